@@ -1,0 +1,166 @@
+/* b2k.h — C ABI of the B200-native online2 hot path (features -> nnet3 -> decoder).
+ *
+ * This is the drop-in boundary: the reference has no FFI, its
+ * boundary is a set of C++ class surfaces; each entry point below names the
+ * reference member function it replaces (file:line under /root/reference/src).
+ * The header-compatible C++ shims in kaldi_b200/host/ forward to these calls;
+ * INTEGRATION.md shows the binding a Kaldi maintainer would add.
+ *
+ * Conventions: every function returns a b2k_status (0 = OK); no exceptions
+ * cross the ABI; handles are opaque; the caller owns every buffer it passes;
+ * pointers named d_* are CUDA device pointers, h_* / unprefixed are host
+ * pointers; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ * There is no CPU fallback: every compute entry point fails with
+ * B2K_ERR_NO_DEVICE when no sm_100 device is present.
+ */
+#ifndef B2K_H_
+#define B2K_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B2K_OK = 0,
+  B2K_ERR_INVALID = 1,      /* bad argument                                   */
+  B2K_ERR_NO_DEVICE = 2,    /* no CUDA device / wrong arch                    */
+  B2K_ERR_CUDA = 3,         /* a CUDA runtime call failed (see b2k_last_error)*/
+  B2K_ERR_OVERFLOW = 4,     /* a decoder arena/queue capacity was exceeded    */
+  B2K_ERR_STATE = 5         /* call sequence error (e.g. advance before init) */
+} b2k_status;
+
+const char *b2k_last_error(void);
+int b2k_version(void);
+/* number of kernels this library has launched since load (bench "gpu_launches") */
+int64_t b2k_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------ decoder */
+
+/* Host-side CSR view of a decoding graph in fst::ConstFst<StdArc> order.
+ * Replaces the argument of CudaFst::CudaFst(const fst::StdFst&, const
+ * TransitionInformation*) (cudadecoder/cuda-fst.h:75-82, cuda-fst.cc:34-198). */
+typedef struct {
+  int32_t num_states;
+  int32_t start;
+  const int32_t *offsets;    /* [num_states+1] arc offsets                    */
+  const int32_t *ilabel;     /* transition-ids, 0 = epsilon                   */
+  const int32_t *olabel;
+  const float *weight;       /* tropical weights (costs)                      */
+  const int32_t *nextstate;
+  const float *final_cost;   /* [num_states], +inf = not final                */
+  const int32_t *tid2pdf;    /* [num_tids] TransitionIdToPdfFast; may be NULL
+                                (then pdf = ilabel - 1)                       */
+  int32_t num_tids;
+} b2k_fst_csr;
+
+typedef struct b2k_fst b2k_fst;
+
+/* CudaFst::CudaFst / Initialize (cuda-fst.cc:34,57-198): builds the device CSR
+ * (emitting arcs and epsilon arcs in separate arrays, tid->pdf pre-applied). */
+int b2k_fst_create(const b2k_fst_csr *csr, b2k_fst **out);
+int b2k_fst_destroy(b2k_fst *fst);
+int32_t b2k_fst_num_states(const b2k_fst *fst);   /* CudaFst::NumStates  cuda-fst.h:81 */
+int32_t b2k_fst_start(const b2k_fst *fst);        /* CudaFst::Start      cuda-fst.h:82 */
+
+/* Decoder options: the union of LatticeFasterDecoderConfig
+ * (decoder/lattice-faster-decoder.h:38-106; the parity semantics) and the
+ * capacity knobs of CudaDecoderConfig (cudadecoder/cuda-decoder.h:58-163). */
+typedef struct {
+  float beam;                 /* --beam            (15)                       */
+  float lattice_beam;         /* --lattice-beam    (8)                        */
+  int32_t max_active;         /* --max-active      (7000)                     */
+  int32_t min_active;         /* --min-active      (200)                      */
+  float beam_delta;           /* --beam-delta      (0.5)                      */
+  int32_t prune_interval;     /* --prune-interval  (25); reserved             */
+  float prune_scale;          /* --prune-scale     (0.1); reserved            */
+  int32_t max_tokens_per_frame; /* per-lane per-frame token capacity (pow2/2) */
+  int32_t max_frames;         /* per-channel frame capacity                   */
+  int64_t max_tokens;         /* per-channel token arena                      */
+  int64_t max_links;          /* per-channel forward-link arena               */
+} b2k_dec_cfg;
+
+void b2k_dec_cfg_default(b2k_dec_cfg *cfg);
+
+typedef struct b2k_dec b2k_dec;
+
+/* CudaDecoder::CudaDecoder(const CudaFst&, const CudaDecoderConfig&, int32
+ * nlanes, int32 nchannels) (cuda-decoder.h:224-225).  The fst is not owned. */
+int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes,
+                   int32_t nchannels, b2k_dec **out);
+int b2k_dec_destroy(b2k_dec *dec);
+
+/* CudaDecoder::InitDecoding(const std::vector<ChannelId>&) (cuda-decoder.h:241;
+ * CPU semantics: LatticeFasterDecoderTpl::InitDecoding lattice-faster-decoder.cc:63-81). */
+int b2k_dec_init_decoding(b2k_dec *dec, const int32_t *channels, int32_t n, void *stream);
+
+/* CudaDecoder::AdvanceDecoding(const std::vector<std::pair<ChannelId,const
+ * BaseFloat*>>&) (cuda-decoder.h:264-265): one frame per listed channel;
+ * d_loglikes[i] points at that frame's [num_pdfs] row (already -log prior,
+ * x acoustic_scale).  CPU semantics: one iteration of AdvanceDecoding's loop,
+ * lattice-faster-decoder.cc:621-627. */
+int b2k_dec_advance_decoding(b2k_dec *dec, const int32_t *channels,
+                             const float *const *d_loglikes, int32_t n, void *stream);
+
+/* Batched multi-frame form (B200-native: one persistent CTA per lane loops
+ * over the frames, no host round trip per frame).  Lane i decodes
+ * num_frames[i] frames whose rows are d_loglikes[i] + f*row_stride. */
+int b2k_dec_advance_decoding_frames(b2k_dec *dec, const int32_t *channels,
+                                    const float *const *d_loglikes,
+                                    const int32_t *num_frames, int32_t row_stride,
+                                    int32_t n, void *stream);
+
+/* CudaDecoder::NumFramesDecoded(ChannelId) (cuda-decoder.h). Synchronizes. */
+int b2k_dec_num_frames_decoded(b2k_dec *dec, int32_t channel, int32_t *out);
+
+/* LatticeFasterDecoderTpl::FinalizeDecoding (lattice-faster-decoder.cc:634-649):
+ * final-cost aware backward pruning of tokens and forward links, on the GPU. */
+int b2k_dec_finalize_decoding(b2k_dec *dec, const int32_t *channels, int32_t n, void *stream);
+
+/* Per-channel counters after a synchronize: [0] status (b2k_status), [1] frames
+ * decoded, [2] tokens in arena, [3] links in arena, [4] emitting arcs examined,
+ * [5] epsilon arcs examined, [6] surviving lattice states, [7] surviving
+ * lattice arcs, [8] number of final states. */
+int b2k_dec_channel_info(b2k_dec *dec, int32_t channel, int64_t info[16]);
+
+/* Raw lattice of a finalized channel — the content of
+ * LatticeFasterDecoderTpl::GetRawLattice (lattice-faster-decoder.cc:114-197) /
+ * CudaDecoder::GetRawLattice (cuda-decoder.h) as flat host arrays.  Lattice
+ * states are surviving tokens; arcs are surviving forward links with
+ * LatticeWeight(graph_cost, acoustic_cost - cost_offset[frame]).
+ * Call once with all pointers NULL to obtain sizes via b2k_dec_channel_info. */
+typedef struct {
+  int64_t num_states, num_arcs, num_finals;
+  int32_t *state_frame;    /* [num_states] frame index (0 = before 1st frame) */
+  int32_t *state_hclg;     /* [num_states] HCLG state of the token            */
+  float *state_tot_cost;   /* [num_states]                                    */
+  float *state_extra_cost; /* [num_states]                                    */
+  int32_t *arc_src;        /* [num_arcs] lattice-state index                  */
+  int32_t *arc_dst;
+  int32_t *arc_ilabel;     /* transition-id (0 for epsilon)                   */
+  int32_t *arc_olabel;
+  float *arc_graph_cost;
+  float *arc_acoustic_cost;
+  int32_t *final_state;    /* [num_finals] lattice-state index                */
+  float *final_cost;       /* [num_finals]                                    */
+} b2k_raw_lattice;
+
+int b2k_dec_get_raw_lattice(b2k_dec *dec, int32_t channel, b2k_raw_lattice *out, void *stream);
+
+/* Debug/parity hook: copies the un-pruned token list of frame `frame_plus_one`
+ * and the links created by that frame step (tests compare these bit-for-bit
+ * against the oracle before any pruning).  links7 rows:
+ * src_state, dst_state, ilabel, olabel, graph bits, acoustic bits, is_eps. */
+int b2k_dec_debug_frame(b2k_dec *dec, int32_t channel, int32_t frame_plus_one,
+                        int32_t *tok_state, float *tok_cost, int64_t *ntok,
+                        int32_t *links7, int64_t *nlink, int64_t cap_tok, int64_t cap_link);
+
+/* Per-frame diagnostics: next_cutoff and cost_offset of frames [0, T). */
+int b2k_dec_frame_info(b2k_dec *dec, int32_t channel, float *cutoff, float *cost_offset,
+                       int32_t *ntoks, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2K_H_ */

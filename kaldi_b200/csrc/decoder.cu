@@ -1,0 +1,1334 @@
+// decoder.cu — B200-native batched WFST lattice decoder (sm_100a).
+//
+// What it computes: the token-passing search of LatticeFasterDecoderTpl
+// (reference decoder/lattice-faster-decoder.cc: InitDecoding :63, GetCutoff
+// :653, ProcessEmitting :723, ProcessNonemitting :830, FinalizeDecoding :634,
+// PruneForwardLinks[Final] :308/:385, GetRawLattice :114) behind the surface of
+// cuda_decoder::CudaDecoder (cudadecoder/cuda-decoder.h:171-346).  It is NOT a
+// port of cudadecoder/cuda-decoder-kernels.cu: that design launches ~25
+// kernels and a blocking D2H per frame and dedups arc-instantiated tokens; this
+// one keeps the CPU decoder's semantics (one token per (frame,state), all
+// admitted links kept, float association (tok + (offset - ll)) + w, per-frame
+// cost_offset) so that finalized lattices are comparable bit-for-bit with the
+// CPU decoder (see oracle/decoder_oracle.cc, mode "order free").
+//
+// Execution model: ONE persistent CTA per lane (utterance).  Utterances are
+// independent, so no grid-wide synchronisation exists anywhere: the CTA loops
+// over all frames of its lane with only __syncthreads() between phases, reads
+// the CSR HCLG and the log-likelihood rows from HBM/L2, and appends tokens and
+// forward links to that channel's arenas in HBM.  Per frame:
+//   1. best/cutoff   block reductions (+ exact radix-select for max/min-active)
+//   2. seed pass     best token's arcs, association of :762-763
+//   3. expand        thread-per-arc over a degree prefix sum (load balanced),
+//                    min-reduction of tot_cost -> FINAL next_cutoff; arcs under
+//                    a running upper bound are staged as candidates
+//   4. admit         candidates with tot < final cutoff: hash insert (CAS),
+//                    atomicMin on the token cost, forward link written (16 B)
+//   5. epsilon       worklist relaxation to the fixpoint, then link generation
+//   6. commit        costs -> arena, link dst slot -> token index, hash cleared
+// Finalisation (backward pruning sweep with final costs) and lattice extraction
+// are separate kernels with the same one-CTA-per-channel shape.
+//
+// Roofline class: HBM (irregular gather/scatter).  Algorithmic bytes per frame
+// (DESIGN.md): 16 B per arc examined + 16 B per source token + 36 B per link
+// admitted + 16 B per token kept.
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2k {
+
+// ------------------------------------------------------------------ data types
+
+struct FstDev {
+  int32_t num_states, start;
+  int32_t num_e, num_ne;
+  const int2 *st_off;       // [N+1] {emitting offset, epsilon offset}
+  const int4 *e_arcs;       // {nextstate, weight bits, pdf, olabel}
+  const int4 *ne_arcs;      // {nextstate, weight bits, olabel, 0}
+  const int32_t *e_ilabel;  // [num_e] transition-id
+  const float *final_cost;  // [N]
+};
+
+struct ChanState {          // per channel, device resident
+  int32_t status;
+  int32_t frames_decoded;   // -1 = InitDecoding not run
+  int32_t ntok, nlink;      // arena fill
+  int32_t finalized;
+  int32_t lat_states, lat_arcs, lat_finals;
+  int32_t any_final;
+  float final_best_cost;
+  unsigned long long arcs_e, arcs_ne;
+};
+
+#define B2K_EPS_FLAG 0x80000000u
+#define B2K_HASH_EMPTY (-1)
+
+struct DecParams {
+  FstDev fst;
+  // config
+  float beam, lattice_beam, beam_delta;
+  int32_t max_active, min_active;
+  int32_t max_tpf;          // tokens per frame capacity
+  int32_t hash_size, hash_log;
+  int32_t cand_cap;
+  int32_t max_frames;
+  int32_t max_tokens, max_links;
+  // channel storage (arrays of [nchannels * capacity])
+  ChanState *chan;
+  int32_t *tok_state;
+  float *tok_cost;
+  float *tok_extra;
+  int4 *links;              // {src tok, dst tok, arc id (bit31 = eps), acoustic bits}
+  int32_t *frame_tok_begin; // [nch * (max_frames+2)]
+  int32_t *frame_link_begin;// [nch * (max_frames+2)]
+  int32_t *frame_link_eps;  // [nch * (max_frames+2)]
+  float *frame_cost_offset; // [nch * (max_frames+1)]
+  float *frame_cutoff;      // [nch * (max_frames+1)]
+  // lane scratch (arrays of [nlanes * capacity])
+  int4 *hash;               // {key state, cost ord, tok idx in frame, stamp}
+  int32_t *tokslot;         // [max_tpf]
+  int32_t *wl;              // [2 * max_tpf]
+  int32_t *cand;            // [5 * cand_cap] src, arc, next, tot bits, ac bits
+  uint32_t *new_extra;      // [max_tpf] (finalize)
+  int32_t *lane_stamp;      // [nlanes]
+  // per launch
+  const int32_t *lane_channel;
+  const float *const *lane_loglikes;
+  const int32_t *lane_nframes;
+  int32_t row_stride;
+  int32_t do_init;
+};
+
+// ------------------------------------------------------------------ block helpers
+
+template <int T>
+__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v,
+                                                            unsigned long long *sh) {
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w < v ? w : v;
+  }
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  unsigned long long r = sh[0];
+#pragma unroll
+  for (int i = 1; i < T / 32; i++) r = sh[i] < r ? sh[i] : r;
+  return r;
+}
+
+template <int T>
+__device__ __forceinline__ uint32_t block_min_u32(uint32_t v, uint32_t *sh) {
+  v = __reduce_min_sync(0xffffffffu, v);
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  uint32_t r = sh[0];
+#pragma unroll
+  for (int i = 1; i < T / 32; i++) r = min(r, sh[i]);
+  return r;
+}
+
+template <int T>
+__device__ __forceinline__ int block_sum_i32(int v, int *sh) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  int r = 0;
+#pragma unroll
+  for (int i = 0; i < T / 32; i++) r += sh[i];
+  return r;
+}
+
+// exclusive scan of one int per thread; returns exclusive prefix, *total = sum
+template <int T>
+__device__ __forceinline__ int block_excl_scan(int v, int *sh /*[T/32+1]*/, int *total) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  __syncthreads();
+  if (lane == 31) sh[warp] = incl;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < T / 32; i++) {
+    int s = sh[i];
+    if (i < warp) base += s;
+    tot += s;
+  }
+  *total = tot;
+  return base + incl - v;
+}
+
+// exact k-th smallest (0-indexed) of n float costs: 4-pass 8-bit radix select
+template <int T>
+__device__ float block_select_kth(const float *vals, int n, int k, uint32_t *hist /*[256]*/,
+                                  uint32_t *sh_pref /*[2]*/) {
+  uint32_t prefix = 0, mask = 0;
+  int krem = k;
+  for (int pass = 3; pass >= 0; pass--) {
+    int shift = pass * 8;
+    for (int i = threadIdx.x; i < 256; i += T) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += T) {
+      uint32_t key = f2ord(vals[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int cum = 0, b = 0;
+      for (; b < 256; b++) {
+        int c = (int)hist[b];
+        if (cum + c > krem) break;
+        cum += c;
+      }
+      if (b > 255) b = 255;
+      sh_pref[0] = (uint32_t)b;
+      sh_pref[1] = (uint32_t)(krem - cum);
+    }
+    __syncthreads();
+    prefix |= sh_pref[0] << shift;
+    mask |= 255u << shift;
+    krem = (int)sh_pref[1];
+    __syncthreads();
+  }
+  return ord2f(prefix);
+}
+
+// ------------------------------------------------------------------ hash
+
+struct LaneCtx {
+  int4 *hash;
+  int32_t *tokslot;
+  int32_t *tok_state;   // channel arena
+  int32_t tbase;
+  int32_t hash_mask, hash_log, max_tpf, max_tokens;
+  int *ntok_new;        // shared
+  int *err;             // shared
+};
+
+__device__ __forceinline__ uint32_t hash_fn(int32_t state, int hash_log) {
+  return ((uint32_t)state * 2654435761u) >> (32 - hash_log);
+}
+
+// find-or-insert; returns slot (or -1 after an overflow was flagged)
+__device__ __forceinline__ int hash_insert(const LaneCtx &c, int32_t state) {
+  uint32_t h = hash_fn(state, c.hash_log);
+  for (int probe = 0; probe <= c.hash_mask; probe++) {
+    int *keyp = reinterpret_cast<int *>(&c.hash[h]);
+    int old = atomicCAS(keyp, B2K_HASH_EMPTY, state);
+    if (old == B2K_HASH_EMPTY) {
+      int idx = atomicAdd(c.ntok_new, 1);
+      if (idx < c.max_tpf && c.tbase + idx < c.max_tokens) {
+        c.tok_state[c.tbase + idx] = state;
+        c.tokslot[idx] = (int)h;
+        keyp[2] = idx;
+      } else {
+        atomicExch(c.err, B2K_ERR_OVERFLOW);
+      }
+      return (int)h;
+    }
+    if (old == state) return (int)h;
+    h = (h + 1) & (uint32_t)c.hash_mask;
+  }
+  atomicExch(c.err, B2K_ERR_OVERFLOW);
+  return -1;
+}
+
+__device__ __forceinline__ int hash_find(const LaneCtx &c, int32_t state) {
+  uint32_t h = hash_fn(state, c.hash_log);
+  for (int probe = 0; probe <= c.hash_mask; probe++) {
+    int key = *reinterpret_cast<volatile int *>(&c.hash[h]);
+    if (key == state) return (int)h;
+    if (key == B2K_HASH_EMPTY) return -1;
+    h = (h + 1) & (uint32_t)c.hash_mask;
+  }
+  return -1;
+}
+
+template <int T>
+__device__ void reset_lane_hash(int4 *hash, int hash_size) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < hash_size; i += T) {
+    hash[i].x = B2K_HASH_EMPTY;
+    hash[i].y = (int)B2K_INF_ORD;
+  }
+}
+
+// ------------------------------------------------------------------ the frame kernel
+
+template <int T>
+struct __align__(16) DecShared {
+  unsigned long long red64[T / 32];
+  uint32_t red32[T / 32];
+  int redi[T / 32 + 1];
+  uint32_t hist[256];
+  uint32_t pref[2];
+  int chunk_off[T + 1];
+  int chunk_ebeg[T];
+  float chunk_cost[T];
+  int ntok_new, nlink_new, ncand, err;
+  int wl_n[2];
+  uint32_t running_ord;
+  int stamp;
+  int cont;
+};
+
+// epsilon closure + link generation + commit of the frame being built.
+// On entry: the emitting phase (or init) has inserted tokens into the hash.
+template <int T>
+__device__ void finish_frame(const DecParams &p, DecShared<T> &s, const LaneCtx &ctx, int lane,
+                             int ch, int list_index, float cutoff, float cost_offset,
+                             int32_t lbase, unsigned long long *arcs_ne_acc) {
+  const int tid = threadIdx.x;
+  const FstDev &g = p.fst;
+  int4 *hash = ctx.hash;
+  int32_t *wl0 = p.wl + (size_t)lane * 2 * p.max_tpf;
+  int32_t *wl1 = wl0 + p.max_tpf;
+  int4 *links = p.links + (size_t)ch * p.max_links;
+  float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
+
+  __syncthreads();
+  const int n_emit_links = s.nlink_new;
+  const int N1 = min(s.ntok_new, p.max_tpf);
+  // initial worklist = every token created so far (eps-degree checked at pop)
+  for (int i = tid; i < N1; i += T) wl0[i] = ctx.tokslot[i];
+  if (tid == 0) { s.wl_n[0] = N1; s.wl_n[1] = 0; s.cont = (N1 > 0 && !s.err); }
+  __syncthreads();
+  int cur = 0;
+  unsigned long long ne_count = 0;
+  while (s.cont) {
+    const int n = s.wl_n[cur];
+    const int stamp = s.stamp + 1;
+    int32_t *in = cur ? wl1 : wl0;
+    int32_t *out = cur ? wl0 : wl1;
+    for (int k = tid; k < n; k += T) {
+      int slot = in[k];
+      int4 *sp = &hash[slot];
+      int state = *reinterpret_cast<volatile int *>(&sp->x);
+      float c = ord2f(*reinterpret_cast<volatile uint32_t *>(&sp->y));
+      if (!(c < cutoff)) continue;
+      int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
+      ne_count += (unsigned long long)(o1.y - o0.y);
+      for (int a = o0.y; a < o1.y; a++) {
+        int4 arc = __ldg(&g.ne_arcs[a]);
+        float tot = c + __int_as_float(arc.y);
+        if (tot < cutoff) {
+          int ds = hash_insert(ctx, arc.x);
+          if (ds < 0) break;
+          uint32_t nv = f2ord(tot);
+          uint32_t old = atomicMin(reinterpret_cast<uint32_t *>(&hash[ds].y), nv);
+          if (nv < old) {
+            if (atomicExch(&hash[ds].w, stamp) != stamp) {
+              int q = atomicAdd(&s.wl_n[cur ^ 1], 1);
+              if (q < p.max_tpf) out[q] = ds;
+              else atomicExch(&s.err, B2K_ERR_OVERFLOW);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      s.wl_n[cur] = 0;
+      s.stamp = stamp;
+      s.cont = (min(s.wl_n[cur ^ 1], p.max_tpf) > 0 && !s.err);
+      if (s.wl_n[cur ^ 1] > p.max_tpf) s.wl_n[cur ^ 1] = p.max_tpf;
+    }
+    cur ^= 1;
+    __syncthreads();
+  }
+  __syncthreads();
+  // epsilon links: {tok, eps arc} with final cost + w < cutoff
+  const int Nall = min(s.ntok_new, p.max_tpf);
+  const int32_t *tok_state = ctx.tok_state;
+  for (int i = tid; i < Nall; i += T) {
+    int slot = ctx.tokslot[i];
+    float c = ord2f((uint32_t)hash[slot].y);
+    if (!(c < cutoff)) continue;
+    int state = tok_state[ctx.tbase + i];
+    int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
+    for (int a = o0.y; a < o1.y; a++) {
+      int4 arc = __ldg(&g.ne_arcs[a]);
+      float tot = c + __int_as_float(arc.y);
+      if (tot < cutoff) {
+        int ds = hash_find(ctx, arc.x);
+        int li = atomicAdd(&s.nlink_new, 1);
+        if (lbase + li < p.max_links && ds >= 0)
+          links[lbase + li] = make_int4(ctx.tbase + i, ds, (int)((uint32_t)a | B2K_EPS_FLAG), 0);
+        else
+          atomicExch(&s.err, B2K_ERR_OVERFLOW);
+      }
+    }
+  }
+  __syncthreads();
+  // commit: costs to arena, link dst slot -> arena token index
+  const int nlink = s.nlink_new;
+  for (int i = tid; i < Nall; i += T) {
+    int slot = ctx.tokslot[i];
+    tok_cost[ctx.tbase + i] = ord2f((uint32_t)hash[slot].y);
+  }
+  if (!s.err) {
+    for (int li = tid; li < nlink; li += T) {
+      int4 *lp = &links[lbase + li];
+      int slot = lp->y;
+      lp->y = ctx.tbase + hash[slot].z;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < Nall; i += T) {
+    int slot = ctx.tokslot[i];
+    hash[slot].x = B2K_HASH_EMPTY;
+    hash[slot].y = (int)B2K_INF_ORD;
+  }
+  if (tid == 0) {
+    size_t fo = (size_t)ch * (p.max_frames + 2);
+    p.frame_tok_begin[fo + list_index] = ctx.tbase;
+    p.frame_tok_begin[fo + list_index + 1] = ctx.tbase + Nall;
+    p.frame_link_begin[fo + list_index] = lbase;
+    p.frame_link_eps[fo + list_index] = lbase + n_emit_links;
+    p.frame_link_begin[fo + list_index + 1] = lbase + nlink;
+    if (list_index > 0) {
+      size_t co = (size_t)ch * (p.max_frames + 1) + (list_index - 1);
+      p.frame_cost_offset[co] = cost_offset;
+      p.frame_cutoff[co] = cutoff;
+    }
+  }
+  // warp-reduce eps arc counter into the caller's accumulator (thread 0 adds)
+  for (int o = 16; o > 0; o >>= 1) ne_count += __shfl_xor_sync(0xffffffffu, ne_count, o);
+  if ((tid & 31) == 0 && ne_count) atomicAdd(arcs_ne_acc, ne_count);
+  __syncthreads();
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
+  __shared__ DecShared<T> s;
+  const int tid = threadIdx.x;
+  const int lane = blockIdx.x;
+  const int ch = p.lane_channel[lane];
+  ChanState *cs = &p.chan[ch];
+  const FstDev &g = p.fst;
+  const float kInf = __int_as_float(0x7f800000);
+
+  if (cs->status != B2K_OK) return;
+  if (!p.do_init && cs->frames_decoded < 0) {
+    if (tid == 0) cs->status = B2K_ERR_STATE;
+    return;
+  }
+
+  int32_t *tok_state = p.tok_state + (size_t)ch * p.max_tokens;
+  float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
+  int4 *links = p.links + (size_t)ch * p.max_links;
+  int32_t *cand = p.cand + (size_t)lane * 5 * p.cand_cap;
+  int32_t *c_src = cand, *c_arc = cand + p.cand_cap, *c_next = cand + 2 * (size_t)p.cand_cap,
+          *c_tot = cand + 3 * (size_t)p.cand_cap, *c_ac = cand + 4 * (size_t)p.cand_cap;
+
+  LaneCtx ctx;
+  ctx.hash = p.hash + (size_t)lane * p.hash_size;
+  ctx.tokslot = p.tokslot + (size_t)lane * p.max_tpf;
+  ctx.tok_state = tok_state;
+  ctx.hash_mask = p.hash_size - 1;
+  ctx.hash_log = p.hash_log;
+  ctx.max_tpf = p.max_tpf;
+  ctx.max_tokens = p.max_tokens;
+  ctx.ntok_new = &s.ntok_new;
+  ctx.err = &s.err;
+
+  if (tid == 0) { s.err = 0; s.stamp = p.lane_stamp[lane]; }
+  __syncthreads();
+
+  if (p.do_init) {
+    // InitDecoding: start token, cost 0, then ProcessNonemitting(config.beam)
+    if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; }
+    __syncthreads();
+    ctx.tbase = 0;
+    if (tid == 0) {
+      int slot = hash_insert(ctx, g.start);
+      if (slot >= 0) atomicMin(reinterpret_cast<uint32_t *>(&ctx.hash[slot].y), f2ord(0.0f));
+    }
+    finish_frame<T>(p, s, ctx, lane, ch, 0, p.beam, 0.0f, 0, &cs->arcs_ne);
+    if (tid == 0) {
+      cs->frames_decoded = 0;
+      cs->ntok = min(s.ntok_new, p.max_tpf);
+      cs->nlink = s.nlink_new;
+      cs->finalized = 0;
+      if (s.err) cs->status = s.err;
+      p.lane_stamp[lane] = s.stamp;
+    }
+    if (s.err) reset_lane_hash<T>(ctx.hash, p.hash_size);
+    return;
+  }
+
+  const int nframes = p.lane_nframes[lane];
+  const float *ll_base = p.lane_loglikes[lane];
+  int frames_decoded = cs->frames_decoded;
+  int32_t tbase = cs->ntok, lbase = cs->nlink;
+  unsigned long long arcs_e_total = 0;   // thread 0 accumulates per-chunk totals
+  const size_t fo = (size_t)ch * (p.max_frames + 2);
+
+  for (int fi = 0; fi < nframes; fi++) {
+    if (frames_decoded >= p.max_frames) { if (tid == 0) s.err = B2K_ERR_OVERFLOW; __syncthreads(); break; }
+    const float *ll = ll_base + (size_t)fi * p.row_stride;
+    const int pb = p.frame_tok_begin[fo + frames_decoded];
+    const int pe = p.frame_tok_begin[fo + frames_decoded + 1];
+    const int K = pe - pb;
+
+    // ---- 1. best token and cutoff (GetCutoff :653-720)
+    unsigned long long local = ~0ull;
+    for (int i = pb + tid; i < pe; i += T) {
+      unsigned long long key = ((unsigned long long)f2ord(tok_cost[i]) << 32) | (uint32_t)tok_state[i];
+      local = key < local ? key : local;
+    }
+    unsigned long long bestkey = block_min_u64<T>(local, s.red64);
+    float best_cost = kInf;
+    int best_state = -1;
+    if (K > 0) { best_cost = ord2f((uint32_t)(bestkey >> 32)); best_state = (int)(uint32_t)(bestkey & 0xffffffffu); }
+    const float beam_cutoff = best_cost + p.beam;
+    float cur_cutoff = beam_cutoff, adaptive_beam = p.beam;
+    if (K > 0 && !(p.max_active == 0x7fffffff && p.min_active == 0)) {
+      int c_lt = 0, c_le = 0;
+      for (int i = pb + tid; i < pe; i += T) {
+        float c = tok_cost[i];
+        c_lt += (c < beam_cutoff);
+        c_le += (c <= beam_cutoff);
+      }
+      c_lt = block_sum_i32<T>(c_lt, s.redi);
+      c_le = block_sum_i32<T>(c_le, s.redi);
+      bool done = false;
+      if (K > p.max_active && c_lt > p.max_active) {
+        // max_active_cutoff < beam_cutoff  (:689-699)
+        float mac = block_select_kth<T>(tok_cost + pb, K, p.max_active, s.hist, s.pref);
+        cur_cutoff = mac;
+        adaptive_beam = mac - best_cost + p.beam_delta;
+        done = true;
+      }
+      if (!done) {
+        float min_active_cutoff = kInf;
+        if (K > p.min_active) {
+          if (p.min_active == 0) min_active_cutoff = best_cost;
+          else if (c_le <= p.min_active)
+            min_active_cutoff = block_select_kth<T>(tok_cost + pb, K, p.min_active, s.hist, s.pref);
+          else min_active_cutoff = beam_cutoff;  // known to be <= beam_cutoff
+        }
+        if (min_active_cutoff > beam_cutoff) {   // :711-714
+          adaptive_beam = min_active_cutoff - best_cost + p.beam_delta;
+          cur_cutoff = min_active_cutoff;
+        }
+      }
+    }
+    const float cost_offset = (K > 0) ? -best_cost : 0.0f;
+
+    // ---- 2. seed next_cutoff from the best token (:753-768)
+    uint32_t seed_local = B2K_INF_ORD;
+    if (K > 0) {
+      int2 o0 = __ldg(&g.st_off[best_state]), o1 = __ldg(&g.st_off[best_state + 1]);
+      for (int a = o0.x + tid; a < o1.x; a += T) {
+        int4 arc = __ldg(&g.e_arcs[a]);
+        float new_weight = __int_as_float(arc.y) + cost_offset - __ldg(&ll[arc.z]) + best_cost;
+        seed_local = min(seed_local, f2ord(new_weight + adaptive_beam));
+      }
+    }
+    const float seed_cutoff = ord2f(block_min_u32<T>(seed_local, s.red32));
+
+    // ---- 3. expand (ProcessEmitting main loop :779-812), pass A
+    if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; s.ncand = 0; s.running_ord = B2K_INF_ORD; }
+    __syncthreads();
+    for (int cb = pb; cb < pe; cb += T) {
+      int i = cb + tid;
+      int deg = 0, ebeg = 0;
+      float c = 0.f;
+      if (i < pe) {
+        c = tok_cost[i];
+        if (c <= cur_cutoff) {
+          int st = tok_state[i];
+          int2 o0 = __ldg(&g.st_off[st]), o1 = __ldg(&g.st_off[st + 1]);
+          ebeg = o0.x;
+          deg = o1.x - o0.x;
+        }
+      }
+      int total;
+      int off = block_excl_scan<T>(deg, s.redi, &total);
+      s.chunk_off[tid] = off;
+      s.chunk_ebeg[tid] = ebeg;
+      s.chunk_cost[tid] = c;
+      if (tid == 0) { s.chunk_off[T] = total; arcs_e_total += (unsigned long long)total; }
+      __syncthreads();
+      const int rounds = (total + T - 1) / T;
+      for (int r = 0; r < rounds; r++) {
+        int j = r * T + tid;
+        bool active = j < total;
+        float tot = kInf, ac = 0.f;
+        int src = 0, a = 0, nexts = 0;
+        if (active) {
+          // largest t with chunk_off[t] <= j
+          int lo = 0, hi = T;
+          while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (s.chunk_off[mid] <= j) lo = mid; else hi = mid;
+          }
+          a = s.chunk_ebeg[lo] + (j - s.chunk_off[lo]);
+          src = cb + lo;
+          int4 arc = __ldg(&g.e_arcs[a]);
+          ac = cost_offset - __ldg(&ll[arc.z]);
+          tot = s.chunk_cost[lo] + ac + __int_as_float(arc.y);
+          nexts = arc.x;
+        }
+        uint32_t wmin = __reduce_min_sync(0xffffffffu, f2ord(tot));
+        uint32_t run = *reinterpret_cast<volatile uint32_t *>(&s.running_ord);
+        if (wmin < run) {
+          if ((tid & 31) == 0) atomicMin(&s.running_ord, wmin);
+          run = wmin;
+        }
+        float bound = fminf(seed_cutoff, ord2f(run) + adaptive_beam);
+        bool is_cand = active && (tot < bound);
+        uint32_t m = __ballot_sync(0xffffffffu, is_cand);
+        if (m) {
+          int lane_id = tid & 31;
+          int base = 0;
+          if (lane_id == 0) base = atomicAdd(&s.ncand, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (is_cand) {
+            int idx = base + __popc(m & ((1u << lane_id) - 1u));
+            if (idx < p.cand_cap) {
+              c_src[idx] = src; c_arc[idx] = a; c_next[idx] = nexts;
+              c_tot[idx] = __float_as_int(tot); c_ac[idx] = __float_as_int(ac);
+            } else {
+              atomicExch(&s.err, B2K_ERR_OVERFLOW);
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // FINAL next_cutoff = min(seed, min_tot + adaptive_beam)
+    const float min_tot = ord2f(s.running_ord);
+    const float next_cutoff = fminf(seed_cutoff, min_tot + adaptive_beam);
+    const int ncand = min(s.ncand, p.cand_cap);
+
+    // ---- 4. admit candidates (FindOrAddToken :261-302 + ForwardLink :804-806)
+    ctx.tbase = tbase;
+    for (int base_i = 0; base_i < ncand; base_i += T) {
+      int idx = base_i + tid;
+      bool adm = false;
+      float tot = 0.f;
+      if (idx < ncand) { tot = __int_as_float(c_tot[idx]); adm = tot < next_cutoff; }
+      int slot = -1;
+      if (adm) {
+        slot = hash_insert(ctx, c_next[idx]);
+        if (slot >= 0) atomicMin(reinterpret_cast<uint32_t *>(&ctx.hash[slot].y), f2ord(tot));
+        else adm = false;
+      }
+      uint32_t m = __ballot_sync(0xffffffffu, adm);
+      if (m) {
+        int lane_id = tid & 31;
+        int lb = 0;
+        if (lane_id == 0) lb = atomicAdd(&s.nlink_new, __popc(m));
+        lb = __shfl_sync(0xffffffffu, lb, 0);
+        if (adm) {
+          int li = lb + __popc(m & ((1u << lane_id) - 1u));
+          if (lbase + li < p.max_links)
+            links[lbase + li] = make_int4(c_src[idx], slot, c_arc[idx], c_ac[idx]);
+          else
+            atomicExch(&s.err, B2K_ERR_OVERFLOW);
+        }
+      }
+    }
+    // ---- 5/6. epsilon closure, eps links, commit
+    finish_frame<T>(p, s, ctx, lane, ch, frames_decoded + 1, next_cutoff, cost_offset, lbase,
+                    &cs->arcs_ne);
+    if (s.err) break;
+    tbase += min(s.ntok_new, p.max_tpf);
+    lbase += s.nlink_new;
+    frames_decoded++;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    cs->frames_decoded = frames_decoded;
+    cs->ntok = tbase;
+    cs->nlink = lbase;
+    cs->arcs_e += arcs_e_total;
+    if (s.err) cs->status = s.err;
+    p.lane_stamp[lane] = s.stamp;
+  }
+  // an overflow can leave uncommitted tokens in the lane's hash: wipe it so the
+  // lane is clean for the next channel it serves
+  if (s.err) reset_lane_hash<T>(ctx.hash, p.hash_size);
+}
+
+// ------------------------------------------------------------------ finalize (backward sweep)
+
+// link_extra_cost of :342-344 / :433-435
+__device__ __forceinline__ float link_extra_cost(float next_extra, float tok_tot, float ac,
+                                                 float graph, float next_tot) {
+  return next_extra + ((tok_tot + ac + graph) - next_tot);
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
+  __shared__ uint32_t red32[T / 32];
+  __shared__ int redi[T / 32];
+  __shared__ int sh_changed;
+  const int tid = threadIdx.x;
+  const int lane = blockIdx.x;
+  const int ch = p.lane_channel[lane];
+  ChanState *cs = &p.chan[ch];
+  const FstDev &g = p.fst;
+  const float kInf = __int_as_float(0x7f800000);
+  if (cs->status != B2K_OK || cs->frames_decoded < 0 || cs->finalized) return;
+
+  const int32_t *tok_state = p.tok_state + (size_t)ch * p.max_tokens;
+  const float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
+  float *tok_extra = p.tok_extra + (size_t)ch * p.max_tokens;
+  int4 *links = p.links + (size_t)ch * p.max_links;
+  uint32_t *nx = p.new_extra + (size_t)lane * p.max_tpf;
+  const size_t fo = (size_t)ch * (p.max_frames + 2);
+  const int last = cs->frames_decoded;
+
+  // ComputeFinalCosts (:545-586) over the last token list
+  const int lb0 = p.frame_tok_begin[fo + last], le0 = p.frame_tok_begin[fo + last + 1];
+  uint32_t bc = B2K_INF_ORD, bcf = B2K_INF_ORD;
+  int anyf = 0;
+  for (int i = lb0 + tid; i < le0; i += T) {
+    float fc = __ldg(&g.final_cost[tok_state[i]]);
+    float c = tok_cost[i];
+    bc = min(bc, f2ord(c));
+    bcf = min(bcf, f2ord(c + fc));
+    anyf |= (fc != kInf);
+  }
+  const float best_cost = ord2f(block_min_u32<T>(bc, red32));
+  const float best_cost_with_final = ord2f(block_min_u32<T>(bcf, red32));
+  const int any_final = block_sum_i32<T>(anyf, redi) > 0;
+  const float final_best_cost = (best_cost_with_final != kInf) ? best_cost_with_final : best_cost;
+
+  int lat_states = 0, lat_arcs = 0, lat_finals = 0;   // per-thread partial counts
+
+  for (int t = last; t >= 0; t--) {
+    const int tb = p.frame_tok_begin[fo + t], te = p.frame_tok_begin[fo + t + 1];
+    const int n = te - tb;
+    const int eps_b = p.frame_link_eps[fo + t], eps_e = p.frame_link_begin[fo + t + 1];
+    // base value per token: final-cost term on the last list (:426), else
+    // +inf (:337) lowered by the emitting links into list t+1
+    for (int i = tid; i < n; i += T) {
+      float base = kInf;
+      if (t == last) {
+        float fc = any_final ? __ldg(&g.final_cost[tok_state[tb + i]]) : 0.0f;
+        base = tok_cost[tb + i] + fc - final_best_cost;
+      }
+      nx[i] = f2ord(base);
+      tok_extra[tb + i] = 0.0f;        // lower bound to start the eps iteration from
+    }
+    __syncthreads();
+    int emit_alive = 0;
+    if (t < last) {
+      const int em_b = p.frame_link_begin[fo + t + 1], em_e = p.frame_link_eps[fo + t + 1];
+      for (int l = em_b + tid; l < em_e; l += T) {
+        int4 lk = links[l];
+        float graph = __int_as_float(__ldg(&g.e_arcs[lk.z]).y);
+        float lec = link_extra_cost(tok_extra[lk.y], tok_cost[lk.x], __int_as_float(lk.w), graph,
+                                    tok_cost[lk.y]);
+        if (lec > p.lattice_beam) {
+          links[l].x = -1;                     // excised (:348-354)
+        } else {
+          if (lec < 0.0f) lec = 0.0f;
+          atomicMin(&nx[lk.x - tb], f2ord(lec));
+          emit_alive++;
+        }
+      }
+    }
+    __syncthreads();
+    // nx now holds the base value of every token (final-cost term or the min
+    // over emitting links).  Iterate the epsilon links of list t to the
+    // fixpoint (Jacobi; unique because eps links form a DAG): old values live
+    // in tok_extra (start at the lower bound 0), new values are built in nx,
+    // the base is kept in a side buffer carved from the idle worklist scratch.
+    uint32_t *base_ord = reinterpret_cast<uint32_t *>(p.wl + (size_t)lane * 2 * p.max_tpf);
+    for (int i = tid; i < n; i += T) base_ord[i] = nx[i];
+    __syncthreads();
+    for (int iter = 0; iter < 100000; iter++) {
+      if (tid == 0) sh_changed = 0;
+      // new = base lowered by alive eps links using OLD extras of dst
+      for (int l = eps_b + tid; l < eps_e; l += T) {
+        int4 lk = links[l];
+        if (lk.x < 0) continue;
+        float graph = __int_as_float(__ldg(&g.ne_arcs[(uint32_t)lk.z & 0x7fffffffu]).y);
+        float lec = link_extra_cost(tok_extra[lk.y], tok_cost[lk.x], 0.0f, graph, tok_cost[lk.y]);
+        if (lec > p.lattice_beam) {
+          links[l].x = -1;
+        } else {
+          if (lec < 0.0f) lec = 0.0f;
+          atomicMin(&nx[lk.x - tb], f2ord(lec));
+        }
+      }
+      __syncthreads();
+      int changed = 0;
+      for (int i = tid; i < n; i += T) {
+        float v = ord2f(nx[i]);
+        if (t == last && v > p.lattice_beam) v = kInf;      // :458-459
+        float old = tok_extra[tb + i];
+        if (!(v == old)) changed = 1;
+        tok_extra[tb + i] = v;
+        nx[i] = base_ord[i];
+      }
+      if (changed) sh_changed = 1;
+      __syncthreads();
+      int ch_any = sh_changed;
+      __syncthreads();
+      if (!ch_any) break;
+    }
+    // counts
+    for (int i = tid; i < n; i += T) {
+      if (tok_extra[tb + i] != kInf) {
+        lat_states++;
+        if (t == last) {
+          if (!any_final) lat_finals++;
+          else if (__ldg(&g.final_cost[tok_state[tb + i]]) != kInf) lat_finals++;
+        }
+      }
+    }
+    for (int l = eps_b + tid; l < eps_e; l += T) if (links[l].x >= 0) lat_arcs++;
+    lat_arcs += emit_alive;
+    __syncthreads();
+  }
+  lat_states = block_sum_i32<T>(lat_states, redi);
+  lat_arcs = block_sum_i32<T>(lat_arcs, redi);
+  lat_finals = block_sum_i32<T>(lat_finals, redi);
+  if (tid == 0) {
+    cs->finalized = 1;
+    cs->lat_states = lat_states;
+    cs->lat_arcs = lat_arcs;
+    cs->lat_finals = lat_finals;
+    cs->any_final = any_final;
+    cs->final_best_cost = final_best_cost;
+  }
+}
+
+// ------------------------------------------------------------------ extraction
+
+struct ExtractOut {
+  int32_t *state_tok;      // arena index (host maps to dense ids)
+  int32_t *state_frame, *state_hclg;
+  float *state_tot, *state_extra;
+  int32_t *arc_src_tok, *arc_dst_tok, *arc_ilabel, *arc_olabel;
+  float *arc_graph, *arc_ac;
+  int32_t *final_tok;
+  float *final_cost;
+  int32_t *counters;       // [3]
+};
+
+template <int T>
+__global__ void __launch_bounds__(T) dec_extract_kernel(DecParams p, int ch, ExtractOut o) {
+  const FstDev &g = p.fst;
+  const ChanState *cs = &p.chan[ch];
+  const float kInf = __int_as_float(0x7f800000);
+  const int32_t *tok_state = p.tok_state + (size_t)ch * p.max_tokens;
+  const float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
+  const float *tok_extra = p.tok_extra + (size_t)ch * p.max_tokens;
+  const int4 *links = p.links + (size_t)ch * p.max_links;
+  const size_t fo = (size_t)ch * (p.max_frames + 2);
+  const float *cost_off = p.frame_cost_offset + (size_t)ch * (p.max_frames + 1);
+  const int last = cs->frames_decoded;
+  const int gtid = blockIdx.x * T + threadIdx.x, gstride = gridDim.x * T;
+  const int32_t *ftb = p.frame_tok_begin + fo;
+  // tokens
+  for (int i = gtid; i < cs->ntok; i += gstride) {
+    float ex = tok_extra[i];
+    if (ex == kInf) continue;
+    int lo = 0, hi = last + 1;           // frame f with ftb[f] <= i < ftb[f+1]
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ftb[mid] <= i) lo = mid; else hi = mid; }
+    int k = atomicAdd(&o.counters[0], 1);
+    o.state_tok[k] = i; o.state_frame[k] = lo; o.state_hclg[k] = tok_state[i];
+    o.state_tot[k] = tok_cost[i]; o.state_extra[k] = ex;
+    if (lo == last) {
+      float fc = __ldg(&g.final_cost[tok_state[i]]);
+      if (!cs->any_final) { int q = atomicAdd(&o.counters[2], 1); o.final_tok[q] = i; o.final_cost[q] = 0.0f; }
+      else if (fc != kInf) { int q = atomicAdd(&o.counters[2], 1); o.final_tok[q] = i; o.final_cost[q] = fc; }
+    }
+  }
+  // links
+  for (int l = gtid; l < cs->nlink; l += gstride) {
+    int4 lk = links[l];
+    if (lk.x < 0) continue;
+    int k = atomicAdd(&o.counters[1], 1);
+    o.arc_src_tok[k] = lk.x; o.arc_dst_tok[k] = lk.y;
+    if ((uint32_t)lk.z & B2K_EPS_FLAG) {
+      int4 arc = __ldg(&g.ne_arcs[(uint32_t)lk.z & 0x7fffffffu]);
+      o.arc_ilabel[k] = 0; o.arc_olabel[k] = arc.z;
+      o.arc_graph[k] = __int_as_float(arc.y); o.arc_ac[k] = 0.0f;    // (:174-181, offset only if emitting)
+    } else {
+      int4 arc = __ldg(&g.e_arcs[lk.z]);
+      // frame of the source token -> cost_offsets_[f]
+      int lo = 0, hi = last + 1;
+      while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ftb[mid] <= lk.x) lo = mid; else hi = mid; }
+      o.arc_ilabel[k] = __ldg(&g.e_ilabel[lk.z]); o.arc_olabel[k] = arc.w;
+      o.arc_graph[k] = __int_as_float(arc.y);
+      o.arc_ac[k] = __int_as_float(lk.w) - cost_off[lo];
+    }
+  }
+}
+
+}  // namespace b2k
+
+// ====================================================================== host side
+
+using namespace b2k;
+
+struct b2k_fst {
+  FstDev dev;
+  int2 *d_st_off = nullptr;
+  int4 *d_e = nullptr, *d_ne = nullptr;
+  int32_t *d_eil = nullptr;
+  float *d_final = nullptr;
+  // host copies for debug/extraction
+  std::vector<int4> h_e, h_ne;
+  std::vector<int32_t> h_eil;
+  int32_t num_pdfs_seen = 0;
+};
+
+struct b2k_dec {
+  const b2k_fst *fst;
+  b2k_dec_cfg cfg;
+  int nlanes, nchannels;
+  DecParams p;
+  // launch-argument staging
+  int32_t *d_lane_channel = nullptr;
+  const float **d_lane_ll = nullptr;
+  int32_t *d_lane_nframes = nullptr;
+  int32_t *h_lane_channel = nullptr;    // pinned
+  const float **h_lane_ll = nullptr;
+  int32_t *h_lane_nframes = nullptr;
+  cudaEvent_t staging_free = nullptr;
+  std::vector<void *> allocs;
+};
+
+namespace b2k {
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launch_count{0};
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_error(B2K_ERR_NO_DEVICE, "no CUDA device: the b2k library has no CPU path",
+                     e != cudaSuccess ? cudaGetErrorString(e) : nullptr);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10)
+    return set_error(B2K_ERR_NO_DEVICE, "b2k kernels are built for sm_100a only");
+  return B2K_OK;
+}
+}  // namespace b2k
+
+extern "C" {
+
+const char *b2k_last_error(void) { return g_last_error.c_str(); }
+int b2k_version(void) { return 100; }
+int64_t b2k_kernel_launch_count(void) { return g_launch_count.load(); }
+
+void b2k_dec_cfg_default(b2k_dec_cfg *c) {
+  c->beam = 15.0f; c->lattice_beam = 8.0f; c->max_active = 7000; c->min_active = 200;
+  c->beam_delta = 0.5f; c->prune_interval = 25; c->prune_scale = 0.1f;
+  c->max_tokens_per_frame = 32768; c->max_frames = 1024;
+  c->max_tokens = 3000000; c->max_links = 6000000;
+}
+
+int b2k_fst_create(const b2k_fst_csr *csr, b2k_fst **out) {
+  if (!csr || !out || csr->num_states <= 0) return set_error(B2K_ERR_INVALID, "b2k_fst_create: bad args");
+  int rc = require_device();
+  if (rc) return rc;
+  const int N = csr->num_states;
+  b2k_fst *f = new b2k_fst();
+  std::vector<int2> st_off(N + 1);
+  int ne_cnt = 0, e_cnt = 0;
+  for (int s = 0; s < N; s++) {
+    st_off[s] = make_int2(e_cnt, ne_cnt);
+    for (int a = csr->offsets[s]; a < csr->offsets[s + 1]; a++) {
+      if (csr->ilabel[a] == 0) ne_cnt++; else e_cnt++;
+    }
+  }
+  st_off[N] = make_int2(e_cnt, ne_cnt);
+  f->h_e.resize(e_cnt); f->h_ne.resize(ne_cnt); f->h_eil.resize(e_cnt);
+  int ei = 0, ni = 0;
+  for (int s = 0; s < N; s++) {
+    for (int a = csr->offsets[s]; a < csr->offsets[s + 1]; a++) {
+      int wbits; memcpy(&wbits, &csr->weight[a], 4);
+      int il = csr->ilabel[a];
+      if (il == 0) {
+        f->h_ne[ni++] = make_int4(csr->nextstate[a], wbits, csr->olabel[a], 0);
+      } else {
+        if (csr->tid2pdf && (il < 0 || il >= csr->num_tids)) { delete f; return set_error(B2K_ERR_INVALID, "ilabel out of tid2pdf range"); }
+        int pdf = csr->tid2pdf ? csr->tid2pdf[il] : il - 1;   // cuda-fst.cc:166-175
+        f->h_eil[ei] = il;
+        f->h_e[ei++] = make_int4(csr->nextstate[a], wbits, pdf, csr->olabel[a]);
+        if (pdf + 1 > f->num_pdfs_seen) f->num_pdfs_seen = pdf + 1;
+      }
+    }
+  }
+  auto up = [&](void **d, const void *h, size_t bytes) -> int {
+    B2K_CUDA_CHECK(cudaMalloc(d, bytes ? bytes : 16));
+    if (bytes) B2K_CUDA_CHECK(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+    return 0;
+  };
+  if ((rc = up((void **)&f->d_st_off, st_off.data(), sizeof(int2) * (N + 1)))) return rc;
+  if ((rc = up((void **)&f->d_e, f->h_e.data(), sizeof(int4) * e_cnt))) return rc;
+  if ((rc = up((void **)&f->d_ne, f->h_ne.data(), sizeof(int4) * ne_cnt))) return rc;
+  if ((rc = up((void **)&f->d_eil, f->h_eil.data(), 4 * (size_t)e_cnt))) return rc;
+  if ((rc = up((void **)&f->d_final, csr->final_cost, 4 * (size_t)N))) return rc;
+  f->dev.num_states = N; f->dev.start = csr->start; f->dev.num_e = e_cnt; f->dev.num_ne = ne_cnt;
+  f->dev.st_off = f->d_st_off; f->dev.e_arcs = f->d_e; f->dev.ne_arcs = f->d_ne;
+  f->dev.e_ilabel = f->d_eil; f->dev.final_cost = f->d_final;
+  *out = f;
+  return B2K_OK;
+}
+
+int b2k_fst_destroy(b2k_fst *f) {
+  if (!f) return B2K_OK;
+  cudaFree(f->d_st_off); cudaFree(f->d_e); cudaFree(f->d_ne); cudaFree(f->d_eil); cudaFree(f->d_final);
+  delete f;
+  return B2K_OK;
+}
+int32_t b2k_fst_num_states(const b2k_fst *f) { return f ? f->dev.num_states : -1; }
+int32_t b2k_fst_start(const b2k_fst *f) { return f ? f->dev.start : -1; }
+
+static int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
+int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, int32_t nchannels,
+                   b2k_dec **out) {
+  if (!fst || !cfg || !out || nlanes <= 0 || nchannels < nlanes)
+    return set_error(B2K_ERR_INVALID, "b2k_dec_create: bad args");
+  if (!(cfg->beam > 0.0f && cfg->max_active > 1 && cfg->lattice_beam > 0.0f &&
+        cfg->min_active <= cfg->max_active && cfg->beam_delta > 0.0f))   // Check() lattice-faster-decoder.h:99-105
+    return set_error(B2K_ERR_INVALID, "b2k_dec_create: invalid decoder config");
+  if (cfg->max_tokens > 0x7fffffffLL || cfg->max_links > 0x7fffffffLL)
+    return set_error(B2K_ERR_INVALID, "arena capacities must fit int32");
+  int rc = require_device();
+  if (rc) return rc;
+  b2k_dec *d = new b2k_dec();
+  d->fst = fst; d->cfg = *cfg; d->nlanes = nlanes; d->nchannels = nchannels;
+  DecParams &p = d->p;
+  memset(&p, 0, sizeof(p));
+  p.fst = fst->dev;
+  p.beam = cfg->beam; p.lattice_beam = cfg->lattice_beam; p.beam_delta = cfg->beam_delta;
+  p.max_active = cfg->max_active; p.min_active = cfg->min_active;
+  p.hash_log = ilog2_ceil(std::max(cfg->max_tokens_per_frame, 1024) * 2);
+  p.hash_size = 1 << p.hash_log;
+  p.max_tpf = p.hash_size / 2;
+  p.cand_cap = p.max_tpf * 4;
+  p.max_frames = cfg->max_frames;
+  p.max_tokens = (int32_t)cfg->max_tokens; p.max_links = (int32_t)cfg->max_links;
+  auto alloc = [&](void **ptr, size_t bytes, int fill) -> int {
+    B2K_CUDA_CHECK(cudaMalloc(ptr, bytes));
+    d->allocs.push_back(*ptr);
+    B2K_CUDA_CHECK(cudaMemset(*ptr, fill, bytes));
+    return 0;
+  };
+  size_t nc = nchannels, nl = nlanes;
+#define A(ptr, bytes, fill) if ((rc = alloc((void **)&(ptr), (bytes), (fill)))) return rc;
+  A(p.chan, sizeof(ChanState) * nc, 0);
+  A(p.tok_state, 4 * nc * p.max_tokens, 0);
+  A(p.tok_cost, 4 * nc * p.max_tokens, 0);
+  A(p.tok_extra, 4 * nc * p.max_tokens, 0);
+  A(p.links, sizeof(int4) * nc * p.max_links, 0);
+  A(p.frame_tok_begin, 4 * nc * (p.max_frames + 2), 0);
+  A(p.frame_link_begin, 4 * nc * (p.max_frames + 2), 0);
+  A(p.frame_link_eps, 4 * nc * (p.max_frames + 2), 0);
+  A(p.frame_cost_offset, 4 * nc * (p.max_frames + 1), 0);
+  A(p.frame_cutoff, 4 * nc * (p.max_frames + 1), 0);
+  A(p.hash, sizeof(int4) * nl * p.hash_size, 0);
+  A(p.tokslot, 4 * nl * p.max_tpf, 0);
+  A(p.wl, 4 * nl * 2 * p.max_tpf, 0);
+  A(p.cand, 4 * nl * 5 * (size_t)p.cand_cap, 0);
+  A(p.new_extra, 4 * nl * p.max_tpf, 0);
+  A(p.lane_stamp, 4 * nl, 0);
+  A(d->d_lane_channel, 4 * nl, 0);
+  A(d->d_lane_ll, sizeof(float *) * nl, 0);
+  A(d->d_lane_nframes, 4 * nl, 0);
+#undef A
+  // hash init: key = EMPTY, cost = +inf (ord), tok = 0, stamp = 0
+  {
+    std::vector<int4> init((size_t)p.hash_size, make_int4(B2K_HASH_EMPTY, (int)B2K_INF_ORD, 0, 0));
+    for (int l = 0; l < nlanes; l++)
+      B2K_CUDA_CHECK(cudaMemcpy(p.hash + (size_t)l * p.hash_size, init.data(),
+                                sizeof(int4) * init.size(), cudaMemcpyHostToDevice));
+  }
+  // channels start un-initialised
+  {
+    std::vector<ChanState> cs(nc);
+    memset(cs.data(), 0, sizeof(ChanState) * nc);
+    for (auto &c : cs) c.frames_decoded = -1;
+    B2K_CUDA_CHECK(cudaMemcpy(p.chan, cs.data(), sizeof(ChanState) * nc, cudaMemcpyHostToDevice));
+  }
+  B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_channel, 4 * nl));
+  B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_ll, sizeof(float *) * nl));
+  B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_nframes, 4 * nl));
+  B2K_CUDA_CHECK(cudaEventCreateWithFlags(&d->staging_free, cudaEventDisableTiming));
+  p.lane_channel = d->d_lane_channel;
+  p.lane_loglikes = d->d_lane_ll;
+  p.lane_nframes = d->d_lane_nframes;
+  *out = d;
+  return B2K_OK;
+}
+
+int b2k_dec_destroy(b2k_dec *d) {
+  if (!d) return B2K_OK;
+  cudaDeviceSynchronize();
+  for (void *p : d->allocs) cudaFree(p);
+  cudaFreeHost(d->h_lane_channel); cudaFreeHost(d->h_lane_ll); cudaFreeHost(d->h_lane_nframes);
+  if (d->staging_free) cudaEventDestroy(d->staging_free);
+  delete d;
+  return B2K_OK;
+}
+
+#define DEC_THREADS 256
+
+static int stage_lanes(b2k_dec *d, const int32_t *channels, const float *const *lls,
+                       const int32_t *nframes, int n, cudaStream_t st) {
+  if (n <= 0 || n > d->nlanes) return set_error(B2K_ERR_INVALID, "number of lanes out of range");
+  // pinned staging is reused: wait until the previous launch consumed it
+  B2K_CUDA_CHECK(cudaEventSynchronize(d->staging_free));
+  for (int i = 0; i < n; i++) {
+    if (channels[i] < 0 || channels[i] >= d->nchannels) return set_error(B2K_ERR_INVALID, "bad channel id");
+    d->h_lane_channel[i] = channels[i];
+    d->h_lane_ll[i] = lls ? lls[i] : nullptr;
+    d->h_lane_nframes[i] = nframes ? nframes[i] : 1;
+  }
+  B2K_CUDA_CHECK(cudaMemcpyAsync(d->d_lane_channel, d->h_lane_channel, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  B2K_CUDA_CHECK(cudaMemcpyAsync((void *)d->d_lane_ll, d->h_lane_ll, sizeof(float *) * (size_t)n, cudaMemcpyHostToDevice, st));
+  B2K_CUDA_CHECK(cudaMemcpyAsync(d->d_lane_nframes, d->h_lane_nframes, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  B2K_CUDA_CHECK(cudaEventRecord(d->staging_free, st));
+  return B2K_OK;
+}
+
+int b2k_dec_init_decoding(b2k_dec *d, const int32_t *channels, int32_t n, void *stream) {
+  if (!d || !channels) return set_error(B2K_ERR_INVALID, "b2k_dec_init_decoding: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  // reset channel state
+  std::vector<ChanState> cs(1);
+  memset(cs.data(), 0, sizeof(ChanState));
+  cs[0].frames_decoded = -1;
+  for (int i = 0; i < n; i++) {
+    if (channels[i] < 0 || channels[i] >= d->nchannels) return set_error(B2K_ERR_INVALID, "bad channel id");
+    B2K_CUDA_CHECK(cudaMemcpyAsync(&d->p.chan[channels[i]], cs.data(), sizeof(ChanState),
+                                   cudaMemcpyHostToDevice, st));
+  }
+  int rc = stage_lanes(d, channels, nullptr, nullptr, n, st);
+  if (rc) return rc;
+  DecParams p = d->p;
+  p.do_init = 1;
+  dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
+  B2K_LAUNCH_CHECK();
+  return B2K_OK;
+}
+
+int b2k_dec_advance_decoding_frames(b2k_dec *d, const int32_t *channels,
+                                    const float *const *d_loglikes, const int32_t *num_frames,
+                                    int32_t row_stride, int32_t n, void *stream) {
+  if (!d || !channels || !d_loglikes) return set_error(B2K_ERR_INVALID, "b2k_dec_advance_decoding: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = stage_lanes(d, channels, d_loglikes, num_frames, n, st);
+  if (rc) return rc;
+  DecParams p = d->p;
+  p.do_init = 0;
+  p.row_stride = row_stride;
+  dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
+  B2K_LAUNCH_CHECK();
+  return B2K_OK;
+}
+
+int b2k_dec_advance_decoding(b2k_dec *d, const int32_t *channels, const float *const *d_loglikes,
+                             int32_t n, void *stream) {
+  return b2k_dec_advance_decoding_frames(d, channels, d_loglikes, nullptr, 0, n, stream);
+}
+
+int b2k_dec_finalize_decoding(b2k_dec *d, const int32_t *channels, int32_t n, void *stream) {
+  if (!d || !channels) return set_error(B2K_ERR_INVALID, "b2k_dec_finalize_decoding: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = stage_lanes(d, channels, nullptr, nullptr, n, st);
+  if (rc) return rc;
+  DecParams p = d->p;
+  dec_finalize_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
+  B2K_LAUNCH_CHECK();
+  return B2K_OK;
+}
+
+static int read_chan(b2k_dec *d, int ch, ChanState *out) {
+  if (ch < 0 || ch >= d->nchannels) return set_error(B2K_ERR_INVALID, "bad channel id");
+  B2K_CUDA_CHECK(cudaDeviceSynchronize());
+  B2K_CUDA_CHECK(cudaMemcpy(out, &d->p.chan[ch], sizeof(ChanState), cudaMemcpyDeviceToHost));
+  return B2K_OK;
+}
+
+int b2k_dec_num_frames_decoded(b2k_dec *d, int32_t channel, int32_t *out) {
+  ChanState cs;
+  int rc = read_chan(d, channel, &cs);
+  if (rc) return rc;
+  *out = cs.frames_decoded;
+  return B2K_OK;
+}
+
+int b2k_dec_channel_info(b2k_dec *d, int32_t channel, int64_t info[16]) {
+  ChanState cs;
+  int rc = read_chan(d, channel, &cs);
+  if (rc) return rc;
+  memset(info, 0, sizeof(int64_t) * 16);
+  info[0] = cs.status; info[1] = cs.frames_decoded; info[2] = cs.ntok; info[3] = cs.nlink;
+  info[4] = (int64_t)cs.arcs_e; info[5] = (int64_t)cs.arcs_ne; info[6] = cs.lat_states;
+  info[7] = cs.lat_arcs; info[8] = cs.lat_finals; info[9] = cs.finalized; info[10] = cs.any_final;
+  return B2K_OK;
+}
+
+int b2k_dec_get_raw_lattice(b2k_dec *d, int32_t channel, b2k_raw_lattice *out, void *stream) {
+  if (!d || !out) return set_error(B2K_ERR_INVALID, "b2k_dec_get_raw_lattice: bad args");
+  ChanState cs;
+  int rc = read_chan(d, channel, &cs);
+  if (rc) return rc;
+  if (cs.status != B2K_OK) return set_error(cs.status, "channel is in an error state");
+  if (!cs.finalized) return set_error(B2K_ERR_STATE, "call b2k_dec_finalize_decoding first");
+  const int64_t ns = cs.lat_states, na = cs.lat_arcs, nf = cs.lat_finals;
+  if (!out->state_frame) { out->num_states = ns; out->num_arcs = na; out->num_finals = nf; return B2K_OK; }
+  if (out->num_states < ns || out->num_arcs < na || out->num_finals < nf)
+    return set_error(B2K_ERR_INVALID, "b2k_dec_get_raw_lattice: output buffers too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  // device scratch
+  size_t bytes = (size_t)(ns + 1) * 5 * 4 + (size_t)(na + 1) * 6 * 4 + (size_t)(nf + 1) * 2 * 4 + 16;
+  char *dbuf = nullptr;
+  B2K_CUDA_CHECK(cudaMalloc((void **)&dbuf, bytes));
+  ExtractOut o;
+  char *q = dbuf;
+  auto take = [&](size_t n) { char *r = q; q += n * 4; return r; };
+  o.counters = (int32_t *)take(4);
+  o.state_tok = (int32_t *)take(ns + 1); o.state_frame = (int32_t *)take(ns + 1);
+  o.state_hclg = (int32_t *)take(ns + 1); o.state_tot = (float *)take(ns + 1);
+  o.state_extra = (float *)take(ns + 1);
+  o.arc_src_tok = (int32_t *)take(na + 1); o.arc_dst_tok = (int32_t *)take(na + 1);
+  o.arc_ilabel = (int32_t *)take(na + 1); o.arc_olabel = (int32_t *)take(na + 1);
+  o.arc_graph = (float *)take(na + 1); o.arc_ac = (float *)take(na + 1);
+  o.final_tok = (int32_t *)take(nf + 1); o.final_cost = (float *)take(nf + 1);
+  cudaError_t e = cudaMemsetAsync(o.counters, 0, 16, st);
+  if (e == cudaSuccess) {
+    dec_extract_kernel<256><<<148 * 2, 256, 0, st>>>(d->p, channel, o);
+    g_launch_count.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  std::vector<int32_t> stok(ns), asrc(na), adst(na), ftok(nf);
+  auto dl = [&](void *h, const void *dv, size_t n) { if (e == cudaSuccess && n) e = cudaMemcpyAsync(h, dv, n * 4, cudaMemcpyDeviceToHost, st); };
+  dl(stok.data(), o.state_tok, ns); dl(out->state_frame, o.state_frame, ns);
+  dl(out->state_hclg, o.state_hclg, ns); dl(out->state_tot_cost, o.state_tot, ns);
+  dl(out->state_extra_cost, o.state_extra, ns);
+  dl(asrc.data(), o.arc_src_tok, na); dl(adst.data(), o.arc_dst_tok, na);
+  dl(out->arc_ilabel, o.arc_ilabel, na); dl(out->arc_olabel, o.arc_olabel, na);
+  dl(out->arc_graph_cost, o.arc_graph, na); dl(out->arc_acoustic_cost, o.arc_ac, na);
+  dl(ftok.data(), o.final_tok, nf); dl(out->final_cost, o.final_cost, nf);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(dbuf);
+  if (e != cudaSuccess) return set_error(B2K_ERR_CUDA, "lattice extraction", cudaGetErrorString(e));
+  // arena index -> dense lattice state id (sorted by arena index = by frame)
+  std::vector<int32_t> order(ns);
+  for (int64_t i = 0; i < ns; i++) order[i] = (int32_t)i;
+  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return stok[a] < stok[b]; });
+  // permute state arrays into arena order so ids are deterministic
+  {
+    std::vector<int32_t> t1(ns), t2(ns); std::vector<float> t3(ns), t4(ns), sorted_tok(ns);
+    for (int64_t i = 0; i < ns; i++) {
+      int32_t j = order[i];
+      t1[i] = out->state_frame[j]; t2[i] = out->state_hclg[j];
+      t3[i] = out->state_tot_cost[j]; t4[i] = out->state_extra_cost[j];
+    }
+    std::vector<int32_t> stok_sorted(ns);
+    for (int64_t i = 0; i < ns; i++) stok_sorted[i] = stok[order[i]];
+    memcpy(out->state_frame, t1.data(), ns * 4); memcpy(out->state_hclg, t2.data(), ns * 4);
+    memcpy(out->state_tot_cost, t3.data(), ns * 4); memcpy(out->state_extra_cost, t4.data(), ns * 4);
+    auto idx_of = [&](int32_t tok) -> int32_t {
+      auto it = std::lower_bound(stok_sorted.begin(), stok_sorted.end(), tok);
+      if (it == stok_sorted.end() || *it != tok) return -1;
+      return (int32_t)(it - stok_sorted.begin());
+    };
+    for (int64_t i = 0; i < na; i++) { out->arc_src[i] = idx_of(asrc[i]); out->arc_dst[i] = idx_of(adst[i]); }
+    for (int64_t i = 0; i < nf; i++) out->final_state[i] = idx_of(ftok[i]);
+  }
+  out->num_states = ns; out->num_arcs = na; out->num_finals = nf;
+  return B2K_OK;
+}
+
+int b2k_dec_debug_frame(b2k_dec *d, int32_t channel, int32_t frame_plus_one, int32_t *tok_state,
+                        float *tok_cost, int64_t *ntok, int32_t *links7, int64_t *nlink,
+                        int64_t cap_tok, int64_t cap_link) {
+  ChanState cs;
+  int rc = read_chan(d, channel, &cs);
+  if (rc) return rc;
+  if (frame_plus_one < 0 || frame_plus_one > cs.frames_decoded) return set_error(B2K_ERR_INVALID, "frame out of range");
+  const DecParams &p = d->p;
+  size_t fo = (size_t)channel * (p.max_frames + 2);
+  int32_t tb[2], lb[2], le;
+  B2K_CUDA_CHECK(cudaMemcpy(tb, p.frame_tok_begin + fo + frame_plus_one, 8, cudaMemcpyDeviceToHost));
+  B2K_CUDA_CHECK(cudaMemcpy(lb, p.frame_link_begin + fo + frame_plus_one, 8, cudaMemcpyDeviceToHost));
+  B2K_CUDA_CHECK(cudaMemcpy(&le, p.frame_link_eps + fo + frame_plus_one, 4, cudaMemcpyDeviceToHost));
+  int64_t nt = tb[1] - tb[0], nl = lb[1] - lb[0];
+  *ntok = nt; *nlink = nl;
+  if (!tok_state) return B2K_OK;
+  if (nt > cap_tok || nl > cap_link) return set_error(B2K_ERR_INVALID, "debug buffers too small");
+  const int32_t *ts = p.tok_state + (size_t)channel * p.max_tokens;
+  const float *tc = p.tok_cost + (size_t)channel * p.max_tokens;
+  B2K_CUDA_CHECK(cudaMemcpy(tok_state, ts + tb[0], nt * 4, cudaMemcpyDeviceToHost));
+  B2K_CUDA_CHECK(cudaMemcpy(tok_cost, tc + tb[0], nt * 4, cudaMemcpyDeviceToHost));
+  std::vector<int4> lk(nl);
+  B2K_CUDA_CHECK(cudaMemcpy(lk.data(), p.links + (size_t)channel * p.max_links + lb[0], nl * sizeof(int4), cudaMemcpyDeviceToHost));
+  // previous list's states for emitting-link sources
+  int32_t ptb = 0;
+  std::vector<int32_t> prev_states;
+  if (frame_plus_one > 0) {
+    B2K_CUDA_CHECK(cudaMemcpy(&ptb, p.frame_tok_begin + fo + frame_plus_one - 1, 4, cudaMemcpyDeviceToHost));
+    prev_states.resize(tb[0] - ptb);
+    B2K_CUDA_CHECK(cudaMemcpy(prev_states.data(), ts + ptb, (size_t)(tb[0] - ptb) * 4, cudaMemcpyDeviceToHost));
+  }
+  auto state_of = [&](int32_t tok) -> int32_t {
+    if (tok >= tb[0]) return tok_state[tok - tb[0]];
+    return prev_states[tok - ptb];
+  };
+  for (int64_t i = 0; i < nl; i++) {
+    int4 l = lk[i];
+    int32_t *r = links7 + i * 7;
+    r[0] = state_of(l.x); r[1] = state_of(l.y);
+    if ((uint32_t)l.z & B2K_EPS_FLAG) {
+      int4 arc = d->fst->h_ne[(uint32_t)l.z & 0x7fffffffu];
+      r[2] = 0; r[3] = arc.z; r[4] = arc.y; r[5] = 0; r[6] = 1;
+    } else {
+      int4 arc = d->fst->h_e[l.z];
+      r[2] = d->fst->h_eil[l.z]; r[3] = arc.w; r[4] = arc.y; r[5] = l.w; r[6] = 0;
+    }
+  }
+  (void)le;
+  return B2K_OK;
+}
+
+int b2k_dec_frame_info(b2k_dec *d, int32_t channel, float *cutoff, float *cost_offset,
+                       int32_t *ntoks, int32_t cap) {
+  ChanState cs;
+  int rc = read_chan(d, channel, &cs);
+  if (rc) return rc;
+  int T = std::min(cap, cs.frames_decoded);
+  if (T <= 0) return B2K_OK;
+  const DecParams &p = d->p;
+  if (cutoff) B2K_CUDA_CHECK(cudaMemcpy(cutoff, p.frame_cutoff + (size_t)channel * (p.max_frames + 1), 4 * (size_t)T, cudaMemcpyDeviceToHost));
+  if (cost_offset) B2K_CUDA_CHECK(cudaMemcpy(cost_offset, p.frame_cost_offset + (size_t)channel * (p.max_frames + 1), 4 * (size_t)T, cudaMemcpyDeviceToHost));
+  if (ntoks) {
+    std::vector<int32_t> tb(T + 2);
+    B2K_CUDA_CHECK(cudaMemcpy(tb.data(), p.frame_tok_begin + (size_t)channel * (p.max_frames + 2), 4 * (size_t)(T + 2), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < T; f++) ntoks[f] = tb[f + 2] - tb[f + 1];
+  }
+  return B2K_OK;
+}
+
+}  // extern "C"

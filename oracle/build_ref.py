@@ -1,0 +1,15 @@
+"""Builds oracle/_ref/ (the reference's OWN sources compiled where they lie under
+/root/reference) — TEST INFRASTRUCTURE ONLY.  Filled in per stage; raises when
+/root/reference is absent (the GPU box uses the prebuilt files)."""
+from __future__ import annotations
+
+import os
+
+REF = "/root/reference"
+
+
+def build_all(quiet: bool = False) -> None:
+    if not os.path.isdir(REF):
+        raise RuntimeError("/root/reference not present")
+    from . import ref_feat
+    ref_feat.build(quiet=quiet)

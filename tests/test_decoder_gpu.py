@@ -1,0 +1,188 @@
+"""GPU parity tests: CUDA decoder (through the C-ABI) vs the oracle, bit-exact.
+
+Compared objects (SURVEY.md §7 hard part 1): (i) the un-pruned token set
+{(state, tot_cost bits)} and link set of EVERY frame, (ii) per-frame
+next_cutoff / cost_offset, (iii) the finalized raw lattice as a canonical set.
+"""
+import numpy as np
+import pytest
+
+from kaldi_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(g, cfg, nlanes=1, nchannels=None, T=64, **kw):
+    from kaldi_b200.decoder import CudaFst, CudaDecoder, CudaDecoderConfig
+    fst = CudaFst(g)
+    c = CudaDecoderConfig.from_dict(cfg, max_frames=max(T + 2, 16), max_tokens=kw.get("max_tokens", 1_500_000),
+                                    max_links=kw.get("max_links", 3_000_000))
+    return fst, CudaDecoder(fst, c, nlanes, nchannels)
+
+
+def _run_gpu(dec, ll_list, chunk=None, one_frame_api=False):
+    import torch
+    n = len(ll_list)
+    d = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in ll_list]
+    ch = list(range(n))
+    dec.InitDecoding(ch)
+    T = [x.shape[0] for x in ll_list]
+    if one_frame_api:
+        for f in range(max(T)):
+            la = [(c, d[c][f].data_ptr()) for c in ch if f < T[c]]
+            dec.AdvanceDecoding(la)
+    elif chunk:
+        done = [0] * n
+        while any(done[c] < T[c] for c in ch):
+            act = [c for c in ch if done[c] < T[c]]
+            nf = [min(chunk, T[c] - done[c]) for c in act]
+            dec.AdvanceDecodingFrames(act, [d[c][done[c]].data_ptr() for c in act], nf, d[0].stride(0))
+            for c, k in zip(act, nf):
+                done[c] += k
+    else:
+        dec.AdvanceDecodingFrames(ch, [x.data_ptr() for x in d], T, d[0].stride(0))
+    dec.FinalizeDecoding(ch)
+    torch.cuda.synchronize()
+
+
+def _check_against_oracle(g, cfg, ll, dec, channel, frames=True):
+    from kaldi_b200.decoder import lattice_to_canonical
+    from oracle import dec_oracle as D
+    o = D.DecoderOracle(g, cfg)
+    o.decode(ll, mode=D.MODE_ORDER_FREE, record_frames=frames)
+    info = dec.ChannelInfo(channel)
+    assert info["status"] == 0, info
+    assert info["frames_decoded"] == ll.shape[0]
+    T = ll.shape[0]
+    fi_o = o.frame_info()
+    fi_g = dec.FrameInfo(channel, T)
+    np.testing.assert_array_equal(fi_g["cost_offset"].view(np.int32), fi_o["cost_offset"].view(np.int32))
+    np.testing.assert_array_equal(fi_g["cutoff"].view(np.int32), fi_o["cutoff"].view(np.int32))
+    np.testing.assert_array_equal(fi_g["ntoks"], fi_o["ntoks"])
+    if frames:
+        for f in range(0, T + 1):
+            ts, tc, lk = dec.DebugFrame(channel, f)
+            got = D.canonical_raw_frame(ts, tc, lk)
+            want = o.raw_frame(f)
+            assert np.array_equal(got["toks"], want["toks"]), f"token set differs on frame {f}"
+            assert np.array_equal(got["links"], want["links"]), f"link set differs on frame {f}"
+    got = lattice_to_canonical(dec.GetRawLattice(channel))
+    want = o.lattice()
+    for k in ("states", "arcs", "finals"):
+        assert got[k].shape == want[k].shape, (k, got[k].shape, want[k].shape)
+        assert np.array_equal(got[k], want[k]), f"finalized lattice differs in {k}"
+    st = o.stats()
+    assert info["arcs_emitting"] == st["arcs_emitting"]
+    return st
+
+
+def test_tiny_graph():
+    from tests.test_decoder_oracle import tiny_graph
+    g = tiny_graph()
+    cfg = dict(synth.DEFAULT_DECODER_CFG, min_active=0)
+    ll = np.array([[0.0, 3.0], [1.0, 0.0]], np.float32)
+    fst, dec = _mk(g, cfg, T=2, max_tokens=1000, max_links=1000)
+    _run_gpu(dec, [ll])
+    _check_against_oracle(g, cfg, ll, dec, 0)
+
+
+@pytest.mark.parametrize("seed,cfgmod", [
+    (0, {}),                                            # recipe settings: beam 15, max-active 7000, min-active 200
+    (1, {"max_active": 2**31 - 1, "min_active": 0, "beam": 11.0}),   # GetCutoff fast path
+    (2, {"max_active": 3000}),                          # max_active fires on most frames
+    (3, {"beam": 10.0, "lattice_beam": 6.0}),
+    (4, {"beam": 8.0, "min_active": 2000}),             # min_active branch
+])
+def test_frames_and_lattice_bit_exact(seed, cfgmod):
+    g = synth.make_hclg(400_000, num_pdfs=800, seed=seed)
+    T = 50
+    ll = synth.make_loglikes(g, T, seed=seed + 100)
+    cfg = dict(synth.DEFAULT_DECODER_CFG, **cfgmod)
+    fst, dec = _mk(g, cfg, T=T)
+    _run_gpu(dec, [ll])
+    st = _check_against_oracle(g, cfg, ll, dec, 0)
+    if "max_active" in cfgmod and cfgmod["max_active"] == 3000:
+        assert st["max_active_branch"] > 5
+    if cfgmod.get("min_active") == 2000:
+        assert st["min_active_branch"] > 0
+
+
+def test_multi_lane_chunked_and_one_frame_api():
+    g = synth.make_hclg(300_000, num_pdfs=500, seed=7)
+    cfg = dict(synth.DEFAULT_DECODER_CFG)
+    lls = [synth.make_loglikes(g, T, seed=20 + i) for i, T in enumerate([30, 17, 25, 30])]
+    # whole-utterance, ragged lengths
+    fst, dec = _mk(g, cfg, nlanes=4, T=32, max_tokens=600_000, max_links=1_200_000)
+    _run_gpu(dec, lls)
+    for c in range(4):
+        _check_against_oracle(g, cfg, lls[c], dec, c, frames=False)
+    # chunked (7 frames per call) must give the same thing; channels are reusable
+    _run_gpu(dec, lls, chunk=7)
+    for c in range(4):
+        _check_against_oracle(g, cfg, lls[c], dec, c, frames=False)
+    # reference-style one-frame AdvanceDecoding(lanes_assignments)
+    _run_gpu(dec, lls, one_frame_api=True)
+    for c in range(4):
+        _check_against_oracle(g, cfg, lls[c], dec, c, frames=(c == 1))
+
+
+def test_dead_end_graph_no_surviving_tokens():
+    g = dict(num_states=2, start=0, num_pdfs=1, offsets=np.array([0, 1, 1], np.int32),
+             ilabel=np.array([1], np.int32), olabel=np.array([0], np.int32),
+             weight=np.array([0.5], np.float32), nextstate=np.array([1], np.int32),
+             final=np.array([np.inf, np.inf], np.float32), tid2pdf=np.array([0, 0], np.int32))
+    cfg = dict(synth.DEFAULT_DECODER_CFG)
+    ll = np.zeros((3, 1), np.float32)
+    fst, dec = _mk(g, cfg, T=3, max_tokens=100, max_links=100)
+    _run_gpu(dec, [ll])
+    info = dec.ChannelInfo(0)
+    assert info["status"] == 0 and info["frames_decoded"] == 3
+    fi = dec.FrameInfo(0, 3)
+    assert fi["ntoks"].tolist() == [1, 0, 0]
+
+
+def test_overflow_is_reported_not_silent():
+    g = synth.make_hclg(300_000, num_pdfs=500, seed=9)
+    cfg = dict(synth.DEFAULT_DECODER_CFG)
+    ll = synth.make_loglikes(g, 20, seed=1)
+    fst, dec = _mk(g, cfg, T=20, max_tokens=5_000, max_links=10_000)   # far too small
+    _run_gpu(dec, [ll])
+    assert dec.ChannelInfo(0)["status"] == 4      # B2K_ERR_OVERFLOW
+    from kaldi_b200._lib import B2kError
+    with pytest.raises(B2kError):
+        dec.GetRawLattice(0)
+
+
+def test_advance_before_init_is_a_state_error():
+    import torch
+    g = synth.make_hclg(50_000, num_pdfs=100, seed=1)
+    fst, dec = _mk(g, dict(synth.DEFAULT_DECODER_CFG), T=4, max_tokens=10_000, max_links=10_000)
+    ll = torch.zeros(4, 100, device="cuda")
+    dec.AdvanceDecodingFrames([0], [ll.data_ptr()], [4], 100)
+    assert dec.ChannelInfo(0)["status"] == 5      # B2K_ERR_STATE
+
+
+def test_full_length_utterance_properties():
+    """BASELINE-size case (333 decoder frames): lattice invariants that do not
+    need the oracle to finish quickly: every arc's endpoints exist, extra_cost
+    in [0, lattice_beam], a zero-extra-cost path exists from start to a final."""
+    g = synth.make_hclg(2_000_000, num_pdfs=2336, seed=11)
+    cfg = dict(synth.DEFAULT_DECODER_CFG)
+    T = 333
+    ll = synth.make_loglikes(g, T, seed=5)
+    fst, dec = _mk(g, cfg, T=T, max_tokens=4_000_000, max_links=8_000_000)
+    _run_gpu(dec, [ll])
+    info = dec.ChannelInfo(0)
+    assert info["status"] == 0 and info["frames_decoded"] == T
+    lat = dec.GetRawLattice(0)
+    ex = lat["state_extra_cost"]
+    assert np.all(ex >= 0) and np.all(ex <= cfg["lattice_beam"])
+    assert lat["arc_src"].min() >= 0 and lat["arc_dst"].min() >= 0
+    assert lat["state_frame"].max() == T and lat["state_frame"].min() == 0
+    assert (lat["state_frame"] == 0).sum() >= 1
+    # frames are non-decreasing along arcs, +1 exactly for emitting arcs
+    df = lat["state_frame"][lat["arc_dst"]] - lat["state_frame"][lat["arc_src"]]
+    assert np.array_equal(df, (lat["arc_ilabel"] != 0).astype(np.int32))
+    assert (ex == 0).sum() >= T + 1          # the best path has extra_cost 0 on every frame
+    # and the whole thing equals the oracle too
+    _check_against_oracle(g, cfg, ll, dec, 0, frames=False)

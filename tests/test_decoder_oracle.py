@@ -1,0 +1,134 @@
+"""CPU tests: the decoder oracle (restatement of lattice-faster-decoder.cc) and
+the C-ABI surface.  No GPU compute."""
+import ctypes as C
+import re
+import os
+
+import numpy as np
+import pytest
+
+from kaldi_b200 import synth
+from oracle import dec_oracle as D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def tiny_graph():
+    """3-state hand-built graph with a known best path.
+    0 --(tid1/pdf0, w=1, o=7)--> 1 ; 0 --(eps, w=0.5)--> 2 ; 2 --(tid2/pdf1,w=0.25,o=9)--> 1
+    1 --(tid1 selfloop w=0.1)--> 1 ; 1 final 0.0"""
+    offsets = np.array([0, 2, 3, 4], np.int32)
+    ilabel = np.array([1, 0, 1, 2], np.int32)
+    olabel = np.array([7, 0, 0, 9], np.int32)
+    weight = np.array([1.0, 0.5, 0.1, 0.25], np.float32)
+    nextstate = np.array([1, 2, 1, 1], np.int32)
+    final = np.array([np.inf, 0.0, np.inf], np.float32)
+    tid2pdf = np.array([0, 0, 1], np.int32)
+    return dict(num_states=3, start=0, num_pdfs=2, offsets=offsets, ilabel=ilabel, olabel=olabel,
+                weight=weight, nextstate=nextstate, final=final, tid2pdf=tid2pdf)
+
+
+def test_tiny_graph_known_answer():
+    g = tiny_graph()
+    cfg = dict(synth.DEFAULT_DECODER_CFG, min_active=0)
+    o = D.DecoderOracle(g, cfg)
+    # frame 0: pdf1 much better -> path 0 -eps-> 2 -tid2-> 1 (cost 0.5+0.25-3) beats 0 -tid1-> 1 (1-0)
+    ll = np.array([[0.0, 3.0], [1.0, 0.0]], np.float32)
+    o.decode(ll, mode=D.MODE_REFERENCE_ORDER)
+    lat = o.lattice()
+    # lattice states: (0,s0) (0,s2) (1,s1) (2,s1); both paths within lattice beam 8
+    assert lat["states"].shape[0] == 4
+    fr_st = {(int(r[0]), int(r[1])) for r in lat["states"]}
+    assert fr_st == {(0, 0), (0, 2), (1, 1), (2, 1)}
+    # arcs: eps 0->2, tid1 0->1, tid2 2->1, selfloop 1->1
+    assert lat["arcs"].shape[0] == 4
+    olabels = sorted(int(r[5]) for r in lat["arcs"])
+    assert olabels == [0, 0, 7, 9]
+    # best token at frame 1 is via eps path: cost_offset0 = 0 -> tot = 0.5 + (0-3) + 0.25
+    tot = {(int(r[0]), int(r[1])): np.int32(r[2]).view(np.float32) for r in lat["states"]}
+    assert tot[(1, 1)] == np.float32(np.float32(0.5) + np.float32(-3.0) + np.float32(0.25))
+    assert lat["finals"].shape[0] == 1
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_reference_order_mode_admits_a_superset(seed):
+    """Mode 0 (literal reference order) admits every link mode 1 (order free)
+    admits plus order-dependent extras with tot in [final cutoff, running
+    cutoff) (lattice-faster-decoder.cc:794-796).  Documented finding
+    (DESIGN.md): those extras can survive into the finalized lattice and, with
+    max_active firing, are counted by the next frame's nth_element (:671-694),
+    so bit-exact parity with the reference needs its iteration order."""
+    g = synth.make_hclg(300_000, num_pdfs=600, seed=seed)
+    ll = synth.make_loglikes(g, 40, seed=seed)
+    o = D.DecoderOracle(g, synth.DEFAULT_DECODER_CFG)
+    st0 = o.decode(ll, mode=D.MODE_REFERENCE_ORDER, record_frames=True)
+    f1_0 = o.raw_frame(1)
+    st1 = o.decode(ll, mode=D.MODE_ORDER_FREE, record_frames=True)
+    f1_1 = o.raw_frame(1)
+    assert st0["lat_states"] > 50 and st1["lat_states"] > 50
+    assert st0["extra_links"] > 0
+    # frame 1 is computed from identical inputs in both modes: superset holds there
+    l0 = set(map(tuple, f1_0["links"].tolist()))
+    l1 = set(map(tuple, f1_1["links"].tolist()))
+    assert l1 <= l0
+
+
+def test_oracle_is_deterministic_and_reusable():
+    g = synth.make_hclg(100_000, num_pdfs=300, seed=3)
+    ll = synth.make_loglikes(g, 30, seed=4)
+    o = D.DecoderOracle(g, synth.DEFAULT_DECODER_CFG)
+    o.decode(ll); a = o.lattice()
+    o.decode(ll); b = o.lattice()
+    assert D.lattices_equal(a, b)
+    o2 = D.DecoderOracle(g, synth.DEFAULT_DECODER_CFG)
+    o2.decode(ll); c = o2.lattice()
+    assert D.lattices_equal(a, c)
+
+
+def test_raw_frames_recorded():
+    g = synth.make_hclg(100_000, num_pdfs=300, seed=3)
+    ll = synth.make_loglikes(g, 10, seed=4)
+    o = D.DecoderOracle(g, synth.DEFAULT_DECODER_CFG)
+    o.decode(ll, mode=D.MODE_ORDER_FREE, record_frames=True)
+    fi = o.frame_info()
+    for f in range(1, 11):
+        r = o.raw_frame(f)
+        assert r["toks"].shape[0] == fi["ntoks"][f - 1]
+        # every link's destination state is a token of this frame
+        assert set(r["links"][:, 1].tolist()) <= set(r["toks"][:, 0].tolist())
+
+
+def test_no_surviving_tokens_is_handled():
+    # graph where start has a single arc to a dead end
+    g = dict(num_states=2, start=0, num_pdfs=1, offsets=np.array([0, 1, 1], np.int32),
+             ilabel=np.array([1], np.int32), olabel=np.array([0], np.int32),
+             weight=np.array([0.5], np.float32), nextstate=np.array([1], np.int32),
+             final=np.array([np.inf, np.inf], np.float32), tid2pdf=np.array([0, 0], np.int32))
+    o = D.DecoderOracle(g, synth.DEFAULT_DECODER_CFG)
+    st = o.decode(np.zeros((3, 1), np.float32))
+    assert st["lat_states"] >= 0   # must not crash; frames 2,3 have no tokens
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b2k.h")).read()
+    names = set(re.findall(r"\b(b2k_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"b2k_status"}
+    so = os.path.join(ROOT, "kaldi_b200", "libb2k.so")
+    if not os.path.exists(so):
+        from kaldi_b200 import build
+        build.build()
+    lib = C.CDLL(so)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, f"libb2k.so does not export: {missing}"
+    assert len(names) >= 15
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from kaldi_b200.decoder import CudaFst
+    from kaldi_b200._lib import B2kError
+    with pytest.raises(B2kError) as e:
+        CudaFst(tiny_graph())
+    assert e.value.code == 2   # B2K_ERR_NO_DEVICE: no CPU fallback exists
