@@ -79,6 +79,14 @@ typedef struct {
   int32_t max_frames;         /* per-channel frame capacity                   */
   int64_t max_tokens;         /* per-channel token arena                      */
   int64_t max_links;          /* per-channel forward-link arena               */
+  int32_t reference_order;    /* 1 (default): bit-exact emulation of the CPU
+                                 decoder's HashList iteration order (running
+                                 next_cutoff, lattice-faster-decoder.cc:794-796);
+                                 0: order-free fast mode (admission against the
+                                 final cutoff; NOT bit-compatible with the
+                                 reference when extras matter)  */
+  float hash_ratio;           /* --hash-ratio (2.0); reference_order only      */
+  int32_t max_arcs_per_frame; /* reference_order: arc-position capacity        */
 } b2k_dec_cfg;
 
 void b2k_dec_cfg_default(b2k_dec_cfg *cfg);

@@ -34,7 +34,34 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(LIB_PATH)
         _lib.b2k_last_error.restype = C.c_char_p
         _lib.b2k_kernel_launch_count.restype = C.c_int64
+        _declare(_lib)
     return _lib
+
+
+def _declare(L) -> None:
+    """argtypes for every entry point of include/b2k.h (64-bit and pointer
+    arguments must not go through ctypes' default int conversion)."""
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    P = C.POINTER
+    sig = {
+        "b2k_fst_create": [vp, P(vp)], "b2k_fst_destroy": [vp],
+        "b2k_fst_num_states": [vp], "b2k_fst_start": [vp],
+        "b2k_dec_cfg_default": [vp],
+        "b2k_dec_create": [vp, vp, i32, i32, P(vp)], "b2k_dec_destroy": [vp],
+        "b2k_dec_init_decoding": [vp, P(i32), i32, vp],
+        "b2k_dec_advance_decoding": [vp, P(i32), vp, i32, vp],
+        "b2k_dec_advance_decoding_frames": [vp, P(i32), vp, P(i32), i32, i32, vp],
+        "b2k_dec_num_frames_decoded": [vp, i32, P(i32)],
+        "b2k_dec_finalize_decoding": [vp, P(i32), i32, vp],
+        "b2k_dec_channel_info": [vp, i32, P(i64)],
+        "b2k_dec_get_raw_lattice": [vp, i32, vp, vp],
+        "b2k_dec_debug_frame": [vp, i32, i32, P(i32), P(f32), P(i64), P(i32), P(i64), i64, i64],
+        "b2k_dec_frame_info": [vp, i32, P(f32), P(f32), P(i32), i32],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int32
 
 
 def check(rc: int) -> None:

@@ -60,10 +60,14 @@ struct ChanState {          // per channel, device resident
   int32_t lat_states, lat_arcs, lat_finals;
   int32_t any_final;
   float final_best_cost;
+  int32_t hc;               // reference-order mode: HashList size (hash-list-inl.h:38), starts at 1000
+  int32_t pad_;
   unsigned long long arcs_e, arcs_ne;
 };
 
 #define B2K_EPS_FLAG 0x80000000u
+#define B2K_DEAD_FLAG 0x40000000u   // link excised by the backward pruning sweep
+#define B2K_ARC_MASK 0x3fffffffu
 #define B2K_HASH_EMPTY (-1)
 
 struct DecParams {
@@ -94,6 +98,16 @@ struct DecParams {
   int32_t *cand;            // [5 * cand_cap] src, arc, next, tot bits, ac bits
   uint32_t *new_extra;      // [max_tpf] (finalize)
   int32_t *lane_stamp;      // [nlanes]
+  // reference-order mode scratch (per lane)
+  uint32_t *x_bm;           // [pos_cap/32] bitmap of first-admission positions
+  int32_t *x_wbase;         // [pos_cap/32]
+  int32_t *x_by_ins;        // [max_tpf] insertion index -> hash slot
+  int32_t *x_bfirst, *x_bcount, *x_bfill;   // [hc_cap] per HashList bucket
+  int32_t *x_sbase;         // [max_tpf]
+  int32_t *x_run;           // [max_tpf]
+  int32_t *x_order;         // [max_tpf] list rank -> hash slot
+  int32_t pos_cap, hc_cap, queue_cap;
+  float hash_ratio;
   // per launch
   const int32_t *lane_channel;
   const float *const *lane_loglikes;
@@ -263,6 +277,7 @@ __device__ void reset_lane_hash(int4 *hash, int hash_size) {
   for (int i = threadIdx.x; i < hash_size; i += T) {
     hash[i].x = B2K_HASH_EMPTY;
     hash[i].y = (int)B2K_INF_ORD;
+    hash[i].z = 0x7fffffff;   // reference-order mode keeps the insertion seq here
   }
 }
 
@@ -283,6 +298,8 @@ struct __align__(16) DecShared {
   uint32_t running_ord;
   int stamp;
   int cont;
+  float scanf_[2][T / 32];
+  int q_n;
 };
 
 // epsilon closure + link generation + commit of the frame being built.
@@ -666,6 +683,547 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
   if (s.err) reset_lane_hash<T>(ctx.hash, p.hash_size);
 }
 
+
+// ====================================================================== reference-order mode
+//
+// Bit-exact emulation of the order dependence of the CPU decoder (DESIGN.md
+// "Why iteration order matters").  ProcessEmitting prunes against a RUNNING
+// next_cutoff (lattice-faster-decoder.cc:794-796) while it walks the previous
+// frame's tokens in HashList order; that running value is exactly an exclusive
+// prefix-min over the (token, arc) sequence:
+//     RC(p) = min(seed, min_{q<p} tot_q + adaptive_beam)
+// (non-admitted arcs cannot lower it because adaptive_beam > 0), so admission
+// is a block-wide scan, not a sequential walk -- PROVIDED each frame's tokens
+// are stored in the arena in HashList iteration order.  That order is
+// (first-occupancy rank of bucket state % hash_size, insertion order within
+// the bucket) (hash-list-inl.h:126-175) and is rebuilt per frame from
+// insertion sequence numbers: for tokens created by ProcessEmitting the
+// sequence number is the position of the first admitted arc (atomicMin), for
+// tokens created by ProcessNonemitting it comes from a literal, single-thread
+// replay of the LIFO worklist (:858-896) -- the one inherently sequential piece.
+
+struct XScratch {
+  uint32_t *bm; int32_t *wbase, *by_ins, *bfirst, *bcount, *bfill, *sbase, *run, *order, *queue;
+};
+
+// find-or-insert without arena write; *created tells whether this call made the token
+__device__ __forceinline__ int hash_insert_x(const LaneCtx &c, int32_t state, bool *created, int *idx_out) {
+  uint32_t h = hash_fn(state, c.hash_log);
+  *created = false;
+  for (int probe = 0; probe <= c.hash_mask; probe++) {
+    int *keyp = reinterpret_cast<int *>(&c.hash[h]);
+    int old = atomicCAS(keyp, B2K_HASH_EMPTY, state);
+    if (old == B2K_HASH_EMPTY) {
+      int idx = atomicAdd(c.ntok_new, 1);
+      if (idx < c.max_tpf) c.tokslot[idx] = (int)h;
+      else atomicExch(c.err, B2K_ERR_OVERFLOW);
+      *created = true;
+      *idx_out = idx;
+      return (int)h;
+    }
+    if (old == state) return (int)h;
+    h = (h + 1) & (uint32_t)c.hash_mask;
+  }
+  atomicExch(c.err, B2K_ERR_OVERFLOW);
+  return -1;
+}
+
+// HashList iteration order of the N tokens by_ins[0..N) (slot.z = insertion index)
+template <int T>
+__device__ void order_tokens(int N, int Hc, int4 *hash, const XScratch &x, DecShared<T> &s) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  for (int k = tid; k < N; k += T) {
+    int slot = x.by_ins[k];
+    uint32_t b = (uint32_t)hash[slot].x % (uint32_t)Hc;
+    atomicMin(&x.bfirst[b], k);
+    atomicAdd(&x.bcount[b], 1);
+  }
+  __syncthreads();
+  int carry = 0;
+  for (int base = 0; base < N; base += T) {
+    int k = base + tid, w = 0;
+    if (k < N) {
+      uint32_t b = (uint32_t)hash[x.by_ins[k]].x % (uint32_t)Hc;
+      if (x.bfirst[b] == k) w = x.bcount[b];
+    }
+    int total;
+    int excl = block_excl_scan<T>(w, s.redi, &total);
+    if (k < N) x.sbase[k] = carry + excl;
+    carry += total;
+  }
+  __syncthreads();
+  for (int k = tid; k < N; k += T) {
+    uint32_t b = (uint32_t)hash[x.by_ins[k]].x % (uint32_t)Hc;
+    int rb = x.sbase[x.bfirst[b]];
+    int q = atomicAdd(&x.bfill[b], 1);
+    x.run[rb + q] = k;
+  }
+  __syncthreads();
+  for (int k = tid; k < N; k += T) {
+    int slot = x.by_ins[k];
+    uint32_t b = (uint32_t)hash[slot].x % (uint32_t)Hc;
+    int rb = x.sbase[x.bfirst[b]];
+    int cnt = x.bcount[b], within = 0;
+    for (int j = 0; j < cnt; j++) within += (x.run[rb + j] < k);
+    x.order[rb + within] = slot;
+  }
+  __syncthreads();
+  for (int k = tid; k < N; k += T) {
+    uint32_t b = (uint32_t)hash[x.by_ins[k]].x % (uint32_t)Hc;
+    x.bfirst[b] = 0x7fffffff; x.bcount[b] = 0; x.bfill[b] = 0;
+  }
+  __syncthreads();
+}
+
+// ProcessNonemitting replay + ordering + eps links + commit (reference order).
+// On entry N1 = s.ntok_new tokens exist with slot.z = insertion index and
+// by_ins filled for them.
+template <int T>
+__device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const LaneCtx &ctx,
+                                   const XScratch &x, int lane, int ch, int list_index, float cutoff,
+                                   float cost_offset, int32_t lbase, int Hc, ChanState *cs) {
+  const int tid = threadIdx.x;
+  const FstDev &g = p.fst;
+  int4 *hash = ctx.hash;
+  int4 *links = p.links + (size_t)ch * p.max_links;
+  int32_t *tok_state = p.tok_state + (size_t)ch * p.max_tokens;
+  float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
+  __syncthreads();
+  if (s.err) return;     // uniform: nothing writes err between the barrier and this read
+  const int n_emit_links = s.nlink_new;
+  const int N1 = min(s.ntok_new, p.max_tpf);
+  // list order after the emitting phase -> initial worklist (:852-856)
+  order_tokens<T>(N1, Hc, hash, x, s);
+  int qcarry = 0;
+  for (int base = 0; base < N1; base += T) {
+    int k = base + tid, flag = 0, slot = 0;
+    if (k < N1) {
+      slot = x.order[k];
+      int st = hash[slot].x;
+      int2 o0 = __ldg(&g.st_off[st]), o1 = __ldg(&g.st_off[st + 1]);
+      flag = (o1.y > o0.y);
+    }
+    int total;
+    int excl = block_excl_scan<T>(flag, s.redi, &total);
+    if (flag) x.queue[qcarry + excl] = slot;
+    qcarry += total;
+  }
+  __syncthreads();
+  // literal LIFO replay by one thread (:858-896)
+  if (tid == 0 && !s.err) {
+    int qn = qcarry;
+    unsigned long long ne = 0;
+    while (qn > 0) {
+      int slot = x.queue[--qn];
+      volatile int4 *sp = &hash[slot];
+      int state = sp->x;
+      float c = ord2f((uint32_t)sp->y);
+      if (c >= cutoff) continue;
+      int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
+      ne += (unsigned long long)(o1.y - o0.y);
+      for (int a = o0.y; a < o1.y; a++) {
+        int4 arc = __ldg(&g.ne_arcs[a]);
+        float tot = c + __int_as_float(arc.y);
+        if (tot < cutoff) {
+          bool created; int idx = 0;
+          int ds = hash_insert_x(ctx, arc.x, &created, &idx);
+          if (ds < 0 || s.err) { qn = 0; break; }
+          volatile int4 *dp = &hash[ds];
+          bool changed = created;
+          if (created) { dp->z = idx; x.by_ins[idx] = ds; }
+          else if (ord2f((uint32_t)dp->y) > tot) changed = true;
+          if (changed) {
+            dp->y = (int)f2ord(tot);
+            int2 d0 = __ldg(&g.st_off[arc.x]), d1 = __ldg(&g.st_off[arc.x + 1]);
+            if (d1.y > d0.y) {
+              if (qn < p.queue_cap) x.queue[qn++] = ds;
+              else { s.err = B2K_ERR_OVERFLOW; qn = 0; break; }
+            }
+          }
+        }
+      }
+    }
+    cs->arcs_ne += ne;
+  }
+  __syncthreads();
+  const int N = min(s.ntok_new, p.max_tpf);
+  order_tokens<T>(N, Hc, hash, x, s);
+  // eps links from final costs
+  for (int i = tid; i < N; i += T) {
+    int slot = ctx.tokslot[i];
+    float c = ord2f((uint32_t)hash[slot].y);
+    if (!(c < cutoff)) continue;
+    int state = hash[slot].x;
+    int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
+    for (int a = o0.y; a < o1.y; a++) {
+      int4 arc = __ldg(&g.ne_arcs[a]);
+      float tot = c + __int_as_float(arc.y);
+      if (tot < cutoff) {
+        int ds = hash_find(ctx, arc.x);
+        int li = atomicAdd(&s.nlink_new, 1);
+        if (lbase + li < p.max_links && ds >= 0)
+          links[lbase + li] = make_int4(slot, ds, (int)((uint32_t)a | B2K_EPS_FLAG), 0);
+        else
+          atomicExch(&s.err, B2K_ERR_OVERFLOW);
+      }
+    }
+  }
+  __syncthreads();
+  const int nlink = s.nlink_new;
+  const bool fits = (ctx.tbase + N <= p.max_tokens);
+  if (!fits && tid == 0) s.err = B2K_ERR_OVERFLOW;
+  __syncthreads();
+  if (!s.err) {
+    for (int r = tid; r < N; r += T) {
+      int slot = x.order[r];
+      tok_state[ctx.tbase + r] = hash[slot].x;
+      tok_cost[ctx.tbase + r] = ord2f((uint32_t)hash[slot].y);
+      hash[slot].w = r;
+    }
+  }
+  __syncthreads();
+  if (!s.err) {
+    for (int li = tid; li < nlink; li += T) {
+      int4 lk = links[lbase + li];
+      if ((uint32_t)lk.z & B2K_EPS_FLAG) lk.x = ctx.tbase + hash[lk.x].w;
+      lk.y = ctx.tbase + hash[lk.y].w;
+      links[lbase + li] = lk;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += T)
+    hash[ctx.tokslot[i]] = make_int4(B2K_HASH_EMPTY, (int)B2K_INF_ORD, 0x7fffffff, 0);
+  if (tid == 0) {
+    size_t fo = (size_t)ch * (p.max_frames + 2);
+    p.frame_tok_begin[fo + list_index] = ctx.tbase;
+    p.frame_tok_begin[fo + list_index + 1] = ctx.tbase + N;
+    p.frame_link_begin[fo + list_index] = lbase;
+    p.frame_link_eps[fo + list_index] = lbase + n_emit_links;
+    p.frame_link_begin[fo + list_index + 1] = lbase + nlink;
+    if (list_index > 0) {
+      size_t co = (size_t)ch * (p.max_frames + 1) + (list_index - 1);
+      p.frame_cost_offset[co] = cost_offset;
+      p.frame_cutoff[co] = cutoff;
+    }
+  }
+  __syncthreads();
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
+  __shared__ DecShared<T> s;
+  constexpr int IT = 4;
+  const int tid = threadIdx.x;
+  const int lane = blockIdx.x;
+  const int ch = p.lane_channel[lane];
+  ChanState *cs = &p.chan[ch];
+  const FstDev &g = p.fst;
+  const float kInf = __int_as_float(0x7f800000);
+
+  if (cs->status != B2K_OK) return;
+  if (!p.do_init && cs->frames_decoded < 0) {
+    if (tid == 0) cs->status = B2K_ERR_STATE;
+    return;
+  }
+  int32_t *tok_state = p.tok_state + (size_t)ch * p.max_tokens;
+  float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
+  int4 *links = p.links + (size_t)ch * p.max_links;
+
+  LaneCtx ctx;
+  ctx.hash = p.hash + (size_t)lane * p.hash_size;
+  ctx.tokslot = p.tokslot + (size_t)lane * p.max_tpf;
+  ctx.tok_state = tok_state;
+  ctx.hash_mask = p.hash_size - 1;
+  ctx.hash_log = p.hash_log;
+  ctx.max_tpf = p.max_tpf;
+  ctx.max_tokens = p.max_tokens;
+  ctx.ntok_new = &s.ntok_new;
+  ctx.err = &s.err;
+  XScratch x;
+  x.bm = p.x_bm + (size_t)lane * (p.pos_cap / 32);
+  x.wbase = p.x_wbase + (size_t)lane * (p.pos_cap / 32);
+  x.by_ins = p.x_by_ins + (size_t)lane * p.max_tpf;
+  x.bfirst = p.x_bfirst + (size_t)lane * p.hc_cap;
+  x.bcount = p.x_bcount + (size_t)lane * p.hc_cap;
+  x.bfill = p.x_bfill + (size_t)lane * p.hc_cap;
+  x.sbase = p.x_sbase + (size_t)lane * p.max_tpf;
+  x.run = p.x_run + (size_t)lane * p.max_tpf;
+  x.order = p.x_order + (size_t)lane * p.max_tpf;
+  x.queue = p.cand + (size_t)lane * 5 * p.cand_cap;     // idle in this mode
+
+  if (tid == 0) { s.err = 0; s.stamp = 0; }
+  __syncthreads();
+
+  if (p.do_init) {
+    if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; }
+    __syncthreads();
+    ctx.tbase = 0;
+    if (tid == 0) {
+      bool created; int idx = 0;
+      int slot = hash_insert_x(ctx, g.start, &created, &idx);
+      if (slot >= 0) { ctx.hash[slot].y = (int)f2ord(0.0f); ctx.hash[slot].z = 0; x.by_ins[0] = slot; }
+    }
+    finish_frame_exact<T>(p, s, ctx, x, lane, ch, 0, p.beam, 0.0f, 0, 1000, cs);
+    if (tid == 0) {
+      cs->frames_decoded = 0;
+      cs->ntok = min(s.ntok_new, p.max_tpf);
+      cs->nlink = s.nlink_new;
+      cs->finalized = 0;
+      cs->hc = 1000;                                   // toks_.SetSize(1000) (:39)
+      if (s.err) cs->status = s.err;
+    }
+    if (s.err) reset_lane_hash<T>(ctx.hash, p.hash_size);
+    return;
+  }
+
+  const int nframes = p.lane_nframes[lane];
+  const float *ll_base = p.lane_loglikes[lane];
+  int frames_decoded = cs->frames_decoded;
+  int32_t tbase = cs->ntok, lbase = cs->nlink;
+  int Hc = cs->hc;
+  unsigned long long arcs_e_total = 0;
+  const size_t fo = (size_t)ch * (p.max_frames + 2);
+
+  for (int fi = 0; fi < nframes; fi++) {
+    if (frames_decoded >= p.max_frames) { if (tid == 0) s.err = B2K_ERR_OVERFLOW; __syncthreads(); break; }
+    const float *ll = ll_base + (size_t)fi * p.row_stride;
+    const int pb = p.frame_tok_begin[fo + frames_decoded];
+    const int pe = p.frame_tok_begin[fo + frames_decoded + 1];
+    const int K = pe - pb;
+
+    // ---- GetCutoff (:653-720); ties -> first in list order (strict < at :662/:675)
+    unsigned long long local = ~0ull;
+    for (int i = pb + tid; i < pe; i += T) {
+      unsigned long long key = ((unsigned long long)f2ord(tok_cost[i]) << 32) | (uint32_t)(i - pb);
+      local = key < local ? key : local;
+    }
+    unsigned long long bestkey = block_min_u64<T>(local, s.red64);
+    float best_cost = kInf;
+    int best_state = -1;
+    if (K > 0) {
+      best_cost = ord2f((uint32_t)(bestkey >> 32));
+      best_state = tok_state[pb + (int)(uint32_t)(bestkey & 0xffffffffu)];
+    }
+    const float beam_cutoff = best_cost + p.beam;
+    float cur_cutoff = beam_cutoff, adaptive_beam = p.beam;
+    if (K > 0 && !(p.max_active == 0x7fffffff && p.min_active == 0)) {
+      int c_lt = 0, c_le = 0;
+      for (int i = pb + tid; i < pe; i += T) {
+        float c = tok_cost[i];
+        c_lt += (c < beam_cutoff);
+        c_le += (c <= beam_cutoff);
+      }
+      c_lt = block_sum_i32<T>(c_lt, s.redi);
+      c_le = block_sum_i32<T>(c_le, s.redi);
+      bool done = false;
+      if (K > p.max_active && c_lt > p.max_active) {
+        float mac = block_select_kth<T>(tok_cost + pb, K, p.max_active, s.hist, s.pref);
+        cur_cutoff = mac;
+        adaptive_beam = mac - best_cost + p.beam_delta;
+        done = true;
+      }
+      if (!done) {
+        float min_active_cutoff = kInf;
+        if (K > p.min_active) {
+          if (p.min_active == 0) min_active_cutoff = best_cost;
+          else if (c_le <= p.min_active)
+            min_active_cutoff = block_select_kth<T>(tok_cost + pb, K, p.min_active, s.hist, s.pref);
+          else min_active_cutoff = beam_cutoff;
+        }
+        if (min_active_cutoff > beam_cutoff) {
+          adaptive_beam = min_active_cutoff - best_cost + p.beam_delta;
+          cur_cutoff = min_active_cutoff;
+        }
+      }
+    }
+    // PossiblyResizeHash(tok_cnt) (:227-233)
+    {
+      long long new_sz = (long long)((float)K * p.hash_ratio);
+      if (new_sz > (long long)Hc) Hc = (int)min(new_sz, (long long)0x7fffffff);
+      if (Hc > p.hc_cap) { if (tid == 0) s.err = B2K_ERR_OVERFLOW; __syncthreads(); break; }
+    }
+    const float cost_offset = (K > 0) ? -best_cost : 0.0f;
+
+    // ---- seed (:753-768)
+    uint32_t seed_local = B2K_INF_ORD;
+    if (K > 0) {
+      int2 o0 = __ldg(&g.st_off[best_state]), o1 = __ldg(&g.st_off[best_state + 1]);
+      for (int a = o0.x + tid; a < o1.x; a += T) {
+        int4 arc = __ldg(&g.e_arcs[a]);
+        float new_weight = __int_as_float(arc.y) + cost_offset - __ldg(&ll[arc.z]) + best_cost;
+        seed_local = min(seed_local, f2ord(new_weight + adaptive_beam));
+      }
+    }
+    const float seed_cutoff = ord2f(block_min_u32<T>(seed_local, s.red32));
+
+    // ---- main loop (:779-812): admission against the exclusive prefix-min
+    if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; }
+    __syncthreads();
+    ctx.tbase = tbase;
+    float carry = kInf;
+    int pos_base = 0;
+    int round_no = 0;
+    for (int cb = pb; cb < pe; cb += T) {
+      int i = cb + tid;
+      int deg = 0, ebeg = 0;
+      float c = 0.f;
+      if (i < pe) {
+        c = tok_cost[i];
+        if (c <= cur_cutoff) {
+          int st = tok_state[i];
+          int2 o0 = __ldg(&g.st_off[st]), o1 = __ldg(&g.st_off[st + 1]);
+          ebeg = o0.x;
+          deg = o1.x - o0.x;
+        }
+      }
+      int total;
+      int off = block_excl_scan<T>(deg, s.redi, &total);
+      s.chunk_off[tid] = off;
+      s.chunk_ebeg[tid] = ebeg;
+      s.chunk_cost[tid] = c;
+      if (tid == 0) { s.chunk_off[T] = total; arcs_e_total += (unsigned long long)total; }
+      __syncthreads();
+      for (int r0 = 0; r0 < total; r0 += T * IT, round_no++) {
+        const int j0 = r0 + tid * IT;
+        float tots[IT], acs[IT];
+        int arcid[IT], nexts[IT], srcs[IT];
+        int lo = 0;
+        if (j0 < total) {
+          int hi = T;
+          while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (s.chunk_off[mid] <= j0) lo = mid; else hi = mid;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+          int j = j0 + k;
+          tots[k] = kInf; acs[k] = 0.f; arcid[k] = 0; nexts[k] = 0; srcs[k] = 0;
+          if (j < total) {
+            while (s.chunk_off[lo + 1] <= j) lo++;
+            int a = s.chunk_ebeg[lo] + (j - s.chunk_off[lo]);
+            int4 arc = __ldg(&g.e_arcs[a]);
+            float ac = cost_offset - __ldg(&ll[arc.z]);
+            tots[k] = s.chunk_cost[lo] + ac + __int_as_float(arc.y);
+            acs[k] = ac; arcid[k] = a; nexts[k] = arc.x; srcs[k] = cb + lo;
+          }
+        }
+        float ex[IT];
+        float pm = kInf;
+#pragma unroll
+        for (int k = 0; k < IT; k++) { ex[k] = pm; pm = fminf(pm, tots[k]); }
+        // block-wide exclusive scan (min) of pm in thread order
+        const int lane_id = tid & 31, warp = tid >> 5;
+        float incl = pm;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          float n = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane_id >= o) incl = fminf(incl, n);
+        }
+        float wexcl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane_id == 0) wexcl = kInf;
+        float *buf = s.scanf_[round_no & 1];
+        if (lane_id == 31) buf[warp] = incl;
+        __syncthreads();
+        float wpre = kInf, tot_all = kInf;
+#pragma unroll
+        for (int w = 0; w < T / 32; w++) {
+          float v = buf[w];
+          if (w < warp) wpre = fminf(wpre, v);
+          tot_all = fminf(tot_all, v);
+        }
+        const float base = fminf(carry, fminf(wpre, wexcl));
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+          int j = j0 + k;
+          float excl = fminf(base, ex[k]);
+          float rc = fminf(seed_cutoff, excl + adaptive_beam);
+          bool adm = (j < total) && (tots[k] < rc);
+          int slot = -1;
+          if (adm) {
+            bool created; int idx;
+            slot = hash_insert_x(ctx, nexts[k], &created, &idx);
+            if (slot >= 0) {
+              atomicMin(reinterpret_cast<uint32_t *>(&ctx.hash[slot].y), f2ord(tots[k]));
+              atomicMin(&ctx.hash[slot].z, pos_base + j);
+            } else adm = false;
+          }
+          uint32_t m = __ballot_sync(0xffffffffu, adm);
+          if (m) {
+            int lb = 0;
+            if (lane_id == 0) lb = atomicAdd(&s.nlink_new, __popc(m));
+            lb = __shfl_sync(0xffffffffu, lb, 0);
+            if (adm) {
+              int li = lb + __popc(m & ((1u << lane_id) - 1u));
+              if (lbase + li < p.max_links)
+                links[lbase + li] = make_int4(srcs[k], slot, arcid[k], __float_as_int(acs[k]));
+              else
+                atomicExch(&s.err, B2K_ERR_OVERFLOW);
+            }
+          }
+        }
+        carry = fminf(carry, tot_all);
+      }
+      pos_base += total;
+      __syncthreads();
+    }
+    const float next_cutoff = fminf(seed_cutoff, carry + adaptive_beam);
+    __syncthreads();
+    // ---- insertion index of the tokens created above = rank of their first
+    //      admitted position (bitmap rank)
+    const int N1 = min(s.ntok_new, p.max_tpf);
+    if (pos_base > p.pos_cap) { if (tid == 0) s.err = B2K_ERR_OVERFLOW; }
+    __syncthreads();
+    if (!s.err) {
+      const int W = (pos_base + 31) >> 5;
+      for (int w = tid; w < W; w += T) x.bm[w] = 0u;
+      __syncthreads();
+      for (int i = tid; i < N1; i += T) {
+        int seq = ctx.hash[ctx.tokslot[i]].z;
+        atomicOr(&x.bm[seq >> 5], 1u << (seq & 31));
+      }
+      __syncthreads();
+      int wc = 0;
+      for (int base = 0; base < W; base += T) {
+        int w = base + tid;
+        int cnt = (w < W) ? __popc(x.bm[w]) : 0;
+        int total;
+        int excl = block_excl_scan<T>(cnt, s.redi, &total);
+        if (w < W) x.wbase[w] = wc + excl;
+        wc += total;
+      }
+      __syncthreads();
+      for (int i = tid; i < N1; i += T) {
+        int slot = ctx.tokslot[i];
+        int seq = ctx.hash[slot].z;
+        int ins = x.wbase[seq >> 5] + __popc(x.bm[seq >> 5] & ((1u << (seq & 31)) - 1u));
+        ctx.hash[slot].z = ins;
+        x.by_ins[ins] = slot;
+      }
+    }
+    finish_frame_exact<T>(p, s, ctx, x, lane, ch, frames_decoded + 1, next_cutoff, cost_offset, lbase,
+                          Hc, cs);
+    if (s.err) break;
+    tbase += min(s.ntok_new, p.max_tpf);
+    lbase += s.nlink_new;
+    frames_decoded++;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    cs->frames_decoded = frames_decoded;
+    cs->ntok = tbase;
+    cs->nlink = lbase;
+    cs->arcs_e += arcs_e_total;
+    cs->hc = Hc;
+    if (s.err) cs->status = s.err;
+  }
+  if (s.err) {
+    reset_lane_hash<T>(ctx.hash, p.hash_size);
+    for (int i = tid; i < p.hc_cap; i += T) { x.bfirst[i] = 0x7fffffff; x.bcount[i] = 0; x.bfill[i] = 0; }
+  }
+}
+
 // ------------------------------------------------------------------ finalize (backward sweep)
 
 // link_extra_cost of :342-344 / :433-435
@@ -738,7 +1296,7 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
         float lec = link_extra_cost(tok_extra[lk.y], tok_cost[lk.x], __int_as_float(lk.w), graph,
                                     tok_cost[lk.y]);
         if (lec > p.lattice_beam) {
-          links[l].x = -1;                     // excised (:348-354)
+          links[l].z = (int)((uint32_t)lk.z | B2K_DEAD_FLAG);   // excised (:348-354)
         } else {
           if (lec < 0.0f) lec = 0.0f;
           atomicMin(&nx[lk.x - tb], f2ord(lec));
@@ -760,11 +1318,11 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
       // new = base lowered by alive eps links using OLD extras of dst
       for (int l = eps_b + tid; l < eps_e; l += T) {
         int4 lk = links[l];
-        if (lk.x < 0) continue;
-        float graph = __int_as_float(__ldg(&g.ne_arcs[(uint32_t)lk.z & 0x7fffffffu]).y);
+        if ((uint32_t)lk.z & B2K_DEAD_FLAG) continue;
+        float graph = __int_as_float(__ldg(&g.ne_arcs[(uint32_t)lk.z & B2K_ARC_MASK]).y);
         float lec = link_extra_cost(tok_extra[lk.y], tok_cost[lk.x], 0.0f, graph, tok_cost[lk.y]);
         if (lec > p.lattice_beam) {
-          links[l].x = -1;
+          links[l].z = (int)((uint32_t)lk.z | B2K_DEAD_FLAG);
         } else {
           if (lec < 0.0f) lec = 0.0f;
           atomicMin(&nx[lk.x - tb], f2ord(lec));
@@ -796,7 +1354,7 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
         }
       }
     }
-    for (int l = eps_b + tid; l < eps_e; l += T) if (links[l].x >= 0) lat_arcs++;
+    for (int l = eps_b + tid; l < eps_e; l += T) if (!((uint32_t)links[l].z & B2K_DEAD_FLAG)) lat_arcs++;
     lat_arcs += emit_alive;
     __syncthreads();
   }
@@ -858,11 +1416,11 @@ __global__ void __launch_bounds__(T) dec_extract_kernel(DecParams p, int ch, Ext
   // links
   for (int l = gtid; l < cs->nlink; l += gstride) {
     int4 lk = links[l];
-    if (lk.x < 0) continue;
+    if ((uint32_t)lk.z & B2K_DEAD_FLAG) continue;
     int k = atomicAdd(&o.counters[1], 1);
     o.arc_src_tok[k] = lk.x; o.arc_dst_tok[k] = lk.y;
     if ((uint32_t)lk.z & B2K_EPS_FLAG) {
-      int4 arc = __ldg(&g.ne_arcs[(uint32_t)lk.z & 0x7fffffffu]);
+      int4 arc = __ldg(&g.ne_arcs[(uint32_t)lk.z & B2K_ARC_MASK]);
       o.arc_ilabel[k] = 0; o.arc_olabel[k] = arc.z;
       o.arc_graph[k] = __int_as_float(arc.y); o.arc_ac[k] = 0.0f;    // (:174-181, offset only if emitting)
     } else {
@@ -942,6 +1500,7 @@ void b2k_dec_cfg_default(b2k_dec_cfg *c) {
   c->beam_delta = 0.5f; c->prune_interval = 25; c->prune_scale = 0.1f;
   c->max_tokens_per_frame = 32768; c->max_frames = 1024;
   c->max_tokens = 3000000; c->max_links = 6000000;
+  c->reference_order = 1; c->hash_ratio = 2.0f; c->max_arcs_per_frame = 1 << 20;
 }
 
 int b2k_fst_create(const b2k_fst_csr *csr, b2k_fst **out) {
@@ -959,6 +1518,7 @@ int b2k_fst_create(const b2k_fst_csr *csr, b2k_fst **out) {
     }
   }
   st_off[N] = make_int2(e_cnt, ne_cnt);
+  if ((uint32_t)e_cnt > B2K_ARC_MASK || (uint32_t)ne_cnt > B2K_ARC_MASK) { delete f; return set_error(B2K_ERR_INVALID, "graphs above 2^30 arcs per class are not supported"); }
   f->h_e.resize(e_cnt); f->h_ne.resize(ne_cnt); f->h_eil.resize(e_cnt);
   int ei = 0, ni = 0;
   for (int s = 0; s < N; s++) {
@@ -1009,7 +1569,8 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
   if (!fst || !cfg || !out || nlanes <= 0 || nchannels < nlanes)
     return set_error(B2K_ERR_INVALID, "b2k_dec_create: bad args");
   if (!(cfg->beam > 0.0f && cfg->max_active > 1 && cfg->lattice_beam > 0.0f &&
-        cfg->min_active <= cfg->max_active && cfg->beam_delta > 0.0f))   // Check() lattice-faster-decoder.h:99-105
+        cfg->min_active <= cfg->max_active && cfg->beam_delta > 0.0f &&
+        (!cfg->reference_order || cfg->hash_ratio >= 1.0f)))   // Check() lattice-faster-decoder.h:99-105
     return set_error(B2K_ERR_INVALID, "b2k_dec_create: invalid decoder config");
   if (cfg->max_tokens > 0x7fffffffLL || cfg->max_links > 0x7fffffffLL)
     return set_error(B2K_ERR_INVALID, "arena capacities must fit int32");
@@ -1052,13 +1613,32 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
   A(p.cand, 4 * nl * 5 * (size_t)p.cand_cap, 0);
   A(p.new_extra, 4 * nl * p.max_tpf, 0);
   A(p.lane_stamp, 4 * nl, 0);
+  if (cfg->reference_order) {
+    p.pos_cap = ((std::max(cfg->max_arcs_per_frame, 1024) + 31) / 32) * 32;
+    p.hc_cap = std::max(1000, (int)((float)p.max_tpf * cfg->hash_ratio) + 1);
+    p.queue_cap = 5 * p.cand_cap;
+    p.hash_ratio = cfg->hash_ratio;
+    A(p.x_bm, 4 * nl * (p.pos_cap / 32), 0);
+    A(p.x_wbase, 4 * nl * (p.pos_cap / 32), 0);
+    A(p.x_by_ins, 4 * nl * p.max_tpf, 0);
+    A(p.x_bfirst, 4 * nl * p.hc_cap, 0);
+    A(p.x_bcount, 4 * nl * p.hc_cap, 0);
+    A(p.x_bfill, 4 * nl * p.hc_cap, 0);
+    A(p.x_sbase, 4 * nl * p.max_tpf, 0);
+    A(p.x_run, 4 * nl * p.max_tpf, 0);
+    A(p.x_order, 4 * nl * p.max_tpf, 0);
+    {
+      std::vector<int32_t> big((size_t)nl * p.hc_cap, 0x7fffffff);
+      B2K_CUDA_CHECK(cudaMemcpy(p.x_bfirst, big.data(), 4 * big.size(), cudaMemcpyHostToDevice));
+    }
+  }
   A(d->d_lane_channel, 4 * nl, 0);
   A(d->d_lane_ll, sizeof(float *) * nl, 0);
   A(d->d_lane_nframes, 4 * nl, 0);
 #undef A
   // hash init: key = EMPTY, cost = +inf (ord), tok = 0, stamp = 0
   {
-    std::vector<int4> init((size_t)p.hash_size, make_int4(B2K_HASH_EMPTY, (int)B2K_INF_ORD, 0, 0));
+    std::vector<int4> init((size_t)p.hash_size, make_int4(B2K_HASH_EMPTY, (int)B2K_INF_ORD, cfg->reference_order ? 0x7fffffff : 0, 0));
     for (int l = 0; l < nlanes; l++)
       B2K_CUDA_CHECK(cudaMemcpy(p.hash + (size_t)l * p.hash_size, init.data(),
                                 sizeof(int4) * init.size(), cudaMemcpyHostToDevice));
@@ -1127,7 +1707,8 @@ int b2k_dec_init_decoding(b2k_dec *d, const int32_t *channels, int32_t n, void *
   if (rc) return rc;
   DecParams p = d->p;
   p.do_init = 1;
-  dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
+  if (d->cfg.reference_order) dec_advance_exact_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
+  else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
   B2K_LAUNCH_CHECK();
   return B2K_OK;
 }
@@ -1142,7 +1723,8 @@ int b2k_dec_advance_decoding_frames(b2k_dec *d, const int32_t *channels,
   DecParams p = d->p;
   p.do_init = 0;
   p.row_stride = row_stride;
-  dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
+  if (d->cfg.reference_order) dec_advance_exact_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
+  else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
   B2K_LAUNCH_CHECK();
   return B2K_OK;
 }
@@ -1293,20 +1875,34 @@ int b2k_dec_debug_frame(b2k_dec *d, int32_t channel, int32_t frame_plus_one, int
     prev_states.resize(tb[0] - ptb);
     B2K_CUDA_CHECK(cudaMemcpy(prev_states.data(), ts + ptb, (size_t)(tb[0] - ptb) * 4, cudaMemcpyDeviceToHost));
   }
+  bool bad = false;
   auto state_of = [&](int32_t tok) -> int32_t {
-    if (tok >= tb[0]) return tok_state[tok - tb[0]];
-    return prev_states[tok - ptb];
+    if (tok >= tb[0] && tok < tb[1]) return tok_state[tok - tb[0]];
+    if (tok >= ptb && tok < tb[0]) return prev_states[tok - ptb];
+    bad = true;
+    return -1;
   };
+  const int64_t n_e = (int64_t)d->fst->h_e.size(), n_ne = (int64_t)d->fst->h_ne.size();
   for (int64_t i = 0; i < nl; i++) {
     int4 l = lk[i];
     int32_t *r = links7 + i * 7;
     r[0] = state_of(l.x); r[1] = state_of(l.y);
+    const int32_t zi = (int32_t)((uint32_t)l.z & B2K_ARC_MASK);
     if ((uint32_t)l.z & B2K_EPS_FLAG) {
-      int4 arc = d->fst->h_ne[(uint32_t)l.z & 0x7fffffffu];
+      int64_t a = zi;
+      if (a >= n_ne) { bad = true; continue; }
+      int4 arc = d->fst->h_ne[a];
       r[2] = 0; r[3] = arc.z; r[4] = arc.y; r[5] = 0; r[6] = 1;
     } else {
-      int4 arc = d->fst->h_e[l.z];
-      r[2] = d->fst->h_eil[l.z]; r[3] = arc.w; r[4] = arc.y; r[5] = l.w; r[6] = 0;
+      if (zi >= n_e) { bad = true; continue; }
+      int4 arc = d->fst->h_e[zi];
+      r[2] = d->fst->h_eil[zi]; r[3] = arc.w; r[4] = arc.y; r[5] = l.w; r[6] = 0;
+    }
+    if (bad) {
+      char buf[256];
+      snprintf(buf, sizeof(buf), "link %lld of frame %d = {%d,%d,%d,%d}; tok ranges prev [%d,%d) cur [%d,%d) links [%d,%d)",
+               (long long)i, frame_plus_one, l.x, l.y, l.z, l.w, ptb, tb[0], tb[0], tb[1], lb[0], lb[1]);
+      return set_error(B2K_ERR_STATE, "inconsistent link record", buf);
     }
   }
   (void)le;

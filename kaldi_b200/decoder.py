@@ -31,7 +31,9 @@ class _DecCfg(C.Structure):
     _fields_ = [("beam", C.c_float), ("lattice_beam", C.c_float), ("max_active", C.c_int32),
                 ("min_active", C.c_int32), ("beam_delta", C.c_float), ("prune_interval", C.c_int32),
                 ("prune_scale", C.c_float), ("max_tokens_per_frame", C.c_int32),
-                ("max_frames", C.c_int32), ("max_tokens", C.c_int64), ("max_links", C.c_int64)]
+                ("max_frames", C.c_int32), ("max_tokens", C.c_int64), ("max_links", C.c_int64),
+                ("reference_order", C.c_int32), ("hash_ratio", C.c_float),
+                ("max_arcs_per_frame", C.c_int32)]
 
 
 class _RawLattice(C.Structure):
@@ -56,7 +58,7 @@ class CudaFst:
                       _p(il, C.c_int32), _p(ol, C.c_int32), _p(w, C.c_float), _p(ns, C.c_int32),
                       _p(fin, C.c_float), _p(t2p, C.c_int32), int(t2p.size))
         self.h = C.c_void_p()
-        _lib.check(L.b2k_fst_create(C.byref(csr), C.byref(self.h)))
+        _lib.check(L.b2k_fst_create(C.cast(C.byref(csr), C.c_void_p), C.byref(self.h)))
         self.num_pdfs = int(graph["num_pdfs"])
 
     def NumStates(self) -> int:
@@ -88,12 +90,16 @@ class CudaDecoderConfig:
     max_frames: int = 1024
     max_tokens: int = 3_000_000
     max_links: int = 6_000_000
+    reference_order: bool = True     # bit-exact HashList-order emulation
+    hash_ratio: float = 2.0
+    max_arcs_per_frame: int = 1 << 20
 
     @classmethod
     def from_dict(cls, d: dict, **kw):
         return cls(default_beam=d["beam"], lattice_beam=d["lattice_beam"], max_active=d["max_active"],
                    min_active=d["min_active"], beam_delta=d["beam_delta"],
-                   prune_interval=d["prune_interval"], prune_scale=d["prune_scale"], **kw)
+                   prune_interval=d["prune_interval"], prune_scale=d["prune_scale"],
+                   hash_ratio=d.get("hash_ratio", 2.0), **kw)
 
 
 class CudaDecoder:
@@ -105,9 +111,10 @@ class CudaDecoder:
         self.fst, self.config, self.nlanes, self.nchannels = fst, config, nlanes, nchannels
         c = _DecCfg(config.default_beam, config.lattice_beam, config.max_active, config.min_active,
                     config.beam_delta, config.prune_interval, config.prune_scale,
-                    config.max_tokens_per_frame, config.max_frames, config.max_tokens, config.max_links)
+                    config.max_tokens_per_frame, config.max_frames, config.max_tokens, config.max_links,
+                    int(config.reference_order), config.hash_ratio, config.max_arcs_per_frame)
         self.h = C.c_void_p()
-        _lib.check(L.b2k_dec_create(fst.h, C.byref(c), nlanes, nchannels, C.byref(self.h)))
+        _lib.check(L.b2k_dec_create(fst.h, C.cast(C.byref(c), C.c_void_p), nlanes, nchannels, C.byref(self.h)))
 
     def __del__(self):
         try:
@@ -129,7 +136,7 @@ class CudaDecoder:
         (cuda-decoder.h:264-265)."""
         ch = self._chan([c for c, _ in lanes_assignments])
         ptrs = (C.c_void_p * len(ch))(*[int(ptr) for _, ptr in lanes_assignments])
-        _lib.check(_lib.lib().b2k_dec_advance_decoding(self.h, _p(ch, C.c_int32), ptrs, len(ch),
+        _lib.check(_lib.lib().b2k_dec_advance_decoding(self.h, _p(ch, C.c_int32), C.cast(ptrs, C.c_void_p), len(ch),
                                                      C.c_void_p(stream)))
 
     def AdvanceDecodingFrames(self, channels, loglike_ptrs, num_frames, row_stride: int, stream: int = 0):
@@ -137,7 +144,7 @@ class CudaDecoder:
         nf = np.ascontiguousarray(num_frames, dtype=np.int32)
         ptrs = (C.c_void_p * len(ch))(*[int(x) for x in loglike_ptrs])
         _lib.check(_lib.lib().b2k_dec_advance_decoding_frames(
-            self.h, _p(ch, C.c_int32), ptrs, _p(nf, C.c_int32), int(row_stride), len(ch),
+            self.h, _p(ch, C.c_int32), C.cast(ptrs, C.c_void_p), _p(nf, C.c_int32), int(row_stride), len(ch),
             C.c_void_p(stream)))
 
     def FinalizeDecoding(self, channels, stream: int = 0):
@@ -151,7 +158,7 @@ class CudaDecoder:
 
     def ChannelInfo(self, channel: int) -> dict:
         info = (C.c_int64 * 16)()
-        _lib.check(_lib.lib().b2k_dec_channel_info(self.h, int(channel), info))
+        _lib.check(_lib.lib().b2k_dec_channel_info(self.h, int(channel), C.cast(info, C.POINTER(C.c_int64))))
         keys = ["status", "frames_decoded", "ntok", "nlink", "arcs_emitting", "arcs_nonemitting",
                 "lat_states", "lat_arcs", "lat_finals", "finalized", "any_final"]
         return {k: int(info[i]) for i, k in enumerate(keys)}
@@ -161,7 +168,7 @@ class CudaDecoder:
         lattice-faster-decoder.cc:114-197)."""
         L = _lib.lib()
         r = _RawLattice()
-        _lib.check(L.b2k_dec_get_raw_lattice(self.h, int(channel), C.byref(r), C.c_void_p(stream)))
+        _lib.check(L.b2k_dec_get_raw_lattice(self.h, int(channel), C.cast(C.byref(r), C.c_void_p), C.c_void_p(stream)))
         ns, na, nf = r.num_states, r.num_arcs, r.num_finals
         out = dict(
             state_frame=np.zeros(ns, np.int32), state_hclg=np.zeros(ns, np.int32),
@@ -172,7 +179,7 @@ class CudaDecoder:
             final_state=np.zeros(nf, np.int32), final_cost=np.zeros(nf, np.float32))
         for k, v in out.items():
             setattr(r, k, _p(v, C.c_float if v.dtype == np.float32 else C.c_int32))
-        _lib.check(L.b2k_dec_get_raw_lattice(self.h, int(channel), C.byref(r), C.c_void_p(stream)))
+        _lib.check(L.b2k_dec_get_raw_lattice(self.h, int(channel), C.cast(C.byref(r), C.c_void_p), C.c_void_p(stream)))
         return out
 
     def DebugFrame(self, channel: int, frame_plus_one: int):

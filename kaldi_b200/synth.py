@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["make_hclg", "make_loglikes", "make_audio", "DEFAULT_DECODER_CFG"]
+__all__ = ["make_hclg", "make_loglikes", "make_audio", "tiny_graph", "DEFAULT_DECODER_CFG"]
 
 # recipe decode settings: egs/wsj/s5/steps/online/nnet3/decode.sh:13-16 and
 # LatticeFasterDecoderConfig defaults (decoder/lattice-faster-decoder.h:38-106)
@@ -142,3 +142,16 @@ def make_audio(num_samples: int, seed: int = 0, sample_rate: float = 16000.0) ->
     x = 3000.0 * env * x + rng.standard_normal(num_samples) * 300.0
     x = np.clip(np.round(x), -32768, 32767)
     return x.astype(np.float32)
+
+
+def tiny_graph() -> dict:
+    """3-state hand-built graph with a known best path (config 1 style plumbing):
+    0 --(tid1/pdf0, w=1, o=7)--> 1 ; 0 --(eps, w=0.5)--> 2 ; 2 --(tid2/pdf1, w=0.25, o=9)--> 1 ;
+    1 --(tid1 self-loop, w=0.1)--> 1 ; state 1 final with cost 0."""
+    return dict(num_states=3, start=0, num_pdfs=2,
+                offsets=np.array([0, 2, 3, 4], np.int32),
+                ilabel=np.array([1, 0, 1, 2], np.int32), olabel=np.array([7, 0, 0, 9], np.int32),
+                weight=np.array([1.0, 0.5, 0.1, 0.25], np.float32),
+                nextstate=np.array([1, 2, 1, 1], np.int32),
+                final=np.array([np.inf, 0.0, np.inf], np.float32),
+                tid2pdf=np.array([0, 0, 1], np.int32))

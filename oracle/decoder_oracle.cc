@@ -725,6 +725,10 @@ struct Oracle {
     n_extra_links_ = n_best_ties_ = n_min_active_branch_ = n_max_active_branch_ = 0;
     n_extras_expanded_ = n_links_admitted_ = n_toks_created_ = 0;
     frame_cutoff_.clear(); frame_ntoks_.clear(); raw_.clear();
+    // the reference tools construct a fresh decoder per utterance
+    // (online2-wav-nnet3-latgen-faster.cc:228): hash size restarts at 1000 (:39)
+    DeleteElems(toks_.Clear());
+    toks_.SetSize(1000);
     InitDecoding();
     while (NumFramesDecoded() < T) {                               // :621-627
       if (NumFramesDecoded() % cfg.prune_interval == 0)

@@ -12,11 +12,15 @@ from kaldi_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def _mk(g, cfg, nlanes=1, nchannels=None, T=64, **kw):
+REF, FREE = True, False      # reference_order=True <-> oracle mode 0; False <-> oracle mode 1
+
+
+def _mk(g, cfg, nlanes=1, nchannels=None, T=64, ref=REF, **kw):
     from kaldi_b200.decoder import CudaFst, CudaDecoder, CudaDecoderConfig
     fst = CudaFst(g)
     c = CudaDecoderConfig.from_dict(cfg, max_frames=max(T + 2, 16), max_tokens=kw.get("max_tokens", 1_500_000),
-                                    max_links=kw.get("max_links", 3_000_000))
+                                    max_links=kw.get("max_links", 3_000_000), reference_order=ref,
+                                    max_tokens_per_frame=kw.get("max_tpf", 32768))
     return fst, CudaDecoder(fst, c, nlanes, nchannels)
 
 
@@ -49,7 +53,8 @@ def _check_against_oracle(g, cfg, ll, dec, channel, frames=True):
     from kaldi_b200.decoder import lattice_to_canonical
     from oracle import dec_oracle as D
     o = D.DecoderOracle(g, cfg)
-    o.decode(ll, mode=D.MODE_ORDER_FREE, record_frames=frames)
+    ref = dec.config.reference_order
+    o.decode(ll, mode=D.MODE_REFERENCE_ORDER if ref else D.MODE_ORDER_FREE, record_frames=frames)
     info = dec.ChannelInfo(channel)
     assert info["status"] == 0, info
     assert info["frames_decoded"] == ll.shape[0]
@@ -73,32 +78,35 @@ def _check_against_oracle(g, cfg, ll, dec, channel, frames=True):
         assert np.array_equal(got[k], want[k]), f"finalized lattice differs in {k}"
     st = o.stats()
     assert info["arcs_emitting"] == st["arcs_emitting"]
+    if ref:   # the eps replay is literal in this mode, so even the visit count matches
+        assert info["arcs_nonemitting"] == st["arcs_nonemitting"]
     return st
 
 
-def test_tiny_graph():
-    from tests.test_decoder_oracle import tiny_graph
-    g = tiny_graph()
+@pytest.mark.parametrize("ref", [REF, FREE])
+def test_tiny_graph(ref):
+    g = synth.tiny_graph()
     cfg = dict(synth.DEFAULT_DECODER_CFG, min_active=0)
     ll = np.array([[0.0, 3.0], [1.0, 0.0]], np.float32)
-    fst, dec = _mk(g, cfg, T=2, max_tokens=1000, max_links=1000)
+    fst, dec = _mk(g, cfg, T=2, max_tokens=1000, max_links=1000, ref=ref)
     _run_gpu(dec, [ll])
     _check_against_oracle(g, cfg, ll, dec, 0)
 
 
+@pytest.mark.parametrize("ref", [REF, FREE])
 @pytest.mark.parametrize("seed,cfgmod", [
     (0, {}),                                            # recipe settings: beam 15, max-active 7000, min-active 200
-    (1, {"max_active": 2**31 - 1, "min_active": 0, "beam": 11.0}),   # GetCutoff fast path
+    (1, {"max_active": 2**31 - 1, "min_active": 0, "beam": 9.0}),    # GetCutoff fast path (up to 61 k tokens/frame)
     (2, {"max_active": 3000}),                          # max_active fires on most frames
     (3, {"beam": 10.0, "lattice_beam": 6.0}),
     (4, {"beam": 8.0, "min_active": 2000}),             # min_active branch
 ])
-def test_frames_and_lattice_bit_exact(seed, cfgmod):
+def test_frames_and_lattice_bit_exact(seed, cfgmod, ref):
     g = synth.make_hclg(400_000, num_pdfs=800, seed=seed)
     T = 50
     ll = synth.make_loglikes(g, T, seed=seed + 100)
     cfg = dict(synth.DEFAULT_DECODER_CFG, **cfgmod)
-    fst, dec = _mk(g, cfg, T=T)
+    fst, dec = _mk(g, cfg, T=T, ref=ref, max_tpf=131072 if cfgmod.get("min_active") == 0 else 32768)
     _run_gpu(dec, [ll])
     st = _check_against_oracle(g, cfg, ll, dec, 0)
     if "max_active" in cfgmod and cfgmod["max_active"] == 3000:
@@ -107,12 +115,13 @@ def test_frames_and_lattice_bit_exact(seed, cfgmod):
         assert st["min_active_branch"] > 0
 
 
-def test_multi_lane_chunked_and_one_frame_api():
+@pytest.mark.parametrize("ref", [REF, FREE])
+def test_multi_lane_chunked_and_one_frame_api(ref):
     g = synth.make_hclg(300_000, num_pdfs=500, seed=7)
     cfg = dict(synth.DEFAULT_DECODER_CFG)
     lls = [synth.make_loglikes(g, T, seed=20 + i) for i, T in enumerate([30, 17, 25, 30])]
     # whole-utterance, ragged lengths
-    fst, dec = _mk(g, cfg, nlanes=4, T=32, max_tokens=600_000, max_links=1_200_000)
+    fst, dec = _mk(g, cfg, nlanes=4, T=32, max_tokens=600_000, max_links=1_200_000, ref=ref)
     _run_gpu(dec, lls)
     for c in range(4):
         _check_against_oracle(g, cfg, lls[c], dec, c, frames=False)
@@ -133,12 +142,13 @@ def test_dead_end_graph_no_surviving_tokens():
              final=np.array([np.inf, np.inf], np.float32), tid2pdf=np.array([0, 0], np.int32))
     cfg = dict(synth.DEFAULT_DECODER_CFG)
     ll = np.zeros((3, 1), np.float32)
-    fst, dec = _mk(g, cfg, T=3, max_tokens=100, max_links=100)
-    _run_gpu(dec, [ll])
-    info = dec.ChannelInfo(0)
-    assert info["status"] == 0 and info["frames_decoded"] == 3
-    fi = dec.FrameInfo(0, 3)
-    assert fi["ntoks"].tolist() == [1, 0, 0]
+    for ref in (REF, FREE):
+        fst, dec = _mk(g, cfg, T=3, max_tokens=100, max_links=100, ref=ref)
+        _run_gpu(dec, [ll])
+        info = dec.ChannelInfo(0)
+        assert info["status"] == 0 and info["frames_decoded"] == 3
+        fi = dec.FrameInfo(0, 3)
+        assert fi["ntoks"].tolist() == [1, 0, 0]
 
 
 def test_overflow_is_reported_not_silent():

@@ -13,19 +13,7 @@ from oracle import dec_oracle as D
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def tiny_graph():
-    """3-state hand-built graph with a known best path.
-    0 --(tid1/pdf0, w=1, o=7)--> 1 ; 0 --(eps, w=0.5)--> 2 ; 2 --(tid2/pdf1,w=0.25,o=9)--> 1
-    1 --(tid1 selfloop w=0.1)--> 1 ; 1 final 0.0"""
-    offsets = np.array([0, 2, 3, 4], np.int32)
-    ilabel = np.array([1, 0, 1, 2], np.int32)
-    olabel = np.array([7, 0, 0, 9], np.int32)
-    weight = np.array([1.0, 0.5, 0.1, 0.25], np.float32)
-    nextstate = np.array([1, 2, 1, 1], np.int32)
-    final = np.array([np.inf, 0.0, np.inf], np.float32)
-    tid2pdf = np.array([0, 0, 1], np.int32)
-    return dict(num_states=3, start=0, num_pdfs=2, offsets=offsets, ilabel=ilabel, olabel=olabel,
-                weight=weight, nextstate=nextstate, final=final, tid2pdf=tid2pdf)
+tiny_graph = synth.tiny_graph
 
 
 def test_tiny_graph_known_answer():
