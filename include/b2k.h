@@ -168,6 +168,67 @@ int b2k_dec_debug_frame(b2k_dec *dec, int32_t channel, int32_t frame_plus_one,
 int b2k_dec_frame_info(b2k_dec *dec, int32_t channel, float *cutoff, float *cost_offset,
                        int32_t *ntoks, int32_t cap);
 
+/* ----------------------------------------------------------------- features */
+
+/* Union of MfccOptions / FbankOptions / FrameExtractionOptions / MelBanksOptions
+ * (feat/feature-mfcc.h:38-60, feature-fbank.h:41-60, feature-window.h:38-66,
+ * mel-computations.h:43-58) — what OnlineNnet2FeaturePipelineInfo reads from
+ * --mfcc-config / --fbank-config (online2/online-nnet2-feature-pipeline.cc:36-60). */
+typedef struct {
+  int32_t feature_type;        /* 0 = mfcc, 1 = fbank                           */
+  float samp_freq, frame_shift_ms, frame_length_ms;
+  float dither;                /* must be 0 (reference dither is unseeded)      */
+  float preemph_coeff;
+  int32_t remove_dc_offset, round_to_power_of_two, snip_edges;
+  int32_t window_type;         /* 0 povey, 1 hamming, 2 hanning, 3 rectangular  */
+  int32_t num_bins;
+  float low_freq, high_freq;
+  int32_t num_ceps, use_energy;
+  float energy_floor;
+  int32_t raw_energy;
+  float cepstral_lifter;
+  int32_t htk_compat, use_log_fbank, use_power, htk_mode;
+  int32_t max_lanes;
+} b2k_feat_cfg;
+
+void b2k_feat_cfg_default(b2k_feat_cfg *cfg);   /* mfcc_hires.conf with --dither=0 */
+
+typedef struct b2k_feat b2k_feat;
+
+/* MfccComputer / FbankComputer constructors (feature-mfcc.cc:82-115): builds the
+ * window, mel-bank, DCT and lifter tables on the host and uploads them. */
+int b2k_feat_create(const b2k_feat_cfg *cfg, b2k_feat **out);
+int b2k_feat_destroy(b2k_feat *f);
+int32_t b2k_feat_dim(const b2k_feat *f);                                    /* Dim()       */
+int32_t b2k_feat_num_frames(const b2k_feat *f, int64_t num_samples, int32_t flush);   /* NumFrames feature-window.cc:42 */
+
+/* OnlineBatchedFeaturePipelineCuda::ComputeFeaturesBatched
+ * (cudafeat/online-batched-feature-pipeline-cuda.h:44-134) /
+ * OnlineGenericBaseFeature::ComputeFeatures (feat/online-feature.cc:162-204):
+ * lane i computes frames [first_frame[i], first_frame[i]+num_frames[i]) of the
+ * utterance whose samples so far are d_wave[i][0..num_samples[i]) (Kaldi's
+ * int16-range float convention) into d_out[i] + frame*row_stride. */
+int b2k_feat_compute_batched(b2k_feat *f, int32_t num_lanes, const float *const *d_wave,
+                             const int32_t *num_samples, const int32_t *first_frame,
+                             const int32_t *num_frames, float *const *d_out, int32_t row_stride,
+                             void *stream);
+
+/* OnlineCmvnOptions (feat/online-feature.h:203-227) */
+typedef struct {
+  int32_t cmn_window, speaker_frames, global_frames, normalize_mean, normalize_variance;
+} b2k_cmvn_cfg;
+
+/* OnlineCmvn::GetFrame for a run of consecutive frames per lane
+ * (feat/online-feature.cc:421-452).  d_state[i]: [2*(dim+1)] doubles, the raw
+ * sliding-window stats after frame first_frame[i]-1 (zero before frame 0),
+ * updated in place; d_global_stats / d_speaker_stats: OnlineCmvnState
+ * global_cmvn_stats / speaker_cmvn_stats as [2*(dim+1)] doubles. */
+int b2k_cmvn_apply_batched(b2k_feat *f, const b2k_cmvn_cfg *cfg, int32_t num_lanes,
+                           const float *const *d_in, float *const *d_out, int32_t in_stride,
+                           int32_t out_stride, const int32_t *first_frame, const int32_t *num_frames,
+                           double *const *d_state, const double *d_global_stats,
+                           const double *d_speaker_stats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

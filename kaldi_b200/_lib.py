@@ -57,6 +57,10 @@ def _declare(L) -> None:
         "b2k_dec_get_raw_lattice": [vp, i32, vp, vp],
         "b2k_dec_debug_frame": [vp, i32, i32, P(i32), P(f32), P(i64), P(i32), P(i64), i64, i64],
         "b2k_dec_frame_info": [vp, i32, P(f32), P(f32), P(i32), i32],
+        "b2k_feat_cfg_default": [vp], "b2k_feat_create": [vp, P(vp)], "b2k_feat_destroy": [vp],
+        "b2k_feat_dim": [vp], "b2k_feat_num_frames": [vp, i64, i32],
+        "b2k_feat_compute_batched": [vp, i32, vp, P(i32), P(i32), P(i32), vp, i32, vp],
+        "b2k_cmvn_apply_batched": [vp, vp, i32, vp, vp, i32, i32, P(i32), P(i32), vp, vp, vp, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)

@@ -1,0 +1,127 @@
+// oracle/ref_wrap/feat_wrap.cc — TEST INFRASTRUCTURE ONLY.
+// Thin extern "C" wrapper (our code) around the reference's OWN feature code,
+// which is compiled from the sources where they lie under /root/reference/src
+// (see oracle/ref_feat.py).  Nothing from the reference is copied here; this
+// file only calls its public API:
+//   Mfcc/Fbank::ComputeFeatures            feat/feature-common-inl.h
+//   OnlineMfcc/OnlineFbank, OnlineCmvn     feat/online-feature.{h,cc}
+//   OnlineMatrixFeature                    feat/online-feature.h
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "feat/feature-fbank.h"
+#include "feat/feature-mfcc.h"
+#include "feat/online-feature.h"
+#include "matrix/kaldi-matrix.h"
+
+using namespace kaldi;
+
+extern "C" {
+
+struct ref_feat_opts {
+  int feature_type;        // 0 mfcc, 1 fbank
+  float samp_freq, frame_shift_ms, frame_length_ms, dither, preemph_coeff;
+  int remove_dc_offset, round_to_power_of_two, snip_edges;
+  int num_bins;
+  float low_freq, high_freq;
+  int num_ceps, use_energy;
+  float energy_floor;
+  int raw_energy;
+  float cepstral_lifter;
+  int htk_compat, use_log_fbank, use_power;
+  int window_type;         // 0 povey, 1 hamming, 2 hanning, 3 rectangular
+  int htk_mode;            // MelBanksOptions::htk_mode (hidden test option)
+};
+
+static void fill_frame(const ref_feat_opts *o, FrameExtractionOptions *f) {
+  f->samp_freq = o->samp_freq; f->frame_shift_ms = o->frame_shift_ms;
+  f->frame_length_ms = o->frame_length_ms; f->dither = o->dither;
+  f->preemph_coeff = o->preemph_coeff; f->remove_dc_offset = o->remove_dc_offset != 0;
+  static const char *kWin[] = {"povey", "hamming", "hanning", "rectangular"};
+  f->window_type = kWin[o->window_type & 3]; f->round_to_power_of_two = o->round_to_power_of_two != 0;
+  f->snip_edges = o->snip_edges != 0;
+}
+static MfccOptions mfcc_opts(const ref_feat_opts *o) {
+  MfccOptions m;
+  fill_frame(o, &m.frame_opts);
+  m.mel_opts.num_bins = o->num_bins; m.mel_opts.low_freq = o->low_freq; m.mel_opts.high_freq = o->high_freq;
+  m.mel_opts.htk_mode = o->htk_mode != 0;
+  m.num_ceps = o->num_ceps; m.use_energy = o->use_energy != 0; m.energy_floor = o->energy_floor;
+  m.raw_energy = o->raw_energy != 0; m.cepstral_lifter = o->cepstral_lifter; m.htk_compat = o->htk_compat != 0;
+  return m;
+}
+static FbankOptions fbank_opts(const ref_feat_opts *o) {
+  FbankOptions m;
+  fill_frame(o, &m.frame_opts);
+  m.mel_opts.num_bins = o->num_bins; m.mel_opts.low_freq = o->low_freq; m.mel_opts.high_freq = o->high_freq;
+  m.mel_opts.htk_mode = o->htk_mode != 0;
+  m.use_energy = o->use_energy != 0; m.energy_floor = o->energy_floor; m.raw_energy = o->raw_energy != 0;
+  m.htk_compat = o->htk_compat != 0; m.use_log_fbank = o->use_log_fbank != 0; m.use_power = o->use_power != 0;
+  return m;
+}
+
+// offline: whole-utterance features.  returns number of frames (or -1), writes dim.
+int ref_feat_compute(const ref_feat_opts *o, const float *wave, int n, float *out, int max_rows, int *dim) {
+  try {
+    SubVector<BaseFloat> w(const_cast<float *>(wave), n);
+    Matrix<BaseFloat> feats;
+    if (o->feature_type == 0) { Mfcc m(mfcc_opts(o)); m.ComputeFeatures(w, o->samp_freq, 1.0, &feats); }
+    else { Fbank m(fbank_opts(o)); m.ComputeFeatures(w, o->samp_freq, 1.0, &feats); }
+    *dim = feats.NumCols();
+    if (feats.NumRows() > max_rows) return -2;
+    for (int r = 0; r < feats.NumRows(); r++) memcpy(out + (size_t)r * feats.NumCols(), feats.RowData(r), 4 * feats.NumCols());
+    return feats.NumRows();
+  } catch (...) { return -1; }
+}
+
+// online: feed `chunk`-sample pieces through OnlineMfcc/OnlineFbank (the path
+// OnlineNnet2FeaturePipeline uses), InputFinished at the end.
+int ref_feat_online(const ref_feat_opts *o, const float *wave, int n, int chunk, float *out, int max_rows, int *dim) {
+  try {
+    std::unique_ptr<OnlineBaseFeature> f;
+    if (o->feature_type == 0) f.reset(new OnlineMfcc(mfcc_opts(o)));
+    else f.reset(new OnlineFbank(fbank_opts(o)));
+    for (int off = 0; off < n; off += chunk) {
+      int len = std::min(chunk, n - off);
+      SubVector<BaseFloat> w(const_cast<float *>(wave) + off, len);
+      f->AcceptWaveform(o->samp_freq, w);
+    }
+    f->InputFinished();
+    int T = f->NumFramesReady(), D = f->Dim();
+    *dim = D;
+    if (T > max_rows) return -2;
+    for (int t = 0; t < T; t++) { SubVector<BaseFloat> row(out + (size_t)t * D, D); f->GetFrame(t, &row); }
+    return T;
+  } catch (...) { return -1; }
+}
+
+// OnlineCmvn over precomputed features (OnlineMatrixFeature source).
+// global_stats: [2 x (D+1)] double (may be NULL -> zero stats); frames are
+// requested in the order given by `order` (NULL = 0..T-1) to exercise the
+// cached-stats paths (online-feature.cc:337-368).
+int ref_cmvn_online(const float *feats, int T, int D, int cmn_window, int speaker_frames, int global_frames,
+                    int normalize_mean, int normalize_variance, const double *global_stats,
+                    const int *order, int n_order, float *out) {
+  try {
+    Matrix<BaseFloat> m(T, D);
+    for (int t = 0; t < T; t++) memcpy(m.RowData(t), feats + (size_t)t * D, 4 * D);
+    OnlineMatrixFeature src(m);
+    OnlineCmvnOptions opts;
+    opts.cmn_window = cmn_window; opts.speaker_frames = speaker_frames; opts.global_frames = global_frames;
+    opts.normalize_mean = normalize_mean != 0; opts.normalize_variance = normalize_variance != 0;
+    Matrix<double> g(2, D + 1);
+    if (global_stats) for (int r = 0; r < 2; r++) for (int c = 0; c <= D; c++) g(r, c) = global_stats[r * (D + 1) + c];
+    OnlineCmvnState state(g);
+    OnlineCmvn cmvn(opts, state, &src);
+    int n = order ? n_order : T;
+    for (int i = 0; i < n; i++) {
+      int t = order ? order[i] : i;
+      SubVector<BaseFloat> row(out + (size_t)i * D, D);
+      cmvn.GetFrame(t, &row);
+    }
+    return n;
+  } catch (...) { return -1; }
+}
+
+}  // extern "C"
