@@ -229,6 +229,63 @@ int b2k_cmvn_apply_batched(b2k_feat *f, const b2k_cmvn_cfg *cfg, int32_t num_lan
                            double *const *d_state, const double *d_global_stats,
                            const double *d_speaker_stats, void *stream);
 
+/* -------------------------------------------------------------------- nnet3 */
+
+/* A compiled forward program for one utterance length: the analogue of the
+ * reference's NnetComputation (nnet3/nnet-computation.h) for the TDNN-F family,
+ * produced by kaldi_b200/nnet_model.py (compile_program).  The executor stands
+ * behind NnetComputer::{AcceptInput,Run,GetOutputDestructive}
+ * (nnet3/nnet-compute.h:95-200) as driven by DecodableNnetLoopedOnlineBase::
+ * AdvanceChunk (nnet3/decodable-online-looped.cc:118-236) and
+ * BatchedStaticNnet3::RunBatch (cudadecoder/batched-static-nnet3.h:59-138). */
+typedef struct {
+  int32_t dim, rows;
+  int32_t kind;          /* 0 internal, 1 "input" features, 2 "ivector" (one row per chunk), 3 "output" */
+  int64_t arena_off;     /* internal nodes: float offset in the per-utterance arena   */
+} b2k_nnet_node;
+
+typedef struct {
+  int32_t src;           /* source node                                              */
+  int32_t ratio, shift;  /* src_row = clamp(out_row*ratio + shift, lo, hi)            */
+  int32_t lo, hi;
+  int32_t ivec;          /* 1: src rows are chunks: row = clamp(floor(t/C) - m, lo, hi) with t = out_row*ratio+shift */
+  int32_t C, m;
+  int32_t k0, klen;      /* GEMM: columns [k0, k0+klen) of W multiply this term       */
+  float scale;           /* EW: coefficient                                          */
+  int32_t block;         /* EW: output column block this term adds into              */
+} b2k_nnet_term;
+
+typedef struct {
+  int32_t type;          /* 0 GEMM (+fused epilogue), 1 elementwise                   */
+  int32_t out, rows, N, K;
+  int32_t n_terms;
+  b2k_nnet_term terms[8];
+  int64_t w, bias, bn_scale, bn_offset, sub_vec;   /* float offsets into the blob, -1 = absent */
+  int32_t relu, has_res;
+  b2k_nnet_term res;     /* bypass input: out = res_alpha*res + bn(...)               */
+  float res_alpha, out_scale;
+  int32_t log_softmax, block_dim;
+} b2k_nnet_op;
+
+typedef struct b2k_nnet b2k_nnet;
+
+int b2k_nnet_create(const b2k_nnet_node *nodes, int32_t n_nodes, const b2k_nnet_op *ops, int32_t n_ops,
+                    const float *blob, int64_t blob_len, int32_t max_batch, b2k_nnet **out);
+int b2k_nnet_destroy(b2k_nnet *nn);
+int32_t b2k_nnet_num_output_frames(const b2k_nnet *nn);
+int32_t b2k_nnet_output_dim(const b2k_nnet *nn);
+double b2k_nnet_flops_per_lane(const b2k_nnet *nn);
+int32_t b2k_nnet_num_launches_per_run(const b2k_nnet *nn);
+
+/* One forward pass for `batch` utterances of the compiled length.  d_input[i]:
+ * [T x feat_dim] features (row stride in_stride); d_ivectors[i]: [n_chunks x
+ * ivector_dim], the i-vector the looped computation received for each chunk;
+ * d_output[i]: [ceil(T/subsampling) x num_pdfs] pseudo log-likelihoods with
+ * -log prior and acoustic scale applied (decodable-online-looped.cc:218-223). */
+int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32_t in_stride,
+                 const float *const *d_ivectors, int32_t iv_stride, float *const *d_output,
+                 int32_t out_stride, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

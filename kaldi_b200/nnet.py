@@ -1,0 +1,121 @@
+"""Host-side mirror of the reference's nnet3 inference surface over the b2k
+C-ABI: the pair (DecodableNnetSimpleLoopedInfo, NnetComputer) of
+nnet3/decodable-simple-looped.h:102-160 / nnet-compute.h:95-200 and the batched
+wrapper cuda_decoder::BatchedStaticNnet3 (cudadecoder/batched-static-nnet3.h)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import nnet_model as NM
+
+
+class _Node(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("rows", C.c_int32), ("kind", C.c_int32), ("arena_off", C.c_int64)]
+
+
+class _Term(C.Structure):
+    _fields_ = [("src", C.c_int32), ("ratio", C.c_int32), ("shift", C.c_int32), ("lo", C.c_int32),
+                ("hi", C.c_int32), ("ivec", C.c_int32), ("C", C.c_int32), ("m", C.c_int32),
+                ("k0", C.c_int32), ("klen", C.c_int32), ("scale", C.c_float), ("block", C.c_int32)]
+
+
+class _Op(C.Structure):
+    _fields_ = [("type", C.c_int32), ("out", C.c_int32), ("rows", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+                ("n_terms", C.c_int32), ("terms", _Term * 8),
+                ("w", C.c_int64), ("bias", C.c_int64), ("bn_scale", C.c_int64), ("bn_offset", C.c_int64),
+                ("sub_vec", C.c_int64), ("relu", C.c_int32), ("has_res", C.c_int32), ("res", _Term),
+                ("res_alpha", C.c_float), ("out_scale", C.c_float), ("log_softmax", C.c_int32),
+                ("block_dim", C.c_int32)]
+
+
+def _term(d: dict, k0=0, klen=0, scale=1.0, block=0) -> _Term:
+    return _Term(d["src"], d["ratio"], d["shift"], d["lo"], d["hi"], d.get("ivec", 0), d.get("C", 1), d.get("m", 0),
+                 d.get("k0", k0), d.get("klen", klen), d.get("scale", scale), block)
+
+
+class NnetComputer:
+    """Compiled, batched forward of one TDNN-F model for utterances of a fixed
+    number of feature frames (the reference compiles one NnetComputation per
+    request shape as well, nnet3/nnet-compile-looped.cc:329)."""
+
+    def __init__(self, arch: dict, W: dict, num_frames: int, max_batch: int, frames_per_chunk: int = 21,
+                 acoustic_scale: float = 1.0, use_priors: bool = True):
+        self.prog = prog = NM.compile_program(arch, W, num_frames, frames_per_chunk, acoustic_scale, use_priors)
+        nodes = (_Node * len(prog["nodes"]))()
+        for i, (name, dim, rows, t0, step) in enumerate(prog["nodes"]):
+            kind = {"input": 1, "ivector": 2, "output": 3}.get(name, 0)
+            nodes[i] = _Node(dim, rows, kind, prog["arena_off"].get(i, 0))
+        ops = (_Op * len(prog["ops"]))()
+        for i, o in enumerate(prog["ops"]):
+            op = _Op()
+            op.out, op.rows = o["out"], o["rows"]
+            op.w = op.bias = op.sub_vec = -1
+            op.bn_scale, op.bn_offset = o.get("bn_scale", -1), o.get("bn_offset", -1)
+            op.out_scale, op.block_dim = 1.0, 1
+            if o["type"] == "gemm":
+                op.type, op.N, op.K = 0, o["N"], o["K"]
+                op.n_terms = len(o["terms"])
+                assert op.n_terms <= 8
+                for j, t in enumerate(o["terms"]):
+                    op.terms[j] = _term(t)
+                op.w, op.bias, op.sub_vec = o["w"], o["bias"], o.get("sub_vec", -1)
+                op.relu, op.log_softmax, op.out_scale = o["relu"], o["log_softmax"], o["out_scale"]
+                if o.get("res"):
+                    op.has_res, op.res, op.res_alpha = 1, _term(o["res"]), o["res_alpha"]
+            else:
+                op.type, op.block_dim = 1, o["block_dim"]
+                flat = [(b, t) for b, blk in enumerate(o["blocks"]) for t in blk]
+                op.n_terms = len(flat)
+                assert op.n_terms <= 8
+                for j, (b, t) in enumerate(flat):
+                    op.terms[j] = _term(t, block=b)
+                op.N = op.K = 0
+            ops[i] = op
+        blob = np.ascontiguousarray(prog["blob"], np.float32)
+        self.h = C.c_void_p()
+        L = _lib.lib()
+        _lib.check(L.b2k_nnet_create(C.cast(nodes, C.c_void_p), len(nodes), C.cast(ops, C.c_void_p), len(ops),
+                                     blob.ctypes.data_as(C.POINTER(C.c_float)), blob.size, int(max_batch),
+                                     C.byref(self.h)))
+        self.max_batch = max_batch
+        self.num_frames = num_frames
+        self.n_out = prog["n_out"]
+        self.n_chunks = prog["n_chunks"]
+        self.output_dim = arch["num_pdfs"]
+        self.feat_dim = arch["feat_dim"]
+        self.ivector_dim = arch["ivector_dim"]
+        self.flops_per_utt = float(L.b2k_nnet_flops_per_lane(self.h))
+        self.launches_per_run = int(L.b2k_nnet_num_launches_per_run(self.h))
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().b2k_nnet_destroy(self.h)
+        except Exception:
+            pass
+
+    def Run(self, input_ptrs, in_stride, ivector_ptrs, iv_stride, output_ptrs, out_stride, stream: int = 0):
+        n = len(input_ptrs)
+
+        def arr(ptrs):
+            a = (C.c_void_p * n)(*[int(p) for p in ptrs])
+            return C.cast(a, C.c_void_p), a
+        ip, k1 = arr(input_ptrs)
+        vp, k2 = arr(ivector_ptrs) if ivector_ptrs is not None else (None, None)
+        op, k3 = arr(output_ptrs)
+        _lib.check(_lib.lib().b2k_nnet_run(self.h, n, ip, int(in_stride), vp, int(iv_stride), op, int(out_stride),
+                                           C.c_void_p(stream)))
+
+    # test convenience
+    def forward(self, feats_list, chunk_ivectors_list):
+        import torch
+        d_in = [torch.from_numpy(np.ascontiguousarray(f, np.float32)).cuda() for f in feats_list]
+        d_iv = [torch.from_numpy(np.ascontiguousarray(v, np.float32)).cuda() for v in chunk_ivectors_list]
+        d_out = [torch.zeros(self.n_out, self.output_dim, device="cuda") for _ in feats_list]
+        self.Run([x.data_ptr() for x in d_in], self.feat_dim, [x.data_ptr() for x in d_iv], self.ivector_dim,
+                 [x.data_ptr() for x in d_out], self.output_dim)
+        torch.cuda.synchronize()
+        return [o.cpu().numpy() for o in d_out]

@@ -1,0 +1,550 @@
+"""TDNN-F chain acoustic models for the nnet3 stage: architecture descriptions
+with the exact layer shapes of the named recipes, seeded synthetic weights
+(there are no trained models in the reference tree, SURVEY.md §7 hard part 8),
+the nnet3 config text the reference itself can read (Nnet::ReadConfig,
+nnet3/nnet-nnet.cc:189), and the compiler from an architecture to the flat op
+program the CUDA executor runs (kaldi_b200/csrc/nnet.cu).
+
+The compile step plays the role of the reference's nnet3 compiler
+(nnet3/nnet-compile.cc, nnet-compile-looped.cc) for this model family: it
+works out, per node, the time grid (step 1 or frame_subsampling_factor) and
+range that the requested outputs need, exactly as the reference only computes
+required Indexes, and turns descriptors (Append/Offset/Sum/Scale/ReplaceIndex,
+nnet3/nnet-descriptor.h) into row mappings of fused GEMM / elementwise ops.
+
+Layer types (xconfig name -> components it expands to, composite_layers.py /
+basic_layers.py / trivial_layers.py of egs/wsj/s5/steps/libs/nnet3/xconfig):
+  idct            FixedAffineComponent
+  batchnorm       BatchNormComponent (test mode)
+  delta           NoOp over Append(Offset..)/Sum/Scale + BatchNorm   (trivial_layers.py:189-257)
+  lda             FixedAffineComponent over Append(-1,0,1,ReplaceIndex(ivector,t,0))
+  relu-batchnorm  NaturalGradientAffine + ReLU + BatchNorm
+  tdnnf           TdnnComponent(linear) + TdnnComponent(affine) + ReLU + BatchNorm + NoOp(Sum(Scale(bypass,in),bn))
+  linear          LinearComponent
+  prefinal        NaturalGradientAffine + ReLU + BatchNorm + Linear + BatchNorm
+  output          NaturalGradientAffine (no log-softmax for chain) [+ LogSoftmax]
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# ----------------------------------------------------------------------------- architectures
+
+
+def arch_tdnnf(name: str, feat_dim: int, ivector_dim: int, num_pdfs: int, dim: int, bottleneck: int,
+               strides, prefinal_small: int, front: str, log_softmax: bool = False) -> dict:
+    layers = []
+    if front == "idct-delta":          # mini_librispeech run_tdnn_1k.sh:176-186
+        layers += [dict(type="idct", name="idct", dim=feat_dim),
+                   dict(type="batchnorm", name="batchnorm0"),
+                   dict(type="delta", name="delta"),
+                   dict(type="relu-batchnorm", name="tdnn1", dim=dim, append_ivector=0.4)]
+    elif front == "lda":               # librispeech run_tdnn_1d.sh:219-226
+        layers += [dict(type="lda", name="lda"),
+                   dict(type="relu-batchnorm", name="tdnn1", dim=dim)]
+    else:
+        raise ValueError(front)
+    for i, s in enumerate(strides):
+        layers.append(dict(type="tdnnf", name=f"tdnnf{i + 2}", dim=dim, bottleneck=bottleneck, stride=s,
+                           bypass=0.66))
+    layers += [dict(type="linear", name="prefinal-l", dim=prefinal_small),
+               dict(type="prefinal", name="prefinal-chain", small=prefinal_small, big=dim),
+               dict(type="output", name="output", dim=num_pdfs, log_softmax=log_softmax)]
+    return dict(name=name, feat_dim=feat_dim, ivector_dim=ivector_dim, num_pdfs=num_pdfs,
+                frame_subsampling_factor=3, layers=layers)
+
+
+def arch_mini_librispeech_1k(num_pdfs: int = 2336) -> dict:
+    """egs/mini_librispeech/s5/local/chain/tuning/run_tdnn_1k.sh:170-207 (5.2 M params)."""
+    return arch_tdnnf("mini_librispeech_tdnn_1k", 40, 100, num_pdfs, 768, 96,
+                      [1, 1, 1, 0, 3, 3, 3, 3, 3, 3, 3, 3], 192, "idct-delta")
+
+
+def arch_librispeech_1d(num_pdfs: int = 6024) -> dict:
+    """egs/librispeech/s5/local/chain/tuning/run_tdnn_1d.sh:219-253 (22.6 M params)."""
+    return arch_tdnnf("librispeech_tdnn_1d", 40, 100, num_pdfs, 1536, 160,
+                      [1, 1, 1, 0, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3], 256, "lda")
+
+
+def arch_tiny(num_pdfs: int = 64, front: str = "idct-delta") -> dict:
+    return arch_tdnnf("tiny_tdnnf", 40, 100, num_pdfs, 64, 16, [1, 0, 3, 3], 32, front)
+
+
+# ----------------------------------------------------------------------------- weights
+
+def random_weights(arch: dict, seed: int = 0) -> dict:
+    """Seeded synthetic parameters: weights N(0, 1/fan_in), biases N(0, 0.1),
+    BatchNorm mean N(0, 0.1), var U(0.5, 1.5)."""
+    rng = np.random.default_rng(seed)
+    W = {}
+
+    def lin(name, out_dim, in_dim, bias=True):
+        W[name + ".w"] = (rng.standard_normal((out_dim, in_dim)) / np.sqrt(in_dim)).astype(np.float32)
+        if bias:
+            W[name + ".b"] = (rng.standard_normal(out_dim) * 0.1).astype(np.float32)
+
+    def bn(name, dim):
+        W[name + ".mean"] = (rng.standard_normal(dim) * 0.1).astype(np.float32)
+        W[name + ".var"] = rng.uniform(0.5, 1.5, dim).astype(np.float32)
+
+    fd, ivd = arch["feat_dim"], arch["ivector_dim"]
+    cur = fd
+    for L in arch["layers"]:
+        t, n = L["type"], L["name"]
+        if t == "idct":
+            lin(n, fd, fd)
+            cur = fd
+        elif t == "batchnorm":
+            bn(n, cur)
+        elif t == "delta":
+            bn(n, 3 * cur)
+            cur = 3 * cur
+        elif t == "lda":
+            k = 3 * fd + ivd
+            lin(n, k, k)
+            cur = k
+        elif t == "relu-batchnorm":
+            k = cur + (ivd if L.get("append_ivector") else 0)
+            lin(n + ".affine", L["dim"], k)
+            bn(n + ".batchnorm", L["dim"])
+            cur = L["dim"]
+        elif t == "tdnnf":
+            nt = 1 if L["stride"] == 0 else 2
+            lin(n + ".linear", L["bottleneck"], cur * nt, bias=False)
+            lin(n + ".affine", L["dim"], L["bottleneck"] * nt)
+            bn(n + ".batchnorm", L["dim"])
+            cur = L["dim"]
+        elif t == "linear":
+            lin(n, L["dim"], cur, bias=False)
+            cur = L["dim"]
+        elif t == "prefinal":
+            lin(n + ".affine", L["big"], cur)
+            bn(n + ".batchnorm1", L["big"])
+            lin(n + ".linear", L["small"], L["big"], bias=False)
+            bn(n + ".batchnorm2", L["small"])
+            cur = L["small"]
+        elif t == "output":
+            lin(n + ".affine", L["dim"], cur)
+            cur = L["dim"]
+        else:
+            raise ValueError(t)
+    p = rng.uniform(0.5, 1.5, arch["num_pdfs"])
+    W["priors"] = (p / p.sum()).astype(np.float32)
+    return W
+
+
+def num_parameters(arch: dict, W: dict) -> int:
+    return int(sum(v.size for k, v in W.items() if k.endswith(".w") or k.endswith(".b")))
+
+
+# ----------------------------------------------------------------------------- nnet3 config text (for the reference)
+
+def _write_kaldi_matrix(path: str, m: np.ndarray) -> None:
+    with open(path, "w") as f:
+        f.write(" [\n")
+        for r in m:
+            f.write("  " + " ".join(repr(float(x)) for x in r) + "\n")
+        f.write(" ]\n")
+
+
+def to_nnet3_config(arch: dict, W: dict, tmpdir: str) -> str:
+    """nnet3 config lines (what steps/nnet3/xconfig_to_configs.py emits for these
+    layers) for Nnet::ReadConfig.  FixedAffine matrices go to files in tmpdir."""
+    fd, ivd = arch["feat_dim"], arch["ivector_dim"]
+    c = [f"input-node name=ivector dim={ivd}", f"input-node name=input dim={fd}"]
+    cur, cur_dim = "input", fd
+    for L in arch["layers"]:
+        t, n = L["type"], L["name"]
+        if t in ("idct", "lda"):
+            path = os.path.join(tmpdir, f"{n}.mat")
+            _write_kaldi_matrix(path, np.concatenate([W[n + ".w"], W[n + ".b"][:, None]], 1))
+            if t == "lda":
+                inp = f"Append(Offset({cur}, -1), {cur}, Offset({cur}, 1), ReplaceIndex(ivector, t, 0))"
+                cur_dim = 3 * fd + ivd
+            else:
+                inp = cur
+            c.append(f"component name={n} type=FixedAffineComponent matrix={path}")
+            c.append(f"component-node name={n} component={n} input={inp}")
+            cur = n
+        elif t == "batchnorm":
+            c.append(f"component name={n} type=BatchNormComponent dim={cur_dim}")
+            c.append(f"component-node name={n} component={n} input={cur}")
+            cur = n
+        elif t == "delta":   # trivial_layers.py:236-256
+            c.append(f"dim-range-node name={cur}_copy1 input-node={cur} dim={cur_dim} dim-offset=0")
+            c.append(f"dim-range-node name={cur}_copy2 input-node={cur} dim={cur_dim} dim-offset=0")
+            c.append(f"component name={cur}_2 type=NoOpComponent dim={3 * cur_dim}")
+            c.append(f"component-node name={cur}_2 component={cur}_2 input=Append(Offset({cur},0),"
+                     f" Sum(Offset(Scale(-1.0,{cur}_copy1),-1), Offset({cur},1)), Sum(Offset({cur},-2), Offset({cur},2),"
+                     f" Offset(Scale(-2.0,{cur}_copy2),0)))")
+            c.append(f"component name={n} type=BatchNormComponent dim={3 * cur_dim}")
+            c.append(f"component-node name={n} component={n} input={cur}_2")
+            cur, cur_dim = n, 3 * cur_dim
+        elif t == "relu-batchnorm":
+            if L.get("append_ivector"):
+                inp = f"Append({cur}, Scale({L['append_ivector']}, ReplaceIndex(ivector, t, 0)))"
+                k = cur_dim + ivd
+            else:
+                inp, k = cur, cur_dim
+            c.append(f"component name={n}.affine type=NaturalGradientAffineComponent input-dim={k} output-dim={L['dim']}")
+            c.append(f"component-node name={n}.affine component={n}.affine input={inp}")
+            c.append(f"component name={n}.relu type=RectifiedLinearComponent dim={L['dim']}")
+            c.append(f"component-node name={n}.relu component={n}.relu input={n}.affine")
+            c.append(f"component name={n}.batchnorm type=BatchNormComponent dim={L['dim']}")
+            c.append(f"component-node name={n}.batchnorm component={n}.batchnorm input={n}.relu")
+            cur, cur_dim = n + ".batchnorm", L["dim"]
+        elif t == "tdnnf":   # composite_layers.py:140-225
+            s = L["stride"]
+            o1 = f"{-s},0" if s else "0"
+            o2 = f"0,{s}" if s else "0"
+            c.append(f"component name={n}.linear type=TdnnComponent input-dim={cur_dim} output-dim={L['bottleneck']} "
+                     f"use-bias=false time-offsets={o1} orthonormal-constraint=-1.0")
+            c.append(f"component-node name={n}.linear component={n}.linear input={cur}")
+            c.append(f"component name={n}.affine type=TdnnComponent input-dim={L['bottleneck']} output-dim={L['dim']} time-offsets={o2}")
+            c.append(f"component-node name={n}.affine component={n}.affine input={n}.linear")
+            c.append(f"component name={n}.relu type=RectifiedLinearComponent dim={L['dim']}")
+            c.append(f"component-node name={n}.relu component={n}.relu input={n}.affine")
+            c.append(f"component name={n}.batchnorm type=BatchNormComponent dim={L['dim']}")
+            c.append(f"component-node name={n}.batchnorm component={n}.batchnorm input={n}.relu")
+            c.append(f"component name={n}.noop type=NoOpComponent dim={L['dim']}")
+            c.append(f"component-node name={n}.noop component={n}.noop input=Sum(Scale({L['bypass']}, {cur}), {n}.batchnorm)")
+            cur, cur_dim = n + ".noop", L["dim"]
+        elif t == "linear":
+            c.append(f"component name={n} type=LinearComponent input-dim={cur_dim} output-dim={L['dim']} orthonormal-constraint=-1.0")
+            c.append(f"component-node name={n} component={n} input={cur}")
+            cur, cur_dim = n, L["dim"]
+        elif t == "prefinal":   # composite_layers.py:280-330
+            c.append(f"component name={n}.affine type=NaturalGradientAffineComponent input-dim={cur_dim} output-dim={L['big']}")
+            c.append(f"component-node name={n}.affine component={n}.affine input={cur}")
+            c.append(f"component name={n}.relu type=RectifiedLinearComponent dim={L['big']}")
+            c.append(f"component-node name={n}.relu component={n}.relu input={n}.affine")
+            c.append(f"component name={n}.batchnorm1 type=BatchNormComponent dim={L['big']}")
+            c.append(f"component-node name={n}.batchnorm1 component={n}.batchnorm1 input={n}.relu")
+            c.append(f"component name={n}.linear type=LinearComponent input-dim={L['big']} output-dim={L['small']} orthonormal-constraint=-1")
+            c.append(f"component-node name={n}.linear component={n}.linear input={n}.batchnorm1")
+            c.append(f"component name={n}.batchnorm2 type=BatchNormComponent dim={L['small']}")
+            c.append(f"component-node name={n}.batchnorm2 component={n}.batchnorm2 input={n}.linear")
+            cur, cur_dim = n + ".batchnorm2", L["small"]
+        elif t == "output":
+            c.append(f"component name={n}.affine type=NaturalGradientAffineComponent input-dim={cur_dim} output-dim={L['dim']}")
+            c.append(f"component-node name={n}.affine component={n}.affine input={cur}")
+            last = n + ".affine"
+            if L.get("log_softmax"):
+                c.append(f"component name={n}.log-softmax type=LogSoftmaxComponent dim={L['dim']}")
+                c.append(f"component-node name={n}.log-softmax component={n}.log-softmax input={n}.affine")
+                last = n + ".log-softmax"
+            c.append(f"output-node name=output input={last}")
+    return "\n".join(c) + "\n"
+
+
+# ----------------------------------------------------------------------------- graph -> op program
+
+BN_EPS = 1e-3      # BatchNormComponent default epsilon (nnet-normalize-component.h)
+
+
+def bn_scale_offset(mean: np.ndarray, var: np.ndarray):
+    """BatchNormComponent::ComputeDerived (nnet-normalize-component.cc:209-246), target_rms = 1."""
+    scale = np.power(np.maximum(var.astype(np.float32), 0.0) + np.float32(BN_EPS), np.float32(-0.5)).astype(np.float32)
+    offset = (-(mean.astype(np.float32)) * scale).astype(np.float32)
+    return scale, offset
+
+
+@dataclass
+class Node:
+    name: str
+    dim: int
+    kind: str                 # "input", "ivector", "gemm", "ew"
+    # consumers fill these during the backward range analysis
+    residues: set = field(default_factory=set)
+    tmin: int = 10**9
+    tmax: int = -10**9
+    step: int = 0
+    t0: int = 0
+    rows: int = 0
+    spec: dict = field(default_factory=dict)
+
+
+def build_graph(arch: dict, W: dict):
+    """Nodes in topological order.  Each non-input node has spec:
+       gemm: terms=[(src, time_offset, w_cols(lo,hi), kind)], w, b, relu, bn=(scale,offset)|None,
+             res=(src, alpha)|None, post=(sub_vec, mul)|None, log_softmax
+       ew:   blocks=[[(src, time_offset, scale), ...] per column block], bn
+    """
+    fd, ivd = arch["feat_dim"], arch["ivector_dim"]
+    nodes = [Node("input", fd, "input"), Node("ivector", ivd, "ivector")]
+    cur = "input"
+    dims = {"input": fd, "ivector": ivd}
+
+    def add(n):
+        nodes.append(n)
+        dims[n.name] = n.dim
+
+    pending_bn = None
+    for L in arch["layers"]:
+        t, n = L["type"], L["name"]
+        if t == "idct":
+            add(Node(n, fd, "gemm", spec=dict(terms=[(cur, 0, (0, fd), "row")], w=W[n + ".w"], b=W[n + ".b"])))
+            cur = n
+        elif t == "batchnorm":
+            # fold into the producing node's epilogue (same arithmetic: x*scale + offset)
+            prod = next(x for x in nodes if x.name == cur)
+            prod.spec["bn"] = bn_scale_offset(W[n + ".mean"], W[n + ".var"])
+        elif t == "delta":
+            d = dims[cur]
+            blocks = [[(cur, 0, 1.0)], [(cur, -1, -1.0), (cur, 1, 1.0)], [(cur, -2, 1.0), (cur, 2, 1.0), (cur, 0, -2.0)]]
+            add(Node(n, 3 * d, "ew", spec=dict(blocks=blocks, block_dim=d, bn=bn_scale_offset(W[n + ".mean"], W[n + ".var"]))))
+            cur = n
+        elif t == "lda":
+            k = 3 * fd + ivd
+            terms = [(cur, -1, (0, fd), "row"), (cur, 0, (fd, 2 * fd), "row"), (cur, 1, (2 * fd, 3 * fd), "row"),
+                     ("ivector", 0, (3 * fd, k), "ivec")]
+            add(Node(n, k, "gemm", spec=dict(terms=terms, w=W[n + ".w"], b=W[n + ".b"])))
+            cur = n
+        elif t == "relu-batchnorm":
+            d = dims[cur]
+            terms = [(cur, 0, (0, d), "row")]
+            if L.get("append_ivector"):
+                # Scale(0.4, ReplaceIndex(ivector,t,0)) is a node of its own so the product keeps the
+                # reference's association (0.4*iv rounded to f32, then the affine)
+                add(Node(n + ".ivscaled", ivd, "ew", spec=dict(blocks=[[("ivector", 0, float(L["append_ivector"]))]],
+                                                             block_dim=ivd, bn=None, ivector_rows=True)))
+                terms.append((n + ".ivscaled", 0, (d, d + ivd), "ivec"))
+            add(Node(n + ".batchnorm", L["dim"], "gemm",
+                     spec=dict(terms=terms, w=W[n + ".affine.w"], b=W[n + ".affine.b"], relu=True,
+                               bn=bn_scale_offset(W[n + ".batchnorm.mean"], W[n + ".batchnorm.var"]))))
+            cur = n + ".batchnorm"
+        elif t == "tdnnf":
+            d, s, bt = dims[cur], L["stride"], L["bottleneck"]
+            o1 = [-s, 0] if s else [0]
+            o2 = [0, s] if s else [0]
+            add(Node(n + ".linear", bt, "gemm",
+                     spec=dict(terms=[(cur, o, (i * d, (i + 1) * d), "row") for i, o in enumerate(o1)],
+                               w=W[n + ".linear.w"], b=None)))
+            add(Node(n + ".noop", L["dim"], "gemm",
+                     spec=dict(terms=[(n + ".linear", o, (i * bt, (i + 1) * bt), "row") for i, o in enumerate(o2)],
+                               w=W[n + ".affine.w"], b=W[n + ".affine.b"], relu=True,
+                               bn=bn_scale_offset(W[n + ".batchnorm.mean"], W[n + ".batchnorm.var"]),
+                               res=(cur, float(L["bypass"])))))
+            cur = n + ".noop"
+        elif t == "linear":
+            d = dims[cur]
+            add(Node(n, L["dim"], "gemm", spec=dict(terms=[(cur, 0, (0, d), "row")], w=W[n + ".w"], b=None)))
+            cur = n
+        elif t == "prefinal":
+            d = dims[cur]
+            add(Node(n + ".batchnorm1", L["big"], "gemm",
+                     spec=dict(terms=[(cur, 0, (0, d), "row")], w=W[n + ".affine.w"], b=W[n + ".affine.b"], relu=True,
+                               bn=bn_scale_offset(W[n + ".batchnorm1.mean"], W[n + ".batchnorm1.var"]))))
+            add(Node(n + ".batchnorm2", L["small"], "gemm",
+                     spec=dict(terms=[(n + ".batchnorm1", 0, (0, L["big"]), "row")], w=W[n + ".linear.w"], b=None,
+                               bn=bn_scale_offset(W[n + ".batchnorm2.mean"], W[n + ".batchnorm2.var"]))))
+            cur = n + ".batchnorm2"
+        elif t == "output":
+            d = dims[cur]
+            add(Node("output", L["dim"], "gemm",
+                     spec=dict(terms=[(cur, 0, (0, d), "row")], w=W[n + ".affine.w"], b=W[n + ".affine.b"],
+                               log_softmax=bool(L.get("log_softmax")))))
+            cur = "output"
+    return nodes
+
+
+def model_context(arch: dict):
+    """(left_context, right_context) of the network = ComputeSimpleNnetContext
+    (nnet3/nnet-utils.cc) for these architectures."""
+    nodes = build_graph(arch, _zero_weights(arch))
+    lo = {n.name: 0 for n in nodes}
+    hi = {n.name: 0 for n in nodes}
+    order = {n.name: i for i, n in enumerate(nodes)}
+    lo["output"], hi["output"] = 0, 0
+    need_lo = {n.name: None for n in nodes}
+    need_hi = {n.name: None for n in nodes}
+    need_lo["output"], need_hi["output"] = 0, 0
+    for n in reversed(nodes):
+        if need_lo[n.name] is None:
+            continue
+        for (src, off) in _deps(n):
+            a, b = need_lo[n.name] + off, need_hi[n.name] + off
+            need_lo[src] = a if need_lo[src] is None else min(need_lo[src], a)
+            need_hi[src] = b if need_hi[src] is None else max(need_hi[src], b)
+    return -need_lo["input"], need_hi["input"]
+
+
+def _deps(n: Node):
+    if n.kind == "gemm":
+        d = [(src, off) for (src, off, _c, kind) in n.spec["terms"] if kind == "row"]
+        if n.spec.get("res"):
+            d.append((n.spec["res"][0], 0))
+        return d
+    if n.kind == "ew":
+        if n.spec.get("ivector_rows"):
+            return []
+        return [(src, off) for blk in n.spec["blocks"] for (src, off, _s) in blk]
+    return []
+
+
+def _zero_weights(arch):
+    class Z(dict):
+        def __missing__(self, k):
+            return np.zeros((1, 1), np.float32) if k.endswith(".w") else np.ones(1, np.float32)
+    return Z()
+
+
+def compile_program(arch: dict, W: dict, num_frames: int, frames_per_chunk: int = 21,
+                    acoustic_scale: float = 1.0, use_priors: bool = True) -> dict:
+    """Compile for utterances of `num_frames` feature frames.  Returns a dict:
+       nodes: [(name, dim, rows, t0, step)], ops: [op dicts], blob: float32 array,
+       left/right context, num_out rows (= ceil(T / subsampling)), ivector chunk mapping.
+    Row mapping of a term: src_row = clamp(out_row * ratio + shift, lo, hi)."""
+    sub = arch["frame_subsampling_factor"]
+    T = int(num_frames)
+    n_out = (T + sub - 1) // sub
+    nodes = build_graph(arch, W)
+    by = {n.name: n for n in nodes}
+    out = by["output"]
+    out.residues, out.tmin, out.tmax = {0}, 0, sub * (n_out - 1)
+    # backward pass: required time range and residues (mod sub) of every node
+    for n in reversed(nodes):
+        if n.tmax < n.tmin:
+            continue
+        for (src, off) in _deps(n):
+            s = by[src]
+            s.tmin = min(s.tmin, n.tmin + off)
+            s.tmax = max(s.tmax, n.tmax + off)
+            if len(n.residues) == 1 and n.kind != "input":
+                r = next(iter(n.residues))
+                s.residues.add((r + off) % sub)
+            else:
+                s.residues |= set(range(sub))
+    L, R = -by["input"].tmin, by["input"].tmax - (sub * (n_out - 1))
+    for n in nodes:
+        if n.kind == "input":
+            n.step, n.t0, n.rows = 1, 0, T            # raw features, reads are clamped
+        elif n.kind == "ivector":
+            n.step, n.t0, n.rows = 0, 0, 0            # set below
+        elif n.tmax < n.tmin:
+            n.rows = 0
+        elif len(n.residues) == 1:
+            r = next(iter(n.residues))
+            n.step = sub
+            n.t0 = n.tmin + ((r - n.tmin) % sub)
+            n.rows = (n.tmax - n.t0) // sub + 1
+        else:
+            n.step, n.t0, n.rows = 1, n.tmin, n.tmax - n.tmin + 1
+    # ivector rows: chunk n of the looped computation supplies one i-vector
+    # (decodable-online-looped.cc:170-205); input time t uses the i-vector of chunk
+    # max(0, floor(t / C) - m), m = floor((C + R - 1) / C)   (nnet-compile-looped.cc:179-205)
+    C = frames_per_chunk
+    assert C % sub == 0
+    Lk, Rk = model_context(arch)
+    m = (C + Rk - 1) // C
+    n_chunks = (n_out * sub + C - 1) // C
+    by["ivector"].rows = n_chunks
+    blob = []
+    blob_off = [0]
+
+    def put(a):
+        a = np.ascontiguousarray(a, np.float32).reshape(-1)
+        off = blob_off[0]
+        blob.append(a)
+        blob_off[0] += a.size
+        return off
+
+    idx = {n.name: i for i, n in enumerate(nodes)}
+    ops = []
+    for n in nodes:
+        if n.kind in ("input", "ivector"):
+            continue
+        if n.rows == 0 and not (n.kind == "ew" and n.spec.get("ivector_rows")):
+            continue
+        if n.kind == "ew" and n.spec.get("ivector_rows"):
+            n.step, n.t0, n.rows = 0, 0, n_chunks
+            ops.append(dict(type="ew", out=idx[n.name], rows=n_chunks, block_dim=n.spec["block_dim"],
+                            blocks=[[dict(src=idx["ivector"], ratio=1, shift=0, lo=0, hi=n_chunks - 1, scale=s, ivec=0)
+                                     for (src, off, s) in blk] for blk in n.spec["blocks"]],
+                            bn_scale=-1, bn_offset=-1))
+            continue
+
+        def rowmap(src, off, kind):
+            s = by[src]
+            if kind == "ivec":
+                # src rows are chunks: row = clamp((t0 + i*step + off) // C - m, 0, n_chunks-1)
+                return dict(src=idx[src], ratio=n.step, shift=n.t0 + off, lo=0, hi=s.rows - 1, ivec=1, C=C, m=m)
+            if s.kind == "input":
+                return dict(src=idx[src], ratio=n.step, shift=n.t0 + off, lo=0, hi=T - 1, ivec=0)
+            assert n.step % s.step == 0 and (n.t0 + off - s.t0) % s.step == 0, (n.name, src)
+            return dict(src=idx[src], ratio=n.step // s.step, shift=(n.t0 + off - s.t0) // s.step, lo=0,
+                        hi=s.rows - 1, ivec=0)
+
+        if n.kind == "ew":
+            blocks = []
+            for blk in n.spec["blocks"]:
+                blocks.append([dict(rowmap(src, off, "row"), scale=float(sc)) for (src, off, sc) in blk])
+            bn = n.spec.get("bn")
+            ops.append(dict(type="ew", out=idx[n.name], rows=n.rows, block_dim=n.spec["block_dim"], blocks=blocks,
+                            bn_scale=put(bn[0]) if bn else -1, bn_offset=put(bn[1]) if bn else -1))
+        else:
+            sp = n.spec
+            w = sp["w"]
+            terms = []
+            for (src, off, (c0, c1), kind) in sp["terms"]:
+                terms.append(dict(rowmap(src, off, kind), k0=c0, klen=c1 - c0))
+            bn = sp.get("bn")
+            res = sp.get("res")
+            op = dict(type="gemm", out=idx[n.name], rows=n.rows, N=w.shape[0], K=w.shape[1], terms=terms,
+                      w=put(w), bias=put(sp["b"]) if sp.get("b") is not None else -1, relu=int(bool(sp.get("relu"))),
+                      bn_scale=put(bn[0]) if bn else -1, bn_offset=put(bn[1]) if bn else -1,
+                      res=None, res_alpha=0.0, sub_vec=-1, out_scale=1.0, log_softmax=int(bool(sp.get("log_softmax"))))
+            if res:
+                op["res"] = rowmap(res[0], 0, "row")
+                op["res_alpha"] = res[1]
+            if n.name == "output":
+                # AddVecToRows(-1, log_priors); Scale(acoustic_scale)  (decodable-online-looped.cc:218-223)
+                if use_priors:
+                    op["sub_vec"] = put(np.log(W["priors"]).astype(np.float32))
+                op["out_scale"] = float(acoustic_scale)
+            ops.append(op)
+    # per-utterance arena with liveness-based reuse (first fit)
+    last_use = {}
+    for oi, op in enumerate(ops):
+        srcs = [t["src"] for t in (op["terms"] if op["type"] == "gemm" else [x for b in op["blocks"] for x in b])]
+        if op.get("res"):
+            srcs.append(op["res"]["src"])
+        for sidx in srcs:
+            last_use[sidx] = oi
+    arena_off = {}
+    live = []           # (offset, size, node_idx)
+    arena_size = 0
+    for oi, op in enumerate(ops):
+        o = op["out"]
+        nd = nodes[o]
+        if nd.name != "output":
+            size = ((nd.rows * nd.dim + 31) // 32) * 32
+            live.sort()
+            pos = 0
+            for (a, sz, _) in live:
+                if pos + size <= a:
+                    break
+                pos = max(pos, a + sz)
+            arena_off[o] = pos
+            live.append((pos, size, o))
+            arena_size = max(arena_size, pos + size)
+        # free nodes whose last use is this op (after allocating the output)
+        live = [(a, sz, ni) for (a, sz, ni) in live if last_use.get(ni, -1) > oi or ni == o]
+    return dict(arch=arch, T=T, n_out=n_out, left_context=L, right_context=R, model_left=Lk, model_right=Rk,
+                arena_off=arena_off, arena_size=arena_size,
+                frames_per_chunk=C, ivector_m=m, n_chunks=n_chunks,
+                nodes=[(n.name, n.dim, n.rows, n.t0, n.step) for n in nodes], ops=ops,
+                blob=np.concatenate(blob) if blob else np.zeros(1, np.float32),
+                node_index=idx)
+
+
+def flops_per_output_frame(prog: dict) -> float:
+    """2 * sum_l K_l * N_l * rows_l / n_out (algorithmic FLOPs counted once)."""
+    tot = 0.0
+    for op in prog["ops"]:
+        if op["type"] == "gemm":
+            tot += 2.0 * op["K"] * op["N"] * op["rows"]
+    return tot / prog["n_out"]

@@ -1,0 +1,148 @@
+// oracle/ref_wrap/nnet_wrap.cc — TEST INFRASTRUCTURE ONLY.
+// Thin extern "C" wrapper (our code) around the reference's OWN nnet3 CPU
+// forward, compiled from /root/reference/src (oracle/ref_nnet.py).  It only
+// calls public reference API:
+//   Nnet::ReadConfig                       nnet3/nnet-nnet.cc:189
+//   UpdatableComponent::{Vectorize,UnVectorize}, Component::ReadNew
+//   SetBatchnormTestMode / SetDropoutTestMode / CollapseModel   nnet3/nnet-utils.cc
+//   AmNnetSimple, DecodableNnetSimpleLoopedInfo, DecodableNnetSimpleLooped
+//                                          nnet3/decodable-simple-looped.{h,cc}
+#include <cstring>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "nnet3/am-nnet-simple.h"
+#include "nnet3/decodable-simple-looped.h"
+#include "nnet3/nnet-nnet.h"
+#include "nnet3/nnet-normalize-component.h"
+#include "nnet3/nnet-simple-component.h"
+#include "nnet3/nnet-utils.h"
+
+using namespace kaldi;
+using namespace kaldi::nnet3;
+
+struct RefNnet {
+  Nnet nnet;
+  std::unique_ptr<AmNnetSimple> am;
+  std::unique_ptr<DecodableNnetSimpleLoopedInfo> info;
+  NnetSimpleLoopedComputationOptions opts;
+  std::string tmp;
+};
+
+extern "C" {
+
+void *ref_nnet_create(const char *config_text) {
+  try {
+    RefNnet *r = new RefNnet();
+    std::istringstream is(config_text);
+    r->nnet.ReadConfig(is);
+    return r;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_nnet_create: %s\n", e.what()); return nullptr; }
+}
+void ref_nnet_destroy(void *h) { delete (RefNnet *)h; }
+
+int ref_nnet_num_components(void *h) { return ((RefNnet *)h)->nnet.NumComponents(); }
+const char *ref_nnet_component_name(void *h, int i) {
+  RefNnet *r = (RefNnet *)h; r->tmp = r->nnet.GetComponentName(i); return r->tmp.c_str();
+}
+const char *ref_nnet_component_type(void *h, int i) {
+  RefNnet *r = (RefNnet *)h; r->tmp = r->nnet.GetComponent(i)->Type(); return r->tmp.c_str();
+}
+// number of parameters of an updatable component (0 if not updatable)
+int ref_nnet_num_params(void *h, int i) {
+  Component *c = ((RefNnet *)h)->nnet.GetComponent(i);
+  if (!(c->Properties() & kUpdatableComponent)) return 0;
+  return dynamic_cast<UpdatableComponent *>(c)->NumParameters();
+}
+int ref_nnet_get_params(void *h, int i, float *out) {
+  try {
+    UpdatableComponent *c = dynamic_cast<UpdatableComponent *>(((RefNnet *)h)->nnet.GetComponent(i));
+    if (!c) return -1;
+    SubVector<BaseFloat> v(out, c->NumParameters());
+    c->Vectorize(&v);
+    return 0;
+  } catch (...) { return -1; }
+}
+int ref_nnet_set_params(void *h, int i, const float *in) {
+  try {
+    UpdatableComponent *c = dynamic_cast<UpdatableComponent *>(((RefNnet *)h)->nnet.GetComponent(i));
+    if (!c) return -1;
+    SubVector<BaseFloat> v(const_cast<float *>(in), c->NumParameters());
+    c->UnVectorize(v);
+    return 0;
+  } catch (...) { return -1; }
+}
+// replace a BatchNormComponent by one with the given stats (text Read path,
+// nnet-normalize-component.cc:591-614)
+int ref_nnet_set_batchnorm(void *h, int i, int dim, float epsilon, float target_rms, float count,
+                           const float *mean, const float *var) {
+  try {
+    RefNnet *r = (RefNnet *)h;
+    std::ostringstream os;
+    os.precision(9);
+    os << "<BatchNormComponent> <Dim> " << dim << " <BlockDim> " << dim << " <Epsilon> " << epsilon
+       << " <TargetRms> " << target_rms << " <TestMode> F <Count> " << count << " <StatsMean> [ ";
+    for (int d = 0; d < dim; d++) os << mean[d] << " ";
+    os << "] <StatsVar> [ ";
+    for (int d = 0; d < dim; d++) os << var[d] << " ";
+    os << "] </BatchNormComponent> ";
+    std::istringstream is(os.str());
+    Component *c = Component::ReadNew(is, false);
+    if (!c) return -1;
+    r->nnet.SetComponent(i, c);
+    return 0;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_nnet_set_batchnorm: %s\n", e.what()); return -1; }
+}
+
+// test-mode + CollapseModel + looped compilation (what online2-wav-nnet3-latgen-faster.cc:162-177 does)
+int ref_nnet_prepare(void *h, int frames_per_chunk, int frame_subsampling_factor, float acoustic_scale,
+                     const float *priors, int num_priors, int collapse) {
+  try {
+    RefNnet *r = (RefNnet *)h;
+    SetBatchnormTestMode(true, &r->nnet);
+    SetDropoutTestMode(true, &r->nnet);
+    if (collapse) CollapseModel(CollapseModelConfig(), &r->nnet);
+    r->am.reset(new AmNnetSimple(r->nnet));
+    if (priors && num_priors > 0) {
+      Vector<BaseFloat> p(num_priors);
+      for (int i = 0; i < num_priors; i++) p(i) = priors[i];
+      r->am->SetPriors(p);
+    }
+    r->opts.frames_per_chunk = frames_per_chunk;
+    r->opts.frame_subsampling_factor = frame_subsampling_factor;
+    r->opts.acoustic_scale = acoustic_scale;
+    r->info.reset(new DecodableNnetSimpleLoopedInfo(r->opts, r->am.get()));
+    return 0;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_nnet_prepare: %s\n", e.what()); return -1; }
+}
+
+// out: [left_context, right_context, frames_per_chunk, output_dim]
+int ref_nnet_info(void *h, int *out) {
+  RefNnet *r = (RefNnet *)h;
+  if (!r->info) return -1;
+  out[0] = r->info->frames_left_context; out[1] = r->info->frames_right_context;
+  out[2] = r->info->frames_per_chunk; out[3] = r->info->output_dim;
+  return 0;
+}
+
+// DecodableNnetSimpleLooped over a whole utterance; ivectors [M x idim] with
+// the given period (decodable-simple-looped.cc:262-279), or M = 0 for none.
+int ref_nnet_forward(void *h, const float *feats, int T, int D, const float *ivectors, int M, int idim,
+                     int period, float *out, int max_rows) {
+  try {
+    RefNnet *r = (RefNnet *)h;
+    Matrix<BaseFloat> f(T, D);
+    for (int t = 0; t < T; t++) memcpy(f.RowData(t), feats + (size_t)t * D, 4 * D);
+    Matrix<BaseFloat> iv;
+    if (M > 0) { iv.Resize(M, idim); for (int m = 0; m < M; m++) memcpy(iv.RowData(m), ivectors + (size_t)m * idim, 4 * idim); }
+    DecodableNnetSimpleLooped dec(*r->info, f, NULL, M > 0 ? &iv : NULL, M > 0 ? period : 1);
+    int n = dec.NumFrames(), P = dec.OutputDim();
+    if (n > max_rows) return -2;
+    for (int t = 0; t < n; t++) { SubVector<BaseFloat> row(out + (size_t)t * P, P); dec.GetOutputForFrame(t, &row); }
+    return n;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_nnet_forward: %s\n", e.what()); return -1; }
+}
+
+}  // extern "C"
