@@ -87,6 +87,8 @@ typedef struct {
                                  reference when extras matter)  */
   float hash_ratio;           /* --hash-ratio (2.0); reference_order only      */
   int32_t max_arcs_per_frame; /* reference_order: arc-position capacity        */
+  int32_t max_lattice_states; /* per-channel capacity of the finalized lattice */
+  int32_t max_lattice_arcs;
 } b2k_dec_cfg;
 
 void b2k_dec_cfg_default(b2k_dec_cfg *cfg);
@@ -155,6 +157,13 @@ typedef struct {
 } b2k_raw_lattice;
 
 int b2k_dec_get_raw_lattice(b2k_dec *dec, int32_t channel, b2k_raw_lattice *out, void *stream);
+
+/* Batched form (CudaDecoder::GetRawLattice(channels, vector<Lattice*>&, ...),
+ * cuda-decoder.h): the lattices of n finalized channels concatenated; lattice i
+ * owns states [state_offs[i], state_offs[i+1]) etc.; arc/final state ids are
+ * relative to the lattice's own first state.  Sizes query: out->state_frame NULL. */
+int b2k_dec_get_raw_lattices(b2k_dec *dec, const int32_t *channels, int32_t n, b2k_raw_lattice *out,
+                             int64_t *state_offs, int64_t *arc_offs, int64_t *final_offs, void *stream);
 
 /* Debug/parity hook: copies the un-pruned token list of frame `frame_plus_one`
  * and the links created by that frame step (tests compare these bit-for-bit

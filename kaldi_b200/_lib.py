@@ -55,6 +55,7 @@ def _declare(L) -> None:
         "b2k_dec_finalize_decoding": [vp, P(i32), i32, vp],
         "b2k_dec_channel_info": [vp, i32, P(i64)],
         "b2k_dec_get_raw_lattice": [vp, i32, vp, vp],
+        "b2k_dec_get_raw_lattices": [vp, P(i32), i32, vp, P(i64), P(i64), P(i64), vp],
         "b2k_dec_debug_frame": [vp, i32, i32, P(i32), P(f32), P(i64), P(i32), P(i64), i64, i64],
         "b2k_dec_frame_info": [vp, i32, P(f32), P(f32), P(i32), i32],
         "b2k_feat_cfg_default": [vp], "b2k_feat_create": [vp, P(vp)], "b2k_feat_destroy": [vp],

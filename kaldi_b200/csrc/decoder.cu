@@ -98,6 +98,12 @@ struct DecParams {
   int32_t *cand;            // [5 * cand_cap] src, arc, next, tot bits, ac bits
   uint32_t *new_extra;      // [max_tpf] (finalize)
   int32_t *lane_stamp;      // [nlanes]
+  // compact lattice of a finalized channel (written by dec_finalize_kernel)
+  int4 *lat_states;         // [nch * cap_ls] {frame, hclg state, tot bits, extra bits}
+  int4 *lat_arcs;           // [nch * cap_la] {src id, dst id, ilabel, olabel}
+  float2 *lat_arcw;         // [nch * cap_la] {graph cost, acoustic cost - cost_offset}
+  int2 *lat_finals;         // [nch * cap_lf] {state id, final cost bits}
+  int32_t cap_ls, cap_la, cap_lf;
   // reference-order mode scratch (per lane)
   uint32_t *x_bm;           // [pos_cap/32] bitmap of first-admission positions
   int32_t *x_wbase;         // [pos_cap/32]
@@ -1269,7 +1275,17 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
   const int any_final = block_sum_i32<T>(anyf, redi) > 0;
   const float final_best_cost = (best_cost_with_final != kInf) ? best_cost_with_final : best_cost;
 
-  int lat_states = 0, lat_arcs = 0, lat_finals = 0;   // per-thread partial counts
+  __shared__ int sh_narcs, sh_nfin;
+  if (tid == 0) { sh_narcs = 0; sh_nfin = 0; }
+  int n_states = 0;                                    // uniform
+  int4 *ls = p.lat_states + (size_t)ch * p.cap_ls;
+  int4 *la = p.lat_arcs + (size_t)ch * p.cap_la;
+  float2 *lw = p.lat_arcw + (size_t)ch * p.cap_la;
+  int2 *lf = p.lat_finals + (size_t)ch * p.cap_lf;
+  int *ids_cur = p.cand + (size_t)lane * 5 * p.cand_cap;          // candidate staging is idle here
+  int *ids_next = ids_cur + p.max_tpf;
+  int tb_next = 0;
+  __syncthreads();
 
   for (int t = last; t >= 0; t--) {
     const int tb = p.frame_tok_begin[fo + t], te = p.frame_tok_begin[fo + t + 1];
@@ -1287,7 +1303,6 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
       tok_extra[tb + i] = 0.0f;        // lower bound to start the eps iteration from
     }
     __syncthreads();
-    int emit_alive = 0;
     if (t < last) {
       const int em_b = p.frame_link_begin[fo + t + 1], em_e = p.frame_link_eps[fo + t + 1];
       for (int l = em_b + tid; l < em_e; l += T) {
@@ -1300,7 +1315,6 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
         } else {
           if (lec < 0.0f) lec = 0.0f;
           atomicMin(&nx[lk.x - tb], f2ord(lec));
-          emit_alive++;
         }
       }
     }
@@ -1344,95 +1358,100 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
       __syncthreads();
       if (!ch_any) break;
     }
-    // counts
-    for (int i = tid; i < n; i += T) {
-      if (tok_extra[tb + i] != kInf) {
-        lat_states++;
-        if (t == last) {
-          if (!any_final) lat_finals++;
-          else if (__ldg(&g.final_cost[tok_state[tb + i]]) != kInf) lat_finals++;
+    // ---- dense lattice-state ids for list t (ids grow as we walk backwards; the
+    //      host flips them so that id 0 is the start state) and emission of the
+    //      surviving states / arcs into the channel's compact lattice region
+    {
+      int carry = 0;
+      for (int base = 0; base < n; base += T) {
+        int k = base + tid;
+        int alive = (k < n) && (tok_extra[tb + k] != kInf);
+        int total;
+        int excl = block_excl_scan<T>(alive, redi, &total);
+        if (k < n) {
+          int id = -1;
+          if (alive) {
+            id = n_states + carry + excl;
+            if (id < p.cap_ls)
+              ls[id] = make_int4(t, tok_state[tb + k], __float_as_int(tok_cost[tb + k]), __float_as_int(tok_extra[tb + k]));
+            if (t == last) {
+              float fc = any_final ? __ldg(&g.final_cost[tok_state[tb + k]]) : 0.0f;
+              if (fc != kInf) {
+                int q = atomicAdd(&sh_nfin, 1);
+                if (q < p.cap_lf) lf[q] = make_int2(id, __float_as_int(fc));
+              }
+            }
+          }
+          ids_cur[k] = id;
+        }
+        carry += total;
+      }
+      n_states += carry;
+    }
+    __syncthreads();
+    if (t < last) {
+      const int em_b = p.frame_link_begin[fo + t + 1], em_e = p.frame_link_eps[fo + t + 1];
+      const float coff = p.frame_cost_offset[(size_t)ch * (p.max_frames + 1) + t];
+      for (int l = em_b + tid; l < em_e; l += T) {
+        int4 lk = links[l];
+        if ((uint32_t)lk.z & B2K_DEAD_FLAG) continue;
+        int4 arc = __ldg(&g.e_arcs[lk.z]);
+        int q = atomicAdd(&sh_narcs, 1);
+        if (q < p.cap_la) {
+          la[q] = make_int4(ids_cur[lk.x - tb], ids_next[lk.y - tb_next], __ldg(&g.e_ilabel[lk.z]), arc.w);
+          lw[q] = make_float2(__int_as_float(arc.y), __int_as_float(lk.w) - coff);   // :174-181
         }
       }
     }
-    for (int l = eps_b + tid; l < eps_e; l += T) if (!((uint32_t)links[l].z & B2K_DEAD_FLAG)) lat_arcs++;
-    lat_arcs += emit_alive;
+    for (int l = eps_b + tid; l < eps_e; l += T) {
+      int4 lk = links[l];
+      if ((uint32_t)lk.z & B2K_DEAD_FLAG) continue;
+      int4 arc = __ldg(&g.ne_arcs[(uint32_t)lk.z & B2K_ARC_MASK]);
+      int q = atomicAdd(&sh_narcs, 1);
+      if (q < p.cap_la) {
+        la[q] = make_int4(ids_cur[lk.x - tb], ids_cur[lk.y - tb], 0, arc.z);
+        lw[q] = make_float2(__int_as_float(arc.y), 0.0f);
+      }
+    }
     __syncthreads();
+    { int *tmp = ids_cur; ids_cur = ids_next; ids_next = tmp; }
+    tb_next = tb;
   }
-  lat_states = block_sum_i32<T>(lat_states, redi);
-  lat_arcs = block_sum_i32<T>(lat_arcs, redi);
-  lat_finals = block_sum_i32<T>(lat_finals, redi);
   if (tid == 0) {
     cs->finalized = 1;
-    cs->lat_states = lat_states;
-    cs->lat_arcs = lat_arcs;
-    cs->lat_finals = lat_finals;
+    cs->lat_states = n_states;
+    cs->lat_arcs = sh_narcs;
+    cs->lat_finals = sh_nfin;
     cs->any_final = any_final;
     cs->final_best_cost = final_best_cost;
+    if (n_states > p.cap_ls || sh_narcs > p.cap_la || sh_nfin > p.cap_lf) cs->status = B2K_ERR_OVERFLOW;
   }
 }
 
-// ------------------------------------------------------------------ extraction
+// ------------------------------------------------------------------ lattice packing
 
-struct ExtractOut {
-  int32_t *state_tok;      // arena index (host maps to dense ids)
-  int32_t *state_frame, *state_hclg;
-  float *state_tot, *state_extra;
-  int32_t *arc_src_tok, *arc_dst_tok, *arc_ilabel, *arc_olabel;
-  float *arc_graph, *arc_ac;
-  int32_t *final_tok;
-  float *final_cost;
-  int32_t *counters;       // [3]
-};
-
-template <int T>
-__global__ void __launch_bounds__(T) dec_extract_kernel(DecParams p, int ch, ExtractOut o) {
-  const FstDev &g = p.fst;
+// Copies the compact lattices of n channels into packed arrays (one D2H each).
+// offs: [3*(n+1)] exclusive prefix sums of states / arcs / finals, computed on the host.
+__global__ void dec_pack_kernel(DecParams p, const int32_t *channels, const int64_t *offs, int n,
+                                int4 *o_states, int4 *o_arcs, float2 *o_arcw, int2 *o_finals) {
+  const int c = blockIdx.y;
+  const int ch = channels[c];
   const ChanState *cs = &p.chan[ch];
-  const float kInf = __int_as_float(0x7f800000);
-  const int32_t *tok_state = p.tok_state + (size_t)ch * p.max_tokens;
-  const float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
-  const float *tok_extra = p.tok_extra + (size_t)ch * p.max_tokens;
-  const int4 *links = p.links + (size_t)ch * p.max_links;
-  const size_t fo = (size_t)ch * (p.max_frames + 2);
-  const float *cost_off = p.frame_cost_offset + (size_t)ch * (p.max_frames + 1);
-  const int last = cs->frames_decoded;
-  const int gtid = blockIdx.x * T + threadIdx.x, gstride = gridDim.x * T;
-  const int32_t *ftb = p.frame_tok_begin + fo;
-  // tokens
-  for (int i = gtid; i < cs->ntok; i += gstride) {
-    float ex = tok_extra[i];
-    if (ex == kInf) continue;
-    int lo = 0, hi = last + 1;           // frame f with ftb[f] <= i < ftb[f+1]
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ftb[mid] <= i) lo = mid; else hi = mid; }
-    int k = atomicAdd(&o.counters[0], 1);
-    o.state_tok[k] = i; o.state_frame[k] = lo; o.state_hclg[k] = tok_state[i];
-    o.state_tot[k] = tok_cost[i]; o.state_extra[k] = ex;
-    if (lo == last) {
-      float fc = __ldg(&g.final_cost[tok_state[i]]);
-      if (!cs->any_final) { int q = atomicAdd(&o.counters[2], 1); o.final_tok[q] = i; o.final_cost[q] = 0.0f; }
-      else if (fc != kInf) { int q = atomicAdd(&o.counters[2], 1); o.final_tok[q] = i; o.final_cost[q] = fc; }
-    }
+  const int ns = min(cs->lat_states, p.cap_ls), na = min(cs->lat_arcs, p.cap_la), nf = min(cs->lat_finals, p.cap_lf);
+  const int4 *ls = p.lat_states + (size_t)ch * p.cap_ls;
+  const int4 *la = p.lat_arcs + (size_t)ch * p.cap_la;
+  const float2 *lw = p.lat_arcw + (size_t)ch * p.cap_la;
+  const int2 *lf = p.lat_finals + (size_t)ch * p.cap_lf;
+  const int64_t so = offs[c], ao = offs[(n + 1) + c], fo = offs[2 * (n + 1) + c];
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  // flip ids so that lattice state 0 is the start state (ids were assigned walking backwards)
+  for (int i = gt; i < ns; i += gs) o_states[so + (ns - 1 - i)] = ls[i];
+  for (int i = gt; i < na; i += gs) {
+    int4 a = la[i];
+    a.x = ns - 1 - a.x; a.y = ns - 1 - a.y;
+    o_arcs[ao + i] = a; o_arcw[ao + i] = lw[i];
   }
-  // links
-  for (int l = gtid; l < cs->nlink; l += gstride) {
-    int4 lk = links[l];
-    if ((uint32_t)lk.z & B2K_DEAD_FLAG) continue;
-    int k = atomicAdd(&o.counters[1], 1);
-    o.arc_src_tok[k] = lk.x; o.arc_dst_tok[k] = lk.y;
-    if ((uint32_t)lk.z & B2K_EPS_FLAG) {
-      int4 arc = __ldg(&g.ne_arcs[(uint32_t)lk.z & B2K_ARC_MASK]);
-      o.arc_ilabel[k] = 0; o.arc_olabel[k] = arc.z;
-      o.arc_graph[k] = __int_as_float(arc.y); o.arc_ac[k] = 0.0f;    // (:174-181, offset only if emitting)
-    } else {
-      int4 arc = __ldg(&g.e_arcs[lk.z]);
-      // frame of the source token -> cost_offsets_[f]
-      int lo = 0, hi = last + 1;
-      while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ftb[mid] <= lk.x) lo = mid; else hi = mid; }
-      o.arc_ilabel[k] = __ldg(&g.e_ilabel[lk.z]); o.arc_olabel[k] = arc.w;
-      o.arc_graph[k] = __int_as_float(arc.y);
-      o.arc_ac[k] = __int_as_float(lk.w) - cost_off[lo];
-    }
-  }
+  for (int i = gt; i < nf; i += gs) { int2 f = lf[i]; f.x = ns - 1 - f.x; o_finals[fo + i] = f; }
 }
 
 }  // namespace b2k
@@ -1467,6 +1486,11 @@ struct b2k_dec {
   int32_t *h_lane_nframes = nullptr;
   cudaEvent_t staging_free = nullptr;
   std::vector<void *> allocs;
+  // batched lattice read-back (grow-only scratch)
+  char *d_pack = nullptr; size_t d_pack_bytes = 0;
+  char *h_pack = nullptr; size_t h_pack_bytes = 0;
+  int32_t *d_pack_ch = nullptr; int64_t *d_pack_offs = nullptr;
+  ChanState *h_chan = nullptr;
 };
 
 extern "C" {
@@ -1477,6 +1501,7 @@ void b2k_dec_cfg_default(b2k_dec_cfg *c) {
   c->max_tokens_per_frame = 32768; c->max_frames = 1024;
   c->max_tokens = 3000000; c->max_links = 6000000;
   c->reference_order = 1; c->hash_ratio = 2.0f; c->max_arcs_per_frame = 1 << 20;
+  c->max_lattice_states = 131072; c->max_lattice_arcs = 262144;
 }
 
 int b2k_fst_create(const b2k_fst_csr *csr, b2k_fst **out) {
@@ -1608,6 +1633,15 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
       B2K_CUDA_CHECK(cudaMemcpy(p.x_bfirst, big.data(), 4 * big.size(), cudaMemcpyHostToDevice));
     }
   }
+  p.cap_ls = cfg->max_lattice_states > 0 ? cfg->max_lattice_states : 131072;
+  p.cap_la = cfg->max_lattice_arcs > 0 ? cfg->max_lattice_arcs : 262144;
+  p.cap_lf = p.max_tpf;
+  A(p.lat_states, sizeof(int4) * nc * p.cap_ls, 0);
+  A(p.lat_arcs, sizeof(int4) * nc * p.cap_la, 0);
+  A(p.lat_arcw, sizeof(float2) * nc * p.cap_la, 0);
+  A(p.lat_finals, sizeof(int2) * nc * p.cap_lf, 0);
+  A(d->d_pack_ch, 4 * nc, 0);
+  A(d->d_pack_offs, 8 * 3 * (nc + 1), 0);
   A(d->d_lane_channel, 4 * nl, 0);
   A(d->d_lane_ll, sizeof(float *) * nl, 0);
   A(d->d_lane_nframes, 4 * nl, 0);
@@ -1626,6 +1660,7 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
     for (auto &c : cs) c.frames_decoded = -1;
     B2K_CUDA_CHECK(cudaMemcpy(p.chan, cs.data(), sizeof(ChanState) * nc, cudaMemcpyHostToDevice));
   }
+  B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_chan, sizeof(ChanState) * nc));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_channel, 4 * nl));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_ll, sizeof(float *) * nl));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_nframes, 4 * nl));
@@ -1642,6 +1677,7 @@ int b2k_dec_destroy(b2k_dec *d) {
   cudaDeviceSynchronize();
   for (void *p : d->allocs) cudaFree(p);
   cudaFreeHost(d->h_lane_channel); cudaFreeHost(d->h_lane_ll); cudaFreeHost(d->h_lane_nframes);
+  cudaFreeHost(d->h_chan); if (d->h_pack) cudaFreeHost(d->h_pack); if (d->d_pack) cudaFree(d->d_pack);
   if (d->staging_free) cudaEventDestroy(d->staging_free);
   delete d;
   return B2K_OK;
@@ -1747,77 +1783,70 @@ int b2k_dec_channel_info(b2k_dec *d, int32_t channel, int64_t info[16]) {
   return B2K_OK;
 }
 
-int b2k_dec_get_raw_lattice(b2k_dec *d, int32_t channel, b2k_raw_lattice *out, void *stream) {
-  if (!d || !out) return set_error(B2K_ERR_INVALID, "b2k_dec_get_raw_lattice: bad args");
-  ChanState cs;
-  int rc = read_chan(d, channel, &cs);
-  if (rc) return rc;
-  if (cs.status != B2K_OK) return set_error(cs.status, "channel is in an error state");
-  if (!cs.finalized) return set_error(B2K_ERR_STATE, "call b2k_dec_finalize_decoding first");
-  const int64_t ns = cs.lat_states, na = cs.lat_arcs, nf = cs.lat_finals;
+// Batched read-back: sizes first (one D2H of the channel states), then one
+// pack kernel and one D2H for all channels.
+int b2k_dec_get_raw_lattices(b2k_dec *d, const int32_t *channels, int32_t n, b2k_raw_lattice *out,
+                             int64_t *state_offs, int64_t *arc_offs, int64_t *final_offs, void *stream) {
+  if (!d || !channels || n <= 0 || n > d->nchannels || !out || !state_offs || !arc_offs || !final_offs)
+    return set_error(B2K_ERR_INVALID, "b2k_dec_get_raw_lattices: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  B2K_CUDA_CHECK(cudaMemcpyAsync(d->h_chan, d->p.chan, sizeof(ChanState) * d->nchannels, cudaMemcpyDeviceToHost, st));
+  B2K_CUDA_CHECK(cudaStreamSynchronize(st));
+  std::vector<int64_t> offs(3 * (size_t)(n + 1), 0);
+  for (int i = 0; i < n; i++) {
+    int ch = channels[i];
+    if (ch < 0 || ch >= d->nchannels) return set_error(B2K_ERR_INVALID, "bad channel id");
+    const ChanState &cs = d->h_chan[ch];
+    if (cs.status != B2K_OK) return set_error(cs.status, "channel is in an error state (capacity overflow?)");
+    if (!cs.finalized) return set_error(B2K_ERR_STATE, "call b2k_dec_finalize_decoding first");
+    offs[i + 1] = offs[i] + cs.lat_states;
+    offs[(n + 1) + i + 1] = offs[(n + 1) + i] + cs.lat_arcs;
+    offs[2 * (n + 1) + i + 1] = offs[2 * (n + 1) + i] + cs.lat_finals;
+  }
+  const int64_t ns = offs[n], na = offs[(n + 1) + n], nf = offs[2 * (n + 1) + n];
+  for (int i = 0; i <= n; i++) { state_offs[i] = offs[i]; arc_offs[i] = offs[(n + 1) + i]; final_offs[i] = offs[2 * (n + 1) + i]; }
   if (!out->state_frame) { out->num_states = ns; out->num_arcs = na; out->num_finals = nf; return B2K_OK; }
   if (out->num_states < ns || out->num_arcs < na || out->num_finals < nf)
-    return set_error(B2K_ERR_INVALID, "b2k_dec_get_raw_lattice: output buffers too small");
-  cudaStream_t st = (cudaStream_t)stream;
-  // device scratch
-  size_t bytes = (size_t)(ns + 1) * 5 * 4 + (size_t)(na + 1) * 6 * 4 + (size_t)(nf + 1) * 2 * 4 + 16;
-  char *dbuf = nullptr;
-  B2K_CUDA_CHECK(cudaMalloc((void **)&dbuf, bytes));
-  ExtractOut o;
-  char *q = dbuf;
-  auto take = [&](size_t n) { char *r = q; q += n * 4; return r; };
-  o.counters = (int32_t *)take(4);
-  o.state_tok = (int32_t *)take(ns + 1); o.state_frame = (int32_t *)take(ns + 1);
-  o.state_hclg = (int32_t *)take(ns + 1); o.state_tot = (float *)take(ns + 1);
-  o.state_extra = (float *)take(ns + 1);
-  o.arc_src_tok = (int32_t *)take(na + 1); o.arc_dst_tok = (int32_t *)take(na + 1);
-  o.arc_ilabel = (int32_t *)take(na + 1); o.arc_olabel = (int32_t *)take(na + 1);
-  o.arc_graph = (float *)take(na + 1); o.arc_ac = (float *)take(na + 1);
-  o.final_tok = (int32_t *)take(nf + 1); o.final_cost = (float *)take(nf + 1);
-  cudaError_t e = cudaMemsetAsync(o.counters, 0, 16, st);
-  if (e == cudaSuccess) {
-    dec_extract_kernel<256><<<148 * 2, 256, 0, st>>>(d->p, channel, o);
-    g_launch_count.fetch_add(1);
-    e = cudaGetLastError();
+    return set_error(B2K_ERR_INVALID, "b2k_dec_get_raw_lattices: output buffers too small");
+  size_t bytes = (size_t)ns * 16 + (size_t)na * 24 + (size_t)nf * 8 + 64;
+  if (bytes > d->d_pack_bytes) {
+    if (d->d_pack) cudaFree(d->d_pack);
+    if (d->h_pack) cudaFreeHost(d->h_pack);
+    size_t cap = bytes + bytes / 4;
+    B2K_CUDA_CHECK(cudaMalloc((void **)&d->d_pack, cap));
+    B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_pack, cap));
+    d->d_pack_bytes = d->h_pack_bytes = cap;
   }
-  std::vector<int32_t> stok(ns), asrc(na), adst(na), ftok(nf);
-  auto dl = [&](void *h, const void *dv, size_t n) { if (e == cudaSuccess && n) e = cudaMemcpyAsync(h, dv, n * 4, cudaMemcpyDeviceToHost, st); };
-  dl(stok.data(), o.state_tok, ns); dl(out->state_frame, o.state_frame, ns);
-  dl(out->state_hclg, o.state_hclg, ns); dl(out->state_tot_cost, o.state_tot, ns);
-  dl(out->state_extra_cost, o.state_extra, ns);
-  dl(asrc.data(), o.arc_src_tok, na); dl(adst.data(), o.arc_dst_tok, na);
-  dl(out->arc_ilabel, o.arc_ilabel, na); dl(out->arc_olabel, o.arc_olabel, na);
-  dl(out->arc_graph_cost, o.arc_graph, na); dl(out->arc_acoustic_cost, o.arc_ac, na);
-  dl(ftok.data(), o.final_tok, nf); dl(out->final_cost, o.final_cost, nf);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(dbuf);
-  if (e != cudaSuccess) return set_error(B2K_ERR_CUDA, "lattice extraction", cudaGetErrorString(e));
-  // arena index -> dense lattice state id (sorted by arena index = by frame)
-  std::vector<int32_t> order(ns);
-  for (int64_t i = 0; i < ns; i++) order[i] = (int32_t)i;
-  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return stok[a] < stok[b]; });
-  // permute state arrays into arena order so ids are deterministic
-  {
-    std::vector<int32_t> t1(ns), t2(ns); std::vector<float> t3(ns), t4(ns), sorted_tok(ns);
-    for (int64_t i = 0; i < ns; i++) {
-      int32_t j = order[i];
-      t1[i] = out->state_frame[j]; t2[i] = out->state_hclg[j];
-      t3[i] = out->state_tot_cost[j]; t4[i] = out->state_extra_cost[j];
-    }
-    std::vector<int32_t> stok_sorted(ns);
-    for (int64_t i = 0; i < ns; i++) stok_sorted[i] = stok[order[i]];
-    memcpy(out->state_frame, t1.data(), ns * 4); memcpy(out->state_hclg, t2.data(), ns * 4);
-    memcpy(out->state_tot_cost, t3.data(), ns * 4); memcpy(out->state_extra_cost, t4.data(), ns * 4);
-    auto idx_of = [&](int32_t tok) -> int32_t {
-      auto it = std::lower_bound(stok_sorted.begin(), stok_sorted.end(), tok);
-      if (it == stok_sorted.end() || *it != tok) return -1;
-      return (int32_t)(it - stok_sorted.begin());
-    };
-    for (int64_t i = 0; i < na; i++) { out->arc_src[i] = idx_of(asrc[i]); out->arc_dst[i] = idx_of(adst[i]); }
-    for (int64_t i = 0; i < nf; i++) out->final_state[i] = idx_of(ftok[i]);
+  int4 *o_states = (int4 *)d->d_pack;
+  int4 *o_arcs = o_states + ns;
+  float2 *o_arcw = (float2 *)(o_arcs + na);
+  int2 *o_finals = (int2 *)(o_arcw + na);
+  B2K_CUDA_CHECK(cudaMemcpyAsync(d->d_pack_ch, channels, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  B2K_CUDA_CHECK(cudaMemcpyAsync(d->d_pack_offs, offs.data(), 8 * offs.size(), cudaMemcpyHostToDevice, st));
+  dec_pack_kernel<<<dim3(8, n), 256, 0, st>>>(d->p, d->d_pack_ch, d->d_pack_offs, n, o_states, o_arcs, o_arcw, o_finals);
+  B2K_LAUNCH_CHECK();
+  B2K_CUDA_CHECK(cudaMemcpyAsync(d->h_pack, d->d_pack, bytes - 64, cudaMemcpyDeviceToHost, st));
+  B2K_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int4 *hs = (const int4 *)d->h_pack;
+  const int4 *ha = hs + ns;
+  const float2 *hw = (const float2 *)(ha + na);
+  const int2 *hf = (const int2 *)(hw + na);
+  for (int64_t i = 0; i < ns; i++) {
+    out->state_frame[i] = hs[i].x; out->state_hclg[i] = hs[i].y;
+    memcpy(&out->state_tot_cost[i], &hs[i].z, 4); memcpy(&out->state_extra_cost[i], &hs[i].w, 4);
   }
+  for (int64_t i = 0; i < na; i++) {
+    out->arc_src[i] = ha[i].x; out->arc_dst[i] = ha[i].y; out->arc_ilabel[i] = ha[i].z; out->arc_olabel[i] = ha[i].w;
+    out->arc_graph_cost[i] = hw[i].x; out->arc_acoustic_cost[i] = hw[i].y;
+  }
+  for (int64_t i = 0; i < nf; i++) { out->final_state[i] = hf[i].x; memcpy(&out->final_cost[i], &hf[i].y, 4); }
   out->num_states = ns; out->num_arcs = na; out->num_finals = nf;
   return B2K_OK;
+}
+
+int b2k_dec_get_raw_lattice(b2k_dec *d, int32_t channel, b2k_raw_lattice *out, void *stream) {
+  int64_t so[2], ao[2], fo[2];
+  return b2k_dec_get_raw_lattices(d, &channel, 1, out, so, ao, fo, stream);
 }
 
 int b2k_dec_debug_frame(b2k_dec *d, int32_t channel, int32_t frame_plus_one, int32_t *tok_state,

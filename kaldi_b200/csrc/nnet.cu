@@ -46,6 +46,7 @@ struct OpDev {
   const float *w, *bias, *bn_scale, *bn_offset, *sub_vec;
   int relu, has_res; TermDev res; float res_alpha, out_scale;
   int block_dim; int term_block[8];
+  int log_softmax;       // output post-processing is then applied after the log-softmax kernel
 };
 
 struct RunCtx {
@@ -160,8 +161,10 @@ __global__ void __launch_bounds__(256) nnet_gemm_kernel(OpDev op, RunCtx c) {
       if (op.relu) v = fmaxf(v, 0.f);
       if (op.bn_scale) v = __fadd_rn(__fmul_rn(v, __ldg(&op.bn_scale[n])), __ldg(&op.bn_offset[n]));
       if (rrow) v = __fadd_rn(__fmul_rn(op.res_alpha, rrow[n]), v);
-      if (op.sub_vec) v = __fadd_rn(v, -__ldg(&op.sub_vec[n]));
-      if (op.out_scale != 1.0f) v = __fmul_rn(v, op.out_scale);
+      if (!op.log_softmax) {
+        if (op.sub_vec) v = __fadd_rn(v, -__ldg(&op.sub_vec[n]));
+        if (op.out_scale != 1.0f) v = __fmul_rn(v, op.out_scale);
+      }
       orow[n] = v;
     }
   }
@@ -207,7 +210,12 @@ __global__ void nnet_logsoftmax_kernel(OpDev op, RunCtx c) {
   for (int n = lane_id; n < op.N; n += 32) s += expf(row[n] - mx);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   float lse = mx + logf(s);
-  for (int n = lane_id; n < op.N; n += 32) row[n] = row[n] - lse;
+  for (int n = lane_id; n < op.N; n += 32) {
+    float v = row[n] - lse;
+    if (op.sub_vec) v = __fadd_rn(v, -__ldg(&op.sub_vec[n]));        // then -log prior, x acoustic_scale
+    if (op.out_scale != 1.0f) v = __fmul_rn(v, op.out_scale);
+    row[n] = v;
+  }
 }
 
 }  // namespace b2k
@@ -272,7 +280,7 @@ int b2k_nnet_create(const b2k_nnet_node *nodes, int32_t n_nodes, const b2k_nnet_
     d.rows = o.rows; d.N = o.N; d.K = o.K; d.n_terms = o.n_terms;
     for (int t = 0; t < o.n_terms; t++) { if ((rc = mk_term(o.terms[t], &d.terms[t]))) return rc; d.term_block[t] = o.terms[t].block; }
     d.w = bp(o.w); d.bias = bp(o.bias); d.bn_scale = bp(o.bn_scale); d.bn_offset = bp(o.bn_offset); d.sub_vec = bp(o.sub_vec);
-    d.relu = o.relu; d.has_res = o.has_res; d.res_alpha = o.res_alpha; d.out_scale = o.out_scale; d.block_dim = o.block_dim > 0 ? o.block_dim : 1;
+    d.log_softmax = o.log_softmax; d.relu = o.relu; d.has_res = o.has_res; d.res_alpha = o.res_alpha; d.out_scale = o.out_scale; d.block_dim = o.block_dim > 0 ? o.block_dim : 1;
     if (o.has_res && (rc = mk_term(o.res, &d.res))) return rc;
     nn->ops.push_back(d);
     nn->log_softmax.push_back(o.log_softmax);

@@ -33,7 +33,8 @@ class _DecCfg(C.Structure):
                 ("prune_scale", C.c_float), ("max_tokens_per_frame", C.c_int32),
                 ("max_frames", C.c_int32), ("max_tokens", C.c_int64), ("max_links", C.c_int64),
                 ("reference_order", C.c_int32), ("hash_ratio", C.c_float),
-                ("max_arcs_per_frame", C.c_int32)]
+                ("max_arcs_per_frame", C.c_int32), ("max_lattice_states", C.c_int32),
+                ("max_lattice_arcs", C.c_int32)]
 
 
 class _RawLattice(C.Structure):
@@ -93,6 +94,8 @@ class CudaDecoderConfig:
     reference_order: bool = True     # bit-exact HashList-order emulation
     hash_ratio: float = 2.0
     max_arcs_per_frame: int = 1 << 20
+    max_lattice_states: int = 131072
+    max_lattice_arcs: int = 262144
 
     @classmethod
     def from_dict(cls, d: dict, **kw):
@@ -112,7 +115,8 @@ class CudaDecoder:
         c = _DecCfg(config.default_beam, config.lattice_beam, config.max_active, config.min_active,
                     config.beam_delta, config.prune_interval, config.prune_scale,
                     config.max_tokens_per_frame, config.max_frames, config.max_tokens, config.max_links,
-                    int(config.reference_order), config.hash_ratio, config.max_arcs_per_frame)
+                    int(config.reference_order), config.hash_ratio, config.max_arcs_per_frame,
+                    config.max_lattice_states, config.max_lattice_arcs)
         self.h = C.c_void_p()
         _lib.check(L.b2k_dec_create(fst.h, C.cast(C.byref(c), C.c_void_p), nlanes, nchannels, C.byref(self.h)))
 
@@ -181,6 +185,48 @@ class CudaDecoder:
             setattr(r, k, _p(v, C.c_float if v.dtype == np.float32 else C.c_int32))
         _lib.check(L.b2k_dec_get_raw_lattice(self.h, int(channel), C.cast(C.byref(r), C.c_void_p), C.c_void_p(stream)))
         return out
+
+    def GetRawLattices(self, channels, stream: int = 0):
+        """Batched read-back of finalized lattices: one pack kernel + one D2H."""
+        L = _lib.lib()
+        ch = self._chan(channels)
+        n = len(ch)
+        so = np.zeros(n + 1, np.int64); ao = np.zeros(n + 1, np.int64); fo = np.zeros(n + 1, np.int64)
+        i64p = C.POINTER(C.c_int64)
+        r = _RawLattice()
+        args = (self.h, _p(ch, C.c_int32), n, C.cast(C.byref(r), C.c_void_p), so.ctypes.data_as(i64p),
+                ao.ctypes.data_as(i64p), fo.ctypes.data_as(i64p), C.c_void_p(stream))
+        _lib.check(L.b2k_dec_get_raw_lattices(*args))
+        ns, na, nf = r.num_states, r.num_arcs, r.num_finals
+        out = dict(
+            state_frame=np.zeros(ns, np.int32), state_hclg=np.zeros(ns, np.int32),
+            state_tot_cost=np.zeros(ns, np.float32), state_extra_cost=np.zeros(ns, np.float32),
+            arc_src=np.zeros(na, np.int32), arc_dst=np.zeros(na, np.int32),
+            arc_ilabel=np.zeros(na, np.int32), arc_olabel=np.zeros(na, np.int32),
+            arc_graph_cost=np.zeros(na, np.float32), arc_acoustic_cost=np.zeros(na, np.float32),
+            final_state=np.zeros(nf, np.int32), final_cost=np.zeros(nf, np.float32))
+        for k, v in out.items():
+            setattr(r, k, _p(v, C.c_float if v.dtype == np.float32 else C.c_int32))
+        _lib.check(L.b2k_dec_get_raw_lattices(*args))
+        out.update(state_offs=so, arc_offs=ao, final_offs=fo)
+        return out
+
+    @staticmethod
+    def SplitLattices(packed: dict):
+        """Views of the individual lattices inside a GetRawLattices result."""
+        so, ao, fo = packed["state_offs"], packed["arc_offs"], packed["final_offs"]
+        res = []
+        for i in range(len(so) - 1):
+            d = {}
+            for k, v in packed.items():
+                if k.startswith("state_") and not k.endswith("offs"):
+                    d[k] = v[so[i]:so[i + 1]]
+                elif k.startswith("arc_") and not k.endswith("offs"):
+                    d[k] = v[ao[i]:ao[i + 1]]
+                elif k.startswith("final_") and not k.endswith("offs"):
+                    d[k] = v[fo[i]:fo[i + 1]]
+            res.append(d)
+        return res
 
     def DebugFrame(self, channel: int, frame_plus_one: int):
         L = _lib.lib()

@@ -125,6 +125,13 @@ def test_multi_lane_chunked_and_one_frame_api(ref):
     _run_gpu(dec, lls)
     for c in range(4):
         _check_against_oracle(g, cfg, lls[c], dec, c, frames=False)
+    # batched packed read-back == per-channel read-back
+    from kaldi_b200.decoder import CudaDecoder, lattice_to_canonical
+    packed = dec.GetRawLattices([0, 1, 2, 3])
+    for c, lat in enumerate(CudaDecoder.SplitLattices(packed)):
+        a, b = lattice_to_canonical(lat), lattice_to_canonical(dec.GetRawLattice(c))
+        assert all(np.array_equal(a[k], b[k]) for k in a)
+        assert lat["state_frame"][0] == 0                     # lattice state 0 is the start state
     # chunked (7 frames per call) must give the same thing; channels are reusable
     _run_gpu(dec, lls, chunk=7)
     for c in range(4):
