@@ -103,7 +103,7 @@ def cpu_reference_one(args):
     if g is None:
         g = _CPU_STATE["graph"] = synth.make_hclg(GRAPH_ARCS, num_pdfs=NUM_PDFS, seed=1)
         arch = NM.arch_mini_librispeech_1k(NUM_PDFS)
-        W = NM.random_weights(arch, seed=arch_seed)
+        W = load_calibrated_weights(arch, arch_seed)
         _CPU_STATE["nnet"] = NO.RefNnet(arch, W)
         _CPU_STATE["feat"] = F.RefFeat()
         _CPU_STATE["dec"] = D.DecoderOracle(g, synth.DEFAULT_DECODER_CFG)
@@ -136,6 +136,19 @@ def cpu_reference_one(args):
 
 
 _CPU_STATE = {}
+CAL_PATH = os.path.join(ROOT, "gpurun_out", "bench_calibration.npz")
+CAL_FALLBACK = os.path.join(ROOT, "tests", "golden", "bench_calibration.npz")
+
+
+def load_calibrated_weights(arch, seed):
+    """Synthetic weights + the output calibration the GPU arm computed (committed
+    fixture so that the CPU arm decodes exactly the same model)."""
+    W = NM.random_weights(arch, seed=seed)
+    for p in (CAL_PATH, CAL_FALLBACK):
+        if os.path.exists(p):
+            c = np.load(p)
+            return NM.apply_output_calibration(W, c["mean"], float(c["scale"]))
+    return W
 
 
 def run_cpu_reference(num_utts: int, workers: int):
@@ -220,6 +233,19 @@ def main():
         ivx = make_synthetic_extractor(seed=0)
     except Exception:
         ivx = None
+    pipe = BatchedPipeline(cfg, arch, W, graph, ivector_extractor=ivx)
+    # prior-style calibration of the synthetic model (see nnet_model.apply_output_calibration)
+    if os.path.exists(CAL_FALLBACK):
+        c = np.load(CAL_FALLBACK)
+        mean, scale = c["mean"], float(c["scale"])
+    else:
+        mean, scale = pipe.output_calibration(build_inputs(min(B, 16), seed0=777_000), target_std=1.0)
+        if rank == 0:
+            os.makedirs(os.path.dirname(CAL_PATH), exist_ok=True)
+            np.savez(CAL_PATH, mean=mean, scale=np.float32(scale))
+    W = NM.apply_output_calibration(W, mean, scale)
+    del pipe
+    torch.cuda.empty_cache()
     pipe = BatchedPipeline(cfg, arch, W, graph, ivector_extractor=ivx)
     # distinct utterances per rank and per step slot (cycled)
     n_sets = 2

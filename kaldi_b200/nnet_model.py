@@ -136,6 +136,20 @@ def random_weights(arch: dict, seed: int = 0) -> dict:
     return W
 
 
+def apply_output_calibration(W: dict, raw_output_mean: np.ndarray, scale: float) -> dict:
+    """Prior-style calibration of a synthetic model: subtract the per-pdf mean of
+    the raw output over calibration data (a random network's output is
+    dominated by a static per-pdf offset, which real systems remove through the
+    priors estimated as the average posterior) and scale the residual so the
+    per-frame spread of the log-likelihoods is speech-like (std ~1).  Without it
+    the beam collapses to < 300 tokens/frame; with it decoding runs in the
+    2-8 k tokens/frame regime of SURVEY.md §8a.  Returns a new weight dict."""
+    W2 = dict(W)
+    W2["output.affine.w"] = (W["output.affine.w"] * np.float32(scale)).astype(np.float32)
+    W2["output.affine.b"] = ((W["output.affine.b"] - raw_output_mean.astype(np.float32)) * np.float32(scale)).astype(np.float32)
+    return W2
+
+
 def num_parameters(arch: dict, W: dict) -> int:
     return int(sum(v.size for k, v in W.items() if k.endswith(".w") or k.endswith(".b")))
 

@@ -46,6 +46,7 @@ class BatchedPipeline:
         self.torch = torch
         self.cfg = cfg
         self.arch = arch
+        self.weights = weights
         self.feat = BatchedFeatures(cfg.feature_opts)
         self.T = self.feat.NumFrames(cfg.num_samples)
         self.nnet = NnetComputer(arch, weights, self.T, cfg.max_batch, cfg.frames_per_chunk, cfg.acoustic_scale)
@@ -98,6 +99,24 @@ class BatchedPipeline:
         self.compute_ivectors(n, stream)
         self.compute_nnet(n, stream)
         self.decode(n, stream)
+
+    def output_calibration(self, waves, target_std: float = 1.0):
+        """(per-pdf mean of the raw nnet output, scale) over a calibration batch,
+        for nnet_model.apply_output_calibration (synthetic models only)."""
+        torch = self.torch
+        n = len(waves)
+        for i, w in enumerate(waves):
+            self.h_wave[i].copy_(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)))
+        self.d_wave[:n].copy_(self.h_wave[:n])
+        self.compute_features(n)
+        self.compute_ivectors(n)
+        self.compute_nnet(n)
+        torch.cuda.synchronize()
+        ll = self.d_loglikes[:n].double()
+        raw = ll / self.cfg.acoustic_scale + torch.log(torch.from_numpy(self.weights["priors"]).double().cuda())[None, None, :]
+        mean = raw.mean(dim=(0, 1))
+        resid_std = float((raw - mean[None, None, :]).std(dim=2).mean())
+        return mean.float().cpu().numpy(), target_std / max(resid_std, 1e-6)
 
     # ---- public entry: host buffers in, host lattices out -------------------------
     def decode_batch(self, waves, want_lattices: bool = True):

@@ -128,18 +128,27 @@ def make_loglikes(graph: dict, num_frames: int, seed: int = 0, sigma: float = 0.
 
 def make_audio(num_samples: int, seed: int = 0, sample_rate: float = 16000.0) -> np.ndarray:
     """Synthetic 16 kHz utterance in Kaldi's int16-range float convention
-    (feat/wave-reader.h:60-62): 5 partials in [100, 4000] Hz, 4 Hz amplitude
-    modulation, N(0, 300^2) noise."""
+    (feat/wave-reader.h:60-62).  Speech-like non-stationarity: a sequence of
+    40-160 ms segments, each with its own 5 partials in [100, 4000] Hz (phase
+    continuous), 4 Hz amplitude modulation, N(0, 300^2) noise (SURVEY.md §8d asks
+    for frames that differ; a stationary tone mixture makes the acoustic scores
+    constant in time and the beam collapses onto self-loops)."""
     rng = np.random.default_rng(seed + 104729)
-    t = np.arange(num_samples, dtype=np.float64) / sample_rate
-    f = rng.uniform(100.0, 4000.0, size=5)
-    a = rng.uniform(0.2, 1.0, size=5)
-    ph = rng.uniform(0, 2 * np.pi, size=5)
-    x = np.zeros(num_samples, dtype=np.float64)
+    n = int(num_samples)
+    bounds = [0]
+    while bounds[-1] < n:
+        bounds.append(bounds[-1] + int(rng.uniform(0.04, 0.16) * sample_rate))
+    nseg = len(bounds) - 1
+    f = rng.uniform(100.0, 4000.0, size=(nseg, 5))
+    a = rng.uniform(0.2, 1.0, size=(nseg, 5))
+    seg = np.searchsorted(np.asarray(bounds[1:]), np.arange(n), side="right")
+    x = np.zeros(n, dtype=np.float64)
     for k in range(5):
-        x += a[k] * np.sin(2 * np.pi * f[k] * t + ph[k])
+        phase = 2 * np.pi * np.cumsum(f[seg, k]) / sample_rate + rng.uniform(0, 2 * np.pi)
+        x += a[seg, k] * np.sin(phase)
+    t = np.arange(n, dtype=np.float64) / sample_rate
     env = 0.6 + 0.4 * np.sin(2 * np.pi * 4.0 * t + rng.uniform(0, 2 * np.pi))
-    x = 3000.0 * env * x + rng.standard_normal(num_samples) * 300.0
+    x = 3000.0 * env * x + rng.standard_normal(n) * 300.0
     x = np.clip(np.round(x), -32768, 32767)
     return x.astype(np.float32)
 
