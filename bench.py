@@ -107,12 +107,8 @@ def cpu_reference_one(args):
         _CPU_STATE["nnet"] = NO.RefNnet(arch, W)
         _CPU_STATE["feat"] = F.RefFeat()
         _CPU_STATE["dec"] = D.DecoderOracle(g, synth.DEFAULT_DECODER_CFG)
-        _CPU_STATE["ivx"] = None
-        try:
-            from oracle import ivector_oracle as IV
-            _CPU_STATE["ivx"] = IV.make_cpu_extractor(arch_seed)
-        except Exception:
-            pass
+        from oracle import ivector_oracle as IV
+        _CPU_STATE["ivx"] = IV.make_cpu_extractor(arch_seed)
     t0 = time.time()
     wave = synth.make_audio(NUM_SAMPLES, seed=seed)
     t1 = time.time()
@@ -227,12 +223,8 @@ def main():
     graph = synth.make_hclg(GRAPH_ARCS, num_pdfs=NUM_PDFS, seed=1)
     B = a.batch
     cfg = PipelineConfig(max_batch=B, num_samples=NUM_SAMPLES, reference_order=not a.order_free)
-    ivx = None
-    try:
-        from kaldi_b200.ivector import make_synthetic_extractor
-        ivx = make_synthetic_extractor(seed=0)
-    except Exception:
-        ivx = None
+    from kaldi_b200.ivector import make_synthetic_extractor
+    ivx = make_synthetic_extractor(seed=0)
     pipe = BatchedPipeline(cfg, arch, W, graph, ivector_extractor=ivx)
     # prior-style calibration of the synthetic model (see nnet_model.apply_output_calibration)
     if os.path.exists(CAL_FALLBACK):
@@ -369,13 +361,17 @@ def main():
                                 model="mini_librispeech tdnn_1k (4.47 M params fwd path, 2336 pdfs)",
                                 graph_arcs=int(graph["offsets"][-1]), beam=15.0, max_active=7000, lattice_beam=8.0,
                                 decoder_mode="order_free" if a.order_free else "reference_order",
-                                ivector="online 100-dim (synthetic extractor)" if ivx is not None else "zeros (extractor not built)",
+                                ivector="online 100-dim, 512-Gaussian UBM, re-estimated per nnet chunk (synthetic extractor)",
                                 cache="inputs larger than L2: log-likes %.0f MB, audio %.0f MB per step" %
                                       (B * pipe.nnet.n_out * NUM_PDFS * 4 / 1e6, B * NUM_SAMPLES * 4 / 1e6),
                                 parallelism=f"dp{world} (utterance shards, no data-path collective)"),
                     e2e=dict(value=e2e_value, unit="RTFx", h2d_bytes_per_step=B * NUM_SAMPLES * 4,
                              d2h_bytes_per_step=int(d2h / a.steps), lattice_states_per_step=int(lat_states / a.steps)),
                     gpu_launches=int(launches), stage_ms={k: round(v, 3) for k, v in stage_ms.items()},
+                    decoder_phase_share=dict(zip(
+                        ["cutoff_seed", "expand", "rank", "order1_queue", "eps_replay", "order2", "links_commit"],
+                        [round(float(sum(i["prof_cycles"][k] for i in infos)) / max(1.0, float(sum(i["prof_cycles"][7] for i in infos))), 3)
+                         for k in range(7)])),
                     decoder=dict(marcs_per_s=arcs / (stage_ms["decoder_advance"] / 1e3) / 1e6 * world,
                                  arcs_per_frame=arcs / (B * pipe.nnet.n_out), tokens_per_frame=ntok / (B * pipe.nnet.n_out),
                                  errors=nerr),

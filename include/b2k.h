@@ -131,8 +131,10 @@ int b2k_dec_finalize_decoding(b2k_dec *dec, const int32_t *channels, int32_t n, 
 /* Per-channel counters after a synchronize: [0] status (b2k_status), [1] frames
  * decoded, [2] tokens in arena, [3] links in arena, [4] emitting arcs examined,
  * [5] epsilon arcs examined, [6] surviving lattice states, [7] surviving
- * lattice arcs, [8] number of final states. */
-int b2k_dec_channel_info(b2k_dec *dec, int32_t channel, int64_t info[16]);
+ * lattice arcs, [8] number of final states; [16..23] reference-order kernel
+ * phase cycle counters (cutoff+seed, expand, rank, order+queue, eps replay,
+ * order, links+commit, total). */
+int b2k_dec_channel_info(b2k_dec *dec, int32_t channel, int64_t info[32]);
 
 /* Raw lattice of a finalized channel — the content of
  * LatticeFasterDecoderTpl::GetRawLattice (lattice-faster-decoder.cc:114-197) /
@@ -237,6 +239,39 @@ int b2k_cmvn_apply_batched(b2k_feat *f, const b2k_cmvn_cfg *cfg, int32_t num_lan
                            int32_t out_stride, const int32_t *first_frame, const int32_t *num_frames,
                            double *const *d_state, const double *d_global_stats,
                            const double *d_speaker_stats, void *stream);
+
+/* ------------------------------------------------------------------ i-vector */
+
+/* OnlineIvectorExtractionInfo (online2/online-ivector-feature.h:165-215): LDA
+ * (splice + transform), diagonal UBM, IvectorExtractor derived quantities
+ * (Sigma_inv_M_, U_; ivector/ivector-extractor.cc:182-218), global CMVN stats. */
+typedef struct {
+  int32_t base_dim, splice_left, splice_right, feat_dim, num_gauss, ivector_dim;
+  int32_t num_gselect;
+  float min_post, posterior_scale, max_count, prior_offset;
+  int32_t num_cg_iters;
+  int32_t cmn_window, speaker_frames, global_frames;   /* OnlineCmvnOptions of the extractor */
+  int32_t max_lanes, max_frames;
+} b2k_ivec_cfg;
+
+typedef struct b2k_ivec b2k_ivec;
+
+int b2k_ivec_create(const b2k_ivec_cfg *cfg, const float *lda /* [feat_dim x (spliced+1)] */,
+                    const float *gconsts, const float *means_invvars, const float *inv_vars,
+                    const double *sigma_inv_m /* [G x feat_dim x ivector_dim] */,
+                    const double *U /* [G x D(D+1)/2] packed */, const double *global_cmvn_stats,
+                    b2k_ivec **out);
+int b2k_ivec_destroy(b2k_ivec *iv);
+
+/* OnlineIvectorFeature::GetFrame as called once per nnet3 chunk
+ * (decodable-online-looped.cc:170-205): for chunk n the statistics of all frames
+ * <= sched[n] are accumulated (UpdateStatsUntilFrame, online-ivector-feature.cc
+ * :248-281) and the i-vector re-estimated by <= num_cg_iters CG iterations from
+ * the previous solution.  d_feats[i]: raw base features [num_frames x base_dim];
+ * d_out[i]: [n_chunks x ivector_dim] (prior offset removed from dim 0). */
+int b2k_ivec_compute_batched(b2k_ivec *iv, int32_t num_lanes, const float *const *d_feats,
+                             int32_t feat_stride, int32_t num_frames, const int32_t *sched,
+                             int32_t n_chunks, float *const *d_out, int32_t out_stride, void *stream);
 
 /* -------------------------------------------------------------------- nnet3 */
 

@@ -62,6 +62,9 @@ def _declare(L) -> None:
         "b2k_feat_dim": [vp], "b2k_feat_num_frames": [vp, i64, i32],
         "b2k_feat_compute_batched": [vp, i32, vp, P(i32), P(i32), P(i32), vp, i32, vp],
         "b2k_cmvn_apply_batched": [vp, vp, i32, vp, vp, i32, i32, P(i32), P(i32), vp, vp, vp, vp],
+        "b2k_ivec_create": [vp, P(f32), P(f32), P(f32), P(f32), P(C.c_double), P(C.c_double), P(C.c_double), P(vp)],
+        "b2k_ivec_destroy": [vp],
+        "b2k_ivec_compute_batched": [vp, i32, vp, i32, i32, P(i32), i32, vp, i32, vp],
         "b2k_nnet_create": [vp, i32, vp, i32, P(f32), i64, i32, P(vp)], "b2k_nnet_destroy": [vp],
         "b2k_nnet_num_output_frames": [vp], "b2k_nnet_output_dim": [vp],
         "b2k_nnet_num_launches_per_run": [vp],

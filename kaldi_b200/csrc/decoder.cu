@@ -47,7 +47,7 @@ struct FstDev {
   int32_t num_e, num_ne;
   const int2 *st_off;       // [N+1] {emitting offset, epsilon offset}
   const int4 *e_arcs;       // {nextstate, weight bits, pdf, olabel}
-  const int4 *ne_arcs;      // {nextstate, weight bits, olabel, 0}
+  const int4 *ne_arcs;      // {nextstate, weight bits, olabel | LAST<<31, eps offset of nextstate or -1}
   const int32_t *e_ilabel;  // [num_e] transition-id
   const float *final_cost;  // [N]
 };
@@ -63,6 +63,7 @@ struct ChanState {          // per channel, device resident
   int32_t hc;               // reference-order mode: HashList size (hash-list-inl.h:38), starts at 1000
   int32_t pad_;
   unsigned long long arcs_e, arcs_ne;
+  unsigned long long prof[8];   // cycles: cutoff+seed, expand, rank, order1+queue, replay, order2, links+commit, total
 };
 
 #define B2K_EPS_FLAG 0x80000000u
@@ -800,61 +801,68 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   const int n_emit_links = s.nlink_new;
   const int N1 = min(s.ntok_new, p.max_tpf);
   // list order after the emitting phase -> initial worklist (:852-856)
+  long long t_o0 = clock64();
   order_tokens<T>(N1, Hc, hash, x, s);
   int qcarry = 0;
   for (int base = 0; base < N1; base += T) {
-    int k = base + tid, flag = 0, slot = 0;
+    int k = base + tid, flag = 0, slot = 0, nb = 0;
     if (k < N1) {
       slot = x.order[k];
       int st = hash[slot].x;
       int2 o0 = __ldg(&g.st_off[st]), o1 = __ldg(&g.st_off[st + 1]);
       flag = (o1.y > o0.y);
+      nb = o0.y;
     }
     int total;
     int excl = block_excl_scan<T>(flag, s.redi, &total);
-    if (flag) x.queue[qcarry + excl] = slot;
+    if (flag) { x.queue[2 * (qcarry + excl)] = slot; x.queue[2 * (qcarry + excl) + 1] = nb; }
     qcarry += total;
   }
   __syncthreads();
-  // literal LIFO replay by one thread (:858-896)
+  // literal LIFO replay by one thread (:858-896).  Queue entries are (slot, first
+  // eps arc); the eps arc record itself says where the destination's eps arcs
+  // start and which arc is the state's last, so the loop touches only the arc
+  // stream and the hash (2 dependent L2 accesses per admitted arc).
+  long long t_rep0 = clock64();
   if (tid == 0 && !s.err) {
     int qn = qcarry;
     unsigned long long ne = 0;
+    const int qcap = p.queue_cap / 2;
     while (qn > 0) {
-      int slot = x.queue[--qn];
-      volatile int4 *sp = &hash[slot];
-      int state = sp->x;
-      float c = ord2f((uint32_t)sp->y);
+      --qn;
+      const int slot = x.queue[2 * qn];
+      int a = x.queue[2 * qn + 1];
+      if (qn > 0) {   // warm the next entry (it is popped next unless this one pushes)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(&g.ne_arcs[x.queue[2 * (qn - 1) + 1]]));
+      }
+      float c = ord2f(*reinterpret_cast<volatile uint32_t *>(&hash[slot].y));
       if (c >= cutoff) continue;
-      int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
-      ne += (unsigned long long)(o1.y - o0.y);
-      for (int a = o0.y; a < o1.y; a++) {
+      for (;; a++) {
         int4 arc = __ldg(&g.ne_arcs[a]);
+        ne++;
         float tot = c + __int_as_float(arc.y);
         if (tot < cutoff) {
           bool created; int idx = 0;
           int ds = hash_insert_x(ctx, arc.x, &created, &idx);
           if (ds < 0 || s.err) { qn = 0; break; }
-          volatile int4 *dp = &hash[ds];
-          bool changed = created;
-          if (created) { dp->z = idx; x.by_ins[idx] = ds; }
-          else if (ord2f((uint32_t)dp->y) > tot) changed = true;
-          if (changed) {
-            dp->y = (int)f2ord(tot);
-            int2 d0 = __ldg(&g.st_off[arc.x]), d1 = __ldg(&g.st_off[arc.x + 1]);
-            if (d1.y > d0.y) {
-              if (qn < p.queue_cap) x.queue[qn++] = ds;
-              else { s.err = B2K_ERR_OVERFLOW; qn = 0; break; }
-            }
+          if (created) { hash[ds].z = idx; x.by_ins[idx] = ds; }
+          uint32_t nv = f2ord(tot);
+          uint32_t old = atomicMin(reinterpret_cast<uint32_t *>(&hash[ds].y), nv);   // FindOrAddToken min-update
+          if (nv < old && arc.w >= 0) {                   // changed, and the destination has eps arcs
+            if (qn < qcap) { x.queue[2 * qn] = ds; x.queue[2 * qn + 1] = arc.w; qn++; }
+            else { s.err = B2K_ERR_OVERFLOW; qn = 0; break; }
           }
         }
+        if (arc.z < 0) break;                             // last eps arc of this state
       }
     }
     cs->arcs_ne += ne;
   }
   __syncthreads();
+  long long t_rep1 = clock64();
   const int N = min(s.ntok_new, p.max_tpf);
   order_tokens<T>(N, Hc, hash, x, s);
+  long long t_o2 = clock64();
   // eps links from final costs
   for (int i = tid; i < N; i += T) {
     int slot = ctx.tokslot[i];
@@ -912,6 +920,11 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
       p.frame_cost_offset[co] = cost_offset;
       p.frame_cutoff[co] = cutoff;
     }
+    long long t_end = clock64();
+    cs->prof[3] += (unsigned long long)(t_rep0 - t_o0);
+    cs->prof[4] += (unsigned long long)(t_rep1 - t_rep0);
+    cs->prof[5] += (unsigned long long)(t_o2 - t_rep1);
+    cs->prof[6] += (unsigned long long)(t_end - t_o2);
   }
   __syncthreads();
 }
@@ -991,12 +1004,15 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
   unsigned long long arcs_e_total = 0;
   const size_t fo = (size_t)ch * (p.max_frames + 2);
 
+  unsigned long long pr_cut = 0, pr_exp = 0, pr_rank = 0, pr_tot = 0;
+  const long long t_kernel0 = clock64();
   for (int fi = 0; fi < nframes; fi++) {
     if (frames_decoded >= p.max_frames) { if (tid == 0) s.err = B2K_ERR_OVERFLOW; __syncthreads(); break; }
     const float *ll = ll_base + (size_t)fi * p.row_stride;
     const int pb = p.frame_tok_begin[fo + frames_decoded];
     const int pe = p.frame_tok_begin[fo + frames_decoded + 1];
     const int K = pe - pb;
+    const long long t_f0 = clock64();
 
     // ---- GetCutoff (:653-720); ties -> first in list order (strict < at :662/:675)
     unsigned long long local = ~0ull;
@@ -1066,6 +1082,7 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
     // ---- main loop (:779-812): admission against the exclusive prefix-min
     if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; }
     __syncthreads();
+    const long long t_f1 = clock64();
     ctx.tbase = tbase;
     float carry = kInf;
     int pos_base = 0;
@@ -1176,6 +1193,7 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
     }
     const float next_cutoff = fminf(seed_cutoff, carry + adaptive_beam);
     __syncthreads();
+    const long long t_f2 = clock64();
     // ---- insertion index of the tokens created above = rank of their first
     //      admitted position (bitmap rank)
     const int N1 = min(s.ntok_new, p.max_tpf);
@@ -1208,6 +1226,9 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
         x.by_ins[ins] = slot;
       }
     }
+    const long long t_f3 = clock64();
+    pr_cut += (unsigned long long)(t_f1 - t_f0); pr_exp += (unsigned long long)(t_f2 - t_f1);
+    pr_rank += (unsigned long long)(t_f3 - t_f2);
     finish_frame_exact<T>(p, s, ctx, x, lane, ch, frames_decoded + 1, next_cutoff, cost_offset, lbase,
                           Hc, cs);
     if (s.err) break;
@@ -1223,6 +1244,8 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
     cs->arcs_e += arcs_e_total;
     cs->hc = Hc;
     if (s.err) cs->status = s.err;
+    cs->prof[0] += pr_cut; cs->prof[1] += pr_exp; cs->prof[2] += pr_rank;
+    cs->prof[7] += (unsigned long long)(clock64() - t_kernel0);
   }
   if (s.err) {
     reset_lane_hash<T>(ctx.hash, p.hash_size);
@@ -1409,7 +1432,7 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
       int4 arc = __ldg(&g.ne_arcs[(uint32_t)lk.z & B2K_ARC_MASK]);
       int q = atomicAdd(&sh_narcs, 1);
       if (q < p.cap_la) {
-        la[q] = make_int4(ids_cur[lk.x - tb], ids_cur[lk.y - tb], 0, arc.z);
+        la[q] = make_int4(ids_cur[lk.x - tb], ids_cur[lk.y - tb], 0, arc.z & 0x7fffffff);
         lw[q] = make_float2(__int_as_float(arc.y), 0.0f);
       }
     }
@@ -1535,6 +1558,17 @@ int b2k_fst_create(const b2k_fst_csr *csr, b2k_fst **out) {
         f->h_e[ei++] = make_int4(csr->nextstate[a], wbits, pdf, csr->olabel[a]);
         if (pdf + 1 > f->num_pdfs_seen) f->num_pdfs_seen = pdf + 1;
       }
+    }
+  }
+  // eps arcs: flag the last eps arc of each state and store where the destination's eps arcs start
+  // (lets the sequential eps replay run without touching the state table)
+  for (int s = 0; s < N; s++) {
+    int b = st_off[s].y, e = st_off[s + 1].y;
+    for (int a = b; a < e; a++) {
+      int ns = f->h_ne[a].x;
+      int nb = st_off[ns].y, ne = st_off[ns + 1].y;
+      f->h_ne[a].w = (ne > nb) ? nb : -1;
+      if (a == e - 1) f->h_ne[a].z = (int)((uint32_t)f->h_ne[a].z | 0x80000000u);
     }
   }
   auto up = [&](void **d, const void *h, size_t bytes) -> int {
@@ -1772,14 +1806,15 @@ int b2k_dec_num_frames_decoded(b2k_dec *d, int32_t channel, int32_t *out) {
   return B2K_OK;
 }
 
-int b2k_dec_channel_info(b2k_dec *d, int32_t channel, int64_t info[16]) {
+int b2k_dec_channel_info(b2k_dec *d, int32_t channel, int64_t info[32]) {
   ChanState cs;
   int rc = read_chan(d, channel, &cs);
   if (rc) return rc;
-  memset(info, 0, sizeof(int64_t) * 16);
+  memset(info, 0, sizeof(int64_t) * 32);
   info[0] = cs.status; info[1] = cs.frames_decoded; info[2] = cs.ntok; info[3] = cs.nlink;
   info[4] = (int64_t)cs.arcs_e; info[5] = (int64_t)cs.arcs_ne; info[6] = cs.lat_states;
   info[7] = cs.lat_arcs; info[8] = cs.lat_finals; info[9] = cs.finalized; info[10] = cs.any_final;
+  for (int k = 0; k < 8; k++) info[16 + k] = (int64_t)cs.prof[k];
   return B2K_OK;
 }
 
@@ -1897,7 +1932,7 @@ int b2k_dec_debug_frame(b2k_dec *d, int32_t channel, int32_t frame_plus_one, int
       int64_t a = zi;
       if (a >= n_ne) { bad = true; continue; }
       int4 arc = d->fst->h_ne[a];
-      r[2] = 0; r[3] = arc.z; r[4] = arc.y; r[5] = 0; r[6] = 1;
+      r[2] = 0; r[3] = arc.z & 0x7fffffff; r[4] = arc.y; r[5] = 0; r[6] = 1;
     } else {
       if (zi >= n_e) { bad = true; continue; }
       int4 arc = d->fst->h_e[zi];

@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "feat_kernels.cuh"
 
 namespace b2k {
 
@@ -270,20 +271,7 @@ feat_kernel(FeatParams p, const FeatLane *lanes, int frames_per_cta) {
   }
 }
 
-// ------------------------------------------------------------------ online CMVN
-struct CmvnLane {
-  const float *in;       // raw features [num_frames_total x dim] (row stride in_stride)
-  float *out;
-  int in_stride, out_stride;
-  int first_frame, num_frames;        // frames to produce in this call
-  double *state;         // [2*(dim+1)] sliding-window stats after frame first_frame-1 (persisted)
-};
-struct CmvnParams {
-  int dim, cmn_window, speaker_frames, global_frames, normalize_mean, normalize_variance;
-  const double *global_stats;   // [2*(dim+1)] or NULL
-  const double *speaker_stats;  // [2*(dim+1)] or NULL
-};
-
+// ------------------------------------------------------------------ online CMVN (structs in feat_kernels.cuh)
 // one thread per (lane, dim); count column handled redundantly by every thread
 __global__ void cmvn_kernel(CmvnParams p, const CmvnLane *lanes) {
   const CmvnLane L = lanes[blockIdx.x];
@@ -345,6 +333,13 @@ __global__ void cmvn_kernel(CmvnParams p, const CmvnLane *lanes) {
   }
   L.state[d] = s0; L.state[(D + 1) + d] = s1;
   if (d == 0) L.state[D] = cnt;
+}
+
+int launch_cmvn(const CmvnParams &cp, const CmvnLane *d_lanes, int num_lanes, cudaStream_t st) {
+  int threads = ((cp.dim + 31) / 32) * 32;
+  cmvn_kernel<<<num_lanes, threads, 0, st>>>(cp, d_lanes);
+  B2K_LAUNCH_CHECK();
+  return B2K_OK;
 }
 
 }  // namespace b2k

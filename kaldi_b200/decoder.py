@@ -161,11 +161,13 @@ class CudaDecoder:
         return out.value
 
     def ChannelInfo(self, channel: int) -> dict:
-        info = (C.c_int64 * 16)()
+        info = (C.c_int64 * 32)()
         _lib.check(_lib.lib().b2k_dec_channel_info(self.h, int(channel), C.cast(info, C.POINTER(C.c_int64))))
         keys = ["status", "frames_decoded", "ntok", "nlink", "arcs_emitting", "arcs_nonemitting",
                 "lat_states", "lat_arcs", "lat_finals", "finalized", "any_final"]
-        return {k: int(info[i]) for i, k in enumerate(keys)}
+        d = {k: int(info[i]) for i, k in enumerate(keys)}
+        d["prof_cycles"] = [int(info[16 + k]) for k in range(8)]
+        return d
 
     def GetRawLattice(self, channel: int, stream: int = 0) -> dict:
         """Finalized raw lattice as flat arrays (content of GetRawLattice,

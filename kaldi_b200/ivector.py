@@ -1,0 +1,165 @@
+"""Online i-vector extraction on the GPU (A12-A16 of SURVEY.md §8a) behind the
+semantics of online2/online-ivector-feature.cc (OnlineIvectorFeature) with the
+defaults of OnlineIvectorExtractionConfig (online-ivector-feature.h:105-111):
+use_most_recent_ivector=true, greedy=false, num_gselect=5, min_post=0.025,
+posterior_scale=0.1, num_cg_iters=15; max_count as in the online recipes' conf.
+
+No trained extractor exists in the reference tree, so `make_synthetic_extractor`
+builds a seeded one with the recipe shapes: 512-Gaussian diagonal UBM over
+40-dim LDA features, splice +-3 (280 -> 40 LDA with offset), 100-dim i-vector;
+derived quantities as IvectorExtractor::ComputeDerivedVars
+(ivector/ivector-extractor.cc:182-218)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def make_synthetic_extractor(seed: int = 0, num_gauss: int = 512, feat_dim: int = 40, ivector_dim: int = 100,
+                             splice: int = 3, base_dim: int = 40, max_count: float = 100.0) -> dict:
+    rng = np.random.default_rng(seed + 4242)
+    K = base_dim * (2 * splice + 1)
+    # LDA-like transform with offset column; inputs are MFCCs of magnitude ~10-100
+    lda = (rng.standard_normal((feat_dim, K)) / np.sqrt(K) * 0.1).astype(np.float32)
+    lda_off = (rng.standard_normal(feat_dim) * 0.1).astype(np.float32)
+    lda_mat = np.concatenate([lda, lda_off[:, None]], axis=1).astype(np.float32)       # [40 x 281]
+    means = (rng.standard_normal((num_gauss, feat_dim)) * 1.0).astype(np.float64)
+    var = rng.uniform(0.5, 2.0, (num_gauss, feat_dim)).astype(np.float64)
+    weights = rng.uniform(0.5, 1.5, num_gauss)
+    weights /= weights.sum()
+    inv_vars = (1.0 / var)
+    means_invvars = means * inv_vars
+    # DiagGmm::ComputeGconsts (gmm/diag-gmm.cc): log w - 0.5*(D log 2pi + sum log var + sum mean^2/var)
+    gconsts = np.log(weights) - 0.5 * (feat_dim * np.log(2 * np.pi) + np.log(var).sum(1) + (means * means * inv_vars).sum(1))
+    # extractor: M_g [feat_dim x ivector_dim], Sigma_inv_g SPD [feat_dim x feat_dim]
+    M = (rng.standard_normal((num_gauss, feat_dim, ivector_dim)) * 0.1).astype(np.float64)
+    M[:, :, 0] += means / 10.0 * 0 + rng.standard_normal((num_gauss, feat_dim)) * 0.05
+    A = rng.standard_normal((num_gauss, feat_dim, feat_dim)) * 0.1
+    sigma_inv = np.einsum("gij,gkj->gik", A, A) + np.eye(feat_dim)[None] * rng.uniform(0.5, 1.5, (num_gauss, 1, 1))
+    prior_offset = 10.0
+    sigma_inv_m = np.einsum("gij,gjk->gik", sigma_inv, M)                                 # [G, 40, 100]
+    U_full = np.einsum("gji,gjk->gik", M, sigma_inv_m)                                    # M^T Sigma_inv M  [G,100,100]
+    il = np.tril_indices(ivector_dim)
+    U = np.ascontiguousarray(U_full[:, il[0], il[1]])                                     # packed lower triangle [G, 5050]
+    return dict(num_gauss=num_gauss, feat_dim=feat_dim, ivector_dim=ivector_dim, splice=splice, base_dim=base_dim,
+                lda_mat=lda_mat, ubm_weights=weights.astype(np.float32), gconsts=gconsts.astype(np.float32),
+                means_invvars=means_invvars.astype(np.float32), inv_vars=inv_vars.astype(np.float32),
+                M=M, sigma_inv=sigma_inv, sigma_inv_m=np.ascontiguousarray(sigma_inv_m), U=U,
+                prior_offset=prior_offset, max_count=max_count, num_gselect=5, min_post=0.025, posterior_scale=0.1,
+                num_cg_iters=15, cmn_window=600, speaker_frames=600, global_frames=200,
+                global_cmvn_stats=_synthetic_global_cmvn(seed, base_dim))
+
+
+def _synthetic_global_cmvn(seed: int, dim: int) -> np.ndarray:
+    rng = np.random.default_rng(seed + 99)
+    cnt = 10000.0
+    mean = rng.standard_normal(dim) * 3.0
+    mean[0] += 60.0
+    var = rng.uniform(20.0, 80.0, dim)
+    g = np.zeros((2, dim + 1), np.float64)
+    g[0, :dim] = mean * cnt
+    g[1, :dim] = (var + mean * mean) * cnt
+    g[0, dim] = cnt
+    return g
+
+
+def online_ivector_schedule(num_samples: int, chunk_samples: int, frame_length: int, frame_shift: int,
+                            num_feature_frames: int, nnet_right_context: int, frames_per_chunk: int, subsampling: int,
+                            splice_right: int = 3):
+    """For each nnet chunk n, the frame index OnlineIvectorFeature::GetFrame is
+    called with when online2-wav-nnet3-latgen-faster feeds `chunk_samples` at a
+    time (online2-wav-nnet3-latgen-faster.cc:245-268): the chunk is computed by
+    the first AdvanceDecoding after which DecodableNnetLoopedOnlineBase::
+    NumFramesReady (decodable-online-looped.cc:56-84) covers it, and it asks for
+    frame min(features_ready - 1, ivector_frames_ready - 1)
+    (decodable-online-looped.cc:185-193), ivector_frames_ready being smaller by
+    the splice right context until the input is finished."""
+    T = num_feature_frames
+    n_out = (T + subsampling - 1) // subsampling
+    n_chunks = (n_out * subsampling + frames_per_chunk - 1) // frames_per_chunk
+    sched = []
+    fed, done_chunks = 0, 0
+    while done_chunks < n_chunks:
+        fed = min(fed + chunk_samples, num_samples)
+        finished = fed >= num_samples
+        ready = 0 if fed < frame_length else 1 + (fed - frame_length) // frame_shift       # snip-edges
+        if finished:
+            ready = T
+            chunks_ready = n_chunks
+            iv_frame = T - 1
+        else:
+            chunks_ready = max(0, ready - nnet_right_context) // frames_per_chunk
+            iv_ready = max(0, ready - splice_right)
+            iv_frame = min(ready - 1, iv_ready - 1)
+        while done_chunks < min(chunks_ready, n_chunks):
+            sched.append(max(iv_frame, 0))
+            done_chunks += 1
+    return np.asarray(sched, np.int32)
+
+
+class _IvecCfg(C.Structure):
+    _fields_ = [("base_dim", C.c_int32), ("splice_left", C.c_int32), ("splice_right", C.c_int32),
+                ("feat_dim", C.c_int32), ("num_gauss", C.c_int32), ("ivector_dim", C.c_int32),
+                ("num_gselect", C.c_int32), ("min_post", C.c_float), ("posterior_scale", C.c_float),
+                ("max_count", C.c_float), ("prior_offset", C.c_float), ("num_cg_iters", C.c_int32),
+                ("cmn_window", C.c_int32), ("speaker_frames", C.c_int32), ("global_frames", C.c_int32),
+                ("max_lanes", C.c_int32), ("max_frames", C.c_int32)]
+
+
+class IvectorExtractorGpu:
+    """GPU OnlineIvectorFeature for batches of equal-length utterances."""
+
+    def __init__(self, ex: dict, max_lanes: int, max_frames: int):
+        self.ex = ex
+        L = _lib.lib()
+        c = _IvecCfg(ex["base_dim"], ex["splice"], ex["splice"], ex["feat_dim"], ex["num_gauss"], ex["ivector_dim"],
+                     ex["num_gselect"], ex["min_post"], ex["posterior_scale"], ex["max_count"], ex["prior_offset"],
+                     ex["num_cg_iters"], ex["cmn_window"], ex["speaker_frames"], ex["global_frames"], max_lanes, max_frames)
+        f32p, f64p = C.POINTER(C.c_float), C.POINTER(C.c_double)
+        self._keep = [np.ascontiguousarray(ex["lda_mat"], np.float32), np.ascontiguousarray(ex["gconsts"], np.float32),
+                      np.ascontiguousarray(ex["means_invvars"], np.float32), np.ascontiguousarray(ex["inv_vars"], np.float32),
+                      np.ascontiguousarray(ex["sigma_inv_m"], np.float64), np.ascontiguousarray(ex["U"], np.float64),
+                      np.ascontiguousarray(ex["global_cmvn_stats"], np.float64)]
+        k = self._keep
+        self.h = C.c_void_p()
+        _lib.check(L.b2k_ivec_create(C.cast(C.byref(c), C.c_void_p), k[0].ctypes.data_as(f32p), k[1].ctypes.data_as(f32p),
+                                     k[2].ctypes.data_as(f32p), k[3].ctypes.data_as(f32p), k[4].ctypes.data_as(f64p),
+                                     k[5].ctypes.data_as(f64p), k[6].ctypes.data_as(f64p), C.byref(self.h)))
+        self.ivector_dim = ex["ivector_dim"]
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().b2k_ivec_destroy(self.h)
+        except Exception:
+            pass
+
+    def Compute(self, feat_ptrs, feat_stride: int, num_frames: int, schedule, out_ptrs, out_stride: int, stream: int = 0):
+        n = len(feat_ptrs)
+        sched = np.ascontiguousarray(schedule, np.int32)
+        fa = (C.c_void_p * n)(*[int(p) for p in feat_ptrs])
+        oa = (C.c_void_p * n)(*[int(p) for p in out_ptrs])
+        _lib.check(_lib.lib().b2k_ivec_compute_batched(
+            self.h, n, C.cast(fa, C.c_void_p), int(feat_stride), int(num_frames),
+            sched.ctypes.data_as(C.POINTER(C.c_int32)), len(sched), C.cast(oa, C.c_void_p), int(out_stride),
+            C.c_void_p(stream)))
+
+    # pipeline hook
+    def compute_chunk_ivectors(self, pipe, n: int, stream: int = 0):
+        T, D = pipe.T, pipe.feat.dim
+        nc, ivd = pipe.nnet.n_chunks, self.ivector_dim
+        if getattr(self, "_sched_key", None) != (T, nc):
+            fo = pipe.cfg.feature_opts
+            self._sched = online_ivector_schedule(
+                pipe.cfg.num_samples, int(round(pipe.cfg.chunk_length_secs * fo.samp_freq)),
+                int(fo.samp_freq * 0.001 * fo.frame_length_ms), int(fo.samp_freq * 0.001 * fo.frame_shift_ms), T,
+                pipe.nnet.prog["model_right"], pipe.cfg.frames_per_chunk, pipe.arch["frame_subsampling_factor"],
+                self.ex["splice"])
+            assert len(self._sched) == nc
+            self._sched_key = (T, nc)
+        fp = [pipe.d_feats.data_ptr() + 4 * T * D * i for i in range(n)]
+        op = [pipe.d_ivec.data_ptr() + 4 * nc * ivd * i for i in range(n)]
+        self.Compute(fp, D, T, self._sched, op, ivd, stream)

@@ -63,6 +63,9 @@ class BatchedPipeline:
         self.d_feats = torch.empty(B, self.T, self.feat.dim, dtype=torch.float32, device="cuda")
         self.d_ivec = torch.zeros(B, self.nnet.n_chunks, arch["ivector_dim"], dtype=torch.float32, device="cuda")
         self.d_loglikes = torch.empty(B, nf, arch["num_pdfs"], dtype=torch.float32, device="cuda")
+        if isinstance(ivector_extractor, dict):      # a synthetic/loaded extractor description
+            from .ivector import IvectorExtractorGpu
+            ivector_extractor = IvectorExtractorGpu(ivector_extractor, cfg.max_batch, self.T)
         self.ivector_extractor = ivector_extractor
         self.audio_seconds_per_utt = cfg.num_samples / cfg.feature_opts.samp_freq
 

@@ -34,13 +34,15 @@ NNET_SOURCES = (
                              "event-map.cc", "tree-renderer.cc")]
     + ["gmm/" + f for f in ("diag-gmm.cc", "am-diag-gmm.cc", "full-gmm.cc", "diag-gmm-normal.cc",
                             "full-gmm-normal.cc", "model-common.cc")]
+    + ["ivector/ivector-extractor.cc"]
 )
 NNET_SOURCES = [s for s in NNET_SOURCES if s != "tree/tree-renderer.cc"]
 
 
 def build(quiet: bool = False, force: bool = False) -> str:
     wrap = os.path.join(HERE, "ref_wrap", "nnet_wrap.cc")
-    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= os.path.getmtime(wrap):
+    wraps = [wrap, os.path.join(HERE, "ref_wrap", "ivector_wrap.cc"), os.path.join(HERE, "ref_wrap", "nnet_stubs.cc")]
+    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(w) for w in wraps):
         return SO
     if not os.path.isdir(RF.SRC):
         raise RuntimeError("/root/reference not present: cannot (re)build oracle/_ref")
@@ -58,9 +60,11 @@ def build(quiet: bool = False, force: bool = False) -> str:
     objs = RF.compile_objects(NNET_SOURCES, os.path.join(OUT_DIR, "obj_nnet"), flags, quiet)
     wobj = os.path.join(OUT_DIR, "obj_nnet", "nnet_wrap.o")
     sobj = os.path.join(OUT_DIR, "obj_nnet", "nnet_stubs.o")
+    iobj = os.path.join(OUT_DIR, "obj_nnet", "ivector_wrap.o")
+    subprocess.check_call(["g++"] + flags + ["-c", os.path.join(HERE, "ref_wrap", "ivector_wrap.cc"), "-o", iobj])
     subprocess.check_call(["g++"] + flags + ["-c", wrap, "-o", wobj])
     subprocess.check_call(["g++"] + flags + ["-c", os.path.join(HERE, "ref_wrap", "nnet_stubs.cc"), "-o", sobj])
-    subprocess.check_call(["g++", "-shared", "-o", SO] + objs + base_objs + [wobj, sobj, blas,
+    subprocess.check_call(["g++", "-shared", "-o", SO] + objs + base_objs + [wobj, sobj, iobj, blas,
                           "-Wl,--disable-new-dtags,-rpath," + os.path.dirname(blas), "-lpthread", "-lm", "-ldl"])
     return SO
 

@@ -1,0 +1,106 @@
+// oracle/ref_wrap/ivector_wrap.cc — TEST INFRASTRUCTURE ONLY.
+// Online i-vector oracle: the arithmetic is the reference's OWN code compiled
+// from /root/reference/src —
+//   IvectorExtractor (text Read + ComputeDerivedVars)   ivector/ivector-extractor.cc:182-218,828-849
+//   OnlineIvectorEstimationStats::{AccStats,GetIvector}  ivector/ivector-extractor.cc:611-668,732-756
+//   LinearCgd<double>                                   matrix/optimization.cc:453-565
+//   DiagGmm::LogLikelihoods                             gmm/diag-gmm.cc:546-562
+//   VectorToPosteriorEntry                              hmm/posterior.cc:440-505
+//   OnlineCmvn / OnlineSpliceFrames / OnlineTransform   feat/online-feature.cc
+// and this file restates only the glue of OnlineIvectorFeature
+// (online2/online-ivector-feature.cc: ctor :399-443, GetMinPost :188-199,
+// UpdateStatsForFrames :201-245, UpdateStatsUntilFrame :248-281, GetFrame
+// :327-355), which cannot be compiled as is because the same translation unit
+// instantiates OnlineSilenceWeighting over the OpenFst-based decoder.
+#include <sstream>
+#include <memory>
+#include <vector>
+
+#include "feat/online-feature.h"
+#include "gmm/diag-gmm.h"
+#include "hmm/posterior.h"
+#include "ivector/ivector-extractor.h"
+
+using namespace kaldi;
+
+struct RefIvec {
+  IvectorExtractor extractor;
+  DiagGmm ubm;
+  Matrix<BaseFloat> lda;
+};
+
+extern "C" {
+
+void *ref_ivector_create(const char *extractor_text, const char *ubm_text, const float *lda, int lda_rows, int lda_cols) {
+  try {
+    RefIvec *r = new RefIvec();
+    { std::istringstream is(extractor_text); r->extractor.Read(is, false); }
+    { std::istringstream is(ubm_text); r->ubm.Read(is, false); }
+    r->lda.Resize(lda_rows, lda_cols);
+    for (int i = 0; i < lda_rows; i++) for (int j = 0; j < lda_cols; j++) r->lda(i, j) = lda[i * lda_cols + j];
+    return r;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_ivector_create: %s\n", e.what()); return nullptr; }
+}
+void ref_ivector_destroy(void *h) { delete (RefIvec *)h; }
+
+// sched[n] = frame index passed to OnlineIvectorFeature::GetFrame for nnet chunk n
+// (non-decreasing).  out: [n_chunks x ivector_dim], prior offset already subtracted from dim 0.
+int ref_ivector_run(void *h, const float *feats, int T, int D, const double *global_cmvn, int cmn_window,
+                    int speaker_frames, int global_frames, int splice_left, int splice_right, int num_gselect,
+                    float min_post, float posterior_scale, float max_count, int num_cg_iters,
+                    int online_cmvn_iextractor, const int *sched, int n_chunks, float *out,
+                    float *debug_lda_raw, float *debug_lda_norm) {
+  try {
+    RefIvec *r = (RefIvec *)h;
+    Matrix<BaseFloat> m(T, D);
+    for (int t = 0; t < T; t++) memcpy(m.RowData(t), feats + (size_t)t * D, 4 * D);
+    OnlineMatrixFeature base(m);
+    OnlineCmvnOptions copts;
+    copts.cmn_window = cmn_window; copts.speaker_frames = speaker_frames; copts.global_frames = global_frames;
+    Matrix<double> g(2, D + 1);
+    for (int i = 0; i < 2; i++) for (int j = 0; j <= D; j++) g(i, j) = global_cmvn[i * (D + 1) + j];
+    OnlineCmvnState cstate(g);
+    OnlineCmvn cmvn(copts, cstate, &base);
+    OnlineSpliceOptions sopts;
+    sopts.left_context = splice_left; sopts.right_context = splice_right;
+    OnlineSpliceFrames splice_norm(sopts, &cmvn), splice_raw(sopts, &base);
+    OnlineTransform lda_norm(r->lda, &splice_norm), lda_raw(r->lda, &splice_raw);
+    const int ivdim = r->extractor.IvectorDim();
+    OnlineIvectorEstimationStats stats(ivdim, r->extractor.PriorOffset(), max_count);
+    Vector<double> current_ivector(ivdim);
+    int num_frames_stats = 0;
+    if (debug_lda_raw) for (int t = 0; t < T; t++) { SubVector<BaseFloat> row(debug_lda_raw + (size_t)t * lda_raw.Dim(), lda_raw.Dim()); lda_raw.GetFrame(t, &row); }
+    if (debug_lda_norm) for (int t = 0; t < T; t++) { SubVector<BaseFloat> row(debug_lda_norm + (size_t)t * lda_norm.Dim(), lda_norm.Dim()); lda_norm.GetFrame(t, &row); }
+    for (int n = 0; n < n_chunks; n++) {
+      int frame = sched[n];
+      // UpdateStatsUntilFrame(frame) with use_most_recent_ivector = true (:248-281)
+      std::vector<int32> frames;
+      for (; num_frames_stats <= frame; num_frames_stats++) frames.push_back(num_frames_stats);
+      if (!frames.empty()) {
+        // UpdateStatsForFrames (:201-245), all frame weights 1.0
+        int nf = frames.size();
+        Matrix<BaseFloat> fe(nf, lda_norm.Dim()), log_likes;
+        lda_norm.GetFrames(frames, &fe);
+        r->ubm.LogLikelihoods(fe, &log_likes);
+        std::vector<std::vector<std::pair<int32, BaseFloat> > > post(nf);
+        BaseFloat mp = min_post;           // GetMinPost(weight = 1.0) (:188-199)
+        if (mp > 0.99) mp = 0.99;
+        for (int i = 0; i < nf; i++) {
+          VectorToPosteriorEntry(log_likes.Row(i), num_gselect, mp, &post[i]);
+          for (size_t j = 0; j < post[i].size(); j++) post[i][j].second *= posterior_scale * 1.0;
+        }
+        if (!online_cmvn_iextractor) lda_raw.GetFrames(frames, &fe); else lda_norm.GetFrames(frames, &fe);
+        stats.AccStats(r->extractor, fe, post);
+        stats.GetIvector(num_cg_iters, &current_ivector);
+      }
+      // GetFrame (:343-349)
+      for (int d = 0; d < ivdim; d++) out[(size_t)n * ivdim + d] = (float)current_ivector(d);
+      out[(size_t)n * ivdim] = (float)current_ivector(0);
+      { Vector<BaseFloat> f(ivdim); f.CopyFromVec(current_ivector); f(0) -= r->extractor.PriorOffset();
+        for (int d = 0; d < ivdim; d++) out[(size_t)n * ivdim + d] = f(d); }
+    }
+    return 0;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_ivector_run: %s\n", e.what()); return -1; }
+}
+
+}  // extern "C"

@@ -48,3 +48,41 @@ def test_end_to_end_small_model_matches_cpu_reference_path():
         want = o.lattice()
         got = lattice_to_canonical(lats[i])
         assert all(np.array_equal(got[k], want[k]) for k in got)
+
+
+def test_end_to_end_with_online_ivectors():
+    """Full chain including the GPU i-vector stage, against the CPU path built
+    from the compiled reference pieces (features, i-vector, nnet3) + decoder oracle."""
+    from kaldi_b200 import ivector as IVM
+    from kaldi_b200.decoder import CudaDecoder, lattice_to_canonical
+    from kaldi_b200.pipeline import BatchedPipeline, PipelineConfig
+    from oracle import dec_oracle as D, feat_oracle as F, ivector_oracle as IO, nnet_oracle as NO
+    P = 300
+    arch = NM.arch_tiny(P)
+    W = NM.random_weights(arch, seed=2)
+    g = synth.make_hclg(200_000, num_pdfs=P, seed=4)
+    S = 48000
+    ex = IVM.make_synthetic_extractor(3, num_gauss=64, ivector_dim=100)
+    cfg = PipelineConfig(max_batch=2, num_samples=S)
+    pipe = BatchedPipeline(cfg, arch, W, g, ivector_extractor=ex)
+    waves = [synth.make_audio(S, seed=10 + i) for i in range(2)]
+    lats = CudaDecoder.SplitLattices(pipe.decode_batch(waves))
+    R, RN, RI = F.RefFeat(), NO.RefNnet(arch, W), IO.RefIvector(ex)
+    for i in range(2):
+        feats = R.compute(waves[i], F.FeatOpts(), online_chunk=2880)
+        sched = IVM.online_ivector_schedule(S, 2880, 400, 160, feats.shape[0], RN.right_context, RN.frames_per_chunk, 3)
+        civ = RI.run(feats, sched)
+        got_iv = pipe.d_ivec[i].cpu().numpy()
+        assert np.abs(got_iv - civ).max() <= 2e-4 * np.linalg.norm(civ, axis=1).max()
+        ends = [(n + 1) * RN.frames_per_chunk + RN.right_context for n in range(len(sched))]
+        mat = np.zeros((ends[-1] + 1, 100), np.float32)
+        prev = 0
+        for n, e in enumerate(ends):
+            mat[prev:e + 1] = civ[n]; prev = e + 1
+        ll_ref = RN.forward(feats, mat, period=1)
+        ll_gpu = pipe.d_loglikes[i].cpu().numpy()
+        assert np.abs(ll_gpu - ll_ref).max() <= 1e-4 * np.abs(ll_ref).max()
+        o = D.DecoderOracle(g, cfg.decoder_cfg)
+        o.decode(ll_gpu, mode=D.MODE_REFERENCE_ORDER)
+        got, want = lattice_to_canonical(lats[i]), o.lattice()
+        assert all(np.array_equal(got[k], want[k]) for k in got)
