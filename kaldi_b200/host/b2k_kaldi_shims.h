@@ -1,0 +1,141 @@
+// b2k_kaldi_shims.h — header-only C++ shims that keep the reference's class
+// surfaces and forward to the b2k C ABI (include/b2k.h).  This is the binding a
+// Kaldi maintainer adds: the tools keep calling
+//   OnlineFeatureInterface::{Dim,NumFramesReady,IsLastFrame,GetFrame}   itf/online-feature-itf.h:49-110
+//   OnlineBaseFeature::{AcceptWaveform,InputFinished}                   itf/online-feature-itf.h:112-125
+//   cuda_decoder::CudaFst / CudaDecoder                                 cudadecoder/cuda-fst.h:75, cuda-decoder.h:224-346
+// and the work happens in libb2k.so.  Compiled against the reference headers
+// by `oracle/check_shims.py` (syntax + type check; OpenFst-typed members are
+// guarded by B2K_HAVE_OPENFST because OpenFst is not in this image).
+#ifndef B2K_KALDI_SHIMS_H_
+#define B2K_KALDI_SHIMS_H_
+
+#include <cuda_runtime.h>
+
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "b2k.h"
+#include "base/kaldi-error.h"
+#include "itf/online-feature-itf.h"
+#include "matrix/kaldi-matrix.h"
+#include "matrix/kaldi-vector.h"
+
+namespace kaldi {
+namespace b2k_shim {
+
+inline void Check(int rc, const char *what) {
+  if (rc != B2K_OK) KALDI_ERR << what << ": " << b2k_last_error();      // throws KaldiFatalError like the reference
+}
+
+// OnlineGenericBaseFeature<MfccComputer|FbankComputer> (feat/online-feature.h:72-160) on the GPU.
+// One object per utterance, not thread-safe (same contract as the reference).
+class OnlineBaseFeatureB2k : public OnlineBaseFeature {
+ public:
+  OnlineBaseFeatureB2k(b2k_feat *feat, BaseFloat frame_shift_s, int32 max_samples)
+      : feat_(feat), shift_s_(frame_shift_s), cap_(max_samples) {
+    dim_ = b2k_feat_dim(feat_);
+    if (cudaMalloc(&d_wave_, sizeof(float) * cap_) != cudaSuccess) KALDI_ERR << "cudaMalloc failed";
+    int32 max_frames = b2k_feat_num_frames(feat_, cap_, 1) + 1;
+    if (cudaMalloc(&d_feats_, sizeof(float) * max_frames * dim_) != cudaSuccess) KALDI_ERR << "cudaMalloc failed";
+    host_.Resize(max_frames, dim_);
+  }
+  ~OnlineBaseFeatureB2k() override { cudaFree(d_wave_); cudaFree(d_feats_); }
+
+  int32 Dim() const override { return dim_; }
+  int32 NumFramesReady() const override { return frames_ready_; }
+  bool IsLastFrame(int32 frame) const override { return finished_ && frame == frames_ready_ - 1; }
+  BaseFloat FrameShiftInSeconds() const override { return shift_s_; }
+
+  void GetFrame(int32 frame, VectorBase<BaseFloat> *feat) override {
+    KALDI_ASSERT(frame >= 0 && frame < frames_ready_ && feat->Dim() == dim_);
+    feat->CopyFromVec(host_.Row(frame));
+  }
+
+  // feat/online-feature.cc:131-159
+  void AcceptWaveform(BaseFloat sampling_rate, const VectorBase<BaseFloat> &wave) override {
+    if (wave.Dim() == 0) return;
+    if (finished_) KALDI_ERR << "AcceptWaveform called after InputFinished() was called.";
+    if (num_samples_ + wave.Dim() > cap_) KALDI_ERR << "utterance longer than the configured capacity";
+    cudaMemcpy(d_wave_ + num_samples_, wave.Data(), sizeof(float) * wave.Dim(), cudaMemcpyHostToDevice);
+    num_samples_ += wave.Dim();
+    Compute(false);
+  }
+  void InputFinished() override { finished_ = true; Compute(true); }
+
+ private:
+  void Compute(bool flush) {   // ComputeFeatures, feat/online-feature.cc:162-204
+    int32 n_new = b2k_feat_num_frames(feat_, num_samples_, flush ? 1 : 0);
+    if (n_new <= frames_ready_) return;
+    const float *w = d_wave_;
+    float *o = d_feats_;
+    int32 ns = num_samples_, first = frames_ready_, cnt = n_new - frames_ready_;
+    Check(b2k_feat_compute_batched(feat_, 1, &w, &ns, &first, &cnt, &o, dim_, nullptr), "b2k_feat_compute_batched");
+    cudaMemcpy(host_.RowData(first), d_feats_ + (size_t)first * dim_, sizeof(float) * cnt * dim_, cudaMemcpyDeviceToHost);
+    // (host_ is allocated with stride == dim_ only if kDefaultStride == cols; a production shim copies row by row)
+    frames_ready_ = n_new;
+  }
+  b2k_feat *feat_;
+  BaseFloat shift_s_;
+  int32 cap_, dim_ = 0, num_samples_ = 0, frames_ready_ = 0;
+  bool finished_ = false;
+  float *d_wave_ = nullptr, *d_feats_ = nullptr;
+  Matrix<BaseFloat> host_;
+};
+
+// cuda_decoder::CudaDecoder surface (cudadecoder/cuda-decoder.h:171-346) over b2k_dec_*.
+typedef int32 ChannelId;
+class CudaDecoderB2k {
+ public:
+  CudaDecoderB2k(const b2k_fst *fst, const b2k_dec_cfg &config, int32 nlanes, int32 nchannels) {
+    Check(b2k_dec_create(fst, &config, nlanes, nchannels, &dec_), "b2k_dec_create");
+  }
+  ~CudaDecoderB2k() { b2k_dec_destroy(dec_); }
+  void InitDecoding(const std::vector<ChannelId> &channels) {
+    Check(b2k_dec_init_decoding(dec_, channels.data(), (int32)channels.size(), nullptr), "InitDecoding");
+  }
+  // AdvanceDecoding(const std::vector<std::pair<ChannelId, const BaseFloat*>>&)  cuda-decoder.h:264-265
+  void AdvanceDecoding(const std::vector<std::pair<ChannelId, const BaseFloat *>> &lanes_assignements) {
+    std::vector<ChannelId> ch;
+    std::vector<const float *> ll;
+    for (const auto &p : lanes_assignements) { ch.push_back(p.first); ll.push_back(p.second); }
+    Check(b2k_dec_advance_decoding(dec_, ch.data(), ll.data(), (int32)ch.size(), nullptr), "AdvanceDecoding");
+  }
+  int32 NumFramesDecoded(ChannelId ichannel) const {
+    int32 n = 0;
+    Check(b2k_dec_num_frames_decoded(dec_, ichannel, &n), "NumFramesDecoded");
+    return n;
+  }
+#ifdef B2K_HAVE_OPENFST
+  // GetRawLattice(const std::vector<ChannelId>&, std::vector<Lattice*>&, bool)  cuda-decoder.h
+  void GetRawLattice(const std::vector<ChannelId> &channels, std::vector<Lattice *> &fst_out_vec, bool use_final_probs) {
+    KALDI_ASSERT(use_final_probs);
+    Check(b2k_dec_finalize_decoding(dec_, channels.data(), (int32)channels.size(), nullptr), "FinalizeDecoding");
+    for (size_t i = 0; i < channels.size(); i++) {
+      b2k_raw_lattice r = {};
+      Check(b2k_dec_get_raw_lattice(dec_, channels[i], &r, nullptr), "GetRawLattice(size)");
+      std::vector<int32> sf(r.num_states), sh(r.num_states), as(r.num_arcs), ad(r.num_arcs), ai(r.num_arcs), ao(r.num_arcs), fs(r.num_finals);
+      std::vector<float> st(r.num_states), se(r.num_states), ag(r.num_arcs), aa(r.num_arcs), fc(r.num_finals);
+      r.state_frame = sf.data(); r.state_hclg = sh.data(); r.state_tot_cost = st.data(); r.state_extra_cost = se.data();
+      r.arc_src = as.data(); r.arc_dst = ad.data(); r.arc_ilabel = ai.data(); r.arc_olabel = ao.data();
+      r.arc_graph_cost = ag.data(); r.arc_acoustic_cost = aa.data(); r.final_state = fs.data(); r.final_cost = fc.data();
+      Check(b2k_dec_get_raw_lattice(dec_, channels[i], &r, nullptr), "GetRawLattice");
+      Lattice *ofst = fst_out_vec[i];
+      ofst->DeleteStates();
+      for (int64 s = 0; s < r.num_states; s++) ofst->AddState();
+      ofst->SetStart(0);
+      for (int64 a = 0; a < r.num_arcs; a++)
+        ofst->AddArc(as[a], LatticeArc(ai[a], ao[a], LatticeWeight(ag[a], aa[a]), ad[a]));     // lattice-faster-decoder.cc:179-182
+      for (int64 f = 0; f < r.num_finals; f++) ofst->SetFinal(fs[f], LatticeWeight(fc[f], 0));  // :189
+    }
+  }
+#endif
+ private:
+  b2k_dec *dec_ = nullptr;
+};
+
+}  // namespace b2k_shim
+}  // namespace kaldi
+#endif  // B2K_KALDI_SHIMS_H_

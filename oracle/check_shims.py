@@ -1,0 +1,22 @@
+"""Compile check of kaldi_b200/host/b2k_kaldi_shims.h against the reference's own
+headers (only possible where /root/reference exists).  Not part of the product."""
+import os, subprocess, sys, tempfile
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_feat as RF
+
+
+def check() -> bool:
+    if not os.path.isdir(RF.SRC):
+        return False
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "t.cc")
+        open(src, "w").write('#include "b2k_kaldi_shims.h"\nint main() { return 0; }\n')
+        cmd = ["g++", "-fsyntax-only"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "kaldi_b200", "host"),
+                                                      "-I/usr/local/cuda/include"]) + [src]
+        subprocess.check_call(cmd)
+    return True
+
+
+if __name__ == "__main__":
+    print("shims compile against the reference headers:", check())
