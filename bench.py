@@ -373,9 +373,10 @@ def main():
                              d2h_bytes_per_step=int(d2h / a.steps), lattice_states_per_step=int(lat_states / a.steps)),
                     gpu_launches=int(launches), stage_ms={k: round(v, 3) for k, v in stage_ms.items()},
                     decoder_phase_share=dict(zip(
-                        ["cutoff_seed", "expand", "rank", "order1_queue", "eps_replay", "order2", "links_commit"],
-                        [round(float(sum(i["prof_cycles"][k] for i in infos)) / max(1.0, float(sum(i["prof_cycles"][7] for i in infos))), 3)
-                         for k in range(7)])),
+                        ["cutoff_seed", "expand", "rank", "order1", "queue_build", "eps_relax", "eps_adjacency", "eps_replay",
+                         "eps_finish", "order2", "eps_links", "commit"],
+                        [round(float(sum(i["prof_cycles"][k] for i in infos)) / max(1.0, float(sum(i["prof_cycles"][15] for i in infos))), 3)
+                         for k in range(12)])),
                     decoder=dict(marcs_per_s=arcs / (stage_ms["decoder_advance"] / 1e3) / 1e6 * world,
                                  arcs_per_frame=arcs / (B * pipe.nnet.n_out), tokens_per_frame=ntok / (B * pipe.nnet.n_out),
                                  errors=nerr),

@@ -34,6 +34,7 @@
 // admitted + 16 B per token kept.
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -63,7 +64,7 @@ struct ChanState {          // per channel, device resident
   int32_t hc;               // reference-order mode: HashList size (hash-list-inl.h:38), starts at 1000
   int32_t pad_;
   unsigned long long arcs_e, arcs_ne;
-  unsigned long long prof[8];   // cycles: cutoff+seed, expand, rank, order1+queue, replay, order2, links+commit, total
+  unsigned long long prof[16];  // cycles per phase of the reference-order kernel (bench.py: decoder_phase_share)
 };
 
 #define B2K_EPS_FLAG 0x80000000u
@@ -113,6 +114,13 @@ struct DecParams {
   int32_t *x_sbase;         // [max_tpf]
   int32_t *x_run;           // [max_tpf]
   int32_t *x_order;         // [max_tpf] list rank -> hash slot
+  float *x_rcost;           // [max_tpf] replay cost per dense token index
+  int32_t *x_adjoff;        // [max_tpf+1] eps adjacency offsets per dense token index
+  int32_t *x_deg;           // [max_tpf] eps out-degree (all arcs) per dense token index
+  int32_t *x_newseq;        // [max_tpf] creation order found by the replay (eps-created tokens)
+  int2 *x_adj;              // [adj_cap] {dest dense index | EPS bit, weight bits}
+  int32_t adj_cap;
+  int32_t rs_rcap, rs_ecap, rs_qcap;   // shared-memory replay capacities (tokens, entries, queue)
   int32_t pos_cap, hc_cap, queue_cap;
   float hash_ratio;
   // per launch
@@ -227,6 +235,9 @@ __device__ float block_select_kth(const float *vals, int n, int k, uint32_t *his
   return ord2f(prefix);
 }
 
+// phase timers (thread 0 only): TICK(s, i) adds the cycles since the previous tick to slot i
+#define B2K_TICK(S, I) do { if (threadIdx.x == 0) { long long _t = clock64(); (S).prof[(I)] += (unsigned long long)(_t - (S).tlast); (S).tlast = _t; } } while (0)
+
 // ------------------------------------------------------------------ hash
 
 struct LaneCtx {
@@ -307,6 +318,8 @@ struct __align__(16) DecShared {
   int cont;
   float scanf_[2][T / 32];
   int q_n;
+  unsigned long long prof[16];
+  long long tlast;
 };
 
 // epsilon closure + link generation + commit of the frame being built.
@@ -711,6 +724,7 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
 
 struct XScratch {
   uint32_t *bm; int32_t *wbase, *by_ins, *bfirst, *bcount, *bfill, *sbase, *run, *order, *queue;
+  float *rcost; int32_t *adjoff, *deg, *newseq; int2 *adj;
 };
 
 // find-or-insert without arena write; *created tells whether this call made the token
@@ -801,8 +815,8 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   const int n_emit_links = s.nlink_new;
   const int N1 = min(s.ntok_new, p.max_tpf);
   // list order after the emitting phase -> initial worklist (:852-856)
-  long long t_o0 = clock64();
   order_tokens<T>(N1, Hc, hash, x, s);
+  B2K_TICK(s, 3);
   int qcarry = 0;
   for (int base = 0; base < N1; base += T) {
     int k = base + tid, flag = 0, slot = 0, nb = 0;
@@ -815,54 +829,270 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
     }
     int total;
     int excl = block_excl_scan<T>(flag, s.redi, &total);
-    if (flag) { x.queue[2 * (qcarry + excl)] = slot; x.queue[2 * (qcarry + excl) + 1] = nb; }
+    (void)nb;
+    if (flag) x.queue[qcarry + excl] = hash[slot].z;          // dense token index (= insertion index)
     qcarry += total;
   }
   __syncthreads();
-  // literal LIFO replay by one thread (:858-896).  Queue entries are (slot, first
-  // eps arc); the eps arc record itself says where the destination's eps arcs
-  // start and which arc is the state's last, so the loop touches only the arc
-  // stream and the hash (2 dependent L2 accesses per admitted arc).
-  long long t_rep0 = clock64();
-  if (tid == 0 && !s.err) {
-    int qn = qcarry;
-    unsigned long long ne = 0;
-    const int qcap = p.queue_cap / 2;
-    while (qn > 0) {
-      --qn;
-      const int slot = x.queue[2 * qn];
-      int a = x.queue[2 * qn + 1];
-      if (qn > 0) {   // warm the next entry (it is popped next unless this one pushes)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(&g.ne_arcs[x.queue[2 * (qn - 1) + 1]]));
-      }
-      float c = ord2f(*reinterpret_cast<volatile uint32_t *>(&hash[slot].y));
-      if (c >= cutoff) continue;
-      for (;; a++) {
-        int4 arc = __ldg(&g.ne_arcs[a]);
-        ne++;
-        float tot = c + __int_as_float(arc.y);
-        if (tot < cutoff) {
-          bool created; int idx = 0;
-          int ds = hash_insert_x(ctx, arc.x, &created, &idx);
-          if (ds < 0 || s.err) { qn = 0; break; }
-          if (created) { hash[ds].z = idx; x.by_ins[idx] = ds; }
-          uint32_t nv = f2ord(tot);
-          uint32_t old = atomicMin(reinterpret_cast<uint32_t *>(&hash[ds].y), nv);   // FindOrAddToken min-update
-          if (nv < old && arc.w >= 0) {                   // changed, and the destination has eps arcs
-            if (qn < qcap) { x.queue[2 * qn] = ds; x.queue[2 * qn + 1] = arc.w; qn++; }
-            else { s.err = B2K_ERR_OVERFLOW; qn = 0; break; }
+  // ---- eps closure.  The final costs and the token set are order independent
+  // (least fixpoint), so they are computed by parallel relaxation; the literal
+  // LIFO replay of ProcessNonemitting (:858-896) is then needed only for the
+  // CREATION ORDER of the eps-created tokens, and runs over small dense
+  // per-frame arrays (replay cost, filtered eps adjacency) that stay in L1
+  // instead of chasing the global hash.  Every arc the replay admits has
+  // cur_cost + w < cutoff with cur_cost >= final cost, so it is in the filtered
+  // adjacency, and every token the relaxation creates is created by the replay.
+  B2K_TICK(s, 4);
+  int32_t *wl0 = p.wl + (size_t)lane * 2 * p.max_tpf;
+  int32_t *wl1 = wl0 + p.max_tpf;
+  for (int d = tid; d < N1; d += T) {
+    int slot = x.by_ins[d];
+    x.rcost[d] = ord2f((uint32_t)hash[slot].y);        // cost after ProcessEmitting
+    wl0[d] = slot;
+  }
+  if (tid == 0) { s.wl_n[0] = N1; s.wl_n[1] = 0; s.cont = (N1 > 0 && !s.err); }
+  __syncthreads();
+  {
+    int cur = 0;
+    while (s.cont) {
+      const int n = s.wl_n[cur];
+      const int stamp = s.stamp + 1;
+      int32_t *in = cur ? wl1 : wl0;
+      int32_t *out = cur ? wl0 : wl1;
+      for (int k = tid; k < n; k += T) {
+        int slot = in[k];
+        int4 *sp = &hash[slot];
+        int state = *reinterpret_cast<volatile int *>(&sp->x);
+        float c = ord2f(*reinterpret_cast<volatile uint32_t *>(&sp->y));
+        if (!(c < cutoff)) continue;
+        int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
+        for (int a = o0.y; a < o1.y; a++) {
+          int4 arc = __ldg(&g.ne_arcs[a]);
+          float tot = c + __int_as_float(arc.y);
+          if (tot < cutoff) {
+            bool created; int idx = 0;
+            int ds = hash_insert_x(ctx, arc.x, &created, &idx);
+            if (ds < 0) break;
+            if (created) hash[ds].z = idx;                 // provisional dense index (>= N1)
+            uint32_t nv = f2ord(tot);
+            uint32_t old = atomicMin(reinterpret_cast<uint32_t *>(&hash[ds].y), nv);
+            if (nv < old && arc.w >= 0) {
+              if (atomicExch(&hash[ds].w, stamp) != stamp) {
+                int q = atomicAdd(&s.wl_n[cur ^ 1], 1);
+                if (q < p.max_tpf) out[q] = ds;
+                else atomicExch(&s.err, B2K_ERR_OVERFLOW);
+              }
+            }
           }
         }
-        if (arc.z < 0) break;                             // last eps arc of this state
+      }
+      __syncthreads();
+      if (tid == 0) {
+        s.wl_n[cur] = 0;
+        s.stamp = stamp;
+        if (s.wl_n[cur ^ 1] > p.max_tpf) s.wl_n[cur ^ 1] = p.max_tpf;
+        s.cont = (s.wl_n[cur ^ 1] > 0 && !s.err);
+      }
+      cur ^= 1;
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  B2K_TICK(s, 5);
+  const int Nall = min(s.ntok_new, p.max_tpf);
+  // dense index -> slot: by_ins for emitting tokens, creation order (tokslot) for eps-created ones
+  for (int d = N1 + tid; d < Nall; d += T) { x.rcost[d] = __int_as_float(0x7f800000); x.newseq[d - N1] = -1; x.by_ins[d] = ctx.tokslot[d]; }
+  __syncthreads();
+  // filtered adjacency, pass 1: counts
+  {
+    int carry = 0;
+    for (int base = 0; base < Nall; base += T) {
+      int d = base + tid, cnt = 0;
+      if (d < Nall) {
+        int slot = x.by_ins[d];
+        int state = hash[slot].x;
+        float cf = ord2f((uint32_t)hash[slot].y);
+        int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
+        x.deg[d] = o1.y - o0.y;
+        if (cf < cutoff)
+          for (int a = o0.y; a < o1.y; a++) cnt += (cf + __int_as_float(__ldg(&g.ne_arcs[a]).y) < cutoff);
+      }
+      int total;
+      int excl = block_excl_scan<T>(cnt, s.redi, &total);
+      if (d < Nall) x.adjoff[d] = carry + excl;
+      carry += total;
+    }
+    if (tid == 0) { x.adjoff[Nall] = carry; if (carry > p.adj_cap) s.err = B2K_ERR_OVERFLOW; }
+  }
+  __syncthreads();
+  if (!s.err) {
+    for (int d = tid; d < Nall; d += T) {
+      int slot = x.by_ins[d];
+      int state = hash[slot].x;
+      float cf = ord2f((uint32_t)hash[slot].y);
+      if (!(cf < cutoff)) continue;
+      int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
+      int pos = x.adjoff[d];
+      for (int a = o0.y; a < o1.y; a++) {
+        int4 arc = __ldg(&g.ne_arcs[a]);
+        if (cf + __int_as_float(arc.y) < cutoff) {
+          int js = hash_find(ctx, arc.x);
+          int jd = (js >= 0) ? hash[js].z : 0;
+          if (js < 0) atomicExch(&s.err, B2K_ERR_STATE);
+          x.adj[pos++] = make_int2(jd | (arc.w >= 0 ? (int)0x40000000 : 0), arc.y);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  B2K_TICK(s, 6);
+  // ---- compact "replay set": tokens of the initial worklist, sources and
+  // destinations of filtered eps arcs, renumbered so that the whole replay state
+  // fits in shared memory (L1-latency steps instead of L2 round trips)
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  float *rc_s = reinterpret_cast<float *>(dyn_smem);
+  int *off_s = reinterpret_cast<int *>(rc_s + p.rs_rcap);
+  float *aw_s = reinterpret_cast<float *>(off_s + p.rs_rcap + 1);
+  unsigned short *aj_s = reinterpret_cast<unsigned short *>(aw_s + p.rs_ecap);
+  unsigned short *deg_s = aj_s + p.rs_ecap;
+  unsigned short *ns_s = deg_s + p.rs_rcap;
+  unsigned short *q_s = ns_s + p.rs_rcap;
+  const int E = s.err ? 0 : x.adjoff[Nall];
+  int *mark = x.run, *ridx = x.sbase;                      // idle until order_tokens below
+  const bool try_smem = p.rs_rcap > 0;
+  if (try_smem) {
+    for (int d = tid; d < Nall; d += T) mark[d] = (x.adjoff[d + 1] > x.adjoff[d]) ? 1 : 0;
+    __syncthreads();
+    for (int k = tid; k < qcarry; k += T) mark[x.queue[k]] = 1;
+    for (int e = tid; e < E; e += T) mark[x.adj[e].x & 0x3fffffff] = 1;
+  }
+  if (tid == 0) s.q_n = 0;
+  __syncthreads();
+  int R = 0;
+  if (try_smem) {
+    int carry = 0, maxdeg = 0;
+    for (int base = 0; base < Nall; base += T) {
+      int d = base + tid, m = (d < Nall) ? mark[d] : 0;
+      if (m) maxdeg = max(maxdeg, x.deg[d]);
+      int total;
+      int excl = block_excl_scan<T>(m, s.redi, &total);
+      if (d < Nall) ridx[d] = carry + excl;
+      carry += total;
+    }
+    R = carry;
+    maxdeg = (int)block_min_u32<T>(~(uint32_t)maxdeg, s.red32);    // block max via min of complement
+    maxdeg = (int)~(uint32_t)maxdeg;
+    if (tid == 0) s.q_n = (R <= p.rs_rcap && E <= p.rs_ecap && qcarry <= p.rs_qcap && maxdeg < 65535 && R < 32767) ? 1 : 0;
+  }
+  __syncthreads();
+  const bool in_smem = s.q_n != 0;
+  if (in_smem && !s.err) {
+    for (int d = tid; d < Nall; d += T) {
+      if (!mark[d]) continue;
+      int r = ridx[d];
+      rc_s[r] = x.rcost[d]; off_s[r] = x.adjoff[d]; deg_s[r] = (unsigned short)x.deg[d]; ns_s[r] = 0xffff;
+    }
+    if (tid == 0) off_s[R] = E;
+    for (int e = tid; e < E; e += T) {
+      int2 en = x.adj[e];
+      aj_s[e] = (unsigned short)(ridx[en.x & 0x3fffffff] | ((en.x & 0x40000000) ? 0x8000 : 0));
+      aw_s[e] = __int_as_float(en.y);
+    }
+    for (int k = tid; k < qcarry; k += T) q_s[k] = (unsigned short)ridx[x.queue[k]];
+    __syncthreads();
+    if (tid == 0) {
+      int qn = qcarry, next = 0;
+      unsigned long long ne = 0;
+      const float kInfF = __int_as_float(0x7f800000);
+      bool ok = true;
+      while (qn > 0) {
+        const int d = q_s[--qn];
+        const float c = rc_s[d];
+        if (c >= cutoff) continue;
+        ne += (unsigned long long)deg_s[d];
+        const int e1 = off_s[d + 1];
+        for (int e = off_s[d]; e < e1; e++) {
+          const float tot = c + aw_s[e];
+          if (tot < cutoff) {
+            const int jj = aj_s[e];
+            const int j = jj & 0x7fff;
+            const float old = rc_s[j];
+            if (tot < old) {                                 // FindOrAddToken: new or improved -> changed
+              rc_s[j] = tot;
+              if (old == kInfF) ns_s[j] = (unsigned short)next++;
+              if (jj & 0x8000) {
+                if (qn < p.rs_qcap) q_s[qn++] = (unsigned short)j;
+                else { ok = false; qn = 0; break; }
+              }
+            }
+          }
+        }
+      }
+      if (ok) {
+        cs->arcs_ne += ne;
+        if (next != Nall - N1) s.err = B2K_ERR_STATE;
+      } else {
+        s.q_n = 0;                                           // worklist outgrew shared memory: redo in global memory
+      }
+    }
+    __syncthreads();
+    if (s.q_n != 0 && !s.err)
+      for (int d = N1 + tid; d < Nall; d += T) x.newseq[d - N1] = (int)ns_s[ridx[d]];
+    __syncthreads();
+  }
+  // fallback: literal LIFO replay by one thread over the dense arrays in global memory
+  if (tid == 0 && !s.err && s.q_n == 0) {
+    int qn = qcarry, next = 0;
+    unsigned long long ne = 0;
+    const float kInfF = __int_as_float(0x7f800000);
+    // (the shared-memory attempt may have consumed nothing persistent: rcost/newseq are untouched)
+    while (qn > 0) {
+      const int d = x.queue[--qn];
+      const float c = x.rcost[d];
+      if (c >= cutoff) continue;
+      ne += (unsigned long long)x.deg[d];
+      const int e1 = x.adjoff[d + 1];
+      for (int e = x.adjoff[d]; e < e1; e++) {
+        const int2 en = x.adj[e];
+        const float tot = c + __int_as_float(en.y);
+        if (tot < cutoff) {
+          const int j = en.x & 0x3fffffff;
+          const float old = x.rcost[j];
+          if (tot < old) {
+            x.rcost[j] = tot;
+            if (old == kInfF) x.newseq[j - N1] = next++;
+            if (en.x & 0x40000000) {
+              if (qn < p.queue_cap) x.queue[qn++] = j;
+              else { s.err = B2K_ERR_OVERFLOW; break; }
+            }
+          }
+        }
       }
     }
     cs->arcs_ne += ne;
+    if (!s.err && next != Nall - N1) s.err = B2K_ERR_STATE;
   }
   __syncthreads();
-  long long t_rep1 = clock64();
+  B2K_TICK(s, 7);
+  // final insertion index of the eps-created tokens
+  if (!s.err) {
+    for (int d = N1 + tid; d < Nall; d += T) {
+      int slot = ctx.tokslot[d];
+      hash[slot].z = N1 + x.newseq[d - N1];
+    }
+  }
+  __syncthreads();
+  if (!s.err) {
+    for (int d = N1 + tid; d < Nall; d += T) {
+      int slot = ctx.tokslot[d];
+      x.by_ins[hash[slot].z] = slot;
+    }
+  }
+  __syncthreads();
+  B2K_TICK(s, 8);
   const int N = min(s.ntok_new, p.max_tpf);
   order_tokens<T>(N, Hc, hash, x, s);
-  long long t_o2 = clock64();
+  B2K_TICK(s, 9);
   // eps links from final costs
   for (int i = tid; i < N; i += T) {
     int slot = ctx.tokslot[i];
@@ -884,6 +1114,7 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
     }
   }
   __syncthreads();
+  B2K_TICK(s, 10);
   const int nlink = s.nlink_new;
   const bool fits = (ctx.tbase + N <= p.max_tokens);
   if (!fits && tid == 0) s.err = B2K_ERR_OVERFLOW;
@@ -920,11 +1151,7 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
       p.frame_cost_offset[co] = cost_offset;
       p.frame_cutoff[co] = cutoff;
     }
-    long long t_end = clock64();
-    cs->prof[3] += (unsigned long long)(t_rep0 - t_o0);
-    cs->prof[4] += (unsigned long long)(t_rep1 - t_rep0);
-    cs->prof[5] += (unsigned long long)(t_o2 - t_rep1);
-    cs->prof[6] += (unsigned long long)(t_end - t_o2);
+    B2K_TICK(s, 11);
   }
   __syncthreads();
 }
@@ -970,6 +1197,11 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
   x.run = p.x_run + (size_t)lane * p.max_tpf;
   x.order = p.x_order + (size_t)lane * p.max_tpf;
   x.queue = p.cand + (size_t)lane * 5 * p.cand_cap;     // idle in this mode
+  x.rcost = p.x_rcost + (size_t)lane * p.max_tpf;
+  x.adjoff = p.x_adjoff + (size_t)lane * (p.max_tpf + 1);
+  x.deg = p.x_deg + (size_t)lane * p.max_tpf;
+  x.newseq = p.x_newseq + (size_t)lane * p.max_tpf;
+  x.adj = p.x_adj + (size_t)lane * p.adj_cap;
 
   if (tid == 0) { s.err = 0; s.stamp = 0; }
   __syncthreads();
@@ -1004,7 +1236,7 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
   unsigned long long arcs_e_total = 0;
   const size_t fo = (size_t)ch * (p.max_frames + 2);
 
-  unsigned long long pr_cut = 0, pr_exp = 0, pr_rank = 0, pr_tot = 0;
+  if (tid == 0) { for (int i = 0; i < 16; i++) s.prof[i] = 0; s.tlast = clock64(); }
   const long long t_kernel0 = clock64();
   for (int fi = 0; fi < nframes; fi++) {
     if (frames_decoded >= p.max_frames) { if (tid == 0) s.err = B2K_ERR_OVERFLOW; __syncthreads(); break; }
@@ -1012,7 +1244,6 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
     const int pb = p.frame_tok_begin[fo + frames_decoded];
     const int pe = p.frame_tok_begin[fo + frames_decoded + 1];
     const int K = pe - pb;
-    const long long t_f0 = clock64();
 
     // ---- GetCutoff (:653-720); ties -> first in list order (strict < at :662/:675)
     unsigned long long local = ~0ull;
@@ -1082,7 +1313,7 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
     // ---- main loop (:779-812): admission against the exclusive prefix-min
     if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; }
     __syncthreads();
-    const long long t_f1 = clock64();
+    B2K_TICK(s, 0);
     ctx.tbase = tbase;
     float carry = kInf;
     int pos_base = 0;
@@ -1193,7 +1424,7 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
     }
     const float next_cutoff = fminf(seed_cutoff, carry + adaptive_beam);
     __syncthreads();
-    const long long t_f2 = clock64();
+    B2K_TICK(s, 1);
     // ---- insertion index of the tokens created above = rank of their first
     //      admitted position (bitmap rank)
     const int N1 = min(s.ntok_new, p.max_tpf);
@@ -1226,9 +1457,7 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
         x.by_ins[ins] = slot;
       }
     }
-    const long long t_f3 = clock64();
-    pr_cut += (unsigned long long)(t_f1 - t_f0); pr_exp += (unsigned long long)(t_f2 - t_f1);
-    pr_rank += (unsigned long long)(t_f3 - t_f2);
+    B2K_TICK(s, 2);
     finish_frame_exact<T>(p, s, ctx, x, lane, ch, frames_decoded + 1, next_cutoff, cost_offset, lbase,
                           Hc, cs);
     if (s.err) break;
@@ -1244,8 +1473,8 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
     cs->arcs_e += arcs_e_total;
     cs->hc = Hc;
     if (s.err) cs->status = s.err;
-    cs->prof[0] += pr_cut; cs->prof[1] += pr_exp; cs->prof[2] += pr_rank;
-    cs->prof[7] += (unsigned long long)(clock64() - t_kernel0);
+    for (int i = 0; i < 15; i++) cs->prof[i] += s.prof[i];
+    cs->prof[15] += (unsigned long long)(clock64() - t_kernel0);
   }
   if (s.err) {
     reset_lane_hash<T>(ctx.hash, p.hash_size);
@@ -1313,6 +1542,13 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
   for (int t = last; t >= 0; t--) {
     const int tb = p.frame_tok_begin[fo + t], te = p.frame_tok_begin[fo + t + 1];
     const int n = te - tb;
+    if (last > p.max_frames || tb < 0 || te < tb || te > p.max_tokens || n > p.max_tpf) {   // corrupted bookkeeping: fail loudly
+      if (tid == 0) {
+        printf("b2k dec_finalize: inconsistent frame table ch=%d lane=%d last=%d t=%d tb=%d te=%d ntok=%d\n", ch, lane, last, t, tb, te, cs->ntok);
+        cs->status = B2K_ERR_STATE;
+      }
+      return;
+    }
     const int eps_b = p.frame_link_eps[fo + t], eps_e = p.frame_link_begin[fo + t + 1];
     // base value per token: final-cost term on the last list (:426), else
     // +inf (:337) lowered by the emitting links into list t+1
@@ -1662,6 +1898,19 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
     A(p.x_sbase, 4 * nl * p.max_tpf, 0);
     A(p.x_run, 4 * nl * p.max_tpf, 0);
     A(p.x_order, 4 * nl * p.max_tpf, 0);
+    p.adj_cap = 2 * p.max_tpf;
+    p.rs_rcap = 0; p.rs_ecap = 0; p.rs_qcap = 0;               // shared-memory replay off by default (measured slower: lower occupancy)
+    if (const char *e = getenv("B2K_DEC_RS_CAPS")) {          // tuning knob: "tokens,entries,queue" (each <= 3072)
+      int a = 0, b = 0, c = 0;
+      if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= 64 && b >= 64 && c >= 64 && a <= 3072 && b <= 3072 && c <= 3072) {
+        p.rs_rcap = a; p.rs_ecap = b; p.rs_qcap = c;
+      }
+    }
+    A(p.x_rcost, 4 * nl * p.max_tpf, 0);
+    A(p.x_adjoff, 4 * nl * (p.max_tpf + 1), 0);
+    A(p.x_deg, 4 * nl * p.max_tpf, 0);
+    A(p.x_newseq, 4 * nl * p.max_tpf, 0);
+    A(p.x_adj, sizeof(int2) * nl * p.adj_cap, 0);
     {
       std::vector<int32_t> big((size_t)nl * p.hc_cap, 0x7fffffff);
       B2K_CUDA_CHECK(cudaMemcpy(p.x_bfirst, big.data(), 4 * big.size(), cudaMemcpyHostToDevice));
@@ -1694,6 +1943,9 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
     for (auto &c : cs) c.frames_decoded = -1;
     B2K_CUDA_CHECK(cudaMemcpy(p.chan, cs.data(), sizeof(ChanState) * nc, cudaMemcpyHostToDevice));
   }
+  if (cfg->reference_order)
+    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(float) * 3072 * 2 + sizeof(int) * 3073 + 2 * (3072 * 4) + 64)));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_chan, sizeof(ChanState) * nc));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_channel, 4 * nl));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_ll, sizeof(float *) * nl));
@@ -1718,6 +1970,12 @@ int b2k_dec_destroy(b2k_dec *d) {
 }
 
 #define DEC_THREADS 256
+
+static size_t exact_smem_bytes(const DecParams &p) {
+  if (p.rs_rcap == 0) return 0;
+  return sizeof(float) * p.rs_rcap + sizeof(int) * (p.rs_rcap + 1) + sizeof(float) * p.rs_ecap +
+         sizeof(unsigned short) * ((size_t)p.rs_ecap + 2 * (size_t)p.rs_rcap + p.rs_qcap) + 16;
+}
 
 static int stage_lanes(b2k_dec *d, const int32_t *channels, const float *const *lls,
                        const int32_t *nframes, int n, cudaStream_t st) {
@@ -1753,7 +2011,7 @@ int b2k_dec_init_decoding(b2k_dec *d, const int32_t *channels, int32_t n, void *
   if (rc) return rc;
   DecParams p = d->p;
   p.do_init = 1;
-  if (d->cfg.reference_order) dec_advance_exact_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
+  if (d->cfg.reference_order) dec_advance_exact_kernel<DEC_THREADS><<<n, DEC_THREADS, exact_smem_bytes(p), st>>>(p);
   else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
   B2K_LAUNCH_CHECK();
   return B2K_OK;
@@ -1769,7 +2027,7 @@ int b2k_dec_advance_decoding_frames(b2k_dec *d, const int32_t *channels,
   DecParams p = d->p;
   p.do_init = 0;
   p.row_stride = row_stride;
-  if (d->cfg.reference_order) dec_advance_exact_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
+  if (d->cfg.reference_order) dec_advance_exact_kernel<DEC_THREADS><<<n, DEC_THREADS, exact_smem_bytes(p), st>>>(p);
   else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
   B2K_LAUNCH_CHECK();
   return B2K_OK;
@@ -1814,7 +2072,7 @@ int b2k_dec_channel_info(b2k_dec *d, int32_t channel, int64_t info[32]) {
   info[0] = cs.status; info[1] = cs.frames_decoded; info[2] = cs.ntok; info[3] = cs.nlink;
   info[4] = (int64_t)cs.arcs_e; info[5] = (int64_t)cs.arcs_ne; info[6] = cs.lat_states;
   info[7] = cs.lat_arcs; info[8] = cs.lat_finals; info[9] = cs.finalized; info[10] = cs.any_final;
-  for (int k = 0; k < 8; k++) info[16 + k] = (int64_t)cs.prof[k];
+  for (int k = 0; k < 16; k++) info[16 + k] = (int64_t)cs.prof[k];
   return B2K_OK;
 }
 

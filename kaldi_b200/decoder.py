@@ -166,7 +166,7 @@ class CudaDecoder:
         keys = ["status", "frames_decoded", "ntok", "nlink", "arcs_emitting", "arcs_nonemitting",
                 "lat_states", "lat_arcs", "lat_finals", "finalized", "any_final"]
         d = {k: int(info[i]) for i, k in enumerate(keys)}
-        d["prof_cycles"] = [int(info[16 + k]) for k in range(8)]
+        d["prof_cycles"] = [int(info[16 + k]) for k in range(16)]
         return d
 
     def GetRawLattice(self, channel: int, stream: int = 0) -> dict:
