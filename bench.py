@@ -178,10 +178,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="utterances per GPU per step")
+    ap.add_argument("--batch", type=int, default=592, help="utterances per GPU per step (592 = 148 SMs x 4 resident decoder CTAs)")
     ap.add_argument("--order-free", action="store_true", help="use the order-free decoder mode (not reference exact)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=6)
+    ap.add_argument("--tok-per-frame", type=int, default=9000, help="decoder token arena sizing (avg tokens/frame)")
+    ap.add_argument("--links-per-frame", type=int, default=16000, help="decoder link arena sizing (avg links/frame)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,7 +228,11 @@ def main():
     W = NM.random_weights(arch, seed=0)
     graph = synth.make_hclg(GRAPH_ARCS, num_pdfs=NUM_PDFS, seed=1)
     B = a.batch
-    cfg = PipelineConfig(max_batch=B, num_samples=NUM_SAMPLES, reference_order=not a.order_free)
+    nf_out = 333
+    from kaldi_b200.feat import FeatureOptions
+    cfg = PipelineConfig(feature_opts=FeatureOptions(max_lanes=max(B, 64)), max_batch=B, num_samples=NUM_SAMPLES,
+                         reference_order=not a.order_free,
+                         max_tokens=nf_out * a.tok_per_frame, max_links=nf_out * a.links_per_frame)
     from kaldi_b200.ivector import make_synthetic_extractor
     ivx = make_synthetic_extractor(seed=0)
     pipe = BatchedPipeline(cfg, arch, W, graph, ivector_extractor=ivx)
@@ -305,7 +311,11 @@ def main():
     d2h = 0
     lat_states = 0
     for s in range(a.steps):
-        lats = pipe.decode_batch(host_sets[s % n_sets], want_lattices=True)
+        try:
+            lats = pipe.decode_batch(host_sets[s % n_sets], want_lattices=True)
+        except Exception as ex:          # e.g. an arena overflow on some channel: report, do not hide
+            print(f"[bench] decode_batch failed: {ex}", file=sys.stderr)
+            raise
         d2h += sum(v.nbytes for k, v in lats.items() if hasattr(v, "nbytes"))
         lat_states += int(lats["state_offs"][-1])
     e3.record()

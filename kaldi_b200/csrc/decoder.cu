@@ -1971,6 +1971,20 @@ int b2k_dec_destroy(b2k_dec *d) {
 
 #define DEC_THREADS 256
 
+static int g_dec_threads = 0;
+static int dec_threads() {
+  if (!g_dec_threads) {
+    g_dec_threads = 256;
+    if (const char *e = getenv("B2K_DEC_THREADS")) { int v = atoi(e); if (v == 128 || v == 256) g_dec_threads = v; }
+  }
+  return g_dec_threads;
+}
+
+static void launch_exact(const DecParams &p, int n, size_t smem, cudaStream_t st) {
+  if (dec_threads() == 128) dec_advance_exact_kernel<128><<<n, 128, smem, st>>>(p);
+  else dec_advance_exact_kernel<256><<<n, 256, smem, st>>>(p);
+}
+
 static size_t exact_smem_bytes(const DecParams &p) {
   if (p.rs_rcap == 0) return 0;
   return sizeof(float) * p.rs_rcap + sizeof(int) * (p.rs_rcap + 1) + sizeof(float) * p.rs_ecap +
@@ -2011,7 +2025,7 @@ int b2k_dec_init_decoding(b2k_dec *d, const int32_t *channels, int32_t n, void *
   if (rc) return rc;
   DecParams p = d->p;
   p.do_init = 1;
-  if (d->cfg.reference_order) dec_advance_exact_kernel<DEC_THREADS><<<n, DEC_THREADS, exact_smem_bytes(p), st>>>(p);
+  if (d->cfg.reference_order) launch_exact(p, n, exact_smem_bytes(p), st);
   else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
   B2K_LAUNCH_CHECK();
   return B2K_OK;
@@ -2027,7 +2041,7 @@ int b2k_dec_advance_decoding_frames(b2k_dec *d, const int32_t *channels,
   DecParams p = d->p;
   p.do_init = 0;
   p.row_stride = row_stride;
-  if (d->cfg.reference_order) dec_advance_exact_kernel<DEC_THREADS><<<n, DEC_THREADS, exact_smem_bytes(p), st>>>(p);
+  if (d->cfg.reference_order) launch_exact(p, n, exact_smem_bytes(p), st);
   else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
   B2K_LAUNCH_CHECK();
   return B2K_OK;
