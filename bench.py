@@ -387,8 +387,13 @@ def main():
                          "eps_finish", "order2", "eps_links", "commit"],
                         [round(float(sum(i["prof_cycles"][k] for i in infos)) / max(1.0, float(sum(i["prof_cycles"][15] for i in infos))), 3)
                          for k in range(12)])),
+                    eps_replay_per_frame=dict(zip(["pops", "arc_visits", "in_shared_memory"],
+                        [round(float(sum(i["prof_cycles"][k] for i in infos)) / max(1.0, float(sum(i["frames_decoded"] for i in infos))), 2)
+                         for k in (12, 13, 14)])),
                     decoder=dict(marcs_per_s=arcs / (stage_ms["decoder_advance"] / 1e3) / 1e6 * world,
-                                 arcs_per_frame=arcs / (B * pipe.nnet.n_out), tokens_per_frame=ntok / (B * pipe.nnet.n_out),
+                                 arcs_per_frame=arcs / (B * pipe.nnet.n_out),
+                                 eps_arcs_per_frame=sum(i["arcs_nonemitting"] for i in infos) / (B * pipe.nnet.n_out),
+                                 links_per_frame=sum(i["nlink"] for i in infos) / (B * pipe.nnet.n_out), tokens_per_frame=ntok / (B * pipe.nnet.n_out),
                                  errors=nerr),
                     nnet3=dict(tflops=pipe.nnet.flops_per_utt * B / (stage_ms["nnet3"] / 1e3) / 1e12 * world,
                                mma="fp32 FFMA (SIMT)"),

@@ -113,14 +113,14 @@ struct DecParams {
   int32_t *x_bfirst, *x_bcount, *x_bfill;   // [hc_cap] per HashList bucket
   int32_t *x_sbase;         // [max_tpf]
   int32_t *x_run;           // [max_tpf]
-  int32_t *x_order;         // [max_tpf] list rank -> hash slot
-  float *x_rcost;           // [max_tpf] replay cost per dense token index
-  int32_t *x_adjoff;        // [max_tpf+1] eps adjacency offsets per dense token index
-  int32_t *x_deg;           // [max_tpf] eps out-degree (all arcs) per dense token index
+  int32_t *x_order;         // [max_tpf] list rank -> insertion index
+  int32_t *x_xb;            // [max_tpf] insertion index -> HashList bucket (state % hash size)
+  int4 *x_rec;              // [max_tpf] per dense token index {record offset, eps out-degree, #arcs admitted, replay cost bits}
   int32_t *x_newseq;        // [max_tpf] creation order found by the replay (eps-created tokens)
-  int2 *x_adj;              // [adj_cap] {dest dense index | EPS bit, weight bits}
+  int4 *x_adj;              // [adj_cap] eps arc entries {dest dense index, weight bits (+inf = not admitted), arc id, dest hash slot}
+  int32_t *x_adjo;          // [adj_cap] owner (source dense index) of each entry
   int32_t adj_cap;
-  int32_t rs_rcap, rs_ecap, rs_qcap;   // shared-memory replay capacities (tokens, entries, queue)
+  int32_t rs_rcap, rs_ecap, rs_qcap;   // shared-memory replay capacities (tokens, arcs, worklist); 0 = off
   int32_t pos_cap, hc_cap, queue_cap;
   float hash_ratio;
   // per launch
@@ -311,6 +311,7 @@ struct __align__(16) DecShared {
   int chunk_off[T + 1];
   int chunk_ebeg[T];
   float chunk_cost[T];
+  int chunk_d[T];
   int ntok_new, nlink_new, ncand, err;
   int wl_n[2];
   uint32_t running_ord;
@@ -318,6 +319,7 @@ struct __align__(16) DecShared {
   int cont;
   float scanf_[2][T / 32];
   int q_n;
+  int rs_n, rs_e, rs_ok;
   unsigned long long prof[16];
   long long tlast;
 };
@@ -723,8 +725,8 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
 // replay of the LIFO worklist (:858-896) -- the one inherently sequential piece.
 
 struct XScratch {
-  uint32_t *bm; int32_t *wbase, *by_ins, *bfirst, *bcount, *bfill, *sbase, *run, *order, *queue;
-  float *rcost; int32_t *adjoff, *deg, *newseq; int2 *adj;
+  uint32_t *bm; int32_t *wbase, *by_ins, *bfirst, *bcount, *bfill, *sbase, *run, *order, *queue, *xb;
+  int4 *rec; int32_t *newseq; int4 *adj; int32_t *adjo;
 };
 
 // find-or-insert without arena write; *created tells whether this call made the token
@@ -749,14 +751,17 @@ __device__ __forceinline__ int hash_insert_x(const LaneCtx &c, int32_t state, bo
   return -1;
 }
 
-// HashList iteration order of the N tokens by_ins[0..N) (slot.z = insertion index)
+// HashList iteration order of the N tokens by_ins[0..N) (slot.z = insertion index):
+// x.order[list rank] = insertion index.  Buckets are ranked by their first
+// insertion (hash-list-inl.h:126-175); a bucket's tokens keep insertion order.
 template <int T>
-__device__ void order_tokens(int N, int Hc, int4 *hash, const XScratch &x, DecShared<T> &s) {
+__device__ void order_tokens(int N, int Hc, const int4 *hash, const XScratch &x, DecShared<T> &s) {
   const int tid = threadIdx.x;
   __syncthreads();
   for (int k = tid; k < N; k += T) {
     int slot = x.by_ins[k];
-    uint32_t b = (uint32_t)hash[slot].x % (uint32_t)Hc;
+    int b = (int)((uint32_t)hash[slot].x % (uint32_t)Hc);
+    x.xb[k] = b;
     atomicMin(&x.bfirst[b], k);
     atomicAdd(&x.bcount[b], 1);
   }
@@ -765,7 +770,7 @@ __device__ void order_tokens(int N, int Hc, int4 *hash, const XScratch &x, DecSh
   for (int base = 0; base < N; base += T) {
     int k = base + tid, w = 0;
     if (k < N) {
-      uint32_t b = (uint32_t)hash[x.by_ins[k]].x % (uint32_t)Hc;
+      int b = x.xb[k];
       if (x.bfirst[b] == k) w = x.bcount[b];
     }
     int total;
@@ -775,23 +780,31 @@ __device__ void order_tokens(int N, int Hc, int4 *hash, const XScratch &x, DecSh
   }
   __syncthreads();
   for (int k = tid; k < N; k += T) {
-    uint32_t b = (uint32_t)hash[x.by_ins[k]].x % (uint32_t)Hc;
-    int rb = x.sbase[x.bfirst[b]];
-    int q = atomicAdd(&x.bfill[b], 1);
-    x.run[rb + q] = k;
+    int b = x.xb[k];
+    int first = x.bfirst[b], cnt = x.bcount[b];
+    int rb = x.sbase[first];
+    if (cnt == 1) {                                  // the common case: done, and the bucket can be reset now
+      x.order[rb] = k;
+      x.bfirst[b] = 0x7fffffff; x.bcount[b] = 0;
+      x.xb[k] = -1;
+    } else {
+      int q = atomicAdd(&x.bfill[b], 1);
+      x.run[rb + q] = k;
+    }
   }
   __syncthreads();
   for (int k = tid; k < N; k += T) {
-    int slot = x.by_ins[k];
-    uint32_t b = (uint32_t)hash[slot].x % (uint32_t)Hc;
+    int b = x.xb[k];
+    if (b < 0) continue;
     int rb = x.sbase[x.bfirst[b]];
     int cnt = x.bcount[b], within = 0;
     for (int j = 0; j < cnt; j++) within += (x.run[rb + j] < k);
-    x.order[rb + within] = slot;
+    x.order[rb + within] = k;
   }
   __syncthreads();
   for (int k = tid; k < N; k += T) {
-    uint32_t b = (uint32_t)hash[x.by_ins[k]].x % (uint32_t)Hc;
+    int b = x.xb[k];
+    if (b < 0) continue;
     x.bfirst[b] = 0x7fffffff; x.bcount[b] = 0; x.bfill[b] = 0;
   }
   __syncthreads();
@@ -814,77 +827,106 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   if (s.err) return;     // uniform: nothing writes err between the barrier and this read
   const int n_emit_links = s.nlink_new;
   const int N1 = min(s.ntok_new, p.max_tpf);
-  // list order after the emitting phase -> initial worklist (:852-856)
+  // list order after the emitting phase (defines the initial worklist, :852-856)
   order_tokens<T>(N1, Hc, hash, x, s);
   B2K_TICK(s, 3);
-  int qcarry = 0;
-  for (int base = 0; base < N1; base += T) {
-    int k = base + tid, flag = 0, slot = 0, nb = 0;
-    if (k < N1) {
-      slot = x.order[k];
-      int st = hash[slot].x;
-      int2 o0 = __ldg(&g.st_off[st]), o1 = __ldg(&g.st_off[st + 1]);
-      flag = (o1.y > o0.y);
-      nb = o0.y;
-    }
-    int total;
-    int excl = block_excl_scan<T>(flag, s.redi, &total);
-    (void)nb;
-    if (flag) x.queue[qcarry + excl] = hash[slot].z;          // dense token index (= insertion index)
-    qcarry += total;
-  }
-  __syncthreads();
   // ---- eps closure.  The final costs and the token set are order independent
   // (least fixpoint), so they are computed by parallel relaxation; the literal
   // LIFO replay of ProcessNonemitting (:858-896) is then needed only for the
-  // CREATION ORDER of the eps-created tokens, and runs over small dense
-  // per-frame arrays (replay cost, filtered eps adjacency) that stay in L1
-  // instead of chasing the global hash.  Every arc the replay admits has
-  // cur_cost + w < cutoff with cur_cost >= final cost, so it is in the filtered
-  // adjacency, and every token the relaxation creates is created by the replay.
-  B2K_TICK(s, 4);
+  // CREATION ORDER of the eps-created tokens.  The relaxation records, for
+  // every token it expands, the eps arcs it admits; the LAST expansion of a
+  // token runs at its final cost, so the last record is exactly
+  // {arcs with final_cost + w < cutoff}: the arcs that become eps links, and a
+  // superset of what the replay can admit (its cur_cost >= final cost).  The
+  // replay then walks those dense records only.
   int32_t *wl0 = p.wl + (size_t)lane * 2 * p.max_tpf;
   int32_t *wl1 = wl0 + p.max_tpf;
   for (int d = tid; d < N1; d += T) {
     int slot = x.by_ins[d];
-    x.rcost[d] = ord2f((uint32_t)hash[slot].y);        // cost after ProcessEmitting
+    x.rec[d] = make_int4(0, 0, 0, __float_as_int(ord2f((uint32_t)hash[slot].y)));   // cost after ProcessEmitting
     wl0[d] = slot;
   }
-  if (tid == 0) { s.wl_n[0] = N1; s.wl_n[1] = 0; s.cont = (N1 > 0 && !s.err); }
+  if (tid == 0) { s.wl_n[0] = N1; s.wl_n[1] = 0; s.cont = (N1 > 0 && !s.err); s.q_n = 0; }
   __syncthreads();
+  B2K_TICK(s, 4);
+  // Each relaxation round expands its worklist ARC-parallel (eps out-degrees are very
+  // skewed: word-boundary hubs carry thousands of eps arcs): a token's record is a
+  // contiguous block of one entry per eps arc, in arc order; arcs that fail the
+  // cutoff get weight +inf so that the replay skips them.
   {
     int cur = 0;
+    const int kInfBits = 0x7f800000;
     while (s.cont) {
       const int n = s.wl_n[cur];
       const int stamp = s.stamp + 1;
       int32_t *in = cur ? wl1 : wl0;
       int32_t *out = cur ? wl0 : wl1;
-      for (int k = tid; k < n; k += T) {
-        int slot = in[k];
-        int4 *sp = &hash[slot];
-        int state = *reinterpret_cast<volatile int *>(&sp->x);
-        float c = ord2f(*reinterpret_cast<volatile uint32_t *>(&sp->y));
-        if (!(c < cutoff)) continue;
-        int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
-        for (int a = o0.y; a < o1.y; a++) {
-          int4 arc = __ldg(&g.ne_arcs[a]);
-          float tot = c + __int_as_float(arc.y);
+      for (int cb = 0; cb < n; cb += T) {
+        const int k = cb + tid;
+        int deg = 0, ebeg = 0, dd = 0;
+        float c = 0.f;
+        if (k < n) {
+          int4 hs = __ldcg(&hash[in[k]]);                     // cost may be lowered concurrently: read at L2
+          c = ord2f((uint32_t)hs.y);
+          if (c < cutoff) {
+            int2 o0 = __ldg(&g.st_off[hs.x]), o1 = __ldg(&g.st_off[hs.x + 1]);
+            ebeg = o0.y; deg = o1.y - o0.y; dd = hs.z;
+          }
+        }
+        int total;
+        const int off = block_excl_scan<T>(deg, s.redi, &total);
+        s.chunk_off[tid] = off; s.chunk_ebeg[tid] = ebeg; s.chunk_cost[tid] = c; s.chunk_d[tid] = dd;
+        if (tid == 0) {
+          s.chunk_off[T] = total;
+          s.ncand = s.q_n;                                    // record space of this chunk
+          s.q_n += total;
+          if (s.q_n > p.adj_cap) s.err = B2K_ERR_OVERFLOW;
+        }
+        __syncthreads();
+        if (s.err) break;                                     // uniform
+        const int ebase = s.ncand;
+        if (deg > 0) {
+          int4 *rp = &x.rec[dd];
+          *reinterpret_cast<int2 *>(rp) = make_int2(ebase + off, deg);
+          rp->z = 0;                                          // arcs admitted by this expansion
+        }
+        __syncthreads();
+        for (int j = tid; j < total; j += T) {
+          int lo = 0, hi = T;
+          while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (s.chunk_off[mid] <= j) lo = mid; else hi = mid;
+          }
+          const int a = s.chunk_ebeg[lo] + (j - s.chunk_off[lo]);
+          const int owner = s.chunk_d[lo];
+          const int4 arc = __ldg(&g.ne_arcs[a]);
+          const float tot = s.chunk_cost[lo] + __int_as_float(arc.y);
+          int4 entry = make_int4(0, kInfBits, a, -1);
           if (tot < cutoff) {
             bool created; int idx = 0;
             int ds = hash_insert_x(ctx, arc.x, &created, &idx);
-            if (ds < 0) break;
-            if (created) hash[ds].z = idx;                 // provisional dense index (>= N1)
-            uint32_t nv = f2ord(tot);
-            uint32_t old = atomicMin(reinterpret_cast<uint32_t *>(&hash[ds].y), nv);
-            if (nv < old && arc.w >= 0) {
-              if (atomicExch(&hash[ds].w, stamp) != stamp) {
-                int q = atomicAdd(&s.wl_n[cur ^ 1], 1);
-                if (q < p.max_tpf) out[q] = ds;
-                else atomicExch(&s.err, B2K_ERR_OVERFLOW);
+            if (ds >= 0) {
+              if (created) {
+                hash[ds].z = idx;                             // provisional dense index (>= N1)
+                if (idx < p.max_tpf) x.rec[idx] = make_int4(0, 0, 0, kInfBits);
+              }
+              entry.y = arc.y; entry.w = ds;
+              atomicAdd(&x.rec[owner].z, 1);
+              uint32_t nv = f2ord(tot);
+              uint32_t old = atomicMin(reinterpret_cast<uint32_t *>(&hash[ds].y), nv);
+              if (nv < old && arc.w >= 0) {
+                if (atomicExch(&hash[ds].w, stamp) != stamp) {
+                  int q = atomicAdd(&s.wl_n[cur ^ 1], 1);
+                  if (q < p.max_tpf) out[q] = ds;
+                  else atomicExch(&s.err, B2K_ERR_OVERFLOW);
+                }
               }
             }
           }
+          x.adj[ebase + j] = entry;
+          x.adjo[ebase + j] = owner;
         }
+        __syncthreads();
       }
       __syncthreads();
       if (tid == 0) {
@@ -900,127 +942,141 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   __syncthreads();
   B2K_TICK(s, 5);
   const int Nall = min(s.ntok_new, p.max_tpf);
-  // dense index -> slot: by_ins for emitting tokens, creation order (tokslot) for eps-created ones
-  for (int d = N1 + tid; d < Nall; d += T) { x.rcost[d] = __int_as_float(0x7f800000); x.newseq[d - N1] = -1; x.by_ins[d] = ctx.tokslot[d]; }
-  __syncthreads();
-  // filtered adjacency, pass 1: counts
-  {
-    int carry = 0;
-    for (int base = 0; base < Nall; base += T) {
-      int d = base + tid, cnt = 0;
-      if (d < Nall) {
-        int slot = x.by_ins[d];
-        int state = hash[slot].x;
-        float cf = ord2f((uint32_t)hash[slot].y);
-        int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
-        x.deg[d] = o1.y - o0.y;
-        if (cf < cutoff)
-          for (int a = o0.y; a < o1.y; a++) cnt += (cf + __int_as_float(__ldg(&g.ne_arcs[a]).y) < cutoff);
+  const int E = s.err ? 0 : min(s.q_n, p.adj_cap);
+  const float kInfF = __int_as_float(0x7f800000);
+  // dest hash slot -> dest dense index (superseded records are converted too; harmless)
+  for (int e = tid; e < E; e += T) {
+    int ds = x.adj[e].w;
+    if (ds >= 0) x.adj[e].x = hash[ds].z;
+  }
+  if (tid == 0) cs->arcs_ne += (unsigned long long)E;        // eps arcs examined by the closure
+  // The replay only has to reproduce the order in which tokens are CREATED.  A token
+  // from which no eps-created token is reachable through admitted arcs can never
+  // influence that order (its pops create nothing, and it only ever modifies its own
+  // descendants), so the walk is restricted to the ancestors of the created tokens:
+  // backward reachability over the final records, then arcs into the rest are disabled.
+  int *mark = x.run;                                         // idle between the two order_tokens calls
+  int qcarry = 0;
+  if (Nall > N1 && !s.err) {
+    for (int d = tid; d < Nall; d += T) { mark[d] = (d >= N1); if (d >= N1) x.newseq[d - N1] = -1; }
+    __syncthreads();
+    for (int it = 0; it < 1000000; it++) {
+      if (tid == 0) s.cont = 0;
+      __syncthreads();
+      for (int e = tid; e < E; e += T) {
+        const int4 en = x.adj[e];
+        if (en.w < 0 || !mark[en.x]) continue;
+        const int o = x.adjo[e];
+        if (mark[o]) continue;
+        const int4 r = x.rec[o];
+        if (e < r.x || e >= r.x + r.y) continue;             // superseded record
+        mark[o] = 1;
+        s.cont = 1;
+      }
+      __syncthreads();
+      const int again = s.cont;
+      __syncthreads();
+      if (!again) break;
+    }
+    for (int e = tid; e < E; e += T) {
+      const int4 en = x.adj[e];
+      if (en.w >= 0 && !mark[en.x]) x.adj[e].y = 0x7f800000;   // the links pass needs only arc id and dest slot
+    }
+    // initial worklist (:852-856) = the emitting tokens in list order, restricted to the
+    // marked tokens whose final record admits something
+    for (int base = 0; base < N1; base += T) {
+      int k = base + tid, flag = 0, d = 0;
+      if (k < N1) {
+        d = x.order[k];
+        flag = mark[d] && x.rec[d].z > 0;
       }
       int total;
-      int excl = block_excl_scan<T>(cnt, s.redi, &total);
-      if (d < Nall) x.adjoff[d] = carry + excl;
-      carry += total;
-    }
-    if (tid == 0) { x.adjoff[Nall] = carry; if (carry > p.adj_cap) s.err = B2K_ERR_OVERFLOW; }
-  }
-  __syncthreads();
-  if (!s.err) {
-    for (int d = tid; d < Nall; d += T) {
-      int slot = x.by_ins[d];
-      int state = hash[slot].x;
-      float cf = ord2f((uint32_t)hash[slot].y);
-      if (!(cf < cutoff)) continue;
-      int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
-      int pos = x.adjoff[d];
-      for (int a = o0.y; a < o1.y; a++) {
-        int4 arc = __ldg(&g.ne_arcs[a]);
-        if (cf + __int_as_float(arc.y) < cutoff) {
-          int js = hash_find(ctx, arc.x);
-          int jd = (js >= 0) ? hash[js].z : 0;
-          if (js < 0) atomicExch(&s.err, B2K_ERR_STATE);
-          x.adj[pos++] = make_int2(jd | (arc.w >= 0 ? (int)0x40000000 : 0), arc.y);
-        }
-      }
+      int excl = block_excl_scan<T>(flag, s.redi, &total);
+      if (flag) x.queue[qcarry + excl] = d;
+      qcarry += total;
     }
   }
   __syncthreads();
   B2K_TICK(s, 6);
-  // ---- compact "replay set": tokens of the initial worklist, sources and
-  // destinations of filtered eps arcs, renumbered so that the whole replay state
-  // fits in shared memory (L1-latency steps instead of L2 round trips)
+  // ---- the replay touches few tokens (sources of admitting records, their
+  // destinations, and the stragglers of the worklist): renumber them compactly
+  // and run the LIFO walk out of shared memory, so that each of its dependent
+  // steps costs a shared-memory access instead of an L2 round trip.  Falls back
+  // to the walk over the global records when the set is too large.
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   float *rc_s = reinterpret_cast<float *>(dyn_smem);
-  int *off_s = reinterpret_cast<int *>(rc_s + p.rs_rcap);
-  float *aw_s = reinterpret_cast<float *>(off_s + p.rs_rcap + 1);
-  unsigned short *aj_s = reinterpret_cast<unsigned short *>(aw_s + p.rs_ecap);
-  unsigned short *deg_s = aj_s + p.rs_ecap;
+  float *aw_s = rc_s + p.rs_rcap;
+  unsigned short *off_s = reinterpret_cast<unsigned short *>(aw_s + p.rs_ecap);
+  unsigned short *cnt_s = off_s + p.rs_rcap;
+  unsigned short *deg_s = cnt_s + p.rs_rcap;
   unsigned short *ns_s = deg_s + p.rs_rcap;
-  unsigned short *q_s = ns_s + p.rs_rcap;
-  const int E = s.err ? 0 : x.adjoff[Nall];
-  int *mark = x.run, *ridx = x.sbase;                      // idle until order_tokens below
-  const bool try_smem = p.rs_rcap > 0;
-  if (try_smem) {
-    for (int d = tid; d < Nall; d += T) mark[d] = (x.adjoff[d + 1] > x.adjoff[d]) ? 1 : 0;
+  unsigned short *aj_s = ns_s + p.rs_rcap;
+  unsigned short *q_s = aj_s + p.rs_ecap;
+  int *cid = x.sbase;                                        // idle between the two order_tokens calls
+  bool replay_done = false;
+  if (p.rs_rcap > 0 && !s.err && Nall > N1 && qcarry <= p.rs_qcap) {
+    if (tid == 0) { s.rs_n = 0; s.rs_e = 0; s.rs_ok = 1; }
+    for (int d = tid; d < Nall; d += T) cid[d] = -1;
     __syncthreads();
-    for (int k = tid; k < qcarry; k += T) mark[x.queue[k]] = 1;
-    for (int e = tid; e < E; e += T) mark[x.adj[e].x & 0x3fffffff] = 1;
-  }
-  if (tid == 0) s.q_n = 0;
-  __syncthreads();
-  int R = 0;
-  if (try_smem) {
-    int carry = 0, maxdeg = 0;
-    for (int base = 0; base < Nall; base += T) {
-      int d = base + tid, m = (d < Nall) ? mark[d] : 0;
-      if (m) maxdeg = max(maxdeg, x.deg[d]);
-      int total;
-      int excl = block_excl_scan<T>(m, s.redi, &total);
-      if (d < Nall) ridx[d] = carry + excl;
-      carry += total;
-    }
-    R = carry;
-    maxdeg = (int)block_min_u32<T>(~(uint32_t)maxdeg, s.red32);    // block max via min of complement
-    maxdeg = (int)~(uint32_t)maxdeg;
-    if (tid == 0) s.q_n = (R <= p.rs_rcap && E <= p.rs_ecap && qcarry <= p.rs_qcap && maxdeg < 65535 && R < 32767) ? 1 : 0;
-  }
-  __syncthreads();
-  const bool in_smem = s.q_n != 0;
-  if (in_smem && !s.err) {
-    for (int d = tid; d < Nall; d += T) {
-      if (!mark[d]) continue;
-      int r = ridx[d];
-      rc_s[r] = x.rcost[d]; off_s[r] = x.adjoff[d]; deg_s[r] = (unsigned short)x.deg[d]; ns_s[r] = 0xffff;
-    }
-    if (tid == 0) off_s[R] = E;
+    auto claim = [&](int d) {
+      if (atomicCAS(&cid[d], -1, -2) != -1) return;
+      const int4 r = x.rec[d];
+      const int cnt = r.z > 0 ? r.y : 0;                     // records that admit nothing are never walked
+      int id = atomicAdd(&s.rs_n, 1);
+      int eo = cnt ? atomicAdd(&s.rs_e, cnt) : 0;
+      if (id < p.rs_rcap && eo + cnt <= p.rs_ecap && r.y < 65536) {
+        rc_s[id] = __int_as_float(r.w);
+        off_s[id] = (unsigned short)eo; cnt_s[id] = (unsigned short)cnt; deg_s[id] = (unsigned short)r.y;
+        ns_s[id] = 0xffff;
+        cid[d] = id;
+      } else {
+        s.rs_ok = 0;
+      }
+    };
+    for (int k = tid; k < qcarry; k += T) claim(x.queue[k]);
     for (int e = tid; e < E; e += T) {
-      int2 en = x.adj[e];
-      aj_s[e] = (unsigned short)(ridx[en.x & 0x3fffffff] | ((en.x & 0x40000000) ? 0x8000 : 0));
-      aw_s[e] = __int_as_float(en.y);
+      int4 en = x.adj[e];
+      if (en.w < 0 || en.y == 0x7f800000) continue;
+      int o = x.adjo[e];
+      if (!mark[o]) continue;
+      if (cid[en.x] == -1) claim(en.x);
+      if (cid[o] == -1) claim(o);
     }
-    for (int k = tid; k < qcarry; k += T) q_s[k] = (unsigned short)ridx[x.queue[k]];
     __syncthreads();
-    if (tid == 0) {
+    if (s.rs_ok) {
+      for (int e = tid; e < E; e += T) {
+        const int o = x.adjo[e];
+        if (cid[o] < 0) continue;
+        const int4 r = x.rec[o];
+        if (r.z == 0 || e < r.x || e >= r.x + r.y) continue;   // superseded record, or nothing admitted
+        const int4 en = x.adj[e];
+        const int pos = off_s[cid[o]] + (e - r.x);
+        aj_s[pos] = (unsigned short)((en.w >= 0 && en.y != 0x7f800000) ? cid[en.x] : 0);
+        aw_s[pos] = __int_as_float(en.y);
+      }
+      for (int k = tid; k < qcarry; k += T) q_s[k] = (unsigned short)cid[x.queue[k]];
+    }
+    __syncthreads();
+    if (s.rs_ok && tid == 0) {
       int qn = qcarry, next = 0;
-      unsigned long long ne = 0;
-      const float kInfF = __int_as_float(0x7f800000);
       bool ok = true;
+      int npop = 0, nvis = 0;
       while (qn > 0) {
         const int d = q_s[--qn];
         const float c = rc_s[d];
+        npop++;
         if (c >= cutoff) continue;
-        ne += (unsigned long long)deg_s[d];
-        const int e1 = off_s[d + 1];
-        for (int e = off_s[d]; e < e1; e++) {
+        nvis += cnt_s[d];
+        const int e0 = off_s[d], e1 = e0 + cnt_s[d];
+        for (int e = e0; e < e1; e++) {
           const float tot = c + aw_s[e];
           if (tot < cutoff) {
-            const int jj = aj_s[e];
-            const int j = jj & 0x7fff;
+            const int j = aj_s[e];
             const float old = rc_s[j];
-            if (tot < old) {                                 // FindOrAddToken: new or improved -> changed
+            if (tot < old) {
               rc_s[j] = tot;
               if (old == kInfF) ns_s[j] = (unsigned short)next++;
-              if (jj & 0x8000) {
+              if (cnt_s[j]) {
                 if (qn < p.rs_qcap) q_s[qn++] = (unsigned short)j;
                 else { ok = false; qn = 0; break; }
               }
@@ -1029,39 +1085,46 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
         }
       }
       if (ok) {
-        cs->arcs_ne += ne;
         if (next != Nall - N1) s.err = B2K_ERR_STATE;
+        s.prof[12] += (unsigned long long)npop; s.prof[13] += (unsigned long long)nvis; s.prof[14] += 1;
       } else {
-        s.q_n = 0;                                           // worklist outgrew shared memory: redo in global memory
+        s.rs_ok = 0;                                         // worklist outgrew shared memory: redo below
       }
     }
     __syncthreads();
-    if (s.q_n != 0 && !s.err)
-      for (int d = N1 + tid; d < Nall; d += T) x.newseq[d - N1] = (int)ns_s[ridx[d]];
+    if (s.rs_ok) {
+      replay_done = true;
+      if (!s.err)
+        for (int d = N1 + tid; d < Nall; d += T) {
+          int id = cid[d];
+          if (id >= 0) x.newseq[d - N1] = (int)ns_s[id];
+          else atomicExch(&s.err, B2K_ERR_STATE);            // an eps-created token is always some record's destination
+        }
+    }
     __syncthreads();
   }
-  // fallback: literal LIFO replay by one thread over the dense arrays in global memory
-  if (tid == 0 && !s.err && s.q_n == 0) {
+  // literal LIFO replay by one thread over the dense records in global memory
+  if (tid == 0 && !s.err && !replay_done && Nall > N1) {
     int qn = qcarry, next = 0;
-    unsigned long long ne = 0;
-    const float kInfF = __int_as_float(0x7f800000);
-    // (the shared-memory attempt may have consumed nothing persistent: rcost/newseq are untouched)
+    int npop = 0, nvis = 0;
     while (qn > 0) {
       const int d = x.queue[--qn];
-      const float c = x.rcost[d];
-      if (c >= cutoff) continue;
-      ne += (unsigned long long)x.deg[d];
-      const int e1 = x.adjoff[d + 1];
-      for (int e = x.adjoff[d]; e < e1; e++) {
-        const int2 en = x.adj[e];
+      const int4 r = x.rec[d];
+      const float c = __int_as_float(r.w);
+      npop++;
+      if (c >= cutoff || r.z == 0) continue;
+      nvis += r.y;
+      for (int e = r.x; e < r.x + r.y; e++) {
+        const int4 en = x.adj[e];
         const float tot = c + __int_as_float(en.y);
         if (tot < cutoff) {
-          const int j = en.x & 0x3fffffff;
-          const float old = x.rcost[j];
-          if (tot < old) {
-            x.rcost[j] = tot;
+          const int j = en.x;
+          const int4 rj = x.rec[j];
+          const float old = __int_as_float(rj.w);
+          if (tot < old) {                                   // FindOrAddToken: new or improved -> changed
+            x.rec[j].w = __float_as_int(tot);
             if (old == kInfF) x.newseq[j - N1] = next++;
-            if (en.x & 0x40000000) {
+            if (rj.z > 0) {
               if (qn < p.queue_cap) x.queue[qn++] = j;
               else { s.err = B2K_ERR_OVERFLOW; break; }
             }
@@ -1069,8 +1132,8 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
         }
       }
     }
-    cs->arcs_ne += ne;
     if (!s.err && next != Nall - N1) s.err = B2K_ERR_STATE;
+    s.prof[12] += (unsigned long long)npop; s.prof[13] += (unsigned long long)nvis;
   }
   __syncthreads();
   B2K_TICK(s, 7);
@@ -1078,38 +1141,45 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   if (!s.err) {
     for (int d = N1 + tid; d < Nall; d += T) {
       int slot = ctx.tokslot[d];
-      hash[slot].z = N1 + x.newseq[d - N1];
-    }
-  }
-  __syncthreads();
-  if (!s.err) {
-    for (int d = N1 + tid; d < Nall; d += T) {
-      int slot = ctx.tokslot[d];
-      x.by_ins[hash[slot].z] = slot;
+      int ins = N1 + x.newseq[d - N1];
+      hash[slot].z = ins;
+      x.by_ins[ins] = slot;
     }
   }
   __syncthreads();
   B2K_TICK(s, 8);
-  const int N = min(s.ntok_new, p.max_tpf);
+  const int N = Nall;
   order_tokens<T>(N, Hc, hash, x, s);
   B2K_TICK(s, 9);
-  // eps links from final costs
-  for (int i = tid; i < N; i += T) {
-    int slot = ctx.tokslot[i];
-    float c = ord2f((uint32_t)hash[slot].y);
-    if (!(c < cutoff)) continue;
-    int state = hash[slot].x;
-    int2 o0 = __ldg(&g.st_off[state]), o1 = __ldg(&g.st_off[state + 1]);
-    for (int a = o0.y; a < o1.y; a++) {
-      int4 arc = __ldg(&g.ne_arcs[a]);
-      float tot = c + __int_as_float(arc.y);
-      if (tot < cutoff) {
-        int ds = hash_find(ctx, arc.x);
-        int li = atomicAdd(&s.nlink_new, 1);
-        if (lbase + li < p.max_links && ds >= 0)
-          links[lbase + li] = make_int4(slot, ds, (int)((uint32_t)a | B2K_EPS_FLAG), 0);
-        else
-          atomicExch(&s.err, B2K_ERR_OVERFLOW);
+  // eps links = the admitted entries of the final records
+  if (!s.err) {
+    const int lane_id = tid & 31;
+    for (int base = 0; base < E; base += T) {
+      const int e = base + tid;
+      bool live = false;
+      int4 en = make_int4(0, 0, 0, -1);
+      int src = 0;
+      if (e < E) {
+        en = x.adj[e];
+        if (en.w >= 0) {
+          const int o = x.adjo[e];
+          const int4 r = x.rec[o];
+          live = (e >= r.x && e < r.x + r.y);
+          src = (o < N1) ? x.by_ins[o] : ctx.tokslot[o];
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, live);
+      if (m) {
+        int lb = 0;
+        if (lane_id == 0) lb = atomicAdd(&s.nlink_new, __popc(m));
+        lb = __shfl_sync(0xffffffffu, lb, 0);
+        if (live) {
+          int li = lb + __popc(m & ((1u << lane_id) - 1u));
+          if (lbase + li < p.max_links)
+            links[lbase + li] = make_int4(src, en.w, (int)((uint32_t)en.z | B2K_EPS_FLAG), 0);
+          else
+            atomicExch(&s.err, B2K_ERR_OVERFLOW);
+        }
       }
     }
   }
@@ -1121,7 +1191,7 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   __syncthreads();
   if (!s.err) {
     for (int r = tid; r < N; r += T) {
-      int slot = x.order[r];
+      int slot = x.by_ins[x.order[r]];
       tok_state[ctx.tbase + r] = hash[slot].x;
       tok_cost[ctx.tbase + r] = ord2f((uint32_t)hash[slot].y);
       hash[slot].w = r;
@@ -1197,11 +1267,11 @@ __global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
   x.run = p.x_run + (size_t)lane * p.max_tpf;
   x.order = p.x_order + (size_t)lane * p.max_tpf;
   x.queue = p.cand + (size_t)lane * 5 * p.cand_cap;     // idle in this mode
-  x.rcost = p.x_rcost + (size_t)lane * p.max_tpf;
-  x.adjoff = p.x_adjoff + (size_t)lane * (p.max_tpf + 1);
-  x.deg = p.x_deg + (size_t)lane * p.max_tpf;
+  x.xb = p.x_xb + (size_t)lane * p.max_tpf;
+  x.rec = p.x_rec + (size_t)lane * p.max_tpf;
   x.newseq = p.x_newseq + (size_t)lane * p.max_tpf;
   x.adj = p.x_adj + (size_t)lane * p.adj_cap;
+  x.adjo = p.x_adjo + (size_t)lane * p.adj_cap;
 
   if (tid == 0) { s.err = 0; s.stamp = 0; }
   __syncthreads();
@@ -1534,8 +1604,13 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
   int4 *la = p.lat_arcs + (size_t)ch * p.cap_la;
   float2 *lw = p.lat_arcw + (size_t)ch * p.cap_la;
   int2 *lf = p.lat_finals + (size_t)ch * p.cap_lf;
-  int *ids_cur = p.cand + (size_t)lane * 5 * p.cand_cap;          // candidate staging is idle here
+  int *ids_cur = p.cand + (size_t)lane * 5 * p.cand_cap;          // candidate staging is idle here (20*max_tpf ints)
   int *ids_next = ids_cur + p.max_tpf;
+  int *has_eps = ids_cur + 2 * p.max_tpf;
+  int *surv_e = ids_cur + 3 * p.max_tpf;                         // surviving emitting links of the segment
+  const int surv_cap = 5 * p.max_tpf;
+  int *surv_p0 = ids_cur + 8 * p.max_tpf, *surv_p1 = ids_cur + 13 * p.max_tpf;   // eps survivors, ping-pong
+  __shared__ int sh_cnt[3];
   int tb_next = 0;
   __syncthreads();
 
@@ -1550,6 +1625,9 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
       return;
     }
     const int eps_b = p.frame_link_eps[fo + t], eps_e = p.frame_link_begin[fo + t + 1];
+    // Almost every token and link dies in this sweep (the lattice keeps ~0.1 % of
+    // them), so the passes exit early on dead destinations and keep compact
+    // survivor lists instead of flagging or re-reading whole link segments.
     // base value per token: final-cost term on the last list (:426), else
     // +inf (:337) lowered by the emitting links into list t+1
     for (int i = tid; i < n; i += T) {
@@ -1559,51 +1637,77 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
         base = tok_cost[tb + i] + fc - final_best_cost;
       }
       nx[i] = f2ord(base);
-      tok_extra[tb + i] = 0.0f;        // lower bound to start the eps iteration from
+      has_eps[i] = 0;
     }
+    if (tid == 0) { sh_cnt[0] = 0; sh_cnt[1] = 0; sh_cnt[2] = 0; }
     __syncthreads();
     if (t < last) {
       const int em_b = p.frame_link_begin[fo + t + 1], em_e = p.frame_link_eps[fo + t + 1];
-      for (int l = em_b + tid; l < em_e; l += T) {
-        int4 lk = links[l];
-        float graph = __int_as_float(__ldg(&g.e_arcs[lk.z]).y);
-        float lec = link_extra_cost(tok_extra[lk.y], tok_cost[lk.x], __int_as_float(lk.w), graph,
-                                    tok_cost[lk.y]);
-        if (lec > p.lattice_beam) {
-          links[l].z = (int)((uint32_t)lk.z | B2K_DEAD_FLAG);   // excised (:348-354)
-        } else {
+      constexpr int U = 4;                                    // independent loads in flight per thread
+      for (int l0 = em_b; l0 < em_e; l0 += U * T) {
+        int4 lk[U];
+        float dex[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          int l = l0 + u * T + tid;
+          lk[u] = (l < em_e) ? __ldcs(&links[l]) : make_int4(0, -1, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) dex[u] = (lk[u].y >= 0) ? tok_extra[lk[u].y] : kInf;   // list t+1 is final
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (dex[u] == kInf) continue;                       // link_extra_cost = inf > lattice_beam
+          float graph = __int_as_float(__ldg(&g.e_arcs[lk[u].z]).y);
+          float lec = link_extra_cost(dex[u], tok_cost[lk[u].x], __int_as_float(lk[u].w), graph, tok_cost[lk[u].y]);
+          if (lec > p.lattice_beam) continue;                 // excised (:348-354)
           if (lec < 0.0f) lec = 0.0f;
-          atomicMin(&nx[lk.x - tb], f2ord(lec));
+          atomicMin(&nx[lk[u].x - tb], f2ord(lec));
+          int q = atomicAdd(&sh_cnt[0], 1);
+          if (q < surv_cap) surv_e[q] = l0 + u * T + tid;
         }
       }
     }
+    for (int l = eps_b + tid; l < eps_e; l += T) has_eps[links[l].x - tb] = 1;
     __syncthreads();
-    // nx now holds the base value of every token (final-cost term or the min
-    // over emitting links).  Iterate the epsilon links of list t to the
-    // fixpoint (Jacobi; unique because eps links form a DAG): old values live
-    // in tok_extra (start at the lower bound 0), new values are built in nx,
-    // the base is kept in a side buffer carved from the idle worklist scratch.
+    // tokens without eps out-links already have their exact extra_cost (= base);
+    // the others start the eps iteration from the lower bound 0.  The iteration
+    // (Jacobi over the surviving eps links; unique fixpoint because eps links
+    // form a DAG) only ever excises a link when a LOWER BOUND of its extra cost
+    // exceeds lattice_beam, so it keeps exactly the links of :308-379.
     uint32_t *base_ord = reinterpret_cast<uint32_t *>(p.wl + (size_t)lane * 2 * p.max_tpf);
-    for (int i = tid; i < n; i += T) base_ord[i] = nx[i];
+    for (int i = tid; i < n; i += T) {
+      uint32_t bo = nx[i];
+      base_ord[i] = bo;
+      float v = ord2f(bo);
+      if (t == last && v > p.lattice_beam) v = kInf;
+      tok_extra[tb + i] = has_eps[i] ? 0.0f : v;
+    }
     __syncthreads();
-    for (int iter = 0; iter < 100000; iter++) {
-      if (tid == 0) sh_changed = 0;
-      // new = base lowered by alive eps links using OLD extras of dst
-      for (int l = eps_b + tid; l < eps_e; l += T) {
+    int n_eps_in = eps_e - eps_b;                             // iteration 0 reads the segment itself
+    int *eps_in = nullptr, *eps_out = surv_p0;
+    for (int iter = 0; iter < 100000 && n_eps_in > 0; iter++) {
+      if (tid == 0) { sh_changed = 0; sh_cnt[1] = 0; }
+      __syncthreads();
+      for (int k = tid; k < n_eps_in; k += T) {
+        int l = eps_in ? eps_in[k] : eps_b + k;
         int4 lk = links[l];
-        if ((uint32_t)lk.z & B2K_DEAD_FLAG) continue;
+        float dex = tok_extra[lk.y];
+        if (dex == kInf) continue;
         float graph = __int_as_float(__ldg(&g.ne_arcs[(uint32_t)lk.z & B2K_ARC_MASK]).y);
-        float lec = link_extra_cost(tok_extra[lk.y], tok_cost[lk.x], 0.0f, graph, tok_cost[lk.y]);
-        if (lec > p.lattice_beam) {
-          links[l].z = (int)((uint32_t)lk.z | B2K_DEAD_FLAG);
-        } else {
-          if (lec < 0.0f) lec = 0.0f;
-          atomicMin(&nx[lk.x - tb], f2ord(lec));
-        }
+        float lec = link_extra_cost(dex, tok_cost[lk.x], 0.0f, graph, tok_cost[lk.y]);
+        if (lec > p.lattice_beam) continue;
+        if (lec < 0.0f) lec = 0.0f;
+        atomicMin(&nx[lk.x - tb], f2ord(lec));
+        int q = atomicAdd(&sh_cnt[1], 1);
+        if (q < surv_cap) eps_out[q] = l;
       }
       __syncthreads();
+      const int n_out = min(sh_cnt[1], surv_cap);
       int changed = 0;
+      // only sources of eps links can change: re-evaluate them via the survivor list plus the
+      // sources whose links all died (their value falls back to base) -> walk the has_eps tokens
       for (int i = tid; i < n; i += T) {
+        if (!has_eps[i]) continue;
         float v = ord2f(nx[i]);
         if (t == last && v > p.lattice_beam) v = kInf;      // :458-459
         float old = tok_extra[tb + i];
@@ -1613,47 +1717,39 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
       }
       if (changed) sh_changed = 1;
       __syncthreads();
-      int ch_any = sh_changed;
+      const int ch_any = sh_changed;
+      if (tid == 0 && sh_cnt[1] > surv_cap) cs->status = B2K_ERR_OVERFLOW;
+      eps_in = eps_out;
+      eps_out = (eps_out == surv_p0) ? surv_p1 : surv_p0;
+      n_eps_in = n_out;
       __syncthreads();
       if (!ch_any) break;
     }
-    // ---- dense lattice-state ids for list t (ids grow as we walk backwards; the
-    //      host flips them so that id 0 is the start state) and emission of the
-    //      surviving states / arcs into the channel's compact lattice region
-    {
-      int carry = 0;
-      for (int base = 0; base < n; base += T) {
-        int k = base + tid;
-        int alive = (k < n) && (tok_extra[tb + k] != kInf);
-        int total;
-        int excl = block_excl_scan<T>(alive, redi, &total);
-        if (k < n) {
-          int id = -1;
-          if (alive) {
-            id = n_states + carry + excl;
-            if (id < p.cap_ls)
-              ls[id] = make_int4(t, tok_state[tb + k], __float_as_int(tok_cost[tb + k]), __float_as_int(tok_extra[tb + k]));
-            if (t == last) {
-              float fc = any_final ? __ldg(&g.final_cost[tok_state[tb + k]]) : 0.0f;
-              if (fc != kInf) {
-                int q = atomicAdd(&sh_nfin, 1);
-                if (q < p.cap_lf) lf[q] = make_int2(id, __float_as_int(fc));
-              }
-            }
-          }
-          ids_cur[k] = id;
+    // ---- lattice-state ids for the surviving tokens of list t (ids grow as we walk
+    //      backwards; the host flips them so that id 0 is the start state) and emission of
+    //      the surviving states / arcs into the channel's compact lattice region
+    for (int k = tid; k < n; k += T) {
+      float ex = tok_extra[tb + k];
+      if (ex == kInf) continue;
+      int id = n_states + atomicAdd(&sh_cnt[2], 1);
+      ids_cur[k] = id;
+      if (id < p.cap_ls) ls[id] = make_int4(t, tok_state[tb + k], __float_as_int(tok_cost[tb + k]), __float_as_int(ex));
+      if (t == last) {
+        float fc = any_final ? __ldg(&g.final_cost[tok_state[tb + k]]) : 0.0f;
+        if (fc != kInf) {
+          int q = atomicAdd(&sh_nfin, 1);
+          if (q < p.cap_lf) lf[q] = make_int2(id, __float_as_int(fc));
         }
-        carry += total;
       }
-      n_states += carry;
     }
     __syncthreads();
+    n_states += sh_cnt[2];
     if (t < last) {
-      const int em_b = p.frame_link_begin[fo + t + 1], em_e = p.frame_link_eps[fo + t + 1];
       const float coff = p.frame_cost_offset[(size_t)ch * (p.max_frames + 1) + t];
-      for (int l = em_b + tid; l < em_e; l += T) {
-        int4 lk = links[l];
-        if ((uint32_t)lk.z & B2K_DEAD_FLAG) continue;
+      const int ns = min(sh_cnt[0], surv_cap);
+      if (tid == 0 && sh_cnt[0] > surv_cap) cs->status = B2K_ERR_OVERFLOW;
+      for (int k = tid; k < ns; k += T) {
+        int4 lk = links[surv_e[k]];
         int4 arc = __ldg(&g.e_arcs[lk.z]);
         int q = atomicAdd(&sh_narcs, 1);
         if (q < p.cap_la) {
@@ -1662,10 +1758,15 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
         }
       }
     }
-    for (int l = eps_b + tid; l < eps_e; l += T) {
+    // surviving eps links: the last input list of the iteration, re-checked against the final extras
+    for (int k = tid; k < n_eps_in; k += T) {
+      int l = eps_in ? eps_in[k] : eps_b + k;
       int4 lk = links[l];
-      if ((uint32_t)lk.z & B2K_DEAD_FLAG) continue;
+      float dex = tok_extra[lk.y];
+      if (dex == kInf) continue;
       int4 arc = __ldg(&g.ne_arcs[(uint32_t)lk.z & B2K_ARC_MASK]);
+      float lec = link_extra_cost(dex, tok_cost[lk.x], 0.0f, __int_as_float(arc.y), tok_cost[lk.y]);
+      if (lec > p.lattice_beam) continue;
       int q = atomicAdd(&sh_narcs, 1);
       if (q < p.cap_la) {
         la[q] = make_int4(ids_cur[lk.x - tb], ids_cur[lk.y - tb], 0, arc.z & 0x7fffffff);
@@ -1899,18 +2000,19 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
     A(p.x_run, 4 * nl * p.max_tpf, 0);
     A(p.x_order, 4 * nl * p.max_tpf, 0);
     p.adj_cap = 2 * p.max_tpf;
-    p.rs_rcap = 0; p.rs_ecap = 0; p.rs_qcap = 0;               // shared-memory replay off by default (measured slower: lower occupancy)
-    if (const char *e = getenv("B2K_DEC_RS_CAPS")) {          // tuning knob: "tokens,entries,queue" (each <= 3072)
+    p.rs_rcap = 0; p.rs_ecap = 0; p.rs_qcap = 0;          // shared-memory walk: off by default
+    if (const char *e = getenv("B2K_DEC_RS_CAPS")) {          // tuning knob: "tokens,arcs,worklist" (each <= 8192; 0,0,0 = off)
       int a = 0, b = 0, c = 0;
-      if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= 64 && b >= 64 && c >= 64 && a <= 3072 && b <= 3072 && c <= 3072) {
+      if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= 0 && b >= 0 && c >= 0 && a <= 8192 && b <= 8192 && c <= 8192) {
         p.rs_rcap = a; p.rs_ecap = b; p.rs_qcap = c;
+        if (!a || !b || !c) { p.rs_rcap = p.rs_ecap = p.rs_qcap = 0; }
       }
     }
-    A(p.x_rcost, 4 * nl * p.max_tpf, 0);
-    A(p.x_adjoff, 4 * nl * (p.max_tpf + 1), 0);
-    A(p.x_deg, 4 * nl * p.max_tpf, 0);
+    A(p.x_xb, 4 * nl * p.max_tpf, 0);
+    A(p.x_rec, sizeof(int4) * nl * p.max_tpf, 0);
     A(p.x_newseq, 4 * nl * p.max_tpf, 0);
-    A(p.x_adj, sizeof(int2) * nl * p.adj_cap, 0);
+    A(p.x_adj, sizeof(int4) * nl * p.adj_cap, 0);
+    A(p.x_adjo, 4 * nl * p.adj_cap, 0);
     {
       std::vector<int32_t> big((size_t)nl * p.hc_cap, 0x7fffffff);
       B2K_CUDA_CHECK(cudaMemcpy(p.x_bfirst, big.data(), 4 * big.size(), cudaMemcpyHostToDevice));
@@ -1980,15 +2082,23 @@ static int dec_threads() {
   return g_dec_threads;
 }
 
-static void launch_exact(const DecParams &p, int n, size_t smem, cudaStream_t st) {
-  if (dec_threads() == 128) dec_advance_exact_kernel<128><<<n, 128, smem, st>>>(p);
-  else dec_advance_exact_kernel<256><<<n, 256, smem, st>>>(p);
-}
-
 static size_t exact_smem_bytes(const DecParams &p) {
   if (p.rs_rcap == 0) return 0;
-  return sizeof(float) * p.rs_rcap + sizeof(int) * (p.rs_rcap + 1) + sizeof(float) * p.rs_ecap +
-         sizeof(unsigned short) * ((size_t)p.rs_ecap + 2 * (size_t)p.rs_rcap + p.rs_qcap) + 16;
+  return sizeof(float) * ((size_t)p.rs_rcap + p.rs_ecap) +
+         sizeof(unsigned short) * (4 * (size_t)p.rs_rcap + p.rs_ecap + p.rs_qcap) + 16;
+}
+
+static int launch_exact(const DecParams &p, int n, cudaStream_t st) {
+  const size_t smem = exact_smem_bytes(p);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  if (dec_threads() == 128) dec_advance_exact_kernel<128><<<n, 128, smem, st>>>(p);
+  else dec_advance_exact_kernel<256><<<n, 256, smem, st>>>(p);
+  return B2K_OK;
 }
 
 static int stage_lanes(b2k_dec *d, const int32_t *channels, const float *const *lls,
@@ -2025,7 +2135,7 @@ int b2k_dec_init_decoding(b2k_dec *d, const int32_t *channels, int32_t n, void *
   if (rc) return rc;
   DecParams p = d->p;
   p.do_init = 1;
-  if (d->cfg.reference_order) launch_exact(p, n, exact_smem_bytes(p), st);
+  if (d->cfg.reference_order) { if ((rc = launch_exact(p, n, st))) return rc; }
   else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
   B2K_LAUNCH_CHECK();
   return B2K_OK;
@@ -2041,7 +2151,7 @@ int b2k_dec_advance_decoding_frames(b2k_dec *d, const int32_t *channels,
   DecParams p = d->p;
   p.do_init = 0;
   p.row_stride = row_stride;
-  if (d->cfg.reference_order) launch_exact(p, n, exact_smem_bytes(p), st);
+  if (d->cfg.reference_order) { if ((rc = launch_exact(p, n, st))) return rc; }
   else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
   B2K_LAUNCH_CHECK();
   return B2K_OK;
