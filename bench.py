@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--order-free", action="store_true", help="use the order-free decoder mode (not reference exact)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=6)
+    ap.add_argument("--max-tpf", type=int, default=32768, help="decoder per-frame token capacity (hash = 2x slots)")
     ap.add_argument("--tok-per-frame", type=int, default=9000, help="decoder token arena sizing (avg tokens/frame)")
     ap.add_argument("--links-per-frame", type=int, default=16000, help="decoder link arena sizing (avg links/frame)")
     a = ap.parse_args()
@@ -232,7 +233,8 @@ def main():
     from kaldi_b200.feat import FeatureOptions
     cfg = PipelineConfig(feature_opts=FeatureOptions(max_lanes=max(B, 64)), max_batch=B, num_samples=NUM_SAMPLES,
                          reference_order=not a.order_free,
-                         max_tokens=nf_out * a.tok_per_frame, max_links=nf_out * a.links_per_frame)
+                         max_tokens=nf_out * a.tok_per_frame, max_links=nf_out * a.links_per_frame,
+                         max_tokens_per_frame=a.max_tpf)
     from kaldi_b200.ivector import make_synthetic_extractor
     ivx = make_synthetic_extractor(seed=0)
     pipe = BatchedPipeline(cfg, arch, W, graph, ivector_extractor=ivx)

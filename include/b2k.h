@@ -130,10 +130,12 @@ int b2k_dec_finalize_decoding(b2k_dec *dec, const int32_t *channels, int32_t n, 
 
 /* Per-channel counters after a synchronize: [0] status (b2k_status), [1] frames
  * decoded, [2] tokens in arena, [3] links in arena, [4] emitting arcs examined,
- * [5] epsilon arcs examined, [6] surviving lattice states, [7] surviving
- * lattice arcs, [8] number of final states; [16..23] reference-order kernel
- * phase cycle counters (cutoff+seed, expand, rank, order+queue, eps replay,
- * order, links+commit, total). */
+ * [5] epsilon arcs examined by the parallel closure, [6] surviving lattice
+ * states, [7] surviving lattice arcs, [8] number of final states, [9] finalized,
+ * [10] any final state reached, [11] source line that raised the channel's
+ * first error (diagnostics for capacity overflows); [16..27] reference-order
+ * kernel cycle counters per phase, [28..30] eps-replay counters (pops, arc
+ * visits, frames walked in shared memory), [31] total kernel cycles. */
 int b2k_dec_channel_info(b2k_dec *dec, int32_t channel, int64_t info[32]);
 
 /* Raw lattice of a finalized channel — the content of

@@ -164,7 +164,7 @@ class CudaDecoder:
         info = (C.c_int64 * 32)()
         _lib.check(_lib.lib().b2k_dec_channel_info(self.h, int(channel), C.cast(info, C.POINTER(C.c_int64))))
         keys = ["status", "frames_decoded", "ntok", "nlink", "arcs_emitting", "arcs_nonemitting",
-                "lat_states", "lat_arcs", "lat_finals", "finalized", "any_final"]
+                "lat_states", "lat_arcs", "lat_finals", "finalized", "any_final", "err_line"]
         d = {k: int(info[i]) for i, k in enumerate(keys)}
         d["prof_cycles"] = [int(info[16 + k]) for k in range(16)]
         return d

@@ -38,6 +38,7 @@ class PipelineConfig:
     extract_ivectors: bool = True
     max_tokens: int = 0                 # 0 = sized from the utterance length
     max_links: int = 0
+    max_tokens_per_frame: int = 32768   # sizes the per-lane token hash (2x this many slots) and per-frame scratch
 
 
 class BatchedPipeline:
@@ -55,7 +56,7 @@ class BatchedPipeline:
         dc = CudaDecoderConfig.from_dict(
             cfg.decoder_cfg, max_frames=nf + 2,
             max_tokens=cfg.max_tokens or int(nf * 9000), max_links=cfg.max_links or int(nf * 16000),
-            reference_order=cfg.reference_order)
+            reference_order=cfg.reference_order, max_tokens_per_frame=cfg.max_tokens_per_frame)
         self.dec = CudaDecoder(self.fst, dc, cfg.max_batch)
         B = cfg.max_batch
         self.h_wave = torch.empty(B, cfg.num_samples, dtype=torch.float32).pin_memory()
