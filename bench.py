@@ -382,7 +382,8 @@ def main():
                                       (B * pipe.nnet.n_out * NUM_PDFS * 4 / 1e6, B * NUM_SAMPLES * 4 / 1e6),
                                 parallelism=f"dp{world} (utterance shards, no data-path collective)"),
                     e2e=dict(value=e2e_value, unit="RTFx", h2d_bytes_per_step=B * NUM_SAMPLES * 4,
-                             d2h_bytes_per_step=int(d2h / a.steps), lattice_states_per_step=int(lat_states / a.steps)),
+                             d2h_bytes_per_step=int(d2h / a.steps), lattice_states_per_step=int(lat_states / a.steps),
+                             host_ms_last_step={k: round(v, 1) for k, v in getattr(pipe, "last_host_ms", {}).items()}),
                     gpu_launches=int(launches), stage_ms={k: round(v, 3) for k, v in stage_ms.items()},
                     decoder_phase_share=dict(zip(
                         ["cutoff_seed", "expand", "rank", "order1", "queue_build", "eps_relax", "eps_adjacency", "eps_replay",

@@ -1012,21 +1012,20 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   }
   __syncthreads();
   B2K_TICK(s, 6);
-  // ---- the replay touches few tokens (sources of admitting records, their
-  // destinations, and the stragglers of the worklist): renumber them compactly
-  // and run the LIFO walk out of shared memory, so that each of its dependent
-  // steps costs a shared-memory access instead of an L2 round trip.  Falls back
-  // to the walk over the global records when the set is too large.
+  // ---- the walk touches few tokens (the marked sources and their destinations) and
+  // few arcs (the enabled ones): renumber the tokens compactly, compact each record
+  // to its enabled arcs (order preserved: one warp per record), and run the LIFO walk
+  // out of shared memory, so that each of its dependent steps costs a shared-memory
+  // access instead of an L2/HBM round trip.  Falls back to the walk over the global
+  // records when the set does not fit.
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  float *rc_s = reinterpret_cast<float *>(dyn_smem);
-  float *aw_s = rc_s + p.rs_rcap;
-  unsigned short *off_s = reinterpret_cast<unsigned short *>(aw_s + p.rs_ecap);
-  unsigned short *cnt_s = off_s + p.rs_rcap;
-  unsigned short *deg_s = cnt_s + p.rs_rcap;
-  unsigned short *ns_s = deg_s + p.rs_rcap;
-  unsigned short *aj_s = ns_s + p.rs_rcap;
-  unsigned short *q_s = aj_s + p.rs_ecap;
+  // per token {replay cost, record offset | count << 16}; per arc {weight, dest id}: one 8-byte load each
+  float2 *tk_s = reinterpret_cast<float2 *>(dyn_smem);
+  float2 *en_s = tk_s + p.rs_rcap;
+  unsigned short *ns_s = reinterpret_cast<unsigned short *>(en_s + p.rs_ecap);
+  unsigned short *q_s = ns_s + p.rs_rcap;
   int *cid = x.sbase;                                        // idle between the two order_tokens calls
+  int *dof = wl0;                                            // compact id -> dense index (worklists are idle now)
   bool replay_done = false;
   if (p.rs_rcap > 0 && !s.err && Nall > N1 && qcarry <= p.rs_qcap) {
     if (tid == 0) { s.rs_n = 0; s.rs_e = 0; s.rs_ok = 1; }
@@ -1034,14 +1033,11 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
     __syncthreads();
     auto claim = [&](int d) {
       if (atomicCAS(&cid[d], -1, -2) != -1) return;
-      const int4 r = x.rec[d];
-      const int cnt = r.z > 0 ? r.y : 0;                     // records that admit nothing are never walked
       int id = atomicAdd(&s.rs_n, 1);
-      int eo = cnt ? atomicAdd(&s.rs_e, cnt) : 0;
-      if (id < p.rs_rcap && eo + cnt <= p.rs_ecap && r.y < 65536) {
-        rc_s[id] = __int_as_float(r.w);
-        off_s[id] = (unsigned short)eo; cnt_s[id] = (unsigned short)cnt; deg_s[id] = (unsigned short)r.y;
+      if (id < p.rs_rcap) {
+        tk_s[id] = make_float2(__int_as_float(x.rec[d].w), __int_as_float(0));
         ns_s[id] = 0xffff;
+        dof[id] = d;
         cid[d] = id;
       } else {
         s.rs_ok = 0;
@@ -1058,15 +1054,36 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
     }
     __syncthreads();
     if (s.rs_ok) {
-      for (int e = tid; e < E; e += T) {
-        const int o = x.adjo[e];
-        if (cid[o] < 0) continue;
-        const int4 r = x.rec[o];
-        if (r.z == 0 || e < r.x || e >= r.x + r.y) continue;   // superseded record, or nothing admitted
-        const int4 en = x.adj[e];
-        const int pos = off_s[cid[o]] + (e - r.x);
-        aj_s[pos] = (unsigned short)((en.w >= 0 && en.y != 0x7f800000) ? cid[en.x] : 0);
-        aw_s[pos] = __int_as_float(en.y);
+      const int R = s.rs_n;
+      const int lane_id = tid & 31;
+      for (int id = tid >> 5; id < R; id += T / 32) {        // one warp per record
+        const int d = dof[id];
+        const int4 r = x.rec[d];
+        if (!mark[d] || r.z == 0) continue;                  // destination only
+        int total = 0;
+        for (int b0 = 0; b0 < r.y; b0 += 32) {
+          int i = b0 + lane_id;
+          int4 en = (i < r.y) ? x.adj[r.x + i] : make_int4(0, 0x7f800000, 0, -1);
+          total += __popc(__ballot_sync(0xffffffffu, en.w >= 0 && en.y != 0x7f800000));
+        }
+        if (!total) continue;
+        int eo = 0;
+        if (lane_id == 0) eo = atomicAdd(&s.rs_e, total);
+        eo = __shfl_sync(0xffffffffu, eo, 0);
+        if (eo + total > p.rs_ecap || total > 0xffff) { if (lane_id == 0) s.rs_ok = 0; continue; }
+        int pos = eo;
+        for (int b0 = 0; b0 < r.y; b0 += 32) {
+          int i = b0 + lane_id;
+          int4 en = (i < r.y) ? x.adj[r.x + i] : make_int4(0, 0x7f800000, 0, -1);
+          bool keep = en.w >= 0 && en.y != 0x7f800000;
+          uint32_t m = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            int q = pos + __popc(m & ((1u << lane_id) - 1u));
+            en_s[q] = make_float2(__int_as_float(en.y), __int_as_float(cid[en.x]));
+          }
+          pos += __popc(m);
+        }
+        if (lane_id == 0) tk_s[id].y = __int_as_float(eo | (total << 16));
       }
       for (int k = tid; k < qcarry; k += T) q_s[k] = (unsigned short)cid[x.queue[k]];
     }
@@ -1077,20 +1094,23 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
       int npop = 0, nvis = 0;
       while (qn > 0) {
         const int d = q_s[--qn];
-        const float c = rc_s[d];
+        const float2 td = tk_s[d];
+        const float c = td.x;
         npop++;
         if (c >= cutoff) continue;
-        nvis += cnt_s[d];
-        const int e0 = off_s[d], e1 = e0 + cnt_s[d];
+        const int oc = __float_as_int(td.y);
+        const int e0 = oc & 0xffff, e1 = e0 + (int)((unsigned)oc >> 16);
+        nvis += e1 - e0;
         for (int e = e0; e < e1; e++) {
-          const float tot = c + aw_s[e];
+          const float2 ent = en_s[e];
+          const float tot = c + ent.x;
           if (tot < cutoff) {
-            const int j = aj_s[e];
-            const float old = rc_s[j];
-            if (tot < old) {
-              rc_s[j] = tot;
-              if (old == kInfF) ns_s[j] = (unsigned short)next++;
-              if (cnt_s[j]) {
+            const int j = __float_as_int(ent.y);
+            const float2 tj = tk_s[j];
+            if (tot < tj.x) {
+              tk_s[j].x = tot;
+              if (tj.x == kInfF) ns_s[j] = (unsigned short)next++;
+              if ((unsigned)__float_as_int(tj.y) >> 16) {
                 if (qn < p.rs_qcap) q_s[qn++] = (unsigned short)j;
                 else { ok = false; qn = 0; break; }
               }
@@ -1112,7 +1132,7 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
         for (int d = N1 + tid; d < Nall; d += T) {
           int id = cid[d];
           if (id >= 0) x.newseq[d - N1] = (int)ns_s[id];
-          else B2K_SET_ERR(s, B2K_ERR_STATE);            // an eps-created token is always some record's destination
+          else B2K_SET_ERR(s, B2K_ERR_STATE);                // an eps-created token is always some record's destination
         }
     }
     __syncthreads();
@@ -1250,7 +1270,7 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
 }
 
 template <int T>
-__global__ void __launch_bounds__(T) dec_advance_exact_kernel(DecParams p) {
+__global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kernel(DecParams p) {
   __shared__ DecShared<T> s;
   constexpr int IT = 4;
   const int tid = threadIdx.x;
@@ -2024,7 +2044,7 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
     A(p.x_run, 4 * nl * p.max_tpf, 0);
     A(p.x_order, 4 * nl * p.max_tpf, 0);
     p.adj_cap = 2 * p.max_tpf;
-    p.rs_rcap = 0; p.rs_ecap = 0; p.rs_qcap = 0;          // shared-memory walk: off by default
+    p.rs_rcap = 4096; p.rs_ecap = 4096; p.rs_qcap = 4096;  // shared-memory walk: 80 KB per CTA (two 512-thread CTAs per SM)
     if (const char *e = getenv("B2K_DEC_TUNE")) p.tune_flags = atoi(e);
     if (const char *e = getenv("B2K_DEC_RS_CAPS")) {          // tuning knob: "tokens,arcs,worklist" (each <= 8192; 0,0,0 = off)
       int a = 0, b = 0, c = 0;
@@ -2070,9 +2090,6 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
     for (auto &c : cs) c.frames_decoded = -1;
     B2K_CUDA_CHECK(cudaMemcpy(p.chan, cs.data(), sizeof(ChanState) * nc, cudaMemcpyHostToDevice));
   }
-  if (cfg->reference_order)
-    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(float) * 3072 * 2 + sizeof(int) * 3073 + 2 * (3072 * 4) + 64)));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_chan, sizeof(ChanState) * nc));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_channel, 4 * nl));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_ll, sizeof(float *) * nl));
@@ -2098,19 +2115,26 @@ int b2k_dec_destroy(b2k_dec *d) {
 
 #define DEC_THREADS 256
 
-static int g_dec_threads = 0;
-static int dec_threads() {
+static int g_dec_threads = 0, g_num_sms = 0;
+// CTA width of the reference-order kernel.  The kernel is bound by the latency/throughput of
+// scattered L2/HBM accesses, so a lane wants as many threads as the SM can give it: one
+// 1024-thread CTA per SM while the batch fits one wave, two 512-thread CTAs per SM beyond
+// that (measured on B200 at 592 lanes: 4x256 790 ms, 1x1024 758 ms, 2x512 743 ms).
+static int dec_threads(int nlanes) {
   if (!g_dec_threads) {
-    g_dec_threads = 256;
-    if (const char *e = getenv("B2K_DEC_THREADS")) { int v = atoi(e); if (v == 128 || v == 256) g_dec_threads = v; }
+    g_dec_threads = -1;
+    if (const char *e = getenv("B2K_DEC_THREADS")) { int v = atoi(e); if (v == 128 || v == 256 || v == 512 || v == 1024) g_dec_threads = v; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  return g_dec_threads;
+  if (g_dec_threads > 0) return g_dec_threads;
+  return nlanes <= g_num_sms ? 1024 : 512;
 }
 
 static size_t exact_smem_bytes(const DecParams &p) {
   if (p.rs_rcap == 0) return 0;
-  return sizeof(float) * ((size_t)p.rs_rcap + p.rs_ecap) +
-         sizeof(unsigned short) * (4 * (size_t)p.rs_rcap + p.rs_ecap + p.rs_qcap) + 16;
+  return sizeof(float2) * ((size_t)p.rs_rcap + p.rs_ecap) + sizeof(unsigned short) * ((size_t)p.rs_rcap + p.rs_qcap) + 16;
 }
 
 static int launch_exact(const DecParams &p, int n, cudaStream_t st) {
@@ -2119,9 +2143,14 @@ static int launch_exact(const DecParams &p, int n, cudaStream_t st) {
   if (smem > 48 * 1024 && smem > configured) {
     B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  if (dec_threads() == 128) dec_advance_exact_kernel<128><<<n, 128, smem, st>>>(p);
+  const int threads = dec_threads(n);
+  if (threads == 128) dec_advance_exact_kernel<128><<<n, 128, smem, st>>>(p);
+  else if (threads == 512) dec_advance_exact_kernel<512><<<n, 512, smem, st>>>(p);
+  else if (threads == 1024) dec_advance_exact_kernel<1024><<<n, 1024, smem, st>>>(p);
   else dec_advance_exact_kernel<256><<<n, 256, smem, st>>>(p);
   return B2K_OK;
 }
