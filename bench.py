@@ -386,8 +386,8 @@ def main():
                              host_ms_last_step={k: round(v, 1) for k, v in getattr(pipe, "last_host_ms", {}).items()}),
                     gpu_launches=int(launches), stage_ms={k: round(v, 3) for k, v in stage_ms.items()},
                     decoder_phase_share=dict(zip(
-                        ["cutoff_seed", "expand", "rank", "order1", "queue_build", "eps_relax", "eps_adjacency", "eps_replay",
-                         "eps_finish", "order2", "eps_links", "commit"],
+                        ["cutoff_seed", "expand", "rank", "bucket_scatter", "eps_init", "eps_closure", "replay_prep", "eps_replay",
+                         "eps_finish", "list_order", "eps_links", "commit"],
                         [round(float(sum(i["prof_cycles"][k] for i in infos)) / max(1.0, float(sum(i["prof_cycles"][15] for i in infos))), 3)
                          for k in range(12)])),
                     eps_replay_per_frame=dict(zip(["pops", "arc_visits", "in_shared_memory"],

@@ -758,17 +758,26 @@ __device__ __forceinline__ int hash_insert_x(const LaneCtx &c, int32_t state, bo
 // HashList iteration order of the N tokens by_ins[0..N) (slot.z = insertion index):
 // x.order[list rank] = insertion index.  Buckets are ranked by their first
 // insertion (hash-list-inl.h:126-175); a bucket's tokens keep insertion order.
+// Two steps: bucket_scatter() records, per bucket, its first insertion index and its
+// population for the tokens [k0, k1) (it can be called again for later insertions:
+// they never lower an existing bucket's first index); order_finish() turns that into
+// the list order of all N tokens and clears the bucket arrays.
 template <int T>
-__device__ void order_tokens(int N, int Hc, const int4 *hash, const XScratch &x, DecShared<T> &s) {
-  const int tid = threadIdx.x;
+__device__ void bucket_scatter(int k0, int k1, int Hc, const int4 *hash, const XScratch &x) {
   __syncthreads();
-  for (int k = tid; k < N; k += T) {
+  for (int k = k0 + threadIdx.x; k < k1; k += T) {
     int slot = x.by_ins[k];
     int b = (int)((uint32_t)hash[slot].x % (uint32_t)Hc);
     x.xb[k] = b;
     atomicMin(&x.bfirst[b], k);
     atomicAdd(&x.bcount[b], 1);
   }
+  __syncthreads();
+}
+
+template <int T>
+__device__ void order_finish(int N, const XScratch &x, DecShared<T> &s) {
+  const int tid = threadIdx.x;
   __syncthreads();
   int carry = 0;
   for (int base = 0; base < N; base += T) {
@@ -831,8 +840,9 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   if (s.err) return;     // uniform: nothing writes err between the barrier and this read
   const int n_emit_links = s.nlink_new;
   const int N1 = min(s.ntok_new, p.max_tpf);
-  // list order after the emitting phase (defines the initial worklist, :852-856)
-  order_tokens<T>(N1, Hc, hash, x, s);
+  // bucket bookkeeping of the emitting tokens: the list order (which defines the initial
+  // worklist, :852-856) is only materialised for the few tokens the replay needs
+  bucket_scatter<T>(0, N1, Hc, hash, x);
   B2K_TICK(s, 3);
   // ---- eps closure.  The final costs and the token set are order independent
   // (least fixpoint), so they are computed by parallel relaxation; the literal
@@ -969,8 +979,10 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   // influence that order (its pops create nothing, and it only ever modifies its own
   // descendants), so the walk is restricted to the ancestors of the created tokens:
   // backward reachability over the final records, then arcs into the rest are disabled.
-  int *mark = x.run;                                         // idle between the two order_tokens calls
+  int *mark = wl1;                                           // the closure's worklists are idle now
   int qcarry = 0;
+  int rescatter_from = N1;                                   // bucket arrays already hold tokens [0, N1)
+  extern __shared__ __align__(16) unsigned char dyn_smem_base[];
   if (Nall > N1 && !s.err) {
     for (int d = tid; d < Nall; d += T) { mark[d] = (d >= N1); if (d >= N1) x.newseq[d - N1] = -1; }
     __syncthreads();
@@ -997,17 +1009,53 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
       if (en.w >= 0 && !mark[en.x]) x.adj[e].y = 0x7f800000;   // the links pass needs only arc id and dest slot
     }
     // initial worklist (:852-856) = the emitting tokens in list order, restricted to the
-    // marked tokens whose final record admits something
-    for (int base = 0; base < N1; base += T) {
-      int k = base + tid, flag = 0, d = 0;
-      if (k < N1) {
-        d = x.order[k];
-        flag = mark[d] && x.rec[d].z > 0;
+    // marked tokens whose final record admits something: collect them with their list
+    // keys (first insertion index of the bucket, own insertion index) and sort the keys
+    // in shared memory; only when they do not fit is the full list order built.
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(dyn_smem_base);
+    const int key_cap = min(4096, p.rs_rcap + p.rs_ecap);     // 8 bytes each, inside the walk's (not yet filled) arrays
+    if (tid == 0) s.rs_n = 0;
+    __syncthreads();
+    for (int d = tid; d < N1; d += T) {
+      if (!mark[d] || x.rec[d].z <= 0) continue;
+      int q = atomicAdd(&s.rs_n, 1);
+      if (q < key_cap) keys[q] = ((unsigned long long)(uint32_t)x.bfirst[x.xb[d]] << 32) | (uint32_t)d;
+    }
+    __syncthreads();
+    qcarry = s.rs_n;
+    if (qcarry <= key_cap) {
+      int P = 1;
+      while (P < qcarry) P <<= 1;
+      for (int i = qcarry + tid; i < P; i += T) keys[i] = ~0ull;
+      __syncthreads();
+      for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < P; i += T) {
+            int ixj = i ^ j;
+            if (ixj > i) {
+              unsigned long long a = keys[i], b = keys[ixj];
+              if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[ixj] = a; }
+            }
+          }
+          __syncthreads();
+        }
+      for (int i = tid; i < qcarry; i += T) x.queue[i] = (int)(uint32_t)keys[i];
+      __syncthreads();
+    } else {
+      order_finish<T>(N1, x, s);                             // (clears the bucket arrays: redone below)
+      rescatter_from = 0;
+      qcarry = 0;
+      for (int base = 0; base < N1; base += T) {
+        int k = base + tid, flag = 0, d = 0;
+        if (k < N1) {
+          d = x.order[k];
+          flag = mark[d] && x.rec[d].z > 0;
+        }
+        int total;
+        int excl = block_excl_scan<T>(flag, s.redi, &total);
+        if (flag) x.queue[qcarry + excl] = d;
+        qcarry += total;
       }
-      int total;
-      int excl = block_excl_scan<T>(flag, s.redi, &total);
-      if (flag) x.queue[qcarry + excl] = d;
-      qcarry += total;
     }
   }
   __syncthreads();
@@ -1018,7 +1066,7 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   // out of shared memory, so that each of its dependent steps costs a shared-memory
   // access instead of an L2/HBM round trip.  Falls back to the walk over the global
   // records when the set does not fit.
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  unsigned char *dyn_smem = dyn_smem_base;
   // per token {replay cost, record offset | count << 16}; per arc {weight, dest id}: one 8-byte load each
   float2 *tk_s = reinterpret_cast<float2 *>(dyn_smem);
   float2 *en_s = tk_s + p.rs_rcap;
@@ -1192,7 +1240,8 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   __syncthreads();
   B2K_TICK(s, 8);
   const int N = Nall;
-  order_tokens<T>(N, Hc, hash, x, s);
+  bucket_scatter<T>(rescatter_from, N, Hc, hash, x);
+  order_finish<T>(N, x, s);
   B2K_TICK(s, 9);
   // eps links = the admitted entries of the final records
   if (!s.err) {

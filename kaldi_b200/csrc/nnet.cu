@@ -23,6 +23,8 @@
 // This first version is a shared-memory tiled SIMT GEMM; see DESIGN.md for the
 // tcgen05 3xTF32 plan that replaces the inner product.
 
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -170,6 +172,163 @@ __global__ void __launch_bounds__(256) nnet_gemm_kernel(OpDev op, RunCtx c) {
   }
 }
 
+// ---------------------------------------------------------------- tensor-core GEMM (3xTF32)
+//
+// Same operator as nnet_gemm_kernel with the inner product on the tensor cores.
+// Every fp32 operand x is split when it is staged in shared memory into
+// hi = tf32(x) and lo = tf32(x - hi); the product is accumulated in fp32 as
+// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (three m16n8k8 TF32 MMAs, small terms
+// first), which keeps the log-likelihoods within ~1e-6 relative of the fp32
+// CPU reference (the dropped a_lo*b_lo term is 2^-22 relative) -- plain TF32
+// (one MMA) would be ~1e-3 and miss the 1e-4 north-star tolerance.
+// CTA tile 64 x 128 x 32, 8 warps of 32 x 32, operands padded to a stride of
+// 36 floats so that the fragment loads are bank-conflict free.
+#define TC_BM 64
+#define TC_BN 128
+#define TC_BK 32
+#define TC_LD 36
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c) {
+  extern __shared__ __align__(16) unsigned char tc_smem[];
+  uint32_t *As_hi = reinterpret_cast<uint32_t *>(tc_smem);          // [TC_BM][TC_LD]
+  uint32_t *As_lo = As_hi + TC_BM * TC_LD;
+  uint32_t *Bs_hi = As_lo + TC_BM * TC_LD;                          // [TC_BN][TC_LD]
+  uint32_t *Bs_lo = Bs_hi + TC_BN * TC_LD;
+  __shared__ const float *rowp[TC_BM];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane_id = tid & 31;
+  const int g = lane_id >> 2, t4 = lane_id & 3;
+  const int wm = warp & 1, wn = warp >> 1;                          // 2 x 4 warps
+  const int M = c.batch * op.rows;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[i][j][q] = 0.f;
+
+  // staging: thread -> (row = idx >> 5, k = idx & 31), 8 A elements and 16 B elements per slab
+  float ra[8], rb[16];
+  for (int ti = 0; ti < op.n_terms; ti++) {
+    const TermDev t = op.terms[ti];
+    __syncthreads();
+    if (tid < TC_BM) {
+      int r = m0 + tid;
+      const float *p = nullptr;
+      if (r < M) {
+        int lane = r / op.rows, i = r - lane * op.rows;
+        p = src_row_ptr(c, t, lane, map_row(t, i));
+      }
+      rowp[tid] = p;
+    }
+    __syncthreads();
+    auto fetch = [&](int kk) {
+      const int k = kk + lane_id;
+      const bool kin = k < t.klen;
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const float *p = rowp[warp + e * 8];
+        ra[e] = (p && kin) ? p[k] : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const int n = n0 + warp + e * 8;
+        rb[e] = (n < op.N && kin) ? __ldg(&op.w[(long long)n * op.K + t.k0 + k]) : 0.f;
+      }
+    };
+    fetch(0);
+    for (int kk = 0; kk < t.klen; kk += TC_BK) {
+      // registers -> shared (split)
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const uint32_t hi = to_tf32(ra[e]);
+        As_hi[(warp + e * 8) * TC_LD + lane_id] = hi;
+        As_lo[(warp + e * 8) * TC_LD + lane_id] = to_tf32(ra[e] - __uint_as_float(hi));
+      }
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const uint32_t hi = to_tf32(rb[e]);
+        Bs_hi[(warp + e * 8) * TC_LD + lane_id] = hi;
+        Bs_lo[(warp + e * 8) * TC_LD + lane_id] = to_tf32(rb[e] - __uint_as_float(hi));
+      }
+      __syncthreads();
+      if (kk + TC_BK < t.klen) fetch(kk + TC_BK);                   // next slab in flight during the MMAs
+#pragma unroll
+      for (int ks = 0; ks < TC_BK; ks += 8) {
+        uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+          const int r = wm * 32 + mi * 16 + g;
+          const int o0 = r * TC_LD + ks + t4, o1 = (r + 8) * TC_LD + ks + t4;
+          ah[mi][0] = As_hi[o0]; ah[mi][1] = As_hi[o1]; ah[mi][2] = As_hi[o0 + 4]; ah[mi][3] = As_hi[o1 + 4];
+          al[mi][0] = As_lo[o0]; al[mi][1] = As_lo[o1]; al[mi][2] = As_lo[o0 + 4]; al[mi][3] = As_lo[o1 + 4];
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+          const int o = (wn * 32 + ni * 8 + g) * TC_LD + ks + t4;
+          bh[ni][0] = Bs_hi[o]; bh[ni][1] = Bs_hi[o + 4];
+          bl[ni][0] = Bs_lo[o]; bl[ni][1] = Bs_lo[o + 4];
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) {
+            mma_tf32(acc[mi][ni], al[mi], bh[ni]);
+            mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
+            mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
+          }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- epilogue (same fused chain as the SIMT kernel); c0,c1 -> row g, c2,c3 -> row g + 8
+#pragma unroll
+  for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const int r = m0 + wm * 32 + mi * 16 + g + half * 8;
+      if (r >= M) continue;
+      const int lane = r / op.rows, ri = r - lane * op.rows;
+      float *orow = (op.out_kind == 0)
+                        ? c.arena + (long long)lane * c.arena_stride + op.out_off + (long long)ri * op.out_dim
+                        : c.d_out[lane] + (long long)ri * c.out_stride;
+      const float *rrow = nullptr;
+      if (op.has_res) rrow = src_row_ptr(c, op.res, lane, map_row(op.res, ri));
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int n = n0 + wn * 32 + ni * 8 + 2 * t4 + q;
+          if (n >= op.N) continue;
+          float v = acc[mi][ni][half * 2 + q];
+          if (op.bias) v = __fadd_rn(v, __ldg(&op.bias[n]));
+          if (op.relu) v = fmaxf(v, 0.f);
+          if (op.bn_scale) v = __fadd_rn(__fmul_rn(v, __ldg(&op.bn_scale[n])), __ldg(&op.bn_offset[n]));
+          if (rrow) v = __fadd_rn(__fmul_rn(op.res_alpha, rrow[n]), v);
+          if (!op.log_softmax) {
+            if (op.sub_vec) v = __fadd_rn(v, -__ldg(&op.sub_vec[n]));
+            if (op.out_scale != 1.0f) v = __fmul_rn(v, op.out_scale);
+          }
+          orow[n] = v;
+        }
+    }
+}
+
 // out[r, blk*block_dim + c] = sum_terms(scale * src[map(r), c]) (+ BatchNorm)
 __global__ void nnet_ew_kernel(OpDev op, RunCtx c) {
   const long long total = (long long)c.batch * op.rows * op.out_dim;
@@ -237,6 +396,13 @@ struct b2k_nnet {
   cudaEvent_t staging_free = nullptr;
   double flops_per_lane = 0;
 };
+
+// B2K_NNET_GEMM=simt selects the fp32 FFMA kernel (kept for A/B numerics and timing)
+static bool use_simt_gemm() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("B2K_NNET_GEMM"); v = (e && !strcmp(e, "simt")) ? 1 : 0; }
+  return v == 1;
+}
 
 extern "C" {
 
@@ -337,8 +503,19 @@ int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32
     const OpDev &op = nn->ops[i];
     long long M = (long long)batch * op.rows;
     if (op.type == 0) {
-      dim3 grid((op.N + GM_BN - 1) / GM_BN, (unsigned)((M + GM_BM - 1) / GM_BM));
-      nnet_gemm_kernel<<<grid, 256, 0, st>>>(op, c);
+      if (use_simt_gemm()) {
+        dim3 grid((op.N + GM_BN - 1) / GM_BN, (unsigned)((M + GM_BM - 1) / GM_BM));
+        nnet_gemm_kernel<<<grid, 256, 0, st>>>(op, c);
+      } else {
+        static bool configured = false;
+        const int smem = (int)(sizeof(uint32_t) * 2 * (TC_BM + TC_BN) * TC_LD);
+        if (!configured) {
+          B2K_CUDA_CHECK(cudaFuncSetAttribute(nnet_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+          configured = true;
+        }
+        dim3 grid((op.N + TC_BN - 1) / TC_BN, (unsigned)((M + TC_BM - 1) / TC_BM));
+        nnet_gemm_tc_kernel<<<grid, 256, smem, st>>>(op, c);
+      }
       B2K_LAUNCH_CHECK();
       if (nn->log_softmax[i]) {
         long long threads = M * 32;
