@@ -111,7 +111,7 @@ struct DecParams {
   uint32_t *x_bm;           // [pos_cap/32] bitmap of first-admission positions
   int32_t *x_wbase;         // [pos_cap/32]
   int32_t *x_by_ins;        // [max_tpf] insertion index -> hash slot
-  int32_t *x_bfirst, *x_bcount, *x_bfill;   // [hc_cap] per HashList bucket
+  int4 *x_bk;               // [hc_cap] per HashList bucket {first insertion index, population, fill cursor, -}
   int32_t *x_sbase;         // [max_tpf]
   int32_t *x_run;           // [max_tpf]
   int32_t *x_order;         // [max_tpf] list rank -> insertion index
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
 // replay of the LIFO worklist (:858-896) -- the one inherently sequential piece.
 
 struct XScratch {
-  uint32_t *bm; int32_t *wbase, *by_ins, *bfirst, *bcount, *bfill, *sbase, *run, *order, *queue, *xb;
+  uint32_t *bm; int32_t *wbase, *by_ins, *sbase, *run, *order, *queue, *xb; int4 *bk;
   int4 *rec; int32_t *newseq; int4 *adj; int32_t *adjo;
 };
 
@@ -769,8 +769,8 @@ __device__ void bucket_scatter(int k0, int k1, int Hc, const int4 *hash, const X
     int slot = x.by_ins[k];
     int b = (int)((uint32_t)hash[slot].x % (uint32_t)Hc);
     x.xb[k] = b;
-    atomicMin(&x.bfirst[b], k);
-    atomicAdd(&x.bcount[b], 1);
+    atomicMin(&x.bk[b].x, k);
+    atomicAdd(&x.bk[b].y, 1);
   }
   __syncthreads();
 }
@@ -778,47 +778,54 @@ __device__ void bucket_scatter(int k0, int k1, int Hc, const int4 *hash, const X
 template <int T>
 __device__ void order_finish(int N, const XScratch &x, DecShared<T> &s) {
   const int tid = threadIdx.x;
+  const int4 kEmptyBucket = make_int4(0x7fffffff, 0, 0, 0);
   __syncthreads();
+  // list position of every bucket head = exclusive scan of the bucket populations in
+  // first-insertion order.  A bucket with one token (the common case) is finished here.
   int carry = 0;
   for (int base = 0; base < N; base += T) {
-    int k = base + tid, w = 0;
+    int k = base + tid, w = 0, b = 0;
     if (k < N) {
-      int b = x.xb[k];
-      if (x.bfirst[b] == k) w = x.bcount[b];
+      b = x.xb[k];
+      int4 bk = x.bk[b];
+      if (bk.x == k) w = bk.y;
     }
     int total;
     int excl = block_excl_scan<T>(w, s.redi, &total);
-    if (k < N) x.sbase[k] = carry + excl;
+    if (k < N) {
+      if (w == 1) {
+        x.order[carry + excl] = k;
+        x.bk[b] = kEmptyBucket;
+        x.xb[k] = -1;
+      } else {
+        x.sbase[k] = carry + excl;                   // only read through bucket heads
+      }
+    }
     carry += total;
   }
   __syncthreads();
   for (int k = tid; k < N; k += T) {
     int b = x.xb[k];
-    int first = x.bfirst[b], cnt = x.bcount[b];
-    int rb = x.sbase[first];
-    if (cnt == 1) {                                  // the common case: done, and the bucket can be reset now
-      x.order[rb] = k;
-      x.bfirst[b] = 0x7fffffff; x.bcount[b] = 0;
-      x.xb[k] = -1;
-    } else {
-      int q = atomicAdd(&x.bfill[b], 1);
-      x.run[rb + q] = k;
-    }
+    if (b < 0) continue;
+    int rb = x.sbase[x.bk[b].x];
+    int q = atomicAdd(&x.bk[b].z, 1);
+    x.run[rb + q] = k;
   }
   __syncthreads();
   for (int k = tid; k < N; k += T) {
     int b = x.xb[k];
     if (b < 0) continue;
-    int rb = x.sbase[x.bfirst[b]];
-    int cnt = x.bcount[b], within = 0;
-    for (int j = 0; j < cnt; j++) within += (x.run[rb + j] < k);
+    int4 bk = x.bk[b];
+    int rb = x.sbase[bk.x];
+    int within = 0;
+    for (int j = 0; j < bk.y; j++) within += (x.run[rb + j] < k);
     x.order[rb + within] = k;
   }
   __syncthreads();
   for (int k = tid; k < N; k += T) {
     int b = x.xb[k];
     if (b < 0) continue;
-    x.bfirst[b] = 0x7fffffff; x.bcount[b] = 0; x.bfill[b] = 0;
+    x.bk[b] = kEmptyBucket;
   }
   __syncthreads();
 }
@@ -1019,7 +1026,7 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
     for (int d = tid; d < N1; d += T) {
       if (!mark[d] || x.rec[d].z <= 0) continue;
       int q = atomicAdd(&s.rs_n, 1);
-      if (q < key_cap) keys[q] = ((unsigned long long)(uint32_t)x.bfirst[x.xb[d]] << 32) | (uint32_t)d;
+      if (q < key_cap) keys[q] = ((unsigned long long)(uint32_t)x.bk[x.xb[d]].x << 32) | (uint32_t)d;
     }
     __syncthreads();
     qcarry = s.rs_n;
@@ -1104,10 +1111,38 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
     if (s.rs_ok) {
       const int R = s.rs_n;
       const int lane_id = tid & 31;
-      for (int id = tid >> 5; id < R; id += T / 32) {        // one warp per record
+      // small records (the vast majority): one thread each; hub records: one warp each
+      if (tid == 0) s.ncand = 0;
+      __syncthreads();
+      int *big_list = x.run;                                 // idle between the two list-order passes
+      for (int id = tid; id < R; id += T) {
         const int d = dof[id];
         const int4 r = x.rec[d];
         if (!mark[d] || r.z == 0) continue;                  // destination only
+        if (r.y > 8) { big_list[atomicAdd(&s.ncand, 1)] = id; continue; }
+        int4 en[8];
+        int total = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          en[i] = (i < r.y) ? x.adj[r.x + i] : make_int4(0, 0x7f800000, 0, -1);
+          total += (en[i].w >= 0 && en[i].y != 0x7f800000);
+        }
+        if (!total) continue;
+        const int eo = atomicAdd(&s.rs_e, total);
+        if (eo + total > p.rs_ecap) { s.rs_ok = 0; continue; }
+        int pos = eo;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (en[i].w >= 0 && en[i].y != 0x7f800000)
+            en_s[pos++] = make_float2(__int_as_float(en[i].y), __int_as_float(cid[en[i].x]));
+        tk_s[id].y = __int_as_float(eo | (total << 16));
+      }
+      __syncthreads();
+      const int nbig = s.ncand;
+      for (int bi = tid >> 5; bi < nbig; bi += T / 32) {     // one warp per hub record
+        const int id = big_list[bi];
+        const int d = dof[id];
+        const int4 r = x.rec[d];
         int total = 0;
         for (int b0 = 0; b0 < r.y; b0 += 32) {
           int i = b0 + lane_id;
@@ -1284,8 +1319,9 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   if (!s.err) {
     for (int r = tid; r < N; r += T) {
       int slot = x.by_ins[x.order[r]];
-      tok_state[ctx.tbase + r] = hash[slot].x;
-      tok_cost[ctx.tbase + r] = ord2f((uint32_t)hash[slot].y);
+      const int4 hs = hash[slot];
+      tok_state[ctx.tbase + r] = hs.x;
+      tok_cost[ctx.tbase + r] = ord2f((uint32_t)hs.y);
       hash[slot].w = r;
     }
   }
@@ -1353,9 +1389,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
   x.bm = p.x_bm + (size_t)lane * (p.pos_cap / 32);
   x.wbase = p.x_wbase + (size_t)lane * (p.pos_cap / 32);
   x.by_ins = p.x_by_ins + (size_t)lane * p.max_tpf;
-  x.bfirst = p.x_bfirst + (size_t)lane * p.hc_cap;
-  x.bcount = p.x_bcount + (size_t)lane * p.hc_cap;
-  x.bfill = p.x_bfill + (size_t)lane * p.hc_cap;
+  x.bk = p.x_bk + (size_t)lane * p.hc_cap;
   x.sbase = p.x_sbase + (size_t)lane * p.max_tpf;
   x.run = p.x_run + (size_t)lane * p.max_tpf;
   x.order = p.x_order + (size_t)lane * p.max_tpf;
@@ -1641,7 +1675,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
   }
   if (s.err) {
     reset_lane_hash<T>(ctx.hash, p.hash_size);
-    for (int i = tid; i < p.hc_cap; i += T) { x.bfirst[i] = 0x7fffffff; x.bcount[i] = 0; x.bfill[i] = 0; }
+    for (int i = tid; i < p.hc_cap; i += T) x.bk[i] = make_int4(0x7fffffff, 0, 0, 0);
   }
 }
 
@@ -2086,9 +2120,7 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
     A(p.x_bm, 4 * nl * (p.pos_cap / 32), 0);
     A(p.x_wbase, 4 * nl * (p.pos_cap / 32), 0);
     A(p.x_by_ins, 4 * nl * p.max_tpf, 0);
-    A(p.x_bfirst, 4 * nl * p.hc_cap, 0);
-    A(p.x_bcount, 4 * nl * p.hc_cap, 0);
-    A(p.x_bfill, 4 * nl * p.hc_cap, 0);
+    A(p.x_bk, sizeof(int4) * nl * p.hc_cap, 0);
     A(p.x_sbase, 4 * nl * p.max_tpf, 0);
     A(p.x_run, 4 * nl * p.max_tpf, 0);
     A(p.x_order, 4 * nl * p.max_tpf, 0);
@@ -2108,8 +2140,9 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
     A(p.x_adj, sizeof(int4) * nl * p.adj_cap, 0);
     A(p.x_adjo, 4 * nl * p.adj_cap, 0);
     {
-      std::vector<int32_t> big((size_t)nl * p.hc_cap, 0x7fffffff);
-      B2K_CUDA_CHECK(cudaMemcpy(p.x_bfirst, big.data(), 4 * big.size(), cudaMemcpyHostToDevice));
+      std::vector<int4> empty((size_t)p.hc_cap, make_int4(0x7fffffff, 0, 0, 0));
+      for (size_t l = 0; l < nl; l++)
+        B2K_CUDA_CHECK(cudaMemcpy(p.x_bk + l * p.hc_cap, empty.data(), sizeof(int4) * empty.size(), cudaMemcpyHostToDevice));
     }
   }
   p.cap_ls = cfg->max_lattice_states > 0 ? cfg->max_lattice_states : 131072;
