@@ -1633,6 +1633,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
       __syncthreads();
       for (int i = tid; i < N1; i += T) {
         int seq = ctx.hash[ctx.tokslot[i]].z;
+        x.sbase[i] = seq;                                     // (scratch: idle until order_finish)
         atomicOr(&x.bm[seq >> 5], 1u << (seq & 31));
       }
       __syncthreads();
@@ -1648,7 +1649,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
       __syncthreads();
       for (int i = tid; i < N1; i += T) {
         int slot = ctx.tokslot[i];
-        int seq = ctx.hash[slot].z;
+        int seq = x.sbase[i];
         int ins = x.wbase[seq >> 5] + __popc(x.bm[seq >> 5] & ((1u << (seq & 31)) - 1u));
         ctx.hash[slot].z = ins;
         x.by_ins[ins] = slot;

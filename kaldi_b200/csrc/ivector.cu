@@ -174,7 +174,7 @@ __device__ __forceinline__ double sp_at(const double *q, int i, int j) {   // pa
   return (i >= j) ? q[(size_t)i * (i + 1) / 2 + j] : q[(size_t)j * (j + 1) / 2 + i];
 }
 
-#define IVS_THREADS 128
+#define IVS_THREADS 512
 
 __global__ void __launch_bounds__(IVS_THREADS) ivec_stats_cg_kernel(IvecParams p, IvecRun r) {
   extern __shared__ double sd[];
@@ -378,7 +378,7 @@ int b2k_ivec_create(const b2k_ivec_cfg *cfg, const float *lda, const float *gcon
   B2K_CUDA_CHECK(cudaMallocHost((void **)&iv->h_sched, 4 * 4096));
   B2K_CUDA_CHECK(cudaEventCreateWithFlags(&iv->staging_free, cudaEventDisableTiming));
   iv->smem_front = sizeof(float) * ((size_t)F * (SD + 1) + IV_WARPS * (2 * (size_t)SD + F));
-  iv->smem_stats = sizeof(double) * ((size_t)Q + 5 * D + F + 8);
+  iv->smem_stats = sizeof(double) * ((size_t)Q + 5 * D + F + 32);
   B2K_CUDA_CHECK(cudaFuncSetAttribute(ivec_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv->smem_front));
   B2K_CUDA_CHECK(cudaFuncSetAttribute(ivec_stats_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv->smem_stats));
   *out = iv;

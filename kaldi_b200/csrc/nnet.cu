@@ -181,10 +181,10 @@ __global__ void __launch_bounds__(256) nnet_gemm_kernel(OpDev op, RunCtx c) {
 // first), which keeps the log-likelihoods within ~1e-6 relative of the fp32
 // CPU reference (the dropped a_lo*b_lo term is 2^-22 relative) -- plain TF32
 // (one MMA) would be ~1e-3 and miss the 1e-4 north-star tolerance.
-// CTA tile 64 x 128 x 32, 8 warps of 32 x 32, operands padded to a stride of
-// 36 floats so that the fragment loads are bank-conflict free.
+// CTA tile 64 x (32*NT) x 32 with NT = 4 or 3 (N = 96 / 192 layers), 8 warps of
+// 32 x (8*NT), operands padded to a stride of 36 floats so that the fragment
+// loads are bank-conflict free.
 #define TC_BM 64
-#define TC_BN 128
 #define TC_BK 32
 #define TC_LD 36
 
@@ -201,7 +201,9 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+template <int NT>
 __global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c) {
+  constexpr int TC_BN = 32 * NT;
   extern __shared__ __align__(16) unsigned char tc_smem[];
   uint32_t *As_hi = reinterpret_cast<uint32_t *>(tc_smem);          // [TC_BM][TC_LD]
   uint32_t *As_lo = As_hi + TC_BM * TC_LD;
@@ -214,16 +216,16 @@ __global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c
   const int wm = warp & 1, wn = warp >> 1;                          // 2 x 4 warps
   const int M = c.batch * op.rows;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
-  float acc[2][4][4];
+  float acc[2][NT][4];
 #pragma unroll
   for (int i = 0; i < 2; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+    for (int j = 0; j < NT; j++)
 #pragma unroll
       for (int q = 0; q < 4; q++) acc[i][j][q] = 0.f;
 
   // staging: thread -> (row = idx >> 5, k = idx & 31), 8 A elements and 16 B elements per slab
-  float ra[8], rb[16];
+  float ra[8], rb[TC_BN / 8];
   for (int ti = 0; ti < op.n_terms; ti++) {
     const TermDev t = op.terms[ti];
     __syncthreads();
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c
         ra[e] = (p && kin) ? p[k] : 0.f;
       }
 #pragma unroll
-      for (int e = 0; e < 16; e++) {
+      for (int e = 0; e < TC_BN / 8; e++) {
         const int n = n0 + warp + e * 8;
         rb[e] = (n < op.N && kin) ? __ldg(&op.w[(long long)n * op.K + t.k0 + k]) : 0.f;
       }
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c
         As_lo[(warp + e * 8) * TC_LD + lane_id] = to_tf32(ra[e] - __uint_as_float(hi));
       }
 #pragma unroll
-      for (int e = 0; e < 16; e++) {
+      for (int e = 0; e < TC_BN / 8; e++) {
         const uint32_t hi = to_tf32(rb[e]);
         Bs_hi[(warp + e * 8) * TC_LD + lane_id] = hi;
         Bs_lo[(warp + e * 8) * TC_LD + lane_id] = to_tf32(rb[e] - __uint_as_float(hi));
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c
       if (kk + TC_BK < t.klen) fetch(kk + TC_BK);                   // next slab in flight during the MMAs
 #pragma unroll
       for (int ks = 0; ks < TC_BK; ks += 8) {
-        uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+        uint32_t ah[2][4], al[2][4], bh[NT][2], bl[NT][2];
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) {
           const int r = wm * 32 + mi * 16 + g;
@@ -279,15 +281,15 @@ __global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c
           al[mi][0] = As_lo[o0]; al[mi][1] = As_lo[o1]; al[mi][2] = As_lo[o0 + 4]; al[mi][3] = As_lo[o1 + 4];
         }
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
-          const int o = (wn * 32 + ni * 8 + g) * TC_LD + ks + t4;
+        for (int ni = 0; ni < NT; ni++) {
+          const int o = (wn * 8 * NT + ni * 8 + g) * TC_LD + ks + t4;
           bh[ni][0] = Bs_hi[o]; bh[ni][1] = Bs_hi[o + 4];
           bl[ni][0] = Bs_lo[o]; bl[ni][1] = Bs_lo[o + 4];
         }
 #pragma unroll
         for (int mi = 0; mi < 2; mi++)
 #pragma unroll
-          for (int ni = 0; ni < 4; ni++) {
+          for (int ni = 0; ni < NT; ni++) {
             mma_tf32(acc[mi][ni], al[mi], bh[ni]);
             mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
             mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
@@ -310,10 +312,10 @@ __global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c
       const float *rrow = nullptr;
       if (op.has_res) rrow = src_row_ptr(c, op.res, lane, map_row(op.res, ri));
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++)
+      for (int ni = 0; ni < NT; ni++)
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-          const int n = n0 + wn * 32 + ni * 8 + 2 * t4 + q;
+          const int n = n0 + wn * 8 * NT + ni * 8 + 2 * t4 + q;
           if (n >= op.N) continue;
           float v = acc[mi][ni][half * 2 + q];
           if (op.bias) v = __fadd_rn(v, __ldg(&op.bias[n]));
@@ -508,13 +510,21 @@ int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32
         nnet_gemm_kernel<<<grid, 256, 0, st>>>(op, c);
       } else {
         static bool configured = false;
-        const int smem = (int)(sizeof(uint32_t) * 2 * (TC_BM + TC_BN) * TC_LD);
+        const int smem4 = (int)(sizeof(uint32_t) * 2 * (TC_BM + 128) * TC_LD), smem3 = (int)(sizeof(uint32_t) * 2 * (TC_BM + 96) * TC_LD);
         if (!configured) {
-          B2K_CUDA_CHECK(cudaFuncSetAttribute(nnet_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+          B2K_CUDA_CHECK(cudaFuncSetAttribute(nnet_gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+          B2K_CUDA_CHECK(cudaFuncSetAttribute(nnet_gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
           configured = true;
         }
-        dim3 grid((op.N + TC_BN - 1) / TC_BN, (unsigned)((M + TC_BM - 1) / TC_BM));
-        nnet_gemm_tc_kernel<<<grid, 256, smem, st>>>(op, c);
+        // column tile 128 or 96, whichever pads N less (the N = 96 / 192 bottlenecks of TDNN-F)
+        const int pad4 = (op.N + 127) / 128 * 128, pad3 = (op.N + 95) / 96 * 96;
+        if (pad3 < pad4) {
+          dim3 grid(pad3 / 96, (unsigned)((M + TC_BM - 1) / TC_BM));
+          nnet_gemm_tc_kernel<3><<<grid, 256, smem3, st>>>(op, c);
+        } else {
+          dim3 grid(pad4 / 128, (unsigned)((M + TC_BM - 1) / TC_BM));
+          nnet_gemm_tc_kernel<4><<<grid, 256, smem4, st>>>(op, c);
+        }
       }
       B2K_LAUNCH_CHECK();
       if (nn->log_softmax[i]) {
