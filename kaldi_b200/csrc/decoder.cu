@@ -862,12 +862,35 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   // replay then walks those dense records only.
   int32_t *wl0 = p.wl + (size_t)lane * 2 * p.max_tpf;
   int32_t *wl1 = wl0 + p.max_tpf;
-  for (int d = tid; d < N1; d += T) {
-    int slot = x.by_ins[d];
-    x.rec[d] = make_int4(0, 0, 0, __float_as_int(ord2f((uint32_t)hash[slot].y)));   // cost after ProcessEmitting
-    wl0[d] = slot;
+  // cost after ProcessEmitting per dense index, and the first worklist: only the tokens
+  // that are below the cutoff and have eps arcs at all (compacted, with what the first
+  // round needs: {cost, first eps arc, eps out-degree, dense index})
+  int4 *wlx = reinterpret_cast<int4 *>(x.queue);              // idle until the replay worklist is built
+  if (tid == 0) { s.wl_n[0] = 0; s.wl_n[1] = 0; s.q_n = 0; }
+  __syncthreads();
+  for (int base = 0; base < N1; base += T) {
+    const int d = base + tid;
+    int deg = 0, ebeg = 0, cbits = 0;
+    if (d < N1) {
+      const int4 hs = hash[x.by_ins[d]];
+      const float c0 = ord2f((uint32_t)hs.y);
+      cbits = __float_as_int(c0);
+      x.rec[d] = make_int4(0, 0, 0, cbits);
+      if (c0 < cutoff) {
+        int2 o0 = __ldg(&g.st_off[hs.x]), o1 = __ldg(&g.st_off[hs.x + 1]);
+        ebeg = o0.y; deg = o1.y - o0.y;
+      }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, deg > 0);
+    if (m) {
+      int wb = 0;
+      if ((tid & 31) == 0) wb = atomicAdd(&s.wl_n[0], __popc(m));
+      wb = __shfl_sync(0xffffffffu, wb, 0);
+      if (deg > 0) wlx[wb + __popc(m & ((1u << (tid & 31)) - 1u))] = make_int4(cbits, ebeg, deg, d);
+    }
   }
-  if (tid == 0) { s.wl_n[0] = N1; s.wl_n[1] = 0; s.cont = (N1 > 0 && !s.err); s.q_n = 0; }
+  __syncthreads();
+  if (tid == 0) s.cont = (s.wl_n[0] > 0 && !s.err);
   __syncthreads();
   B2K_TICK(s, 4);
   // Each relaxation round expands its worklist ARC-parallel (eps out-degrees are very
@@ -876,6 +899,7 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   // cutoff get weight +inf so that the replay skips them.
   {
     int cur = 0;
+    bool first_round = true;
     const int kInfBits = 0x7f800000;
     while (s.cont) {
       const int n = s.wl_n[cur];
@@ -887,11 +911,17 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
         int deg = 0, ebeg = 0, dd = 0;
         float c = 0.f;
         if (k < n) {
-          int4 hs = __ldcg(&hash[in[k]]);                     // cost may be lowered concurrently: read at L2
-          c = ord2f((uint32_t)hs.y);
-          if (c < cutoff) {
-            int2 o0 = __ldg(&g.st_off[hs.x]), o1 = __ldg(&g.st_off[hs.x + 1]);
-            ebeg = o0.y; deg = o1.y - o0.y; dd = hs.z;
+          if (first_round) {
+            // (a cost lowered since the snapshot re-queues the token, so the snapshot is as good as a fresh read)
+            const int4 w = wlx[k];
+            c = __int_as_float(w.x); ebeg = w.y; deg = w.z; dd = w.w;
+          } else {
+            int4 hs = __ldcg(&hash[in[k]]);                   // cost may be lowered concurrently: read at L2
+            c = ord2f((uint32_t)hs.y);
+            if (c < cutoff) {
+              int2 o0 = __ldg(&g.st_off[hs.x]), o1 = __ldg(&g.st_off[hs.x + 1]);
+              ebeg = o0.y; deg = o1.y - o0.y; dd = hs.z;
+            }
           }
         }
         int total;
@@ -957,6 +987,7 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
         s.cont = (s.wl_n[cur ^ 1] > 0 && !s.err);
       }
       cur ^= 1;
+      first_round = false;
       __syncthreads();
     }
   }
