@@ -311,9 +311,12 @@ struct __align__(16) DecShared {
   int redi[T / 32 + 1];
   uint32_t hist[256];
   uint32_t pref[2];
-  int chunk_off[T + 1];
-  int chunk_ebeg[T];
-  float chunk_cost[T];
+  static constexpr int TPT = (T >= 512) ? 1024 / T : 4;   // tokens per thread in an expansion chunk (shared memory is
+                                                          // also L1: 2048-token chunks cost more in hit rate than they save)
+  static constexpr int CT = T * TPT;                      // tokens per expansion chunk
+  int chunk_off[CT + 1];
+  int chunk_ebeg[CT];
+  float chunk_cost[CT];
   int chunk_d[T];
   int ntok_new, nlink_new, ncand, err, err_line;
   int wl_n[2];
@@ -1546,25 +1549,37 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
     float carry = kInf;
     int pos_base = 0;
     int round_no = 0;
-    for (int cb = pb; cb < pe; cb += T) {
-      int i = cb + tid;
-      int deg = 0, ebeg = 0;
-      float c = 0.f;
-      if (i < pe) {
-        c = tok_cost[i];
-        if (c <= cur_cutoff) {
-          int st = tok_state[i];
-          int2 o0 = __ldg(&g.st_off[st]), o1 = __ldg(&g.st_off[st + 1]);
-          ebeg = o0.x;
-          deg = o1.x - o0.x;
+    // Tokens are expanded in chunks of CT = T * TPT: the chunk's out-degrees are scanned
+    // once, then its arcs are processed ARC-parallel in list order (rounds of T * IT arcs).
+    constexpr int TPT = DecShared<T>::TPT, CT = DecShared<T>::CT;
+    for (int cb = pb; cb < pe; cb += CT) {
+#pragma unroll
+      for (int u = 0; u < TPT; u++) {                       // striped (coalesced) loads
+        const int q = u * T + tid, i = cb + q;
+        int deg = 0, ebeg = 0;
+        float c = 0.f;
+        if (i < pe) {
+          c = tok_cost[i];
+          if (c <= cur_cutoff) {
+            int st = tok_state[i];
+            int2 o0 = __ldg(&g.st_off[st]), o1 = __ldg(&g.st_off[st + 1]);
+            ebeg = o0.x;
+            deg = o1.x - o0.x;
+          }
         }
+        s.chunk_off[q] = deg; s.chunk_ebeg[q] = ebeg; s.chunk_cost[q] = c;
       }
+      __syncthreads();
       int total;
-      int off = block_excl_scan<T>(deg, s.redi, &total);
-      s.chunk_off[tid] = off;
-      s.chunk_ebeg[tid] = ebeg;
-      s.chunk_cost[tid] = c;
-      if (tid == 0) { s.chunk_off[T] = total; arcs_e_total += (unsigned long long)total; }
+      {                                                      // blocked exclusive scan of the degrees
+        int dloc[TPT], sum = 0;
+#pragma unroll
+        for (int u = 0; u < TPT; u++) { dloc[u] = s.chunk_off[tid * TPT + u]; sum += dloc[u]; }
+        int off = block_excl_scan<T>(sum, s.redi, &total);
+#pragma unroll
+        for (int u = 0; u < TPT; u++) { s.chunk_off[tid * TPT + u] = off; off += dloc[u]; }
+      }
+      if (tid == 0) { s.chunk_off[CT] = total; arcs_e_total += (unsigned long long)total; }
       __syncthreads();
       for (int r0 = 0; r0 < total; r0 += T * IT, round_no++) {
         const int j0 = r0 + tid * IT;
@@ -1572,7 +1587,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
         int arcid[IT], nexts[IT], srcs[IT];
         int lo = 0;
         if (j0 < total) {
-          int hi = T;
+          int hi = CT;
           while (hi - lo > 1) {
             int mid = (lo + hi) >> 1;
             if (s.chunk_off[mid] <= j0) lo = mid; else hi = mid;
@@ -2254,7 +2269,7 @@ static size_t exact_smem_bytes(const DecParams &p) {
 static int launch_exact(const DecParams &p, int n, cudaStream_t st) {
   const size_t smem = exact_smem_bytes(p);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > configured) {                                   // static + dynamic may exceed 48 KB: always opt in
     B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -34,7 +34,7 @@ struct IvecParams {
   const float *lda;            // [feat_dim x (spliced_dim+1)]
   const float *gconsts;        // [G]
   const float *means_invvars;  // [G x feat_dim]
-  const float *inv_vars;       // [G x feat_dim]
+  const float *inv_vars;       // [feat_dim x G] (transposed at creation, like means_invvars)
   const double *sigma_inv_m;   // [G x feat_dim x ivector_dim]
   const double *U;             // [G x ivd*(ivd+1)/2] packed lower triangle (row-major rows of growing length)
 };
@@ -98,9 +98,13 @@ __global__ void __launch_bounds__(IV_WARPS * 32) ivec_front_kernel(IvecParams p,
       int g = lane_id + 32 * i;
       float v = -INFINITY;
       if (g < p.num_gauss) {
-        const float *mv = p.means_invvars + (size_t)g * p.feat_dim, *iv = p.inv_vars + (size_t)g * p.feat_dim;
+        const float *mv = p.means_invvars + g, *iv = p.inv_vars + g;      // [feat_dim][G]
         float a1 = 0.f, a2 = 0.f;
-        for (int d = 0; d < p.feat_dim; d++) { float x = xa[d]; a1 = fmaf(__ldg(&mv[d]), x, a1); a2 = fmaf(__ldg(&iv[d]), x * x, a2); }
+        for (int d = 0; d < p.feat_dim; d++) {
+          float x = xa[d];
+          a1 = fmaf(__ldg(&mv[(size_t)d * p.num_gauss]), x, a1);
+          a2 = fmaf(__ldg(&iv[(size_t)d * p.num_gauss]), x * x, a2);
+        }
         v = __ldg(&p.gconsts[g]) + a1;
         v = v + (-0.5f) * a2;
       }
@@ -351,8 +355,18 @@ int b2k_ivec_create(const b2k_ivec_cfg *cfg, const float *lda, const float *gcon
   };
   if ((rc = up(lda, 4 * (size_t)F * (SD + 1), (const void **)&p.lda))) return rc;
   if ((rc = up(gconsts, 4 * (size_t)G, (const void **)&p.gconsts))) return rc;
-  if ((rc = up(means_invvars, 4 * (size_t)G * F, (const void **)&p.means_invvars))) return rc;
-  if ((rc = up(inv_vars, 4 * (size_t)G * F, (const void **)&p.inv_vars))) return rc;
+  {
+    // the posterior kernel reads Gaussian g = lane + 32 i: keep the UBM parameters [feat_dim][G]
+    // so that a warp's 32 Gaussians are one coalesced row segment
+    std::vector<float> mvT((size_t)G * F), ivT((size_t)G * F);
+    for (int g = 0; g < G; g++)
+      for (int d = 0; d < F; d++) {
+        mvT[(size_t)d * G + g] = means_invvars[(size_t)g * F + d];
+        ivT[(size_t)d * G + g] = inv_vars[(size_t)g * F + d];
+      }
+    if ((rc = up(mvT.data(), 4 * (size_t)G * F, (const void **)&p.means_invvars))) return rc;
+    if ((rc = up(ivT.data(), 4 * (size_t)G * F, (const void **)&p.inv_vars))) return rc;
+  }
   if ((rc = up(sigma_inv_m, 8 * (size_t)G * F * D, (const void **)&p.sigma_inv_m))) return rc;
   if ((rc = up(U, 8 * (size_t)G * Q, (const void **)&p.U))) return rc;
   if ((rc = up(global_cmvn_stats, 8 * 2 * (size_t)(cfg->base_dim + 1), (const void **)&iv->d_global))) return rc;
