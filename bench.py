@@ -172,6 +172,10 @@ def make_cpu_pool(workers: int):
 
 # ----------------------------------------------------------------------------- main
 
+# dram__bytes_read.sum + dram__bytes_write.sum of dec_advance_exact_kernel per (lane, frame), profiles/r01_final_ncu_summary.md
+NCU_DRAM_BYTES_PER_LANE_FRAME = 3.66e6
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,7 +350,11 @@ def main():
         alg_bytes = 16.0 * arcs + 16.0 * ntok + 36.0 * nlink + 16.0 * ntok
         achieved = alg_bytes / (stage_ms["decoder_advance"] / 1e3) / 1e9
         roof = dict(kernel="dec_advance_exact_kernel" if not a.order_free else "dec_advance_kernel", bound="hbm",
-                    achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"], traffic=None,
+                    achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
+                    traffic=(NCU_DRAM_BYTES_PER_LANE_FRAME * B * pipe.nnet.n_out) if not a.order_free else None,
+                    traffic_source="ncu --set full (profiles/r01_final_ncu_summary.md): dram read+write per lane-frame at 592 lanes "
+                                   "on the decoder-only synthetic load, scaled to this launch's lane-frames",
+                    algorithmic_bytes=alg_bytes,
                     peak_source=peaks["source"], marcs_per_s=arcs / (stage_ms["decoder_advance"] / 1e3) / 1e6,
                     share_of_step=stage_ms["decoder_advance"] / sum(stage_ms.values()))
     elif dom == "nnet3":
@@ -399,7 +407,7 @@ def main():
                                  links_per_frame=sum(i["nlink"] for i in infos) / (B * pipe.nnet.n_out), tokens_per_frame=ntok / (B * pipe.nnet.n_out),
                                  errors=nerr),
                     nnet3=dict(tflops=pipe.nnet.flops_per_utt * B / (stage_ms["nnet3"] / 1e3) / 1e12 * world,
-                               mma="fp32 FFMA (SIMT)"),
+                               mma="3xTF32 mma.sync m16n8k8, fp32 accumulate" if os.environ.get("B2K_NNET_GEMM") != "simt" else "fp32 FFMA (SIMT)"),
                     roofline=roof, clocks=clk)
         if cpu_base:
             line["cpu_baseline"] = cpu_base

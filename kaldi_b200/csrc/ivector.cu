@@ -180,14 +180,15 @@ __device__ __forceinline__ double sp_at(const double *q, int i, int j) {   // pa
 
 #define IVS_THREADS 512
 
-__global__ void __launch_bounds__(IVS_THREADS) ivec_stats_cg_kernel(IvecParams p, IvecRun r) {
+__global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParams p, IvecRun r) {
   extern __shared__ double sd[];
   const int D = p.ivector_dim, Q = D * (D + 1) / 2, F = p.feat_dim;
   double *quad = sd;            // Q
   double *lin = quad + Q;       // D
   double *x = lin + D, *rr = x + D, *pp = rr + D, *Ap = pp + D;   // D each
   double *xf = Ap + D;          // F (current frame features as double)
-  double *red = xf + F;         // 8
+  double *red = xf + F;         // 32
+  double *sa = red + 32;        // 8 * D: per-Gaussian dot products of the current frame
   const int tid = threadIdx.x, L = blockIdx.x;
   // OnlineIvectorEstimationStats ctor (:786-795): linear(0) = prior_offset, quadratic = I
   for (int k = tid; k < Q; k += IVS_THREADS) quad[k] = 0.0;
@@ -208,19 +209,43 @@ __global__ void __launch_bounds__(IVS_THREADS) ivec_stats_cg_kernel(IvecParams p
       const int cnt = r.post_cnt[(size_t)L * r.T + t];
       for (int d = tid; d < F; d += IVS_THREADS) xf[d] = (double)lda_raw[(size_t)t * F + d];
       __syncthreads();
-      for (int j = 0; j < cnt; j++) {
-        const int g = r.post_idx[((size_t)L * r.T + t) * 8 + j];
-        const double w = (double)r.post_val[((size_t)L * r.T + t) * 8 + j];
-        const double *SiM = p.sigma_inv_m + (size_t)g * F * D;
-        for (int i = tid; i < D; i += IVS_THREADS) {
-          double a = 0.0;
-          for (int d = 0; d < F; d++) a += SiM[(size_t)d * D + i] * xf[d];
-          lin[i] += w * a;
-        }
-        const double *Ug = p.U + (size_t)g * Q;
-        for (int k = tid; k < Q; k += IVS_THREADS) quad[k] += w * Ug[k];
-        tot_weight += w;
+      // AccStats (ivector-extractor.cc:600-648) for the <= 8 selected Gaussians of the frame.
+      // The per-Gaussian dot products run side by side (one thread per (Gaussian, dim)); the
+      // accumulations then add the Gaussians in posterior order, i.e. exactly the sequence of
+      // fused multiply-adds of a Gaussian-by-Gaussian loop.
+      const size_t pb = ((size_t)L * r.T + t) * 8;
+      int gj[8];
+      double wj[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        gj[j] = (j < cnt) ? r.post_idx[pb + j] : 0;
+        wj[j] = (j < cnt) ? (double)r.post_val[pb + j] : 0.0;
       }
+      for (int q = tid; q < cnt * D; q += IVS_THREADS) {
+        const int j = q / D, i = q - j * D;
+        const double *SiM = p.sigma_inv_m + (size_t)r.post_idx[pb + j] * F * D;
+        double a = 0.0;
+        for (int d = 0; d < F; d++) a += SiM[(size_t)d * D + i] * xf[d];
+        sa[q] = a;
+      }
+      __syncthreads();
+      for (int i = tid; i < D; i += IVS_THREADS) {
+        double l = lin[i];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (j < cnt) l += wj[j] * sa[j * D + i];
+        lin[i] = l;
+      }
+      for (int k = tid; k < Q; k += IVS_THREADS) {
+        double qv = quad[k];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (j < cnt) qv += wj[j] * __ldg(&p.U[(size_t)gj[j] * Q + k]);
+        quad[k] = qv;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < cnt) tot_weight += wj[j];
       __syncthreads();
     }
     if (any) {
@@ -392,7 +417,7 @@ int b2k_ivec_create(const b2k_ivec_cfg *cfg, const float *lda, const float *gcon
   B2K_CUDA_CHECK(cudaMallocHost((void **)&iv->h_sched, 4 * 4096));
   B2K_CUDA_CHECK(cudaEventCreateWithFlags(&iv->staging_free, cudaEventDisableTiming));
   iv->smem_front = sizeof(float) * ((size_t)F * (SD + 1) + IV_WARPS * (2 * (size_t)SD + F));
-  iv->smem_stats = sizeof(double) * ((size_t)Q + 5 * D + F + 32);
+  iv->smem_stats = sizeof(double) * ((size_t)Q + 5 * D + F + 32 + 8 * (size_t)D);
   B2K_CUDA_CHECK(cudaFuncSetAttribute(ivec_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv->smem_front));
   B2K_CUDA_CHECK(cudaFuncSetAttribute(ivec_stats_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv->smem_stats));
   *out = iv;

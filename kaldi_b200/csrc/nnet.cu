@@ -18,10 +18,11 @@
 // commands per chunk (nnet3/nnet-compute.cc:236-459) and its three-pass
 // ReLU/BatchNorm kernels with ~35 launches per batch.
 //
-// Numerics: float32 inputs, float32 accumulation (FFMA), so log-likelihoods
-// stay within ~1e-6 relative of the CPU reference (north star: 1e-4).
-// This first version is a shared-memory tiled SIMT GEMM; see DESIGN.md for the
-// tcgen05 3xTF32 plan that replaces the inner product.
+// Numerics: float32 inputs; the GEMM runs on the tensor cores as 3xTF32 (hi/lo
+// operand split, fp32 accumulation: nnet_gemm_tc_kernel below), which keeps the
+// log-likelihoods within ~1e-6 relative of the CPU reference (north star: 1e-4).
+// The fp32 FFMA kernel (nnet_gemm_kernel) is kept for A/B checks (B2K_NNET_GEMM=simt).
+// Round 2 replaces mma.sync by tcgen05 kind::tf32.
 
 #include <cstdlib>
 #include <cstring>

@@ -41,7 +41,7 @@ for mode in a.modes.split(","):
         e2.record()
         torch.cuda.synchronize()
         t_adv, t_fin = e0.elapsed_time(e1) / 1e3, e1.elapsed_time(e2) / 1e3
-        if rep > 0 and (best is None or t_adv < best[0]):
+        if (rep > 0 or a.reps == 0) and (best is None or t_adv < best[0]):
             best = (t_adv, t_fin)
     infos = [dec.ChannelInfo(c) for c in ch]
     bad = [i["status"] for i in infos if i["status"] != 0]
