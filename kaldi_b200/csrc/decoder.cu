@@ -2011,6 +2011,7 @@ struct b2k_dec {
   b2k_dec_cfg cfg;
   int nlanes, nchannels;
   DecParams p;
+  int threads_override = 0, fin_threads = 1024, num_sms = 0;   // tuning knobs, read from the environment at creation
   // launch-argument staging
   int32_t *d_lane_channel = nullptr;
   const float **d_lane_ll = nullptr;
@@ -2124,6 +2125,15 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
   if (rc) return rc;
   b2k_dec *d = new b2k_dec();
   d->fst = fst; d->cfg = *cfg; d->nlanes = nlanes; d->nchannels = nchannels;
+  {
+    // tuning knobs (defaults = measured best); read per decoder so that tests can vary them
+    if (const char *e = getenv("B2K_DEC_THREADS")) { int v = atoi(e); if (v == 128 || v == 256 || v == 512 || v == 1024) d->threads_override = v; }
+    d->fin_threads = 1024;   // one 1024-thread CTA per SM: measured 4x faster than four 256-thread CTAs
+    if (const char *e = getenv("B2K_FIN_THREADS")) { int v = atoi(e); if (v == 256 || v == 512 || v == 1024) d->fin_threads = v; }
+    int dev = 0;
+    B2K_CUDA_CHECK(cudaGetDevice(&dev));
+    B2K_CUDA_CHECK(cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   DecParams &p = d->p;
   memset(&p, 0, sizeof(p));
   p.fst = fst->dev;
@@ -2244,21 +2254,13 @@ int b2k_dec_destroy(b2k_dec *d) {
 
 #define DEC_THREADS 256
 
-static int g_dec_threads = 0, g_num_sms = 0;
 // CTA width of the reference-order kernel.  The kernel is bound by the latency/throughput of
 // scattered L2/HBM accesses, so a lane wants as many threads as the SM can give it: one
 // 1024-thread CTA per SM while the batch fits one wave, two 512-thread CTAs per SM beyond
 // that (measured on B200 at 592 lanes: 4x256 790 ms, 1x1024 758 ms, 2x512 743 ms).
-static int dec_threads(int nlanes) {
-  if (!g_dec_threads) {
-    g_dec_threads = -1;
-    if (const char *e = getenv("B2K_DEC_THREADS")) { int v = atoi(e); if (v == 128 || v == 256 || v == 512 || v == 1024) g_dec_threads = v; }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  if (g_dec_threads > 0) return g_dec_threads;
-  return nlanes <= g_num_sms ? 1024 : 512;
+static int dec_threads(const b2k_dec *d, int nlanes) {
+  if (d->threads_override > 0) return d->threads_override;
+  return nlanes <= d->num_sms ? 1024 : 512;
 }
 
 static size_t exact_smem_bytes(const DecParams &p) {
@@ -2266,7 +2268,7 @@ static size_t exact_smem_bytes(const DecParams &p) {
   return sizeof(float2) * ((size_t)p.rs_rcap + p.rs_ecap) + sizeof(unsigned short) * ((size_t)p.rs_rcap + p.rs_qcap) + 16;
 }
 
-static int launch_exact(const DecParams &p, int n, cudaStream_t st) {
+static int launch_exact(const b2k_dec *d, const DecParams &p, int n, cudaStream_t st) {
   const size_t smem = exact_smem_bytes(p);
   static size_t configured = 0;
   if (smem > configured) {                                   // static + dynamic may exceed 48 KB: always opt in
@@ -2276,7 +2278,7 @@ static int launch_exact(const DecParams &p, int n, cudaStream_t st) {
     B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const int threads = dec_threads(n);
+  const int threads = dec_threads(d, n);
   if (threads == 128) dec_advance_exact_kernel<128><<<n, 128, smem, st>>>(p);
   else if (threads == 512) dec_advance_exact_kernel<512><<<n, 512, smem, st>>>(p);
   else if (threads == 1024) dec_advance_exact_kernel<1024><<<n, 1024, smem, st>>>(p);
@@ -2318,7 +2320,7 @@ int b2k_dec_init_decoding(b2k_dec *d, const int32_t *channels, int32_t n, void *
   if (rc) return rc;
   DecParams p = d->p;
   p.do_init = 1;
-  if (d->cfg.reference_order) { if ((rc = launch_exact(p, n, st))) return rc; }
+  if (d->cfg.reference_order) { if ((rc = launch_exact(d, p, n, st))) return rc; }
   else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
   B2K_LAUNCH_CHECK();
   return B2K_OK;
@@ -2334,7 +2336,7 @@ int b2k_dec_advance_decoding_frames(b2k_dec *d, const int32_t *channels,
   DecParams p = d->p;
   p.do_init = 0;
   p.row_stride = row_stride;
-  if (d->cfg.reference_order) { if ((rc = launch_exact(p, n, st))) return rc; }
+  if (d->cfg.reference_order) { if ((rc = launch_exact(d, p, n, st))) return rc; }
   else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
   B2K_LAUNCH_CHECK();
   return B2K_OK;
@@ -2352,11 +2354,7 @@ int b2k_dec_finalize_decoding(b2k_dec *d, const int32_t *channels, int32_t n, vo
   if (rc) return rc;
   DecParams p = d->p;
   {
-    static int fin_threads = 0;
-    if (!fin_threads) {
-      fin_threads = 1024;          // one 1024-thread CTA per SM: measured 4x faster than four 256-thread CTAs (cache thrash)
-      if (const char *e = getenv("B2K_FIN_THREADS")) { int v = atoi(e); if (v == 256 || v == 512 || v == 1024) fin_threads = v; }
-    }
+    const int fin_threads = d->fin_threads;
     if (fin_threads == 1024) dec_finalize_kernel<1024><<<n, 1024, 0, st>>>(p);
     else if (fin_threads == 512) dec_finalize_kernel<512><<<n, 512, 0, st>>>(p);
     else dec_finalize_kernel<256><<<n, 256, 0, st>>>(p);

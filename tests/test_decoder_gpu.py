@@ -165,10 +165,33 @@ def test_overflow_is_reported_not_silent():
     ll = synth.make_loglikes(g, 20, seed=1)
     fst, dec = _mk(g, cfg, T=20, max_tokens=5_000, max_links=10_000)   # far too small
     _run_gpu(dec, [ll])
-    assert dec.ChannelInfo(0)["status"] == 4      # B2K_ERR_OVERFLOW
+    info = dec.ChannelInfo(0)
+    assert info["status"] == 4                    # B2K_ERR_OVERFLOW
+    assert info["err_line"] > 0                   # which capacity check fired (source line of decoder.cu)
     from kaldi_b200._lib import B2kError
-    with pytest.raises(B2kError):
+    with pytest.raises(B2kError, match=r"decoder\.cu:\d+"):
         dec.GetRawLattice(0)
+
+
+@pytest.mark.parametrize("env", [
+    {"B2K_DEC_THREADS": "512"},                    # the CTA shape used for batches larger than one wave
+    {"B2K_DEC_THREADS": "256"},
+    {"B2K_DEC_RS_CAPS": "0,0,0"},                  # replay walk over the global records, full first list order
+    {"B2K_DEC_RS_CAPS": "64,64,64"},               # small frames in shared memory, the others fall back mid-utterance
+    {"B2K_FIN_THREADS": "256"},
+], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_tuning_knobs_do_not_change_results(env, monkeypatch):
+    """Every alternative code path behind a tuning knob (CTA width, shared-memory replay
+    capacities and their fallbacks) must stay bit-exact."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = synth.make_hclg(400_000, num_pdfs=800, seed=0)
+    T = 40
+    ll = synth.make_loglikes(g, T, seed=100)
+    cfg = dict(synth.DEFAULT_DECODER_CFG)
+    fst, dec = _mk(g, cfg, T=T)
+    _run_gpu(dec, [ll])
+    _check_against_oracle(g, cfg, ll, dec, 0)
 
 
 def test_advance_before_init_is_a_state_error():
