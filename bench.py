@@ -94,8 +94,9 @@ class ClockSampler:
 # ----------------------------------------------------------------------------- CPU reference path
 
 def cpu_reference_one(args):
-    """One utterance through the reference's CPU path: compiled reference
-    features + compiled reference nnet3 (oracle/_ref) + decoder restatement."""
+    """One utterance through the reference's CPU path, all of it the reference's own
+    sources compiled in oracle/_ref: features, i-vector, nnet3 looped forward and
+    LatticeFasterDecoder (InitDecoding / AdvanceDecoding / FinalizeDecoding)."""
     seed, arch_seed = args
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     from oracle import dec_oracle as D, feat_oracle as F, nnet_oracle as NO
@@ -106,7 +107,8 @@ def cpu_reference_one(args):
         W = load_calibrated_weights(arch, arch_seed)
         _CPU_STATE["nnet"] = NO.RefNnet(arch, W)
         _CPU_STATE["feat"] = F.RefFeat()
-        _CPU_STATE["dec"] = D.DecoderOracle(g, synth.DEFAULT_DECODER_CFG)
+        from oracle import ref_decoder as RD
+        _CPU_STATE["dec"] = RD.RefDecoder(g, synth.DEFAULT_DECODER_CFG)
         from oracle import ivector_oracle as IV
         _CPU_STATE["ivx"] = IV.make_cpu_extractor(arch_seed)
     t0 = time.time()
@@ -126,9 +128,10 @@ def cpu_reference_one(args):
         mat[prev:e + 1] = civ[n]
         prev = e + 1
     ll = R.forward(feats, mat, period=1)
-    st = _CPU_STATE["dec"].decode(ll, mode=D.MODE_REFERENCE_ORDER)
+    _CPU_STATE["dec"].decode(ll, record=False)
     t2 = time.time()
-    return (t2 - t1, st["lat_states"], st["arcs_emitting"] + st["arcs_nonemitting"])
+    ns, na, _ = _CPU_STATE["dec"].lattice_sizes()
+    return (t2 - t1, ns, na)
 
 
 _CPU_STATE = {}
@@ -215,7 +218,7 @@ def main():
                     cpu_baseline=dict(value=v, unit="RTFx", cores=cores, kind="reference",
                                       sample=f"{per_step} x 10 s utterances per step, one per worker process; features+nnet3 = "
                                              "the reference's own sources compiled in oracle/_ref (OpenBLAS, 1 thread/worker), "
-                                             "decoder = oracle restatement (OpenFst absent); lattice determinization excluded"),
+                                             "decoder = the reference's lattice-faster-decoder.cc compiled against a container-only OpenFst stand-in; lattice determinization excluded"),
                     e2e=dict(value=v, unit="RTFx", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return 0
@@ -373,10 +376,10 @@ def main():
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         r = run_cpu_reference(a.cpu_utts, 1)
-        cpu_base = dict(value=r["rtfx"], unit="RTFx", cores=1, kind="port",
+        cpu_base = dict(value=r["rtfx"], unit="RTFx", cores=1, kind="reference",
                         sample=f"{a.cpu_utts} x 10 s utterances, single thread: features + nnet3 are the reference's own "
-                               "sources compiled in oracle/_ref (OpenBLAS 1 thread), decoder is the oracle restatement "
-                               "(lattice-faster-decoder.cc cannot be built without OpenFst); determinization excluded")
+                               "sources compiled in oracle/_ref (OpenBLAS 1 thread), decoder = the reference's lattice-faster-decoder.cc "
+                               "compiled against a container-only OpenFst stand-in; determinization excluded")
     if rank == 0:
         line = dict(metric="real-time factor (audio-sec/wall-sec)", value=value, unit="RTFx", n_gpus=world, steps=a.steps,
                     warmup=a.warmup, ms_per_step=1e3 * t_dev / a.steps, higher_is_better=True, scaling="weak",

@@ -84,6 +84,37 @@ def _check_against_oracle(g, cfg, ll, dec, channel, frames=True):
     return st
 
 
+def _check_against_compiled_reference(g, cfg, ll, dec, channel):
+    """Directly against the reference's own lattice-faster-decoder.cc (oracle/_ref, built by
+    oracle/ref_decoder.py): every frame's token list IN HASHLIST ORDER (= the order of the
+    channel's token arena) and the finalized raw lattice, bit for bit."""
+    from kaldi_b200.decoder import lattice_to_canonical
+    from oracle import dec_oracle as D
+    from oracle import ref_decoder as R
+    if not R.available():
+        pytest.skip("oracle/_ref decoder library not present")
+    r = R.RefDecoder(g, cfg)
+    r.decode(ll)
+    for f in range(ll.shape[0] + 1):
+        ts, tc, _ = dec.DebugFrame(channel, f)
+        st, co = r.frame_tokens(f)
+        assert np.array_equal(ts, st), f"token list order of frame {f} differs from the reference's HashList order"
+        assert np.array_equal(tc.view(np.int32), co.view(np.int32)), f"token costs of frame {f} differ"
+    assert D.lattices_equal(lattice_to_canonical(dec.GetRawLattice(channel)), r.lattice())
+
+
+@pytest.mark.parametrize("seed,cfgmod", [(0, {}), (2, {"max_active": 3000}), (4, {"beam": 8.0, "min_active": 2000})])
+def test_gpu_equals_compiled_reference_decoder(seed, cfgmod):
+    g = synth.make_hclg(400_000, num_pdfs=800, seed=seed)
+    T = 50
+    ll = synth.make_loglikes(g, T, seed=seed + 100)
+    cfg = dict(synth.DEFAULT_DECODER_CFG, **cfgmod)
+    fst, dec = _mk(g, cfg, T=T, ref=REF)
+    _run_gpu(dec, [ll])
+    assert dec.ChannelInfo(0)["status"] == 0
+    _check_against_compiled_reference(g, cfg, ll, dec, 0)
+
+
 @pytest.mark.parametrize("ref", [REF, FREE])
 def test_tiny_graph(ref):
     g = synth.tiny_graph()

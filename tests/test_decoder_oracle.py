@@ -120,3 +120,72 @@ def test_product_fails_loudly_without_gpu():
     with pytest.raises(B2kError) as e:
         CudaFst(tiny_graph())
     assert e.value.code == 2   # B2K_ERR_NO_DEVICE: no CPU fallback exists
+
+
+# ----------------------------------------------------------------------------- pinned to the reference
+#
+# oracle/_ref/libkaldi_ref_decoder.so is the reference's OWN lattice-faster-decoder.cc and
+# hash-list-inl.h, compiled where they lie against a container-only OpenFst stand-in
+# (oracle/ref_decoder.py).  The restatement must reproduce it bit for bit: every frame's
+# un-pruned token set {(state, tot_cost bits)} and the finalized raw lattice.
+
+def _ref_decoder_or_skip():
+    from oracle import ref_decoder as R
+    if not R.available():
+        pytest.skip("oracle/_ref decoder library not built and /root/reference absent")
+    return R
+
+
+def _sorted_rows(a):
+    return a[np.lexsort(a.T[::-1])] if len(a) else a
+
+
+@pytest.mark.parametrize("seed,cfgmod", [
+    (0, {}),                                                        # recipe settings
+    (1, {"max_active": 2**31 - 1, "min_active": 0, "beam": 9.0}),   # GetCutoff fast path
+    (2, {"max_active": 3000}),                                      # max_active fires on most frames
+    (3, {"beam": 10.0, "lattice_beam": 6.0}),
+    (4, {"beam": 8.0, "min_active": 2000}),                         # min_active branch
+    (5, {"prune_interval": 7}),                                     # interim PruneActiveTokens every 7 frames
+])
+def test_restatement_equals_compiled_reference_decoder(seed, cfgmod):
+    R = _ref_decoder_or_skip()
+    g = synth.make_hclg(400_000, num_pdfs=800, seed=seed)
+    T = 60
+    ll = synth.make_loglikes(g, T, seed=seed + 100)
+    cfg = dict(synth.DEFAULT_DECODER_CFG, **cfgmod)
+    r = R.RefDecoder(g, cfg)
+    r.decode(ll)
+    o = D.DecoderOracle(g, cfg)
+    o.decode(ll, mode=D.MODE_REFERENCE_ORDER, record_frames=True)
+    for f in range(T + 1):
+        st, co = r.frame_tokens(f)
+        want = _sorted_rows(np.stack([st, co.view(np.int32)], axis=1))
+        got = o.raw_frame(f)["toks"]
+        assert np.array_equal(got, want), f"token set of frame {f} differs from the reference decoder"
+    assert D.lattices_equal(o.lattice(), r.lattice())
+
+
+def test_compiled_reference_decoder_on_the_known_answer_graph():
+    R = _ref_decoder_or_skip()
+    g = synth.tiny_graph()
+    cfg = dict(synth.DEFAULT_DECODER_CFG, min_active=0)
+    ll = np.array([[0.0, 3.0], [1.0, 0.0]], np.float32)
+    r = R.RefDecoder(g, cfg)
+    r.decode(ll)
+    o = D.DecoderOracle(g, cfg)
+    o.decode(ll, mode=D.MODE_REFERENCE_ORDER)
+    assert D.lattices_equal(o.lattice(), r.lattice())
+
+
+def test_compiled_reference_decoder_full_length():
+    """BASELINE-size utterance (333 frames, 2 M-arc graph, recipe settings)."""
+    R = _ref_decoder_or_skip()
+    g = synth.make_hclg(2_000_000, num_pdfs=2336, seed=11)
+    cfg = dict(synth.DEFAULT_DECODER_CFG)
+    ll = synth.make_loglikes(g, 333, seed=5)
+    r = R.RefDecoder(g, cfg)
+    r.decode(ll)
+    o = D.DecoderOracle(g, cfg)
+    o.decode(ll, mode=D.MODE_REFERENCE_ORDER)
+    assert D.lattices_equal(o.lattice(), r.lattice())
