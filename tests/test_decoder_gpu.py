@@ -103,7 +103,8 @@ def _check_against_compiled_reference(g, cfg, ll, dec, channel):
     assert D.lattices_equal(lattice_to_canonical(dec.GetRawLattice(channel)), r.lattice())
 
 
-@pytest.mark.parametrize("seed,cfgmod", [(0, {}), (2, {"max_active": 3000}), (4, {"beam": 8.0, "min_active": 2000})])
+@pytest.mark.parametrize("seed,cfgmod", [(0, {}), (2, {"max_active": 3000}), (4, {"beam": 8.0, "min_active": 2000}),
+                                         (5, {"prune_interval": 7})])   # the reference prunes every 7 frames; the GPU only at the end
 def test_gpu_equals_compiled_reference_decoder(seed, cfgmod):
     g = synth.make_hclg(400_000, num_pdfs=800, seed=seed)
     T = 50
