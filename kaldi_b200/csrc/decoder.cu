@@ -69,7 +69,6 @@ struct ChanState {          // per channel, device resident
 
 #define B2K_SET_ERR(S, code) do { if (atomicCAS(&(S).err, 0, (code)) == 0) (S).err_line = __LINE__; } while (0)
 #define B2K_EPS_FLAG 0x80000000u
-#define B2K_DEAD_FLAG 0x40000000u   // link excised by the backward pruning sweep
 #define B2K_ARC_MASK 0x3fffffffu
 #define B2K_HASH_EMPTY (-1)
 
@@ -130,7 +129,6 @@ struct DecParams {
   const int32_t *lane_nframes;
   int32_t row_stride;
   int32_t do_init;
-  int32_t tune_flags;       // bit 0: prefetch the replay working set into L1 before the walk
 };
 
 // ------------------------------------------------------------------ block helpers
@@ -779,7 +777,7 @@ __device__ void bucket_scatter(int k0, int k1, int Hc, const int4 *hash, const X
 }
 
 template <int T>
-__device__ void order_finish(int N, const XScratch &x, DecShared<T> &s) {
+__device__ void order_finish(int N, const XScratch &x, DecShared<T> &s, int *order_slot = nullptr) {
   const int tid = threadIdx.x;
   const int4 kEmptyBucket = make_int4(0x7fffffff, 0, 0, 0);
   __syncthreads();
@@ -798,6 +796,7 @@ __device__ void order_finish(int N, const XScratch &x, DecShared<T> &s) {
     if (k < N) {
       if (w == 1) {
         x.order[carry + excl] = k;
+        if (order_slot) order_slot[carry + excl] = x.by_ins[k];
         x.bk[b] = kEmptyBucket;
         x.xb[k] = -1;
       } else {
@@ -823,6 +822,7 @@ __device__ void order_finish(int N, const XScratch &x, DecShared<T> &s) {
     int within = 0;
     for (int j = 0; j < bk.y; j++) within += (x.run[rb + j] < k);
     x.order[rb + within] = k;
+    if (order_slot) order_slot[rb + within] = x.by_ins[k];
   }
   __syncthreads();
   for (int k = tid; k < N; k += T) {
@@ -1254,15 +1254,6 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
     }
     __syncthreads();
   }
-  if ((p.tune_flags & 1) && !replay_done && Nall > N1 && !s.err) {
-    for (int k = tid; k < qcarry; k += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(&x.rec[x.queue[k]]));
-    for (int e = tid; e < E; e += T) {
-      const int4 en = x.adj[e];
-      if (en.w < 0 || en.y == 0x7f800000) continue;
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(&x.rec[en.x]));
-    }
-    __syncthreads();
-  }
   // literal LIFO replay by one thread over the dense records in global memory
   if (tid == 0 && !s.err && !replay_done && Nall > N1) {
     int qn = qcarry, next = 0;
@@ -1310,7 +1301,8 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   B2K_TICK(s, 8);
   const int N = Nall;
   bucket_scatter<T>(rescatter_from, N, Hc, hash, x);
-  order_finish<T>(N, x, s);
+  int *order_slot = x.queue;                                 // (the replay worklist is done) list rank -> hash slot
+  order_finish<T>(N, x, s, order_slot);
   B2K_TICK(s, 9);
   // eps links = the admitted entries of the final records
   if (!s.err) {
@@ -1352,7 +1344,7 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   __syncthreads();
   if (!s.err) {
     for (int r = tid; r < N; r += T) {
-      int slot = x.by_ins[x.order[r]];
+      const int slot = order_slot[r];
       const int4 hs = hash[slot];
       tok_state[ctx.tbase + r] = hs.x;
       tok_cost[ctx.tbase + r] = ord2f((uint32_t)hs.y);
@@ -2183,7 +2175,6 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
     A(p.x_order, 4 * nl * p.max_tpf, 0);
     p.adj_cap = 2 * p.max_tpf;
     p.rs_rcap = 4096; p.rs_ecap = 4096; p.rs_qcap = 4096;  // shared-memory walk: 80 KB per CTA (two 512-thread CTAs per SM)
-    if (const char *e = getenv("B2K_DEC_TUNE")) p.tune_flags = atoi(e);
     if (const char *e = getenv("B2K_DEC_RS_CAPS")) {          // tuning knob: "tokens,arcs,worklist" (each <= 8192; 0,0,0 = off)
       int a = 0, b = 0, c = 0;
       if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= 0 && b >= 0 && c >= 0 && a <= 8192 && b <= 8192 && c <= 8192) {
