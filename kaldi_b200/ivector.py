@@ -163,3 +163,29 @@ class IvectorExtractorGpu:
         fp = [pipe.d_feats.data_ptr() + 4 * T * D * i for i in range(n)]
         op = [pipe.d_ivec.data_ptr() + 4 * nc * ivd * i for i in range(n)]
         self.Compute(fp, D, T, self._sched, op, ivd, stream)
+
+
+def extractor_from_kaldi_files(ie_path: str, dubm_path: str, lda_mat_path: str, global_cmvn_path: str,
+                               splice: int = 3, base_dim: int = 40, num_gselect: int = 5, min_post: float = 0.025,
+                               posterior_scale: float = 0.1, max_count: float = 100.0, num_cg_iters: int = 15,
+                               cmn_window: int = 600, speaker_frames: int = 600, global_frames: int = 200) -> dict:
+    """The extractor description IvectorExtractorGpu consumes, from the files of an
+    ivector_extractor directory (final.ie, final.dubm, final.mat, global_cmvn.stats;
+    steps/online/nnet2/train_ivector_extractor.sh) and the options of its
+    conf/ivector_extractor.conf (defaults of OnlineIvectorExtractionConfig,
+    online2/online-ivector-feature.h:55-140)."""
+    from . import kaldi_io as KIO
+    ie = KIO.read_ivector_extractor(ie_path)
+    ubm = KIO.read_diag_gmm(dubm_path)
+    lda_mat = KIO.read_matrix(lda_mat_path).astype(np.float32)
+    if ubm["num_gauss"] != ie["num_gauss"] or ubm["feat_dim"] != ie["feat_dim"]:
+        raise ValueError("final.dubm and final.ie disagree on the number of Gaussians / feature dimension")
+    if lda_mat.shape != (ie["feat_dim"], base_dim * (2 * splice + 1) + 1):
+        raise ValueError(f"final.mat is {lda_mat.shape}, expected ({ie['feat_dim']}, {base_dim * (2 * splice + 1) + 1})")
+    return dict(num_gauss=ie["num_gauss"], feat_dim=ie["feat_dim"], ivector_dim=ie["ivector_dim"], splice=splice,
+                base_dim=base_dim, lda_mat=lda_mat, ubm_weights=ubm["ubm_weights"], gconsts=ubm["gconsts"],
+                means_invvars=ubm["means_invvars"], inv_vars=ubm["inv_vars"], M=ie["M"], sigma_inv=ie["sigma_inv"],
+                sigma_inv_m=ie["sigma_inv_m"], U=ie["U"], prior_offset=ie["prior_offset"], max_count=max_count,
+                num_gselect=num_gselect, min_post=min_post, posterior_scale=posterior_scale, num_cg_iters=num_cg_iters,
+                cmn_window=cmn_window, speaker_frames=speaker_frames, global_frames=global_frames,
+                global_cmvn_stats=KIO.read_cmvn_stats(global_cmvn_path))

@@ -1,0 +1,559 @@
+"""Readers (and the writers the tests need) for the Kaldi on-disk formats that sit
+on the input side of the hot path — SURVEY.md §8(f) row 2, built without
+Kaldi/OpenFst:
+
+* basic types, tokens, float/double matrices and vectors in binary and text mode
+  (base/io-funcs{,-inl.h}.cc, matrix/kaldi-matrix.cc Read/Write :1375-1545,
+  kaldi-vector.cc :1130-1260),
+* "raw" nnet3 models as Nnet::Write emits them (nnet3/nnet-nnet.cc:630-656):
+  config lines + components, every component parsed generically into
+  {token: value}, and the mapping of a TDNN-F chain model (the xconfig layer
+  names of steps/libs/nnet3/xconfig) onto the arch/weights dictionaries of
+  kaldi_b200.nnet_model,
+* DiagGmm (gmm/diag-gmm.cc:835-895), IvectorExtractor (ivector/ivector-extractor.cc:
+  807-870), global CMVN stats.
+
+Pinned by tests/test_kaldi_io.py against files written by the reference's own
+writers (oracle/_ref).  Host-side only; nothing here touches the GPU.
+"""
+from __future__ import annotations
+
+import io
+import re
+import struct
+
+import numpy as np
+
+
+class KaldiFormatError(ValueError):
+    pass
+
+
+class Reader:
+    """Sequential reader over a Kaldi object file (binary files start with "\\0B")."""
+
+    def __init__(self, data: bytes):
+        self.d = data
+        self.p = 0
+        self.binary = data[:2] == b"\0B"
+        if self.binary:
+            self.p = 2
+
+    @classmethod
+    def open(cls, path: str) -> "Reader":
+        with open(path, "rb") as f:
+            return cls(f.read())
+
+    # ---- low level
+    def _ws(self):
+        while self.p < len(self.d) and self.d[self.p:self.p + 1].isspace():
+            self.p += 1
+
+    def eof(self) -> bool:
+        if not self.binary:
+            self._ws()
+        return self.p >= len(self.d)
+
+    def peek_byte(self) -> int:
+        if not self.binary:
+            self._ws()
+        if self.p >= len(self.d):
+            raise KaldiFormatError("unexpected end of file")
+        return self.d[self.p]
+
+    def read_token(self) -> str:
+        """ReadToken (io-funcs.cc:154): whitespace-delimited, one trailing space consumed."""
+        self._ws() if not self.binary else None
+        # tokens are written as "<tok> " in both modes; in binary mode there is no leading whitespace,
+        # except the newline Nnet::Write puts after the config section
+        while self.p < len(self.d) and self.d[self.p:self.p + 1].isspace():
+            self.p += 1
+        e = self.p
+        while e < len(self.d) and not self.d[e:e + 1].isspace():
+            e += 1
+        tok = self.d[self.p:e].decode("ascii")
+        self.p = e + 1
+        if not tok:
+            raise KaldiFormatError("empty token")
+        return tok
+
+    def expect_token(self, want: str):
+        got = self.read_token()
+        if got != want:
+            raise KaldiFormatError(f"expected token {want}, got {got} at byte {self.p}")
+
+    def read_line(self) -> str:
+        e = self.d.index(b"\n", self.p)
+        s = self.d[self.p:e].decode("ascii")
+        self.p = e + 1
+        return s
+
+    def _text_number(self) -> str:
+        self._ws()
+        e = self.p
+        while e < len(self.d) and not self.d[e:e + 1].isspace():
+            e += 1
+        s = self.d[self.p:e].decode("ascii")
+        self.p = e
+        return s
+
+    # ---- basic types (io-funcs-inl.h:34-110, io-funcs.cc:26-130)
+    def read_int(self) -> int:
+        if not self.binary:
+            return int(self._text_number())
+        n = struct.unpack_from("b", self.d, self.p)[0]
+        self.p += 1
+        size = abs(n)
+        fmt = {1: "b", 2: "h", 4: "i", 8: "q"}[size] if n > 0 else {1: "B", 2: "H", 4: "I", 8: "Q"}[size]
+        v = struct.unpack_from("<" + fmt, self.d, self.p)[0]
+        self.p += size
+        return v
+
+    def read_float(self) -> float:
+        if not self.binary:
+            s = self._text_number()
+            return float({"inf": "inf", "-inf": "-inf", "nan": "nan"}.get(s.lower(), s))
+        size = self.d[self.p]
+        self.p += 1
+        if size == 4:
+            v = struct.unpack_from("<f", self.d, self.p)[0]
+        elif size == 8:
+            v = struct.unpack_from("<d", self.d, self.p)[0]
+        else:
+            raise KaldiFormatError(f"expected a float, saw size byte {size}")
+        self.p += size
+        return v
+
+    def read_bool(self) -> bool:
+        c = chr(self.peek_byte())
+        if c not in "TF":
+            raise KaldiFormatError(f"expected T/F, saw {c!r}")
+        self.p += 1
+        return c == "T"
+
+    def read_int_vector(self) -> np.ndarray:
+        """ReadIntegerVector (io-funcs-inl.h:232-290)."""
+        if self.binary:
+            size = self.d[self.p]
+            self.p += 1
+            n = struct.unpack_from("<i", self.d, self.p)[0]
+            self.p += 4
+            dt = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[size]
+            v = np.frombuffer(self.d, dt, n, self.p).copy()
+            self.p += n * size
+            return v
+        self._ws()
+        if self.d[self.p:self.p + 1] != b"[":
+            raise KaldiFormatError("expected [ at the start of an integer vector")
+        e = self.d.index(b"]", self.p)
+        v = np.array(self.d[self.p + 1:e].split(), dtype=np.int64)
+        self.p = e + 1
+        return v
+
+    # ---- matrices and vectors
+    def _text_brackets(self) -> np.ndarray:
+        self._ws()
+        if self.d[self.p:self.p + 1] != b"[":
+            raise KaldiFormatError(f"expected [ at byte {self.p}")
+        e = self.d.index(b"]", self.p)
+        body = self.d[self.p + 1:e].decode("ascii")
+        self.p = e + 1
+        rows = [r.split() for r in body.split("\n") if r.strip()]
+        return rows
+
+    def read_vector(self) -> np.ndarray:
+        if self.binary:
+            tag = self.d[self.p:self.p + 3]
+            if tag not in (b"FV ", b"DV "):
+                raise KaldiFormatError(f"expected FV/DV, saw {tag!r}")
+            self.p += 3
+            n = self.read_int()
+            dt = np.float32 if tag == b"FV " else np.float64
+            v = np.frombuffer(self.d, dt, n, self.p).copy()
+            self.p += n * v.itemsize
+            return v
+        rows = self._text_brackets()
+        flat = [x for r in rows for x in r]
+        return np.array(flat, dtype=np.float64).astype(np.float32) if flat else np.zeros(0, np.float32)
+
+    def read_matrix(self) -> np.ndarray:
+        if self.binary:
+            tag = self.d[self.p:self.p + 3]
+            if tag[:2] == b"CM":
+                raise KaldiFormatError("compressed matrices are not supported")
+            if tag not in (b"FM ", b"DM "):
+                raise KaldiFormatError(f"expected FM/DM, saw {tag!r}")
+            self.p += 3
+            r, c = self.read_int(), self.read_int()
+            dt = np.float32 if tag == b"FM " else np.float64
+            m = np.frombuffer(self.d, dt, r * c, self.p).reshape(r, c).copy()
+            self.p += r * c * m.itemsize
+            return m
+        rows = self._text_brackets()
+        if not rows:
+            return np.zeros((0, 0), np.float32)
+        return np.array(rows, dtype=np.float64).astype(np.float32)
+
+    def read_packed(self) -> np.ndarray:
+        """SpMatrix/TpMatrix (matrix/packed-matrix.cc:236-330): packed lower triangle -> full symmetric matrix."""
+        if self.binary:
+            tag = self.d[self.p:self.p + 3]
+            if tag not in (b"FP ", b"DP "):
+                raise KaldiFormatError(f"expected FP/DP, saw {tag!r}")
+            self.p += 3
+            n = self.read_int()
+            dt = np.float32 if tag == b"FP " else np.float64
+            ne = n * (n + 1) // 2
+            flat = np.frombuffer(self.d, dt, ne, self.p).copy()
+            self.p += ne * flat.itemsize
+        else:
+            rows = self._text_brackets()
+            n = len(rows)
+            flat = np.array([x for r in rows for x in r], dtype=np.float64)
+        m = np.zeros((n, n), flat.dtype)
+        il = np.tril_indices(n)
+        m[il] = flat
+        m[(il[1], il[0])] = flat
+        return m
+
+    # ---- generic "<Token> value value ..." records
+    def _binary_value(self):
+        b = self.d[self.p]
+        nxt = self.d[self.p:self.p + 3]
+        if nxt in (b"FM ", b"DM "):
+            return self.read_matrix()
+        if nxt in (b"FV ", b"DV "):
+            return self.read_vector()
+        if nxt[:2] == b"CM":
+            raise KaldiFormatError("compressed matrices are not supported")
+        if b in (ord("T"), ord("F")):
+            return self.read_bool()
+        if b in (4, 8):                 # float/double or int32/int64: keep the raw bytes, typed on demand
+            raw = self.d[self.p + 1:self.p + 1 + b]
+            self.p += 1 + b
+            return RawScalar(raw)
+        if b in (1, 2, 0xFF, 0xFE, 0xFC):
+            return self.read_int()
+        raise KaldiFormatError(f"cannot parse a value at byte {self.p} (0x{b:02x})")
+
+    def read_fields(self, end_token: str, int_vector_tokens=("<TimeOffsets>",)) -> dict:
+        """Parses "<A> v <B> v v ... </End>" into {"<A>": [values], ...} (order kept)."""
+        out = {}
+        while True:
+            tok = self.read_token()
+            if tok == end_token:
+                return out
+            if not tok.startswith("<"):
+                raise KaldiFormatError(f"expected a token, got {tok!r}")
+            vals = []
+            while True:
+                if self.binary:
+                    if self.d[self.p:self.p + 1] == b"<":
+                        break
+                    vals.append(self.read_int_vector() if tok in int_vector_tokens else self._binary_value())
+                else:
+                    self._ws()
+                    c = self.d[self.p:self.p + 1]
+                    if c == b"<":
+                        break
+                    if c == b"[":
+                        rows = self._text_brackets()
+                        if tok in int_vector_tokens:
+                            vals.append(np.array([x for r in rows for x in r], dtype=np.int64))
+                        elif len(rows) <= 1:
+                            vals.append(np.array(rows[0] if rows else [], dtype=np.float64).astype(np.float32))
+                        else:
+                            vals.append(np.array(rows, dtype=np.float64).astype(np.float32))
+                    else:
+                        s = self._text_number()
+                        vals.append(True if s == "T" else False if s == "F" else RawScalar(text=s))
+            out[tok] = vals
+
+
+class RawScalar:
+    """A 4/8-byte binary scalar (or a text number) whose type the format does not reveal."""
+
+    def __init__(self, raw: bytes = b"", text: str | None = None):
+        self.raw, self.text = raw, text
+
+    def as_int(self) -> int:
+        if self.text is not None:
+            return int(self.text)
+        return struct.unpack("<i" if len(self.raw) == 4 else "<q", self.raw)[0]
+
+    def as_float(self) -> float:
+        if self.text is not None:
+            return float(self.text)
+        return struct.unpack("<f" if len(self.raw) == 4 else "<d", self.raw)[0]
+
+    def __repr__(self):
+        return f"RawScalar({self.text if self.text is not None else self.raw.hex()})"
+
+
+# ----------------------------------------------------------------------------- files
+
+def read_matrix(path: str) -> np.ndarray:
+    return Reader.open(path).read_matrix()
+
+
+def read_vector(path: str) -> np.ndarray:
+    return Reader.open(path).read_vector()
+
+
+def write_matrix(path: str, m: np.ndarray, binary: bool = True) -> None:
+    m = np.ascontiguousarray(m)
+    with open(path, "wb") as f:
+        if binary:
+            tag = b"DM " if m.dtype == np.float64 else b"FM "
+            mm = m if m.dtype == np.float64 else m.astype(np.float32)
+            f.write(b"\0B" + tag + b"\4" + struct.pack("<i", m.shape[0]) + b"\4" + struct.pack("<i", m.shape[1]))
+            f.write(mm.tobytes())
+        else:
+            f.write(b" [\n")
+            for r in m:
+                f.write(("  " + " ".join(repr(float(np.float32(x))) for x in r) + "\n").encode())
+            f.seek(-1, io.SEEK_END)
+            f.write(b" ]\n")
+
+
+def write_vector(path: str, v: np.ndarray, binary: bool = True) -> None:
+    v = np.ascontiguousarray(v)
+    with open(path, "wb") as f:
+        if binary:
+            tag = b"DV " if v.dtype == np.float64 else b"FV "
+            vv = v if v.dtype == np.float64 else v.astype(np.float32)
+            f.write(b"\0B" + tag + b"\4" + struct.pack("<i", v.shape[0]) + vv.tobytes())
+        else:
+            f.write((" [ " + " ".join(repr(float(x)) for x in v) + " ]\n").encode())
+
+
+# ----------------------------------------------------------------------------- nnet3 raw models
+
+def read_nnet3_raw(path: str) -> dict:
+    """{"config": [lines], "components": {name: {"type": T, "<Token>": [values], ...}}} (Nnet::Read, nnet-nnet.cc:586)."""
+    r = Reader.open(path)
+    r.expect_token("<Nnet3>")
+    lines = []
+    # config-like section: text lines up to the first blank line, in both modes
+    if r.d[r.p:r.p + 1] == b"\n":
+        r.p += 1
+    while True:
+        line = r.read_line()
+        if not line.strip():
+            if lines:
+                break
+            continue
+        lines.append(line.strip())
+    r.expect_token("<NumComponents>")
+    n = r.read_int()
+    comps = {}
+    for _ in range(n):
+        r.expect_token("<ComponentName>")
+        name = r.read_token()
+        typ = r.read_token()
+        if not (typ.startswith("<") and typ.endswith(">")):
+            raise KaldiFormatError(f"bad component type token {typ!r}")
+        fields = r.read_fields("</" + typ[1:])
+        fields["type"] = typ[1:-1]
+        comps[name] = fields
+    r.expect_token("</Nnet3>")
+    return {"config": lines, "components": comps}
+
+
+def _f(fields: dict, tok: str, i: int = 0):
+    return fields[tok][i]
+
+
+def _parse_config_line(line: str) -> tuple[str, dict]:
+    kind, rest = line.split(" ", 1)
+    kv = {}
+    for m in re.finditer(r"(\S+?)=(.*?)(?=\s+\S+?=|$)", rest):
+        kv[m.group(1)] = m.group(2).strip()
+    return kind, kv
+
+
+def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
+    """Maps a parsed TDNN-F chain model onto (arch, weights) of kaldi_b200.nnet_model.
+
+    Recognises the node patterns that steps/libs/nnet3/xconfig emits for: idct-layer /
+    FixedAffine lda, batchnorm-component, spec-augment-free delta-layer, relu-batchnorm-layer
+    (optionally with Scale(s, ReplaceIndex(ivector, t, 0)) appended), tdnnf-layer,
+    linear-component, prefinal-layer, output-layer; anything else raises."""
+    comps = parsed["components"]
+    nodes = []
+    dims = {}
+    for line in parsed["config"]:
+        kind, kv = _parse_config_line(line)
+        if kind == "input-node":
+            dims[kv["name"]] = int(kv["dim"])
+        elif kind in ("component-node", "dim-range-node", "output-node"):
+            nodes.append((kind, kv))
+    W = {}
+    layers = []
+    arch = {"name": name, "feat_dim": dims["input"], "ivector_dim": dims.get("ivector", 0)}
+
+    def mat(c, tok):
+        f = comps[c]
+        if tok == "<LinearParams>" and tok not in f:      # LinearComponent calls its matrix <Params>
+            tok = "<Params>"
+        return np.ascontiguousarray(_f(f, tok), np.float32)
+
+    def bn(c, key):
+        f = comps[c]
+        assert f["type"] == "BatchNormComponent", (c, f["type"])
+        count = _f(f, "<Count>").as_float()
+        mean, var = np.asarray(_f(f, "<StatsMean>"), np.float64), np.asarray(_f(f, "<StatsVar>"), np.float64)
+        # BatchNormComponent::Write stores mean and uncentered variance times nothing: Read() (nnet-normalize-component.cc
+        # :591-614) takes <StatsMean> as the mean and <StatsVar> as the variance when written after ComputeDerived.
+        W[key + ".mean"] = mean.astype(np.float32)
+        W[key + ".var"] = var.astype(np.float32)
+        return count
+
+    cn = [(kv["name"], kv) for kind, kv in nodes if kind == "component-node"]
+    names = [n for n, _ in cn]
+    inputs = {n: kv["input"] for n, kv in cn}
+    i = 0
+    sub = None
+    while i < len(cn):
+        n, kv = cn[i]
+        c = comps[kv["component"]]
+        t = c["type"]
+        if t == "FixedAffineComponent" and inputs[n] == "input":
+            W[n + ".w"], W[n + ".b"] = mat(n, "<LinearParams>"), mat(n, "<BiasParams>")
+            layers.append({"type": "idct", "name": n, "dim": int(W[n + ".w"].shape[0])})
+            i += 1
+        elif t == "FixedAffineComponent":
+            layers.append({"type": "lda", "name": n})
+            W[n + ".w"], W[n + ".b"] = mat(n, "<LinearParams>"), mat(n, "<BiasParams>")
+            i += 1
+        elif t == "BatchNormComponent" and i + 1 < len(cn) and comps[cn[i + 1][1]["component"]]["type"] == "NoOpComponent" \
+                and cn[i + 1][0] == n + "_2":
+            # batchnorm-component followed by delta-layer (its NoOp is named <input>_2, trivial_layers.py:236-256)
+            layers.append({"type": "batchnorm", "name": n})
+            bn(n, n)
+            dn = cn[i + 2][0]
+            layers.append({"type": "delta", "name": dn})
+            bn(dn, dn)
+            i += 3
+        elif t == "BatchNormComponent":
+            layers.append({"type": "batchnorm", "name": n})
+            bn(n, n)
+            i += 1
+        elif t in ("NaturalGradientAffineComponent", "AffineComponent") and n.endswith(".affine") \
+                and i + 2 < len(cn) and cn[i + 1][0] == n[:-7] + ".relu":
+            base = n[:-7]
+            nxt = [x[0] for x in cn[i:i + 8]]
+            if base + ".batchnorm1" in nxt:     # prefinal-layer: affine relu batchnorm1 linear batchnorm2
+                big = mat(n, "<LinearParams>").shape[0]
+                small = mat(base + ".linear", "<LinearParams>").shape[0]
+                layers.append({"type": "prefinal", "name": base, "big": int(big), "small": int(small)})
+                W[n + ".w"], W[n + ".b"] = mat(n, "<LinearParams>"), mat(n, "<BiasParams>")
+                bn(base + ".batchnorm1", base + ".batchnorm1")
+                W[base + ".linear.w"] = mat(base + ".linear", "<LinearParams>")
+                bn(base + ".batchnorm2", base + ".batchnorm2")
+                i += 5
+            else:                               # relu-batchnorm-layer
+                L = {"type": "relu-batchnorm", "name": base, "dim": int(mat(n, "<LinearParams>").shape[0])}
+                m = re.search(r"Scale\(([0-9.eE+-]+),\s*ivector\)", inputs[n]) or \
+                    re.search(r"Scale\(([0-9.eE+-]+),\s*ReplaceIndex\(ivector", inputs[n])
+                if "ivector" in inputs[n]:
+                    L["append_ivector"] = float(m.group(1)) if m else 1.0
+                layers.append(L)
+                W[n + ".w"], W[n + ".b"] = mat(n, "<LinearParams>"), mat(n, "<BiasParams>")
+                bn(base + ".batchnorm", base + ".batchnorm")
+                i += 3
+        elif t == "TdnnComponent" and n.endswith(".linear"):
+            base = n[:-7]
+            offs = np.asarray(_f(c, "<TimeOffsets>")).tolist()
+            stride = int(max(abs(o) for o in offs))
+            if stride == 3 and sub is None:
+                sub = 3
+            m = re.search(r"Scale\(([0-9.eE+-]+),", inputs[base + ".noop"])
+            wl = mat(n, "<LinearParams>")
+            wa = mat(base + ".affine", "<LinearParams>")
+            layers.append({"type": "tdnnf", "name": base, "dim": int(wa.shape[0]), "bottleneck": int(wl.shape[0]),
+                           "stride": stride, "bypass": float(m.group(1)) if m else 0.0})
+            W[n + ".w"] = wl
+            W[base + ".affine.w"], W[base + ".affine.b"] = wa, mat(base + ".affine", "<BiasParams>")
+            bn(base + ".batchnorm", base + ".batchnorm")
+            i += 5
+        elif t == "LinearComponent":
+            w = mat(n, "<LinearParams>")
+            layers.append({"type": "linear", "name": n, "dim": int(w.shape[0])})
+            W[n + ".w"] = w
+            i += 1
+        elif t in ("NaturalGradientAffineComponent", "AffineComponent") and n.endswith(".affine"):
+            base = n[:-7]                       # output-layer: <name>.affine (+ log-softmax for xent outputs)
+            w = mat(n, "<LinearParams>")
+            L = {"type": "output", "name": base, "dim": int(w.shape[0]), "log_softmax": False}
+            W[n + ".w"], W[n + ".b"] = w, mat(n, "<BiasParams>")
+            i += 1
+            if i < len(cn) and comps[cn[i][1]["component"]]["type"] == "LogSoftmaxComponent":
+                L["log_softmax"] = True
+                i += 1
+            layers.append(L)
+        else:
+            raise KaldiFormatError(f"unsupported node pattern at {n} ({t})")
+    arch["layers"] = layers
+    out = [L for L in layers if L["type"] == "output"]
+    arch["num_pdfs"] = out[0]["dim"] if out else 0
+    arch["frame_subsampling_factor"] = 3 if any(L["type"] == "tdnnf" and L["stride"] == 3 for L in layers) else 1
+    return arch, W
+
+
+# ----------------------------------------------------------------------------- i-vector extractor side
+
+def read_diag_gmm(path: str) -> dict:
+    """DiagGmm::Read (gmm/diag-gmm.cc:758-800): final.dubm."""
+    r = Reader.open(path)
+    tok = r.read_token()
+    if tok not in ("<DiagGMM>", "<DiagGMMBegin>"):
+        raise KaldiFormatError(f"not a DiagGmm: {tok}")
+    out = {}
+    while True:
+        tok = r.read_token()
+        if tok in ("</DiagGMM>", "<DiagGMMEnd>"):
+            break
+        if tok == "<GCONSTS>":
+            out["gconsts"] = r.read_vector().astype(np.float32)
+        elif tok == "<WEIGHTS>":
+            out["ubm_weights"] = r.read_vector().astype(np.float32)
+        elif tok == "<MEANS_INVVARS>":
+            out["means_invvars"] = r.read_matrix().astype(np.float32)
+        elif tok == "<INV_VARS>":
+            out["inv_vars"] = r.read_matrix().astype(np.float32)
+        else:
+            raise KaldiFormatError(f"unexpected token {tok} in DiagGmm")
+    out["num_gauss"], out["feat_dim"] = out["means_invvars"].shape
+    return out
+
+
+def read_ivector_extractor(path: str) -> dict:
+    """IvectorExtractor::Read (ivector/ivector-extractor.cc:828-848) + ComputeDerivedVars (:182-230): final.ie.
+    Returns M [G, F, D], sigma_inv [G, F, F], w_vec, prior_offset and the derived
+    sigma_inv_m [G, F, D] and U [G, D(D+1)/2] (packed lower triangles of M^T Sigma^-1 M), all float64."""
+    r = Reader.open(path)
+    r.expect_token("<IvectorExtractor>")
+    r.expect_token("<w>")
+    w = r.read_matrix()
+    r.expect_token("<w_vec>")
+    w_vec = r.read_vector().astype(np.float64)
+    r.expect_token("<M>")
+    G = r.read_int()
+    M = np.stack([r.read_matrix().astype(np.float64) for _ in range(G)])
+    r.expect_token("<SigmaInv>")
+    sigma_inv = np.stack([r.read_packed().astype(np.float64) for _ in range(G)])
+    r.expect_token("<IvectorOffset>")
+    prior_offset = r.read_float()
+    r.expect_token("</IvectorExtractor>")
+    sigma_inv_m = np.einsum("gij,gjk->gik", sigma_inv, M)
+    U_full = np.einsum("gji,gjk->gik", M, sigma_inv_m)
+    il = np.tril_indices(M.shape[2])
+    return dict(num_gauss=G, feat_dim=M.shape[1], ivector_dim=M.shape[2], w=w, w_vec=w_vec, M=M, sigma_inv=sigma_inv,
+                prior_offset=float(prior_offset), sigma_inv_m=np.ascontiguousarray(sigma_inv_m),
+                U=np.ascontiguousarray(U_full[:, il[0], il[1]]))
+
+
+def read_cmvn_stats(path: str) -> np.ndarray:
+    """global_cmvn.stats: a 2 x (dim + 1) double matrix (transform/cmvn.cc)."""
+    return np.asarray(read_matrix(path), np.float64)

@@ -562,3 +562,13 @@ def flops_per_output_frame(prog: dict) -> float:
         if op["type"] == "gemm":
             tot += 2.0 * op["K"] * op["N"] * op["rows"]
     return tot / prog["n_out"]
+
+
+def load_kaldi_raw(path: str, priors: np.ndarray | None = None, name: str | None = None) -> tuple[dict, dict]:
+    """(arch, weights) of a TDNN-F chain model stored as a raw nnet3 file (nnet3-am-copy --raw=true final.mdl
+    final.raw; text or binary).  `priors` (AmNnetSimple::Priors, the <Priors> vector of final.mdl) default to
+    none, which is what chain models ship."""
+    from . import kaldi_io as KIO
+    arch, W = KIO.nnet3_to_arch(KIO.read_nnet3_raw(path), name=name or os.path.basename(path))
+    W["priors"] = (np.ones(arch["num_pdfs"], np.float32) if priors is None else np.ascontiguousarray(priors, np.float32))
+    return arch, W

@@ -20,6 +20,7 @@
 #include "gmm/diag-gmm.h"
 #include "hmm/posterior.h"
 #include "ivector/ivector-extractor.h"
+#include "util/kaldi-io.h"
 
 using namespace kaldi;
 
@@ -101,6 +102,17 @@ int ref_ivector_run(void *h, const float *feats, int T, int D, const double *glo
     }
     return 0;
   } catch (const std::exception &e) { fprintf(stderr, "ref_ivector_run: %s\n", e.what()); return -1; }
+}
+
+// IvectorExtractor::Write (ivector/ivector-extractor.cc:807) and DiagGmm::Write (gmm/diag-gmm.cc:728) with the
+// Kaldi binary header, as final.ie / final.dubm are stored: what kaldi_b200/kaldi_io.py's readers are pinned against.
+int ref_ivector_write(void *h, const char *extractor_path, const char *ubm_path, int binary) {
+  try {
+    RefIvec *r = (RefIvec *)h;
+    { Output ko(extractor_path, binary != 0); r->extractor.Write(ko.Stream(), binary != 0); if (!ko.Close()) return -1; }
+    { Output ko(ubm_path, binary != 0); r->ubm.Write(ko.Stream(), binary != 0); if (!ko.Close()) return -1; }
+    return 0;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_ivector_write: %s\n", e.what()); return -1; }
 }
 
 }  // extern "C"

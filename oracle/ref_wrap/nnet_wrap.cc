@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "nnet3/am-nnet-simple.h"
+#include "util/kaldi-io.h"
 #include "nnet3/decodable-simple-looped.h"
 #include "nnet3/nnet-nnet.h"
 #include "nnet3/nnet-normalize-component.h"
@@ -143,6 +144,18 @@ int ref_nnet_forward(void *h, const float *feats, int T, int D, const float *ive
     for (int t = 0; t < n; t++) { SubVector<BaseFloat> row(out + (size_t)t * P, P); dec.GetOutputForFrame(t, &row); }
     return n;
   } catch (const std::exception &e) { fprintf(stderr, "ref_nnet_forward: %s\n", e.what()); return -1; }
+}
+
+// Nnet::Write (nnet3/nnet-nnet.cc:630) of the model as it stands (call before ref_nnet_prepare for the
+// un-collapsed training-form model): the "raw" nnet3 file the readers in kaldi_b200/kaldi_io.py are
+// pinned against.
+int ref_nnet_write(void *h, const char *path, int binary) {
+  try {
+    RefNnet *r = (RefNnet *)h;
+    Output ko(path, binary != 0);     // with the "\\0B" header, as nnet3-copy writes final.raw
+    r->nnet.Write(ko.Stream(), binary != 0);
+    return ko.Close() ? 0 : -1;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_nnet_write: %s\n", e.what()); return -1; }
 }
 
 }  // extern "C"

@@ -1,0 +1,101 @@
+"""kaldi_b200/kaldi_io.py against files written by the reference's OWN writers
+(oracle/_ref: Nnet::Write, Matrix/Vector::Write): binary and text mode must give
+back exactly the parameters that were put into the reference model."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from kaldi_b200 import kaldi_io as KIO
+from kaldi_b200 import nnet_model as NM
+
+
+def _ref_model_files(tmp_path, arch, W):
+    from oracle import nnet_oracle as NO
+    if not (os.path.exists(NO._SO) or os.path.isdir("/root/reference")):
+        pytest.skip("oracle/_ref nnet3 library not present")
+    R = NO.RefNnet(arch, W, collapse=False)     # the model as trained (CollapseModel renames and merges components)
+    if not hasattr(R.lib, "ref_nnet_write"):
+        pytest.skip("oracle/_ref nnet3 library predates ref_nnet_write")
+    R.lib.ref_nnet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    out = {}
+    for mode, binary in (("bin", 1), ("txt", 0)):
+        p = str(tmp_path / f"model.{mode}")
+        assert R.lib.ref_nnet_write(R.h, p.encode(), binary) == 0
+        out[mode] = p
+    return out
+
+
+@pytest.mark.parametrize("front", ["idct-delta", "lda"])
+def test_nnet3_raw_model_round_trip_through_the_reference_writer(tmp_path, front):
+    arch = NM.arch_tiny(front=front)
+    W = NM.random_weights(arch, seed=3)
+    files = _ref_model_files(tmp_path, arch, W)
+    a3, W3 = NM.load_kaldi_raw(files["bin"])
+    assert a3["num_pdfs"] == arch["num_pdfs"] and W3["priors"].shape == (arch["num_pdfs"],)
+    for mode, path in files.items():
+        parsed = KIO.read_nnet3_raw(path)
+        arch2, W2 = KIO.nnet3_to_arch(parsed, name=arch["name"])
+        assert [(L["type"], L["name"]) for L in arch2["layers"]] == [(L["type"], L["name"]) for L in arch["layers"]]
+        for L, L2 in zip(arch["layers"], arch2["layers"]):
+            for k, v in L.items():
+                if isinstance(v, float):
+                    assert abs(L2[k] - v) < 1e-6, (L["name"], k)
+                else:
+                    assert L2.get(k) == v, (L["name"], k, L2.get(k), v)
+        assert arch2["feat_dim"] == arch["feat_dim"] and arch2["ivector_dim"] == arch["ivector_dim"]
+        assert arch2["num_pdfs"] == arch["num_pdfs"]
+        assert arch2["frame_subsampling_factor"] == arch["frame_subsampling_factor"]
+        for k, v in W.items():
+            if k == "priors":
+                continue
+            assert k in W2, k
+            if mode == "bin" and not k.endswith((".mean", ".var")):
+                np.testing.assert_array_equal(W2[k], v, err_msg=k)
+            elif mode == "bin":
+                # BatchNormComponent keeps sum and sum-of-squares (x count) and Write() divides again
+                # (nnet-normalize-component.cc:591-650): the stats come back within an ulp or two
+                np.testing.assert_allclose(W2[k], v, rtol=1e-6, atol=1e-7, err_msg=k)
+            else:   # text mode prints ~6 significant digits
+                np.testing.assert_allclose(W2[k], v, rtol=2e-5, atol=1e-6, err_msg=k)
+
+
+def test_matrix_and_vector_files(tmp_path):
+    rng = np.random.default_rng(0)
+    m = rng.standard_normal((7, 5)).astype(np.float32)
+    v = rng.standard_normal(9).astype(np.float32)
+    for binary in (True, False):
+        KIO.write_matrix(str(tmp_path / "m"), m, binary)
+        KIO.write_vector(str(tmp_path / "v"), v, binary)
+        np.testing.assert_array_equal(KIO.read_matrix(str(tmp_path / "m")), m)
+        np.testing.assert_array_equal(KIO.read_vector(str(tmp_path / "v")), v)
+    md = rng.standard_normal((3, 4))
+    KIO.write_matrix(str(tmp_path / "md"), md, True)
+    np.testing.assert_array_equal(KIO.read_matrix(str(tmp_path / "md")), md)
+
+
+def test_ivector_extractor_and_ubm_files_written_by_the_reference(tmp_path):
+    from kaldi_b200.ivector import make_synthetic_extractor
+    from oracle import ivector_oracle as IV
+    from oracle import nnet_oracle as NO
+    if not (os.path.exists(NO._SO) or os.path.isdir("/root/reference")):
+        pytest.skip("oracle/_ref library not present")
+    ex = make_synthetic_extractor(seed=1, num_gauss=6, feat_dim=8, ivector_dim=5, splice=1, base_dim=8)
+    R = IV.RefIvector(ex)
+    if not hasattr(R.lib, "ref_ivector_write"):
+        pytest.skip("oracle/_ref library predates ref_ivector_write")
+    R.lib.ref_ivector_write.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+    for binary in (1, 0):
+        pe, pu = str(tmp_path / f"final{binary}.ie"), str(tmp_path / f"final{binary}.dubm")
+        assert R.lib.ref_ivector_write(R.h, pe.encode(), pu.encode(), binary) == 0
+        got = KIO.read_ivector_extractor(pe)
+        ubm = KIO.read_diag_gmm(pu)
+        tol = dict(rtol=0, atol=0) if binary else dict(rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(got["M"], ex["M"], **tol)
+        np.testing.assert_allclose(got["sigma_inv"], ex["sigma_inv"], **tol)
+        assert abs(got["prior_offset"] - ex["prior_offset"]) < 1e-6
+        np.testing.assert_allclose(got["sigma_inv_m"], ex["sigma_inv_m"], rtol=1e-4 if not binary else 1e-12, atol=1e-6 if not binary else 1e-12)
+        np.testing.assert_allclose(got["U"], ex["U"], rtol=1e-4 if not binary else 1e-12, atol=1e-5 if not binary else 1e-12)
+        for k in ("gconsts", "ubm_weights", "means_invvars", "inv_vars"):
+            np.testing.assert_allclose(ubm[k], ex[k], rtol=1e-5 if not binary else 1e-6, atol=1e-6, err_msg=k)
