@@ -2103,6 +2103,8 @@ int32_t b2k_fst_start(const b2k_fst *f) { return f ? f->dev.start : -1; }
 
 static int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
+static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, int32_t nchannels);
+
 int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, int32_t nchannels,
                    b2k_dec **out) {
   if (!fst || !cfg || !out || nlanes <= 0 || nchannels < nlanes)
@@ -2116,6 +2118,18 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
   int rc = require_device();
   if (rc) return rc;
   b2k_dec *d = new b2k_dec();
+  rc = dec_create_impl(d, fst, cfg, nlanes, nchannels);
+  if (rc) {                       // e.g. cudaMalloc failed half way (arenas are sized by the caller): release what exists
+    b2k_dec_destroy(d);
+    *out = nullptr;
+    return rc;
+  }
+  *out = d;
+  return B2K_OK;
+}
+
+static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, int32_t nchannels) {
+  int rc = 0;
   d->fst = fst; d->cfg = *cfg; d->nlanes = nlanes; d->nchannels = nchannels;
   {
     // tuning knobs (defaults = measured best); read per decoder so that tests can vary them
@@ -2228,7 +2242,6 @@ int b2k_dec_create(const b2k_fst *fst, const b2k_dec_cfg *cfg, int32_t nlanes, i
   p.lane_channel = d->d_lane_channel;
   p.lane_loglikes = d->d_lane_ll;
   p.lane_nframes = d->d_lane_nframes;
-  *out = d;
   return B2K_OK;
 }
 
@@ -2236,8 +2249,12 @@ int b2k_dec_destroy(b2k_dec *d) {
   if (!d) return B2K_OK;
   cudaDeviceSynchronize();
   for (void *p : d->allocs) cudaFree(p);
-  cudaFreeHost(d->h_lane_channel); cudaFreeHost(d->h_lane_ll); cudaFreeHost(d->h_lane_nframes);
-  cudaFreeHost(d->h_chan); if (d->h_pack) cudaFreeHost(d->h_pack); if (d->d_pack) cudaFree(d->d_pack);
+  if (d->h_lane_channel) cudaFreeHost(d->h_lane_channel);
+  if (d->h_lane_ll) cudaFreeHost(d->h_lane_ll);
+  if (d->h_lane_nframes) cudaFreeHost(d->h_lane_nframes);
+  if (d->h_chan) cudaFreeHost(d->h_chan);
+  if (d->h_pack) cudaFreeHost(d->h_pack);
+  if (d->d_pack) cudaFree(d->d_pack);
   if (d->staging_free) cudaEventDestroy(d->staging_free);
   delete d;
   return B2K_OK;

@@ -331,7 +331,10 @@ def write_vector(path: str, v: np.ndarray, binary: bool = True) -> None:
 
 def read_nnet3_raw(path: str) -> dict:
     """{"config": [lines], "components": {name: {"type": T, "<Token>": [values], ...}}} (Nnet::Read, nnet-nnet.cc:586)."""
-    r = Reader.open(path)
+    return _read_nnet3(Reader.open(path))
+
+
+def _read_nnet3(r: Reader) -> dict:
     r.expect_token("<Nnet3>")
     lines = []
     # config-like section: text lines up to the first blank line, in both modes
@@ -557,3 +560,137 @@ def read_ivector_extractor(path: str) -> dict:
 def read_cmvn_stats(path: str) -> np.ndarray:
     """global_cmvn.stats: a 2 x (dim + 1) double matrix (transform/cmvn.cc)."""
     return np.asarray(read_matrix(path), np.float64)
+
+
+# ----------------------------------------------------------------------------- transition model, final.mdl
+
+def _read_topology(r: Reader) -> dict:
+    """HmmTopology::Read (hmm/hmm-topology.cc:38-163).  entries[i] = list of states
+    {forward_pdf_class, self_loop_pdf_class, transitions [(dst, prob)]}."""
+    r.expect_token("<Topology>")
+    entries, phone2idx, phones = [], {}, []
+    if not r.binary:
+        while True:
+            tok = r.read_token()
+            if tok == "</Topology>":
+                break
+            if tok != "<TopologyEntry>":
+                raise KaldiFormatError(f"expected <TopologyEntry>, got {tok}")
+            r.expect_token("<ForPhones>")
+            ph = []
+            while True:
+                t = r.read_token()
+                if t == "</ForPhones>":
+                    break
+                ph.append(int(t))
+            states = []
+            while True:
+                t = r.read_token()
+                if t == "</TopologyEntry>":
+                    break
+                if t != "<State>":
+                    raise KaldiFormatError(f"expected <State>, got {t}")
+                idx = r.read_int()
+                if idx != len(states):
+                    raise KaldiFormatError("states out of order in topology")
+                st = {"forward_pdf_class": -1, "self_loop_pdf_class": -1, "transitions": []}
+                while True:
+                    t = r.read_token()
+                    if t == "</State>":
+                        break
+                    if t == "<PdfClass>":
+                        st["forward_pdf_class"] = st["self_loop_pdf_class"] = r.read_int()
+                    elif t == "<ForwardPdfClass>":
+                        st["forward_pdf_class"] = r.read_int()
+                    elif t == "<SelfLoopPdfClass>":
+                        st["self_loop_pdf_class"] = r.read_int()
+                    elif t in ("<Transition>", "<Final>"):
+                        if t == "<Transition>":
+                            dst = r.read_int()
+                            st["transitions"].append((dst, r.read_float()))
+                        else:
+                            r.read_float()
+                    else:
+                        raise KaldiFormatError(f"unexpected token {t} in topology state")
+                states.append(st)
+            for p in ph:
+                phone2idx[p] = len(entries)
+            phones += ph
+            entries.append(states)
+        return {"phones": sorted(phones), "phone2idx": phone2idx, "entries": entries}
+    phones = r.read_int_vector().tolist()
+    p2i = r.read_int_vector().tolist()
+    n = r.read_int()
+    is_hmm = True
+    if n == -1:                          # the extended format with self-loop pdf classes (:213)
+        is_hmm = False
+        n = r.read_int()
+    for _ in range(n):
+        ns = r.read_int()
+        states = []
+        for _ in range(ns):
+            fwd = r.read_int()
+            sl = fwd if is_hmm else r.read_int()
+            nt = r.read_int()
+            tr = []
+            for _ in range(nt):
+                dst = r.read_int()
+                tr.append((dst, r.read_float()))
+            states.append({"forward_pdf_class": fwd, "self_loop_pdf_class": sl, "transitions": tr})
+        entries.append(states)
+    r.expect_token("</Topology>")
+    return {"phones": phones, "phone2idx": {p: i for p, i in enumerate(p2i) if i >= 0}, "entries": entries}
+
+
+def _read_transition_model(r: Reader) -> dict:
+    """TransitionModel::Read + ComputeDerived (hmm/transition-model.cc:394-420,144-188).
+    tid2pdf[t] for t = 1..num_tids (index 0 is a 0 placeholder, as CudaFst's table wants it)."""
+    r.expect_token("<TransitionModel>")
+    topo = _read_topology(r)
+    tok = r.read_token()
+    if tok not in ("<Triples>", "<Tuples>"):
+        raise KaldiFormatError(f"expected <Triples>/<Tuples>, got {tok}")
+    has_sl = tok == "<Tuples>"
+    n = r.read_int()
+    tuples = []
+    for _ in range(n):
+        phone, hs, fwd = r.read_int(), r.read_int(), r.read_int()
+        sl = r.read_int() if has_sl else fwd
+        tuples.append((phone, hs, fwd, sl))
+    r.expect_token("</Triples>" if not has_sl else "</Tuples>")
+    r.expect_token("<LogProbs>")
+    log_probs = r.read_vector()
+    r.expect_token("</LogProbs>")
+    r.expect_token("</TransitionModel>")
+    tid2pdf, tid2phone, self_loop = [0], [0], [False]
+    for phone, hs, fwd, sl in tuples:
+        state = topo["entries"][topo["phone2idx"][phone]][hs]
+        for dst, _p in state["transitions"]:
+            is_sl = dst == hs
+            tid2pdf.append(sl if is_sl else fwd)
+            tid2phone.append(phone)
+            self_loop.append(is_sl)
+    if len(log_probs) != len(tid2pdf):
+        raise KaldiFormatError("transition model: <LogProbs> does not match the number of transition-ids")
+    return dict(topology=topo, tuples=tuples, log_probs=log_probs, tid2pdf=np.array(tid2pdf, np.int32),
+                tid2phone=np.array(tid2phone, np.int32), is_self_loop=np.array(self_loop, bool),
+                num_pdfs=int(max(max(t[2], t[3]) for t in tuples) + 1))
+
+
+def read_transition_model(path: str) -> dict:
+    return _read_transition_model(Reader.open(path))
+
+
+def read_final_mdl(path: str) -> dict:
+    """final.mdl of an nnet3 acoustic model: TransitionModel + AmNnetSimple (nnet3/am-nnet-simple.cc:47-57).
+    {"transition_model": ..., "nnet": parsed raw nnet3, "left_context", "right_context", "priors"}."""
+    r = Reader.open(path)
+    tm = _read_transition_model(r)
+    nnet = _read_nnet3(r)
+    r.expect_token("<LeftContext>")
+    lc = r.read_int()
+    r.expect_token("<RightContext>")
+    rc = r.read_int()
+    r.expect_token("<Priors>")
+    priors = r.read_vector()
+    return dict(transition_model=tm, nnet=nnet, left_context=lc, right_context=rc, priors=priors)

@@ -13,7 +13,10 @@
 #include <string>
 #include <vector>
 
+#include "hmm/hmm-topology.h"
+#include "hmm/transition-model.h"
 #include "nnet3/am-nnet-simple.h"
+#include "tree/context-dep.h"
 #include "util/kaldi-io.h"
 #include "nnet3/decodable-simple-looped.h"
 #include "nnet3/nnet-nnet.h"
@@ -156,6 +159,39 @@ int ref_nnet_write(void *h, const char *path, int binary) {
     r->nnet.Write(ko.Stream(), binary != 0);
     return ko.Close() ? 0 : -1;
   } catch (const std::exception &e) { fprintf(stderr, "ref_nnet_write: %s\n", e.what()); return -1; }
+}
+
+// final.mdl as nnet3-am-init / nnet3-am-copy write it: TransitionModel::Write (hmm/transition-model.cc:422)
+// followed by AmNnetSimple::Write (nnet3/am-nnet-simple.cc:34).  The transition model is built by the reference
+// from a topology text and a monophone tree (tree/context-dep.cc:331); tid2pdf_out[t] = TransitionIdToPdf(t)
+// for t = 1..NumTransitionIds (index 0 unused) is returned for the reader's parity test.
+int ref_write_final_mdl(void *h, const char *path, int binary, const char *topo_text, int num_phones,
+                        int pdf_classes_per_phone, const float *priors, int num_priors,
+                        int *tid2pdf_out, int max_tids) {
+  try {
+    RefNnet *r = (RefNnet *)h;
+    HmmTopology topo;
+    { std::istringstream is(topo_text); topo.Read(is, false); }
+    std::vector<int32> phones, num_classes(num_phones + 1, 0);
+    for (int p = 1; p <= num_phones; p++) { phones.push_back(p); num_classes[p] = pdf_classes_per_phone; }
+    std::unique_ptr<ContextDependency> ctx(MonophoneContextDependency(phones, num_classes));
+    TransitionModel tm(*ctx, topo);
+    AmNnetSimple am(r->nnet);
+    if (priors && num_priors > 0) {
+      Vector<BaseFloat> pv(num_priors);
+      for (int i = 0; i < num_priors; i++) pv(i) = priors[i];
+      am.SetPriors(pv);
+    }
+    Output ko(path, binary != 0);
+    tm.Write(ko.Stream(), binary != 0);
+    am.Write(ko.Stream(), binary != 0);
+    if (!ko.Close()) return -1;
+    const int n = tm.NumTransitionIds();
+    if (n + 1 > max_tids) return -2;
+    tid2pdf_out[0] = 0;
+    for (int t = 1; t <= n; t++) tid2pdf_out[t] = tm.TransitionIdToPdf(t);
+    return n;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_write_final_mdl: %s\n", e.what()); return -1; }
 }
 
 }  // extern "C"

@@ -99,3 +99,52 @@ def test_ivector_extractor_and_ubm_files_written_by_the_reference(tmp_path):
         np.testing.assert_allclose(got["U"], ex["U"], rtol=1e-4 if not binary else 1e-12, atol=1e-5 if not binary else 1e-12)
         for k in ("gconsts", "ubm_weights", "means_invvars", "inv_vars"):
             np.testing.assert_allclose(ubm[k], ex[k], rtol=1e-5 if not binary else 1e-6, atol=1e-6, err_msg=k)
+
+
+CHAIN_TOPO = """<Topology>
+<TopologyEntry>
+<ForPhones> 1 2 3 4 5 </ForPhones>
+<State> 0 <ForwardPdfClass> 0 <SelfLoopPdfClass> 1 <Transition> 0 0.5 <Transition> 1 0.5 </State>
+<State> 1 </State>
+</TopologyEntry>
+</Topology>
+"""
+HMM3_TOPO = """<Topology>
+<TopologyEntry>
+<ForPhones> 1 2 3 4 5 </ForPhones>
+<State> 0 <PdfClass> 0 <Transition> 0 0.75 <Transition> 1 0.25 </State>
+<State> 1 <PdfClass> 1 <Transition> 1 0.75 <Transition> 2 0.25 </State>
+<State> 2 <PdfClass> 2 <Transition> 2 0.75 <Transition> 3 0.25 </State>
+<State> 3 </State>
+</TopologyEntry>
+</Topology>
+"""
+
+
+@pytest.mark.parametrize("topo,classes", [(CHAIN_TOPO, 2), (HMM3_TOPO, 3)], ids=["chain", "hmm3"])
+def test_final_mdl_written_by_the_reference(tmp_path, topo, classes):
+    from oracle import nnet_oracle as NO
+    if not (os.path.exists(NO._SO) or os.path.isdir("/root/reference")):
+        pytest.skip("oracle/_ref nnet3 library not present")
+    arch = NM.arch_tiny()
+    W = NM.random_weights(arch, seed=5)
+    R = NO.RefNnet(arch, W, collapse=False)
+    if not hasattr(R.lib, "ref_write_final_mdl"):
+        pytest.skip("oracle/_ref nnet3 library predates ref_write_final_mdl")
+    R.lib.ref_write_final_mdl.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    pri = np.ascontiguousarray(W["priors"], np.float32)
+    for binary in (1, 0):
+        path = str(tmp_path / f"final{binary}.mdl")
+        tid2pdf = np.zeros(256, np.int32)
+        n = R.lib.ref_write_final_mdl(R.h, path.encode(), binary, topo.encode(), 5, classes, pri.ctypes.data, pri.size,
+                                      tid2pdf.ctypes.data, tid2pdf.size)
+        assert n > 0
+        m = KIO.read_final_mdl(path)
+        tm = m["transition_model"]
+        np.testing.assert_array_equal(tm["tid2pdf"], tid2pdf[:n + 1])      # TransitionIdToPdf of the reference
+        assert tm["num_pdfs"] == 5 * classes
+        np.testing.assert_allclose(m["priors"], pri, rtol=0 if binary else 2e-5, atol=0 if binary else 1e-7)
+        arch2, W2 = KIO.nnet3_to_arch(m["nnet"])
+        assert [(L["type"], L["name"]) for L in arch2["layers"]] == [(L["type"], L["name"]) for L in arch["layers"]]
+        np.testing.assert_allclose(W2["output.affine.w"], W["output.affine.w"], rtol=0 if binary else 2e-5, atol=0 if binary else 1e-6)
