@@ -23,6 +23,9 @@ basic_layers.py / trivial_layers.py of egs/wsj/s5/steps/libs/nnet3/xconfig):
   linear          LinearComponent
   prefinal        NaturalGradientAffine + ReLU + BatchNorm + Linear + BatchNorm
   output          NaturalGradientAffine (no log-softmax for chain) [+ LogSoftmax]
+  ivector-linear-bn  LinearComponent over ReplaceIndex(ivector,t,0) + BatchNorm(target-rms)   (CNN-TDNN-F front)
+  combine         PermuteComponent interleaving the feature map of `cur` with a side node (combine-feature-maps-layer)
+  conv            TimeHeightConvolutionComponent + ReLU + BatchNorm(block-dim = filters) (conv-relu-batchnorm-layer)
 """
 from __future__ import annotations
 
@@ -55,6 +58,44 @@ def arch_tdnnf(name: str, feat_dim: int, ivector_dim: int, num_pdfs: int, dim: i
                dict(type="output", name="output", dim=num_pdfs, log_softmax=log_softmax)]
     return dict(name=name, feat_dim=feat_dim, ivector_dim=ivector_dim, num_pdfs=num_pdfs,
                 frame_subsampling_factor=3, layers=layers)
+
+
+def arch_cnn_tdnnf(name: str, feat_dim: int, ivector_dim: int, num_pdfs: int, ivector_linear_dim: int, convs,
+                   dim: int, bottleneck_first: int, bottleneck: int, n_tdnnf: int, prefinal_small: int) -> dict:
+    """egs/librispeech/s5/local/chain/tuning/run_cnn_tdnn_1a.sh:127-165.  convs: list of
+    (height_in, height_out, height_subsample_out, num_filters_out); 3x3 patches (time and height offsets -1,0,1)."""
+    assert ivector_linear_dim % feat_dim == 0
+    f2 = ivector_linear_dim // feat_dim
+    layers = [dict(type="idct", name="idct", dim=feat_dim),
+              dict(type="ivector-linear-bn", name="ivector", dim=ivector_linear_dim, target_rms=0.025),
+              dict(type="batchnorm", name="idct-batchnorm"),
+              dict(type="combine", name="combine_inputs", side="ivector-batchnorm", height=feat_dim, filters1=1, filters2=f2)]
+    fin = 1 + f2
+    for i, (hi, ho, sub, fo) in enumerate(convs):
+        layers.append(dict(type="conv", name=f"cnn{i + 1}", height_in=hi, height_out=ho, height_subsample_out=sub,
+                           filters_in=fin, filters_out=fo, time_offsets=[-1, 0, 1], height_offsets=[-1, 0, 1]))
+        fin = fo
+    first = len(convs) + 1
+    layers.append(dict(type="tdnnf", name=f"tdnnf{first}", dim=dim, bottleneck=bottleneck_first, stride=0, bypass=0.0))
+    for i in range(n_tdnnf - 1):
+        layers.append(dict(type="tdnnf", name=f"tdnnf{first + 1 + i}", dim=dim, bottleneck=bottleneck, stride=3, bypass=0.75))
+    layers += [dict(type="linear", name="prefinal-l", dim=prefinal_small),
+               dict(type="prefinal", name="prefinal-chain", small=prefinal_small, big=dim),
+               dict(type="output", name="output", dim=num_pdfs, log_softmax=False)]
+    return dict(name=name, feat_dim=feat_dim, ivector_dim=ivector_dim, num_pdfs=num_pdfs,
+                frame_subsampling_factor=3, layers=layers)
+
+
+def arch_librispeech_cnn_tdnn_1a(num_pdfs: int = 6024) -> dict:
+    """BASELINE config 3: librispeech CNN-TDNN-F (run_cnn_tdnn_1a.sh)."""
+    return arch_cnn_tdnnf("librispeech_cnn_tdnn_1a", 40, 100, num_pdfs, 200,
+                          [(40, 40, 1, 64), (40, 40, 1, 64), (40, 20, 2, 128), (20, 20, 1, 128), (20, 10, 2, 256), (10, 10, 1, 256)],
+                          1536, 256, 160, 12, 256)
+
+
+def arch_tiny_cnn(num_pdfs: int = 48) -> dict:
+    return arch_cnn_tdnnf("tiny_cnn_tdnnf", 40, 100, num_pdfs, 80, [(40, 40, 1, 4), (40, 20, 2, 6), (20, 10, 2, 8)],
+                          48, 16, 12, 3, 24)
 
 
 def arch_mini_librispeech_1k(num_pdfs: int = 2336) -> dict:
@@ -129,6 +170,16 @@ def random_weights(arch: dict, seed: int = 0) -> dict:
         elif t == "output":
             lin(n + ".affine", L["dim"], cur)
             cur = L["dim"]
+        elif t == "ivector-linear-bn":
+            lin(n + "-linear", L["dim"], ivd, bias=False)
+            bn(n + "-batchnorm", L["dim"])
+        elif t == "combine":
+            cur = cur + L["height"] * L["filters2"]
+        elif t == "conv":
+            k = len(L["time_offsets"]) * len(L["height_offsets"]) * L["filters_in"]
+            lin(n + ".conv", L["filters_out"], k)
+            bn(n + ".batchnorm", L["filters_out"])        # block-dim = filters_out: one statistic per filter
+            cur = L["height_out"] * L["filters_out"]
         else:
             raise ValueError(t)
     p = rng.uniform(0.5, 1.5, arch["num_pdfs"])
@@ -223,9 +274,12 @@ def to_nnet3_config(arch: dict, W: dict, tmpdir: str) -> str:
             c.append(f"component-node name={n}.relu component={n}.relu input={n}.affine")
             c.append(f"component name={n}.batchnorm type=BatchNormComponent dim={L['dim']}")
             c.append(f"component-node name={n}.batchnorm component={n}.batchnorm input={n}.relu")
-            c.append(f"component name={n}.noop type=NoOpComponent dim={L['dim']}")
-            c.append(f"component-node name={n}.noop component={n}.noop input=Sum(Scale({L['bypass']}, {cur}), {n}.batchnorm)")
-            cur, cur_dim = n + ".noop", L["dim"]
+            if L["bypass"] != 0.0:
+                c.append(f"component name={n}.noop type=NoOpComponent dim={L['dim']}")
+                c.append(f"component-node name={n}.noop component={n}.noop input=Sum(Scale({L['bypass']}, {cur}), {n}.batchnorm)")
+                cur, cur_dim = n + ".noop", L["dim"]
+            else:                # bypass-scale=0.0: tdnnf-layer emits no NoOp (composite_layers.py:213-222)
+                cur, cur_dim = n + ".batchnorm", L["dim"]
         elif t == "linear":
             c.append(f"component name={n} type=LinearComponent input-dim={cur_dim} output-dim={L['dim']} orthonormal-constraint=-1.0")
             c.append(f"component-node name={n} component={n} input={cur}")
@@ -242,6 +296,31 @@ def to_nnet3_config(arch: dict, W: dict, tmpdir: str) -> str:
             c.append(f"component name={n}.batchnorm2 type=BatchNormComponent dim={L['small']}")
             c.append(f"component-node name={n}.batchnorm2 component={n}.batchnorm2 input={n}.linear")
             cur, cur_dim = n + ".batchnorm2", L["small"]
+        elif t == "ivector-linear-bn":   # linear-component + batchnorm-component on ReplaceIndex(ivector, t, 0)
+            c.append(f"component name={n}-linear type=LinearComponent input-dim={ivd} output-dim={L['dim']}")
+            c.append(f"component-node name={n}-linear component={n}-linear input=ReplaceIndex(ivector, t, 0)")
+            c.append(f"component name={n}-batchnorm type=BatchNormComponent dim={L['dim']} target-rms={L['target_rms']}")
+            c.append(f"component-node name={n}-batchnorm component={n}-batchnorm input={n}-linear")
+        elif t == "combine":             # trivial_layers.py:402-430
+            h, f1, f2 = L["height"], L["filters1"], L["filters2"]
+            cmap = []
+            for hh in range(h):
+                cmap += [hh * f1 + f for f in range(f1)] + [h * f1 + hh * f2 + f for f in range(f2)]
+            c.append(f"component name={n} type=PermuteComponent column-map={','.join(map(str, cmap))}")
+            c.append(f"component-node name={n} component={n} input=Append({cur}, {L['side']})")
+            cur, cur_dim = n, h * (f1 + f2)
+        elif t == "conv":                # convolution.py:260-310 (conv-relu-batchnorm-layer)
+            od = L["height_out"] * L["filters_out"]
+            c.append(f"component name={n}.conv type=TimeHeightConvolutionComponent height-in={L['height_in']} "
+                     f"height-out={L['height_out']} height-subsample-out={L['height_subsample_out']} "
+                     f"num-filters-in={L['filters_in']} num-filters-out={L['filters_out']} "
+                     f"time-offsets={','.join(map(str, L['time_offsets']))} height-offsets={','.join(map(str, L['height_offsets']))}")
+            c.append(f"component-node name={n}.conv component={n}.conv input={cur}")
+            c.append(f"component name={n}.relu type=RectifiedLinearComponent dim={od} block-dim={L['filters_out']}")
+            c.append(f"component-node name={n}.relu component={n}.relu input={n}.conv")
+            c.append(f"component name={n}.batchnorm type=BatchNormComponent dim={od} block-dim={L['filters_out']}")
+            c.append(f"component-node name={n}.batchnorm component={n}.batchnorm input={n}.relu")
+            cur, cur_dim = n + ".batchnorm", od
         elif t == "output":
             c.append(f"component name={n}.affine type=NaturalGradientAffineComponent input-dim={cur_dim} output-dim={L['dim']}")
             c.append(f"component-node name={n}.affine component={n}.affine input={cur}")
@@ -259,11 +338,49 @@ def to_nnet3_config(arch: dict, W: dict, tmpdir: str) -> str:
 BN_EPS = 1e-3      # BatchNormComponent default epsilon (nnet-normalize-component.h)
 
 
-def bn_scale_offset(mean: np.ndarray, var: np.ndarray):
-    """BatchNormComponent::ComputeDerived (nnet-normalize-component.cc:209-246), target_rms = 1."""
+def bn_scale_offset(mean: np.ndarray, var: np.ndarray, target_rms: float = 1.0):
+    """BatchNormComponent::ComputeDerived (nnet-normalize-component.cc:209-246):
+    scale = (var + eps)^-0.5 * target_rms, offset = -mean * scale."""
     scale = np.power(np.maximum(var.astype(np.float32), 0.0) + np.float32(BN_EPS), np.float32(-0.5)).astype(np.float32)
+    if target_rms != 1.0:
+        scale = (scale * np.float32(target_rms)).astype(np.float32)
     offset = (-(mean.astype(np.float32)) * scale).astype(np.float32)
     return scale, offset
+
+
+def expand_conv_weights(L: dict, w: np.ndarray, b: np.ndarray, combine: dict | None):
+    """TimeHeightConvolutionComponent (nnet3/nnet-convolutional-component.cc:282-299, convolution.h:88-130) as a
+    dense affine map per time offset: returns (W_exp [H_out*F_out, n_t * K_in], b_exp, K_main, K_side) with
+      out[t, h*F_out + f] = b[f] + sum_{ti, dh, c} w[f, (ti*n_h + dhi)*F_in + c] * in[t + dt_ti, (h*sub + dh)*F_in + c]
+    (inputs outside 0 <= h_in < H_in are zero padding).  With `combine` (combine-feature-maps-layer in front:
+    the input map interleaves f1 filters of the main node with f2 of a side node) the columns of each time
+    block are reordered to [main node columns | side node columns] so the permutation costs nothing.
+    This is a first, functional mapping onto the GEMM kernel (it multiplies the structural zeros too:
+    ~n_h/H_in density); a patch-gather convolution kernel is the follow-up."""
+    Hi, Ho, sub = L["height_in"], L["height_out"], L["height_subsample_out"]
+    Fi, Fo = L["filters_in"], L["filters_out"]
+    toffs, hoffs = L["time_offsets"], L["height_offsets"]
+    K = Hi * Fi
+    if combine:
+        f1, f2 = combine["filters1"], combine["filters2"]
+        assert f1 + f2 == Fi and combine["height"] == Hi
+        k_main, k_side = Hi * f1, Hi * f2
+    else:
+        f1, f2, k_main, k_side = Fi, 0, K, 0
+    We = np.zeros((Ho * Fo, len(toffs) * K), np.float32)
+    for ti in range(len(toffs)):
+        for hi_, dh in enumerate(hoffs):
+            blk = w[:, (ti * len(hoffs) + hi_) * Fi:(ti * len(hoffs) + hi_ + 1) * Fi]      # [Fo, Fi]
+            for ho in range(Ho):
+                h_in = ho * sub + dh
+                if not (0 <= h_in < Hi):
+                    continue
+                rows = slice(ho * Fo, (ho + 1) * Fo)
+                base = ti * K
+                We[rows, base + h_in * f1: base + h_in * f1 + f1] = blk[:, :f1]
+                if f2:
+                    We[rows, base + k_main + h_in * f2: base + k_main + h_in * f2 + f2] = blk[:, f1:]
+    return We, np.tile(b.astype(np.float32), Ho), k_main, k_side
 
 
 @dataclass
@@ -281,7 +398,7 @@ class Node:
     spec: dict = field(default_factory=dict)
 
 
-def build_graph(arch: dict, W: dict):
+def build_graph(arch: dict, W: dict, structural: bool = False):
     """Nodes in topological order.  Each non-input node has spec:
        gemm: terms=[(src, time_offset, w_cols(lo,hi), kind)], w, b, relu, bn=(scale,offset)|None,
              res=(src, alpha)|None, post=(sub_vec, mul)|None, log_softmax
@@ -296,7 +413,7 @@ def build_graph(arch: dict, W: dict):
         nodes.append(n)
         dims[n.name] = n.dim
 
-    pending_bn = None
+    pending_combine = None
     for L in arch["layers"]:
         t, n = L["type"], L["name"]
         if t == "idct":
@@ -341,7 +458,7 @@ def build_graph(arch: dict, W: dict):
                      spec=dict(terms=[(n + ".linear", o, (i * bt, (i + 1) * bt), "row") for i, o in enumerate(o2)],
                                w=W[n + ".affine.w"], b=W[n + ".affine.b"], relu=True,
                                bn=bn_scale_offset(W[n + ".batchnorm.mean"], W[n + ".batchnorm.var"]),
-                               res=(cur, float(L["bypass"])))))
+                               res=(cur, float(L["bypass"])) if L["bypass"] != 0.0 else None)))
             cur = n + ".noop"
         elif t == "linear":
             d = dims[cur]
@@ -356,6 +473,33 @@ def build_graph(arch: dict, W: dict):
                      spec=dict(terms=[(n + ".batchnorm1", 0, (0, L["big"]), "row")], w=W[n + ".linear.w"], b=None,
                                bn=bn_scale_offset(W[n + ".batchnorm2.mean"], W[n + ".batchnorm2.var"]))))
             cur = n + ".batchnorm2"
+        elif t == "ivector-linear-bn":
+            # evaluated once per nnet chunk (the rows of the ivector input), like Scale(0.4, ReplaceIndex(ivector, t, 0))
+            add(Node(n + "-batchnorm", L["dim"], "gemm",
+                     spec=dict(terms=[("ivector", 0, (0, ivd), "chunk")], w=W[n + "-linear.w"], b=None, ivector_rows=True,
+                               bn=bn_scale_offset(W[n + "-batchnorm.mean"], W[n + "-batchnorm.var"], L["target_rms"]))))
+        elif t == "combine":
+            pending_combine = dict(L)
+        elif t == "conv":
+            if structural:       # context / range analysis only: no weights needed
+                f2 = pending_combine["filters2"] if pending_combine else 0
+                k_side = L["height_in"] * f2
+                k_main = L["height_in"] * L["filters_in"] - k_side
+                we, be = np.zeros((1, 1), np.float32), np.zeros(1, np.float32)
+            else:
+                we, be, k_main, k_side = expand_conv_weights(L, W[n + ".conv.w"], W[n + ".conv.b"], pending_combine)
+            K = k_main + k_side
+            terms = []
+            for ti, dt in enumerate(L["time_offsets"]):
+                terms.append((cur, dt, (ti * K, ti * K + k_main), "row"))
+                if k_side:
+                    terms.append((pending_combine["side"], dt, (ti * K + k_main, (ti + 1) * K), "ivec"))
+            sc, of = bn_scale_offset(W[n + ".batchnorm.mean"], W[n + ".batchnorm.var"])
+            add(Node(n + ".batchnorm", L["height_out"] * L["filters_out"], "gemm",
+                     spec=dict(terms=terms, w=we, b=be, relu=True,
+                               bn=(np.tile(sc, L["height_out"]), np.tile(of, L["height_out"])))))
+            pending_combine = None
+            cur = n + ".batchnorm"
         elif t == "output":
             d = dims[cur]
             add(Node("output", L["dim"], "gemm",
@@ -368,7 +512,7 @@ def build_graph(arch: dict, W: dict):
 def model_context(arch: dict):
     """(left_context, right_context) of the network = ComputeSimpleNnetContext
     (nnet3/nnet-utils.cc) for these architectures."""
-    nodes = build_graph(arch, _zero_weights(arch))
+    nodes = build_graph(arch, _zero_weights(arch), structural=True)
     lo = {n.name: 0 for n in nodes}
     hi = {n.name: 0 for n in nodes}
     order = {n.name: i for i, n in enumerate(nodes)}
@@ -388,6 +532,8 @@ def model_context(arch: dict):
 
 def _deps(n: Node):
     if n.kind == "gemm":
+        if n.spec.get("ivector_rows"):
+            return []
         d = [(src, off) for (src, off, _c, kind) in n.spec["terms"] if kind == "row"]
         if n.spec.get("res"):
             d.append((n.spec["res"][0], 0))
@@ -471,7 +617,18 @@ def compile_program(arch: dict, W: dict, num_frames: int, frames_per_chunk: int 
     for n in nodes:
         if n.kind in ("input", "ivector"):
             continue
-        if n.rows == 0 and not (n.kind == "ew" and n.spec.get("ivector_rows")):
+        if n.rows == 0 and not n.spec.get("ivector_rows"):
+            continue
+        if n.kind == "gemm" and n.spec.get("ivector_rows"):
+            n.step, n.t0, n.rows = 0, 0, n_chunks
+            sp = n.spec
+            bn = sp.get("bn")
+            ops.append(dict(type="gemm", out=idx[n.name], rows=n_chunks, N=sp["w"].shape[0], K=sp["w"].shape[1],
+                            terms=[dict(src=idx["ivector"], ratio=1, shift=0, lo=0, hi=n_chunks - 1, ivec=0, k0=c0, klen=c1 - c0)
+                                   for (_src, _off, (c0, c1), _kind) in sp["terms"]],
+                            w=put(sp["w"]), bias=put(sp["b"]) if sp.get("b") is not None else -1, relu=int(bool(sp.get("relu"))),
+                            bn_scale=put(bn[0]) if bn else -1, bn_offset=put(bn[1]) if bn else -1,
+                            res=None, res_alpha=0.0, sub_vec=-1, out_scale=1.0, log_softmax=0))
             continue
         if n.kind == "ew" and n.spec.get("ivector_rows"):
             n.step, n.t0, n.rows = 0, 0, n_chunks

@@ -58,16 +58,25 @@ class RefNnet:
             self.h = C.c_void_p(L.ref_nnet_create(cfg.encode()))
         if not self.h:
             raise RuntimeError("reference Nnet::ReadConfig failed")
+        # BatchNorm components whose dim differs from their statistics (block-dim) or with a target rms
+        bn_shape = {}
+        for Ly in arch["layers"]:
+            if Ly["type"] == "conv":
+                bn_shape[Ly["name"] + ".batchnorm"] = (Ly["height_out"] * Ly["filters_out"], 1.0)
+            elif Ly["type"] == "ivector-linear-bn":
+                bn_shape[Ly["name"] + "-batchnorm"] = (Ly["dim"], float(Ly["target_rms"]))
         n = L.ref_nnet_num_components(self.h)
         for i in range(n):
             name = L.ref_nnet_component_name(self.h, i).decode()
             typ = L.ref_nnet_component_type(self.h, i).decode()
             if typ == "BatchNormComponent":
                 mean, var = W[name + ".mean"], W[name + ".var"]
-                r = L.ref_nnet_set_batchnorm(self.h, i, C.c_int(mean.size), C.c_float(NM.BN_EPS), C.c_float(1.0),
-                                             C.c_float(1000.0), _p(mean, C.c_float), _p(var, C.c_float))
+                dim, target_rms = bn_shape.get(name, (mean.size, 1.0))
+                r = L.ref_nnet_set_batchnorm(self.h, i, C.c_int(dim), C.c_int(mean.size), C.c_float(NM.BN_EPS),
+                                             C.c_float(target_rms), C.c_float(1000.0), _p(mean, C.c_float), _p(var, C.c_float))
                 assert r == 0, name
-            elif typ in ("NaturalGradientAffineComponent", "AffineComponent", "TdnnComponent", "LinearComponent"):
+            elif typ in ("NaturalGradientAffineComponent", "AffineComponent", "TdnnComponent", "LinearComponent",
+                         "TimeHeightConvolutionComponent"):
                 w = W[name + ".w"]
                 vec = w.reshape(-1)
                 if name + ".b" in W:

@@ -1,0 +1,72 @@
+"""TEST INFRASTRUCTURE ONLY: a numpy interpreter of the op program that
+kaldi_b200.nnet_model.compile_program emits and kaldi_b200/csrc/nnet.cu executes
+(same row maps, same epilogue order).  It lets the tests check a compiled program
+against the reference's compiled nnet3 forward (oracle/_ref) on the CPU, so that
+a new layer type (e.g. the dense-expanded TimeHeightConvolutionComponent) is
+validated before any GPU time is spent; the GPU tests then only have to show
+that the kernels execute the same program.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _rows(term: dict, n_rows: int) -> np.ndarray:
+    i = np.arange(n_rows, dtype=np.int64)
+    j = i * term["ratio"] + term["shift"]
+    if term.get("ivec"):
+        j = np.floor_divide(j, term["C"]) - term["m"]          # floor division, also for negative times
+    return np.clip(j, term["lo"], term["hi"])
+
+
+def run_program(prog: dict, feats: np.ndarray, chunk_ivectors: np.ndarray | None) -> np.ndarray:
+    blob = prog["blob"]
+    nodes = prog["nodes"]                                       # (name, dim, rows, t0, step)
+    val = {}
+    for i, (name, dim, rows, _t0, _step) in enumerate(nodes):
+        if name == "input":
+            val[i] = np.ascontiguousarray(feats, np.float32)
+        elif name == "ivector":
+            val[i] = (np.zeros((prog["n_chunks"], dim), np.float32) if chunk_ivectors is None
+                      else np.ascontiguousarray(chunk_ivectors, np.float32))
+    out = None
+    for op in prog["ops"]:
+        name, dim, _r, _t0, _step = nodes[op["out"]]
+        R = op["rows"]
+        if op["type"] == "gemm":
+            N, K = op["N"], op["K"]
+            w = blob[op["w"]:op["w"] + N * K].reshape(N, K)
+            acc = np.zeros((R, N), np.float32)
+            for t in op["terms"]:
+                src = val[t["src"]][_rows(t, R)][:, :t["klen"]]
+                acc += src @ w[:, t["k0"]:t["k0"] + t["klen"]].T
+            v = acc
+            if op["bias"] >= 0:
+                v = v + blob[op["bias"]:op["bias"] + N]
+            if op["relu"]:
+                v = np.maximum(v, 0.0)
+            if op["bn_scale"] >= 0:
+                v = v * blob[op["bn_scale"]:op["bn_scale"] + N] + blob[op["bn_offset"]:op["bn_offset"] + N]
+            if op.get("res"):
+                v = np.float32(op["res_alpha"]) * val[op["res"]["src"]][_rows(op["res"], R)] + v
+            if op["log_softmax"]:
+                m = v.max(axis=1, keepdims=True)
+                v = v - (m + np.log(np.exp(v - m).sum(axis=1, keepdims=True)))
+            if op["sub_vec"] >= 0:
+                v = v - blob[op["sub_vec"]:op["sub_vec"] + N]
+            if op["out_scale"] != 1.0:
+                v = v * np.float32(op["out_scale"])
+            v = v.astype(np.float32)
+        else:
+            bd = op["block_dim"]
+            v = np.zeros((R, dim), np.float32)
+            for bi, blk in enumerate(op["blocks"]):
+                for t in blk:
+                    v[:, bi * bd:(bi + 1) * bd] += np.float32(t["scale"]) * val[t["src"]][_rows(t, R)][:, :bd]
+            if op["bn_scale"] >= 0:
+                v = v * blob[op["bn_scale"]:op["bn_scale"] + dim] + blob[op["bn_offset"]:op["bn_offset"] + dim]
+            v = v.astype(np.float32)
+        val[op["out"]] = v
+        if name == "output":
+            out = v
+    return out

@@ -80,17 +80,17 @@ int ref_nnet_set_params(void *h, int i, const float *in) {
 }
 // replace a BatchNormComponent by one with the given stats (text Read path,
 // nnet-normalize-component.cc:591-614)
-int ref_nnet_set_batchnorm(void *h, int i, int dim, float epsilon, float target_rms, float count,
+int ref_nnet_set_batchnorm(void *h, int i, int dim, int block_dim, float epsilon, float target_rms, float count,
                            const float *mean, const float *var) {
   try {
     RefNnet *r = (RefNnet *)h;
     std::ostringstream os;
     os.precision(9);
-    os << "<BatchNormComponent> <Dim> " << dim << " <BlockDim> " << dim << " <Epsilon> " << epsilon
+    os << "<BatchNormComponent> <Dim> " << dim << " <BlockDim> " << block_dim << " <Epsilon> " << epsilon
        << " <TargetRms> " << target_rms << " <TestMode> F <Count> " << count << " <StatsMean> [ ";
-    for (int d = 0; d < dim; d++) os << mean[d] << " ";
+    for (int d = 0; d < block_dim; d++) os << mean[d] << " ";      // statistics are per block element
     os << "] <StatsVar> [ ";
-    for (int d = 0; d < dim; d++) os << var[d] << " ";
+    for (int d = 0; d < block_dim; d++) os << var[d] << " ";
     os << "] </BatchNormComponent> ";
     std::istringstream is(os.str());
     Component *c = Component::ReadNew(is, false);

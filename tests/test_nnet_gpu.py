@@ -92,3 +92,31 @@ def test_missing_ivectors_is_an_error():
     x = torch.zeros(30, 40, device="cuda"); o = torch.zeros(10, 64, device="cuda")
     with pytest.raises(B2kError):
         nc.Run([x.data_ptr()], 40, None, 0, [o.data_ptr()], 64)
+
+
+@pytest.mark.parametrize("T", [90, 23])
+def test_cnn_tdnnf_front_end_vs_compiled_reference(T):
+    """CNN-TDNN-F (BASELINE config 3 family): TimeHeightConvolutionComponent + ReLU + block BatchNorm layers,
+    combine-feature-maps, the per-chunk i-vector linear+batchnorm branch, a no-bypass TDNN-F layer."""
+    from kaldi_b200.nnet import NnetComputer
+    from oracle import nnet_oracle as NO
+    from oracle.program_interp import run_program
+    arch = NM.arch_tiny_cnn()
+    W = NM.random_weights(arch, seed=7)
+    nc = NnetComputer(arch, W, num_frames=T, max_batch=2, acoustic_scale=0.9)
+    R = NO.RefNnet(arch, W, frames_per_chunk=20, acoustic_scale=0.9)
+    batch = [_inputs(T, s, nc.n_chunks) for s in range(2)]
+    outs = nc.forward([b[0] for b in batch], [b[1] for b in batch])
+    prog = NM.compile_program(arch, W, T, 21, acoustic_scale=0.9)
+    for (feats, civ), o in zip(batch, outs):
+        ends = [(n + 1) * R.frames_per_chunk + R.right_context for n in range(nc.n_chunks)]
+        mat = np.zeros((ends[-1] + 1, 100), np.float32)
+        prev = 0
+        for n, e in enumerate(ends):
+            mat[prev:e + 1] = civ[n]
+            prev = e + 1
+        ref = R.forward(feats, mat, period=1)
+        scale = np.abs(ref).max()
+        assert o.shape == ref.shape
+        assert np.abs(o - ref).max() <= RTOL_SCALE * scale
+        assert np.abs(o - run_program(prog, feats, civ)).max() <= RTOL_SCALE * scale

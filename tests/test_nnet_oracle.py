@@ -70,3 +70,35 @@ def test_compile_program_shapes():
     names = {n[0]: n for n in p["nodes"]}
     assert names["tdnnf6.noop"][4] == 3 and names["tdnnf3.noop"][4] == 1    # time grids: step 3 after tdnnf4
     assert NM.num_parameters(arch, W) == 4466056
+
+
+def _ref_forward(R, feats, civ, n_chunks):
+    """The reference's looped forward with chunk n reading civ[n] (online_ivectors matrix of period 1)."""
+    ends = [(n + 1) * R.frames_per_chunk + R.right_context for n in range(n_chunks)]
+    mat = np.zeros((ends[-1] + 1, civ.shape[1]), np.float32)
+    prev = 0
+    for n, e in enumerate(ends):
+        mat[prev:e + 1] = civ[n]
+        prev = e + 1
+    return R.forward(feats, mat, period=1)
+
+
+@pytest.mark.parametrize("which,T", [("tdnnf", 64), ("cnn", 90), ("cnn", 23)])
+def test_compiled_program_vs_compiled_reference(which, T):
+    """The op program itself (what the CUDA executor runs), interpreted in numpy, against the reference's
+    compiled nnet3: covers the CNN-TDNN-F front end (TimeHeightConvolutionComponent as a dense map per
+    time offset, combine-feature-maps permutation folded into the weights, per-chunk i-vector branch)."""
+    from oracle import nnet_oracle as NO
+    from oracle.program_interp import run_program
+    arch = NM.arch_tiny_cnn() if which == "cnn" else NM.arch_tiny(64)
+    W = NM.random_weights(arch, seed=7)
+    prog = NM.compile_program(arch, W, T, 21, acoustic_scale=0.9)
+    R = NO.RefNnet(arch, W, frames_per_chunk=20, acoustic_scale=0.9)
+    assert (prog["model_left"], prog["model_right"]) == (R.left_context, R.right_context)
+    rng = np.random.default_rng(5)
+    feats = (rng.standard_normal((T, 40)) * 10).astype(np.float32)
+    civ = rng.standard_normal((prog["n_chunks"], 100)).astype(np.float32)
+    mine = run_program(prog, feats, civ)
+    ref = _ref_forward(R, feats, civ, prog["n_chunks"])
+    assert mine.shape == ref.shape
+    assert np.abs(mine - ref).max() <= 1e-4 * np.abs(ref).max()
