@@ -299,18 +299,25 @@ typedef struct {
   int32_t k0, klen;      /* GEMM: columns [k0, k0+klen) of W multiply this term       */
   float scale;           /* EW: coefficient                                          */
   int32_t block;         /* EW: output column block this term adds into              */
+  /* GEMM ops with hsplit > 1 (time-height convolution): the term reads klen columns starting at
+   * column h*col_step + col_off of the source row, or zeros when that lies outside [0, col_lim)
+   * (height zero padding); col_lim = 0 means a plain term                                     */
+  int32_t col_step, col_off, col_lim;
 } b2k_nnet_term;
 
 typedef struct {
   int32_t type;          /* 0 GEMM (+fused epilogue), 1 elementwise                   */
   int32_t out, rows, N, K;
   int32_t n_terms;
-  b2k_nnet_term terms[8];
+  b2k_nnet_term terms[12];
   int64_t w, bias, bn_scale, bn_offset, sub_vec;   /* float offsets into the blob, -1 = absent */
   int32_t relu, has_res;
   b2k_nnet_term res;     /* bypass input: out = res_alpha*res + bn(...)               */
   float res_alpha, out_scale;
   int32_t log_softmax, block_dim;
+  /* > 1: TimeHeightConvolutionComponent (nnet3/nnet-convolutional-component.cc:282): every output row is
+   * hsplit GEMM rows (one per output height h), written to columns [h*N, (h+1)*N) of the node's row     */
+  int32_t hsplit;
 } b2k_nnet_op;
 
 typedef struct b2k_nnet b2k_nnet;

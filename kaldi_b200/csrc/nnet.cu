@@ -39,17 +39,19 @@ struct TermDev {
   int ratio, shift, lo, hi, ivec, C, m;
   int k0, klen;
   float scale;
+  int col_step, col_off, col_lim;   // hsplit ops: source column window per output height (col_lim 0 = plain)
 };
 
 struct OpDev {
   int type;              // 0 gemm, 1 ew
   long long out_off; int out_dim; int out_kind;   // out_kind 0 internal, 3 external output
   int rows, N, K;
-  int n_terms; TermDev terms[8];
+  int n_terms; TermDev terms[12];
   const float *w, *bias, *bn_scale, *bn_offset, *sub_vec;
   int relu, has_res; TermDev res; float res_alpha, out_scale;
-  int block_dim; int term_block[8];
+  int block_dim; int term_block[12];
   int log_softmax;       // output post-processing is then applied after the log-softmax kernel
+  int hsplit;            // > 1: time-height convolution, hsplit GEMM rows (output heights) per node row
 };
 
 struct RunCtx {
@@ -70,6 +72,19 @@ __device__ __forceinline__ int map_row(const TermDev &t, int i) {
   return min(max(j, t.lo), t.hi);
 }
 
+// GEMM row r -> (utterance lane, node row, output height) and the term's source pointer for it
+struct RowIdx { int lane, i, h; };
+__device__ __forceinline__ RowIdx split_row(const OpDev &op, int r) {
+  const int H = op.hsplit > 1 ? op.hsplit : 1;
+  const int per_lane = op.rows * H;
+  RowIdx x;
+  x.lane = r / per_lane;
+  const int rem = r - x.lane * per_lane;
+  x.i = rem / H;
+  x.h = rem - x.i * H;
+  return x;
+}
+
 __device__ __forceinline__ const float *src_row_ptr(const RunCtx &c, const TermDev &t, int lane, int row) {
   if (t.src_kind == 0) return c.arena + (long long)lane * c.arena_stride + t.src_off + (long long)row * t.src_dim;
   if (t.src_kind == 1) return c.d_input[lane] + (long long)row * c.in_stride;
@@ -86,8 +101,8 @@ __global__ void __launch_bounds__(256) nnet_gemm_kernel(OpDev op, RunCtx c) {
   __shared__ float Bs[GM_BK][GM_BN + 4];
   __shared__ const float *rowp[GM_BM];
   const int tid = threadIdx.x;
-  const int M = c.batch * op.rows;
-  const int m0 = blockIdx.y * GM_BM, n0 = blockIdx.x * GM_BN;
+  const int M = c.batch * op.rows * (op.hsplit > 1 ? op.hsplit : 1);
+  const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * GM_BN;    // x = row tiles (can exceed 65535 with hsplit)
   const int tx = tid & 15, ty = tid >> 4;         // 16 x 16 thread grid
   float acc[4][4];
 #pragma unroll
@@ -102,8 +117,12 @@ __global__ void __launch_bounds__(256) nnet_gemm_kernel(OpDev op, RunCtx c) {
       int r = m0 + tid;
       const float *p = nullptr;
       if (r < M) {
-        int lane = r / op.rows, i = r - lane * op.rows;
-        p = src_row_ptr(c, t, lane, map_row(t, i));
+        const RowIdx x = split_row(op, r);
+        p = src_row_ptr(c, t, x.lane, map_row(t, x.i));
+        if (t.col_lim > 0) {                              // convolution patch: column window of this output height
+          const int cb = x.h * t.col_step + t.col_off;
+          p = (cb >= 0 && cb < t.col_lim) ? p + cb : nullptr;   // outside = height zero padding
+        }
       }
       rowp[tid] = p;
     }
@@ -149,9 +168,10 @@ __global__ void __launch_bounds__(256) nnet_gemm_kernel(OpDev op, RunCtx c) {
   for (int i = 0; i < 4; i++) {
     int r = m0 + ty * 4 + i;
     if (r >= M) continue;
-    int lane = r / op.rows, ri = r - lane * op.rows;
+    const RowIdx x = split_row(op, r);
+    const int lane = x.lane, ri = x.i;
     float *orow = (op.out_kind == 0)
-                      ? c.arena + (long long)lane * c.arena_stride + op.out_off + (long long)ri * op.out_dim
+                      ? c.arena + (long long)lane * c.arena_stride + op.out_off + (long long)ri * op.out_dim + (long long)x.h * op.N
                       : c.d_out[lane] + (long long)ri * c.out_stride;
     const float *rrow = nullptr;
     if (op.has_res) rrow = src_row_ptr(c, op.res, lane, map_row(op.res, ri));
@@ -215,8 +235,8 @@ __global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c
   const int warp = tid >> 5, lane_id = tid & 31;
   const int g = lane_id >> 2, t4 = lane_id & 3;
   const int wm = warp & 1, wn = warp >> 1;                          // 2 x 4 warps
-  const int M = c.batch * op.rows;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int M = c.batch * op.rows * (op.hsplit > 1 ? op.hsplit : 1);
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;    // x = row tiles (can exceed 65535 with hsplit)
   float acc[2][NT][4];
 #pragma unroll
   for (int i = 0; i < 2; i++)
@@ -234,8 +254,12 @@ __global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c
       int r = m0 + tid;
       const float *p = nullptr;
       if (r < M) {
-        int lane = r / op.rows, i = r - lane * op.rows;
-        p = src_row_ptr(c, t, lane, map_row(t, i));
+        const RowIdx x = split_row(op, r);
+        p = src_row_ptr(c, t, x.lane, map_row(t, x.i));
+        if (t.col_lim > 0) {                              // convolution patch: column window of this output height
+          const int cb = x.h * t.col_step + t.col_off;
+          p = (cb >= 0 && cb < t.col_lim) ? p + cb : nullptr;   // outside = height zero padding
+        }
       }
       rowp[tid] = p;
     }
@@ -306,9 +330,10 @@ __global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c
     for (int half = 0; half < 2; half++) {
       const int r = m0 + wm * 32 + mi * 16 + g + half * 8;
       if (r >= M) continue;
-      const int lane = r / op.rows, ri = r - lane * op.rows;
+      const RowIdx x = split_row(op, r);
+      const int lane = x.lane, ri = x.i;
       float *orow = (op.out_kind == 0)
-                        ? c.arena + (long long)lane * c.arena_stride + op.out_off + (long long)ri * op.out_dim
+                        ? c.arena + (long long)lane * c.arena_stride + op.out_off + (long long)ri * op.out_dim + (long long)x.h * op.N
                         : c.d_out[lane] + (long long)ri * c.out_stride;
       const float *rrow = nullptr;
       if (op.has_res) rrow = src_row_ptr(c, op.res, lane, map_row(op.res, ri));
@@ -437,11 +462,13 @@ int b2k_nnet_create(const b2k_nnet_node *nodes, int32_t n_nodes, const b2k_nnet_
     d->src_kind = s.kind == 3 ? 0 : s.kind; d->src_off = s.arena_off; d->src_dim = s.dim;
     d->ratio = t.ratio; d->shift = t.shift; d->lo = t.lo; d->hi = t.hi; d->ivec = t.ivec; d->C = t.C > 0 ? t.C : 1;
     d->m = t.m; d->k0 = t.k0; d->klen = t.klen; d->scale = t.scale;
+    d->col_step = t.col_step; d->col_off = t.col_off; d->col_lim = t.col_lim;
+    if (t.col_lim < 0 || (t.col_lim > 0 && (t.klen > s.dim || t.col_lim > s.dim))) return set_error(B2K_ERR_INVALID, "bad column window");
     return 0;
   };
   for (int i = 0; i < n_ops; i++) {
     const b2k_nnet_op &o = ops[i];
-    if (o.n_terms < 1 || o.n_terms > 8 || o.out < 0 || o.out >= n_nodes) { return set_error(B2K_ERR_INVALID, "bad op"); }
+    if (o.n_terms < 1 || o.n_terms > 12 || o.out < 0 || o.out >= n_nodes || o.hsplit < 0) { return set_error(B2K_ERR_INVALID, "bad op"); }
     OpDev d;
     memset(&d, 0, sizeof(d));
     d.type = o.type; d.out_off = nodes[o.out].arena_off; d.out_dim = nodes[o.out].dim;
@@ -449,11 +476,14 @@ int b2k_nnet_create(const b2k_nnet_node *nodes, int32_t n_nodes, const b2k_nnet_
     d.rows = o.rows; d.N = o.N; d.K = o.K; d.n_terms = o.n_terms;
     for (int t = 0; t < o.n_terms; t++) { if ((rc = mk_term(o.terms[t], &d.terms[t]))) return rc; d.term_block[t] = o.terms[t].block; }
     d.w = bp(o.w); d.bias = bp(o.bias); d.bn_scale = bp(o.bn_scale); d.bn_offset = bp(o.bn_offset); d.sub_vec = bp(o.sub_vec);
+    d.hsplit = o.hsplit > 1 ? o.hsplit : 1;
+    if (d.hsplit > 1 && (o.type != 0 || o.log_softmax || o.has_res || nodes[o.out].kind == 3 || (long long)d.hsplit * o.N != nodes[o.out].dim))
+      return set_error(B2K_ERR_INVALID, "hsplit is for internal convolution GEMM ops whose node dim is hsplit * N");
     d.log_softmax = o.log_softmax; d.relu = o.relu; d.has_res = o.has_res; d.res_alpha = o.res_alpha; d.out_scale = o.out_scale; d.block_dim = o.block_dim > 0 ? o.block_dim : 1;
     if (o.has_res && (rc = mk_term(o.res, &d.res))) return rc;
     nn->ops.push_back(d);
     nn->log_softmax.push_back(o.log_softmax);
-    if (o.type == 0) nn->flops_per_lane += 2.0 * o.K * o.N * o.rows;
+    if (o.type == 0) nn->flops_per_lane += 2.0 * o.K * o.N * o.rows * d.hsplit;
   }
   size_t pb = sizeof(void *) * max_batch;
   B2K_CUDA_CHECK(cudaMalloc((void **)&nn->d_in, pb)); B2K_CUDA_CHECK(cudaMalloc((void **)&nn->d_iv, pb));
@@ -504,10 +534,10 @@ int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32
   c.d_ivec = nn->d_iv; c.iv_stride = iv_stride; c.d_out = nn->d_outp; c.out_stride = out_stride; c.batch = batch;
   for (size_t i = 0; i < nn->ops.size(); i++) {
     const OpDev &op = nn->ops[i];
-    long long M = (long long)batch * op.rows;
+    long long M = (long long)batch * op.rows * (op.type == 0 && op.hsplit > 1 ? op.hsplit : 1);
     if (op.type == 0) {
       if (use_simt_gemm()) {
-        dim3 grid((op.N + GM_BN - 1) / GM_BN, (unsigned)((M + GM_BM - 1) / GM_BM));
+        dim3 grid((unsigned)((M + GM_BM - 1) / GM_BM), (op.N + GM_BN - 1) / GM_BN);
         nnet_gemm_kernel<<<grid, 256, 0, st>>>(op, c);
       } else {
         static bool configured = false;
@@ -520,10 +550,10 @@ int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32
         // column tile 128 or 96, whichever pads N less (the N = 96 / 192 bottlenecks of TDNN-F)
         const int pad4 = (op.N + 127) / 128 * 128, pad3 = (op.N + 95) / 96 * 96;
         if (pad3 < pad4) {
-          dim3 grid(pad3 / 96, (unsigned)((M + TC_BM - 1) / TC_BM));
+          dim3 grid((unsigned)((M + TC_BM - 1) / TC_BM), pad3 / 96);
           nnet_gemm_tc_kernel<3><<<grid, 256, smem3, st>>>(op, c);
         } else {
-          dim3 grid(pad4 / 128, (unsigned)((M + TC_BM - 1) / TC_BM));
+          dim3 grid((unsigned)((M + TC_BM - 1) / TC_BM), pad4 / 128);
           nnet_gemm_tc_kernel<4><<<grid, 256, smem4, st>>>(op, c);
         }
       }

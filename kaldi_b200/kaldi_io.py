@@ -150,6 +150,23 @@ class Reader:
         self.p = e + 1
         return v
 
+    def read_int_pair_vector(self) -> np.ndarray:
+        """ReadIntegerPairVector (io-funcs-inl.h:113-190): [n, 2]; text form "[ a,b c,d ]"."""
+        if self.binary:
+            size = self.d[self.p]
+            self.p += 1
+            n = struct.unpack_from("<i", self.d, self.p)[0]
+            self.p += 4
+            dt = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[size]
+            v = np.frombuffer(self.d, dt, 2 * n, self.p).reshape(n, 2).copy()
+            self.p += 2 * n * size
+            return v
+        self._ws()
+        e = self.d.index(b"]", self.p)
+        items = self.d[self.p + 1:e].split()
+        self.p = e + 1
+        return np.array([[int(x) for x in it.split(b",")] for it in items], dtype=np.int64).reshape(-1, 2)
+
     # ---- matrices and vectors
     def _text_brackets(self) -> np.ndarray:
         self._ws()
@@ -236,7 +253,8 @@ class Reader:
             return self.read_int()
         raise KaldiFormatError(f"cannot parse a value at byte {self.p} (0x{b:02x})")
 
-    def read_fields(self, end_token: str, int_vector_tokens=("<TimeOffsets>",)) -> dict:
+    def read_fields(self, end_token: str, int_vector_tokens=("<TimeOffsets>", "<RequiredTimeOffsets>", "<ColumnMap>"),
+                    pair_vector_tokens=("<Offsets>",)) -> dict:
         """Parses "<A> v <B> v v ... </End>" into {"<A>": [values], ...} (order kept)."""
         out = {}
         while True:
@@ -250,13 +268,20 @@ class Reader:
                 if self.binary:
                     if self.d[self.p:self.p + 1] == b"<":
                         break
-                    vals.append(self.read_int_vector() if tok in int_vector_tokens else self._binary_value())
+                    if tok in pair_vector_tokens:
+                        vals.append(self.read_int_pair_vector())
+                    elif tok in int_vector_tokens:
+                        vals.append(self.read_int_vector())
+                    else:
+                        vals.append(self._binary_value())
                 else:
                     self._ws()
                     c = self.d[self.p:self.p + 1]
                     if c == b"<":
                         break
-                    if c == b"[":
+                    if c == b"[" and tok in pair_vector_tokens:
+                        vals.append(self.read_int_pair_vector())
+                    elif c == b"[":
                         rows = self._text_brackets()
                         if tok in int_vector_tokens:
                             vals.append(np.array([x for r in rows for x in r], dtype=np.int64))
@@ -412,6 +437,7 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
         W[key + ".var"] = var.astype(np.float32)
         return count
 
+    node_dim = {"input": dims["input"], "ivector": dims.get("ivector", 0)}
     cn = [(kv["name"], kv) for kind, kv in nodes if kind == "component-node"]
     names = [n for n, _ in cn]
     inputs = {n: kv["input"] for n, kv in cn}
@@ -421,9 +447,57 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
         n, kv = cn[i]
         c = comps[kv["component"]]
         t = c["type"]
-        if t == "FixedAffineComponent" and inputs[n] == "input":
+        if t == "LinearComponent" and "ivector" in inputs[n] and i + 1 < len(cn) \
+                and comps[cn[i + 1][1]["component"]]["type"] == "BatchNormComponent" and n.endswith("-linear"):
+            base = n[:-7]                       # linear-component + batchnorm-component on ReplaceIndex(ivector, t, 0)
+            w = mat(n, "<LinearParams>")
+            bnn = cn[i + 1][0]
+            layers.append({"type": "ivector-linear-bn", "name": base, "dim": int(w.shape[0]),
+                           "target_rms": round(_f(comps[bnn], "<TargetRms>").as_float(), 6)})
+            W[n + ".w"] = w
+            bn(bnn, bnn)
+            node_dim[bnn] = int(w.shape[0])
+            i += 2
+        elif t == "PermuteComponent":
+            m = re.match(r"Append\((\S+),\s*(\S+)\)", inputs[n])
+            if not m:
+                raise KaldiFormatError(f"unsupported PermuteComponent input {inputs[n]}")
+            main, side = m.group(1), m.group(2)
+            nxt = comps[cn[i + 1][1]["component"]]
+            if nxt["type"] != "TimeHeightConvolutionComponent":
+                raise KaldiFormatError("PermuteComponent is only supported as combine-feature-maps in front of a convolution")
+            h = _f(nxt, "<HeightIn>").as_int()
+            f1, f2 = node_dim[main] // h, node_dim[side] // h
+            want = []
+            for hh in range(h):
+                want += [hh * f1 + f for f in range(f1)] + [h * f1 + hh * f2 + f for f in range(f2)]
+            if np.asarray(_f(c, "<ColumnMap>")).tolist() != want:
+                raise KaldiFormatError("PermuteComponent column map is not a combine-feature-maps interleave")
+            layers.append({"type": "combine", "name": n, "side": side, "height": h, "filters1": f1, "filters2": f2})
+            node_dim[n] = node_dim[main] + node_dim[side]
+            i += 1
+        elif t == "TimeHeightConvolutionComponent" and n.endswith(".conv"):
+            base = n[:-5]
+            offs = np.asarray(_f(c, "<Offsets>"))
+            L = {"type": "conv", "name": base, "height_in": _f(c, "<HeightIn>").as_int(),
+                 "height_out": _f(c, "<HeightOut>").as_int(), "height_subsample_out": _f(c, "<HeightSubsampleOut>").as_int(),
+                 "filters_in": _f(c, "<NumFiltersIn>").as_int(), "filters_out": _f(c, "<NumFiltersOut>").as_int(),
+                 "time_offsets": sorted(set(offs[:, 0].tolist())), "height_offsets": sorted(set(offs[:, 1].tolist()))}
+            if len(offs) != len(L["time_offsets"]) * len(L["height_offsets"]):
+                raise KaldiFormatError("convolution offsets are not a full time x height grid")
+            if sorted(np.asarray(_f(c, "<RequiredTimeOffsets>")).tolist()) != L["time_offsets"]:
+                raise KaldiFormatError("time zero-padding (required-time-offsets) is not supported")
+            if [x[0] for x in cn[i + 1:i + 3]] != [base + ".relu", base + ".batchnorm"]:
+                raise KaldiFormatError(f"expected conv-relu-batchnorm at {base}")
+            layers.append(L)
+            W[n + ".w"], W[n + ".b"] = mat(n, "<LinearParams>"), mat(n, "<BiasParams>")
+            bn(base + ".batchnorm", base + ".batchnorm")
+            node_dim[base + ".batchnorm"] = L["height_out"] * L["filters_out"]
+            i += 3
+        elif t == "FixedAffineComponent" and inputs[n] == "input":
             W[n + ".w"], W[n + ".b"] = mat(n, "<LinearParams>"), mat(n, "<BiasParams>")
             layers.append({"type": "idct", "name": n, "dim": int(W[n + ".w"].shape[0])})
+            node_dim[n] = int(W[n + ".w"].shape[0])
             i += 1
         elif t == "FixedAffineComponent":
             layers.append({"type": "lda", "name": n})
@@ -441,6 +515,7 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
         elif t == "BatchNormComponent":
             layers.append({"type": "batchnorm", "name": n})
             bn(n, n)
+            node_dim[n] = _f(c, "<Dim>").as_int()
             i += 1
         elif t in ("NaturalGradientAffineComponent", "AffineComponent") and n.endswith(".affine") \
                 and i + 2 < len(cn) and cn[i + 1][0] == n[:-7] + ".relu":
@@ -471,7 +546,8 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
             stride = int(max(abs(o) for o in offs))
             if stride == 3 and sub is None:
                 sub = 3
-            m = re.search(r"Scale\(([0-9.eE+-]+),", inputs[base + ".noop"])
+            has_noop = base + ".noop" in inputs
+            m = re.search(r"Scale\(([0-9.eE+-]+),", inputs[base + ".noop"]) if has_noop else None
             wl = mat(n, "<LinearParams>")
             wa = mat(base + ".affine", "<LinearParams>")
             layers.append({"type": "tdnnf", "name": base, "dim": int(wa.shape[0]), "bottleneck": int(wl.shape[0]),
@@ -479,7 +555,7 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
             W[n + ".w"] = wl
             W[base + ".affine.w"], W[base + ".affine.b"] = wa, mat(base + ".affine", "<BiasParams>")
             bn(base + ".batchnorm", base + ".batchnorm")
-            i += 5
+            i += 5 if has_noop else 4           # bypass-scale 0: no NoOp node
         elif t == "LinearComponent":
             w = mat(n, "<LinearParams>")
             layers.append({"type": "linear", "name": n, "dim": int(w.shape[0])})

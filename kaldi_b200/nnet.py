@@ -19,21 +19,23 @@ class _Node(C.Structure):
 class _Term(C.Structure):
     _fields_ = [("src", C.c_int32), ("ratio", C.c_int32), ("shift", C.c_int32), ("lo", C.c_int32),
                 ("hi", C.c_int32), ("ivec", C.c_int32), ("C", C.c_int32), ("m", C.c_int32),
-                ("k0", C.c_int32), ("klen", C.c_int32), ("scale", C.c_float), ("block", C.c_int32)]
+                ("k0", C.c_int32), ("klen", C.c_int32), ("scale", C.c_float), ("block", C.c_int32),
+                ("col_step", C.c_int32), ("col_off", C.c_int32), ("col_lim", C.c_int32)]
 
 
 class _Op(C.Structure):
     _fields_ = [("type", C.c_int32), ("out", C.c_int32), ("rows", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
-                ("n_terms", C.c_int32), ("terms", _Term * 8),
+                ("n_terms", C.c_int32), ("terms", _Term * 12),
                 ("w", C.c_int64), ("bias", C.c_int64), ("bn_scale", C.c_int64), ("bn_offset", C.c_int64),
                 ("sub_vec", C.c_int64), ("relu", C.c_int32), ("has_res", C.c_int32), ("res", _Term),
                 ("res_alpha", C.c_float), ("out_scale", C.c_float), ("log_softmax", C.c_int32),
-                ("block_dim", C.c_int32)]
+                ("block_dim", C.c_int32), ("hsplit", C.c_int32)]
 
 
 def _term(d: dict, k0=0, klen=0, scale=1.0, block=0) -> _Term:
     return _Term(d["src"], d["ratio"], d["shift"], d["lo"], d["hi"], d.get("ivec", 0), d.get("C", 1), d.get("m", 0),
-                 d.get("k0", k0), d.get("klen", klen), d.get("scale", scale), block)
+                 d.get("k0", k0), d.get("klen", klen), d.get("scale", scale), block,
+                 d.get("col_step", 0), d.get("col_off", 0), d.get("col_lim", 0))
 
 
 class NnetComputer:
@@ -42,8 +44,9 @@ class NnetComputer:
     request shape as well, nnet3/nnet-compile-looped.cc:329)."""
 
     def __init__(self, arch: dict, W: dict, num_frames: int, max_batch: int, frames_per_chunk: int = 21,
-                 acoustic_scale: float = 1.0, use_priors: bool = True):
-        self.prog = prog = NM.compile_program(arch, W, num_frames, frames_per_chunk, acoustic_scale, use_priors)
+                 acoustic_scale: float = 1.0, use_priors: bool = True, conv_mode: str | None = None):
+        self.prog = prog = NM.compile_program(arch, W, num_frames, frames_per_chunk, acoustic_scale, use_priors,
+                                              conv_mode=conv_mode)
         nodes = (_Node * len(prog["nodes"]))()
         for i, (name, dim, rows, t0, step) in enumerate(prog["nodes"]):
             kind = {"input": 1, "ivector": 2, "output": 3}.get(name, 0)
@@ -58,7 +61,8 @@ class NnetComputer:
             if o["type"] == "gemm":
                 op.type, op.N, op.K = 0, o["N"], o["K"]
                 op.n_terms = len(o["terms"])
-                assert op.n_terms <= 8
+                assert op.n_terms <= 12
+                op.hsplit = o.get("hsplit", 1)
                 for j, t in enumerate(o["terms"]):
                     op.terms[j] = _term(t)
                 op.w, op.bias, op.sub_vec = o["w"], o["bias"], o.get("sub_vec", -1)
@@ -69,7 +73,7 @@ class NnetComputer:
                 op.type, op.block_dim = 1, o["block_dim"]
                 flat = [(b, t) for b, blk in enumerate(o["blocks"]) for t in blk]
                 op.n_terms = len(flat)
-                assert op.n_terms <= 8
+                assert op.n_terms <= 12
                 for j, (b, t) in enumerate(flat):
                     op.terms[j] = _term(t, block=b)
                 op.N = op.K = 0

@@ -398,7 +398,12 @@ class Node:
     spec: dict = field(default_factory=dict)
 
 
-def build_graph(arch: dict, W: dict, structural: bool = False):
+CONV_MODE_DEFAULT = "patch"      # time-height convolutions as hsplit GEMM ops (true convolution FLOPs); "dense": one dense
+                                 # [H_out*F_out, H_in*F_in] map per time offset (kept for A/B checks and for the first layer,
+                                 # whose combine-feature-maps permutation is folded into the weights)
+
+
+def build_graph(arch: dict, W: dict, structural: bool = False, conv_mode: str | None = None):
     """Nodes in topological order.  Each non-input node has spec:
        gemm: terms=[(src, time_offset, w_cols(lo,hi), kind)], w, b, relu, bn=(scale,offset)|None,
              res=(src, alpha)|None, post=(sub_vec, mul)|None, log_softmax
@@ -481,6 +486,23 @@ def build_graph(arch: dict, W: dict, structural: bool = False):
         elif t == "combine":
             pending_combine = dict(L)
         elif t == "conv":
+            mode = conv_mode or CONV_MODE_DEFAULT
+            if mode == "patch" and not pending_combine and not structural:
+                # one GEMM row per (time, output height): 9 terms of klen = filters_in, each reading the source
+                # row's column window of height h*subsample + dh (zeros outside = height padding)
+                Fi, Fo, Hi, Ho = L["filters_in"], L["filters_out"], L["height_in"], L["height_out"]
+                nh = len(L["height_offsets"])
+                terms, cols = [], []
+                for ti, dt in enumerate(L["time_offsets"]):
+                    for hi_, dh in enumerate(L["height_offsets"]):
+                        k0 = (ti * nh + hi_) * Fi
+                        terms.append((cur, dt, (k0, k0 + Fi), "row"))
+                        cols.append((L["height_subsample_out"] * Fi, dh * Fi, Hi * Fi))
+                add(Node(n + ".batchnorm", Ho * Fo, "gemm",
+                         spec=dict(terms=terms, term_cols=cols, hsplit=Ho, w=W[n + ".conv.w"], b=W[n + ".conv.b"], relu=True,
+                                   bn=bn_scale_offset(W[n + ".batchnorm.mean"], W[n + ".batchnorm.var"]))))
+                cur = n + ".batchnorm"
+                continue
             if structural:       # context / range analysis only: no weights needed
                 f2 = pending_combine["filters2"] if pending_combine else 0
                 k_side = L["height_in"] * f2
@@ -553,7 +575,7 @@ def _zero_weights(arch):
 
 
 def compile_program(arch: dict, W: dict, num_frames: int, frames_per_chunk: int = 21,
-                    acoustic_scale: float = 1.0, use_priors: bool = True) -> dict:
+                    acoustic_scale: float = 1.0, use_priors: bool = True, conv_mode: str | None = None) -> dict:
     """Compile for utterances of `num_frames` feature frames.  Returns a dict:
        nodes: [(name, dim, rows, t0, step)], ops: [op dicts], blob: float32 array,
        left/right context, num_out rows (= ceil(T / subsampling)), ivector chunk mapping.
@@ -561,7 +583,7 @@ def compile_program(arch: dict, W: dict, num_frames: int, frames_per_chunk: int 
     sub = arch["frame_subsampling_factor"]
     T = int(num_frames)
     n_out = (T + sub - 1) // sub
-    nodes = build_graph(arch, W)
+    nodes = build_graph(arch, W, conv_mode=conv_mode)
     by = {n.name: n for n in nodes}
     out = by["output"]
     out.residues, out.tmin, out.tmax = {0}, 0, sub * (n_out - 1)
@@ -660,14 +682,18 @@ def compile_program(arch: dict, W: dict, num_frames: int, frames_per_chunk: int 
             sp = n.spec
             w = sp["w"]
             terms = []
-            for (src, off, (c0, c1), kind) in sp["terms"]:
-                terms.append(dict(rowmap(src, off, kind), k0=c0, klen=c1 - c0))
+            for ti_, (src, off, (c0, c1), kind) in enumerate(sp["terms"]):
+                td = dict(rowmap(src, off, kind), k0=c0, klen=c1 - c0)
+                if sp.get("term_cols"):
+                    td["col_step"], td["col_off"], td["col_lim"] = sp["term_cols"][ti_]
+                terms.append(td)
             bn = sp.get("bn")
             res = sp.get("res")
             op = dict(type="gemm", out=idx[n.name], rows=n.rows, N=w.shape[0], K=w.shape[1], terms=terms,
                       w=put(w), bias=put(sp["b"]) if sp.get("b") is not None else -1, relu=int(bool(sp.get("relu"))),
                       bn_scale=put(bn[0]) if bn else -1, bn_offset=put(bn[1]) if bn else -1,
-                      res=None, res_alpha=0.0, sub_vec=-1, out_scale=1.0, log_softmax=int(bool(sp.get("log_softmax"))))
+                      res=None, res_alpha=0.0, sub_vec=-1, out_scale=1.0, log_softmax=int(bool(sp.get("log_softmax"))),
+                      hsplit=int(sp.get("hsplit", 1)))
             if res:
                 op["res"] = rowmap(res[0], 0, "row")
                 op["res_alpha"] = res[1]
@@ -717,7 +743,7 @@ def flops_per_output_frame(prog: dict) -> float:
     tot = 0.0
     for op in prog["ops"]:
         if op["type"] == "gemm":
-            tot += 2.0 * op["K"] * op["N"] * op["rows"]
+            tot += 2.0 * op["K"] * op["N"] * op["rows"] * op.get("hsplit", 1)
     return tot / prog["n_out"]
 
 

@@ -36,11 +36,20 @@ def run_program(prog: dict, feats: np.ndarray, chunk_ivectors: np.ndarray | None
         if op["type"] == "gemm":
             N, K = op["N"], op["K"]
             w = blob[op["w"]:op["w"] + N * K].reshape(N, K)
-            acc = np.zeros((R, N), np.float32)
+            H = op.get("hsplit", 1)
+            acc = np.zeros((R, H, N), np.float32)
             for t in op["terms"]:
-                src = val[t["src"]][_rows(t, R)][:, :t["klen"]]
-                acc += src @ w[:, t["k0"]:t["k0"] + t["klen"]].T
-            v = acc
+                rows = val[t["src"]][_rows(t, R)]
+                wt = w[:, t["k0"]:t["k0"] + t["klen"]].T
+                for h in range(H):
+                    if t.get("col_lim", 0) > 0:                 # convolution patch window of output height h
+                        cb = h * t["col_step"] + t["col_off"]
+                        if not (0 <= cb < t["col_lim"]):
+                            continue                            # height zero padding
+                        acc[:, h] += rows[:, cb:cb + t["klen"]] @ wt
+                    else:
+                        acc[:, h] += rows[:, :t["klen"]] @ wt
+            v = acc.reshape(R * H, N)
             if op["bias"] >= 0:
                 v = v + blob[op["bias"]:op["bias"] + N]
             if op["relu"]:
@@ -48,6 +57,7 @@ def run_program(prog: dict, feats: np.ndarray, chunk_ivectors: np.ndarray | None
             if op["bn_scale"] >= 0:
                 v = v * blob[op["bn_scale"]:op["bn_scale"] + N] + blob[op["bn_offset"]:op["bn_offset"] + N]
             if op.get("res"):
+                assert H == 1
                 v = np.float32(op["res_alpha"]) * val[op["res"]["src"]][_rows(op["res"], R)] + v
             if op["log_softmax"]:
                 m = v.max(axis=1, keepdims=True)
@@ -56,7 +66,7 @@ def run_program(prog: dict, feats: np.ndarray, chunk_ivectors: np.ndarray | None
                 v = v - blob[op["sub_vec"]:op["sub_vec"] + N]
             if op["out_scale"] != 1.0:
                 v = v * np.float32(op["out_scale"])
-            v = v.astype(np.float32)
+            v = v.astype(np.float32).reshape(R, H * N)
         else:
             bd = op["block_dim"]
             v = np.zeros((R, dim), np.float32)

@@ -94,8 +94,9 @@ def test_missing_ivectors_is_an_error():
         nc.Run([x.data_ptr()], 40, None, 0, [o.data_ptr()], 64)
 
 
+@pytest.mark.parametrize("conv_mode", ["dense", "patch"])
 @pytest.mark.parametrize("T", [90, 23])
-def test_cnn_tdnnf_front_end_vs_compiled_reference(T):
+def test_cnn_tdnnf_front_end_vs_compiled_reference(T, conv_mode):
     """CNN-TDNN-F (BASELINE config 3 family): TimeHeightConvolutionComponent + ReLU + block BatchNorm layers,
     combine-feature-maps, the per-chunk i-vector linear+batchnorm branch, a no-bypass TDNN-F layer."""
     from kaldi_b200.nnet import NnetComputer
@@ -103,11 +104,11 @@ def test_cnn_tdnnf_front_end_vs_compiled_reference(T):
     from oracle.program_interp import run_program
     arch = NM.arch_tiny_cnn()
     W = NM.random_weights(arch, seed=7)
-    nc = NnetComputer(arch, W, num_frames=T, max_batch=2, acoustic_scale=0.9)
+    nc = NnetComputer(arch, W, num_frames=T, max_batch=2, acoustic_scale=0.9, conv_mode=conv_mode)
     R = NO.RefNnet(arch, W, frames_per_chunk=20, acoustic_scale=0.9)
     batch = [_inputs(T, s, nc.n_chunks) for s in range(2)]
     outs = nc.forward([b[0] for b in batch], [b[1] for b in batch])
-    prog = NM.compile_program(arch, W, T, 21, acoustic_scale=0.9)
+    prog = NM.compile_program(arch, W, T, 21, acoustic_scale=0.9, conv_mode=conv_mode)
     for (feats, civ), o in zip(batch, outs):
         ends = [(n + 1) * R.frames_per_chunk + R.right_context for n in range(nc.n_chunks)]
         mat = np.zeros((ends[-1] + 1, 100), np.float32)

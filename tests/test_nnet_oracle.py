@@ -83,16 +83,16 @@ def _ref_forward(R, feats, civ, n_chunks):
     return R.forward(feats, mat, period=1)
 
 
-@pytest.mark.parametrize("which,T", [("tdnnf", 64), ("cnn", 90), ("cnn", 23)])
+@pytest.mark.parametrize("which,T", [("tdnnf", 64), ("cnn", 90), ("cnn", 23), ("cnn-patch", 90), ("cnn-patch", 23)])
 def test_compiled_program_vs_compiled_reference(which, T):
     """The op program itself (what the CUDA executor runs), interpreted in numpy, against the reference's
     compiled nnet3: covers the CNN-TDNN-F front end (TimeHeightConvolutionComponent as a dense map per
     time offset, combine-feature-maps permutation folded into the weights, per-chunk i-vector branch)."""
     from oracle import nnet_oracle as NO
     from oracle.program_interp import run_program
-    arch = NM.arch_tiny_cnn() if which == "cnn" else NM.arch_tiny(64)
+    arch = NM.arch_tiny_cnn() if which.startswith("cnn") else NM.arch_tiny(64)
     W = NM.random_weights(arch, seed=7)
-    prog = NM.compile_program(arch, W, T, 21, acoustic_scale=0.9)
+    prog = NM.compile_program(arch, W, T, 21, acoustic_scale=0.9, conv_mode="patch" if which == "cnn-patch" else "dense")
     R = NO.RefNnet(arch, W, frames_per_chunk=20, acoustic_scale=0.9)
     assert (prog["model_left"], prog["model_right"]) == (R.left_context, R.right_context)
     rng = np.random.default_rng(5)
