@@ -770,3 +770,133 @@ def read_final_mdl(path: str) -> dict:
     r.expect_token("<Priors>")
     priors = r.read_vector()
     return dict(transition_model=tm, nnet=nnet, left_context=lc, right_context=rc, priors=priors)
+
+
+# ----------------------------------------------------------------------------- OpenFst binary FSTs (HCLG.fst)
+#
+# PARITY UNPINNED: OpenFst (1.8.4, tools/Makefile:10) is absent from this image and the reference tree holds no
+# binary FST, so this reader follows the published on-disk layout of fst/fst.h (FstHeader::Write),
+# fst/vector-fst.h (VectorFstImpl::Write, file version 2) and fst/const-fst.h (ConstFstImpl::Write, file version
+# 2, aligned version 1) for StdArc ("standard") and has only been checked against its own writer below.
+
+_FST_MAGIC = 2125659606
+_SYMTAB_MAGIC = 2125658996
+_FST_HAS_ISYMBOLS, _FST_HAS_OSYMBOLS, _FST_IS_ALIGNED = 1, 2, 4
+
+
+def _fst_string(d: bytes, p: int):
+    n = struct.unpack_from("<i", d, p)[0]
+    return d[p + 4:p + 4 + n].decode("ascii"), p + 4 + n
+
+
+def _skip_symbol_table(d: bytes, p: int) -> int:
+    magic = struct.unpack_from("<i", d, p)[0]
+    if magic != _SYMTAB_MAGIC:
+        raise KaldiFormatError("bad symbol table magic")
+    _name, p = _fst_string(d, p + 4)
+    _avail, size = struct.unpack_from("<qq", d, p)
+    p += 16
+    for _ in range(size):
+        _sym, p = _fst_string(d, p)
+        p += 8
+    return p
+
+
+def read_openfst(path: str) -> dict:
+    """An OpenFst binary "vector" or "const" FST over StdArc as the CSR dictionary CudaFst takes:
+    num_states, start, offsets [S+1], ilabel/olabel/nextstate [A] int32, weight [A] float32, final [S] float32
+    (+inf = not final).  Arc order is file order (= ConstFst arc order, which the decoder's results depend on)."""
+    with open(path, "rb") as f:
+        d = f.read()
+    if struct.unpack_from("<i", d, 0)[0] != _FST_MAGIC:
+        raise KaldiFormatError("not an OpenFst binary file (bad magic number)")
+    fsttype, p = _fst_string(d, 4)
+    arctype, p = _fst_string(d, p)
+    version, flags = struct.unpack_from("<ii", d, p)
+    p += 8
+    _props, start, nstates, narcs = struct.unpack_from("<Qqqq", d, p)
+    p += 32
+    if arctype != "standard":
+        raise KaldiFormatError(f"arc type {arctype!r} is not supported (only StdArc)")
+    if flags & _FST_HAS_ISYMBOLS:
+        p = _skip_symbol_table(d, p)
+    if flags & _FST_HAS_OSYMBOLS:
+        p = _skip_symbol_table(d, p)
+    arc_dt = np.dtype([("ilabel", "<i4"), ("olabel", "<i4"), ("weight", "<f4"), ("nextstate", "<i4")])
+    if fsttype == "vector":
+        finals, offs, chunks = [], [0], []
+        s = 0
+        while (nstates < 0 or s < nstates) and p + 12 <= len(d):
+            fw = struct.unpack_from("<f", d, p)[0]
+            na = struct.unpack_from("<q", d, p + 4)[0]
+            p += 12
+            chunks.append(np.frombuffer(d, arc_dt, na, p))
+            p += na * 16
+            finals.append(fw)
+            offs.append(offs[-1] + na)
+            s += 1
+        arcs = np.concatenate(chunks) if chunks else np.zeros(0, arc_dt)
+        final = np.array(finals, np.float32)
+        offsets = np.array(offs, np.int64)
+    elif fsttype == "const":
+        if (flags & _FST_IS_ALIGNED) or version == 1:
+            p = (p + 15) // 16 * 16
+        st_dt = np.dtype([("final", "<f4"), ("pos", "<u4"), ("narcs", "<u4"), ("nieps", "<u4"), ("noeps", "<u4")])
+        st = np.frombuffer(d, st_dt, nstates, p)
+        p += nstates * st_dt.itemsize
+        if (flags & _FST_IS_ALIGNED) or version == 1:
+            p = (p + 15) // 16 * 16
+        arcs = np.frombuffer(d, arc_dt, narcs, p)
+        final = st["final"].astype(np.float32)
+        offsets = np.concatenate([st["pos"].astype(np.int64), [narcs]])
+        if nstates and not np.array_equal(np.diff(offsets), st["narcs"].astype(np.int64)):
+            raise KaldiFormatError("const FST: state table is not contiguous")
+    else:
+        raise KaldiFormatError(f"FST type {fsttype!r} is not supported (vector, const)")
+    if offsets[-1] > np.iinfo(np.int32).max:
+        raise KaldiFormatError("more than 2^31 arcs")
+    return dict(num_states=int(len(final)), start=int(start), offsets=offsets.astype(np.int32),
+                ilabel=np.ascontiguousarray(arcs["ilabel"]), olabel=np.ascontiguousarray(arcs["olabel"]),
+                weight=np.ascontiguousarray(arcs["weight"]), nextstate=np.ascontiguousarray(arcs["nextstate"]),
+                final=final, fst_type=fsttype)
+
+
+def write_openfst(path: str, g: dict, fst_type: str = "const", aligned: bool = False) -> None:
+    """Writer for the same layout (used by the self-consistency test and to hand graphs to OpenFst tools)."""
+    S, A = int(g["num_states"]), int(g["offsets"][-1])
+    arc_dt = np.dtype([("ilabel", "<i4"), ("olabel", "<i4"), ("weight", "<f4"), ("nextstate", "<i4")])
+    arcs = np.zeros(A, arc_dt)
+    for k in ("ilabel", "olabel", "weight", "nextstate"):
+        arcs[k] = g[k][:A]
+    fin = np.asarray(g["final"], np.float32)
+    off = np.asarray(g["offsets"], np.int64)
+
+    def fstr(x):
+        return struct.pack("<i", len(x)) + x.encode("ascii")
+    version = 2 if not (aligned and fst_type == "const") else 1
+    flags = _FST_IS_ALIGNED if (aligned and fst_type == "const") else 0
+    hdr = struct.pack("<i", _FST_MAGIC) + fstr(fst_type) + fstr("standard") + struct.pack("<ii", version, flags) + \
+        struct.pack("<Qqqq", 0, int(g["start"]), S, A)
+    with open(path, "wb") as f:
+        f.write(hdr)
+        if fst_type == "vector":
+            for s_ in range(S):
+                f.write(struct.pack("<f", float(fin[s_])) + struct.pack("<q", int(off[s_ + 1] - off[s_])))
+                f.write(arcs[off[s_]:off[s_ + 1]].tobytes())
+        else:
+            pos = len(hdr)
+            if aligned:
+                f.write(b"\0" * ((-pos) % 16))
+                pos += (-pos) % 16
+            st_dt = np.dtype([("final", "<f4"), ("pos", "<u4"), ("narcs", "<u4"), ("nieps", "<u4"), ("noeps", "<u4")])
+            st = np.zeros(S, st_dt)
+            st["final"], st["pos"], st["narcs"] = fin, off[:-1], np.diff(off)
+            ie = np.add.reduceat((arcs["ilabel"] == 0).astype(np.int64), off[:-1].clip(max=max(A - 1, 0))) if A else np.zeros(S, np.int64)
+            oe = np.add.reduceat((arcs["olabel"] == 0).astype(np.int64), off[:-1].clip(max=max(A - 1, 0))) if A else np.zeros(S, np.int64)
+            empty = np.diff(off) == 0
+            st["nieps"], st["noeps"] = np.where(empty, 0, ie), np.where(empty, 0, oe)
+            f.write(st.tobytes())
+            pos += S * st_dt.itemsize
+            if aligned:
+                f.write(b"\0" * ((-pos) % 16))
+            f.write(arcs.tobytes())

@@ -148,3 +148,19 @@ def test_final_mdl_written_by_the_reference(tmp_path, topo, classes):
         arch2, W2 = KIO.nnet3_to_arch(m["nnet"])
         assert [(L["type"], L["name"]) for L in arch2["layers"]] == [(L["type"], L["name"]) for L in arch["layers"]]
         np.testing.assert_allclose(W2["output.affine.w"], W["output.affine.w"], rtol=0 if binary else 2e-5, atol=0 if binary else 1e-6)
+
+
+@pytest.mark.parametrize("fst_type,aligned", [("const", False), ("const", True), ("vector", False)])
+def test_openfst_binary_layout_self_consistency(tmp_path, fst_type, aligned):
+    """PARITY UNPINNED (no OpenFst in this image): reader and writer agree with each other on the published
+    layout; the arrays come back bit for bit, arc order preserved."""
+    from kaldi_b200 import synth
+    g = synth.make_hclg(20_000, num_pdfs=50, seed=3)
+    p = str(tmp_path / "HCLG.fst")
+    KIO.write_openfst(p, g, fst_type, aligned)
+    h = KIO.read_openfst(p)
+    assert h["num_states"] == g["num_states"] and h["start"] == g["start"] and h["fst_type"] == fst_type
+    for k in ("offsets", "ilabel", "olabel", "nextstate"):
+        np.testing.assert_array_equal(h[k], np.asarray(g[k], np.int32)[:len(h[k])], err_msg=k)
+    np.testing.assert_array_equal(h["weight"].view(np.int32), np.asarray(g["weight"], np.float32).view(np.int32))
+    np.testing.assert_array_equal(h["final"].view(np.int32), np.asarray(g["final"], np.float32).view(np.int32))
