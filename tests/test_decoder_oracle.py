@@ -189,3 +189,28 @@ def test_compiled_reference_decoder_full_length():
     o = D.DecoderOracle(g, cfg)
     o.decode(ll, mode=D.MODE_REFERENCE_ORDER)
     assert D.lattices_equal(o.lattice(), r.lattice())
+
+
+def test_restatement_equals_compiled_reference_decoder_randomised():
+    """24 random (graph, utterance, config) draws: small and medium graphs, beams 4-16, lattice beams 2-10,
+    max_active from 50 (fires on every frame) to unlimited, min_active 0-200, interim pruning every 3 or 25 frames."""
+    R = _ref_decoder_or_skip()
+    rng = np.random.default_rng(0)
+    for it in range(24):
+        g = synth.make_hclg(int(rng.choice([2000, 8000, 40000])), num_pdfs=int(rng.choice([20, 60, 200])), seed=100 + it)
+        T = int(rng.integers(5, 40))
+        ll = synth.make_loglikes(g, T, seed=500 + it)
+        cfg = dict(synth.DEFAULT_DECODER_CFG, beam=float(rng.choice([4, 8, 12, 16])),
+                   lattice_beam=float(rng.choice([2, 6, 10])), max_active=int(rng.choice([50, 300, 2000, 2**31 - 1])),
+                   min_active=int(rng.choice([0, 20, 200])), prune_interval=int(rng.choice([3, 25])))
+        if cfg["min_active"] > cfg["max_active"]:
+            cfg["min_active"] = 0
+        r = R.RefDecoder(g, cfg)
+        r.decode(ll)
+        o = D.DecoderOracle(g, cfg)
+        o.decode(ll, mode=D.MODE_REFERENCE_ORDER, record_frames=True)
+        for f in range(T + 1):
+            st, co = r.frame_tokens(f)
+            want = _sorted_rows(np.stack([st, co.view(np.int32)], axis=1)) if len(st) else np.zeros((0, 2), np.int32)
+            assert np.array_equal(o.raw_frame(f)["toks"], want), (it, f, cfg)
+        assert D.lattices_equal(o.lattice(), r.lattice()), (it, cfg)
