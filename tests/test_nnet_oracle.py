@@ -102,3 +102,22 @@ def test_compiled_program_vs_compiled_reference(which, T):
     ref = _ref_forward(R, feats, civ, prog["n_chunks"])
     assert mine.shape == ref.shape
     assert np.abs(mine - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("which", ["librispeech_tdnn_1d", "librispeech_cnn_tdnn_1a"])
+def test_baseline_config_architectures_vs_compiled_reference(which):
+    """BASELINE.json configs 2 and 3 at full width (fewer pdfs to keep it quick): the compiled op program vs the
+    reference's compiled nnet3, and ComputeSimpleNnetContext."""
+    from oracle import nnet_oracle as NO
+    from oracle.program_interp import run_program
+    arch = (NM.arch_librispeech_1d if which == "librispeech_tdnn_1d" else NM.arch_librispeech_cnn_tdnn_1a)(num_pdfs=512)
+    W = NM.random_weights(arch, seed=1)
+    T = 50
+    prog = NM.compile_program(arch, W, T, 21)
+    R = NO.RefNnet(arch, W, frames_per_chunk=20)
+    assert (prog["model_left"], prog["model_right"]) == (R.left_context, R.right_context)
+    rng = np.random.default_rng(2)
+    feats = (rng.standard_normal((T, 40)) * 10).astype(np.float32)
+    civ = rng.standard_normal((prog["n_chunks"], 100)).astype(np.float32)
+    ref = _ref_forward(R, feats, civ, prog["n_chunks"])
+    assert np.abs(run_program(prog, feats, civ) - ref).max() <= 1e-4 * np.abs(ref).max()
