@@ -20,6 +20,11 @@
 #include "b2k.h"
 #include "base/kaldi-error.h"
 #include "itf/online-feature-itf.h"
+#include "itf/transition-information.h"
+#ifdef B2K_HAVE_OPENFST
+#include "fst/fstlib.h"
+#include "lat/kaldi-lattice.h"
+#endif
 #include "matrix/kaldi-matrix.h"
 #include "matrix/kaldi-vector.h"
 
@@ -84,6 +89,49 @@ class OnlineBaseFeatureB2k : public OnlineBaseFeature {
   float *d_wave_ = nullptr, *d_feats_ = nullptr;
   Matrix<BaseFloat> host_;
 };
+
+#ifdef B2K_HAVE_OPENFST
+// cuda_decoder::CudaFst (cudadecoder/cuda-fst.h:62-82): CSR of the decoding graph in arc (file) order, with the
+// transition-id -> pdf table pre-applied on the device as CudaFst::ApplyTransitionModelOnIlabels does (cuda-fst.cc:34-198).
+class CudaFstB2k {
+ public:
+  CudaFstB2k(const fst::StdFst &fst, const TransitionInformation *trans_model = nullptr) {
+    std::vector<int32> offsets(1, 0), ilabel, olabel, nextstate;
+    std::vector<float> weight, final_cost;
+    for (fst::StateIterator<fst::StdFst> siter(fst); !siter.Done(); siter.Next()) {
+      const fst::StdArc::StateId s = siter.Value();
+      for (fst::ArcIterator<fst::StdFst> aiter(fst, s); !aiter.Done(); aiter.Next()) {
+        const fst::StdArc &arc = aiter.Value();
+        ilabel.push_back(arc.ilabel); olabel.push_back(arc.olabel);
+        weight.push_back(arc.weight.Value()); nextstate.push_back(arc.nextstate);
+      }
+      offsets.push_back(static_cast<int32>(ilabel.size()));
+      final_cost.push_back(fst.Final(s).Value());
+    }
+    b2k_fst_csr csr = {};
+    csr.num_states = static_cast<int32>(final_cost.size());
+    csr.start = fst.Start();
+    csr.offsets = offsets.data(); csr.ilabel = ilabel.data(); csr.olabel = olabel.data();
+    csr.weight = weight.data(); csr.nextstate = nextstate.data(); csr.final_cost = final_cost.data();
+    if (trans_model) {   // TransitionIdToPdfArray(): index = transition-id (itf/transition-information.h:94)
+      const std::vector<int32_t> &t2p = trans_model->TransitionIdToPdfArray();
+      csr.tid2pdf = t2p.data();
+      csr.num_tids = static_cast<int32>(t2p.size());
+      Check(b2k_fst_create(&csr, &fst_), "b2k_fst_create");
+    } else {
+      Check(b2k_fst_create(&csr, &fst_), "b2k_fst_create");
+    }
+  }
+  ~CudaFstB2k() { b2k_fst_destroy(fst_); }
+  CudaFstB2k(const CudaFstB2k &) = delete;
+  CudaFstB2k &operator=(const CudaFstB2k &) = delete;
+  uint32_t NumStates() const { return static_cast<uint32_t>(b2k_fst_num_states(fst_)); }
+  fst::StdArc::StateId Start() const { return b2k_fst_start(fst_); }
+  const b2k_fst *Handle() const { return fst_; }
+ private:
+  b2k_fst *fst_ = nullptr;
+};
+#endif
 
 // cuda_decoder::CudaDecoder surface (cudadecoder/cuda-decoder.h:171-346) over b2k_dec_*.
 typedef int32 ChannelId;

@@ -15,6 +15,13 @@ def check() -> bool:
         cmd = ["g++", "-fsyntax-only"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "kaldi_b200", "host"),
                                                       "-I/usr/local/cuda/include"]) + [src]
         subprocess.check_call(cmd)
+        # the OpenFst-typed members (CudaFstB2k, CudaDecoderB2k::GetRawLattice), type-checked against the
+        # container-only stand-in of oracle/ref_wrap/fst_stub (OpenFst itself is not in this image)
+        stub = os.path.join(ROOT, "oracle", "ref_wrap", "fst_stub")
+        flags = RF.cxxflags(["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "kaldi_b200", "host"),
+                             "-I/usr/local/cuda/include"])
+        flags = [f for f in flags if not f.startswith("-I")] + ["-I" + stub] + [f for f in flags if f.startswith("-I")]
+        subprocess.check_call(["g++", "-fsyntax-only", "-DB2K_HAVE_OPENFST"] + flags + [src])
     return True
 
 

@@ -106,6 +106,18 @@ class ArcIterator {
   size_t i_;
 };
 
+template <class F>
+class StateIterator {
+ public:
+  typedef typename F::Arc::StateId StateId;
+  explicit StateIterator(const F &fst) : n_(fst.NumStates()), s_(0) {}
+  bool Done() const { return s_ >= n_; }
+  void Next() { ++s_; }
+  StateId Value() const { return s_; }
+ private:
+  StateId n_, s_;
+};
+
 // fst/memory.h: fixed-size object pool (block size is only a hint in the reference too)
 template <class T>
 class MemoryPool {
