@@ -2189,13 +2189,14 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     A(p.x_order, 4 * nl * p.max_tpf, 0);
     p.adj_cap = 2 * p.max_tpf;
     p.rs_rcap = 4096; p.rs_ecap = 4096; p.rs_qcap = 4096;  // shared-memory walk: 80 KB per CTA (two 512-thread CTAs per SM)
-    if (const char *e = getenv("B2K_DEC_RS_CAPS")) {          // tuning knob: "tokens,arcs,worklist" (each <= 8192; 0,0,0 = off)
+    if (const char *e = getenv("B2K_DEC_RS_CAPS")) {          // tuning knob: "tokens,arcs,worklist" (powers of two <= 8192, tokens == arcs; 0,0,0 = off)
       int a = 0, b = 0, c = 0;
       if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= 0 && b >= 0 && c >= 0 && a <= 8192 && b <= 8192 && c <= 8192) {
         // powers of two only: the kernel's key sort pads the replay worklist to a power of two inside
         // the (tokens + arcs) * 8-byte area
         auto pow2_floor = [](int v) { int q = 1; while (q * 2 <= v) q *= 2; return v > 0 ? q : 0; };
         p.rs_rcap = pow2_floor(a); p.rs_ecap = pow2_floor(b); p.rs_qcap = pow2_floor(c);
+        if (p.rs_rcap != p.rs_ecap) p.rs_rcap = p.rs_ecap = std::min(p.rs_rcap, p.rs_ecap);   // (their sum must be one too)
         if (!a || !b || !c) { p.rs_rcap = p.rs_ecap = p.rs_qcap = 0; }
       }
     }
