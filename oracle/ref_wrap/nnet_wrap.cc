@@ -194,4 +194,30 @@ int ref_write_final_mdl(void *h, const char *path, int binary, const char *topo_
   } catch (const std::exception &e) { fprintf(stderr, "ref_write_final_mdl: %s\n", e.what()); return -1; }
 }
 
+// Matrix<float>::Read / Vector<float>::Read through Input (util/kaldi-io.h), binary or text: the reference-side
+// check of the writers in kaldi_b200/kaldi_io.py.  Returns rows (matrix) or dim (vector), -1 on failure.
+int ref_read_matrix(const char *path, float *out, int max_elems, int *cols) {
+  try {
+    bool binary;
+    Input ki(path, &binary);
+    Matrix<BaseFloat> m;
+    m.Read(ki.Stream(), binary);
+    if ((long long)m.NumRows() * m.NumCols() > max_elems) return -2;
+    for (int r = 0; r < m.NumRows(); r++) memcpy(out + (size_t)r * m.NumCols(), m.RowData(r), sizeof(float) * m.NumCols());
+    *cols = m.NumCols();
+    return m.NumRows();
+  } catch (const std::exception &e) { fprintf(stderr, "ref_read_matrix: %s\n", e.what()); return -1; }
+}
+int ref_read_vector(const char *path, float *out, int max_elems) {
+  try {
+    bool binary;
+    Input ki(path, &binary);
+    Vector<BaseFloat> v;
+    v.Read(ki.Stream(), binary);
+    if (v.Dim() > max_elems) return -2;
+    memcpy(out, v.Data(), sizeof(float) * v.Dim());
+    return v.Dim();
+  } catch (const std::exception &e) { fprintf(stderr, "ref_read_vector: %s\n", e.what()); return -1; }
+}
+
 }  // extern "C"

@@ -164,3 +164,30 @@ def test_openfst_binary_layout_self_consistency(tmp_path, fst_type, aligned):
         np.testing.assert_array_equal(h[k], np.asarray(g[k], np.int32)[:len(h[k])], err_msg=k)
     np.testing.assert_array_equal(h["weight"].view(np.int32), np.asarray(g["weight"], np.float32).view(np.int32))
     np.testing.assert_array_equal(h["final"].view(np.int32), np.asarray(g["final"], np.float32).view(np.int32))
+
+
+def test_written_matrices_are_read_by_the_reference(tmp_path):
+    """The other direction: what kaldi_io writes, the reference's Matrix/Vector::Read must accept, bit for bit."""
+    from oracle import nnet_oracle as NO
+    if not (os.path.exists(NO._SO) or os.path.isdir("/root/reference")):
+        pytest.skip("oracle/_ref library not present")
+    L = C.CDLL(NO._SO)
+    if not hasattr(L, "ref_read_matrix"):
+        pytest.skip("oracle/_ref library predates ref_read_matrix")
+    L.ref_read_matrix.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ref_read_vector.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(4)
+    m = rng.standard_normal((6, 9)).astype(np.float32)
+    v = rng.standard_normal(11).astype(np.float32)
+    for binary in (True, False):
+        pm, pv = str(tmp_path / f"m{int(binary)}"), str(tmp_path / f"v{int(binary)}")
+        KIO.write_matrix(pm, m, binary)
+        KIO.write_vector(pv, v, binary)
+        out = np.zeros(m.size, np.float32)
+        cols = C.c_int()
+        rows = L.ref_read_matrix(pm.encode(), out.ctypes.data, out.size, C.addressof(cols))
+        assert (rows, cols.value) == m.shape
+        np.testing.assert_array_equal(out.reshape(m.shape), m)
+        outv = np.zeros(v.size, np.float32)
+        assert L.ref_read_vector(pv.encode(), outv.ctypes.data, outv.size) == v.size
+        np.testing.assert_array_equal(outv, v)
