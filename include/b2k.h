@@ -339,6 +339,56 @@ int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32
                  const float *const *d_ivectors, int32_t iv_stride, float *const *d_output,
                  int32_t out_stride, void *stream);
 
+/* ------------------------------------------------------------------ nnet3 program compiler (host only)
+ *
+ * From a chain-model layer list (the xconfig layers of the TDNN-F and CNN-TDNN-F recipes) and its parameters
+ * to the op program b2k_nnet_create executes: the role of nnet3's compiler for this family
+ * (nnet3/nnet-compile.cc, nnet-compile-looped.cc:329, nnet-optimize.cc) for utterances of `num_frames`
+ * feature frames.  Needs no device.  kaldi_b200/nnet_model.py holds the same algorithm in Python as its
+ * test oracle (identical nodes / ops / blob). */
+typedef struct {
+  char type[24];   /* idct | batchnorm | delta | lda | relu-batchnorm | tdnnf | linear | prefinal | output |
+                      ivector-linear-bn | combine | conv  (steps/libs/nnet3/xconfig layer kinds)          */
+  char name[48];
+  char side[48];   /* combine: the node appended to the current one before the interleave                 */
+  int32_t dim, bottleneck, stride, big, small, log_softmax;
+  float bypass, append_ivector, target_rms;          /* append_ivector: 0 = none, else the Scale() factor */
+  int32_t height, filters1, filters2;                /* combine-feature-maps-layer                        */
+  int32_t height_in, height_out, height_subsample_out, filters_in, filters_out;   /* conv-relu-batchnorm-layer */
+  int32_t n_time_offsets, time_offsets[8], n_height_offsets, height_offsets[8];
+} b2k_nnet_layer;
+
+typedef struct {
+  const char *name;      /* "<component>.w" [rows x cols], ".b" [rows], ".mean" / ".var" (BatchNorm stats), "priors" */
+  const float *data;
+  int64_t size;
+  int32_t rows, cols;
+} b2k_nnet_weight;
+
+typedef struct {
+  int32_t feat_dim, ivector_dim, num_pdfs, frame_subsampling_factor;
+  int32_t num_frames;        /* feature frames per utterance the program is compiled for                  */
+  int32_t frames_per_chunk;  /* --frames-per-chunk of the looped computation, a multiple of the subsampling factor */
+  int32_t use_priors;        /* subtract log priors at the output (decodable-online-looped.cc:218-223)     */
+  int32_t conv_dense;        /* 1: every convolution as a dense map per time offset (A/B checks)           */
+  float acoustic_scale;
+} b2k_nnet_compile_cfg;
+
+typedef struct b2k_nnet_program b2k_nnet_program;
+
+int b2k_nnet_compile(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers,
+                     const b2k_nnet_weight *weights, int32_t n_weights, b2k_nnet_program **out);
+int b2k_nnet_program_destroy(b2k_nnet_program *prog);
+int b2k_nnet_program_sizes(const b2k_nnet_program *prog, int32_t *n_nodes, int32_t *n_ops, int64_t *blob_len);
+const b2k_nnet_node *b2k_nnet_program_nodes(const b2k_nnet_program *prog);
+const b2k_nnet_op *b2k_nnet_program_ops(const b2k_nnet_program *prog);
+const float *b2k_nnet_program_blob(const b2k_nnet_program *prog);
+/* info: [0] output rows, [1] nnet chunks, [2]/[3] input frames needed left/right of the utterance,
+ * [4]/[5] model left/right context (ComputeSimpleNnetContext), [6] chunk lag m of the i-vector, [7] arena floats per utterance */
+int b2k_nnet_program_info(const b2k_nnet_program *prog, int64_t info[8]);
+/* b2k_nnet_create on a compiled program (needs the device) */
+int b2k_nnet_create_from_program(const b2k_nnet_program *prog, int32_t max_batch, b2k_nnet **out);
+
 #ifdef __cplusplus
 }
 #endif
