@@ -339,6 +339,14 @@ int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32
                  const float *const *d_ivectors, int32_t iv_stride, float *const *d_output,
                  int32_t out_stride, void *stream);
 
+/* Which feature frame OnlineIvectorFeature::GetFrame is asked for by each nnet chunk when the CPU tool feeds
+ * `chunk_samples` of audio at a time (online2-wav-nnet3-latgen-faster.cc:245-268, decodable-online-looped.cc:
+ * 56-84,185-193): the schedule b2k_ivec_compute_batched takes.  Host only. */
+int b2k_ivec_online_schedule(int64_t num_samples, int32_t chunk_samples, int32_t frame_length, int32_t frame_shift,
+                             int32_t num_feature_frames, int32_t nnet_right_context, int32_t frames_per_chunk,
+                             int32_t subsampling, int32_t splice_right, int32_t *sched, int32_t max_chunks,
+                             int32_t *n_chunks);
+
 /* ------------------------------------------------------------------ nnet3 program compiler (host only)
  *
  * From a chain-model layer list (the xconfig layers of the TDNN-F and CNN-TDNN-F recipes) and its parameters
