@@ -397,6 +397,23 @@ int b2k_nnet_program_info(const b2k_nnet_program *prog, int64_t info[8]);
 /* b2k_nnet_create on a compiled program (needs the device) */
 int b2k_nnet_create_from_program(const b2k_nnet_program *prog, int32_t max_batch, b2k_nnet **out);
 
+/* ------------------------------------------------------------------ Kaldi model files (host only)
+ *
+ * Raw nnet3 models as Nnet::Write emits them (nnet3/nnet-nnet.cc:630-656) and final.mdl = TransitionModel
+ * (hmm/transition-model.cc:394-453) + AmNnetSimple (nnet3/am-nnet-simple.cc:34-57), binary or text, without
+ * Kaldi/OpenFst: parsed and mapped onto the layer list / named weights of b2k_nnet_compile (TDNN-F and
+ * CNN-TDNN-F recipe layers; anything else is B2K_ERR_INVALID).  The arrays live as long as the handle.
+ * kaldi_b200/kaldi_io.py is the Python twin; both are pinned to files written by the reference's own Write(). */
+typedef struct b2k_model b2k_model;
+int b2k_model_read(const char *path, int32_t is_mdl /* 1: final.mdl, 0: raw nnet3 */, b2k_model **out);
+int b2k_model_destroy(b2k_model *model);
+/* info: [0] feat_dim, [1] ivector_dim, [2] num_pdfs, [3] frame subsampling factor, [4] layers, [5] weights,
+ * [6] size of the transition-id -> pdf table (0 for raw models), [7] 1 if the file carried priors */
+int b2k_model_info(const b2k_model *model, int32_t info[8]);
+const b2k_nnet_layer *b2k_model_layers(const b2k_model *model);
+const b2k_nnet_weight *b2k_model_weights(const b2k_model *model);    /* includes "priors" (ones when absent) */
+const int32_t *b2k_model_tid2pdf(const b2k_model *model);           /* [tid], index 0 unused; b2k_fst_csr.tid2pdf */
+
 #ifdef __cplusplus
 }
 #endif

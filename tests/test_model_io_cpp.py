@@ -1,0 +1,143 @@
+"""The C++ model-file reader of libb2k.so (kaldi_b200/csrc/model_io.cu: b2k_model_read) on files written by the
+reference's own Write() methods (oracle/_ref), against the architecture and weights that were put into the
+reference model and against the Python reader; then straight into the C++ program compiler."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from kaldi_b200 import nnet_model as NM
+
+
+def _lib():
+    try:
+        from kaldi_b200 import _lib as L
+        return L.lib()
+    except Exception as e:
+        pytest.skip(str(e))
+
+
+def _read(L, path, is_mdl):
+    from kaldi_b200.nnet_compile import _Layer, _Weight
+    h = C.c_void_p()
+    L.b2k_model_read.argtypes = [C.c_char_p, C.c_int32, C.c_void_p]
+    rc = L.b2k_model_read(path.encode(), int(is_mdl), C.byref(h))
+    if rc:
+        L.b2k_last_error.restype = C.c_char_p
+        raise RuntimeError(L.b2k_last_error().decode())
+    info = (C.c_int32 * 8)()
+    L.b2k_model_info.argtypes = [C.c_void_p, C.c_void_p]
+    assert L.b2k_model_info(h, info) == 0
+    L.b2k_model_layers.restype = C.POINTER(_Layer)
+    L.b2k_model_layers.argtypes = [C.c_void_p]
+    L.b2k_model_weights.restype = C.POINTER(_Weight)
+    L.b2k_model_weights.argtypes = [C.c_void_p]
+    L.b2k_model_tid2pdf.restype = C.POINTER(C.c_int32)
+    L.b2k_model_tid2pdf.argtypes = [C.c_void_p]
+    layers = [L.b2k_model_layers(h)[i] for i in range(info[4])]
+    W = {}
+    for i in range(info[5]):
+        w = L.b2k_model_weights(h)[i]
+        a = np.ctypeslib.as_array(C.cast(w.data, C.POINTER(C.c_float)), shape=(w.size,)).copy()
+        W[w.name.decode()] = a.reshape(w.rows, w.cols) if w.cols > 1 else a
+    t2p = np.ctypeslib.as_array(L.b2k_model_tid2pdf(h), shape=(info[6],)).copy() if info[6] else None
+    return h, list(info), layers, W, t2p
+
+
+def _layer_dict(x):
+    d = {f[0]: getattr(x, f[0]) for f in x._fields_}
+    d["type"], d["name"], d["side"] = d["type"].decode(), d["name"].decode(), d["side"].decode()
+    d["time_offsets"] = list(d["time_offsets"])[:d["n_time_offsets"]]
+    d["height_offsets"] = list(d["height_offsets"])[:d["n_height_offsets"]]
+    return d
+
+
+CHAIN_TOPO = """<Topology>
+<TopologyEntry>
+<ForPhones> 1 2 3 4 5 </ForPhones>
+<State> 0 <ForwardPdfClass> 0 <SelfLoopPdfClass> 1 <Transition> 0 0.5 <Transition> 1 0.5 </State>
+<State> 1 </State>
+</TopologyEntry>
+</Topology>
+"""
+
+
+@pytest.mark.parametrize("which", ["idct-delta", "lda", "cnn"])
+@pytest.mark.parametrize("binary", [1, 0])
+def test_cpp_reader_on_reference_written_models(tmp_path, which, binary):
+    L = _lib()
+    from kaldi_b200.nnet_compile import _layer, CompiledProgram, _Cfg
+    from oracle import nnet_oracle as NO
+    if not (os.path.exists(NO._SO) or os.path.isdir("/root/reference")):
+        pytest.skip("oracle/_ref nnet3 library not present")
+    arch = NM.arch_tiny_cnn() if which == "cnn" else NM.arch_tiny(front=which)
+    Wt = NM.random_weights(arch, seed=3)
+    R = NO.RefNnet(arch, Wt, collapse=False)
+    if not hasattr(R.lib, "ref_write_final_mdl"):
+        pytest.skip("oracle/_ref library predates the writers")
+    R.lib.ref_nnet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    R.lib.ref_write_final_mdl.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    raw, mdl = str(tmp_path / "final.raw"), str(tmp_path / "final.mdl")
+    assert R.lib.ref_nnet_write(R.h, raw.encode(), binary) == 0
+    pri = np.ascontiguousarray(Wt["priors"], np.float32)
+    tid2pdf = np.zeros(64, np.int32)
+    n_tids = R.lib.ref_write_final_mdl(R.h, mdl.encode(), binary, CHAIN_TOPO.encode(), 5, 2, pri.ctypes.data, pri.size,
+                                       tid2pdf.ctypes.data, tid2pdf.size)
+    assert n_tids > 0
+    for path, is_mdl in ((raw, 0), (mdl, 1)):
+        h, info, layers, W, t2p = _read(L, path, is_mdl)
+        try:
+            assert info[:4] == [arch["feat_dim"], arch["ivector_dim"], arch["num_pdfs"], arch["frame_subsampling_factor"]]
+            want = [_layer_dict(_layer(x)) for x in arch["layers"]]
+            got = [_layer_dict(x) for x in layers]
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                for k in b:
+                    if isinstance(b[k], float):
+                        assert abs(a[k] - b[k]) < 1e-6, (b["name"], k, a[k], b[k])
+                    else:
+                        assert a[k] == b[k], (b["name"], k, a[k], b[k])
+            for k, v in Wt.items():
+                if k == "priors" and not is_mdl:
+                    np.testing.assert_array_equal(W[k], np.ones_like(v))
+                    continue
+                tol = dict(rtol=0, atol=0) if (binary and not k.endswith((".mean", ".var"))) else dict(rtol=2e-5, atol=1e-6)
+                np.testing.assert_allclose(W[k].reshape(v.shape), v, err_msg=k, **tol)
+            if is_mdl:
+                np.testing.assert_array_equal(t2p, tid2pdf[:n_tids + 1])
+            else:
+                assert t2p is None
+            if binary and is_mdl:
+                # straight into the C++ compiler: same program as compiling the original arch/weights
+                cfg = _Cfg(info[0], info[1], info[2], info[3], 120, 21, 1, 0, 1.0)
+                prog = C.c_void_p()
+                L.b2k_nnet_compile.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+                L.b2k_model_layers.restype = C.c_void_p
+                L.b2k_model_weights.restype = C.c_void_p
+                assert L.b2k_nnet_compile(C.byref(cfg), L.b2k_model_layers(h), info[4], L.b2k_model_weights(h), info[5], C.byref(prog)) == 0
+                nn, no, bl = C.c_int32(), C.c_int32(), C.c_int64()
+                L.b2k_nnet_program_sizes.argtypes = [C.c_void_p] * 4
+                assert L.b2k_nnet_program_sizes(prog, C.byref(nn), C.byref(no), C.byref(bl)) == 0
+                ref = CompiledProgram(arch, Wt, 120, 21)
+                assert (nn.value, no.value, bl.value) == (len(ref.nodes), len(ref.ops), ref.blob.size)
+                L.b2k_nnet_program_blob.restype = C.POINTER(C.c_float)
+                L.b2k_nnet_program_blob.argtypes = [C.c_void_p]
+                blob = np.ctypeslib.as_array(L.b2k_nnet_program_blob(prog), shape=(bl.value,))
+                np.testing.assert_allclose(blob, ref.blob, rtol=2e-6, atol=1e-7)
+                L.b2k_nnet_program_destroy.argtypes = [C.c_void_p]
+                L.b2k_nnet_program_destroy(prog)
+        finally:
+            L.b2k_model_destroy.argtypes = [C.c_void_p]
+            L.b2k_model_destroy(h)
+
+
+def test_cpp_reader_rejects_garbage(tmp_path):
+    L = _lib()
+    p = str(tmp_path / "junk")
+    open(p, "wb").write(b"\0B<Nnet3> \nnot a model\n\n")
+    h = C.c_void_p()
+    L.b2k_model_read.argtypes = [C.c_char_p, C.c_int32, C.c_void_p]
+    assert L.b2k_model_read(p.encode(), 0, C.byref(h)) != 0
+    assert L.b2k_model_read(str(tmp_path / "missing").encode(), 0, C.byref(h)) != 0
