@@ -1,0 +1,76 @@
+"""Model files through the C++ reader of libb2k.so (kaldi_b200/csrc/model_io.cu, include/b2k.h b2k_model_*):
+`final.mdl` (TransitionModel + AmNnetSimple, hmm/transition-model.cc:394, nnet3/am-nnet-simple.cc:34) or a raw
+nnet3 model (nnet3/nnet-nnet.cc:630), binary or text → the layer list, named weights and transition-id → pdf table
+that b2k_nnet_compile / b2k_fst_create take.  kaldi_io.py holds the same readers in Python as the test oracle."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class KaldiModel:
+    """Owns a b2k_model handle.  `NnetComputer.from_model(m, ...)` compiles and uploads it without going through
+    the Python compiler; `m.tid2pdf` feeds `CudaFst`."""
+
+    def __init__(self, path: str, is_mdl: bool | None = None):
+        L = _lib.lib()
+        if is_mdl is None:
+            is_mdl = str(path).endswith(".mdl")
+        self.h = C.c_void_p()
+        L.b2k_model_read.argtypes = [C.c_char_p, C.c_int32, C.c_void_p]
+        _lib.check(L.b2k_model_read(str(path).encode(), int(bool(is_mdl)), C.byref(self.h)))
+        info = (C.c_int32 * 8)()
+        L.b2k_model_info.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.check(L.b2k_model_info(self.h, info))
+        (self.feat_dim, self.ivector_dim, self.num_pdfs, self.frame_subsampling_factor, self.n_layers, self.n_weights,
+         n_tid, has_priors) = [int(x) for x in info]
+        self.has_priors = bool(has_priors)
+        for f in ("b2k_model_layers", "b2k_model_weights", "b2k_model_tid2pdf"):
+            getattr(L, f).restype = C.c_void_p
+            getattr(L, f).argtypes = [C.c_void_p]
+        self.layers_ptr = L.b2k_model_layers(self.h)
+        self.weights_ptr = L.b2k_model_weights(self.h)
+        self.tid2pdf = None
+        if n_tid:
+            p = C.cast(L.b2k_model_tid2pdf(self.h), C.POINTER(C.c_int32))
+            self.tid2pdf = np.ctypeslib.as_array(p, shape=(n_tid,)).copy()
+
+    def layer_types(self) -> list[tuple[str, str]]:
+        from .nnet_compile import _Layer
+        a = C.cast(self.layers_ptr, C.POINTER(_Layer))
+        return [(a[i].type.decode(), a[i].name.decode()) for i in range(self.n_layers)]
+
+    def weights(self) -> dict[str, np.ndarray]:
+        from .nnet_compile import _Weight
+        a = C.cast(self.weights_ptr, C.POINTER(_Weight))
+        out = {}
+        for i in range(self.n_weights):
+            w = a[i]
+            v = np.ctypeslib.as_array(C.cast(w.data, C.POINTER(C.c_float)), shape=(w.size,)).copy()
+            out[w.name.decode()] = v.reshape(w.rows, w.cols) if w.cols > 1 else v
+        return out
+
+    def compile(self, num_frames: int, frames_per_chunk: int = 21, acoustic_scale: float = 1.0, use_priors: bool = True,
+                conv_mode: str | None = None) -> "C.c_void_p":
+        """b2k_nnet_compile on the model's own arrays → a b2k_nnet_program handle (caller destroys it)."""
+        from .nnet_compile import _Cfg
+        L = _lib.lib()
+        cfg = _Cfg(self.feat_dim, self.ivector_dim, self.num_pdfs, self.frame_subsampling_factor, int(num_frames),
+                   int(frames_per_chunk), int(use_priors), int((conv_mode or "patch") == "dense"), float(acoustic_scale))
+        prog = C.c_void_p()
+        L.b2k_nnet_compile.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        _lib.check(L.b2k_nnet_compile(C.byref(cfg), C.c_void_p(self.layers_ptr), self.n_layers,
+                                      C.c_void_p(self.weights_ptr), self.n_weights, C.byref(prog)))
+        return prog
+
+    def close(self):
+        if getattr(self, "h", None):
+            L = _lib.lib()
+            L.b2k_model_destroy.argtypes = [C.c_void_p]
+            L.b2k_model_destroy(self.h)
+            self.h = None
+
+    __del__ = close

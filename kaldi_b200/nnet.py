@@ -94,6 +94,35 @@ class NnetComputer:
         self.flops_per_utt = float(L.b2k_nnet_flops_per_lane(self.h))
         self.launches_per_run = int(L.b2k_nnet_num_launches_per_run(self.h))
 
+    @classmethod
+    def from_model(cls, model, num_frames: int, max_batch: int, frames_per_chunk: int = 21,
+                   acoustic_scale: float = 1.0, use_priors: bool = True, conv_mode: str | None = None):
+        """The C++ route: model.KaldiModel (b2k_model_read) → b2k_nnet_compile → b2k_nnet_create_from_program; the
+        Python compiler is not involved (it is this route's test oracle)."""
+        L = _lib.lib()
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        self.prog = None
+        prog = model.compile(num_frames, frames_per_chunk, acoustic_scale, use_priors, conv_mode)
+        try:
+            info = (C.c_int64 * 8)()
+            L.b2k_nnet_program_info.argtypes = [C.c_void_p, C.c_void_p]
+            _lib.check(L.b2k_nnet_program_info(prog, info))
+            L.b2k_nnet_create_from_program.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+            _lib.check(L.b2k_nnet_create_from_program(prog, int(max_batch), C.byref(self.h)))
+        finally:
+            L.b2k_nnet_program_destroy.argtypes = [C.c_void_p]
+            L.b2k_nnet_program_destroy(prog)
+        self.max_batch = max_batch
+        self.num_frames = num_frames
+        self.n_out, self.n_chunks = int(info[0]), int(info[1])
+        self.output_dim = model.num_pdfs
+        self.feat_dim = model.feat_dim
+        self.ivector_dim = model.ivector_dim
+        self.flops_per_utt = float(L.b2k_nnet_flops_per_lane(self.h))
+        self.launches_per_run = int(L.b2k_nnet_num_launches_per_run(self.h))
+        return self
+
     def __del__(self):
         try:
             if self.h:

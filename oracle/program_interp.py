@@ -80,3 +80,30 @@ def run_program(prog: dict, feats: np.ndarray, chunk_ivectors: np.ndarray | None
         if name == "output":
             out = v
     return out
+
+
+def program_from_abi(nodes, ops, blob) -> dict:
+    """The same program, rebuilt from the C-ABI structs (b2k_nnet_node / b2k_nnet_op arrays as b2k_nnet_create
+    takes them, include/b2k.h): lets the tests interpret exactly what the device executes, including programs
+    that never existed as a Python dictionary (the C++ compiler's output)."""
+    kinds = {1: "input", 2: "ivector", 3: "output"}
+
+    def term(t):
+        return dict(src=t.src, ratio=t.ratio, shift=t.shift, lo=t.lo, hi=t.hi, ivec=t.ivec, C=t.C, m=t.m, k0=t.k0,
+                    klen=t.klen, scale=t.scale, col_step=t.col_step, col_off=t.col_off, col_lim=t.col_lim)
+    pn = [(kinds.get(n.kind, "n%d" % i), n.dim, n.rows, 0, 0) for i, n in enumerate(nodes)]
+    po = []
+    for o in ops:
+        d = dict(out=o.out, rows=o.rows, bn_scale=o.bn_scale, bn_offset=o.bn_offset)
+        if o.type == 0:
+            d.update(type="gemm", N=o.N, K=o.K, hsplit=max(o.hsplit, 1), terms=[term(o.terms[j]) for j in range(o.n_terms)],
+                     w=o.w, bias=o.bias, sub_vec=o.sub_vec, relu=o.relu, log_softmax=o.log_softmax, out_scale=o.out_scale)
+            if o.has_res:
+                d.update(res=term(o.res), res_alpha=o.res_alpha)
+        else:
+            nb = 1 + max(o.terms[j].block for j in range(o.n_terms))
+            d.update(type="sum", block_dim=o.block_dim,
+                     blocks=[[term(o.terms[j]) for j in range(o.n_terms) if o.terms[j].block == b] for b in range(nb)])
+        po.append(d)
+    n_chunks = max([n.rows for n in nodes if n.kind == 2] + [0])
+    return dict(nodes=pn, ops=po, blob=np.asarray(blob, np.float32), n_chunks=n_chunks)

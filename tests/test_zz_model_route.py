@@ -1,0 +1,100 @@
+"""The C/C++ route from a model file to log-likelihoods — b2k_model_read → b2k_nnet_compile →
+b2k_nnet_create_from_program → b2k_nnet_run — on tests/golden/tiny_final.mdl, a binary final.mdl written by the
+reference's own TransitionModel::Write + AmNnetSimple::Write (tests/golden/make_model_golden.py), against
+tests/golden/nnet_golden.npz = the reference's own forward of that model.  CPU: reader, compiler and the ABI program
+(interpreted in numpy); GPU: the same through the device.  Tolerance 1e-4 of the output scale (north star)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from kaldi_b200 import nnet_model as NM
+
+HERE = os.path.dirname(__file__)
+MDL = os.path.join(HERE, "golden", "tiny_final.mdl")
+GOLD = os.path.join(HERE, "golden", "nnet_golden.npz")
+T2P = os.path.join(HERE, "golden", "tiny_final_tid2pdf.npy")
+RTOL_SCALE = 1e-4
+
+
+def _model():
+    try:
+        from kaldi_b200.model import KaldiModel
+        return KaldiModel(MDL)
+    except OSError as e:                       # libb2k.so not built
+        pytest.skip(str(e))
+
+
+def test_reader_returns_the_model_that_was_written():
+    m = _model()
+    arch = NM.arch_tiny(64)
+    W = NM.random_weights(arch, seed=11)
+    assert (m.feat_dim, m.ivector_dim, m.num_pdfs, m.frame_subsampling_factor) == (
+        arch["feat_dim"], arch["ivector_dim"], arch["num_pdfs"], arch["frame_subsampling_factor"])
+    assert m.has_priors
+    assert [t for t, _ in m.layer_types()] == [L["type"] for L in arch["layers"]]
+    got = m.weights()
+    for k, v in W.items():
+        tol = dict(rtol=2e-5, atol=1e-6) if k.endswith((".mean", ".var")) else dict(rtol=0, atol=0)
+        np.testing.assert_allclose(got[k].reshape(v.shape), v, err_msg=k, **tol)
+    np.testing.assert_array_equal(m.tid2pdf, np.load(T2P))
+    # and the Python reader agrees
+    arch2, W2, t2p2 = NM.load_kaldi_mdl(MDL)
+    np.testing.assert_array_equal(t2p2, m.tid2pdf)
+    for k in W2:
+        np.testing.assert_array_equal(np.asarray(W2[k], np.float32).reshape(-1), got[k].reshape(-1), err_msg=k)
+
+
+def test_compiled_abi_program_reproduces_the_reference_forward_on_cpu():
+    from kaldi_b200 import _lib
+    from kaldi_b200.nnet import _Node, _Op
+    from oracle import program_interp as PI
+    m = _model()
+    g = np.load(GOLD)
+    L = _lib.lib()
+    prog = m.compile(num_frames=g["feats"].shape[0])
+    try:
+        nn, no, bl = C.c_int32(), C.c_int32(), C.c_int64()
+        L.b2k_nnet_program_sizes.argtypes = [C.c_void_p] * 4
+        assert L.b2k_nnet_program_sizes(prog, C.byref(nn), C.byref(no), C.byref(bl)) == 0
+        for f, rt in (("b2k_nnet_program_nodes", C.POINTER(_Node)), ("b2k_nnet_program_ops", C.POINTER(_Op)),
+                      ("b2k_nnet_program_blob", C.POINTER(C.c_float))):
+            getattr(L, f).restype = rt
+            getattr(L, f).argtypes = [C.c_void_p]
+        nodes = [L.b2k_nnet_program_nodes(prog)[i] for i in range(nn.value)]
+        ops = [L.b2k_nnet_program_ops(prog)[i] for i in range(no.value)]
+        blob = np.ctypeslib.as_array(L.b2k_nnet_program_blob(prog), shape=(bl.value,)).copy()
+        out = PI.run_program(PI.program_from_abi(nodes, ops, blob), g["feats"], g["chunk_ivectors"])
+    finally:
+        L.b2k_nnet_program_destroy.argtypes = [C.c_void_p]
+        L.b2k_nnet_program_destroy(prog)
+    assert out.shape == g["ref_out"].shape
+    assert np.abs(out - g["ref_out"]).max() <= RTOL_SCALE * np.abs(g["ref_out"]).max()
+
+
+def test_device_creation_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from kaldi_b200.nnet import NnetComputer
+    with pytest.raises(Exception):
+        NnetComputer.from_model(_model(), num_frames=100, max_batch=1)
+
+
+@pytest.mark.gpu
+def test_model_file_to_loglikes_on_the_device():
+    from kaldi_b200.model import KaldiModel
+    from kaldi_b200.nnet import NnetComputer
+    g = np.load(GOLD)
+    m = KaldiModel(MDL)
+    nc = NnetComputer.from_model(m, num_frames=g["feats"].shape[0], max_batch=2)
+    assert (nc.n_out, nc.n_chunks) == (g["ref_out"].shape[0], g["chunk_ivectors"].shape[0])
+    out = nc.forward([g["feats"], g["feats"]], [g["chunk_ivectors"], g["chunk_ivectors"]])
+    for o in out:
+        assert np.abs(o - g["ref_out"]).max() <= RTOL_SCALE * np.abs(g["ref_out"]).max()
+    # the Python-compiled program of the same model gives the same numbers
+    arch = NM.arch_tiny(64)
+    ref = NnetComputer(arch, NM.random_weights(arch, seed=11), num_frames=g["feats"].shape[0], max_batch=2)
+    out2 = ref.forward([g["feats"], g["feats"]], [g["chunk_ivectors"], g["chunk_ivectors"]])
+    np.testing.assert_allclose(out[0], out2[0], rtol=1e-5, atol=1e-5)
