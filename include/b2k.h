@@ -414,6 +414,64 @@ const b2k_nnet_layer *b2k_model_layers(const b2k_model *model);
 const b2k_nnet_weight *b2k_model_weights(const b2k_model *model);    /* includes "priors" (ones when absent) */
 const int32_t *b2k_model_tid2pdf(const b2k_model *model);           /* [tid], index 0 unused; b2k_fst_csr.tid2pdf */
 
+/* ------------------------------------------------------------------ the batched pipeline (host waveforms -> lattices)
+ *
+ * BatchedThreadedNnet3CudaOnlinePipeline::DecodeBatch (cudadecoder/batched-threaded-nnet3-cuda-online-pipeline.cc:
+ * 316-377: ComputeGPUFeatureExtraction -> RunNnet3 -> RunDecoder -> finalize) for batches of utterances bucketed to one
+ * length, with the numerical semantics of online2-wav-nnet3-latgen-faster (online2bin/online2-wav-nnet3-latgen-faster.cc:
+ * 199-299).  C++ above the stage calls of this header (kaldi_b200/csrc/pipeline.cu); kaldi_b200/pipeline.py spells the
+ * same sequence in Python. */
+typedef struct {
+  b2k_feat_cfg feat;            /* max_lanes is set from max_batch                                           */
+  b2k_dec_cfg dec;              /* max_frames / max_tokens / max_links <= 0: sized from the utterance length */
+  int32_t frames_per_chunk;     /* 21 = --frames-per-chunk=20 rounded up to the subsampling factor           */
+  float acoustic_scale;         /* 1.0 for chain models                                                      */
+  int32_t max_batch;
+  int64_t num_samples;          /* every utterance of a batch has exactly this many samples                  */
+  float chunk_length_secs;      /* 0.18: the CPU tool's --chunk-length, decides which i-vector a chunk sees   */
+  int32_t ivector_splice_right; /* --splice-config right context of the extractor (3)                        */
+  int32_t use_priors, conv_dense;
+} b2k_pipeline_cfg;
+
+void b2k_pipeline_cfg_default(b2k_pipeline_cfg *cfg);
+
+typedef struct {
+  int32_t num_feature_frames, feat_dim, num_output_frames, num_chunks, num_pdfs, ivector_dim;
+  int32_t model_right_context;  /* filled by b2k_pipeline_create (0 in a bare plan)                          */
+  int32_t chunk_samples;
+  b2k_dec_cfg dec;              /* with the capacities resolved                                              */
+  int64_t device_bytes, pinned_bytes;   /* the pipeline's own buffers (decoder arenas and model not included) */
+} b2k_pipeline_plan;
+
+typedef struct b2k_pipeline b2k_pipeline;
+
+/* The sizes the pipeline will use for (cfg, model).  Host only. */
+int b2k_pipeline_plan_for(const b2k_pipeline_cfg *cfg, const b2k_model *model, b2k_pipeline_plan *plan);
+/* Compiles the model for the utterance length, creates the feature / nnet3 / decoder stages (max_batch lanes,
+ * channel i = batch slot i) and the buffers.  fst and ivec (may be NULL: zero i-vectors) are not owned; an
+ * extractor must have been created with max_lanes >= max_batch and max_frames >= plan.num_feature_frames. */
+int b2k_pipeline_create(const b2k_pipeline_cfg *cfg, const b2k_model *model, const b2k_fst *fst, b2k_ivec *ivec,
+                        b2k_pipeline **out);
+int b2k_pipeline_destroy(b2k_pipeline *p);
+int b2k_pipeline_get_plan(const b2k_pipeline *p, b2k_pipeline_plan *plan);
+/* DecodeBatch: h_waves[i] = num_samples samples of utterance i (float in int16 range, or int16).  Stages them through
+ * pinned memory, copies, and queues all four stages + FinalizeDecoding on `stream`; returns without waiting. */
+int b2k_pipeline_decode_batch(b2k_pipeline *p, int32_t n, const float *const *h_waves, void *stream);
+int b2k_pipeline_decode_batch_i16(b2k_pipeline *p, int32_t n, const int16_t *const *h_waves, void *stream);
+/* Same with the waveforms already on the device ([n x num_samples], NULL = the pipeline's own buffer as is). */
+int b2k_pipeline_run_device(b2k_pipeline *p, int32_t n, const float *d_waves, void *stream);
+/* The finalized raw lattices of batch slots 0..n-1 (b2k_dec_get_raw_lattices; waits for the stream). */
+int b2k_pipeline_get_raw_lattices(b2k_pipeline *p, int32_t n, b2k_raw_lattice *out, int64_t *state_offs,
+                                  int64_t *arc_offs, int64_t *final_offs, void *stream);
+/* Stage handles / device buffers for diagnostics: the decoder (channel info, frame info), [max_batch x frames x dim]
+ * features, [max_batch x chunks x ivector_dim] i-vectors, [max_batch x output frames x pdfs] log-likelihoods. */
+/* Copies a stage output of batch slots 0..n-1 to the host and waits: what = 0 features, 1 i-vectors, 2 log-likelihoods. */
+int b2k_pipeline_read(b2k_pipeline *p, int32_t what, int32_t n, float *h_out, void *stream);
+b2k_dec *b2k_pipeline_decoder(b2k_pipeline *p);
+const float *b2k_pipeline_features(const b2k_pipeline *p);
+const float *b2k_pipeline_ivectors(const b2k_pipeline *p);
+const float *b2k_pipeline_loglikes(const b2k_pipeline *p);
+
 #ifdef __cplusplus
 }
 #endif

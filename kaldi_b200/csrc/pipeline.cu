@@ -1,0 +1,287 @@
+// pipeline.cu — the batched online2 pipeline in C++ above the stage entry points of this library: host waveforms in,
+// finalized raw lattices out.  It stands behind cuda_decoder::BatchedThreadedNnet3CudaOnlinePipeline::DecodeBatch
+// (cudadecoder/batched-threaded-nnet3-cuda-online-pipeline.cc:316-377: ComputeGPUFeatureExtraction -> RunNnet3 ->
+// RunDecoder -> finalize) with the numerical semantics of online2-wav-nnet3-latgen-faster
+// (online2bin/online2-wav-nnet3-latgen-faster.cc:199-299): per-chunk i-vectors as the looped decodable would have
+// received them, CPU decoder search semantics, one finalized raw lattice per utterance.  No device code of its own:
+// CUDA runtime calls for the buffers and copies, the b2k stage calls for the work.  kaldi_b200/pipeline.py
+// (BatchedPipeline) is the Python spelling of the same sequence; the sizing rules are shared through
+// b2k_pipeline_plan_for, which needs no device (tests/test_pipeline_plan.py).
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+using b2k::set_error;
+
+struct b2k_pipeline {
+  b2k_pipeline_cfg cfg;
+  b2k_pipeline_plan plan;
+  b2k_feat *feat = nullptr;
+  b2k_nnet *nnet = nullptr;
+  b2k_dec *dec = nullptr;
+  b2k_ivec *ivec = nullptr;          // not owned
+  float *h_wave = nullptr;           // pinned [max_batch x num_samples]
+  float *d_wave = nullptr, *d_feats = nullptr, *d_ivec = nullptr, *d_loglikes = nullptr;
+  std::vector<int32_t> sched, channels, ns, zeros, nframes, nout;
+  std::vector<const float *> p_wave, p_feats, p_ivec, p_ll;
+  std::vector<float *> p_feats_out, p_ivec_out, p_ll_out;
+  int32_t last_n = 0;
+};
+
+namespace {
+
+int frame_count(const b2k_feat_cfg &f, int64_t num_samples) {   // NumFrames, flush = true (feat/feature-window.cc:42-87)
+  const int64_t length = (int)(f.samp_freq * 0.001f * f.frame_length_ms), shift = (int)(f.samp_freq * 0.001f * f.frame_shift_ms);
+  if (shift <= 0 || length <= 0) return -1;
+  if (f.snip_edges) return num_samples < length ? 0 : (int)(1 + (num_samples - length) / shift);
+  return (int)((num_samples + shift / 2) / shift);
+}
+
+template <typename S>
+void stage_rows(float *dst, const S *const *src, int32_t n, int64_t len) {
+  // float input: plain copies; int16 input: widened on the way (Kaldi keeps int16-range values in floats)
+  auto work = [&](int32_t a, int32_t b) {
+    for (int32_t i = a; i < b; i++) {
+      float *d = dst + (size_t)i * len;
+      const S *s = src[i];
+      for (int64_t k = 0; k < len; k++) d[k] = (float)s[k];
+    }
+  };
+  const int64_t total = (int64_t)n * len;
+  unsigned nt = total < (1 << 21) ? 1u : std::min<unsigned>({8u, std::max(1u, std::thread::hardware_concurrency()), (unsigned)n});
+  if (nt <= 1) { work(0, n); return; }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++) th.emplace_back(work, (int32_t)((int64_t)n * t / nt), (int32_t)((int64_t)n * (t + 1) / nt));
+  for (auto &t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+void b2k_pipeline_cfg_default(b2k_pipeline_cfg *c) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  b2k_feat_cfg_default(&c->feat);
+  b2k_dec_cfg_default(&c->dec);
+  c->dec.max_frames = 0; c->dec.max_tokens = 0; c->dec.max_links = 0;   // sized from the utterance length
+  c->frames_per_chunk = 21;          // --frames-per-chunk=20 rounded up to a multiple of 3 (GetChunkSize, nnet3/nnet-compile-looped.cc:81; decodable-simple-looped.cc:66)
+  c->acoustic_scale = 1.0f;          // chain models decode with --acwt 1.0
+  c->max_batch = 64;
+  c->num_samples = 160000;
+  c->chunk_length_secs = 0.18f;      // online2-wav-nnet3-latgen-faster --chunk-length
+  c->ivector_splice_right = 3;
+  c->use_priors = 1;
+}
+
+int b2k_pipeline_plan_for(const b2k_pipeline_cfg *cfg, const b2k_model *model, b2k_pipeline_plan *plan) {
+  if (!cfg || !model || !plan) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: bad args");
+  if (cfg->max_batch <= 0 || cfg->num_samples <= 0 || cfg->frames_per_chunk <= 0)
+    return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: max_batch, num_samples and frames_per_chunk must be positive");
+  int32_t mi[8];
+  int rc = b2k_model_info(model, mi);
+  if (rc) return rc;
+  memset(plan, 0, sizeof(*plan));
+  const int T = frame_count(cfg->feat, cfg->num_samples);
+  if (T <= 0) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: the utterance length gives no feature frame");
+  const int D = cfg->feat.feature_type == 0 ? cfg->feat.num_ceps : cfg->feat.num_bins + (cfg->feat.use_energy ? 1 : 0);
+  if (D != mi[0]) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: feature dimension differs from the model's input dimension");
+  const int sub = mi[3];
+  if (cfg->frames_per_chunk % sub) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: frames_per_chunk must be a multiple of the frame subsampling factor");
+  plan->num_feature_frames = T;
+  plan->feat_dim = D;
+  plan->num_output_frames = (T + sub - 1) / sub;
+  plan->num_chunks = (plan->num_output_frames * sub + cfg->frames_per_chunk - 1) / cfg->frames_per_chunk;
+  plan->num_pdfs = mi[2];
+  plan->ivector_dim = mi[1];
+  plan->chunk_samples = (int32_t)(cfg->chunk_length_secs * cfg->feat.samp_freq + 0.5f);
+  plan->dec = cfg->dec;
+  const int64_t nf = plan->num_output_frames;
+  if (plan->dec.max_frames <= 0) plan->dec.max_frames = (int32_t)(nf + 2);
+  if (plan->dec.max_tokens <= 0) plan->dec.max_tokens = nf * 9000;
+  if (plan->dec.max_links <= 0) plan->dec.max_links = nf * 16000;
+  const int64_t B = cfg->max_batch;
+  plan->device_bytes = 4 * B * (cfg->num_samples + (int64_t)T * D + (int64_t)plan->num_chunks * std::max(1, plan->ivector_dim) +
+                                nf * plan->num_pdfs);
+  plan->pinned_bytes = 4 * B * cfg->num_samples;
+  return B2K_OK;
+}
+
+int b2k_pipeline_destroy(b2k_pipeline *p) {
+  if (!p) return B2K_OK;
+  if (p->dec) b2k_dec_destroy(p->dec);
+  if (p->nnet) b2k_nnet_destroy(p->nnet);
+  if (p->feat) b2k_feat_destroy(p->feat);
+  if (p->h_wave) cudaFreeHost(p->h_wave);
+  for (float *d : {p->d_wave, p->d_feats, p->d_ivec, p->d_loglikes}) if (d) cudaFree(d);
+  delete p;
+  return B2K_OK;
+}
+
+static int pipeline_create_impl(b2k_pipeline *p, const b2k_model *model, const b2k_fst *fst) {
+  const b2k_pipeline_cfg &cfg = p->cfg;
+  const b2k_pipeline_plan &pl = p->plan;
+  int32_t mi[8];
+  int rc = b2k_model_info(model, mi);
+  if (rc) return rc;
+  // nnet3: compile for this utterance length, upload
+  b2k_nnet_compile_cfg cc;
+  memset(&cc, 0, sizeof(cc));
+  cc.feat_dim = mi[0]; cc.ivector_dim = mi[1]; cc.num_pdfs = mi[2]; cc.frame_subsampling_factor = mi[3];
+  cc.num_frames = pl.num_feature_frames; cc.frames_per_chunk = cfg.frames_per_chunk; cc.use_priors = cfg.use_priors;
+  cc.conv_dense = cfg.conv_dense; cc.acoustic_scale = cfg.acoustic_scale;
+  b2k_nnet_program *prog = nullptr;
+  rc = b2k_nnet_compile(&cc, b2k_model_layers(model), mi[4], b2k_model_weights(model), mi[5], &prog);
+  if (rc) return rc;
+  int64_t pi[8];
+  b2k_nnet_program_info(prog, pi);
+  rc = b2k_nnet_create_from_program(prog, cfg.max_batch, &p->nnet);
+  b2k_nnet_program_destroy(prog);
+  if (rc) return rc;
+  if (pi[0] != pl.num_output_frames || pi[1] != pl.num_chunks)
+    return set_error(B2K_ERR_STATE, "b2k_pipeline_create: the compiled program disagrees with the plan");
+  p->plan.model_right_context = (int32_t)pi[5];
+  // features
+  b2k_feat_cfg fc = cfg.feat;
+  fc.max_lanes = cfg.max_batch;
+  rc = b2k_feat_create(&fc, &p->feat);
+  if (rc) return rc;
+  if (b2k_feat_num_frames(p->feat, cfg.num_samples, 1) != pl.num_feature_frames || b2k_feat_dim(p->feat) != pl.feat_dim)
+    return set_error(B2K_ERR_STATE, "b2k_pipeline_create: the feature stage disagrees with the plan");
+  // decoder: one lane per batch slot, channel = lane
+  rc = b2k_dec_create(fst, &pl.dec, cfg.max_batch, cfg.max_batch, &p->dec);
+  if (rc) return rc;
+  // buffers
+  const size_t B = (size_t)cfg.max_batch, S = (size_t)cfg.num_samples, T = (size_t)pl.num_feature_frames, D = (size_t)pl.feat_dim;
+  const size_t NC = (size_t)pl.num_chunks, IV = (size_t)std::max(1, pl.ivector_dim), NF = (size_t)pl.num_output_frames, P = (size_t)pl.num_pdfs;
+  B2K_CUDA_CHECK(cudaMallocHost((void **)&p->h_wave, 4 * B * S));
+  B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_wave, 4 * B * S));
+  B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_feats, 4 * B * T * D));
+  B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_ivec, 4 * B * NC * IV));
+  B2K_CUDA_CHECK(cudaMemset(p->d_ivec, 0, 4 * B * NC * IV));      // no extractor: the network sees zero i-vectors
+  B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_loglikes, 4 * B * NF * P));
+  p->channels.resize(B); p->ns.assign(B, (int32_t)S); p->zeros.assign(B, 0); p->nframes.assign(B, (int32_t)T); p->nout.assign(B, (int32_t)NF);
+  p->p_wave.resize(B); p->p_feats.resize(B); p->p_ivec.resize(B); p->p_ll.resize(B);
+  p->p_feats_out.resize(B); p->p_ivec_out.resize(B); p->p_ll_out.resize(B);
+  for (size_t i = 0; i < B; i++) {
+    p->channels[i] = (int32_t)i;
+    p->p_wave[i] = p->d_wave + i * S;
+    p->p_feats[i] = p->p_feats_out[i] = p->d_feats + i * T * D;
+    p->p_ivec[i] = p->p_ivec_out[i] = p->d_ivec + i * NC * IV;
+    p->p_ll[i] = p->p_ll_out[i] = p->d_loglikes + i * NF * P;
+  }
+  if (p->ivec) {
+    p->sched.resize(NC);
+    int32_t nc = 0;
+    const b2k_feat_cfg &f = cfg.feat;
+    rc = b2k_ivec_online_schedule(cfg.num_samples, pl.chunk_samples, (int)(f.samp_freq * 0.001f * f.frame_length_ms),
+                                  (int)(f.samp_freq * 0.001f * f.frame_shift_ms), pl.num_feature_frames, p->plan.model_right_context,
+                                  cfg.frames_per_chunk, mi[3], cfg.ivector_splice_right, p->sched.data(), (int32_t)NC, &nc);
+    if (rc) return rc;
+    if (nc != (int32_t)NC) return set_error(B2K_ERR_STATE, "b2k_pipeline_create: i-vector schedule length differs from the chunk count");
+  }
+  return B2K_OK;
+}
+
+int b2k_pipeline_create(const b2k_pipeline_cfg *cfg, const b2k_model *model, const b2k_fst *fst, b2k_ivec *ivec,
+                        b2k_pipeline **out) {
+  if (!cfg || !model || !fst || !out) return set_error(B2K_ERR_INVALID, "b2k_pipeline_create: bad args");
+  *out = nullptr;
+  b2k_pipeline_plan plan;
+  int rc = b2k_pipeline_plan_for(cfg, model, &plan);
+  if (rc) return rc;
+  if (ivec && plan.ivector_dim <= 0) return set_error(B2K_ERR_INVALID, "b2k_pipeline_create: an extractor was given but the model takes no i-vector");
+  rc = b2k::require_device();
+  if (rc) return rc;
+  b2k_pipeline *p = new b2k_pipeline();
+  p->cfg = *cfg; p->plan = plan; p->ivec = ivec;
+  rc = pipeline_create_impl(p, model, fst);
+  if (rc) { const std::string keep = b2k::g_last_error; b2k_pipeline_destroy(p); b2k::g_last_error = keep; return rc; }
+  *out = p;
+  return B2K_OK;
+}
+
+int b2k_pipeline_get_plan(const b2k_pipeline *p, b2k_pipeline_plan *plan) {
+  if (!p || !plan) return set_error(B2K_ERR_INVALID, "b2k_pipeline_get_plan: bad args");
+  *plan = p->plan;
+  return B2K_OK;
+}
+
+b2k_dec *b2k_pipeline_decoder(b2k_pipeline *p) { return p ? p->dec : nullptr; }
+const float *b2k_pipeline_loglikes(const b2k_pipeline *p) { return p ? p->d_loglikes : nullptr; }
+const float *b2k_pipeline_features(const b2k_pipeline *p) { return p ? p->d_feats : nullptr; }
+const float *b2k_pipeline_ivectors(const b2k_pipeline *p) { return p ? p->d_ivec : nullptr; }
+
+}  // extern "C"
+
+// All stages for the first n batch slots, inputs already in d_wave; asynchronous on `stream`.
+static int run_device(b2k_pipeline *p, int32_t n, void *stream) {
+  const b2k_pipeline_plan &pl = p->plan;
+  int rc = b2k_feat_compute_batched(p->feat, n, p->p_wave.data(), p->ns.data(), p->zeros.data(), p->nframes.data(),
+                                    p->p_feats_out.data(), pl.feat_dim, stream);
+  if (rc) return rc;
+  if (p->ivec) {
+    rc = b2k_ivec_compute_batched(p->ivec, n, p->p_feats.data(), pl.feat_dim, pl.num_feature_frames, p->sched.data(),
+                                  pl.num_chunks, p->p_ivec_out.data(), pl.ivector_dim, stream);
+    if (rc) return rc;
+  }
+  rc = b2k_nnet_run(p->nnet, n, p->p_feats.data(), pl.feat_dim, pl.ivector_dim > 0 ? p->p_ivec.data() : nullptr, pl.ivector_dim,
+                    p->p_ll_out.data(), pl.num_pdfs, stream);
+  if (rc) return rc;
+  rc = b2k_dec_init_decoding(p->dec, p->channels.data(), n, stream);
+  if (rc) return rc;
+  rc = b2k_dec_advance_decoding_frames(p->dec, p->channels.data(), p->p_ll.data(), p->nout.data(), pl.num_pdfs, n, stream);
+  if (rc) return rc;
+  return b2k_dec_finalize_decoding(p->dec, p->channels.data(), n, stream);
+}
+
+template <typename S>
+static int decode_batch(b2k_pipeline *p, int32_t n, const S *const *h_waves, void *stream) {
+  if (!p || n <= 0 || n > p->cfg.max_batch || !h_waves) return set_error(B2K_ERR_INVALID, "b2k_pipeline_decode_batch: bad args");
+  for (int32_t i = 0; i < n; i++) if (!h_waves[i]) return set_error(B2K_ERR_INVALID, "b2k_pipeline_decode_batch: null waveform");
+  cudaStream_t st = (cudaStream_t)stream;
+  // the previous batch's H2D copy reads the pinned buffer: it must have completed (it has if the caller read lattices)
+  B2K_CUDA_CHECK(cudaStreamSynchronize(st));
+  stage_rows<S>(p->h_wave, h_waves, n, p->cfg.num_samples);
+  B2K_CUDA_CHECK(cudaMemcpyAsync(p->d_wave, p->h_wave, 4 * (size_t)n * (size_t)p->cfg.num_samples, cudaMemcpyHostToDevice, st));
+  p->last_n = n;
+  return run_device(p, n, stream);
+}
+
+extern "C" {
+
+int b2k_pipeline_decode_batch(b2k_pipeline *p, int32_t n, const float *const *h_waves, void *stream) {
+  return decode_batch<float>(p, n, h_waves, stream);
+}
+int b2k_pipeline_decode_batch_i16(b2k_pipeline *p, int32_t n, const int16_t *const *h_waves, void *stream) {
+  return decode_batch<int16_t>(p, n, h_waves, stream);
+}
+
+int b2k_pipeline_run_device(b2k_pipeline *p, int32_t n, const float *d_waves, void *stream) {
+  if (!p || n <= 0 || n > p->cfg.max_batch) return set_error(B2K_ERR_INVALID, "b2k_pipeline_run_device: bad args");
+  if (d_waves && d_waves != p->d_wave)
+    B2K_CUDA_CHECK(cudaMemcpyAsync(p->d_wave, d_waves, 4 * (size_t)n * (size_t)p->cfg.num_samples, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  p->last_n = n;
+  return run_device(p, n, stream);
+}
+
+int b2k_pipeline_read(b2k_pipeline *p, int32_t what, int32_t n, float *h_out, void *stream) {
+  if (!p || n <= 0 || n > p->cfg.max_batch || !h_out || what < 0 || what > 2) return set_error(B2K_ERR_INVALID, "b2k_pipeline_read: bad args");
+  const b2k_pipeline_plan &pl = p->plan;
+  const float *src = what == 0 ? p->d_feats : what == 1 ? p->d_ivec : p->d_loglikes;
+  const size_t per = what == 0 ? (size_t)pl.num_feature_frames * pl.feat_dim
+                   : what == 1 ? (size_t)pl.num_chunks * std::max(1, pl.ivector_dim) : (size_t)pl.num_output_frames * pl.num_pdfs;
+  B2K_CUDA_CHECK(cudaMemcpyAsync(h_out, src, 4 * per * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  B2K_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return B2K_OK;
+}
+
+int b2k_pipeline_get_raw_lattices(b2k_pipeline *p, int32_t n, b2k_raw_lattice *out, int64_t *state_offs, int64_t *arc_offs,
+                                  int64_t *final_offs, void *stream) {
+  if (!p || n <= 0 || n > p->cfg.max_batch) return set_error(B2K_ERR_INVALID, "b2k_pipeline_get_raw_lattices: bad args");
+  return b2k_dec_get_raw_lattices(p->dec, p->channels.data(), n, out, state_offs, arc_offs, final_offs, stream);
+}
+
+}  // extern "C"

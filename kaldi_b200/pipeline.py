@@ -149,3 +149,144 @@ class BatchedPipeline:
         # host-side wall time of the three parts (the last one includes waiting for the GPU)
         self.last_host_ms = dict(stage_to_pinned=(t1 - t0) * 1e3, submit=(t2 - t1) * 1e3, wait_and_readback=(t3 - t2) * 1e3)
         return out
+
+
+# ---- the same pipeline in C++ (kaldi_b200/csrc/pipeline.cu, include/b2k.h b2k_pipeline_*) ---------------------------
+
+def _native_structs():
+    import ctypes as C
+    from .decoder import _DecCfg
+    from .feat import _FeatCfg
+
+    class _PipelineCfg(C.Structure):
+        _fields_ = [("feat", _FeatCfg), ("dec", _DecCfg), ("frames_per_chunk", C.c_int32), ("acoustic_scale", C.c_float),
+                    ("max_batch", C.c_int32), ("num_samples", C.c_int64), ("chunk_length_secs", C.c_float),
+                    ("ivector_splice_right", C.c_int32), ("use_priors", C.c_int32), ("conv_dense", C.c_int32)]
+
+    class _PipelinePlan(C.Structure):
+        _fields_ = [("num_feature_frames", C.c_int32), ("feat_dim", C.c_int32), ("num_output_frames", C.c_int32),
+                    ("num_chunks", C.c_int32), ("num_pdfs", C.c_int32), ("ivector_dim", C.c_int32),
+                    ("model_right_context", C.c_int32), ("chunk_samples", C.c_int32), ("dec", _DecCfg),
+                    ("device_bytes", C.c_int64), ("pinned_bytes", C.c_int64)]
+    return _PipelineCfg, _PipelinePlan
+
+
+def native_cfg(cfg: PipelineConfig, ivector_splice_right: int = 3):
+    """PipelineConfig -> b2k_pipeline_cfg (defaults from b2k_pipeline_cfg_default, then every field of cfg)."""
+    import ctypes as C
+    from dataclasses import fields
+    from . import _lib
+    PC, _ = _native_structs()
+    L = _lib.lib()
+    c = PC()
+    L.b2k_pipeline_cfg_default.argtypes = [C.c_void_p]
+    L.b2k_pipeline_cfg_default.restype = None
+    L.b2k_pipeline_cfg_default(C.byref(c))
+    for f in fields(cfg.feature_opts):
+        setattr(c.feat, f.name, getattr(cfg.feature_opts, f.name))
+    d = cfg.decoder_cfg
+    c.dec.beam, c.dec.lattice_beam, c.dec.max_active, c.dec.min_active = d["beam"], d["lattice_beam"], d["max_active"], d["min_active"]
+    c.dec.beam_delta, c.dec.prune_interval, c.dec.prune_scale = d["beam_delta"], d["prune_interval"], d["prune_scale"]
+    c.dec.hash_ratio = d.get("hash_ratio", 2.0)
+    c.dec.reference_order = int(cfg.reference_order)
+    c.dec.max_tokens_per_frame = cfg.max_tokens_per_frame
+    c.dec.max_tokens, c.dec.max_links, c.dec.max_frames = cfg.max_tokens, cfg.max_links, 0
+    c.frames_per_chunk, c.acoustic_scale, c.max_batch = cfg.frames_per_chunk, cfg.acoustic_scale, cfg.max_batch
+    c.num_samples, c.chunk_length_secs, c.ivector_splice_right = cfg.num_samples, cfg.chunk_length_secs, ivector_splice_right
+    return c
+
+
+def native_plan(cfg: PipelineConfig, model, ivector_splice_right: int = 3) -> dict:
+    """b2k_pipeline_plan_for: the sizes the C++ pipeline derives for (cfg, model); needs no device."""
+    import ctypes as C
+    from . import _lib
+    _, PP = _native_structs()
+    L = _lib.lib()
+    c, pl = native_cfg(cfg, ivector_splice_right), PP()
+    L.b2k_pipeline_plan_for.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    _lib.check(L.b2k_pipeline_plan_for(C.byref(c), model.h, C.byref(pl)))
+    out = {f[0]: getattr(pl, f[0]) for f in pl._fields_ if f[0] != "dec"}
+    out["dec"] = {f[0]: getattr(pl.dec, f[0]) for f in pl.dec._fields_}
+    return out
+
+
+class NativeBatchedPipeline:
+    """BatchedPipeline with the orchestration in C++: model.KaldiModel (a model file) + CudaFst (+ IvectorExtractorGpu)
+    -> b2k_pipeline_create; decode_batch(waves) -> b2k_pipeline_decode_batch + b2k_pipeline_get_raw_lattices.  Returns
+    the same packed dictionary as BatchedPipeline.decode_batch."""
+
+    def __init__(self, cfg: PipelineConfig, model, fst: CudaFst, ivector_extractor=None):
+        import ctypes as C
+        from . import _lib
+        self.cfg, self.model, self.fst, self.ivector_extractor = cfg, model, fst, ivector_extractor
+        L = self._L = _lib.lib()
+        splice = ivector_extractor.ex["splice"] if ivector_extractor is not None else 3
+        c = native_cfg(cfg, splice)
+        self.h = C.c_void_p()
+        L.b2k_pipeline_create.argtypes = [C.c_void_p] * 5
+        _lib.check(L.b2k_pipeline_create(C.byref(c), model.h, fst.h,
+                                         ivector_extractor.h if ivector_extractor is not None else None, C.byref(self.h)))
+        _, PP = _native_structs()
+        pl = PP()
+        L.b2k_pipeline_get_plan.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.check(L.b2k_pipeline_get_plan(self.h, C.byref(pl)))
+        self.plan = pl
+        self.audio_seconds_per_utt = cfg.num_samples / cfg.feature_opts.samp_freq
+
+    def __del__(self):
+        try:
+            if self.h:
+                import ctypes as C
+                self._L.b2k_pipeline_destroy.argtypes = [C.c_void_p]
+                self._L.b2k_pipeline_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def decode_batch(self, waves, stream: int = 0):
+        import ctypes as C
+        from . import _lib
+        from .decoder import _RawLattice, _p
+        L = self._L
+        n = len(waves)
+        i16 = all(getattr(w, "dtype", None) == np.int16 for w in waves)
+        keep = [np.ascontiguousarray(w, np.int16 if i16 else np.float32) for w in waves]
+        for w in keep:
+            assert w.ndim == 1 and len(w) == self.cfg.num_samples, "utterances are bucketed by length before batching"
+        ptrs = (C.c_void_p * n)(*[w.ctypes.data for w in keep])
+        fn = L.b2k_pipeline_decode_batch_i16 if i16 else L.b2k_pipeline_decode_batch
+        fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        _lib.check(fn(self.h, n, ptrs, C.c_void_p(stream)))
+        so = np.zeros(n + 1, np.int64); ao = np.zeros(n + 1, np.int64); fo = np.zeros(n + 1, np.int64)
+        i64p = C.POINTER(C.c_int64)
+        r = _RawLattice()
+        L.b2k_pipeline_get_raw_lattices.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, i64p, i64p, i64p, C.c_void_p]
+        args = (self.h, n, C.cast(C.byref(r), C.c_void_p), so.ctypes.data_as(i64p), ao.ctypes.data_as(i64p),
+                fo.ctypes.data_as(i64p), C.c_void_p(stream))
+        _lib.check(L.b2k_pipeline_get_raw_lattices(*args))          # sizes
+        ns, na, nf = r.num_states, r.num_arcs, r.num_finals
+        out = dict(
+            state_frame=np.zeros(ns, np.int32), state_hclg=np.zeros(ns, np.int32),
+            state_tot_cost=np.zeros(ns, np.float32), state_extra_cost=np.zeros(ns, np.float32),
+            arc_src=np.zeros(na, np.int32), arc_dst=np.zeros(na, np.int32),
+            arc_ilabel=np.zeros(na, np.int32), arc_olabel=np.zeros(na, np.int32),
+            arc_graph_cost=np.zeros(na, np.float32), arc_acoustic_cost=np.zeros(na, np.float32),
+            final_state=np.zeros(nf, np.int32), final_cost=np.zeros(nf, np.float32))
+        for k, v in out.items():
+            setattr(r, k, _p(v, C.c_float if v.dtype == np.float32 else C.c_int32))
+        _lib.check(L.b2k_pipeline_get_raw_lattices(*args))
+        out.update(state_offs=so, arc_offs=ao, final_offs=fo)
+        return out
+
+    def read(self, what: str, n: int) -> np.ndarray:
+        """Stage outputs of batch slots 0..n-1 on the host: 'features', 'ivectors' or 'loglikes'."""
+        import ctypes as C
+        from . import _lib
+        pl = self.plan
+        idx, shape = {"features": (0, (n, pl.num_feature_frames, pl.feat_dim)),
+                      "ivectors": (1, (n, pl.num_chunks, max(1, pl.ivector_dim))),
+                      "loglikes": (2, (n, pl.num_output_frames, pl.num_pdfs))}[what]
+        out = np.zeros(shape, np.float32)
+        self._L.b2k_pipeline_read.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        _lib.check(self._L.b2k_pipeline_read(self.h, idx, n, out.ctypes.data, None))
+        return out
