@@ -414,6 +414,26 @@ const b2k_nnet_layer *b2k_model_layers(const b2k_model *model);
 const b2k_nnet_weight *b2k_model_weights(const b2k_model *model);    /* includes "priors" (ones when absent) */
 const int32_t *b2k_model_tid2pdf(const b2k_model *model);           /* [tid], index 0 unused; b2k_fst_csr.tid2pdf */
 
+/* The files of an ivector_extractor directory (steps/online/nnet2/train_ivector_extractor.sh): final.ie
+ * (IvectorExtractor::Read, ivector/ivector-extractor.cc:828-848, + ComputeDerivedVars :182-230), final.dubm
+ * (DiagGmm::Read, gmm/diag-gmm.cc:758-800), final.mat (LDA over spliced frames, with offset column) and
+ * global_cmvn.stats.  Host only; kaldi_io.read_ivector_extractor / read_diag_gmm are the Python twins. */
+typedef struct b2k_ivec_files b2k_ivec_files;
+int b2k_ivec_files_read(const char *ie_path, const char *dubm_path, const char *lda_mat_path,
+                        const char *global_cmvn_path, b2k_ivec_files **out);
+int b2k_ivec_files_destroy(b2k_ivec_files *files);
+/* info: [0] Gaussians, [1] feature dim, [2] i-vector dim, [3]/[4] rows/cols of final.mat, [5] dim of the CMVN stats,
+ * [6] number of UBM weights */
+int b2k_ivec_files_info(const b2k_ivec_files *files, int32_t info[8], float *prior_offset);
+/* which: 0 lda [rows x cols], 1 gconsts [G], 2 means_invvars [G x F], 3 inv_vars [G x F], 4 UBM weights [G] */
+const float *b2k_ivec_files_f32(const b2k_ivec_files *files, int32_t which);
+/* which: 0 Sigma_inv_M [G x F x D], 1 U [G x D(D+1)/2], 2 global CMVN stats [2 x (dim+1)] */
+const double *b2k_ivec_files_f64(const b2k_ivec_files *files, int32_t which);
+/* b2k_ivec_create on the parsed files; cfg carries what ivector_extractor.conf / splice.conf say (base_dim, splice,
+ * num_gselect, min_post, posterior_scale, max_count, num_cg_iters, CMVN options, capacities); the dimensions and the
+ * prior offset come from the files.  Needs the device. */
+int b2k_ivec_create_from_files(const b2k_ivec_cfg *cfg, const b2k_ivec_files *files, b2k_ivec **out);
+
 /* ------------------------------------------------------------------ the batched pipeline (host waveforms -> lattices)
  *
  * BatchedThreadedNnet3CudaOnlinePipeline::DecodeBatch (cudadecoder/batched-threaded-nnet3-cuda-online-pipeline.cc:

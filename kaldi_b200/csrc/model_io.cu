@@ -158,6 +158,39 @@ struct Reader {
     v->f.clear();
     for (auto &r : rows) { if ((int)r.size() != v->cols) throw FormatError("ragged matrix"); for (auto &x : r) v->f.push_back((float)atof(x.c_str())); }
   }
+  // double-precision forms for the i-vector extractor files (values kept as stored; floats are widened)
+  void read_dense_d(char kind /* 'M' | 'V' | 'P' */, std::vector<double> *out, int *rows, int *cols) {
+    out->clear();
+    if (binary) {
+      need(3);
+      const bool dbl = d[p] == 'D';
+      if (!((d[p] == 'F' || dbl) && d[p + 1] == (unsigned char)kind && d[p + 2] == ' ')) {
+        if (d[p] == 'C' && d[p + 1] == 'M') throw FormatError("compressed matrices are not supported");
+        throw FormatError(std::string("expected a binary F") + kind + "/D" + kind + " object");
+      }
+      p += 3;
+      long long r = read_int(), c = kind == 'M' ? read_int() : 1;
+      if (r < 0 || c < 0) throw FormatError("negative matrix size");
+      const long long n = kind == 'P' ? r * (r + 1) / 2 : r * c;
+      out->resize((size_t)n);
+      if (dbl) { need(8 * n); memcpy(out->data(), &d[p], 8 * n); p += 8 * n; }
+      else { need(4 * n); for (long long i = 0; i < n; i++) { float x; memcpy(&x, &d[p + 4 * i], 4); (*out)[i] = x; } p += 4 * n; }
+      *rows = (int)r; *cols = kind == 'P' ? (int)r : (int)c;
+      return;
+    }
+    std::vector<std::vector<std::string>> rw;
+    text_brackets(&rw);
+    for (auto &r : rw) for (auto &x : r) out->push_back(atof(x.c_str()));
+    if (kind == 'V') { *rows = (int)out->size(); *cols = 1; return; }
+    *rows = (int)rw.size();
+    if (kind == 'P') {
+      for (size_t i = 0; i < rw.size(); i++) if (rw[i].size() != i + 1) throw FormatError("bad packed matrix row");
+      *cols = *rows;
+    } else {
+      *cols = rw.empty() ? 0 : (int)rw[0].size();
+      for (auto &r : rw) if ((int)r.size() != *cols) throw FormatError("ragged matrix");
+    }
+  }
   void read_int_vector(Value *v, bool pairs) {   // ReadIntegerVector / ReadIntegerPairVector (io-funcs-inl.h:113-290)
     v->kind = pairs ? Value::PAIRS : Value::IVEC;
     v->iv.clear();
@@ -345,6 +378,13 @@ static void read_transition_model(Reader &r, std::vector<int32_t> *tid2pdf) {
 }
 
 }  // namespace
+
+struct b2k_ivec_files {
+  int num_gauss = 0, feat_dim = 0, ivector_dim = 0, lda_rows = 0, lda_cols = 0, cmvn_dim = 0;
+  double prior_offset = 0.0;
+  std::vector<float> lda, gconsts, ubm_weights, means_invvars, inv_vars;
+  std::vector<double> sigma_inv_m, U, cmvn;
+};
 
 struct b2k_model {
   int32_t feat_dim = 0, ivector_dim = 0, num_pdfs = 0, subsampling = 1;
@@ -652,5 +692,144 @@ int b2k_model_info(const b2k_model *m, int32_t info[8]) {
 const b2k_nnet_layer *b2k_model_layers(const b2k_model *m) { return m ? m->layers.data() : nullptr; }
 const b2k_nnet_weight *b2k_model_weights(const b2k_model *m) { return m ? m->weights.data() : nullptr; }
 const int32_t *b2k_model_tid2pdf(const b2k_model *m) { return m && !m->tid2pdf.empty() ? m->tid2pdf.data() : nullptr; }
+
+
+// ------------------------------------------------------------------ i-vector extractor directory
+// final.ie = IvectorExtractor::Read (ivector/ivector-extractor.cc:828-848), final.dubm = DiagGmm::Read
+// (gmm/diag-gmm.cc:758-800), final.mat = the LDA/splice transform (a Matrix), global_cmvn.stats (a 2 x (dim+1) double
+// Matrix).  Derived quantities as IvectorExtractor::ComputeDerivedVars (ivector-extractor.cc:182-230):
+// Sigma_inv_M_[g] = Sigma_inv_[g] M_[g],  U_[g] = packed lower triangle of M_[g]^T Sigma_inv_[g] M_[g].
+
+int b2k_ivec_files_read(const char *ie_path, const char *dubm_path, const char *lda_mat_path, const char *global_cmvn_path,
+                        b2k_ivec_files **out) {
+  if (!ie_path || !dubm_path || !lda_mat_path || !global_cmvn_path || !out)
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_ivec_files_read: bad args");
+  b2k_ivec_files *F = new b2k_ivec_files();
+  try {
+    int r = 0, c = 0;
+    {   // final.ie
+      Reader rd(ie_path);
+      rd.expect("<IvectorExtractor>");
+      rd.expect("<w>");
+      std::vector<double> w; rd.read_dense_d('M', &w, &r, &c);
+      rd.expect("<w_vec>");
+      rd.read_dense_d('V', &w, &r, &c);
+      rd.expect("<M>");
+      const long long G = rd.read_int();
+      if (G <= 0) throw FormatError("final.ie: no Gaussians");
+      std::vector<std::vector<double>> M((size_t)G), S((size_t)G);
+      int Fd = 0, D = 0;
+      for (long long g = 0; g < G; g++) {
+        rd.read_dense_d('M', &M[g], &r, &c);
+        if (g == 0) { Fd = r; D = c; } else if (r != Fd || c != D) throw FormatError("final.ie: M_ sizes differ");
+      }
+      rd.expect("<SigmaInv>");
+      for (long long g = 0; g < G; g++) { rd.read_dense_d('P', &S[g], &r, &c); if (r != Fd) throw FormatError("final.ie: SigmaInv size"); }
+      rd.expect("<IvectorOffset>");
+      F->prior_offset = rd.read_float();
+      rd.expect("</IvectorExtractor>");
+      F->num_gauss = (int)G; F->feat_dim = Fd; F->ivector_dim = D;
+      F->sigma_inv_m.assign((size_t)G * Fd * D, 0.0);
+      const int DP = D * (D + 1) / 2;
+      F->U.assign((size_t)G * DP, 0.0);
+      std::vector<double> full((size_t)Fd * Fd);
+      for (long long g = 0; g < G; g++) {
+        for (int i = 0, k = 0; i < Fd; i++) for (int j = 0; j <= i; j++, k++) full[(size_t)i * Fd + j] = full[(size_t)j * Fd + i] = S[g][k];
+        double *sm = &F->sigma_inv_m[(size_t)g * Fd * D];
+        for (int i = 0; i < Fd; i++)
+          for (int j = 0; j < Fd; j++) {
+            const double a = full[(size_t)i * Fd + j];
+            const double *mr = &M[g][(size_t)j * D];
+            for (int k = 0; k < D; k++) sm[(size_t)i * D + k] += a * mr[k];
+          }
+        double *u = &F->U[(size_t)g * DP];
+        for (int i = 0, k = 0; i < D; i++)
+          for (int j = 0; j <= i; j++, k++) {
+            double acc = 0.0;
+            for (int f = 0; f < Fd; f++) acc += M[g][(size_t)f * D + i] * sm[(size_t)f * D + j];
+            u[k] = acc;
+          }
+      }
+    }
+    {   // final.dubm
+      Reader rd(dubm_path);
+      std::string tok = rd.token();
+      if (tok != "<DiagGMM>" && tok != "<DiagGMMBegin>") throw FormatError("final.dubm: not a DiagGmm: " + tok);
+      bool have[4] = {false, false, false, false};
+      while (true) {
+        tok = rd.token();
+        if (tok == "</DiagGMM>" || tok == "<DiagGMMEnd>") break;
+        Value v;
+        if (tok == "<GCONSTS>") { rd.read_vector(&v); F->gconsts = v.f; have[0] = true; }
+        else if (tok == "<WEIGHTS>") { rd.read_vector(&v); F->ubm_weights = v.f; have[1] = true; }
+        else if (tok == "<MEANS_INVVARS>") { rd.read_matrix(&v); F->means_invvars = v.f; have[2] = true; if (v.rows != F->num_gauss || v.cols != F->feat_dim) throw FormatError("final.dubm and final.ie disagree on the number of Gaussians / feature dimension"); }
+        else if (tok == "<INV_VARS>") { rd.read_matrix(&v); F->inv_vars = v.f; have[3] = true; if (v.rows != F->num_gauss || v.cols != F->feat_dim) throw FormatError("final.dubm and final.ie disagree on the number of Gaussians / feature dimension"); }
+        else throw FormatError("unexpected token " + tok + " in DiagGmm");
+      }
+      if (!(have[0] && have[2] && have[3]) || (int)F->gconsts.size() != F->num_gauss) throw FormatError("final.dubm: incomplete DiagGmm");
+    }
+    {   // final.mat
+      Reader rd(lda_mat_path);
+      Value v;
+      rd.read_matrix(&v);
+      F->lda = v.f; F->lda_rows = v.rows; F->lda_cols = v.cols;
+      if (v.rows != F->feat_dim) throw FormatError("final.mat: row count differs from the extractor's feature dimension");
+    }
+    {   // global_cmvn.stats
+      Reader rd(global_cmvn_path);
+      rd.read_dense_d('M', &F->cmvn, &r, &c);
+      if (r != 2 || c < 2) throw FormatError("global_cmvn.stats: expected a 2 x (dim + 1) matrix");
+      F->cmvn_dim = c - 1;
+    }
+  } catch (const std::exception &e) {
+    delete F;
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_ivec_files_read", e.what());
+  }
+  *out = F;
+  return B2K_OK;
+}
+
+int b2k_ivec_files_destroy(b2k_ivec_files *f) { delete f; return B2K_OK; }
+
+int b2k_ivec_files_info(const b2k_ivec_files *f, int32_t info[8], float *prior_offset) {
+  if (!f || !info) return b2k::set_error(B2K_ERR_INVALID, "b2k_ivec_files_info: bad args");
+  info[0] = f->num_gauss; info[1] = f->feat_dim; info[2] = f->ivector_dim; info[3] = f->lda_rows; info[4] = f->lda_cols;
+  info[5] = f->cmvn_dim; info[6] = (int32_t)f->ubm_weights.size(); info[7] = 0;
+  if (prior_offset) *prior_offset = (float)f->prior_offset;
+  return B2K_OK;
+}
+
+const float *b2k_ivec_files_f32(const b2k_ivec_files *f, int32_t which) {
+  if (!f) return nullptr;
+  switch (which) {
+    case 0: return f->lda.data();
+    case 1: return f->gconsts.data();
+    case 2: return f->means_invvars.data();
+    case 3: return f->inv_vars.data();
+    case 4: return f->ubm_weights.empty() ? nullptr : f->ubm_weights.data();
+    default: return nullptr;
+  }
+}
+
+const double *b2k_ivec_files_f64(const b2k_ivec_files *f, int32_t which) {
+  if (!f) return nullptr;
+  switch (which) {
+    case 0: return f->sigma_inv_m.data();
+    case 1: return f->U.data();
+    case 2: return f->cmvn.data();
+    default: return nullptr;
+  }
+}
+
+int b2k_ivec_create_from_files(const b2k_ivec_cfg *cfg, const b2k_ivec_files *f, b2k_ivec **out) {
+  if (!cfg || !f || !out) return b2k::set_error(B2K_ERR_INVALID, "b2k_ivec_create_from_files: bad args");
+  b2k_ivec_cfg c = *cfg;
+  c.feat_dim = f->feat_dim; c.num_gauss = f->num_gauss; c.ivector_dim = f->ivector_dim; c.prior_offset = (float)f->prior_offset;
+  if (f->lda_cols != c.base_dim * (c.splice_left + c.splice_right + 1) + 1)
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_ivec_create_from_files: final.mat does not match base_dim x (splice_left + 1 + splice_right) + 1 columns");
+  if (f->cmvn_dim != c.base_dim) return b2k::set_error(B2K_ERR_INVALID, "b2k_ivec_create_from_files: global_cmvn.stats dimension differs from base_dim");
+  return b2k_ivec_create(&c, f->lda.data(), f->gconsts.data(), f->means_invvars.data(), f->inv_vars.data(), f->sigma_inv_m.data(),
+                         f->U.data(), f->cmvn.data(), out);
+}
 
 }  // extern "C"

@@ -128,7 +128,6 @@ static bool build_graph(const b2k_nnet_compile_cfg &cfg, const b2k_nnet_layer *l
   std::string cur = "input";
   const b2k_nnet_layer *pending_combine = nullptr;
   auto add = [&](Node &n) { g->dims[n.name] = n.dim; g->nodes.push_back(std::move(n)); };
-  auto W_or_null = [&](const std::string &k) -> const b2k_nnet_weight * { return structural ? nullptr : W.get(k); };
   for (int li = 0; li < n_layers; li++) {
     const b2k_nnet_layer &L = layers[li];
     const std::string t = S(L.type, sizeof(L.type)), n = S(L.name, sizeof(L.name));
@@ -255,7 +254,6 @@ static bool build_graph(const b2k_nnet_compile_cfg &cfg, const b2k_nnet_layer *l
       err = "unknown layer type " + t;
       return false;
     }
-    (void)W_or_null;
   }
   return true;
 }

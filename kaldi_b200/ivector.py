@@ -189,3 +189,73 @@ def extractor_from_kaldi_files(ie_path: str, dubm_path: str, lda_mat_path: str, 
                 num_gselect=num_gselect, min_post=min_post, posterior_scale=posterior_scale, num_cg_iters=num_cg_iters,
                 cmn_window=cmn_window, speaker_frames=speaker_frames, global_frames=global_frames,
                 global_cmvn_stats=KIO.read_cmvn_stats(global_cmvn_path))
+
+
+class IvectorFiles:
+    """The same four files through the C++ reader of libb2k.so (kaldi_b200/csrc/model_io.cu, b2k_ivec_files_*);
+    `IvectorExtractorGpu.from_files` uploads them without going through numpy."""
+
+    def __init__(self, ie_path: str, dubm_path: str, lda_mat_path: str, global_cmvn_path: str):
+        L = _lib.lib()
+        self.h = C.c_void_p()
+        L.b2k_ivec_files_read.argtypes = [C.c_char_p] * 4 + [C.c_void_p]
+        _lib.check(L.b2k_ivec_files_read(str(ie_path).encode(), str(dubm_path).encode(), str(lda_mat_path).encode(),
+                                         str(global_cmvn_path).encode(), C.byref(self.h)))
+        info, po = (C.c_int32 * 8)(), C.c_float()
+        L.b2k_ivec_files_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.check(L.b2k_ivec_files_info(self.h, info, C.byref(po)))
+        (self.num_gauss, self.feat_dim, self.ivector_dim, self.lda_rows, self.lda_cols, self.cmvn_dim,
+         self.num_weights) = [int(x) for x in info][:7]
+        self.prior_offset = float(po.value)
+
+    def arrays(self) -> dict:
+        L = _lib.lib()
+        L.b2k_ivec_files_f32.restype = C.POINTER(C.c_float)
+        L.b2k_ivec_files_f32.argtypes = [C.c_void_p, C.c_int32]
+        L.b2k_ivec_files_f64.restype = C.POINTER(C.c_double)
+        L.b2k_ivec_files_f64.argtypes = [C.c_void_p, C.c_int32]
+        G, F, D = self.num_gauss, self.feat_dim, self.ivector_dim
+
+        def f32(i, shape):
+            return np.ctypeslib.as_array(L.b2k_ivec_files_f32(self.h, i), shape=shape).copy()
+
+        def f64(i, shape):
+            return np.ctypeslib.as_array(L.b2k_ivec_files_f64(self.h, i), shape=shape).copy()
+        out = dict(lda_mat=f32(0, (self.lda_rows, self.lda_cols)), gconsts=f32(1, (G,)), means_invvars=f32(2, (G, F)),
+                   inv_vars=f32(3, (G, F)), sigma_inv_m=f64(0, (G, F, D)), U=f64(1, (G, D * (D + 1) // 2)),
+                   global_cmvn_stats=f64(2, (2, self.cmvn_dim + 1)))
+        if self.num_weights:
+            out["ubm_weights"] = f32(4, (self.num_weights,))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            L = _lib.lib()
+            L.b2k_ivec_files_destroy.argtypes = [C.c_void_p]
+            L.b2k_ivec_files_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def _from_files(cls, files: IvectorFiles, max_lanes: int, max_frames: int, splice: int = 3, base_dim: int = 40,
+                num_gselect: int = 5, min_post: float = 0.025, posterior_scale: float = 0.1, max_count: float = 100.0,
+                num_cg_iters: int = 15, cmn_window: int = 600, speaker_frames: int = 600, global_frames: int = 200):
+    """b2k_ivec_create_from_files: options = defaults of OnlineIvectorExtractionConfig
+    (online2/online-ivector-feature.h:55-140), everything else from the files."""
+    self = cls.__new__(cls)
+    c = _IvecCfg(base_dim, splice, splice, files.feat_dim, files.num_gauss, files.ivector_dim, num_gselect, min_post,
+                 posterior_scale, max_count, files.prior_offset, num_cg_iters, cmn_window, speaker_frames, global_frames,
+                 max_lanes, max_frames)
+    self.h = C.c_void_p()
+    self.ex = dict(splice=splice, base_dim=base_dim, feat_dim=files.feat_dim, num_gauss=files.num_gauss,
+                   ivector_dim=files.ivector_dim)
+    self.ivector_dim = files.ivector_dim
+    self._keep = []
+    L = _lib.lib()
+    L.b2k_ivec_create_from_files.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    _lib.check(L.b2k_ivec_create_from_files(C.byref(c), files.h, C.byref(self.h)))
+    return self
+
+
+IvectorExtractorGpu.from_files = classmethod(_from_files)

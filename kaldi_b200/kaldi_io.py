@@ -193,7 +193,9 @@ class Reader:
         flat = [x for r in rows for x in r]
         return np.array(flat, dtype=np.float64).astype(np.float32) if flat else np.zeros(0, np.float32)
 
-    def read_matrix(self) -> np.ndarray:
+    def read_matrix(self, text_dtype=np.float32) -> np.ndarray:
+        """text_dtype: a text matrix carries no type tag; the reference parses it into the precision of the object it
+        is read into (Matrix<double> for the i-vector extractor), so the caller says which."""
         if self.binary:
             tag = self.d[self.p:self.p + 3]
             if tag[:2] == b"CM":
@@ -209,7 +211,7 @@ class Reader:
         rows = self._text_brackets()
         if not rows:
             return np.zeros((0, 0), np.float32)
-        return np.array(rows, dtype=np.float64).astype(np.float32)
+        return np.array(rows, dtype=np.float64).astype(text_dtype)
 
     def read_packed(self) -> np.ndarray:
         """SpMatrix/TpMatrix (matrix/packed-matrix.cc:236-330): packed lower triangle -> full symmetric matrix."""
@@ -619,7 +621,7 @@ def read_ivector_extractor(path: str) -> dict:
     w_vec = r.read_vector().astype(np.float64)
     r.expect_token("<M>")
     G = r.read_int()
-    M = np.stack([r.read_matrix().astype(np.float64) for _ in range(G)])
+    M = np.stack([r.read_matrix(text_dtype=np.float64).astype(np.float64) for _ in range(G)])
     r.expect_token("<SigmaInv>")
     sigma_inv = np.stack([r.read_packed().astype(np.float64) for _ in range(G)])
     r.expect_token("<IvectorOffset>")
