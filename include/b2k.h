@@ -414,6 +414,18 @@ const b2k_nnet_layer *b2k_model_layers(const b2k_model *model);
 const b2k_nnet_weight *b2k_model_weights(const b2k_model *model);    /* includes "priors" (ones when absent) */
 const int32_t *b2k_model_tid2pdf(const b2k_model *model);           /* [tid], index 0 unused; b2k_fst_csr.tid2pdf */
 
+/* HCLG.fst: an OpenFst binary "vector" or "const" FST over StdArc -> the CSR view of b2k_fst_create (arc order = file
+ * order = the order ConstFst iterates in, which the decoder's results depend on).  Host only, no OpenFst.
+ * PARITY UNPINNED: follows the published layout (fst/fst.h, vector-fst.h, const-fst.h); OpenFst is absent from this
+ * image, so the reader is checked against kaldi_io.read_openfst / write_openfst only. */
+typedef struct b2k_fst_file b2k_fst_file;
+int b2k_fst_file_read(const char *path, b2k_fst_file **out);
+int b2k_fst_file_destroy(b2k_fst_file *file);
+/* csr: views into the file object (tid2pdf NULL); is_const (may be NULL): 1 for a "const" file */
+int b2k_fst_file_csr(const b2k_fst_file *file, b2k_fst_csr *csr, int32_t *is_const);
+/* b2k_fst_create on the file with the transition-id -> pdf table of the model (b2k_model_tid2pdf); needs the device */
+int b2k_fst_create_from_file(const b2k_fst_file *file, const int32_t *tid2pdf, int32_t num_tids, b2k_fst **out);
+
 /* The files of an ivector_extractor directory (steps/online/nnet2/train_ivector_extractor.sh): final.ie
  * (IvectorExtractor::Read, ivector/ivector-extractor.cc:828-848, + ComputeDerivedVars :182-230), final.dubm
  * (DiagGmm::Read, gmm/diag-gmm.cc:758-800), final.mat (LDA over spliced frames, with offset column) and

@@ -62,6 +62,26 @@ class CudaFst:
         _lib.check(L.b2k_fst_create(C.cast(C.byref(csr), C.c_void_p), C.byref(self.h)))
         self.num_pdfs = int(graph["num_pdfs"])
 
+    @classmethod
+    def from_file(cls, path: str, tid2pdf=None, num_pdfs: int | None = None):
+        """HCLG.fst through the C++ reader (kaldi_b200/csrc/fst_io.cu): b2k_fst_file_read -> b2k_fst_create_from_file."""
+        L = _lib.lib()
+        fh = C.c_void_p()
+        L.b2k_fst_file_read.argtypes = [C.c_char_p, C.c_void_p]
+        _lib.check(L.b2k_fst_file_read(str(path).encode(), C.byref(fh)))
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        try:
+            t2p = None if tid2pdf is None else np.ascontiguousarray(tid2pdf, np.int32)
+            L.b2k_fst_create_from_file.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+            _lib.check(L.b2k_fst_create_from_file(fh, None if t2p is None else t2p.ctypes.data,
+                                                  0 if t2p is None else int(t2p.size), C.byref(self.h)))
+        finally:
+            L.b2k_fst_file_destroy.argtypes = [C.c_void_p]
+            L.b2k_fst_file_destroy(fh)
+        self.num_pdfs = int(num_pdfs) if num_pdfs is not None else (int(t2p.max()) + 1 if t2p is not None else 0)
+        return self
+
     def NumStates(self) -> int:
         return int(_lib.lib().b2k_fst_num_states(self.h))
 
@@ -266,3 +286,29 @@ def lattice_to_canonical(lat: dict) -> dict:
         return m[np.lexsort(m.T[::-1])] if m.shape[0] else m
     return dict(states=srt(states.astype(np.int32)), arcs=srt(arcs.astype(np.int32)),
                 finals=srt(finals.astype(np.int32)))
+
+
+def read_fst_file(path: str) -> dict:
+    """The CSR arrays of an OpenFst binary file as the C++ reader sees them (b2k_fst_file_read / b2k_fst_file_csr);
+    same dictionary as kaldi_io.read_openfst.  Host only."""
+    L = _lib.lib()
+    fh = C.c_void_p()
+    L.b2k_fst_file_read.argtypes = [C.c_char_p, C.c_void_p]
+    _lib.check(L.b2k_fst_file_read(str(path).encode(), C.byref(fh)))
+    try:
+        csr, is_const = _FstCsr(), C.c_int32()
+        L.b2k_fst_file_csr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.check(L.b2k_fst_file_csr(fh, C.byref(csr), C.byref(is_const)))
+        S = csr.num_states
+        offsets = np.ctypeslib.as_array(csr.offsets, shape=(S + 1,)).copy()
+        A = int(offsets[-1])
+
+        def arr(ptr, n):
+            return np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.zeros(0, np.int32)
+        return dict(num_states=int(S), start=int(csr.start), offsets=offsets, ilabel=arr(csr.ilabel, A),
+                    olabel=arr(csr.olabel, A), weight=arr(csr.weight, A).astype(np.float32, copy=False),
+                    nextstate=arr(csr.nextstate, A), final=arr(csr.final_cost, S).astype(np.float32, copy=False),
+                    fst_type="const" if is_const.value else "vector")
+    finally:
+        L.b2k_fst_file_destroy.argtypes = [C.c_void_p]
+        L.b2k_fst_file_destroy(fh)

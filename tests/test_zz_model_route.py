@@ -138,3 +138,28 @@ def test_cpp_pipeline_equals_python_pipeline(with_ivectors, int16):
         o.decode(ll[i], mode=D.MODE_REFERENCE_ORDER)
         want, got = o.lattice(), lattice_to_canonical(lats[i])
         assert all(np.array_equal(got[k], want[k]) for k in got)
+
+
+@pytest.mark.gpu
+def test_graph_file_route_gives_the_same_decoder(tmp_path):
+    """HCLG.fst -> b2k_fst_file_read -> b2k_fst_create_from_file against b2k_fst_create on the in-memory CSR: the
+    decoder's raw lattice is identical."""
+    import torch
+    from kaldi_b200 import kaldi_io as KIO, synth
+    from kaldi_b200.decoder import CudaDecoder, CudaDecoderConfig, CudaFst, lattice_to_canonical
+    g = synth.make_hclg(50_000, num_pdfs=64, seed=4)
+    p = str(tmp_path / "HCLG.fst")
+    KIO.write_openfst(p, g, "const")
+    rng = np.random.default_rng(3)
+    ll = torch.from_numpy((rng.standard_normal((40, 64)) * 2.0).astype(np.float32)).cuda()
+    lats = []
+    for fst in (CudaFst(g), CudaFst.from_file(p, g["tid2pdf"], num_pdfs=64)):
+        dc = CudaDecoderConfig.from_dict(synth.DEFAULT_DECODER_CFG, max_frames=64, max_tokens=1_500_000, max_links=3_000_000)
+        dec = CudaDecoder(fst, dc, 1)
+        dec.InitDecoding([0])
+        dec.AdvanceDecodingFrames([0], [ll.data_ptr()], [40], 64)
+        dec.FinalizeDecoding([0])
+        assert dec.ChannelInfo(0)["status"] == 0
+        lats.append(lattice_to_canonical(dec.GetRawLattice(0)))
+    assert all(np.array_equal(lats[0][k], lats[1][k]) for k in lats[0])
+    assert lats[0]["states"].shape[0] > 0
