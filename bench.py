@@ -128,7 +128,7 @@ def cpu_reference_one(args):
         mat[prev:e + 1] = civ[n]
         prev = e + 1
     ll = R.forward(feats, mat, period=1)
-    _CPU_STATE["dec"].decode(ll, record=False)
+    _CPU_STATE["dec"].decode(ll, record=_CPU_STATE.get("record", False))   # record: tools/bench_lattice_det.py
     t2 = time.time()
     ns, na, _ = _CPU_STATE["dec"].lattice_sizes()
     return (t2 - t1, ns, na)

@@ -446,6 +446,39 @@ const double *b2k_ivec_files_f64(const b2k_ivec_files *files, int32_t which);
  * prior offset come from the files.  Needs the device. */
 int b2k_ivec_create_from_files(const b2k_ivec_cfg *cfg, const b2k_ivec_files *files, b2k_ivec **out);
 
+/* ------------------------------------------------------------------ raw lattice -> compact lattice (host only)
+ *
+ * Where SingleUtteranceNnet3DecoderTpl::GetLattice calls DeterminizeLatticePhonePrunedWrapper
+ * (online2/online-nnet3-decoding.cc:60-78, lat/determinize-lattice-pruned.h:284): the finalized raw lattice
+ * (b2k_dec_get_raw_lattice; state 0 = start) becomes an acceptor over words, deterministic (one arc per word per
+ * state, word epsilons absorbed), each arc / final weight carrying LatticeWeight (graph, acoustic) and the
+ * transition-id string of the best path (CompactLatticeWeight, fstext/lattice-weight.h:387-604).  Every word
+ * sequence whose best cost is within `beam` of the best path is kept, with exactly the weight and alignment of its
+ * best path in the raw lattice; sequences outside the beam may or may not survive (as in the reference).
+ * PARITY: equivalence-tested against the raw lattice (tests/test_lattice_det.py); the state numbering of the
+ * reference's own determinizer is not reproduced (it needs OpenFst, absent here) — see kaldi_b200/csrc/lattice_det.cu. */
+typedef struct {
+  int64_t num_states, num_arcs, num_finals, num_tids;   /* state 0 = start */
+  int32_t *arc_src, *arc_dst, *arc_word;                /* [num_arcs]                                   */
+  float *arc_graph_cost, *arc_acoustic_cost;
+  int64_t *arc_tids_off;                                /* [num_arcs + 1] offsets into tids             */
+  int32_t *final_state;                                 /* [num_finals]                                 */
+  float *final_graph_cost, *final_acoustic_cost;
+  int64_t *final_tids_off;                              /* [num_finals + 1] offsets into tids           */
+  int32_t *tids;                                        /* [num_tids] transition-ids, arcs then finals  */
+} b2k_compact_lattice;
+
+typedef struct b2k_clat b2k_clat;
+/* max_states > 0: budget of determinized states; when it is exceeded the work is redone with 3/4 of the beam (the
+ * reference reduces its beam when max_mem is hit, determinize-lattice-pruned.h:126-160) — see b2k_clat_effective_beam */
+int b2k_lat_determinize_pruned(const b2k_raw_lattice *raw, float beam, int64_t max_states, b2k_clat **out);
+float b2k_clat_effective_beam(const b2k_clat *clat);
+int b2k_clat_destroy(b2k_clat *clat);
+/* sizes: [0] states, [1] arcs, [2] finals, [3] transition-ids, [4] subsets expanded, [5] subset elements in total */
+int b2k_clat_sizes(const b2k_clat *clat, int64_t sizes[6]);
+/* fills the counts and every non-NULL array of `out` (caller-allocated from b2k_clat_sizes) */
+int b2k_clat_copy(const b2k_clat *clat, b2k_compact_lattice *out);
+
 /* ------------------------------------------------------------------ the batched pipeline (host waveforms -> lattices)
  *
  * BatchedThreadedNnet3CudaOnlinePipeline::DecodeBatch (cudadecoder/batched-threaded-nnet3-cuda-online-pipeline.cc:

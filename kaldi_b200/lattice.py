@@ -125,3 +125,112 @@ def raw_lattice_from_canonical(c: dict) -> dict:
                 arc_graph_cost=arcs[:, 6].view(np.float32).copy(), arc_acoustic_cost=arcs[:, 7].view(np.float32).copy(),
                 final_state=np.array([sid[(last, int(r[0]))] for r in c["finals"]], np.int32),
                 final_cost=c["finals"][:, 1].view(np.float32).copy())
+
+
+# ---- raw lattice -> compact lattice (kaldi_b200/csrc/lattice_det.cu through the C ABI; host only) -------------------
+
+def determinize_pruned(lat: dict, beam: float, max_states: int = 0) -> dict:
+    """DeterminizeLatticePhonePrunedWrapper's role (lat/determinize-lattice-pruned.h:284) for one finalized raw
+    lattice: returns the compact lattice as flat arrays — arc_src/arc_dst/arc_word/arc_graph_cost/arc_acoustic_cost,
+    arc_tids (list of int32 arrays), final_state/final_graph_cost/final_acoustic_cost/final_tids, num_states (state 0
+    = start) — plus `stats` (subsets expanded, elements).  See include/b2k.h b2k_lat_determinize_pruned."""
+    import ctypes as C
+    from . import _lib
+    from .decoder import _RawLattice, _p
+    L = _lib.lib()
+    keep = {k: np.ascontiguousarray(lat[k], np.float32 if lat[k].dtype.kind == "f" else np.int32) for k in
+            ("state_frame", "state_hclg", "state_tot_cost", "state_extra_cost", "arc_src", "arc_dst", "arc_ilabel",
+             "arc_olabel", "arc_graph_cost", "arc_acoustic_cost", "final_state", "final_cost")}
+    r = _RawLattice()
+    r.num_states, r.num_arcs, r.num_finals = len(keep["state_frame"]), len(keep["arc_src"]), len(keep["final_state"])
+    for k, v in keep.items():
+        setattr(r, k, _p(v, C.c_float if v.dtype == np.float32 else C.c_int32))
+    h = C.c_void_p()
+    L.b2k_lat_determinize_pruned.argtypes = [C.c_void_p, C.c_float, C.c_int64, C.c_void_p]
+    _lib.check(L.b2k_lat_determinize_pruned(C.byref(r), float(beam), int(max_states), C.byref(h)))
+    L.b2k_clat_effective_beam.restype = C.c_float
+    L.b2k_clat_effective_beam.argtypes = [C.c_void_p]
+    eff = float(L.b2k_clat_effective_beam(h))
+    try:
+        sz = (C.c_int64 * 6)()
+        L.b2k_clat_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.check(L.b2k_clat_sizes(h, sz))
+        ns, na, nf, nt = int(sz[0]), int(sz[1]), int(sz[2]), int(sz[3])
+
+        class _CL(C.Structure):
+            _fields_ = [("num_states", C.c_int64), ("num_arcs", C.c_int64), ("num_finals", C.c_int64), ("num_tids", C.c_int64),
+                        ("arc_src", C.c_void_p), ("arc_dst", C.c_void_p), ("arc_word", C.c_void_p),
+                        ("arc_graph_cost", C.c_void_p), ("arc_acoustic_cost", C.c_void_p), ("arc_tids_off", C.c_void_p),
+                        ("final_state", C.c_void_p), ("final_graph_cost", C.c_void_p), ("final_acoustic_cost", C.c_void_p),
+                        ("final_tids_off", C.c_void_p), ("tids", C.c_void_p)]
+        out = dict(arc_src=np.zeros(na, np.int32), arc_dst=np.zeros(na, np.int32), arc_word=np.zeros(na, np.int32),
+                   arc_graph_cost=np.zeros(na, np.float32), arc_acoustic_cost=np.zeros(na, np.float32),
+                   arc_tids_off=np.zeros(na + 1, np.int64), final_state=np.zeros(nf, np.int32),
+                   final_graph_cost=np.zeros(nf, np.float32), final_acoustic_cost=np.zeros(nf, np.float32),
+                   final_tids_off=np.zeros(nf + 1, np.int64), tids=np.zeros(nt, np.int32))
+        cl = _CL()
+        for k, v in out.items():
+            setattr(cl, k, v.ctypes.data)
+        L.b2k_clat_copy.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.check(L.b2k_clat_copy(h, C.byref(cl)))
+    finally:
+        L.b2k_clat_destroy.argtypes = [C.c_void_p]
+        L.b2k_clat_destroy(h)
+    t, ao, fo = out.pop("tids"), out.pop("arc_tids_off"), out.pop("final_tids_off")
+    out["arc_tids"] = [t[ao[i]:ao[i + 1]] for i in range(na)]
+    out["final_tids"] = [t[fo[i]:fo[i + 1]] for i in range(nf)]
+    out["num_states"] = ns
+    out["stats"] = dict(subsets_expanded=int(sz[4]), elements_total=int(sz[5]))
+    out["effective_beam"] = eff
+    return out
+
+
+def compact_best_path(clat: dict) -> dict:
+    """CompactLatticeShortestPath + the word / transition-id read-out of online2-wav-nnet3-latgen-faster.cc:43-54."""
+    ns = clat["num_states"]
+    if ns == 0 or len(clat["final_state"]) == 0:
+        return dict(words=np.zeros(0, np.int32), tids=np.zeros(0, np.int32), graph_cost=np.inf, acoustic_cost=np.inf,
+                    total_cost=np.inf)
+    src, dst = clat["arc_src"].astype(np.int64), clat["arc_dst"].astype(np.int64)
+    w = clat["arc_graph_cost"].astype(np.float64) + clat["arc_acoustic_cost"].astype(np.float64)
+    dist, back = np.full(ns, np.inf), np.full(ns, -1, np.int64)
+    dist[0] = 0.0
+    order = np.argsort(src, kind="stable")
+    starts = np.searchsorted(src[order], np.arange(ns + 1))
+    for s in _topological_order(ns, src, dst):
+        if np.isfinite(dist[s]):
+            for a in order[starts[s]:starts[s + 1]]:
+                if dist[s] + w[a] < dist[dst[a]]:
+                    dist[dst[a]], back[dst[a]] = dist[s] + w[a], a
+    fs = clat["final_state"].astype(np.int64)
+    tot = dist[fs] + clat["final_graph_cost"].astype(np.float64) + clat["final_acoustic_cost"].astype(np.float64)
+    k = int(np.argmin(tot))
+    arcs, s = [], int(fs[k])
+    while s != 0:
+        arcs.append(int(back[s]))
+        s = int(src[arcs[-1]])
+    arcs = arcs[::-1]
+    tids = [clat["arc_tids"][a] for a in arcs] + [clat["final_tids"][k]]
+    return dict(words=clat["arc_word"][arcs].astype(np.int32),
+                tids=np.concatenate(tids).astype(np.int32) if tids else np.zeros(0, np.int32),
+                graph_cost=float(clat["arc_graph_cost"][arcs].astype(np.float64).sum() + clat["final_graph_cost"][k]),
+                acoustic_cost=float(clat["arc_acoustic_cost"][arcs].astype(np.float64).sum() + clat["final_acoustic_cost"][k]),
+                total_cost=float(tot[k]))
+
+
+def write_compact_lattice_text(f, key: str, clat: dict) -> None:
+    """One entry of a text-mode CompactLattice table (lat/kaldi-lattice.cc WriteCompactLattice, text mode): key line,
+    `src dst word graph,acoustic,tid_tid_...` per arc, `state graph,acoustic,tid_...` per final state, blank line."""
+    f.write(key + "\n")
+    order = np.argsort(clat["arc_src"], kind="stable")
+    starts = np.searchsorted(clat["arc_src"][order], np.arange(clat["num_states"] + 1))
+    fin = {int(s): i for i, s in enumerate(clat["final_state"])}
+    for s in range(clat["num_states"]):
+        for a in order[starts[s]:starts[s + 1]]:
+            f.write(f"{s}\t{int(clat['arc_dst'][a])}\t{int(clat['arc_word'][a])}\t{_num(clat['arc_graph_cost'][a])},"
+                    f"{_num(clat['arc_acoustic_cost'][a])},{'_'.join(str(int(t)) for t in clat['arc_tids'][a])}\n")
+        if s in fin:
+            i = fin[s]
+            f.write(f"{s}\t{_num(clat['final_graph_cost'][i])},{_num(clat['final_acoustic_cost'][i])},"
+                    f"{'_'.join(str(int(t)) for t in clat['final_tids'][i])}\n")
+    f.write("\n")

@@ -1,0 +1,264 @@
+"""Raw lattice -> compact lattice (kaldi_b200/csrc/lattice_det.cu, b2k_lat_determinize_pruned).  PARITY: structure
+unpinned (the reference's determinizer needs OpenFst); the properties checked are the ones the reference's own
+determinize-lattice-pruned-test.cc checks (deterministic output, equivalent to the input within the beam), here
+exhaustively on small lattices (every path enumerated) and by path sampling on decoder output."""
+import io
+import itertools
+
+import numpy as np
+import pytest
+
+
+def _det(lat, beam):
+    try:
+        from kaldi_b200.lattice import determinize_pruned
+        return determinize_pruned(lat, beam)
+    except OSError as e:
+        pytest.skip(str(e))
+
+
+def _random_lattice(rng, n_states, n_arcs, vocab=3, eps_frac=0.4, tid_eps_frac=0.2):
+    """Acyclic by construction (src < dst after a random relabelling that keeps state 0 first)."""
+    src = rng.integers(0, n_states - 1, n_arcs)
+    dst = np.array([rng.integers(s + 1, n_states) for s in src])
+    perm = np.concatenate([[0], 1 + rng.permutation(n_states - 1)])      # hide the topological order
+    ol = np.where(rng.random(n_arcs) < eps_frac, 0, rng.integers(1, vocab + 1, n_arcs))
+    il = np.where(rng.random(n_arcs) < tid_eps_frac, 0, rng.integers(1, 50, n_arcs))
+    nf = max(1, n_states // 4)
+    fs = np.unique(np.concatenate([[n_states - 1], rng.integers(1, n_states, nf)]))
+    return dict(state_frame=np.zeros(n_states, np.int32), state_hclg=np.arange(n_states, dtype=np.int32),
+                state_tot_cost=np.zeros(n_states, np.float32), state_extra_cost=np.zeros(n_states, np.float32),
+                arc_src=perm[src].astype(np.int32), arc_dst=perm[dst].astype(np.int32), arc_ilabel=il.astype(np.int32),
+                arc_olabel=ol.astype(np.int32), arc_graph_cost=rng.uniform(0, 3, n_arcs).astype(np.float32),
+                arc_acoustic_cost=rng.uniform(-2, 4, n_arcs).astype(np.float32),
+                final_state=perm[fs].astype(np.int32), final_cost=rng.uniform(0, 1, len(fs)).astype(np.float32))
+
+
+def _enumerate_raw(lat):
+    """word sequence -> (total, graph, acoustic, tids, runner-up total) of its best path (float32 sums in path order)."""
+    out_arcs = {}
+    for a in range(len(lat["arc_src"])):
+        out_arcs.setdefault(int(lat["arc_src"][a]), []).append(a)
+    finals = dict(zip(lat["final_state"].tolist(), lat["final_cost"].tolist()))
+    best = {}
+
+    def walk(s, g, ac, words, tids):
+        if s in finals:
+            gg = np.float32(g + np.float32(finals[s]))
+            cand = (float(np.float32(gg + ac)), float(gg), float(ac), tuple(tids))
+            key = tuple(words)
+            order = lambda c: (c[0], c[1], len(c[3]), c[3])
+            if key not in best:
+                best[key] = cand + (np.inf,)
+            elif order(cand) < order(best[key]):
+                best[key] = cand + (best[key][0],)            # last field: cost of the runner-up path
+            else:
+                best[key] = best[key][:4] + (min(best[key][4], cand[0]),)
+        for a in out_arcs.get(s, []):
+            il, ol = int(lat["arc_ilabel"][a]), int(lat["arc_olabel"][a])
+            walk(int(lat["arc_dst"][a]), np.float32(g + lat["arc_graph_cost"][a]), np.float32(ac + lat["arc_acoustic_cost"][a]),
+                 words + ([ol] if ol else []), tids + ([il] if il else []))
+    walk(0, np.float32(0), np.float32(0), [], [])
+    return best
+
+
+def _enumerate_compact(c):
+    out_arcs = {}
+    for a in range(len(c["arc_src"])):
+        out_arcs.setdefault(int(c["arc_src"][a]), []).append(a)
+    for s, arcs in out_arcs.items():                       # deterministic, no word epsilons
+        words = [int(c["arc_word"][a]) for a in arcs]
+        assert 0 not in words and len(set(words)) == len(words), (s, words)
+    fin = {int(s): i for i, s in enumerate(c["final_state"])}
+    assert len(fin) == len(c["final_state"])
+    res = {}
+
+    def walk(s, g, ac, words, tids):
+        if s in fin:
+            i = fin[s]
+            key = tuple(words)
+            assert key not in res
+            gg, aa = g + float(c["final_graph_cost"][i]), ac + float(c["final_acoustic_cost"][i])
+            res[key] = (gg + aa, gg, aa, tuple(tids + c["final_tids"][i].tolist()))
+        for a in out_arcs.get(s, []):
+            walk(int(c["arc_dst"][a]), g + float(c["arc_graph_cost"][a]), ac + float(c["arc_acoustic_cost"][a]),
+                 words + [int(c["arc_word"][a])], tids + c["arc_tids"][a].tolist())
+    if c["num_states"]:
+        walk(0, 0.0, 0.0, [], [])
+    return res
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_exhaustive_equivalence_on_small_lattices(seed):
+    rng = np.random.default_rng(seed)
+    lat = _random_lattice(rng, n_states=int(rng.integers(3, 11)), n_arcs=int(rng.integers(3, 26)),
+                          vocab=int(rng.integers(1, 4)))
+    want = _enumerate_raw(lat)
+    got = _enumerate_compact(_det(lat, 1e9))
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k][0] == pytest.approx(want[k][0], abs=2e-4), k
+        assert got[k][1] == pytest.approx(want[k][1], abs=2e-4) and got[k][2] == pytest.approx(want[k][2], abs=2e-4)
+        if want[k][4] - want[k][0] > 1e-3:                   # no near-tie: the alignment is the best path's
+            assert got[k][3] == want[k][3], k
+
+
+@pytest.mark.parametrize("seed", range(40, 70))
+def test_pruning_keeps_everything_within_the_beam(seed):
+    rng = np.random.default_rng(seed)
+    lat = _random_lattice(rng, n_states=int(rng.integers(4, 11)), n_arcs=int(rng.integers(6, 26)), vocab=3)
+    want = _enumerate_raw(lat)
+    if not want:
+        pytest.skip("no accepting path")
+    best = min(v[0] for v in want.values())
+    beam = float(rng.uniform(0.5, 4.0))
+    got = _enumerate_compact(_det(lat, beam))
+    inside = {k for k, v in want.items() if v[0] <= best + beam - 1e-3}
+    assert inside <= set(got)
+    assert set(got) <= set(want)                             # nothing invented
+    for k, v in got.items():
+        assert v[0] == pytest.approx(want[k][0], abs=2e-4)   # and whatever survives carries its true best cost
+    assert min(v[0] for v in got.values()) == pytest.approx(best, abs=2e-4)
+
+
+def test_alignment_strings_are_those_of_the_best_paths():
+    """Hand-made: two paths for word sequence (7,), one cheaper; a word epsilon path; transition-id epsilons dropped."""
+    f32, i32 = np.float32, np.int32
+    lat = dict(state_frame=np.zeros(4, i32), state_hclg=np.arange(4, dtype=i32), state_tot_cost=np.zeros(4, f32),
+               state_extra_cost=np.zeros(4, f32),
+               arc_src=np.array([0, 0, 1, 2, 0], i32), arc_dst=np.array([1, 2, 3, 3, 3], i32),
+               arc_ilabel=np.array([11, 12, 0, 14, 15], i32), arc_olabel=np.array([7, 7, 0, 0, 0], i32),
+               arc_graph_cost=np.array([1.0, 0.5, 0.25, 0.25, 5.0], f32), arc_acoustic_cost=np.array([1.0, 1.0, 0.0, 0.0, 0.0], f32),
+               final_state=np.array([3], i32), final_cost=np.array([0.5], f32))
+    c = _det(lat, 100.0)
+    got = _enumerate_compact(c)
+    assert set(got) == {(7,), ()}
+    assert got[(7,)][3] == (12, 14) and got[(7,)][0] == pytest.approx(0.5 + 1.0 + 0.25 + 0.5)
+    assert got[()][3] == (15,) and got[()][0] == pytest.approx(5.5)
+    from kaldi_b200.lattice import compact_best_path, write_compact_lattice_text
+    bp = compact_best_path(c)
+    assert bp["words"].tolist() == [7] and bp["tids"].tolist() == [12, 14] and bp["total_cost"] == pytest.approx(2.25)
+    buf = io.StringIO()
+    write_compact_lattice_text(buf, "utt1", c)
+    lines = buf.getvalue().split("\n")
+    assert lines[0] == "utt1" and lines[-2] == "" and any("\t7\t" in l for l in lines)
+    c2 = _det(lat, 1.0)                                      # the epsilon-word path (5.5) is outside a beam of 1
+    assert set(_enumerate_compact(c2)) == {(7,)}
+
+
+def test_empty_and_degenerate_inputs():
+    f32, i32 = np.float32, np.int32
+    empty = dict(state_frame=np.zeros(0, i32), state_hclg=np.zeros(0, i32), state_tot_cost=np.zeros(0, f32),
+                 state_extra_cost=np.zeros(0, f32), arc_src=np.zeros(0, i32), arc_dst=np.zeros(0, i32),
+                 arc_ilabel=np.zeros(0, i32), arc_olabel=np.zeros(0, i32), arc_graph_cost=np.zeros(0, f32),
+                 arc_acoustic_cost=np.zeros(0, f32), final_state=np.zeros(0, i32), final_cost=np.zeros(0, f32))
+    c = _det(empty, 8.0)
+    assert c["num_states"] == 0 and len(c["arc_src"]) == 0
+    one = dict(empty, state_frame=np.zeros(1, i32), state_hclg=np.zeros(1, i32), state_tot_cost=np.zeros(1, f32),
+               state_extra_cost=np.zeros(1, f32), final_state=np.array([0], i32), final_cost=np.array([0.25], f32))
+    c = _det(one, 8.0)
+    assert c["num_states"] == 1 and _enumerate_compact(c) == {(): (0.25, 0.25, 0.0, ())}
+    cyc = dict(one, state_frame=np.zeros(2, i32), state_hclg=np.zeros(2, i32), state_tot_cost=np.zeros(2, f32),
+               state_extra_cost=np.zeros(2, f32), arc_src=np.array([0, 1], i32), arc_dst=np.array([1, 0], i32),
+               arc_ilabel=np.array([1, 1], i32), arc_olabel=np.array([1, 1], i32), arc_graph_cost=np.zeros(2, f32),
+               arc_acoustic_cost=np.zeros(2, f32))
+    with pytest.raises(RuntimeError):
+        _det(cyc, 8.0)
+    with pytest.raises(RuntimeError):
+        _det(one, 0.0)
+
+
+def test_decoder_output_best_path_and_sampled_paths():
+    """A finalized raw lattice of the decoder (CPU oracle on a synthetic graph): the compact lattice has the same
+    best path, is deterministic, and accepts every sampled raw path's word sequence at a cost no larger than the path's."""
+    from kaldi_b200 import synth
+    from kaldi_b200.lattice import best_path, compact_best_path, raw_lattice_from_canonical
+    from oracle import dec_oracle as D
+    g = synth.make_hclg(30_000, num_pdfs=60, seed=7, olabel_frac=0.3)
+    cfg = dict(synth.DEFAULT_DECODER_CFG)
+    rng = np.random.default_rng(5)
+    ll = (rng.standard_normal((40, 60)) * 2.0).astype(np.float32)
+    o = D.DecoderOracle(g, cfg)
+    o.decode(ll, mode=D.MODE_REFERENCE_ORDER)
+    lat = raw_lattice_from_canonical(o.lattice())
+    assert len(lat["arc_src"]) > 100
+    beam = float(cfg["lattice_beam"])
+    c = _det(lat, beam)
+    bp_raw, bp = best_path(lat), compact_best_path(c)
+    assert bp["total_cost"] == pytest.approx(bp_raw["total_cost"], abs=1e-3)
+    assert bp["words"].tolist() == bp_raw["olabels"].tolist()
+    assert bp["tids"].tolist() == bp_raw["ilabels"].tolist()
+    # determinism
+    key = c["arc_src"].astype(np.int64) * (1 << 32) + c["arc_word"]
+    assert len(np.unique(key)) == len(key) and (c["arc_word"] != 0).all()
+    # sampled paths
+    out_arcs = {}
+    for a in range(len(lat["arc_src"])):
+        out_arcs.setdefault(int(lat["arc_src"][a]), []).append(a)
+    finals = dict(zip(lat["final_state"].tolist(), lat["final_cost"].tolist()))
+    cout = {}
+    for a in range(len(c["arc_src"])):
+        cout[(int(c["arc_src"][a]), int(c["arc_word"][a]))] = a
+    cfin = {int(s): i for i, s in enumerate(c["final_state"])}
+    # backward best costs, so that the walk can stay inside the beam
+    from kaldi_b200.lattice import _topological_order
+    ns = len(lat["state_frame"])
+    beta = np.full(ns, np.inf)
+    for s_, fc in finals.items():
+        beta[s_] = fc
+    aw = lat["arc_graph_cost"].astype(np.float64) + lat["arc_acoustic_cost"].astype(np.float64)
+    for s_ in _topological_order(ns, lat["arc_src"].astype(np.int64), lat["arc_dst"].astype(np.int64))[::-1]:
+        for a in out_arcs.get(int(s_), []):
+            beta[s_] = min(beta[s_], aw[a] + beta[lat["arc_dst"][a]])
+    limit = bp_raw["total_cost"] + beam - 0.05
+    checked = 0
+    for _ in range(300):
+        s, cost, words = 0, 0.0, []
+        while True:
+            moves = [a for a in out_arcs.get(s, []) if cost + aw[a] + beta[lat["arc_dst"][a]] <= limit]
+            can_stop = s in finals and cost + finals[s] <= limit
+            if can_stop and (not moves or rng.random() < 0.3):
+                cost += finals[s]
+                break
+            assert moves, "the walk is kept inside the beam, so a continuation exists"
+            a = moves[int(rng.integers(len(moves)))]
+            cost += aw[a]
+            if lat["arc_olabel"][a]:
+                words.append(int(lat["arc_olabel"][a]))
+            s = int(lat["arc_dst"][a])
+        q, ccost = 0, 0.0
+        for w in words:
+            a = cout.get((q, w))
+            assert a is not None, "a word sequence within the beam is missing from the compact lattice"
+            ccost += float(c["arc_graph_cost"][a]) + float(c["arc_acoustic_cost"][a])
+            q = int(c["arc_dst"][a])
+        assert q in cfin
+        ccost += float(c["final_graph_cost"][cfin[q]]) + float(c["final_acoustic_cost"][cfin[q]])
+        assert ccost <= cost + 1e-2
+        checked += 1
+    assert checked == 300
+
+
+def test_state_budget_reduces_the_beam_instead_of_blowing_up():
+    """A dense small-vocabulary DAG (exponentially many word sequences): with a state budget the result stays small,
+    reports the beam it could afford, still holds the best path, and is still correct for what it contains."""
+    from kaldi_b200.lattice import best_path, compact_best_path
+    rng = np.random.default_rng(1)
+    ns, na = 600, 4800
+    lat = _random_lattice(rng, ns, na, vocab=6)
+    src = rng.integers(0, ns - 1, na)
+    lat["arc_src"] = src.astype(np.int32)
+    lat["arc_dst"] = np.minimum(src + 1 + rng.integers(0, 12, na), ns - 1).astype(np.int32)
+    lat["final_state"], lat["final_cost"] = np.array([ns - 1], np.int32), np.zeros(1, np.float32)
+    full = _det(lat, 6.0)
+    c = _det_budget(lat, 6.0, 2000)
+    assert full["num_states"] > 2000 >= c["num_states"] and c["effective_beam"] < 6.0 == full["effective_beam"]
+    a, b = best_path(lat), compact_best_path(c)
+    assert b["total_cost"] == pytest.approx(a["total_cost"], abs=1e-3) and b["words"].tolist() == a["olabels"].tolist()
+    key = c["arc_src"].astype(np.int64) * (1 << 32) + c["arc_word"]
+    assert len(np.unique(key)) == len(key)
+
+
+def _det_budget(lat, beam, max_states):
+    from kaldi_b200.lattice import determinize_pruned
+    return determinize_pruned(lat, beam, max_states=max_states)
