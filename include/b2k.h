@@ -278,8 +278,9 @@ int b2k_ivec_compute_batched(b2k_ivec *iv, int32_t num_lanes, const float *const
 /* -------------------------------------------------------------------- nnet3 */
 
 /* A compiled forward program for one utterance length: the analogue of the
- * reference's NnetComputation (nnet3/nnet-computation.h) for the TDNN-F family,
- * produced by kaldi_b200/nnet_model.py (compile_program).  The executor stands
+ * reference's NnetComputation (nnet3/nnet-computation.h) for the TDNN-F and CNN-TDNN-F
+ * families, produced by b2k_nnet_compile below (kaldi_b200/nnet_model.py holds the same
+ * compiler in Python as its test oracle).  The executor stands
  * behind NnetComputer::{AcceptInput,Run,GetOutputDestructive}
  * (nnet3/nnet-compute.h:95-200) as driven by DecodableNnetLoopedOnlineBase::
  * AdvanceChunk (nnet3/decodable-online-looped.cc:118-236) and

@@ -4,6 +4,7 @@
 //   OnlineFeatureInterface::{Dim,NumFramesReady,IsLastFrame,GetFrame}   itf/online-feature-itf.h:49-110
 //   OnlineBaseFeature::{AcceptWaveform,InputFinished}                   itf/online-feature-itf.h:112-125
 //   cuda_decoder::CudaFst / CudaDecoder                                 cudadecoder/cuda-fst.h:75, cuda-decoder.h:224-346
+//   cuda_decoder::BatchedThreadedNnet3CudaOnlinePipeline                cudadecoder/batched-threaded-nnet3-cuda-online-pipeline.h:127-275
 // and the work happens in libb2k.so.  Compiled against the reference headers
 // by `oracle/check_shims.py` (syntax + type check; OpenFst-typed members are
 // guarded by B2K_HAVE_OPENFST because OpenFst is not in this image).
@@ -17,7 +18,10 @@
 #include <utility>
 #include <vector>
 
+#include <functional>
+
 #include "b2k.h"
+#include "b2k_pipeline_shim.h"
 #include "base/kaldi-error.h"
 #include "itf/online-feature-itf.h"
 #include "itf/transition-information.h"
@@ -182,6 +186,91 @@ class CudaDecoderB2k {
 #endif
  private:
   b2k_dec *dec_ = nullptr;
+};
+
+// cuda_decoder::BatchedThreadedNnet3CudaOnlinePipeline surface (cudadecoder/batched-threaded-nnet3-cuda-online-
+// pipeline.h:127-275) over b2k_host::UtteranceBatcher + B2kPipelineBackend (b2k_batcher.h, b2k_pipeline_shim.h):
+// TryInitCorrID / SetLatticeCallback / DecodeBatch(corr_ids, wave_samples, is_first_chunk, is_last_chunk) /
+// WaitForLatticeCallbacks keep their names and argument meaning.  Results are those of the CPU tool
+// online2-wav-nnet3-latgen-faster for each utterance; what differs from the reference GPU pipeline (no partial
+// hypotheses, callbacks from the calling thread, utterances decoded when complete) is listed in b2k_batcher.h.
+class BatchedOnlinePipelineB2k {
+ public:
+  using CorrelationID = uint64_t;
+  // the compact lattice in ABI form; with OpenFst present use SetLatticeCallback(corr_id, LatticeCallback) below
+  typedef std::function<void(CorrelationID, const b2k_clat *)> ClatCallback;
+
+  BatchedOnlinePipelineB2k(const b2k_pipeline_cfg &config, const b2k_model *model, const b2k_fst *decode_fst,
+                           const b2k_ivec_files *ivector_files, const b2k_ivec_cfg *ivector_opts, BaseFloat lattice_beam,
+                           int32 num_channels)
+      : backend_(config, model, decode_fst, ivector_files, ivector_opts, lattice_beam),
+        batcher_(&backend_, config.max_batch, num_channels) {}
+
+  bool TryInitCorrID(CorrelationID corr_id, int /*wait_for*/ = 0) { return batcher_.TryInitCorrId(corr_id); }
+
+  void SetClatCallback(CorrelationID corr_id, ClatCallback cb) {
+    batcher_.SetCallback(corr_id, [cb](CorrelationID id, b2k_host::B2kPipelineBackend::Result &r) { cb(id, r.clat.get()); });
+  }
+
+#if defined(B2K_HAVE_OPENFST) && !defined(B2K_OPENFST_IS_STANDIN)
+  typedef std::function<void(CompactLattice &)> LatticeCallback;      // …online-pipeline.h:131
+  void SetLatticeCallback(CorrelationID corr_id, const LatticeCallback &callback) {
+    batcher_.SetCallback(corr_id, [callback](CorrelationID, b2k_host::B2kPipelineBackend::Result &r) {
+      CompactLattice clat;
+      FillCompactLattice(r.clat.get(), &clat);
+      callback(clat);
+    });
+  }
+  // b2k_clat -> CompactLattice: arcs CompactLatticeArc(word, word, CompactLatticeWeight(LatticeWeight(g, a), tids), dst)
+  static void FillCompactLattice(const b2k_clat *c, CompactLattice *out) {
+    int64_t sz[6];
+    Check(b2k_clat_sizes(c, sz), "b2k_clat_sizes");
+    std::vector<int32> as(sz[1]), ad(sz[1]), aw(sz[1]), fs(sz[2]), tids(sz[3]);
+    std::vector<float> ag(sz[1]), aa(sz[1]), fg(sz[2]), fa(sz[2]);
+    std::vector<int64_t> ao(sz[1] + 1), fo(sz[2] + 1);
+    b2k_compact_lattice v = {};
+    v.arc_src = as.data(); v.arc_dst = ad.data(); v.arc_word = aw.data(); v.arc_graph_cost = ag.data(); v.arc_acoustic_cost = aa.data();
+    v.arc_tids_off = ao.data(); v.final_state = fs.data(); v.final_graph_cost = fg.data(); v.final_acoustic_cost = fa.data();
+    v.final_tids_off = fo.data(); v.tids = tids.data();
+    Check(b2k_clat_copy(c, &v), "b2k_clat_copy");
+    out->DeleteStates();
+    for (int64_t s = 0; s < sz[0]; s++) out->AddState();
+    if (sz[0] > 0) out->SetStart(0);
+    for (int64_t a = 0; a < sz[1]; a++) {
+      std::vector<int32> str(tids.begin() + ao[a], tids.begin() + ao[a + 1]);
+      out->AddArc(as[a], CompactLatticeArc(aw[a], aw[a], CompactLatticeWeight(LatticeWeight(ag[a], aa[a]), str), ad[a]));
+    }
+    for (int64_t f = 0; f < sz[2]; f++) {
+      std::vector<int32> str(tids.begin() + fo[f], tids.begin() + fo[f + 1]);
+      out->SetFinal(fs[f], CompactLatticeWeight(LatticeWeight(fg[f], fa[f]), str));
+    }
+  }
+#endif
+
+  // …online-pipeline.h:209-215.  partial_hypotheses / end_point are not offered (see b2k_batcher.h)
+  void DecodeBatch(const std::vector<CorrelationID> &corr_ids, const std::vector<SubVector<BaseFloat>> &wave_samples,
+                   const std::vector<bool> &is_first_chunk, const std::vector<bool> &is_last_chunk) {
+    KALDI_ASSERT(corr_ids.size() == wave_samples.size());
+    std::vector<std::pair<const float *, int64_t>> chunks;
+    for (const SubVector<BaseFloat> &w : wave_samples) chunks.push_back({w.Data(), (int64_t)w.Dim()});
+    try {
+      batcher_.AcceptChunks(corr_ids, chunks, is_first_chunk, is_last_chunk);
+    } catch (const std::exception &e) {
+      KALDI_ERR << "DecodeBatch: " << e.what();
+    }
+  }
+
+  void WaitForLatticeCallbacks() {
+    try {
+      batcher_.Flush();
+    } catch (const std::exception &e) {
+      KALDI_ERR << "WaitForLatticeCallbacks: " << e.what();
+    }
+  }
+
+ private:
+  b2k_host::B2kPipelineBackend backend_;
+  b2k_host::B2kBatcher batcher_;
 };
 
 }  // namespace b2k_shim

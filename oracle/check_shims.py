@@ -21,7 +21,7 @@ def check() -> bool:
         flags = RF.cxxflags(["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "kaldi_b200", "host"),
                              "-I/usr/local/cuda/include"])
         flags = [f for f in flags if not f.startswith("-I")] + ["-I" + stub] + [f for f in flags if f.startswith("-I")]
-        subprocess.check_call(["g++", "-fsyntax-only", "-DB2K_HAVE_OPENFST"] + flags + [src])
+        subprocess.check_call(["g++", "-fsyntax-only", "-DB2K_HAVE_OPENFST", "-DB2K_OPENFST_IS_STANDIN"] + flags + [src])
     return True
 
 
