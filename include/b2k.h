@@ -456,8 +456,9 @@ int b2k_ivec_create_from_files(const b2k_ivec_cfg *cfg, const b2k_ivec_files *fi
  * transition-id string of the best path (CompactLatticeWeight, fstext/lattice-weight.h:387-604).  Every word
  * sequence whose best cost is within `beam` of the best path is kept, with exactly the weight and alignment of its
  * best path in the raw lattice; sequences outside the beam may or may not survive (as in the reference).
- * PARITY: equivalence-tested against the raw lattice (tests/test_lattice_det.py); the state numbering of the
- * reference's own determinizer is not reproduced (it needs OpenFst, absent here) — see kaldi_b200/csrc/lattice_det.cu. */
+ * PARITY: pinned by equivalence against the reference's own determinizer compiled in oracle/_ref (same word sequences
+ * within the beam, same weights, same alignments; tests/test_lattice_det.py); the reference's state numbering is not
+ * reproduced — see kaldi_b200/csrc/lattice_det.cu. */
 typedef struct {
   int64_t num_states, num_arcs, num_finals, num_tids;   /* state 0 = start */
   int32_t *arc_src, *arc_dst, *arc_word;                /* [num_arcs]                                   */

@@ -14,9 +14,11 @@
 // Not reproduced: the phone-level first pass of the wrapper (an efficiency device: it does not change the
 // accepted language), max_mem / max_loop early stopping, minimization (off by default, DeterminizeLatticePhone-
 // PrunedOptions), and therefore the STATE NUMBERING of the reference's output.
-// PARITY: structure unpinned (the reference's determinizer needs OpenFst, absent from this image); equivalence
-// with the raw lattice is tested exhaustively on small lattices and by path sampling on decoder output
-// (tests/test_lattice_det.py), the way the reference's own determinize-lattice-pruned-test.cc checks itself.
+// PARITY: pinned by equivalence.  The reference's own lat/determinize-lattice-pruned.cc is compiled in oracle/_ref
+// against a container-only OpenFst stand-in (oracle/ref_det.py, oracle/ref_wrap/fst_stub_det/) and run on the same raw
+// lattices, with and without its phone-level pass: same word sequences within the beam, same weights, same
+// transition-id strings (tests/test_lattice_det.py; also exhaustively against path enumeration on small lattices, the
+// property the reference's determinize-lattice-pruned-test.cc checks).  The state numbering is not compared.
 #include <algorithm>
 #include <cmath>
 #include <cstring>

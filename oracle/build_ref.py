@@ -11,7 +11,8 @@ REF = "/root/reference"
 def build_all(quiet: bool = False) -> None:
     if not os.path.isdir(REF):
         raise RuntimeError("/root/reference not present")
-    from . import ref_decoder, ref_feat, ref_nnet
+    from . import ref_decoder, ref_det, ref_feat, ref_nnet
     ref_feat.build(quiet=quiet)
     ref_nnet.build(quiet=quiet)
     ref_decoder.build(quiet=quiet)
+    ref_det.build(quiet=quiet)

@@ -262,3 +262,122 @@ def test_state_budget_reduces_the_beam_instead_of_blowing_up():
 def _det_budget(lat, beam, max_states):
     from kaldi_b200.lattice import determinize_pruned
     return determinize_pruned(lat, beam, max_states=max_states)
+
+
+# ---- against the reference's own determinizer (lat/determinize-lattice-pruned.cc compiled in oracle/_ref against a
+# ---- container-only OpenFst stand-in, oracle/ref_det.py): same accepted language within the beam, same weights, same
+# ---- alignments; the state numbering is not compared
+
+def _ref_det():
+    try:
+        from oracle import ref_det
+        if not ref_det.available():
+            pytest.skip("oracle/_ref determinizer not present")
+        ref_det.lib()
+        return ref_det
+    except (OSError, RuntimeError) as e:
+        pytest.skip(str(e))
+
+
+_T = np.arange(64)
+PHONES = dict(phone_of=(1 + _T % 5).astype(np.int32), self_loop=(_T % 2).astype(np.uint8), phone_start=(_T % 3 == 0).astype(np.uint8))
+
+
+@pytest.mark.parametrize("seed", range(100, 140))
+def test_reference_determinizer_agrees_without_pruning(seed):
+    RD = _ref_det()
+    rng = np.random.default_rng(seed)
+    lat = _random_lattice(rng, n_states=int(rng.integers(3, 11)), n_arcs=int(rng.integers(3, 26)), vocab=int(rng.integers(1, 4)))
+    want = _enumerate_raw(lat)
+    for phone_pass in (False, True):
+        r = RD.determinize(lat, 1e9, phone_determinize=phone_pass, **PHONES)
+        assert r["ok"] == 1
+        ref, mine = _enumerate_compact(r), _enumerate_compact(_det(lat, 1e9))
+        assert set(ref) == set(mine) == set(want)
+        for k in want:
+            assert ref[k][0] == pytest.approx(mine[k][0], abs=2e-4) and ref[k][1] == pytest.approx(mine[k][1], abs=2e-4)
+            if want[k][4] - want[k][0] > 1e-3:
+                assert ref[k][3] == mine[k][3] == want[k][3], k
+
+
+@pytest.mark.parametrize("seed", range(140, 200))
+def test_reference_determinizer_agrees_within_the_beam(seed):
+    RD = _ref_det()
+    rng = np.random.default_rng(seed)
+    lat = _random_lattice(rng, n_states=int(rng.integers(4, 12)), n_arcs=int(rng.integers(6, 30)), vocab=3)
+    want = _enumerate_raw(lat)
+    if not want:
+        pytest.skip("no accepting path")
+    best = min(v[0] for v in want.values())
+    beam = float(rng.uniform(0.5, 4.0))
+    mine = _enumerate_compact(_det(lat, beam))
+    inside = {k for k, v in want.items() if v[0] <= best + beam - 1e-3}
+    for phone_pass in (False, True):
+        r = RD.determinize(lat, beam, phone_determinize=phone_pass, **PHONES)
+        assert r["ok"] == 1
+        ref = _enumerate_compact(r)
+        assert inside <= set(ref) and inside <= set(mine)       # both keep everything within the beam
+        assert set(ref) <= set(want) and set(mine) <= set(want)  # (each may keep a few sequences just outside it)
+        for k in set(ref) & set(mine):
+            assert ref[k][0] == pytest.approx(mine[k][0], abs=2e-4)
+            if want[k][4] - want[k][0] > 1e-3:
+                assert ref[k][3] == mine[k][3], k
+
+
+def test_reference_determinizer_agrees_on_decoder_output():
+    RD = _ref_det()
+    from kaldi_b200 import synth
+    from kaldi_b200.lattice import compact_best_path, raw_lattice_from_canonical
+    from oracle import dec_oracle as D
+    g = synth.make_hclg(30_000, num_pdfs=60, seed=7, olabel_frac=0.3)
+    cfg = dict(synth.DEFAULT_DECODER_CFG)
+    rng = np.random.default_rng(5)
+    ll = (rng.standard_normal((40, 60)) * 2.0).astype(np.float32)
+    o = D.DecoderOracle(g, cfg)
+    o.decode(ll, mode=D.MODE_REFERENCE_ORDER)
+    lat = raw_lattice_from_canonical(o.lattice())
+    beam = float(cfg["lattice_beam"])
+    mine = _det(lat, beam)
+    # phone structure of the synthetic graph: transition-ids 2*pdf+1 (forward) and 2*pdf+2 (self-loop), synth.make_hclg
+    ntid = int(lat["arc_ilabel"].max()) + 2
+    t = np.arange(ntid)
+    phones = dict(phone_of=(1 + np.maximum(t - 1, 0) // 2 % 40).astype(np.int32), self_loop=((t % 2 == 0) & (t > 0)).astype(np.uint8),
+                  phone_start=(t % 2 == 1).astype(np.uint8))
+    for phone_pass in (False, True):
+        r = RD.determinize(lat, beam, phone_determinize=phone_pass, **phones)
+        assert r["ok"] == 1
+        a, b = compact_best_path(r), compact_best_path(mine)
+        assert a["words"].tolist() == b["words"].tolist() and a["tids"].tolist() == b["tids"].tolist()
+        assert a["total_cost"] == pytest.approx(b["total_cost"], abs=1e-3)
+        # every word sequence of the reference's compact lattice that is safely inside the beam is in ours at the same cost,
+        # and the other way round (walk both automata in lock step from the start state)
+        for x, y in ((r, mine), (mine, r)):
+            xo, yo = {}, {}
+            for i in range(len(x["arc_src"])):
+                xo.setdefault(int(x["arc_src"][i]), []).append(i)
+            for i in range(len(y["arc_src"])):
+                yo[(int(y["arc_src"][i]), int(y["arc_word"][i]))] = i
+            xf = {int(s): i for i, s in enumerate(x["final_state"])}
+            yf = {int(s): i for i, s in enumerate(y["final_state"])}
+            limit = a["total_cost"] + beam - 0.05
+            stack, seen, finals_checked = [(0, 0, 0.0, 0.0)], set(), 0
+            while stack:
+                sx, sy, cx, cy = stack.pop()
+                if sx in xf:
+                    tx = cx + float(x["final_graph_cost"][xf[sx]]) + float(x["final_acoustic_cost"][xf[sx]])
+                    if tx <= limit:
+                        assert sy in yf
+                        ty = cy + float(y["final_graph_cost"][yf[sy]]) + float(y["final_acoustic_cost"][yf[sy]])
+                        assert ty == pytest.approx(tx, abs=2e-3)
+                        finals_checked += 1
+                for i in xo.get(sx, []):
+                    j = yo.get((sy, int(x["arc_word"][i])))
+                    if j is None:
+                        continue                                 # only sequences outside the beam may be missing: checked at finals
+                    nxt = (int(x["arc_dst"][i]), int(y["arc_dst"][j]))
+                    if nxt in seen:
+                        continue
+                    seen.add(nxt)
+                    stack.append((nxt[0], nxt[1], cx + float(x["arc_graph_cost"][i]) + float(x["arc_acoustic_cost"][i]),
+                                  cy + float(y["arc_graph_cost"][j]) + float(y["arc_acoustic_cost"][j])))
+            assert finals_checked > 0
