@@ -234,3 +234,153 @@ def write_compact_lattice_text(f, key: str, clat: dict) -> None:
             f.write(f"{s}\t{_num(clat['final_graph_cost'][i])},{_num(clat['final_acoustic_cost'][i])},"
                     f"{'_'.join(str(int(t)) for t in clat['final_tids'][i])}\n")
     f.write("\n")
+
+
+# ---- binary table entries (lat/kaldi-lattice.cc WriteLattice / WriteCompactLattice with binary = true) ---------------
+#
+# `key` + ' ' + "\0B" + VectorFst<Arc>::Write: FstHeader {int32 magic 2125659606, "vector", arc type ("lattice4" =
+# LatticeWeightTpl<float>::Type(), lattice-weight.h:86-89; "compactlattice44", :470-474), int32 version 2, int32 flags 0,
+# uint64 properties, int64 start, int64 numstates, int64 numarcs 0}, then per state: final weight, int64 narcs, arcs
+# {int32 ilabel, int32 olabel, weight, int32 nextstate}.  LatticeWeight = 2 floats (lattice-weight.h:141-146);
+# CompactLatticeWeight = LatticeWeight + int32 length + int32 transition-ids (:531-540).  The weight encodings are
+# checked against the reference's own Write() (oracle/_ref, tests/test_lattice_utils.py); the container layout is
+# OpenFst's published one and, OpenFst being absent here, PARITY UNPINNED like the HCLG reader.
+
+import struct as _struct
+
+_FST_MAGIC = 2125659606
+_INF32 = _struct.pack("<f", float("inf"))
+
+
+def _fst_header(arctype: str, start: int, num_states: int) -> bytes:
+    def s(x):
+        return _struct.pack("<i", len(x)) + x.encode("ascii")
+    return (_struct.pack("<i", _FST_MAGIC) + s("vector") + s(arctype) + _struct.pack("<ii", 2, 0) +
+            _struct.pack("<Qqqq", 0x3, start, num_states, 0))          # properties: kExpanded | kMutable
+
+
+def lattice_weight_bytes(g: float, a: float) -> bytes:
+    return _struct.pack("<ff", g, a)
+
+
+def compact_weight_bytes(g: float, a: float, tids) -> bytes:
+    t = np.ascontiguousarray(tids, np.int32)
+    return _struct.pack("<ff", g, a) + _struct.pack("<i", len(t)) + t.astype("<i4").tobytes()
+
+
+def write_lattice_binary(f, key: str, lat: dict) -> None:
+    """One binary `Lattice` table entry (a raw lattice: state 0 = start)."""
+    ns = len(lat["state_frame"])
+    f.write(key.encode() + b" \0B" + _fst_header("lattice4", 0 if ns else -1, ns))
+    order = np.argsort(lat["arc_src"], kind="stable")
+    starts = np.searchsorted(lat["arc_src"][order], np.arange(ns + 1))
+    fin = dict(zip(lat["final_state"].tolist(), lat["final_cost"].tolist()))
+    arc_dt = np.dtype([("i", "<i4"), ("o", "<i4"), ("g", "<f4"), ("a", "<f4"), ("n", "<i4")])
+    for s in range(ns):
+        f.write(lattice_weight_bytes(fin[s], 0.0) if s in fin else _INF32 * 2)
+        idx = order[starts[s]:starts[s + 1]]
+        f.write(_struct.pack("<q", len(idx)))
+        rec = np.zeros(len(idx), arc_dt)
+        rec["i"], rec["o"] = lat["arc_ilabel"][idx], lat["arc_olabel"][idx]
+        rec["g"], rec["a"], rec["n"] = lat["arc_graph_cost"][idx], lat["arc_acoustic_cost"][idx], lat["arc_dst"][idx]
+        f.write(rec.tobytes())
+
+
+def write_compact_lattice_binary(f, key: str, clat: dict) -> None:
+    """One binary `CompactLattice` table entry (acceptor: ilabel = olabel = word)."""
+    ns = clat["num_states"]
+    f.write(key.encode() + b" \0B" + _fst_header("compactlattice44", 0 if ns else -1, ns))
+    order = np.argsort(clat["arc_src"], kind="stable")
+    starts = np.searchsorted(clat["arc_src"][order], np.arange(ns + 1))
+    fin = {int(s): i for i, s in enumerate(clat["final_state"])}
+    for s in range(ns):
+        if s in fin:
+            i = fin[s]
+            f.write(compact_weight_bytes(clat["final_graph_cost"][i], clat["final_acoustic_cost"][i], clat["final_tids"][i]))
+        else:
+            f.write(_INF32 * 2 + _struct.pack("<i", 0))
+        idx = order[starts[s]:starts[s + 1]]
+        f.write(_struct.pack("<q", len(idx)))
+        for a in idx:
+            w = int(clat["arc_word"][a])
+            f.write(_struct.pack("<ii", w, w) + compact_weight_bytes(clat["arc_graph_cost"][a], clat["arc_acoustic_cost"][a],
+                                                                     clat["arc_tids"][a]) + _struct.pack("<i", int(clat["arc_dst"][a])))
+
+
+def read_lattice_archive(data: bytes) -> list:
+    """Entries of a binary Lattice / CompactLattice archive as written above: [(key, 'lattice' | 'compact', dict)]."""
+    out, p = [], 0
+    while p < len(data):
+        e = data.index(b" ", p)
+        key = data[p:e].decode()
+        if data[e + 1:e + 3] != b"\0B":
+            raise ValueError("not a binary table entry")
+        p = e + 3
+
+        def rd(fmt):
+            nonlocal p
+            v = _struct.unpack_from(fmt, data, p)
+            p += _struct.calcsize(fmt)
+            return v
+
+        def rs():
+            nonlocal p
+            (n,) = rd("<i")
+            s = data[p:p + n].decode("ascii")
+            p += n
+            return s
+        if rd("<i")[0] != _FST_MAGIC:
+            raise ValueError("bad FST magic")
+        fsttype, arctype = rs(), rs()
+        _ver, _flags = rd("<ii")
+        _props, start, ns, _na = rd("<Qqqq")
+        if fsttype != "vector" or arctype not in ("lattice4", "compactlattice44"):
+            raise ValueError(f"unsupported FST {fsttype}/{arctype}")
+        compact = arctype.startswith("compact")
+
+        def rw():
+            g, a = rd("<ff")
+            if not compact:
+                return g, a, None
+            (n,) = rd("<i")
+            t = np.frombuffer(data, "<i4", n, p).copy()
+            nonlocal_p_advance(4 * n)
+            return g, a, t
+
+        def nonlocal_p_advance(k):
+            nonlocal p
+            p += k
+        src, dst, il, ol, g_, a_, tids, fs, fg, fa, ft = [], [], [], [], [], [], [], [], [], [], []
+        for s in range(ns):
+            g, a, t = rw()
+            if np.isfinite(g) or np.isfinite(a):
+                fs.append(s); fg.append(g); fa.append(a); ft.append(t)
+            (na,) = rd("<q")
+            for _ in range(na):
+                i, o = rd("<ii")
+                g, a, t = rw()
+                (n,) = rd("<i")
+                src.append(s); dst.append(n); il.append(i); ol.append(o); g_.append(g); a_.append(a); tids.append(t)
+        i32, f32 = np.int32, np.float32
+        if compact:
+            d = dict(num_states=int(ns), arc_src=np.array(src, i32), arc_dst=np.array(dst, i32), arc_word=np.array(il, i32),
+                     arc_graph_cost=np.array(g_, f32), arc_acoustic_cost=np.array(a_, f32), arc_tids=tids,
+                     final_state=np.array(fs, i32), final_graph_cost=np.array(fg, f32), final_acoustic_cost=np.array(fa, f32),
+                     final_tids=ft)
+        else:
+            d = dict(num_states=int(ns), arc_src=np.array(src, i32), arc_dst=np.array(dst, i32), arc_ilabel=np.array(il, i32),
+                     arc_olabel=np.array(ol, i32), arc_graph_cost=np.array(g_, f32), arc_acoustic_cost=np.array(a_, f32),
+                     final_state=np.array(fs, i32), final_cost=np.array(fg, f32))
+        d["start"] = int(start)
+        out.append((key, "compact" if compact else "lattice", d))
+    return out
+
+
+def scale_compact_lattice(clat: dict, graph_scale: float = 1.0, acoustic_scale: float = 1.0) -> dict:
+    """fst::ScaleLattice with a diagonal scale (AcousticLatticeScale / GraphLatticeScale, fstext/lattice-utils.h): what
+    online2-wav-nnet3-latgen-faster does with 1/acoustic_scale before writing (online2-wav-nnet3-latgen-faster.cc:289-291)."""
+    out = dict(clat)
+    for k, s in (("arc_graph_cost", graph_scale), ("final_graph_cost", graph_scale), ("arc_acoustic_cost", acoustic_scale),
+                 ("final_acoustic_cost", acoustic_scale)):
+        out[k] = (clat[k].astype(np.float32) * np.float32(s)).astype(np.float32)
+    return out

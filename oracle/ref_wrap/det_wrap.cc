@@ -5,6 +5,8 @@
 // and comes back as flat compact-lattice arrays.  Oracle of kaldi_b200/csrc/lattice_det.cu (tests/test_lattice_det.py).
 #include <cstdint>
 #include <cstring>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #include "lat/determinize-lattice-pruned.h"
@@ -103,5 +105,21 @@ void ref_det_copy(void *h, int32_t *arc_src, int32_t *arc_dst, int32_t *arc_word
 }
 
 void ref_det_free(void *h) { delete (Out *)h; }
+
+// The reference's own binary encodings: CompactLatticeWeightTpl::Write (fstext/lattice-weight.h:531-540) when n >= 0,
+// LatticeWeightTpl::Write (:141-146) when n < 0; and the arc type strings of the two lattice types.  Returns the byte count.
+int32_t ref_lattice_weight_bytes(float g, float a, const int32_t *tids, int32_t n, uint8_t *out, int32_t cap) {
+  std::ostringstream os(std::ios::binary);
+  if (n >= 0) kaldi::CompactLatticeWeight(kaldi::LatticeWeight(g, a), std::vector<int32_t>(tids, tids + n)).Write(os);
+  else kaldi::LatticeWeight(g, a).Write(os);
+  const std::string s = os.str();
+  if ((int32_t)s.size() <= cap) memcpy(out, s.data(), s.size());
+  return (int32_t)s.size();
+}
+int32_t ref_lattice_type_strings(char *out, int32_t cap) {
+  const std::string s = kaldi::LatticeWeight::Type() + " " + kaldi::CompactLatticeWeight::Type();
+  if ((int32_t)s.size() + 1 <= cap) memcpy(out, s.c_str(), s.size() + 1);
+  return (int32_t)s.size();
+}
 
 }  // extern "C"

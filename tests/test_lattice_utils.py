@@ -71,3 +71,83 @@ def test_lattice_text_round_trip():
     want = sorted(zip(lat["arc_src"].tolist(), lat["arc_dst"].tolist(), lat["arc_ilabel"].tolist(), lat["arc_olabel"].tolist(),
                       lat["arc_graph_cost"].view(np.int32).tolist(), lat["arc_acoustic_cost"].view(np.int32).tolist()))
     assert got == want                     # repr(float32) round-trips bit for bit
+
+
+def _small_raw_and_compact():
+    from kaldi_b200.lattice import determinize_pruned
+    f32, i32 = np.float32, np.int32
+    lat = dict(state_frame=np.zeros(4, i32), state_hclg=np.arange(4, dtype=i32), state_tot_cost=np.zeros(4, f32),
+               state_extra_cost=np.zeros(4, f32),
+               arc_src=np.array([0, 0, 1, 2, 0], i32), arc_dst=np.array([1, 2, 3, 3, 3], i32),
+               arc_ilabel=np.array([11, 12, 0, 14, 15], i32), arc_olabel=np.array([7, 7, 0, 0, 9], i32),
+               arc_graph_cost=np.array([1.0, 0.5, 0.25, 0.25, 5.0], f32), arc_acoustic_cost=np.array([1.0, 1.0, 0.0, 0.0, -0.5], f32),
+               final_state=np.array([3], i32), final_cost=np.array([0.5], f32))
+    try:
+        return lat, determinize_pruned(lat, 100.0)
+    except OSError as e:
+        pytest.skip(str(e))
+
+
+def test_binary_archives_round_trip():
+    import io
+    from kaldi_b200.lattice import read_lattice_archive, write_compact_lattice_binary, write_lattice_binary
+    lat, clat = _small_raw_and_compact()
+    buf = io.BytesIO()
+    write_lattice_binary(buf, "utt-a", lat)
+    write_compact_lattice_binary(buf, "utt-b", clat)
+    write_lattice_binary(buf, "utt-c", lat)
+    entries = read_lattice_archive(buf.getvalue())
+    assert [(k, kind) for k, kind, _ in entries] == [("utt-a", "lattice"), ("utt-b", "compact"), ("utt-c", "lattice")]
+    a = entries[0][2]
+    order = np.argsort(lat["arc_src"], kind="stable")
+    for k in ("arc_src", "arc_dst", "arc_ilabel", "arc_olabel", "arc_graph_cost", "arc_acoustic_cost"):
+        np.testing.assert_array_equal(a[k], lat[k][order], err_msg=k)
+    assert a["start"] == 0 and a["final_state"].tolist() == [3] and a["final_cost"].tolist() == [0.5]
+    b = entries[1][2]
+    order = np.argsort(clat["arc_src"], kind="stable")
+    for k in ("arc_src", "arc_dst", "arc_word", "arc_graph_cost", "arc_acoustic_cost"):
+        np.testing.assert_array_equal(b[k], clat[k][order], err_msg=k)
+    assert [t.tolist() for t in b["arc_tids"]] == [clat["arc_tids"][i].tolist() for i in order]
+    assert b["final_state"].tolist() == clat["final_state"].tolist()
+    assert [t.tolist() for t in b["final_tids"]] == [t.tolist() for t in clat["final_tids"]]
+    # the first byte after the "\0B" marker is 214 = the low byte of the FST magic (kaldi-lattice.cc:381 relies on it)
+    raw = buf.getvalue()
+    assert raw[raw.index(b"\0B") + 2] == 214
+
+
+def test_weight_encodings_equal_the_references_own_write():
+    """LatticeWeightTpl::Write / CompactLatticeWeightTpl::Write and the arc type strings, from the reference's
+    fstext/lattice-weight.h compiled in oracle/_ref."""
+    import ctypes as C
+    from kaldi_b200.lattice import _fst_header, compact_weight_bytes, lattice_weight_bytes
+    try:
+        from oracle import ref_det
+        if not ref_det.available():
+            pytest.skip("oracle/_ref determinizer library not present")
+        L = ref_det.lib()
+    except (OSError, RuntimeError) as e:
+        pytest.skip(str(e))
+    if not hasattr(L, "ref_lattice_weight_bytes"):
+        pytest.skip("oracle/_ref library predates ref_lattice_weight_bytes")
+    L.ref_lattice_weight_bytes.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    buf = (C.c_uint8 * 256)()
+    for g, a, tids in [(1.5, -2.25, [3, 1, 4, 1, 5]), (0.0, 0.0, []), (float("inf"), float("inf"), []), (7.0, 0.125, [2 ** 30])]:
+        t = np.array(tids, np.int32)
+        n = L.ref_lattice_weight_bytes(g, a, t.ctypes.data, len(t), buf, 256)
+        assert bytes(buf[:n]) == compact_weight_bytes(g, a, t)
+        n = L.ref_lattice_weight_bytes(g, a, None, -1, buf, 256)
+        assert bytes(buf[:n]) == lattice_weight_bytes(g, a)
+    s = C.create_string_buffer(64)
+    L.ref_lattice_type_strings.argtypes = [C.c_void_p, C.c_int32]
+    L.ref_lattice_type_strings(s, 64)
+    assert s.value.decode().split() == ["lattice4", "compactlattice44"]
+    assert b"lattice4" in _fst_header("lattice4", 0, 1) and b"compactlattice44" in _fst_header("compactlattice44", 0, 1)
+
+
+def test_scale_compact_lattice():
+    from kaldi_b200.lattice import compact_best_path, scale_compact_lattice
+    _, clat = _small_raw_and_compact()
+    s = scale_compact_lattice(clat, acoustic_scale=0.5)
+    np.testing.assert_array_equal(s["arc_acoustic_cost"], clat["arc_acoustic_cost"] * np.float32(0.5))
+    np.testing.assert_array_equal(s["arc_graph_cost"], clat["arc_graph_cost"])
+    assert compact_best_path(s)["acoustic_cost"] == pytest.approx(0.5 * compact_best_path(clat)["acoustic_cost"])
