@@ -163,3 +163,71 @@ def test_graph_file_route_gives_the_same_decoder(tmp_path):
         lats.append(lattice_to_canonical(dec.GetRawLattice(0)))
     assert all(np.array_equal(lats[0][k], lats[1][k]) for k in lats[0])
     assert lats[0]["states"].shape[0] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="host C++ above the ABI (b2k_batcher.h / b2k_pipeline_shim.h over csrc/pipeline.cu) was written "
+                                        "after this round's GPU budget was spent: its first device run is the round-end test run")
+def test_pure_cpp_route_from_files_to_compact_lattices(tmp_path):
+    """tests/cabi/pipeline_device_route.cc: model file + graph file + chunked audio -> UtteranceBatcher ->
+    B2kPipelineBackend -> compact lattices, no Python in between; against the ctypes view of the same C++ pipeline
+    (NativeBatchedPipeline) followed by lattice.determinize_pruned."""
+    import shutil
+    import subprocess
+    from kaldi_b200 import kaldi_io as KIO, synth
+    from kaldi_b200.decoder import CudaDecoder, CudaFst
+    from kaldi_b200.lattice import determinize_pruned
+    from kaldi_b200.model import KaldiModel
+    from kaldi_b200.pipeline import NativeBatchedPipeline, PipelineConfig
+    if not shutil.which("g++"):
+        pytest.skip("g++ missing")
+    root = os.path.dirname(HERE)
+    S, n = 32000, 3
+    g = synth.make_hclg(50_000, num_pdfs=64, seed=4)
+    fst_path, wav_path, t2p_path, out_path = (str(tmp_path / x) for x in ("HCLG.fst", "waves.f32", "tid2pdf.i32", "out.bin"))
+    KIO.write_openfst(fst_path, g, "const")
+    waves = [synth.make_audio(S, seed=40 + i).astype(np.float32) for i in range(n)]
+    np.concatenate(waves).astype("<f4").tofile(wav_path)
+    np.asarray(g["tid2pdf"], "<i4").tofile(t2p_path)
+    exe = str(tmp_path / "pipeline_device_route")
+    so_dir = os.path.join(root, "kaldi_b200")
+    r = subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(root, "include"), "-I" + os.path.join(so_dir, "host"),
+                        os.path.join(HERE, "cabi", "pipeline_device_route.cc"), "-o", exe, "-L" + so_dir, "-lb2k",
+                        "-Wl,-rpath," + so_dir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, MDL, fst_path, wav_path, str(n), str(S), out_path, t2p_path], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # read back: per utterance in callback order
+    d = open(out_path, "rb").read()
+    p, got = 0, {}
+    while p < len(d):
+        cid, ns, na, nf, nt = np.frombuffer(d, "<i8", 5, p)
+        p += 40
+
+        def take(dt, k):
+            nonlocal p
+            a = np.frombuffer(d, dt, int(k), p).copy()
+            p += a.nbytes
+            return a
+        rec = dict(num_states=int(ns), arc_src=take("<i4", na), arc_dst=take("<i4", na), arc_word=take("<i4", na),
+                   arc_graph_cost=take("<f4", na), arc_acoustic_cost=take("<f4", na), arc_off=take("<i8", na + 1),
+                   final_state=take("<i4", nf), final_graph_cost=take("<f4", nf), final_acoustic_cost=take("<f4", nf),
+                   final_off=take("<i8", nf + 1), tids=take("<i4", nt))
+        got[int(cid)] = rec
+    assert sorted(got) == [100, 101, 102]
+    # the same C++ pipeline through ctypes, then the determinizer
+    cfg = PipelineConfig(max_batch=2, num_samples=S, extract_ivectors=False)
+    nat = NativeBatchedPipeline(cfg, KaldiModel(MDL), CudaFst(g), None)
+    beam = float(cfg.decoder_cfg["lattice_beam"])
+    for first in (0, 2):                                     # the batcher decoded utterances {0,1} and then {2}
+        batch = waves[first:first + 2]
+        lats = CudaDecoder.SplitLattices(nat.decode_batch(batch))
+        for j, lat in enumerate(lats):
+            want, rec = determinize_pruned(lat, beam), got[100 + first + j]
+            assert rec["num_states"] == want["num_states"]
+            for k in ("arc_src", "arc_dst", "arc_word", "arc_graph_cost", "arc_acoustic_cost", "final_state",
+                      "final_graph_cost", "final_acoustic_cost"):
+                np.testing.assert_array_equal(rec[k], want[k], err_msg=k)
+            tids = np.concatenate([np.concatenate(want["arc_tids"]) if want["arc_tids"] else np.zeros(0, np.int32),
+                                   np.concatenate(want["final_tids"]) if want["final_tids"] else np.zeros(0, np.int32)])
+            np.testing.assert_array_equal(rec["tids"], tids)
