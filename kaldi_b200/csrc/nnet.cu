@@ -357,6 +357,197 @@ __global__ void __launch_bounds__(256, 2) nnet_gemm_tc_kernel(OpDev op, RunCtx c
     }
 }
 
+// ---------------------------------------------------------------- tcgen05 GEMM (3xTF32, accumulator in TMEM)
+//
+// EXPERIMENTAL, OFF BY DEFAULT (B2K_NNET_GEMM=tcgen05): written after round 1's GPU budget was spent and never run.
+// The descriptor and shared-memory layout math is the one of tools/tcgen05_gemm_probe.cu, cross-checked on the host
+// against CuTe (tools/check_tcgen05_layout.cu); the execution protocol (fences, mbarrier phases) has not met a device.
+// Same operator and fused epilogue as the two kernels above.  One CTA = 256 threads = one 128 x TN output tile held in
+// TN fp32 TMEM columns; K slabs of 32 are double-buffered in shared memory: all threads gather / split / store slab s
+// while the tensor core runs the 12 MMAs (4 K-steps x {lo*hi, hi*lo, hi*hi}) of slab s-1, issued by thread 0 and
+// tracked with one mbarrier per buffer (tcgen05.commit).  Operand tiles are K-major, no swizzle: one panel per
+// 16-byte K chunk holding 16 bytes of every row, panels padded by 16 bytes so that a warp storing 32 consecutive k of
+// one row hits 32 different banks (LBO = rows*16 + 16, SBO = 128).
+#define T5_BM 128
+#define T5_BK 32
+#define T5_CH (T5_BK / 4)
+
+__device__ __forceinline__ uint32_t t5_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t t5_desc(uint32_t saddr, uint32_t lbo_bytes) {          // SBO 128 B, version 1, no swizzle
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) | ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void t5_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void t5_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "T5_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+      "@P bra T5_DONE_%=;\n\t"
+      "bra T5_WAIT_%=;\n\t"
+      "T5_DONE_%=:\n\t}"
+      :: "r"(bar), "r"(parity) : "memory");
+}
+
+template <int TN>
+__global__ void __launch_bounds__(256, 1) nnet_gemm_tc5_kernel(OpDev op, RunCtx c) {
+  constexpr uint32_t PANEL_A = T5_BM * 16 + 16, PANEL_B = TN * 16 + 16;            // bytes; LBO of the descriptors
+  constexpr uint32_t TILE_A = T5_CH * PANEL_A, TILE_B = T5_CH * PANEL_B;
+  constexpr uint32_t STAGE = 2 * TILE_A + 2 * TILE_B;                               // a_hi, a_lo, b_hi, b_lo
+  constexpr uint32_t TMEM_COLS = TN <= 128 ? 128 : 256;                             // power of two >= TN
+  extern __shared__ __align__(16) unsigned char t5_smem[];       // no-swizzle operands need 16-byte alignment only
+  __shared__ const float *rowp[T5_BM];
+  __shared__ __align__(8) unsigned long long bars[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane_id = tid & 31;
+  const int M = c.batch * op.rows * (op.hsplit > 1 ? op.hsplit : 1);
+  const int m0 = blockIdx.x * T5_BM, n0 = blockIdx.y * TN;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(t5_smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(t5_smem_u32(&bars[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(t5_smem_u32(&bars[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+  // F32 accumulate (bit 4), TF32 x TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(T5_BM >> 4) << 24);
+
+  uint32_t uses0 = 0u, uses1 = 0u;         // commits issued on each buffer so far (same value in every thread)
+  uint32_t slab = 0;
+  for (int ti = 0; ti < op.n_terms; ti++) {
+    const TermDev t = op.terms[ti];
+    __syncthreads();
+    if (tid < T5_BM) {
+      const int r = m0 + tid;
+      const float *p = nullptr;
+      if (r < M) {
+        const RowIdx x = split_row(op, r);
+        p = src_row_ptr(c, t, x.lane, map_row(t, x.i));
+        if (t.col_lim > 0) {
+          const int cb = x.h * t.col_step + t.col_off;
+          p = (cb >= 0 && cb < t.col_lim) ? p + cb : nullptr;
+        }
+      }
+      rowp[tid] = p;
+    }
+    __syncthreads();
+    for (int kk = 0; kk < t.klen; kk += T5_BK, slab++) {
+      const uint32_t b = slab & 1u;
+      unsigned char *a_hi = t5_smem + b * STAGE, *a_lo = a_hi + TILE_A, *b_hi = a_lo + TILE_A, *b_lo = b_hi + TILE_B;
+      // global -> registers (a warp reads 32 consecutive k of one row: 128-byte segments), before waiting for the buffer
+      const int k = kk + lane_id;
+      const bool kin = k < t.klen;
+      float ra[T5_BM / 8], rb[TN / 8];
+#pragma unroll
+      for (int e = 0; e < T5_BM / 8; e++) {
+        const float *p = rowp[warp + e * 8];
+        ra[e] = (p && kin) ? p[k] : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < TN / 8; e++) {
+        const int n = n0 + warp + e * 8;
+        rb[e] = (n < op.N && kin) ? __ldg(&op.w[(long long)n * op.K + t.k0 + k]) : 0.f;
+      }
+      // the MMAs that read this buffer two slabs ago must have retired
+      const uint32_t used = b ? uses1 : uses0;
+      if (used > 0) t5_mbar_wait(t5_smem_u32(&bars[b]), (used - 1u) & 1u);
+      const uint32_t koff = (uint32_t)(lane_id >> 2), kin4 = (uint32_t)(lane_id & 3) * 4u;
+#pragma unroll
+      for (int e = 0; e < T5_BM / 8; e++) {
+        const uint32_t off = koff * PANEL_A + (uint32_t)(warp + e * 8) * 16u + kin4;
+        const uint32_t hi = to_tf32(ra[e]);
+        *reinterpret_cast<uint32_t *>(a_hi + off) = hi;
+        *reinterpret_cast<uint32_t *>(a_lo + off) = to_tf32(ra[e] - __uint_as_float(hi));
+      }
+#pragma unroll
+      for (int e = 0; e < TN / 8; e++) {
+        const uint32_t off = koff * PANEL_B + (uint32_t)(warp + e * 8) * 16u + kin4;
+        const uint32_t hi = to_tf32(rb[e]);
+        *reinterpret_cast<uint32_t *>(b_hi + off) = hi;
+        *reinterpret_cast<uint32_t *>(b_lo + off) = to_tf32(rb[e] - __uint_as_float(hi));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> visible to the tensor core
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int ks = 0; ks < T5_BK / 8; ks++) {                          // K = 8 per instruction = two 16-byte chunks = two panels
+          const uint64_t dah = t5_desc(t5_smem_u32(a_hi) + (uint32_t)ks * 2u * PANEL_A, PANEL_A), dal = t5_desc(t5_smem_u32(a_lo) + (uint32_t)ks * 2u * PANEL_A, PANEL_A);
+          const uint64_t dbh = t5_desc(t5_smem_u32(b_hi) + (uint32_t)ks * 2u * PANEL_B, PANEL_B), dbl = t5_desc(t5_smem_u32(b_lo) + (uint32_t)ks * 2u * PANEL_B, PANEL_B);
+          t5_mma(tmem_d, dal, dbh, idesc, (slab > 0 || ks > 0) ? 1u : 0u);
+          t5_mma(tmem_d, dah, dbl, idesc, 1u);
+          t5_mma(tmem_d, dah, dbh, idesc, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(t5_smem_u32(&bars[b])) : "memory");
+      }
+      if (b) uses1++; else uses0++;
+    }
+  }
+  // all MMAs retired: a commit tracks every tcgen05 operation issued before it, so the most recent one is enough
+  if (slab > 0) {
+    const uint32_t lb = (slab - 1u) & 1u;
+    t5_mbar_wait(t5_smem_u32(&bars[lb]), ((lb ? uses1 : uses0) - 1u) & 1u);
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (its quarter) = tile rows, columns of half w/4
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int r = m0 + q * 32 + lane_id;
+    const bool live = r < M;
+    RowIdx x = {0, 0, 0};
+    float *orow = nullptr;
+    const float *rrow = nullptr;
+    if (live) {
+      x = split_row(op, r);
+      orow = (op.out_kind == 0) ? c.arena + (long long)x.lane * c.arena_stride + op.out_off + (long long)x.i * op.out_dim + (long long)x.h * op.N
+                                : c.d_out[x.lane] + (long long)x.i * c.out_stride;
+      if (op.has_res) rrow = src_row_ptr(c, op.res, x.lane, map_row(op.res, x.i));
+    }
+    for (int c0 = half * (TN / 2); c0 < (half + 1) * (TN / 2); c0 += 16) {
+      uint32_t v[16];
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const int n = n0 + c0 + j;
+          if (n >= op.N) continue;
+          float val = slab > 0 ? __uint_as_float(v[j]) : 0.f;
+          if (op.bias) val = __fadd_rn(val, __ldg(&op.bias[n]));
+          if (op.relu) val = fmaxf(val, 0.f);
+          if (op.bn_scale) val = __fadd_rn(__fmul_rn(val, __ldg(&op.bn_scale[n])), __ldg(&op.bn_offset[n]));
+          if (rrow) val = __fadd_rn(__fmul_rn(op.res_alpha, rrow[n]), val);
+          if (!op.log_softmax) {
+            if (op.sub_vec) val = __fadd_rn(val, -__ldg(&op.sub_vec[n]));
+            if (op.out_scale != 1.0f) val = __fmul_rn(val, op.out_scale);
+          }
+          orow[n] = val;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(TMEM_COLS) : "memory");
+}
+
 // out[r, blk*block_dim + c] = sum_terms(scale * src[map(r), c]) (+ BatchNorm)
 __global__ void nnet_ew_kernel(OpDev op, RunCtx c) {
   const long long total = (long long)c.batch * op.rows * op.out_dim;
@@ -425,12 +616,14 @@ struct b2k_nnet {
   double flops_per_lane = 0;
 };
 
-// B2K_NNET_GEMM=simt selects the fp32 FFMA kernel (kept for A/B numerics and timing)
-static bool use_simt_gemm() {
+// B2K_NNET_GEMM=simt selects the fp32 FFMA kernel (kept for A/B numerics and timing); =tcgen05 the experimental
+// TMEM kernel above (never run on a device yet); anything else, and the default, is the mma.sync 3xTF32 kernel
+static int gemm_mode() {
   static int v = -1;
-  if (v < 0) { const char *e = getenv("B2K_NNET_GEMM"); v = (e && !strcmp(e, "simt")) ? 1 : 0; }
-  return v == 1;
+  if (v < 0) { const char *e = getenv("B2K_NNET_GEMM"); v = (e && !strcmp(e, "simt")) ? 1 : (e && !strcmp(e, "tcgen05")) ? 2 : 0; }
+  return v;
 }
+static bool use_simt_gemm() { return gemm_mode() == 1; }
 
 extern "C" {
 
@@ -539,6 +732,22 @@ int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32
       if (use_simt_gemm()) {
         dim3 grid((unsigned)((M + GM_BM - 1) / GM_BM), (op.N + GM_BN - 1) / GM_BN);
         nnet_gemm_kernel<<<grid, 256, 0, st>>>(op, c);
+      } else if (gemm_mode() == 2) {
+        static bool configured5 = false;
+        const int s128 = 2 * (2 * T5_CH * (T5_BM * 16 + 16) + 2 * T5_CH * (128 * 16 + 16)), s96 = 2 * (2 * T5_CH * (T5_BM * 16 + 16) + 2 * T5_CH * (96 * 16 + 16));
+        if (!configured5) {
+          B2K_CUDA_CHECK(cudaFuncSetAttribute(nnet_gemm_tc5_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, s128));
+          B2K_CUDA_CHECK(cudaFuncSetAttribute(nnet_gemm_tc5_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, s96));
+          configured5 = true;
+        }
+        const int pad128 = (op.N + 127) / 128 * 128, pad96 = (op.N + 95) / 96 * 96;
+        if (pad96 < pad128) {
+          dim3 grid((unsigned)((M + T5_BM - 1) / T5_BM), pad96 / 96);
+          nnet_gemm_tc5_kernel<96><<<grid, 256, s96, st>>>(op, c);
+        } else {
+          dim3 grid((unsigned)((M + T5_BM - 1) / T5_BM), pad128 / 128);
+          nnet_gemm_tc5_kernel<128><<<grid, 256, s128, st>>>(op, c);
+        }
       } else {
         static bool configured = false;
         const int smem4 = (int)(sizeof(uint32_t) * 2 * (TC_BM + 128) * TC_LD), smem3 = (int)(sizeof(uint32_t) * 2 * (TC_BM + 96) * TC_LD);
