@@ -6,6 +6,7 @@
 // nnet3_to_arch), which stays as its test oracle; both are pinned to files written by the reference's own
 // Write() methods (tests/test_model_io_cpp.py, tests/test_kaldi_io.py).
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -468,6 +469,12 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
   Arch A{M, P, {}};
   std::vector<std::pair<std::string, std::map<std::string, std::string>>> cn;     // component-nodes in file order
   std::map<std::string, std::string> inputs;
+  // every node line, then the view a decoder has of a trained recipe model (kaldi_io._inference_view): dropout
+  // components are the identity in test mode (SetDropoutTestMode, online2-wav-nnet3-latgen-faster.cc:147), so their
+  // nodes are replaced by their inputs; and only what the output node "output" depends on is kept (chain recipes
+  // leave the cross-entropy branch, output-xent, in final.mdl)
+  struct NodeLine { std::string kind; std::map<std::string, std::string> kv; };
+  std::vector<NodeLine> lines;
   for (const std::string &l : P.config) {
     size_t sp = l.find(' ');
     if (sp == std::string::npos) continue;
@@ -476,8 +483,80 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
     if (kind == "input-node") {
       if (kv["name"] == "input") M->feat_dim = atoi(kv["dim"].c_str());
       if (kv["name"] == "ivector") M->ivector_dim = atoi(kv["dim"].c_str());
-    } else if (kind == "component-node") { inputs[kv["name"]] = kv["input"]; cn.push_back({kv["name"], kv}); }
+    } else if (kind == "component-node" || kind == "dim-range-node" || kind == "output-node") lines.push_back({kind, kv});
   }
+  auto is_word_char = [](char ch) { return isalnum((unsigned char)ch) || ch == '_' || ch == '.' || ch == '-'; };
+  auto descriptor_nodes = [&](const std::string &d) {
+    static const std::set<std::string> words = {"Append", "Offset", "Sum", "Scale", "ReplaceIndex", "Round", "IfDefined", "Failover", "Switch", "Const", "t", "x"};
+    std::vector<std::string> out;
+    for (size_t i = 0; i < d.size();) {
+      if (isalpha((unsigned char)d[i]) || d[i] == '_') {
+        size_t j = i;
+        while (j < d.size() && is_word_char(d[j])) j++;
+        const std::string w = d.substr(i, j - i);
+        if (!words.count(w)) out.push_back(w);
+        i = j;
+      } else if (is_word_char(d[i])) { while (i < d.size() && is_word_char(d[i])) i++; }   // a number
+      else i++;
+    }
+    return out;
+  };
+  std::map<std::string, std::string> alias;
+  for (auto &ln : lines)
+    if (ln.kind == "component-node") {
+      const Component *c = P.get(ln.kv["component"]);
+      if (c && (c->type == "GeneralDropoutComponent" || c->type == "DropoutComponent" || c->type == "SpecAugmentTimeMaskComponent")) {
+        std::string src = ln.kv["input"];
+        while (!src.empty() && src.front() == ' ') src.erase(0, 1);
+        while (!src.empty() && src.back() == ' ') src.pop_back();
+        const auto names = descriptor_nodes(src);
+        if (names.size() != 1 || names[0] != src) throw FormatError("dropout node " + ln.kv["name"] + " has a compound input descriptor: " + src);
+        alias[ln.kv["name"]] = src;
+      }
+    }
+  auto resolve = [&](std::string n) { while (alias.count(n)) n = alias[n]; return n; };
+  auto subst = [&](const std::string &d) {
+    std::string out;
+    for (size_t i = 0; i < d.size();) {
+      if (isalpha((unsigned char)d[i]) || d[i] == '_') {
+        size_t j = i;
+        while (j < d.size() && is_word_char(d[j])) j++;
+        const std::string w = d.substr(i, j - i);
+        out += alias.count(w) ? resolve(w) : w;
+        i = j;
+      } else if (is_word_char(d[i])) { while (i < d.size() && is_word_char(d[i])) out.push_back(d[i++]); }
+      else out.push_back(d[i++]);
+    }
+    return out;
+  };
+  std::vector<NodeLine> view;
+  for (auto &ln : lines) {
+    if (ln.kind == "component-node" && alias.count(ln.kv["name"])) continue;
+    NodeLine v = ln;
+    for (const char *key : {"input", "input-node"}) if (v.kv.count(key)) v.kv[key] = subst(v.kv[key]);
+    view.push_back(v);
+  }
+  std::set<std::string> keep;
+  bool have_root = false;
+  for (auto &ln : view) if (ln.kind == "output-node" && ln.kv["name"] == "output") have_root = true;
+  if (have_root) {
+    std::map<std::string, const NodeLine *> by_name;
+    for (auto &ln : view) by_name[ln.kv["name"]] = &ln;
+    std::vector<std::string> todo(1, "output");
+    while (!todo.empty()) {
+      const std::string n = todo.back();
+      todo.pop_back();
+      if (keep.count(n) || !by_name.count(n)) continue;
+      keep.insert(n);
+      const NodeLine *ln = by_name[n];
+      for (const char *key : {"input", "input-node"}) {
+        auto it = ln->kv.find(key);
+        if (it != ln->kv.end()) for (auto &w : descriptor_nodes(it->second)) todo.push_back(w);
+      }
+    }
+  }
+  for (auto &ln : view)
+    if (ln.kind == "component-node" && (!have_root || keep.count(ln.kv["name"]))) { inputs[ln.kv["name"]] = ln.kv["input"]; cn.push_back({ln.kv["name"], ln.kv}); }
   A.node_dim["input"] = M->feat_dim; A.node_dim["ivector"] = M->ivector_dim;
   auto comp_of = [&](size_t i) -> const Component & {
     const Component *c = P.get(cn[i].second.at("component"));
@@ -557,7 +636,8 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
       A.add_w(n + ".b", A.field(c, "<BiasParams>"));
       A.node_dim[n] = w.rows;
       i += 1;
-    } else if (t == "BatchNormComponent" && next_type(1) == "NoOpComponent" && next_name(1) == n + "_2") {
+    } else if (t == "BatchNormComponent" && next_type(1) == "NoOpComponent" && ends_with(next_name(1), "_2") &&
+               inputs[next_name(1)].find("_copy1") != std::string::npos) {
       new_layer("batchnorm", n);                      // batchnorm-component followed by delta-layer (trivial_layers.py:236-256)
       A.bn(n, n);
       const std::string dn = next_name(2);

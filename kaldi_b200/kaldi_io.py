@@ -402,6 +402,57 @@ def _parse_config_line(line: str) -> tuple[str, dict]:
     return kind, kv
 
 
+_DESCRIPTOR_WORDS = {"Append", "Offset", "Sum", "Scale", "ReplaceIndex", "Round", "IfDefined", "Failover", "Switch", "Const", "t", "x"}
+_IDENTITY_AT_TEST_TIME = ("GeneralDropoutComponent", "DropoutComponent", "SpecAugmentTimeMaskComponent")   # SetDropoutTestMode(true), online2-wav-nnet3-latgen-faster.cc:147
+
+
+def _descriptor_nodes(desc: str) -> list[str]:
+    return [w for w in re.findall(r"[A-Za-z_][A-Za-z0-9_.\-]*", desc) if w not in _DESCRIPTOR_WORDS]
+
+
+def _inference_view(nodes: list, comps: dict) -> list:
+    """What a trained recipe model looks like to the decoder: (1) dropout components are the identity in test mode, so
+    every reference to such a node is replaced by the node's own input; (2) only what the output node named "output"
+    depends on is kept (chain recipes leave their cross-entropy branch, output-xent, in final.mdl)."""
+    alias = {}
+    for kind, kv in nodes:
+        if kind == "component-node" and comps[kv["component"]]["type"] in _IDENTITY_AT_TEST_TIME:
+            src = kv["input"].strip()
+            if _descriptor_nodes(src) != [src]:
+                raise KaldiFormatError(f"dropout node {kv['name']} has a compound input descriptor: {src}")
+            alias[kv["name"]] = src
+
+    def resolve(n):
+        while n in alias:
+            n = alias[n]
+        return n
+
+    def subst(desc):
+        return re.sub(r"[A-Za-z_][A-Za-z0-9_.\-]*", lambda m: resolve(m.group(0)) if m.group(0) in alias else m.group(0), desc)
+    out = []
+    for kind, kv in nodes:
+        if kind == "component-node" and kv["name"] in alias:
+            continue
+        kv = dict(kv)
+        for key in ("input", "input-node"):
+            if key in kv:
+                kv[key] = subst(kv[key])
+        out.append((kind, kv))
+    roots = [kv for kind, kv in out if kind == "output-node" and kv["name"] == "output"]
+    if not roots:
+        return out
+    by_name = {kv["name"]: (kind, kv) for kind, kv in out}
+    keep, todo = set(), ["output"]
+    while todo:
+        n = todo.pop()
+        if n in keep or n not in by_name:
+            continue
+        keep.add(n)
+        kind, kv = by_name[n]
+        todo += _descriptor_nodes(kv.get("input", "")) + _descriptor_nodes(kv.get("input-node", ""))
+    return [(kind, kv) for kind, kv in out if kv["name"] in keep]
+
+
 def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
     """Maps a parsed TDNN-F chain model onto (arch, weights) of kaldi_b200.nnet_model.
 
@@ -440,6 +491,7 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
         return count
 
     node_dim = {"input": dims["input"], "ivector": dims.get("ivector", 0)}
+    nodes = _inference_view(nodes, comps)
     cn = [(kv["name"], kv) for kind, kv in nodes if kind == "component-node"]
     names = [n for n, _ in cn]
     inputs = {n: kv["input"] for n, kv in cn}
@@ -506,8 +558,10 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
             W[n + ".w"], W[n + ".b"] = mat(n, "<LinearParams>"), mat(n, "<BiasParams>")
             i += 1
         elif t == "BatchNormComponent" and i + 1 < len(cn) and comps[cn[i + 1][1]["component"]]["type"] == "NoOpComponent" \
-                and cn[i + 1][0] == n + "_2":
-            # batchnorm-component followed by delta-layer (its NoOp is named <input>_2, trivial_layers.py:236-256)
+                and cn[i + 1][0].endswith("_2") and "_copy1" in inputs[cn[i + 1][0]]:
+            # batchnorm-component followed by delta-layer (its NoOp is named <input descriptor>_2 and reads the
+            # dim-range copies <input descriptor>_copy1/2, trivial_layers.py:236-256; the input descriptor is the
+            # batchnorm itself or a spec-augment-layer behind it)
             layers.append({"type": "batchnorm", "name": n})
             bn(n, n)
             dn = cn[i + 2][0]

@@ -221,6 +221,8 @@ def to_nnet3_config(arch: dict, W: dict, tmpdir: str) -> str:
     fd, ivd = arch["feat_dim"], arch["ivector_dim"]
     c = [f"input-node name=ivector dim={ivd}", f"input-node name=input dim={fd}"]
     cur, cur_dim = "input", fd
+    extras = bool(arch.get("recipe_extras"))     # tests: dropout components and the xent branch of a trained recipe model
+    xent_from = None
     for L in arch["layers"]:
         t, n = L["type"], L["name"]
         if t in ("idct", "lda"):
@@ -238,6 +240,13 @@ def to_nnet3_config(arch: dict, W: dict, tmpdir: str) -> str:
             c.append(f"component name={n} type=BatchNormComponent dim={cur_dim}")
             c.append(f"component-node name={n} component={n} input={cur}")
             cur = n
+            if extras:       # spec-augment-layer (basic_layers.py:1277-1360): two masking components, identity in test mode
+                sa = n + "-spec-augment"
+                c.append(f"component name={sa}.freq-mask type=GeneralDropoutComponent dim={cur_dim} specaugment-max-proportion=0.5")
+                c.append(f"component-node name={sa}.freq-mask component={sa}.freq-mask input={cur}")
+                c.append(f"component name={sa}.time-mask type=SpecAugmentTimeMaskComponent dim={cur_dim} zeroed-proportion=0.2 time-mask-max-frames=20")
+                c.append(f"component-node name={sa}.time-mask component={sa}.time-mask input={sa}.freq-mask")
+                cur = sa + ".time-mask"
         elif t == "delta":   # trivial_layers.py:236-256
             c.append(f"dim-range-node name={cur}_copy1 input-node={cur} dim={cur_dim} dim-offset=0")
             c.append(f"dim-range-node name={cur}_copy2 input-node={cur} dim={cur_dim} dim-offset=0")
@@ -261,6 +270,10 @@ def to_nnet3_config(arch: dict, W: dict, tmpdir: str) -> str:
             c.append(f"component name={n}.batchnorm type=BatchNormComponent dim={L['dim']}")
             c.append(f"component-node name={n}.batchnorm component={n}.batchnorm input={n}.relu")
             cur, cur_dim = n + ".batchnorm", L["dim"]
+            if extras:       # relu-batchnorm-dropout-layer: GeneralDropoutComponent, identity at test time
+                c.append(f"component name={n}.dropout type=GeneralDropoutComponent dim={L['dim']} dropout-proportion=0.0 continuous=true")
+                c.append(f"component-node name={n}.dropout component={n}.dropout input={n}.batchnorm")
+                cur = n + ".dropout"
         elif t == "tdnnf":   # composite_layers.py:140-225
             s = L["stride"]
             o1 = f"{-s},0" if s else "0"
@@ -274,17 +287,23 @@ def to_nnet3_config(arch: dict, W: dict, tmpdir: str) -> str:
             c.append(f"component-node name={n}.relu component={n}.relu input={n}.affine")
             c.append(f"component name={n}.batchnorm type=BatchNormComponent dim={L['dim']}")
             c.append(f"component-node name={n}.batchnorm component={n}.batchnorm input={n}.relu")
+            last_bn = n + ".batchnorm"
+            if extras:       # tdnnf-layer with dropout-proportion set: the dropout sits between batchnorm and the bypass sum
+                c.append(f"component name={n}.dropout type=GeneralDropoutComponent dim={L['dim']} dropout-proportion=0.0 continuous=true")
+                c.append(f"component-node name={n}.dropout component={n}.dropout input={n}.batchnorm")
+                last_bn = n + ".dropout"
             if L["bypass"] != 0.0:
                 c.append(f"component name={n}.noop type=NoOpComponent dim={L['dim']}")
-                c.append(f"component-node name={n}.noop component={n}.noop input=Sum(Scale({L['bypass']}, {cur}), {n}.batchnorm)")
+                c.append(f"component-node name={n}.noop component={n}.noop input=Sum(Scale({L['bypass']}, {cur}), {last_bn})")
                 cur, cur_dim = n + ".noop", L["dim"]
             else:                # bypass-scale=0.0: tdnnf-layer emits no NoOp (composite_layers.py:213-222)
-                cur, cur_dim = n + ".batchnorm", L["dim"]
+                cur, cur_dim = last_bn, L["dim"]
         elif t == "linear":
             c.append(f"component name={n} type=LinearComponent input-dim={cur_dim} output-dim={L['dim']} orthonormal-constraint=-1.0")
             c.append(f"component-node name={n} component={n} input={cur}")
             cur, cur_dim = n, L["dim"]
         elif t == "prefinal":   # composite_layers.py:280-330
+            xent_from = (cur, cur_dim)                   # the xent branch forks where the chain prefinal does
             c.append(f"component name={n}.affine type=NaturalGradientAffineComponent input-dim={cur_dim} output-dim={L['big']}")
             c.append(f"component-node name={n}.affine component={n}.affine input={cur}")
             c.append(f"component name={n}.relu type=RectifiedLinearComponent dim={L['big']}")
@@ -322,6 +341,19 @@ def to_nnet3_config(arch: dict, W: dict, tmpdir: str) -> str:
             c.append(f"component-node name={n}.batchnorm component={n}.batchnorm input={n}.relu")
             cur, cur_dim = n + ".batchnorm", od
         elif t == "output":
+            if extras:       # the cross-entropy branch chain recipes train with and leave in final.mdl (run_tdnn_1k.sh:205-207)
+                xin, xdim = (xent_from if xent_from else (cur, cur_dim))
+                c.append(f"component name=prefinal-xent.affine type=NaturalGradientAffineComponent input-dim={xdim} output-dim=32")
+                c.append(f"component-node name=prefinal-xent.affine component=prefinal-xent.affine input={xin}")
+                c.append("component name=prefinal-xent.relu type=RectifiedLinearComponent dim=32")
+                c.append("component-node name=prefinal-xent.relu component=prefinal-xent.relu input=prefinal-xent.affine")
+                c.append("component name=prefinal-xent.batchnorm1 type=BatchNormComponent dim=32")
+                c.append("component-node name=prefinal-xent.batchnorm1 component=prefinal-xent.batchnorm1 input=prefinal-xent.relu")
+                c.append(f"component name=output-xent.affine type=NaturalGradientAffineComponent input-dim=32 output-dim={L['dim']}")
+                c.append("component-node name=output-xent.affine component=output-xent.affine input=prefinal-xent.batchnorm1")
+                c.append(f"component name=output-xent.log-softmax type=LogSoftmaxComponent dim={L['dim']}")
+                c.append("component-node name=output-xent.log-softmax component=output-xent.log-softmax input=output-xent.affine")
+                c.append("output-node name=output-xent input=output-xent.log-softmax objective=linear")
             c.append(f"component name={n}.affine type=NaturalGradientAffineComponent input-dim={cur_dim} output-dim={L['dim']}")
             c.append(f"component-node name={n}.affine component={n}.affine input={cur}")
             last = n + ".affine"

@@ -70,13 +70,18 @@ class RefNnet:
             name = L.ref_nnet_component_name(self.h, i).decode()
             typ = L.ref_nnet_component_type(self.h, i).decode()
             if typ == "BatchNormComponent":
-                mean, var = W[name + ".mean"], W[name + ".var"]
+                if name + ".mean" not in W and arch.get("recipe_extras"):
+                    mean, var = np.zeros(32, np.float32), np.ones(32, np.float32)      # prefinal-xent.batchnorm1
+                else:
+                    mean, var = W[name + ".mean"], W[name + ".var"]
                 dim, target_rms = bn_shape.get(name, (mean.size, 1.0))
                 r = L.ref_nnet_set_batchnorm(self.h, i, C.c_int(dim), C.c_int(mean.size), C.c_float(NM.BN_EPS),
                                              C.c_float(target_rms), C.c_float(1000.0), _p(mean, C.c_float), _p(var, C.c_float))
                 assert r == 0, name
             elif typ in ("NaturalGradientAffineComponent", "AffineComponent", "TdnnComponent", "LinearComponent",
                          "TimeHeightConvolutionComponent"):
+                if name + ".w" not in W and arch.get("recipe_extras"):
+                    continue                                  # the xent branch keeps the reference's own initialisation
                 w = W[name + ".w"]
                 vec = w.reshape(-1)
                 if name + ".b" in W:

@@ -141,3 +141,70 @@ def test_cpp_reader_rejects_garbage(tmp_path):
     L.b2k_model_read.argtypes = [C.c_char_p, C.c_int32, C.c_void_p]
     assert L.b2k_model_read(p.encode(), 0, C.byref(h)) != 0
     assert L.b2k_model_read(str(tmp_path / "missing").encode(), 0, C.byref(h)) != 0
+
+
+@pytest.mark.parametrize("which", ["idct-delta", "lda", "cnn"])
+@pytest.mark.parametrize("binary", [1, 0])
+def test_trained_recipe_model_with_dropout_and_xent_branch(tmp_path, binary, which):
+    """What final.mdl of a chain recipe really contains besides the layers: GeneralDropoutComponent nodes (identity in test
+    mode) after every batchnorm, and the cross-entropy branch (prefinal-xent / output-xent) next to the chain output.
+    Both readers must see the same network as without them, and the program compiled from what the C++ reader returns
+    must reproduce the reference's forward of that very model."""
+    L = _lib()
+    from kaldi_b200 import kaldi_io as KIO
+    from kaldi_b200.model import KaldiModel
+    from kaldi_b200.nnet import _Node, _Op
+    from oracle import nnet_oracle as NO
+    from oracle import program_interp as PI
+    if not (os.path.exists(NO._SO) or os.path.isdir("/root/reference")):
+        pytest.skip("oracle/_ref nnet3 library not present")
+    plain = NM.arch_tiny_cnn() if which == "cnn" else NM.arch_tiny(64, front=which)
+    arch = dict(plain, recipe_extras=True)
+    Wt = NM.random_weights(plain, seed=5)
+    R = NO.RefNnet(arch, Wt, collapse=False)
+    if not hasattr(R.lib, "ref_nnet_write"):
+        pytest.skip("oracle/_ref library predates the writers")
+    R.lib.ref_nnet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    raw = str(tmp_path / "final.raw")
+    assert R.lib.ref_nnet_write(R.h, raw.encode(), binary) == 0
+    text = open(raw, "rb").read()
+    assert b"GeneralDropoutComponent" in text and b"output-xent" in text
+    assert (b"SpecAugmentTimeMaskComponent" in text) == (which != "lda")
+    # Python reader
+    arch2, W2 = NM.load_kaldi_raw(raw)
+    assert [(x["type"], x["name"]) for x in arch2["layers"]] == [(x["type"], x["name"]) for x in plain["layers"]]
+    assert not any("xent" in k for k in W2)
+    # C++ reader -> C++ compiler -> numpy interpreter of the ABI program == the reference's forward of this model
+    m = KaldiModel(raw, is_mdl=False)
+    assert [t for t, _ in m.layer_types()] == [x["type"] for x in plain["layers"]]
+    got = m.weights()
+    for k, v in Wt.items():
+        if k == "priors":
+            continue
+        tol = dict(rtol=0, atol=0) if (binary and not k.endswith((".mean", ".var"))) else dict(rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(got[k].reshape(v.shape), v, err_msg=k, **tol)
+    T = 60
+    rng = np.random.default_rng(0)
+    feats = (rng.standard_normal((T, plain["feat_dim"])) * 10).astype(np.float32)
+    iv = rng.standard_normal((T, plain["ivector_dim"])).astype(np.float32)
+    Rp = NO.RefNnet(arch, Wt, use_priors=False)
+    ref = Rp.forward(feats, iv, period=1)
+    rows = Rp.chunk_ivector_rows(T, T, 1)
+    prog = m.compile(num_frames=T, frames_per_chunk=21, use_priors=False)
+    try:
+        nn, no, bl = C.c_int32(), C.c_int32(), C.c_int64()
+        L.b2k_nnet_program_sizes.argtypes = [C.c_void_p] * 4
+        assert L.b2k_nnet_program_sizes(prog, C.byref(nn), C.byref(no), C.byref(bl)) == 0
+        for f, rt in (("b2k_nnet_program_nodes", C.POINTER(_Node)), ("b2k_nnet_program_ops", C.POINTER(_Op)),
+                      ("b2k_nnet_program_blob", C.POINTER(C.c_float))):
+            getattr(L, f).restype = rt
+            getattr(L, f).argtypes = [C.c_void_p]
+        nodes = [L.b2k_nnet_program_nodes(prog)[i] for i in range(nn.value)]
+        ops = [L.b2k_nnet_program_ops(prog)[i] for i in range(no.value)]
+        blob = np.ctypeslib.as_array(L.b2k_nnet_program_blob(prog), shape=(bl.value,)).copy()
+        out = PI.run_program(PI.program_from_abi(nodes, ops, blob), feats, iv[rows])
+    finally:
+        L.b2k_nnet_program_destroy.argtypes = [C.c_void_p]
+        L.b2k_nnet_program_destroy(prog)
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max()
