@@ -415,6 +415,22 @@ const b2k_nnet_layer *b2k_model_layers(const b2k_model *model);
 const b2k_nnet_weight *b2k_model_weights(const b2k_model *model);    /* includes "priors" (ones when absent) */
 const int32_t *b2k_model_tid2pdf(const b2k_model *model);           /* [tid], index 0 unused; b2k_fst_csr.tid2pdf */
 
+/* Kaldi option files (ParseOptions::ReadConfigFile, util/parse-options.cc:460-497) for the two configurations the tool is
+ * pointed at: --mfcc-config / --fbank-config (MfccOptions / FbankOptions with their frame and mel options) and
+ * --ivector-extraction-config (OnlineIvectorExtractionConfig, online2/online-ivector-feature.h:55-160, with the splice and
+ * CMVN option files it names).  Values not in the file keep the REFERENCE'S defaults (e.g. dither 1.0, 23 mel bins, 13
+ * cepstra — not mfcc_hires.conf); an unknown option is an error, as in the reference.  Host only; pinned to the reference's
+ * own ParseOptions on the same files (tests/test_conf_cpp.py). */
+int b2k_feat_cfg_from_conf(const char *conf_path, int32_t feature_type /* 0 mfcc, 1 fbank */, b2k_feat_cfg *cfg);
+typedef struct {
+  char lda_matrix[512], global_cmvn_stats[512], splice_config[512], cmvn_config[512], diag_ubm[512], ivector_extractor[512];
+  int32_t ivector_period, use_most_recent_ivector, greedy_ivector_extractor, online_cmvn_iextractor;
+  float max_remembered_frames;
+} b2k_ivec_paths;
+/* cfg: in = the caller's base_dim / capacities, out = + every option of the three files; paths: the files to hand to
+ * b2k_ivec_files_read and the options that only matter to a streaming front end */
+int b2k_ivec_cfg_from_conf(const char *conf_path, b2k_ivec_cfg *cfg, b2k_ivec_paths *paths);
+
 /* HCLG.fst: an OpenFst binary "vector" or "const" FST over StdArc -> the CSR view of b2k_fst_create (arc order = file
  * order = the order ConstFst iterates in, which the decoder's results depend on).  Host only, no OpenFst.
  * PARITY UNPINNED: follows the published layout (fst/fst.h, vector-fst.h, const-fst.h); OpenFst is absent from this

@@ -44,3 +44,160 @@ int b2k_ivec_online_schedule(int64_t num_samples, int32_t chunk_samples, int32_t
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ Kaldi option files (conf/*.conf)
+//
+// ParseOptions::ReadConfigFile (util/parse-options.cc:460-497): '#' starts a comment, lines are trimmed, every non-empty
+// line is --name=value or --name (a bool set to true), names are lower-cased with '_' -> '-' (NormalizeArgName, :523-536),
+// bools accept true/t/1/"" and false/f/0 (ToBool, :569-586), an unknown name is an error.  The option names and defaults
+// below are the ones MfccOptions / FbankOptions / FrameExtractionOptions / MelBanksOptions, OnlineIvectorExtractionConfig,
+// OnlineSpliceOptions and OnlineCmvnOptions register (feat/feature-window.h:69-104, mel-computations.h:60-74,
+// feature-mfcc.h:62-79, feature-fbank.h:62-80, online2/online-ivector-feature.h:112-160, feat/online-feature.h:234-251,
+// :446-456); tests/test_conf_cpp.py compares with the reference's own ParseOptions on the same files.
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct ConfError { std::string msg; };
+
+static std::string trim(const std::string &s) {
+  const char *ws = " \t\n\r\f\v";
+  const size_t a = s.find_first_not_of(ws);
+  if (a == std::string::npos) return "";
+  return s.substr(a, s.find_last_not_of(ws) - a + 1);
+}
+
+static std::map<std::string, std::pair<std::string, bool>> read_conf(const char *path) {     // name -> (value, has '=')
+  std::ifstream is(path);
+  if (!is.good()) throw ConfError{std::string("Cannot open config file: ") + path};
+  std::map<std::string, std::pair<std::string, bool>> out;
+  std::string line;
+  int ln = 0;
+  while (std::getline(is, line)) {
+    ln++;
+    const size_t h = line.find('#');
+    if (h != std::string::npos) line.erase(h);
+    line = trim(line);
+    if (line.empty()) continue;
+    if (line.compare(0, 2, "--") != 0) throw ConfError{std::string(path) + ": line " + std::to_string(ln) + " is not of the form --x=y"};
+    const size_t eq = line.find('=');
+    std::string key = eq == std::string::npos ? line.substr(2) : line.substr(2, eq - 2), val = eq == std::string::npos ? "" : trim(line.substr(eq + 1));
+    for (auto &c : key) c = c == '_' ? '-' : (char)std::tolower((unsigned char)c);
+    if (key.empty()) throw ConfError{std::string(path) + ": line " + std::to_string(ln) + ": empty option name"};
+    out[key] = {val, eq != std::string::npos};
+  }
+  return out;
+}
+
+static bool to_bool(const std::string &name, std::string v) {
+  for (auto &c : v) c = (char)std::tolower((unsigned char)c);
+  if (v == "true" || v == "t" || v == "1" || v == "") return true;
+  if (v == "false" || v == "f" || v == "0") return false;
+  throw ConfError{"Invalid format for boolean argument --" + name + ": " + v};
+}
+static double to_num(const std::string &name, const std::string &v, bool integer) {
+  char *end = nullptr;
+  const double d = integer ? (double)strtol(v.c_str(), &end, 10) : strtod(v.c_str(), &end);
+  if (v.empty() || !end || *end != 0) throw ConfError{"Invalid " + std::string(integer ? "integer" : "floating-point") + " option --" + name + "=" + v};
+  return d;
+}
+
+// one table entry per registered option: where it goes and what kind it is
+struct Opt { const char *name; char kind; void *dst; };   // kind: b bool->int32, i int32, f float, s string (char[512]), x parsed but unused
+
+static void apply(const char *path, const std::map<std::string, std::pair<std::string, bool>> &kv, const Opt *opts, size_t n) {
+  for (auto &e : kv) {
+    const Opt *o = nullptr;
+    for (size_t i = 0; i < n; i++) if (e.first == opts[i].name) o = &opts[i];
+    if (!o) throw ConfError{"Invalid option --" + e.first + " in config file " + path};
+    const std::string &v = e.second.first;
+    switch (o->kind) {
+      case 'b': *(int32_t *)o->dst = to_bool(e.first, v) ? 1 : 0; break;
+      case 'i': *(int32_t *)o->dst = (int32_t)to_num(e.first, v, true); break;
+      case 'f': *(float *)o->dst = (float)to_num(e.first, v, false); break;
+      case 's': { char *d = (char *)o->dst; if (v.size() >= 512) throw ConfError{"value of --" + e.first + " is too long"}; memcpy(d, v.c_str(), v.size() + 1); break; }
+      default: break;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2k_feat_cfg_from_conf(const char *conf_path, int32_t feature_type, b2k_feat_cfg *cfg) {
+  if (!conf_path || !cfg || (feature_type != 0 && feature_type != 1)) return b2k::set_error(B2K_ERR_INVALID, "b2k_feat_cfg_from_conf: bad args");
+  // the reference's own defaults (NOT mfcc_hires.conf): MfccOptions() / FbankOptions(), FrameExtractionOptions(), MelBanksOptions(23)
+  b2k_feat_cfg c;
+  memset(&c, 0, sizeof(c));
+  c.feature_type = feature_type; c.samp_freq = 16000.f; c.frame_shift_ms = 10.f; c.frame_length_ms = 25.f; c.dither = 1.0f;
+  c.preemph_coeff = 0.97f; c.remove_dc_offset = 1; c.round_to_power_of_two = 1; c.snip_edges = 1; c.window_type = 0;
+  c.num_bins = 23; c.low_freq = 20.f; c.high_freq = 0.f; c.num_ceps = 13; c.use_energy = feature_type == 0 ? 1 : 0;
+  c.energy_floor = 0.f; c.raw_energy = 1; c.cepstral_lifter = 22.f; c.htk_compat = 0; c.use_log_fbank = 1; c.use_power = 1; c.htk_mode = 0;
+  c.max_lanes = cfg->max_lanes > 0 ? cfg->max_lanes : 1024;
+  char window[512] = "povey";
+  float blackman = 0.42f, vtln_low = 100.f, vtln_high = -500.f;
+  int32_t allow_down = 0, allow_up = 0, max_fv = -1, debug_mel = 0;
+  std::vector<Opt> o = {
+      {"sample-frequency", 'f', &c.samp_freq}, {"frame-length", 'f', &c.frame_length_ms}, {"frame-shift", 'f', &c.frame_shift_ms},
+      {"preemphasis-coefficient", 'f', &c.preemph_coeff}, {"remove-dc-offset", 'b', &c.remove_dc_offset}, {"dither", 'f', &c.dither},
+      {"window-type", 's', window}, {"blackman-coeff", 'f', &blackman}, {"round-to-power-of-two", 'b', &c.round_to_power_of_two},
+      {"snip-edges", 'b', &c.snip_edges}, {"allow-downsample", 'b', &allow_down}, {"allow-upsample", 'b', &allow_up},
+      {"max-feature-vectors", 'i', &max_fv}, {"num-mel-bins", 'i', &c.num_bins}, {"low-freq", 'f', &c.low_freq}, {"high-freq", 'f', &c.high_freq},
+      {"vtln-low", 'f', &vtln_low}, {"vtln-high", 'f', &vtln_high}, {"debug-mel", 'b', &debug_mel},
+      {"use-energy", 'b', &c.use_energy}, {"energy-floor", 'f', &c.energy_floor}, {"raw-energy", 'b', &c.raw_energy}, {"htk-compat", 'b', &c.htk_compat}};
+  if (feature_type == 0) { o.push_back({"num-ceps", 'i', &c.num_ceps}); o.push_back({"cepstral-lifter", 'f', &c.cepstral_lifter}); }
+  else { o.push_back({"use-log-fbank", 'b', &c.use_log_fbank}); o.push_back({"use-power", 'b', &c.use_power}); }
+  try {
+    apply(conf_path, read_conf(conf_path), o.data(), o.size());
+    const std::string w = window;
+    c.window_type = w == "povey" ? 0 : w == "hamming" ? 1 : w == "hanning" ? 2 : w == "rectangular" ? 3 : -1;
+    if (c.window_type < 0) throw ConfError{"window type " + w + " is not supported (povey, hamming, hanning, rectangular)"};
+  } catch (const ConfError &e) {
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_feat_cfg_from_conf", e.msg.c_str());
+  }
+  *cfg = c;
+  return B2K_OK;
+}
+
+int b2k_ivec_cfg_from_conf(const char *conf_path, b2k_ivec_cfg *cfg, b2k_ivec_paths *paths) {
+  if (!conf_path || !cfg || !paths) return b2k::set_error(B2K_ERR_INVALID, "b2k_ivec_cfg_from_conf: bad args");
+  b2k_ivec_cfg c = *cfg;                       // base_dim, max_lanes, max_frames and the dimensions stay the caller's
+  b2k_ivec_paths p;
+  memset(&p, 0, sizeof(p));
+  // OnlineIvectorExtractionConfig(): online-ivector-feature.h:104-111
+  c.num_gselect = 5; c.min_post = 0.025f; c.posterior_scale = 0.1f; c.max_count = 0.0f; c.num_cg_iters = 15;
+  // OnlineSpliceOptions(): 4 / 4;  OnlineCmvnOptions(): 600 / 600 / 200
+  c.splice_left = 4; c.splice_right = 4; c.cmn_window = 600; c.speaker_frames = 600; c.global_frames = 200;
+  p.ivector_period = 10; p.use_most_recent_ivector = 1; p.max_remembered_frames = 1000.f;
+  int32_t norm_vars = 0, norm_means = 1;
+  char skip_dims[512] = "";
+  const Opt top[] = {
+      {"lda-matrix", 's', p.lda_matrix}, {"global-cmvn-stats", 's', p.global_cmvn_stats}, {"cmvn-config", 's', p.cmvn_config},
+      {"online-cmvn-iextractor", 'b', &p.online_cmvn_iextractor}, {"splice-config", 's', p.splice_config}, {"diag-ubm", 's', p.diag_ubm},
+      {"ivector-extractor", 's', p.ivector_extractor}, {"ivector-period", 'i', &p.ivector_period}, {"num-gselect", 'i', &c.num_gselect},
+      {"min-post", 'f', &c.min_post}, {"posterior-scale", 'f', &c.posterior_scale}, {"max-count", 'f', &c.max_count},
+      {"use-most-recent-ivector", 'b', &p.use_most_recent_ivector}, {"greedy-ivector-extractor", 'b', &p.greedy_ivector_extractor},
+      {"max-remembered-frames", 'f', &p.max_remembered_frames}};
+  const Opt splice[] = {{"left-context", 'i', &c.splice_left}, {"right-context", 'i', &c.splice_right}};
+  const Opt cmvn[] = {{"cmn-window", 'i', &c.cmn_window}, {"global-frames", 'i', &c.global_frames}, {"speaker-frames", 'i', &c.speaker_frames},
+                      {"norm-vars", 'b', &norm_vars}, {"norm-means", 'b', &norm_means}, {"skip-dims", 's', skip_dims}};
+  try {
+    apply(conf_path, read_conf(conf_path), top, sizeof(top) / sizeof(top[0]));
+    if (p.splice_config[0]) apply(p.splice_config, read_conf(p.splice_config), splice, 2);     // OnlineIvectorExtractionInfo::Init reads both
+    if (p.cmvn_config[0]) apply(p.cmvn_config, read_conf(p.cmvn_config), cmvn, sizeof(cmvn) / sizeof(cmvn[0]));
+    if (norm_vars || !norm_means || skip_dims[0]) throw ConfError{"the extractor's online CMVN must be mean-only over all dimensions (norm-vars / skip-dims are not supported)"};
+    if (p.online_cmvn_iextractor) throw ConfError{"--online-cmvn-iextractor=true is not supported"};
+  } catch (const ConfError &e) {
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_ivec_cfg_from_conf", e.msg.c_str());
+  }
+  *cfg = c;
+  *paths = p;
+  return B2K_OK;
+}
+
+}  // extern "C"

@@ -6,6 +6,7 @@
 //   Mfcc/Fbank::ComputeFeatures            feat/feature-common-inl.h
 //   OnlineMfcc/OnlineFbank, OnlineCmvn     feat/online-feature.{h,cc}
 //   OnlineMatrixFeature                    feat/online-feature.h
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "feat/feature-mfcc.h"
 #include "feat/online-feature.h"
 #include "matrix/kaldi-matrix.h"
+#include "util/parse-options.h"
 
 using namespace kaldi;
 
@@ -122,6 +124,34 @@ int ref_cmvn_online(const float *feats, int T, int D, int cmn_window, int speake
     }
     return n;
   } catch (...) { return -1; }
+}
+
+// MfccOptions / FbankOptions as the reference's own ParseOptions::ReadConfigFile fills them from an option file
+// (util/parse-options.cc:460-497): the oracle of b2k_feat_cfg_from_conf.  out: samp_freq, frame_shift_ms, frame_length_ms,
+// dither, preemph, remove_dc, round_pow2, snip_edges, num_bins, low_freq, high_freq, num_ceps, use_energy, energy_floor,
+// raw_energy, cepstral_lifter, htk_compat, use_log_fbank, use_power.  Returns 0, or 1 if the reference rejected the file.
+int ref_feat_opts_from_conf(const char *path, int feature_type, float *out, char *window, int window_cap) {
+  try {
+    kaldi::ParseOptions po("");
+    kaldi::MfccOptions m;
+    kaldi::FbankOptions f;
+    if (feature_type == 0) m.Register(&po); else f.Register(&po);
+    po.ReadConfigFile(path);
+    const kaldi::FrameExtractionOptions &fr = feature_type == 0 ? m.frame_opts : f.frame_opts;
+    const kaldi::MelBanksOptions &mel = feature_type == 0 ? m.mel_opts : f.mel_opts;
+    int i = 0;
+    out[i++] = fr.samp_freq; out[i++] = fr.frame_shift_ms; out[i++] = fr.frame_length_ms; out[i++] = fr.dither; out[i++] = fr.preemph_coeff;
+    out[i++] = fr.remove_dc_offset; out[i++] = fr.round_to_power_of_two; out[i++] = fr.snip_edges;
+    out[i++] = mel.num_bins; out[i++] = mel.low_freq; out[i++] = mel.high_freq;
+    out[i++] = feature_type == 0 ? m.num_ceps : 0; out[i++] = feature_type == 0 ? m.use_energy : f.use_energy;
+    out[i++] = feature_type == 0 ? m.energy_floor : f.energy_floor; out[i++] = feature_type == 0 ? m.raw_energy : f.raw_energy;
+    out[i++] = feature_type == 0 ? m.cepstral_lifter : 0; out[i++] = feature_type == 0 ? m.htk_compat : f.htk_compat;
+    out[i++] = feature_type == 0 ? 1 : f.use_log_fbank; out[i++] = feature_type == 0 ? 1 : f.use_power;
+    snprintf(window, window_cap, "%s", fr.window_type.c_str());
+    return 0;
+  } catch (const std::exception &) {
+    return 1;
+  }
 }
 
 }  // extern "C"
