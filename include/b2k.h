@@ -431,6 +431,18 @@ typedef struct {
  * b2k_ivec_files_read and the options that only matter to a streaming front end */
 int b2k_ivec_cfg_from_conf(const char *conf_path, b2k_ivec_cfg *cfg, b2k_ivec_paths *paths);
 
+/* conf/online.conf, the --config file of online2-wav-nnet3-latgen-faster: the feature group
+ * (OnlineNnet2FeaturePipelineConfig::Register, online2/online-nnet2-feature-pipeline.h:101-126); options of the other
+ * groups the tool registers (--endpoint.*, --ivector-silence-weighting.*, decoder and decodable options) are passed
+ * through in `rest`, one per line. */
+typedef struct {
+  int32_t feature_type;               /* 0 mfcc, 1 fbank ("plp" is rejected) */
+  int32_t add_pitch;                  /* must be false                       */
+  char mfcc_config[512], fbank_config[512], cmvn_config[512], global_cmvn_stats[512], ivector_extraction_config[512];
+  char rest[4096];
+} b2k_online_conf;
+int b2k_online_conf_read(const char *conf_path, b2k_online_conf *out);
+
 /* HCLG.fst: an OpenFst binary "vector" or "const" FST over StdArc -> the CSR view of b2k_fst_create (arc order = file
  * order = the order ConstFst iterates in, which the decoder's results depend on).  Host only, no OpenFst.
  * PARITY UNPINNED: follows the published layout (fst/fst.h, vector-fst.h, const-fst.h); OpenFst is absent from this

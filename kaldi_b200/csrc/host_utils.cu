@@ -200,4 +200,42 @@ int b2k_ivec_cfg_from_conf(const char *conf_path, b2k_ivec_cfg *cfg, b2k_ivec_pa
   return B2K_OK;
 }
 
+
+// conf/online.conf: the --config file of online2-wav-nnet3-latgen-faster.  The tool registers several option groups into
+// one ParseOptions; this reader takes the feature group (OnlineNnet2FeaturePipelineConfig::Register,
+// online2/online-nnet2-feature-pipeline.h:101-126) and lets the other groups a recipe puts in the same file pass
+// (--endpoint.*, --ivector-silence-weighting.*, the decoder / decodable options): they are returned verbatim in `rest`.
+int b2k_online_conf_read(const char *conf_path, b2k_online_conf *out) {
+  if (!conf_path || !out) return b2k::set_error(B2K_ERR_INVALID, "b2k_online_conf_read: bad args");
+  b2k_online_conf c;
+  memset(&c, 0, sizeof(c));
+  char feature_type[512] = "mfcc", plp_config[512] = "", pitch_config[512] = "";
+  const Opt opts[] = {{"feature-type", 's', feature_type}, {"mfcc-config", 's', c.mfcc_config}, {"plp-config", 's', plp_config},
+                      {"fbank-config", 's', c.fbank_config}, {"cmvn-config", 's', c.cmvn_config}, {"global-cmvn-stats", 's', c.global_cmvn_stats},
+                      {"add-pitch", 'b', &c.add_pitch}, {"online-pitch-config", 's', pitch_config},
+                      {"ivector-extraction-config", 's', c.ivector_extraction_config}};
+  try {
+    auto kv = read_conf(conf_path);
+    std::map<std::string, std::pair<std::string, bool>> mine;
+    std::string rest;
+    for (auto &e : kv) {
+      bool known = false;
+      for (auto &o : opts) known = known || e.first == o.name;
+      if (known) mine[e.first] = e.second;
+      else rest += "--" + e.first + (e.second.second ? "=" + e.second.first : "") + "\n";
+    }
+    apply(conf_path, mine, opts, sizeof(opts) / sizeof(opts[0]));
+    const std::string ft = feature_type;
+    c.feature_type = ft == "mfcc" ? 0 : ft == "fbank" ? 1 : -1;
+    if (c.feature_type < 0) throw ConfError{"feature type " + ft + " is not supported (mfcc, fbank)"};     // "plp": SURVEY section 8(f) row 4
+    if (c.add_pitch) throw ConfError{"--add-pitch=true is not supported"};
+    if (rest.size() >= sizeof(c.rest)) throw ConfError{"too many other options in the file"};
+    memcpy(c.rest, rest.c_str(), rest.size() + 1);
+  } catch (const ConfError &e) {
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_online_conf_read", e.msg.c_str());
+  }
+  *out = c;
+  return B2K_OK;
+}
+
 }  // extern "C"

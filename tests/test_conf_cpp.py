@@ -194,3 +194,38 @@ def test_ivector_option_names_are_the_ones_the_reference_registers():
                 conf = os.path.join(d, "top.conf")
                 open(conf, "w").write(top)
                 assert _ivec(L, conf)[0] == 0, (g, n)
+
+
+class _OnlineConf(C.Structure):
+    _fields_ = [("feature_type", C.c_int32), ("add_pitch", C.c_int32)] + \
+               [(k, C.c_char * 512) for k in ("mfcc_config", "fbank_config", "cmvn_config", "global_cmvn_stats", "ivector_extraction_config")] + \
+               [("rest", C.c_char * 4096)]
+
+
+def test_online_conf_as_prepare_online_decoding_writes_it(tmp_path):
+    L = _lib()
+    p = str(tmp_path / "online.conf")
+    open(p, "w").write("--feature-type=mfcc\n--mfcc-config=/exp/conf/mfcc.conf\n--ivector-extraction-config=/exp/conf/ivector_extractor.conf\n"
+                       "--endpoint.silence-phones=1:2:3:4:5\n--endpoint.rule1.min-trailing-silence=0.5\n")
+    c = _OnlineConf()
+    L.b2k_online_conf_read.argtypes = [C.c_char_p, C.c_void_p]
+    assert L.b2k_online_conf_read(p.encode(), C.byref(c)) == 0
+    assert c.feature_type == 0 and c.mfcc_config.decode() == "/exp/conf/mfcc.conf"
+    assert c.ivector_extraction_config.decode() == "/exp/conf/ivector_extractor.conf"
+    assert sorted(c.rest.decode().split()) == ["--endpoint.rule1.min-trailing-silence=0.5", "--endpoint.silence-phones=1:2:3:4:5"]
+    open(p, "w").write("--feature-type=plp\n")
+    assert L.b2k_online_conf_read(p.encode(), C.byref(c)) != 0
+    open(p, "w").write("--feature-type=fbank\n--add-pitch=true\n")
+    assert L.b2k_online_conf_read(p.encode(), C.byref(c)) != 0
+    # the feature group's names are the ones the reference registers
+    hdr = "/root/reference/src/online2/online-nnet2-feature-pipeline.h"
+    if os.path.exists(hdr):
+        text = open(hdr).read()
+        text = text[text.index("struct OnlineNnet2FeaturePipelineConfig"):text.index("struct OnlineNnet2FeaturePipelineInfo")]
+        names = set(re.findall(r'Register\("([a-z\-]+)"', text))
+        assert {"feature-type", "mfcc-config", "ivector-extraction-config", "add-pitch"} <= names
+        for n in sorted(names):
+            val = "false" if n == "add-pitch" else ("mfcc" if n == "feature-type" else "x")
+            open(p, "w").write(f"--{n}={val}\n")
+            assert L.b2k_online_conf_read(p.encode(), C.byref(c)) == 0, n
+            assert c.rest.decode() == "", n                    # recognised, not passed through
