@@ -443,6 +443,15 @@ typedef struct {
 } b2k_online_conf;
 int b2k_online_conf_read(const char *conf_path, b2k_online_conf *out);
 
+/* RIFF/WAVE input as WaveData::Read takes it (feat/wave-reader.cc:107-321): 16-bit PCM (plain or WAVE_FORMAT_EXTENSIBLE), RIFF or
+ * RIFX, extra chunks skipped, "stream mode" sizes, truncated files; samples as floats in the int16 range, one row per channel
+ * ([channels x samples]).  Host only; pinned to the reference's own reader (tests/test_wave_cpp.py). */
+typedef struct b2k_wave b2k_wave;
+int b2k_wave_read(const char *path, b2k_wave **out);
+int b2k_wave_destroy(b2k_wave *wave);
+int b2k_wave_info(const b2k_wave *wave, float *samp_freq, int32_t *channels, int64_t *samples);
+const float *b2k_wave_data(const b2k_wave *wave);
+
 /* HCLG.fst: an OpenFst binary "vector" or "const" FST over StdArc -> the CSR view of b2k_fst_create (arc order = file
  * order = the order ConstFst iterates in, which the decoder's results depend on).  Host only, no OpenFst.
  * PARITY UNPINNED: follows the published layout (fst/fst.h, vector-fst.h, const-fst.h); OpenFst is absent from this

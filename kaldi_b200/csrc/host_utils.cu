@@ -56,6 +56,7 @@ int b2k_ivec_online_schedule(int64_t num_samples, int32_t chunk_samples, int32_t
 // :446-456); tests/test_conf_cpp.py compares with the reference's own ParseOptions on the same files.
 #include <cstdlib>
 #include <fstream>
+#include <iterator>
 #include <map>
 #include <string>
 #include <vector>
@@ -237,5 +238,104 @@ int b2k_online_conf_read(const char *conf_path, b2k_online_conf *out) {
   *out = c;
   return B2K_OK;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ RIFF/WAVE input
+//
+// WaveData::Read (feat/wave-reader.cc:107-321) in our own words: RIFF or RIFX (byte-swapped), any chunks before "fmt " and
+// between "fmt " and "data" skipped, format 1 (PCM) or 0xFFFE (extensible with the PCM sub-format GUID), 16 bits only,
+// byte rate and block align must be consistent, "stream mode" (read to the end of the file) when the RIFF or data size is
+// 0 / 0xFFFFFFFF / 0x7FFFF000 (SoX), a short file gives the samples that are there, no data at all is an error.  Samples
+// stay in the int16 range as floats (Kaldi's convention, feat/wave-reader.h:60-62), one row per channel.
+struct b2k_wave { float samp_freq = 0; int32_t channels = 0; int64_t samples = 0; std::vector<float> data; };
+
+namespace {
+struct WavIn {
+  std::vector<unsigned char> d; size_t p = 0; bool swap = false;
+  void need(size_t n) const { if (p + n > d.size()) throw ConfError{"WaveData: unexpected end of file or read error"}; }
+  std::string tag() { need(4); std::string t((const char *)&d[p], 4); p += 4; return t; }
+  uint32_t u32() { need(4); uint32_t v; unsigned char b[4] = {d[p], d[p + 1], d[p + 2], d[p + 3]}; if (swap) { std::swap(b[0], b[3]); std::swap(b[1], b[2]); } memcpy(&v, b, 4); p += 4; return v; }
+  uint16_t u16() { need(2); uint16_t v; unsigned char b[2] = {d[p], d[p + 1]}; if (swap) std::swap(b[0], b[1]); memcpy(&v, b, 2); p += 2; return v; }
+  void skip(uint32_t n) { p = std::min(d.size(), p + (size_t)n); }      // the reference's is.get() loop does not fail at EOF either
+};
+}  // namespace
+
+extern "C" {
+
+int b2k_wave_read(const char *path, b2k_wave **out) {
+  if (!path || !out) return b2k::set_error(B2K_ERR_INVALID, "b2k_wave_read: bad args");
+  b2k_wave *W = new b2k_wave();
+  try {
+    WavIn r;
+    {
+      std::ifstream is(path, std::ios::binary);
+      if (!is.good()) throw ConfError{std::string("cannot open ") + path};
+      r.d.assign(std::istreambuf_iterator<char>(is), std::istreambuf_iterator<char>());
+    }
+    const std::string riff = r.tag();
+    if (riff == "RIFX") r.swap = true;
+    else if (riff != "RIFF") throw ConfError{"WaveData: expected RIFF or RIFX, got " + riff};
+    const uint32_t riff_size = r.u32();
+    if (r.tag() != "WAVE") throw ConfError{"WaveData: expected WAVE"};
+    std::string t = r.tag();
+    while (t != "fmt ") { r.skip(r.u32()); t = r.tag(); }
+    const uint32_t fmt_size = r.u32();
+    const uint16_t format = r.u16();
+    const uint16_t channels = r.u16();
+    const uint32_t rate = r.u32(), byte_rate = r.u32();
+    const uint32_t block_align = r.u16(), bits = r.u16();
+    uint32_t fmt_read = 16;
+    if (format == 1) {
+      if (fmt_size < 16) throw ConfError{"WaveData: expect PCM format data to have fmt chunk of at least size 16."};
+    } else if (format == 0xFFFE) {
+      const uint16_t extra = r.u16();
+      if (fmt_size < 40 || extra < 22) throw ConfError{"WaveData: malformed WAVE_FORMAT_EXTENSIBLE format data."};
+      r.u16(); r.u32();
+      const uint32_t g1 = r.u32(), g2 = r.u32(), g3 = r.u32(), g4 = r.u32();
+      fmt_read = 40;
+      if (g1 != 0x00000001u || g2 != 0x00100000u || g3 != 0xAA000080u || g4 != 0x719B3800u) throw ConfError{"WaveData: unsupported WAVE_FORMAT_EXTENSIBLE format."};
+    } else {
+      throw ConfError{"WaveData: can read only PCM data, format id in file is: " + std::to_string(format)};
+    }
+    if (fmt_size > fmt_read) r.skip(fmt_size - fmt_read);
+    if (channels == 0) throw ConfError{"WaveData: no channels present"};
+    if (bits != 16) throw ConfError{"WaveData: unsupported bits_per_sample = " + std::to_string(bits)};
+    if (byte_rate != rate * (bits / 8) * channels) throw ConfError{"WaveData: unexpected byte rate"};
+    if (block_align != (uint32_t)channels * (bits / 8)) throw ConfError{"WaveData: unexpected block_align"};
+    t = r.tag();
+    while (t != "data") { r.skip(r.u32()); t = r.tag(); }
+    const uint32_t data_size = r.u32();
+    const bool stream = riff_size == 0 || riff_size == 0xFFFFFFFFu || data_size == 0 || data_size == 0xFFFFFFFFu || data_size == 0x7FFFF000u;
+    size_t avail = r.d.size() - r.p;
+    if (!stream) avail = std::min<size_t>(avail, (size_t)(data_size / block_align) * block_align);   // DataBytes() = samp_count * BlockAlign()
+    if (avail == 0) throw ConfError{"WaveData: empty file (no data)"};
+    const size_t ns = avail / block_align;
+    W->samp_freq = (float)rate; W->channels = channels; W->samples = (int64_t)ns;
+    W->data.resize((size_t)channels * ns);
+    for (size_t i = 0; i < ns; i++)
+      for (int j = 0; j < channels; j++) {
+        unsigned char b0 = r.d[r.p], b1 = r.d[r.p + 1];
+        r.p += 2;
+        if (r.swap) std::swap(b0, b1);
+        W->data[(size_t)j * ns + i] = (float)(int16_t)((uint16_t)b0 | ((uint16_t)b1 << 8));
+      }
+  } catch (const ConfError &e) {
+    delete W;
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_wave_read", e.msg.c_str());
+  }
+  *out = W;
+  return B2K_OK;
+}
+
+int b2k_wave_destroy(b2k_wave *w) { delete w; return B2K_OK; }
+int b2k_wave_info(const b2k_wave *w, float *samp_freq, int32_t *channels, int64_t *samples) {
+  if (!w) return b2k::set_error(B2K_ERR_INVALID, "b2k_wave_info: bad args");
+  if (samp_freq) *samp_freq = w->samp_freq;
+  if (channels) *channels = w->channels;
+  if (samples) *samples = w->samples;
+  return B2K_OK;
+}
+const float *b2k_wave_data(const b2k_wave *w) { return w ? w->data.data() : nullptr; }
 
 }  // extern "C"

@@ -8,6 +8,7 @@
 //   OnlineMatrixFeature                    feat/online-feature.h
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <vector>
 
@@ -15,6 +16,7 @@
 #include "feat/feature-mfcc.h"
 #include "feat/online-feature.h"
 #include "matrix/kaldi-matrix.h"
+#include "feat/wave-reader.h"
 #include "util/parse-options.h"
 
 using namespace kaldi;
@@ -148,6 +150,24 @@ int ref_feat_opts_from_conf(const char *path, int feature_type, float *out, char
     out[i++] = feature_type == 0 ? m.cepstral_lifter : 0; out[i++] = feature_type == 0 ? m.htk_compat : f.htk_compat;
     out[i++] = feature_type == 0 ? 1 : f.use_log_fbank; out[i++] = feature_type == 0 ? 1 : f.use_power;
     snprintf(window, window_cap, "%s", fr.window_type.c_str());
+    return 0;
+  } catch (const std::exception &) {
+    return 1;
+  }
+}
+
+// WaveData::Read (feat/wave-reader.cc) on a file: the oracle of b2k_wave_read.  Returns 0, 1 if the reference rejected the
+// file, 2 if `cap` floats are not enough.
+int ref_wave_read(const char *path, float *out, long long cap, int *channels, long long *samples, float *samp_freq) {
+  try {
+    std::ifstream is(path, std::ios::binary);
+    if (!is.good()) return 1;
+    kaldi::WaveData w;
+    w.Read(is);
+    *channels = w.Data().NumRows(); *samples = w.Data().NumCols(); *samp_freq = w.SampFreq();
+    if ((long long)w.Data().NumRows() * w.Data().NumCols() > cap) return 2;
+    for (int j = 0; j < w.Data().NumRows(); j++)
+      for (int i = 0; i < w.Data().NumCols(); i++) out[(long long)j * w.Data().NumCols() + i] = w.Data()(j, i);
     return 0;
   } catch (const std::exception &) {
     return 1;
