@@ -213,6 +213,7 @@ typedef struct b2k_feat b2k_feat;
 int b2k_feat_create(const b2k_feat_cfg *cfg, b2k_feat **out);
 int b2k_feat_destroy(b2k_feat *f);
 int32_t b2k_feat_dim(const b2k_feat *f);                                    /* Dim()       */
+float b2k_feat_samp_freq(const b2k_feat *f);                                /* GetFrameOptions().samp_freq: AcceptWaveform checks it (online-feature.cc:135-150) */
 int32_t b2k_feat_num_frames(const b2k_feat *f, int64_t num_samples, int32_t flush);   /* NumFrames feature-window.cc:42 */
 
 /* OnlineBatchedFeaturePipelineCuda::ComputeFeaturesBatched

@@ -498,6 +498,7 @@ int b2k_feat_destroy(b2k_feat *f) {
 }
 
 int32_t b2k_feat_dim(const b2k_feat *f) { return f ? f->p.dim : -1; }
+float b2k_feat_samp_freq(const b2k_feat *f) { return f ? f->cfg.samp_freq : -1.0f; }
 
 // NumFrames (feat/feature-window.cc:42-87)
 int32_t b2k_feat_num_frames(const b2k_feat *f, int64_t num_samples, int32_t flush) {

@@ -67,6 +67,8 @@ class OnlineBaseFeatureB2k : public OnlineBaseFeature {
   void AcceptWaveform(BaseFloat sampling_rate, const VectorBase<BaseFloat> &wave) override {
     if (wave.Dim() == 0) return;
     if (finished_) KALDI_ERR << "AcceptWaveform called after InputFinished() was called.";
+    if (sampling_rate != b2k_feat_samp_freq(feat_))          // no resampler here (allow-downsample / allow-upsample, :138-150)
+      KALDI_ERR << "Sampling frequency mismatch, expected " << b2k_feat_samp_freq(feat_) << ", got " << sampling_rate;
     if (num_samples_ + wave.Dim() > cap_) KALDI_ERR << "utterance longer than the configured capacity";
     cudaMemcpy(d_wave_ + num_samples_, wave.Data(), sizeof(float) * wave.Dim(), cudaMemcpyHostToDevice);
     num_samples_ += wave.Dim();
