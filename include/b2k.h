@@ -508,6 +508,16 @@ typedef struct {
   int32_t *tids;                                        /* [num_tids] transition-ids, arcs then finals  */
 } b2k_compact_lattice;
 
+/* LatticeFasterDecoderTpl::GetBestPath (lattice-faster-decoder.cc:102-108) / CudaDecoder::GetBestPath on a finalized raw
+ * lattice: word ids and transition-ids (epsilons removed) of the cheapest path, its graph cost (final cost included, as
+ * LatticeWeight(final, 0) does) and acoustic cost.  cap = capacity of words[] and tids[]; with too small a cap the sizes
+ * are returned with B2K_ERR_OVERFLOW.  Host only. */
+int b2k_lat_best_path(const b2k_raw_lattice *raw, int32_t *words, int32_t *n_words, int32_t *tids, int32_t *n_tids, int32_t cap,
+                      float *graph_cost, float *acoustic_cost);
+/* The same path as indices into the raw lattice's arc arrays (in path order) and the index of its final entry (-1: empty
+ * lattice): what a shim needs to build the linear Lattice GetBestPath returns, weights included. */
+int b2k_lat_best_path_arcs(const b2k_raw_lattice *raw, int64_t *arcs, int64_t *n_arcs, int64_t cap, int64_t *final_index);
+
 typedef struct b2k_clat b2k_clat;
 /* max_states > 0: budget of determinized states; when it is exceeded the work is redone with 3/4 of the beam (the
  * reference reduces its beam when max_mem is hit, determinize-lattice-pruned.h:126-160) — see b2k_clat_effective_beam */

@@ -290,6 +290,99 @@ int b2k_lat_determinize_pruned(const b2k_raw_lattice *in, float beam, int64_t ma
 
 int b2k_clat_destroy(b2k_clat *c) { delete c; return B2K_OK; }
 
+// LatticeFasterDecoderTpl::GetBestPath (decoder/lattice-faster-decoder.cc:102-108 = GetRawLattice + ShortestPath over
+// graph + acoustic) / CudaDecoder::GetBestPath (cudadecoder/cuda-decoder.h): the cheapest path from state 0 to a final
+// state of a finalized raw lattice.  Ties: the first minimum in topological order of states and input order of arcs.
+}  // extern "C"
+
+// shared by the two entry points below: arcs of the cheapest start -> final path (in path order) and the final's index
+static int best_path_core(const b2k_raw_lattice *in, std::vector<int64_t> *path_out, int64_t *best_final) {
+  const int64_t N = in->num_states, A = in->num_arcs;
+  path_out->clear();
+  *best_final = -1;
+  if (N == 0 || in->num_finals == 0) return B2K_OK;
+  std::vector<int64_t> off(N + 1, 0);
+  for (int64_t a = 0; a < A; a++) {
+    if (in->arc_src[a] < 0 || in->arc_src[a] >= N || in->arc_dst[a] < 0 || in->arc_dst[a] >= N) return b2k::set_error(B2K_ERR_INVALID, "best path: arc endpoint out of range");
+    off[in->arc_src[a] + 1]++;
+  }
+  for (int64_t s = 0; s < N; s++) off[s + 1] += off[s];
+  std::vector<int64_t> arcs(A), fill(off.begin(), off.end() - 1);
+  for (int64_t a = 0; a < A; a++) arcs[fill[in->arc_src[a]]++] = a;
+  std::vector<int32_t> indeg(N, 0), topo;
+  for (int64_t a = 0; a < A; a++) indeg[in->arc_dst[a]]++;
+  for (int64_t s = 0; s < N; s++) if (!indeg[s]) topo.push_back((int32_t)s);
+  for (size_t i = 0; i < topo.size(); i++)
+    for (int64_t k = off[topo[i]]; k < off[topo[i] + 1]; k++) if (--indeg[in->arc_dst[arcs[k]]] == 0) topo.push_back(in->arc_dst[arcs[k]]);
+  if ((int64_t)topo.size() != N) return b2k::set_error(B2K_ERR_INVALID, "best path: the raw lattice has a cycle");
+  const double INF = std::numeric_limits<double>::infinity();
+  std::vector<double> dist(N, INF);
+  std::vector<int64_t> back(N, -1);
+  dist[0] = 0.0;
+  for (int32_t s : topo) {
+    if (!(dist[s] < INF)) continue;
+    for (int64_t k = off[s]; k < off[s + 1]; k++) {
+      const int64_t a = arcs[k];
+      const double nd = dist[s] + (double)in->arc_graph_cost[a] + (double)in->arc_acoustic_cost[a];
+      if (nd < dist[in->arc_dst[a]]) { dist[in->arc_dst[a]] = nd; back[in->arc_dst[a]] = a; }
+    }
+  }
+  int64_t best = -1;
+  double best_cost = INF;
+  for (int64_t f = 0; f < in->num_finals; f++) {
+    const int32_t s = in->final_state[f];
+    if (s < 0 || s >= N) return b2k::set_error(B2K_ERR_INVALID, "best path: final state out of range");
+    const double c = dist[s] + (double)in->final_cost[f];
+    if (c < best_cost) { best_cost = c; best = f; }
+  }
+  if (best < 0) return b2k::set_error(B2K_ERR_STATE, "best path: no final state is reachable from the start state");
+  for (int32_t s = in->final_state[best]; s != 0;) { path_out->push_back(back[s]); s = in->arc_src[back[s]]; }
+  std::reverse(path_out->begin(), path_out->end());
+  *best_final = best;
+  return B2K_OK;
+}
+
+extern "C" {
+
+int b2k_lat_best_path(const b2k_raw_lattice *in, int32_t *words, int32_t *n_words, int32_t *tids, int32_t *n_tids, int32_t cap,
+                      float *graph_cost, float *acoustic_cost) {
+  if (!in || !n_words || !n_tids || cap < 0 || (cap > 0 && (!words || !tids)))
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_lat_best_path: bad args");
+  *n_words = 0; *n_tids = 0;
+  if (graph_cost) *graph_cost = std::numeric_limits<float>::infinity();
+  if (acoustic_cost) *acoustic_cost = std::numeric_limits<float>::infinity();
+  std::vector<int64_t> path;
+  int64_t best = -1;
+  const int rc = best_path_core(in, &path, &best);
+  if (rc) return rc;
+  if (best < 0) return B2K_OK;
+  double g = (double)in->final_cost[best], ac = 0.0;
+  int32_t nw = 0, nt = 0;
+  for (const int64_t a : path) {
+    g += (double)in->arc_graph_cost[a]; ac += (double)in->arc_acoustic_cost[a];
+    if (in->arc_olabel[a] != 0) { if (nw < cap) words[nw] = in->arc_olabel[a]; nw++; }
+    if (in->arc_ilabel[a] != 0) { if (nt < cap) tids[nt] = in->arc_ilabel[a]; nt++; }
+  }
+  *n_words = nw; *n_tids = nt;
+  if (graph_cost) *graph_cost = (float)g;
+  if (acoustic_cost) *acoustic_cost = (float)ac;
+  if (nw > cap || nt > cap) return b2k::set_error(B2K_ERR_OVERFLOW, "b2k_lat_best_path: output buffers too small (sizes returned)");
+  return B2K_OK;
+}
+
+int b2k_lat_best_path_arcs(const b2k_raw_lattice *in, int64_t *arcs, int64_t *n_arcs, int64_t cap, int64_t *final_index) {
+  if (!in || !n_arcs || cap < 0 || (cap > 0 && !arcs)) return b2k::set_error(B2K_ERR_INVALID, "b2k_lat_best_path_arcs: bad args");
+  std::vector<int64_t> path;
+  int64_t best = -1;
+  const int rc = best_path_core(in, &path, &best);
+  if (rc) return rc;
+  *n_arcs = (int64_t)path.size();
+  if (final_index) *final_index = best;
+  if ((int64_t)path.size() > cap) return b2k::set_error(B2K_ERR_OVERFLOW, "b2k_lat_best_path_arcs: output buffer too small (size returned)");
+  if (!path.empty()) memcpy(arcs, path.data(), 8 * path.size());
+  return B2K_OK;
+}
+
 float b2k_clat_effective_beam(const b2k_clat *c) { return c ? c->effective_beam : 0.f; }
 
 int b2k_clat_sizes(const b2k_clat *c, int64_t sizes[6]) {

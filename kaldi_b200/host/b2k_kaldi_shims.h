@@ -185,6 +185,36 @@ class CudaDecoderB2k {
       for (int64 f = 0; f < r.num_finals; f++) ofst->SetFinal(fs[f], LatticeWeight(fc[f], 0));  // :189
     }
   }
+  // GetBestPath(const std::vector<ChannelId>&, std::vector<Lattice*>&, bool)  cuda-decoder.h; CPU semantics
+  // LatticeFasterDecoderTpl::GetBestPath = GetRawLattice + ShortestPath (lattice-faster-decoder.cc:102-108): a linear
+  // lattice, one state per path position, the final weight on the last state
+  void GetBestPath(const std::vector<ChannelId> &channels, std::vector<Lattice *> &fst_out_vec, bool use_final_probs) {
+    KALDI_ASSERT(use_final_probs);
+    Check(b2k_dec_finalize_decoding(dec_, channels.data(), (int32)channels.size(), nullptr), "FinalizeDecoding");
+    for (size_t i = 0; i < channels.size(); i++) {
+      b2k_raw_lattice r = {};
+      Check(b2k_dec_get_raw_lattice(dec_, channels[i], &r, nullptr), "GetRawLattice(size)");
+      std::vector<int32> sf(r.num_states), sh(r.num_states), as(r.num_arcs), ad(r.num_arcs), ai(r.num_arcs), ao(r.num_arcs), fs(r.num_finals);
+      std::vector<float> st(r.num_states), se(r.num_states), ag(r.num_arcs), aa(r.num_arcs), fc(r.num_finals);
+      r.state_frame = sf.data(); r.state_hclg = sh.data(); r.state_tot_cost = st.data(); r.state_extra_cost = se.data();
+      r.arc_src = as.data(); r.arc_dst = ad.data(); r.arc_ilabel = ai.data(); r.arc_olabel = ao.data();
+      r.arc_graph_cost = ag.data(); r.arc_acoustic_cost = aa.data(); r.final_state = fs.data(); r.final_cost = fc.data();
+      Check(b2k_dec_get_raw_lattice(dec_, channels[i], &r, nullptr), "GetRawLattice");
+      std::vector<int64_t> path((size_t)r.num_arcs + 1);
+      int64_t n = 0, fin = -1;
+      Check(b2k_lat_best_path_arcs(&r, path.data(), &n, (int64_t)path.size(), &fin), "b2k_lat_best_path_arcs");
+      Lattice *ofst = fst_out_vec[i];
+      ofst->DeleteStates();
+      if (fin < 0) continue;                                   // empty lattice: empty FST, as ShortestPath gives
+      for (int64_t k = 0; k <= n; k++) ofst->AddState();
+      ofst->SetStart(0);
+      for (int64_t k = 0; k < n; k++) {
+        const int64_t a = path[k];
+        ofst->AddArc((int32)k, LatticeArc(ai[a], ao[a], LatticeWeight(ag[a], aa[a]), (int32)(k + 1)));
+      }
+      ofst->SetFinal((int32)n, LatticeWeight(fc[fin], 0));
+    }
+  }
 #endif
  private:
   b2k_dec *dec_ = nullptr;

@@ -151,3 +151,64 @@ def test_scale_compact_lattice():
     np.testing.assert_array_equal(s["arc_acoustic_cost"], clat["arc_acoustic_cost"] * np.float32(0.5))
     np.testing.assert_array_equal(s["arc_graph_cost"], clat["arc_graph_cost"])
     assert compact_best_path(s)["acoustic_cost"] == pytest.approx(0.5 * compact_best_path(clat)["acoustic_cost"])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_cpp_best_path_equals_python_best_path(seed):
+    import ctypes as C
+    try:
+        from kaldi_b200 import _lib
+        from kaldi_b200.decoder import _RawLattice, _p
+        L = _lib.lib()
+    except OSError as e:
+        pytest.skip(str(e))
+    lat = _lattice(seed)
+    want = LT.best_path(lat)
+    keep = {k: np.ascontiguousarray(lat[k], np.float32 if lat[k].dtype.kind == "f" else np.int32) for k in
+            ("state_frame", "state_hclg", "state_tot_cost", "state_extra_cost", "arc_src", "arc_dst", "arc_ilabel", "arc_olabel",
+             "arc_graph_cost", "arc_acoustic_cost", "final_state", "final_cost")}
+    r = _RawLattice()
+    r.num_states, r.num_arcs, r.num_finals = len(keep["state_frame"]), len(keep["arc_src"]), len(keep["final_state"])
+    for k, v in keep.items():
+        setattr(r, k, _p(v, C.c_float if v.dtype == np.float32 else C.c_int32))
+    L.b2k_lat_best_path.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    nw, nt, g, a = C.c_int32(), C.c_int32(), C.c_float(), C.c_float()
+    assert L.b2k_lat_best_path(C.byref(r), None, C.byref(nw), None, C.byref(nt), 0, C.byref(g), C.byref(a)) in (0, 4)   # sizes query
+    words, tids = np.zeros(max(nw.value, 1), np.int32), np.zeros(max(nt.value, 1), np.int32)
+    cap = max(nw.value, nt.value, 1)
+    words, tids = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    assert L.b2k_lat_best_path(C.byref(r), words.ctypes.data, C.byref(nw), tids.ctypes.data, C.byref(nt), cap, C.byref(g), C.byref(a)) == 0
+    assert words[:nw.value].tolist() == want["olabels"].tolist()
+    assert tids[:nt.value].tolist() == want["ilabels"].tolist()
+    assert g.value == pytest.approx(want["graph_cost"], abs=1e-3) and a.value == pytest.approx(want["acoustic_cost"], abs=1e-3)
+
+
+def test_cpp_best_path_arcs_trace_the_same_path():
+    import ctypes as C
+    try:
+        from kaldi_b200 import _lib
+        from kaldi_b200.decoder import _RawLattice, _p
+        L = _lib.lib()
+    except OSError as e:
+        pytest.skip(str(e))
+    lat = _lattice(1)
+    want = LT.best_path(lat)
+    keep = {k: np.ascontiguousarray(lat[k], np.float32 if lat[k].dtype.kind == "f" else np.int32) for k in
+            ("state_frame", "state_hclg", "state_tot_cost", "state_extra_cost", "arc_src", "arc_dst", "arc_ilabel", "arc_olabel",
+             "arc_graph_cost", "arc_acoustic_cost", "final_state", "final_cost")}
+    r = _RawLattice()
+    r.num_states, r.num_arcs, r.num_finals = len(keep["state_frame"]), len(keep["arc_src"]), len(keep["final_state"])
+    for k, v in keep.items():
+        setattr(r, k, _p(v, C.c_float if v.dtype == np.float32 else C.c_int32))
+    L.b2k_lat_best_path_arcs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    n, fi = C.c_int64(), C.c_int64()
+    assert L.b2k_lat_best_path_arcs(C.byref(r), None, C.byref(n), 0, C.byref(fi)) == 4       # B2K_ERR_OVERFLOW: size returned
+    arcs = np.zeros(n.value, np.int64)
+    assert L.b2k_lat_best_path_arcs(C.byref(r), arcs.ctypes.data, C.byref(n), n.value, C.byref(fi)) == 0
+    states = [0] + [int(lat["arc_dst"][a]) for a in arcs]
+    assert states == want["states"].tolist()
+    assert all(int(lat["arc_src"][a]) == s for a, s in zip(arcs, states[:-1]))
+    assert int(lat["final_state"][fi.value]) == states[-1]
+    # empty lattice: nothing, no error
+    e = _RawLattice()
+    assert L.b2k_lat_best_path_arcs(C.byref(e), None, C.byref(n), 0, C.byref(fi)) == 0 and n.value == 0 and fi.value == -1
