@@ -546,6 +546,11 @@ typedef struct {
   float chunk_length_secs;      /* 0.18: the CPU tool's --chunk-length, decides which i-vector a chunk sees   */
   int32_t ivector_splice_right; /* --splice-config right context of the extractor (3)                        */
   int32_t use_priors, conv_dense;
+  /* OnlineNnet2FeaturePipelineInfo::use_cmvn (online-nnet2-feature-pipeline.cc:108-123): the network reads OnlineCmvn of the
+   * base features (the i-vector stage keeps the base features); global_cmvn_stats: host [2 x (feat_dim + 1)] doubles */
+  int32_t use_cmvn;
+  b2k_cmvn_cfg cmvn;
+  const double *global_cmvn_stats;
 } b2k_pipeline_cfg;
 
 void b2k_pipeline_cfg_default(b2k_pipeline_cfg *cfg);

@@ -24,6 +24,11 @@ struct b2k_pipeline {
   b2k_ivec *ivec = nullptr;          // not owned
   float *h_wave = nullptr;           // pinned [max_batch x num_samples]
   float *d_wave = nullptr, *d_feats = nullptr, *d_ivec = nullptr, *d_loglikes = nullptr;
+  float *d_feats_cmvn = nullptr;     // use_cmvn: what the network reads (the i-vector stage keeps reading d_feats)
+  double *d_cmvn_state = nullptr, *d_cmvn_global = nullptr;
+  std::vector<const float *> p_nnet_in;
+  std::vector<float *> p_cmvn_out;
+  std::vector<double *> p_cmvn_state;
   std::vector<int32_t> sched, channels, ns, zeros, nframes, nout;
   std::vector<const float *> p_wave, p_feats, p_ivec, p_ll;
   std::vector<float *> p_feats_out, p_ivec_out, p_ll_out;
@@ -74,6 +79,8 @@ void b2k_pipeline_cfg_default(b2k_pipeline_cfg *c) {
   c->chunk_length_secs = 0.18f;      // online2-wav-nnet3-latgen-faster --chunk-length
   c->ivector_splice_right = 3;
   c->use_priors = 1;
+  c->use_cmvn = 0;                   // OnlineNnet2FeaturePipelineInfo::use_cmvn: off unless --cmvn-config is given
+  c->cmvn.cmn_window = 600; c->cmvn.speaker_frames = 600; c->cmvn.global_frames = 200; c->cmvn.normalize_mean = 1; c->cmvn.normalize_variance = 0;
 }
 
 int b2k_pipeline_plan_for(const b2k_pipeline_cfg *cfg, const b2k_model *model, b2k_pipeline_plan *plan) {
@@ -88,6 +95,7 @@ int b2k_pipeline_plan_for(const b2k_pipeline_cfg *cfg, const b2k_model *model, b
   if (T <= 0) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: the utterance length gives no feature frame");
   const int D = cfg->feat.feature_type == 0 ? cfg->feat.num_ceps : cfg->feat.num_bins + (cfg->feat.use_energy ? 1 : 0);
   if (D != mi[0]) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: feature dimension differs from the model's input dimension");
+  if (cfg->use_cmvn && !cfg->global_cmvn_stats) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: use_cmvn needs global_cmvn_stats (online-feature.cc:417)");
   const int sub = mi[3];
   if (cfg->frames_per_chunk % sub) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: frames_per_chunk must be a multiple of the frame subsampling factor");
   plan->num_feature_frames = T;
@@ -105,6 +113,7 @@ int b2k_pipeline_plan_for(const b2k_pipeline_cfg *cfg, const b2k_model *model, b
   const int64_t B = cfg->max_batch;
   plan->device_bytes = 4 * B * (cfg->num_samples + (int64_t)T * D + (int64_t)plan->num_chunks * std::max(1, plan->ivector_dim) +
                                 nf * plan->num_pdfs);
+  if (cfg->use_cmvn) plan->device_bytes += 4 * B * (int64_t)T * D + 8 * (B + 1) * 2 * (D + 1);
   plan->pinned_bytes = 4 * B * cfg->num_samples;
   return B2K_OK;
 }
@@ -115,7 +124,8 @@ int b2k_pipeline_destroy(b2k_pipeline *p) {
   if (p->nnet) b2k_nnet_destroy(p->nnet);
   if (p->feat) b2k_feat_destroy(p->feat);
   if (p->h_wave) cudaFreeHost(p->h_wave);
-  for (float *d : {p->d_wave, p->d_feats, p->d_ivec, p->d_loglikes}) if (d) cudaFree(d);
+  for (float *d : {p->d_wave, p->d_feats, p->d_ivec, p->d_loglikes, p->d_feats_cmvn}) if (d) cudaFree(d);
+  for (double *d : {p->d_cmvn_state, p->d_cmvn_global}) if (d) cudaFree(d);
   delete p;
   return B2K_OK;
 }
@@ -162,6 +172,16 @@ static int pipeline_create_impl(b2k_pipeline *p, const b2k_model *model, const b
   B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_ivec, 4 * B * NC * IV));
   B2K_CUDA_CHECK(cudaMemset(p->d_ivec, 0, 4 * B * NC * IV));      // no extractor: the network sees zero i-vectors
   B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_loglikes, 4 * B * NF * P));
+  p->p_nnet_in.resize(B);
+  if (cfg.use_cmvn) {      // OnlineNnet2FeaturePipeline: base -> OnlineCmvn -> network input (online-nnet2-feature-pipeline.cc:108-123)
+    const size_t SD = 2 * (D + 1);
+    B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_feats_cmvn, 4 * B * T * D));
+    B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_cmvn_state, 8 * B * SD));
+    B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_cmvn_global, 8 * SD));
+    B2K_CUDA_CHECK(cudaMemcpy(p->d_cmvn_global, cfg.global_cmvn_stats, 8 * SD, cudaMemcpyHostToDevice));
+    p->p_cmvn_out.resize(B); p->p_cmvn_state.resize(B);
+    for (size_t i = 0; i < B; i++) { p->p_cmvn_out[i] = p->d_feats_cmvn + i * T * D; p->p_cmvn_state[i] = p->d_cmvn_state + i * SD; }
+  }
   p->channels.resize(B); p->ns.assign(B, (int32_t)S); p->zeros.assign(B, 0); p->nframes.assign(B, (int32_t)T); p->nout.assign(B, (int32_t)NF);
   p->p_wave.resize(B); p->p_feats.resize(B); p->p_ivec.resize(B); p->p_ll.resize(B);
   p->p_feats_out.resize(B); p->p_ivec_out.resize(B); p->p_ll_out.resize(B);
@@ -171,6 +191,7 @@ static int pipeline_create_impl(b2k_pipeline *p, const b2k_model *model, const b
     p->p_feats[i] = p->p_feats_out[i] = p->d_feats + i * T * D;
     p->p_ivec[i] = p->p_ivec_out[i] = p->d_ivec + i * NC * IV;
     p->p_ll[i] = p->p_ll_out[i] = p->d_loglikes + i * NF * P;
+    p->p_nnet_in[i] = cfg.use_cmvn ? p->d_feats_cmvn + i * T * D : p->d_feats + i * T * D;
   }
   if (p->ivec) {
     p->sched.resize(NC);
@@ -227,7 +248,14 @@ static int run_device(b2k_pipeline *p, int32_t n, void *stream) {
                                   pl.num_chunks, p->p_ivec_out.data(), pl.ivector_dim, stream);
     if (rc) return rc;
   }
-  rc = b2k_nnet_run(p->nnet, n, p->p_feats.data(), pl.feat_dim, pl.ivector_dim > 0 ? p->p_ivec.data() : nullptr, pl.ivector_dim,
+  if (p->cfg.use_cmvn) {                     // every utterance starts from empty sliding-window stats and no speaker stats
+    const size_t SD = 2 * ((size_t)pl.feat_dim + 1);
+    B2K_CUDA_CHECK(cudaMemsetAsync(p->d_cmvn_state, 0, 8 * (size_t)n * SD, (cudaStream_t)stream));
+    rc = b2k_cmvn_apply_batched(p->feat, &p->cfg.cmvn, n, p->p_feats.data(), p->p_cmvn_out.data(), pl.feat_dim, pl.feat_dim,
+                                p->zeros.data(), p->nframes.data(), p->p_cmvn_state.data(), p->d_cmvn_global, nullptr, stream);
+    if (rc) return rc;
+  }
+  rc = b2k_nnet_run(p->nnet, n, p->p_nnet_in.data(), pl.feat_dim, pl.ivector_dim > 0 ? p->p_ivec.data() : nullptr, pl.ivector_dim,
                     p->p_ll_out.data(), pl.num_pdfs, stream);
   if (rc) return rc;
   rc = b2k_dec_init_decoding(p->dec, p->channels.data(), n, stream);

@@ -156,12 +156,13 @@ class BatchedPipeline:
 def _native_structs():
     import ctypes as C
     from .decoder import _DecCfg
-    from .feat import _FeatCfg
+    from .feat import _CmvnCfg, _FeatCfg
 
     class _PipelineCfg(C.Structure):
         _fields_ = [("feat", _FeatCfg), ("dec", _DecCfg), ("frames_per_chunk", C.c_int32), ("acoustic_scale", C.c_float),
                     ("max_batch", C.c_int32), ("num_samples", C.c_int64), ("chunk_length_secs", C.c_float),
-                    ("ivector_splice_right", C.c_int32), ("use_priors", C.c_int32), ("conv_dense", C.c_int32)]
+                    ("ivector_splice_right", C.c_int32), ("use_priors", C.c_int32), ("conv_dense", C.c_int32),
+                    ("use_cmvn", C.c_int32), ("cmvn", _CmvnCfg), ("global_cmvn_stats", C.c_void_p)]
 
     class _PipelinePlan(C.Structure):
         _fields_ = [("num_feature_frames", C.c_int32), ("feat_dim", C.c_int32), ("num_output_frames", C.c_int32),

@@ -68,3 +68,24 @@ def test_pipeline_creation_fails_loudly_without_a_gpu():
     fake_fst = C.c_void_p(8)                 # never dereferenced: the device check comes first
     assert L.b2k_pipeline_create(C.byref(c), m.h, fake_fst, None, C.byref(h)) == 2      # B2K_ERR_NO_DEVICE
     assert not h.value
+
+
+def test_cmvn_option_is_validated_and_sized():
+    """use_cmvn (OnlineNnet2FeaturePipelineInfo::use_cmvn): global stats are mandatory, one more feature buffer is planned."""
+    from kaldi_b200 import _lib
+    from kaldi_b200.pipeline import PipelineConfig, native_cfg, _native_structs
+    m = _model()
+    L = _lib.lib()
+    _, PP = _native_structs()
+    c, pl = native_cfg(PipelineConfig(max_batch=2, num_samples=16000)), PP()
+    L.b2k_pipeline_plan_for.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    assert L.b2k_pipeline_plan_for(C.byref(c), m.h, C.byref(pl)) == 0
+    base = pl.device_bytes
+    assert (c.use_cmvn, c.cmvn.cmn_window, c.cmvn.speaker_frames, c.cmvn.global_frames, c.cmvn.normalize_mean) == (0, 600, 600, 200, 1)
+    c.use_cmvn = 1
+    assert L.b2k_pipeline_plan_for(C.byref(c), m.h, C.byref(pl)) == 1                    # no global stats
+    stats = np.zeros((2, 41), np.float64)
+    c.global_cmvn_stats = stats.ctypes.data
+    assert L.b2k_pipeline_plan_for(C.byref(c), m.h, C.byref(pl)) == 0
+    T = pl.num_feature_frames
+    assert pl.device_bytes == base + 4 * 2 * T * 40 + 8 * 3 * 2 * 41
