@@ -523,6 +523,10 @@ typedef struct b2k_clat b2k_clat;
  * reference reduces its beam when max_mem is hit, determinize-lattice-pruned.h:126-160) — see b2k_clat_effective_beam */
 int b2k_lat_determinize_pruned(const b2k_raw_lattice *raw, float beam, int64_t max_states, b2k_clat **out);
 float b2k_clat_effective_beam(const b2k_clat *clat);
+/* n lattices on up to num_threads host threads (0 = all cores); out[i], status[i] per lattice (status may be NULL); returns the
+ * first non-zero status.  Same results as n single calls. */
+int b2k_lat_determinize_pruned_batch(const b2k_raw_lattice *raws, int32_t n, float beam, int64_t max_states, int32_t num_threads,
+                                     b2k_clat **out, int32_t *status);
 int b2k_clat_destroy(b2k_clat *clat);
 /* sizes: [0] states, [1] arcs, [2] finals, [3] transition-ids, [4] subsets expanded, [5] subset elements in total */
 int b2k_clat_sizes(const b2k_clat *clat, int64_t sizes[6]);

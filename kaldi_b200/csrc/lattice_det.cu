@@ -20,11 +20,14 @@
 // transition-id strings (tests/test_lattice_det.py; also exhaustively against path enumeration on small lattices, the
 // property the reference's determinize-lattice-pruned-test.cc checks).  The state numbering is not compared.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <limits>
 #include <map>
 #include <queue>
+#include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -286,6 +289,37 @@ int b2k_lat_determinize_pruned(const b2k_raw_lattice *in, float beam, int64_t ma
     b *= 0.75f;
   }
   return b2k::set_error(B2K_ERR_OVERFLOW, "b2k_lat_determinize_pruned: the state budget cannot be met even with a tiny beam");
+}
+
+// n independent lattices on up to num_threads host threads (the reference determinizes on a thread pool as well,
+// cudadecoder/batched-threaded-nnet3-cuda-online-pipeline.cc:727-790).  out[i] / status[i] per lattice; returns the
+// first non-zero status.  Results are those of the single-lattice call: nothing is shared between lattices.
+int b2k_lat_determinize_pruned_batch(const b2k_raw_lattice *in, int32_t n, float beam, int64_t max_states, int32_t num_threads,
+                                     b2k_clat **out, int32_t *status) {
+  if (!in || !out || n < 0) return b2k::set_error(B2K_ERR_INVALID, "b2k_lat_determinize_pruned_batch: bad args");
+  for (int32_t i = 0; i < n; i++) out[i] = nullptr;
+  std::vector<int> rc((size_t)n, 0);
+  std::vector<std::string> msg((size_t)n);
+  std::atomic<int32_t> next{0};
+  auto work = [&]() {
+    for (int32_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
+      rc[i] = b2k_lat_determinize_pruned(&in[i], beam, max_states, &out[i]);
+      if (rc[i]) msg[i] = b2k::g_last_error;                   // thread-local in the worker: carry it to the caller
+    }
+  };
+  const int32_t nt = std::max<int32_t>(1, std::min<int32_t>(num_threads > 0 ? num_threads : (int32_t)std::thread::hardware_concurrency(), n));
+  if (nt <= 1) work();
+  else {
+    std::vector<std::thread> th;
+    for (int32_t t = 0; t < nt; t++) th.emplace_back(work);
+    for (auto &t : th) t.join();
+  }
+  int first = 0;
+  for (int32_t i = 0; i < n; i++) {
+    if (status) status[i] = rc[i];
+    if (rc[i] && !first) { first = rc[i]; b2k::g_last_error = msg[i]; }
+  }
+  return first;
 }
 
 int b2k_clat_destroy(b2k_clat *c) { delete c; return B2K_OK; }

@@ -62,23 +62,34 @@ class B2kPipelineBackend {
     all.arc_src = as.data(); all.arc_dst = ad.data(); all.arc_ilabel = ai.data(); all.arc_olabel = ao_.data();
     all.arc_graph_cost = ag.data(); all.arc_acoustic_cost = aa.data(); all.final_state = fs.data(); all.final_cost = fc.data();
     Check(b2k_pipeline_get_raw_lattices(e.pipe, n, &all, so.data(), ao.data(), fo.data(), nullptr), "b2k_pipeline_get_raw_lattices");
+    std::vector<b2k_raw_lattice> ones((size_t)n);
     for (int32_t i = 0; i < n; i++) {
-      b2k_raw_lattice one = {};                                // views into the packed arrays; ids are lattice-relative
+      b2k_raw_lattice &one = ones[i];                         // views into the packed arrays; ids are lattice-relative
+      one = b2k_raw_lattice{};
       one.num_states = so[i + 1] - so[i]; one.num_arcs = ao[i + 1] - ao[i]; one.num_finals = fo[i + 1] - fo[i];
       one.state_frame = sf.data() + so[i]; one.state_hclg = sh.data() + so[i];
       one.state_tot_cost = st.data() + so[i]; one.state_extra_cost = se.data() + so[i];
       one.arc_src = as.data() + ao[i]; one.arc_dst = ad.data() + ao[i]; one.arc_ilabel = ai.data() + ao[i]; one.arc_olabel = ao_.data() + ao[i];
       one.arc_graph_cost = ag.data() + ao[i]; one.arc_acoustic_cost = aa.data() + ao[i];
       one.final_state = fs.data() + fo[i]; one.final_cost = fc.data() + fo[i];
-      b2k_clat *c = nullptr;
-      Check(b2k_lat_determinize_pruned(&one, det_beam_, det_max_states_, &c), "b2k_lat_determinize_pruned");
+    }
+    std::vector<b2k_clat *> clats((size_t)n, nullptr);       // determinized on the host cores, one lattice per task
+    const int rc = b2k_lat_determinize_pruned_batch(ones.data(), n, det_beam_, det_max_states_, det_threads_, clats.data(), nullptr);
+    if (rc != B2K_OK) {
+      const std::string msg = b2k_last_error();
+      for (b2k_clat *c : clats) if (c) b2k_clat_destroy(c);
+      throw std::runtime_error("b2k_lat_determinize_pruned_batch: " + msg);
+    }
+    for (int32_t i = 0; i < n; i++) {
       Result r;
-      r.clat.reset(c);
-      r.effective_beam = b2k_clat_effective_beam(c);
-      r.raw_states = one.num_states; r.raw_arcs = one.num_arcs;
+      r.clat.reset(clats[i]);
+      r.effective_beam = b2k_clat_effective_beam(clats[i]);
+      r.raw_states = ones[i].num_states; r.raw_arcs = ones[i].num_arcs;
       out->push_back(std::move(r));
     }
   }
+
+  void SetDeterminizeThreads(int32_t n) { det_threads_ = n; }   // 0 = all host cores
 
   size_t NumPipelines() const { return pipes_.size(); }
 
@@ -119,6 +130,7 @@ class B2kPipelineBackend {
   float det_beam_;
   int64_t det_max_states_;
   size_t max_pipelines_;
+  int32_t det_threads_ = 0;
   std::list<Entry> pipes_;
 };
 
