@@ -2023,6 +2023,7 @@ struct b2k_dec {
 extern "C" {
 
 void b2k_dec_cfg_default(b2k_dec_cfg *c) {
+  if (!c) return;
   c->beam = 15.0f; c->lattice_beam = 8.0f; c->max_active = 7000; c->min_active = 200;
   c->beam_delta = 0.5f; c->prune_interval = 25; c->prune_scale = 0.1f;
   c->max_tokens_per_frame = 32768; c->max_frames = 1024;
@@ -2376,6 +2377,7 @@ int b2k_dec_finalize_decoding(b2k_dec *d, const int32_t *channels, int32_t n, vo
 }
 
 static int read_chan(b2k_dec *d, int ch, ChanState *out) {
+  if (!d) return set_error(B2K_ERR_INVALID, "null decoder handle");
   if (ch < 0 || ch >= d->nchannels) return set_error(B2K_ERR_INVALID, "bad channel id");
   B2K_CUDA_CHECK(cudaDeviceSynchronize());
   B2K_CUDA_CHECK(cudaMemcpy(out, &d->p.chan[ch], sizeof(ChanState), cudaMemcpyDeviceToHost));
@@ -2383,6 +2385,7 @@ static int read_chan(b2k_dec *d, int ch, ChanState *out) {
 }
 
 int b2k_dec_num_frames_decoded(b2k_dec *d, int32_t channel, int32_t *out) {
+  if (!out) return set_error(B2K_ERR_INVALID, "b2k_dec_num_frames_decoded: bad args");
   ChanState cs;
   int rc = read_chan(d, channel, &cs);
   if (rc) return rc;
@@ -2391,6 +2394,7 @@ int b2k_dec_num_frames_decoded(b2k_dec *d, int32_t channel, int32_t *out) {
 }
 
 int b2k_dec_channel_info(b2k_dec *d, int32_t channel, int64_t info[32]) {
+  if (!info) return set_error(B2K_ERR_INVALID, "b2k_dec_channel_info: bad args");
   ChanState cs;
   int rc = read_chan(d, channel, &cs);
   if (rc) return rc;

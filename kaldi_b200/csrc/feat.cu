@@ -363,6 +363,7 @@ static inline float melscale_f(float f) { return 1127.0f * logf(1.0f + f / 700.0
 extern "C" {
 
 void b2k_feat_cfg_default(b2k_feat_cfg *c) {
+  if (!c) return;
   memset(c, 0, sizeof(*c));
   c->feature_type = 0; c->samp_freq = 16000.f; c->frame_shift_ms = 10.f; c->frame_length_ms = 25.f;
   c->dither = 0.f; c->preemph_coeff = 0.97f; c->remove_dc_offset = 1; c->round_to_power_of_two = 1;
