@@ -56,25 +56,39 @@ struct Reader {
   }
   static bool sp(unsigned char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\f' || c == '\v'; }
   void ws() { while (p < d.size() && sp(d[p])) p++; }
-  void need(size_t n) const { if (p + n > d.size()) throw FormatError("unexpected end of file"); }
+  void need(size_t n) const { if (p > d.size() || n > d.size() - p) throw FormatError("unexpected end of file"); }
+  // a count read from the file: non-negative and small enough for the bytes that are left (checked BEFORE anything is allocated)
+  size_t count(long long n, size_t elem_bytes) const {
+    if (n < 0 || p > d.size() || (unsigned long long)n > (d.size() - p) / elem_bytes) throw FormatError("implausible element count in the file");
+    return (size_t)n;
+  }
   std::string token() {                       // ReadToken (io-funcs.cc:154)
     ws();
     size_t e = p;
     while (e < d.size() && !sp(d[e])) e++;
     if (e == p) throw FormatError("empty token");
     std::string t((const char *)&d[p], e - p);
-    p = e + 1;
+    p = std::min(e + 1, d.size());
     return t;
   }
   void expect(const char *t) { std::string g = token(); if (g != t) throw FormatError(std::string("expected ") + t + ", got " + g); }
   std::string line() {
+    if (p >= d.size()) throw FormatError("unexpected end of file");
     size_t e = p;
     while (e < d.size() && d[e] != '\n') e++;
     std::string s((const char *)&d[p], e - p);
-    p = e + 1;
+    p = std::min(e + 1, d.size());
     return s;
   }
-  std::string text_number() { ws(); size_t e = p; while (e < d.size() && !sp(d[e])) e++; std::string s((const char *)&d[p], e - p); p = e; return s; }
+  std::string text_number() {
+    ws();
+    size_t e = p;
+    while (e < d.size() && !sp(d[e])) e++;
+    if (e == p) throw FormatError("unexpected end of file (number expected)");
+    std::string s((const char *)&d[p], e - p);
+    p = e;
+    return s;
+  }
   long long read_int() {                      // ReadBasicType<integer> (io-funcs-inl.h:34-110)
     if (!binary) return atoll(text_number().c_str());
     need(1);
@@ -125,10 +139,10 @@ struct Reader {
       const bool dbl = d[p] == 'D';
       if (!((d[p] == 'F' || dbl) && d[p + 1] == 'V' && d[p + 2] == ' ')) throw FormatError("expected FV/DV");
       p += 3;
-      const long long n = read_int();
-      v->f.resize((size_t)n);
-      if (dbl) { need(8 * n); for (long long i = 0; i < n; i++) { double x; memcpy(&x, &d[p + 8 * i], 8); v->f[i] = (float)x; } p += 8 * n; }
-      else { need(4 * n); memcpy(v->f.data(), &d[p], 4 * n); p += 4 * n; }
+      const size_t n = count(read_int(), dbl ? 8 : 4);
+      v->f.resize(n);
+      if (dbl) { for (size_t i = 0; i < n; i++) { double x; memcpy(&x, &d[p + 8 * i], 8); v->f[i] = (float)x; } p += 8 * n; }
+      else { if (n) memcpy(v->f.data(), &d[p], 4 * n); p += 4 * n; }
       v->rows = (int)n; v->cols = 1;
       return;
     }
@@ -146,10 +160,12 @@ struct Reader {
       const bool dbl = d[p] == 'D';
       if (!((d[p] == 'F' || dbl) && d[p + 1] == 'M' && d[p + 2] == ' ')) throw FormatError("expected FM/DM");
       p += 3;
-      const long long r = read_int(), c = read_int(), n = r * c;
-      v->f.resize((size_t)n);
-      if (dbl) { need(8 * n); for (long long i = 0; i < n; i++) { double x; memcpy(&x, &d[p + 8 * i], 8); v->f[i] = (float)x; } p += 8 * n; }
-      else { need(4 * n); memcpy(v->f.data(), &d[p], 4 * n); p += 4 * n; }
+      const long long r = read_int(), c = read_int();
+      if (r < 0 || c < 0 || r > 0x7fffffffLL || c > 0x7fffffffLL) throw FormatError("implausible matrix size in the file");
+      const size_t n = count(r * c, dbl ? 8 : 4);
+      v->f.resize(n);
+      if (dbl) { for (size_t i = 0; i < n; i++) { double x; memcpy(&x, &d[p + 8 * i], 8); v->f[i] = (float)x; } p += 8 * n; }
+      else { if (n) memcpy(v->f.data(), &d[p], 4 * n); p += 4 * n; }
       v->rows = (int)r; v->cols = (int)c;
       return;
     }
@@ -171,11 +187,11 @@ struct Reader {
       }
       p += 3;
       long long r = read_int(), c = kind == 'M' ? read_int() : 1;
-      if (r < 0 || c < 0) throw FormatError("negative matrix size");
-      const long long n = kind == 'P' ? r * (r + 1) / 2 : r * c;
-      out->resize((size_t)n);
-      if (dbl) { need(8 * n); memcpy(out->data(), &d[p], 8 * n); p += 8 * n; }
-      else { need(4 * n); for (long long i = 0; i < n; i++) { float x; memcpy(&x, &d[p + 4 * i], 4); (*out)[i] = x; } p += 4 * n; }
+      if (r < 0 || c < 0 || r > 0x7fffffffLL || c > 0x7fffffffLL) throw FormatError("implausible matrix size in the file");
+      const size_t n = count(kind == 'P' ? r * (r + 1) / 2 : r * c, dbl ? 8 : 4);
+      out->resize(n);
+      if (dbl) { if (n) memcpy(out->data(), &d[p], 8 * n); p += 8 * n; }
+      else { for (size_t i = 0; i < n; i++) { float x; memcpy(&x, &d[p + 4 * i], 4); (*out)[i] = x; } p += 4 * n; }
       *rows = (int)r; *cols = kind == 'P' ? (int)r : (int)c;
       return;
     }
@@ -199,8 +215,8 @@ struct Reader {
       need(5);
       const int sz = d[p++];
       int32_t n; memcpy(&n, &d[p], 4); p += 4;
-      const long long cnt = (long long)n * (pairs ? 2 : 1);
-      need((size_t)cnt * sz);
+      if (sz != 1 && sz != 2 && sz != 4 && sz != 8) throw FormatError("bad integer vector element size");
+      const long long cnt = (long long)count((long long)n * (pairs ? 2 : 1), (size_t)sz);
       for (long long i = 0; i < cnt; i++) {
         long long x = 0;
         if (sz == 4) { int32_t y; memcpy(&y, &d[p + 4 * i], 4); x = y; } else if (sz == 8) memcpy(&x, &d[p + 8 * i], 8);
@@ -366,7 +382,8 @@ static void read_transition_model(Reader &r, std::vector<int32_t> *tid2pdf) {
     const int phone = (int)r.read_int(), hs = (int)r.read_int(), fwd = (int)r.read_int();
     const int sl = has_sl ? (int)r.read_int() : fwd;
     auto it = p2i.find(phone);
-    if (it == p2i.end() || hs < 0 || hs >= (int)entries[it->second].size()) throw FormatError("transition model: bad tuple");
+    if (it == p2i.end() || it->second < 0 || it->second >= (int)entries.size() || hs < 0 || hs >= (int)entries[it->second].size())
+      throw FormatError("transition model: bad tuple");
     for (auto &tr : entries[it->second][hs].tr) tid2pdf->push_back(tr.first == hs ? sl : fwd);
   }
   r.expect(has_sl ? "</Tuples>" : "</Triples>");
@@ -796,7 +813,7 @@ int b2k_ivec_files_read(const char *ie_path, const char *dubm_path, const char *
       rd.read_dense_d('V', &w, &r, &c);
       rd.expect("<M>");
       const long long G = rd.read_int();
-      if (G <= 0) throw FormatError("final.ie: no Gaussians");
+      if (G <= 0 || (unsigned long long)G > rd.d.size()) throw FormatError("final.ie: implausible number of Gaussians");
       std::vector<std::vector<double>> M((size_t)G), S((size_t)G);
       int Fd = 0, D = 0;
       for (long long g = 0; g < G; g++) {

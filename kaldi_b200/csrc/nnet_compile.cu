@@ -39,7 +39,7 @@ struct Node {
   int hsplit = 1;
   const float *w = nullptr; int w_rows = 0, w_cols = 0;
   std::vector<float> w_own;     // expanded convolution weights
-  const float *b = nullptr; std::vector<float> b_own; bool has_b = false;
+  const float *b = nullptr; std::vector<float> b_own; bool has_b = false; long long b_size = 0;
   bool relu = false, has_bn = false, has_res = false, log_softmax = false, ivector_rows = false;
   std::vector<float> bn_scale, bn_offset;
   std::string res_src; float res_alpha = 0.f;
@@ -114,7 +114,7 @@ static void expand_conv(const b2k_nnet_layer &L, const float *w, const float *b,
   n->w = n->w_own.data(); n->w_rows = Ho * Fo; n->w_cols = wc;
   n->b_own.resize((size_t)Ho * Fo);
   for (int ho = 0; ho < Ho; ho++) for (int fo = 0; fo < Fo; fo++) n->b_own[(size_t)ho * Fo + fo] = b[fo];
-  n->b = n->b_own.data(); n->has_b = true;
+  n->b = n->b_own.data(); n->has_b = true; n->b_size = (long long)n->b_own.size();
 }
 
 static bool build_graph(const b2k_nnet_compile_cfg &cfg, const b2k_nnet_layer *layers, int n_layers, const Weights &W,
@@ -142,7 +142,7 @@ static bool build_graph(const b2k_nnet_compile_cfg &cfg, const b2k_nnet_layer *l
       const b2k_nnet_weight *w = W.get(wname + ".w");
       NEED(w, wname + ".w");
       set_w(nd, w);
-      if (bias) { const b2k_nnet_weight *b = W.get(wname + ".b"); NEED(b, wname + ".b"); nd->b = b->data; nd->has_b = true; }
+      if (bias) { const b2k_nnet_weight *b = W.get(wname + ".b"); NEED(b, wname + ".b"); nd->b = b->data; nd->has_b = true; nd->b_size = b->size; }
       return true;
     };
     if (t == "idct") {
@@ -233,6 +233,12 @@ static bool build_graph(const b2k_nnet_compile_cfg &cfg, const b2k_nnet_layer *l
       } else {
         const b2k_nnet_weight *w = W.get(n + ".conv.w"), *b = W.get(n + ".conv.b");
         NEED(w, n + ".conv.w"); NEED(b, n + ".conv.b");
+        if (w->size != (long long)L.filters_out * L.n_time_offsets * L.n_height_offsets * L.filters_in || b->size != L.filters_out) {
+          err = "convolution parameters of " + n + " do not match the layer's filter and offset counts"; return false;
+        }
+        if (pending_combine && (pending_combine->filters1 + pending_combine->filters2 != L.filters_in || pending_combine->height != L.height_in)) {
+          err = "combine-feature-maps in front of " + n + " does not match its input maps"; return false;
+        }
         expand_conv(L, w->data, b->data, pending_combine, &x, &k_main, &k_side);
         if (!bn(&x, n + ".batchnorm", 1.0f, L.height_out)) return false;
       }
@@ -253,6 +259,72 @@ static bool build_graph(const b2k_nnet_compile_cfg &cfg, const b2k_nnet_layer *l
     } else {
       err = "unknown layer type " + t;
       return false;
+    }
+  }
+  return true;
+}
+
+// The layer list and the weights come from the caller (or from a file): everything the later stages index with is
+// checked here, so that an inconsistent model is B2K_ERR_INVALID instead of an out-of-bounds read.
+static bool validate_layers(const b2k_nnet_compile_cfg &cfg, const b2k_nnet_layer *layers, int n_layers, std::string &err) {
+  const int kMaxDim = 1 << 20;
+  if (cfg.feat_dim <= 0 || cfg.feat_dim > kMaxDim || cfg.ivector_dim < 0 || cfg.ivector_dim > kMaxDim || cfg.num_pdfs <= 0 || cfg.num_pdfs > kMaxDim ||
+      cfg.num_frames > (1 << 24) || n_layers > 4096) { err = "dimensions out of range"; return false; }
+  for (int i = 0; i < n_layers; i++) {
+    const b2k_nnet_layer &L = layers[i];
+    const std::string t = S(L.type, sizeof(L.type)), n = S(L.name, sizeof(L.name));
+    auto dim_ok = [&](int d) { return d > 0 && d <= kMaxDim; };
+    bool ok = true;
+    if (t == "relu-batchnorm" || t == "linear" || t == "output" || t == "ivector-linear-bn") ok = dim_ok(L.dim);
+    else if (t == "tdnnf") ok = dim_ok(L.dim) && dim_ok(L.bottleneck) && L.stride >= 0 && L.stride <= 64;
+    else if (t == "prefinal") ok = dim_ok(L.big) && dim_ok(L.small);
+    else if (t == "combine") ok = L.height > 0 && L.filters1 > 0 && L.filters2 >= 0 && (long long)L.height * (L.filters1 + (long long)L.filters2) <= kMaxDim;
+    else if (t == "conv") {
+      ok = L.height_in > 0 && L.height_out > 0 && L.height_subsample_out > 0 && L.filters_in > 0 && L.filters_out > 0 &&
+           L.n_time_offsets > 0 && L.n_time_offsets <= 8 && L.n_height_offsets > 0 && L.n_height_offsets <= 8 &&
+           (long long)L.height_in * L.filters_in <= kMaxDim && (long long)L.height_out * L.filters_out <= kMaxDim;
+      for (int k = 0; ok && k < L.n_time_offsets; k++) ok = L.time_offsets[k] >= -64 && L.time_offsets[k] <= 64;
+      for (int k = 0; ok && k < L.n_height_offsets; k++) ok = L.height_offsets[k] >= -64 && L.height_offsets[k] <= 64;
+    }
+    if (!ok) { err = "layer " + n + " (" + t + ") has dimensions out of range"; return false; }
+  }
+  return true;
+}
+
+static bool validate_graph(Graph &g, std::string &err) {
+  std::map<std::string, const Node *> by;
+  for (auto &n : g.nodes) {
+    if (by.count(n.name)) { err = "two nodes are called " + n.name; return false; }
+    by[n.name] = &n;
+  }
+  auto src_dim = [&](const std::string &s) -> int { auto it = by.find(s); return it == by.end() ? -1 : it->second->dim; };
+  for (auto &n : g.nodes) {
+    if (n.kind == 2) {
+      const int H = std::max(1, n.hsplit);
+      if (!n.w || n.dim <= 0 || n.dim % H != 0 || n.w_rows != n.dim / H || n.w_cols <= 0) { err = "parameters of " + n.name + " do not match its output dimension"; return false; }
+      int K = 0;
+      for (size_t i = 0; i < n.terms.size(); i++) {
+        const Term &t = n.terms[i];
+        const int sd = src_dim(t.src);
+        if (sd < 0) { err = n.name + " reads the unknown node " + t.src; return false; }
+        const int len = t.c1 - t.c0;
+        if (t.c0 < 0 || len <= 0) { err = "bad column range in " + n.name; return false; }
+        if (i < n.term_cols.size()) {                      // convolution patch: a window of the source row
+          const ColWin &c = n.term_cols[i];
+          if (c.lim <= 0 || c.lim > sd || c.step <= 0) { err = "bad convolution window in " + n.name; return false; }
+          // every in-range window start leaves len columns inside [0, lim)
+          for (int h = 0; h < H; h++) { const int cb = h * c.step + c.off; if (cb >= 0 && cb < c.lim && cb + len > sd) { err = "convolution window of " + n.name + " leaves its source row"; return false; } }
+        } else if (len > sd) { err = n.name + " reads more columns than " + t.src + " has"; return false; }
+        K = std::max(K, t.c1);
+      }
+      if (K != n.w_cols) { err = "parameters of " + n.name + " do not match its input dimension"; return false; }
+      if (n.has_b && n.b_size != n.w_rows) { err = "bias of " + n.name + " has the wrong length"; return false; }
+      if (n.has_bn && ((int)n.bn_scale.size() != n.w_rows || (int)n.bn_offset.size() != n.w_rows)) { err = "batchnorm statistics of " + n.name + " have the wrong length"; return false; }
+      if (n.has_res && src_dim(n.res_src) != n.dim) { err = "bypass input of " + n.name + " has a different dimension"; return false; }
+    } else if (n.kind == 3) {
+      if (n.block_dim <= 0 || (long long)n.block_dim * (long long)n.blocks.size() != n.dim) { err = "block layout of " + n.name + " does not match its dimension"; return false; }
+      for (auto &blk : n.blocks) for (auto &t : blk) if (src_dim(t.src) < n.block_dim) { err = n.name + " reads more columns than " + t.src + " has"; return false; }
+      if (n.has_bn && ((int)n.bn_scale.size() != n.dim || (int)n.bn_offset.size() != n.dim)) { err = "batchnorm statistics of " + n.name + " have the wrong length"; return false; }
     }
   }
   return true;
@@ -317,10 +389,17 @@ int b2k_nnet_compile(const b2k_nnet_compile_cfg *cfgp, const b2k_nnet_layer *lay
   const int sub = cfg.frame_subsampling_factor, T = cfg.num_frames, C = cfg.frames_per_chunk;
   if (sub <= 0 || T <= 0 || C <= 0 || C % sub != 0) return set_error(B2K_ERR_INVALID, "b2k_nnet_compile: frames_per_chunk must be a positive multiple of the subsampling factor");
   Weights W;
-  for (int i = 0; i < n_weights; i++) W.m[weights[i].name] = &weights[i];
+  for (int i = 0; i < n_weights; i++) {
+    const b2k_nnet_weight &w = weights[i];
+    if (!w.name || !w.data || w.size < 0 || w.rows < 0 || w.cols < 0 || (long long)w.rows * std::max(w.cols, 1) != w.size)
+      return set_error(B2K_ERR_INVALID, "b2k_nnet_compile: a weight's size does not match its shape", w.name ? w.name : "(unnamed)");
+    W.m[w.name] = &w;
+  }
   std::string err;
   Graph g;
+  if (!validate_layers(cfg, layers, n_layers, err)) return set_error(B2K_ERR_INVALID, "b2k_nnet_compile", err.c_str());
   if (!build_graph(cfg, layers, n_layers, W, false, &g, err)) return set_error(B2K_ERR_INVALID, "b2k_nnet_compile", err.c_str());
+  if (!validate_graph(g, err)) return set_error(B2K_ERR_INVALID, "b2k_nnet_compile", err.c_str());
   std::map<std::string, Node *> by;
   for (auto &n : g.nodes) by[n.name] = &n;
   if (!by.count("output")) return set_error(B2K_ERR_INVALID, "b2k_nnet_compile: no output layer");

@@ -1,0 +1,110 @@
+"""Truncated and corrupted input files must make the C++ readers of libb2k.so return an error (or a valid object), never
+crash, hang or ask for absurd amounts of memory: model files, graph files, WAVE files, option files.  Each family runs in a
+child process with an address-space limit, so that a crash shows up as a failed test."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = textwrap.dedent(r'''
+    import ctypes as C, os, resource, sys
+    import numpy as np
+    sys.path.insert(0, %(root)r)
+    resource.setrlimit(resource.RLIMIT_AS, (6 << 30, 6 << 30))
+    from kaldi_b200 import _lib
+    L = _lib.lib()
+    kind, src, tmp = %(kind)r, %(src)r, %(tmp)r
+    data = open(src, "rb").read()
+    rng = np.random.default_rng(1234)
+
+    def variants():
+        n = len(data)
+        for k in sorted(set([0, 1, 2, 3, 7, 16, 40, n // 3, n // 2, n - 5, n - 1] + rng.integers(0, n, 60).tolist())):
+            if 0 <= k < n:
+                yield data[:k]                                  # truncations
+        for _ in range(150):                                    # byte flips, mostly near the start where the structure is
+            b = bytearray(data)
+            for _ in range(int(rng.integers(1, 4))):
+                pos = int(rng.integers(0, min(n, 4096))) if rng.random() < 0.7 else int(rng.integers(0, n))
+                b[pos] = int(rng.integers(0, 256))
+            yield bytes(b)
+        for _ in range(40):                                     # 4-byte fields overwritten with extreme values
+            b = bytearray(data)
+            pos = int(rng.integers(0, max(1, min(n, 2048) - 4)))
+            b[pos:pos + 4] = [(0xff, 0xff, 0xff, 0x7f), (0xff, 0xff, 0xff, 0xff), (0, 0, 0, 0x80), (0, 0, 0, 0)][int(rng.integers(0, 4))]
+            yield bytes(b)
+
+    def call(path):
+        h = C.c_void_p()
+        if kind == "mdl":
+            L.b2k_model_read.argtypes = [C.c_char_p, C.c_int32, C.c_void_p]
+            rc = L.b2k_model_read(path, 1, C.byref(h))
+            if rc == 0:
+                L.b2k_model_destroy.argtypes = [C.c_void_p]; L.b2k_model_destroy(h)
+        elif kind == "fst":
+            L.b2k_fst_file_read.argtypes = [C.c_char_p, C.c_void_p]
+            rc = L.b2k_fst_file_read(path, C.byref(h))
+            if rc == 0:
+                L.b2k_fst_file_destroy.argtypes = [C.c_void_p]; L.b2k_fst_file_destroy(h)
+        elif kind == "wav":
+            L.b2k_wave_read.argtypes = [C.c_char_p, C.c_void_p]
+            rc = L.b2k_wave_read(path, C.byref(h))
+            if rc == 0:
+                L.b2k_wave_destroy.argtypes = [C.c_void_p]; L.b2k_wave_destroy(h)
+        elif kind == "conf":
+            buf = (C.c_char * 4096)()
+            L.b2k_feat_cfg_from_conf.argtypes = [C.c_char_p, C.c_int32, C.c_void_p]
+            rc = L.b2k_feat_cfg_from_conf(path, 0, buf)
+        return rc
+
+    ok = bad = 0
+    p = os.path.join(tmp, "fuzz.bin").encode()
+    for v in variants():
+        open(p, "wb").write(v)
+        if call(p) == 0: ok += 1
+        else: bad += 1
+    print("accepted", ok, "rejected", bad)
+''')
+
+
+def _run(kind, src, tmp_path):
+    so = os.path.join(ROOT, "kaldi_b200", "libb2k.so")
+    if not os.path.exists(so):
+        pytest.skip("libb2k.so not built")
+    r = subprocess.run([sys.executable, "-c", CHILD % dict(root=ROOT, kind=kind, src=src, tmp=str(tmp_path))], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, f"{kind}: child ended with {r.returncode}\n" + r.stdout[-1000:] + r.stderr[-3000:]
+    words = r.stdout.strip().split()
+    assert int(words[-1]) > 5 and int(words[1]) + int(words[-1]) > 200, r.stdout   # some variants are rejected, flips in payload bytes are fine
+
+
+def test_model_file_reader(tmp_path):
+    _run("mdl", os.path.join(ROOT, "tests", "golden", "tiny_final.mdl"), tmp_path)
+
+
+@pytest.mark.parametrize("fst_type", ["const", "vector"])
+def test_graph_file_reader(tmp_path, fst_type):
+    from kaldi_b200 import kaldi_io as KIO, synth
+    p = str(tmp_path / "HCLG.fst")
+    KIO.write_openfst(p, synth.make_hclg(3_000, num_pdfs=20, seed=5), fst_type)
+    _run("fst", p, tmp_path)
+
+
+def test_wave_reader(tmp_path):
+    import struct
+    x = np.random.default_rng(0).integers(-32768, 32768, 4000).astype("<i2").tobytes()
+    body = b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, 16000, 32000, 2, 16) + b"data" + struct.pack("<I", len(x)) + x
+    p = str(tmp_path / "a.wav")
+    open(p, "wb").write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    _run("wav", p, tmp_path)
+
+
+def test_option_file_reader(tmp_path):
+    p = str(tmp_path / "mfcc.conf")
+    open(p, "w").write("--use-energy=false   # comment\n--num-mel-bins=40\n--num-ceps=40\n--low-freq=20\n--high-freq=-400\n--dither=0\n" * 3)
+    _run("conf", p, tmp_path)
