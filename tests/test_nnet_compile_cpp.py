@@ -105,3 +105,31 @@ def test_cpp_compiler_equals_python_compiler(which, kw, T):
     # weights are copied bit for bit; the derived BatchNorm scales (powf) and log priors (logf) may differ from numpy by an ulp
     np.testing.assert_allclose(cp.blob, prog["blob"], rtol=1e-6, atol=0)
     assert (cp.blob != prog["blob"]).mean() < 0.05
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 4, 7, 20, 21, 22, 63, 64])
+def test_very_short_utterances_against_the_reference_forward(T):
+    """Utterances shorter than the model context and around the chunk boundaries: both compilers agree, and the compiled
+    program (numpy interpreter) reproduces the reference's looped forward (north-star tolerance 1e-4; observed ~1e-6)."""
+    try:
+        from kaldi_b200.nnet_compile import CompiledProgram
+    except Exception as e:
+        pytest.skip(str(e))
+    import os
+    from oracle import nnet_oracle as NO
+    from oracle import program_interp as PI
+    if not (os.path.exists(NO._SO) or os.path.isdir("/root/reference")):
+        pytest.skip("oracle/_ref nnet3 library not present")
+    arch = NM.arch_tiny(64)
+    W = NM.random_weights(arch, seed=9)
+    prog = NM.compile_program(arch, W, T, 21, use_priors=False)
+    cp = CompiledProgram(arch, W, T, 21, use_priors=False)
+    assert (cp.n_out, cp.n_chunks) == (prog["n_out"], prog["n_chunks"]) == ((T + 2) // 3, (((T + 2) // 3) * 3 + 20) // 21)
+    np.testing.assert_allclose(cp.blob, prog["blob"], rtol=1e-6, atol=0)
+    rng = np.random.default_rng(T)
+    feats = (rng.standard_normal((T, 40)) * 10).astype(np.float32)
+    iv = rng.standard_normal((T, 100)).astype(np.float32)
+    R = NO.RefNnet(arch, W, use_priors=False)
+    ref = R.forward(feats, iv, period=1)
+    out = PI.run_program(prog, feats, iv[R.chunk_ivector_rows(T, T, 1)])
+    assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max()
