@@ -81,12 +81,26 @@ def best_path(lat: dict) -> dict:
                 total_cost=float(tot[k]), states=np.array(states[::-1], np.int32))
 
 
-def _num(x: float) -> str:
-    return repr(float(np.float32(x))) if np.isfinite(x) else "Infinity"
+def _num(x: float, exact: bool = False) -> str:
+    """A float as the reference's weight printer writes it (LatticeWeightTpl::WriteFloatType, fstext/lattice-weight.h:148-160,
+    on a default-precision ostream): six significant digits, "Infinity" / "-Infinity" / "BadNumber"."""
+    x = float(np.float32(x))
+    if exact and x == x and abs(x) != float("inf"):
+        return repr(x)                                       # shortest text that reads back to the same float32
+    if x == float("inf"):
+        return "Infinity"
+    if x == float("-inf"):
+        return "-Infinity"
+    if x != x:
+        return "BadNumber"
+    return "%g" % x
 
 
-def write_lattice_text(f, key: str, lat: dict) -> None:
-    """One entry of a text-mode Lattice table (`ark,t`): arcs grouped by source state as an FST printer emits them."""
+def write_lattice_text(f, key: str, lat: dict, exact: bool = False) -> None:
+    """One entry of a text-mode Lattice table (`ark,t`): arcs grouped by source state as an FST printer emits them.  Numbers are
+    printed as the reference prints them (six significant digits); exact=True prints every float32 in full instead (the
+    reference's reader accepts both), for archives that must read back bit for bit."""
+    num = lambda x: _num(x, exact)
     f.write(key + "\n")
     src = lat["arc_src"]
     order = np.argsort(src, kind="stable")
@@ -95,9 +109,9 @@ def write_lattice_text(f, key: str, lat: dict) -> None:
     for s in range(len(lat["state_frame"])):
         for a in order[starts[s]:starts[s + 1]]:
             f.write(f"{s}\t{int(lat['arc_dst'][a])}\t{int(lat['arc_ilabel'][a])}\t{int(lat['arc_olabel'][a])}\t"
-                    f"{_num(lat['arc_graph_cost'][a])},{_num(lat['arc_acoustic_cost'][a])}\n")
+                    f"{num(lat['arc_graph_cost'][a])},{num(lat['arc_acoustic_cost'][a])}\n")
         if s in finals:
-            f.write(f"{s}\t{_num(finals[s])},0\n")
+            f.write(f"{s}\t{num(finals[s])},0\n")
     f.write("\n")
 
 
@@ -218,20 +232,21 @@ def compact_best_path(clat: dict) -> dict:
                 total_cost=float(tot[k]))
 
 
-def write_compact_lattice_text(f, key: str, clat: dict) -> None:
+def write_compact_lattice_text(f, key: str, clat: dict, exact: bool = False) -> None:
     """One entry of a text-mode CompactLattice table (lat/kaldi-lattice.cc WriteCompactLattice, text mode): key line,
     `src dst word graph,acoustic,tid_tid_...` per arc, `state graph,acoustic,tid_...` per final state, blank line."""
+    num = lambda x: _num(x, exact)
     f.write(key + "\n")
     order = np.argsort(clat["arc_src"], kind="stable")
     starts = np.searchsorted(clat["arc_src"][order], np.arange(clat["num_states"] + 1))
     fin = {int(s): i for i, s in enumerate(clat["final_state"])}
     for s in range(clat["num_states"]):
         for a in order[starts[s]:starts[s + 1]]:
-            f.write(f"{s}\t{int(clat['arc_dst'][a])}\t{int(clat['arc_word'][a])}\t{_num(clat['arc_graph_cost'][a])},"
-                    f"{_num(clat['arc_acoustic_cost'][a])},{'_'.join(str(int(t)) for t in clat['arc_tids'][a])}\n")
+            f.write(f"{s}\t{int(clat['arc_dst'][a])}\t{int(clat['arc_word'][a])}\t{num(clat['arc_graph_cost'][a])},"
+                    f"{num(clat['arc_acoustic_cost'][a])},{'_'.join(str(int(t)) for t in clat['arc_tids'][a])}\n")
         if s in fin:
             i = fin[s]
-            f.write(f"{s}\t{_num(clat['final_graph_cost'][i])},{_num(clat['final_acoustic_cost'][i])},"
+            f.write(f"{s}\t{num(clat['final_graph_cost'][i])},{num(clat['final_acoustic_cost'][i])},"
                     f"{'_'.join(str(int(t)) for t in clat['final_tids'][i])}\n")
     f.write("\n")
 

@@ -116,6 +116,16 @@ int32_t ref_lattice_weight_bytes(float g, float a, const int32_t *tids, int32_t 
   if ((int32_t)s.size() <= cap) memcpy(out, s.data(), s.size());
   return (int32_t)s.size();
 }
+// The text form of the two weight types: the reference's own operator<< (fstext/lattice-weight.h:396-403, 726-741), i.e. what
+// FstPrinter puts into the weight column of a text-mode lattice.  n < 0: LatticeWeight.
+int32_t ref_lattice_weight_text(float g, float a, const int32_t *tids, int32_t n, char *out, int32_t cap) {
+  std::ostringstream os;
+  if (n >= 0) os << kaldi::CompactLatticeWeight(kaldi::LatticeWeight(g, a), std::vector<int32_t>(tids, tids + n));
+  else os << kaldi::LatticeWeight(g, a);
+  const std::string s = os.str();
+  if ((int32_t)s.size() + 1 <= cap) memcpy(out, s.c_str(), s.size() + 1);
+  return (int32_t)s.size();
+}
 int32_t ref_lattice_type_strings(char *out, int32_t cap) {
   const std::string s = kaldi::LatticeWeight::Type() + " " + kaldi::CompactLatticeWeight::Type();
   if ((int32_t)s.size() + 1 <= cap) memcpy(out, s.c_str(), s.size() + 1);

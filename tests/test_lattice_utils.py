@@ -60,7 +60,7 @@ def test_best_path_is_the_cheapest_path(seed, cfgmod):
 def test_lattice_text_round_trip():
     lat = _lattice(1)
     buf = io.StringIO()
-    LT.write_lattice_text(buf, "utt1", lat)
+    LT.write_lattice_text(buf, "utt1", lat, exact=True)
     lines = buf.getvalue().split("\n")
     assert lines[0] == "utt1" and lines[-2] == "" and lines[-1] == ""
     arcs = [l.split("\t") for l in lines[1:] if l.count("\t") == 4]
@@ -70,7 +70,11 @@ def test_lattice_text_round_trip():
                   np.float32(a[4].split(",")[1]).view(np.int32).item()) for a in arcs)
     want = sorted(zip(lat["arc_src"].tolist(), lat["arc_dst"].tolist(), lat["arc_ilabel"].tolist(), lat["arc_olabel"].tolist(),
                       lat["arc_graph_cost"].view(np.int32).tolist(), lat["arc_acoustic_cost"].view(np.int32).tolist()))
-    assert got == want                     # repr(float32) round-trips bit for bit
+    assert got == want                     # exact=True: repr(float32) round-trips bit for bit
+    buf = io.StringIO()
+    LT.write_lattice_text(buf, "utt1", lat)            # default: the reference's six significant digits
+    w = [l.split("\t")[4].split(",") for l in buf.getvalue().split("\n")[1:] if l.count("\t") == 4]
+    assert all(len(x.replace("-", "").replace(".", "").split("e")[0].lstrip("0")) <= 6 for pair in w for x in pair)
 
 
 def _small_raw_and_compact():
@@ -212,3 +216,30 @@ def test_cpp_best_path_arcs_trace_the_same_path():
     # empty lattice: nothing, no error
     e = _RawLattice()
     assert L.b2k_lat_best_path_arcs(C.byref(e), None, C.byref(n), 0, C.byref(fi)) == 0 and n.value == 0 and fi.value == -1
+
+
+def test_text_weights_equal_the_references_printer():
+    """The weight column of text-mode lattices: the reference's own operator<< for LatticeWeight / CompactLatticeWeight."""
+    import ctypes as C
+    try:
+        from oracle import ref_det
+        if not ref_det.available():
+            pytest.skip("oracle/_ref determinizer library not present")
+        L = ref_det.lib()
+    except (OSError, RuntimeError) as e:
+        pytest.skip(str(e))
+    if not hasattr(L, "ref_lattice_weight_text"):
+        pytest.skip("oracle/_ref library predates ref_lattice_weight_text")
+    L.ref_lattice_weight_text.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    buf = C.create_string_buffer(512)
+    rng = np.random.default_rng(0)
+    cases = [(1.5, -2.25, [3, 1, 4]), (0.1, 1e-7, []), (123456.789, 0.30000001, [7]), (float("inf"), float("inf"), []),
+             (0.0, 0.0, [2 ** 30]), (1e10, -1e-10, [1, 2]), (float("-inf"), 3.0, [5])]
+    cases += [(float(np.float32(rng.normal() * 10.0 ** int(rng.integers(-6, 7)))), float(np.float32(rng.normal())), rng.integers(1, 999, rng.integers(0, 5)).tolist())
+              for _ in range(200)]
+    for g, a, tids in cases:
+        t = np.array(tids, np.int32)
+        L.ref_lattice_weight_text(g, a, t.ctypes.data, len(t), buf, 512)
+        assert buf.value.decode() == f"{LT._num(g)},{LT._num(a)},{'_'.join(str(int(x)) for x in tids)}"
+        L.ref_lattice_weight_text(g, a, None, -1, buf, 512)
+        assert buf.value.decode() == f"{LT._num(g)},{LT._num(a)}"
