@@ -108,10 +108,13 @@ def write_lattice_text(f, key: str, lat: dict, exact: bool = False) -> None:
     starts = np.searchsorted(src[order], np.arange(len(lat["state_frame"]) + 1))
     for s in range(len(lat["state_frame"])):
         for a in order[starts[s]:starts[s + 1]]:
-            f.write(f"{s}\t{int(lat['arc_dst'][a])}\t{int(lat['arc_ilabel'][a])}\t{int(lat['arc_olabel'][a])}\t"
-                    f"{num(lat['arc_graph_cost'][a])},{num(lat['arc_acoustic_cost'][a])}\n")
+            g, ac = float(lat["arc_graph_cost"][a]), float(lat["arc_acoustic_cost"][a])
+            # fst::FstPrinter with show_weight_one = false (kaldi-lattice.cc:406-409) leaves the weight column out when the
+            # weight is One(); the reference's reader accepts both forms (PARITY of this detail unpinned: no OpenFst here)
+            w = "" if (g == 0.0 and ac == 0.0) else f"\t{num(g)},{num(ac)}"
+            f.write(f"{s}\t{int(lat['arc_dst'][a])}\t{int(lat['arc_ilabel'][a])}\t{int(lat['arc_olabel'][a])}{w}\n")
         if s in finals:
-            f.write(f"{s}\t{num(finals[s])},0\n")
+            f.write(f"{s}\n" if finals[s] == 0.0 else f"{s}\t{num(finals[s])},0\n")
     f.write("\n")
 
 
@@ -242,10 +245,14 @@ def write_compact_lattice_text(f, key: str, clat: dict, exact: bool = False) -> 
     fin = {int(s): i for i, s in enumerate(clat["final_state"])}
     for s in range(clat["num_states"]):
         for a in order[starts[s]:starts[s + 1]]:
-            f.write(f"{s}\t{int(clat['arc_dst'][a])}\t{int(clat['arc_word'][a])}\t{num(clat['arc_graph_cost'][a])},"
-                    f"{num(clat['arc_acoustic_cost'][a])},{'_'.join(str(int(t)) for t in clat['arc_tids'][a])}\n")
+            g, ac, t = float(clat["arc_graph_cost"][a]), float(clat["arc_acoustic_cost"][a]), clat["arc_tids"][a]
+            w = "" if (g == 0.0 and ac == 0.0 and len(t) == 0) else f"\t{num(g)},{num(ac)},{'_'.join(str(int(x)) for x in t)}"   # One() omitted
+            f.write(f"{s}\t{int(clat['arc_dst'][a])}\t{int(clat['arc_word'][a])}{w}\n")
         if s in fin:
             i = fin[s]
+            if float(clat["final_graph_cost"][i]) == 0.0 and float(clat["final_acoustic_cost"][i]) == 0.0 and len(clat["final_tids"][i]) == 0:
+                f.write(f"{s}\n")
+                continue
             f.write(f"{s}\t{num(clat['final_graph_cost'][i])},{num(clat['final_acoustic_cost'][i])},"
                     f"{'_'.join(str(int(t)) for t in clat['final_tids'][i])}\n")
     f.write("\n")

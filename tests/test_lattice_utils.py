@@ -243,3 +243,15 @@ def test_text_weights_equal_the_references_printer():
         assert buf.value.decode() == f"{LT._num(g)},{LT._num(a)},{'_'.join(str(int(x)) for x in tids)}"
         L.ref_lattice_weight_text(g, a, None, -1, buf, 512)
         assert buf.value.decode() == f"{LT._num(g)},{LT._num(a)}"
+
+
+def test_text_tables_leave_out_unit_weights():
+    """FstPrinter with show_weight_one = false: an arc / final weight equal to One() has no weight column."""
+    f32, i32 = np.float32, np.int32
+    lat = dict(state_frame=np.zeros(3, i32), state_hclg=np.arange(3, dtype=i32), state_tot_cost=np.zeros(3, f32),
+               state_extra_cost=np.zeros(3, f32), arc_src=np.array([0, 1], i32), arc_dst=np.array([1, 2], i32),
+               arc_ilabel=np.array([4, 5], i32), arc_olabel=np.array([0, 9], i32), arc_graph_cost=np.array([0.0, 1.25], f32),
+               arc_acoustic_cost=np.array([0.0, -3.0], f32), final_state=np.array([2], i32), final_cost=np.array([0.0], f32))
+    buf = io.StringIO()
+    LT.write_lattice_text(buf, "u", lat)
+    assert buf.getvalue() == "u\n0\t1\t4\t0\n1\t2\t5\t9\t1.25,-3\n2\n\n"
