@@ -523,6 +523,11 @@ typedef struct b2k_clat b2k_clat;
  * reference reduces its beam when max_mem is hit, determinize-lattice-pruned.h:126-160) — see b2k_clat_effective_beam */
 int b2k_lat_determinize_pruned(const b2k_raw_lattice *raw, float beam, int64_t max_states, b2k_clat **out);
 float b2k_clat_effective_beam(const b2k_clat *clat);
+/* One table entry (lat/kaldi-lattice.cc WriteLattice / WriteCompactLattice) written or appended to `path`: binary = 1: key, ' ',
+ * "\0B", OpenFst VectorFst container (published layout, unpinned) with the reference's weight encodings; binary = 0: the text form
+ * (weights as the reference's printer writes them, unit weights left out).  kaldi_b200/lattice.py writes the same bytes. */
+int b2k_lat_write(const b2k_raw_lattice *raw, const char *key, const char *path, int32_t binary, int32_t append);
+int b2k_clat_write(const b2k_clat *clat, const char *key, const char *path, int32_t binary, int32_t append);
 /* n lattices on up to num_threads host threads (0 = all cores); out[i], status[i] per lattice (status may be NULL); returns the
  * first non-zero status.  Same results as n single calls. */
 int b2k_lat_determinize_pruned_batch(const b2k_raw_lattice *raws, int32_t n, float beam, int64_t max_states, int32_t num_threads,

@@ -22,10 +22,12 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <map>
 #include <queue>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -414,6 +416,149 @@ int b2k_lat_best_path_arcs(const b2k_raw_lattice *in, int64_t *arcs, int64_t *n_
   if (final_index) *final_index = best;
   if ((int64_t)path.size() > cap) return b2k::set_error(B2K_ERR_OVERFLOW, "b2k_lat_best_path_arcs: output buffer too small (size returned)");
   if (!path.empty()) memcpy(arcs, path.data(), 8 * path.size());
+  return B2K_OK;
+}
+
+// ---- table entries (lat/kaldi-lattice.cc WriteLattice / WriteCompactLattice): `key` + ' ' + "\0B" + VectorFst binary, or the
+// text form an FstPrinter gives (weights printed by the reference's own operator<<: "%g"-style floats, "Infinity", strings
+// joined by '_'; unit weights left out).  kaldi_b200/lattice.py writes the same bytes and is the test oracle of these two.
+}  // extern "C"
+
+namespace {
+struct Out {
+  FILE *f;
+  void bytes(const void *p, size_t n) { if (n && fwrite(p, 1, n, f) != n) throw std::runtime_error("write failed"); }
+  template <typename T> void put(T v) { bytes(&v, sizeof(T)); }
+  void str(const std::string &s) { put<int32_t>((int32_t)s.size()); bytes(s.data(), s.size()); }
+  void text(const std::string &s) { bytes(s.data(), s.size()); }
+};
+std::string num_text(float x) {
+  if (x == std::numeric_limits<float>::infinity()) return "Infinity";
+  if (x == -std::numeric_limits<float>::infinity()) return "-Infinity";
+  if (x != x) return "BadNumber";
+  char b[64];
+  snprintf(b, sizeof(b), "%g", (double)x);
+  return b;
+}
+void fst_header(Out &o, const char *arctype, int64_t start, int64_t ns) {
+  o.put<int32_t>(2125659606); o.str("vector"); o.str(arctype); o.put<int32_t>(2); o.put<int32_t>(0);
+  o.put<uint64_t>(0x3); o.put<int64_t>(start); o.put<int64_t>(ns); o.put<int64_t>(0);
+}
+// arcs grouped by source state, input order kept inside a state
+void group_by_src(const int32_t *src, int64_t na, int64_t ns, std::vector<int64_t> *off, std::vector<int64_t> *order) {
+  off->assign((size_t)ns + 1, 0);
+  for (int64_t a = 0; a < na; a++) { if (src[a] < 0 || src[a] >= ns) throw std::runtime_error("arc source out of range"); (*off)[src[a] + 1]++; }
+  for (int64_t s = 0; s < ns; s++) (*off)[s + 1] += (*off)[s];
+  order->resize((size_t)na);
+  std::vector<int64_t> fill(off->begin(), off->end() - 1);
+  for (int64_t a = 0; a < na; a++) (*order)[fill[src[a]]++] = a;
+}
+FILE *open_out(const char *path, int32_t append) {
+  FILE *f = fopen(path, append ? "ab" : "wb");
+  if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+  return f;
+}
+}  // namespace
+
+extern "C" {
+
+int b2k_lat_write(const b2k_raw_lattice *in, const char *key, const char *path, int32_t binary, int32_t append) {
+  if (!in || !key || !path || in->num_states < 0 || in->num_arcs < 0 || in->num_finals < 0) return b2k::set_error(B2K_ERR_INVALID, "b2k_lat_write: bad args");
+  FILE *f = nullptr;
+  try {
+    std::vector<int64_t> off, order;
+    group_by_src(in->arc_src, in->num_arcs, in->num_states, &off, &order);
+    const float inf = std::numeric_limits<float>::infinity();
+    std::vector<float> fin((size_t)in->num_states, inf);
+    for (int64_t k = 0; k < in->num_finals; k++) { if (in->final_state[k] < 0 || in->final_state[k] >= in->num_states) throw std::runtime_error("final state out of range"); fin[in->final_state[k]] = in->final_cost[k]; }
+    f = open_out(path, append);
+    Out o{f};
+    if (binary) {
+      o.text(std::string(key) + " "); o.put<char>(0); o.put<char>('B');
+      fst_header(o, "lattice4", in->num_states ? 0 : -1, in->num_states);
+      for (int64_t s = 0; s < in->num_states; s++) {
+        if (fin[s] != inf) { o.put<float>(fin[s]); o.put<float>(0.f); } else { o.put<float>(inf); o.put<float>(inf); }
+        o.put<int64_t>(off[s + 1] - off[s]);
+        for (int64_t k = off[s]; k < off[s + 1]; k++) {
+          const int64_t a = order[k];
+          o.put<int32_t>(in->arc_ilabel[a]); o.put<int32_t>(in->arc_olabel[a]); o.put<float>(in->arc_graph_cost[a]); o.put<float>(in->arc_acoustic_cost[a]); o.put<int32_t>(in->arc_dst[a]);
+        }
+      }
+    } else {
+      o.text(std::string(key) + "\n");
+      for (int64_t s = 0; s < in->num_states; s++) {
+        for (int64_t k = off[s]; k < off[s + 1]; k++) {
+          const int64_t a = order[k];
+          const float g = in->arc_graph_cost[a], ac = in->arc_acoustic_cost[a];
+          std::string l = std::to_string(s) + "\t" + std::to_string(in->arc_dst[a]) + "\t" + std::to_string(in->arc_ilabel[a]) + "\t" + std::to_string(in->arc_olabel[a]);
+          if (!(g == 0.f && ac == 0.f)) l += "\t" + num_text(g) + "," + num_text(ac);
+          o.text(l + "\n");
+        }
+        if (fin[s] != inf) o.text(fin[s] == 0.f ? std::to_string(s) + "\n" : std::to_string(s) + "\t" + num_text(fin[s]) + ",0\n");
+      }
+      o.text("\n");
+    }
+    fclose(f);
+  } catch (const std::exception &e) {
+    if (f) fclose(f);
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_lat_write", e.what());
+  }
+  return B2K_OK;
+}
+
+int b2k_clat_write(const b2k_clat *c, const char *key, const char *path, int32_t binary, int32_t append) {
+  if (!c || !key || !path) return b2k::set_error(B2K_ERR_INVALID, "b2k_clat_write: bad args");
+  FILE *f = nullptr;
+  try {
+    const int64_t ns = c->num_states, na = (int64_t)c->arc_src.size(), nf = (int64_t)c->final_state.size();
+    std::vector<int64_t> off, order;
+    group_by_src(c->arc_src.data(), na, ns, &off, &order);
+    std::vector<int64_t> fin((size_t)ns, -1);
+    for (int64_t k = 0; k < nf; k++) fin[c->final_state[k]] = k;
+    auto tids_of_arc = [&](int64_t a, const int32_t **p, int64_t *n) { *p = c->tids.data() + c->arc_str_off[a]; *n = c->arc_str_off[a + 1] - c->arc_str_off[a]; };
+    auto tids_of_final = [&](int64_t k, const int32_t **p, int64_t *n) { *p = c->tids.data() + c->final_str_off[k]; *n = c->final_str_off[k + 1] - c->final_str_off[k]; };
+    auto joined = [](const int32_t *p, int64_t n) { std::string s; for (int64_t i = 0; i < n; i++) { if (i) s += "_"; s += std::to_string(p[i]); } return s; };
+    f = open_out(path, append);
+    Out o{f};
+    const float inf = std::numeric_limits<float>::infinity();
+    if (binary) {
+      o.text(std::string(key) + " "); o.put<char>(0); o.put<char>('B');
+      fst_header(o, "compactlattice44", ns ? 0 : -1, ns);
+      auto weight = [&](float g, float a, const int32_t *p, int64_t n) { o.put<float>(g); o.put<float>(a); o.put<int32_t>((int32_t)n); o.bytes(p, 4 * (size_t)n); };
+      for (int64_t s = 0; s < ns; s++) {
+        const int32_t *p; int64_t n;
+        if (fin[s] >= 0) { tids_of_final(fin[s], &p, &n); weight(c->final_g[fin[s]], c->final_a[fin[s]], p, n); } else weight(inf, inf, nullptr, 0);
+        o.put<int64_t>(off[s + 1] - off[s]);
+        for (int64_t k = off[s]; k < off[s + 1]; k++) {
+          const int64_t a = order[k];
+          tids_of_arc(a, &p, &n);
+          o.put<int32_t>(c->arc_word[a]); o.put<int32_t>(c->arc_word[a]); weight(c->arc_g[a], c->arc_a[a], p, n); o.put<int32_t>(c->arc_dst[a]);
+        }
+      }
+    } else {
+      o.text(std::string(key) + "\n");
+      for (int64_t s = 0; s < ns; s++) {
+        const int32_t *p; int64_t n;
+        for (int64_t k = off[s]; k < off[s + 1]; k++) {
+          const int64_t a = order[k];
+          tids_of_arc(a, &p, &n);
+          std::string l = std::to_string(s) + "\t" + std::to_string(c->arc_dst[a]) + "\t" + std::to_string(c->arc_word[a]);
+          if (!(c->arc_g[a] == 0.f && c->arc_a[a] == 0.f && n == 0)) l += "\t" + num_text(c->arc_g[a]) + "," + num_text(c->arc_a[a]) + "," + joined(p, n);
+          o.text(l + "\n");
+        }
+        if (fin[s] >= 0) {
+          tids_of_final(fin[s], &p, &n);
+          const float g = c->final_g[fin[s]], a = c->final_a[fin[s]];
+          o.text((g == 0.f && a == 0.f && n == 0) ? std::to_string(s) + "\n" : std::to_string(s) + "\t" + num_text(g) + "," + num_text(a) + "," + joined(p, n) + "\n");
+        }
+      }
+      o.text("\n");
+    }
+    fclose(f);
+  } catch (const std::exception &e) {
+    if (f) fclose(f);
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_clat_write", e.what());
+  }
   return B2K_OK;
 }
 

@@ -255,3 +255,46 @@ def test_text_tables_leave_out_unit_weights():
     buf = io.StringIO()
     LT.write_lattice_text(buf, "u", lat)
     assert buf.getvalue() == "u\n0\t1\t4\t0\n1\t2\t5\t9\t1.25,-3\n2\n\n"
+
+
+@pytest.mark.parametrize("binary", [0, 1])
+def test_cpp_table_writers_write_the_same_bytes_as_the_python_ones(tmp_path, binary):
+    import ctypes as C
+    try:
+        from kaldi_b200 import _lib
+        from kaldi_b200.decoder import _RawLattice, _p
+        L = _lib.lib()
+    except OSError as e:
+        pytest.skip(str(e))
+    lat = _lattice(2)
+    lat["arc_graph_cost"][:3] = 0.0
+    lat["arc_acoustic_cost"][:3] = 0.0                      # a few unit weights
+    keep = {k: np.ascontiguousarray(lat[k], np.float32 if lat[k].dtype.kind == "f" else np.int32) for k in
+            ("state_frame", "state_hclg", "state_tot_cost", "state_extra_cost", "arc_src", "arc_dst", "arc_ilabel", "arc_olabel",
+             "arc_graph_cost", "arc_acoustic_cost", "final_state", "final_cost")}
+    r = _RawLattice()
+    r.num_states, r.num_arcs, r.num_finals = len(keep["state_frame"]), len(keep["arc_src"]), len(keep["final_state"])
+    for k, v in keep.items():
+        setattr(r, k, _p(v, C.c_float if v.dtype == np.float32 else C.c_int32))
+    p = str(tmp_path / "lat.ark")
+    L.b2k_lat_write.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32]
+    L.b2k_clat_write.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32]
+    assert L.b2k_lat_write(C.byref(r), b"utt-1", p.encode(), binary, 0) == 0
+    h = C.c_void_p()
+    L.b2k_lat_determinize_pruned.argtypes = [C.c_void_p, C.c_float, C.c_int64, C.c_void_p]
+    assert L.b2k_lat_determinize_pruned(C.byref(r), 8.0, 0, C.byref(h)) == 0
+    assert L.b2k_clat_write(h, b"utt-1", p.encode(), binary, 1) == 0            # appended
+    L.b2k_clat_destroy.argtypes = [C.c_void_p]
+    L.b2k_clat_destroy(h)
+    clat = LT.determinize_pruned(lat, 8.0)
+    buf = io.BytesIO() if binary else io.StringIO()
+    if binary:
+        LT.write_lattice_binary(buf, "utt-1", lat)
+        LT.write_compact_lattice_binary(buf, "utt-1", clat)
+        want = buf.getvalue()
+    else:
+        LT.write_lattice_text(buf, "utt-1", lat)
+        LT.write_compact_lattice_text(buf, "utt-1", clat)
+        want = buf.getvalue().encode()
+    assert open(p, "rb").read() == want
+    assert L.b2k_lat_write(C.byref(r), b"k", str(tmp_path / "no" / "such" / "dir").encode(), binary, 0) != 0
