@@ -452,6 +452,11 @@ int b2k_wave_read(const char *path, b2k_wave **out);
 int b2k_wave_destroy(b2k_wave *wave);
 int b2k_wave_info(const b2k_wave *wave, float *samp_freq, int32_t *channels, int64_t *samples);
 const float *b2k_wave_data(const b2k_wave *wave);
+/* ResampleWaveform (feat/resample.cc:368-376; LinearResample, low-pass at 0.99 x Nyquist of the lower rate, 6 zero crossings,
+ * flush): what AcceptWaveform applies under --allow-downsample / --allow-upsample (feat/online-feature.cc:138-150).  n_out is
+ * always set; with cap too small the call returns B2K_ERR_OVERFLOW.  Host only; within 1e-5 of the reference's output scale
+ * (its dot products run in BLAS order), tests/test_wave_cpp.py. */
+int b2k_resample_waveform(float orig_freq, const float *in, int64_t n_in, float new_freq, float *out, int64_t cap, int64_t *n_out);
 
 /* HCLG.fst: an OpenFst binary "vector" or "const" FST over StdArc -> the CSR view of b2k_fst_create (arc order = file
  * order = the order ConstFst iterates in, which the decoder's results depend on).  Host only, no OpenFst.

@@ -1,6 +1,7 @@
 // host_utils.cu — small host-only pieces of the online2 control flow that the batched pipeline needs
 // (no device code).  Python twins in kaldi_b200/ivector.py are the test oracles (tests/test_host_utils.py).
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -339,3 +340,64 @@ int b2k_wave_info(const b2k_wave *w, float *samp_freq, int32_t *channels, int64_
 const float *b2k_wave_data(const b2k_wave *w) { return w ? w->data.data() : nullptr; }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ sample-rate conversion of a whole waveform
+//
+// ResampleWaveform (feat/resample.cc:368-376): LinearResample with a low-pass at 0.99 * Nyquist of the lower rate and 6
+// zero crossings, flush = true.  What OnlineGenericBaseFeature::AcceptWaveform applies when --allow-downsample /
+// --allow-upsample lets a file of another rate in (feat/online-feature.cc:138-150).  Output sample k sits at time k / new_rate;
+// it is the dot product of the input around that time with a Hann-windowed sinc (resample.h:40-106), whose weights repeat
+// with the period of gcd(orig_rate, new_rate) and are computed once per phase.  The filter function is evaluated in float
+// like the reference's (FilterFunc takes and returns BaseFloat), the weights' time arguments in double.
+extern "C" int b2k_resample_waveform(float orig_freq, const float *in, int64_t n_in, float new_freq, float *out, int64_t cap, int64_t *n_out) {
+  if (!n_out || n_in < 0 || (n_in > 0 && !in) || cap < 0 || (cap > 0 && !out) || !(orig_freq > 0.f) || !(new_freq > 0.f) ||
+      orig_freq != (float)(int32_t)orig_freq || new_freq != (float)(int32_t)new_freq)
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_resample_waveform: bad args (rates must be positive whole numbers of Hz)");
+  const int32_t rin = (int32_t)orig_freq, rout = (int32_t)new_freq;
+  const float min_freq = std::min(orig_freq, new_freq);
+  const float cutoff = 0.99f * 0.5f * min_freq;              // BaseFloat arithmetic, as in ResampleWaveform
+  const int32_t num_zeros = 6;
+  auto gcd = [](int32_t a, int32_t b) { while (b) { const int32_t t = a % b; a = b; b = t; } return a; };
+  const int32_t base = gcd(rin, rout), in_unit = rin / base, out_unit = rout / base;
+  // number of output samples: the largest k with k / rout < n_in / rin (GetNumOutputSamples with flush = true)
+  const int64_t tick = (int64_t)rin / base * rout;            // lcm
+  const int64_t per_in = tick / rin, per_out = tick / rout, interval = n_in * per_in;
+  int64_t total = 0;
+  if (interval > 0) { int64_t last = interval / per_out; if (last * per_out == interval) last--; total = last + 1; }
+  *n_out = total;
+  if (total > cap) return b2k::set_error(B2K_ERR_OVERFLOW, "b2k_resample_waveform: output buffer too small (size returned)");
+  auto filter_func = [&](float t) -> float {                  // LinearResample::FilterFunc (resample.cc:246-259)
+    float window, filter;
+    if (fabs(t) < num_zeros / (2.0 * cutoff)) window = (float)(0.5 * (1 + cos(6.283185307179586476925286766559005 * cutoff / num_zeros * t)));
+    else window = 0.0f;
+    if (t != 0) filter = (float)(sin(6.283185307179586476925286766559005 * cutoff * t) / (3.1415926535897932384626433832795 * t));
+    else filter = 2 * cutoff;
+    return filter * window;
+  };
+  const double window_width = num_zeros / (2.0 * cutoff);
+  std::vector<int32_t> first((size_t)out_unit);
+  std::vector<std::vector<float>> weights((size_t)out_unit);
+  for (int32_t i = 0; i < out_unit; i++) {
+    const double output_t = i / (double)rout, min_t = output_t - window_width, max_t = output_t + window_width;
+    const int32_t lo = (int32_t)ceil(min_t * rin), hi = (int32_t)floor(max_t * rin);
+    first[i] = lo;
+    weights[i].resize((size_t)std::max(0, hi - lo + 1));
+    for (int32_t j = 0; j <= hi - lo; j++) {
+      const double input_t = (lo + j) / (double)rin, delta_t = input_t - output_t;
+      weights[i][j] = filter_func((float)delta_t) / rin;
+    }
+  }
+  for (int64_t k = 0; k < total; k++) {
+    const int64_t unit = k / out_unit;
+    const int32_t ph = (int32_t)(k - unit * out_unit);
+    const int64_t f0 = first[ph] + unit * in_unit;
+    const std::vector<float> &w = weights[ph];
+    float acc = 0.0f;
+    for (size_t j = 0; j < w.size(); j++) {
+      const int64_t idx = f0 + (int64_t)j;
+      if (idx >= 0 && idx < n_in) acc += w[j] * in[idx];      // beyond either end: zero (flush = true, no remainder)
+    }
+    out[k] = acc;
+  }
+  return B2K_OK;
+}

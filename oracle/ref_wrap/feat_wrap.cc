@@ -16,6 +16,7 @@
 #include "feat/feature-mfcc.h"
 #include "feat/online-feature.h"
 #include "matrix/kaldi-matrix.h"
+#include "feat/resample.h"
 #include "feat/wave-reader.h"
 #include "util/parse-options.h"
 
@@ -171,6 +172,19 @@ int ref_wave_read(const char *path, float *out, long long cap, int *channels, lo
     return 0;
   } catch (const std::exception &) {
     return 1;
+  }
+}
+
+// ResampleWaveform (feat/resample.cc:368): the oracle of b2k_resample_waveform.  Returns the number of output samples (-1 on error).
+long long ref_resample_waveform(float orig_freq, const float *in, long long n, float new_freq, float *out, long long cap) {
+  try {
+    kaldi::Vector<kaldi::BaseFloat> w(n), o;
+    for (long long i = 0; i < n; i++) w(i) = in[i];
+    kaldi::ResampleWaveform(orig_freq, w, new_freq, &o);
+    for (long long i = 0; i < o.Dim() && i < cap; i++) out[i] = o(i);
+    return o.Dim();
+  } catch (const std::exception &) {
+    return -1;
   }
 }
 

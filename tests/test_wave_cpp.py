@@ -125,3 +125,52 @@ def test_both_reject_invalid_files(tmp_path, name):
     open(p, "wb").write(BAD[name])
     assert _reference(p) is None, "the reference accepts this file: fix the test"
     assert _mine(p) is None
+
+
+@pytest.mark.parametrize("rin,rout,n", [(8000, 16000, 4000), (44100, 16000, 9000), (48000, 16000, 4801), (16000, 8000, 3000),
+                                        (22050, 16000, 5000), (16000, 16000, 1000), (8000, 16000, 1), (44100, 16000, 2), (11025, 16000, 0)])
+def test_resampler_equals_the_references(rin, rout, n):
+    """ResampleWaveform (feat/resample.cc): same number of output samples, values within 1e-5 of the output scale (the
+    reference's dot products are BLAS calls, ours a plain left-to-right loop)."""
+    try:
+        from kaldi_b200 import _lib
+        L = _lib.lib()
+    except OSError as e:
+        pytest.skip(str(e))
+    from oracle import feat_oracle as F
+    R = F.RefFeat()
+    if not hasattr(R.lib, "ref_resample_waveform"):
+        pytest.skip("oracle/_ref feature library predates ref_resample_waveform")
+    rng = np.random.default_rng(rin + rout + n)
+    t = np.arange(n) / rin
+    x = (3000 * np.sin(2 * np.pi * 440 * t) + 1000 * np.sin(2 * np.pi * 3100 * t) + rng.normal(0, 300, n)).astype(np.float32)
+    ref = np.zeros(int(n * rout / rin) + 16, np.float32)
+    R.lib.ref_resample_waveform.restype = C.c_longlong
+    R.lib.ref_resample_waveform.argtypes = [C.c_float, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p, C.c_longlong]
+    nr = R.lib.ref_resample_waveform(float(rin), x.ctypes.data, n, float(rout), ref.ctypes.data, ref.size)
+    assert 0 <= nr <= ref.size
+    L.b2k_resample_waveform.argtypes = [C.c_float, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
+    no = C.c_int64()
+    rc = L.b2k_resample_waveform(float(rin), x.ctypes.data, n, float(rout), None, 0, C.byref(no))
+    assert no.value == nr and rc == (0 if nr == 0 else 4)      # size query: B2K_ERR_OVERFLOW with the size set
+    out = np.zeros(max(nr, 1), np.float32)
+    assert L.b2k_resample_waveform(float(rin), x.ctypes.data, n, float(rout), out.ctypes.data, out.size, C.byref(no)) == 0
+    if nr:
+        scale = max(1.0, float(np.abs(ref[:nr]).max()))
+        assert np.abs(out[:nr] - ref[:nr]).max() <= 1e-5 * scale
+    if rin == rout and n:
+        np.testing.assert_allclose(out[:nr], x[:nr], rtol=0, atol=1e-5 * 4000 + 0.05 * 4000)   # an (almost) identity low-pass
+
+
+def test_resampler_rejects_bad_arguments():
+    try:
+        from kaldi_b200 import _lib
+        L = _lib.lib()
+    except OSError as e:
+        pytest.skip(str(e))
+    L.b2k_resample_waveform.argtypes = [C.c_float, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
+    x = np.zeros(10, np.float32)
+    n = C.c_int64()
+    assert L.b2k_resample_waveform(0.0, x.ctypes.data, 10, 16000.0, None, 0, C.byref(n)) == 1
+    assert L.b2k_resample_waveform(8000.5, x.ctypes.data, 10, 16000.0, None, 0, C.byref(n)) == 1
+    assert L.b2k_resample_waveform(8000.0, None, 10, 16000.0, None, 0, C.byref(n)) == 1
