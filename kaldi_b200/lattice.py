@@ -406,3 +406,29 @@ def scale_compact_lattice(clat: dict, graph_scale: float = 1.0, acoustic_scale: 
                  ("final_acoustic_cost", acoustic_scale)):
         out[k] = (clat[k].astype(np.float32) * np.float32(s)).astype(np.float32)
     return out
+
+
+def read_symbol_table(path: str) -> dict:
+    """words.txt / phones.txt (fst::SymbolTable::ReadText: one `symbol id` pair per line, whitespace separated) as {id: symbol}:
+    what online2-wav-nnet3-latgen-faster uses to print the transcript of the best path (online2-wav-nnet3-latgen-faster.cc:66-76)."""
+    out = {}
+    with open(path, encoding="utf-8") as f:
+        for ln, line in enumerate(f, 1):
+            parts = line.split()
+            if not parts:
+                continue
+            if len(parts) != 2:
+                raise ValueError(f"{path}:{ln}: expected `symbol id`")
+            try:
+                out[int(parts[1])] = parts[0]
+            except ValueError:
+                raise ValueError(f"{path}:{ln}: the id is not an integer") from None
+    return out
+
+
+def transcript(word_ids, symbols: dict) -> str:
+    """The words of a best path, separated by single spaces, as the tool prints them after the utterance id."""
+    missing = [int(w) for w in word_ids if int(w) not in symbols]
+    if missing:
+        raise KeyError(f"Word-id {missing[0]} not in symbol table.")              # the tool's own message (:73)
+    return " ".join(symbols[int(w)] for w in word_ids)

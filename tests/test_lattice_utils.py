@@ -298,3 +298,16 @@ def test_cpp_table_writers_write_the_same_bytes_as_the_python_ones(tmp_path, bin
         want = buf.getvalue().encode()
     assert open(p, "rb").read() == want
     assert L.b2k_lat_write(C.byref(r), b"k", str(tmp_path / "no" / "such" / "dir").encode(), binary, 0) != 0
+
+
+def test_symbol_table_and_transcript(tmp_path):
+    p = str(tmp_path / "words.txt")
+    open(p, "w", encoding="utf-8").write("<eps> 0\nhello 1\nwörld\t2\n\n#0 3\n")
+    st = LT.read_symbol_table(p)
+    assert st == {0: "<eps>", 1: "hello", 2: "wörld", 3: "#0"}
+    assert LT.transcript(np.array([1, 2, 1], np.int32), st) == "hello wörld hello" and LT.transcript([], st) == ""
+    with pytest.raises(KeyError):
+        LT.transcript([7], st)
+    open(p, "w").write("only-one-column\n")
+    with pytest.raises(ValueError):
+        LT.read_symbol_table(p)
