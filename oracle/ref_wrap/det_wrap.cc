@@ -4,6 +4,7 @@
 // (determinize-lattice-pruned.cc:1486-1506: Invert, TopSort, ArcSort, [phone-level pass,] word-level pass, Connect)
 // and comes back as flat compact-lattice arrays.  Oracle of kaldi_b200/csrc/lattice_det.cu (tests/test_lattice_det.py).
 #include <cstdint>
+#include <chrono>
 #include <cstring>
 #include <sstream>
 #include <string>
@@ -30,6 +31,8 @@ class ArrayTransitionInformation : public kaldi::TransitionInformation {
   std::vector<uint8_t> loop_, start_;
   std::vector<int32_t> pdf_;
 };
+
+double g_last_ms = 0.0;   // wall time of the last DeterminizeLatticePhonePrunedWrapper call alone
 
 struct Out {
   std::vector<int32_t> arc_src, arc_dst, arc_word, final_state, tids;
@@ -64,7 +67,9 @@ void *ref_det_run(int32_t num_states, int64_t num_arcs, const int32_t *src, cons
   if (max_mem > 0) opts.max_mem = max_mem;
   CompactLattice clat;
   Out *o = new Out();
+  const auto t0 = std::chrono::steady_clock::now();
   o->ok = fst::DeterminizeLatticePhonePrunedWrapper(tm, &lat, beam, &clat, opts) ? 1 : 0;
+  g_last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   o->num_states = clat.NumStates();
   o->arc_off.push_back(0);
   // the start state is made state 0 (Connect keeps relative order; TopSort put the start first)
@@ -105,6 +110,7 @@ void ref_det_copy(void *h, int32_t *arc_src, int32_t *arc_dst, int32_t *arc_word
 }
 
 void ref_det_free(void *h) { delete (Out *)h; }
+double ref_det_last_ms() { return g_last_ms; }
 
 // The reference's own binary encodings: CompactLatticeWeightTpl::Write (fstext/lattice-weight.h:531-540) when n >= 0,
 // LatticeWeightTpl::Write (:141-146) when n < 0; and the arc type strings of the two lattice types.  Returns the byte count.
