@@ -39,7 +39,7 @@ def _build(d):
     n_tids = R.lib.ref_write_final_mdl(R.h, os.path.join(d, "final.mdl").encode(), 1, CHAIN_TOPO.encode(), 5, 2, pri.ctypes.data, pri.size,
                                        t2p.ctypes.data, t2p.size)
     assert n_tids > 0
-    ex = make_synthetic_extractor(seed=1, num_gauss=6, feat_dim=8, ivector_dim=100, splice=3, base_dim=40)
+    ex = make_synthetic_extractor(seed=1, num_gauss=64, feat_dim=40, ivector_dim=100, splice=3, base_dim=40)   # sizes the GPU tests use
     RI = IV.RefIvector(ex)
     RI.lib.ref_ivector_write.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
     ie = os.path.join(d, "ivector_extractor")
@@ -74,7 +74,7 @@ def test_consistent_directory_is_accepted_and_sized(tmp_path):
     assert r["ok"] and r["feature_type"] == "mfcc" and r["other_options"] == ["--endpoint.silence-phones=1:2"]
     assert r["features"]["dim"] == 40 and r["features"]["dither"] == 0.0
     assert r["model"]["num_pdfs"] == 10 and r["model"]["ivector_dim"] == 100 and r["model"]["transition_ids"] == n_tids
-    assert r["ivector_extractor"]["splice"] == [3, 3] and r["ivector_extractor"]["lda"] == [8, 281] and r["ivector_extractor"]["max_count"] == 100.0
+    assert r["ivector_extractor"]["splice"] == [3, 3] and r["ivector_extractor"]["lda"] == [40, 281] and r["ivector_extractor"]["max_count"] == 100.0
     assert r["graph_info"]["type"] == "const" and r["graph_info"]["max_ilabel"] <= n_tids
     assert r["plan"]["feature_frames"] == 1 + (32000 - 400) // 160 and r["plan"]["output_frames"] == (r["plan"]["feature_frames"] + 2) // 3
     assert r["warnings"] == []
