@@ -48,15 +48,16 @@ inline int cmp_w(const W &x, const W &y) {                  // 1: x better (latt
 }
 inline W times(const W &x, const W &y) { return W{x.g + y.g, x.a + y.a}; }
 inline W divide(const W &x, const W &y) { return W{x.g - y.g, x.a - y.a}; }
-inline int cmp_str(const std::vector<int32_t> &x, const std::vector<int32_t> &y) {   // 1: x better (:594-603)
-  if (x.size() > y.size()) return -1;
-  if (x.size() < y.size()) return 1;
-  for (size_t i = 0; i < x.size(); i++) { if (x[i] < y[i]) return -1; if (x[i] > y[i]) return 1; }
+
+// an element's transition-id string lives in one append-only pool per call: (offset, length) — taking a prefix off is a
+// change of offset, extending copies into the pool's tail, nothing is allocated per element
+struct Elem { int32_t state; W w; int64_t s_off = 0; int32_t s_len = 0; };
+inline int cmp_span(const int32_t *x, int32_t nx, const int32_t *y, int32_t ny) {     // 1: x better (:594-603)
+  if (nx > ny) return -1;
+  if (nx < ny) return 1;
+  for (int32_t i = 0; i < nx; i++) { if (x[i] < y[i]) return -1; if (x[i] > y[i]) return 1; }
   return 0;
 }
-
-struct Elem { int32_t state; W w; std::vector<int32_t> str; };
-inline bool better(const Elem &x, const Elem &y) { int c = cmp_w(x.w, y.w); return c ? c > 0 : cmp_str(x.str, y.str) > 0; }
 
 struct Key {                                               // identity of a determinized state
   std::vector<int32_t> ints;                                // per element: state, g bits, a bits, len, string...
@@ -125,6 +126,22 @@ static int determinize_once(const b2k_raw_lattice *in, float beam, int64_t max_s
   }
   if (!std::isfinite(beta[0])) { C->final_str_off.push_back(0); *out = C; return B2K_OK; }   // no final state reachable
   const double cutoff = beta[0] + (double)beam;
+  std::vector<int32_t> pool;
+  pool.reserve((size_t)A * 4 + 1024);
+  auto better = [&](const Elem &x, const Elem &y) {
+    const int c = cmp_w(x.w, y.w);
+    return c ? c > 0 : cmp_span(pool.data() + x.s_off, x.s_len, pool.data() + y.s_off, y.s_len) > 0;
+  };
+  // string of `src` plus one transition-id (0 = nothing to add) for a new element
+  auto extend = [&](const Elem &src, int32_t tid, Elem *dst) {
+    if (tid == 0) { dst->s_off = src.s_off; dst->s_len = src.s_len; return; }
+    const size_t off = pool.size(), need = off + (size_t)src.s_len + 1;
+    if (pool.capacity() < need) pool.reserve(std::max(need, 2 * pool.capacity()));
+    pool.resize(need);                                       // no reallocation after the reserve: source and target do not overlap
+    if (src.s_len) memcpy(&pool[off], &pool[(size_t)src.s_off], 4 * (size_t)src.s_len);
+    pool[off + (size_t)src.s_len] = tid;
+    dst->s_off = (int64_t)off; dst->s_len = src.s_len + 1;
+  };
 
   // closure over word-epsilon arcs in topological order, best element per input state; elements that cannot lie on a
   // path within the beam are dropped; then the common weight and the common string prefix are split off
@@ -159,8 +176,7 @@ static int determinize_once(const b2k_raw_lattice *in, float beam, int64_t max_s
         Elem e;
         e.state = in->arc_dst[a];
         e.w = times(cur.w, W{in->arc_graph_cost[a], in->arc_acoustic_cost[a]});
-        e.str = cur.str;
-        if (in->arc_ilabel[a] != 0) e.str.push_back(in->arc_ilabel[a]);
+        extend(cur, in->arc_ilabel[a], &e);
         const bool wasnew = tmp_slot[e.state] < 0;
         offer(std::move(e));
         if (wasnew && tmp_slot[in->arc_dst[a]] >= 0) pq.push({rank[in->arc_dst[a]], in->arc_dst[a]});
@@ -172,14 +188,14 @@ static int determinize_once(const b2k_raw_lattice *in, float beam, int64_t max_s
     std::sort(kept.begin(), kept.end(), [](const Elem &x, const Elem &y) { return x.state < y.state; });
     W cw = kept[0].w;
     for (auto &e : kept) if (cmp_w(e.w, cw) > 0) cw = e.w;
-    size_t pre = kept[0].str.size();
+    int32_t pre = kept[0].s_len;
     for (auto &e : kept) {
-      size_t k = 0;
-      while (k < pre && k < e.str.size() && e.str[k] == kept[0].str[k]) k++;
+      int32_t k = 0;
+      while (k < pre && k < e.s_len && pool[e.s_off + k] == pool[kept[0].s_off + k]) k++;
       pre = k;
     }
-    common_s->assign(kept[0].str.begin(), kept[0].str.begin() + pre);
-    for (auto &e : kept) { e.w = divide(e.w, cw); e.str.erase(e.str.begin(), e.str.begin() + pre); }
+    common_s->assign(pool.begin() + kept[0].s_off, pool.begin() + kept[0].s_off + pre);
+    for (auto &e : kept) { e.w = divide(e.w, cw); e.s_off += pre; e.s_len -= pre; }
     *common_w = cw;
     seed.swap(kept);
     return true;
@@ -196,8 +212,8 @@ static int determinize_once(const b2k_raw_lattice *in, float beam, int64_t max_s
     for (auto &e : elems) {
       int32_t gb, ab;
       memcpy(&gb, &e.w.g, 4); memcpy(&ab, &e.w.a, 4);
-      k.ints.push_back(e.state); k.ints.push_back(gb); k.ints.push_back(ab); k.ints.push_back((int32_t)e.str.size());
-      k.ints.insert(k.ints.end(), e.str.begin(), e.str.end());
+      k.ints.push_back(e.state); k.ints.push_back(gb); k.ints.push_back(ab); k.ints.push_back(e.s_len);
+      k.ints.insert(k.ints.end(), pool.begin() + e.s_off, pool.begin() + e.s_off + e.s_len);
       mr = std::min(mr, rank[e.state]);
     }
     auto it = index.find(k);
@@ -230,11 +246,11 @@ static int determinize_once(const b2k_raw_lattice *in, float beam, int64_t max_s
     {
       bool have = false; Elem bestf;
       for (auto &e : elems) if (std::isfinite(final_cost[e.state])) {
-        Elem f; f.state = e.state; f.w = times(e.w, W{final_cost[e.state], 0.f}); f.str = e.str;
+        Elem f = e; f.w = times(e.w, W{final_cost[e.state], 0.f});
         if (!have || better(f, bestf)) { bestf = std::move(f); have = true; }
       }
       if (have && alpha + (double)bestf.w.g + (double)bestf.w.a <= cutoff) {
-        W w = bestf.w; std::vector<int32_t> s = bestf.str;
+        W w = bestf.w; std::vector<int32_t> s(pool.begin() + bestf.s_off, pool.begin() + bestf.s_off + bestf.s_len);
         if (cur == 0) { w = times(start_w, w); s.insert(s.begin(), start_s.begin(), start_s.end()); }
         fin_state.push_back((int32_t)cur); fin_g.push_back(w.g); fin_a.push_back(w.a); fin_str.push_back(std::move(s));
       }
@@ -248,8 +264,7 @@ static int determinize_once(const b2k_raw_lattice *in, float beam, int64_t max_s
         if (word == 0) continue;
         Elem n; n.state = in->arc_dst[a];
         n.w = times(e.w, W{in->arc_graph_cost[a], in->arc_acoustic_cost[a]});
-        n.str = e.str;
-        if (in->arc_ilabel[a] != 0) n.str.push_back(in->arc_ilabel[a]);
+        extend(e, in->arc_ilabel[a], &n);
         by_word[word].push_back(std::move(n));
       }
     for (auto &kv : by_word) {
