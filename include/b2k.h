@@ -601,6 +601,13 @@ int b2k_pipeline_get_raw_lattices(b2k_pipeline *p, int32_t n, b2k_raw_lattice *o
  * features, [max_batch x chunks x ivector_dim] i-vectors, [max_batch x output frames x pdfs] log-likelihoods. */
 /* Copies a stage output of batch slots 0..n-1 to the host and waits: what = 0 features, 1 i-vectors, 2 log-likelihoods. */
 int b2k_pipeline_read(b2k_pipeline *p, int32_t what, int32_t n, float *h_out, void *stream);
+/* Decoder / decodable / tool options in the tool's own spelling ("--beam=15 --lattice-beam=8 --acoustic-scale=1.0
+ * --frames-per-chunk=20 ...", one per line or blank-separated, e.g. b2k_online_conf.rest or a command line): applied to cfg as
+ * LatticeFasterDecoderConfig / NnetSimpleLoopedComputationOptions would take them (decoder/lattice-faster-decoder.h:75-98,
+ * nnet3/decodable-simple-looped.h:66-88; --frames-per-chunk is rounded up to the subsampling factor as GetChunkSize does).
+ * endpoint.* / ivector-silence-weighting.* / det.* and the options without effect here are accepted and ignored; an unknown
+ * option is an error.  Host only. */
+int b2k_pipeline_cfg_apply_options(const char *text, b2k_pipeline_cfg *cfg);
 b2k_dec *b2k_pipeline_decoder(b2k_pipeline *p);
 const float *b2k_pipeline_features(const b2k_pipeline *p);
 const float *b2k_pipeline_ivectors(const b2k_pipeline *p);

@@ -242,6 +242,65 @@ int b2k_online_conf_read(const char *conf_path, b2k_online_conf *out) {
 
 }  // extern "C"
 
+// The decoder / decodable / tool options that may sit beside the feature group in the same option file or on the tool's command
+// line: LatticeFasterDecoderConfig::Register (decoder/lattice-faster-decoder.h:75-98), NnetSimpleLoopedComputationOptions::Register
+// (nnet3/decodable-simple-looped.h:66-88) and the tool's own --chunk-length (online2-wav-nnet3-latgen-faster.cc:112).  `text` is one
+// option per line or blank-separated (b2k_online_conf.rest has that form).  Option groups this library does not act on are accepted
+// and ignored by prefix (endpoint.*, ivector-silence-weighting.*, det.*) or by name (word-symbol-table, do-endpointing, online,
+// num-threads-startup, determinize-lattice, memory-pool-*, debug-computation); values that would change what is computed and
+// are not supported are errors (extra-left-context-initial != 0, a frame-subsampling-factor other than the model's is caught
+// later by b2k_pipeline_plan_for through frames_per_chunk).
+extern "C" int b2k_pipeline_cfg_apply_options(const char *text, b2k_pipeline_cfg *cfg) {
+  if (!text || !cfg) return b2k::set_error(B2K_ERR_INVALID, "b2k_pipeline_cfg_apply_options: bad args");
+  b2k_pipeline_cfg c = *cfg;
+  int32_t prune_interval = c.dec.prune_interval, sub = 3, fpc = 20, extra_left = 0, ign_i = 0;
+  float ign_f = 0.f;
+  char ign_s[512] = "";
+  const Opt opts[] = {{"beam", 'f', &c.dec.beam}, {"max-active", 'i', &c.dec.max_active}, {"min-active", 'i', &c.dec.min_active},
+                      {"lattice-beam", 'f', &c.dec.lattice_beam}, {"prune-interval", 'i', &prune_interval}, {"beam-delta", 'f', &c.dec.beam_delta},
+                      {"hash-ratio", 'f', &c.dec.hash_ratio}, {"acoustic-scale", 'f', &c.acoustic_scale}, {"frames-per-chunk", 'i', &fpc},
+                      {"frame-subsampling-factor", 'i', &sub}, {"extra-left-context-initial", 'i', &extra_left}, {"chunk-length", 'f', &c.chunk_length_secs},
+                      {"determinize-lattice", 'b', &ign_i}, {"memory-pool-tokens-block-size", 'i', &ign_i}, {"memory-pool-links-block-size", 'i', &ign_i},
+                      {"debug-computation", 'b', &ign_i}, {"word-symbol-table", 's', ign_s}, {"do-endpointing", 'b', &ign_i}, {"online", 'b', &ign_i},
+                      {"num-threads-startup", 'i', &ign_i}};
+  (void)ign_f;
+  try {
+    std::map<std::string, std::pair<std::string, bool>> kv;
+    bool fpc_given = false;
+    std::string t(text), tok;
+    size_t i = 0;
+    while (i <= t.size()) {
+      const bool end = i == t.size() || t[i] == '\n' || t[i] == ' ' || t[i] == '\t' || t[i] == '\r';
+      if (!end) tok.push_back(t[i]);
+      else if (!tok.empty()) {
+        if (tok.compare(0, 2, "--") != 0) throw ConfError{"option " + tok + " does not start with --"};
+        const size_t eq = tok.find('=');
+        std::string key = eq == std::string::npos ? tok.substr(2) : tok.substr(2, eq - 2);
+        for (auto &ch : key) ch = ch == '_' ? '-' : (char)std::tolower((unsigned char)ch);
+        const std::string val = eq == std::string::npos ? "" : tok.substr(eq + 1);
+        if (key.compare(0, 9, "endpoint.") != 0 && key.compare(0, 26, "ivector-silence-weighting.") != 0 && key.compare(0, 4, "det.") != 0) {
+          kv[key] = {val, eq != std::string::npos};
+          if (key == "frames-per-chunk") fpc_given = true;
+        }
+        tok.clear();
+      }
+      i++;
+    }
+    apply("(options)", kv, opts, sizeof(opts) / sizeof(opts[0]));
+    if (extra_left != 0) throw ConfError{"--extra-left-context-initial other than 0 is not supported"};
+    if (sub <= 0) throw ConfError{"--frame-subsampling-factor must be positive"};
+    c.dec.prune_interval = prune_interval;
+    if (fpc_given) {                                          // GetChunkSize (nnet-compile-looped.cc:81): rounded up to a multiple of the subsampling factor
+      if (fpc <= 0) throw ConfError{"--frames-per-chunk must be positive"};
+      c.frames_per_chunk = (fpc + sub - 1) / sub * sub;
+    }
+  } catch (const ConfError &e) {
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_pipeline_cfg_apply_options", e.msg.c_str());
+  }
+  *cfg = c;
+  return B2K_OK;
+}
+
 // ------------------------------------------------------------------ RIFF/WAVE input
 //
 // WaveData::Read (feat/wave-reader.cc:107-321) in our own words: RIFF or RIFX (byte-swapped), any chunks before "fmt " and

@@ -229,3 +229,34 @@ def test_online_conf_as_prepare_online_decoding_writes_it(tmp_path):
             open(p, "w").write(f"--{n}={val}\n")
             assert L.b2k_online_conf_read(p.encode(), C.byref(c)) == 0, n
             assert c.rest.decode() == "", n                    # recognised, not passed through
+
+
+def test_decoder_and_decodable_options_in_the_tools_spelling():
+    from kaldi_b200.pipeline import PipelineConfig, native_cfg
+    L = _lib()
+    L.b2k_pipeline_cfg_apply_options.argtypes = [C.c_char_p, C.c_void_p]
+    c = native_cfg(PipelineConfig(max_batch=2, num_samples=16000))
+    text = b"--beam=13.5 --Max_Active=5000\n--min-active=100 --lattice-beam=6 --beam-delta=0.25 --hash-ratio=3\n--acoustic-scale=0.9 " \
+           b"--frames-per-chunk=50 --chunk-length=0.3 --endpoint.silence-phones=1:2:3 --do-endpointing=false --det.max-mem=1000 " \
+           b"--ivector-silence-weighting.silence-weight=0.5 --word-symbol-table=/x/words.txt --online=true --prune-interval=10\n"
+    assert L.b2k_pipeline_cfg_apply_options(text, C.byref(c)) == 0
+    assert (c.dec.beam, c.dec.max_active, c.dec.min_active, c.dec.lattice_beam, c.dec.prune_interval) == (13.5, 5000, 100, 6.0, 10)
+    assert c.dec.beam_delta == 0.25 and c.dec.hash_ratio == 3.0 and c.acoustic_scale == pytest.approx(0.9)
+    assert c.frames_per_chunk == 51 and c.chunk_length_secs == pytest.approx(0.3)       # 50 rounded up to a multiple of 3
+    before = bytes(c)
+    for bad in (b"--no-such-option=1", b"beam=3", b"--beam=wide", b"--extra-left-context-initial=5", b"--frames-per-chunk=0"):
+        assert L.b2k_pipeline_cfg_apply_options(bad, C.byref(c)) != 0
+        assert bytes(c) == before                             # a rejected text changes nothing
+    # the names are the ones the reference registers
+    src = "/root/reference/src"
+    if os.path.isdir(src):
+        def names(path, start, end):
+            t = open(os.path.join(src, path)).read()
+            t = t[t.index(start):]
+            return set(re.findall(r'Register\("([a-z\-]+)"', t[:t.index(end)]))
+        dec = names("decoder/lattice-faster-decoder.h", "struct LatticeFasterDecoderConfig", "void Check() const")
+        nn = names("nnet3/decodable-simple-looped.h", "struct NnetSimpleLoopedComputationOptions", "class DecodableNnetSimpleLoopedInfo")
+        assert {"beam", "lattice-beam", "hash-ratio"} <= dec and {"acoustic-scale", "frames-per-chunk"} <= nn
+        for n in sorted(dec | nn):
+            val = {"determinize-lattice": "true", "debug-computation": "false", "extra-left-context-initial": "0", "frame-subsampling-factor": "3"}.get(n, "7")
+            assert L.b2k_pipeline_cfg_apply_options(f"--{n}={val}".encode(), C.byref(c)) == 0, n
