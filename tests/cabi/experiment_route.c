@@ -21,6 +21,7 @@ int main(int argc, char **argv) {
   b2k_pipeline_cfg_default(&cfg);
   cfg.feat.max_lanes = 1;
   CHECK(b2k_feat_cfg_from_conf(oc.feature_type == 0 ? oc.mfcc_config : oc.fbank_config, oc.feature_type, &cfg.feat));
+  CHECK(b2k_pipeline_cfg_apply_options(oc.rest, &cfg));   /* --beam, --lattice-beam, --acoustic-scale ... if the file carries them */
   cfg.feat.dither = 0.0f;                         /* the reference's dither is unseeded: results are defined only without it */
   /* model, graph, waveform */
   b2k_model *model = NULL;
