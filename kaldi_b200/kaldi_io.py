@@ -29,6 +29,22 @@ class KaldiFormatError(ValueError):
     pass
 
 
+def _format_errors(fn):
+    """Readers see files that may be cut short or corrupted: whatever goes wrong while parsing (a struct that cannot be
+    unpacked, bytes that are not ASCII, a field that is missing, an index outside a table) is reported as KaldiFormatError."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **kw):
+        try:
+            return fn(*a, **kw)
+        except KaldiFormatError:
+            raise
+        except (ValueError, KeyError, IndexError, struct.error, UnicodeDecodeError, OverflowError, AttributeError, TypeError) as e:
+            raise KaldiFormatError(f"{fn.__name__}: malformed file ({type(e).__name__}: {e})") from e
+    return wrapped
+
+
 class Reader:
     """Sequential reader over a Kaldi object file (binary files start with "\\0B")."""
 
@@ -60,6 +76,13 @@ class Reader:
         if self.p >= len(self.d):
             raise KaldiFormatError("unexpected end of file")
         return self.d[self.p]
+
+    def _count(self, n: int, elem_bytes: int) -> int:
+        """A count read from the file: non-negative and no larger than the bytes that are left (np.frombuffer would read
+        count = -1 as 'everything', and a position that moves backwards never reaches the end of the file)."""
+        if n < 0 or n * elem_bytes > len(self.d) - self.p:
+            raise KaldiFormatError(f"implausible element count {n} at byte {self.p}")
+        return n
 
     def read_token(self) -> str:
         """ReadToken (io-funcs.cc:154): whitespace-delimited, one trailing space consumed."""
@@ -93,6 +116,8 @@ class Reader:
         e = self.p
         while e < len(self.d) and not self.d[e:e + 1].isspace():
             e += 1
+        if e == self.p:
+            raise KaldiFormatError("unexpected end of file (number expected)")
         s = self.d[self.p:e].decode("ascii")
         self.p = e
         return s
@@ -139,7 +164,7 @@ class Reader:
             n = struct.unpack_from("<i", self.d, self.p)[0]
             self.p += 4
             dt = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[size]
-            v = np.frombuffer(self.d, dt, n, self.p).copy()
+            v = np.frombuffer(self.d, dt, self._count(n, size), self.p).copy()
             self.p += n * size
             return v
         self._ws()
@@ -158,7 +183,7 @@ class Reader:
             n = struct.unpack_from("<i", self.d, self.p)[0]
             self.p += 4
             dt = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[size]
-            v = np.frombuffer(self.d, dt, 2 * n, self.p).reshape(n, 2).copy()
+            v = np.frombuffer(self.d, dt, self._count(2 * n, size) if n >= 0 else self._count(n, size), self.p).reshape(n, 2).copy()
             self.p += 2 * n * size
             return v
         self._ws()
@@ -186,7 +211,7 @@ class Reader:
             self.p += 3
             n = self.read_int()
             dt = np.float32 if tag == b"FV " else np.float64
-            v = np.frombuffer(self.d, dt, n, self.p).copy()
+            v = np.frombuffer(self.d, dt, self._count(n, np.dtype(dt).itemsize), self.p).copy()
             self.p += n * v.itemsize
             return v
         rows = self._text_brackets()
@@ -205,7 +230,9 @@ class Reader:
             self.p += 3
             r, c = self.read_int(), self.read_int()
             dt = np.float32 if tag == b"FM " else np.float64
-            m = np.frombuffer(self.d, dt, r * c, self.p).reshape(r, c).copy()
+            if r < 0 or c < 0:
+                raise KaldiFormatError("negative matrix size")
+            m = np.frombuffer(self.d, dt, self._count(r * c, np.dtype(dt).itemsize), self.p).reshape(r, c).copy()
             self.p += r * c * m.itemsize
             return m
         rows = self._text_brackets()
@@ -223,7 +250,9 @@ class Reader:
             n = self.read_int()
             dt = np.float32 if tag == b"FP " else np.float64
             ne = n * (n + 1) // 2
-            flat = np.frombuffer(self.d, dt, ne, self.p).copy()
+            if n < 0:
+                raise KaldiFormatError("negative matrix size")
+            flat = np.frombuffer(self.d, dt, self._count(ne, np.dtype(dt).itemsize), self.p).copy()
             self.p += ne * flat.itemsize
         else:
             rows = self._text_brackets()
@@ -319,10 +348,12 @@ class RawScalar:
 
 # ----------------------------------------------------------------------------- files
 
+@_format_errors
 def read_matrix(path: str) -> np.ndarray:
     return Reader.open(path).read_matrix()
 
 
+@_format_errors
 def read_vector(path: str) -> np.ndarray:
     return Reader.open(path).read_vector()
 
@@ -356,6 +387,7 @@ def write_vector(path: str, v: np.ndarray, binary: bool = True) -> None:
 
 # ----------------------------------------------------------------------------- nnet3 raw models
 
+@_format_errors
 def read_nnet3_raw(path: str) -> dict:
     """{"config": [lines], "components": {name: {"type": T, "<Token>": [values], ...}}} (Nnet::Read, nnet-nnet.cc:586)."""
     return _read_nnet3(Reader.open(path))
@@ -453,6 +485,7 @@ def _inference_view(nodes: list, comps: dict) -> list:
     return [(kind, kv) for kind, kv in out if kv["name"] in keep]
 
 
+@_format_errors
 def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
     """Maps a parsed TDNN-F chain model onto (arch, weights) of kaldi_b200.nnet_model.
 
@@ -638,6 +671,7 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
 
 # ----------------------------------------------------------------------------- i-vector extractor side
 
+@_format_errors
 def read_diag_gmm(path: str) -> dict:
     """DiagGmm::Read (gmm/diag-gmm.cc:758-800): final.dubm."""
     r = Reader.open(path)
@@ -663,6 +697,7 @@ def read_diag_gmm(path: str) -> dict:
     return out
 
 
+@_format_errors
 def read_ivector_extractor(path: str) -> dict:
     """IvectorExtractor::Read (ivector/ivector-extractor.cc:828-848) + ComputeDerivedVars (:182-230): final.ie.
     Returns M [G, F, D], sigma_inv [G, F, F], w_vec, prior_offset and the derived
@@ -689,6 +724,7 @@ def read_ivector_extractor(path: str) -> dict:
                 U=np.ascontiguousarray(U_full[:, il[0], il[1]]))
 
 
+@_format_errors
 def read_cmvn_stats(path: str) -> np.ndarray:
     """global_cmvn.stats: a 2 x (dim + 1) double matrix (transform/cmvn.cc)."""
     return np.asarray(read_matrix(path), np.float64)
@@ -809,10 +845,12 @@ def _read_transition_model(r: Reader) -> dict:
                 num_pdfs=int(max(max(t[2], t[3]) for t in tuples) + 1))
 
 
+@_format_errors
 def read_transition_model(path: str) -> dict:
     return _read_transition_model(Reader.open(path))
 
 
+@_format_errors
 def read_final_mdl(path: str) -> dict:
     """final.mdl of an nnet3 acoustic model: TransitionModel + AmNnetSimple (nnet3/am-nnet-simple.cc:47-57).
     {"transition_model": ..., "nnet": parsed raw nnet3, "left_context", "right_context", "priors"}."""
@@ -858,6 +896,7 @@ def _skip_symbol_table(d: bytes, p: int) -> int:
     return p
 
 
+@_format_errors
 def read_openfst(path: str) -> dict:
     """An OpenFst binary "vector" or "const" FST over StdArc as the CSR dictionary CudaFst takes:
     num_states, start, offsets [S+1], ilabel/olabel/nextstate [A] int32, weight [A] float32, final [S] float32
@@ -886,6 +925,8 @@ def read_openfst(path: str) -> dict:
             fw = struct.unpack_from("<f", d, p)[0]
             na = struct.unpack_from("<q", d, p + 4)[0]
             p += 12
+            if na < 0 or na * 16 > len(d) - p:
+                raise KaldiFormatError("vector FST: implausible arc count")
             chunks.append(np.frombuffer(d, arc_dt, na, p))
             p += na * 16
             finals.append(fw)
@@ -898,10 +939,14 @@ def read_openfst(path: str) -> dict:
         if (flags & _FST_IS_ALIGNED) or version == 1:
             p = (p + 15) // 16 * 16
         st_dt = np.dtype([("final", "<f4"), ("pos", "<u4"), ("narcs", "<u4"), ("nieps", "<u4"), ("noeps", "<u4")])
+        if nstates < 0 or narcs < 0 or nstates * st_dt.itemsize > len(d) - p:
+            raise KaldiFormatError("const FST: implausible sizes")
         st = np.frombuffer(d, st_dt, nstates, p)
         p += nstates * st_dt.itemsize
         if (flags & _FST_IS_ALIGNED) or version == 1:
             p = (p + 15) // 16 * 16
+        if narcs * 16 > len(d) - p:
+            raise KaldiFormatError("const FST: the arc table is cut short")
         arcs = np.frombuffer(d, arc_dt, narcs, p)
         final = st["final"].astype(np.float32)
         offsets = np.concatenate([st["pos"].astype(np.int64), [narcs]])

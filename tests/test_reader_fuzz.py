@@ -108,3 +108,62 @@ def test_option_file_reader(tmp_path):
     p = str(tmp_path / "mfcc.conf")
     open(p, "w").write("--use-energy=false   # comment\n--num-mel-bins=40\n--num-ceps=40\n--low-freq=20\n--high-freq=-400\n--dither=0\n" * 3)
     _run("conf", p, tmp_path)
+
+
+def test_python_readers_reject_corrupt_files_without_hanging(tmp_path):
+    """The Python twins (kaldi_io.py) on truncated / bit-flipped / extreme-count variants of a reference-written text and binary
+    model and of a graph file: every variant is either read or raises KaldiFormatError, within a time limit per file."""
+    import signal
+    from kaldi_b200 import kaldi_io as KIO, nnet_model as NM, synth
+
+    class Timeout(Exception):
+        pass
+
+    def alarm(sig, frm):
+        raise Timeout()
+    old = signal.signal(signal.SIGALRM, alarm)
+    try:
+        golden = os.path.join(ROOT, "tests", "golden", "tiny_final.mdl")
+        arch, W, t2p = NM.load_kaldi_mdl(golden)
+        # a text twin of the golden model, written through our own text writer of matrices is not available for whole models:
+        # corrupt the binary model and a const / vector graph file instead, plus the text form of one matrix
+        g = synth.make_hclg(3_000, num_pdfs=20, seed=5)
+        files = {"mdl": open(golden, "rb").read()}
+        for t in ("const", "vector"):
+            p = str(tmp_path / (t + ".fst"))
+            KIO.write_openfst(p, g, t)
+            files[t] = open(p, "rb").read()
+        p = str(tmp_path / "m.txt")
+        KIO.write_matrix(p, np.random.default_rng(0).standard_normal((6, 5)).astype(np.float32), binary=False)
+        files["matrix-text"] = open(p, "rb").read()
+        rng = np.random.default_rng(99)
+        for kind, data in files.items():
+            n = len(data)
+            variants = [data[:k] for k in sorted(set([0, 1, 2, 3, 7, 16, 40, n // 2, n - 1] + rng.integers(0, n, 40).tolist())) if 0 <= k < n]
+            for _ in range(120):
+                b = bytearray(data)
+                for _ in range(int(rng.integers(1, 4))):
+                    b[int(rng.integers(0, min(n, 4096)))] = int(rng.integers(0, 256))
+                variants.append(bytes(b))
+            for _ in range(40):
+                b = bytearray(data)
+                pos = int(rng.integers(0, max(1, min(n, 2048) - 4)))
+                b[pos:pos + 4] = [(0xff, 0xff, 0xff, 0x7f), (0xff, 0xff, 0xff, 0xff), (0, 0, 0, 0x80)][int(rng.integers(0, 3))]
+                variants.append(bytes(b))
+            reader = {"mdl": NM.load_kaldi_mdl, "const": KIO.read_openfst, "vector": KIO.read_openfst, "matrix-text": KIO.read_matrix}[kind]
+            q = str(tmp_path / "v.bin")
+            rejected = 0
+            for v in variants:
+                open(q, "wb").write(v)
+                signal.alarm(20)
+                try:
+                    reader(q)
+                except KIO.KaldiFormatError:
+                    rejected += 1
+                except MemoryError:
+                    rejected += 1
+                finally:
+                    signal.alarm(0)
+            assert rejected > 5, kind
+    finally:
+        signal.signal(signal.SIGALRM, old)
