@@ -2034,6 +2034,20 @@ void b2k_dec_cfg_default(b2k_dec_cfg *c) {
 
 int b2k_fst_create(const b2k_fst_csr *csr, b2k_fst **out) {
   if (!csr || !out || csr->num_states <= 0) return set_error(B2K_ERR_INVALID, "b2k_fst_create: bad args");
+  {   // the CSR comes from the caller: everything the kernels will index with is checked here, before any upload
+    const int N0 = csr->num_states;
+    if (!csr->offsets || !csr->final_cost || csr->start < 0 || csr->start >= N0 || csr->offsets[0] != 0)
+      return set_error(B2K_ERR_INVALID, "b2k_fst_create: bad start state or offsets");
+    for (int s = 0; s < N0; s++) if (csr->offsets[s + 1] < csr->offsets[s]) return set_error(B2K_ERR_INVALID, "b2k_fst_create: arc offsets are not non-decreasing");
+    const int A0 = csr->offsets[N0];
+    if (A0 > 0 && (!csr->ilabel || !csr->olabel || !csr->weight || !csr->nextstate)) return set_error(B2K_ERR_INVALID, "b2k_fst_create: arc arrays missing");
+    if (csr->tid2pdf && csr->num_tids <= 0) return set_error(B2K_ERR_INVALID, "b2k_fst_create: empty transition-id table");
+    for (int a = 0; a < A0; a++) {
+      if (csr->nextstate[a] < 0 || csr->nextstate[a] >= N0) return set_error(B2K_ERR_INVALID, "b2k_fst_create: arc to a state outside the graph");
+      if (csr->ilabel[a] < 0 || csr->olabel[a] < 0) return set_error(B2K_ERR_INVALID, "b2k_fst_create: negative label");
+      if (csr->weight[a] != csr->weight[a]) return set_error(B2K_ERR_INVALID, "b2k_fst_create: NaN arc weight");
+    }
+  }
   int rc = require_device();
   if (rc) return rc;
   const int N = csr->num_states;

@@ -214,3 +214,39 @@ def test_restatement_equals_compiled_reference_decoder_randomised():
             want = _sorted_rows(np.stack([st, co.view(np.int32)], axis=1)) if len(st) else np.zeros((0, 2), np.int32)
             assert np.array_equal(o.raw_frame(f)["toks"], want), (it, f, cfg)
         assert D.lattices_equal(o.lattice(), r.lattice()), (it, cfg)
+
+
+def test_graph_is_validated_before_the_device_is_touched():
+    """b2k_fst_create checks the caller's CSR (offsets, arc endpoints, labels, weights) before any device call: an inconsistent
+    graph is B2K_ERR_INVALID even on a machine without a GPU, a consistent one gets as far as the device check."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    try:
+        from kaldi_b200 import _lib
+        from kaldi_b200.decoder import CudaFst
+        _lib.lib()
+    except OSError as e:
+        pytest.skip(str(e))
+    from kaldi_b200 import synth
+
+    def code(g):
+        try:
+            CudaFst(g)
+        except _lib.B2kError as e:
+            return e.args[0] if isinstance(e.args[0], int) else int(str(e).split("b2k error ")[1].split(":")[0])
+        return 0
+    good = [synth.make_hclg(3_000, num_pdfs=20, seed=5), synth.tiny_graph()]
+    for g in good:
+        assert code(g) == 2                                   # B2K_ERR_NO_DEVICE: the graph itself was accepted
+    g = synth.make_hclg(3_000, num_pdfs=20, seed=5)
+    for field, idx, val in (("nextstate", 7, 10 ** 6), ("nextstate", 3, -1), ("ilabel", 2, -5), ("olabel", 9, -1), ("weight", 4, np.nan)):
+        bad = dict(g)
+        bad[field] = np.array(g[field]).copy()
+        bad[field][idx] = val
+        assert code(bad) == 1, field
+    bad = dict(g)
+    bad["offsets"] = np.array(g["offsets"]).copy()
+    bad["offsets"][5] = bad["offsets"][6] + 1                 # not non-decreasing
+    assert code(bad) == 1
+    assert code(dict(g, start=g["num_states"])) == 1
