@@ -527,6 +527,10 @@ typedef struct b2k_clat b2k_clat;
 /* max_states > 0: budget of determinized states; when it is exceeded the work is redone with 3/4 of the beam (the
  * reference reduces its beam when max_mem is hit, determinize-lattice-pruned.h:126-160) — see b2k_clat_effective_beam */
 int b2k_lat_determinize_pruned(const b2k_raw_lattice *raw, float beam, int64_t max_states, b2k_clat **out);
+/* CompactLatticeShortestPath + read-out (online2-wav-nnet3-latgen-faster.cc:43-76): words and transition-ids of the best path
+ * of the compact lattice, graph / acoustic cost with the final weight included; too small capacities: sizes + B2K_ERR_OVERFLOW */
+int b2k_clat_best_path(const b2k_clat *clat, int32_t *words, int32_t *n_words, int32_t *tids, int32_t *n_tids, int32_t cap_words,
+                       int32_t cap_tids, float *graph_cost, float *acoustic_cost);
 float b2k_clat_effective_beam(const b2k_clat *clat);
 /* One table entry (lat/kaldi-lattice.cc WriteLattice / WriteCompactLattice) written or appended to `path`: binary = 1: key, ' ',
  * "\0B", OpenFst VectorFst container (published layout, unpinned) with the reference's weight encodings; binary = 0: the text form

@@ -577,6 +577,63 @@ int b2k_clat_write(const b2k_clat *c, const char *key, const char *path, int32_t
   return B2K_OK;
 }
 
+// CompactLatticeShortestPath + the read-out of online2-wav-nnet3-latgen-faster.cc:43-76: the cheapest path of the compact lattice
+// (word ids, the concatenated transition-id strings, graph and acoustic cost with the final weight included).
+int b2k_clat_best_path(const b2k_clat *c, int32_t *words, int32_t *n_words, int32_t *tids, int32_t *n_tids, int32_t cap_words, int32_t cap_tids,
+                       float *graph_cost, float *acoustic_cost) {
+  if (!c || !n_words || !n_tids || cap_words < 0 || cap_tids < 0 || (cap_words > 0 && !words) || (cap_tids > 0 && !tids))
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_clat_best_path: bad args");
+  *n_words = 0; *n_tids = 0;
+  if (graph_cost) *graph_cost = std::numeric_limits<float>::infinity();
+  if (acoustic_cost) *acoustic_cost = std::numeric_limits<float>::infinity();
+  const int64_t N = c->num_states, A = (int64_t)c->arc_src.size(), F = (int64_t)c->final_state.size();
+  if (N == 0 || F == 0) return B2K_OK;
+  std::vector<int64_t> off(N + 1, 0);
+  for (int64_t a = 0; a < A; a++) off[c->arc_src[a] + 1]++;
+  for (int64_t s = 0; s < N; s++) off[s + 1] += off[s];
+  std::vector<int64_t> arcs(A), fill(off.begin(), off.end() - 1);
+  for (int64_t a = 0; a < A; a++) arcs[fill[c->arc_src[a]]++] = a;
+  std::vector<int32_t> indeg(N, 0), topo;
+  for (int64_t a = 0; a < A; a++) indeg[c->arc_dst[a]]++;
+  for (int64_t s = 0; s < N; s++) if (!indeg[s]) topo.push_back((int32_t)s);
+  for (size_t i = 0; i < topo.size(); i++)
+    for (int64_t k = off[topo[i]]; k < off[topo[i] + 1]; k++) if (--indeg[c->arc_dst[arcs[k]]] == 0) topo.push_back(c->arc_dst[arcs[k]]);
+  const double INF = std::numeric_limits<double>::infinity();
+  std::vector<double> dist(N, INF);
+  std::vector<int64_t> back(N, -1);
+  dist[0] = 0.0;
+  for (int32_t s : topo) {
+    if (!(dist[s] < INF)) continue;
+    for (int64_t k = off[s]; k < off[s + 1]; k++) {
+      const int64_t a = arcs[k];
+      const double nd = dist[s] + (double)c->arc_g[a] + (double)c->arc_a[a];
+      if (nd < dist[c->arc_dst[a]]) { dist[c->arc_dst[a]] = nd; back[c->arc_dst[a]] = a; }
+    }
+  }
+  int64_t best = -1;
+  double best_cost = INF;
+  for (int64_t f = 0; f < F; f++) { const double v = dist[c->final_state[f]] + (double)c->final_g[f] + (double)c->final_a[f]; if (v < best_cost) { best_cost = v; best = f; } }
+  if (best < 0) return b2k::set_error(B2K_ERR_STATE, "b2k_clat_best_path: no final state is reachable");
+  std::vector<int64_t> path;
+  for (int32_t s = c->final_state[best]; s != 0;) { path.push_back(back[s]); s = c->arc_src[back[s]]; }
+  std::reverse(path.begin(), path.end());
+  double g = (double)c->final_g[best], ac = (double)c->final_a[best];
+  int64_t nw = 0, nt = 0;
+  auto emit = [&](int64_t b, int64_t e) { for (int64_t i = b; i < e; i++) { if (nt < cap_tids) tids[nt] = c->tids[i]; nt++; } };
+  for (int64_t a : path) {
+    g += (double)c->arc_g[a]; ac += (double)c->arc_a[a];
+    if (nw < cap_words) words[nw] = c->arc_word[a];
+    nw++;
+    emit(c->arc_str_off[a], c->arc_str_off[a + 1]);
+  }
+  emit(c->final_str_off[best], c->final_str_off[best + 1]);
+  *n_words = (int32_t)nw; *n_tids = (int32_t)nt;
+  if (graph_cost) *graph_cost = (float)g;
+  if (acoustic_cost) *acoustic_cost = (float)ac;
+  if (nw > cap_words || nt > cap_tids) return b2k::set_error(B2K_ERR_OVERFLOW, "b2k_clat_best_path: output buffers too small (sizes returned)");
+  return B2K_OK;
+}
+
 float b2k_clat_effective_beam(const b2k_clat *c) { return c ? c->effective_beam : 0.f; }
 
 int b2k_clat_sizes(const b2k_clat *c, int64_t sizes[6]) {

@@ -81,6 +81,10 @@ int main(int argc, char **argv) {
   b2k_clat *clat = NULL;
   CHECK(b2k_lat_determinize_pruned(&raw, cfg.dec.lattice_beam, 0, &clat));              /* GetLattice */
   CHECK(b2k_clat_write(clat, "utt", argv[5], 1, 0));                                    /* ark:out.ark */
+  int32_t words[256], tids[4096], nw = 0, nt = 0;
+  float g = 0.f, a = 0.f;
+  CHECK(b2k_clat_best_path(clat, words, &nw, tids, &nt, 256, 4096, &g, &a));             /* CompactLatticeShortestPath */
+  printf("best path: %d words, %d transition-ids, graph cost %g, acoustic cost %g\n", nw, nt, g, a);
   int64_t sz[6];
   b2k_clat_sizes(clat, sz);
   printf("lattice: %lld raw arcs -> %lld compact arcs, written to %s\n", (long long)raw.num_arcs, (long long)sz[1], argv[5]);

@@ -311,3 +311,37 @@ def test_symbol_table_and_transcript(tmp_path):
     open(p, "w").write("only-one-column\n")
     with pytest.raises(ValueError):
         LT.read_symbol_table(p)
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_cpp_compact_best_path_equals_python(seed):
+    import ctypes as C
+    try:
+        from kaldi_b200 import _lib
+        from kaldi_b200.decoder import _RawLattice, _p
+        L = _lib.lib()
+    except OSError as e:
+        pytest.skip(str(e))
+    lat = _lattice(seed)
+    want = LT.compact_best_path(LT.determinize_pruned(lat, 8.0))
+    keep = {k: np.ascontiguousarray(lat[k], np.float32 if lat[k].dtype.kind == "f" else np.int32) for k in
+            ("state_frame", "state_hclg", "state_tot_cost", "state_extra_cost", "arc_src", "arc_dst", "arc_ilabel", "arc_olabel",
+             "arc_graph_cost", "arc_acoustic_cost", "final_state", "final_cost")}
+    r = _RawLattice()
+    r.num_states, r.num_arcs, r.num_finals = len(keep["state_frame"]), len(keep["arc_src"]), len(keep["final_state"])
+    for k, v in keep.items():
+        setattr(r, k, _p(v, C.c_float if v.dtype == np.float32 else C.c_int32))
+    h = C.c_void_p()
+    L.b2k_lat_determinize_pruned.argtypes = [C.c_void_p, C.c_float, C.c_int64, C.c_void_p]
+    assert L.b2k_lat_determinize_pruned(C.byref(r), 8.0, 0, C.byref(h)) == 0
+    L.b2k_clat_best_path.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    nw, nt, g, a = C.c_int32(), C.c_int32(), C.c_float(), C.c_float()
+    assert L.b2k_clat_best_path(h, None, C.byref(nw), None, C.byref(nt), 0, 0, C.byref(g), C.byref(a)) in (0, 4)
+    words, tids = np.zeros(max(nw.value, 1), np.int32), np.zeros(max(nt.value, 1), np.int32)
+    assert L.b2k_clat_best_path(h, words.ctypes.data, C.byref(nw), tids.ctypes.data, C.byref(nt), words.size, tids.size, C.byref(g), C.byref(a)) == 0
+    L.b2k_clat_destroy.argtypes = [C.c_void_p]
+    L.b2k_clat_destroy(h)
+    assert words[:nw.value].tolist() == want["words"].tolist() and tids[:nt.value].tolist() == want["tids"].tolist()
+    assert g.value == pytest.approx(want["graph_cost"], abs=1e-3) and a.value == pytest.approx(want["acoustic_cost"], abs=1e-3)
+    bp = LT.best_path(lat)                                   # and it is the raw lattice's best path
+    assert words[:nw.value].tolist() == bp["olabels"].tolist() and tids[:nt.value].tolist() == bp["ilabels"].tolist()
