@@ -518,20 +518,8 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
     }
     return out;
   };
+  // name -> descriptor text that replaces it; nodes are defined before they are used, so one pass in file order is enough
   std::map<std::string, std::string> alias;
-  for (auto &ln : lines)
-    if (ln.kind == "component-node") {
-      const Component *c = P.get(ln.kv["component"]);
-      if (c && (c->type == "GeneralDropoutComponent" || c->type == "DropoutComponent" || c->type == "SpecAugmentTimeMaskComponent")) {
-        std::string src = ln.kv["input"];
-        while (!src.empty() && src.front() == ' ') src.erase(0, 1);
-        while (!src.empty() && src.back() == ' ') src.pop_back();
-        const auto names = descriptor_nodes(src);
-        if (names.size() != 1 || names[0] != src) throw FormatError("dropout node " + ln.kv["name"] + " has a compound input descriptor: " + src);
-        alias[ln.kv["name"]] = src;
-      }
-    }
-  auto resolve = [&](std::string n) { while (alias.count(n)) n = alias[n]; return n; };
   auto subst = [&](const std::string &d) {
     std::string out;
     for (size_t i = 0; i < d.size();) {
@@ -539,7 +527,8 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
         size_t j = i;
         while (j < d.size() && is_word_char(d[j])) j++;
         const std::string w = d.substr(i, j - i);
-        out += alias.count(w) ? resolve(w) : w;
+        auto it = alias.find(w);
+        out += it != alias.end() ? it->second : w;
         i = j;
       } else if (is_word_char(d[i])) { while (i < d.size() && is_word_char(d[i])) out.push_back(d[i++]); }
       else out.push_back(d[i++]);
@@ -548,9 +537,27 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
   };
   std::vector<NodeLine> view;
   for (auto &ln : lines) {
-    if (ln.kind == "component-node" && alias.count(ln.kv["name"])) continue;
     NodeLine v = ln;
     for (const char *key : {"input", "input-node"}) if (v.kv.count(key)) v.kv[key] = subst(v.kv[key]);
+    if (v.kind == "component-node") {
+      const Component *c = P.get(v.kv["component"]);
+      std::string src = v.kv["input"];
+      while (!src.empty() && src.front() == ' ') src.erase(0, 1);
+      while (!src.empty() && src.back() == ' ') src.pop_back();
+      const std::string &nm = v.kv["name"];
+      if (c && (c->type == "GeneralDropoutComponent" || c->type == "DropoutComponent" || c->type == "SpecAugmentTimeMaskComponent")) {
+        const auto names = descriptor_nodes(src);
+        if (names.size() != 1 || names[0] != src) throw FormatError("dropout node " + nm + " has a compound input descriptor: " + src);
+        alias[nm] = src;
+        continue;
+      }
+      // no-op-component: a name for a descriptor (input2 = Append(delta, Scale(0.4, ivector)), run_tdnn_1k.sh:181); the NoOp nodes
+      // that belong to a layer pattern stay: the delta-layer's "<input>_2" and the tdnnf-layer's "<name>.noop"
+      if (c && c->type == "NoOpComponent" && !ends_with(nm, ".noop") && !(ends_with(nm, "_2") && src.find("_copy1") != std::string::npos)) {
+        alias[nm] = src;
+        continue;
+      }
+    }
     view.push_back(v);
   }
   std::set<std::string> keep;

@@ -446,29 +446,31 @@ def _inference_view(nodes: list, comps: dict) -> list:
     """What a trained recipe model looks like to the decoder: (1) dropout components are the identity in test mode, so
     every reference to such a node is replaced by the node's own input; (2) only what the output node named "output"
     depends on is kept (chain recipes leave their cross-entropy branch, output-xent, in final.mdl)."""
+    # name -> descriptor text that replaces it.  Nodes are defined before they are used, so one pass in file order is enough.
     alias = {}
-    for kind, kv in nodes:
-        if kind == "component-node" and comps[kv["component"]]["type"] in _IDENTITY_AT_TEST_TIME:
-            src = kv["input"].strip()
-            if _descriptor_nodes(src) != [src]:
-                raise KaldiFormatError(f"dropout node {kv['name']} has a compound input descriptor: {src}")
-            alias[kv["name"]] = src
-
-    def resolve(n):
-        while n in alias:
-            n = alias[n]
-        return n
 
     def subst(desc):
-        return re.sub(r"[A-Za-z_][A-Za-z0-9_.\-]*", lambda m: resolve(m.group(0)) if m.group(0) in alias else m.group(0), desc)
+        return re.sub(r"[A-Za-z_][A-Za-z0-9_.\-]*", lambda m: alias.get(m.group(0), m.group(0)), desc)
     out = []
     for kind, kv in nodes:
-        if kind == "component-node" and kv["name"] in alias:
-            continue
         kv = dict(kv)
         for key in ("input", "input-node"):
             if key in kv:
                 kv[key] = subst(kv[key])
+        if kind == "component-node":
+            typ = comps[kv["component"]]["type"]
+            src = kv["input"].strip()
+            if typ in _IDENTITY_AT_TEST_TIME:
+                if _descriptor_nodes(src) != [src]:
+                    raise KaldiFormatError(f"dropout node {kv['name']} has a compound input descriptor: {src}")
+                alias[kv["name"]] = src
+                continue
+            # no-op-component (trivial_layers.py): a name for a descriptor, e.g. input2 = Append(delta, Scale(0.4, ivector)) in
+            # run_tdnn_1k.sh:181.  The NoOp nodes that belong to a layer pattern stay: the delta-layer's "<input>_2" and the
+            # tdnnf-layer's "<name>.noop".
+            if typ == "NoOpComponent" and not kv["name"].endswith(".noop") and not (kv["name"].endswith("_2") and "_copy1" in src):
+                alias[kv["name"]] = src
+                continue
         out.append((kind, kv))
     roots = [kv for kind, kv in out if kind == "output-node" and kv["name"] == "output"]
     if not roots:

@@ -186,3 +186,83 @@ def test_cnn_tdnnf_built_by_the_references_xconfig_library(tmp_path):
         prog = NM.compile_program(arch, dict(W, priors=np.ones(48, np.float32)), T, 21, use_priors=False, conv_mode=mode)
         out = PI.run_program(prog, feats, iv[R.chunk_ivector_rows(T, T, 1)])
         assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max(), mode
+
+
+TDNN_1K_XCONFIG = """input dim=100 name=ivector
+input dim=40 name=input
+idct-layer name=idct input=input dim=40 cepstral-lifter=22 affine-transform-file={idct}
+batchnorm-component name=batchnorm0 input=idct
+spec-augment-layer name=spec-augment freq-max-proportion=0.5 time-zeroed-proportion=0.2 time-mask-max-frames=20
+delta-layer name=delta input=spec-augment
+no-op-component name=input2 input=Append(delta, Scale(0.4, ReplaceIndex(ivector, t, 0)))
+relu-batchnorm-layer name=tdnn1 l2-regularize=0.03 dim=64 input=input2
+tdnnf-layer name=tdnnf2 l2-regularize=0.03 bypass-scale=0.66 dim=64 bottleneck-dim=16 time-stride=1
+tdnnf-layer name=tdnnf3 l2-regularize=0.03 bypass-scale=0.66 dim=64 bottleneck-dim=16 time-stride=0
+tdnnf-layer name=tdnnf4 l2-regularize=0.03 bypass-scale=0.66 dim=64 bottleneck-dim=16 time-stride=3
+linear-component name=prefinal-l dim=32 l2-regularize=0.03 orthonormal-constraint=-1.0
+prefinal-layer name=prefinal-chain input=prefinal-l l2-regularize=0.03 small-dim=32 big-dim=64
+output-layer name=output include-log-softmax=false dim=48 l2-regularize=0.015
+prefinal-layer name=prefinal-xent input=prefinal-l l2-regularize=0.03 small-dim=32 big-dim=64
+output-layer name=output-xent dim=48 learning-rate-factor=5.0 l2-regularize=0.015
+"""
+TDNN_1K_BN = {"batchnorm0": 40, "delta": 120, "tdnn1.batchnorm": 64, "tdnnf2.batchnorm": 64, "tdnnf3.batchnorm": 64, "tdnnf4.batchnorm": 64,
+              "prefinal-chain.batchnorm1": 64, "prefinal-chain.batchnorm2": 32, "prefinal-xent.batchnorm1": 64, "prefinal-xent.batchnorm2": 32}
+
+
+def test_mini_librispeech_tdnn_1k_shape_from_the_references_xconfig_library(tmp_path):
+    """The network of the headline configuration (egs/mini_librispeech/s5/local/chain/tuning/run_tdnn_1k.sh:170-207): idct,
+    batchnorm, spec-augment, delta-layer, the no-op node that appends the scaled i-vector, relu-batchnorm, TDNN-F, both branches."""
+    if not os.path.isdir(STEPS):
+        pytest.skip("the reference's xconfig library exists in the build container only")
+    from oracle import nnet_oracle as NO
+    from oracle import program_interp as PI
+    sys.path.insert(0, STEPS)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import libs.nnet3.xconfig.parser as xparser
+    rng = np.random.default_rng(7)
+    idct = str(tmp_path / "idct.mat")
+    KIO.write_matrix(idct, np.concatenate([np.linalg.qr(rng.standard_normal((40, 40)))[0], np.zeros((40, 1))], 1).astype(np.float32), binary=False)
+    xc = str(tmp_path / "network.xconfig")
+    open(xc, "w").write(TDNN_1K_XCONFIG.format(idct=idct))
+    lines = [line for layer in xparser.read_xconfig_file(xc) for base, line in layer.get_full_config() if base == "final"]
+    R = NO.RefNnet.__new__(NO.RefNnet)
+    L = R.lib = C.CDLL(NO._SO)
+    L.ref_nnet_create.restype = C.c_void_p
+    L.ref_nnet_component_name.restype = C.c_char_p
+    L.ref_nnet_component_type.restype = C.c_char_p
+    R.h = C.c_void_p(L.ref_nnet_create(("\n".join(lines) + "\n").encode()))
+    assert R.h
+    R.arch = {"frame_subsampling_factor": 3}
+    f32p = C.POINTER(C.c_float)
+    for i in range(L.ref_nnet_num_components(R.h)):
+        name, typ = L.ref_nnet_component_name(R.h, i).decode(), L.ref_nnet_component_type(R.h, i).decode()
+        if typ == "BatchNormComponent":
+            d = TDNN_1K_BN[name]
+            mean, var = (rng.standard_normal(d) * 0.1).astype(np.float32), rng.uniform(0.5, 1.5, d).astype(np.float32)
+            assert L.ref_nnet_set_batchnorm(R.h, i, C.c_int(d), C.c_int(d), C.c_float(1e-3), C.c_float(1.0), C.c_float(1000.0),
+                                            mean.ctypes.data_as(f32p), var.ctypes.data_as(f32p)) == 0, name
+    raw = str(tmp_path / "final.raw")
+    L.ref_nnet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    assert L.ref_nnet_write(R.h, raw.encode(), 1) == 0
+    arch, W = NM.load_kaldi_raw(raw)
+    assert [(x["type"], x["name"]) for x in arch["layers"]] == [
+        ("idct", "idct"), ("batchnorm", "batchnorm0"), ("delta", "delta"), ("relu-batchnorm", "tdnn1"), ("tdnnf", "tdnnf2"), ("tdnnf", "tdnnf3"),
+        ("tdnnf", "tdnnf4"), ("linear", "prefinal-l"), ("prefinal", "prefinal-chain"), ("output", "output")]
+    assert arch["layers"][3]["append_ivector"] == pytest.approx(0.4)
+    try:
+        from kaldi_b200.model import KaldiModel
+        assert KaldiModel(raw, is_mdl=False).layer_types() == [(x["type"], x["name"]) for x in arch["layers"]]
+    except OSError:
+        pass
+    assert L.ref_nnet_prepare(R.h, C.c_int(20), C.c_int(3), C.c_float(1.0), None, C.c_int(0), C.c_int(1)) == 0
+    info = (C.c_int * 4)()
+    L.ref_nnet_info(R.h, info)
+    R.left_context, R.right_context, R.frames_per_chunk, R.output_dim = list(info)
+    T = 64
+    feats = (rng.standard_normal((T, 40)) * 10).astype(np.float32)
+    iv = rng.standard_normal((T, 100)).astype(np.float32)
+    ref = R.forward(feats, iv, period=1)
+    prog = NM.compile_program(arch, dict(W, priors=np.ones(48, np.float32)), T, 21, use_priors=False)
+    out = PI.run_program(prog, feats, iv[R.chunk_ivector_rows(T, T, 1)])
+    assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max()
