@@ -14,6 +14,16 @@ from kaldi_b200 import kaldi_io as KIO, nnet_model as NM
 
 STEPS = "/root/reference/egs/wsj/s5/steps"
 
+def _randomise_parameters(L, h, rng):
+    """Kaldi initialises output layers to zero: give every updatable component seeded random parameters so that the forward
+    comparison is not 0 == 0."""
+    for i in range(L.ref_nnet_num_components(h)):
+        n = L.ref_nnet_num_params(h, i)
+        if n > 0:
+            v = (rng.standard_normal(n) * 0.1).astype(np.float32)
+            assert L.ref_nnet_set_params(h, i, v.ctypes.data_as(C.POINTER(C.c_float))) == 0
+
+
 XCONFIG = """input dim=100 name=ivector
 input dim=40 name=input
 fixed-affine-layer name=lda input=Append(-1,0,1,ReplaceIndex(ivector, t, 0)) affine-transform-file={lda}
@@ -59,6 +69,7 @@ def test_model_built_by_the_references_xconfig_library(tmp_path, binary):
     R.h = C.c_void_p(L.ref_nnet_create(config.encode()))
     assert R.h, "the reference rejected its own xconfig output"
     R.arch = {"frame_subsampling_factor": 3}
+    _randomise_parameters(L, R.h, rng)
     f32p = C.POINTER(C.c_float)
     for i in range(L.ref_nnet_num_components(R.h)):
         name, typ = L.ref_nnet_component_name(R.h, i).decode(), L.ref_nnet_component_type(R.h, i).decode()
@@ -99,6 +110,7 @@ def test_model_built_by_the_references_xconfig_library(tmp_path, binary):
     ref = R.forward(feats, iv, period=1)
     prog = NM.compile_program(arch, dict(W, priors=pri), T, 21, use_priors=False)
     out = PI.run_program(prog, feats, iv[R.chunk_ivector_rows(T, T, 1)])
+    assert np.abs(ref).max() > 1e-2 and ref.std() > 1e-3                                  # a real comparison, not 0 == 0
     assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max()
     assert (R.left_context, R.right_context) == (prog["model_left"], prog["model_right"])
 
@@ -151,6 +163,7 @@ def test_cnn_tdnnf_built_by_the_references_xconfig_library(tmp_path):
     R.h = C.c_void_p(L.ref_nnet_create(("\n".join(lines) + "\n").encode()))
     assert R.h
     R.arch = {"frame_subsampling_factor": 3}
+    _randomise_parameters(L, R.h, rng)
     f32p = C.POINTER(C.c_float)
     for i in range(L.ref_nnet_num_components(R.h)):
         name, typ = L.ref_nnet_component_name(R.h, i).decode(), L.ref_nnet_component_type(R.h, i).decode()
@@ -185,6 +198,7 @@ def test_cnn_tdnnf_built_by_the_references_xconfig_library(tmp_path):
     for mode in ("patch", "dense"):
         prog = NM.compile_program(arch, dict(W, priors=np.ones(48, np.float32)), T, 21, use_priors=False, conv_mode=mode)
         out = PI.run_program(prog, feats, iv[R.chunk_ivector_rows(T, T, 1)])
+        assert np.abs(ref).max() > 1e-2 and ref.std() > 1e-3
         assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max(), mode
 
 
@@ -234,6 +248,7 @@ def test_mini_librispeech_tdnn_1k_shape_from_the_references_xconfig_library(tmp_
     R.h = C.c_void_p(L.ref_nnet_create(("\n".join(lines) + "\n").encode()))
     assert R.h
     R.arch = {"frame_subsampling_factor": 3}
+    _randomise_parameters(L, R.h, rng)
     f32p = C.POINTER(C.c_float)
     for i in range(L.ref_nnet_num_components(R.h)):
         name, typ = L.ref_nnet_component_name(R.h, i).decode(), L.ref_nnet_component_type(R.h, i).decode()
@@ -265,4 +280,5 @@ def test_mini_librispeech_tdnn_1k_shape_from_the_references_xconfig_library(tmp_
     ref = R.forward(feats, iv, period=1)
     prog = NM.compile_program(arch, dict(W, priors=np.ones(48, np.float32)), T, 21, use_priors=False)
     out = PI.run_program(prog, feats, iv[R.chunk_ivector_rows(T, T, 1)])
+    assert np.abs(ref).max() > 1e-2 and ref.std() > 1e-3                                  # a real comparison, not 0 == 0
     assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max()
