@@ -415,6 +415,7 @@ int b2k_model_info(const b2k_model *model, int32_t info[8]);
 const b2k_nnet_layer *b2k_model_layers(const b2k_model *model);
 const b2k_nnet_weight *b2k_model_weights(const b2k_model *model);    /* includes "priors" (ones when absent) */
 const int32_t *b2k_model_tid2pdf(const b2k_model *model);           /* [tid], index 0 unused; b2k_fst_csr.tid2pdf */
+const int32_t *b2k_model_tid2phone(const b2k_model *model);         /* [tid], index 0 unused; TransitionIdToPhone (hmm/transition-model.cc:798) */
 
 /* Kaldi option files (ParseOptions::ReadConfigFile, util/parse-options.cc:460-497) for the two configurations the tool is
  * pointed at: --mfcc-config / --fbank-config (MfccOptions / FbankOptions with their frame and mel options) and
@@ -443,6 +444,39 @@ typedef struct {
   char rest[4096];
 } b2k_online_conf;
 int b2k_online_conf_read(const char *conf_path, b2k_online_conf *out);
+
+/* Endpointing (online2/online-endpoint.h:54-186, online-endpoint.cc:28-135): the five-rule disjunction, its option group
+ * (--endpoint.silence-phones, --endpoint.ruleN.{must-contain-nonsilence, min-trailing-silence, max-relative-cost,
+ * min-utterance-length}) and the trailing-silence count the rules are evaluated on.  Host only; pinned to the reference's own
+ * online-endpoint.cc (tests/test_endpoint_cpp.py). */
+typedef struct {
+  int32_t must_contain_nonsilence;
+  float min_trailing_silence, max_relative_cost, min_utterance_length;
+} b2k_endpoint_rule;
+typedef struct {
+  b2k_endpoint_rule rule[5];          /* rule1 .. rule5 */
+  char silence_phones[512];           /* colon-separated, e.g. "1:2:3:4:5" */
+} b2k_endpoint_cfg;
+int b2k_endpoint_cfg_default(b2k_endpoint_cfg *cfg);                          /* OnlineEndpointConfig() (online-endpoint.h:146-151) */
+/* the endpoint.* options of an option file (the other groups a tool keeps in the same file are not looked at; an endpoint.*
+ * name the group does not register is an error), on top of the defaults */
+int b2k_endpoint_cfg_from_conf(const char *conf_path, b2k_endpoint_cfg *cfg);
+/* the same for options given as text ("--endpoint.rule2.min-trailing-silence=0.8 ...", e.g. b2k_online_conf.rest), on top of *cfg */
+int b2k_endpoint_cfg_apply_options(const char *text, b2k_endpoint_cfg *cfg);
+/* EndpointDetected(config, num_frames_decoded, trailing_silence_frames, frame_shift, final_relative_cost) (online-endpoint.cc:47-76);
+ * *detected = 0 / 1.  num_frames_decoded < trailing_silence_frames is an error (the reference asserts). */
+int b2k_endpoint_detected(const b2k_endpoint_cfg *cfg, int32_t num_frames_decoded, int32_t trailing_silence_frames,
+                          float frame_shift_in_seconds, float final_relative_cost, int32_t *detected);
+/* TrailingSilenceLength (online-endpoint.cc:78-114) on a best path given as its input labels in time order (epsilons allowed, as
+ * b2k_lat_best_path_arcs returns them): the number of silence frames at the end, counting stops at the first non-silence phone.
+ * tid2phone = b2k_model_tid2phone.  A malformed, empty or duplicated silence list and an out-of-range transition-id are errors. */
+int b2k_trailing_silence_frames(const int32_t *tid2phone, int32_t num_tids, const char *silence_phones, const int32_t *ilabels,
+                                int64_t n, int32_t *frames);
+/* EndpointDetected(config, tmodel, frame_shift, decoder) (online-endpoint.cc:116-135) with the decoder's best path, frame count and
+ * final relative cost passed in; 0 frames decoded -> not detected.  trailing_silence_frames may be NULL. */
+int b2k_endpoint_detected_on_path(const b2k_endpoint_cfg *cfg, const int32_t *tid2phone, int32_t num_tids, const int32_t *ilabels, int64_t n,
+                                  int32_t num_frames_decoded, float frame_shift_in_seconds, float final_relative_cost,
+                                  int32_t *detected, int32_t *trailing_silence_frames);
 
 /* RIFF/WAVE input as WaveData::Read takes it (feat/wave-reader.cc:107-321): 16-bit PCM (plain or WAVE_FORMAT_EXTENSIBLE), RIFF or
  * RIFX, extra chunks skipped, "stream mode" sizes, truncated files; samples as floats in the int16 range, one row per channel

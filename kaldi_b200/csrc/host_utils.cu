@@ -55,7 +55,9 @@ int b2k_ivec_online_schedule(int64_t num_samples, int32_t chunk_samples, int32_t
 // OnlineSpliceOptions and OnlineCmvnOptions register (feat/feature-window.h:69-104, mel-computations.h:60-74,
 // feature-mfcc.h:62-79, feature-fbank.h:62-80, online2/online-ivector-feature.h:112-160, feat/online-feature.h:234-251,
 // :446-456); tests/test_conf_cpp.py compares with the reference's own ParseOptions on the same files.
+#include <cerrno>
 #include <cstdlib>
+#include <limits>
 #include <fstream>
 #include <iterator>
 #include <map>
@@ -460,3 +462,171 @@ extern "C" int b2k_resample_waveform(float orig_freq, const float *in, int64_t n
   }
   return B2K_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Endpointing (online2/online-endpoint.{h,cc}): the rule set, its option group and the two quantities the rules are
+// evaluated on.  Host only.  The best path comes from b2k_lat_best_path_arcs / CudaDecoderB2k::GetBestPath; the relative
+// cost of the final states is the caller's (FinalRelativeCost of the decoder, lattice-faster-decoder.cc:283).
+namespace {
+
+static void endpoint_defaults(b2k_endpoint_cfg *c) {            // OnlineEndpointConfig() (online-endpoint.h:146-151)
+  const float inf = std::numeric_limits<float>::infinity();
+  memset(c, 0, sizeof(*c));
+  c->rule[0] = {0, 5.0f, inf, 0.0f};
+  c->rule[1] = {1, 0.5f, 2.0f, 0.0f};
+  c->rule[2] = {1, 1.0f, 8.0f, 0.0f};
+  c->rule[3] = {1, 2.0f, inf, 0.0f};
+  c->rule[4] = {0, 0.0f, inf, 20.0f};
+}
+
+// the endpoint.* entries of `kv` -> cfg; an endpoint.* name the group does not register is an error, other names are not looked at
+static void endpoint_apply(const char *where, const std::map<std::string, std::pair<std::string, bool>> &kv, b2k_endpoint_cfg *c) {
+  std::vector<Opt> o = {{"endpoint.silence-phones", 's', c->silence_phones}};
+  static const char *const names[5][4] = {
+      {"endpoint.rule1.must-contain-nonsilence", "endpoint.rule1.min-trailing-silence", "endpoint.rule1.max-relative-cost", "endpoint.rule1.min-utterance-length"},
+      {"endpoint.rule2.must-contain-nonsilence", "endpoint.rule2.min-trailing-silence", "endpoint.rule2.max-relative-cost", "endpoint.rule2.min-utterance-length"},
+      {"endpoint.rule3.must-contain-nonsilence", "endpoint.rule3.min-trailing-silence", "endpoint.rule3.max-relative-cost", "endpoint.rule3.min-utterance-length"},
+      {"endpoint.rule4.must-contain-nonsilence", "endpoint.rule4.min-trailing-silence", "endpoint.rule4.max-relative-cost", "endpoint.rule4.min-utterance-length"},
+      {"endpoint.rule5.must-contain-nonsilence", "endpoint.rule5.min-trailing-silence", "endpoint.rule5.max-relative-cost", "endpoint.rule5.min-utterance-length"}};
+  for (int r = 0; r < 5; r++) {
+    o.push_back({names[r][0], 'b', &c->rule[r].must_contain_nonsilence});
+    o.push_back({names[r][1], 'f', &c->rule[r].min_trailing_silence});
+    o.push_back({names[r][2], 'f', &c->rule[r].max_relative_cost});
+    o.push_back({names[r][3], 'f', &c->rule[r].min_utterance_length});
+  }
+  std::map<std::string, std::pair<std::string, bool>> mine;
+  for (auto &e : kv) if (e.first.compare(0, 9, "endpoint.") == 0) mine[e.first] = e.second;
+  apply(where, mine, o.data(), o.size());
+}
+
+// "1:2:3" -> sorted phones; SplitStringToIntegers(":", omit_empty = false) + the two asserts of TrailingSilenceLength
+// (online-endpoint.cc:82-91): no empty fields, no trailing characters after a number, no duplicates, not empty
+static std::vector<int32_t> silence_set(const char *str) {
+  std::vector<int32_t> out;
+  const std::string s(str);
+  size_t a = 0;
+  while (!s.empty()) {
+    const size_t b = s.find(':', a);
+    const std::string f = s.substr(a, b == std::string::npos ? std::string::npos : b - a);
+    char *end = nullptr;
+    errno = 0;
+    const long long v = strtoll(f.c_str(), &end, 10);
+    if (end == f.c_str() || *end != 0 || v != (long long)(int32_t)v) throw ConfError{"Bad --silence-phones option in endpointing config: " + s};
+    out.push_back((int32_t)v);
+    if (b == std::string::npos) break;
+    a = b + 1;
+  }
+  if (out.empty()) throw ConfError{"Endpointing requires nonempty --endpoint.silence-phones option"};
+  std::sort(out.begin(), out.end());
+  if (std::adjacent_find(out.begin(), out.end()) != out.end()) throw ConfError{"Duplicates in --silence-phones option in endpointing config"};
+  return out;
+}
+
+static bool rule_activated(const b2k_endpoint_rule &r, float trailing_silence, float relative_cost, float utterance_length) {
+  const bool contains_nonsilence = utterance_length > trailing_silence;           // online-endpoint.cc:31-37
+  return (contains_nonsilence || !r.must_contain_nonsilence) && trailing_silence >= r.min_trailing_silence &&
+         relative_cost <= r.max_relative_cost && utterance_length >= r.min_utterance_length;
+}
+
+static int32_t trailing_silence(const int32_t *tid2phone, int32_t num_tids, const std::vector<int32_t> &sil, const int32_t *ilabels, int64_t n) {
+  int32_t count = 0;
+  for (int64_t i = n - 1; i >= 0; i--) {                                            // backwards in time from the last decoded frame
+    const int32_t t = ilabels[i];
+    if (t == 0) continue;
+    if (t < 0 || t >= num_tids) throw ConfError{"best path holds a transition-id outside the model's range"};
+    if (!std::binary_search(sil.begin(), sil.end(), tid2phone[t])) break;
+    count++;
+  }
+  return count;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2k_endpoint_cfg_default(b2k_endpoint_cfg *cfg) {
+  if (!cfg) return b2k::set_error(B2K_ERR_INVALID, "b2k_endpoint_cfg_default: bad args");
+  endpoint_defaults(cfg);
+  return B2K_OK;
+}
+
+int b2k_endpoint_cfg_from_conf(const char *conf_path, b2k_endpoint_cfg *cfg) {
+  if (!conf_path || !cfg) return b2k::set_error(B2K_ERR_INVALID, "b2k_endpoint_cfg_from_conf: bad args");
+  b2k_endpoint_cfg c;
+  endpoint_defaults(&c);
+  try {
+    endpoint_apply(conf_path, read_conf(conf_path), &c);
+  } catch (const ConfError &e) {
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_endpoint_cfg_from_conf", e.msg.c_str());
+  }
+  *cfg = c;
+  return B2K_OK;
+}
+
+int b2k_endpoint_cfg_apply_options(const char *text, b2k_endpoint_cfg *cfg) {
+  if (!text || !cfg) return b2k::set_error(B2K_ERR_INVALID, "b2k_endpoint_cfg_apply_options: bad args");
+  b2k_endpoint_cfg c = *cfg;
+  try {
+    std::map<std::string, std::pair<std::string, bool>> kv;
+    std::string t(text), tok;
+    for (size_t i = 0; i <= t.size(); i++) {
+      const bool end = i == t.size() || t[i] == '\n' || t[i] == ' ' || t[i] == '\t' || t[i] == '\r';
+      if (!end) { tok.push_back(t[i]); continue; }
+      if (tok.empty()) continue;
+      if (tok.compare(0, 2, "--") != 0) throw ConfError{"option " + tok + " does not start with --"};
+      const size_t eq = tok.find('=');
+      std::string key = eq == std::string::npos ? tok.substr(2) : tok.substr(2, eq - 2);
+      for (auto &ch : key) ch = ch == '_' ? '-' : (char)std::tolower((unsigned char)ch);
+      kv[key] = {eq == std::string::npos ? "" : tok.substr(eq + 1), eq != std::string::npos};
+      tok.clear();
+    }
+    endpoint_apply("(options)", kv, &c);
+  } catch (const ConfError &e) {
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_endpoint_cfg_apply_options", e.msg.c_str());
+  }
+  *cfg = c;
+  return B2K_OK;
+}
+
+int b2k_endpoint_detected(const b2k_endpoint_cfg *cfg, int32_t num_frames_decoded, int32_t trailing_silence_frames,
+                          float frame_shift_in_seconds, float final_relative_cost, int32_t *detected) {
+  if (!cfg || !detected) return b2k::set_error(B2K_ERR_INVALID, "b2k_endpoint_detected: bad args");
+  if (num_frames_decoded < trailing_silence_frames)              // KALDI_ASSERT (online-endpoint.cc:52)
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_endpoint_detected: more trailing silence than decoded frames");
+  const float utterance_length = num_frames_decoded * frame_shift_in_seconds, trailing = trailing_silence_frames * frame_shift_in_seconds;
+  int32_t ans = 0;
+  for (int r = 0; r < 5 && !ans; r++) ans = rule_activated(cfg->rule[r], trailing, final_relative_cost, utterance_length) ? 1 : 0;
+  *detected = ans;
+  return B2K_OK;
+}
+
+int b2k_trailing_silence_frames(const int32_t *tid2phone, int32_t num_tids, const char *silence_phones, const int32_t *ilabels,
+                                int64_t n, int32_t *frames) {
+  if (!tid2phone || num_tids <= 0 || !silence_phones || (!ilabels && n > 0) || n < 0 || !frames)
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_trailing_silence_frames: bad args");
+  try {
+    *frames = trailing_silence(tid2phone, num_tids, silence_set(silence_phones), ilabels, n);
+  } catch (const ConfError &e) {
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_trailing_silence_frames", e.msg.c_str());
+  }
+  return B2K_OK;
+}
+
+int b2k_endpoint_detected_on_path(const b2k_endpoint_cfg *cfg, const int32_t *tid2phone, int32_t num_tids, const int32_t *ilabels, int64_t n,
+                                  int32_t num_frames_decoded, float frame_shift_in_seconds, float final_relative_cost,
+                                  int32_t *detected, int32_t *trailing_silence_frames) {
+  if (!cfg || !tid2phone || num_tids <= 0 || (!ilabels && n > 0) || n < 0 || num_frames_decoded < 0 || !detected)
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_endpoint_detected_on_path: bad args");
+  if (trailing_silence_frames) *trailing_silence_frames = 0;
+  if (num_frames_decoded == 0) { *detected = 0; return B2K_OK; }                  // online-endpoint.cc:123
+  int32_t sil = 0;
+  try {
+    sil = trailing_silence(tid2phone, num_tids, silence_set(cfg->silence_phones), ilabels, n);
+  } catch (const ConfError &e) {
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_endpoint_detected_on_path", e.msg.c_str());
+  }
+  if (trailing_silence_frames) *trailing_silence_frames = sil;
+  return b2k_endpoint_detected(cfg, num_frames_decoded, sil, frame_shift_in_seconds, final_relative_cost, detected);
+}
+
+}  // extern "C"

@@ -368,7 +368,7 @@ static void read_topology(Reader &r, std::vector<std::vector<TopoState>> *entrie
 }
 
 // TransitionModel::Read + ComputeDerived (hmm/transition-model.cc:394-420,144-188): tid2pdf[t], t = 1..num_tids, [0] = 0
-static void read_transition_model(Reader &r, std::vector<int32_t> *tid2pdf) {
+static void read_transition_model(Reader &r, std::vector<int32_t> *tid2pdf, std::vector<int32_t> *tid2phone) {
   r.expect("<TransitionModel>");
   std::vector<std::vector<TopoState>> entries;
   std::map<int, int> p2i;
@@ -378,13 +378,17 @@ static void read_transition_model(Reader &r, std::vector<int32_t> *tid2pdf) {
   const bool has_sl = tok == "<Tuples>";
   const long long n = r.read_int();
   tid2pdf->assign(1, 0);
+  tid2phone->assign(1, 0);
   for (long long i = 0; i < n; i++) {
     const int phone = (int)r.read_int(), hs = (int)r.read_int(), fwd = (int)r.read_int();
     const int sl = has_sl ? (int)r.read_int() : fwd;
     auto it = p2i.find(phone);
     if (it == p2i.end() || it->second < 0 || it->second >= (int)entries.size() || hs < 0 || hs >= (int)entries[it->second].size())
       throw FormatError("transition model: bad tuple");
-    for (auto &tr : entries[it->second][hs].tr) tid2pdf->push_back(tr.first == hs ? sl : fwd);
+    for (auto &tr : entries[it->second][hs].tr) {
+      tid2pdf->push_back(tr.first == hs ? sl : fwd);
+      tid2phone->push_back(phone);                           // TransitionIdToPhone (transition-model.cc:798)
+    }
   }
   r.expect(has_sl ? "</Tuples>" : "</Triples>");
   r.expect("<LogProbs>");
@@ -411,7 +415,7 @@ struct b2k_model {
   std::vector<std::vector<float>> wdata;
   std::vector<std::pair<int, int>> wshape;
   std::vector<b2k_nnet_weight> weights;       // views into the three above
-  std::vector<int32_t> tid2pdf;
+  std::vector<int32_t> tid2pdf, tid2phone;
   int32_t has_priors = 0;
 };
 
@@ -764,7 +768,7 @@ int b2k_model_read(const char *path, int32_t is_mdl, b2k_model **out) {
     ParsedNnet P;
     std::vector<float> priors;
     if (is_mdl) {
-      read_transition_model(r, &M->tid2pdf);
+      read_transition_model(r, &M->tid2pdf, &M->tid2phone);
       read_nnet3(r, &P);
       r.expect("<LeftContext>"); r.read_int();
       r.expect("<RightContext>"); r.read_int();
@@ -796,6 +800,7 @@ int b2k_model_info(const b2k_model *m, int32_t info[8]) {
 const b2k_nnet_layer *b2k_model_layers(const b2k_model *m) { return m ? m->layers.data() : nullptr; }
 const b2k_nnet_weight *b2k_model_weights(const b2k_model *m) { return m ? m->weights.data() : nullptr; }
 const int32_t *b2k_model_tid2pdf(const b2k_model *m) { return m && !m->tid2pdf.empty() ? m->tid2pdf.data() : nullptr; }
+const int32_t *b2k_model_tid2phone(const b2k_model *m) { return m && !m->tid2phone.empty() ? m->tid2phone.data() : nullptr; }
 
 
 // ------------------------------------------------------------------ i-vector extractor directory

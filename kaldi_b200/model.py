@@ -28,15 +28,17 @@ class KaldiModel:
         (self.feat_dim, self.ivector_dim, self.num_pdfs, self.frame_subsampling_factor, self.n_layers, self.n_weights,
          n_tid, has_priors) = [int(x) for x in info]
         self.has_priors = bool(has_priors)
-        for f in ("b2k_model_layers", "b2k_model_weights", "b2k_model_tid2pdf"):
+        for f in ("b2k_model_layers", "b2k_model_weights", "b2k_model_tid2pdf", "b2k_model_tid2phone"):
             getattr(L, f).restype = C.c_void_p
             getattr(L, f).argtypes = [C.c_void_p]
         self.layers_ptr = L.b2k_model_layers(self.h)
         self.weights_ptr = L.b2k_model_weights(self.h)
-        self.tid2pdf = None
+        self.tid2pdf = self.tid2phone = None
         if n_tid:
             p = C.cast(L.b2k_model_tid2pdf(self.h), C.POINTER(C.c_int32))
             self.tid2pdf = np.ctypeslib.as_array(p, shape=(n_tid,)).copy()
+            p = C.cast(L.b2k_model_tid2phone(self.h), C.POINTER(C.c_int32))
+            self.tid2phone = np.ctypeslib.as_array(p, shape=(n_tid,)).copy()       # TransitionIdToPhone, for endpointing
 
     def layer_types(self) -> list[tuple[str, str]]:
         from .nnet_compile import _Layer

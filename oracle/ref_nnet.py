@@ -41,7 +41,8 @@ NNET_SOURCES = [s for s in NNET_SOURCES if s != "tree/tree-renderer.cc"]
 
 def build(quiet: bool = False, force: bool = False) -> str:
     wrap = os.path.join(HERE, "ref_wrap", "nnet_wrap.cc")
-    wraps = [wrap, os.path.join(HERE, "ref_wrap", "ivector_wrap.cc"), os.path.join(HERE, "ref_wrap", "nnet_stubs.cc")]
+    wraps = [wrap, os.path.join(HERE, "ref_wrap", "ivector_wrap.cc"), os.path.join(HERE, "ref_wrap", "nnet_stubs.cc"),
+             os.path.join(HERE, "ref_wrap", "endpoint_wrap.cc")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(w) for w in wraps):
         return SO
     if not os.path.isdir(RF.SRC):
@@ -63,8 +64,10 @@ def build(quiet: bool = False, force: bool = False) -> str:
     iobj = os.path.join(OUT_DIR, "obj_nnet", "ivector_wrap.o")
     subprocess.check_call(["g++"] + flags + ["-c", os.path.join(HERE, "ref_wrap", "ivector_wrap.cc"), "-o", iobj])
     subprocess.check_call(["g++"] + flags + ["-c", wrap, "-o", wobj])
+    eobj = os.path.join(OUT_DIR, "obj_nnet", "endpoint_wrap.o")
+    subprocess.check_call(["g++"] + flags + ["-c", os.path.join(HERE, "ref_wrap", "endpoint_wrap.cc"), "-o", eobj])
     subprocess.check_call(["g++"] + flags + ["-c", os.path.join(HERE, "ref_wrap", "nnet_stubs.cc"), "-o", sobj])
-    subprocess.check_call(["g++", "-shared", "-o", SO] + objs + base_objs + [wobj, sobj, iobj, blas,
+    subprocess.check_call(["g++", "-shared", "-o", SO] + objs + base_objs + [wobj, sobj, iobj, eobj, blas,
                           "-Wl,--disable-new-dtags,-rpath," + os.path.dirname(blas), "-lpthread", "-lm", "-ldl"])
     return SO
 
