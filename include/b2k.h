@@ -351,7 +351,7 @@ int b2k_ivec_online_schedule(int64_t num_samples, int32_t chunk_samples, int32_t
 
 /* ------------------------------------------------------------------ nnet3 program compiler (host only)
  *
- * From a chain-model layer list (the xconfig layers of the TDNN-F and CNN-TDNN-F recipes) and its parameters
+ * From a chain-model layer list (the xconfig layers of the TDNN, TDNN-F and CNN-TDNN-F recipes) and its parameters
  * to the op program b2k_nnet_create executes: the role of nnet3's compiler for this family
  * (nnet3/nnet-compile.cc, nnet-compile-looped.cc:329, nnet-optimize.cc) for utterances of `num_frames`
  * feature frames.  Needs no device.  kaldi_b200/nnet_model.py holds the same algorithm in Python as its
@@ -366,6 +366,8 @@ typedef struct {
   int32_t height, filters1, filters2;                /* combine-feature-maps-layer                        */
   int32_t height_in, height_out, height_subsample_out, filters_in, filters_out;   /* conv-relu-batchnorm-layer */
   int32_t n_time_offsets, time_offsets[8], n_height_offsets, height_offsets[8];
+  /* time_offsets, besides conv: the splice of the input of an lda / relu-batchnorm layer (input=Append(-1,0,1) of the chain TDNN
+   * recipes); n_time_offsets = 0 means the TDNN-F recipes' form: -1,0,1 in front of lda, none for relu-batchnorm */
 } b2k_nnet_layer;
 
 typedef struct {

@@ -591,6 +591,62 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
     if (!c) throw FormatError("missing component " + cn[i].second.at("component"));
     return *c;
   };
+  // The time offsets over which an input descriptor splices ONE source node: x -> {0}; Append(Offset(x, -1), x, Offset(x, 1)) ->
+  // {-1, 0, 1} (what xconfig writes for input=Append(-1,0,1)); a trailing term on the ivector input is not part of the splice.
+  auto trim = [](const std::string &x) -> std::string {
+    const size_t a = x.find_first_not_of(" \t");
+    return a == std::string::npos ? std::string() : x.substr(a, x.find_last_not_of(" \t") - a + 1);
+  };
+  auto splice_offsets = [&](const std::string &desc) -> std::vector<int> {
+    const std::string d = trim(desc);
+    if (d.size() < 8 || d.compare(0, 7, "Append(") != 0 || d.back() != ')') return {0};
+    std::vector<std::string> terms;
+    int depth = 0;
+    size_t start = 7;
+    for (size_t p = 7; p + 1 < d.size(); p++) {
+      if (d[p] == '(') depth++;
+      else if (d[p] == ')') depth--;
+      else if (d[p] == ',' && depth == 0) { terms.push_back(d.substr(start, p - start)); start = p + 1; }
+    }
+    terms.push_back(d.substr(start, d.size() - 1 - start));
+    auto is_name = [](const std::string &w) {
+      if (w.empty() || !(std::isalpha((unsigned char)w[0]) || w[0] == '_')) return false;
+      for (char ch : w) if (!(std::isalnum((unsigned char)ch) || ch == '_' || ch == '.' || ch == '-')) return false;
+      return true;
+    };
+    std::vector<int> offs;
+    std::string src;
+    for (size_t k = 0; k < terms.size(); k++) {
+      const std::string term = trim(terms[k]);
+      bool on_ivector = false;
+      for (auto &w : descriptor_nodes(term)) on_ivector = on_ivector || w == "ivector";
+      if (on_ivector) {
+        if (k + 1 != terms.size()) throw FormatError("unsupported input descriptor " + desc);
+        continue;
+      }
+      std::string node = term;
+      long o = 0;
+      if (term.compare(0, 7, "Offset(") == 0 && term.back() == ')') {
+        const size_t comma = term.find(',');
+        if (comma == std::string::npos) throw FormatError("unsupported input descriptor " + desc);
+        node = trim(term.substr(7, comma - 7));
+        const std::string num = trim(term.substr(comma + 1, term.size() - 2 - comma));
+        char *end = nullptr;
+        o = strtol(num.c_str(), &end, 10);
+        if (num.empty() || !end || *end != 0 || o < -64 || o > 64) throw FormatError("unsupported input descriptor " + desc);
+      }
+      if (!is_name(node) || (!src.empty() && node != src)) throw FormatError("unsupported input descriptor " + desc);
+      src = node;
+      offs.push_back((int)o);
+    }
+    if (offs.empty() || offs.size() > 8) throw FormatError("unsupported input descriptor " + desc);
+    return offs;
+  };
+  auto set_splice = [&](b2k_nnet_layer &L, const std::vector<int> &sp, const std::vector<int> &dflt) {
+    if (sp == dflt) return;
+    L.n_time_offsets = (int32_t)sp.size();
+    for (size_t k = 0; k < sp.size(); k++) L.time_offsets[k] = sp[k];
+  };
   auto new_layer = [&](const char *type, const std::string &name) -> b2k_nnet_layer & {
     b2k_nnet_layer L;
     memset(&L, 0, sizeof(L));
@@ -660,6 +716,7 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
       const Value &w = A.field(c, "<LinearParams>");
       b2k_nnet_layer &L = new_layer(idct ? "idct" : "lda", n);
       if (idct) L.dim = w.rows;
+      else set_splice(L, splice_offsets(inputs[n]), {-1, 0, 1});
       A.add_w(n + ".w", w);
       A.add_w(n + ".b", A.field(c, "<BiasParams>"));
       A.node_dim[n] = w.rows;
@@ -697,6 +754,7 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
         b2k_nnet_layer &L = new_layer("relu-batchnorm", base);
         L.dim = w.rows;
         if (inputs[n].find("ivector") != std::string::npos) { float s = 1.0f; scale_in(inputs[n], &s); L.append_ivector = s; }
+        set_splice(L, splice_offsets(inputs[n]), {0});
         A.add_w(n + ".w", w); A.add_w(n + ".b", A.field(c, "<BiasParams>"));
         A.bn(base + ".batchnorm", base + ".batchnorm");
         i += 3;
@@ -739,7 +797,10 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
     }
   }
   M->subsampling = 1;
-  for (auto &L : M->layers) if (!strcmp(L.type, "tdnnf") && L.stride == 3) M->subsampling = 3;
+  for (auto &L : M->layers) {                          // not stored in the file (the tools take --frame-subsampling-factor): a layer that
+    if (!strcmp(L.type, "tdnnf") && L.stride == 3) M->subsampling = 3;           // looks 3 frames away marks a chain model
+    if (!strcmp(L.type, "relu-batchnorm")) for (int k = 0; k < L.n_time_offsets; k++) if (L.time_offsets[k] == 3 || L.time_offsets[k] == -3) M->subsampling = 3;
+  }
 }
 
 static void finish(b2k_model *M, const std::vector<float> *priors) {

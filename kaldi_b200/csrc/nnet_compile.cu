@@ -81,6 +81,11 @@ struct Graph {
 };
 
 static std::string S(const char *c, size_t cap) { return std::string(c, strnlen(c, cap)); }
+// the time offsets a layer splices its input over: time_offsets when given, else the recipe default of the layer kind
+static std::vector<int> splice_of(const b2k_nnet_layer &L, std::vector<int> dflt) {
+  if (L.n_time_offsets <= 0) return dflt;
+  return std::vector<int>(L.time_offsets, L.time_offsets + std::min(L.n_time_offsets, 8));
+}
 
 #define NEED(ptr, what) do { if (!(ptr)) { err = std::string("missing weight ") + (what); return false; } } while (0)
 
@@ -160,15 +165,20 @@ static bool build_graph(const b2k_nnet_compile_cfg &cfg, const b2k_nnet_layer *l
       if (!bn(&x, n, 1.0f, 1)) return false;
       add(x); cur = n;
     } else if (t == "lda") {
-      const int k = 3 * fd + ivd;
+      const int d = g->dims[cur];
+      const std::vector<int> sp = splice_of(L, {-1, 0, 1});
+      const int k = (int)sp.size() * d + ivd;
       Node x; x.name = n; x.dim = k; x.kind = 2;
-      x.terms = {{cur, -1, 0, fd, 0}, {cur, 0, fd, 2 * fd, 0}, {cur, 1, 2 * fd, 3 * fd, 0}, {"ivector", 0, 3 * fd, k, 1}};
+      for (size_t i = 0; i < sp.size(); i++) x.terms.push_back({cur, sp[i], (int)i * d, (int)(i + 1) * d, 0});
+      x.terms.push_back({"ivector", 0, (int)sp.size() * d, k, 1});
       if (!lin(&x, n, true)) return false;
       add(x); cur = n;
     } else if (t == "relu-batchnorm") {
-      const int d = g->dims[cur];
+      const int d0 = g->dims[cur];
+      const std::vector<int> sp = splice_of(L, {0});
+      const int d = (int)sp.size() * d0;
       Node x; x.name = n + ".batchnorm"; x.dim = L.dim; x.kind = 2; x.relu = true;
-      x.terms = {{cur, 0, 0, d, 0}};
+      for (size_t i = 0; i < sp.size(); i++) x.terms.push_back({cur, sp[i], (int)i * d0, (int)(i + 1) * d0, 0});
       if (L.append_ivector != 0.0f) {     // Scale(s, ReplaceIndex(ivector, t, 0)) is a node of its own (reference's association)
         Node s; s.name = n + ".ivscaled"; s.dim = ivd; s.kind = 3; s.block_dim = ivd; s.ivector_rows = true;
         s.blocks = {{{"ivector", 0, L.append_ivector}}};
@@ -275,7 +285,11 @@ static bool validate_layers(const b2k_nnet_compile_cfg &cfg, const b2k_nnet_laye
     const std::string t = S(L.type, sizeof(L.type)), n = S(L.name, sizeof(L.name));
     auto dim_ok = [&](int d) { return d > 0 && d <= kMaxDim; };
     bool ok = true;
-    if (t == "relu-batchnorm" || t == "linear" || t == "output" || t == "ivector-linear-bn") ok = dim_ok(L.dim);
+    if (t == "linear" || t == "output" || t == "ivector-linear-bn") ok = dim_ok(L.dim);
+    else if (t == "relu-batchnorm" || t == "lda") {          // time_offsets: the splice of the layer's input (0 = the recipe default)
+      ok = (t == "lda" || dim_ok(L.dim)) && L.n_time_offsets >= 0 && L.n_time_offsets <= 8;
+      for (int k = 0; ok && k < L.n_time_offsets; k++) ok = L.time_offsets[k] >= -64 && L.time_offsets[k] <= 64;
+    }
     else if (t == "tdnnf") ok = dim_ok(L.dim) && dim_ok(L.bottleneck) && L.stride >= 0 && L.stride <= 64;
     else if (t == "prefinal") ok = dim_ok(L.big) && dim_ok(L.small);
     else if (t == "combine") ok = L.height > 0 && L.filters1 > 0 && L.filters2 >= 0 && (long long)L.height * (L.filters1 + (long long)L.filters2) <= kMaxDim;

@@ -442,6 +442,39 @@ def _descriptor_nodes(desc: str) -> list[str]:
     return [w for w in re.findall(r"[A-Za-z_][A-Za-z0-9_.\-]*", desc) if w not in _DESCRIPTOR_WORDS]
 
 
+def _splice_offsets(desc: str) -> list[int]:
+    """The time offsets over which an input descriptor splices ONE source node: `x` -> [0];
+    `Append(Offset(x, -1), x, Offset(x, 1))` -> [-1, 0, 1] (what xconfig writes for input=Append(-1,0,1)); a trailing
+    term on the ivector input is not part of the splice.  Anything else (two sources, nested expressions) raises."""
+    d = desc.strip()
+    if not (d.startswith("Append(") and d.endswith(")")):
+        return [0]
+    terms, depth, start = [], 0, 7
+    for p in range(7, len(d) - 1):
+        depth += d[p] == "("
+        depth -= d[p] == ")"
+        if d[p] == "," and depth == 0:
+            terms.append(d[start:p])
+            start = p + 1
+    terms.append(d[start:len(d) - 1])
+    offs, src = [], None
+    for k, term in enumerate(terms):
+        term = term.strip()
+        if "ivector" in _descriptor_nodes(term):
+            if k != len(terms) - 1:
+                raise KaldiFormatError(f"unsupported input descriptor {desc}")
+            continue
+        m = re.fullmatch(r"Offset\(\s*([^,()\s]+)\s*,\s*(-?\d+)\s*\)", term)
+        node, o = (m.group(1), int(m.group(2))) if m else (term, 0)
+        if not re.fullmatch(r"[A-Za-z_][A-Za-z0-9_.\-]*", node) or (src is not None and node != src):
+            raise KaldiFormatError(f"unsupported input descriptor {desc}")
+        src = node
+        offs.append(o)
+    if not offs or len(offs) > 8:
+        raise KaldiFormatError(f"unsupported input descriptor {desc}")
+    return offs
+
+
 def _inference_view(nodes: list, comps: dict) -> list:
     """What a trained recipe model looks like to the decoder: (1) dropout components are the identity in test mode, so
     every reference to such a node is replaced by the node's own input; (2) only what the output node named "output"
@@ -589,7 +622,11 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
             node_dim[n] = int(W[n + ".w"].shape[0])
             i += 1
         elif t == "FixedAffineComponent":
-            layers.append({"type": "lda", "name": n})
+            L = {"type": "lda", "name": n}
+            sp = _splice_offsets(inputs[n])
+            if sp != [-1, 0, 1]:
+                L["time_offsets"] = sp
+            layers.append(L)
             W[n + ".w"], W[n + ".b"] = mat(n, "<LinearParams>"), mat(n, "<BiasParams>")
             i += 1
         elif t == "BatchNormComponent" and i + 1 < len(cn) and comps[cn[i + 1][1]["component"]]["type"] == "NoOpComponent" \
@@ -627,6 +664,9 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
                     re.search(r"Scale\(([0-9.eE+-]+),\s*ReplaceIndex\(ivector", inputs[n])
                 if "ivector" in inputs[n]:
                     L["append_ivector"] = float(m.group(1)) if m else 1.0
+                sp = _splice_offsets(inputs[n])
+                if sp != [0]:
+                    L["time_offsets"] = sp
                 layers.append(L)
                 W[n + ".w"], W[n + ".b"] = mat(n, "<LinearParams>"), mat(n, "<BiasParams>")
                 bn(base + ".batchnorm", base + ".batchnorm")
@@ -667,7 +707,10 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
     arch["layers"] = layers
     out = [L for L in layers if L["type"] == "output"]
     arch["num_pdfs"] = out[0]["dim"] if out else 0
-    arch["frame_subsampling_factor"] = 3 if any(L["type"] == "tdnnf" and L["stride"] == 3 for L in layers) else 1
+    # not stored in the file (the tools take --frame-subsampling-factor): a layer that looks 3 frames away marks a chain model
+    arch["frame_subsampling_factor"] = 3 if any((L["type"] == "tdnnf" and L["stride"] == 3) or
+                                                (L["type"] == "relu-batchnorm" and 3 in map(abs, L.get("time_offsets", [])))
+                                                for L in layers) else 1
     return arch, W
 
 

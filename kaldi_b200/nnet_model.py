@@ -17,8 +17,10 @@ basic_layers.py / trivial_layers.py of egs/wsj/s5/steps/libs/nnet3/xconfig):
   idct            FixedAffineComponent
   batchnorm       BatchNormComponent (test mode)
   delta           NoOp over Append(Offset..)/Sum/Scale + BatchNorm   (trivial_layers.py:189-257)
-  lda             FixedAffineComponent over Append(-1,0,1,ReplaceIndex(ivector,t,0))
-  relu-batchnorm  NaturalGradientAffine + ReLU + BatchNorm
+  lda             FixedAffineComponent over Append(-1,0,1,ReplaceIndex(ivector,t,0)); `time_offsets` gives another splice
+                  (Append(-2,-1,0,1,2,...) of the chain TDNN recipes, wsj run_tdnn_1f.sh:171)
+  relu-batchnorm  NaturalGradientAffine + ReLU + BatchNorm; `time_offsets` = the input=Append(-1,0,1) / Append(-3,0,3) /
+                  Append(-6,-3,0) splice of a TDNN layer without factorisation
   tdnnf           TdnnComponent(linear) + TdnnComponent(affine) + ReLU + BatchNorm + NoOp(Sum(Scale(bypass,in),bn))
   linear          LinearComponent
   prefinal        NaturalGradientAffine + ReLU + BatchNorm + Linear + BatchNorm
@@ -110,6 +112,38 @@ def arch_librispeech_1d(num_pdfs: int = 6024) -> dict:
                       [1, 1, 1, 0, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3], 256, "lda")
 
 
+def splice_of(L: dict) -> list:
+    """Time offsets a layer splices its input over (the Append(-1,0,1) of an xconfig `input=`): `time_offsets` when given,
+    else what the TDNN-F recipes use: -1,0,1 in front of the LDA-like transform, none for a relu-batchnorm-layer."""
+    v = L.get("time_offsets")
+    return [int(o) for o in v] if v else ([-1, 0, 1] if L["type"] == "lda" else [0])
+
+
+def arch_tdnn(name: str, feat_dim: int, ivector_dim: int, num_pdfs: int, dim: int, splices, lda_splice=(-2, -1, 0, 1, 2)) -> dict:
+    """The chain TDNN without factorisation (egs/wsj/s5/local/chain/tuning/run_tdnn_1f.sh:165-186 and 89 more recipes):
+    fixed-affine-layer over Append(-2..2, ivector), relu-batchnorm-layers whose inputs are spliced Append(-1,0,1) /
+    Append(-3,0,3) / Append(-6,-3,0), prefinal-chain, output-layer."""
+    layers = [dict(type="lda", name="lda", time_offsets=list(lda_splice))]
+    for i, sp in enumerate(splices):
+        L = dict(type="relu-batchnorm", name=f"tdnn{i + 1}", dim=dim)
+        if list(sp) != [0]:
+            L["time_offsets"] = list(sp)
+        layers.append(L)
+    layers += [dict(type="relu-batchnorm", name="prefinal-chain", dim=dim),
+               dict(type="output", name="output", dim=num_pdfs, log_softmax=False)]
+    return dict(name=name, feat_dim=feat_dim, ivector_dim=ivector_dim, num_pdfs=num_pdfs, frame_subsampling_factor=3, layers=layers)
+
+
+def arch_wsj_tdnn_1f(num_pdfs: int = 2880, dim: int = 448) -> dict:
+    """egs/wsj/s5/local/chain/tuning/run_tdnn_1f.sh:165-186."""
+    return arch_tdnn("wsj_tdnn_1f", 40, 100, num_pdfs, dim,
+                     [[0], [-1, 0, 1], [0], [-1, 0, 1], [0], [-3, 0, 3], [-3, 0, 3], [-6, -3, 0]])
+
+
+def arch_tiny_tdnn(num_pdfs: int = 56) -> dict:
+    return arch_tdnn("tiny_tdnn", 40, 100, num_pdfs, 48, [[0], [-1, 0, 1], [-3, 0, 3], [-6, -3, 0]])
+
+
 def arch_tiny(num_pdfs: int = 64, front: str = "idct-delta") -> dict:
     return arch_tdnnf("tiny_tdnnf", 40, 100, num_pdfs, 64, 16, [1, 0, 3, 3], 32, front)
 
@@ -144,11 +178,11 @@ def random_weights(arch: dict, seed: int = 0) -> dict:
             bn(n, 3 * cur)
             cur = 3 * cur
         elif t == "lda":
-            k = 3 * fd + ivd
+            k = len(splice_of(L)) * cur + ivd
             lin(n, k, k)
             cur = k
         elif t == "relu-batchnorm":
-            k = cur + (ivd if L.get("append_ivector") else 0)
+            k = cur * len(splice_of(L)) + (ivd if L.get("append_ivector") else 0)
             lin(n + ".affine", L["dim"], k)
             bn(n + ".batchnorm", L["dim"])
             cur = L["dim"]
@@ -229,8 +263,9 @@ def to_nnet3_config(arch: dict, W: dict, tmpdir: str) -> str:
             path = os.path.join(tmpdir, f"{n}.mat")
             _write_kaldi_matrix(path, np.concatenate([W[n + ".w"], W[n + ".b"][:, None]], 1))
             if t == "lda":
-                inp = f"Append(Offset({cur}, -1), {cur}, Offset({cur}, 1), ReplaceIndex(ivector, t, 0))"
-                cur_dim = 3 * fd + ivd
+                sp = ", ".join(cur if o == 0 else f"Offset({cur}, {o})" for o in splice_of(L))
+                inp = f"Append({sp}, ReplaceIndex(ivector, t, 0))"
+                cur_dim = len(splice_of(L)) * cur_dim + ivd
             else:
                 inp = cur
             c.append(f"component name={n} type=FixedAffineComponent matrix={path}")
@@ -258,11 +293,13 @@ def to_nnet3_config(arch: dict, W: dict, tmpdir: str) -> str:
             c.append(f"component-node name={n} component={n} input={cur}_2")
             cur, cur_dim = n, 3 * cur_dim
         elif t == "relu-batchnorm":
+            sp = splice_of(L)
+            spliced = ", ".join(cur if o == 0 else f"Offset({cur}, {o})" for o in sp)
             if L.get("append_ivector"):
-                inp = f"Append({cur}, Scale({L['append_ivector']}, ReplaceIndex(ivector, t, 0)))"
-                k = cur_dim + ivd
+                inp = f"Append({spliced}, Scale({L['append_ivector']}, ReplaceIndex(ivector, t, 0)))"
+                k = len(sp) * cur_dim + ivd
             else:
-                inp, k = cur, cur_dim
+                inp, k = (cur if sp == [0] else f"Append({spliced})"), len(sp) * cur_dim
             c.append(f"component name={n}.affine type=NaturalGradientAffineComponent input-dim={k} output-dim={L['dim']}")
             c.append(f"component-node name={n}.affine component={n}.affine input={inp}")
             c.append(f"component name={n}.relu type=RectifiedLinearComponent dim={L['dim']}")
@@ -466,14 +503,15 @@ def build_graph(arch: dict, W: dict, structural: bool = False, conv_mode: str | 
             add(Node(n, 3 * d, "ew", spec=dict(blocks=blocks, block_dim=d, bn=bn_scale_offset(W[n + ".mean"], W[n + ".var"]))))
             cur = n
         elif t == "lda":
-            k = 3 * fd + ivd
-            terms = [(cur, -1, (0, fd), "row"), (cur, 0, (fd, 2 * fd), "row"), (cur, 1, (2 * fd, 3 * fd), "row"),
-                     ("ivector", 0, (3 * fd, k), "ivec")]
+            d, sp = dims[cur], splice_of(L)
+            k = len(sp) * d + ivd
+            terms = [(cur, o, (i * d, (i + 1) * d), "row") for i, o in enumerate(sp)] + [("ivector", 0, (len(sp) * d, k), "ivec")]
             add(Node(n, k, "gemm", spec=dict(terms=terms, w=W[n + ".w"], b=W[n + ".b"])))
             cur = n
         elif t == "relu-batchnorm":
-            d = dims[cur]
-            terms = [(cur, 0, (0, d), "row")]
+            d0, sp = dims[cur], splice_of(L)
+            d = len(sp) * d0
+            terms = [(cur, o, (i * d0, (i + 1) * d0), "row") for i, o in enumerate(sp)]
             if L.get("append_ivector"):
                 # Scale(0.4, ReplaceIndex(ivector,t,0)) is a node of its own so the product keeps the
                 # reference's association (0.4*iv rounded to f32, then the affine)

@@ -185,11 +185,12 @@ def forward_dense(arch: dict, W: dict, feats: np.ndarray, chunk_ivectors: np.nda
             b2 = (shift(cur, -2) + shift(cur, 2)).astype(f32) + (f32(-2.0) * cur).astype(f32)
             cur = bn(np.concatenate([b0, b1, b2], 1).astype(f32), n)
         elif t == "lda":
-            cur = affine(np.concatenate([shift(cur, -1), cur, shift(cur, 1), iv_t], 1).astype(f32), n)
+            cur = affine(np.concatenate([shift(cur, o) for o in NM.splice_of(L)] + [iv_t], 1).astype(f32), n)
         elif t == "relu-batchnorm":
-            a = cur
+            sp = NM.splice_of(L)
+            a = cur if sp == [0] else np.concatenate([shift(cur, o) for o in sp], 1)
             if L.get("append_ivector"):
-                a = np.concatenate([cur, (f32(L["append_ivector"]) * iv_t).astype(f32)], 1)
+                a = np.concatenate([a, (f32(L["append_ivector"]) * iv_t).astype(f32)], 1)
             cur = bn(np.maximum(affine(a, n + ".affine"), 0), n + ".batchnorm")
         elif t == "tdnnf":
             s = L["stride"]

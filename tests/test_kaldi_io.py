@@ -27,9 +27,9 @@ def _ref_model_files(tmp_path, arch, W):
     return out
 
 
-@pytest.mark.parametrize("front", ["idct-delta", "lda", "cnn"])
+@pytest.mark.parametrize("front", ["idct-delta", "lda", "cnn", "tdnn"])
 def test_nnet3_raw_model_round_trip_through_the_reference_writer(tmp_path, front):
-    arch = NM.arch_tiny_cnn() if front == "cnn" else NM.arch_tiny(front=front)
+    arch = NM.arch_tiny_cnn() if front == "cnn" else NM.arch_tiny_tdnn() if front == "tdnn" else NM.arch_tiny(front=front)
     W = NM.random_weights(arch, seed=3)
     files = _ref_model_files(tmp_path, arch, W)
     a3, W3 = NM.load_kaldi_raw(files["bin"])

@@ -63,7 +63,7 @@ CHAIN_TOPO = """<Topology>
 """
 
 
-@pytest.mark.parametrize("which", ["idct-delta", "lda", "cnn"])
+@pytest.mark.parametrize("which", ["idct-delta", "lda", "cnn", "tdnn"])
 @pytest.mark.parametrize("binary", [1, 0])
 def test_cpp_reader_on_reference_written_models(tmp_path, which, binary):
     L = _lib()
@@ -71,7 +71,7 @@ def test_cpp_reader_on_reference_written_models(tmp_path, which, binary):
     from oracle import nnet_oracle as NO
     if not (os.path.exists(NO._SO) or os.path.isdir("/root/reference")):
         pytest.skip("oracle/_ref nnet3 library not present")
-    arch = NM.arch_tiny_cnn() if which == "cnn" else NM.arch_tiny(front=which)
+    arch = NM.arch_tiny_cnn() if which == "cnn" else NM.arch_tiny_tdnn() if which == "tdnn" else NM.arch_tiny(front=which)
     Wt = NM.random_weights(arch, seed=3)
     R = NO.RefNnet(arch, Wt, collapse=False)
     if not hasattr(R.lib, "ref_write_final_mdl"):

@@ -51,7 +51,7 @@ def _term_tuple(t):
 
 
 CASES = [("tiny-idct", {}), ("tiny-lda", {}), ("tiny-logsoftmax", {}), ("cnn-patch", {"conv_mode": "patch"}),
-         ("cnn-dense", {"conv_mode": "dense"}), ("mini", {}), ("libri-1d", {}), ("libri-cnn", {})]
+         ("cnn-dense", {"conv_mode": "dense"}), ("mini", {}), ("libri-1d", {}), ("libri-cnn", {}), ("tiny-tdnn", {}), ("wsj-1f", {})]
 
 
 @pytest.mark.parametrize("which,kw", CASES, ids=[c[0] for c in CASES])
@@ -68,6 +68,10 @@ def test_cpp_compiler_equals_python_compiler(which, kw, T):
     elif which == "tiny-logsoftmax":
         arch = NM.arch_tiny(64)
         arch["layers"][-1]["log_softmax"] = True
+    elif which == "tiny-tdnn":
+        arch = NM.arch_tiny_tdnn()
+    elif which == "wsj-1f":
+        arch = NM.arch_wsj_tdnn_1f(256)
     elif which == "mini":
         arch = NM.arch_mini_librispeech_1k(256)
     elif which == "libri-1d":

@@ -83,14 +83,14 @@ def _ref_forward(R, feats, civ, n_chunks):
     return R.forward(feats, mat, period=1)
 
 
-@pytest.mark.parametrize("which,T", [("tdnnf", 64), ("cnn", 90), ("cnn", 23), ("cnn-patch", 90), ("cnn-patch", 23)])
+@pytest.mark.parametrize("which,T", [("tdnnf", 64), ("cnn", 90), ("cnn", 23), ("cnn-patch", 90), ("cnn-patch", 23), ("tdnn", 64), ("tdnn", 23)])
 def test_compiled_program_vs_compiled_reference(which, T):
     """The op program itself (what the CUDA executor runs), interpreted in numpy, against the reference's
     compiled nnet3: covers the CNN-TDNN-F front end (TimeHeightConvolutionComponent as a dense map per
     time offset, combine-feature-maps permutation folded into the weights, per-chunk i-vector branch)."""
     from oracle import nnet_oracle as NO
     from oracle.program_interp import run_program
-    arch = NM.arch_tiny_cnn() if which.startswith("cnn") else NM.arch_tiny(64)
+    arch = NM.arch_tiny_cnn() if which.startswith("cnn") else NM.arch_tiny_tdnn() if which == "tdnn" else NM.arch_tiny(64)
     W = NM.random_weights(arch, seed=7)
     prog = NM.compile_program(arch, W, T, 21, acoustic_scale=0.9, conv_mode="patch" if which == "cnn-patch" else "dense")
     R = NO.RefNnet(arch, W, frames_per_chunk=20, acoustic_scale=0.9)
@@ -104,13 +104,14 @@ def test_compiled_program_vs_compiled_reference(which, T):
     assert np.abs(mine - ref).max() <= 1e-4 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("which", ["librispeech_tdnn_1d", "librispeech_cnn_tdnn_1a"])
+@pytest.mark.parametrize("which", ["librispeech_tdnn_1d", "librispeech_cnn_tdnn_1a", "wsj_tdnn_1f"])
 def test_baseline_config_architectures_vs_compiled_reference(which):
     """BASELINE.json configs 2 and 3 at full width (fewer pdfs to keep it quick): the compiled op program vs the
     reference's compiled nnet3, and ComputeSimpleNnetContext."""
     from oracle import nnet_oracle as NO
     from oracle.program_interp import run_program
-    arch = (NM.arch_librispeech_1d if which == "librispeech_tdnn_1d" else NM.arch_librispeech_cnn_tdnn_1a)(num_pdfs=512)
+    arch = {"librispeech_tdnn_1d": NM.arch_librispeech_1d, "librispeech_cnn_tdnn_1a": NM.arch_librispeech_cnn_tdnn_1a,
+            "wsj_tdnn_1f": NM.arch_wsj_tdnn_1f}[which](num_pdfs=512)
     W = NM.random_weights(arch, seed=1)
     T = 50
     prog = NM.compile_program(arch, W, T, 21)

@@ -282,3 +282,115 @@ def test_mini_librispeech_tdnn_1k_shape_from_the_references_xconfig_library(tmp_
     out = PI.run_program(prog, feats, iv[R.chunk_ivector_rows(T, T, 1)])
     assert np.abs(ref).max() > 1e-2 and ref.std() > 1e-3                                  # a real comparison, not 0 == 0
     assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+WSJ_TDNN_1F_XCONFIG = """input dim=100 name=ivector
+input dim=40 name=input
+fixed-affine-layer name=lda input=Append(-2,-1,0,1,2,ReplaceIndex(ivector, t, 0)) affine-transform-file={lda}
+relu-batchnorm-layer name=tdnn1 l2-regularize=0.01 dim=56
+relu-batchnorm-layer name=tdnn2 l2-regularize=0.01 dim=56 input=Append(-1,0,1)
+relu-batchnorm-layer name=tdnn3 l2-regularize=0.01 dim=56
+relu-batchnorm-layer name=tdnn4 l2-regularize=0.01 dim=56 input=Append(-1,0,1)
+relu-batchnorm-layer name=tdnn5 l2-regularize=0.01 dim=56
+relu-batchnorm-layer name=tdnn6 l2-regularize=0.01 dim=56 input=Append(-3,0,3)
+relu-batchnorm-layer name=tdnn7 l2-regularize=0.01 dim=56 input=Append(-3,0,3)
+relu-batchnorm-layer name=tdnn8 l2-regularize=0.01 dim=56 input=Append(-6,-3,0)
+relu-batchnorm-layer name=prefinal-chain l2-regularize=0.01 dim=56
+output-layer name=output l2-regularize=0.005 include-log-softmax=false dim=48
+relu-batchnorm-layer name=prefinal-xent l2-regularize=0.01 input=tdnn8 dim=56
+output-layer name=output-xent l2-regularize=0.005 dim=48 learning-rate-factor=5.0
+"""
+
+
+@pytest.mark.parametrize("binary", [1, 0])
+def test_wsj_tdnn_1f_shape_from_the_references_xconfig_library(tmp_path, binary):
+    """The chain TDNN without factorisation (egs/wsj/s5/local/chain/tuning/run_tdnn_1f.sh:165-186; 90 tuning scripts of the
+    reference use this layer form): LDA over Append(-2..2, ivector), relu-batchnorm-layers over Append(-1,0,1), Append(-3,0,3),
+    Append(-6,-3,0), both output branches; narrower layers, same structure."""
+    if not os.path.isdir(STEPS):
+        pytest.skip("the reference's xconfig library exists in the build container only")
+    from oracle import nnet_oracle as NO
+    from oracle import program_interp as PI
+    sys.path.insert(0, STEPS)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import libs.nnet3.xconfig.parser as xparser
+    rng = np.random.default_rng(11)
+    lda = str(tmp_path / "lda.mat")
+    KIO.write_matrix(lda, (rng.standard_normal((300, 301)) / 17).astype(np.float32), binary=False)
+    xc = str(tmp_path / "network.xconfig")
+    open(xc, "w").write(WSJ_TDNN_1F_XCONFIG.format(lda=lda))
+    lines = [line for layer in xparser.read_xconfig_file(xc) for base, line in layer.get_full_config() if base == "final"]
+    config = "\n".join(lines) + "\n"
+    assert "Append(Offset(tdnn7.batchnorm, -6), Offset(tdnn7.batchnorm, -3), tdnn7.batchnorm)" in config
+    R = NO.RefNnet.__new__(NO.RefNnet)
+    L = R.lib = C.CDLL(NO._SO)
+    L.ref_nnet_create.restype = C.c_void_p
+    L.ref_nnet_component_name.restype = C.c_char_p
+    L.ref_nnet_component_type.restype = C.c_char_p
+    R.h = C.c_void_p(L.ref_nnet_create(config.encode()))
+    assert R.h, "the reference rejected its own xconfig output"
+    R.arch = {"frame_subsampling_factor": 3}
+    _randomise_parameters(L, R.h, rng)
+    f32p = C.POINTER(C.c_float)
+    for i in range(L.ref_nnet_num_components(R.h)):
+        name, typ = L.ref_nnet_component_name(R.h, i).decode(), L.ref_nnet_component_type(R.h, i).decode()
+        if typ == "BatchNormComponent":
+            mean, var = (rng.standard_normal(56) * 0.1).astype(np.float32), rng.uniform(0.5, 1.5, 56).astype(np.float32)
+            assert L.ref_nnet_set_batchnorm(R.h, i, C.c_int(56), C.c_int(56), C.c_float(1e-3), C.c_float(1.0), C.c_float(1000.0),
+                                            mean.ctypes.data_as(f32p), var.ctypes.data_as(f32p)) == 0, name
+    raw = str(tmp_path / "final.raw")
+    L.ref_nnet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    assert L.ref_nnet_write(R.h, raw.encode(), binary) == 0
+    arch, W = NM.load_kaldi_raw(raw)
+    want = NM.arch_wsj_tdnn_1f(48, dim=56)
+    assert [(x["type"], x["name"], x.get("time_offsets")) for x in arch["layers"]] == \
+           [(x["type"], x["name"], x.get("time_offsets")) for x in want["layers"]]
+    assert (arch["feat_dim"], arch["ivector_dim"], arch["num_pdfs"], arch["frame_subsampling_factor"]) == (40, 100, 48, 3)
+    try:
+        from kaldi_b200.model import KaldiModel
+        from kaldi_b200.nnet_compile import _Layer
+        m = KaldiModel(raw, is_mdl=False)
+    except OSError as e:
+        pytest.skip(str(e))
+    assert m.layer_types() == [(x["type"], x["name"]) for x in want["layers"]]
+    a = C.cast(m.layers_ptr, C.POINTER(_Layer))
+    assert [list(a[i].time_offsets[:a[i].n_time_offsets]) for i in range(m.n_layers)] == [x.get("time_offsets", []) for x in want["layers"]]
+    got = m.weights()
+    for k, v in W.items():
+        np.testing.assert_array_equal(got[k].reshape(-1), np.asarray(v, np.float32).reshape(-1), err_msg=k)
+    # forward: the reference's looped computation of ITS model against the programs compiled (Python and C++) from what was read
+    assert L.ref_nnet_prepare(R.h, C.c_int(20), C.c_int(3), C.c_float(1.0), None, C.c_int(0), C.c_int(1)) == 0
+    info = (C.c_int * 4)()
+    L.ref_nnet_info(R.h, info)
+    R.left_context, R.right_context, R.frames_per_chunk, R.output_dim = list(info)
+    assert (R.left_context, R.right_context) == NM.model_context(arch) == (16, 10)        # 2+1+1+3+3+6 / 2+1+1+3+3
+    T = 70
+    feats = (rng.standard_normal((T, 40)) * 10).astype(np.float32)
+    iv = rng.standard_normal((T, 100)).astype(np.float32)
+    ref = R.forward(feats, iv, period=1)
+    assert np.abs(ref).max() > 1e-2 and ref.std() > 1e-3
+    civ = iv[R.chunk_ivector_rows(T, T, 1)]
+    prog = NM.compile_program(arch, dict(W, priors=np.ones(48, np.float32)), T, 21, use_priors=False)
+    out = PI.run_program(prog, feats, civ)
+    assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max()
+    from kaldi_b200 import _lib as LB
+    from kaldi_b200.nnet_compile import _Node, _Op
+    B = LB.lib()
+    hp = m.compile(T, 21, use_priors=False)
+    try:
+        nn, no, bl = C.c_int32(), C.c_int32(), C.c_int64()
+        B.b2k_nnet_program_sizes.argtypes = [C.c_void_p] * 4
+        assert B.b2k_nnet_program_sizes(hp, C.byref(nn), C.byref(no), C.byref(bl)) == 0
+        for f, rt in (("b2k_nnet_program_nodes", C.POINTER(_Node)), ("b2k_nnet_program_ops", C.POINTER(_Op)),
+                      ("b2k_nnet_program_blob", C.POINTER(C.c_float))):
+            getattr(B, f).restype = rt
+            getattr(B, f).argtypes = [C.c_void_p]
+        nodes = [B.b2k_nnet_program_nodes(hp)[i] for i in range(nn.value)]
+        ops = [B.b2k_nnet_program_ops(hp)[i] for i in range(no.value)]
+        blob = np.ctypeslib.as_array(B.b2k_nnet_program_blob(hp), shape=(bl.value,)).copy()
+        out2 = PI.run_program(PI.program_from_abi(nodes, ops, blob), feats, civ)
+    finally:
+        B.b2k_nnet_program_destroy.argtypes = [C.c_void_p]
+        B.b2k_nnet_program_destroy(hp)
+    assert out2.shape == ref.shape and np.abs(out2 - ref).max() <= 1e-4 * np.abs(ref).max()
