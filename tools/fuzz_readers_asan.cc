@@ -11,6 +11,8 @@
 // recipe extras, const / aligned / vector graphs, WAVE, option files, final.ie / final.dubm): clean after fixing, in model_io.cu,
 // counts that were trusted before being checked against the bytes left, a phone index outside the topology table and an
 // end-of-file loop in text mode, and, in nnet_compile.cu, weights whose sizes were not checked against the layer dimensions.
+// The input-descriptor parser (splices of the chain TDNN layers) was run the same way on 800 variants of a reference-written chain
+// TDNN model whose config section was mutated (flipped bytes, deleted spans, inserted "Offset(" / "Append(" fragments, huge offsets): clean.
 #include "b2k.h"
 #include <cstdio>
 #include <cstring>
