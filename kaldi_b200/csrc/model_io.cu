@@ -597,9 +597,14 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
     const size_t a = x.find_first_not_of(" \t");
     return a == std::string::npos ? std::string() : x.substr(a, x.find_last_not_of(" \t") - a + 1);
   };
-  auto splice_offsets = [&](const std::string &desc) -> std::vector<int> {
+  // A source other than `expect` (the layer before) is a skip connection: not supported, and an error rather than a wrong network.
+  auto splice_offsets = [&](const std::string &desc, const std::string &expect) -> std::vector<int> {
     const std::string d = trim(desc);
-    if (d.size() < 8 || d.compare(0, 7, "Append(") != 0 || d.back() != ')') return {0};
+    auto skip = [&]() { return FormatError("input " + desc + " is not the layer before (" + expect + "): skip connections are not supported"); };
+    if (d.size() < 8 || d.compare(0, 7, "Append(") != 0 || d.back() != ')') {
+      if (d != expect) throw skip();
+      return {0};
+    }
     std::vector<std::string> terms;
     int depth = 0;
     size_t start = 7;
@@ -640,6 +645,7 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
       offs.push_back((int)o);
     }
     if (offs.empty() || offs.size() > 8) throw FormatError("unsupported input descriptor " + desc);
+    if (src != expect) throw skip();
     return offs;
   };
   auto set_splice = [&](b2k_nnet_layer &L, const std::vector<int> &sp, const std::vector<int> &dflt) {
@@ -716,7 +722,7 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
       const Value &w = A.field(c, "<LinearParams>");
       b2k_nnet_layer &L = new_layer(idct ? "idct" : "lda", n);
       if (idct) L.dim = w.rows;
-      else set_splice(L, splice_offsets(inputs[n]), {-1, 0, 1});
+      else set_splice(L, splice_offsets(inputs[n], i ? cn[i - 1].first : std::string("input")), {-1, 0, 1});
       A.add_w(n + ".w", w);
       A.add_w(n + ".b", A.field(c, "<BiasParams>"));
       A.node_dim[n] = w.rows;
@@ -754,7 +760,7 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
         b2k_nnet_layer &L = new_layer("relu-batchnorm", base);
         L.dim = w.rows;
         if (inputs[n].find("ivector") != std::string::npos) { float s = 1.0f; scale_in(inputs[n], &s); L.append_ivector = s; }
-        set_splice(L, splice_offsets(inputs[n]), {0});
+        set_splice(L, splice_offsets(inputs[n], i ? cn[i - 1].first : std::string("input")), {0});
         A.add_w(n + ".w", w); A.add_w(n + ".b", A.field(c, "<BiasParams>"));
         A.bn(base + ".batchnorm", base + ".batchnorm");
         i += 3;

@@ -442,12 +442,15 @@ def _descriptor_nodes(desc: str) -> list[str]:
     return [w for w in re.findall(r"[A-Za-z_][A-Za-z0-9_.\-]*", desc) if w not in _DESCRIPTOR_WORDS]
 
 
-def _splice_offsets(desc: str) -> list[int]:
+def _splice_offsets(desc: str, expect_src: str | None = None) -> list[int]:
     """The time offsets over which an input descriptor splices ONE source node: `x` -> [0];
     `Append(Offset(x, -1), x, Offset(x, 1))` -> [-1, 0, 1] (what xconfig writes for input=Append(-1,0,1)); a trailing
-    term on the ivector input is not part of the splice.  Anything else (two sources, nested expressions) raises."""
+    term on the ivector input is not part of the splice.  Anything else (two sources, nested expressions, a source other than
+    `expect_src` = the layer before, i.e. a skip connection) raises."""
     d = desc.strip()
     if not (d.startswith("Append(") and d.endswith(")")):
+        if expect_src is not None and d != expect_src:
+            raise KaldiFormatError(f"input {desc} is not the layer before ({expect_src}): skip connections are not supported")
         return [0]
     terms, depth, start = [], 0, 7
     for p in range(7, len(d) - 1):
@@ -472,6 +475,8 @@ def _splice_offsets(desc: str) -> list[int]:
         offs.append(o)
     if not offs or len(offs) > 8:
         raise KaldiFormatError(f"unsupported input descriptor {desc}")
+    if expect_src is not None and src != expect_src:
+        raise KaldiFormatError(f"input {desc} is not the layer before ({expect_src}): skip connections are not supported")
     return offs
 
 
@@ -623,7 +628,7 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
             i += 1
         elif t == "FixedAffineComponent":
             L = {"type": "lda", "name": n}
-            sp = _splice_offsets(inputs[n])
+            sp = _splice_offsets(inputs[n], cn[i - 1][0] if i else "input")
             if sp != [-1, 0, 1]:
                 L["time_offsets"] = sp
             layers.append(L)
@@ -664,7 +669,7 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
                     re.search(r"Scale\(([0-9.eE+-]+),\s*ReplaceIndex\(ivector", inputs[n])
                 if "ivector" in inputs[n]:
                     L["append_ivector"] = float(m.group(1)) if m else 1.0
-                sp = _splice_offsets(inputs[n])
+                sp = _splice_offsets(inputs[n], cn[i - 1][0] if i else "input")
                 if sp != [0]:
                     L["time_offsets"] = sp
                 layers.append(L)

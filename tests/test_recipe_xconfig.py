@@ -394,3 +394,51 @@ def test_wsj_tdnn_1f_shape_from_the_references_xconfig_library(tmp_path, binary)
         B.b2k_nnet_program_destroy.argtypes = [C.c_void_p]
         B.b2k_nnet_program_destroy(hp)
     assert out2.shape == ref.shape and np.abs(out2 - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("edit", ["dead-layer", "two-sources", "skip"])
+def test_skip_connections_are_an_error_not_a_different_network(tmp_path, edit):
+    """A layer that reads a layer other than the one before it (dense / skip TDNNs) is outside the supported families: both
+    readers must refuse the file instead of returning the chain without the skip.  A layer nothing reads any more is not a
+    skip: it is dropped like the cross-entropy branch, and what remains is the network the reference computes."""
+    from oracle import nnet_oracle as NO
+    if not os.path.exists(NO._SO):
+        pytest.skip("oracle/_ref nnet3 library not present")
+    arch = NM.arch_tiny_tdnn()
+    W = NM.random_weights(arch, seed=1)
+    config = NM.to_nnet3_config(arch, W, str(tmp_path))
+    old = "input=Append(Offset(tdnn2.batchnorm, -3), tdnn2.batchnorm, Offset(tdnn2.batchnorm, 3))"
+    assert config.count(old) == 1
+    new = {"dead-layer": "input=Append(Offset(tdnn1.batchnorm, -3), tdnn1.batchnorm, Offset(tdnn1.batchnorm, 3))",
+           "two-sources": "input=Append(Offset(tdnn1.batchnorm, -3), tdnn2.batchnorm, Offset(tdnn2.batchnorm, 3))",
+           "skip": old}[edit]
+    config = config.replace(old, new)
+    if edit == "skip":           # tdnn4 reads tdnn2 past tdnn3, and tdnn3 stays alive through the xent-like second output
+        old4 = "input=Append(Offset(tdnn3.batchnorm, -6), Offset(tdnn3.batchnorm, -3), tdnn3.batchnorm)"
+        assert config.count(old4) == 1
+        config = config.replace(old4, "input=Append(Offset(tdnn2.batchnorm, -6), Offset(tdnn2.batchnorm, -3), tdnn2.batchnorm)")
+        config = config.replace("component-node name=prefinal-chain.affine component=prefinal-chain.affine input=tdnn4.batchnorm",
+                                "component-node name=prefinal-chain.affine component=prefinal-chain.affine input=Sum(tdnn4.batchnorm, tdnn3.batchnorm)")
+        assert "Sum(tdnn4.batchnorm, tdnn3.batchnorm)" in config
+    L = C.CDLL(NO._SO)
+    L.ref_nnet_create.restype = C.c_void_p
+    h = C.c_void_p(L.ref_nnet_create(config.encode()))
+    assert h, "the reference accepts the network"
+    raw = str(tmp_path / "skip.raw")
+    L.ref_nnet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    assert L.ref_nnet_write(h, raw.encode(), 1) == 0
+    try:
+        from kaldi_b200 import _lib as LB
+        from kaldi_b200.model import KaldiModel
+        LB.lib()
+    except OSError as e:
+        pytest.skip(str(e))
+    if edit == "dead-layer":
+        want = [x["name"] for x in arch["layers"] if x["name"] != "tdnn2"]
+        assert [x["name"] for x in NM.load_kaldi_raw(raw)[0]["layers"]] == want
+        assert [n for _, n in KaldiModel(raw, is_mdl=False).layer_types()] == want
+        return
+    with pytest.raises(KIO.KaldiFormatError):
+        NM.load_kaldi_raw(raw)
+    with pytest.raises(LB.B2kError):
+        KaldiModel(raw, is_mdl=False)
