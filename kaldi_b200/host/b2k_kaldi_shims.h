@@ -13,6 +13,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -304,6 +305,53 @@ class BatchedOnlinePipelineB2k {
   b2k_host::B2kPipelineBackend backend_;
   b2k_host::B2kBatcher batcher_;
 };
+
+// ------------------------------------------------------------------------------------------------ endpointing
+// online2/online-endpoint.h:128-190.  Templates on the configuration type so that this header does not have to include
+// online-endpoint.h (which pulls both online decoders, hence OpenFst, in): instantiate them with kaldi::OnlineEndpointConfig.
+template <class EndpointConfig>
+inline b2k_endpoint_cfg ToB2kEndpointConfig(const EndpointConfig &config) {
+  b2k_endpoint_cfg c;
+  Check(b2k_endpoint_cfg_default(&c), "b2k_endpoint_cfg_default");
+  const decltype(config.rule1) *rules[5] = {&config.rule1, &config.rule2, &config.rule3, &config.rule4, &config.rule5};
+  for (int r = 0; r < 5; r++) {
+    c.rule[r].must_contain_nonsilence = rules[r]->must_contain_nonsilence ? 1 : 0;
+    c.rule[r].min_trailing_silence = rules[r]->min_trailing_silence;
+    c.rule[r].max_relative_cost = rules[r]->max_relative_cost;
+    c.rule[r].min_utterance_length = rules[r]->min_utterance_length;
+  }
+  if (config.silence_phones.size() >= sizeof(c.silence_phones)) KALDI_ERR << "--endpoint.silence-phones is too long";
+  config.silence_phones.copy(c.silence_phones, config.silence_phones.size());
+  c.silence_phones[config.silence_phones.size()] = 0;
+  return c;
+}
+
+// EndpointDetected(config, num_frames_decoded, trailing_silence_frames, frame_shift_in_seconds, final_relative_cost)  online-endpoint.h:171
+template <class EndpointConfig>
+inline bool EndpointDetectedB2k(const EndpointConfig &config, int32 num_frames_decoded, int32 trailing_silence_frames,
+                                BaseFloat frame_shift_in_seconds, BaseFloat final_relative_cost) {
+  const b2k_endpoint_cfg c = ToB2kEndpointConfig(config);
+  int32_t hit = 0;
+  Check(b2k_endpoint_detected(&c, num_frames_decoded, trailing_silence_frames, frame_shift_in_seconds, final_relative_cost, &hit), "EndpointDetected");
+  return hit != 0;
+}
+
+// EndpointDetected(config, tmodel, frame_shift_in_seconds, decoder)  online-endpoint.h:185: the decoder's part is passed in as the
+// best path's input labels in time order (CudaDecoderB2k::GetBestPath / b2k_lat_best_path_arcs), the frame count and the final
+// relative cost; TransitionIdToPhone comes from the reference's own transition model.
+template <class EndpointConfig>
+inline bool EndpointDetectedB2k(const EndpointConfig &config, const TransitionInformation &tmodel, BaseFloat frame_shift_in_seconds,
+                                const std::vector<int32> &best_path_ilabels, int32 num_frames_decoded, BaseFloat final_relative_cost) {
+  const b2k_endpoint_cfg c = ToB2kEndpointConfig(config);
+  int32 max_tid = 0;
+  for (int32 t : best_path_ilabels) max_tid = std::max(max_tid, t);
+  std::vector<int32_t> tid2phone((size_t)max_tid + 1, 0);
+  for (int32 t : best_path_ilabels) if (t > 0) tid2phone[t] = tmodel.TransitionIdToPhone(t);
+  int32_t hit = 0;
+  Check(b2k_endpoint_detected_on_path(&c, tid2phone.data(), (int32_t)tid2phone.size(), best_path_ilabels.data(), (int64_t)best_path_ilabels.size(),
+                                      num_frames_decoded, frame_shift_in_seconds, final_relative_cost, &hit, nullptr), "EndpointDetected");
+  return hit != 0;
+}
 
 }  // namespace b2k_shim
 }  // namespace kaldi

@@ -22,6 +22,20 @@ def check() -> bool:
                              "-I/usr/local/cuda/include"])
         flags = [f for f in flags if not f.startswith("-I")] + ["-I" + stub] + [f for f in flags if f.startswith("-I")]
         subprocess.check_call(["g++", "-fsyntax-only", "-DB2K_HAVE_OPENFST", "-DB2K_OPENFST_IS_STANDIN"] + flags + [src])
+        # the endpointing templates, instantiated with the reference's own OnlineEndpointConfig.  online-endpoint.h includes both
+        # online decoders (OpenFst); their include guards are pre-defined, as in oracle/ref_wrap/endpoint_wrap.cc
+        ep = os.path.join(td, "e.cc")
+        open(ep, "w").write(
+            "#define KALDI_LAT_KALDI_LATTICE_H_\n#define KALDI_DECODER_LATTICE_FASTER_ONLINE_DECODER_H_\n"
+            "#define KALDI_DECODER_LATTICE_INCREMENTAL_ONLINE_DECODER_H_\n"
+            '#include "online2/online-endpoint.h"\n#include "hmm/transition-model.h"\n#include "b2k_kaldi_shims.h"\n'
+            "bool f(const kaldi::OnlineEndpointConfig &c, const kaldi::TransitionModel &tm, const std::vector<kaldi::int32> &path) {\n"
+            "  b2k_endpoint_cfg x = kaldi::b2k_shim::ToB2kEndpointConfig(c); (void)x;\n"
+            "  return kaldi::b2k_shim::EndpointDetectedB2k(c, 100, 10, 0.03f, 0.0f) ||\n"
+            "         kaldi::b2k_shim::EndpointDetectedB2k(c, tm, 0.03f, path, 100, 0.0f);\n}\n")
+        subprocess.check_call(["g++", "-fsyntax-only"] + RF.cxxflags(["-DHAVE_CUDA=0", "-I" + os.path.join(ROOT, "include"),
+                              "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include",
+                              "-I" + os.path.join(ROOT, "oracle", "_ref", "inc")]) + [ep])
     return True
 
 
