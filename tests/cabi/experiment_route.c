@@ -23,6 +23,9 @@ int main(int argc, char **argv) {
   CHECK(b2k_feat_cfg_from_conf(oc.feature_type == 0 ? oc.mfcc_config : oc.fbank_config, oc.feature_type, &cfg.feat));
   CHECK(b2k_pipeline_cfg_apply_options(oc.rest, &cfg));   /* --beam, --lattice-beam, --acoustic-scale ... if the file carries them */
   cfg.feat.dither = 0.0f;                         /* the reference's dither is unseeded: results are defined only without it */
+  b2k_endpoint_cfg ep;                            /* the --endpoint.* group of the same file (online2-wav-nnet3-latgen-faster.cc:128) */
+  CHECK(b2k_endpoint_cfg_default(&ep));
+  CHECK(b2k_endpoint_cfg_apply_options(oc.rest, &ep));
   /* model, graph, waveform */
   b2k_model *model = NULL;
   CHECK(b2k_model_read(argv[2], 1, &model));
@@ -57,6 +60,12 @@ int main(int argc, char **argv) {
     CHECK(b2k_ivec_cfg_from_conf(oc.ivector_extraction_config, &icfg, &ip));
     CHECK(b2k_ivec_files_read(ip.ivector_extractor, ip.diag_ubm, ip.lda_matrix, ip.global_cmvn_stats, &ivf));
     cfg.ivector_splice_right = icfg.splice_right;
+  }
+  {
+    /* what the endpoint rules say about 2 s of speech followed by 0.6 s of silence, had the decoder produced that path */
+    int32_t hit = 0;
+    CHECK(b2k_endpoint_detected(&ep, 87, 20, 0.03f, 0.0f, &hit));
+    printf("endpointing: silence phones %s, rule2 fires after 0.6 s of trailing silence: %s\n", ep.silence_phones, hit ? "yes" : "no");
   }
   printf("host side ready: %d feature frames -> %d decoder frames, %d pdfs, %lld transition-ids\n", plan.num_feature_frames,
          plan.num_output_frames, plan.num_pdfs, (long long)mi[6] - 1);

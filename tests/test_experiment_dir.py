@@ -123,6 +123,7 @@ def test_c99_program_drives_the_directory_through_the_abi(tmp_path):
                        capture_output=True, text=True, timeout=300)
     frames = 1 + (16000 - 400) // 160                        # 8000 samples at 8 kHz -> 16000 at 16 kHz
     assert f"host side ready: {frames} feature frames -> {(frames + 2) // 3} decoder frames, 10 pdfs, {n_tids} transition-ids" in r.stdout, r.stdout + r.stderr
+    assert "endpointing: silence phones 1:2, rule2 fires after 0.6 s of trailing silence: yes" in r.stdout, r.stdout
     import torch
     if torch.cuda.is_available():
         assert r.returncode == 0, r.stdout + r.stderr
