@@ -9,8 +9,10 @@
 //    the shorter then the lexicographically smaller string (:590-604);
 //  * the result accepts word sequences; for each sequence it carries the best path's weight and transition-id
 //    string; word epsilons (olabel 0) are absorbed; every state has at most one arc per word;
-//  * pruning: a sequence is kept iff its best cost <= best cost of the lattice + beam
-//    (determinize-lattice-pruned.h:126-140: "--beam" relative to the best path).
+//  * pruning: every sequence whose best cost <= best cost of the lattice + beam is kept, with that cost and its string
+//    (determinize-lattice-pruned.h:126-140: "--beam" relative to the best path).  A sequence outside the beam can survive
+//    where its states are shared with sequences inside it; it then carries the weight of its best SURVIVING derivation,
+//    which is never below its true best cost (pruned determinization does not promise more, in the reference either).
 // Not reproduced: the phone-level first pass of the wrapper (an efficiency device: it does not change the
 // accepted language), max_mem / max_loop early stopping, minimization (off by default, DeterminizeLatticePhone-
 // PrunedOptions), and therefore the STATE NUMBERING of the reference's output.

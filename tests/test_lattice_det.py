@@ -103,7 +103,7 @@ def test_exhaustive_equivalence_on_small_lattices(seed):
             assert got[k][3] == want[k][3], k
 
 
-@pytest.mark.parametrize("seed", range(40, 70))
+@pytest.mark.parametrize("seed", list(range(40, 70)) + [12531, 12780, 13110])      # the last three: out-of-beam survivors (soak run)
 def test_pruning_keeps_everything_within_the_beam(seed):
     rng = np.random.default_rng(seed)
     lat = _random_lattice(rng, n_states=int(rng.integers(4, 11)), n_arcs=int(rng.integers(6, 26)), vocab=3)
@@ -117,7 +117,11 @@ def test_pruning_keeps_everything_within_the_beam(seed):
     assert inside <= set(got)
     assert set(got) <= set(want)                             # nothing invented
     for k, v in got.items():
-        assert v[0] == pytest.approx(want[k][0], abs=2e-4)   # and whatever survives carries its true best cost
+        if k in inside:
+            assert v[0] == pytest.approx(want[k][0], abs=2e-4)   # within the beam: the true best cost
+        else:                                                    # outside: the best surviving derivation, never cheaper than the truth,
+            assert v[0] >= want[k][0] - 2e-4                     # and only sequences that really are outside the beam
+            assert want[k][0] > best + beam - 2e-3
     assert min(v[0] for v in got.values()) == pytest.approx(best, abs=2e-4)
 
 
