@@ -103,11 +103,32 @@ static bool to_bool(const std::string &name, std::string v) {
   if (v == "false" || v == "f" || v == "0") return false;
   throw ConfError{"Invalid format for boolean argument --" + name + ": " + v};
 }
+// ConvertStringToInteger / ConvertStringToReal<float> (util/text-utils.h:118-136, text-utils.cc:165-246) as ParseOptions applies
+// them: integers through strtoll with a range check (no hex prefix games: base 10), reals through istream >> float, i.e. only
+// decimal notation, overflow is an error, and the spellings of infinity / NaN the reference lists are accepted by name.
 static double to_num(const std::string &name, const std::string &v, bool integer) {
+  const std::string what = "Invalid " + std::string(integer ? "integer" : "floating-point") + " option --" + name + "=" + v;
+  if (v.empty()) throw ConfError{what};
   char *end = nullptr;
-  const double d = integer ? (double)strtol(v.c_str(), &end, 10) : strtod(v.c_str(), &end);
-  if (v.empty() || !end || *end != 0) throw ConfError{"Invalid " + std::string(integer ? "integer" : "floating-point") + " option --" + name + "=" + v};
-  return d;
+  if (integer) {
+    errno = 0;
+    const long long i = strtoll(v.c_str(), &end, 10);
+    if (end == v.c_str() || *end != 0 || errno != 0 || i != (long long)(int32_t)i) throw ConfError{what};
+    return (double)i;
+  }
+  if (v.find_first_not_of("0123456789+-.eE") == std::string::npos) {
+    const float f = strtof(v.c_str(), &end);
+    if (end == v.c_str() || *end != 0 || std::isinf(f)) throw ConfError{what};
+    return (double)f;
+  }
+  std::string u = v;
+  for (auto &c : u) c = (char)std::toupper((unsigned char)c);
+  const double inf = std::numeric_limits<double>::infinity(), nan = std::numeric_limits<double>::quiet_NaN();
+  if (u == "INF" || u == "+INF" || u == "INFINITY" || u == "+INFINITY" || u == "1.#INF") return inf;
+  if (u == "-INF" || u == "-INFINITY" || u == "-1.#INF") return -inf;
+  if (u == "NAN" || u == "+NAN" || u == "1.#QNAN") return nan;
+  if (u == "-NAN" || u == "-1.#QNAN") return -nan;
+  throw ConfError{what};
 }
 
 // one table entry per registered option: where it goes and what kind it is
@@ -120,7 +141,10 @@ static void apply(const char *path, const std::map<std::string, std::pair<std::s
     if (!o) throw ConfError{"Invalid option --" + e.first + " in config file " + path};
     const std::string &v = e.second.first;
     switch (o->kind) {
-      case 'b': *(int32_t *)o->dst = to_bool(e.first, v) ? 1 : 0; break;
+      case 'b':
+        if (e.second.second && v.empty()) throw ConfError{"Invalid option --" + e.first + "="};      // parse-options.cc:545: --x is true, --x= is not
+        *(int32_t *)o->dst = to_bool(e.first, v) ? 1 : 0;
+        break;
       case 'i': *(int32_t *)o->dst = (int32_t)to_num(e.first, v, true); break;
       case 'f': *(float *)o->dst = (float)to_num(e.first, v, false); break;
       case 's': { char *d = (char *)o->dst; if (v.size() >= 512) throw ConfError{"value of --" + e.first + " is too long"}; memcpy(d, v.c_str(), v.size() + 1); break; }

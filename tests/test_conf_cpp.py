@@ -29,6 +29,8 @@ ODD = """
 --raw-energy=0   # trailing comment
 --energy-floor=1.5
 """
+# spellings of numbers the reference's ConvertStringToReal / ConvertStringToInteger take (found by a soak run against its ParseOptions)
+NUMBERS = "--energy-floor=INF\n--low-freq=+20\n--high-freq=-.5e3\n--dither=5.\n--num-mel-bins=+30\n--cepstral-lifter=1E1\n--preemphasis-coefficient=-infinity\n"
 FBANK = "--num-mel-bins=64\n--use-log-fbank=false\n--use-power=t\n--use-energy=true\n--dither=0.0\n--htk-compat=TRUE\n"
 
 
@@ -65,8 +67,8 @@ FIELDS = ["samp_freq", "frame_shift_ms", "frame_length_ms", "dither", "preemph_c
 WINDOWS = {"povey": 0, "hamming": 1, "hanning": 2, "rectangular": 3}
 
 
-@pytest.mark.parametrize("text,feature_type", [(HIRES, 0), (ODD, 0), ("", 0), (FBANK, 1), (ODD, 1), ("", 1)],
-                         ids=["hires", "odd-spelling", "defaults-mfcc", "fbank", "odd-fbank", "defaults-fbank"])
+@pytest.mark.parametrize("text,feature_type", [(HIRES, 0), (ODD, 0), ("", 0), (FBANK, 1), (ODD, 1), ("", 1), (NUMBERS, 0)],
+                         ids=["hires", "odd-spelling", "defaults-mfcc", "fbank", "odd-fbank", "defaults-fbank", "number-spellings"])
 def test_feature_options_equal_the_references_parse(tmp_path, text, feature_type):
     L = _lib()
     p = str(tmp_path / "feat.conf")
@@ -79,12 +81,13 @@ def test_feature_options_equal_the_references_parse(tmp_path, text, feature_type
             continue                                          # FbankOptions has no such option
         if feature_type == 0 and k in ("use_log_fbank", "use_power"):
             continue
-        assert float(getattr(c, k)) == pytest.approx(ref[i], abs=1e-6), k
+        assert float(getattr(c, k)) == ref[i] or float(getattr(c, k)) == pytest.approx(ref[i], abs=1e-6), k
     assert c.window_type == WINDOWS[win] and c.feature_type == feature_type
 
 
 @pytest.mark.parametrize("text", ["--no-such-option=3\n", "num-ceps=13\n", "--frame-length = 20\n", "--num-ceps=thirteen\n", "--use-energy=maybe\n",
-                                  "--use-log-fbank=true\n"])
+                                  "--use-log-fbank=true\n", "--htk-compat=\n", "--dither=0x10\n", "--dither=1e400\n", "--num-ceps=2147483648\n",
+                                  "--num-ceps=3.0\n", "--dither=1.0f\n", "--frame-shift=\n"])
 def test_both_reject_the_same_files(tmp_path, text):
     L = _lib()
     p = str(tmp_path / "bad.conf")
