@@ -368,7 +368,9 @@ int b2k_wave_read(const char *path, b2k_wave **out) {
     while (t != "fmt ") { r.skip(r.u32()); t = r.tag(); }
     const uint32_t fmt_size = r.u32();
     const uint16_t format = r.u16();
-    const uint16_t channels = r.u16();
+    // WaveInfo keeps the channel count in a uint8 (wave-reader.h:101): the 16-bit field of the file is truncated, and every later check
+    // (no channels, byte rate, block_align) sees the truncated value.  Mirrored, so that the same files are accepted with the same shape.
+    const uint16_t channels = (uint16_t)(r.u16() & 0xFFu);
     const uint32_t rate = r.u32(), byte_rate = r.u32();
     const uint32_t block_align = r.u16(), bits = r.u16();
     uint32_t fmt_read = 16;
@@ -397,6 +399,7 @@ int b2k_wave_read(const char *path, b2k_wave **out) {
     if (!stream) avail = std::min<size_t>(avail, (size_t)(data_size / block_align) * block_align);   // DataBytes() = samp_count * BlockAlign()
     if (avail == 0) throw ConfError{"WaveData: empty file (no data)"};
     const size_t ns = avail / block_align;
+    if (ns == 0) throw ConfError{"WaveData: less than one sample block of data"};     // the reference cannot read such a file either (Matrix::Resize(channels, 0) asserts)
     W->samp_freq = (float)rate; W->channels = channels; W->samples = (int64_t)ns;
     W->data.resize((size_t)channels * ns);
     for (size_t i = 0; i < ns; i++)

@@ -174,3 +174,19 @@ def test_resampler_rejects_bad_arguments():
     assert L.b2k_resample_waveform(0.0, x.ctypes.data, 10, 16000.0, None, 0, C.byref(n)) == 1
     assert L.b2k_resample_waveform(8000.5, x.ctypes.data, 10, 16000.0, None, 0, C.byref(n)) == 1
     assert L.b2k_resample_waveform(8000.0, None, 10, 16000.0, None, 0, C.byref(n)) == 1
+
+
+def test_channel_count_is_read_as_the_reference_reads_it(tmp_path):
+    """WaveInfo keeps the channel count in 8 bits (wave-reader.h:101): a header that says 258 channels with the byte rate and block size
+    of 2 is a two-channel file to the reference, and one that says 256 has no channels.  Found by a soak run against WaveData::Read."""
+    x, b = _samples(40, channels=2, seed=3)
+    p = str(tmp_path / "c258.wav")
+    open(p, "wb").write(_riff(_fmt(channels=258, byte_rate=16000 * 4, block_align=4), b))
+    mine, ref = _mine(p), _reference(p)
+    assert mine is not None and ref is not None
+    assert mine[0] == ref[0] and mine[1].shape == ref[1].shape == (2, 40) and np.array_equal(mine[1], ref[1])
+    open(p, "wb").write(_riff(_fmt(channels=256, byte_rate=0, block_align=0), b))
+    assert _mine(p) is None and _reference(p) is None
+    # less than one sample block of data: the reference asserts (it cannot be called on it), this reader reports an error
+    open(p, "wb").write(_riff(_fmt(channels=2), b[:3], data_size=3))
+    assert _mine(p) is None
