@@ -396,7 +396,7 @@ def main():
                              d2h_bytes_per_step=int(d2h / a.steps), lattice_states_per_step=int(lat_states / a.steps),
                              host_ms_last_step={k: round(v, 1) for k, v in getattr(pipe, "last_host_ms", {}).items()}),
                     gpu_launches=int(launches), stage_ms={k: round(v, 3) for k, v in stage_ms.items()},
-                    decoder_phase_share=dict(zip(
+                    decoder_phase_share=None if not os.environ.get("B2K_DEC_PROF") else dict(zip(
                         ["cutoff_seed", "expand", "rank", "bucket_scatter", "eps_init", "eps_closure", "replay_prep", "eps_replay",
                          "eps_finish", "list_order", "eps_links", "commit"],
                         [round(float(sum(i["prof_cycles"][k] for i in infos)) / max(1.0, float(sum(i["prof_cycles"][15] for i in infos))), 3)

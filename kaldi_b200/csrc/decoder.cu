@@ -93,13 +93,13 @@ struct DecParams {
   int32_t *frame_link_eps;  // [nch * (max_frames+2)]
   float *frame_cost_offset; // [nch * (max_frames+1)]
   float *frame_cutoff;      // [nch * (max_frames+1)]
-  // lane scratch (arrays of [nlanes * capacity])
+  // CTA scratch (arrays of [nslots * capacity]; a slot = one resident CTA of the persistent launch)
   int4 *hash;               // {key state, cost ord, tok idx in frame, stamp}
   int32_t *tokslot;         // [max_tpf]
   int32_t *wl;              // [2 * max_tpf]
   int32_t *cand;            // [5 * cand_cap] src, arc, next, tot bits, ac bits
   uint32_t *new_extra;      // [max_tpf] (finalize)
-  int32_t *lane_stamp;      // [nlanes]
+  int32_t *lane_stamp;      // [nslots]
   // compact lattice of a finalized channel (written by dec_finalize_kernel)
   int4 *lat_states;         // [nch * cap_ls] {frame, hclg state, tot bits, extra bits}
   int4 *lat_arcs;           // [nch * cap_la] {src id, dst id, ilabel, olabel}
@@ -110,7 +110,7 @@ struct DecParams {
   uint32_t *x_bm;           // [pos_cap/32] bitmap of first-admission positions
   int32_t *x_wbase;         // [pos_cap/32]
   int32_t *x_by_ins;        // [max_tpf] insertion index -> hash slot
-  int4 *x_bk;               // [hc_cap] per HashList bucket {first insertion index, population, fill cursor, -}
+  int2 *x_bk;               // [hc_cap] per HashList bucket {first insertion index, population | fill cursor << 16}
   int32_t *x_sbase;         // [max_tpf]
   int32_t *x_run;           // [max_tpf]
   int32_t *x_order;         // [max_tpf] list rank -> insertion index
@@ -129,6 +129,17 @@ struct DecParams {
   const int32_t *lane_nframes;
   int32_t row_stride;
   int32_t do_init;
+  // persistent launch: a CTA serves lanes until the counter runs out; its scratch is indexed by blockIdx.x
+  int32_t n_lanes;
+  int32_t *lane_counter;
+  int32_t num_pdfs;         // log-likelihood columns the graph reads
+  int32_t ll_smem;          // 1 = the frame's log-likelihood row is staged in shared memory (after the replay arrays)
+  int32_t rs_bytes;         // bytes of the replay arrays at the start of dynamic shared memory
+  // second-generation reference-order frame step (per-CTA scratch; see struct X2)
+  int4 *v2_trec, *v2_tok4;
+  uint32_t *v2_c0, *v2_adjc, *v2_qstamp, *v2_hw;
+  int32_t *v2_pf;
+  int32_t v2_hw_len;
 };
 
 // ------------------------------------------------------------------ block helpers
@@ -236,7 +247,7 @@ __device__ float block_select_kth(const float *vals, int n, int k, uint32_t *his
 }
 
 // phase timers (thread 0 only): TICK(s, i) adds the cycles since the previous tick to slot i
-#define B2K_TICK(S, I) do { if (threadIdx.x == 0) { long long _t = clock64(); (S).prof[(I)] += (unsigned long long)(_t - (S).tlast); (S).tlast = _t; } } while (0)
+#define B2K_TICK(S, I) do { if (PROF && threadIdx.x == 0) { long long _t = clock64(); (S).prof[(I)] += (unsigned long long)(_t - (S).tlast); (S).tlast = _t; } } while (0)
 
 // ------------------------------------------------------------------ hash
 
@@ -246,19 +257,41 @@ struct LaneCtx {
   int32_t *tok_state;   // channel arena
   int32_t tbase;
   int32_t hash_mask, hash_log, max_tpf, max_tokens;
+  int32_t l1_mask, l1_log;   // level-1 window of the table for this frame (see probe_slot)
   int *ntok_new;        // shared
   int *err;             // shared
   int *err_line;        // shared
 };
 
-__device__ __forceinline__ uint32_t hash_fn(int32_t state, int hash_log) {
-  return ((uint32_t)state * 2654435761u) >> (32 - hash_log);
+// Two-level open addressing.  A CTA's table has hash_size slots (capacity), but a frame only
+// ever holds a few thousand tokens: the first B2K_L1_PROBES probes of a state stay inside the
+// first l1_size slots (l1_size ~ 3x the previous frame's token count, chosen per frame), so the
+// slots a frame touches are a small, L2-resident prefix of the table; only a state whose whole
+// level-1 window is occupied goes on to linear probing over the full table with a second hash.
+// Slots are never freed inside a frame, so a state's position is stable: if it is in its
+// level-1 window every later lookup finds it there, and if it is not, the window was full when
+// it was inserted and is still full, so later lookups also fall through to level 2.
+#define B2K_L1_PROBES 16
+
+__device__ __forceinline__ uint32_t probe_slot(const LaneCtx &c, int32_t state, int i) {
+  if (i < B2K_L1_PROBES) return ((((uint32_t)state * 2654435761u) >> (32 - c.l1_log)) + (uint32_t)i) & (uint32_t)c.l1_mask;
+  return ((((uint32_t)state * 0x85ebca6bu) >> (32 - c.hash_log)) + (uint32_t)(i - B2K_L1_PROBES)) & (uint32_t)c.hash_mask;
+}
+
+// level-1 size for a frame.  Measured (profiles/r02_decoder_history.md): a level-1 window sized to the frame made probe
+// sequences longer and did not make the table L2 resident (a resident CTA touches ~0.85 MB of scratch per frame, 296 of
+// them 2x the L2), so the first-generation kernels use the whole table as level 1; the bucket-keyed table of the
+// second-generation frame step (probe_slot_b) sizes its window from the reference's own HashList size.
+__device__ __forceinline__ void set_l1(LaneCtx &c, int K) {
+  (void)K;
+  c.l1_log = c.hash_log;
+  c.l1_mask = c.hash_mask;
 }
 
 // find-or-insert; returns slot (or -1 after an overflow was flagged)
 __device__ __forceinline__ int hash_insert(const LaneCtx &c, int32_t state) {
-  uint32_t h = hash_fn(state, c.hash_log);
-  for (int probe = 0; probe <= c.hash_mask; probe++) {
+  for (int probe = 0; probe <= c.hash_mask + B2K_L1_PROBES; probe++) {
+    const uint32_t h = probe_slot(c, state, probe);
     int *keyp = reinterpret_cast<int *>(&c.hash[h]);
     int old = atomicCAS(keyp, B2K_HASH_EMPTY, state);
     if (old == B2K_HASH_EMPTY) {
@@ -273,19 +306,17 @@ __device__ __forceinline__ int hash_insert(const LaneCtx &c, int32_t state) {
       return (int)h;
     }
     if (old == state) return (int)h;
-    h = (h + 1) & (uint32_t)c.hash_mask;
   }
   do { if (atomicCAS(c.err, 0, B2K_ERR_OVERFLOW) == 0) *c.err_line = __LINE__; } while (0);
   return -1;
 }
 
 __device__ __forceinline__ int hash_find(const LaneCtx &c, int32_t state) {
-  uint32_t h = hash_fn(state, c.hash_log);
-  for (int probe = 0; probe <= c.hash_mask; probe++) {
+  for (int probe = 0; probe <= c.hash_mask + B2K_L1_PROBES; probe++) {
+    const uint32_t h = probe_slot(c, state, probe);
     int key = *reinterpret_cast<volatile int *>(&c.hash[h]);
     if (key == state) return (int)h;
     if (key == B2K_HASH_EMPTY) return -1;
-    h = (h + 1) & (uint32_t)c.hash_mask;
   }
   return -1;
 }
@@ -455,10 +486,8 @@ __device__ void finish_frame(const DecParams &p, DecShared<T> &s, const LaneCtx 
 }
 
 template <int T>
-__global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
-  __shared__ DecShared<T> s;
+__device__ void dec_advance_lane(const DecParams &p, DecShared<T> &s, const int lane, const int slot) {
   const int tid = threadIdx.x;
-  const int lane = blockIdx.x;
   const int ch = p.lane_channel[lane];
   ChanState *cs = &p.chan[ch];
   const FstDev &g = p.fst;
@@ -473,13 +502,13 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
   int32_t *tok_state = p.tok_state + (size_t)ch * p.max_tokens;
   float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
   int4 *links = p.links + (size_t)ch * p.max_links;
-  int32_t *cand = p.cand + (size_t)lane * 5 * p.cand_cap;
+  int32_t *cand = p.cand + (size_t)slot * 5 * p.cand_cap;
   int32_t *c_src = cand, *c_arc = cand + p.cand_cap, *c_next = cand + 2 * (size_t)p.cand_cap,
           *c_tot = cand + 3 * (size_t)p.cand_cap, *c_ac = cand + 4 * (size_t)p.cand_cap;
 
   LaneCtx ctx;
-  ctx.hash = p.hash + (size_t)lane * p.hash_size;
-  ctx.tokslot = p.tokslot + (size_t)lane * p.max_tpf;
+  ctx.hash = p.hash + (size_t)slot * p.hash_size;
+  ctx.tokslot = p.tokslot + (size_t)slot * p.max_tpf;
   ctx.tok_state = tok_state;
   ctx.hash_mask = p.hash_size - 1;
   ctx.hash_log = p.hash_log;
@@ -488,8 +517,9 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
   ctx.ntok_new = &s.ntok_new;
   ctx.err = &s.err;
   ctx.err_line = &s.err_line;
+  set_l1(ctx, 0);
 
-  if (tid == 0) { s.err = 0; s.err_line = 0; s.stamp = p.lane_stamp[lane]; }
+  if (tid == 0) { s.err = 0; s.err_line = 0; s.stamp = p.lane_stamp[slot]; }
   __syncthreads();
 
   if (p.do_init) {
@@ -501,14 +531,14 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
       int slot = hash_insert(ctx, g.start);
       if (slot >= 0) atomicMin(reinterpret_cast<uint32_t *>(&ctx.hash[slot].y), f2ord(0.0f));
     }
-    finish_frame<T>(p, s, ctx, lane, ch, 0, p.beam, 0.0f, 0, &cs->arcs_ne);
+    finish_frame<T>(p, s, ctx, slot, ch, 0, p.beam, 0.0f, 0, &cs->arcs_ne);
     if (tid == 0) {
       cs->frames_decoded = 0;
       cs->ntok = min(s.ntok_new, p.max_tpf);
       cs->nlink = s.nlink_new;
       cs->finalized = 0;
       if (s.err) { cs->status = s.err; cs->err_line = s.err_line; }
-      p.lane_stamp[lane] = s.stamp;
+      p.lane_stamp[slot] = s.stamp;
     }
     if (s.err) reset_lane_hash<T>(ctx.hash, p.hash_size);
     return;
@@ -527,6 +557,7 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
     const int pb = p.frame_tok_begin[fo + frames_decoded];
     const int pe = p.frame_tok_begin[fo + frames_decoded + 1];
     const int K = pe - pb;
+    set_l1(ctx, K);
 
     // ---- 1. best token and cutoff (GetCutoff :653-720)
     unsigned long long local = ~0ull;
@@ -689,7 +720,7 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
       }
     }
     // ---- 5/6. epsilon closure, eps links, commit
-    finish_frame<T>(p, s, ctx, lane, ch, frames_decoded + 1, next_cutoff, cost_offset, lbase,
+    finish_frame<T>(p, s, ctx, slot, ch, frames_decoded + 1, next_cutoff, cost_offset, lbase,
                     &cs->arcs_ne);
     if (s.err) break;
     tbase += min(s.ntok_new, p.max_tpf);
@@ -703,11 +734,32 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
     cs->nlink = lbase;
     cs->arcs_e += arcs_e_total;
     if (s.err) { cs->status = s.err; cs->err_line = s.err_line; }
-    p.lane_stamp[lane] = s.stamp;
+    p.lane_stamp[slot] = s.stamp;
   }
-  // an overflow can leave uncommitted tokens in the lane's hash: wipe it so the
-  // lane is clean for the next channel it serves
+  // an overflow can leave uncommitted tokens in the CTA's hash: wipe it so the
+  // table is clean for the next lane it serves
   if (s.err) reset_lane_hash<T>(ctx.hash, p.hash_size);
+}
+
+// Persistent launch shared by the three per-lane kernels: the grid is at most the number of CTAs the
+// device keeps resident, every CTA owns one scratch slot (hash table, per-frame arrays: indexed by
+// blockIdx.x) and serves lanes until the launch's counter runs out.  The scratch a launch touches is
+// therefore (resident CTAs) x (what a frame touches), which stays in L2, instead of growing with the batch.
+#define B2K_PERSISTENT_LANES(BODY)                                            \
+  __shared__ int s_lane_;                                                     \
+  for (;;) {                                                                  \
+    __syncthreads();                                                          \
+    if (threadIdx.x == 0) s_lane_ = atomicAdd(p.lane_counter, 1);             \
+    __syncthreads();                                                          \
+    const int lane_ = s_lane_;                                                \
+    if (lane_ >= p.n_lanes) break;                                            \
+    BODY;                                                                     \
+  }
+
+template <int T>
+__global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
+  __shared__ DecShared<T> s;
+  B2K_PERSISTENT_LANES(dec_advance_lane<T>(p, s, lane_, (int)blockIdx.x))
 }
 
 
@@ -730,15 +782,15 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
 // replay of the LIFO worklist (:858-896) -- the one inherently sequential piece.
 
 struct XScratch {
-  uint32_t *bm; int32_t *wbase, *by_ins, *sbase, *run, *order, *queue, *xb; int4 *bk;
+  uint32_t *bm; int32_t *wbase, *by_ins, *sbase, *run, *order, *queue, *xb; int2 *bk;
   int4 *rec; int32_t *newseq; int4 *adj; int32_t *adjo;
 };
 
 // find-or-insert without arena write; *created tells whether this call made the token
 __device__ __forceinline__ int hash_insert_x(const LaneCtx &c, int32_t state, bool *created, int *idx_out) {
-  uint32_t h = hash_fn(state, c.hash_log);
   *created = false;
-  for (int probe = 0; probe <= c.hash_mask; probe++) {
+  for (int probe = 0; probe <= c.hash_mask + B2K_L1_PROBES; probe++) {
+    const uint32_t h = probe_slot(c, state, probe);
     int *keyp = reinterpret_cast<int *>(&c.hash[h]);
     int old = atomicCAS(keyp, B2K_HASH_EMPTY, state);
     if (old == B2K_HASH_EMPTY) {
@@ -750,7 +802,6 @@ __device__ __forceinline__ int hash_insert_x(const LaneCtx &c, int32_t state, bo
       return (int)h;
     }
     if (old == state) return (int)h;
-    h = (h + 1) & (uint32_t)c.hash_mask;
   }
   do { if (atomicCAS(c.err, 0, B2K_ERR_OVERFLOW) == 0) *c.err_line = __LINE__; } while (0);
   return -1;
@@ -771,7 +822,7 @@ __device__ void bucket_scatter(int k0, int k1, int Hc, const int4 *hash, const X
     int b = (int)((uint32_t)hash[slot].x % (uint32_t)Hc);
     x.xb[k] = b;
     atomicMin(&x.bk[b].x, k);
-    atomicAdd(&x.bk[b].y, 1);
+    atomicAdd(&x.bk[b].y, 1);                           // population: low 16 bits (a frame holds < 65536 tokens)
   }
   __syncthreads();
 }
@@ -779,7 +830,7 @@ __device__ void bucket_scatter(int k0, int k1, int Hc, const int4 *hash, const X
 template <int T>
 __device__ void order_finish(int N, const XScratch &x, DecShared<T> &s, int *order_slot = nullptr) {
   const int tid = threadIdx.x;
-  const int4 kEmptyBucket = make_int4(0x7fffffff, 0, 0, 0);
+  const int2 kEmptyBucket = make_int2(0x7fffffff, 0);
   __syncthreads();
   // list position of every bucket head = exclusive scan of the bucket populations in
   // first-insertion order.  A bucket with one token (the common case) is finished here.
@@ -788,8 +839,8 @@ __device__ void order_finish(int N, const XScratch &x, DecShared<T> &s, int *ord
     int k = base + tid, w = 0, b = 0;
     if (k < N) {
       b = x.xb[k];
-      int4 bk = x.bk[b];
-      if (bk.x == k) w = bk.y;
+      int2 bk = x.bk[b];
+      if (bk.x == k) w = bk.y & 0xffff;
     }
     int total;
     int excl = block_excl_scan<T>(w, s.redi, &total);
@@ -810,17 +861,18 @@ __device__ void order_finish(int N, const XScratch &x, DecShared<T> &s, int *ord
     int b = x.xb[k];
     if (b < 0) continue;
     int rb = x.sbase[x.bk[b].x];
-    int q = atomicAdd(&x.bk[b].z, 1);
+    int q = (int)((uint32_t)atomicAdd(&x.bk[b].y, 0x10000) >> 16);   // fill cursor: high 16 bits
     x.run[rb + q] = k;
   }
   __syncthreads();
   for (int k = tid; k < N; k += T) {
     int b = x.xb[k];
     if (b < 0) continue;
-    int4 bk = x.bk[b];
+    int2 bk = x.bk[b];
     int rb = x.sbase[bk.x];
     int within = 0;
-    for (int j = 0; j < bk.y; j++) within += (x.run[rb + j] < k);
+    const int pop = bk.y & 0xffff;
+    for (int j = 0; j < pop; j++) within += (x.run[rb + j] < k);
     x.order[rb + within] = k;
     if (order_slot) order_slot[rb + within] = x.by_ins[k];
   }
@@ -836,7 +888,7 @@ __device__ void order_finish(int N, const XScratch &x, DecShared<T> &s, int *ord
 // ProcessNonemitting replay + ordering + eps links + commit (reference order).
 // On entry N1 = s.ntok_new tokens exist with slot.z = insertion index and
 // by_ins filled for them.
-template <int T>
+template <int T, bool PROF>
 __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const LaneCtx &ctx,
                                    const XScratch &x, int lane, int ch, int list_index, float cutoff,
                                    float cost_offset, int32_t lbase, int Hc, ChanState *cs) {
@@ -1380,12 +1432,10 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
   __syncthreads();
 }
 
-template <int T>
-__global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kernel(DecParams p) {
-  __shared__ DecShared<T> s;
+template <int T, bool PROF>
+__device__ void dec_advance_exact_lane(const DecParams &p, DecShared<T> &s, const int lane, const int slot) {
   constexpr int IT = 4;
   const int tid = threadIdx.x;
-  const int lane = blockIdx.x;
   const int ch = p.lane_channel[lane];
   ChanState *cs = &p.chan[ch];
   const FstDev &g = p.fst;
@@ -1401,8 +1451,8 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
   int4 *links = p.links + (size_t)ch * p.max_links;
 
   LaneCtx ctx;
-  ctx.hash = p.hash + (size_t)lane * p.hash_size;
-  ctx.tokslot = p.tokslot + (size_t)lane * p.max_tpf;
+  ctx.hash = p.hash + (size_t)slot * p.hash_size;
+  ctx.tokslot = p.tokslot + (size_t)slot * p.max_tpf;
   ctx.tok_state = tok_state;
   ctx.hash_mask = p.hash_size - 1;
   ctx.hash_log = p.hash_log;
@@ -1411,20 +1461,21 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
   ctx.ntok_new = &s.ntok_new;
   ctx.err = &s.err;
   ctx.err_line = &s.err_line;
+  set_l1(ctx, 0);
   XScratch x;
-  x.bm = p.x_bm + (size_t)lane * (p.pos_cap / 32);
-  x.wbase = p.x_wbase + (size_t)lane * (p.pos_cap / 32);
-  x.by_ins = p.x_by_ins + (size_t)lane * p.max_tpf;
-  x.bk = p.x_bk + (size_t)lane * p.hc_cap;
-  x.sbase = p.x_sbase + (size_t)lane * p.max_tpf;
-  x.run = p.x_run + (size_t)lane * p.max_tpf;
-  x.order = p.x_order + (size_t)lane * p.max_tpf;
-  x.queue = p.cand + (size_t)lane * 5 * p.cand_cap;     // idle in this mode
-  x.xb = p.x_xb + (size_t)lane * p.max_tpf;
-  x.rec = p.x_rec + (size_t)lane * p.max_tpf;
-  x.newseq = p.x_newseq + (size_t)lane * p.max_tpf;
-  x.adj = p.x_adj + (size_t)lane * p.adj_cap;
-  x.adjo = p.x_adjo + (size_t)lane * p.adj_cap;
+  x.bm = p.x_bm + (size_t)slot * (p.pos_cap / 32);
+  x.wbase = p.x_wbase + (size_t)slot * (p.pos_cap / 32);
+  x.by_ins = p.x_by_ins + (size_t)slot * p.max_tpf;
+  x.bk = p.x_bk + (size_t)slot * p.hc_cap;
+  x.sbase = p.x_sbase + (size_t)slot * p.max_tpf;
+  x.run = p.x_run + (size_t)slot * p.max_tpf;
+  x.order = p.x_order + (size_t)slot * p.max_tpf;
+  x.queue = p.cand + (size_t)slot * 5 * p.cand_cap;     // idle in this mode
+  x.xb = p.x_xb + (size_t)slot * p.max_tpf;
+  x.rec = p.x_rec + (size_t)slot * p.max_tpf;
+  x.newseq = p.x_newseq + (size_t)slot * p.max_tpf;
+  x.adj = p.x_adj + (size_t)slot * p.adj_cap;
+  x.adjo = p.x_adjo + (size_t)slot * p.adj_cap;
 
   if (tid == 0) { s.err = 0; s.err_line = 0; s.stamp = 0; }
   __syncthreads();
@@ -1438,7 +1489,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
       int slot = hash_insert_x(ctx, g.start, &created, &idx);
       if (slot >= 0) { ctx.hash[slot].y = (int)f2ord(0.0f); ctx.hash[slot].z = 0; x.by_ins[0] = slot; }
     }
-    finish_frame_exact<T>(p, s, ctx, x, lane, ch, 0, p.beam, 0.0f, 0, 1000, cs);
+    finish_frame_exact<T, PROF>(p, s, ctx, x, slot, ch, 0, p.beam, 0.0f, 0, 1000, cs);
     if (tid == 0) {
       cs->frames_decoded = 0;
       cs->ntok = min(s.ntok_new, p.max_tpf);
@@ -1459,14 +1510,20 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
   unsigned long long arcs_e_total = 0;
   const size_t fo = (size_t)ch * (p.max_frames + 2);
 
-  if (tid == 0) { for (int i = 0; i < 16; i++) s.prof[i] = 0; s.tlast = clock64(); }
-  const long long t_kernel0 = clock64();
+  if (tid == 0) { for (int i = 0; i < 16; i++) s.prof[i] = 0; s.tlast = PROF ? clock64() : 0; }
+  const long long t_kernel0 = PROF ? clock64() : 0;
+  extern __shared__ __align__(16) unsigned char dyn_smem_base[];
+  float *ll_s = reinterpret_cast<float *>(dyn_smem_base + p.rs_bytes);
   for (int fi = 0; fi < nframes; fi++) {
     if (frames_decoded >= p.max_frames) { if (tid == 0) B2K_SET_ERR(s, B2K_ERR_OVERFLOW); __syncthreads(); break; }
-    const float *ll = ll_base + (size_t)fi * p.row_stride;
+    const float *llg = ll_base + (size_t)fi * p.row_stride;
+    // the frame's log-likelihood row is gathered once per arc: stage it in shared memory (the block
+    // reductions of the cutoff below are the barrier between this fill and the first reader)
+    if (p.ll_smem) for (int i = tid; i < p.num_pdfs; i += T) ll_s[i] = __ldcs(&llg[i]);
     const int pb = p.frame_tok_begin[fo + frames_decoded];
     const int pe = p.frame_tok_begin[fo + frames_decoded + 1];
     const int K = pe - pb;
+    set_l1(ctx, K);
 
     // ---- GetCutoff (:653-720); ties -> first in list order (strict < at :662/:675)
     unsigned long long local = ~0ull;
@@ -1527,7 +1584,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
       int2 o0 = __ldg(&g.st_off[best_state]), o1 = __ldg(&g.st_off[best_state + 1]);
       for (int a = o0.x + tid; a < o1.x; a += T) {
         int4 arc = __ldg(&g.e_arcs[a]);
-        float new_weight = __int_as_float(arc.y) + cost_offset - __ldg(&ll[arc.z]) + best_cost;
+        float new_weight = __int_as_float(arc.y) + cost_offset - (p.ll_smem ? ll_s[arc.z] : __ldg(&llg[arc.z])) + best_cost;
         seed_local = min(seed_local, f2ord(new_weight + adaptive_beam));
       }
     }
@@ -1593,7 +1650,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
             while (s.chunk_off[lo + 1] <= j) lo++;
             int a = s.chunk_ebeg[lo] + (j - s.chunk_off[lo]);
             int4 arc = __ldg(&g.e_arcs[a]);
-            float ac = cost_offset - __ldg(&ll[arc.z]);
+            float ac = cost_offset - (p.ll_smem ? ll_s[arc.z] : __ldg(&llg[arc.z]));
             tots[k] = s.chunk_cost[lo] + ac + __int_as_float(arc.y);
             acs[k] = ac; arcid[k] = a; nexts[k] = arc.x; srcs[k] = cb + lo;
           }
@@ -1694,7 +1751,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
       }
     }
     B2K_TICK(s, 2);
-    finish_frame_exact<T>(p, s, ctx, x, lane, ch, frames_decoded + 1, next_cutoff, cost_offset, lbase,
+    finish_frame_exact<T, PROF>(p, s, ctx, x, slot, ch, frames_decoded + 1, next_cutoff, cost_offset, lbase,
                           Hc, cs);
     if (s.err) break;
     tbase += min(s.ntok_new, p.max_tpf);
@@ -1710,12 +1767,1014 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kerne
     cs->hc = Hc;
     if (s.err) { cs->status = s.err; cs->err_line = s.err_line; }
     for (int i = 0; i < 15; i++) cs->prof[i] += s.prof[i];
-    cs->prof[15] += (unsigned long long)(clock64() - t_kernel0);
+    if (PROF) cs->prof[15] += (unsigned long long)(clock64() - t_kernel0);
   }
   if (s.err) {
     reset_lane_hash<T>(ctx.hash, p.hash_size);
-    for (int i = tid; i < p.hc_cap; i += T) x.bk[i] = make_int4(0x7fffffff, 0, 0, 0);
+    for (int i = tid; i < p.hc_cap; i += T) x.bk[i] = make_int2(0x7fffffff, 0);
   }
+}
+
+// PROF = per-phase cycle counters (bench.py's decoder_phase_share pass; B2K_DEC_PROF=1), compiled out otherwise
+template <int T, bool PROF>
+__global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_exact_kernel(DecParams p) {
+  __shared__ DecShared<T> s;
+  B2K_PERSISTENT_LANES((dec_advance_exact_lane<T, PROF>(p, s, lane_, (int)blockIdx.x)))
+}
+
+// ====================================================================== reference-order mode, second generation
+//
+// Same results as the frame step above (bit for bit: tests/test_decoder_gpu.py runs both), built around what the
+// round-2 profile showed (profiles/r02_decoder_history.md): the first generation visits every token's hash slot ~9
+// times and its HashList bucket record ~5 times per frame, reads the state table twice per token, and spends 46 % of
+// its time in the epsilon phases although they examine 10 % of the arcs.  Here
+//   * the token table is keyed by the reference's OWN bucket (state % hash size, hash-list-inl.h:130): all tokens of a
+//     bucket lie on one probe sequence before its first empty slot, so the HashList order (first insertion of the
+//     bucket, insertion within the bucket) is read off the table by walking that run -- no bucket array, no scatter,
+//     no per-bucket atomics;
+//   * a token's insertion key is the position of its first admitted arc (tokens created by ProcessNonemitting:
+//     positions after all arcs, in replay order); list positions come from ONE exclusive scan over that key space;
+//   * the thread that creates a token reads the state table once and leaves {emitting arcs, epsilon arcs} in a dense
+//     per-frame record: the closure finds its epsilon sources there, and the commit hands the emitting ranges to the
+//     next frame's expansion in list order, so the expansion never touches the state table;
+//   * the cost a token had before the closure is reconstructed from the values atomicMin returned (the largest one a
+//     successful lowering saw), so no per-token snapshot pass exists; a destination the closure never lowered cannot
+//     fire in the replay at all;
+//   * epsilon links are written with final arena indices; emitting links are remapped once.
+// A slot is {state, cost (ordered bits), insertion key, creation index}.
+
+struct X2 {
+  int4 *trec;          // [max_tpf] creation index -> {emitting arc begin, emitting degree, eps arc begin, eps degree}
+  int4 *rec;           // [max_tpf] closure record {offset, eps degree, #admitted, replay cost bits (global walk only)}
+  uint32_t *c0;        // [max_tpf] cost before the closure (ordered bits) if the closure lowered it; 0 = never lowered; +inf = created by the closure
+  int32_t *newseq;     // [max_tpf]
+  int4 *adj; int32_t *adjo; uint32_t *adjc;   // [adj_cap] eps arc entries, their owners, the cost the destination had before this entry lowered it (0 = did not)
+  int32_t *wl0, *wl1;  // [max_tpf]
+  int32_t *queue;      // [5 * cand_cap]
+  uint32_t *qstamp;    // [hash_size] re-queue filter of the closure rounds
+  int4 *tok4;          // [max_tpf] creation index -> {state, cost bits, first key of the bucket, rank inside the bucket}
+  uint32_t *hw;        // [pos_cap + max_tpf + 32] key -> bucket population at bucket heads, then its exclusive scan
+  int32_t *rank;       // [max_tpf] creation index -> list rank
+  int32_t *pf_ebeg, *pf_edeg;   // [max_tpf] list rank -> emitting arcs (input of the next frame's expansion)
+  int32_t *cid, *big;  // [max_tpf]
+};
+
+#define B2K_V2_L1_PROBES 32
+
+// i-th slot of bucket b's probe sequence (see the note at probe_slot: positions are stable because slots are never
+// freed inside a frame).  Level 1 = a window of the table sized from the reference's HashList size (>= 2x the previous
+// token count), level 2 = the whole table.
+__device__ __forceinline__ uint32_t probe_slot_b(const LaneCtx &c, uint32_t b, int i) {
+  if (i < B2K_V2_L1_PROBES) return (((b * 2654435761u) >> (32 - c.l1_log)) + (uint32_t)i) & (uint32_t)c.l1_mask;
+  return (((b * 0x85ebca6bu) >> (32 - c.hash_log)) + (uint32_t)(i - B2K_V2_L1_PROBES)) & (uint32_t)c.hash_mask;
+}
+
+__device__ __forceinline__ void set_l1_b(LaneCtx &c, uint32_t Hc) {
+  int lg = 12;
+  while ((1u << lg) < Hc && lg < c.hash_log) lg++;
+  c.l1_log = lg;
+  c.l1_mask = (1 << lg) - 1;
+}
+
+// find-or-insert on the bucket-keyed table; the creator records slot <-> creation index
+__device__ __forceinline__ int hash_insert_b(const LaneCtx &c, int32_t state, uint32_t Hc, bool *created, int *idx_out) {
+  const uint32_t b = (uint32_t)state % Hc;
+  *created = false;
+  for (int probe = 0; probe <= c.hash_mask + B2K_V2_L1_PROBES; probe++) {
+    const uint32_t h = probe_slot_b(c, b, probe);
+    int *keyp = reinterpret_cast<int *>(&c.hash[h]);
+    int old = atomicCAS(keyp, B2K_HASH_EMPTY, state);
+    if (old == B2K_HASH_EMPTY) {
+      int idx = atomicAdd(c.ntok_new, 1);
+      if (idx < c.max_tpf) { c.tokslot[idx] = (int)h; keyp[3] = idx; }
+      else do { if (atomicCAS(c.err, 0, B2K_ERR_OVERFLOW) == 0) *c.err_line = __LINE__; } while (0);
+      *created = true;
+      *idx_out = idx;
+      return (int)h;
+    }
+    if (old == state) return (int)h;
+  }
+  do { if (atomicCAS(c.err, 0, B2K_ERR_OVERFLOW) == 0) *c.err_line = __LINE__; } while (0);
+  return -1;
+}
+
+// in-place exclusive scan of a[0, n): every warp owns a contiguous range (coalesced), one block-level step
+template <int T>
+__device__ void block_excl_scan_array(uint32_t *a, int n, int *sh /*[T/32+1]*/) {
+  constexpr int W = T / 32;
+  const int warp = threadIdx.x >> 5, lane_id = threadIdx.x & 31;
+  const int per = ((n + W * 32 - 1) / (W * 32)) * 32;
+  const int b0 = min(n, warp * per), b1 = min(n, b0 + per);
+  uint32_t sum = 0;
+  for (int i = b0 + lane_id; i < b1; i += 32) sum += a[i];
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  __syncthreads();
+  if (lane_id == 0) sh[warp] = (int)sum;
+  __syncthreads();
+  uint32_t carry = 0;
+  for (int w = 0; w < warp; w++) carry += (uint32_t)sh[w];
+  for (int i0 = b0; i0 < b1; i0 += 32) {
+    const int i = i0 + lane_id;
+    const uint32_t v = (i < b1) ? a[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane_id >= o) incl += nb;
+    }
+    if (i < b1) a[i] = carry + incl - v;
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncthreads();
+}
+
+// ascending bitonic sort of keys[0, P2) (P2 a power of two; padding = ~0); keys may live in shared or global memory
+template <int T>
+__device__ void block_bitonic_sort_u64(unsigned long long *keys, int P2) {
+  for (int k = 2; k <= P2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P2; i += T) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = keys[i], b = keys[ixj];
+          if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+// ProcessNonemitting (closure, creation order by replay), list order, commit.  On entry the emitting pass has
+// inserted N1 = s.ntok_new tokens (slot.z = first admitted position < P, slot.w = creation index, trec filled).
+template <int T, bool PROF>
+__device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneCtx &ctx, const X2 &x, int ch,
+                                int list_index, float cutoff, float cost_offset, int32_t lbase, uint32_t Hc, int P,
+                                ChanState *cs) {
+  const int tid = threadIdx.x;
+  const FstDev &g = p.fst;
+  int4 *hash = ctx.hash;
+  const int32_t *tokslot = ctx.tokslot;
+  int4 *links = p.links + (size_t)ch * p.max_links;
+  int32_t *tok_state = p.tok_state + (size_t)ch * p.max_tokens;
+  float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
+  const int kInfBits = 0x7f800000;
+  const float kInfF = __int_as_float(kInfBits);
+  __syncthreads();
+  if (s.err) return;     // uniform: nothing writes err between the barrier and this read
+  const int n_emit_links = s.nlink_new;
+  const int N1 = min(s.ntok_new, p.max_tpf);
+  B2K_TICK(s, 3);
+  // ---- first worklist of the closure: the tokens that have eps arcs (dense records) and are below the cutoff
+  int32_t *wl0 = x.wl0, *wl1 = x.wl1;
+  int4 *wlx = reinterpret_cast<int4 *>(x.queue);              // idle until the replay worklist is built
+  if (tid == 0) { s.wl_n[0] = 0; s.wl_n[1] = 0; s.q_n = 0; }
+  __syncthreads();
+  for (int base = 0; base < N1; base += T) {
+    const int d = base + tid;
+    int deg = 0, ebeg = 0, cbits = 0;
+    if (d < N1) {
+      const int4 t = x.trec[d];
+      x.rec[d] = make_int4(0, 0, 0, 0);
+      x.c0[d] = 0u;
+      if (t.w > 0) {
+        const float c = ord2f((uint32_t)hash[tokslot[d]].y);
+        if (c < cutoff) { deg = t.w; ebeg = t.z; cbits = __float_as_int(c); }
+      }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, deg > 0);
+    if (m) {
+      int wb = 0;
+      if ((tid & 31) == 0) wb = atomicAdd(&s.wl_n[0], __popc(m));
+      wb = __shfl_sync(0xffffffffu, wb, 0);
+      if (deg > 0) wlx[wb + __popc(m & ((1u << (tid & 31)) - 1u))] = make_int4(cbits, ebeg, deg, d);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) s.cont = (s.wl_n[0] > 0 && !s.err);
+  __syncthreads();
+  B2K_TICK(s, 4);
+  // ---- closure by parallel relaxation, ARC-parallel per round (see the first generation for why the LAST record of a
+  //      token is exactly its set of eps links and a superset of what the replay can admit)
+  {
+    int cur = 0;
+    bool first_round = true;
+    while (s.cont) {
+      const int n = s.wl_n[cur];
+      const int stamp = s.stamp + 1;
+      int32_t *in = cur ? wl1 : wl0;
+      int32_t *out = cur ? wl0 : wl1;
+      for (int cb = 0; cb < n; cb += T) {
+        const int k = cb + tid;
+        int deg = 0, ebeg = 0, dd = 0;
+        float c = 0.f;
+        if (k < n) {
+          if (first_round) {
+            const int4 w = wlx[k];
+            c = __int_as_float(w.x); ebeg = w.y; deg = w.z; dd = w.w;
+          } else {
+            const int4 hs = __ldcg(&hash[in[k]]);             // cost may be lowered concurrently: read at L2
+            c = ord2f((uint32_t)hs.y);
+            if (c < cutoff) {
+              dd = hs.w;
+              const int4 t = x.trec[dd];
+              ebeg = t.z; deg = t.w;
+            }
+          }
+        }
+        int total;
+        const int off = block_excl_scan<T>(deg, s.redi, &total);
+        s.chunk_off[tid] = off; s.chunk_ebeg[tid] = ebeg; s.chunk_cost[tid] = c; s.chunk_d[tid] = dd;
+        if (tid == 0) {
+          s.chunk_off[T] = total;
+          s.ncand = s.q_n;                                    // record space of this chunk
+          s.q_n += total;
+          if (s.q_n > p.adj_cap) B2K_SET_ERR(s, B2K_ERR_OVERFLOW);
+        }
+        __syncthreads();
+        if (s.err) break;                                     // uniform
+        const int ebase = s.ncand;
+        if (deg > 0) {
+          int4 *rp = &x.rec[dd];
+          *reinterpret_cast<int2 *>(rp) = make_int2(ebase + off, deg);
+          rp->z = 0;                                          // arcs admitted by this expansion
+        }
+        __syncthreads();
+        for (int j = tid; j < total; j += T) {
+          int lo = 0, hi = T;
+          while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (s.chunk_off[mid] <= j) lo = mid; else hi = mid;
+          }
+          const int a = s.chunk_ebeg[lo] + (j - s.chunk_off[lo]);
+          const int owner = s.chunk_d[lo];
+          const int4 arc = __ldg(&g.ne_arcs[a]);
+          const float tot = s.chunk_cost[lo] + __int_as_float(arc.y);
+          int4 entry = make_int4(0, kInfBits, a, -1);
+          uint32_t lowered_from = 0u;
+          if (tot < cutoff) {
+            bool created; int idx = 0;
+            const int ds = hash_insert_b(ctx, arc.x, Hc, &created, &idx);
+            if (ds >= 0) {
+              if (created && idx < p.max_tpf) {
+                x.rec[idx] = make_int4(0, 0, 0, 0);
+                x.c0[idx] = B2K_INF_ORD;
+                const int2 o0 = __ldg(&g.st_off[arc.x]), o1 = __ldg(&g.st_off[arc.x + 1]);
+                x.trec[idx] = make_int4(o0.x, o1.x - o0.x, o0.y, o1.y - o0.y);
+              }
+              entry.x = __float_as_int(tot); entry.y = arc.y; entry.w = ds;
+              atomicAdd(&x.rec[owner].z, 1);
+              const uint32_t nv = f2ord(tot);
+              const uint32_t old = atomicMin(reinterpret_cast<uint32_t *>(&hash[ds].y), nv);
+              if (nv < old) {
+                lowered_from = old;
+                if (arc.w >= 0) {
+                  if (atomicExch(&x.qstamp[ds], (uint32_t)stamp) != (uint32_t)stamp) {
+                    int q = atomicAdd(&s.wl_n[cur ^ 1], 1);
+                    if (q < p.max_tpf) out[q] = ds;
+                    else B2K_SET_ERR(s, B2K_ERR_OVERFLOW);
+                  }
+                }
+              }
+            }
+          }
+          x.adj[ebase + j] = entry;
+          x.adjo[ebase + j] = owner;
+          x.adjc[ebase + j] = lowered_from;
+        }
+        __syncthreads();
+      }
+      __syncthreads();
+      if (tid == 0) {
+        s.wl_n[cur] = 0;
+        s.stamp = stamp;
+        if (s.wl_n[cur ^ 1] > p.max_tpf) s.wl_n[cur ^ 1] = p.max_tpf;
+        s.cont = (s.wl_n[cur ^ 1] > 0 && !s.err);
+      }
+      cur ^= 1;
+      first_round = false;
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  B2K_TICK(s, 5);
+  const int Nall = min(s.ntok_new, p.max_tpf);
+  const int E = s.err ? 0 : min(s.q_n, p.adj_cap);
+  // destination slot -> creation index; the cost a lowered token had before the closure = the largest value a
+  // successful atomicMin returned for it (the values a slot takes are decreasing)
+  for (int e = tid; e < E; e += T) {
+    const int dsl = x.adj[e].w;
+    if (dsl < 0) continue;
+    const int jd = hash[dsl].w;
+    x.adj[e].w = jd;
+    const uint32_t ov = x.adjc[e];
+    if (ov) atomicMax(&x.c0[jd], ov);
+  }
+  __syncthreads();
+  // An arc can only ever fire in the replay if final_cost(src) + w < cost(dest) after ProcessEmitting.  A destination
+  // the closure never lowered keeps that cost, which is <= every admitted tot: none of its arcs can fire.
+  for (int e = tid; e < E; e += T) {
+    int4 en = x.adj[e];
+    if (en.w < 0) continue;
+    const uint32_t c0b = x.c0[en.w];
+    if (!(c0b != 0u && __int_as_float(en.x) < ord2f(c0b))) x.adj[e].y = kInfBits;
+    x.adj[e].x = en.w;
+  }
+  __syncthreads();
+  if (tid == 0) cs->arcs_ne += (unsigned long long)E;        // eps arcs examined by the closure
+  // ---- replay (creation order of the eps-created tokens), restricted to the ancestors of created tokens
+  int *mark = wl1;                                           // the closure's worklists are idle now
+  int qcarry = 0;
+  extern __shared__ __align__(16) unsigned char dyn_smem_base[];
+  auto cost_before_closure = [&](int d) -> float {
+    const uint32_t c0b = x.c0[d];
+    return c0b ? ord2f(c0b) : ord2f((uint32_t)hash[tokslot[d]].y);
+  };
+  if (Nall > N1 && !s.err) {
+    for (int d = tid; d < Nall; d += T) { mark[d] = (d >= N1); if (d >= N1) x.newseq[d - N1] = -1; }
+    __syncthreads();
+    for (int it = 0; it < 1000000; it++) {
+      if (tid == 0) s.cont = 0;
+      __syncthreads();
+      for (int e = tid; e < E; e += T) {
+        const int4 en = x.adj[e];
+        if (en.w < 0 || en.y == kInfBits || !mark[en.x]) continue;
+        const int o = x.adjo[e];
+        if (mark[o]) continue;
+        const int4 r = x.rec[o];
+        if (e < r.x || e >= r.x + r.y) continue;             // superseded record
+        mark[o] = 1;
+        s.cont = 1;
+      }
+      __syncthreads();
+      const int again = s.cont;
+      __syncthreads();
+      if (!again) break;
+    }
+    for (int e = tid; e < E; e += T) {
+      const int4 en = x.adj[e];
+      if (en.w >= 0 && !mark[en.x]) x.adj[e].y = kInfBits;
+    }
+    // initial worklist (:852-856) = the emitting tokens in list order, restricted to the marked tokens whose final
+    // record admits something.  List order = (first key of the token's bucket, own key): both are read off the table.
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(dyn_smem_base);
+    const int key_cap = min(4096, p.rs_rcap + p.rs_ecap);     // 8 bytes each, inside the walk's (not yet filled) arrays
+    if (tid == 0) s.rs_n = 0;
+    __syncthreads();
+    int *pend = x.big;                                        // tokens to key (idle until the walk arrays are built)
+    for (int d = tid; d < N1; d += T) {
+      if (!mark[d] || x.rec[d].z <= 0) continue;
+      pend[atomicAdd(&s.rs_n, 1)] = d;
+    }
+    __syncthreads();
+    qcarry = s.rs_n;
+    int P2 = 1;
+    while (P2 < qcarry) P2 <<= 1;
+    if (qcarry > key_cap || P2 > key_cap) keys = reinterpret_cast<unsigned long long *>(x.hw);   // (idle until the list-order pass)
+    for (int q = tid; q < P2; q += T) {
+      unsigned long long key = ~0ull;
+      if (q < qcarry) {
+        const int d = pend[q];
+        const int4 hs = hash[tokslot[d]];
+        const uint32_t b = (uint32_t)hs.x % Hc;
+        uint32_t F = (uint32_t)hs.z;
+        for (int i = 0; i <= ctx.hash_mask + B2K_V2_L1_PROBES; i++) {
+          const int4 o = hash[probe_slot_b(ctx, b, i)];
+          if (o.x == B2K_HASH_EMPTY) break;
+          if ((uint32_t)o.x % Hc == b) F = min(F, (uint32_t)o.z);   // (eps-created tokens still carry the largest key)
+        }
+        key = ((unsigned long long)F << 37) | ((unsigned long long)(uint32_t)hs.z << 17) | (unsigned long long)(uint32_t)d;
+      }
+      keys[q] = key;
+    }
+    __syncthreads();
+    block_bitonic_sort_u64<T>(keys, P2);
+    for (int i = tid; i < qcarry; i += T) x.queue[i] = (int)(uint32_t)(keys[i] & 0x1ffffull);
+    __syncthreads();
+  }
+  __syncthreads();
+  B2K_TICK(s, 6);
+  // ---- compact walk out of shared memory (same construction as the first generation; falls back to the walk over the
+  //      global records when the set does not fit)
+  unsigned char *dyn_smem = dyn_smem_base;
+  float2 *tk_s = reinterpret_cast<float2 *>(dyn_smem);        // per token {replay cost, record offset | count << 16}
+  float2 *en_s = tk_s + p.rs_rcap;                            // per arc {weight, dest id}
+  unsigned short *ns_s = reinterpret_cast<unsigned short *>(en_s + p.rs_ecap);
+  unsigned short *q_s = ns_s + p.rs_rcap;
+  int *cid = x.cid;
+  int *dof = wl0;                                            // compact id -> creation index (worklists are idle now)
+  bool replay_done = false;
+  if (p.rs_rcap > 0 && !s.err && Nall > N1 && qcarry <= p.rs_qcap) {
+    if (tid == 0) { s.rs_n = 0; s.rs_e = 0; s.rs_ok = 1; }
+    for (int d = tid; d < Nall; d += T) cid[d] = -1;
+    __syncthreads();
+    auto claim = [&](int d) {
+      if (atomicCAS(&cid[d], -1, -2) != -1) return;
+      int id = atomicAdd(&s.rs_n, 1);
+      if (id < p.rs_rcap) {
+        tk_s[id] = make_float2(cost_before_closure(d), __int_as_float(0));
+        ns_s[id] = 0xffff;
+        dof[id] = d;
+        cid[d] = id;
+      } else {
+        s.rs_ok = 0;
+      }
+    };
+    for (int k = tid; k < qcarry; k += T) claim(x.queue[k]);
+    for (int e = tid; e < E; e += T) {
+      int4 en = x.adj[e];
+      if (en.w < 0 || en.y == kInfBits) continue;
+      int o = x.adjo[e];
+      if (!mark[o]) continue;
+      if (cid[en.x] == -1) claim(en.x);
+      if (cid[o] == -1) claim(o);
+    }
+    __syncthreads();
+    if (s.rs_ok) {
+      const int R = s.rs_n;
+      const int lane_id = tid & 31;
+      if (tid == 0) s.ncand = 0;
+      __syncthreads();
+      int *big_list = x.big;
+      for (int id = tid; id < R; id += T) {
+        const int d = dof[id];
+        const int4 r = x.rec[d];
+        if (!mark[d] || r.z == 0) continue;                  // destination only
+        if (r.y > 8) { big_list[atomicAdd(&s.ncand, 1)] = id; continue; }
+        int4 en[8];
+        int total = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          en[i] = (i < r.y) ? x.adj[r.x + i] : make_int4(0, kInfBits, 0, -1);
+          total += (en[i].w >= 0 && en[i].y != kInfBits);
+        }
+        if (!total) continue;
+        const int eo = atomicAdd(&s.rs_e, total);
+        if (eo + total > p.rs_ecap) { s.rs_ok = 0; continue; }
+        int pos = eo;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (en[i].w >= 0 && en[i].y != kInfBits)
+            en_s[pos++] = make_float2(__int_as_float(en[i].y), __int_as_float(cid[en[i].x]));
+        tk_s[id].y = __int_as_float(eo | (total << 16));
+      }
+      __syncthreads();
+      const int nbig = s.ncand;
+      for (int bi = tid >> 5; bi < nbig; bi += T / 32) {     // one warp per hub record
+        const int id = big_list[bi];
+        const int d = dof[id];
+        const int4 r = x.rec[d];
+        int total = 0;
+        for (int b0 = 0; b0 < r.y; b0 += 32) {
+          int i = b0 + lane_id;
+          int4 en = (i < r.y) ? x.adj[r.x + i] : make_int4(0, kInfBits, 0, -1);
+          total += __popc(__ballot_sync(0xffffffffu, en.w >= 0 && en.y != kInfBits));
+        }
+        if (!total) continue;
+        int eo = 0;
+        if (lane_id == 0) eo = atomicAdd(&s.rs_e, total);
+        eo = __shfl_sync(0xffffffffu, eo, 0);
+        if (eo + total > p.rs_ecap || total > 0xffff) { if (lane_id == 0) s.rs_ok = 0; continue; }
+        int pos = eo;
+        for (int b0 = 0; b0 < r.y; b0 += 32) {
+          int i = b0 + lane_id;
+          int4 en = (i < r.y) ? x.adj[r.x + i] : make_int4(0, kInfBits, 0, -1);
+          bool keep = en.w >= 0 && en.y != kInfBits;
+          uint32_t m = __ballot_sync(0xffffffffu, keep);
+          if (keep) {
+            int q = pos + __popc(m & ((1u << lane_id) - 1u));
+            en_s[q] = make_float2(__int_as_float(en.y), __int_as_float(cid[en.x]));
+          }
+          pos += __popc(m);
+        }
+        if (lane_id == 0) tk_s[id].y = __int_as_float(eo | (total << 16));
+      }
+      for (int k = tid; k < qcarry; k += T) q_s[k] = (unsigned short)cid[x.queue[k]];
+    }
+    __syncthreads();
+    if (s.rs_ok && tid == 0) {
+      int qn = qcarry, next = 0;
+      bool ok = true;
+      int npop = 0, nvis = 0;
+      while (qn > 0) {
+        const int d = q_s[--qn];
+        const float2 td = tk_s[d];
+        const float c = td.x;
+        npop++;
+        if (c >= cutoff) continue;
+        const int oc = __float_as_int(td.y);
+        const int e0 = oc & 0xffff, e1 = e0 + (int)((unsigned)oc >> 16);
+        nvis += e1 - e0;
+        for (int e = e0; e < e1; e++) {
+          const float2 ent = en_s[e];
+          const float tot = c + ent.x;
+          if (tot < cutoff) {
+            const int j = __float_as_int(ent.y);
+            const float2 tj = tk_s[j];
+            if (tot < tj.x) {
+              tk_s[j].x = tot;
+              if (tj.x == kInfF) ns_s[j] = (unsigned short)next++;
+              if ((unsigned)__float_as_int(tj.y) >> 16) {
+                if (qn < p.rs_qcap) q_s[qn++] = (unsigned short)j;
+                else { ok = false; qn = 0; break; }
+              }
+            }
+          }
+        }
+      }
+      if (ok) {
+        if (next != Nall - N1) B2K_SET_ERR(s, B2K_ERR_STATE);
+        s.prof[12] += (unsigned long long)npop; s.prof[13] += (unsigned long long)nvis; s.prof[14] += 1;
+      } else {
+        s.rs_ok = 0;                                         // worklist outgrew shared memory: redo below
+      }
+    }
+    __syncthreads();
+    if (s.rs_ok) {
+      replay_done = true;
+      if (!s.err)
+        for (int d = N1 + tid; d < Nall; d += T) {
+          int id = cid[d];
+          if (id >= 0) x.newseq[d - N1] = (int)ns_s[id];
+          else B2K_SET_ERR(s, B2K_ERR_STATE);                // an eps-created token is always some record's destination
+        }
+    }
+    __syncthreads();
+  }
+  // literal LIFO replay by one thread over the dense records in global memory (rec.w = replay cost)
+  if (!s.err && !replay_done && Nall > N1) {
+    for (int d = tid; d < Nall; d += T) x.rec[d].w = __float_as_int(cost_before_closure(d));
+    __syncthreads();
+    if (tid == 0) {
+      int qn = qcarry, next = 0;
+      int npop = 0, nvis = 0;
+      while (qn > 0) {
+        const int d = x.queue[--qn];
+        const int4 r = x.rec[d];
+        const float c = __int_as_float(r.w);
+        npop++;
+        if (c >= cutoff || r.z == 0) continue;
+        nvis += r.y;
+        for (int e = r.x; e < r.x + r.y; e++) {
+          const int4 en = x.adj[e];
+          if (en.w < 0) continue;
+          const float tot = c + __int_as_float(en.y);
+          if (tot < cutoff) {
+            const int j = en.x;
+            const int4 rj = x.rec[j];
+            const float old = __int_as_float(rj.w);
+            if (tot < old) {                                   // FindOrAddToken: new or improved -> changed
+              x.rec[j].w = __float_as_int(tot);
+              if (old == kInfF) x.newseq[j - N1] = next++;
+              if (rj.z > 0) {
+                if (qn < p.queue_cap) x.queue[qn++] = j;
+                else { B2K_SET_ERR(s, B2K_ERR_OVERFLOW); break; }
+              }
+            }
+          }
+        }
+      }
+      if (!s.err && next != Nall - N1) B2K_SET_ERR(s, B2K_ERR_STATE);
+      s.prof[12] += (unsigned long long)npop; s.prof[13] += (unsigned long long)nvis;
+    }
+  }
+  __syncthreads();
+  B2K_TICK(s, 7);
+  if (s.err) return;                                         // uniform (the caller resets the table)
+  // ---- insertion keys of the eps-created tokens: after every arc position, in replay order
+  const int PP = P + (Nall - N1);
+  for (int d = N1 + tid; d < Nall; d += T) hash[tokslot[d]].z = P + x.newseq[d - N1];
+  for (int w = tid; w < PP; w += T) x.hw[w] = 0u;
+  __syncthreads();
+  B2K_TICK(s, 8);
+  // ---- HashList order (hash-list-inl.h:126-175): buckets by first insertion, insertion order inside a bucket.  Every
+  //      token walks its bucket's probe run: first key of the bucket, its own rank inside it, the population.
+  for (int d = tid; d < Nall; d += T) {
+    const int sl = tokslot[d];
+    const int4 hs = hash[sl];
+    const uint32_t b = (uint32_t)hs.x % Hc;
+    uint32_t F = (uint32_t)hs.z;
+    int within = 0, pop = 0;
+    for (int i = 0; i <= ctx.hash_mask + B2K_V2_L1_PROBES; i++) {
+      const int4 o = hash[probe_slot_b(ctx, b, i)];
+      if (o.x == B2K_HASH_EMPTY) break;
+      if ((uint32_t)o.x % Hc == b) {
+        pop++;
+        F = min(F, (uint32_t)o.z);
+        within += ((uint32_t)o.z < (uint32_t)hs.z);
+      }
+    }
+    x.tok4[d] = make_int4(hs.x, __float_as_int(ord2f((uint32_t)hs.y)), (int)F, within);
+    if (F == (uint32_t)hs.z) x.hw[F] = (uint32_t)pop;
+  }
+  __syncthreads();
+  block_excl_scan_array<T>(x.hw, PP, s.redi);
+  B2K_TICK(s, 9);
+  const bool fits = (ctx.tbase + Nall <= p.max_tokens);
+  if (!fits) { if (tid == 0) B2K_SET_ERR(s, B2K_ERR_OVERFLOW); __syncthreads(); return; }
+  // ---- commit: tokens to the arena in list order, the emitting ranges for the next frame's expansion
+  for (int d = tid; d < Nall; d += T) {
+    const int4 t = x.tok4[d];
+    const int r = (int)x.hw[t.z] + t.w;
+    tok_state[ctx.tbase + r] = t.x;
+    tok_cost[ctx.tbase + r] = __int_as_float(t.y);
+    const int4 tr = x.trec[d];
+    x.pf_ebeg[r] = tr.x;
+    x.pf_edeg[r] = tr.y;
+    x.rank[d] = r;
+  }
+  __syncthreads();
+  // ---- eps links = the admitted entries of the final records, written with arena indices
+  {
+    const int lane_id = tid & 31;
+    for (int base = 0; base < E; base += T) {
+      const int e = base + tid;
+      bool live = false;
+      int4 en = make_int4(0, 0, 0, -1);
+      int o = 0;
+      if (e < E) {
+        en = x.adj[e];
+        if (en.w >= 0) {
+          o = x.adjo[e];
+          const int4 r = x.rec[o];
+          live = (e >= r.x && e < r.x + r.y);
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, live);
+      if (m) {
+        int lb = 0;
+        if (lane_id == 0) lb = atomicAdd(&s.nlink_new, __popc(m));
+        lb = __shfl_sync(0xffffffffu, lb, 0);
+        if (live) {
+          int li = lb + __popc(m & ((1u << lane_id) - 1u));
+          if (lbase + li < p.max_links)
+            links[lbase + li] = make_int4(ctx.tbase + x.rank[o], ctx.tbase + x.rank[en.w], (int)((uint32_t)en.z | B2K_EPS_FLAG), 0);
+          else
+            B2K_SET_ERR(s, B2K_ERR_OVERFLOW);
+        }
+      }
+    }
+  }
+  // emitting links: destination slot -> arena index
+  for (int li = tid; li < n_emit_links; li += T) {
+    int4 *lp = &links[lbase + li];
+    lp->y = ctx.tbase + x.rank[hash[lp->y].w];
+  }
+  __syncthreads();
+  B2K_TICK(s, 10);
+  const int nlink = s.nlink_new;
+  for (int d = tid; d < Nall; d += T)
+    hash[tokslot[d]] = make_int4(B2K_HASH_EMPTY, (int)B2K_INF_ORD, 0x7fffffff, 0);
+  if (tid == 0) {
+    size_t fo = (size_t)ch * (p.max_frames + 2);
+    p.frame_tok_begin[fo + list_index] = ctx.tbase;
+    p.frame_tok_begin[fo + list_index + 1] = ctx.tbase + Nall;
+    p.frame_link_begin[fo + list_index] = lbase;
+    p.frame_link_eps[fo + list_index] = lbase + n_emit_links;
+    p.frame_link_begin[fo + list_index + 1] = lbase + nlink;
+    if (list_index > 0) {
+      size_t co = (size_t)ch * (p.max_frames + 1) + (list_index - 1);
+      p.frame_cost_offset[co] = cost_offset;
+      p.frame_cutoff[co] = cutoff;
+    }
+    B2K_TICK(s, 11);
+  }
+  __syncthreads();
+}
+
+template <int T, bool PROF>
+__device__ void dec_advance_v2_lane(const DecParams &p, DecShared<T> &s, const int lane, const int slot) {
+  constexpr int IT = 4;
+  const int tid = threadIdx.x;
+  const int ch = p.lane_channel[lane];
+  ChanState *cs = &p.chan[ch];
+  const FstDev &g = p.fst;
+  const float kInf = __int_as_float(0x7f800000);
+
+  if (cs->status != B2K_OK) return;
+  if (!p.do_init && cs->frames_decoded < 0) {
+    if (tid == 0) { cs->status = B2K_ERR_STATE; cs->err_line = __LINE__; }
+    return;
+  }
+  int32_t *tok_state = p.tok_state + (size_t)ch * p.max_tokens;
+  float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
+  int4 *links = p.links + (size_t)ch * p.max_links;
+
+  LaneCtx ctx;
+  ctx.hash = p.hash + (size_t)slot * p.hash_size;
+  ctx.tokslot = p.tokslot + (size_t)slot * p.max_tpf;
+  ctx.tok_state = tok_state;
+  ctx.hash_mask = p.hash_size - 1;
+  ctx.hash_log = p.hash_log;
+  ctx.max_tpf = p.max_tpf;
+  ctx.max_tokens = p.max_tokens;
+  ctx.ntok_new = &s.ntok_new;
+  ctx.err = &s.err;
+  ctx.err_line = &s.err_line;
+  set_l1_b(ctx, 1000u);
+  X2 x;
+  x.trec = p.v2_trec + (size_t)slot * p.max_tpf;
+  x.rec = p.x_rec + (size_t)slot * p.max_tpf;
+  x.c0 = p.v2_c0 + (size_t)slot * p.max_tpf;
+  x.newseq = p.x_newseq + (size_t)slot * p.max_tpf;
+  x.adj = p.x_adj + (size_t)slot * p.adj_cap;
+  x.adjo = p.x_adjo + (size_t)slot * p.adj_cap;
+  x.adjc = p.v2_adjc + (size_t)slot * p.adj_cap;
+  x.wl0 = p.wl + (size_t)slot * 2 * p.max_tpf;
+  x.wl1 = x.wl0 + p.max_tpf;
+  x.queue = p.cand + (size_t)slot * 5 * p.cand_cap;
+  x.qstamp = p.v2_qstamp + (size_t)slot * p.hash_size;
+  x.tok4 = p.v2_tok4 + (size_t)slot * p.max_tpf;
+  x.hw = p.v2_hw + (size_t)slot * p.v2_hw_len;
+  x.rank = p.x_order + (size_t)slot * p.max_tpf;
+  x.pf_ebeg = p.v2_pf + (size_t)slot * 2 * p.max_tpf;
+  x.pf_edeg = x.pf_ebeg + p.max_tpf;
+  x.cid = p.x_sbase + (size_t)slot * p.max_tpf;
+  x.big = p.x_run + (size_t)slot * p.max_tpf;
+
+  if (tid == 0) { s.err = 0; s.err_line = 0; s.stamp = p.lane_stamp[slot]; }
+  __syncthreads();
+
+  if (p.do_init) {
+    if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; }
+    __syncthreads();
+    ctx.tbase = 0;
+    if (tid == 0) {
+      bool created; int idx = 0;
+      int sl = hash_insert_b(ctx, g.start, 1000u, &created, &idx);
+      if (sl >= 0) {
+        ctx.hash[sl].y = (int)f2ord(0.0f); ctx.hash[sl].z = 0;
+        const int2 o0 = __ldg(&g.st_off[g.start]), o1 = __ldg(&g.st_off[g.start + 1]);
+        x.trec[0] = make_int4(o0.x, o1.x - o0.x, o0.y, o1.y - o0.y);
+      }
+    }
+    finish_frame_v2<T, PROF>(p, s, ctx, x, ch, 0, p.beam, 0.0f, 0, 1000u, 1, cs);
+    if (tid == 0) {
+      cs->frames_decoded = 0;
+      cs->ntok = min(s.ntok_new, p.max_tpf);
+      cs->nlink = s.nlink_new;
+      cs->finalized = 0;
+      cs->hc = 1000;                                   // toks_.SetSize(1000) (:39)
+      if (s.err) { cs->status = s.err; cs->err_line = s.err_line; }
+      p.lane_stamp[slot] = s.stamp;
+    }
+    if (s.err) reset_lane_hash<T>(ctx.hash, p.hash_size);
+    return;
+  }
+
+  const int nframes = p.lane_nframes[lane];
+  const float *ll_base = p.lane_loglikes[lane];
+  int frames_decoded = cs->frames_decoded;
+  int32_t tbase = cs->ntok, lbase = cs->nlink;
+  int Hc = cs->hc;
+  unsigned long long arcs_e_total = 0;
+  const size_t fo = (size_t)ch * (p.max_frames + 2);
+
+  if (tid == 0) { for (int i = 0; i < 16; i++) s.prof[i] = 0; s.tlast = PROF ? clock64() : 0; }
+  const long long t_kernel0 = PROF ? clock64() : 0;
+  extern __shared__ __align__(16) unsigned char dyn_smem_base[];
+  float *ll_s = reinterpret_cast<float *>(dyn_smem_base);    // shares the replay arrays' space: they are idle during the expansion
+  bool have_pf = false;                                      // x.pf_* describe the previous list (true after one frame of this launch)
+  for (int fi = 0; fi < nframes; fi++) {
+    if (frames_decoded >= p.max_frames) { if (tid == 0) B2K_SET_ERR(s, B2K_ERR_OVERFLOW); __syncthreads(); break; }
+    const float *llg = ll_base + (size_t)fi * p.row_stride;
+    if (p.ll_smem) for (int i = tid; i < p.num_pdfs; i += T) ll_s[i] = __ldcs(&llg[i]);
+    const int pb = p.frame_tok_begin[fo + frames_decoded];
+    const int pe = p.frame_tok_begin[fo + frames_decoded + 1];
+    const int K = pe - pb;
+
+    // ---- GetCutoff (:653-720); ties -> first in list order (strict < at :662/:675)
+    unsigned long long local = ~0ull;
+    for (int i = pb + tid; i < pe; i += T) {
+      unsigned long long key = ((unsigned long long)f2ord(tok_cost[i]) << 32) | (uint32_t)(i - pb);
+      local = key < local ? key : local;
+    }
+    unsigned long long bestkey = block_min_u64<T>(local, s.red64);
+    float best_cost = kInf;
+    int best_i = -1;
+    if (K > 0) {
+      best_cost = ord2f((uint32_t)(bestkey >> 32));
+      best_i = (int)(uint32_t)(bestkey & 0xffffffffu);
+    }
+    const float beam_cutoff = best_cost + p.beam;
+    float cur_cutoff = beam_cutoff, adaptive_beam = p.beam;
+    if (K > 0 && !(p.max_active == 0x7fffffff && p.min_active == 0)) {
+      int c_lt = 0, c_le = 0;
+      for (int i = pb + tid; i < pe; i += T) {
+        float c = tok_cost[i];
+        c_lt += (c < beam_cutoff);
+        c_le += (c <= beam_cutoff);
+      }
+      c_lt = block_sum_i32<T>(c_lt, s.redi);
+      c_le = block_sum_i32<T>(c_le, s.redi);
+      bool done = false;
+      if (K > p.max_active && c_lt > p.max_active) {
+        float mac = block_select_kth<T>(tok_cost + pb, K, p.max_active, s.hist, s.pref);
+        cur_cutoff = mac;
+        adaptive_beam = mac - best_cost + p.beam_delta;
+        done = true;
+      }
+      if (!done) {
+        float min_active_cutoff = kInf;
+        if (K > p.min_active) {
+          if (p.min_active == 0) min_active_cutoff = best_cost;
+          else if (c_le <= p.min_active)
+            min_active_cutoff = block_select_kth<T>(tok_cost + pb, K, p.min_active, s.hist, s.pref);
+          else min_active_cutoff = beam_cutoff;
+        }
+        if (min_active_cutoff > beam_cutoff) {
+          adaptive_beam = min_active_cutoff - best_cost + p.beam_delta;
+          cur_cutoff = min_active_cutoff;
+        }
+      }
+    }
+    // PossiblyResizeHash(tok_cnt) (:227-233)
+    {
+      long long new_sz = (long long)((float)K * p.hash_ratio);
+      if (new_sz > (long long)Hc) Hc = (int)min(new_sz, (long long)0x7fffffff);
+    }
+    set_l1_b(ctx, (uint32_t)Hc);
+    const float cost_offset = (K > 0) ? -best_cost : 0.0f;
+
+    // ---- seed (:753-768)
+    uint32_t seed_local = B2K_INF_ORD;
+    if (K > 0) {
+      int sb, se;
+      if (have_pf) { sb = x.pf_ebeg[best_i]; se = sb + x.pf_edeg[best_i]; }
+      else { const int bs = tok_state[pb + best_i]; sb = __ldg(&g.st_off[bs]).x; se = __ldg(&g.st_off[bs + 1]).x; }
+      for (int a = sb + tid; a < se; a += T) {
+        int4 arc = __ldg(&g.e_arcs[a]);
+        float new_weight = __int_as_float(arc.y) + cost_offset - (p.ll_smem ? ll_s[arc.z] : __ldg(&llg[arc.z])) + best_cost;
+        seed_local = min(seed_local, f2ord(new_weight + adaptive_beam));
+      }
+    }
+    const float seed_cutoff = ord2f(block_min_u32<T>(seed_local, s.red32));
+
+    // ---- main loop (:779-812): admission against the exclusive prefix-min
+    if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; }
+    __syncthreads();
+    B2K_TICK(s, 0);
+    ctx.tbase = tbase;
+    float carry = kInf;
+    int pos_base = 0;
+    int round_no = 0;
+    constexpr int TPT = DecShared<T>::TPT, CT = DecShared<T>::CT;
+    for (int cb = pb; cb < pe; cb += CT) {
+#pragma unroll
+      for (int u = 0; u < TPT; u++) {                       // striped (coalesced) loads
+        const int q = u * T + tid, i = cb + q;
+        int deg = 0, ebeg = 0;
+        float c = 0.f;
+        if (i < pe) {
+          c = tok_cost[i];
+          if (c <= cur_cutoff) {
+            if (have_pf) { ebeg = x.pf_ebeg[i - pb]; deg = x.pf_edeg[i - pb]; }
+            else {
+              int st = tok_state[i];
+              int2 o0 = __ldg(&g.st_off[st]), o1 = __ldg(&g.st_off[st + 1]);
+              ebeg = o0.x;
+              deg = o1.x - o0.x;
+            }
+          }
+        }
+        s.chunk_off[q] = deg; s.chunk_ebeg[q] = ebeg; s.chunk_cost[q] = c;
+      }
+      __syncthreads();
+      int total;
+      {                                                      // blocked exclusive scan of the degrees
+        int dloc[TPT], sum = 0;
+#pragma unroll
+        for (int u = 0; u < TPT; u++) { dloc[u] = s.chunk_off[tid * TPT + u]; sum += dloc[u]; }
+        int off = block_excl_scan<T>(sum, s.redi, &total);
+#pragma unroll
+        for (int u = 0; u < TPT; u++) { s.chunk_off[tid * TPT + u] = off; off += dloc[u]; }
+      }
+      if (tid == 0) { s.chunk_off[CT] = total; arcs_e_total += (unsigned long long)total; }
+      __syncthreads();
+      for (int r0 = 0; r0 < total; r0 += T * IT, round_no++) {
+        const int j0 = r0 + tid * IT;
+        float tots[IT], acs[IT];
+        int arcid[IT], nexts[IT], srcs[IT];
+        int lo = 0;
+        if (j0 < total) {
+          int hi = CT;
+          while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (s.chunk_off[mid] <= j0) lo = mid; else hi = mid;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+          int j = j0 + k;
+          tots[k] = kInf; acs[k] = 0.f; arcid[k] = 0; nexts[k] = 0; srcs[k] = 0;
+          if (j < total) {
+            while (s.chunk_off[lo + 1] <= j) lo++;
+            int a = s.chunk_ebeg[lo] + (j - s.chunk_off[lo]);
+            int4 arc = __ldg(&g.e_arcs[a]);
+            float ac = cost_offset - (p.ll_smem ? ll_s[arc.z] : __ldg(&llg[arc.z]));
+            tots[k] = s.chunk_cost[lo] + ac + __int_as_float(arc.y);
+            acs[k] = ac; arcid[k] = a; nexts[k] = arc.x; srcs[k] = cb + lo;
+          }
+        }
+        float ex[IT];
+        float pm = kInf;
+#pragma unroll
+        for (int k = 0; k < IT; k++) { ex[k] = pm; pm = fminf(pm, tots[k]); }
+        // block-wide exclusive scan (min) of pm in thread order
+        const int lane_id = tid & 31, warp = tid >> 5;
+        float incl = pm;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          float n = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane_id >= o) incl = fminf(incl, n);
+        }
+        float wexcl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane_id == 0) wexcl = kInf;
+        float *buf = s.scanf_[round_no & 1];
+        if (lane_id == 31) buf[warp] = incl;
+        __syncthreads();
+        float wpre = kInf, tot_all = kInf;
+#pragma unroll
+        for (int w = 0; w < T / 32; w++) {
+          float v = buf[w];
+          if (w < warp) wpre = fminf(wpre, v);
+          tot_all = fminf(tot_all, v);
+        }
+        const float base = fminf(carry, fminf(wpre, wexcl));
+        int cr[IT];                                           // creation index of a token this thread created, else -1
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+          int j = j0 + k;
+          float excl = fminf(base, ex[k]);
+          float rc = fminf(seed_cutoff, excl + adaptive_beam);
+          bool adm = (j < total) && (tots[k] < rc);
+          int sl = -1;
+          cr[k] = -1;
+          if (adm) {
+            bool created; int idx;
+            sl = hash_insert_b(ctx, nexts[k], (uint32_t)Hc, &created, &idx);
+            if (sl >= 0) {
+              atomicMin(reinterpret_cast<uint32_t *>(&ctx.hash[sl].y), f2ord(tots[k]));
+              atomicMin(&ctx.hash[sl].z, pos_base + j);
+              if (created && idx < p.max_tpf) cr[k] = idx;
+            } else adm = false;
+          }
+          uint32_t m = __ballot_sync(0xffffffffu, adm);
+          if (m) {
+            int lb = 0;
+            if (lane_id == 0) lb = atomicAdd(&s.nlink_new, __popc(m));
+            lb = __shfl_sync(0xffffffffu, lb, 0);
+            if (adm) {
+              int li = lb + __popc(m & ((1u << lane_id) - 1u));
+              if (lbase + li < p.max_links)
+                links[lbase + li] = make_int4(srcs[k], sl, arcid[k], __float_as_int(acs[k]));
+              else
+                B2K_SET_ERR(s, B2K_ERR_OVERFLOW);
+            }
+          }
+        }
+        // the creator of a token reads the state table for it, once per token and off the admission path
+#pragma unroll
+        for (int k = 0; k < IT; k++)
+          if (cr[k] >= 0) {
+            const int2 o0 = __ldg(&g.st_off[nexts[k]]), o1 = __ldg(&g.st_off[nexts[k] + 1]);
+            x.trec[cr[k]] = make_int4(o0.x, o1.x - o0.x, o0.y, o1.y - o0.y);
+          }
+        carry = fminf(carry, tot_all);
+      }
+      pos_base += total;
+      __syncthreads();
+    }
+    const float next_cutoff = fminf(seed_cutoff, carry + adaptive_beam);
+    if (pos_base > p.pos_cap) { if (tid == 0) B2K_SET_ERR(s, B2K_ERR_OVERFLOW); }
+    __syncthreads();
+    B2K_TICK(s, 1);
+    finish_frame_v2<T, PROF>(p, s, ctx, x, ch, frames_decoded + 1, next_cutoff, cost_offset, lbase, (uint32_t)Hc,
+                             pos_base, cs);
+    if (s.err) break;
+    tbase += min(s.ntok_new, p.max_tpf);
+    lbase += s.nlink_new;
+    frames_decoded++;
+    have_pf = true;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    cs->frames_decoded = frames_decoded;
+    cs->ntok = tbase;
+    cs->nlink = lbase;
+    cs->arcs_e += arcs_e_total;
+    cs->hc = Hc;
+    if (s.err) { cs->status = s.err; cs->err_line = s.err_line; }
+    for (int i = 0; i < 15; i++) cs->prof[i] += s.prof[i];
+    if (PROF) cs->prof[15] += (unsigned long long)(clock64() - t_kernel0);
+    p.lane_stamp[slot] = s.stamp;
+  }
+  if (s.err) reset_lane_hash<T>(ctx.hash, p.hash_size);
+}
+
+template <int T, bool PROF>
+__global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_v2_kernel(DecParams p) {
+  __shared__ DecShared<T> s;
+  B2K_PERSISTENT_LANES((dec_advance_v2_lane<T, PROF>(p, s, lane_, (int)blockIdx.x)))
 }
 
 // ------------------------------------------------------------------ finalize (backward sweep)
@@ -1727,12 +2786,11 @@ __device__ __forceinline__ float link_extra_cost(float next_extra, float tok_tot
 }
 
 template <int T>
-__global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
+__device__ void dec_finalize_lane(const DecParams &p, const int lane, const int slot) {
   __shared__ uint32_t red32[T / 32];
   __shared__ int redi[T / 32];
   __shared__ int sh_changed;
   const int tid = threadIdx.x;
-  const int lane = blockIdx.x;
   const int ch = p.lane_channel[lane];
   ChanState *cs = &p.chan[ch];
   const FstDev &g = p.fst;
@@ -1743,7 +2801,7 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
   const float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
   float *tok_extra = p.tok_extra + (size_t)ch * p.max_tokens;
   int4 *links = p.links + (size_t)ch * p.max_links;
-  uint32_t *nx = p.new_extra + (size_t)lane * p.max_tpf;
+  uint32_t *nx = p.new_extra + (size_t)slot * p.max_tpf;
   const size_t fo = (size_t)ch * (p.max_frames + 2);
   const int last = cs->frames_decoded;
 
@@ -1770,7 +2828,7 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
   int4 *la = p.lat_arcs + (size_t)ch * p.cap_la;
   float2 *lw = p.lat_arcw + (size_t)ch * p.cap_la;
   int2 *lf = p.lat_finals + (size_t)ch * p.cap_lf;
-  int *ids_cur = p.cand + (size_t)lane * 5 * p.cand_cap;          // candidate staging is idle here (20*max_tpf ints)
+  int *ids_cur = p.cand + (size_t)slot * 5 * p.cand_cap;          // candidate staging is idle here (20*max_tpf ints)
   int *ids_next = ids_cur + p.max_tpf;
   int *has_eps = ids_cur + 2 * p.max_tpf;
   int *surv_e = ids_cur + 3 * p.max_tpf;                         // surviving emitting links of the segment
@@ -1840,7 +2898,7 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
     // (Jacobi over the surviving eps links; unique fixpoint because eps links
     // form a DAG) only ever excises a link when a LOWER BOUND of its extra cost
     // exceeds lattice_beam, so it keeps exactly the links of :308-379.
-    uint32_t *base_ord = reinterpret_cast<uint32_t *>(p.wl + (size_t)lane * 2 * p.max_tpf);
+    uint32_t *base_ord = reinterpret_cast<uint32_t *>(p.wl + (size_t)slot * 2 * p.max_tpf);
     for (int i = tid; i < n; i += T) {
       uint32_t bo = nx[i];
       base_ord[i] = bo;
@@ -1954,6 +3012,11 @@ __global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
   }
 }
 
+template <int T>
+__global__ void __launch_bounds__(T) dec_finalize_kernel(DecParams p) {
+  B2K_PERSISTENT_LANES(dec_finalize_lane<T>(p, lane_, (int)blockIdx.x))
+}
+
 // ------------------------------------------------------------------ lattice packing
 
 // Copies the compact lattices of n channels into packed arrays (one D2H each).
@@ -2004,6 +3067,11 @@ struct b2k_dec {
   int nlanes, nchannels;
   DecParams p;
   int threads_override = 0, fin_threads = 1024, num_sms = 0;   // tuning knobs, read from the environment at creation
+  int nslots = 0;                       // scratch slots = the largest grid any per-lane launch uses (resident CTAs)
+  int prof = 0;                         // B2K_DEC_PROF=1: per-phase cycle counters in the reference-order kernel
+  int ll_smem_off = 0;                  // B2K_DEC_LL_SMEM=0: leave the log-likelihood rows in global memory
+  int use_v2 = 0;                       // second-generation reference-order frame step (B2K_DEC_V1=1 selects the first)
+  int32_t *d_lane_counter = nullptr;
   // launch-argument staging
   int32_t *d_lane_channel = nullptr;
   const float **d_lane_ll = nullptr;
@@ -2154,7 +3222,15 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     int dev = 0;
     B2K_CUDA_CHECK(cudaGetDevice(&dev));
     B2K_CUDA_CHECK(cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (const char *e = getenv("B2K_DEC_PROF")) d->prof = atoi(e) != 0;
+    if (const char *e = getenv("B2K_DEC_LL_SMEM")) d->ll_smem_off = atoi(e) == 0;
+    // Persistent launches: at most two CTAs per SM are ever resident (512-thread reference-order CTAs; the
+    // order-free and finalize kernels use one slot per CTA of their own, smaller grids), so that is the
+    // number of scratch slots, whatever the batch size.
+    d->nslots = std::min(nlanes, 2 * d->num_sms);
   }
+  if (cfg->reference_order && cfg->max_tokens_per_frame > 32768)
+    return set_error(B2K_ERR_INVALID, "reference_order: max_tokens_per_frame above 32768 is not supported (16-bit bucket populations)");
   DecParams &p = d->p;
   memset(&p, 0, sizeof(p));
   p.fst = fst->dev;
@@ -2172,7 +3248,7 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     B2K_CUDA_CHECK(cudaMemset(*ptr, fill, bytes));
     return 0;
   };
-  size_t nc = nchannels, nl = nlanes;
+  size_t nc = nchannels, nl = (size_t)d->nslots, nlanes_sz = (size_t)nlanes;
 #define A(ptr, bytes, fill) if ((rc = alloc((void **)&(ptr), (bytes), (fill)))) return rc;
   A(p.chan, sizeof(ChanState) * nc, 0);
   A(p.tok_state, 4 * nc * p.max_tokens, 0);
@@ -2198,7 +3274,7 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     A(p.x_bm, 4 * nl * (p.pos_cap / 32), 0);
     A(p.x_wbase, 4 * nl * (p.pos_cap / 32), 0);
     A(p.x_by_ins, 4 * nl * p.max_tpf, 0);
-    A(p.x_bk, sizeof(int4) * nl * p.hc_cap, 0);
+    A(p.x_bk, sizeof(int2) * nl * p.hc_cap, 0);
     A(p.x_sbase, 4 * nl * p.max_tpf, 0);
     A(p.x_run, 4 * nl * p.max_tpf, 0);
     A(p.x_order, 4 * nl * p.max_tpf, 0);
@@ -2221,9 +3297,24 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     A(p.x_adj, sizeof(int4) * nl * p.adj_cap, 0);
     A(p.x_adjo, 4 * nl * p.adj_cap, 0);
     {
-      std::vector<int4> empty((size_t)p.hc_cap, make_int4(0x7fffffff, 0, 0, 0));
+      const char *e = getenv("B2K_DEC_V1");
+      // the second generation packs (key, key, creation index) into 64 bits for the replay's initial worklist
+      d->use_v2 = !(e && atoi(e) != 0) && p.pos_cap <= (1 << 20) && p.max_tpf <= (1 << 17);
+    }
+    if (d->use_v2) {
+      p.v2_hw_len = ((p.pos_cap + 2 * p.max_tpf + 64 + 63) / 64) * 64;
+      A(p.v2_trec, sizeof(int4) * nl * p.max_tpf, 0);
+      A(p.v2_tok4, sizeof(int4) * nl * p.max_tpf, 0);
+      A(p.v2_c0, 4 * nl * p.max_tpf, 0);
+      A(p.v2_adjc, 4 * nl * p.adj_cap, 0);
+      A(p.v2_qstamp, 4 * nl * p.hash_size, 0);
+      A(p.v2_hw, 4 * nl * (size_t)p.v2_hw_len, 0);
+      A(p.v2_pf, 4 * nl * 2 * p.max_tpf, 0);
+    }
+    {
+      std::vector<int2> empty((size_t)p.hc_cap, make_int2(0x7fffffff, 0));
       for (size_t l = 0; l < nl; l++)
-        B2K_CUDA_CHECK(cudaMemcpy(p.x_bk + l * p.hc_cap, empty.data(), sizeof(int4) * empty.size(), cudaMemcpyHostToDevice));
+        B2K_CUDA_CHECK(cudaMemcpy(p.x_bk + l * p.hc_cap, empty.data(), sizeof(int2) * empty.size(), cudaMemcpyHostToDevice));
     }
   }
   p.cap_ls = cfg->max_lattice_states > 0 ? cfg->max_lattice_states : 131072;
@@ -2235,14 +3326,17 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
   A(p.lat_finals, sizeof(int2) * nc * p.cap_lf, 0);
   A(d->d_pack_ch, 4 * nc, 0);
   A(d->d_pack_offs, 8 * 3 * (nc + 1), 0);
-  A(d->d_lane_channel, 4 * nl, 0);
-  A(d->d_lane_ll, sizeof(float *) * nl, 0);
-  A(d->d_lane_nframes, 4 * nl, 0);
+  A(d->d_lane_channel, 4 * nlanes_sz, 0);
+  A(d->d_lane_ll, sizeof(float *) * nlanes_sz, 0);
+  A(d->d_lane_nframes, 4 * nlanes_sz, 0);
+  A(d->d_lane_counter, 4, 0);
+  p.lane_counter = d->d_lane_counter;
+  p.num_pdfs = fst->num_pdfs_seen;
 #undef A
   // hash init: key = EMPTY, cost = +inf (ord), tok = 0, stamp = 0
   {
     std::vector<int4> init((size_t)p.hash_size, make_int4(B2K_HASH_EMPTY, (int)B2K_INF_ORD, cfg->reference_order ? 0x7fffffff : 0, 0));
-    for (int l = 0; l < nlanes; l++)
+    for (int l = 0; l < d->nslots; l++)
       B2K_CUDA_CHECK(cudaMemcpy(p.hash + (size_t)l * p.hash_size, init.data(),
                                 sizeof(int4) * init.size(), cudaMemcpyHostToDevice));
   }
@@ -2254,9 +3348,9 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     B2K_CUDA_CHECK(cudaMemcpy(p.chan, cs.data(), sizeof(ChanState) * nc, cudaMemcpyHostToDevice));
   }
   B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_chan, sizeof(ChanState) * nc));
-  B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_channel, 4 * nl));
-  B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_ll, sizeof(float *) * nl));
-  B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_nframes, 4 * nl));
+  B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_channel, 4 * nlanes_sz));
+  B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_ll, sizeof(float *) * nlanes_sz));
+  B2K_CUDA_CHECK(cudaMallocHost((void **)&d->h_lane_nframes, 4 * nlanes_sz));
   B2K_CUDA_CHECK(cudaEventCreateWithFlags(&d->staging_free, cudaEventDisableTiming));
   p.lane_channel = d->d_lane_channel;
   p.lane_loglikes = d->d_lane_ll;
@@ -2295,22 +3389,94 @@ static size_t exact_smem_bytes(const DecParams &p) {
   return sizeof(float2) * ((size_t)p.rs_rcap + p.rs_ecap) + sizeof(unsigned short) * ((size_t)p.rs_rcap + p.rs_qcap) + 16;
 }
 
-static int launch_exact(const b2k_dec *d, const DecParams &p, int n, cudaStream_t st) {
-  const size_t smem = exact_smem_bytes(p);
+// every per-lane launch is persistent: zero the lane counter, at most `max_grid` CTAs
+static int begin_persistent(const b2k_dec *d, DecParams &p, int n, cudaStream_t st) {
+  p.n_lanes = n;
+  B2K_CUDA_CHECK(cudaMemsetAsync(d->d_lane_counter, 0, 4, st));
+  return B2K_OK;
+}
+
+extern "C++" {
+template <int T, bool PROF>
+static int launch_exact_t(const b2k_dec *d, DecParams p, int n, int ctas_per_sm, cudaStream_t st) {
   static size_t configured = 0;
+  static size_t static_smem = 0;
+  if (!static_smem) {
+    cudaFuncAttributes fa;
+    B2K_CUDA_CHECK(cudaFuncGetAttributes(&fa, dec_advance_exact_kernel<T, PROF>));
+    static_smem = fa.sharedSizeBytes;
+  }
+  p.rs_bytes = (int32_t)exact_smem_bytes(p);
+  size_t smem = (size_t)p.rs_bytes;
+  // the log-likelihood row goes to shared memory when it fits beside the replay arrays at this occupancy
+  const size_t ll_bytes = ((size_t)p.num_pdfs * 4 + 15) / 16 * 16;
+  const size_t per_cta = (size_t)227 * 1024 / (size_t)ctas_per_sm - 1024;
+  p.ll_smem = (!d->ll_smem_off && p.num_pdfs > 0 && !p.do_init && p.row_stride >= p.num_pdfs &&
+               static_smem + smem + ll_bytes <= per_cta) ? 1 : 0;
+  if (p.ll_smem) smem += ll_bytes;
   if (smem > configured) {                                   // static + dynamic may exceed 48 KB: always opt in
-    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_exact_kernel<T, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const int threads = dec_threads(d, n);
-  if (threads == 128) dec_advance_exact_kernel<128><<<n, 128, smem, st>>>(p);
-  else if (threads == 512) dec_advance_exact_kernel<512><<<n, 512, smem, st>>>(p);
-  else if (threads == 1024) dec_advance_exact_kernel<1024><<<n, 1024, smem, st>>>(p);
-  else dec_advance_exact_kernel<256><<<n, 256, smem, st>>>(p);
+  const int grid = std::min(n, std::min(d->nslots, d->num_sms * ctas_per_sm));
+  dec_advance_exact_kernel<T, PROF><<<grid, T, smem, st>>>(p);
   return B2K_OK;
+}
+}  // extern "C++"
+
+extern "C++" {
+template <int T, bool PROF>
+static int launch_v2_t(const b2k_dec *d, DecParams p, int n, int ctas_per_sm, cudaStream_t st) {
+  static size_t configured = 0;
+  static size_t static_smem = 0;
+  if (!static_smem) {
+    cudaFuncAttributes fa;
+    B2K_CUDA_CHECK(cudaFuncGetAttributes(&fa, dec_advance_v2_kernel<T, PROF>));
+    static_smem = fa.sharedSizeBytes;
+  }
+  p.rs_bytes = (int32_t)exact_smem_bytes(p);
+  // the log-likelihood row shares the replay arrays' space (idle during the expansion): it only costs shared memory
+  // when it is larger than them
+  const size_t ll_bytes = ((size_t)p.num_pdfs * 4 + 15) / 16 * 16;
+  const size_t per_cta = (size_t)227 * 1024 / (size_t)ctas_per_sm - 1024;
+  size_t smem = (size_t)p.rs_bytes;
+  p.ll_smem = (!d->ll_smem_off && p.num_pdfs > 0 && !p.do_init && p.row_stride >= p.num_pdfs &&
+               static_smem + std::max(smem, ll_bytes) <= per_cta) ? 1 : 0;
+  if (p.ll_smem) smem = std::max(smem, ll_bytes);
+  if (smem > configured) {
+    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_v2_kernel<T, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int grid = std::min(n, std::min(d->nslots, d->num_sms * ctas_per_sm));
+  dec_advance_v2_kernel<T, PROF><<<grid, T, smem, st>>>(p);
+  return B2K_OK;
+}
+}  // extern "C++"
+
+static int launch_exact(const b2k_dec *d, DecParams p, int n, cudaStream_t st) {
+  int rc = begin_persistent(d, p, n, st);
+  if (rc) return rc;
+  const int threads = dec_threads(d, n);
+  if (d->use_v2) {
+    if (d->prof) {
+      if (threads == 1024) return launch_v2_t<1024, true>(d, p, n, 1, st);
+      if (threads == 512) return launch_v2_t<512, true>(d, p, n, 2, st);
+      return launch_v2_t<256, true>(d, p, n, 2, st);
+    }
+    if (threads == 1024) return launch_v2_t<1024, false>(d, p, n, 1, st);
+    if (threads == 512) return launch_v2_t<512, false>(d, p, n, 2, st);
+    if (threads == 128) return launch_v2_t<128, false>(d, p, n, 2, st);
+    return launch_v2_t<256, false>(d, p, n, 2, st);
+  }
+  if (d->prof) {
+    if (threads == 1024) return launch_exact_t<1024, true>(d, p, n, 1, st);
+    if (threads == 512) return launch_exact_t<512, true>(d, p, n, 2, st);
+    return launch_exact_t<256, true>(d, p, n, 2, st);
+  }
+  if (threads == 1024) return launch_exact_t<1024, false>(d, p, n, 1, st);
+  if (threads == 512) return launch_exact_t<512, false>(d, p, n, 2, st);
+  if (threads == 128) return launch_exact_t<128, false>(d, p, n, 2, st);
+  return launch_exact_t<256, false>(d, p, n, 2, st);
 }
 
 static int stage_lanes(b2k_dec *d, const int32_t *channels, const float *const *lls,
@@ -2348,7 +3514,10 @@ int b2k_dec_init_decoding(b2k_dec *d, const int32_t *channels, int32_t n, void *
   DecParams p = d->p;
   p.do_init = 1;
   if (d->cfg.reference_order) { if ((rc = launch_exact(d, p, n, st))) return rc; }
-  else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
+  else {
+    if ((rc = begin_persistent(d, p, n, st))) return rc;
+    dec_advance_kernel<DEC_THREADS><<<std::min(n, d->nslots), DEC_THREADS, 0, st>>>(p);
+  }
   B2K_LAUNCH_CHECK();
   return B2K_OK;
 }
@@ -2364,7 +3533,10 @@ int b2k_dec_advance_decoding_frames(b2k_dec *d, const int32_t *channels,
   p.do_init = 0;
   p.row_stride = row_stride;
   if (d->cfg.reference_order) { if ((rc = launch_exact(d, p, n, st))) return rc; }
-  else dec_advance_kernel<DEC_THREADS><<<n, DEC_THREADS, 0, st>>>(p);
+  else {
+    if ((rc = begin_persistent(d, p, n, st))) return rc;
+    dec_advance_kernel<DEC_THREADS><<<std::min(n, d->nslots), DEC_THREADS, 0, st>>>(p);
+  }
   B2K_LAUNCH_CHECK();
   return B2K_OK;
 }
@@ -2382,9 +3554,11 @@ int b2k_dec_finalize_decoding(b2k_dec *d, const int32_t *channels, int32_t n, vo
   DecParams p = d->p;
   {
     const int fin_threads = d->fin_threads;
-    if (fin_threads == 1024) dec_finalize_kernel<1024><<<n, 1024, 0, st>>>(p);
-    else if (fin_threads == 512) dec_finalize_kernel<512><<<n, 512, 0, st>>>(p);
-    else dec_finalize_kernel<256><<<n, 256, 0, st>>>(p);
+    if ((rc = begin_persistent(d, p, n, st))) return rc;
+    const int grid = std::min(n, d->nslots);                 // one resident CTA per scratch slot
+    if (fin_threads == 1024) dec_finalize_kernel<1024><<<std::min(grid, d->num_sms), 1024, 0, st>>>(p);
+    else if (fin_threads == 512) dec_finalize_kernel<512><<<grid, 512, 0, st>>>(p);
+    else dec_finalize_kernel<256><<<grid, 256, 0, st>>>(p);
   }
   B2K_LAUNCH_CHECK();
   return B2K_OK;
