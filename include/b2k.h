@@ -414,6 +414,11 @@ int b2k_model_destroy(b2k_model *model);
 /* info: [0] feat_dim, [1] ivector_dim, [2] num_pdfs, [3] frame subsampling factor, [4] layers, [5] weights,
  * [6] size of the transition-id -> pdf table (0 for raw models), [7] 1 if the file carried priors */
 int b2k_model_info(const b2k_model *model, int32_t info[8]);
+/* The frame subsampling factor is not stored in a model file.  1 = the layer shapes do not decide it (splices at +-3
+ * without a stride-3 TDNN-F layer: chain and non-chain recipes both have them): the compile routes refuse the model
+ * until b2k_model_set_frame_subsampling_factor states it (the tool's --frame-subsampling-factor). */
+int32_t b2k_model_frame_subsampling_ambiguous(const b2k_model *m);
+int b2k_model_set_frame_subsampling_factor(b2k_model *m, int32_t factor);
 const b2k_nnet_layer *b2k_model_layers(const b2k_model *model);
 const b2k_nnet_weight *b2k_model_weights(const b2k_model *model);    /* includes "priors" (ones when absent) */
 const int32_t *b2k_model_tid2pdf(const b2k_model *model);           /* [tid], index 0 unused; b2k_fst_csr.tid2pdf */
@@ -605,6 +610,10 @@ typedef struct {
   int32_t use_cmvn;
   b2k_cmvn_cfg cmvn;
   const double *global_cmvn_stats;
+  /* --frame-subsampling-factor (nnet3/decodable-simple-looped.h:75; the reference's default is 1, chain recipes pass 3).
+   * 0 = not given: the model's own factor is used when its layers decide it (b2k_model_frame_subsampling_ambiguous == 0),
+   * otherwise creating the pipeline is an error.  A value that contradicts the model (TDNN-F time-stride 3) is an error. */
+  int32_t frame_subsampling_factor;
 } b2k_pipeline_cfg;
 
 void b2k_pipeline_cfg_default(b2k_pipeline_cfg *cfg);

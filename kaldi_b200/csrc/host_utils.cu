@@ -279,7 +279,7 @@ int b2k_online_conf_read(const char *conf_path, b2k_online_conf *out) {
 extern "C" int b2k_pipeline_cfg_apply_options(const char *text, b2k_pipeline_cfg *cfg) {
   if (!text || !cfg) return b2k::set_error(B2K_ERR_INVALID, "b2k_pipeline_cfg_apply_options: bad args");
   b2k_pipeline_cfg c = *cfg;
-  int32_t prune_interval = c.dec.prune_interval, sub = 3, fpc = 20, extra_left = 0, ign_i = 0;
+  int32_t prune_interval = c.dec.prune_interval, sub = 3, fpc = 20, extra_left = 0, ign_i = 0, online_flag = 1, do_endpointing = 0;
   float ign_f = 0.f;
   char ign_s[512] = "";
   const Opt opts[] = {{"beam", 'f', &c.dec.beam}, {"max-active", 'i', &c.dec.max_active}, {"min-active", 'i', &c.dec.min_active},
@@ -287,7 +287,7 @@ extern "C" int b2k_pipeline_cfg_apply_options(const char *text, b2k_pipeline_cfg
                       {"hash-ratio", 'f', &c.dec.hash_ratio}, {"acoustic-scale", 'f', &c.acoustic_scale}, {"frames-per-chunk", 'i', &fpc},
                       {"frame-subsampling-factor", 'i', &sub}, {"extra-left-context-initial", 'i', &extra_left}, {"chunk-length", 'f', &c.chunk_length_secs},
                       {"determinize-lattice", 'b', &ign_i}, {"memory-pool-tokens-block-size", 'i', &ign_i}, {"memory-pool-links-block-size", 'i', &ign_i},
-                      {"debug-computation", 'b', &ign_i}, {"word-symbol-table", 's', ign_s}, {"do-endpointing", 'b', &ign_i}, {"online", 'b', &ign_i},
+                      {"debug-computation", 'b', &ign_i}, {"word-symbol-table", 's', ign_s}, {"do-endpointing", 'b', &do_endpointing}, {"online", 'b', &online_flag},
                       {"num-threads-startup", 'i', &ign_i}};
   (void)ign_f;
   try {
@@ -314,8 +314,12 @@ extern "C" int b2k_pipeline_cfg_apply_options(const char *text, b2k_pipeline_cfg
     }
     apply("(options)", kv, opts, sizeof(opts) / sizeof(opts[0]));
     if (extra_left != 0) throw ConfError{"--extra-left-context-initial other than 0 is not supported"};
+    if (do_endpointing) throw ConfError{"--do-endpointing=true is not supported by the batched pipeline (whole utterances are decoded; the endpoint rules are b2k_endpoint_*)"};
+    if (!online_flag) c.chunk_length_secs = -1.0f;         // --online=false: the tool sets chunk_length_secs = -1 = the whole file in one call (:128-130)
     if (sub <= 0) throw ConfError{"--frame-subsampling-factor must be positive"};
     c.dec.prune_interval = prune_interval;
+    if (kv.count("frame-subsampling-factor")) c.frame_subsampling_factor = sub;   // carried to the compile (never inferred from a default)
+    else if (c.frame_subsampling_factor > 0) sub = c.frame_subsampling_factor;
     if (fpc_given) {                                          // GetChunkSize (nnet-compile-looped.cc:81): rounded up to a multiple of the subsampling factor
       if (fpc <= 0) throw ConfError{"--frames-per-chunk must be positive"};
       c.frames_per_chunk = (fpc + sub - 1) / sub * sub;

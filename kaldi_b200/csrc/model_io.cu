@@ -410,6 +410,8 @@ struct b2k_ivec_files {
 
 struct b2k_model {
   int32_t feat_dim = 0, ivector_dim = 0, num_pdfs = 0, subsampling = 1;
+  int32_t subsampling_ambiguous = 0;          // the layer shapes do not decide the factor (see b2k_model_set_frame_subsampling_factor)
+  int32_t has_stride3_tdnnf = 0;
   std::vector<b2k_nnet_layer> layers;
   std::vector<std::string> wnames;
   std::vector<std::vector<float>> wdata;
@@ -802,11 +804,18 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
       throw FormatError("unsupported node pattern at " + n + " (" + t + ")");
     }
   }
+  // The factor is NOT stored in the file: the tools take --frame-subsampling-factor (default 1,
+  // nnet3/decodable-simple-looped.h:75).  A TDNN-F layer with time-stride 3 only exists in chain recipes (factor 3).
+  // Splices at +-3 in relu-batchnorm layers do not decide it: chain TDNNs (egs/wsj/s5/local/chain/tuning/run_tdnn_1f.sh,
+  // factor 3) and plain nnet3 TDNNs (egs/aishell/s5/local/nnet3/tuning/run_tdnn_1a.sh, factor 1) both have them: such a
+  // model is marked ambiguous and refuses to compile until the caller states the factor.
   M->subsampling = 1;
-  for (auto &L : M->layers) {                          // not stored in the file (the tools take --frame-subsampling-factor): a layer that
-    if (!strcmp(L.type, "tdnnf") && L.stride == 3) M->subsampling = 3;           // looks 3 frames away marks a chain model
-    if (!strcmp(L.type, "relu-batchnorm")) for (int k = 0; k < L.n_time_offsets; k++) if (L.time_offsets[k] == 3 || L.time_offsets[k] == -3) M->subsampling = 3;
+  for (auto &L : M->layers) {
+    if (!strcmp(L.type, "tdnnf") && L.stride == 3) { M->subsampling = 3; M->has_stride3_tdnnf = 1; }
+    if (!strcmp(L.type, "relu-batchnorm")) for (int k = 0; k < L.n_time_offsets; k++) if (L.time_offsets[k] == 3 || L.time_offsets[k] == -3) M->subsampling_ambiguous = 1;
   }
+  if (M->has_stride3_tdnnf) M->subsampling_ambiguous = 0;
+  if (M->subsampling_ambiguous) M->subsampling = 3;     // what the chain recipes use; only consulted after the caller confirms it
 }
 
 static void finish(b2k_model *M, const std::vector<float> *priors) {
@@ -862,6 +871,15 @@ int b2k_model_info(const b2k_model *m, int32_t info[8]) {
   if (!m || !info) return b2k::set_error(B2K_ERR_INVALID, "b2k_model_info: bad args");
   info[0] = m->feat_dim; info[1] = m->ivector_dim; info[2] = m->num_pdfs; info[3] = m->subsampling;
   info[4] = (int32_t)m->layers.size(); info[5] = (int32_t)m->weights.size(); info[6] = (int32_t)m->tid2pdf.size(); info[7] = m->has_priors;
+  return B2K_OK;
+}
+int32_t b2k_model_frame_subsampling_ambiguous(const b2k_model *m) { return m ? m->subsampling_ambiguous : -1; }
+int b2k_model_set_frame_subsampling_factor(b2k_model *m, int32_t factor) {
+  if (!m || factor <= 0) return b2k::set_error(B2K_ERR_INVALID, "b2k_model_set_frame_subsampling_factor: bad args");
+  if (m->has_stride3_tdnnf && factor != 3)
+    return b2k::set_error(B2K_ERR_INVALID, "--frame-subsampling-factor disagrees with the model: its TDNN-F layers have time-stride 3 (a chain model, factor 3)");
+  m->subsampling = factor;
+  m->subsampling_ambiguous = 0;
   return B2K_OK;
 }
 const b2k_nnet_layer *b2k_model_layers(const b2k_model *m) { return m ? m->layers.data() : nullptr; }

@@ -83,6 +83,31 @@ void b2k_pipeline_cfg_default(b2k_pipeline_cfg *c) {
   c->cmvn.cmn_window = 600; c->cmvn.speaker_frames = 600; c->cmvn.global_frames = 200; c->cmvn.normalize_mean = 1; c->cmvn.normalize_variance = 0;
 }
 
+// --frame-subsampling-factor: the caller's value if given, else the model's when its layers decide it
+// (b2k_model_frame_subsampling_ambiguous); never a silent guess.
+static int resolve_subsampling(const b2k_pipeline_cfg *cfg, const b2k_model *model, int model_factor, int32_t *out) {
+  const int amb = b2k_model_frame_subsampling_ambiguous(model);
+  if (cfg->frame_subsampling_factor < 0) return set_error(B2K_ERR_INVALID, "frame_subsampling_factor must be positive (0 = take the model's)");
+  if (cfg->frame_subsampling_factor == 0) {
+    if (amb) return set_error(B2K_ERR_INVALID, "the model's layers do not decide the frame subsampling factor (splices at +-3 without a stride-3 TDNN-F layer): "
+                                              "pass --frame-subsampling-factor (3 for chain models, 1 otherwise)");
+    *out = model_factor;
+    return B2K_OK;
+  }
+  if (!amb && model_factor == 3 && cfg->frame_subsampling_factor != 3)
+    return set_error(B2K_ERR_INVALID, "--frame-subsampling-factor disagrees with the model (TDNN-F layers with time-stride 3: a chain model, factor 3)");
+  *out = cfg->frame_subsampling_factor;
+  return B2K_OK;
+}
+
+// samples per AcceptWaveform call of online2-wav-nnet3-latgen-faster (:234-240): int32(samp_freq * chunk_length_secs)
+// in float arithmetic (truncated, not rounded), 0 becomes 1, and chunk_length_secs <= 0 (--online=false) = the whole file
+static int32_t chunk_samples_of(float samp_freq, float chunk_length_secs, int64_t num_samples) {
+  if (chunk_length_secs <= 0.0f) return (int32_t)std::min<int64_t>(num_samples, 0x7fffffff);
+  int32_t c = (int32_t)(samp_freq * chunk_length_secs);
+  return c == 0 ? 1 : c;
+}
+
 int b2k_pipeline_plan_for(const b2k_pipeline_cfg *cfg, const b2k_model *model, b2k_pipeline_plan *plan) {
   if (!cfg || !model || !plan) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: bad args");
   if (cfg->max_batch <= 0 || cfg->num_samples <= 0 || cfg->frames_per_chunk <= 0)
@@ -96,7 +121,8 @@ int b2k_pipeline_plan_for(const b2k_pipeline_cfg *cfg, const b2k_model *model, b
   const int D = cfg->feat.feature_type == 0 ? cfg->feat.num_ceps : cfg->feat.num_bins + (cfg->feat.use_energy ? 1 : 0);
   if (D != mi[0]) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: feature dimension differs from the model's input dimension");
   if (cfg->use_cmvn && !cfg->global_cmvn_stats) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: use_cmvn needs global_cmvn_stats (online-feature.cc:417)");
-  const int sub = mi[3];
+  int sub = 0;
+  if ((rc = resolve_subsampling(cfg, model, mi[3], &sub))) return rc;
   if (cfg->frames_per_chunk % sub) return set_error(B2K_ERR_INVALID, "b2k_pipeline_plan_for: frames_per_chunk must be a multiple of the frame subsampling factor");
   plan->num_feature_frames = T;
   plan->feat_dim = D;
@@ -104,7 +130,7 @@ int b2k_pipeline_plan_for(const b2k_pipeline_cfg *cfg, const b2k_model *model, b
   plan->num_chunks = (plan->num_output_frames * sub + cfg->frames_per_chunk - 1) / cfg->frames_per_chunk;
   plan->num_pdfs = mi[2];
   plan->ivector_dim = mi[1];
-  plan->chunk_samples = (int32_t)(cfg->chunk_length_secs * cfg->feat.samp_freq + 0.5f);
+  plan->chunk_samples = chunk_samples_of(cfg->feat.samp_freq, cfg->chunk_length_secs, cfg->num_samples);
   plan->dec = cfg->dec;
   const int64_t nf = plan->num_output_frames;
   if (plan->dec.max_frames <= 0) plan->dec.max_frames = (int32_t)(nf + 2);
@@ -139,7 +165,8 @@ static int pipeline_create_impl(b2k_pipeline *p, const b2k_model *model, const b
   // nnet3: compile for this utterance length, upload
   b2k_nnet_compile_cfg cc;
   memset(&cc, 0, sizeof(cc));
-  cc.feat_dim = mi[0]; cc.ivector_dim = mi[1]; cc.num_pdfs = mi[2]; cc.frame_subsampling_factor = mi[3];
+  cc.feat_dim = mi[0]; cc.ivector_dim = mi[1]; cc.num_pdfs = mi[2];
+  if ((rc = resolve_subsampling(&cfg, model, mi[3], &cc.frame_subsampling_factor))) return rc;
   cc.num_frames = pl.num_feature_frames; cc.frames_per_chunk = cfg.frames_per_chunk; cc.use_priors = cfg.use_priors;
   cc.conv_dense = cfg.conv_dense; cc.acoustic_scale = cfg.acoustic_scale;
   b2k_nnet_program *prog = nullptr;

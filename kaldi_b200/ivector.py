@@ -66,6 +66,15 @@ def _synthetic_global_cmvn(seed: int, dim: int) -> np.ndarray:
     return g
 
 
+def chunk_samples_of(samp_freq: float, chunk_length_secs: float, num_samples: int) -> int:
+    """Samples per AcceptWaveform call of online2-wav-nnet3-latgen-faster (:234-240): int32(samp_freq *
+    chunk_length_secs) in float32 arithmetic (truncated), 0 becomes 1, chunk_length_secs <= 0 = the whole file."""
+    if chunk_length_secs <= 0:
+        return int(num_samples)
+    c = int(np.float32(samp_freq) * np.float32(chunk_length_secs))
+    return 1 if c == 0 else c
+
+
 def online_ivector_schedule(num_samples: int, chunk_samples: int, frame_length: int, frame_shift: int,
                             num_feature_frames: int, nnet_right_context: int, frames_per_chunk: int, subsampling: int,
                             splice_right: int = 3):
@@ -154,7 +163,7 @@ class IvectorExtractorGpu:
         if getattr(self, "_sched_key", None) != (T, nc):
             fo = pipe.cfg.feature_opts
             self._sched = online_ivector_schedule(
-                pipe.cfg.num_samples, int(round(pipe.cfg.chunk_length_secs * fo.samp_freq)),
+                pipe.cfg.num_samples, chunk_samples_of(fo.samp_freq, pipe.cfg.chunk_length_secs, pipe.cfg.num_samples),
                 int(fo.samp_freq * 0.001 * fo.frame_length_ms), int(fo.samp_freq * 0.001 * fo.frame_shift_ms), T,
                 pipe.nnet.prog["model_right"], pipe.cfg.frames_per_chunk, pipe.arch["frame_subsampling_factor"],
                 self.ex["splice"])

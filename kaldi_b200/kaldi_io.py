@@ -526,7 +526,7 @@ def _inference_view(nodes: list, comps: dict) -> list:
 
 
 @_format_errors
-def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
+def nnet3_to_arch(parsed: dict, name: str = "from_file", frame_subsampling_factor: int | None = None) -> tuple[dict, dict]:
     """Maps a parsed TDNN-F chain model onto (arch, weights) of kaldi_b200.nnet_model.
 
     Recognises the node patterns that steps/libs/nnet3/xconfig emits for: idct-layer /
@@ -712,10 +712,22 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file") -> tuple[dict, dict]:
     arch["layers"] = layers
     out = [L for L in layers if L["type"] == "output"]
     arch["num_pdfs"] = out[0]["dim"] if out else 0
-    # not stored in the file (the tools take --frame-subsampling-factor): a layer that looks 3 frames away marks a chain model
-    arch["frame_subsampling_factor"] = 3 if any((L["type"] == "tdnnf" and L["stride"] == 3) or
-                                                (L["type"] == "relu-batchnorm" and 3 in map(abs, L.get("time_offsets", [])))
-                                                for L in layers) else 1
+    # The factor is not stored in the file (the tools take --frame-subsampling-factor, default 1).  A TDNN-F layer with
+    # time-stride 3 only exists in chain recipes (factor 3); +-3 splices of relu-batchnorm layers do not decide it (chain
+    # run_tdnn_1f.sh has them and so does the plain nnet3 aishell run_tdnn_1a.sh): the caller must then state it.
+    stride3 = any(L["type"] == "tdnnf" and L["stride"] == 3 for L in layers)
+    splice3 = any(L["type"] == "relu-batchnorm" and 3 in map(abs, L.get("time_offsets", [])) for L in layers)
+    arch["frame_subsampling_ambiguous"] = bool(splice3 and not stride3)
+    if frame_subsampling_factor is not None:
+        if int(frame_subsampling_factor) <= 0 or (stride3 and int(frame_subsampling_factor) != 3):
+            raise KaldiFormatError("--frame-subsampling-factor disagrees with the model (TDNN-F layers with time-stride 3: factor 3)")
+        arch["frame_subsampling_factor"] = int(frame_subsampling_factor)
+        arch["frame_subsampling_ambiguous"] = False
+    elif arch["frame_subsampling_ambiguous"]:
+        raise KaldiFormatError("the layers do not decide the frame subsampling factor (splices at +-3 without a stride-3 TDNN-F "
+                               "layer): pass frame_subsampling_factor (3 for chain models, 1 otherwise)")
+    else:
+        arch["frame_subsampling_factor"] = 3 if stride3 else 1
     return arch, W
 
 

@@ -15,13 +15,18 @@ class KaldiModel:
     """Owns a b2k_model handle.  `NnetComputer.from_model(m, ...)` compiles and uploads it without going through
     the Python compiler; `m.tid2pdf` feeds `CudaFst`."""
 
-    def __init__(self, path: str, is_mdl: bool | None = None):
+    def __init__(self, path: str, is_mdl: bool | None = None, frame_subsampling_factor: int | None = None):
         L = _lib.lib()
         if is_mdl is None:
             is_mdl = str(path).endswith(".mdl")
         self.h = C.c_void_p()
         L.b2k_model_read.argtypes = [C.c_char_p, C.c_int32, C.c_void_p]
         _lib.check(L.b2k_model_read(str(path).encode(), int(bool(is_mdl)), C.byref(self.h)))
+        if frame_subsampling_factor is not None:               # the tool's --frame-subsampling-factor (not stored in the file)
+            L.b2k_model_set_frame_subsampling_factor.argtypes = [C.c_void_p, C.c_int32]
+            _lib.check(L.b2k_model_set_frame_subsampling_factor(self.h, int(frame_subsampling_factor)))
+        L.b2k_model_frame_subsampling_ambiguous.argtypes = [C.c_void_p]
+        self.frame_subsampling_ambiguous = bool(L.b2k_model_frame_subsampling_ambiguous(self.h))
         info = (C.c_int32 * 8)()
         L.b2k_model_info.argtypes = [C.c_void_p, C.c_void_p]
         _lib.check(L.b2k_model_info(self.h, info))
@@ -60,6 +65,10 @@ class KaldiModel:
         """b2k_nnet_compile on the model's own arrays → a b2k_nnet_program handle (caller destroys it)."""
         from .nnet_compile import _Cfg
         L = _lib.lib()
+        if self.frame_subsampling_ambiguous:
+            raise _lib.B2kError(_lib.B2K_ERR_INVALID,
+                                "the model's layers do not decide the frame subsampling factor: construct KaldiModel with "
+                                "frame_subsampling_factor (3 for chain models, 1 otherwise)")
         cfg = _Cfg(self.feat_dim, self.ivector_dim, self.num_pdfs, self.frame_subsampling_factor, int(num_frames),
                    int(frames_per_chunk), int(use_priors), int((conv_mode or "patch") == "dense"), float(acoustic_scale))
         prog = C.c_void_p()

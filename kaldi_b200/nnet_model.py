@@ -817,23 +817,25 @@ def flops_per_output_frame(prog: dict) -> float:
     return tot / prog["n_out"]
 
 
-def load_kaldi_raw(path: str, priors: np.ndarray | None = None, name: str | None = None) -> tuple[dict, dict]:
+def load_kaldi_raw(path: str, priors: np.ndarray | None = None, name: str | None = None,
+                   frame_subsampling_factor: int | None = None) -> tuple[dict, dict]:
     """(arch, weights) of a TDNN-F chain model stored as a raw nnet3 file (nnet3-am-copy --raw=true final.mdl
     final.raw; text or binary).  `priors` (AmNnetSimple::Priors, the <Priors> vector of final.mdl) default to
     none, which is what chain models ship."""
     from . import kaldi_io as KIO
-    arch, W = KIO.nnet3_to_arch(KIO.read_nnet3_raw(path), name=name or os.path.basename(path))
+    arch, W = KIO.nnet3_to_arch(KIO.read_nnet3_raw(path), name=name or os.path.basename(path),
+                                frame_subsampling_factor=frame_subsampling_factor)
     W["priors"] = (np.ones(arch["num_pdfs"], np.float32) if priors is None else np.ascontiguousarray(priors, np.float32))
     return arch, W
 
 
-def load_kaldi_mdl(path: str, name: str | None = None) -> tuple[dict, dict, np.ndarray]:
+def load_kaldi_mdl(path: str, name: str | None = None, frame_subsampling_factor: int | None = None) -> tuple[dict, dict, np.ndarray]:
     """(arch, weights, tid2pdf) from a final.mdl (TransitionModel + AmNnetSimple).  tid2pdf[tid] is what
     CudaFst applies to the ilabels of HCLG (cudadecoder/cuda-fst.cc: TransitionIdToPdf); an empty <Priors>
     vector (chain models) means no prior subtraction."""
     from . import kaldi_io as KIO
     m = KIO.read_final_mdl(path)
-    arch, W = KIO.nnet3_to_arch(m["nnet"], name=name or os.path.basename(path))
+    arch, W = KIO.nnet3_to_arch(m["nnet"], name=name or os.path.basename(path), frame_subsampling_factor=frame_subsampling_factor)
     pri = m["priors"]
     W["priors"] = np.ones(arch["num_pdfs"], np.float32) if len(pri) == 0 else np.ascontiguousarray(pri, np.float32)
     return arch, W, m["transition_model"]["tid2pdf"]

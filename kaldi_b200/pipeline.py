@@ -35,6 +35,7 @@ class PipelineConfig:
     num_samples: int = 160000           # utterances are padded/truncated to this many samples per batch
     reference_order: bool = True
     chunk_length_secs: float = 0.18     # the CPU tool's --chunk-length (drives which i-vector a chunk sees)
+    frame_subsampling_factor: int = 0   # --frame-subsampling-factor; 0 = the model's own when its layers decide it
     extract_ivectors: bool = True
     max_tokens: int = 0                 # 0 = sized from the utterance length
     max_links: int = 0
@@ -162,7 +163,8 @@ def _native_structs():
         _fields_ = [("feat", _FeatCfg), ("dec", _DecCfg), ("frames_per_chunk", C.c_int32), ("acoustic_scale", C.c_float),
                     ("max_batch", C.c_int32), ("num_samples", C.c_int64), ("chunk_length_secs", C.c_float),
                     ("ivector_splice_right", C.c_int32), ("use_priors", C.c_int32), ("conv_dense", C.c_int32),
-                    ("use_cmvn", C.c_int32), ("cmvn", _CmvnCfg), ("global_cmvn_stats", C.c_void_p)]
+                    ("use_cmvn", C.c_int32), ("cmvn", _CmvnCfg), ("global_cmvn_stats", C.c_void_p),
+                    ("frame_subsampling_factor", C.c_int32)]
 
     class _PipelinePlan(C.Structure):
         _fields_ = [("num_feature_frames", C.c_int32), ("feat_dim", C.c_int32), ("num_output_frames", C.c_int32),
@@ -194,6 +196,7 @@ def native_cfg(cfg: PipelineConfig, ivector_splice_right: int = 3):
     c.dec.max_tokens, c.dec.max_links, c.dec.max_frames = cfg.max_tokens, cfg.max_links, 0
     c.frames_per_chunk, c.acoustic_scale, c.max_batch = cfg.frames_per_chunk, cfg.acoustic_scale, cfg.max_batch
     c.num_samples, c.chunk_length_secs, c.ivector_splice_right = cfg.num_samples, cfg.chunk_length_secs, ivector_splice_right
+    c.frame_subsampling_factor = cfg.frame_subsampling_factor
     return c
 
 

@@ -32,11 +32,12 @@ def test_nnet3_raw_model_round_trip_through_the_reference_writer(tmp_path, front
     arch = NM.arch_tiny_cnn() if front == "cnn" else NM.arch_tiny_tdnn() if front == "tdnn" else NM.arch_tiny(front=front)
     W = NM.random_weights(arch, seed=3)
     files = _ref_model_files(tmp_path, arch, W)
-    a3, W3 = NM.load_kaldi_raw(files["bin"])
+    sub = arch["frame_subsampling_factor"] if front == "tdnn" else None      # +-3 splices alone do not decide it: stated by the caller
+    a3, W3 = NM.load_kaldi_raw(files["bin"], frame_subsampling_factor=sub)
     assert a3["num_pdfs"] == arch["num_pdfs"] and W3["priors"].shape == (arch["num_pdfs"],)
     for mode, path in files.items():
         parsed = KIO.read_nnet3_raw(path)
-        arch2, W2 = KIO.nnet3_to_arch(parsed, name=arch["name"])
+        arch2, W2 = KIO.nnet3_to_arch(parsed, name=arch["name"], frame_subsampling_factor=sub)
         assert [(L["type"], L["name"]) for L in arch2["layers"]] == [(L["type"], L["name"]) for L in arch["layers"]]
         for L, L2 in zip(arch["layers"], arch2["layers"]):
             for k, v in L.items():

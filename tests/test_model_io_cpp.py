@@ -90,6 +90,16 @@ def test_cpp_reader_on_reference_written_models(tmp_path, which, binary):
         h, info, layers, W, t2p = _read(L, path, is_mdl)
         try:
             assert info[:4] == [arch["feat_dim"], arch["ivector_dim"], arch["num_pdfs"], arch["frame_subsampling_factor"]]
+            # +-3 splices without a stride-3 TDNN-F layer do not decide --frame-subsampling-factor: flagged, and settled by the caller
+            L.b2k_model_frame_subsampling_ambiguous.argtypes = [C.c_void_p]
+            L.b2k_model_set_frame_subsampling_factor.argtypes = [C.c_void_p, C.c_int32]
+            assert L.b2k_model_frame_subsampling_ambiguous(h) == (1 if which == "tdnn" else 0)
+            if which == "tdnn":
+                assert L.b2k_model_set_frame_subsampling_factor(h, 1) == 0 and L.b2k_model_frame_subsampling_ambiguous(h) == 0
+                i2 = (C.c_int32 * 8)(); L.b2k_model_info(h, i2); assert i2[3] == 1
+                assert L.b2k_model_set_frame_subsampling_factor(h, 3) == 0
+            elif any(x["type"] == "tdnnf" and x.get("stride") == 3 for x in arch["layers"]):
+                assert L.b2k_model_set_frame_subsampling_factor(h, 1) != 0           # contradicts the stride-3 TDNN-F layers
             want = [_layer_dict(_layer(x)) for x in arch["layers"]]
             got = [_layer_dict(x) for x in layers]
             assert len(got) == len(want)

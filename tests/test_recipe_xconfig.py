@@ -342,7 +342,13 @@ def test_wsj_tdnn_1f_shape_from_the_references_xconfig_library(tmp_path, binary)
     raw = str(tmp_path / "final.raw")
     L.ref_nnet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     assert L.ref_nnet_write(R.h, raw.encode(), binary) == 0
-    arch, W = NM.load_kaldi_raw(raw)
+    # +-3 splices without a stride-3 TDNN-F layer do not decide --frame-subsampling-factor (chain run_tdnn_1f.sh: 3, the plain
+    # nnet3 aishell run_tdnn_1a.sh with the same Append(-3,0,3): 1): both readers refuse to guess, and take what the caller states
+    from kaldi_b200.kaldi_io import KaldiFormatError
+    with pytest.raises(KaldiFormatError, match="frame subsampling factor"):
+        NM.load_kaldi_raw(raw)
+    assert NM.load_kaldi_raw(raw, frame_subsampling_factor=1)[0]["frame_subsampling_factor"] == 1
+    arch, W = NM.load_kaldi_raw(raw, frame_subsampling_factor=3)
     want = NM.arch_wsj_tdnn_1f(48, dim=56)
     assert [(x["type"], x["name"], x.get("time_offsets")) for x in arch["layers"]] == \
            [(x["type"], x["name"], x.get("time_offsets")) for x in want["layers"]]
@@ -350,7 +356,14 @@ def test_wsj_tdnn_1f_shape_from_the_references_xconfig_library(tmp_path, binary)
     try:
         from kaldi_b200.model import KaldiModel
         from kaldi_b200.nnet_compile import _Layer
-        m = KaldiModel(raw, is_mdl=False)
+        m0 = KaldiModel(raw, is_mdl=False)
+        assert m0.frame_subsampling_ambiguous
+        from kaldi_b200._lib import B2kError
+        with pytest.raises(B2kError, match="frame subsampling factor"):
+            m0.compile(70)
+        assert KaldiModel(raw, is_mdl=False, frame_subsampling_factor=1).frame_subsampling_factor == 1
+        m = KaldiModel(raw, is_mdl=False, frame_subsampling_factor=3)
+        assert not m.frame_subsampling_ambiguous and m.frame_subsampling_factor == 3
     except OSError as e:
         pytest.skip(str(e))
     assert m.layer_types() == [(x["type"], x["name"]) for x in want["layers"]]
@@ -435,10 +448,10 @@ def test_skip_connections_are_an_error_not_a_different_network(tmp_path, edit):
         pytest.skip(str(e))
     if edit == "dead-layer":
         want = [x["name"] for x in arch["layers"] if x["name"] != "tdnn2"]
-        assert [x["name"] for x in NM.load_kaldi_raw(raw)[0]["layers"]] == want
+        assert [x["name"] for x in NM.load_kaldi_raw(raw, frame_subsampling_factor=3)[0]["layers"]] == want
         assert [n for _, n in KaldiModel(raw, is_mdl=False).layer_types()] == want
         return
-    with pytest.raises(KIO.KaldiFormatError):
-        NM.load_kaldi_raw(raw)
+    with pytest.raises(KIO.KaldiFormatError, match="unsupported|skip|source"):
+        NM.load_kaldi_raw(raw, frame_subsampling_factor=3)
     with pytest.raises(LB.B2kError):
         KaldiModel(raw, is_mdl=False)
