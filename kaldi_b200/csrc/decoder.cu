@@ -110,7 +110,7 @@ struct DecParams {
   uint32_t *x_bm;           // [pos_cap/32] bitmap of first-admission positions
   int32_t *x_wbase;         // [pos_cap/32]
   int32_t *x_by_ins;        // [max_tpf] insertion index -> hash slot
-  int2 *x_bk;               // [hc_cap] per HashList bucket {first insertion index, population | fill cursor << 16}
+  int4 *x_bk;               // [hc_cap] per HashList bucket {first insertion index, population, fill cursor, -}
   int32_t *x_sbase;         // [max_tpf]
   int32_t *x_run;           // [max_tpf]
   int32_t *x_order;         // [max_tpf] list rank -> insertion index
@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(T) dec_advance_kernel(DecParams p) {
 // replay of the LIFO worklist (:858-896) -- the one inherently sequential piece.
 
 struct XScratch {
-  uint32_t *bm; int32_t *wbase, *by_ins, *sbase, *run, *order, *queue, *xb; int2 *bk;
+  uint32_t *bm; int32_t *wbase, *by_ins, *sbase, *run, *order, *queue, *xb; int4 *bk;
   int4 *rec; int32_t *newseq; int4 *adj; int32_t *adjo;
 };
 
@@ -822,7 +822,7 @@ __device__ void bucket_scatter(int k0, int k1, int Hc, const int4 *hash, const X
     int b = (int)((uint32_t)hash[slot].x % (uint32_t)Hc);
     x.xb[k] = b;
     atomicMin(&x.bk[b].x, k);
-    atomicAdd(&x.bk[b].y, 1);                           // population: low 16 bits (a frame holds < 65536 tokens)
+    atomicAdd(&x.bk[b].y, 1);
   }
   __syncthreads();
 }
@@ -830,7 +830,7 @@ __device__ void bucket_scatter(int k0, int k1, int Hc, const int4 *hash, const X
 template <int T>
 __device__ void order_finish(int N, const XScratch &x, DecShared<T> &s, int *order_slot = nullptr) {
   const int tid = threadIdx.x;
-  const int2 kEmptyBucket = make_int2(0x7fffffff, 0);
+  const int4 kEmptyBucket = make_int4(0x7fffffff, 0, 0, 0);
   __syncthreads();
   // list position of every bucket head = exclusive scan of the bucket populations in
   // first-insertion order.  A bucket with one token (the common case) is finished here.
@@ -839,8 +839,8 @@ __device__ void order_finish(int N, const XScratch &x, DecShared<T> &s, int *ord
     int k = base + tid, w = 0, b = 0;
     if (k < N) {
       b = x.xb[k];
-      int2 bk = x.bk[b];
-      if (bk.x == k) w = bk.y & 0xffff;
+      int4 bk = x.bk[b];
+      if (bk.x == k) w = bk.y;
     }
     int total;
     int excl = block_excl_scan<T>(w, s.redi, &total);
@@ -861,17 +861,17 @@ __device__ void order_finish(int N, const XScratch &x, DecShared<T> &s, int *ord
     int b = x.xb[k];
     if (b < 0) continue;
     int rb = x.sbase[x.bk[b].x];
-    int q = (int)((uint32_t)atomicAdd(&x.bk[b].y, 0x10000) >> 16);   // fill cursor: high 16 bits
+    int q = atomicAdd(&x.bk[b].z, 1);
     x.run[rb + q] = k;
   }
   __syncthreads();
   for (int k = tid; k < N; k += T) {
     int b = x.xb[k];
     if (b < 0) continue;
-    int2 bk = x.bk[b];
+    int4 bk = x.bk[b];
     int rb = x.sbase[bk.x];
     int within = 0;
-    const int pop = bk.y & 0xffff;
+    const int pop = bk.y;
     for (int j = 0; j < pop; j++) within += (x.run[rb + j] < k);
     x.order[rb + within] = k;
     if (order_slot) order_slot[rb + within] = x.by_ins[k];
@@ -1771,7 +1771,7 @@ __device__ void dec_advance_exact_lane(const DecParams &p, DecShared<T> &s, cons
   }
   if (s.err) {
     reset_lane_hash<T>(ctx.hash, p.hash_size);
-    for (int i = tid; i < p.hc_cap; i += T) x.bk[i] = make_int2(0x7fffffff, 0);
+    for (int i = tid; i < p.hc_cap; i += T) x.bk[i] = make_int4(0x7fffffff, 0, 0, 0);
   }
 }
 
@@ -1827,6 +1827,13 @@ struct X2 {
 __device__ __forceinline__ uint32_t probe_slot_b(const LaneCtx &c, uint32_t b, int i) {
   if (i < B2K_V2_L1_PROBES) return (((b * 2654435761u) >> (32 - c.l1_log)) + (uint32_t)i) & (uint32_t)c.l1_mask;
   return (((b * 0x85ebca6bu) >> (32 - c.hash_log)) + (uint32_t)(i - B2K_V2_L1_PROBES)) & (uint32_t)c.hash_mask;
+}
+
+// true if the level-2 part of bucket b's sequence passes over a slot of its own level-1 window (already visited)
+__device__ __forceinline__ bool probe_revisits_b(const LaneCtx &c, uint32_t b, int i, uint32_t slot) {
+  if (i < B2K_V2_L1_PROBES || slot > (uint32_t)c.l1_mask) return false;
+  const uint32_t w0 = ((b * 2654435761u) >> (32 - c.l1_log)) & (uint32_t)c.l1_mask;
+  return ((slot - w0) & (uint32_t)c.l1_mask) < (uint32_t)B2K_V2_L1_PROBES;
 }
 
 __device__ __forceinline__ void set_l1_b(LaneCtx &c, uint32_t Hc) {
@@ -2138,8 +2145,10 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
         const uint32_t b = (uint32_t)hs.x % Hc;
         uint32_t F = (uint32_t)hs.z;
         for (int i = 0; i <= ctx.hash_mask + B2K_V2_L1_PROBES; i++) {
-          const int4 o = hash[probe_slot_b(ctx, b, i)];
+          const uint32_t ps = probe_slot_b(ctx, b, i);
+          const int4 o = hash[ps];
           if (o.x == B2K_HASH_EMPTY) break;
+          if (probe_revisits_b(ctx, b, i, ps)) continue;
           if ((uint32_t)o.x % Hc == b) F = min(F, (uint32_t)o.z);   // (eps-created tokens still carry the largest key)
         }
         key = ((unsigned long long)F << 37) | ((unsigned long long)(uint32_t)hs.z << 17) | (unsigned long long)(uint32_t)d;
@@ -2355,8 +2364,10 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     uint32_t F = (uint32_t)hs.z;
     int within = 0, pop = 0;
     for (int i = 0; i <= ctx.hash_mask + B2K_V2_L1_PROBES; i++) {
-      const int4 o = hash[probe_slot_b(ctx, b, i)];
+      const uint32_t ps = probe_slot_b(ctx, b, i);
+      const int4 o = hash[ps];
       if (o.x == B2K_HASH_EMPTY) break;
+      if (probe_revisits_b(ctx, b, i, ps)) continue;
       if ((uint32_t)o.x % Hc == b) {
         pop++;
         F = min(F, (uint32_t)o.z);
@@ -3071,6 +3082,7 @@ struct b2k_dec {
   int prof = 0;                         // B2K_DEC_PROF=1: per-phase cycle counters in the reference-order kernel
   int ll_smem_off = 0;                  // B2K_DEC_LL_SMEM=0: leave the log-likelihood rows in global memory
   int use_v2 = 0;                       // second-generation reference-order frame step (B2K_DEC_V1=1 selects the first)
+  int grid_cap = 0;                     // B2K_DEC_GRID: cap on the resident CTAs of the reference-order launches (experiments)
   int32_t *d_lane_counter = nullptr;
   // launch-argument staging
   int32_t *d_lane_channel = nullptr;
@@ -3223,14 +3235,14 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     B2K_CUDA_CHECK(cudaGetDevice(&dev));
     B2K_CUDA_CHECK(cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (const char *e = getenv("B2K_DEC_PROF")) d->prof = atoi(e) != 0;
+    if (const char *e = getenv("B2K_DEC_GRID")) d->grid_cap = atoi(e);
     if (const char *e = getenv("B2K_DEC_LL_SMEM")) d->ll_smem_off = atoi(e) == 0;
     // Persistent launches: at most two CTAs per SM are ever resident (512-thread reference-order CTAs; the
     // order-free and finalize kernels use one slot per CTA of their own, smaller grids), so that is the
     // number of scratch slots, whatever the batch size.
     d->nslots = std::min(nlanes, 2 * d->num_sms);
   }
-  if (cfg->reference_order && cfg->max_tokens_per_frame > 32768)
-    return set_error(B2K_ERR_INVALID, "reference_order: max_tokens_per_frame above 32768 is not supported (16-bit bucket populations)");
+
   DecParams &p = d->p;
   memset(&p, 0, sizeof(p));
   p.fst = fst->dev;
@@ -3274,7 +3286,7 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     A(p.x_bm, 4 * nl * (p.pos_cap / 32), 0);
     A(p.x_wbase, 4 * nl * (p.pos_cap / 32), 0);
     A(p.x_by_ins, 4 * nl * p.max_tpf, 0);
-    A(p.x_bk, sizeof(int2) * nl * p.hc_cap, 0);
+    A(p.x_bk, sizeof(int4) * nl * p.hc_cap, 0);
     A(p.x_sbase, 4 * nl * p.max_tpf, 0);
     A(p.x_run, 4 * nl * p.max_tpf, 0);
     A(p.x_order, 4 * nl * p.max_tpf, 0);
@@ -3312,9 +3324,9 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
       A(p.v2_pf, 4 * nl * 2 * p.max_tpf, 0);
     }
     {
-      std::vector<int2> empty((size_t)p.hc_cap, make_int2(0x7fffffff, 0));
+      std::vector<int4> empty((size_t)p.hc_cap, make_int4(0x7fffffff, 0, 0, 0));
       for (size_t l = 0; l < nl; l++)
-        B2K_CUDA_CHECK(cudaMemcpy(p.x_bk + l * p.hc_cap, empty.data(), sizeof(int2) * empty.size(), cudaMemcpyHostToDevice));
+        B2K_CUDA_CHECK(cudaMemcpy(p.x_bk + l * p.hc_cap, empty.data(), sizeof(int4) * empty.size(), cudaMemcpyHostToDevice));
     }
   }
   p.cap_ls = cfg->max_lattice_states > 0 ? cfg->max_lattice_states : 131072;
@@ -3447,7 +3459,8 @@ static int launch_v2_t(const b2k_dec *d, DecParams p, int n, int ctas_per_sm, cu
     B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_v2_kernel<T, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const int grid = std::min(n, std::min(d->nslots, d->num_sms * ctas_per_sm));
+  int grid = std::min(n, std::min(d->nslots, d->num_sms * ctas_per_sm));
+  if (d->grid_cap > 0) grid = std::min(grid, d->grid_cap);
   dec_advance_v2_kernel<T, PROF><<<grid, T, smem, st>>>(p);
   return B2K_OK;
 }

@@ -28,6 +28,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace b2k {
@@ -548,6 +550,285 @@ __global__ void __launch_bounds__(256, 1) nnet_gemm_tc5_kernel(OpDev op, RunCtx 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(TMEM_COLS) : "memory");
 }
 
+// ---------------------------------------------------------------- tcgen05 GEMM, A in TMEM, W by TMA (the default)
+//
+// Same operator and fused epilogue as the kernels above; the structure was validated stand-alone first
+// (tools/tcgen05_gemm_probe2.cu, profiles/r02_nnet_gemm.md).  One CTA = one 128 x TN output tile, accumulator in TN
+// fp32 TMEM columns, 3xTF32: D += A_lo*W_hi + A_hi*W_lo + A_hi*W_hi per K step of 8.
+//   * W is split ONCE, when the network is uploaded, into W_hi = tf32(W) and W_lo = tf32(W - W_hi) (both are valid
+//     TF32 bit patterns, rows padded to a multiple of 4 floats); a K slab of 32 (TN rows x 128 bytes of each) is
+//     fetched by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, zero fill outside the matrix) into a 3-stage ring and read
+//     by the tensor core through K-major SW128 descriptors.  A slab that runs past a term's columns reads the next
+//     term's weights against zeros of A.
+//   * A is gathered by two groups of four loader warps (even / odd slabs): thread = tile row (row maps, clamping, the
+//     convolution's column windows and zero padding are per-thread pointer arithmetic), 128 bytes per slab, split in
+//     registers, written straight into TMEM (tcgen05.st 32x32b: lane = row, column = k) and consumed by tcgen05.mma with
+//     the A operand in TMEM (.ts form): A never touches shared memory.  TMEM: TN accumulator columns + 2 stages x
+//     (32 hi + 32 lo) = 256 columns for TN <= 128, so two CTAs share an SM and one's epilogue overlaps the other's MMAs.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one thread; tcgen05.commit frees the stages), warps 2..9 = loaders,
+//     then epilogue: TMEM -> registers -> 32 x 32 transposes in the (now idle) W ring -> the fused bias / ReLU /
+//     BatchNorm / bypass / prior / scale chain with one column per thread -> 128-byte row segments to global memory.
+#define TS_BM 128
+#define TS_BK 32
+#define TS_THREADS 320
+
+struct TsMaps { CUtensorMap hi, lo; };
+
+__device__ __forceinline__ void ts_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void ts_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+__device__ __forceinline__ void ts_mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void ts_tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void ts_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// K-major SWIZZLE_128B operand: 8-row groups of 1024 B (SBO), LBO field 1 (unused for swizzled K-major), version 1, layout 2
+__device__ __forceinline__ uint64_t ts_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void ts_mma(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               :: "r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void ts_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+         "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+         "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void ts_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// slab s of the op -> (term, k offset inside the term); terms are walked in order by every role
+struct TsSlab { int ti, kk; };
+__device__ __forceinline__ TsSlab ts_slab(const int *term_slab0, int n_terms, int s) {
+  int ti = 0;
+  while (ti + 1 < n_terms && term_slab0[ti + 1] <= s) ti++;
+  return {ti, (s - term_slab0[ti]) * TS_BK};
+}
+
+template <int TN, int SB>
+__global__ void __launch_bounds__(TS_THREADS, (TN <= 128 ? 2 : 1))
+nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __grid_constant__ TsMaps maps) {
+  constexpr uint32_t B_TILE = TN * 128;                       // bytes of one hi (or lo) tile: TN rows x 32 floats
+  constexpr uint32_t B_STAGE = 2 * B_TILE;
+  constexpr uint32_t TMEM_COLS = (TN + 128 <= 256) ? 256 : 512;
+  static_assert(SB * B_STAGE >= 8 * 32 * 33 * 4, "the W ring doubles as the epilogue's transpose space");
+  extern __shared__ __align__(1024) unsigned char ts_smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ts_smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long bars[2 * SB + 5];   // b_full[SB], b_empty[SB], a_full[2], a_empty[2], acc_full
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int term_slab0[13];
+  const int tid = threadIdx.x, warp = tid >> 5, lane_id = tid & 31;
+  const int M = c.batch * op.rows * (op.hsplit > 1 ? op.hsplit : 1);
+  const int m0 = blockIdx.x * TS_BM, n0 = blockIdx.y * TN;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[0]);
+  auto B_FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto B_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(SB + s); };
+  auto A_FULL = [&](int s) { return bar0 + 8u * (uint32_t)(2 * SB + s); };
+  auto A_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(2 * SB + 2 + s); };
+  const uint32_t ACC_FULL = bar0 + 8u * (uint32_t)(2 * SB + 4);
+
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < SB; s++) { ts_mbar_init(B_FULL(s), 1); ts_mbar_init(B_EMPTY(s), 1); }
+    for (int s = 0; s < 2; s++) { ts_mbar_init(A_FULL(s), 128); ts_mbar_init(A_EMPTY(s), 1); }
+    ts_mbar_init(ACC_FULL, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&maps.hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&maps.lo) : "memory");
+    int acc = 0;
+    for (int ti = 0; ti < op.n_terms; ti++) { term_slab0[ti] = acc; acc += (op.terms[ti].klen + TS_BK - 1) / TS_BK; }
+    term_slab0[op.n_terms] = acc;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int nslabs = term_slab0[op.n_terms];
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_acc = tmem_base;                        // TN columns
+  const uint32_t tmem_a = tmem_base + (uint32_t)TN;           // 2 stages x 64 columns
+  // F32 accumulate (bit 4), TF32 x TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TS_BM >> 4) << 24);
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane_id == 0) {
+      for (int s = 0; s < nslabs; s++) {
+        const int st = s % SB;
+        const TsSlab sl = ts_slab(term_slab0, op.n_terms, s);
+        t5_mbar_wait(B_EMPTY(st), (((uint32_t)(s / SB)) & 1u) ^ 1u);
+        ts_mbar_expect_tx(B_FULL(st), B_STAGE);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem + (size_t)st * B_STAGE);
+        const int kcol = op.terms[sl.ti].k0 + sl.kk;
+        ts_tma_load_2d(dst, &maps.hi, B_FULL(st), kcol, n0);
+        ts_tma_load_2d(dst + B_TILE, &maps.lo, B_FULL(st), kcol, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (lane_id == 0) {
+      for (int s = 0; s < nslabs; s++) {
+        const int st = s % SB, as = s & 1;
+        t5_mbar_wait(B_FULL(st), ((uint32_t)(s / SB)) & 1u);
+        t5_mbar_wait(A_FULL(as), ((uint32_t)(s >> 1)) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t bh = (uint32_t)__cvta_generic_to_shared(smem + (size_t)st * B_STAGE), bl = bh + B_TILE;
+#pragma unroll
+        for (int ks = 0; ks < TS_BK / 8; ks++) {
+          const uint64_t dbh = ts_desc_sw128(bh + (uint32_t)ks * 32u), dbl = ts_desc_sw128(bl + (uint32_t)ks * 32u);
+          const uint32_t ah = tmem_a + (uint32_t)as * 64u + (uint32_t)ks * 8u, al = ah + 32u;
+          ts_mma(tmem_acc, al, dbh, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+          ts_mma(tmem_acc, ah, dbl, idesc, 1u);
+          ts_mma(tmem_acc, ah, dbh, idesc, 1u);
+        }
+        ts_commit(B_EMPTY(st));
+        ts_commit(A_EMPTY(as));
+      }
+      ts_commit(ACC_FULL);
+    }
+  } else {
+    // ------------------------------------------------ A loaders (group g = even / odd slabs), then the epilogue
+    const int g = (warp - 2) >> 2, q = warp & 3;             // q = the TMEM lane quarter this warp may access
+    const int r = q * 32 + lane_id;                           // tile row owned by this thread
+    const bool live = m0 + r < M;
+    RowIdx x = {0, 0, 0};
+    if (live) x = split_row(op, m0 + r);
+    float cur[32];
+    int cur_ti = -1;
+    const float *arow = nullptr;
+    auto fetch = [&](int s) {
+      const TsSlab sl = ts_slab(term_slab0, op.n_terms, s);
+      const TermDev &t = op.terms[sl.ti];
+      if (sl.ti != cur_ti) {                                  // this thread's source row for the term
+        cur_ti = sl.ti;
+        arow = nullptr;
+        if (live) {
+          arow = src_row_ptr(c, t, x.lane, map_row(t, x.i));
+          if (t.col_lim > 0) {                                // convolution patch: column window of this output height
+            const int cb = x.h * t.col_step + t.col_off;
+            arow = (cb >= 0 && cb < t.col_lim) ? arow + cb : nullptr;   // outside = height zero padding
+          }
+        }
+      }
+      const int kk = sl.kk, klen = t.klen;
+      if (!arow) {
+#pragma unroll
+        for (int e = 0; e < 32; e++) cur[e] = 0.f;
+      } else if (kk + 32 <= klen && ((reinterpret_cast<uintptr_t>(arow + kk) & 15) == 0)) {
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) {
+          const float4 v = *reinterpret_cast<const float4 *>(arow + kk + cc * 4);
+          cur[cc * 4 + 0] = v.x; cur[cc * 4 + 1] = v.y; cur[cc * 4 + 2] = v.z; cur[cc * 4 + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; e++) cur[e] = (kk + e < klen) ? arow[kk + e] : 0.f;
+      }
+    };
+    if (g < nslabs) fetch(g);
+    for (int s = g; s < nslabs; s += 2) {
+      uint32_t hv[32];
+      t5_mbar_wait(A_EMPTY(g), (((uint32_t)(s >> 1)) & 1u) ^ 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t t0 = tmem_a + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 64u;
+#pragma unroll
+      for (int e = 0; e < 32; e++) hv[e] = to_tf32(cur[e]);
+      ts_tmem_st32(t0, hv);
+#pragma unroll
+      for (int e = 0; e < 32; e++) hv[e] = to_tf32(cur[e] - __uint_as_float(hv[e]));
+      ts_tmem_st32(t0 + 32u, hv);
+      if (s + 2 < nslabs) fetch(s + 2);                       // next slab of this group in flight while the MMAs run
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      ts_mbar_arrive(A_FULL(g));
+    }
+    // ---- epilogue.  Warp (q, g): rows 32q .. 32q+31, columns g*TN/2 .. +TN/2, 32 columns at a time: TMEM gives a
+    //      thread its row's 32 columns; a 32 x 32 transpose in shared memory gives it one column of the 32 rows, so the
+    //      per-column parameters are loaded once and every row is stored as one 128-byte segment.
+    if (nslabs > 0) t5_mbar_wait(ACC_FULL, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float *tsp = reinterpret_cast<float *>(smem) + (size_t)(warp - 2) * (32 * 33);   // the W ring is idle now
+    float *orow = nullptr;
+    const float *rrow = nullptr;
+    if (live) {
+      orow = (op.out_kind == 0) ? c.arena + (long long)x.lane * c.arena_stride + op.out_off + (long long)x.i * op.out_dim + (long long)x.h * op.N
+                                : c.d_out[x.lane] + (long long)x.i * c.out_stride;
+      if (op.has_res) rrow = src_row_ptr(c, op.res, x.lane, map_row(op.res, x.i));
+    }
+    const unsigned long long orow_u = reinterpret_cast<unsigned long long>(orow), rrow_u = reinterpret_cast<unsigned long long>(rrow);
+    constexpr int HALF = TN / 2;
+    for (int c0 = g * HALF; c0 < (g + 1) * HALF; c0 += 32) {
+      uint32_t v[32];
+      const int ncols = min(32, (g + 1) * HALF - c0);         // TN / 2 need not be a multiple of 32 (TN = 96, 160)
+      if (nslabs > 0) {
+        if (ncols == 32) ts_tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        else {                                                // 16 columns
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              : "r"(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 16; j < 32; j++) v[j] = 0u;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = 0u;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; j++) tsp[lane_id * 33 + j] = __uint_as_float(v[j]);   // (row = lane, column j): conflict free
+      __syncwarp();
+      const int n = n0 + c0 + lane_id;                        // this thread's column
+      const bool ncol_ok = lane_id < ncols && n < op.N;
+      float bias = 0.f, bsc = 1.f, bof = 0.f, sub = 0.f;
+      if (ncol_ok) {
+        if (op.bias) bias = __ldg(&op.bias[n]);
+        if (op.bn_scale) { bsc = __ldg(&op.bn_scale[n]); bof = __ldg(&op.bn_offset[n]); }
+        if (op.sub_vec) sub = __ldg(&op.sub_vec[n]);
+      }
+#pragma unroll 4
+      for (int rr = 0; rr < 32; rr++) {
+        const unsigned long long ou = __shfl_sync(0xffffffffu, orow_u, rr), ru = __shfl_sync(0xffffffffu, rrow_u, rr);
+        if (!ou || !ncol_ok) continue;
+        float val = tsp[rr * 33 + lane_id];
+        if (op.bias) val = __fadd_rn(val, bias);
+        if (op.relu) val = fmaxf(val, 0.f);
+        if (op.bn_scale) val = __fadd_rn(__fmul_rn(val, bsc), bof);
+        if (ru) val = __fadd_rn(__fmul_rn(op.res_alpha, reinterpret_cast<const float *>(ru)[n]), val);
+        if (!op.log_softmax) {
+          if (op.sub_vec) val = __fadd_rn(val, -sub);
+          if (op.out_scale != 1.0f) val = __fmul_rn(val, op.out_scale);
+        }
+        reinterpret_cast<float *>(ou)[n] = val;
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
 // out[r, blk*block_dim + c] = sum_terms(scale * src[map(r), c]) (+ BatchNorm)
 __global__ void nnet_ew_kernel(OpDev op, RunCtx c) {
   const long long total = (long long)c.batch * op.rows * op.out_dim;
@@ -614,15 +895,66 @@ struct b2k_nnet {
   float **h_outp = nullptr;
   cudaEvent_t staging_free = nullptr;
   double flops_per_lane = 0;
+  // tcgen05 path: W split once into hi / lo TF32 matrices (rows padded to 4 floats) + their TMA descriptors, per GEMM op
+  float *d_wsplit = nullptr;
+  std::vector<TsMaps> ts_maps;       // per op (unused entries for non-GEMM ops)
+  std::vector<int> ts_tn;            // column tile per op: 96, 128 (two CTAs per SM) or 160
 };
 
-// B2K_NNET_GEMM=simt selects the fp32 FFMA kernel (kept for A/B numerics and timing); =tcgen05 the experimental
-// TMEM kernel above (never run on a device yet); anything else, and the default, is the mma.sync 3xTF32 kernel
+// The default is the tcgen05 kernel with A in TMEM and W by TMA (nnet_gemm_ts_kernel).  B2K_NNET_GEMM selects the others
+// for A/B numerics and timing: mma = mma.sync 3xTF32 (round 1's measured kernel), simt = fp32 FFMA, tcgen05 = the first
+// TMEM kernel (both operands staged through shared memory by the CTA's threads).
 static int gemm_mode() {
   static int v = -1;
-  if (v < 0) { const char *e = getenv("B2K_NNET_GEMM"); v = (e && !strcmp(e, "simt")) ? 1 : (e && !strcmp(e, "tcgen05")) ? 2 : 0; }
+  if (v < 0) {
+    const char *e = getenv("B2K_NNET_GEMM");
+    v = !e ? 3 : !strcmp(e, "simt") ? 1 : !strcmp(e, "tcgen05") ? 2 : !strcmp(e, "mma") ? 0 : 3;
+  }
   return v;
 }
+
+static float host_tf32_rna(float x) {                        // cvt.rna.tf32.f32
+  uint32_t u; memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;            // inf / nan unchanged
+  u = (u + 0x1000u) & 0xffffe000u;
+  float r; memcpy(&r, &u, 4);
+  return r;
+}
+
+static int ts_pick_tn(int N) {
+  const int cand[3] = {128, 96, 160};                        // ties go to 128, then 96 (both keep two CTAs per SM)
+  int best = 128, best_pad = (N + 127) / 128 * 128;
+  for (int i = 1; i < 3; i++) { const int pad = (N + cand[i] - 1) / cand[i] * cand[i]; if (pad < best_pad) { best = cand[i]; best_pad = pad; } }
+  return best;
+}
+
+static int ts_make_map(CUtensorMap *m, const float *dptr, int N, int Kp, int TN) {
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)TN};
+  cuuint32_t es[2] = {1, 1};
+  CUresult rc = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)dptr, dims, strides, box, es,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return set_error(B2K_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight matrix");
+  return B2K_OK;
+}
+
+extern "C++" {
+template <int TN, int SB>
+static int ts_launch(const OpDev &op, const RunCtx &c, const TsMaps &maps, long long M, cudaStream_t st) {
+  static bool configured = false;
+  const int smem = SB * 2 * TN * 128 + 1024;
+  if (!configured) {
+    B2K_CUDA_CHECK(cudaFuncSetAttribute(nnet_gemm_ts_kernel<TN, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((unsigned)((M + TS_BM - 1) / TS_BM), (unsigned)((op.N + TN - 1) / TN));
+  nnet_gemm_ts_kernel<TN, SB><<<grid, TS_THREADS, smem, st>>>(op, c, maps);
+  return B2K_OK;
+}
+}  // extern "C++"
+
 static bool use_simt_gemm() { return gemm_mode() == 1; }
 
 extern "C" {
@@ -678,6 +1010,47 @@ int b2k_nnet_create(const b2k_nnet_node *nodes, int32_t n_nodes, const b2k_nnet_
     nn->log_softmax.push_back(o.log_softmax);
     if (o.type == 0) nn->flops_per_lane += 2.0 * o.K * o.N * o.rows * d.hsplit;
   }
+  {
+    // W -> W_hi, W_lo (TF32 bit patterns, rows padded to a multiple of 4 floats for TMA's 16-byte stride rule)
+    size_t total = 0;
+    std::vector<size_t> off(nn->ops.size(), 0);
+    for (size_t i = 0; i < nn->ops.size(); i++) {
+      if (nn->ops[i].type != 0) continue;
+      const size_t Kp = ((size_t)nn->ops[i].K + 3) / 4 * 4;
+      off[i] = total;
+      total += 2 * (size_t)nn->ops[i].N * Kp;
+      total = (total + 63) / 64 * 64;                        // 256-byte aligned matrices
+    }
+    nn->ts_maps.resize(nn->ops.size());
+    nn->ts_tn.assign(nn->ops.size(), 0);
+    if (total) {
+      std::vector<float> split(total, 0.f);
+      for (size_t i = 0; i < nn->ops.size(); i++) {
+        const OpDev &d = nn->ops[i];
+        if (d.type != 0) continue;
+        const size_t Kp = ((size_t)d.K + 3) / 4 * 4;
+        const float *w = blob + (d.w - nn->d_blob);          // the same offset in the host blob
+        float *hi = split.data() + off[i], *lo = hi + (size_t)d.N * Kp;
+        for (int n = 0; n < d.N; n++)
+          for (int k = 0; k < d.K; k++) {
+            const float v = w[(size_t)n * d.K + k], h = host_tf32_rna(v);
+            hi[(size_t)n * Kp + k] = h;
+            lo[(size_t)n * Kp + k] = host_tf32_rna(v - h);
+          }
+      }
+      B2K_CUDA_CHECK(cudaMalloc((void **)&nn->d_wsplit, sizeof(float) * total));
+      B2K_CUDA_CHECK(cudaMemcpy(nn->d_wsplit, split.data(), sizeof(float) * total, cudaMemcpyHostToDevice));
+      for (size_t i = 0; i < nn->ops.size(); i++) {
+        const OpDev &d = nn->ops[i];
+        if (d.type != 0) continue;
+        const int Kp = (d.K + 3) / 4 * 4;
+        nn->ts_tn[i] = ts_pick_tn(d.N);
+        const float *hi = nn->d_wsplit + off[i], *lo = hi + (size_t)d.N * Kp;
+        if ((rc = ts_make_map(&nn->ts_maps[i].hi, hi, d.N, Kp, nn->ts_tn[i]))) return rc;
+        if ((rc = ts_make_map(&nn->ts_maps[i].lo, lo, d.N, Kp, nn->ts_tn[i]))) return rc;
+      }
+    }
+  }
   size_t pb = sizeof(void *) * max_batch;
   B2K_CUDA_CHECK(cudaMalloc((void **)&nn->d_in, pb)); B2K_CUDA_CHECK(cudaMalloc((void **)&nn->d_iv, pb));
   B2K_CUDA_CHECK(cudaMalloc((void **)&nn->d_outp, pb));
@@ -691,7 +1064,7 @@ int b2k_nnet_create(const b2k_nnet_node *nodes, int32_t n_nodes, const b2k_nnet_
 int b2k_nnet_destroy(b2k_nnet *nn) {
   if (!nn) return B2K_OK;
   cudaDeviceSynchronize();
-  cudaFree(nn->d_blob); cudaFree(nn->d_arena); cudaFree(nn->d_in); cudaFree(nn->d_iv); cudaFree(nn->d_outp);
+  cudaFree(nn->d_blob); cudaFree(nn->d_arena); cudaFree(nn->d_in); cudaFree(nn->d_iv); cudaFree(nn->d_outp); cudaFree(nn->d_wsplit);
   cudaFreeHost(nn->h_in); cudaFreeHost(nn->h_iv); cudaFreeHost(nn->h_outp);
   if (nn->staging_free) cudaEventDestroy(nn->staging_free);
   delete nn;
@@ -732,6 +1105,12 @@ int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32
       if (use_simt_gemm()) {
         dim3 grid((unsigned)((M + GM_BM - 1) / GM_BM), (op.N + GM_BN - 1) / GM_BN);
         nnet_gemm_kernel<<<grid, 256, 0, st>>>(op, c);
+      } else if (gemm_mode() == 3) {
+        int rc2;
+        if (nn->ts_tn[i] == 96) rc2 = ts_launch<96, 3>(op, c, nn->ts_maps[i], M, st);
+        else if (nn->ts_tn[i] == 160) rc2 = ts_launch<160, 3>(op, c, nn->ts_maps[i], M, st);
+        else rc2 = ts_launch<128, 3>(op, c, nn->ts_maps[i], M, st);
+        if (rc2) return rc2;
       } else if (gemm_mode() == 2) {
         static bool configured5 = false;
         const int s128 = 2 * (2 * T5_CH * (T5_BM * 16 + 16) + 2 * T5_CH * (128 * 16 + 16)), s96 = 2 * (2 * T5_CH * (T5_BM * 16 + 16) + 2 * T5_CH * (96 * 16 + 16));
