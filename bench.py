@@ -1,25 +1,28 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the online2 inference hot path on B200.
 
-Metric (BASELINE.json): real-time factor RTFx = audio-seconds / wall-seconds, on
-config[1]: mini_librispeech TDNN-F chain model (run_tdnn_1k.sh shapes, 2336
-pdfs, synthetic weights), synthetic 16 kHz 10 s utterances, beam 15 /
-max-active 7000 / lattice-beam 8, synthetic 5 M-arc HCLG.  A "step" is one
-batch of utterances through features -> i-vectors -> nnet3 -> decoder ->
-finalized raw lattices.
+Metric (BASELINE.json): real-time factor RTFx = audio-seconds / wall-seconds.  A "step" is one batch of synthetic
+16 kHz 10 s utterances through features -> online i-vectors -> nnet3 -> lattice decoder -> finalized raw lattices.
 
-  python bench.py --gpus N --steps K --warmup W          # our arm
-  python bench.py --impl reference --gpus N ...           # the reference's CPU path on the host cores
+  python bench.py --gpus N --steps K --warmup W            # our arm; default workload = BASELINE configs[1]
+  python bench.py --impl reference --gpus N ...             # the reference's own CPU path on the host cores
+  python bench.py --workload librispeech_tdnn_1d/hclg50M/batch512   # BASELINE configs[2] (one GPU's share)
+  python bench.py --workload decoder_sweep                  # BASELINE configs[4]: Marcs/s per (graph size, beam)
 
-`value`  : whole-job RTFx with the audio already resident in HBM (CUDA events).
-`e2e`    : same through BatchedPipeline.decode_batch with HOST buffers: pinned
-           host audio -> H2D -> ... -> finalized lattices packed -> D2H, all timed.
-`roofline`: the dominant kernel (largest share of the step, measured live).
-`cpu_baseline`: the reference CPU path on a bounded sample (rank 0, N=1 only).
+Everything on the GPU side goes through the C ABI (include/b2k.h): b2k_pipeline_* over libb2k.so.
+`value`       : whole-job RTFx with the audio already resident in HBM (b2k_pipeline_run_device, CUDA events).
+`e2e`         : the same through b2k_pipeline_submit_i16 / b2k_pipeline_collect with HOST int16 buffers: staging to
+                pinned memory, H2D, all stages, packed lattices D2H and unpacking are inside the timed region; batch
+                k+1 is submitted before batch k is collected (the calls a serving loop makes).
+`roofline`    : the dominant kernel (largest share of the step, measured live with CUDA events).
+`cpu_baseline`: the reference CPU path (oracle/_ref: the reference's own sources) on a bounded sample, one thread.
+`parity_checked`: utterances of the last end-to-end batch whose lattices were compared, outside the timed region, with
+                the compiled reference decoder run on the device's log-likelihoods (bit-identical or the bench fails).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -35,10 +38,19 @@ sys.path.insert(0, ROOT)
 from kaldi_b200 import nnet_model as NM  # noqa: E402
 from kaldi_b200 import synth  # noqa: E402
 
-WORKLOAD = "mini_librispeech_tdnn_1k/10s-utts/beam15/hclg5M"
 NUM_SAMPLES = 160000
-GRAPH_ARCS = 5_000_000
-NUM_PDFS = 2336
+
+WORKLOADS = {
+    # BASELINE configs[1]: the configuration the metric is quoted on at N = 1
+    "mini_librispeech_tdnn_1k/10s-utts/beam15/hclg5M": dict(
+        arch="mini_librispeech_1k", num_pdfs=2336, graph_arcs=5_000_000, batch=592, cal="bench_calibration.npz",
+        model="mini_librispeech tdnn_1k (4.47 M params fwd path, 2336 pdfs)"),
+    # BASELINE configs[2]: one GPU's share of the 8-GPU target configuration
+    "librispeech_tdnn_1d/hclg50M/batch512": dict(
+        arch="librispeech_1d", num_pdfs=6024, graph_arcs=50_000_000, batch=512, cal="bench_calibration_1d.npz",
+        model="librispeech tdnn_1d (1536/160 x 17 layers, 6024 pdfs)"),
+}
+DEFAULT_WORKLOAD = "mini_librispeech_tdnn_1k/10s-utts/beam15/hclg5M"
 
 
 def load_peaks():
@@ -50,8 +62,47 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
 
 
-def build_inputs(batch: int, seed0: int):
-    return [synth.make_audio(NUM_SAMPLES, seed=seed0 + i) for i in range(batch)]
+def usable_cores():
+    """Host threads this process can really use: the affinity mask AND the cgroup CPU quota (a 1-GPU lease of this pool
+    shows 128 CPUs in the mask with cpu.max = 16 CPUs: round 1 started 128 workers on it, profiles/r02_reference_arm.md)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = max(1, int(int(q) / int(per)))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = max(1, q // per)
+        except Exception:
+            pass
+    return dict(affinity=n, cgroup_quota=quota, usable=min(n, quota) if quota else n)
+
+
+def graph_for(arcs: int, num_pdfs: int):
+    """Synthetic HCLG (kaldi_b200/synth.py), cached under gpurun_out/ because the 50 M-arc one takes minutes to draw."""
+    cache = os.path.join(ROOT, "gpurun_out", f"hclg_{arcs}_{num_pdfs}.npz")
+    if arcs >= 20_000_000 and os.path.exists(cache):
+        z = np.load(cache)
+        g = {k: z[k] for k in z.files}
+        for k in ("num_states", "start", "num_pdfs"):
+            g[k] = int(g[k])
+        return g
+    g = synth.make_hclg(arcs, num_pdfs=num_pdfs, seed=1)
+    if arcs >= 20_000_000:
+        try:
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
+            np.savez(cache, **g)
+        except Exception:
+            pass
+    return g
+
+
+def arch_for(w):
+    return getattr(NM, "arch_" + w["arch"])(w["num_pdfs"])
 
 
 class ClockSampler:
@@ -93,34 +144,49 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU reference path
 
-def cpu_reference_one(args):
-    """One utterance through the reference's CPU path, all of it the reference's own
-    sources compiled in oracle/_ref: features, i-vector, nnet3 looped forward and
-    LatticeFasterDecoder (InitDecoding / AdvanceDecoding / FinalizeDecoding)."""
-    seed, arch_seed = args
+_CPU_STATE = {}
+
+
+def load_calibrated_weights(arch, seed, cal_name):
+    """Synthetic weights + the prior-style output calibration (committed fixture: both arms decode the same model)."""
+    W = NM.random_weights(arch, seed=seed)
+    for p in (os.path.join(ROOT, "gpurun_out", cal_name), os.path.join(ROOT, "tests", "golden", cal_name)):
+        if os.path.exists(p):
+            c = np.load(p)
+            return NM.apply_output_calibration(W, c["mean"], float(c["scale"]))
+    return W
+
+
+def _cpu_setup(wname):
+    """Graph, model, extractor, features and decoder of the reference's CPU path (oracle/_ref), once per process."""
+    if _CPU_STATE.get("workload") == wname:
+        return
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    from oracle import dec_oracle as D, feat_oracle as F, nnet_oracle as NO
+    from oracle import feat_oracle as F, nnet_oracle as NO, ref_decoder as RD, ivector_oracle as IV
+    w = WORKLOADS[wname]
     g = _CPU_STATE.get("graph")
     if g is None:
-        g = _CPU_STATE["graph"] = synth.make_hclg(GRAPH_ARCS, num_pdfs=NUM_PDFS, seed=1)
-        arch = NM.arch_mini_librispeech_1k(NUM_PDFS)
-        W = load_calibrated_weights(arch, arch_seed)
-        _CPU_STATE["nnet"] = NO.RefNnet(arch, W)
-        _CPU_STATE["feat"] = F.RefFeat()
-        from oracle import ref_decoder as RD
-        _CPU_STATE["dec"] = RD.RefDecoder(g, synth.DEFAULT_DECODER_CFG)
-        from oracle import ivector_oracle as IV
-        _CPU_STATE["ivx"] = IV.make_cpu_extractor(arch_seed)
-    t0 = time.time()
-    wave = synth.make_audio(NUM_SAMPLES, seed=seed)
+        g = graph_for(w["graph_arcs"], w["num_pdfs"])
+    arch = arch_for(w)
+    W = load_calibrated_weights(arch, 0, w["cal"])
+    _CPU_STATE.update(workload=wname, graph=g, nnet=NO.RefNnet(arch, W), feat=F.RefFeat(), F=F,
+                      dec=RD.RefDecoder(g, synth.DEFAULT_DECODER_CFG), ivx=IV.make_cpu_extractor(0))
+
+
+def cpu_reference_one(args):
+    """One utterance through the reference's CPU path, all of it the reference's own sources compiled in oracle/_ref:
+    features (online, 0.18 s chunks), i-vector, nnet3 looped forward and LatticeFasterDecoder."""
+    idx, wname = args
+    _cpu_setup(wname)
+    S = _CPU_STATE
+    F = S["F"]
+    wave = S["waves"][idx]                                          # drawn before the clock started (fork-shared)
     t1 = time.time()
-    feats = _CPU_STATE["feat"].compute(wave, F.FeatOpts(), online_chunk=2880)
-    R = _CPU_STATE["nnet"]
+    feats = S["feat"].compute(wave, F.FeatOpts(), online_chunk=2880)
+    R = S["nnet"]
     n_chunks = len(R.chunk_ivector_rows(feats.shape[0], feats.shape[0], 1))
-    if _CPU_STATE["ivx"] is not None:
-        civ = _CPU_STATE["ivx"].chunk_ivectors(feats, n_chunks, R.frames_per_chunk, R.right_context)
-    else:
-        civ = np.zeros((n_chunks, 100), np.float32)
+    civ = S["ivx"].chunk_ivectors(feats, n_chunks, R.frames_per_chunk, R.right_context) if S["ivx"] is not None \
+        else np.zeros((n_chunks, 100), np.float32)
     ends = [(n + 1) * R.frames_per_chunk + R.right_context for n in range(n_chunks)]
     mat = np.zeros((ends[-1] + 1, 100), np.float32)
     prev = 0
@@ -128,55 +194,124 @@ def cpu_reference_one(args):
         mat[prev:e + 1] = civ[n]
         prev = e + 1
     ll = R.forward(feats, mat, period=1)
-    _CPU_STATE["dec"].decode(ll, record=_CPU_STATE.get("record", False))   # record: tools/bench_lattice_det.py
+    S["dec"].decode(ll, record=S.get("record", False))              # record: tools/bench_lattice_det.py
     t2 = time.time()
-    ns, na, _ = _CPU_STATE["dec"].lattice_sizes()
+    ns, na, _ = S["dec"].lattice_sizes()
     return (t2 - t1, ns, na)
 
 
-_CPU_STATE = {}
-CAL_PATH = os.path.join(ROOT, "gpurun_out", "bench_calibration.npz")
-CAL_FALLBACK = os.path.join(ROOT, "tests", "golden", "bench_calibration.npz")
-
-
-def load_calibrated_weights(arch, seed):
-    """Synthetic weights + the output calibration the GPU arm computed (committed
-    fixture so that the CPU arm decodes exactly the same model)."""
-    W = NM.random_weights(arch, seed=seed)
-    for p in (CAL_PATH, CAL_FALLBACK):
-        if os.path.exists(p):
-            c = np.load(p)
-            return NM.apply_output_calibration(W, c["mean"], float(c["scale"]))
-    return W
-
-
-def run_cpu_reference(num_utts: int, workers: int, pool=None, seed0: int = 1000):
-    t0 = time.time()
-    if workers <= 1:
-        cpu_reference_one((900, 0))                                   # builds graph/model/extractor once (untimed)
-        res = [cpu_reference_one((seed0 + i, 0)) for i in range(num_utts)]
-        t_total = sum(r[0] for r in res)
-    else:
-        t0 = time.time()
-        res = pool.map(cpu_reference_one, [(seed0 + i, 0) for i in range(num_utts)], chunksize=1)
-        t_total = time.time() - t0
-    audio = num_utts * NUM_SAMPLES / 16000.0
-    return dict(rtfx=audio / t_total, wall_s=t_total, utts=num_utts, arcs=sum(r[2] for r in res))
-
-
-def make_cpu_pool(workers: int):
+def run_reference_arm(a, wname):
+    """`--impl reference`: the reference's CPU path on every host thread this process may use; utterances are drawn
+    before the pool forks, each step is `2 x workers` utterances."""
     import multiprocessing as mp
+    cores = usable_cores()
+    workers = cores["usable"]
+    per_step = 2 * workers
+    n_steps = a.warmup + a.steps
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     os.environ["OMP_NUM_THREADS"] = "1"
+    _CPU_STATE["waves"] = [synth.make_audio(NUM_SAMPLES, seed=1000 + i) for i in range(per_step * n_steps + workers)]
+    _cpu_setup(wname)                                               # before the fork: workers share graph and model
     pool = mp.get_context("fork").Pool(workers)
-    pool.map(cpu_reference_one, [(900 + i, 0) for i in range(workers)], chunksize=1)   # warm every worker
-    return pool
+    base = per_step * n_steps
+    pool.map(cpu_reference_one, [(base + i, wname) for i in range(workers)], chunksize=1)   # warm every worker
+    vals, t_all = [], 0.0
+    for s in range(n_steps):
+        t0 = time.time()
+        pool.map(cpu_reference_one, [(s * per_step + i, wname) for i in range(per_step)], chunksize=1)
+        dt = time.time() - t0
+        if s >= a.warmup:
+            vals.append(per_step * NUM_SAMPLES / 16000.0 / dt)
+            t_all += dt
+    pool.close()
+    v = float(np.mean(vals))
+    sample = (f"{per_step} x 10 s utterances per step on {workers} worker processes (affinity {cores['affinity']}, cgroup quota "
+              f"{cores['cgroup_quota']}), audio drawn before the clock; features + i-vector + nnet3 + LatticeFasterDecoder are the "
+              "reference's own sources compiled in oracle/_ref (OpenBLAS 1 thread per worker; decoder against a container-only "
+              "OpenFst stand-in); lattice determinization excluded on both arms")
+    w = WORKLOADS[wname]
+    return dict(metric="real-time factor (audio-sec/wall-sec)", value=v, unit="RTFx", n_gpus=a.gpus, steps=a.steps,
+                warmup=a.warmup, ms_per_step=1e3 * t_all / max(a.steps, 1), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=wname, model=w["model"], graph_arcs=w["graph_arcs"], beam=15.0, max_active=7000,
+                            lattice_beam=8.0, sample=f"{per_step} utterances of 10 s per step"),
+                cpu_baseline=dict(value=v, unit="RTFx", cores=workers, kind="reference", sample=sample),
+                e2e=dict(value=v, unit="RTFx", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
 
 
-# ----------------------------------------------------------------------------- main
+def run_cpu_baseline(num_utts, wname):
+    _CPU_STATE["waves"] = [synth.make_audio(NUM_SAMPLES, seed=900 + i) for i in range(num_utts + 1)]
+    _cpu_setup(wname)
+    cpu_reference_one((num_utts, wname))                            # warm (untimed)
+    res = [cpu_reference_one((i, wname)) for i in range(num_utts)]
+    t = sum(r[0] for r in res)
+    return dict(value=num_utts * NUM_SAMPLES / 16000.0 / t, unit="RTFx", cores=1, kind="reference",
+                sample=f"{num_utts} x 10 s utterances, single thread: features + i-vector + nnet3 + LatticeFasterDecoder are the "
+                       "reference's own sources compiled in oracle/_ref (OpenBLAS 1 thread; decoder against a container-only "
+                       "OpenFst stand-in); determinization excluded")
 
-# dram__bytes_read.sum + dram__bytes_write.sum of dec_advance_exact_kernel per (lane, frame), profiles/r01_final_ncu_summary.md
-NCU_DRAM_BYTES_PER_LANE_FRAME = 3.66e6
+
+# ----------------------------------------------------------------------------- GPU arm
+
+def dec_infos(L, dec_handle, n):
+    L.b2k_dec_channel_info.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    out = []
+    info = (C.c_int64 * 32)()
+    for c in range(n):
+        L.b2k_dec_channel_info(dec_handle, c, info)
+        out.append([int(x) for x in info])
+    return out
+
+
+def decoder_sweep(a, rank, world, local_rank):
+    """BASELINE configs[4]: decoder only, fixed precomputed log-likelihoods, graph 5 M -> 200 M arcs, beam 10 -> 20."""
+    import torch
+    from kaldi_b200.decoder import CudaDecoder, CudaDecoderConfig, CudaFst
+    torch.cuda.set_device(local_rank)
+    peaks = load_peaks()
+    B, T, P = a.batch or 296, 333, 2336
+    sizes = [int(x) for x in (a.sweep_arcs or "5000000,20000000,50000000").split(",")]
+    beams = [float(x) for x in (a.sweep_beams or "10,13,15,17,20").split(",")]
+    rows = []
+    for arcs in sizes:
+        g = graph_for(arcs, P)
+        fst = CudaFst(g)
+        ll = torch.from_numpy(np.stack([synth.make_loglikes(g, T, seed=100 + i) for i in range(min(B, 16))])).cuda()
+        ll = ll.repeat((B + ll.shape[0] - 1) // ll.shape[0], 1, 1)[:B].contiguous()
+        for beam in beams:
+            cfg = dict(synth.DEFAULT_DECODER_CFG, beam=beam)
+            dc = CudaDecoderConfig.from_dict(cfg, max_frames=T + 2, max_tokens=T * 9000, max_links=T * 16000,
+                                             reference_order=True, max_tokens_per_frame=a.max_tpf)
+            dec = CudaDecoder(fst, dc, B)
+            ch = list(range(B))
+            lp = [ll.data_ptr() + 4 * T * P * i for i in range(B)]
+            ts = []
+            for it in range(1 + max(1, a.steps)):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dec.InitDecoding(ch)
+                e0.record()
+                dec.AdvanceDecodingFrames(ch, lp, [T] * B, P)
+                e1.record()
+                torch.cuda.synchronize()
+                if it > 0:
+                    ts.append(e0.elapsed_time(e1) / 1e3)
+            infos = [dec.ChannelInfo(c) for c in range(B)]
+            arcs_x = sum(i["arcs_emitting"] + i["arcs_nonemitting"] for i in infos)
+            ntok, nlink = sum(i["ntok"] for i in infos), sum(i["nlink"] for i in infos)
+            t = float(np.mean(ts))
+            alg = 16.0 * arcs_x + 32.0 * ntok + 36.0 * nlink
+            rows.append(dict(graph_arcs=int(g["offsets"][-1]), beam=beam, marcs_per_s=arcs_x / t / 1e6, ms=1e3 * t,
+                             tokens_per_frame=ntok / (B * T), arcs_per_frame=arcs_x / (B * T), gbs=alg / t / 1e9,
+                             frac_of_hbm=alg / t / 1e9 / peaks["hbm_gbs"], errors=sum(1 for i in infos if i["status"] != 0)))
+            del dec
+        del fst
+    if rank == 0:
+        best = max(r["marcs_per_s"] for r in rows)
+        print(json.dumps(dict(metric="decoder Marcs/s (arcs examined per second)", value=best, unit="Marcs/s", n_gpus=world,
+                              steps=a.steps, warmup=1, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                              data="synthetic", config=dict(workload="decoder_sweep", lanes=B, frames=T, pdfs=P,
+                                                            decoder_mode="reference_order"), sweep=rows)))
+    return 0
 
 
 def main():
@@ -185,13 +320,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=592, help="utterances per GPU per step (592 = 148 SMs x 4 resident decoder CTAs)")
-    ap.add_argument("--order-free", action="store_true", help="use the order-free decoder mode (not reference exact)")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["decoder_sweep"])
+    ap.add_argument("--batch", type=int, default=0, help="utterances per GPU per step (0 = the workload's own)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=6)
+    ap.add_argument("--parity-utts", type=int, default=2, help="utterances of the last e2e batch checked against the compiled reference decoder")
     ap.add_argument("--max-tpf", type=int, default=32768, help="decoder per-frame token capacity (hash = 2x slots)")
     ap.add_argument("--tok-per-frame", type=int, default=9000, help="decoder token arena sizing (avg tokens/frame)")
     ap.add_argument("--links-per-frame", type=int, default=16000, help="decoder link arena sizing (avg links/frame)")
+    ap.add_argument("--sweep-arcs", default="")
+    ap.add_argument("--sweep-beams", default="")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -200,68 +338,60 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        cores = os.cpu_count() or 1
-        per_step = 2 * cores
-        pool = make_cpu_pool(cores)
-        vals = []
-        t_all = 0.0
-        for s in range(a.warmup + a.steps):
-            r = run_cpu_reference(per_step, cores, pool, seed0=1000 + 100 * s)
-            if s >= a.warmup:
-                vals.append(r["rtfx"]); t_all += r["wall_s"]
-        pool.close()
-        v = float(np.mean(vals))
-        line = dict(metric="real-time factor (audio-sec/wall-sec)", value=v, unit="RTFx", n_gpus=a.gpus, steps=a.steps,
-                    warmup=a.warmup, ms_per_step=1e3 * t_all / max(a.steps, 1), higher_is_better=True, scaling="weak",
-                    vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                    config=dict(workload=WORKLOAD, sample=f"{per_step} utterances of 10 s per step"),
-                    cpu_baseline=dict(value=v, unit="RTFx", cores=cores, kind="reference",
-                                      sample=f"{per_step} x 10 s utterances per step, one per worker process; features+nnet3 = "
-                                             "the reference's own sources compiled in oracle/_ref (OpenBLAS, 1 thread/worker), "
-                                             "decoder = the reference's lattice-faster-decoder.cc compiled against a container-only OpenFst stand-in; lattice determinization excluded"),
-                    e2e=dict(value=v, unit="RTFx", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
+        wname = a.workload if a.workload in WORKLOADS else DEFAULT_WORKLOAD
+        print(json.dumps(run_reference_arm(a, wname)))
         return 0
+    if a.workload == "decoder_sweep":
+        return decoder_sweep(a, rank, world, local_rank)
 
     import torch
     import torch.distributed as dist
     from kaldi_b200 import _lib
-    from kaldi_b200.pipeline import BatchedPipeline, PipelineConfig
+    from kaldi_b200.decoder import CudaDecoder, CudaFst, lattice_to_canonical
+    from kaldi_b200.feat import FeatureOptions
+    from kaldi_b200.ivector import IvectorExtractorGpu, make_synthetic_extractor
+    from kaldi_b200.model import KaldiModel
+    from kaldi_b200.pipeline import NativeBatchedPipeline, PipelineConfig
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl")
+    L = _lib.lib()
     peaks = load_peaks()
-    arch = NM.arch_mini_librispeech_1k(NUM_PDFS)
-    W = NM.random_weights(arch, seed=0)
-    graph = synth.make_hclg(GRAPH_ARCS, num_pdfs=NUM_PDFS, seed=1)
-    B = a.batch
+    wname = a.workload
+    w = WORKLOADS[wname]
+    P = w["num_pdfs"]
+    arch = arch_for(w)
+    W = load_calibrated_weights(arch, 0, w["cal"])
+    graph = graph_for(w["graph_arcs"], P)
+    _CPU_STATE["graph"] = graph
+    B = a.batch or w["batch"]
     nf_out = 333
-    from kaldi_b200.feat import FeatureOptions
     cfg = PipelineConfig(feature_opts=FeatureOptions(max_lanes=max(B, 64)), max_batch=B, num_samples=NUM_SAMPLES,
-                         reference_order=not a.order_free,
-                         max_tokens=nf_out * a.tok_per_frame, max_links=nf_out * a.links_per_frame,
+                         reference_order=True, max_tokens=nf_out * a.tok_per_frame, max_links=nf_out * a.links_per_frame,
                          max_tokens_per_frame=a.max_tpf)
-    from kaldi_b200.ivector import make_synthetic_extractor
-    ivx = make_synthetic_extractor(seed=0)
-    pipe = BatchedPipeline(cfg, arch, W, graph, ivector_extractor=ivx)
-    # prior-style calibration of the synthetic model (see nnet_model.apply_output_calibration)
-    if os.path.exists(CAL_FALLBACK):
-        c = np.load(CAL_FALLBACK)
-        mean, scale = c["mean"], float(c["scale"])
-    else:
-        mean, scale = pipe.output_calibration(build_inputs(min(B, 16), seed0=777_000), target_std=1.0)
-        if rank == 0:
-            os.makedirs(os.path.dirname(CAL_PATH), exist_ok=True)
-            np.savez(CAL_PATH, mean=mean, scale=np.float32(scale))
-    W = NM.apply_output_calibration(W, mean, scale)
-    del pipe
-    torch.cuda.empty_cache()
-    pipe = BatchedPipeline(cfg, arch, W, graph, ivector_extractor=ivx)
-    # distinct utterances per rank and per step slot (cycled)
+    model = KaldiModel.from_arch(arch, W)
+    fst = CudaFst(graph)
+    T_feat = 1 + (NUM_SAMPLES - 400) // 160
+    ivx = IvectorExtractorGpu(make_synthetic_extractor(seed=0), B, T_feat)
+    pipe = NativeBatchedPipeline(cfg, model, fst, ivx)
+    nf = pipe.plan.num_output_frames
+    L.b2k_pipeline_enable_stage_timing.argtypes = [C.c_void_p, C.c_int32]
+    L.b2k_pipeline_stage_times.argtypes = [C.c_void_p, C.c_void_p]
+    L.b2k_pipeline_run_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.b2k_pipeline_nnet_flops_per_utterance.restype = C.c_double
+    L.b2k_pipeline_nnet_flops_per_utterance.argtypes = [C.c_void_p]
+    L.b2k_pipeline_decoder.restype = C.c_void_p
+    L.b2k_pipeline_decoder.argtypes = [C.c_void_p]
+    _lib.check(L.b2k_pipeline_enable_stage_timing(pipe.h, 1))
+
+    # distinct utterances per rank and per step slot (cycled); int16 on the host, float on the device
     n_sets = 2
-    host_sets = [build_inputs(B, seed0=10_000 * rank + 1000 * s) for s in range(n_sets)]
-    dev_sets = [torch.from_numpy(np.stack(hs)).cuda() for hs in host_sets]
+    host_sets = [np.stack([synth.make_audio(NUM_SAMPLES, seed=10_000 * rank + 1000 * s + i) for i in range(B)]).astype(np.int16)
+                 for s in range(n_sets)]
+    host_ptrs = [NativeBatchedPipeline.row_pointers(hs) for hs in host_sets]
+    dev_sets = [torch.from_numpy(hs.astype(np.float32)).cuda() for hs in host_sets]
+    stream = torch.cuda.current_stream().cuda_stream
 
     def sync_all():
         torch.cuda.synchronize()
@@ -270,25 +400,7 @@ def main():
             torch.cuda.synchronize()
 
     def step_device(s):
-        pipe.d_wave[:B].copy_(dev_sets[s % n_sets])
-        pipe.run_device(B)
-
-    stage_ms = dict(features=0.0, ivector=0.0, nnet3=0.0, decoder_advance=0.0, decoder_finalize=0.0)
-
-    def step_device_staged(s):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-        pipe.d_wave[:B].copy_(dev_sets[s % n_sets])
-        ev[0].record(); pipe.compute_features(B)
-        ev[1].record(); pipe.compute_ivectors(B)
-        ev[2].record(); pipe.compute_nnet(B)
-        ev[3].record()
-        ch = list(range(B)); P, nf = arch["num_pdfs"], pipe.nnet.n_out
-        pipe.dec.InitDecoding(ch)
-        lp = [pipe.d_loglikes.data_ptr() + 4 * nf * P * i for i in range(B)]
-        pipe.dec.AdvanceDecodingFrames(ch, lp, [nf] * B, P)
-        ev[4].record(); pipe.dec.FinalizeDecoding(ch)
-        ev[5].record()
-        return ev
+        _lib.check(L.b2k_pipeline_run_device(pipe.h, B, C.c_void_p(dev_sets[s % n_sets].data_ptr()), C.c_void_p(stream)))
 
     # ---- warm-up
     for s in range(a.warmup):
@@ -298,76 +410,102 @@ def main():
     clocks = ClockSampler(local_rank); clocks.start()
     launches0 = _lib.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_names = ["features", "ivector", "nnet3", "decoder_advance", "decoder_finalize"]
+    stage_ms = dict.fromkeys(stage_names, 0.0)
     sync_all()
     e0.record()
-    evs = [step_device_staged(s) for s in range(a.steps)]
+    for s in range(a.steps):
+        step_device(s)
     e1.record()
     sync_all()
     launches = _lib.kernel_launch_count() - launches0
     t_dev = e0.elapsed_time(e1) / 1e3
-    for ev in evs:
-        for k, (i, j) in zip(stage_ms, [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5)]):
-            stage_ms[k] += ev[i].elapsed_time(ev[j]) / a.steps
-    infos = [pipe.dec.ChannelInfo(c) for c in range(B)]
-    errs = [i["status"] for i in infos if i["status"] != 0]
-    # ---- timed: end to end through the public API with host buffers
+    ms5 = (C.c_float * 5)()
+    _lib.check(L.b2k_pipeline_stage_times(pipe.h, ms5))            # (the last step's split; the steps are alike)
+    for k, v in zip(stage_names, ms5):
+        stage_ms[k] = float(v)
+    infos = dec_infos(L, L.b2k_pipeline_decoder(pipe.h), B)
+    nerr_local = sum(1 for i in infos if i[0] != 0)
+    # ---- timed: end to end through the C ABI with host buffers, batch k+1 submitted before batch k is collected
     for s in range(min(a.warmup, 2)):
-        pipe.decode_batch(host_sets[s % n_sets], want_lattices=True)
+        pipe.submit(None, ptrs=host_ptrs[s % n_sets])
+        pipe.collect(copy=False)
     sync_all()
     t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
     d2h = 0
     lat_states = 0
-    for s in range(a.steps):
-        try:
-            lats = pipe.decode_batch(host_sets[s % n_sets], want_lattices=True)
-        except Exception as ex:          # e.g. an arena overflow on some channel: report, do not hide
-            print(f"[bench] decode_batch failed: {ex}", file=sys.stderr)
-            raise
-        d2h += sum(v.nbytes for k, v in lats.items() if hasattr(v, "nbytes"))
-        lat_states += int(lats["state_offs"][-1])
-    e3.record()
-    sync_all()
-    t_e2e = max(e2.elapsed_time(e3) / 1e3, time.perf_counter() - t0)
+    last = None
+    pipe.submit(None, ptrs=host_ptrs[0])
+    for s in range(1, a.steps + 1):
+        if s < a.steps:
+            pipe.submit(None, ptrs=host_ptrs[s % n_sets])
+        last = pipe.collect(copy=(s == a.steps))
+        d2h += sum(v.nbytes for v in last.values())
+        lat_states += int(last["state_offs"][-1])
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
     clk = clocks.stop()
     # max over ranks
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(t[0]), float(t[1])
-        e = torch.tensor([len(errs)], device="cuda"); dist.all_reduce(e); nerr = int(e[0])
+        e = torch.tensor([nerr_local], device="cuda"); dist.all_reduce(e); nerr = int(e[0])
     else:
-        nerr = len(errs)
+        nerr = nerr_local
     audio_per_step = world * B * NUM_SAMPLES / 16000.0
     value = audio_per_step * a.steps / t_dev
     e2e_value = audio_per_step * a.steps / t_e2e
 
+    # ---- parity spot check (outside the timed regions): the last e2e batch's first k lattices against the reference's own
+    #      LatticeFasterDecoder (oracle/_ref) run on the log-likelihoods the device computed for them
+    parity_checked = 0
+    if rank == 0 and a.parity_utts > 0:
+        from oracle import ref_decoder as RD
+        k = min(a.parity_utts, B)
+        ll = pipe.read("loglikes", k)
+        rd = RD.RefDecoder(graph, synth.DEFAULT_DECODER_CFG)
+        lats = CudaDecoder.SplitLattices(last)
+        for i in range(k):
+            rd.decode(ll[i])
+            want, have = rd.lattice(), lattice_to_canonical(lats[i])
+            for key in have:
+                if not np.array_equal(have[key], want[key]):
+                    raise SystemExit(f"[bench] parity check failed: utterance {i}, lattice field {key} differs from the compiled reference decoder")
+            parity_checked += 1
+
     # ---- roofline of the dominant kernel (by measured share of the step)
     dom = max(stage_ms, key=stage_ms.get)
-    arcs = sum(i["arcs_emitting"] + i["arcs_nonemitting"] for i in infos)
-    ntok = sum(i["ntok"] for i in infos)
-    nlink = sum(i["nlink"] for i in infos)
+    arcs = sum(i[4] + i[5] for i in infos)
+    ntok = sum(i[2] for i in infos)
+    nlink = sum(i[3] for i in infos)
+    traffic_file = os.path.join(ROOT, "profiles", "r02_decoder_dram.json")
+    traffic = None
+    traffic_source = None
+    if os.path.exists(traffic_file):
+        tj = json.load(open(traffic_file))
+        if tj.get("workload") == wname:
+            traffic = float(tj["dram_bytes_per_lane_frame"]) * B * nf
+            traffic_source = tj.get("source")
     if dom.startswith("decoder"):
         # 16 B/arc examined + 16 B/source token + 36 B/link admitted + 16 B/token kept
         alg_bytes = 16.0 * arcs + 16.0 * ntok + 36.0 * nlink + 16.0 * ntok
         achieved = alg_bytes / (stage_ms["decoder_advance"] / 1e3) / 1e9
-        roof = dict(kernel="dec_advance_exact_kernel" if not a.order_free else "dec_advance_kernel", bound="hbm",
+        roof = dict(kernel="dec_advance_v2_kernel" if not os.environ.get("B2K_DEC_V1") else "dec_advance_exact_kernel", bound="hbm",
                     achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
-                    traffic=(NCU_DRAM_BYTES_PER_LANE_FRAME * B * pipe.nnet.n_out) if not a.order_free else None,
-                    traffic_source="ncu --set full (profiles/r01_final_ncu_summary.md): dram read+write per lane-frame at 592 lanes "
-                                   "on the decoder-only synthetic load, scaled to this launch's lane-frames",
-                    algorithmic_bytes=alg_bytes,
+                    traffic=traffic, traffic_source=traffic_source, algorithmic_bytes=alg_bytes,
                     peak_source=peaks["source"], marcs_per_s=arcs / (stage_ms["decoder_advance"] / 1e3) / 1e6,
                     share_of_step=stage_ms["decoder_advance"] / sum(stage_ms.values()))
     elif dom == "nnet3":
-        fl = pipe.nnet.flops_per_utt * B
+        fl = L.b2k_pipeline_nnet_flops_per_utterance(pipe.h) * B
         achieved = fl / (stage_ms["nnet3"] / 1e3) / 1e12
-        roof = dict(kernel="nnet_gemm_kernel", bound="tensor", achieved=achieved, peak=peaks["bf16_tflops"], unit="TFLOP/s",
+        roof = dict(kernel="nnet_gemm_ts_kernel", bound="tensor", achieved=achieved, peak=peaks["bf16_tflops"], unit="TFLOP/s",
                     frac=achieved / peaks["bf16_tflops"], traffic=None, peak_source=peaks["source"],
                     share_of_step=stage_ms["nnet3"] / sum(stage_ms.values()))
     else:
-        frames = B * pipe.T
+        frames = B * pipe.plan.num_feature_frames
         achieved = frames * 800.0 / (stage_ms["features"] / 1e3) / 1e9
         roof = dict(kernel="feat_kernel", bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
                     frac=achieved / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"],
@@ -375,43 +513,40 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        r = run_cpu_reference(a.cpu_utts, 1)
-        cpu_base = dict(value=r["rtfx"], unit="RTFx", cores=1, kind="reference",
-                        sample=f"{a.cpu_utts} x 10 s utterances, single thread: features + nnet3 are the reference's own "
-                               "sources compiled in oracle/_ref (OpenBLAS 1 thread), decoder = the reference's lattice-faster-decoder.cc "
-                               "compiled against a container-only OpenFst stand-in; determinization excluded")
+        cpu_base = run_cpu_baseline(a.cpu_utts, wname)
     if rank == 0:
+        gemm = os.environ.get("B2K_NNET_GEMM", "ts")
         line = dict(metric="real-time factor (audio-sec/wall-sec)", value=value, unit="RTFx", n_gpus=world, steps=a.steps,
                     warmup=a.warmup, ms_per_step=1e3 * t_dev / a.steps, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=WORKLOAD, utterances_per_gpu_per_step=B, audio_s_per_step=audio_per_step,
-                                model="mini_librispeech tdnn_1k (4.47 M params fwd path, 2336 pdfs)",
-                                graph_arcs=int(graph["offsets"][-1]), beam=15.0, max_active=7000, lattice_beam=8.0,
-                                decoder_mode="order_free" if a.order_free else "reference_order",
+                    config=dict(workload=wname, utterances_per_gpu_per_step=B, audio_s_per_step=audio_per_step,
+                                model=w["model"], graph_arcs=int(graph["offsets"][-1]), beam=15.0, max_active=7000, lattice_beam=8.0,
+                                decoder_mode="reference_order",
                                 ivector="online 100-dim, 512-Gaussian UBM, re-estimated per nnet chunk (synthetic extractor)",
                                 cache="inputs larger than L2: log-likes %.0f MB, audio %.0f MB per step" %
-                                      (B * pipe.nnet.n_out * NUM_PDFS * 4 / 1e6, B * NUM_SAMPLES * 4 / 1e6),
+                                      (B * nf * P * 4 / 1e6, B * NUM_SAMPLES * 4 / 1e6),
                                 parallelism=f"dp{world} (utterance shards, no data-path collective)"),
-                    e2e=dict(value=e2e_value, unit="RTFx", h2d_bytes_per_step=B * NUM_SAMPLES * 4,
+                    e2e=dict(value=e2e_value, unit="RTFx", h2d_bytes_per_step=B * NUM_SAMPLES * 2,
                              d2h_bytes_per_step=int(d2h / a.steps), lattice_states_per_step=int(lat_states / a.steps),
-                             host_ms_last_step={k: round(v, 1) for k, v in getattr(pipe, "last_host_ms", {}).items()}),
+                             api="b2k_pipeline_submit_i16 / b2k_pipeline_collect (C ABI), int16 host buffers, two batches in flight"),
                     gpu_launches=int(launches), stage_ms={k: round(v, 3) for k, v in stage_ms.items()},
                     decoder_phase_share=None if not os.environ.get("B2K_DEC_PROF") else dict(zip(
-                        ["cutoff_seed", "expand", "rank", "bucket_scatter", "eps_init", "eps_closure", "replay_prep", "eps_replay",
-                         "eps_finish", "list_order", "eps_links", "commit"],
-                        [round(float(sum(i["prof_cycles"][k] for i in infos)) / max(1.0, float(sum(i["prof_cycles"][15] for i in infos))), 3)
+                        ["cutoff_seed", "expand", "rank", "closure_init", "closure", "replay_prep", "replay", "keys_hw_clear",
+                         "list_order", "commit_links", "clear", "frame_end"],
+                        [round(float(sum(i[16 + k] for i in infos)) / max(1.0, float(sum(i[16 + 15] for i in infos))), 3)
                          for k in range(12)])),
                     eps_replay_per_frame=dict(zip(["pops", "arc_visits", "in_shared_memory"],
-                        [round(float(sum(i["prof_cycles"][k] for i in infos)) / max(1.0, float(sum(i["frames_decoded"] for i in infos))), 2)
+                        [round(float(sum(i[16 + k] for i in infos)) / max(1.0, float(sum(i[1] for i in infos))), 2)
                          for k in (12, 13, 14)])),
                     decoder=dict(marcs_per_s=arcs / (stage_ms["decoder_advance"] / 1e3) / 1e6 * world,
-                                 arcs_per_frame=arcs / (B * pipe.nnet.n_out),
-                                 eps_arcs_per_frame=sum(i["arcs_nonemitting"] for i in infos) / (B * pipe.nnet.n_out),
-                                 links_per_frame=sum(i["nlink"] for i in infos) / (B * pipe.nnet.n_out), tokens_per_frame=ntok / (B * pipe.nnet.n_out),
-                                 errors=nerr),
-                    nnet3=dict(tflops=pipe.nnet.flops_per_utt * B / (stage_ms["nnet3"] / 1e3) / 1e12 * world,
-                               mma="3xTF32 mma.sync m16n8k8, fp32 accumulate" if os.environ.get("B2K_NNET_GEMM") != "simt" else "fp32 FFMA (SIMT)"),
-                    roofline=roof, clocks=clk)
+                                 arcs_per_frame=arcs / (B * nf),
+                                 eps_arcs_per_frame=sum(i[5] for i in infos) / (B * nf),
+                                 links_per_frame=nlink / (B * nf), tokens_per_frame=ntok / (B * nf), errors=nerr),
+                    nnet3=dict(tflops=L.b2k_pipeline_nnet_flops_per_utterance(pipe.h) * B / (stage_ms["nnet3"] / 1e3) / 1e12 * world,
+                               mma={"ts": "3xTF32 tcgen05.mma kind::tf32 (A in TMEM, W by TMA), fp32 accumulate in TMEM",
+                                    "tcgen05": "3xTF32 tcgen05.mma kind::tf32 (operands staged by threads)",
+                                    "mma": "3xTF32 mma.sync m16n8k8", "simt": "fp32 FFMA (SIMT)"}.get(gemm, gemm)),
+                    roofline=roof, clocks=clk, parity_checked=parity_checked, host=usable_cores())
         if cpu_base:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))

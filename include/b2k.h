@@ -169,6 +169,16 @@ int b2k_dec_get_raw_lattice(b2k_dec *dec, int32_t channel, b2k_raw_lattice *out,
 int b2k_dec_get_raw_lattices(b2k_dec *dec, const int32_t *channels, int32_t n, b2k_raw_lattice *out,
                              int64_t *state_offs, int64_t *arc_offs, int64_t *final_offs, void *stream);
 
+/* The batched read-back without a host round trip before the copy (pipelined pipelines: b2k_pipeline_submit / collect).
+ * b2k_dec_pack_lattices_async packs the lattices of n finalized channels (d_channels: device array) into d_buf on `stream`:
+ * a header of b2k_dec_pack_header_bytes(n) bytes (offsets, status, bytes needed) followed by the body; a channel in error /
+ * not finalized / a buffer that is too small is reported in the header (and by b2k_dec_unpack_lattices), nothing is written
+ * past the header then.  b2k_dec_unpack_lattices reads a HOST copy of that buffer; sizes query: out->state_frame NULL. */
+int64_t b2k_dec_pack_header_bytes(int32_t n);
+int b2k_dec_pack_lattices_async(b2k_dec *dec, const int32_t *d_channels, int32_t n, void *d_buf, int64_t cap_bytes, void *stream);
+int b2k_dec_unpack_lattices(const void *h_buf, int32_t n, b2k_raw_lattice *out, int64_t *state_offs, int64_t *arc_offs,
+                            int64_t *final_offs);
+
 /* Debug/parity hook: copies the un-pruned token list of frame `frame_plus_one`
  * and the links created by that frame step (tests compare these bit-for-bit
  * against the oracle before any pruning).  links7 rows:
@@ -411,6 +421,11 @@ int b2k_nnet_create_from_program(const b2k_nnet_program *prog, int32_t max_batch
 typedef struct b2k_model b2k_model;
 int b2k_model_read(const char *path, int32_t is_mdl /* 1: final.mdl, 0: raw nnet3 */, b2k_model **out);
 int b2k_model_destroy(b2k_model *model);
+/* The same object from arrays the caller already holds (synthetic models; everything is copied; "priors" optional, tid2pdf
+ * may be NULL): the input of b2k_pipeline_create without a model file. */
+int b2k_model_from_arrays(int32_t feat_dim, int32_t ivector_dim, int32_t num_pdfs, int32_t frame_subsampling_factor,
+                          const b2k_nnet_layer *layers, int32_t n_layers, const b2k_nnet_weight *weights, int32_t n_weights,
+                          const int32_t *tid2pdf, int32_t n_tids, b2k_model **out);
 /* info: [0] feat_dim, [1] ivector_dim, [2] num_pdfs, [3] frame subsampling factor, [4] layers, [5] weights,
  * [6] size of the transition-id -> pdf table (0 for raw models), [7] 1 if the file carried priors */
 int b2k_model_info(const b2k_model *model, int32_t info[8]);
@@ -641,6 +656,16 @@ int b2k_pipeline_get_plan(const b2k_pipeline *p, b2k_pipeline_plan *plan);
  * pinned memory, copies, and queues all four stages + FinalizeDecoding on `stream`; returns without waiting. */
 int b2k_pipeline_decode_batch(b2k_pipeline *p, int32_t n, const float *const *h_waves, void *stream);
 int b2k_pipeline_decode_batch_i16(b2k_pipeline *p, int32_t n, const int16_t *const *h_waves, void *stream);
+/* Pipelined form (what bench.py's end-to-end number times): b2k_pipeline_submit_i16 stages batch k (int16 PCM) into one of
+ * two pinned buffers, copies it on the pipeline's copy stream and queues all stages + lattice packing on its compute
+ * stream; it returns without waiting, so batch k+1 can be submitted (its staging and copy overlap batch k's kernels)
+ * before b2k_pipeline_collect(k) copies batch k's packed lattices back (overlapping batch k+1's kernels) and unpacks
+ * them.  At most two batches may be outstanding; collect returns them in submission order.  The arrays collect fills
+ * belong to the pipeline and stay valid until the next collect.  (DecodeBatch + the lattice callbacks of
+ * cudadecoder/batched-threaded-nnet3-cuda-online-pipeline.cc:316-377,727-790 in one thread.) */
+int b2k_pipeline_submit_i16(b2k_pipeline *p, int32_t n, const int16_t *const *h_waves);
+int b2k_pipeline_collect(b2k_pipeline *p, int32_t *n_out, b2k_raw_lattice *view, const int64_t **state_offs,
+                         const int64_t **arc_offs, const int64_t **final_offs);
 /* Same with the waveforms already on the device ([n x num_samples], NULL = the pipeline's own buffer as is). */
 int b2k_pipeline_run_device(b2k_pipeline *p, int32_t n, const float *d_waves, void *stream);
 /* The finalized raw lattices of batch slots 0..n-1 (b2k_dec_get_raw_lattices; waits for the stream). */
@@ -657,6 +682,11 @@ int b2k_pipeline_read(b2k_pipeline *p, int32_t what, int32_t n, float *h_out, vo
  * endpoint.* / ivector-silence-weighting.* / det.* and the options without effect here are accepted and ignored; an unknown
  * option is an error.  Host only. */
 int b2k_pipeline_cfg_apply_options(const char *text, b2k_pipeline_cfg *cfg);
+/* Stage timing for benchmarks: CUDA events between the stages of every run; b2k_pipeline_stage_times waits for the last
+ * run and returns ms of {features, i-vectors (+ CMVN), nnet3, decoder init + advance, decoder finalize}. */
+int b2k_pipeline_enable_stage_timing(b2k_pipeline *p, int32_t on);
+int b2k_pipeline_stage_times(b2k_pipeline *p, float ms[5]);
+double b2k_pipeline_nnet_flops_per_utterance(const b2k_pipeline *p);
 b2k_dec *b2k_pipeline_decoder(b2k_pipeline *p);
 const float *b2k_pipeline_features(const b2k_pipeline *p);
 const float *b2k_pipeline_ivectors(const b2k_pipeline *p);

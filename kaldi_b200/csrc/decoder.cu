@@ -3054,6 +3054,88 @@ __global__ void dec_pack_kernel(DecParams p, const int32_t *channels, const int6
   for (int i = gt; i < nf; i += gs) { int2 f = lf[i]; f.x = ns - 1 - f.x; o_finals[fo + i] = f; }
 }
 
+__global__ void dec_reset_channels_kernel(DecParams p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ChanState *cs = &p.chan[p.lane_channel[i]];
+  ChanState z;
+  memset(&z, 0, sizeof(z));
+  z.frames_decoded = -1;
+  *cs = z;
+}
+
+// ---- the same packing without a host round trip: offsets computed on the device into the buffer's header.
+// Buffer layout: int64 header[3 * (n + 1) + 4] = {state offsets, arc offsets, final offsets, status, bytes needed, n, -},
+// padded to 16 bytes, then int4 states[ns], int4 arcs[na], float2 arc weights[na], int2 finals[nf].
+__host__ __device__ inline int64_t pack_header_bytes(int n) { return (int64_t)((8 * (3 * ((int64_t)n + 1) + 4) + 15) / 16 * 16); }
+
+__global__ void dec_pack_header_kernel(DecParams p, const int32_t *channels, int n, int64_t *hdr, int64_t cap_bytes) {
+  // one block: exclusive prefix sums of the per-channel lattice sizes (n is at most a few thousand)
+  __shared__ long long carry[3];
+  __shared__ int status;
+  if (threadIdx.x == 0) { carry[0] = carry[1] = carry[2] = 0; status = B2K_OK; }
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    int v[3] = {0, 0, 0};
+    if (i < n) {
+      const ChanState *cs = &p.chan[channels[i]];
+      if (cs->status != B2K_OK) atomicCAS(&status, B2K_OK, cs->status);
+      else if (!cs->finalized) atomicCAS(&status, B2K_OK, B2K_ERR_STATE);
+      v[0] = min(cs->lat_states, p.cap_ls); v[1] = min(cs->lat_arcs, p.cap_la); v[2] = min(cs->lat_finals, p.cap_lf);
+    }
+    for (int k = 0; k < 3; k++) {
+      // block-wide exclusive scan by a shared array (n is small; simplicity over speed)
+      __shared__ int sc[1024];
+      sc[threadIdx.x] = v[k];
+      __syncthreads();
+      for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+        int t = threadIdx.x >= (unsigned)o ? sc[threadIdx.x - o] : 0;
+        __syncthreads();
+        sc[threadIdx.x] += t;
+        __syncthreads();
+      }
+      if (i < n) hdr[(size_t)k * (n + 1) + i] = carry[k] + sc[threadIdx.x] - v[k];
+      __syncthreads();
+      if (threadIdx.x == blockDim.x - 1) carry[k] += sc[threadIdx.x];
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 3; k++) hdr[(size_t)k * (n + 1) + n] = carry[k];
+    const int64_t need = pack_header_bytes(n) + carry[0] * 16 + carry[1] * 24 + carry[2] * 8;
+    if (need > cap_bytes && status == B2K_OK) status = B2K_ERR_OVERFLOW;
+    int64_t *tail = hdr + 3 * ((size_t)n + 1);
+    tail[0] = status; tail[1] = need; tail[2] = n; tail[3] = 0;
+  }
+}
+
+__global__ void dec_pack_body_kernel(DecParams p, const int32_t *channels, int n, const int64_t *hdr, char *buf) {
+  if (hdr[3 * ((size_t)n + 1)] != B2K_OK) return;             // error or overflow: the header says so, nothing is written
+  const int64_t ns_all = hdr[n], na_all = hdr[(n + 1) + n];
+  int4 *o_states = reinterpret_cast<int4 *>(buf + pack_header_bytes(n));
+  int4 *o_arcs = o_states + ns_all;
+  float2 *o_arcw = reinterpret_cast<float2 *>(o_arcs + na_all);
+  int2 *o_finals = reinterpret_cast<int2 *>(o_arcw + na_all);
+  const int c = blockIdx.y;
+  const int ch = channels[c];
+  const ChanState *cs = &p.chan[ch];
+  const int ns = min(cs->lat_states, p.cap_ls), na = min(cs->lat_arcs, p.cap_la), nf = min(cs->lat_finals, p.cap_lf);
+  const int4 *ls = p.lat_states + (size_t)ch * p.cap_ls;
+  const int4 *la = p.lat_arcs + (size_t)ch * p.cap_la;
+  const float2 *lw = p.lat_arcw + (size_t)ch * p.cap_la;
+  const int2 *lf = p.lat_finals + (size_t)ch * p.cap_lf;
+  const int64_t so = hdr[c], ao = hdr[(n + 1) + c], fo = hdr[2 * (n + 1) + c];
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  for (int i = gt; i < ns; i += gs) o_states[so + (ns - 1 - i)] = ls[i];
+  for (int i = gt; i < na; i += gs) {
+    int4 a = la[i];
+    a.x = ns - 1 - a.x; a.y = ns - 1 - a.y;
+    o_arcs[ao + i] = a; o_arcw[ao + i] = lw[i];
+  }
+  for (int i = gt; i < nf; i += gs) { int2 f = lf[i]; f.x = ns - 1 - f.x; o_finals[fo + i] = f; }
+}
+
 }  // namespace b2k
 
 // ====================================================================== host side
@@ -3513,18 +3595,11 @@ static int stage_lanes(b2k_dec *d, const int32_t *channels, const float *const *
 int b2k_dec_init_decoding(b2k_dec *d, const int32_t *channels, int32_t n, void *stream) {
   if (!d || !channels) return set_error(B2K_ERR_INVALID, "b2k_dec_init_decoding: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  // reset channel state
-  std::vector<ChanState> cs(1);
-  memset(cs.data(), 0, sizeof(ChanState));
-  cs[0].frames_decoded = -1;
-  for (int i = 0; i < n; i++) {
-    if (channels[i] < 0 || channels[i] >= d->nchannels) return set_error(B2K_ERR_INVALID, "bad channel id");
-    B2K_CUDA_CHECK(cudaMemcpyAsync(&d->p.chan[channels[i]], cs.data(), sizeof(ChanState),
-                                   cudaMemcpyHostToDevice, st));
-  }
-  int rc = stage_lanes(d, channels, nullptr, nullptr, n, st);
+  int rc = stage_lanes(d, channels, nullptr, nullptr, n, st);          // (validates the channel ids)
   if (rc) return rc;
   DecParams p = d->p;
+  dec_reset_channels_kernel<<<(n + 127) / 128, 128, 0, st>>>(p, n);       // channel state as b2k_dec_create leaves it
+  B2K_LAUNCH_CHECK();
   p.do_init = 1;
   if (d->cfg.reference_order) { if ((rc = launch_exact(d, p, n, st))) return rc; }
   else {
@@ -3604,6 +3679,58 @@ int b2k_dec_channel_info(b2k_dec *d, int32_t channel, int64_t info[32]) {
   info[4] = (int64_t)cs.arcs_e; info[5] = (int64_t)cs.arcs_ne; info[6] = cs.lat_states;
   info[7] = cs.lat_arcs; info[8] = cs.lat_finals; info[9] = cs.finalized; info[10] = cs.any_final; info[11] = cs.err_line;
   for (int k = 0; k < 16; k++) info[16 + k] = (int64_t)cs.prof[k];
+  return B2K_OK;
+}
+
+// Asynchronous packing for pipelined read-back (kaldi_b200/csrc/pipeline.cu: submit / collect): the lattices of n
+// finalized channels are packed into d_buf entirely on the device; the host later copies the header, learns the sizes,
+// copies the body and unpacks it with b2k_dec_unpack_lattices.
+int64_t b2k_dec_pack_header_bytes(int32_t n) { return n < 0 ? 0 : (int64_t)b2k::pack_header_bytes(n); }
+
+int b2k_dec_pack_lattices_async(b2k_dec *d, const int32_t *d_channels, int32_t n, void *d_buf, int64_t cap_bytes, void *stream) {
+  if (!d || !d_channels || n <= 0 || n > d->nchannels || !d_buf || cap_bytes < (int64_t)b2k::pack_header_bytes(n))
+    return set_error(B2K_ERR_INVALID, "b2k_dec_pack_lattices_async: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  dec_pack_header_kernel<<<1, 1024, 0, st>>>(d->p, d_channels, n, (int64_t *)d_buf, cap_bytes);
+  B2K_LAUNCH_CHECK();
+  dec_pack_body_kernel<<<dim3(8, n), 256, 0, st>>>(d->p, d_channels, n, (const int64_t *)d_buf, (char *)d_buf);
+  B2K_LAUNCH_CHECK();
+  return B2K_OK;
+}
+
+// h_buf: a host copy of the packed buffer (header, then body).  out arrays must hold the totals the header states
+// (query them with out->state_frame == NULL).
+int b2k_dec_unpack_lattices(const void *h_buf, int32_t n, b2k_raw_lattice *out, int64_t *state_offs, int64_t *arc_offs, int64_t *final_offs) {
+  if (!h_buf || n <= 0 || !out) return set_error(B2K_ERR_INVALID, "b2k_dec_unpack_lattices: bad args");
+  const int64_t *hdr = (const int64_t *)h_buf;
+  const int64_t *tail = hdr + 3 * ((size_t)n + 1);
+  if (tail[2] != n) return set_error(B2K_ERR_INVALID, "b2k_dec_unpack_lattices: the buffer was packed for another channel count");
+  if (tail[0] != B2K_OK) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "packed lattices carry status %lld (%lld bytes needed): a channel is in error, not finalized, or the buffer was too small", (long long)tail[0], (long long)tail[1]);
+    return set_error((int)tail[0], msg);
+  }
+  const int64_t ns = hdr[n], na = hdr[(n + 1) + n], nf = hdr[2 * (n + 1) + n];
+  if (state_offs) for (int i = 0; i <= n; i++) state_offs[i] = hdr[i];
+  if (arc_offs) for (int i = 0; i <= n; i++) arc_offs[i] = hdr[(n + 1) + i];
+  if (final_offs) for (int i = 0; i <= n; i++) final_offs[i] = hdr[2 * (n + 1) + i];
+  if (!out->state_frame) { out->num_states = ns; out->num_arcs = na; out->num_finals = nf; return B2K_OK; }
+  if (out->num_states < ns || out->num_arcs < na || out->num_finals < nf)
+    return set_error(B2K_ERR_INVALID, "b2k_dec_unpack_lattices: output buffers too small");
+  const int4 *hs = (const int4 *)((const char *)h_buf + b2k::pack_header_bytes(n));
+  const int4 *ha = hs + ns;
+  const float2 *hw = (const float2 *)(ha + na);
+  const int2 *hf = (const int2 *)(hw + na);
+  for (int64_t i = 0; i < ns; i++) {
+    out->state_frame[i] = hs[i].x; out->state_hclg[i] = hs[i].y;
+    memcpy(&out->state_tot_cost[i], &hs[i].z, 4); memcpy(&out->state_extra_cost[i], &hs[i].w, 4);
+  }
+  for (int64_t i = 0; i < na; i++) {
+    out->arc_src[i] = ha[i].x; out->arc_dst[i] = ha[i].y; out->arc_ilabel[i] = ha[i].z; out->arc_olabel[i] = ha[i].w;
+    out->arc_graph_cost[i] = hw[i].x; out->arc_acoustic_cost[i] = hw[i].y;
+  }
+  for (int64_t i = 0; i < nf; i++) { out->final_state[i] = hf[i].x; memcpy(&out->final_cost[i], &hf[i].y, 4); }
+  out->num_states = ns; out->num_arcs = na; out->num_finals = nf;
   return B2K_OK;
 }
 

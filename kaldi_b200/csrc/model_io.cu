@@ -867,6 +867,43 @@ int b2k_model_read(const char *path, int32_t is_mdl, b2k_model **out) {
 
 int b2k_model_destroy(b2k_model *m) { delete m; return B2K_OK; }
 
+// A model that never was a file: the layer list and named weights a caller already holds (synthetic models of bench.py
+// and the tests; what b2k_nnet_compile takes).  Everything is copied.  "priors" may be absent (ones are used);
+// tid2pdf may be NULL (raw model).
+int b2k_model_from_arrays(int32_t feat_dim, int32_t ivector_dim, int32_t num_pdfs, int32_t frame_subsampling_factor,
+                          const b2k_nnet_layer *layers, int32_t n_layers, const b2k_nnet_weight *weights, int32_t n_weights,
+                          const int32_t *tid2pdf, int32_t n_tids, b2k_model **out) {
+  if (!out || !layers || !weights || n_layers <= 0 || n_weights <= 0 || feat_dim <= 0 || num_pdfs <= 0 || ivector_dim < 0 ||
+      frame_subsampling_factor <= 0 || n_tids < 0)
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_model_from_arrays: bad args");
+  b2k_model *M = new b2k_model();
+  M->feat_dim = feat_dim; M->ivector_dim = ivector_dim; M->num_pdfs = num_pdfs; M->subsampling = frame_subsampling_factor;
+  M->layers.assign(layers, layers + n_layers);
+  for (auto &L : M->layers) if (!strcmp(L.type, "tdnnf") && L.stride == 3) M->has_stride3_tdnnf = 1;
+  bool have_priors = false;
+  for (int i = 0; i < n_weights; i++) {
+    const b2k_nnet_weight &w = weights[i];
+    if (!w.name || !w.data || w.size <= 0 || (int64_t)w.rows * std::max(1, w.cols) != w.size) { delete M; return b2k::set_error(B2K_ERR_INVALID, "b2k_model_from_arrays: bad weight entry"); }
+    M->wnames.push_back(w.name);
+    M->wdata.emplace_back(w.data, w.data + w.size);
+    M->wshape.push_back({w.rows, w.cols});
+    if (!strcmp(w.name, "priors")) have_priors = true;
+  }
+  if (!have_priors) { M->wnames.push_back("priors"); M->wdata.emplace_back((size_t)num_pdfs, 1.0f); M->wshape.push_back({num_pdfs, 1}); }
+  M->has_priors = have_priors;
+  M->weights.resize(M->wnames.size());
+  for (size_t i = 0; i < M->wnames.size(); i++) {
+    M->weights[i].name = M->wnames[i].c_str();
+    M->weights[i].data = M->wdata[i].data();
+    M->weights[i].size = (int64_t)M->wdata[i].size();
+    M->weights[i].rows = M->wshape[i].first; M->weights[i].cols = M->wshape[i].second;
+  }
+  if (tid2pdf && n_tids > 0) M->tid2pdf.assign(tid2pdf, tid2pdf + n_tids);
+  if (M->has_stride3_tdnnf && frame_subsampling_factor != 3) { delete M; return b2k::set_error(B2K_ERR_INVALID, "b2k_model_from_arrays: TDNN-F layers with time-stride 3 need frame_subsampling_factor 3"); }
+  *out = M;
+  return B2K_OK;
+}
+
 int b2k_model_info(const b2k_model *m, int32_t info[8]) {
   if (!m || !info) return b2k::set_error(B2K_ERR_INVALID, "b2k_model_info: bad args");
   info[0] = m->feat_dim; info[1] = m->ivector_dim; info[2] = m->num_pdfs; info[3] = m->subsampling;

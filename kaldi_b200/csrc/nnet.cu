@@ -933,9 +933,22 @@ static int ts_make_map(CUtensorMap *m, const float *dptr, int N, int Kp, int TN)
   cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
   cuuint32_t box[2] = {32, (cuuint32_t)TN};
   cuuint32_t es[2] = {1, 1};
-  CUresult rc = cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)dptr, dims, strides, box, es,
-                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // the driver entry point is looked up at run time: libb2k.so must load (host-only functions, CPU tests) where no
+  // libcuda.so.1 exists
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    B2K_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return set_error(B2K_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = (EncodeTiledFn)fn;
+  }
+  CUresult rc = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)dptr, dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) return set_error(B2K_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight matrix");
   return B2K_OK;
 }
@@ -1146,6 +1159,15 @@ int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32
         }
       }
       B2K_LAUNCH_CHECK();
+      if (getenv("B2K_NNET_SYNC")) {                          // debugging aid: find the op whose kernel faults
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+          char msg[256];
+          snprintf(msg, sizeof(msg), "op %zu (N %d K %d rows %d hsplit %d terms %d klen0 %d mode %d tn %d): %s", i, op.N, op.K, op.rows, op.hsplit,
+                   op.n_terms, op.terms[0].klen, gemm_mode(), nn->ts_tn[i], cudaGetErrorString(e));
+          return set_error(B2K_ERR_CUDA, "b2k_nnet_run", msg);
+        }
+      }
       if (nn->log_softmax[i]) {
         long long threads = M * 32;
         nnet_logsoftmax_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(op, c);

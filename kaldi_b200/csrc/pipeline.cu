@@ -33,6 +33,25 @@ struct b2k_pipeline {
   std::vector<const float *> p_wave, p_feats, p_ivec, p_ll;
   std::vector<float *> p_feats_out, p_ivec_out, p_ll_out;
   int32_t last_n = 0;
+  // pipelined operation (submit / collect): two batches in flight
+  struct Slot {
+    int16_t *h_wave16 = nullptr;      // pinned [max_batch x num_samples]
+    int16_t *d_wave16 = nullptr;
+    char *d_pack = nullptr, *h_pack = nullptr; size_t pack_cap = 0, h_pack_cap = 0;
+    cudaEvent_t h2d_done = nullptr, wave_consumed = nullptr, packed = nullptr, pack_read = nullptr;
+    int32_t n = 0;
+    bool busy = false;
+  } slot[2];
+  cudaStream_t st_copy = nullptr, st_compute = nullptr;
+  int32_t *d_channels = nullptr;
+  int64_t n_submitted = 0, n_collected = 0;
+  size_t pack_floor = 0;
+  // optional stage timing (bench.py): events around the stages of the last run_device
+  bool timing = false;
+  cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};             // lower bound for the packed-lattice buffers, raised when a batch comes close to the capacity
+  // host result of the last collect
+  std::vector<int32_t> r_i32[7]; std::vector<float> r_f32[5];
+  std::vector<int64_t> r_offs[3];
 };
 
 namespace {
@@ -150,6 +169,17 @@ int b2k_pipeline_destroy(b2k_pipeline *p) {
   if (p->nnet) b2k_nnet_destroy(p->nnet);
   if (p->feat) b2k_feat_destroy(p->feat);
   if (p->h_wave) cudaFreeHost(p->h_wave);
+  for (auto &sl : p->slot) {
+    if (sl.h_wave16) cudaFreeHost(sl.h_wave16);
+    if (sl.d_wave16) cudaFree(sl.d_wave16);
+    if (sl.d_pack) cudaFree(sl.d_pack);
+    if (sl.h_pack) cudaFreeHost(sl.h_pack);
+    for (cudaEvent_t e : {sl.h2d_done, sl.wave_consumed, sl.packed, sl.pack_read}) if (e) cudaEventDestroy(e);
+  }
+  if (p->d_channels) cudaFree(p->d_channels);
+  for (cudaEvent_t e : p->tev) if (e) cudaEventDestroy(e);
+  if (p->st_copy) cudaStreamDestroy(p->st_copy);
+  if (p->st_compute) cudaStreamDestroy(p->st_compute);
   for (float *d : {p->d_wave, p->d_feats, p->d_ivec, p->d_loglikes, p->d_feats_cmvn}) if (d) cudaFree(d);
   for (double *d : {p->d_cmvn_state, p->d_cmvn_global}) if (d) cudaFree(d);
   delete p;
@@ -267,9 +297,12 @@ const float *b2k_pipeline_ivectors(const b2k_pipeline *p) { return p ? p->d_ivec
 // All stages for the first n batch slots, inputs already in d_wave; asynchronous on `stream`.
 static int run_device(b2k_pipeline *p, int32_t n, void *stream) {
   const b2k_pipeline_plan &pl = p->plan;
+  auto tick = [&](int i) { if (p->timing) cudaEventRecord(p->tev[i], (cudaStream_t)stream); };
+  tick(0);
   int rc = b2k_feat_compute_batched(p->feat, n, p->p_wave.data(), p->ns.data(), p->zeros.data(), p->nframes.data(),
                                     p->p_feats_out.data(), pl.feat_dim, stream);
   if (rc) return rc;
+  tick(1);
   if (p->ivec) {
     rc = b2k_ivec_compute_batched(p->ivec, n, p->p_feats.data(), pl.feat_dim, pl.num_feature_frames, p->sched.data(),
                                   pl.num_chunks, p->p_ivec_out.data(), pl.ivector_dim, stream);
@@ -282,15 +315,35 @@ static int run_device(b2k_pipeline *p, int32_t n, void *stream) {
                                 p->zeros.data(), p->nframes.data(), p->p_cmvn_state.data(), p->d_cmvn_global, nullptr, stream);
     if (rc) return rc;
   }
+  tick(2);
   rc = b2k_nnet_run(p->nnet, n, p->p_nnet_in.data(), pl.feat_dim, pl.ivector_dim > 0 ? p->p_ivec.data() : nullptr, pl.ivector_dim,
                     p->p_ll_out.data(), pl.num_pdfs, stream);
   if (rc) return rc;
+  tick(3);
   rc = b2k_dec_init_decoding(p->dec, p->channels.data(), n, stream);
   if (rc) return rc;
   rc = b2k_dec_advance_decoding_frames(p->dec, p->channels.data(), p->p_ll.data(), p->nout.data(), pl.num_pdfs, n, stream);
   if (rc) return rc;
-  return b2k_dec_finalize_decoding(p->dec, p->channels.data(), n, stream);
+  tick(4);
+  rc = b2k_dec_finalize_decoding(p->dec, p->channels.data(), n, stream);
+  tick(5);
+  return rc;
 }
+
+extern "C" int b2k_pipeline_enable_stage_timing(b2k_pipeline *p, int32_t on) {
+  if (!p) return set_error(B2K_ERR_INVALID, "b2k_pipeline_enable_stage_timing: bad args");
+  if (on && !p->tev[0]) for (auto &e : p->tev) B2K_CUDA_CHECK(cudaEventCreate(&e));
+  p->timing = on != 0;
+  return B2K_OK;
+}
+// ms of {features, i-vectors (+ CMVN), nnet3, decoder init + advance, decoder finalize} of the last run (waits for it)
+extern "C" int b2k_pipeline_stage_times(b2k_pipeline *p, float ms[5]) {
+  if (!p || !ms || !p->timing) return set_error(B2K_ERR_INVALID, "b2k_pipeline_stage_times: timing is not enabled");
+  B2K_CUDA_CHECK(cudaEventSynchronize(p->tev[5]));
+  for (int i = 0; i < 5; i++) B2K_CUDA_CHECK(cudaEventElapsedTime(&ms[i], p->tev[i], p->tev[i + 1]));
+  return B2K_OK;
+}
+extern "C" double b2k_pipeline_nnet_flops_per_utterance(const b2k_pipeline *p) { return p && p->nnet ? b2k_nnet_flops_per_lane(p->nnet) : 0.0; }
 
 template <typename S>
 static int decode_batch(b2k_pipeline *p, int32_t n, const S *const *h_waves, void *stream) {
@@ -303,6 +356,174 @@ static int decode_batch(b2k_pipeline *p, int32_t n, const S *const *h_waves, voi
   B2K_CUDA_CHECK(cudaMemcpyAsync(p->d_wave, p->h_wave, 4 * (size_t)n * (size_t)p->cfg.num_samples, cudaMemcpyHostToDevice, st));
   p->last_n = n;
   return run_device(p, n, stream);
+}
+
+// ---------------------------------------------------------------- pipelined operation
+__global__ void i16_to_f32_kernel(const int16_t *__restrict__ src, float *__restrict__ dst, size_t n) {
+  // 8 samples per thread: one 16-byte load, two 16-byte stores (the waveform stays in the int16 range as floats)
+  const size_t i8 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i8 + 8 <= n) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(src + i8);
+    const int16_t *h = reinterpret_cast<const int16_t *>(&v);
+    float4 a = make_float4(h[0], h[1], h[2], h[3]), b = make_float4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<float4 *>(dst + i8) = a;
+    *reinterpret_cast<float4 *>(dst + i8 + 4) = b;
+  } else {
+    for (size_t i = i8; i < n; i++) dst[i] = (float)src[i];
+  }
+}
+
+static int ensure_pipelined(b2k_pipeline *p) {
+  if (p->st_copy) return B2K_OK;
+  B2K_CUDA_CHECK(cudaStreamCreateWithFlags(&p->st_copy, cudaStreamNonBlocking));
+  B2K_CUDA_CHECK(cudaStreamCreateWithFlags(&p->st_compute, cudaStreamNonBlocking));
+  const size_t B = (size_t)p->cfg.max_batch, S = (size_t)p->cfg.num_samples;
+  for (auto &sl : p->slot) {
+    B2K_CUDA_CHECK(cudaMallocHost((void **)&sl.h_wave16, 2 * B * S));
+    B2K_CUDA_CHECK(cudaMalloc((void **)&sl.d_wave16, 2 * B * S + 16));
+    for (cudaEvent_t *e : {&sl.h2d_done, &sl.wave_consumed, &sl.packed, &sl.pack_read})
+      B2K_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_channels, 4 * B));
+  B2K_CUDA_CHECK(cudaMemcpy(p->d_channels, p->channels.data(), 4 * B, cudaMemcpyHostToDevice));
+  return B2K_OK;
+}
+
+extern "C" int b2k_pipeline_submit_i16(b2k_pipeline *p, int32_t n, const int16_t *const *h_waves) {
+  if (!p || n <= 0 || n > p->cfg.max_batch || !h_waves) return set_error(B2K_ERR_INVALID, "b2k_pipeline_submit_i16: bad args");
+  for (int32_t i = 0; i < n; i++) if (!h_waves[i]) return set_error(B2K_ERR_INVALID, "b2k_pipeline_submit_i16: null waveform");
+  if (p->n_submitted - p->n_collected >= 2) return set_error(B2K_ERR_STATE, "b2k_pipeline_submit_i16: two batches are outstanding, collect one first");
+  int rc = ensure_pipelined(p);
+  if (rc) return rc;
+  b2k_pipeline::Slot &sl = p->slot[p->n_submitted & 1];
+  const size_t S = (size_t)p->cfg.num_samples, total = (size_t)n * S;
+  // the pinned buffer of this slot was last read by the copy of batch k-2
+  if (p->n_submitted >= 2) B2K_CUDA_CHECK(cudaEventSynchronize(sl.h2d_done));
+  {
+    auto work = [&](int32_t a, int32_t b) { for (int32_t i = a; i < b; i++) memcpy(sl.h_wave16 + (size_t)i * S, h_waves[i], 2 * S); };
+    const unsigned nt = total < (1u << 21) ? 1u : std::min<unsigned>({8u, std::max(1u, std::thread::hardware_concurrency()), (unsigned)n});
+    if (nt <= 1) work(0, n);
+    else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nt; t++) th.emplace_back(work, (int32_t)((int64_t)n * t / nt), (int32_t)((int64_t)n * (t + 1) / nt));
+      for (auto &t : th) t.join();
+    }
+  }
+  // copy stream: the device buffer of this slot was last read by the conversion of batch k-2
+  if (p->n_submitted >= 2) B2K_CUDA_CHECK(cudaStreamWaitEvent(p->st_copy, sl.wave_consumed, 0));
+  B2K_CUDA_CHECK(cudaMemcpyAsync(sl.d_wave16, sl.h_wave16, 2 * total, cudaMemcpyHostToDevice, p->st_copy));
+  B2K_CUDA_CHECK(cudaEventRecord(sl.h2d_done, p->st_copy));
+  // compute stream: int16 -> float (Kaldi keeps int16-range values in floats), the four stages, finalize, pack
+  B2K_CUDA_CHECK(cudaStreamWaitEvent(p->st_compute, sl.h2d_done, 0));
+  {
+    const size_t threads = (total + 7) / 8;
+    i16_to_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, p->st_compute>>>(sl.d_wave16, p->d_wave, total);
+    B2K_LAUNCH_CHECK();
+  }
+  B2K_CUDA_CHECK(cudaEventRecord(sl.wave_consumed, p->st_compute));
+  p->last_n = n;
+  rc = run_device(p, n, (void *)p->st_compute);
+  if (rc) return rc;
+  // packed lattices: capacity from the decoder's own per-channel limits would be far too large; start from 64 MB or
+  // 1.5x the last batch's need and grow when the header reports an overflow (collect then falls back to the synchronous copy)
+  const size_t want = std::max<size_t>({sl.pack_cap, p->pack_floor, (size_t)64 << 20, (size_t)n * ((size_t)512 << 10)});
+  if (want > sl.pack_cap) {
+    if (sl.d_pack) { B2K_CUDA_CHECK(cudaStreamSynchronize(p->st_copy)); cudaFree(sl.d_pack); sl.d_pack = nullptr; }
+    B2K_CUDA_CHECK(cudaMalloc((void **)&sl.d_pack, want));
+    sl.pack_cap = want;
+  }
+  // the buffer of this slot was last read by the D2H of batch k-2
+  if (p->n_submitted >= 2) B2K_CUDA_CHECK(cudaStreamWaitEvent(p->st_compute, sl.pack_read, 0));
+  rc = b2k_dec_pack_lattices_async(p->dec, p->d_channels, n, sl.d_pack, (int64_t)sl.pack_cap, (void *)p->st_compute);
+  if (rc) return rc;
+  B2K_CUDA_CHECK(cudaEventRecord(sl.packed, p->st_compute));
+  sl.n = n; sl.busy = true;
+  p->n_submitted++;
+  return B2K_OK;
+}
+
+extern "C" int b2k_pipeline_collect(b2k_pipeline *p, int32_t *n_out, b2k_raw_lattice *view, const int64_t **state_offs,
+                                    const int64_t **arc_offs, const int64_t **final_offs) {
+  if (!p || !view) return set_error(B2K_ERR_INVALID, "b2k_pipeline_collect: bad args");
+  if (p->n_collected >= p->n_submitted) return set_error(B2K_ERR_STATE, "b2k_pipeline_collect: nothing was submitted");
+  b2k_pipeline::Slot &sl = p->slot[p->n_collected & 1];
+  const int32_t n = sl.n;
+  const size_t hb = (size_t)b2k_dec_pack_header_bytes(n);
+  auto need_host = [&](size_t bytes) -> int {
+    if (bytes <= sl.h_pack_cap) return B2K_OK;
+    if (sl.h_pack) cudaFreeHost(sl.h_pack);
+    sl.h_pack = nullptr; sl.h_pack_cap = 0;
+    const size_t cap = bytes + bytes / 4;
+    B2K_CUDA_CHECK(cudaMallocHost((void **)&sl.h_pack, cap));
+    sl.h_pack_cap = cap;
+    return B2K_OK;
+  };
+  int rc = need_host(std::max<size_t>(hb, (size_t)1 << 20));
+  if (rc) return rc;
+  // header first (sizes), then exactly the body; both on the copy stream, so the next batch's kernels keep running
+  B2K_CUDA_CHECK(cudaStreamWaitEvent(p->st_copy, sl.packed, 0));
+  B2K_CUDA_CHECK(cudaMemcpyAsync(sl.h_pack, sl.d_pack, hb, cudaMemcpyDeviceToHost, p->st_copy));
+  B2K_CUDA_CHECK(cudaStreamSynchronize(p->st_copy));
+  const int64_t *tail = (const int64_t *)sl.h_pack + 3 * ((size_t)n + 1);
+  const int64_t status = tail[0], need = tail[1];
+  if (status == B2K_ERR_OVERFLOW && need > (int64_t)sl.pack_cap) {
+    // the packed form did not fit: grow the buffer for the next batches and repack this one (the channels still hold
+    // it as long as no later batch was submitted after it; with one already running the lattices are gone)
+    if (p->n_submitted - p->n_collected > 1) { sl.busy = false; p->n_collected++; sl.pack_cap = 0; cudaFree(sl.d_pack); sl.d_pack = nullptr;
+      return set_error(B2K_ERR_OVERFLOW, "b2k_pipeline_collect: the packed lattices outgrew the buffer while the next batch was already running; the buffer grows for the following batches"); }
+    B2K_CUDA_CHECK(cudaStreamSynchronize(p->st_compute));
+    cudaFree(sl.d_pack); sl.d_pack = nullptr;
+    const size_t want = (size_t)need + (size_t)need / 2;
+    B2K_CUDA_CHECK(cudaMalloc((void **)&sl.d_pack, want));
+    sl.pack_cap = want;
+    rc = b2k_dec_pack_lattices_async(p->dec, p->d_channels, n, sl.d_pack, (int64_t)sl.pack_cap, (void *)p->st_compute);
+    if (rc) return rc;
+    B2K_CUDA_CHECK(cudaStreamSynchronize(p->st_compute));
+    B2K_CUDA_CHECK(cudaMemcpy(sl.h_pack, sl.d_pack, hb, cudaMemcpyDeviceToHost));
+  }
+  {
+    const int64_t *t2 = (const int64_t *)sl.h_pack + 3 * ((size_t)n + 1);
+    if (t2[0] == B2K_OK) {
+      const size_t bytes = (size_t)t2[1];
+      const size_t cap_before = sl.h_pack_cap;
+      if (bytes > cap_before) {                               // keep the header while the host buffer grows
+        std::vector<char> keep(sl.h_pack, sl.h_pack + hb);
+        if ((rc = need_host(bytes))) return rc;
+        memcpy(sl.h_pack, keep.data(), hb);
+      }
+      B2K_CUDA_CHECK(cudaMemcpyAsync(sl.h_pack + hb, sl.d_pack + hb, bytes - hb, cudaMemcpyDeviceToHost, p->st_copy));
+    }
+    B2K_CUDA_CHECK(cudaEventRecord(sl.pack_read, p->st_copy));
+    B2K_CUDA_CHECK(cudaStreamSynchronize(p->st_copy));
+  }
+  sl.busy = false;
+  p->n_collected++;
+  // (the device buffer grows on the next submit when a batch came within 2/3 of its capacity)
+  {
+    const int64_t need_now = ((const int64_t *)sl.h_pack)[3 * ((size_t)n + 1) + 1];
+    if (need_now > 0 && (size_t)need_now * 3 / 2 > sl.pack_cap) p->pack_floor = std::max(p->pack_floor, (size_t)need_now * 2);
+  }
+  b2k_raw_lattice q;
+  memset(&q, 0, sizeof(q));
+  for (int k = 0; k < 3; k++) p->r_offs[k].resize((size_t)n + 1);
+  rc = b2k_dec_unpack_lattices(sl.h_pack, n, &q, p->r_offs[0].data(), p->r_offs[1].data(), p->r_offs[2].data());
+  if (rc) return rc;
+  p->r_i32[0].resize(q.num_states); p->r_i32[1].resize(q.num_states); p->r_f32[0].resize(q.num_states); p->r_f32[1].resize(q.num_states);
+  for (int k = 2; k < 6; k++) p->r_i32[k].resize(q.num_arcs);
+  p->r_f32[2].resize(q.num_arcs); p->r_f32[3].resize(q.num_arcs);
+  p->r_i32[6].resize(q.num_finals); p->r_f32[4].resize(q.num_finals);
+  q.state_frame = p->r_i32[0].data(); q.state_hclg = p->r_i32[1].data(); q.state_tot_cost = p->r_f32[0].data(); q.state_extra_cost = p->r_f32[1].data();
+  q.arc_src = p->r_i32[2].data(); q.arc_dst = p->r_i32[3].data(); q.arc_ilabel = p->r_i32[4].data(); q.arc_olabel = p->r_i32[5].data();
+  q.arc_graph_cost = p->r_f32[2].data(); q.arc_acoustic_cost = p->r_f32[3].data();
+  q.final_state = p->r_i32[6].data(); q.final_cost = p->r_f32[4].data();
+  rc = b2k_dec_unpack_lattices(sl.h_pack, n, &q, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  *view = q;
+  if (n_out) *n_out = n;
+  if (state_offs) *state_offs = p->r_offs[0].data();
+  if (arc_offs) *arc_offs = p->r_offs[1].data();
+  if (final_offs) *final_offs = p->r_offs[2].data();
+  return B2K_OK;
 }
 
 extern "C" {

@@ -25,6 +25,9 @@ class KaldiModel:
         if frame_subsampling_factor is not None:               # the tool's --frame-subsampling-factor (not stored in the file)
             L.b2k_model_set_frame_subsampling_factor.argtypes = [C.c_void_p, C.c_int32]
             _lib.check(L.b2k_model_set_frame_subsampling_factor(self.h, int(frame_subsampling_factor)))
+        self._finish_init(L)
+
+    def _finish_init(self, L):
         L.b2k_model_frame_subsampling_ambiguous.argtypes = [C.c_void_p]
         self.frame_subsampling_ambiguous = bool(L.b2k_model_frame_subsampling_ambiguous(self.h))
         info = (C.c_int32 * 8)()
@@ -44,6 +47,27 @@ class KaldiModel:
             self.tid2pdf = np.ctypeslib.as_array(p, shape=(n_tid,)).copy()
             p = C.cast(L.b2k_model_tid2phone(self.h), C.POINTER(C.c_int32))
             self.tid2phone = np.ctypeslib.as_array(p, shape=(n_tid,)).copy()       # TransitionIdToPhone, for endpointing
+
+    @classmethod
+    def from_arch(cls, arch: dict, W: dict, tid2pdf=None) -> "KaldiModel":
+        """b2k_model_from_arrays: a model that never was a file (synthetic weights of bench.py / tests)."""
+        from .nnet_compile import _Layer, _Weight, _layer
+        L = _lib.lib()
+        self = cls.__new__(cls)
+        layers = (_Layer * len(arch["layers"]))(*[_layer(x) for x in arch["layers"]])
+        keep = {k: np.ascontiguousarray(v, np.float32) for k, v in W.items()}
+        ws = (_Weight * len(keep))()
+        for i, (k, v) in enumerate(keep.items()):
+            rows, cols = (v.shape if v.ndim == 2 else (v.shape[0], 1))
+            ws[i] = _Weight(k.encode(), v.ctypes.data, v.size, int(rows), int(cols))
+        t2p = None if tid2pdf is None else np.ascontiguousarray(tid2pdf, np.int32)
+        self.h = C.c_void_p()
+        L.b2k_model_from_arrays.argtypes = [C.c_int32] * 4 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        _lib.check(L.b2k_model_from_arrays(arch["feat_dim"], arch["ivector_dim"], arch["num_pdfs"], arch["frame_subsampling_factor"],
+                                           layers, len(layers), ws, len(ws), None if t2p is None else t2p.ctypes.data,
+                                           0 if t2p is None else len(t2p), C.byref(self.h)))
+        self._finish_init(L)
+        return self
 
     def layer_types(self) -> list[tuple[str, str]]:
         from .nnet_compile import _Layer

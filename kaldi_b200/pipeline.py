@@ -282,6 +282,60 @@ class NativeBatchedPipeline:
         out.update(state_offs=so, arc_offs=ao, final_offs=fo)
         return out
 
+    # ---- pipelined form: submit(k+1) before collect(k) overlaps batch k+1's staging / copy with batch k's kernels and
+    #      batch k's lattice read-back with batch k+1's kernels (b2k_pipeline_submit_i16 / b2k_pipeline_collect)
+    def submit(self, waves_i16, ptrs=None):
+        """waves_i16: a [n x num_samples] int16 array (or a list of int16 rows).  Returns immediately."""
+        import ctypes as C
+        from . import _lib
+        L = self._L
+        if ptrs is None:
+            rows = [np.ascontiguousarray(w, np.int16) for w in waves_i16]
+            for w in rows:
+                assert w.ndim == 1 and len(w) == self.cfg.num_samples, "utterances are bucketed by length before batching"
+            self._keep = rows
+            ptrs = (C.c_void_p * len(rows))(*[w.ctypes.data for w in rows])
+        L.b2k_pipeline_submit_i16.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        _lib.check(L.b2k_pipeline_submit_i16(self.h, len(ptrs), ptrs))
+
+    @staticmethod
+    def row_pointers(waves_i16: np.ndarray):
+        """ctypes pointer table of a C-contiguous [n x num_samples] int16 array (build once, reuse per step)."""
+        import ctypes as C
+        assert waves_i16.dtype == np.int16 and waves_i16.flags["C_CONTIGUOUS"] and waves_i16.ndim == 2
+        base, stride = waves_i16.ctypes.data, waves_i16.strides[0]
+        return (C.c_void_p * waves_i16.shape[0])(*[base + i * stride for i in range(waves_i16.shape[0])])
+
+    def collect(self, copy: bool = True):
+        """The oldest outstanding batch's raw lattices (same dictionary as decode_batch).  copy=False returns views of
+        the pipeline's own arrays, valid until the next collect."""
+        import ctypes as C
+        from . import _lib
+        from .decoder import _RawLattice
+        L = self._L
+        r = _RawLattice()
+        n = C.c_int32()
+        i64p = C.POINTER(C.c_int64)
+        so, ao, fo = i64p(), i64p(), i64p()
+        L.b2k_pipeline_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.check(L.b2k_pipeline_collect(self.h, C.byref(n), C.byref(r), C.byref(so), C.byref(ao), C.byref(fo)))
+        ns, na, nf, nn = r.num_states, r.num_arcs, r.num_finals, n.value
+
+        def arr(ptr, count, dt):
+            if count == 0:
+                return np.zeros(0, dt)
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float if dt == np.float32 else C.c_int64 if dt == np.int64 else C.c_int32)), shape=(count,))
+            return a.copy() if copy else a
+        out = dict(
+            state_frame=arr(r.state_frame, ns, np.int32), state_hclg=arr(r.state_hclg, ns, np.int32),
+            state_tot_cost=arr(r.state_tot_cost, ns, np.float32), state_extra_cost=arr(r.state_extra_cost, ns, np.float32),
+            arc_src=arr(r.arc_src, na, np.int32), arc_dst=arr(r.arc_dst, na, np.int32),
+            arc_ilabel=arr(r.arc_ilabel, na, np.int32), arc_olabel=arr(r.arc_olabel, na, np.int32),
+            arc_graph_cost=arr(r.arc_graph_cost, na, np.float32), arc_acoustic_cost=arr(r.arc_acoustic_cost, na, np.float32),
+            final_state=arr(r.final_state, nf, np.int32), final_cost=arr(r.final_cost, nf, np.float32),
+            state_offs=arr(so, nn + 1, np.int64), arc_offs=arr(ao, nn + 1, np.int64), final_offs=arr(fo, nn + 1, np.int64))
+        return out
+
     def read(self, what: str, n: int) -> np.ndarray:
         """Stage outputs of batch slots 0..n-1 on the host: 'features', 'ivectors' or 'loglikes'."""
         import ctypes as C

@@ -23,6 +23,7 @@ from kaldi_b200.lattice import best_path, compact_best_path, determinize_pruned,
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     bench._CPU_STATE["record"] = True          # keep the keyed lattice of each utterance
+    bench._CPU_STATE["waves"] = [synth.make_audio(bench.NUM_SAMPLES, seed=1000 + i) for i in range(n)]
     L = _lib.lib()
     L.b2k_lat_determinize_pruned.argtypes = [C.c_void_p, C.c_float, C.c_int64, C.c_void_p]
     L.b2k_clat_destroy.argtypes = [C.c_void_p]
@@ -35,7 +36,7 @@ def main():
     beam = float(synth.DEFAULT_DECODER_CFG["lattice_beam"])
     rows = []
     for i in range(n):
-        bench.cpu_reference_one((1000 + i, 0))
+        bench.cpu_reference_one((i, bench.DEFAULT_WORKLOAD))
         lat = raw_lattice_from_canonical(bench._CPU_STATE["dec"].lattice())
         keep = {k: np.ascontiguousarray(lat[k], np.float32 if lat[k].dtype.kind == "f" else np.int32) for k in lat}
         r = _RawLattice()
