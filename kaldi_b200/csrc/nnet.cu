@@ -1059,6 +1059,7 @@ int b2k_nnet_create(const b2k_nnet_node *nodes, int32_t n_nodes, const b2k_nnet_
         const int Kp = (d.K + 3) / 4 * 4;
         nn->ts_tn[i] = ts_pick_tn(d.N);
         const float *hi = nn->d_wsplit + off[i], *lo = hi + (size_t)d.N * Kp;
+        if (getenv("B2K_NNET_SYNC")) fprintf(stderr, "[b2k nnet] op %zu: N %d K %d Kp %d rows %d hsplit %d terms %d tn %d hi %p lo %p\n", i, d.N, d.K, Kp, d.rows, d.hsplit, d.n_terms, nn->ts_tn[i], (const void *)hi, (const void *)lo);
         if ((rc = ts_make_map(&nn->ts_maps[i].hi, hi, d.N, Kp, nn->ts_tn[i]))) return rc;
         if ((rc = ts_make_map(&nn->ts_maps[i].lo, lo, d.N, Kp, nn->ts_tn[i]))) return rc;
       }
