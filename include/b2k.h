@@ -666,6 +666,10 @@ int b2k_pipeline_decode_batch_i16(b2k_pipeline *p, int32_t n, const int16_t *con
 int b2k_pipeline_submit_i16(b2k_pipeline *p, int32_t n, const int16_t *const *h_waves);
 int b2k_pipeline_collect(b2k_pipeline *p, int32_t *n_out, b2k_raw_lattice *view, const int64_t **state_offs,
                          const int64_t **arc_offs, const int64_t **final_offs);
+/* Multi-GPU shards (kaldi_b200/ingest.py): int16 PCM that is already on the device (received from the ingest rank), and
+ * the finalized lattices packed into a caller-owned device buffer (sent back to it; layout: b2k_dec_pack_lattices_async). */
+int b2k_pipeline_run_device_i16(b2k_pipeline *p, int32_t n, const int16_t *d_waves, void *stream);
+int b2k_pipeline_pack_device(b2k_pipeline *p, int32_t n, void *d_buf, int64_t cap_bytes, void *stream);
 /* Same with the waveforms already on the device ([n x num_samples], NULL = the pipeline's own buffer as is). */
 int b2k_pipeline_run_device(b2k_pipeline *p, int32_t n, const float *d_waves, void *stream);
 /* The finalized raw lattices of batch slots 0..n-1 (b2k_dec_get_raw_lattices; waits for the stream). */

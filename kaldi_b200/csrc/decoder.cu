@@ -1865,39 +1865,6 @@ __device__ __forceinline__ int hash_insert_b(const LaneCtx &c, int32_t state, ui
   return -1;
 }
 
-// The same insert with the first probe's CAS already issued by the caller (the expansion issues the first CAS of its
-// four arcs back to back, so their round trips overlap): first_old is what that CAS returned for slot first_slot.
-__device__ __forceinline__ int hash_insert_b_finish(const LaneCtx &c, int32_t state, uint32_t Hc, uint32_t first_slot, int first_old,
-                                                   bool *created, int *idx_out) {
-  *created = false;
-  if (first_old == B2K_HASH_EMPTY) {
-    int idx = atomicAdd(c.ntok_new, 1);
-    if (idx < c.max_tpf) { c.tokslot[idx] = (int)first_slot; reinterpret_cast<int *>(&c.hash[first_slot])[3] = idx; }
-    else do { if (atomicCAS(c.err, 0, B2K_ERR_OVERFLOW) == 0) *c.err_line = __LINE__; } while (0);
-    *created = true;
-    *idx_out = idx;
-    return (int)first_slot;
-  }
-  if (first_old == state) return (int)first_slot;
-  const uint32_t b = (uint32_t)state % Hc;
-  for (int probe = 1; probe <= c.hash_mask + B2K_V2_L1_PROBES; probe++) {
-    const uint32_t h = probe_slot_b(c, b, probe);
-    int *keyp = reinterpret_cast<int *>(&c.hash[h]);
-    int old = atomicCAS(keyp, B2K_HASH_EMPTY, state);
-    if (old == B2K_HASH_EMPTY) {
-      int idx = atomicAdd(c.ntok_new, 1);
-      if (idx < c.max_tpf) { c.tokslot[idx] = (int)h; keyp[3] = idx; }
-      else do { if (atomicCAS(c.err, 0, B2K_ERR_OVERFLOW) == 0) *c.err_line = __LINE__; } while (0);
-      *created = true;
-      *idx_out = idx;
-      return (int)h;
-    }
-    if (old == state) return (int)h;
-  }
-  do { if (atomicCAS(c.err, 0, B2K_ERR_OVERFLOW) == 0) *c.err_line = __LINE__; } while (0);
-  return -1;
-}
-
 // in-place exclusive scan of a[0, n): every warp owns a contiguous range (coalesced), one block-level step
 template <int T>
 __device__ void block_excl_scan_array(uint32_t *a, int n, int *sh /*[T/32+1]*/) {
@@ -2194,57 +2161,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     __syncthreads();
   }
   __syncthreads();
-  // key space of the list-order pass: arc positions, then the eps-created tokens in replay order
-  const int PP = P + (Nall - N1);
-  for (int w = tid; w < PP; w += T) x.hw[w] = 0u;             // (the replay's key sort is done with this array)
-  __syncthreads();
   B2K_TICK(s, 6);
-  // ---- HashList order (hash-list-inl.h:126-175): buckets by first insertion, insertion order inside a bucket.  Every
-  //      token walks its bucket's probe run: first key of the bucket, its own rank inside it, the population.  Two
-  //      tokens per iteration with the first two probes of each run loaded up front, so that the dependent round trips
-  //      of different tokens overlap.  For the tokens ProcessEmitting created the result does not depend on the replay
-  //      (eps-created tokens of the bucket carry the largest key until then: counted in the population, never before an
-  //      emitting token), so their pass runs WHILE one thread walks the replay.
-  auto list_pass = [&](int d0, int d1, int t0, int tstride) {
-    for (int base = d0 + t0; base < d1; base += 2 * tstride) {
-      int sl[2];
-      int4 hs[2], o0[2], o1[2];
-      uint32_t b[2];
-#pragma unroll
-      for (int u = 0; u < 2; u++) { const int d = base + u * tstride; sl[u] = d < d1 ? tokslot[d] : -1; }
-#pragma unroll
-      for (int u = 0; u < 2; u++) if (sl[u] >= 0) hs[u] = hash[sl[u]];
-#pragma unroll
-      for (int u = 0; u < 2; u++)
-        if (sl[u] >= 0) {
-          b[u] = (uint32_t)hs[u].x % Hc;
-          o0[u] = hash[probe_slot_b(ctx, b[u], 0)];
-          o1[u] = hash[probe_slot_b(ctx, b[u], 1)];
-        }
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        if (sl[u] < 0) continue;
-        const int d = base + u * tstride;
-        const uint32_t key = (uint32_t)hs[u].z;
-        uint32_t F = key;
-        int within = 0, pop = 0;
-        for (int i = 0; i <= ctx.hash_mask + B2K_V2_L1_PROBES; i++) {
-          const uint32_t ps = probe_slot_b(ctx, b[u], i);
-          const int4 o = i == 0 ? o0[u] : i == 1 ? o1[u] : hash[ps];
-          if (o.x == B2K_HASH_EMPTY) break;
-          if (probe_revisits_b(ctx, b[u], i, ps)) continue;
-          if ((uint32_t)o.x % Hc == b[u]) {
-            pop++;
-            F = min(F, (uint32_t)o.z);
-            within += ((uint32_t)o.z < key);
-          }
-        }
-        x.tok4[d] = make_int4(hs[u].x, __float_as_int(ord2f((uint32_t)hs[u].y)), (int)F, within);
-        if (F == key) x.hw[F] = (uint32_t)pop;
-      }
-    }
-  };
-  bool emitting_listed = false;
   // ---- compact walk out of shared memory (same construction as the first generation; falls back to the walk over the
   //      global records when the set does not fit)
   unsigned char *dyn_smem = dyn_smem_base;
@@ -2343,8 +2260,6 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       for (int k = tid; k < qcarry; k += T) q_s[k] = (unsigned short)cid[x.queue[k]];
     }
     __syncthreads();
-    emitting_listed = true;                                  // (uniform)
-    if (tid >= 32) list_pass(0, N1, tid - 32, T - 32);       // every warp but the first: the emitting tokens' list pass
     if (s.rs_ok && tid == 0) {
       int qn = qcarry, next = 0;
       bool ok = true;
@@ -2435,36 +2350,48 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
   B2K_TICK(s, 7);
   if (s.err) return;                                         // uniform (the caller resets the table)
   // ---- insertion keys of the eps-created tokens: after every arc position, in replay order
+  const int PP = P + (Nall - N1);
   for (int d = N1 + tid; d < Nall; d += T) hash[tokslot[d]].z = P + x.newseq[d - N1];
-  if (!emitting_listed) list_pass(0, N1, tid, T);            // (no replay ran this frame)
+  for (int w = tid; w < PP; w += T) x.hw[w] = 0u;
   __syncthreads();
   B2K_TICK(s, 8);
-  list_pass(N1, Nall, tid, T);                               // the eps-created tokens, now that their keys exist
+  // ---- HashList order (hash-list-inl.h:126-175): buckets by first insertion, insertion order inside a bucket.  Every
+  //      token walks its bucket's probe run: first key of the bucket, its own rank inside it, the population.
+  for (int d = tid; d < Nall; d += T) {
+    const int sl = tokslot[d];
+    const int4 hs = hash[sl];
+    const uint32_t b = (uint32_t)hs.x % Hc;
+    uint32_t F = (uint32_t)hs.z;
+    int within = 0, pop = 0;
+    for (int i = 0; i <= ctx.hash_mask + B2K_V2_L1_PROBES; i++) {
+      const uint32_t ps = probe_slot_b(ctx, b, i);
+      const int4 o = hash[ps];
+      if (o.x == B2K_HASH_EMPTY) break;
+      if (probe_revisits_b(ctx, b, i, ps)) continue;
+      if ((uint32_t)o.x % Hc == b) {
+        pop++;
+        F = min(F, (uint32_t)o.z);
+        within += ((uint32_t)o.z < (uint32_t)hs.z);
+      }
+    }
+    x.tok4[d] = make_int4(hs.x, __float_as_int(ord2f((uint32_t)hs.y)), (int)F, within);
+    if (F == (uint32_t)hs.z) x.hw[F] = (uint32_t)pop;
+  }
   __syncthreads();
   block_excl_scan_array<T>(x.hw, PP, s.redi);
   B2K_TICK(s, 9);
   const bool fits = (ctx.tbase + Nall <= p.max_tokens);
   if (!fits) { if (tid == 0) B2K_SET_ERR(s, B2K_ERR_OVERFLOW); __syncthreads(); return; }
   // ---- commit: tokens to the arena in list order, the emitting ranges for the next frame's expansion
-  for (int base = tid; base < Nall; base += 2 * T) {          // two tokens per iteration: their loads overlap
-    int4 t[2];
-    uint32_t hp[2];
-#pragma unroll
-    for (int u = 0; u < 2; u++) { const int d = base + u * T; if (d < Nall) t[u] = x.tok4[d]; }
-#pragma unroll
-    for (int u = 0; u < 2; u++) { const int d = base + u * T; hp[u] = d < Nall ? x.hw[t[u].z] : 0u; }
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int d = base + u * T;
-      if (d >= Nall) continue;
-      const int r = (int)hp[u] + t[u].w;
-      const int2 tr = *reinterpret_cast<const int2 *>(&x.trec[d]);
-      tok_state[ctx.tbase + r] = t[u].x;
-      tok_cost[ctx.tbase + r] = __int_as_float(t[u].y);
-      x.pf_ebeg[r] = tr.x;
-      x.pf_edeg[r] = tr.y;
-      x.rank[d] = r;
-    }
+  for (int d = tid; d < Nall; d += T) {
+    const int4 t = x.tok4[d];
+    const int r = (int)x.hw[t.z] + t.w;
+    tok_state[ctx.tbase + r] = t.x;
+    tok_cost[ctx.tbase + r] = __int_as_float(t.y);
+    const int4 tr = x.trec[d];
+    x.pf_ebeg[r] = tr.x;
+    x.pf_edeg[r] = tr.y;
+    x.rank[d] = r;
   }
   __syncthreads();
   // ---- eps links = the admitted entries of the final records, written with arena indices
@@ -2499,14 +2426,9 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     }
   }
   // emitting links: destination slot -> arena index
-  for (int base = tid; base < n_emit_links; base += 4 * T) {
-    int ds[4], di[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) { const int li = base + u * T; ds[u] = li < n_emit_links ? links[lbase + li].y : -1; }
-#pragma unroll
-    for (int u = 0; u < 4; u++) di[u] = ds[u] >= 0 ? hash[ds[u]].w : 0;
-#pragma unroll
-    for (int u = 0; u < 4; u++) { const int li = base + u * T; if (li < n_emit_links) links[lbase + li].y = ctx.tbase + x.rank[di[u]]; }
+  for (int li = tid; li < n_emit_links; li += T) {
+    int4 *lp = &links[lbase + li];
+    lp->y = ctx.tbase + x.rank[hash[lp->y].w];
   }
   __syncthreads();
   B2K_TICK(s, 10);
@@ -2790,42 +2712,29 @@ __device__ void dec_advance_v2_lane(const DecParams &p, DecShared<T> &s, const i
         }
         const float base = fminf(carry, fminf(wpre, wexcl));
         int cr[IT];                                           // creation index of a token this thread created, else -1
-        bool adm[IT];
-        uint32_t fslot[IT];
-        int fold[IT];
-        // first probe of every admitted arc issued back to back: the four CAS round trips overlap
 #pragma unroll
         for (int k = 0; k < IT; k++) {
-          const int j = j0 + k;
-          const float excl = fminf(base, ex[k]);
-          const float rc = fminf(seed_cutoff, excl + adaptive_beam);
-          adm[k] = (j < total) && (tots[k] < rc);
-          fslot[k] = 0u; fold[k] = 0;
-          if (adm[k]) {
-            fslot[k] = probe_slot_b(ctx, (uint32_t)nexts[k] % (uint32_t)Hc, 0);
-            fold[k] = atomicCAS(reinterpret_cast<int *>(&ctx.hash[fslot[k]]), B2K_HASH_EMPTY, nexts[k]);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < IT; k++) {
-          const int j = j0 + k;
+          int j = j0 + k;
+          float excl = fminf(base, ex[k]);
+          float rc = fminf(seed_cutoff, excl + adaptive_beam);
+          bool adm = (j < total) && (tots[k] < rc);
           int sl = -1;
           cr[k] = -1;
-          if (adm[k]) {
+          if (adm) {
             bool created; int idx;
-            sl = hash_insert_b_finish(ctx, nexts[k], (uint32_t)Hc, fslot[k], fold[k], &created, &idx);
+            sl = hash_insert_b(ctx, nexts[k], (uint32_t)Hc, &created, &idx);
             if (sl >= 0) {
               atomicMin(reinterpret_cast<uint32_t *>(&ctx.hash[sl].y), f2ord(tots[k]));
               atomicMin(&ctx.hash[sl].z, pos_base + j);
               if (created && idx < p.max_tpf) cr[k] = idx;
-            } else adm[k] = false;
+            } else adm = false;
           }
-          uint32_t m = __ballot_sync(0xffffffffu, adm[k]);
+          uint32_t m = __ballot_sync(0xffffffffu, adm);
           if (m) {
             int lb = 0;
             if (lane_id == 0) lb = atomicAdd(&s.nlink_new, __popc(m));
             lb = __shfl_sync(0xffffffffu, lb, 0);
-            if (adm[k]) {
+            if (adm) {
               int li = lb + __popc(m & ((1u << lane_id) - 1u));
               if (lbase + li < p.max_links)
                 links[lbase + li] = make_int4(srcs[k], sl, arcid[k], __float_as_int(acs[k]));

@@ -613,7 +613,11 @@ __device__ __forceinline__ void ts_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// slab s of the op -> (term, k offset inside the term); terms are walked in order by every role
+// slab s of the op -> (term, k offset inside the term); terms are walked in order by every role.
+// TMA fetches 16-byte aligned row segments only: the box of a term whose first weight column k0 is not a multiple of 4
+// starts at the aligned column below it, d = k0 & 3 columns early, and the loaders place the term's A values d positions
+// later in the slab (zeros in front: those columns belong to the previous term).  kk is the slab's offset from the
+// ALIGNED start, so slab position e holds term element kk + e - d.
 struct TsSlab { int ti, kk; };
 __device__ __forceinline__ TsSlab ts_slab(const int *term_slab0, int n_terms, int s) {
   int ti = 0;
@@ -655,7 +659,7 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
     asm volatile("prefetch.tensormap [%0];" :: "l"(&maps.hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&maps.lo) : "memory");
     int acc = 0;
-    for (int ti = 0; ti < op.n_terms; ti++) { term_slab0[ti] = acc; acc += (op.terms[ti].klen + TS_BK - 1) / TS_BK; }
+    for (int ti = 0; ti < op.n_terms; ti++) { term_slab0[ti] = acc; acc += (op.terms[ti].klen + (op.terms[ti].k0 & 3) + TS_BK - 1) / TS_BK; }
     term_slab0[op.n_terms] = acc;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -677,7 +681,7 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
         t5_mbar_wait(B_EMPTY(st), (((uint32_t)(s / SB)) & 1u) ^ 1u);
         ts_mbar_expect_tx(B_FULL(st), B_STAGE);
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem + (size_t)st * B_STAGE);
-        const int kcol = op.terms[sl.ti].k0 + sl.kk;
+        const int kcol = (op.terms[sl.ti].k0 & ~3) + sl.kk;     // 16-byte aligned box start
         ts_tma_load_2d(dst, &maps.hi, B_FULL(st), kcol, n0);
         ts_tma_load_2d(dst + B_TILE, &maps.lo, B_FULL(st), kcol, n0);
       }
@@ -728,19 +732,20 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
           }
         }
       }
-      const int kk = sl.kk, klen = t.klen;
+      const int klen = t.klen;
+      const int k0e = sl.kk - (t.k0 & 3);                     // term element held by slab position 0 (may be negative)
       if (!arow) {
 #pragma unroll
         for (int e = 0; e < 32; e++) cur[e] = 0.f;
-      } else if (kk + 32 <= klen && ((reinterpret_cast<uintptr_t>(arow + kk) & 15) == 0)) {
+      } else if (k0e >= 0 && k0e + 32 <= klen && ((reinterpret_cast<uintptr_t>(arow + k0e) & 15) == 0)) {
 #pragma unroll
         for (int cc = 0; cc < 8; cc++) {
-          const float4 v = *reinterpret_cast<const float4 *>(arow + kk + cc * 4);
+          const float4 v = *reinterpret_cast<const float4 *>(arow + k0e + cc * 4);
           cur[cc * 4 + 0] = v.x; cur[cc * 4 + 1] = v.y; cur[cc * 4 + 2] = v.z; cur[cc * 4 + 3] = v.w;
         }
       } else {
 #pragma unroll
-        for (int e = 0; e < 32; e++) cur[e] = (kk + e < klen) ? arow[kk + e] : 0.f;
+        for (int e = 0; e < 32; e++) { const int ke = k0e + e; cur[e] = (ke >= 0 && ke < klen) ? arow[ke] : 0.f; }
       }
     };
     if (g < nslabs) fetch(g);

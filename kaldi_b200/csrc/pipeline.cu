@@ -384,8 +384,10 @@ static int ensure_pipelined(b2k_pipeline *p) {
     for (cudaEvent_t *e : {&sl.h2d_done, &sl.wave_consumed, &sl.packed, &sl.pack_read})
       B2K_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   }
-  B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_channels, 4 * B));
-  B2K_CUDA_CHECK(cudaMemcpy(p->d_channels, p->channels.data(), 4 * B, cudaMemcpyHostToDevice));
+  if (!p->d_channels) {
+    B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_channels, 4 * B));
+    B2K_CUDA_CHECK(cudaMemcpy(p->d_channels, p->channels.data(), 4 * B, cudaMemcpyHostToDevice));
+  }
   return B2K_OK;
 }
 
@@ -440,6 +442,29 @@ extern "C" int b2k_pipeline_submit_i16(b2k_pipeline *p, int32_t n, const int16_t
   sl.n = n; sl.busy = true;
   p->n_submitted++;
   return B2K_OK;
+}
+
+// int16 PCM already on the device (a shard received over NVLink, kaldi_b200/ingest.py): widen, run all stages.
+extern "C" int b2k_pipeline_run_device_i16(b2k_pipeline *p, int32_t n, const int16_t *d_waves, void *stream) {
+  if (!p || n <= 0 || n > p->cfg.max_batch || !d_waves) return set_error(B2K_ERR_INVALID, "b2k_pipeline_run_device_i16: bad args");
+  if (reinterpret_cast<uintptr_t>(d_waves) & 15) return set_error(B2K_ERR_INVALID, "b2k_pipeline_run_device_i16: the waveform block must be 16-byte aligned");
+  const size_t total = (size_t)n * (size_t)p->cfg.num_samples, threads = (total + 7) / 8;
+  i16_to_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_waves, p->d_wave, total);
+  B2K_LAUNCH_CHECK();
+  p->last_n = n;
+  return run_device(p, n, stream);
+}
+
+// The finalized lattices of batch slots 0..n-1 packed into a caller-owned device buffer (b2k_dec_pack_lattices_async):
+// what a rank sends to the ingest rank.  *bytes_out (host) = header + body once the stream has run; a too small buffer
+// is reported by the header's status (b2k_dec_unpack_lattices on a host copy returns B2K_ERR_OVERFLOW).
+extern "C" int b2k_pipeline_pack_device(b2k_pipeline *p, int32_t n, void *d_buf, int64_t cap_bytes, void *stream) {
+  if (!p || n <= 0 || n > p->cfg.max_batch || !d_buf) return set_error(B2K_ERR_INVALID, "b2k_pipeline_pack_device: bad args");
+  if (!p->d_channels) {
+    B2K_CUDA_CHECK(cudaMalloc((void **)&p->d_channels, 4 * (size_t)p->cfg.max_batch));
+    B2K_CUDA_CHECK(cudaMemcpy(p->d_channels, p->channels.data(), 4 * (size_t)p->cfg.max_batch, cudaMemcpyHostToDevice));
+  }
+  return b2k_dec_pack_lattices_async(p->dec, p->d_channels, n, d_buf, cap_bytes, stream);
 }
 
 extern "C" int b2k_pipeline_collect(b2k_pipeline *p, int32_t *n_out, b2k_raw_lattice *view, const int64_t **state_offs,
