@@ -85,8 +85,10 @@ class OnlineBaseFeatureB2k : public OnlineBaseFeature {
     float *o = d_feats_;
     int32 ns = num_samples_, first = frames_ready_, cnt = n_new - frames_ready_;
     Check(b2k_feat_compute_batched(feat_, 1, &w, &ns, &first, &cnt, &o, dim_, nullptr), "b2k_feat_compute_batched");
-    cudaMemcpy(host_.RowData(first), d_feats_ + (size_t)first * dim_, sizeof(float) * cnt * dim_, cudaMemcpyDeviceToHost);
-    // (host_ is allocated with stride == dim_ only if kDefaultStride == cols; a production shim copies row by row)
+    // Matrix rows are padded (kDefaultStride: Stride() >= NumCols(), e.g. 16 floats for a 13-dim MFCC): a pitched copy
+    if (cudaMemcpy2D(host_.RowData(first), sizeof(float) * host_.Stride(), d_feats_ + (size_t)first * dim_, sizeof(float) * dim_,
+                     sizeof(float) * dim_, cnt, cudaMemcpyDeviceToHost) != cudaSuccess)
+      KALDI_ERR << "copying the new feature frames to the host failed";
     frames_ready_ = n_new;
   }
   b2k_feat *feat_;
@@ -140,12 +142,53 @@ class CudaFstB2k {
 };
 #endif
 
+// cuda_decoder::CudaDecoderConfig (cudadecoder/cuda-decoder.h:58-163): the same fields, option names, Check() and
+// ComputeConfig(), so that a pipeline config that embeds it keeps registering "--beam --lattice-beam --max-active
+// --ntokens-pre-allocated --main-q-capacity --aux-q-capacity" (+ the endpointing group when the caller registers its
+// own OnlineEndpointConfig beside it).  ToB2k() maps it onto the b2k decoder: this decoder keeps the CPU decoder's
+// one-token-per-state semantics, so the queue capacities size its per-frame hash instead of arc-instantiated queues.
+struct CudaDecoderConfigB2k {
+  BaseFloat default_beam = 15.0f, lattice_beam = 10.0f;
+  int32 ntokens_pre_allocated = 1000000, main_q_capacity = -1, aux_q_capacity = -1, max_active = 10000;
+  template <class Opts>                                      // OptionsItf (itf/options-itf.h) or anything with its Register()
+  void Register(Opts *opts) {
+    opts->Register("beam", &default_beam, "Decoding beam. Larger->slower, more accurate.");
+    opts->Register("lattice-beam", &lattice_beam, "The width of the lattice beam");
+    opts->Register("max-active", &max_active, "At the end of each frame computation, we keep only its best max-active tokens.");
+    opts->Register("ntokens-pre-allocated", &ntokens_pre_allocated, "Advanced - Number of tokens pre-allocated per channel (token arena).");
+    opts->Register("main-q-capacity", &main_q_capacity, "Advanced - tokens that can be stored after pruning for each frame (-1 = 4*max-active).");
+    opts->Register("aux-q-capacity", &aux_q_capacity, "Advanced - raw tokens that can be stored before pruning for each frame (-1 = 3*main-q-capacity).");
+  }
+  void Check() const { KALDI_ASSERT(default_beam > 0.0 && ntokens_pre_allocated >= 0 && lattice_beam >= 0.0f && max_active > 0); }
+  void ComputeConfig() {                                     // KALDI_CUDA_DECODER_MAX_ACTIVE_MAIN_Q_CAPACITY_FACTOR 4, ..._AUX_Q_MAIN_Q_CAPACITIES_FACTOR 3
+    if (main_q_capacity == -1) main_q_capacity = max_active * 4;
+    if (aux_q_capacity == -1) aux_q_capacity = main_q_capacity * 3;
+  }
+  b2k_dec_cfg ToB2k(int32 max_frames) const {
+    b2k_dec_cfg c;
+    b2k_dec_cfg_default(&c);
+    c.beam = default_beam; c.lattice_beam = lattice_beam; c.max_active = max_active;
+    const int32 mq = main_q_capacity > 0 ? main_q_capacity : max_active * 4;
+    c.max_tokens_per_frame = std::min<int32>(131072, std::max<int32>(1024, mq));
+    c.max_frames = max_frames;
+    c.max_tokens = std::max<int64_t>(ntokens_pre_allocated, (int64_t)max_frames * 9000);
+    c.max_links = 2 * c.max_tokens;
+    return c;
+  }
+};
+
 // cuda_decoder::CudaDecoder surface (cudadecoder/cuda-decoder.h:171-346) over b2k_dec_*.
 typedef int32 ChannelId;
 class CudaDecoderB2k {
  public:
   CudaDecoderB2k(const b2k_fst *fst, const b2k_dec_cfg &config, int32 nlanes, int32 nchannels) {
     Check(b2k_dec_create(fst, &config, nlanes, nchannels, &dec_), "b2k_dec_create");
+  }
+  // CudaDecoder(const CudaFst &fst, const CudaDecoderConfig &config, int32 nlanes, int32 nchannels)  cuda-decoder.h:224
+  CudaDecoderB2k(const b2k_fst *fst, const CudaDecoderConfigB2k &config, int32 nlanes, int32 nchannels, int32 max_frames = 4096) {
+    config.Check();
+    const b2k_dec_cfg c = config.ToB2k(max_frames);
+    Check(b2k_dec_create(fst, &c, nlanes, nchannels, &dec_), "b2k_dec_create");
   }
   ~CudaDecoderB2k() { b2k_dec_destroy(dec_); }
   void InitDecoding(const std::vector<ChannelId> &channels) {

@@ -36,6 +36,16 @@ def check() -> bool:
         subprocess.check_call(["g++", "-fsyntax-only"] + RF.cxxflags(["-DHAVE_CUDA=0", "-I" + os.path.join(ROOT, "include"),
                               "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include",
                               "-I" + os.path.join(ROOT, "oracle", "_ref", "inc")]) + [ep])
+        # CudaDecoderConfig's stand-in registers on the reference's own ParseOptions (util/parse-options.h) and its
+        # defaults / ComputeConfig() equal the reference's constants (cudadecoder/cuda-decoder-common.h)
+        cc = os.path.join(td, "c.cc")
+        open(cc, "w").write(
+            '#include "util/parse-options.h"\n#include "b2k_kaldi_shims.h"\n'
+            "int f(int argc, const char *const *argv) {\n"
+            '  kaldi::ParseOptions po("x");\n  kaldi::b2k_shim::CudaDecoderConfigB2k c;\n  c.Register(&po);\n  po.Read(argc, argv);\n'
+            "  c.Check(); c.ComputeConfig();\n  b2k_dec_cfg d = c.ToB2k(400);\n  return d.max_active + c.main_q_capacity;\n}\n")
+        subprocess.check_call(["g++", "-fsyntax-only"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"),
+                              "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include"]) + [cc])
     return True
 
 
