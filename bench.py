@@ -426,25 +426,84 @@ def main():
         stage_ms[k] = float(v)
     infos = dec_infos(L, L.b2k_pipeline_decoder(pipe.h), B)
     nerr_local = sum(1 for i in infos if i[0] != 0)
-    # ---- timed: end to end through the C ABI with host buffers, batch k+1 submitted before batch k is collected
-    for s in range(min(a.warmup, 2)):
-        pipe.submit(None, ptrs=host_ptrs[s % n_sets])
-        pipe.collect(copy=False)
-    sync_all()
-    t0 = time.perf_counter()
-    d2h = 0
-    lat_states = 0
-    last = None
-    pipe.submit(None, ptrs=host_ptrs[0])
-    for s in range(1, a.steps + 1):
-        if s < a.steps:
+    collective_bytes = 0
+    e2e_api = "b2k_pipeline_submit_i16 / b2k_pipeline_collect (C ABI), int16 host buffers, two batches in flight"
+    if world == 1:
+        # ---- timed: end to end through the C ABI with host buffers, batch k+1 submitted before batch k is collected
+        for s in range(min(a.warmup, 2)):
             pipe.submit(None, ptrs=host_ptrs[s % n_sets])
-        last = pipe.collect(copy=(s == a.steps))
-        d2h += sum(v.nbytes for v in last.values())
-        lat_states += int(last["state_offs"][-1])
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    if world > 1:
+            pipe.collect(copy=False)
+        sync_all()
+        t0 = time.perf_counter()
+        d2h = 0
+        lat_states = 0
+        last = None
+        pipe.submit(None, ptrs=host_ptrs[0])
+        for s in range(1, a.steps + 1):
+            if s < a.steps:
+                pipe.submit(None, ptrs=host_ptrs[s % n_sets])
+            last = pipe.collect(copy=(s == a.steps))
+            d2h += sum(v.nbytes for v in last.values())
+            lat_states += int(last["state_offs"][-1])
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        h2d_per_step = B * NUM_SAMPLES * 2
+    else:
+        # ---- timed: the whole step enters and leaves through rank 0 (kaldi_b200/ingest.py): rank 0 copies the
+        #      packed int16 PCM of ALL ranks' utterances to its GPU, scatters the shards over NVLink (grouped ncclSend/Recv),
+        #      every rank runs the pipeline on its shard and packs its lattices on the device, rank 0 gathers the packed
+        #      buffers (size all-gather + grouped send/recv), copies them to the host and unpacks them.
+        from kaldi_b200 import ingest
+        e2e_api = ("rank 0: H2D of every rank's int16 PCM -> scatter (grouped ncclSend/ncclRecv) -> b2k_pipeline_run_device_i16 + "
+                   "b2k_pipeline_pack_device on every rank -> size all-gather + grouped gather to rank 0 -> D2H + b2k_dec_unpack_lattices")
+        dev = torch.device("cuda", local_rank)
+        U = world * B
+        speakers = [f"spk{u // 4}" for u in range(U)]               # four utterances per speaker: a speaker stays on one rank
+        lengths = [NUM_SAMPLES] * U
+        pcm_host = None
+        if rank == 0:
+            pcm_host = torch.from_numpy(np.concatenate([host_sets[0]] * world, axis=0)).pin_memory()
+        pack_cap = max(64 << 20, B * (512 << 10))
+        pack_buf = torch.empty(pack_cap, dtype=torch.uint8, device=dev)
+
+        def compute(shard):
+            n = int(shard.shape[0])
+            pipe.run_device_i16(shard.data_ptr(), n, stream)
+            pipe.pack_device(n, pack_buf.data_ptr(), pack_cap, stream)
+            hb = int(L.b2k_dec_pack_header_bytes(n))
+            hdr = pack_buf[:hb].cpu().numpy().view(np.int64)          # (waits for the stream: the sizes are needed to send)
+            status, need = NativeBatchedPipeline.packed_bytes_needed(hdr, n)
+            if status != 0:
+                raise SystemExit(f"[bench] rank {rank}: packed lattices carry status {status} ({need} bytes needed, capacity {pack_cap})")
+            return pack_buf[:need]
+        L.b2k_dec_pack_header_bytes.restype = C.c_int64
+        L.b2k_dec_pack_header_bytes.argtypes = [C.c_int32]
+
+        def one_step():
+            pcm_dev = pcm_host.to(dev, non_blocking=True) if rank == 0 else None
+            parts, shards, nbytes = ingest.run_step(pcm_dev, speakers if rank == 0 else None, lengths if rank == 0 else None,
+                                                    rank, world, compute, dev)
+            got = None
+            if rank == 0:
+                got = [NativeBatchedPipeline.unpack_lattices(p_.cpu().numpy(), len(ids)) for p_, ids in zip(parts, shards)]
+            return got, nbytes
+        for s in range(min(a.warmup, 1)):
+            one_step()
+        sync_all()
+        t0 = time.perf_counter()
+        d2h = 0
+        lat_states = 0
+        last = None
+        for s in range(a.steps):
+            got, nbytes = one_step()
+            if rank == 0:
+                collective_bytes += nbytes
+                d2h += sum(v.nbytes for g_ in got for v in g_.values())
+                lat_states += sum(int(g_["state_offs"][-1]) for g_ in got)
+                last = got[0]
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        h2d_per_step = U * NUM_SAMPLES * 2
         dist.barrier()
     clk = clocks.stop()
     # max over ranks
@@ -525,10 +584,11 @@ def main():
                                 ivector="online 100-dim, 512-Gaussian UBM, re-estimated per nnet chunk (synthetic extractor)",
                                 cache="inputs larger than L2: log-likes %.0f MB, audio %.0f MB per step" %
                                       (B * nf * P * 4 / 1e6, B * NUM_SAMPLES * 4 / 1e6),
-                                parallelism=f"dp{world} (utterance shards, no data-path collective)"),
-                    e2e=dict(value=e2e_value, unit="RTFx", h2d_bytes_per_step=B * NUM_SAMPLES * 2,
+                                parallelism=f"dp{world} (speaker-ordered utterance shards; replicas of model / extractor / HCLG; "
+                                            "collectives only at ingest (PCM scatter) and egress (lattice gather) of the e2e path)"),
+                    e2e=dict(value=e2e_value, unit="RTFx", h2d_bytes_per_step=h2d_per_step,
                              d2h_bytes_per_step=int(d2h / a.steps), lattice_states_per_step=int(lat_states / a.steps),
-                             api="b2k_pipeline_submit_i16 / b2k_pipeline_collect (C ABI), int16 host buffers, two batches in flight"),
+                             collective_bytes_per_step=int(collective_bytes / a.steps), api=e2e_api),
                     gpu_launches=int(launches), stage_ms={k: round(v, 3) for k, v in stage_ms.items()},
                     decoder_phase_share=None if not os.environ.get("B2K_DEC_PROF") else dict(zip(
                         ["cutoff_seed", "expand", "rank", "closure_init", "closure", "replay_prep", "replay", "keys_hw_clear",

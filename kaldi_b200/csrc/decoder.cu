@@ -140,6 +140,7 @@ struct DecParams {
   uint32_t *v2_c0, *v2_adjc, *v2_qstamp, *v2_hw;
   int32_t *v2_pf;
   int32_t v2_hw_len;
+  int32_t v2_l1_shift;      // level-1 window = 2^shift x the reference's HashList size (rounded up to a power of two)
 };
 
 // ------------------------------------------------------------------ block helpers
@@ -258,6 +259,7 @@ struct LaneCtx {
   int32_t tbase;
   int32_t hash_mask, hash_log, max_tpf, max_tokens;
   int32_t l1_mask, l1_log;   // level-1 window of the table for this frame (see probe_slot)
+  int *used_l2;              // shared: set when a bucket-keyed insert went past its level-1 window this frame
   int *ntok_new;        // shared
   int *err;             // shared
   int *err_line;        // shared
@@ -354,6 +356,7 @@ struct __align__(16) DecShared {
   int cont;
   float scanf_[2][T / 32];
   int q_n;
+  int used_l2;
   int rs_n, rs_e, rs_ok;
   unsigned long long prof[16];
   long long tlast;
@@ -1836,9 +1839,9 @@ __device__ __forceinline__ bool probe_revisits_b(const LaneCtx &c, uint32_t b, i
   return ((slot - w0) & (uint32_t)c.l1_mask) < (uint32_t)B2K_V2_L1_PROBES;
 }
 
-__device__ __forceinline__ void set_l1_b(LaneCtx &c, uint32_t Hc) {
+__device__ __forceinline__ void set_l1_b(LaneCtx &c, uint32_t Hc, int shift) {
   int lg = 12;
-  while ((1u << lg) < Hc && lg < c.hash_log) lg++;
+  while ((1ull << lg) < ((unsigned long long)Hc << shift) && lg < c.hash_log) lg++;
   c.l1_log = lg;
   c.l1_mask = (1 << lg) - 1;
 }
@@ -1849,6 +1852,7 @@ __device__ __forceinline__ int hash_insert_b(const LaneCtx &c, int32_t state, ui
   *created = false;
   for (int probe = 0; probe <= c.hash_mask + B2K_V2_L1_PROBES; probe++) {
     const uint32_t h = probe_slot_b(c, b, probe);
+    if (probe == B2K_V2_L1_PROBES) *c.used_l2 = 1;          // (the table scan of the list order needs every bucket inside one level-1 run)
     int *keyp = reinterpret_cast<int *>(&c.hash[h]);
     int old = atomicCAS(keyp, B2K_HASH_EMPTY, state);
     if (old == B2K_HASH_EMPTY) {
@@ -2022,11 +2026,12 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
             bool created; int idx = 0;
             const int ds = hash_insert_b(ctx, arc.x, Hc, &created, &idx);
             if (ds >= 0) {
-              if (created && idx < p.max_tpf) {
+              const bool fill = created && idx < p.max_tpf;
+              int2 o0 = make_int2(0, 0), o1 = make_int2(0, 0);
+              if (fill) {                                     // loads now, the store that needs them after the atomics below
                 x.rec[idx] = make_int4(0, 0, 0, 0);
                 x.c0[idx] = B2K_INF_ORD;
-                const int2 o0 = __ldg(&g.st_off[arc.x]), o1 = __ldg(&g.st_off[arc.x + 1]);
-                x.trec[idx] = make_int4(o0.x, o1.x - o0.x, o0.y, o1.y - o0.y);
+                o0 = __ldg(&g.st_off[arc.x]); o1 = __ldg(&g.st_off[arc.x + 1]);
               }
               entry.x = __float_as_int(tot); entry.y = arc.y; entry.w = ds;
               atomicAdd(&x.rec[owner].z, 1);
@@ -2042,6 +2047,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
                   }
                 }
               }
+              if (fill) x.trec[idx] = make_int4(o0.x, o1.x - o0.x, o0.y, o1.y - o0.y);
             }
           }
           x.adj[ebase + j] = entry;
@@ -2156,8 +2162,18 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       keys[q] = key;
     }
     __syncthreads();
-    block_bitonic_sort_u64<T>(keys, P2);
-    for (int i = tid; i < qcarry; i += T) x.queue[i] = (int)(uint32_t)(keys[i] & 0x1ffffull);
+    if (qcarry <= 1024) {
+      // the keys are distinct: a key's position is the number of smaller keys (one pass, no barriers inside)
+      for (int i = tid; i < qcarry; i += T) {
+        const unsigned long long k = keys[i];
+        int r = 0;
+        for (int j = 0; j < qcarry; j++) r += (keys[j] < k);
+        x.queue[r] = (int)(uint32_t)(k & 0x1ffffull);
+      }
+    } else {
+      block_bitonic_sort_u64<T>(keys, P2);
+      for (int i = tid; i < qcarry; i += T) x.queue[i] = (int)(uint32_t)(keys[i] & 0x1ffffull);
+    }
     __syncthreads();
   }
   __syncthreads();
@@ -2355,8 +2371,59 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
   for (int w = tid; w < PP; w += T) x.hw[w] = 0u;
   __syncthreads();
   B2K_TICK(s, 8);
-  // ---- HashList order (hash-list-inl.h:126-175): buckets by first insertion, insertion order inside a bucket.  Every
-  //      token walks its bucket's probe run: first key of the bucket, its own rank inside it, the population.
+  // ---- HashList order (hash-list-inl.h:126-175): buckets by first insertion, insertion order inside a bucket.
+  //      All tokens of a bucket sit in ONE occupied run of the level-1 window (as long as no insert of this frame went to
+  //      level 2), so the order is read off the table by scanning the window once: every thread owns a contiguous range
+  //      of slots, finds the runs that start in it (one pass of independent loads builds an occupancy mask) and, per run,
+  //      the bucket of every entry once (the slow integer modulo is paid per token, not per probe; the source-level
+  //      profile had 30 % of all stall samples in the per-token walk this replaces, profiles/r02_dec_v2_source_stalls.md).
+  bool scanned = false;
+  {
+    const int S1 = ctx.l1_mask + 1;
+    const int per = (S1 + T - 1) / T;
+    const int RMAX = min(16, p.rs_bytes / (8 * T));           // run entries cached in the (idle) replay arrays' space
+    if (!s.used_l2 && per <= 64 && RMAX >= 4 && Nall < S1) {  // uniform
+      scanned = true;
+      uint32_t *rb_s = reinterpret_cast<uint32_t *>(dyn_smem_base), *rk_s = rb_s + RMAX * T;
+      const int p0 = tid * per;
+      const uint32_t mask = (uint32_t)ctx.l1_mask;
+      unsigned long long occ = 0ull;
+      for (int i = 0; i < per; i++) {
+        const int q = p0 + i;
+        if (q < S1 && hash[q].x != B2K_HASH_EMPTY) occ |= 1ull << i;
+      }
+      int i = 0;
+      if (p0 < S1 && hash[(uint32_t)(p0 + S1 - 1) & mask].x != B2K_HASH_EMPTY)
+        while (i < per && ((occ >> i) & 1ull)) i++;           // the tail of a run that started in an earlier range
+      while (i < per) {
+        if (!((occ >> i) & 1ull)) { i++; continue; }
+        int Lr = 0;                                           // the run that starts at p0 + i (it may leave the range and wrap)
+        for (;;) {
+          const uint32_t q = (uint32_t)(p0 + i + Lr) & mask;
+          const int4 o = hash[q];
+          if (o.x == B2K_HASH_EMPTY || Lr >= S1) break;
+          if (Lr < RMAX) { rb_s[Lr * T + tid] = (uint32_t)o.x % Hc; rk_s[Lr * T + tid] = (uint32_t)o.z; }
+          Lr++;
+        }
+        for (int a2 = 0; a2 < Lr; a2++) {
+          const int4 o = hash[(uint32_t)(p0 + i + a2) & mask];
+          const uint32_t ba = a2 < RMAX ? rb_s[a2 * T + tid] : (uint32_t)o.x % Hc, ka = (uint32_t)o.z;
+          uint32_t F = ka;
+          int within = 0, pop = 0;
+          for (int c2 = 0; c2 < Lr; c2++) {
+            uint32_t bc, kc;
+            if (c2 < RMAX) { bc = rb_s[c2 * T + tid]; kc = rk_s[c2 * T + tid]; }
+            else { const int4 o2 = hash[(uint32_t)(p0 + i + c2) & mask]; bc = (uint32_t)o2.x % Hc; kc = (uint32_t)o2.z; }
+            if (bc == ba) { pop++; F = min(F, kc); within += (kc < ka); }
+          }
+          x.tok4[o.w] = make_int4(o.x, __float_as_int(ord2f((uint32_t)o.y)), (int)F, within);
+          if (F == ka) x.hw[F] = (uint32_t)pop;
+        }
+        i += Lr;
+      }
+    }
+  }
+  if (!scanned)
   for (int d = tid; d < Nall; d += T) {
     const int sl = tokslot[d];
     const int4 hs = hash[sl];
@@ -2481,7 +2548,8 @@ __device__ void dec_advance_v2_lane(const DecParams &p, DecShared<T> &s, const i
   ctx.ntok_new = &s.ntok_new;
   ctx.err = &s.err;
   ctx.err_line = &s.err_line;
-  set_l1_b(ctx, 1000u);
+  set_l1_b(ctx, 1000u, p.v2_l1_shift);
+  ctx.used_l2 = &s.used_l2;
   X2 x;
   x.trec = p.v2_trec + (size_t)slot * p.max_tpf;
   x.rec = p.x_rec + (size_t)slot * p.max_tpf;
@@ -2506,7 +2574,7 @@ __device__ void dec_advance_v2_lane(const DecParams &p, DecShared<T> &s, const i
   __syncthreads();
 
   if (p.do_init) {
-    if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; }
+    if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; s.used_l2 = 0; }
     __syncthreads();
     ctx.tbase = 0;
     if (tid == 0) {
@@ -2603,7 +2671,7 @@ __device__ void dec_advance_v2_lane(const DecParams &p, DecShared<T> &s, const i
       long long new_sz = (long long)((float)K * p.hash_ratio);
       if (new_sz > (long long)Hc) Hc = (int)min(new_sz, (long long)0x7fffffff);
     }
-    set_l1_b(ctx, (uint32_t)Hc);
+    set_l1_b(ctx, (uint32_t)Hc, p.v2_l1_shift);
     const float cost_offset = (K > 0) ? -best_cost : 0.0f;
 
     // ---- seed (:753-768)
@@ -2621,7 +2689,7 @@ __device__ void dec_advance_v2_lane(const DecParams &p, DecShared<T> &s, const i
     const float seed_cutoff = ord2f(block_min_u32<T>(seed_local, s.red32));
 
     // ---- main loop (:779-812): admission against the exclusive prefix-min
-    if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; }
+    if (tid == 0) { s.ntok_new = 0; s.nlink_new = 0; s.used_l2 = 0; }
     __syncthreads();
     B2K_TICK(s, 0);
     ctx.tbase = tbase;
@@ -3394,6 +3462,7 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
       const char *e = getenv("B2K_DEC_V1");
       // the second generation packs (key, key, creation index) into 64 bits for the replay's initial worklist
       d->use_v2 = !(e && atoi(e) != 0) && p.pos_cap <= (1 << 20) && p.max_tpf <= (1 << 17);
+      if (const char *lx = getenv("B2K_DEC_L1X")) p.v2_l1_shift = std::max(0, std::min(3, atoi(lx)));   // level-1 window = 2^x times the HashList size
     }
     if (d->use_v2) {
       p.v2_hw_len = ((p.pos_cap + 2 * p.max_tpf + 64 + 63) / 64) * 64;

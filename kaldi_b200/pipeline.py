@@ -336,6 +336,55 @@ class NativeBatchedPipeline:
             state_offs=arr(so, nn + 1, np.int64), arc_offs=arr(ao, nn + 1, np.int64), final_offs=arr(fo, nn + 1, np.int64))
         return out
 
+    # ---- multi-GPU shards (kaldi_b200/ingest.py): device int16 in, device-packed lattices out
+    def run_device_i16(self, d_ptr: int, n: int, stream: int = 0):
+        import ctypes as C
+        from . import _lib
+        L = self._L
+        L.b2k_pipeline_run_device_i16.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        _lib.check(L.b2k_pipeline_run_device_i16(self.h, n, C.c_void_p(d_ptr), C.c_void_p(stream)))
+
+    def pack_device(self, n: int, d_buf_ptr: int, cap_bytes: int, stream: int = 0):
+        import ctypes as C
+        from . import _lib
+        L = self._L
+        L.b2k_pipeline_pack_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        _lib.check(L.b2k_pipeline_pack_device(self.h, n, C.c_void_p(d_buf_ptr), cap_bytes, C.c_void_p(stream)))
+
+    @staticmethod
+    def packed_bytes_needed(header: np.ndarray, n: int) -> tuple[int, int]:
+        """(status, bytes) from a host copy of a packed buffer's header (int64 view)."""
+        tail = header[3 * (n + 1):]
+        return int(tail[0]), int(tail[1])
+
+    @staticmethod
+    def unpack_lattices(h_buf: np.ndarray, n: int) -> dict:
+        """b2k_dec_unpack_lattices on a host copy (uint8 array) of a packed buffer: the same dictionary as decode_batch."""
+        import ctypes as C
+        from . import _lib
+        from .decoder import _RawLattice, _p
+        L = _lib.lib()
+        h_buf = np.ascontiguousarray(h_buf, np.uint8)
+        r = _RawLattice()
+        so = np.zeros(n + 1, np.int64); ao = np.zeros(n + 1, np.int64); fo = np.zeros(n + 1, np.int64)
+        i64p = C.POINTER(C.c_int64)
+        L.b2k_dec_unpack_lattices.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, i64p, i64p, i64p]
+        args = (h_buf.ctypes.data, n, C.cast(C.byref(r), C.c_void_p), so.ctypes.data_as(i64p), ao.ctypes.data_as(i64p), fo.ctypes.data_as(i64p))
+        _lib.check(L.b2k_dec_unpack_lattices(*args))            # sizes
+        ns, na, nf = r.num_states, r.num_arcs, r.num_finals
+        out = dict(
+            state_frame=np.zeros(ns, np.int32), state_hclg=np.zeros(ns, np.int32),
+            state_tot_cost=np.zeros(ns, np.float32), state_extra_cost=np.zeros(ns, np.float32),
+            arc_src=np.zeros(na, np.int32), arc_dst=np.zeros(na, np.int32),
+            arc_ilabel=np.zeros(na, np.int32), arc_olabel=np.zeros(na, np.int32),
+            arc_graph_cost=np.zeros(na, np.float32), arc_acoustic_cost=np.zeros(na, np.float32),
+            final_state=np.zeros(nf, np.int32), final_cost=np.zeros(nf, np.float32))
+        for k, v in out.items():
+            setattr(r, k, _p(v, C.c_float if v.dtype == np.float32 else C.c_int32))
+        _lib.check(L.b2k_dec_unpack_lattices(*args))
+        out.update(state_offs=so, arc_offs=ao, final_offs=fo)
+        return out
+
     def read(self, what: str, n: int) -> np.ndarray:
         """Stage outputs of batch slots 0..n-1 on the host: 'features', 'ivectors' or 'loglikes'."""
         import ctypes as C
