@@ -260,6 +260,8 @@ struct LaneCtx {
   int32_t hash_mask, hash_log, max_tpf, max_tokens;
   int32_t l1_mask, l1_log;   // level-1 window of the table for this frame (see probe_slot)
   int *used_l2;              // shared: set when a bucket-keyed insert went past its level-1 window this frame
+  uint32_t hc;               // the reference's HashList size of this frame and its fastmod constant (bucket_b)
+  unsigned long long hc_m;
   int *ntok_new;        // shared
   int *err;             // shared
   int *err_line;        // shared
@@ -1839,7 +1841,16 @@ __device__ __forceinline__ bool probe_revisits_b(const LaneCtx &c, uint32_t b, i
   return ((slot - w0) & (uint32_t)c.l1_mask) < (uint32_t)B2K_V2_L1_PROBES;
 }
 
+// state % Hc (hash-list-inl.h:130) without the generic 32-bit modulo (the source-level profile had 9 % of all stall samples
+// on it): Lemire's fastmod, exact for every 32-bit numerator and divisor.  M = floor(2^64 / d) + 1 (0 for d = 1).
+__device__ __forceinline__ uint32_t bucket_b(const LaneCtx &c, int32_t state) {
+  const unsigned long long low = c.hc_m * (unsigned long long)(uint32_t)state;
+  return (uint32_t)__umul64hi(low, (unsigned long long)c.hc);
+}
+
 __device__ __forceinline__ void set_l1_b(LaneCtx &c, uint32_t Hc, int shift) {
+  c.hc = Hc;
+  c.hc_m = 0xffffffffffffffffull / (unsigned long long)Hc + 1ull;
   int lg = 12;
   while ((1ull << lg) < ((unsigned long long)Hc << shift) && lg < c.hash_log) lg++;
   c.l1_log = lg;
@@ -1848,7 +1859,7 @@ __device__ __forceinline__ void set_l1_b(LaneCtx &c, uint32_t Hc, int shift) {
 
 // find-or-insert on the bucket-keyed table; the creator records slot <-> creation index
 __device__ __forceinline__ int hash_insert_b(const LaneCtx &c, int32_t state, uint32_t Hc, bool *created, int *idx_out) {
-  const uint32_t b = (uint32_t)state % Hc;
+  const uint32_t b = bucket_b(c, state);
   *created = false;
   for (int probe = 0; probe <= c.hash_mask + B2K_V2_L1_PROBES; probe++) {
     const uint32_t h = probe_slot_b(c, b, probe);
@@ -2148,14 +2159,14 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       if (q < qcarry) {
         const int d = pend[q];
         const int4 hs = hash[tokslot[d]];
-        const uint32_t b = (uint32_t)hs.x % Hc;
+        const uint32_t b = bucket_b(ctx, hs.x);
         uint32_t F = (uint32_t)hs.z;
         for (int i = 0; i <= ctx.hash_mask + B2K_V2_L1_PROBES; i++) {
           const uint32_t ps = probe_slot_b(ctx, b, i);
           const int4 o = hash[ps];
           if (o.x == B2K_HASH_EMPTY) break;
           if (probe_revisits_b(ctx, b, i, ps)) continue;
-          if ((uint32_t)o.x % Hc == b) F = min(F, (uint32_t)o.z);   // (eps-created tokens still carry the largest key)
+          if (bucket_b(ctx, o.x) == b) F = min(F, (uint32_t)o.z);   // (eps-created tokens still carry the largest key)
         }
         key = ((unsigned long long)F << 37) | ((unsigned long long)(uint32_t)hs.z << 17) | (unsigned long long)(uint32_t)d;
       }
@@ -2371,63 +2382,14 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
   for (int w = tid; w < PP; w += T) x.hw[w] = 0u;
   __syncthreads();
   B2K_TICK(s, 8);
-  // ---- HashList order (hash-list-inl.h:126-175): buckets by first insertion, insertion order inside a bucket.
-  //      All tokens of a bucket sit in ONE occupied run of the level-1 window (as long as no insert of this frame went to
-  //      level 2), so the order is read off the table by scanning the window once: every thread owns a contiguous range
-  //      of slots, finds the runs that start in it (one pass of independent loads builds an occupancy mask) and, per run,
-  //      the bucket of every entry once (the slow integer modulo is paid per token, not per probe; the source-level
-  //      profile had 30 % of all stall samples in the per-token walk this replaces, profiles/r02_dec_v2_source_stalls.md).
-  bool scanned = false;
-  {
-    const int S1 = ctx.l1_mask + 1;
-    const int per = (S1 + T - 1) / T;
-    const int RMAX = min(16, p.rs_bytes / (8 * T));           // run entries cached in the (idle) replay arrays' space
-    if (!s.used_l2 && per <= 64 && RMAX >= 4 && Nall < S1) {  // uniform
-      scanned = true;
-      uint32_t *rb_s = reinterpret_cast<uint32_t *>(dyn_smem_base), *rk_s = rb_s + RMAX * T;
-      const int p0 = tid * per;
-      const uint32_t mask = (uint32_t)ctx.l1_mask;
-      unsigned long long occ = 0ull;
-      for (int i = 0; i < per; i++) {
-        const int q = p0 + i;
-        if (q < S1 && hash[q].x != B2K_HASH_EMPTY) occ |= 1ull << i;
-      }
-      int i = 0;
-      if (p0 < S1 && hash[(uint32_t)(p0 + S1 - 1) & mask].x != B2K_HASH_EMPTY)
-        while (i < per && ((occ >> i) & 1ull)) i++;           // the tail of a run that started in an earlier range
-      while (i < per) {
-        if (!((occ >> i) & 1ull)) { i++; continue; }
-        int Lr = 0;                                           // the run that starts at p0 + i (it may leave the range and wrap)
-        for (;;) {
-          const uint32_t q = (uint32_t)(p0 + i + Lr) & mask;
-          const int4 o = hash[q];
-          if (o.x == B2K_HASH_EMPTY || Lr >= S1) break;
-          if (Lr < RMAX) { rb_s[Lr * T + tid] = (uint32_t)o.x % Hc; rk_s[Lr * T + tid] = (uint32_t)o.z; }
-          Lr++;
-        }
-        for (int a2 = 0; a2 < Lr; a2++) {
-          const int4 o = hash[(uint32_t)(p0 + i + a2) & mask];
-          const uint32_t ba = a2 < RMAX ? rb_s[a2 * T + tid] : (uint32_t)o.x % Hc, ka = (uint32_t)o.z;
-          uint32_t F = ka;
-          int within = 0, pop = 0;
-          for (int c2 = 0; c2 < Lr; c2++) {
-            uint32_t bc, kc;
-            if (c2 < RMAX) { bc = rb_s[c2 * T + tid]; kc = rk_s[c2 * T + tid]; }
-            else { const int4 o2 = hash[(uint32_t)(p0 + i + c2) & mask]; bc = (uint32_t)o2.x % Hc; kc = (uint32_t)o2.z; }
-            if (bc == ba) { pop++; F = min(F, kc); within += (kc < ka); }
-          }
-          x.tok4[o.w] = make_int4(o.x, __float_as_int(ord2f((uint32_t)o.y)), (int)F, within);
-          if (F == ka) x.hw[F] = (uint32_t)pop;
-        }
-        i += Lr;
-      }
-    }
-  }
-  if (!scanned)
+  // ---- HashList order (hash-list-inl.h:126-175): buckets by first insertion, insertion order inside a bucket.  Every
+  //      token walks its bucket's probe run: first key of the bucket, its own rank inside it, the population.
+  //      (A scan of the whole level-1 window with the runs analysed per thread was measured slower, 578 vs 533 ms:
+  //      profiles/r02_decoder_history.md.)
   for (int d = tid; d < Nall; d += T) {
     const int sl = tokslot[d];
     const int4 hs = hash[sl];
-    const uint32_t b = (uint32_t)hs.x % Hc;
+    const uint32_t b = bucket_b(ctx, hs.x);
     uint32_t F = (uint32_t)hs.z;
     int within = 0, pop = 0;
     for (int i = 0; i <= ctx.hash_mask + B2K_V2_L1_PROBES; i++) {
@@ -2435,7 +2397,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       const int4 o = hash[ps];
       if (o.x == B2K_HASH_EMPTY) break;
       if (probe_revisits_b(ctx, b, i, ps)) continue;
-      if ((uint32_t)o.x % Hc == b) {
+      if (bucket_b(ctx, o.x) == b) {
         pop++;
         F = min(F, (uint32_t)o.z);
         within += ((uint32_t)o.z < (uint32_t)hs.z);

@@ -811,15 +811,25 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
         if (op.bn_scale) { bsc = __ldg(&op.bn_scale[n]); bof = __ldg(&op.bn_offset[n]); }
         if (op.sub_vec) sub = __ldg(&op.sub_vec[n]);
       }
-#pragma unroll 4
+      // the bypass term's 32 loads (one per row, 128 contiguous bytes per warp) are all issued before the first is used:
+      // one memory latency per chunk instead of one per group of rows (the epilogue was the longest part of a short-K tile)
+      float resv[32];
+      if (op.has_res) {
+#pragma unroll
+        for (int rr = 0; rr < 32; rr++) {
+          const unsigned long long ru = __shfl_sync(0xffffffffu, rrow_u, rr);
+          resv[rr] = (ru && ncol_ok) ? reinterpret_cast<const float *>(ru)[n] : 0.f;
+        }
+      }
+#pragma unroll
       for (int rr = 0; rr < 32; rr++) {
-        const unsigned long long ou = __shfl_sync(0xffffffffu, orow_u, rr), ru = __shfl_sync(0xffffffffu, rrow_u, rr);
+        const unsigned long long ou = __shfl_sync(0xffffffffu, orow_u, rr);
         if (!ou || !ncol_ok) continue;
         float val = tsp[rr * 33 + lane_id];
         if (op.bias) val = __fadd_rn(val, bias);
         if (op.relu) val = fmaxf(val, 0.f);
         if (op.bn_scale) val = __fadd_rn(__fmul_rn(val, bsc), bof);
-        if (ru) val = __fadd_rn(__fmul_rn(op.res_alpha, reinterpret_cast<const float *>(ru)[n]), val);
+        if (op.has_res) val = __fadd_rn(__fmul_rn(op.res_alpha, resv[rr]), val);
         if (!op.log_softmax) {
           if (op.sub_vec) val = __fadd_rn(val, -sub);
           if (op.out_scale != 1.0f) val = __fmul_rn(val, op.out_scale);
