@@ -186,9 +186,13 @@ __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParam
   double *quad = sd;            // Q
   double *lin = quad + Q;       // D
   double *x = lin + D, *rr = x + D, *pp = rr + D, *Ap = pp + D;   // D each
-  double *xf = Ap + D;          // F (current frame features as double)
-  double *red = xf + F;         // 32
-  double *sa = red + 32;        // 8 * D: per-Gaussian dot products of the current frame
+  double *xf = Ap + D;          // 8 * F: weighted_feats of up to 8 Gaussians of the chunk
+  double *red = xf + 8 * F;     // 32
+  double *sa = red + 32;        // 8 * D: Sigma_inv_M_g^T weighted_feats of those Gaussians
+  float *occ_s = reinterpret_cast<float *>(sa + 8 * D);        // num_gauss: a Gaussian's summed frame weights (float, as GaussInfo::tot_weight)
+  int *glist = reinterpret_cast<int *>(occ_s + p.num_gauss);   // num_gauss: the chunk's distinct Gaussians
+  int *wcnt_s = glist + p.num_gauss;                           // IVS_THREADS / 32
+  int *nd_s = wcnt_s + IVS_THREADS / 32;
   const int tid = threadIdx.x, L = blockIdx.x;
   // OnlineIvectorEstimationStats ctor (:786-795): linear(0) = prior_offset, quadratic = I
   for (int k = tid; k < Q; k += IVS_THREADS) quad[k] = 0.0;
@@ -203,50 +207,94 @@ __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParam
   for (int n = 0; n < r.n_chunks; n++) {
     const int upto = min(r.sched[n], r.T - 1);
     double tot_weight = 0.0;
-    bool any = next_t <= upto;
-    for (; next_t <= upto; next_t++) {
-      const int t = next_t;
-      const int cnt = r.post_cnt[(size_t)L * r.T + t];
-      for (int d = tid; d < F; d += IVS_THREADS) xf[d] = (double)lda_raw[(size_t)t * F + d];
+    const bool any = next_t <= upto;
+    if (any) {
+      // OnlineIvectorEstimationStats::AccStats(extractor, features, gauss_post) (ivector-extractor.cc:611-668) over the
+      // frames of this request, as the reference does it: PER GAUSSIAN.  ConvertPostToGaussInfo sums a Gaussian's frame
+      // weights in float, in frame order; weighted_feats = sum_t weight * x_t in double; then ONE
+      // linear += Sigma_inv_M_g^T weighted_feats and ONE quadratic += tot_weight_g * U_g per distinct Gaussian, so a
+      // 40 KB U_g row and a 32 KB Sigma_inv_M_g block are read once per chunk instead of once per frame that selects g
+      // (round 1 read them per frame: 213 GB of L2 traffic per 592-utterance step, the kernel sat at L2 bandwidth).
+      const int t0 = next_t;
+      const int G = p.num_gauss;
+      for (int g = tid; g < G; g += IVS_THREADS) {
+        float o = 0.f;
+        for (int t = t0; t <= upto; t++) {
+          const int cnt = r.post_cnt[(size_t)L * r.T + t];
+          const size_t pb = ((size_t)L * r.T + t) * 8;
+          for (int j = 0; j < cnt; j++)
+            if (r.post_idx[pb + j] == g) o += r.post_val[pb + j];
+        }
+        occ_s[g] = o;
+      }
+      if (tid == 0) *nd_s = 0;
       __syncthreads();
-      // AccStats (ivector-extractor.cc:600-648) for the <= 8 selected Gaussians of the frame.
-      // The per-Gaussian dot products run side by side (one thread per (Gaussian, dim)); the
-      // accumulations then add the Gaussians in posterior order, i.e. exactly the sequence of
-      // fused multiply-adds of a Gaussian-by-Gaussian loop.
-      const size_t pb = ((size_t)L * r.T + t) * 8;
-      int gj[8];
-      double wj[8];
+      // distinct Gaussians of the chunk, in index order (one pass: G <= 512 = the CTA width)
+      for (int gb = 0; gb < G; gb += IVS_THREADS) {
+        const int g = gb + tid;
+        const bool on = g < G && occ_s[g] != 0.f;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        __syncthreads();
+        if ((tid & 31) == 0) wcnt_s[tid >> 5] = __popc(m);
+        __syncthreads();
+        int base = *nd_s;
+        for (int w = 0; w < (tid >> 5); w++) base += wcnt_s[w];
+        if (on) glist[base + __popc(m & ((1u << (tid & 31)) - 1u))] = g;
+        __syncthreads();
+        if (tid == 0) { int tot = 0; for (int w = 0; w < IVS_THREADS / 32; w++) tot += wcnt_s[w]; *nd_s += tot; }
+        __syncthreads();
+      }
+      const int nd = *nd_s;
+      for (int gb = 0; gb < nd; gb += 8) {
+        const int nj = min(8, nd - gb);
+        // weighted_feats of up to 8 Gaussians side by side: thread (j, d)
+        for (int q = tid; q < nj * F; q += IVS_THREADS) {
+          const int j = q / F, d = q - j * F, g = glist[gb + j];
+          double a = 0.0;
+          for (int t = t0; t <= upto; t++) {
+            const int cnt = r.post_cnt[(size_t)L * r.T + t];
+            const size_t pb = ((size_t)L * r.T + t) * 8;
+            for (int jj = 0; jj < cnt; jj++)
+              if (r.post_idx[pb + jj] == g) a += (double)r.post_val[pb + jj] * (double)lda_raw[(size_t)t * F + d];
+          }
+          xf[q] = a;
+        }
+        __syncthreads();
+        for (int q = tid; q < nj * D; q += IVS_THREADS) {
+          const int j = q / D, i = q - j * D;
+          const double *SiM = p.sigma_inv_m + (size_t)glist[gb + j] * F * D;
+          double a = 0.0;
+          for (int d = 0; d < F; d++) a += SiM[(size_t)d * D + i] * xf[j * F + d];
+          sa[q] = a;
+        }
+        __syncthreads();
+        int gj[8];
+        double wj[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        gj[j] = (j < cnt) ? r.post_idx[pb + j] : 0;
-        wj[j] = (j < cnt) ? (double)r.post_val[pb + j] : 0.0;
-      }
-      for (int q = tid; q < cnt * D; q += IVS_THREADS) {
-        const int j = q / D, i = q - j * D;
-        const double *SiM = p.sigma_inv_m + (size_t)r.post_idx[pb + j] * F * D;
-        double a = 0.0;
-        for (int d = 0; d < F; d++) a += SiM[(size_t)d * D + i] * xf[d];
-        sa[q] = a;
-      }
-      __syncthreads();
-      for (int i = tid; i < D; i += IVS_THREADS) {
-        double l = lin[i];
+        for (int j = 0; j < 8; j++) {
+          gj[j] = (j < nj) ? glist[gb + j] : 0;
+          wj[j] = (j < nj) ? (double)occ_s[gj[j]] : 0.0;
+        }
+        for (int i = tid; i < D; i += IVS_THREADS) {
+          double l = lin[i];
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (j < nj) l += sa[j * D + i];
+          lin[i] = l;
+        }
+        for (int k = tid; k < Q; k += IVS_THREADS) {
+          double qv = quad[k];
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (j < nj) qv += wj[j] * __ldg(&p.U[(size_t)gj[j] * Q + k]);
+          quad[k] = qv;
+        }
 #pragma unroll
         for (int j = 0; j < 8; j++)
-          if (j < cnt) l += wj[j] * sa[j * D + i];
-        lin[i] = l;
+          if (j < nj) tot_weight += wj[j];
+        __syncthreads();
       }
-      for (int k = tid; k < Q; k += IVS_THREADS) {
-        double qv = quad[k];
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-          if (j < cnt) qv += wj[j] * __ldg(&p.U[(size_t)gj[j] * Q + k]);
-        quad[k] = qv;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (j < cnt) tot_weight += wj[j];
-      __syncthreads();
+      next_t = upto + 1;
     }
     if (any) {
       // max_count prior scaling (:650-664)
@@ -417,7 +465,7 @@ int b2k_ivec_create(const b2k_ivec_cfg *cfg, const float *lda, const float *gcon
   B2K_CUDA_CHECK(cudaMallocHost((void **)&iv->h_sched, 4 * 4096));
   B2K_CUDA_CHECK(cudaEventCreateWithFlags(&iv->staging_free, cudaEventDisableTiming));
   iv->smem_front = sizeof(float) * ((size_t)F * (SD + 1) + IV_WARPS * (2 * (size_t)SD + F));
-  iv->smem_stats = sizeof(double) * ((size_t)Q + 5 * D + F + 32 + 8 * (size_t)D);
+  iv->smem_stats = sizeof(double) * ((size_t)Q + 5 * D + 8 * (size_t)F + 32 + 8 * (size_t)D) + 4 * (2 * (size_t)G + IVS_THREADS / 32 + 4);
   B2K_CUDA_CHECK(cudaFuncSetAttribute(ivec_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv->smem_front));
   B2K_CUDA_CHECK(cudaFuncSetAttribute(ivec_stats_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv->smem_stats));
   *out = iv;
