@@ -3424,7 +3424,8 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
       const char *e = getenv("B2K_DEC_V1");
       // the second generation packs (key, key, creation index) into 64 bits for the replay's initial worklist
       d->use_v2 = !(e && atoi(e) != 0) && p.pos_cap <= (1 << 20) && p.max_tpf <= (1 << 17);
-      if (const char *lx = getenv("B2K_DEC_L1X")) p.v2_l1_shift = std::max(0, std::min(3, atoi(lx)));   // level-1 window = 2^x times the HashList size
+      p.v2_l1_shift = 2;      // measured (profiles/r02_decoder_history.md, r2j): 552 ms at 1x / 2x, 472 ms at 4x the HashList size
+      if (const char *lx = getenv("B2K_DEC_L1X")) p.v2_l1_shift = std::max(0, std::min(6, atoi(lx)));   // level-1 window = 2^x times the HashList size
     }
     if (d->use_v2) {
       p.v2_hw_len = ((p.pos_cap + 2 * p.max_tpf + 64 + 63) / 64) * 64;
