@@ -1111,7 +1111,7 @@ __device__ void finish_frame_exact(const DecParams &p, DecShared<T> &s, const La
     // keys (first insertion index of the bucket, own insertion index) and sort the keys
     // in shared memory; only when they do not fit is the full list order built.
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(dyn_smem_base);
-    const int key_cap = min(4096, p.rs_rcap + p.rs_ecap);     // 8 bytes each, inside the walk's (not yet filled) arrays
+    const int key_cap = 1 << (31 - __clz(max(1, min(4096, p.rs_rcap + p.rs_ecap))));   // 8 bytes each, inside the walk's (not yet filled) arrays; a power of two
     if (tid == 0) s.rs_n = 0;
     __syncthreads();
     for (int d = tid; d < N1; d += T) {
@@ -2141,7 +2141,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     // initial worklist (:852-856) = the emitting tokens in list order, restricted to the marked tokens whose final
     // record admits something.  List order = (first key of the token's bucket, own key): both are read off the table.
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(dyn_smem_base);
-    const int key_cap = min(4096, p.rs_rcap + p.rs_ecap);     // 8 bytes each, inside the walk's (not yet filled) arrays
+    const int key_cap = 1 << (31 - __clz(max(1, min(4096, p.rs_rcap + p.rs_ecap))));   // 8 bytes each, inside the walk's (not yet filled) arrays; a power of two
     if (tid == 0) s.rs_n = 0;
     __syncthreads();
     int *pend = x.big;                                        // tokens to key (idle until the walk arrays are built)
@@ -2290,8 +2290,9 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     if (s.rs_ok && tid == 0) {
       int qn = qcarry, next = 0;
       bool ok = true;
-      int npop = 0, nvis = 0;
+      int npop = 0, nvis = 0, qmax = qcarry;
       while (qn > 0) {
+        if (PROF) qmax = max(qmax, qn);
         const int d = q_s[--qn];
         const float2 td = tk_s[d];
         const float c = td.x;
@@ -2320,6 +2321,8 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       if (ok) {
         if (next != Nall - N1) B2K_SET_ERR(s, B2K_ERR_STATE);
         s.prof[12] += (unsigned long long)npop; s.prof[13] += (unsigned long long)nvis; s.prof[14] += 1;
+        // sizing data for the shared-memory walk (three 20-bit counters: frames with > 2048 tokens / arcs / worklist entries)
+        if (PROF) s.prof[2] += (unsigned long long)(s.rs_n > 2048) | ((unsigned long long)(s.rs_e > 2048) << 20) | ((unsigned long long)(qmax > 2048) << 40);
       } else {
         s.rs_ok = 0;                                         // worklist outgrew shared memory: redo below
       }
@@ -2813,7 +2816,7 @@ __device__ void dec_advance_v2_lane(const DecParams &p, DecShared<T> &s, const i
 }
 
 template <int T, bool PROF>
-__global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) dec_advance_v2_kernel(DecParams p) {
+__global__ void __launch_bounds__(T, (T == 512 ? 2 : (T == 256 ? 3 : 1))) dec_advance_v2_kernel(DecParams p) {
   __shared__ DecShared<T> s;
   B2K_PERSISTENT_LANES((dec_advance_v2_lane<T, PROF>(p, s, lane_, (int)blockIdx.x)))
 }
@@ -3095,7 +3098,7 @@ __global__ void dec_reset_channels_kernel(DecParams p, int n) {
 }
 
 // ---- the same packing without a host round trip: offsets computed on the device into the buffer's header.
-// Buffer layout: int64 header[3 * (n + 1) + 4] = {state offsets, arc offsets, final offsets, status, bytes needed, n, -},
+// Buffer layout: int64 header[3 * (n + 1) + 4] = {state offsets, arc offsets, final offsets, status, bytes needed, n, first failing entry (line << 32 | index) or -1},
 // padded to 16 bytes, then int4 states[ns], int4 arcs[na], float2 arc weights[na], int2 finals[nf].
 __host__ __device__ inline int64_t pack_header_bytes(int n) { return (int64_t)((8 * (3 * ((int64_t)n + 1) + 4) + 15) / 16 * 16); }
 
@@ -3103,15 +3106,16 @@ __global__ void dec_pack_header_kernel(DecParams p, const int32_t *channels, int
   // one block: exclusive prefix sums of the per-channel lattice sizes (n is at most a few thousand)
   __shared__ long long carry[3];
   __shared__ int status;
-  if (threadIdx.x == 0) { carry[0] = carry[1] = carry[2] = 0; status = B2K_OK; }
+  __shared__ long long culprit;                               // first failing entry: (source line << 32) | index in `channels`
+  if (threadIdx.x == 0) { carry[0] = carry[1] = carry[2] = 0; status = B2K_OK; culprit = -1; }
   __syncthreads();
   for (int base = 0; base < n; base += blockDim.x) {
     const int i = base + threadIdx.x;
     int v[3] = {0, 0, 0};
     if (i < n) {
       const ChanState *cs = &p.chan[channels[i]];
-      if (cs->status != B2K_OK) atomicCAS(&status, B2K_OK, cs->status);
-      else if (!cs->finalized) atomicCAS(&status, B2K_OK, B2K_ERR_STATE);
+      if (cs->status != B2K_OK) { if (atomicCAS(&status, B2K_OK, cs->status) == B2K_OK) culprit = ((long long)cs->err_line << 32) | (unsigned)i; }
+      else if (!cs->finalized) { if (atomicCAS(&status, B2K_OK, B2K_ERR_STATE) == B2K_OK) culprit = (long long)(unsigned)i; }
       v[0] = min(cs->lat_states, p.cap_ls); v[1] = min(cs->lat_arcs, p.cap_la); v[2] = min(cs->lat_finals, p.cap_lf);
     }
     for (int k = 0; k < 3; k++) {
@@ -3136,7 +3140,7 @@ __global__ void dec_pack_header_kernel(DecParams p, const int32_t *channels, int
     const int64_t need = pack_header_bytes(n) + carry[0] * 16 + carry[1] * 24 + carry[2] * 8;
     if (need > cap_bytes && status == B2K_OK) status = B2K_ERR_OVERFLOW;
     int64_t *tail = hdr + 3 * ((size_t)n + 1);
-    tail[0] = status; tail[1] = need; tail[2] = n; tail[3] = 0;
+    tail[0] = status; tail[1] = need; tail[2] = n; tail[3] = culprit;
   }
 }
 
@@ -3190,6 +3194,7 @@ struct b2k_dec {
   int nlanes, nchannels;
   DecParams p;
   int threads_override = 0, fin_threads = 1024, num_sms = 0;   // tuning knobs, read from the environment at creation
+  int ctas_override = 0;                // B2K_DEC_CTAS (256-thread CTAs only)
   int nslots = 0;                       // scratch slots = the largest grid any per-lane launch uses (resident CTAs)
   int prof = 0;                         // B2K_DEC_PROF=1: per-phase cycle counters in the reference-order kernel
   int ll_smem_off = 0;                  // B2K_DEC_LL_SMEM=0: leave the log-likelihood rows in global memory
@@ -3352,7 +3357,8 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     // Persistent launches: at most two CTAs per SM are ever resident (512-thread reference-order CTAs; the
     // order-free and finalize kernels use one slot per CTA of their own, smaller grids), so that is the
     // number of scratch slots, whatever the batch size.
-    d->nslots = std::min(nlanes, 2 * d->num_sms);
+    if (const char *e = getenv("B2K_DEC_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 3) d->ctas_override = v; }   // experiments: 256-thread CTAs, three per SM
+    d->nslots = std::min(nlanes, std::max(2, d->ctas_override) * d->num_sms);
   }
 
   DecParams &p = d->p;
@@ -3404,14 +3410,13 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     A(p.x_order, 4 * nl * p.max_tpf, 0);
     p.adj_cap = 2 * p.max_tpf;
     p.rs_rcap = 4096; p.rs_ecap = 4096; p.rs_qcap = 4096;  // shared-memory walk: 80 KB per CTA (two 512-thread CTAs per SM)
-    if (const char *e = getenv("B2K_DEC_RS_CAPS")) {          // tuning knob: "tokens,arcs,worklist" (powers of two <= 8192, tokens == arcs; 0,0,0 = off)
+    if (const char *e = getenv("B2K_DEC_RS_CAPS")) {          // tuning knob: "tokens,arcs,worklist" (powers of two <= 8192; 0,0,0 = off)
       int a = 0, b = 0, c = 0;
       if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= 0 && b >= 0 && c >= 0 && a <= 8192 && b <= 8192 && c <= 8192) {
         // powers of two only: the kernel's key sort pads the replay worklist to a power of two inside
         // the (tokens + arcs) * 8-byte area
         auto pow2_floor = [](int v) { int q = 1; while (q * 2 <= v) q *= 2; return v > 0 ? q : 0; };
         p.rs_rcap = pow2_floor(a); p.rs_ecap = pow2_floor(b); p.rs_qcap = pow2_floor(c);
-        if (p.rs_rcap != p.rs_ecap) p.rs_rcap = p.rs_ecap = std::min(p.rs_rcap, p.rs_ecap);   // (their sum must be one too)
         if (!a || !b || !c) { p.rs_rcap = p.rs_ecap = p.rs_qcap = 0; }
       }
     }
@@ -3424,7 +3429,7 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
       const char *e = getenv("B2K_DEC_V1");
       // the second generation packs (key, key, creation index) into 64 bits for the replay's initial worklist
       d->use_v2 = !(e && atoi(e) != 0) && p.pos_cap <= (1 << 20) && p.max_tpf <= (1 << 17);
-      p.v2_l1_shift = 2;      // measured (profiles/r02_decoder_history.md, r2j): 552 ms at 1x / 2x, 472 ms at 4x the HashList size
+      p.v2_l1_shift = 3;      // measured (profiles/r02_decoder_history.md, r2j-r2k): 552 ms at 1x / 2x, 472 ms at 4x, 463 ms at 8x the HashList size
       if (const char *lx = getenv("B2K_DEC_L1X")) p.v2_l1_shift = std::max(0, std::min(6, atoi(lx)));   // level-1 window = 2^x times the HashList size
     }
     if (d->use_v2) {
@@ -3588,12 +3593,12 @@ static int launch_exact(const b2k_dec *d, DecParams p, int n, cudaStream_t st) {
     if (d->prof) {
       if (threads == 1024) return launch_v2_t<1024, true>(d, p, n, 1, st);
       if (threads == 512) return launch_v2_t<512, true>(d, p, n, 2, st);
-      return launch_v2_t<256, true>(d, p, n, 2, st);
+      return launch_v2_t<256, true>(d, p, n, d->ctas_override > 0 ? d->ctas_override : 2, st);
     }
     if (threads == 1024) return launch_v2_t<1024, false>(d, p, n, 1, st);
     if (threads == 512) return launch_v2_t<512, false>(d, p, n, 2, st);
     if (threads == 128) return launch_v2_t<128, false>(d, p, n, 2, st);
-    return launch_v2_t<256, false>(d, p, n, 2, st);
+    return launch_v2_t<256, false>(d, p, n, d->ctas_override > 0 ? d->ctas_override : 2, st);
   }
   if (d->prof) {
     if (threads == 1024) return launch_exact_t<1024, true>(d, p, n, 1, st);
@@ -3738,8 +3743,12 @@ int b2k_dec_unpack_lattices(const void *h_buf, int32_t n, b2k_raw_lattice *out, 
   const int64_t *tail = hdr + 3 * ((size_t)n + 1);
   if (tail[2] != n) return set_error(B2K_ERR_INVALID, "b2k_dec_unpack_lattices: the buffer was packed for another channel count");
   if (tail[0] != B2K_OK) {
-    char msg[160];
-    snprintf(msg, sizeof(msg), "packed lattices carry status %lld (%lld bytes needed): a channel is in error, not finalized, or the buffer was too small", (long long)tail[0], (long long)tail[1]);
+    char msg[240];
+    if (tail[3] >= 0)
+      snprintf(msg, sizeof(msg), "packed lattices carry status %lld: entry %lld of the channel list is in error (raised at decoder.cu:%lld; 0 = not finalized)",
+               (long long)tail[0], (long long)(tail[3] & 0xffffffffll), (long long)(tail[3] >> 32));
+    else
+      snprintf(msg, sizeof(msg), "packed lattices carry status %lld: the buffer was too small (%lld bytes needed)", (long long)tail[0], (long long)tail[1]);
     return set_error((int)tail[0], msg);
   }
   const int64_t ns = hdr[n], na = hdr[(n + 1) + n], nf = hdr[2 * (n + 1) + n];

@@ -178,7 +178,23 @@ __device__ __forceinline__ double sp_at(const double *q, int i, int j) {   // pa
   return (i >= j) ? q[(size_t)i * (i + 1) / 2 + j] : q[(size_t)j * (j + 1) / 2 + i];
 }
 
+// (A v)_i of a packed symmetric matrix, FOUR threads per row (row = tid / 4, each sums a contiguous quarter of the
+// columns, the quarters are added as (q0 + q1) + (q2 + q3)): the dependent chain of double FMAs is D / 4 long instead of
+// D.  Every thread of the warps that hold rows gets the row's value; rows >= D return 0.  4 * D <= the CTA width.
+__device__ __forceinline__ double sp_matvec_row4(const double *q, const double *v, int D) {
+  const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
+  double a = 0.0;
+  if (i < D) {
+    const int per = (D + 3) >> 2, j0 = part * per, j1 = min(D, j0 + per);
+    for (int j = j0; j < j1; j++) a += sp_at(q, i, j) * v[j];
+  }
+  a += __shfl_xor_sync(0xffffffffu, a, 1);
+  a += __shfl_xor_sync(0xffffffffu, a, 2);
+  return a;
+}
+
 #define IVS_THREADS 512
+#define IVS_STAGE 64
 
 __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParams p, IvecRun r) {
   extern __shared__ double sd[];
@@ -192,7 +208,12 @@ __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParam
   float *occ_s = reinterpret_cast<float *>(sa + 8 * D);        // num_gauss: a Gaussian's summed frame weights (float, as GaussInfo::tot_weight)
   int *glist = reinterpret_cast<int *>(occ_s + p.num_gauss);   // num_gauss: the chunk's distinct Gaussians
   int *wcnt_s = glist + p.num_gauss;                           // IVS_THREADS / 32
-  int *nd_s = wcnt_s + IVS_THREADS / 32;
+  int *nd_s = wcnt_s + IVS_THREADS / 32;                       // 4
+  // a chunk of up to IVS_STAGE frames is staged once: posteriors and the LDA-transformed frames
+  int *pcnt_s = nd_s + 4;                                      // IVS_STAGE
+  int *pidx_s = pcnt_s + IVS_STAGE;                            // 8 * IVS_STAGE
+  float *pval_s = reinterpret_cast<float *>(pidx_s + 8 * IVS_STAGE);   // 8 * IVS_STAGE
+  float *feat_s = pval_s + 8 * IVS_STAGE;                      // IVS_STAGE * F
   const int tid = threadIdx.x, L = blockIdx.x;
   // OnlineIvectorEstimationStats ctor (:786-795): linear(0) = prior_offset, quadratic = I
   for (int k = tid; k < Q; k += IVS_THREADS) quad[k] = 0.0;
@@ -217,13 +238,26 @@ __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParam
       // (round 1 read them per frame: 213 GB of L2 traffic per 592-utterance step, the kernel sat at L2 bandwidth).
       const int t0 = next_t;
       const int G = p.num_gauss;
+      const int nfr = upto - t0 + 1;
+      // the chunk's posteriors and frames: out of shared memory when the chunk fits (every thread scans them several
+      // times), else where the front kernel left them (same code: generic pointers, indexed from the chunk's first frame)
+      const int *cntp = r.post_cnt + (size_t)L * r.T + t0;
+      const int *idxp = r.post_idx + ((size_t)L * r.T + t0) * 8;
+      const float *valp = r.post_val + ((size_t)L * r.T + t0) * 8;
+      const float *featp = lda_raw + (size_t)t0 * F;
+      if (nfr <= IVS_STAGE) {
+        for (int q = tid; q < nfr; q += IVS_THREADS) pcnt_s[q] = cntp[q];
+        for (int q = tid; q < nfr * 8; q += IVS_THREADS) { pidx_s[q] = idxp[q]; pval_s[q] = valp[q]; }
+        for (int q = tid; q < nfr * F; q += IVS_THREADS) feat_s[q] = featp[q];
+        cntp = pcnt_s; idxp = pidx_s; valp = pval_s; featp = feat_s;
+        __syncthreads();
+      }
       for (int g = tid; g < G; g += IVS_THREADS) {
         float o = 0.f;
-        for (int t = t0; t <= upto; t++) {
-          const int cnt = r.post_cnt[(size_t)L * r.T + t];
-          const size_t pb = ((size_t)L * r.T + t) * 8;
+        for (int t = 0; t < nfr; t++) {
+          const int cnt = cntp[t];
           for (int j = 0; j < cnt; j++)
-            if (r.post_idx[pb + j] == g) o += r.post_val[pb + j];
+            if (idxp[t * 8 + j] == g) o += valp[t * 8 + j];
         }
         occ_s[g] = o;
       }
@@ -251,11 +285,10 @@ __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParam
         for (int q = tid; q < nj * F; q += IVS_THREADS) {
           const int j = q / F, d = q - j * F, g = glist[gb + j];
           double a = 0.0;
-          for (int t = t0; t <= upto; t++) {
-            const int cnt = r.post_cnt[(size_t)L * r.T + t];
-            const size_t pb = ((size_t)L * r.T + t) * 8;
+          for (int t = 0; t < nfr; t++) {
+            const int cnt = cntp[t];
             for (int jj = 0; jj < cnt; jj++)
-              if (r.post_idx[pb + jj] == g) a += (double)r.post_val[pb + jj] * (double)lda_raw[(size_t)t * F + d];
+              if (idxp[t * 8 + jj] == g) a += (double)valp[t * 8 + jj] * (double)featp[(size_t)t * F + d];
           }
           xf[q] = a;
         }
@@ -315,11 +348,9 @@ __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParam
         if (tid == 0 && x[0] == 0.0) x[0] = (double)p.prior_offset;
         __syncthreads();
         // p_0 = b - A x_0 ; r_0 = -p_0
-        for (int i = tid; i < D; i += IVS_THREADS) {
-          double a = 0.0;
-          for (int j = 0; j < D; j++) a += sp_at(quad, i, j) * x[j];
-          pp[i] = lin[i] - a;
-          rr[i] = -pp[i];
+        {
+          const double a = sp_matvec_row4(quad, x, D);
+          if ((tid & 3) == 0 && (tid >> 2) < D) { pp[tid >> 2] = lin[tid >> 2] - a; rr[tid >> 2] = -pp[tid >> 2]; }
         }
         __syncthreads();
         double loc = 0.0;
@@ -329,10 +360,9 @@ __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParam
         const double max_error_sq = 2.2250738585072014e-308;          // max(0*0, DBL_MIN)
         const double residual_factor = 0.01 * 0.01, inv_residual_factor = 1.0 / residual_factor;
         for (int k = 0; k < D + 5 && k != p.num_cg_iters; k++) {
-          for (int i = tid; i < D; i += IVS_THREADS) {
-            double a = 0.0;
-            for (int j = 0; j < D; j++) a += sp_at(quad, i, j) * pp[j];
-            Ap[i] = a;
+          {
+            const double a = sp_matvec_row4(quad, pp, D);
+            if ((tid & 3) == 0 && (tid >> 2) < D) Ap[tid >> 2] = a;
           }
           __syncthreads();
           double l1 = 0.0, l2 = 0.0;
@@ -346,10 +376,9 @@ __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParam
           for (int i = tid; i < D; i += IVS_THREADS) loc += rr[i] * rr[i];
           double r_next = block_sum_d(loc, red, IVS_THREADS);
           if (r_next < residual_factor * r_recompute || r_next > inv_residual_factor * r_recompute) {
-            for (int i = tid; i < D; i += IVS_THREADS) {
-              double a = 0.0;
-              for (int j = 0; j < D; j++) a += sp_at(quad, i, j) * x[j];
-              Ap[i] = a - lin[i];
+            {
+              const double a = sp_matvec_row4(quad, x, D);
+              if ((tid & 3) == 0 && (tid >> 2) < D) Ap[tid >> 2] = a - lin[tid >> 2];
             }
             __syncthreads();
             for (int i = tid; i < D; i += IVS_THREADS) rr[i] = Ap[i];
@@ -465,7 +494,8 @@ int b2k_ivec_create(const b2k_ivec_cfg *cfg, const float *lda, const float *gcon
   B2K_CUDA_CHECK(cudaMallocHost((void **)&iv->h_sched, 4 * 4096));
   B2K_CUDA_CHECK(cudaEventCreateWithFlags(&iv->staging_free, cudaEventDisableTiming));
   iv->smem_front = sizeof(float) * ((size_t)F * (SD + 1) + IV_WARPS * (2 * (size_t)SD + F));
-  iv->smem_stats = sizeof(double) * ((size_t)Q + 5 * D + 8 * (size_t)F + 32 + 8 * (size_t)D) + 4 * (2 * (size_t)G + IVS_THREADS / 32 + 4);
+  iv->smem_stats = sizeof(double) * ((size_t)Q + 5 * D + 8 * (size_t)F + 32 + 8 * (size_t)D) + 4 * (2 * (size_t)G + IVS_THREADS / 32 + 4) +
+                   4 * ((size_t)IVS_STAGE * (1 + 8 + 8) + (size_t)IVS_STAGE * F);
   B2K_CUDA_CHECK(cudaFuncSetAttribute(ivec_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv->smem_front));
   B2K_CUDA_CHECK(cudaFuncSetAttribute(ivec_stats_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv->smem_stats));
   *out = iv;

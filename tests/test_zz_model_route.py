@@ -101,8 +101,6 @@ def test_model_file_to_loglikes_on_the_device():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="the C++ pipeline (csrc/pipeline.cu) was written after this round's GPU budget "
-                                        "was spent: its first device run is the round-end test run")
 @pytest.mark.parametrize("with_ivectors,int16", [(True, False), (False, True)])
 def test_cpp_pipeline_equals_python_pipeline(with_ivectors, int16):
     """b2k_pipeline_* (model file -> C++ orchestration) against BatchedPipeline (Python orchestration of the same
@@ -166,8 +164,6 @@ def test_graph_file_route_gives_the_same_decoder(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="host C++ above the ABI (b2k_batcher.h / b2k_pipeline_shim.h over csrc/pipeline.cu) was written "
-                                        "after this round's GPU budget was spent: its first device run is the round-end test run")
 def test_pure_cpp_route_from_files_to_compact_lattices(tmp_path):
     """tests/cabi/pipeline_device_route.cc: model file + graph file + chunked audio -> UtteranceBatcher ->
     B2kPipelineBackend -> compact lattices, no Python in between; against the ctypes view of the same C++ pipeline
@@ -234,8 +230,6 @@ def test_pure_cpp_route_from_files_to_compact_lattices(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="tests/cabi/experiment_route.c drives csrc/pipeline.cu and the file-based i-vector extractor, "
-                                        "written after this round's GPU budget was spent: first device run at round end")
 def test_c99_program_decodes_a_directory_on_the_device(tmp_path):
     """The complete C route (option files, final.mdl, HCLG.fst, 8 kHz WAVE resampled, extractor files) down to a binary
     CompactLattice archive that reads back."""
@@ -271,9 +265,6 @@ def test_c99_program_decodes_a_directory_on_the_device(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="the spliced relu-batchnorm / 5-frame LDA programs of the chain TDNN were added after this round's GPU "
-                                        "budget was spent: same kernels as the TDNN-F programs, first device run pending (CPU: the op program "
-                                        "interpreted in numpy equals the reference's forward, tests/test_recipe_xconfig.py)")
 @pytest.mark.parametrize("T", [64, 23])
 def test_chain_tdnn_without_factorisation_on_the_device(T):
     from kaldi_b200.nnet import NnetComputer

@@ -13,7 +13,7 @@
 //     groups of four warps (even / odd K slabs), which also run the epilogue (tcgen05.ld -> global).
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/_bin/tc5b tools/tcgen05_gemm_probe2.cu -lcuda
-//   tools/_bin/tc5b [mode] [M] [N] [K]
+//   tools/_bin/tc5b [mode] [M] [N] [K] [accmode 0|1|2] [dist 0|1]
 //
 // prints max relative error against a double-precision CPU product and the TFLOP/s of the kernel.
 #include <cstdint>
@@ -82,13 +82,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 
 // MODE 1: A in TMEM (two stages of 64 columns: 32 hi + 32 lo);  MODE 0: A in shared memory (two stages of hi + lo panels)
 template <int MODE, int TN, int SB>
-__global__ void __launch_bounds__(NTHREADS, MODE == 1 ? 2 : 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc5b(const float *__restrict__ A, float *__restrict__ C, int M, int N, int K,
-          const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+          const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, int accmode) {
   constexpr uint32_t B_TILE = TN * 128;                       // bytes of one hi (or lo) tile: TN rows x 32 floats
   constexpr uint32_t B_STAGE = 2 * B_TILE;
   constexpr uint32_t A_PANEL = TM * 16, A_TILE = (TK / 4) * A_PANEL, A_STAGE = 2 * A_TILE;   // MODE 0 only
-  constexpr uint32_t TMEM_COLS = (MODE == 1) ? (TN + 128 <= 256 ? 256 : 512) : (TN <= 128 ? 128 : 256);
+  constexpr uint32_t TMEM_COLS = (MODE == 1) ? 512 : (TN <= 128 ? 128 : 256);   // (probe: room for the accumulation experiments)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *b_st = smem;                                 // SB stages of {hi, lo}
@@ -152,9 +152,19 @@ gemm_tc5b(const float *__restrict__ A, float *__restrict__ C, int M, int N, int 
           const uint32_t acc0 = (s > 0 || ks > 0) ? 1u : 0u;
           if (MODE == 1) {
             const uint32_t ah = tmem_a + (uint32_t)as * 64u + (uint32_t)ks * 8u, al = ah + 32u;
-            mma_ts(tmem_acc, al, dbh, idesc, acc0);
-            mma_ts(tmem_acc, ah, dbl, idesc, 1u);
-            mma_ts(tmem_acc, ah, dbh, idesc, 1u);
+            // accmode 0: one accumulator.  1: the two correction products in their own accumulator (TN + 128 ...).
+            // 2: also the main products alternate between two accumulators by k-step parity.
+            if (accmode == 0) {
+              mma_ts(tmem_acc, al, dbh, idesc, acc0);
+              mma_ts(tmem_acc, ah, dbl, idesc, 1u);
+              mma_ts(tmem_acc, ah, dbh, idesc, 1u);
+            } else {
+              const uint32_t cross = tmem_base + (uint32_t)TN + 128u, main2 = cross + (uint32_t)TN;
+              mma_ts(cross, al, dbh, idesc, acc0);
+              mma_ts(cross, ah, dbl, idesc, 1u);
+              if (accmode == 2 && (ks & 1)) mma_ts(main2, ah, dbh, idesc, (s > 0 || ks > 1) ? 1u : 0u);
+              else mma_ts(tmem_acc, ah, dbh, idesc, acc0);
+            }
           } else {
             const uint32_t ah = smem_u32(a_st + (size_t)as * A_STAGE) + (uint32_t)ks * 2u * A_PANEL, al = ah + A_TILE;
             mma_ss(tmem_acc, desc_nosw(al, A_PANEL), dbh, idesc, acc0);
@@ -230,6 +240,29 @@ gemm_tc5b(const float *__restrict__ A, float *__restrict__ C, int M, int N, int 
             "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int extra = 0; extra < accmode; extra++) {           // main + (main2 +) cross, added in fp32 (round to nearest)
+        uint32_t w[16];
+        const uint32_t ta2 = taddr + (uint32_t)TN + 128u + (uint32_t)(extra == 0 ? 0 : TN);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+              "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+            : "r"(ta2));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (accmode == 2 && extra == 0) continue;              // (order: main + main2 first, then cross)
+        for (int j = 0; j < 16; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      }
+      if (accmode == 2) {                                      // cross last
+        uint32_t w[16];
+        const uint32_t ta2 = taddr + (uint32_t)TN + 128u;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+              "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+            : "r"(ta2));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 16; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      }
       if (row < M)
         for (int j = 0; j < 16; j++)
           if (n0 + c0 + j < N) C[(size_t)row * N + n0 + c0 + j] = __uint_as_float(v[j]);
@@ -261,11 +294,11 @@ static CUtensorMap make_map(const float *dptr, int N, int Kp, int TN) {
 }
 
 template <int MODE, int TN, int SB>
-static void run(int M, int N, int K) {
+static void run(int M, int N, int K, int accmode, int dist) {
   const int Kp = (K + 3) / 4 * 4;
   std::vector<float> hA((size_t)M * K), hW((size_t)N * K), hWh((size_t)N * Kp, 0.f), hWl((size_t)N * Kp, 0.f), hC((size_t)M * N);
   srand(1);
-  for (auto &x : hA) x = (float)rand() / RAND_MAX - 0.5f;
+  for (auto &x : hA) x = (float)rand() / RAND_MAX - (dist == 1 ? 0.0f : 0.5f);   // dist 1: non-negative activations (after ReLU)
   for (auto &x : hW) x = (float)rand() / RAND_MAX - 0.5f;
   for (int n = 0; n < N; n++)
     for (int k = 0; k < K; k++) {
@@ -282,19 +315,19 @@ static void run(int M, int N, int K) {
   const size_t smem = (size_t)SB * 2 * TN * 128 + (MODE == 0 ? 2 * 2 * (TK / 4) * TM * 16 : 0) + 1024;
   CHECK(cudaFuncSetAttribute(gemm_tc5b<MODE, TN, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
-  gemm_tc5b<MODE, TN, SB><<<grid, NTHREADS, smem>>>(dA, dC, M, N, K, mh, ml);
+  gemm_tc5b<MODE, TN, SB><<<grid, NTHREADS, smem>>>(dA, dC, M, N, K, mh, ml, accmode);
   CHECK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
   const int reps = 20;
-  for (int i = 0; i < reps; i++) gemm_tc5b<MODE, TN, SB><<<grid, NTHREADS, smem>>>(dA, dC, M, N, K, mh, ml);
+  for (int i = 0; i < reps; i++) gemm_tc5b<MODE, TN, SB><<<grid, NTHREADS, smem>>>(dA, dC, M, N, K, mh, ml, accmode);
   cudaEventRecord(e1);
   CHECK(cudaDeviceSynchronize());
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   CHECK(cudaMemcpy(hC.data(), dC, hC.size() * 4, cudaMemcpyDeviceToHost));
-  double max_err = 0, max_ref = 0;
+  double max_err = 0, max_ref = 0, se = 0, sr = 0;
   int bad = 0;
   for (int i = 0; i < M; i += (M > 512 ? 37 : 1))
     for (int j = 0; j < N; j += (N > 256 ? 11 : 1)) {
@@ -304,20 +337,22 @@ static void run(int M, int N, int K) {
       if (!(e == e)) { bad++; e = 1e30; }
       max_err = fmax(max_err, e);
       max_ref = fmax(max_ref, fabs(ref));
+      if (e < 1e29) { se += e * e; sr += ref * ref; }
     }
-  printf("mode %d TN %d SB %d  M %d N %d K %d: max |err| / max |ref| = %.3e  nan %d   %.1f TFLOP/s fp32-equivalent (%.3f ms)\n",
-         MODE, TN, SB, M, N, K, max_err / max_ref, bad, 2.0 * M * N * K * reps / (ms * 1e-3) / 1e12, ms / reps);
+  printf("mode %d acc %d dist %d TN %d SB %d  M %d N %d K %d: max |err| / max |ref| = %.3e  rms err / rms ref = %.3e  nan %d   %.1f TFLOP/s fp32-equivalent (%.3f ms)\n",
+         MODE, accmode, dist, TN, SB, M, N, K, max_err / max_ref, sqrt(se / sr), bad, 2.0 * M * N * K * reps / (ms * 1e-3) / 1e12, ms / reps);
   cudaFree(dA); cudaFree(dWh); cudaFree(dWl); cudaFree(dC);
 }
 
 int main(int argc, char **argv) {
   const int mode = argc > 1 ? atoi(argv[1]) : 1;
   const int M = argc > 2 ? atoi(argv[2]) : 16384, N = argc > 3 ? atoi(argv[3]) : 1536, K = argc > 4 ? atoi(argv[4]) : 320;
+  const int accmode = argc > 5 ? atoi(argv[5]) : 0, dist = argc > 6 ? atoi(argv[6]) : 0;
   CHECK(cudaFree(0));
-  if (mode == 0) run<0, 128, 2>(M, N, K);
-  else if (mode == 1) run<1, 128, 3>(M, N, K);
-  else if (mode == 2) run<1, 96, 3>(M, N, K);
-  else if (mode == 3) run<1, 256, 2>(M, N, K);
-  else if (mode == 4) run<1, 160, 3>(M, N, K);
+  if (mode == 0) run<0, 128, 2>(M, N, K, 0, dist);
+  else if (mode == 1) run<1, 128, 3>(M, N, K, accmode == 2 ? 1 : accmode, dist);   // (three accumulators of 128 do not fit)
+  else if (mode == 2) run<1, 96, 3>(M, N, K, accmode, dist);
+  else if (mode == 3) run<1, 256, 2>(M, N, K, 0, dist);
+  else if (mode == 4) run<1, 160, 3>(M, N, K, accmode == 2 ? 1 : accmode, dist);
   return 0;
 }
