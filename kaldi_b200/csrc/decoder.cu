@@ -2018,7 +2018,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
         if (deg > 0) {
           int4 *rp = &x.rec[dd];
           *reinterpret_cast<int2 *>(rp) = make_int2(ebase + off, deg);
-          rp->z = 0;                                          // arcs admitted by this expansion
+          rp->z = 0;                                          // set when this expansion admits an arc
         }
         __syncthreads();
         for (int j = tid; j < total; j += T) {
@@ -2045,7 +2045,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
                 o0 = __ldg(&g.st_off[arc.x]); o1 = __ldg(&g.st_off[arc.x + 1]);
               }
               entry.x = __float_as_int(tot); entry.y = arc.y; entry.w = ds;
-              atomicAdd(&x.rec[owner].z, 1);
+              x.rec[owner].z = 1;                             // only zero / non-zero is ever read: a plain store, no atomic round trip
               const uint32_t nv = f2ord(tot);
               const uint32_t old = atomicMin(reinterpret_cast<uint32_t *>(&hash[ds].y), nv);
               if (nv < old) {
@@ -2114,6 +2114,44 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     return c0b ? ord2f(c0b) : ord2f((uint32_t)hash[tokslot[d]].y);
   };
   if (Nall > N1 && !s.err) {
+    if ((size_t)E * 8 + (size_t)Nall + 16 <= (size_t)p.rs_bytes) {
+      // the fixed point runs out of shared memory (the replay arrays are not built yet): one pass reads the entries,
+      // the iterations touch no scratch
+      uint2 *ent_s = reinterpret_cast<uint2 *>(dyn_smem_base);      // {destination or ~0, owner | 1 << 31 if it cannot propagate}
+      unsigned char *mark_s = reinterpret_cast<unsigned char *>(ent_s + E);
+      for (int d = tid; d < Nall; d += T) { mark_s[d] = (d >= N1); if (d >= N1) x.newseq[d - N1] = -1; }
+      for (int e = tid; e < E; e += T) {
+        const int4 en = x.adj[e];
+        uint2 v = make_uint2(0xffffffffu, 0x80000000u);
+        if (en.w >= 0) {
+          const int o = x.adjo[e];
+          bool prop = en.y != kInfBits;
+          if (prop) { const int4 r = x.rec[o]; prop = (e >= r.x && e < r.x + r.y); }   // not a superseded record
+          v = make_uint2((uint32_t)en.x, (uint32_t)o | (prop ? 0u : 0x80000000u));
+        }
+        ent_s[e] = v;
+      }
+      __syncthreads();
+      for (int it = 0; it < 1000000; it++) {
+        if (tid == 0) s.cont = 0;
+        __syncthreads();
+        for (int e = tid; e < E; e += T) {
+          const uint2 v = ent_s[e];
+          if ((v.y & 0x80000000u) || !mark_s[v.x] || mark_s[v.y]) continue;
+          mark_s[v.y] = 1;
+          s.cont = 1;
+        }
+        __syncthreads();
+        const int again = s.cont;
+        __syncthreads();
+        if (!again) break;
+      }
+      for (int d = tid; d < Nall; d += T) mark[d] = mark_s[d];
+      for (int e = tid; e < E; e += T) {
+        const uint2 v = ent_s[e];
+        if (v.x != 0xffffffffu && !mark_s[v.x]) x.adj[e].y = kInfBits;
+      }
+    } else {
     for (int d = tid; d < Nall; d += T) { mark[d] = (d >= N1); if (d >= N1) x.newseq[d - N1] = -1; }
     __syncthreads();
     for (int it = 0; it < 1000000; it++) {
@@ -2138,6 +2176,8 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       const int4 en = x.adj[e];
       if (en.w >= 0 && !mark[en.x]) x.adj[e].y = kInfBits;
     }
+    }
+    __syncthreads();                                         // (mark / adj are read below; the key area reuses the shared arrays)
     // initial worklist (:852-856) = the emitting tokens in list order, restricted to the marked tokens whose final
     // record admits something.  List order = (first key of the token's bucket, own key): both are read off the table.
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(dyn_smem_base);
@@ -2382,7 +2422,10 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
   // ---- insertion keys of the eps-created tokens: after every arc position, in replay order
   const int PP = P + (Nall - N1);
   for (int d = N1 + tid; d < Nall; d += T) hash[tokslot[d]].z = P + x.newseq[d - N1];
-  for (int w = tid; w < PP; w += T) x.hw[w] = 0u;
+  // the key space fits the (now idle) replay arrays in most frames: bucket heads, their scan and the commit's look-ups
+  // stay in shared memory instead of three round trips to scratch that misses L2
+  uint32_t *hwp = ((size_t)PP * 4 <= (size_t)p.rs_bytes) ? reinterpret_cast<uint32_t *>(dyn_smem_base) : x.hw;
+  for (int w = tid; w < PP; w += T) hwp[w] = 0u;
   __syncthreads();
   B2K_TICK(s, 8);
   // ---- HashList order (hash-list-inl.h:126-175): buckets by first insertion, insertion order inside a bucket.  Every
@@ -2407,17 +2450,17 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       }
     }
     x.tok4[d] = make_int4(hs.x, __float_as_int(ord2f((uint32_t)hs.y)), (int)F, within);
-    if (F == (uint32_t)hs.z) x.hw[F] = (uint32_t)pop;
+    if (F == (uint32_t)hs.z) hwp[F] = (uint32_t)pop;
   }
   __syncthreads();
-  block_excl_scan_array<T>(x.hw, PP, s.redi);
+  block_excl_scan_array<T>(hwp, PP, s.redi);
   B2K_TICK(s, 9);
   const bool fits = (ctx.tbase + Nall <= p.max_tokens);
   if (!fits) { if (tid == 0) B2K_SET_ERR(s, B2K_ERR_OVERFLOW); __syncthreads(); return; }
   // ---- commit: tokens to the arena in list order, the emitting ranges for the next frame's expansion
   for (int d = tid; d < Nall; d += T) {
     const int4 t = x.tok4[d];
-    const int r = (int)x.hw[t.z] + t.w;
+    const int r = (int)hwp[t.z] + t.w;
     tok_state[ctx.tbase + r] = t.x;
     tok_cost[ctx.tbase + r] = __int_as_float(t.y);
     const int4 tr = x.trec[d];
