@@ -625,7 +625,12 @@ __device__ __forceinline__ TsSlab ts_slab(const int *term_slab0, int n_terms, in
   return {ti, (s - term_slab0[ti]) * TS_BK};
 }
 
-template <int TN, int SB>
+// FL > 0: the accumulator is emptied every FL slabs (K = 32 FL).  The tensor core adds into its fp32 accumulator with
+// truncation, so the error of a long contraction grows with the number of additions into the same accumulator (full-width
+// tdnn_1d, K up to 3072: 1.8e-4 of the output scale against 1.9e-6 for the FFMA kernel, tools/nnet_precision_probe.py).
+// With the flush a segment's partial sum is read out of TMEM and added to a running tile in shared memory in fp32,
+// round to nearest, as the software-accumulation schemes for 3xTF32 do; short contractions (<= FL slabs) never flush.
+template <int TN, int SB, int FL>
 __global__ void __launch_bounds__(TS_THREADS, (TN <= 128 ? 2 : 1))
 nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __grid_constant__ TsMaps maps) {
   constexpr uint32_t B_TILE = TN * 128;                       // bytes of one hi (or lo) tile: TN rows x 32 floats
@@ -634,18 +639,21 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
   static_assert(SB * B_STAGE >= 8 * 32 * 33 * 4, "the W ring doubles as the epilogue's transpose space");
   extern __shared__ __align__(1024) unsigned char ts_smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ts_smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) unsigned long long bars[2 * SB + 5];   // b_full[SB], b_empty[SB], a_full[2], a_empty[2], acc_full
+  __shared__ __align__(8) unsigned long long bars[2 * SB + 7];   // b_full[SB], b_empty[SB], a_full[2], a_empty[2], acc_full, flush_full, flush_done
   __shared__ uint32_t tmem_base_s;
   __shared__ int term_slab0[13];
   const int tid = threadIdx.x, warp = tid >> 5, lane_id = tid & 31;
   const int M = c.batch * op.rows * (op.hsplit > 1 ? op.hsplit : 1);
-  const int m0 = blockIdx.x * TS_BM, n0 = blockIdx.y * TN;
+  const int ntn_ = (op.N + TN - 1) / TN;
+  const int m0 = (int)(blockIdx.x / (unsigned)ntn_) * TS_BM, n0 = (int)(blockIdx.x % (unsigned)ntn_) * TN;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[0]);
   auto B_FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
   auto B_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(SB + s); };
   auto A_FULL = [&](int s) { return bar0 + 8u * (uint32_t)(2 * SB + s); };
   auto A_EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(2 * SB + 2 + s); };
   const uint32_t ACC_FULL = bar0 + 8u * (uint32_t)(2 * SB + 4);
+  const uint32_t FLUSH_FULL = bar0 + 8u * (uint32_t)(2 * SB + 5), FLUSH_DONE = bar0 + 8u * (uint32_t)(2 * SB + 6);
+  float *run_s = reinterpret_cast<float *>(smem + (size_t)SB * B_STAGE);   // FL > 0: running sums [TN][128], column major
 
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
@@ -655,6 +663,7 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
     for (int s = 0; s < SB; s++) { ts_mbar_init(B_FULL(s), 1); ts_mbar_init(B_EMPTY(s), 1); }
     for (int s = 0; s < 2; s++) { ts_mbar_init(A_FULL(s), 128); ts_mbar_init(A_EMPTY(s), 1); }
     ts_mbar_init(ACC_FULL, 1);
+    ts_mbar_init(FLUSH_FULL, 1); ts_mbar_init(FLUSH_DONE, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&maps.hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&maps.lo) : "memory");
@@ -691,6 +700,12 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
     if (lane_id == 0) {
       for (int s = 0; s < nslabs; s++) {
         const int st = s % SB, as = s & 1;
+        bool fresh = (s == 0);
+        if (FL > 0 && s > 0 && s % (FL > 0 ? FL : 1) == 0) {                 // segment boundary: hand the accumulator to the flush, start a new sum
+          ts_commit(FLUSH_FULL);
+          t5_mbar_wait(FLUSH_DONE, ((uint32_t)(s / (FL > 0 ? FL : 1) - 1)) & 1u);
+          fresh = true;
+        }
         t5_mbar_wait(B_FULL(st), ((uint32_t)(s / SB)) & 1u);
         t5_mbar_wait(A_FULL(as), ((uint32_t)(s >> 1)) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -699,7 +714,7 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
         for (int ks = 0; ks < TS_BK / 8; ks++) {
           const uint64_t dbh = ts_desc_sw128(bh + (uint32_t)ks * 32u), dbl = ts_desc_sw128(bl + (uint32_t)ks * 32u);
           const uint32_t ah = tmem_a + (uint32_t)as * 64u + (uint32_t)ks * 8u, al = ah + 32u;
-          ts_mma(tmem_acc, al, dbh, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+          ts_mma(tmem_acc, al, dbh, idesc, (!fresh || ks > 0) ? 1u : 0u);
           ts_mma(tmem_acc, ah, dbl, idesc, 1u);
           ts_mma(tmem_acc, ah, dbh, idesc, 1u);
         }
@@ -748,6 +763,30 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
         for (int e = 0; e < 32; e++) { const int ke = k0e + e; cur[e] = (ke >= 0 && ke < klen) ? arow[ke] : 0.f; }
       }
     };
+    constexpr int HALF = TN / 2;
+    const int n_flush = (FL > 0 && nslabs > 0) ? (nslabs - 1) / (FL > 0 ? FL : 1) : 0;
+    int flushed = 0;
+    auto flush = [&]() {                                      // this thread's row, its group's column half: TMEM -> running tile
+      t5_mbar_wait(FLUSH_FULL, (uint32_t)flushed & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c0 = g * HALF; c0 < (g + 1) * HALF; c0 += 16) {   // 16 columns at a time (HALF = 48 or 80): the next slab's 32 values stay in registers
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          float *rp = run_s + (size_t)(c0 + j) * TS_BM + r;    // consecutive rows across a warp: conflict free
+          *rp = flushed ? __fadd_rn(*rp, __uint_as_float(v[j])) : __uint_as_float(v[j]);
+        }
+      }
+      flushed++;
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      ts_mbar_arrive(FLUSH_DONE);
+    };
     if (g < nslabs) fetch(g);
     for (int s = g; s < nslabs; s += 2) {
       uint32_t hv[32];
@@ -764,10 +803,14 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       ts_mbar_arrive(A_FULL(g));
+      // boundaries lie before slabs FL, 2 FL, ...: this slab's A is already in place, so the flush costs the tensor core only
+      // the read-out itself
+      if (FL > 0) while (flushed < s / (FL > 0 ? FL : 1)) flush();
     }
     // ---- epilogue.  Warp (q, g): rows 32q .. 32q+31, columns g*TN/2 .. +TN/2, 32 columns at a time: TMEM gives a
     //      thread its row's 32 columns; a 32 x 32 transpose in shared memory gives it one column of the 32 rows, so the
     //      per-column parameters are loaded once and every row is stored as one 128-byte segment.
+    if (FL > 0) while (flushed < n_flush) flush();             // (a group whose last slab lies before the last boundary)
     if (nslabs > 0) t5_mbar_wait(ACC_FULL, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float *tsp = reinterpret_cast<float *>(smem) + (size_t)(warp - 2) * (32 * 33);   // the W ring is idle now
@@ -779,7 +822,6 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
       if (op.has_res) rrow = src_row_ptr(c, op.res, x.lane, map_row(op.res, x.i));
     }
     const unsigned long long orow_u = reinterpret_cast<unsigned long long>(orow), rrow_u = reinterpret_cast<unsigned long long>(rrow);
-    constexpr int HALF = TN / 2;
     for (int c0 = g * HALF; c0 < (g + 1) * HALF; c0 += 32) {
       uint32_t v[32];
       const int ncols = min(32, (g + 1) * HALF - c0);         // TN / 2 need not be a multiple of 32 (TN = 96, 160)
@@ -798,6 +840,11 @@ nnet_gemm_ts_kernel(const __grid_constant__ OpDev op, const RunCtx c, const __gr
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = 0u;
+      }
+      if (FL > 0 && n_flush > 0) {                             // last segment + the running sums of the earlier ones
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          if (j < ncols) v[j] = __float_as_uint(__fadd_rn(run_s[(size_t)(c0 + j) * TS_BM + r], __uint_as_float(v[j])));
       }
       __syncwarp();
 #pragma unroll
@@ -936,6 +983,19 @@ static float host_tf32_rna(float x) {                        // cvt.rna.tf32.f32
   return r;
 }
 
+// Accumulator flush interval of the long contractions, in K slabs of 32 (B2K_NNET_FLUSH=0 switches it off for A/B runs).
+#define TS_FL 16
+static int ts_flush_slabs() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("B2K_NNET_FLUSH"); v = (e && atoi(e) == 0) ? 0 : TS_FL; }
+  return v;
+}
+static int ts_num_slabs(const OpDev &op) {
+  int n = 0;
+  for (int ti = 0; ti < op.n_terms; ti++) n += (op.terms[ti].klen + (op.terms[ti].k0 & 3) + TS_BK - 1) / TS_BK;
+  return n;
+}
+
 static int ts_pick_tn(int N) {
   const int cand[3] = {128, 96, 160};                        // ties go to 128, then 96 (both keep two CTAs per SM)
   int best = 128, best_pad = (N + 127) / 128 * 128;
@@ -969,16 +1029,19 @@ static int ts_make_map(CUtensorMap *m, const float *dptr, int N, int Kp, int TN)
 }
 
 extern "C++" {
-template <int TN, int SB>
+template <int TN, int SB, int FL>
 static int ts_launch(const OpDev &op, const RunCtx &c, const TsMaps &maps, long long M, cudaStream_t st) {
   static bool configured = false;
-  const int smem = SB * 2 * TN * 128 + 1024;
+  const int smem = SB * 2 * TN * 128 + (FL > 0 ? TN * TS_BM * 4 : 0) + 1024;
   if (!configured) {
-    B2K_CUDA_CHECK(cudaFuncSetAttribute(nnet_gemm_ts_kernel<TN, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B2K_CUDA_CHECK(cudaFuncSetAttribute(nnet_gemm_ts_kernel<TN, SB, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((unsigned)((M + TS_BM - 1) / TS_BM), (unsigned)((op.N + TN - 1) / TN));
-  nnet_gemm_ts_kernel<TN, SB><<<grid, TS_THREADS, smem, st>>>(op, c, maps);
+  // one-dimensional grid, column tile fastest: the CTAs that share a block of A rows are launched together, so the
+  // rows come out of L2 for all but the first of them (with the column tile in blockIdx.y they were N/TN waves apart
+  // and every column tile re-read its A rows from HBM)
+  const long long ntn = (op.N + TN - 1) / TN, ntm = (M + TS_BM - 1) / TS_BM;
+  nnet_gemm_ts_kernel<TN, SB, FL><<<(unsigned)(ntm * ntn), TS_THREADS, smem, st>>>(op, c, maps);
   return B2K_OK;
 }
 }  // extern "C++"
@@ -1073,6 +1136,10 @@ int b2k_nnet_create(const b2k_nnet_node *nodes, int32_t n_nodes, const b2k_nnet_
         if (d.type != 0) continue;
         const int Kp = (d.K + 3) / 4 * 4;
         nn->ts_tn[i] = ts_pick_tn(d.N);
+        if (nn->ts_tn[i] == 128 && ts_flush_slabs() > 0 && ts_num_slabs(d) > ts_flush_slabs()) {
+          // the running tile of a flushed 128-column tile does not fit beside the weight ring at two CTAs per SM
+          nn->ts_tn[i] = ((d.N + 159) / 160 * 160 < (d.N + 95) / 96 * 96) ? 160 : 96;
+        }
         const float *hi = nn->d_wsplit + off[i], *lo = hi + (size_t)d.N * Kp;
         if (getenv("B2K_NNET_SYNC")) fprintf(stderr, "[b2k nnet] op %zu: N %d K %d Kp %d rows %d hsplit %d terms %d tn %d hi %p lo %p\n", i, d.N, d.K, Kp, d.rows, d.hsplit, d.n_terms, nn->ts_tn[i], (const void *)hi, (const void *)lo);
         if ((rc = ts_make_map(&nn->ts_maps[i].hi, hi, d.N, Kp, nn->ts_tn[i]))) return rc;
@@ -1136,9 +1203,10 @@ int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32
         nnet_gemm_kernel<<<grid, 256, 0, st>>>(op, c);
       } else if (gemm_mode() == 3) {
         int rc2;
-        if (nn->ts_tn[i] == 96) rc2 = ts_launch<96, 3>(op, c, nn->ts_maps[i], M, st);
-        else if (nn->ts_tn[i] == 160) rc2 = ts_launch<160, 3>(op, c, nn->ts_maps[i], M, st);
-        else rc2 = ts_launch<128, 3>(op, c, nn->ts_maps[i], M, st);
+        const bool long_k = ts_flush_slabs() > 0 && ts_num_slabs(op) > ts_flush_slabs();   // (create() gave such ops a 96 / 160 tile)
+        if (nn->ts_tn[i] == 96) rc2 = long_k ? ts_launch<96, 2, TS_FL>(op, c, nn->ts_maps[i], M, st) : ts_launch<96, 3, 0>(op, c, nn->ts_maps[i], M, st);
+        else if (nn->ts_tn[i] == 160) rc2 = long_k ? ts_launch<160, 3, TS_FL>(op, c, nn->ts_maps[i], M, st) : ts_launch<160, 3, 0>(op, c, nn->ts_maps[i], M, st);
+        else rc2 = ts_launch<128, 3, 0>(op, c, nn->ts_maps[i], M, st);
         if (rc2) return rc2;
       } else if (gemm_mode() == 2) {
         static bool configured5 = false;
