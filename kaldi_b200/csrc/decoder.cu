@@ -140,6 +140,7 @@ struct DecParams {
   uint32_t *v2_c0, *v2_adjc, *v2_qstamp, *v2_hw;
   int32_t *v2_pf;
   int32_t v2_hw_len;
+  int32_t cid_smem;         // second generation: 16-bit compact ids of the replay in the upper half of the shared arc area
   int32_t v2_l1_shift;      // level-1 window = 2^shift x the reference's HashList size (rounded up to a power of two)
 };
 
@@ -359,7 +360,7 @@ struct __align__(16) DecShared {
   float scanf_[2][T / 32];
   int q_n;
   int used_l2;
-  int rs_n, rs_e, rs_ok;
+  int rs_n, rs_e, rs_ok, rs_eov;
   unsigned long long prof[16];
   long long tlast;
 };
@@ -2113,8 +2114,10 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     const uint32_t c0b = x.c0[d];
     return c0b ? ord2f(c0b) : ord2f((uint32_t)hash[tokslot[d]].y);
   };
+  bool owners_marked = false;                                // every entry left alive has a marked owner (shared-memory marking ran)
   if (Nall > N1 && !s.err) {
     if ((size_t)E * 8 + (size_t)Nall + 16 <= (size_t)p.rs_bytes) {
+      owners_marked = true;
       // the fixed point runs out of shared memory (the replay arrays are not built yet): one pass reads the entries,
       // the iterations touch no scratch
       uint2 *ent_s = reinterpret_cast<uint2 *>(dyn_smem_base);      // {destination or ~0, owner | 1 << 31 if it cannot propagate}
@@ -2149,7 +2152,9 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       for (int d = tid; d < Nall; d += T) mark[d] = mark_s[d];
       for (int e = tid; e < E; e += T) {
         const uint2 v = ent_s[e];
-        if (v.x != 0xffffffffu && !mark_s[v.x]) x.adj[e].y = kInfBits;
+        // dead for the replay: destination not an ancestor of a created token, or the entry cannot propagate (superseded
+        // record / cannot fire) -- the links pass reads only arc id and destination of the final records
+        if (v.x != 0xffffffffu && (!mark_s[v.x] || (v.y & 0x80000000u))) x.adj[e].y = kInfBits;
       }
     } else {
     for (int d = tid; d < Nall; d += T) { mark[d] = (d >= N1); if (d >= N1) x.newseq[d - N1] = -1; }
@@ -2240,7 +2245,41 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
   int *dof = wl0;                                            // compact id -> creation index (worklists are idle now)
   bool replay_done = false;
   if (p.rs_rcap > 0 && !s.err && Nall > N1 && qcarry <= p.rs_qcap) {
-    if (tid == 0) { s.rs_n = 0; s.rs_e = 0; s.rs_ok = 1; }
+    if (tid == 0) { s.rs_n = 0; s.rs_e = 0; s.rs_ok = 1; s.rs_eov = 0; }
+    // compact ids of the replay's tokens: 16-bit, in shared memory behind the walk's arrays when the frame fits
+    // They live in the upper half of the arc area (2 x ecap ids): the walk's arcs fit the lower half in almost every
+    // frame; when they do not, the ids are spilled to scratch and the arcs are compacted again into the whole area.
+    unsigned short *cid_s = reinterpret_cast<unsigned short *>(en_s + p.rs_ecap / 2);
+    const bool cid_in_smem = owners_marked && p.cid_smem && p.rs_ecap >= 2 && Nall <= 2 * p.rs_ecap;
+    bool use_s = cid_in_smem;
+    auto cidv = [&](int d) -> int {
+      if (use_s) { const unsigned v = cid_s[d]; return v >= 0xfffeu ? -1 : (int)v; }
+      return cid[d];
+    };
+    if (cid_in_smem) {
+      for (int d = tid; d < Nall; d += T) cid_s[d] = 0xffffu;
+      __syncthreads();
+      for (int k = tid; k < qcarry; k += T) cid_s[x.queue[k]] = 0xfffeu;
+      for (int e = tid; e < E; e += T) {
+        const int4 en = x.adj[e];
+        if (en.w < 0 || en.y == kInfBits) continue;
+        cid_s[en.x] = 0xfffeu;
+        cid_s[x.adjo[e]] = 0xfffeu;
+      }
+      __syncthreads();
+      for (int d = tid; d < Nall; d += T) {
+        if (cid_s[d] != 0xfffeu) continue;
+        const int id = atomicAdd(&s.rs_n, 1);
+        if (id < p.rs_rcap) {
+          tk_s[id] = make_float2(cost_before_closure(d), __int_as_float(0));
+          ns_s[id] = 0xffff;
+          dof[id] = d;
+          cid_s[d] = (unsigned short)id;
+        } else {
+          s.rs_ok = 0;
+        }
+      }
+    } else {
     for (int d = tid; d < Nall; d += T) cid[d] = -1;
     __syncthreads();
     auto claim = [&](int d) {
@@ -2264,7 +2303,10 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       if (cid[en.x] == -1) claim(en.x);
       if (cid[o] == -1) claim(o);
     }
+    }
     __syncthreads();
+    for (int attempt = 0; attempt < 2; attempt++) {
+    const int ecap_eff = use_s ? p.rs_ecap / 2 : p.rs_ecap;
     if (s.rs_ok) {
       const int R = s.rs_n;
       const int lane_id = tid & 31;
@@ -2285,12 +2327,12 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
         }
         if (!total) continue;
         const int eo = atomicAdd(&s.rs_e, total);
-        if (eo + total > p.rs_ecap) { s.rs_ok = 0; continue; }
+        if (eo + total > ecap_eff) { s.rs_ok = 0; s.rs_eov = 1; continue; }
         int pos = eo;
 #pragma unroll
         for (int i = 0; i < 8; i++)
           if (en[i].w >= 0 && en[i].y != kInfBits)
-            en_s[pos++] = make_float2(__int_as_float(en[i].y), __int_as_float(cid[en[i].x]));
+            en_s[pos++] = make_float2(__int_as_float(en[i].y), __int_as_float(cidv(en[i].x)));
         tk_s[id].y = __int_as_float(eo | (total << 16));
       }
       __syncthreads();
@@ -2309,7 +2351,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
         int eo = 0;
         if (lane_id == 0) eo = atomicAdd(&s.rs_e, total);
         eo = __shfl_sync(0xffffffffu, eo, 0);
-        if (eo + total > p.rs_ecap || total > 0xffff) { if (lane_id == 0) s.rs_ok = 0; continue; }
+        if (eo + total > ecap_eff || total > 0xffff) { if (lane_id == 0) { s.rs_ok = 0; if (total <= 0xffff) s.rs_eov = 1; } continue; }
         int pos = eo;
         for (int b0 = 0; b0 < r.y; b0 += 32) {
           int i = b0 + lane_id;
@@ -2318,15 +2360,24 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
           uint32_t m = __ballot_sync(0xffffffffu, keep);
           if (keep) {
             int q = pos + __popc(m & ((1u << lane_id) - 1u));
-            en_s[q] = make_float2(__int_as_float(en.y), __int_as_float(cid[en.x]));
+            en_s[q] = make_float2(__int_as_float(en.y), __int_as_float(cidv(en.x)));
           }
           pos += __popc(m);
         }
         if (lane_id == 0) tk_s[id].y = __int_as_float(eo | (total << 16));
       }
-      for (int k = tid; k < qcarry; k += T) q_s[k] = (unsigned short)cid[x.queue[k]];
+      for (int k = tid; k < qcarry; k += T) q_s[k] = (unsigned short)cidv(x.queue[k]);
     }
     __syncthreads();
+    if (!(use_s && s.rs_eov && attempt == 0)) break;         // uniform
+    // the arcs did not fit beside the ids: ids to scratch, arcs again into the whole area
+    for (int d = tid; d < Nall; d += T) cid[d] = cidv(d);
+    for (int id = tid; id < min(s.rs_n, p.rs_rcap); id += T) tk_s[id].y = __int_as_float(0);
+    __syncthreads();
+    if (tid == 0) { s.rs_e = 0; s.rs_ok = 1; s.rs_eov = 0; }
+    use_s = false;
+    __syncthreads();
+    }
     if (s.rs_ok && tid == 0) {
       int qn = qcarry, next = 0;
       bool ok = true;
@@ -2372,7 +2423,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       replay_done = true;
       if (!s.err)
         for (int d = N1 + tid; d < Nall; d += T) {
-          int id = cid[d];
+          int id = cidv(d);
           if (id >= 0) x.newseq[d - N1] = (int)ns_s[id];
           else B2K_SET_ERR(s, B2K_ERR_STATE);                // an eps-created token is always some record's destination
         }
@@ -3238,6 +3289,7 @@ struct b2k_dec {
   DecParams p;
   int threads_override = 0, fin_threads = 1024, num_sms = 0;   // tuning knobs, read from the environment at creation
   int ctas_override = 0;                // B2K_DEC_CTAS (256-thread CTAs only)
+  bool cid_smem_off = false;            // B2K_DEC_CID_SMEM=0
   int nslots = 0;                       // scratch slots = the largest grid any per-lane launch uses (resident CTAs)
   int prof = 0;                         // B2K_DEC_PROF=1: per-phase cycle counters in the reference-order kernel
   int ll_smem_off = 0;                  // B2K_DEC_LL_SMEM=0: leave the log-likelihood rows in global memory
@@ -3397,6 +3449,7 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     if (const char *e = getenv("B2K_DEC_PROF")) d->prof = atoi(e) != 0;
     if (const char *e = getenv("B2K_DEC_GRID")) d->grid_cap = atoi(e);
     if (const char *e = getenv("B2K_DEC_LL_SMEM")) d->ll_smem_off = atoi(e) == 0;
+    if (const char *e = getenv("B2K_DEC_CID_SMEM")) d->cid_smem_off = atoi(e) == 0;
     // Persistent launches: at most two CTAs per SM are ever resident (512-thread reference-order CTAs; the
     // order-free and finalize kernels use one slot per CTA of their own, smaller grids), so that is the
     // number of scratch slots, whatever the batch size.
@@ -3617,6 +3670,7 @@ static int launch_v2_t(const b2k_dec *d, DecParams p, int n, int ctas_per_sm, cu
   p.ll_smem = (!d->ll_smem_off && p.num_pdfs > 0 && !p.do_init && p.row_stride >= p.num_pdfs &&
                static_smem + std::max(smem, ll_bytes) <= per_cta) ? 1 : 0;
   if (p.ll_smem) smem = std::max(smem, ll_bytes);
+  p.cid_smem = d->cid_smem_off ? 0 : 1;
   if (smem > configured) {
     B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_v2_kernel<T, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -140,6 +140,8 @@ static void apply(const char *path, const std::map<std::string, std::pair<std::s
     for (size_t i = 0; i < n; i++) if (e.first == opts[i].name) o = &opts[i];
     if (!o) throw ConfError{"Invalid option --" + e.first + " in config file " + path};
     const std::string &v = e.second.first;
+    // parse-options.cc:540-547: only a bool may be given without '=' (--x means true); "--x" for any other type is an error
+    if (o->kind != 'b' && !e.second.second) throw ConfError{"Invalid option --" + e.first + " (option format is --x=y)."};
     switch (o->kind) {
       case 'b':
         if (e.second.second && v.empty()) throw ConfError{"Invalid option --" + e.first + "="};      // parse-options.cc:545: --x is true, --x= is not
@@ -220,6 +222,11 @@ int b2k_ivec_cfg_from_conf(const char *conf_path, b2k_ivec_cfg *cfg, b2k_ivec_pa
     if (p.cmvn_config[0]) apply(p.cmvn_config, read_conf(p.cmvn_config), cmvn, sizeof(cmvn) / sizeof(cmvn[0]));
     if (norm_vars || !norm_means || skip_dims[0]) throw ConfError{"the extractor's online CMVN must be mean-only over all dimensions (norm-vars / skip-dims are not supported)"};
     if (p.online_cmvn_iextractor) throw ConfError{"--online-cmvn-iextractor=true is not supported"};
+    // OnlineIvectorFeature has two more modes this library has no kernel for: an i-vector per requested frame instead of the
+    // most recent one (online-ivector-feature.cc:327-349) and the greedy stats update (:392-402).  Values that would change
+    // what the reference computes are errors, not silently ignored.
+    if (!p.use_most_recent_ivector) throw ConfError{"--use-most-recent-ivector=false is not supported (the i-vector of a chunk is the most recent estimate)"};
+    if (p.greedy_ivector_extractor) throw ConfError{"--greedy-ivector-extractor=true is not supported"};
   } catch (const ConfError &e) {
     return b2k::set_error(B2K_ERR_INVALID, "b2k_ivec_cfg_from_conf", e.msg.c_str());
   }
@@ -293,6 +300,8 @@ extern "C" int b2k_pipeline_cfg_apply_options(const char *text, b2k_pipeline_cfg
   try {
     std::map<std::string, std::pair<std::string, bool>> kv;
     bool fpc_given = false;
+    std::string sil_phones;
+    float sil_weight = 1.0f;
     std::string t(text), tok;
     size_t i = 0;
     while (i <= t.size()) {
@@ -308,12 +317,18 @@ extern "C" int b2k_pipeline_cfg_apply_options(const char *text, b2k_pipeline_cfg
           kv[key] = {val, eq != std::string::npos};
           if (key == "frames-per-chunk") fpc_given = true;
         }
+        // OnlineSilenceWeightingConfig::Active() (online-ivector-feature.h:414): silence-phones given and silence-weight != 1
+        // re-weights the i-vector statistics from the decoder's traceback, which this pipeline does not do
+        if (key == "ivector-silence-weighting.silence-phones") sil_phones = val;
+        if (key == "ivector-silence-weighting.silence-weight") sil_weight = (float)to_num(key, val, false);
         tok.clear();
       }
       i++;
     }
     apply("(options)", kv, opts, sizeof(opts) / sizeof(opts[0]));
     if (extra_left != 0) throw ConfError{"--extra-left-context-initial other than 0 is not supported"};
+    if (!sil_phones.empty() && sil_weight != 1.0f)
+      throw ConfError{"--ivector-silence-weighting.silence-weight other than 1 with silence phones is not supported (i-vector statistics are not re-weighted from the traceback)"};
     if (do_endpointing) throw ConfError{"--do-endpointing=true is not supported by the batched pipeline (whole utterances are decoded; the endpoint rules are b2k_endpoint_*)"};
     if (!online_flag) c.chunk_length_secs = -1.0f;         // --online=false: the tool sets chunk_length_secs = -1 = the whole file in one call (:128-130)
     if (sub <= 0) throw ConfError{"--frame-subsampling-factor must be positive"};

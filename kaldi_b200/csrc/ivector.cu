@@ -52,6 +52,7 @@ struct IvecRun {
 };
 
 #define IV_WARPS 8
+#define IV_FR 4
 
 __global__ void __launch_bounds__(IV_WARPS * 32) ivec_front_kernel(IvecParams p, IvecRun r, int frames_per_cta) {
   extern __shared__ float sm[];
@@ -59,107 +60,130 @@ __global__ void __launch_bounds__(IV_WARPS * 32) ivec_front_kernel(IvecParams p,
   const int LW = SD + 1;                    // lda row length
   float *s_lda = sm;                        // feat_dim * LW
   float *s_w = s_lda + p.feat_dim * LW;     // per warp: 2*SD + feat_dim
-  const int per_warp = 2 * SD + p.feat_dim;
+  const int per_warp = 2 * SD + IV_FR * p.feat_dim;
   const int tid = threadIdx.x, lane_id = tid & 31, warp = tid >> 5;
   for (int i = tid; i < p.feat_dim * LW; i += blockDim.x) s_lda[i] = p.lda[i];
   __syncthreads();
-  float *spl_raw = s_w + warp * per_warp, *spl_norm = spl_raw + SD, *xa = spl_norm + SD;
+  float *spl_raw = s_w + warp * per_warp, *spl_norm = spl_raw + SD, *xa0 = spl_norm + SD;   // xa0: IV_FR frames x feat_dim
   const int L = blockIdx.y;
   const float *feats = r.d_feats[L];
   const float *cm = r.cmvn + (size_t)L * r.T * p.base_dim;
   const int f0 = blockIdx.x * frames_per_cta, f1 = min(f0 + frames_per_cta, r.T);
   const int W = p.splice_left + p.splice_right + 1;
-  for (int t = f0 + warp; t < f1; t += IV_WARPS) {
-    // splice with edge clamping (online-feature.cc:504-519)
-    for (int k = lane_id; k < SD; k += 32) {
-      int w = k / p.base_dim, d = k - w * p.base_dim;
-      int t2 = t - p.splice_left + w;
-      t2 = min(max(t2, 0), r.T - 1);
-      spl_raw[k] = feats[(size_t)t2 * r.feat_stride + d];
-      spl_norm[k] = cm[(size_t)t2 * p.base_dim + d];
+  (void)W;
+  // IV_FR frames per warp pass: the UBM parameters (164 KB for 512 Gaussians x 40 dims, more than L1) are loaded once per
+  // pass and applied to all of them, so the L2 -> SM traffic of the kernel is 1 / IV_FR of one-frame-per-pass (97 GB per
+  // 592-utterance step, the kernel sat at L2 bandwidth: 15.6 ms).  Every (Gaussian, frame) sum keeps its order over d.
+  for (int t0 = f0 + warp * IV_FR; t0 < f1; t0 += IV_WARPS * IV_FR) {
+    const int nfr = min(IV_FR, f1 - t0);
+    for (int f = 0; f < nfr; f++) {
+      const int t = t0 + f;
+      float *xa = xa0 + f * p.feat_dim;
+      // splice with edge clamping (online-feature.cc:504-519)
+      for (int k = lane_id; k < SD; k += 32) {
+        int w = k / p.base_dim, d = k - w * p.base_dim;
+        int t2 = t - p.splice_left + w;
+        t2 = min(max(t2, 0), r.T - 1);
+        spl_raw[k] = feats[(size_t)t2 * r.feat_stride + d];
+        spl_norm[k] = cm[(size_t)t2 * p.base_dim + d];
+      }
+      __syncwarp();
+      // OnlineTransform: y = offset + A x, both paths
+      float *lraw = r.lda_raw + ((size_t)L * r.T + t) * p.feat_dim;
+      for (int j = lane_id; j < p.feat_dim; j += 32) {
+        const float *row = s_lda + j * LW;
+        float a0 = 0.f, a1 = 0.f;
+        for (int k = 0; k < SD; k++) { float w = row[k]; a0 = fmaf(w, spl_raw[k], a0); a1 = fmaf(w, spl_norm[k], a1); }
+        lraw[j] = row[SD] + a0;
+        xa[j] = row[SD] + a1;
+      }
+      __syncwarp();
     }
-    (void)W;
-    __syncwarp();
-    // OnlineTransform: y = offset + A x, both paths
-    float *lraw = r.lda_raw + ((size_t)L * r.T + t) * p.feat_dim;
-    for (int j = lane_id; j < p.feat_dim; j += 32) {
-      const float *row = s_lda + j * LW;
-      float a0 = 0.f, a1 = 0.f;
-      for (int k = 0; k < SD; k++) { float w = row[k]; a0 = fmaf(w, spl_raw[k], a0); a1 = fmaf(w, spl_norm[k], a1); }
-      lraw[j] = row[SD] + a0;
-      xa[j] = row[SD] + a1;
-    }
-    __syncwarp();
-    // DiagGmm log-likelihoods of the normalised path
-    float best = -INFINITY;
-    float ll[16];
+    // DiagGmm log-likelihoods of the normalised path, IV_FR frames against one load of the parameters
+    float llf[IV_FR][16];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-      int g = lane_id + 32 * i;
-      float v = -INFINITY;
+      const int g = lane_id + 32 * i;
+      float a1[IV_FR], a2[IV_FR];
+#pragma unroll
+      for (int f = 0; f < IV_FR; f++) { a1[f] = 0.f; a2[f] = 0.f; }
       if (g < p.num_gauss) {
         const float *mv = p.means_invvars + g, *iv = p.inv_vars + g;      // [feat_dim][G]
-        float a1 = 0.f, a2 = 0.f;
         for (int d = 0; d < p.feat_dim; d++) {
-          float x = xa[d];
-          a1 = fmaf(__ldg(&mv[(size_t)d * p.num_gauss]), x, a1);
-          a2 = fmaf(__ldg(&iv[(size_t)d * p.num_gauss]), x * x, a2);
+          const float m = __ldg(&mv[(size_t)d * p.num_gauss]), v = __ldg(&iv[(size_t)d * p.num_gauss]);
+#pragma unroll
+          for (int f = 0; f < IV_FR; f++) {
+            const float x = xa0[f * p.feat_dim + d];          // (frames beyond nfr: stale values, results unused)
+            a1[f] = fmaf(m, x, a1[f]);
+            a2[f] = fmaf(v, x * x, a2[f]);
+          }
         }
-        v = __ldg(&p.gconsts[g]) + a1;
-        v = v + (-0.5f) * a2;
-      }
-      ll[i] = v;
-      best = fmaxf(best, v);
-    }
-    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-    // VectorToPosteriorEntry: candidates like > max + log(min_post), post = exp(like - max)
-    const float cutoff = best + logf(p.min_post);
-    float post[16];
-    int ncand = 0;
+        const float gc = __ldg(&p.gconsts[g]);
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-      bool c = (p.min_post != 0.0f) && (ll[i] > cutoff);
-      post[i] = c ? expf(ll[i] - best) : -1.0f;
-      ncand += c;
-    }
-    ncand = __reduce_add_sync(0xffffffffu, ncand);
-    if (ncand == 0) {     // none reached the threshold (or min_post == 0): take them all (:467-473)
+        for (int f = 0; f < IV_FR; f++) { float v = gc + a1[f]; llf[f][i] = v + (-0.5f) * a2[f]; }
+      } else {
 #pragma unroll
-      for (int i = 0; i < 16; i++) post[i] = (lane_id + 32 * i < p.num_gauss) ? expf(ll[i] - best) : -1.0f;
-    }
-    // top num_gselect by posterior (descending)
-    float sel_v[8]; int sel_i[8]; int nsel = 0;
-    for (int s = 0; s < p.num_gselect && s < 8; s++) {
-      float bv = -1.0f; int bi = -1;
-#pragma unroll
-      for (int i = 0; i < 16; i++) if (post[i] > bv) { bv = post[i]; bi = lane_id + 32 * i; }
-      // warp arg-max (ties -> lowest index)
-      for (int o = 16; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi >= 0 && (bi < 0 || oi < bi))) { bv = ov; bi = oi; }
-      }
-      if (bi < 0 || bv < 0.f) break;
-      sel_v[nsel] = bv; sel_i[nsel] = bi; nsel++;
-      if ((bi & 31) == lane_id) {
-        int slot = bi >> 5;
-#pragma unroll
-        for (int i = 0; i < 16; i++) if (i == slot) post[i] = -1.0f;
+        for (int f = 0; f < IV_FR; f++) llf[f][i] = -INFINITY;
       }
     }
-    // tail pruning and renormalisation (:492-503)
-    float tot = 0.f;
-    for (int s = 0; s < nsel; s++) tot += sel_v[s];
-    const float cut2 = p.min_post * tot;
-    while (nsel > 1 && sel_v[nsel - 1] < cut2) { tot -= sel_v[nsel - 1]; nsel--; }
-    const float inv_tot = 1.0f / tot;
-    if (lane_id == 0) {
-      size_t o = ((size_t)L * r.T + t) * 8;
-      const float sc = p.posterior_scale * 1.0f;           // posterior_scale * frame weight (1.0)
-      for (int s = 0; s < nsel; s++) { r.post_idx[o + s] = sel_i[s]; r.post_val[o + s] = (sel_v[s] * inv_tot) * sc; }
-      r.post_cnt[(size_t)L * r.T + t] = nsel;
+#pragma unroll
+    for (int f = 0; f < IV_FR; f++) {
+      if (f >= nfr) break;
+      const int t = t0 + f;
+      float (&ll)[16] = llf[f];
+      float best = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 16; i++) best = fmaxf(best, ll[i]);
+      for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+      // VectorToPosteriorEntry: candidates like > max + log(min_post), post = exp(like - max)
+      const float cutoff = best + logf(p.min_post);
+      float post[16];
+      int ncand = 0;
+  #pragma unroll
+      for (int i = 0; i < 16; i++) {
+        bool c = (p.min_post != 0.0f) && (ll[i] > cutoff);
+        post[i] = c ? expf(ll[i] - best) : -1.0f;
+        ncand += c;
+      }
+      ncand = __reduce_add_sync(0xffffffffu, ncand);
+      if (ncand == 0) {     // none reached the threshold (or min_post == 0): take them all (:467-473)
+  #pragma unroll
+        for (int i = 0; i < 16; i++) post[i] = (lane_id + 32 * i < p.num_gauss) ? expf(ll[i] - best) : -1.0f;
+      }
+      // top num_gselect by posterior (descending)
+      float sel_v[8]; int sel_i[8]; int nsel = 0;
+      for (int s = 0; s < p.num_gselect && s < 8; s++) {
+        float bv = -1.0f; int bi = -1;
+  #pragma unroll
+        for (int i = 0; i < 16; i++) if (post[i] > bv) { bv = post[i]; bi = lane_id + 32 * i; }
+        // warp arg-max (ties -> lowest index)
+        for (int o = 16; o > 0; o >>= 1) {
+          float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi >= 0 && (bi < 0 || oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (bi < 0 || bv < 0.f) break;
+        sel_v[nsel] = bv; sel_i[nsel] = bi; nsel++;
+        if ((bi & 31) == lane_id) {
+          int slot = bi >> 5;
+  #pragma unroll
+          for (int i = 0; i < 16; i++) if (i == slot) post[i] = -1.0f;
+        }
+      }
+      // tail pruning and renormalisation (:492-503)
+      float tot = 0.f;
+      for (int s = 0; s < nsel; s++) tot += sel_v[s];
+      const float cut2 = p.min_post * tot;
+      while (nsel > 1 && sel_v[nsel - 1] < cut2) { tot -= sel_v[nsel - 1]; nsel--; }
+      const float inv_tot = 1.0f / tot;
+      if (lane_id == 0) {
+        size_t o = ((size_t)L * r.T + t) * 8;
+        const float sc = p.posterior_scale * 1.0f;           // posterior_scale * frame weight (1.0)
+        for (int s = 0; s < nsel; s++) { r.post_idx[o + s] = sel_i[s]; r.post_val[o + s] = (sel_v[s] * inv_tot) * sc; }
+        r.post_cnt[(size_t)L * r.T + t] = nsel;
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -493,7 +517,7 @@ int b2k_ivec_create(const b2k_ivec_cfg *cfg, const float *lda, const float *gcon
   B2K_CUDA_CHECK(cudaMallocHost((void **)&iv->h_outp, sizeof(void *) * NL));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&iv->h_sched, 4 * 4096));
   B2K_CUDA_CHECK(cudaEventCreateWithFlags(&iv->staging_free, cudaEventDisableTiming));
-  iv->smem_front = sizeof(float) * ((size_t)F * (SD + 1) + IV_WARPS * (2 * (size_t)SD + F));
+  iv->smem_front = sizeof(float) * ((size_t)F * (SD + 1) + IV_WARPS * (2 * (size_t)SD + IV_FR * (size_t)F));
   iv->smem_stats = sizeof(double) * ((size_t)Q + 5 * D + 8 * (size_t)F + 32 + 8 * (size_t)D) + 4 * (2 * (size_t)G + IVS_THREADS / 32 + 4) +
                    4 * ((size_t)IVS_STAGE * (1 + 8 + 8) + (size_t)IVS_STAGE * F);
   B2K_CUDA_CHECK(cudaFuncSetAttribute(ivec_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iv->smem_front));

@@ -181,8 +181,8 @@ def test_ivector_option_names_are_the_ones_the_reference_registers():
                 for f in sub.values():
                     open(f, "w").write("\n")
                 val = {"top": "1", "splice": "2", "cmvn": "5"}[g]
-                if n in ("norm-vars", "online-cmvn-iextractor"):
-                    val = "false"
+                if n in ("norm-vars", "online-cmvn-iextractor", "greedy-ivector-extractor"):
+                    val = "false"                             # accepted by name; true has no kernel behind it and is an error
                 if n == "norm-means":
                     val = "true"
                 if n == "skip-dims":
@@ -197,6 +197,10 @@ def test_ivector_option_names_are_the_ones_the_reference_registers():
                 conf = os.path.join(d, "top.conf")
                 open(conf, "w").write(top)
                 assert _ivec(L, conf)[0] == 0, (g, n)
+        # values that would change what the reference computes are refused, not ignored
+        for bad in ("--use-most-recent-ivector=false", "--greedy-ivector-extractor=true", "--num-gselect"):
+            open(conf, "w").write(bad + "\n")
+            assert _ivec(L, conf)[0] != 0, bad
 
 
 class _OnlineConf(C.Structure):
@@ -247,7 +251,10 @@ def test_decoder_and_decodable_options_in_the_tools_spelling():
     assert c.dec.beam_delta == 0.25 and c.dec.hash_ratio == 3.0 and c.acoustic_scale == pytest.approx(0.9)
     assert c.frames_per_chunk == 51 and c.chunk_length_secs == pytest.approx(0.3)       # 50 rounded up to a multiple of 3
     before = bytes(c)
-    for bad in (b"--no-such-option=1", b"beam=3", b"--beam=wide", b"--extra-left-context-initial=5", b"--frames-per-chunk=0"):
+    # (silence weighting without silence phones is inactive, OnlineSilenceWeightingConfig::Active(): accepted above; active = refused)
+    for bad in (b"--no-such-option=1", b"beam=3", b"--beam=wide", b"--extra-left-context-initial=5", b"--frames-per-chunk=0",
+                b"--ivector-silence-weighting.silence-weight=0.5 --ivector-silence-weighting.silence-phones=1:2:3",
+                b"--do-endpointing=true", b"--word-symbol-table", b"--beam"):
         assert L.b2k_pipeline_cfg_apply_options(bad, C.byref(c)) != 0
         assert bytes(c) == before                             # a rejected text changes nothing
     # the names are the ones the reference registers

@@ -223,7 +223,8 @@ def test_pure_cpp_route_from_files_to_compact_lattices(tmp_path):
             assert rec["num_states"] == want["num_states"]
             for k in ("arc_src", "arc_dst", "arc_word", "arc_graph_cost", "arc_acoustic_cost", "final_state",
                       "final_graph_cost", "final_acoustic_cost"):
-                np.testing.assert_array_equal(rec[k], want[k], err_msg=k)
+                np.testing.assert_array_equal(rec[k], want[k], err_msg="%s (utterance %d; finals here %s / %s, there %s / %s)" % (
+                    k, first + j, rec["final_graph_cost"], rec["final_acoustic_cost"], want["final_graph_cost"], want["final_acoustic_cost"]))
             tids = np.concatenate([np.concatenate(want["arc_tids"]) if want["arc_tids"] else np.zeros(0, np.int32),
                                    np.concatenate(want["final_tids"]) if want["final_tids"] else np.zeros(0, np.int32)])
             np.testing.assert_array_equal(rec["tids"], tids)
