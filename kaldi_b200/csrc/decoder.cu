@@ -140,6 +140,7 @@ struct DecParams {
   uint32_t *v2_c0, *v2_adjc, *v2_qstamp, *v2_hw;
   int32_t *v2_pf;
   int32_t v2_hw_len;
+  int32_t fin_scap;         // finalize: tokens of a list whose sweep state is held in shared memory (0 = off)
   int32_t cid_smem;         // second generation: 16-bit compact ids of the replay in the upper half of the shared arc area
   int32_t v2_l1_shift;      // level-1 window = 2^shift x the reference's HashList size (rounded up to a power of two)
 };
@@ -2940,6 +2941,15 @@ __device__ void dec_finalize_lane(const DecParams &p, const int lane, const int 
   float *tok_extra = p.tok_extra + (size_t)ch * p.max_tokens;
   int4 *links = p.links + (size_t)ch * p.max_links;
   uint32_t *nx = p.new_extra + (size_t)slot * p.max_tpf;
+  // A token list that fits (p.fin_scap tokens; one 1024-thread CTA per SM has the room) keeps its per-token sweep state in
+  // shared memory: the running minima, their base values, the has-eps flags as a bitmap, and a bitmap of the tokens of
+  // list t+1 that survived -- 99.8 % of the links point at dead tokens and now die on a shared-memory bit instead of a
+  // random 4-byte read of the arena.  Larger lists use the scratch arrays as before (same code through the pointers).
+  extern __shared__ __align__(16) unsigned char fin_smem[];
+  const int scap = p.fin_scap, bmw = (scap + 31) / 32;
+  uint32_t *nx_s = reinterpret_cast<uint32_t *>(fin_smem), *base_s = nx_s + scap;
+  uint32_t *eps_bm = base_s + scap, *alive_next = eps_bm + bmw, *alive_cur = alive_next + bmw;
+  bool have_next_bm = false;
   const size_t fo = (size_t)ch * (p.max_frames + 2);
   const int last = cs->frames_decoded;
 
@@ -2987,6 +2997,10 @@ __device__ void dec_finalize_lane(const DecParams &p, const int lane, const int 
       return;
     }
     const int eps_b = p.frame_link_eps[fo + t], eps_e = p.frame_link_begin[fo + t + 1];
+    const bool in_s = n <= scap;                              // uniform
+    uint32_t *nxp = in_s ? nx_s : nx;
+    auto get_eps = [&](int i) -> bool { return in_s ? ((eps_bm[i >> 5] >> (i & 31)) & 1u) != 0u : has_eps[i] != 0; };
+    if (in_s) for (int w = tid; w < (n + 31) / 32; w += T) { eps_bm[w] = 0u; alive_cur[w] = 0u; }
     // Almost every token and link dies in this sweep (the lattice keeps ~0.1 % of
     // them), so the passes exit early on dead destinations and keep compact
     // survivor lists instead of flagging or re-reading whole link segments.
@@ -2998,8 +3012,8 @@ __device__ void dec_finalize_lane(const DecParams &p, const int lane, const int 
         float fc = any_final ? __ldg(&g.final_cost[tok_state[tb + i]]) : 0.0f;
         base = tok_cost[tb + i] + fc - final_best_cost;
       }
-      nx[i] = f2ord(base);
-      has_eps[i] = 0;
+      nxp[i] = f2ord(base);
+      if (!in_s) has_eps[i] = 0;
     }
     if (tid == 0) { sh_cnt[0] = 0; sh_cnt[1] = 0; sh_cnt[2] = 0; }
     __syncthreads();
@@ -3015,7 +3029,11 @@ __device__ void dec_finalize_lane(const DecParams &p, const int lane, const int 
           lk[u] = (l < em_e) ? __ldcs(&links[l]) : make_int4(0, -1, 0, 0);
         }
 #pragma unroll
-        for (int u = 0; u < U; u++) dex[u] = (lk[u].y >= 0) ? tok_extra[lk[u].y] : kInf;   // list t+1 is final
+        for (int u = 0; u < U; u++) {                         // list t+1 is final
+          bool alive = lk[u].y >= 0;
+          if (alive && have_next_bm) { const int j = lk[u].y - tb_next; alive = ((alive_next[j >> 5] >> (j & 31)) & 1u) != 0u; }
+          dex[u] = alive ? tok_extra[lk[u].y] : kInf;
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {
           if (dex[u] == kInf) continue;                       // link_extra_cost = inf > lattice_beam
@@ -3023,26 +3041,29 @@ __device__ void dec_finalize_lane(const DecParams &p, const int lane, const int 
           float lec = link_extra_cost(dex[u], tok_cost[lk[u].x], __int_as_float(lk[u].w), graph, tok_cost[lk[u].y]);
           if (lec > p.lattice_beam) continue;                 // excised (:348-354)
           if (lec < 0.0f) lec = 0.0f;
-          atomicMin(&nx[lk[u].x - tb], f2ord(lec));
+          atomicMin(&nxp[lk[u].x - tb], f2ord(lec));
           int q = atomicAdd(&sh_cnt[0], 1);
           if (q < surv_cap) surv_e[q] = l0 + u * T + tid;
         }
       }
     }
-    for (int l = eps_b + tid; l < eps_e; l += T) has_eps[links[l].x - tb] = 1;
+    for (int l = eps_b + tid; l < eps_e; l += T) {
+      const int i = links[l].x - tb;
+      if (in_s) atomicOr(&eps_bm[i >> 5], 1u << (i & 31)); else has_eps[i] = 1;
+    }
     __syncthreads();
     // tokens without eps out-links already have their exact extra_cost (= base);
     // the others start the eps iteration from the lower bound 0.  The iteration
     // (Jacobi over the surviving eps links; unique fixpoint because eps links
     // form a DAG) only ever excises a link when a LOWER BOUND of its extra cost
     // exceeds lattice_beam, so it keeps exactly the links of :308-379.
-    uint32_t *base_ord = reinterpret_cast<uint32_t *>(p.wl + (size_t)slot * 2 * p.max_tpf);
+    uint32_t *base_ord = in_s ? base_s : reinterpret_cast<uint32_t *>(p.wl + (size_t)slot * 2 * p.max_tpf);
     for (int i = tid; i < n; i += T) {
-      uint32_t bo = nx[i];
+      uint32_t bo = nxp[i];
       base_ord[i] = bo;
       float v = ord2f(bo);
       if (t == last && v > p.lattice_beam) v = kInf;
-      tok_extra[tb + i] = has_eps[i] ? 0.0f : v;
+      tok_extra[tb + i] = get_eps(i) ? 0.0f : v;
     }
     __syncthreads();
     int n_eps_in = eps_e - eps_b;                             // iteration 0 reads the segment itself
@@ -3059,7 +3080,7 @@ __device__ void dec_finalize_lane(const DecParams &p, const int lane, const int 
         float lec = link_extra_cost(dex, tok_cost[lk.x], 0.0f, graph, tok_cost[lk.y]);
         if (lec > p.lattice_beam) continue;
         if (lec < 0.0f) lec = 0.0f;
-        atomicMin(&nx[lk.x - tb], f2ord(lec));
+        atomicMin(&nxp[lk.x - tb], f2ord(lec));
         int q = atomicAdd(&sh_cnt[1], 1);
         if (q < surv_cap) eps_out[q] = l;
       }
@@ -3069,13 +3090,13 @@ __device__ void dec_finalize_lane(const DecParams &p, const int lane, const int 
       // only sources of eps links can change: re-evaluate them via the survivor list plus the
       // sources whose links all died (their value falls back to base) -> walk the has_eps tokens
       for (int i = tid; i < n; i += T) {
-        if (!has_eps[i]) continue;
-        float v = ord2f(nx[i]);
+        if (!get_eps(i)) continue;
+        float v = ord2f(nxp[i]);
         if (t == last && v > p.lattice_beam) v = kInf;      // :458-459
         float old = tok_extra[tb + i];
         if (!(v == old)) changed = 1;
         tok_extra[tb + i] = v;
-        nx[i] = base_ord[i];
+        nxp[i] = base_ord[i];
       }
       if (changed) sh_changed = 1;
       __syncthreads();
@@ -3095,6 +3116,7 @@ __device__ void dec_finalize_lane(const DecParams &p, const int lane, const int 
       if (ex == kInf) continue;
       int id = n_states + atomicAdd(&sh_cnt[2], 1);
       ids_cur[k] = id;
+      if (in_s) atomicOr(&alive_cur[k >> 5], 1u << (k & 31));
       if (id < p.cap_ls) ls[id] = make_int4(t, tok_state[tb + k], __float_as_int(tok_cost[tb + k]), __float_as_int(ex));
       if (t == last) {
         float fc = any_final ? __ldg(&g.final_cost[tok_state[tb + k]]) : 0.0f;
@@ -3137,6 +3159,8 @@ __device__ void dec_finalize_lane(const DecParams &p, const int lane, const int 
     }
     __syncthreads();
     { int *tmp = ids_cur; ids_cur = ids_next; ids_next = tmp; }
+    { uint32_t *tmp = alive_cur; alive_cur = alive_next; alive_next = tmp; }
+    have_next_bm = in_s;
     tb_next = tb;
   }
   if (tid == 0) {
@@ -3290,6 +3314,7 @@ struct b2k_dec {
   int threads_override = 0, fin_threads = 1024, num_sms = 0;   // tuning knobs, read from the environment at creation
   int ctas_override = 0;                // B2K_DEC_CTAS (256-thread CTAs only)
   bool cid_smem_off = false;            // B2K_DEC_CID_SMEM=0
+  bool fin_smem_off = false;            // B2K_FIN_SMEM=0
   int nslots = 0;                       // scratch slots = the largest grid any per-lane launch uses (resident CTAs)
   int prof = 0;                         // B2K_DEC_PROF=1: per-phase cycle counters in the reference-order kernel
   int ll_smem_off = 0;                  // B2K_DEC_LL_SMEM=0: leave the log-likelihood rows in global memory
@@ -3450,6 +3475,7 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     if (const char *e = getenv("B2K_DEC_GRID")) d->grid_cap = atoi(e);
     if (const char *e = getenv("B2K_DEC_LL_SMEM")) d->ll_smem_off = atoi(e) == 0;
     if (const char *e = getenv("B2K_DEC_CID_SMEM")) d->cid_smem_off = atoi(e) == 0;
+    if (const char *e = getenv("B2K_FIN_SMEM")) d->fin_smem_off = atoi(e) == 0;
     // Persistent launches: at most two CTAs per SM are ever resident (512-thread reference-order CTAs; the
     // order-free and finalize kernels use one slot per CTA of their own, smaller grids), so that is the
     // number of scratch slots, whatever the batch size.
@@ -3778,7 +3804,19 @@ int b2k_dec_finalize_decoding(b2k_dec *d, const int32_t *channels, int32_t n, vo
     const int fin_threads = d->fin_threads;
     if ((rc = begin_persistent(d, p, n, st))) return rc;
     const int grid = std::min(n, d->nslots);                 // one resident CTA per scratch slot
-    if (fin_threads == 1024) dec_finalize_kernel<1024><<<std::min(grid, d->num_sms), 1024, 0, st>>>(p);
+    p.fin_scap = 0;
+    if (fin_threads == 1024) {
+      // one CTA per SM: 16 K tokens per list in shared memory (2 x 64 KB + three bitmaps, inside the 164 KB carve-out)
+      static bool configured = false;
+      const int scap = d->fin_smem_off ? 0 : 16384;
+      const size_t smem = (size_t)scap * 8 + 3 * (size_t)((scap + 31) / 32) * 4;
+      if (!configured) {
+        B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_finalize_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)16384 * 8 + 3 * 512 * 4)));
+        configured = true;
+      }
+      p.fin_scap = scap;
+      dec_finalize_kernel<1024><<<std::min(grid, d->num_sms), 1024, smem, st>>>(p);
+    }
     else if (fin_threads == 512) dec_finalize_kernel<512><<<grid, 512, 0, st>>>(p);
     else dec_finalize_kernel<256><<<grid, 256, 0, st>>>(p);
   }
