@@ -2579,9 +2579,8 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
   __syncthreads();
 }
 
-template <int T, bool PROF>
+template <int T, bool PROF, int IT>
 __device__ void dec_advance_v2_lane(const DecParams &p, DecShared<T> &s, const int lane, const int slot) {
-  constexpr int IT = 4;
   const int tid = threadIdx.x;
   const int ch = p.lane_channel[lane];
   ChanState *cs = &p.chan[ch];
@@ -2910,10 +2909,10 @@ __device__ void dec_advance_v2_lane(const DecParams &p, DecShared<T> &s, const i
   if (s.err) reset_lane_hash<T>(ctx.hash, p.hash_size);
 }
 
-template <int T, bool PROF>
+template <int T, bool PROF, int IT>
 __global__ void __launch_bounds__(T, (T == 512 ? 2 : (T == 256 ? 3 : 1))) dec_advance_v2_kernel(DecParams p) {
   __shared__ DecShared<T> s;
-  B2K_PERSISTENT_LANES((dec_advance_v2_lane<T, PROF>(p, s, lane_, (int)blockIdx.x)))
+  B2K_PERSISTENT_LANES((dec_advance_v2_lane<T, PROF, IT>(p, s, lane_, (int)blockIdx.x)))
 }
 
 // ------------------------------------------------------------------ finalize (backward sweep)
@@ -3315,6 +3314,7 @@ struct b2k_dec {
   int ctas_override = 0;                // B2K_DEC_CTAS (256-thread CTAs only)
   bool cid_smem_off = false;            // B2K_DEC_CID_SMEM=0
   bool fin_smem_off = false;            // B2K_FIN_SMEM=0
+  int arcs_per_thread = 4;              // B2K_DEC_IT (512-thread CTAs)
   int nslots = 0;                       // scratch slots = the largest grid any per-lane launch uses (resident CTAs)
   int prof = 0;                         // B2K_DEC_PROF=1: per-phase cycle counters in the reference-order kernel
   int ll_smem_off = 0;                  // B2K_DEC_LL_SMEM=0: leave the log-likelihood rows in global memory
@@ -3476,6 +3476,7 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     if (const char *e = getenv("B2K_DEC_LL_SMEM")) d->ll_smem_off = atoi(e) == 0;
     if (const char *e = getenv("B2K_DEC_CID_SMEM")) d->cid_smem_off = atoi(e) == 0;
     if (const char *e = getenv("B2K_FIN_SMEM")) d->fin_smem_off = atoi(e) == 0;
+    if (const char *e = getenv("B2K_DEC_IT")) { int v = atoi(e); if (v >= 2 && v <= 4) d->arcs_per_thread = v; }
     // Persistent launches: at most two CTAs per SM are ever resident (512-thread reference-order CTAs; the
     // order-free and finalize kernels use one slot per CTA of their own, smaller grids), so that is the
     // number of scratch slots, whatever the batch size.
@@ -3678,13 +3679,13 @@ static int launch_exact_t(const b2k_dec *d, DecParams p, int n, int ctas_per_sm,
 }  // extern "C++"
 
 extern "C++" {
-template <int T, bool PROF>
+template <int T, bool PROF, int IT = 4>
 static int launch_v2_t(const b2k_dec *d, DecParams p, int n, int ctas_per_sm, cudaStream_t st) {
   static size_t configured = 0;
   static size_t static_smem = 0;
   if (!static_smem) {
     cudaFuncAttributes fa;
-    B2K_CUDA_CHECK(cudaFuncGetAttributes(&fa, dec_advance_v2_kernel<T, PROF>));
+    B2K_CUDA_CHECK(cudaFuncGetAttributes(&fa, dec_advance_v2_kernel<T, PROF, IT>));
     static_smem = fa.sharedSizeBytes;
   }
   p.rs_bytes = (int32_t)exact_smem_bytes(p);
@@ -3698,12 +3699,12 @@ static int launch_v2_t(const b2k_dec *d, DecParams p, int n, int ctas_per_sm, cu
   if (p.ll_smem) smem = std::max(smem, ll_bytes);
   p.cid_smem = d->cid_smem_off ? 0 : 1;
   if (smem > configured) {
-    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_v2_kernel<T, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_v2_kernel<T, PROF, IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   int grid = std::min(n, std::min(d->nslots, d->num_sms * ctas_per_sm));
   if (d->grid_cap > 0) grid = std::min(grid, d->grid_cap);
-  dec_advance_v2_kernel<T, PROF><<<grid, T, smem, st>>>(p);
+  dec_advance_v2_kernel<T, PROF, IT><<<grid, T, smem, st>>>(p);
   return B2K_OK;
 }
 }  // extern "C++"
@@ -3719,7 +3720,11 @@ static int launch_exact(const b2k_dec *d, DecParams p, int n, cudaStream_t st) {
       return launch_v2_t<256, true>(d, p, n, d->ctas_override > 0 ? d->ctas_override : 2, st);
     }
     if (threads == 1024) return launch_v2_t<1024, false>(d, p, n, 1, st);
-    if (threads == 512) return launch_v2_t<512, false>(d, p, n, 2, st);
+    if (threads == 512) {
+      if (d->arcs_per_thread == 2) return launch_v2_t<512, false, 2>(d, p, n, 2, st);   // B2K_DEC_IT: arcs per thread and admission round
+      if (d->arcs_per_thread == 3) return launch_v2_t<512, false, 3>(d, p, n, 2, st);
+      return launch_v2_t<512, false>(d, p, n, 2, st);
+    }
     if (threads == 128) return launch_v2_t<128, false>(d, p, n, 2, st);
     return launch_v2_t<256, false>(d, p, n, d->ctas_override > 0 ? d->ctas_override : 2, st);
   }
