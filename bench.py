@@ -609,8 +609,9 @@ def main():
                              collective_bytes_per_step=int(collective_bytes / a.steps), api=e2e_api),
                     gpu_launches=int(launches), stage_ms={k: round(v, 3) for k, v in stage_ms.items()},
                     decoder_phase_share=None if not os.environ.get("B2K_DEC_PROF") else dict(zip(
-                        ["cutoff_seed", "expand", "rank", "closure_init", "closure", "replay_prep", "replay", "keys_hw_clear",
-                         "list_order", "commit_links", "clear", "frame_end"],
+                        # slots of dec_advance_v2_lane / finish_frame_v2 (B2K_TICK): 2 carries the walk's sizing counters, not cycles
+                        ["cutoff_seed", "expand", "(walk_size_counters)", "walk_arrays_build", "closure_start", "closure_rounds", "replay_prep",
+                         "walk_single_thread", "eps_keys_zero", "list_order_scan", "commit_links_remap", "clear"],
                         [round(float(sum(i[16 + k] for i in infos)) / max(1.0, float(sum(i[16 + 15] for i in infos))), 3)
                          for k in range(12)])),
                     eps_replay_per_frame=dict(zip(["pops", "arc_visits", "in_shared_memory"],

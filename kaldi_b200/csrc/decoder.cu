@@ -2379,6 +2379,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     use_s = false;
     __syncthreads();
     }
+    B2K_TICK(s, 3);                                          // (profile: slot 3 = building the compact arrays, slot 7 = the walk)
     if (s.rs_ok && tid == 0) {
       int qn = qcarry, next = 0;
       bool ok = true;
