@@ -2117,13 +2117,14 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
   };
   bool owners_marked = false;                                // every entry left alive has a marked owner (shared-memory marking ran)
   if (Nall > N1 && !s.err) {
-    if ((size_t)E * 8 + (size_t)Nall + 16 <= (size_t)p.rs_bytes) {
+    if ((size_t)E * 8 + 2 * (size_t)Nall + 16 <= (size_t)p.rs_bytes) {
       owners_marked = true;
       // the fixed point runs out of shared memory (the replay arrays are not built yet): one pass reads the entries,
       // the iterations touch no scratch
       uint2 *ent_s = reinterpret_cast<uint2 *>(dyn_smem_base);      // {destination or ~0, owner | 1 << 31 if it cannot propagate}
       unsigned char *mark_s = reinterpret_cast<unsigned char *>(ent_s + E);
-      for (int d = tid; d < Nall; d += T) { mark_s[d] = (d >= N1); if (d >= N1) x.newseq[d - N1] = -1; }
+      unsigned char *live_s = mark_s + Nall;                        // owner of at least one entry that can fire in the replay
+      for (int d = tid; d < Nall; d += T) { mark_s[d] = (d >= N1); live_s[d] = 0; if (d >= N1) x.newseq[d - N1] = -1; }
       for (int e = tid; e < E; e += T) {
         const int4 en = x.adj[e];
         uint2 v = make_uint2(0xffffffffu, 0x80000000u);
@@ -2155,7 +2156,9 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
         const uint2 v = ent_s[e];
         // dead for the replay: destination not an ancestor of a created token, or the entry cannot propagate (superseded
         // record / cannot fire) -- the links pass reads only arc id and destination of the final records
-        if (v.x != 0xffffffffu && (!mark_s[v.x] || (v.y & 0x80000000u))) x.adj[e].y = kInfBits;
+        if (v.x == 0xffffffffu) continue;
+        if (!mark_s[v.x] || (v.y & 0x80000000u)) x.adj[e].y = kInfBits;
+        else live_s[v.y] = 1;
       }
     } else {
     for (int d = tid; d < Nall; d += T) { mark[d] = (d >= N1); if (d >= N1) x.newseq[d - N1] = -1; }
@@ -2191,9 +2194,16 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     if (tid == 0) s.rs_n = 0;
     __syncthreads();
     int *pend = x.big;                                        // tokens to key (idle until the walk arrays are built)
-    for (int d = tid; d < N1; d += T) {
-      if (!mark[d] || x.rec[d].z <= 0) continue;
-      pend[atomicAdd(&s.rs_n, 1)] = d;
+    if (owners_marked) {
+      // a token none of whose entries can fire would be popped and visit no arc: left out (the order of the others is unchanged)
+      const unsigned char *live_s = reinterpret_cast<const unsigned char *>(reinterpret_cast<uint2 *>(dyn_smem_base) + E) + Nall;
+      for (int d = tid; d < N1; d += T)
+        if (live_s[d]) pend[atomicAdd(&s.rs_n, 1)] = d;
+    } else {
+      for (int d = tid; d < N1; d += T) {
+        if (!mark[d] || x.rec[d].z <= 0) continue;
+        pend[atomicAdd(&s.rs_n, 1)] = d;
+      }
     }
     __syncthreads();
     qcarry = s.rs_n;
@@ -2384,32 +2394,47 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       int qn = qcarry, next = 0;
       bool ok = true;
       int npop = 0, nvis = 0, qmax = qcarry;
+      // One thread, a chain of dependent shared-memory loads per pop (stack entry -> token -> arc -> destination): the
+      // entry BELOW the top and its token are loaded while the top is processed; they are what the next pop needs unless
+      // this pop pushes (then the next pop is the pushed token, whose record is in registers already) or lowers that very
+      // token (patched in the register copy).
+      int d_top = qn > 0 ? (int)q_s[qn - 1] : 0;
+      float2 t_top = tk_s[d_top];
       while (qn > 0) {
         if (PROF) qmax = max(qmax, qn);
-        const int d = q_s[--qn];
-        const float2 td = tk_s[d];
+        const int d = d_top;
+        const float2 td = t_top;
+        --qn;
+        int d_below = qn > 0 ? (int)q_s[qn - 1] : 0;
+        float2 t_below = tk_s[d_below];
+        bool pushed = false;
         const float c = td.x;
         npop++;
-        if (c >= cutoff) continue;
-        const int oc = __float_as_int(td.y);
-        const int e0 = oc & 0xffff, e1 = e0 + (int)((unsigned)oc >> 16);
-        nvis += e1 - e0;
-        for (int e = e0; e < e1; e++) {
-          const float2 ent = en_s[e];
-          const float tot = c + ent.x;
-          if (tot < cutoff) {
-            const int j = __float_as_int(ent.y);
-            const float2 tj = tk_s[j];
-            if (tot < tj.x) {
-              tk_s[j].x = tot;
-              if (tj.x == kInfF) ns_s[j] = (unsigned short)next++;
-              if ((unsigned)__float_as_int(tj.y) >> 16) {
-                if (qn < p.rs_qcap) q_s[qn++] = (unsigned short)j;
-                else { ok = false; qn = 0; break; }
+        if (c < cutoff) {
+          const int oc = __float_as_int(td.y);
+          const int e0 = oc & 0xffff, e1 = e0 + (int)((unsigned)oc >> 16);
+          nvis += e1 - e0;
+          for (int e = e0; e < e1; e++) {
+            const float2 ent = en_s[e];
+            const float tot = c + ent.x;
+            if (tot < cutoff) {
+              const int j = __float_as_int(ent.y);
+              const float2 tj = tk_s[j];
+              if (tot < tj.x) {
+                tk_s[j].x = tot;
+                if (j == d_below) t_below.x = tot;
+                if (tj.x == kInfF) ns_s[j] = (unsigned short)next++;
+                if ((unsigned)__float_as_int(tj.y) >> 16) {
+                  if (qn < p.rs_qcap) {
+                    q_s[qn++] = (unsigned short)j;
+                    d_top = j; t_top = make_float2(tot, tj.y); pushed = true;
+                  } else { ok = false; qn = 0; break; }
+                }
               }
             }
           }
         }
+        if (!pushed) { d_top = d_below; t_top = t_below; }
       }
       if (ok) {
         if (next != Nall - N1) B2K_SET_ERR(s, B2K_ERR_STATE);
@@ -3314,7 +3339,7 @@ struct b2k_dec {
   int threads_override = 0, fin_threads = 1024, num_sms = 0;   // tuning knobs, read from the environment at creation
   int ctas_override = 0;                // B2K_DEC_CTAS (256-thread CTAs only)
   bool cid_smem_off = false;            // B2K_DEC_CID_SMEM=0
-  bool fin_smem_off = false;            // B2K_FIN_SMEM=0
+  bool fin_smem_off = true;             // B2K_FIN_SMEM=1 turns the shared-memory sweep state on (measured slower: 94 vs 58 ms, it shrinks L1 to 92 KB)
   int arcs_per_thread = 4;              // B2K_DEC_IT (512-thread CTAs)
   int nslots = 0;                       // scratch slots = the largest grid any per-lane launch uses (resident CTAs)
   int prof = 0;                         // B2K_DEC_PROF=1: per-phase cycle counters in the reference-order kernel
