@@ -141,6 +141,7 @@ struct DecParams {
   int32_t *v2_pf;
   int32_t v2_hw_len;
   int32_t fin_scap;         // finalize: tokens of a list whose sweep state is held in shared memory (0 = off)
+  int32_t par_walk;         // second generation: replay by connected components (one thread each)
   int32_t cid_smem;         // second generation: 16-bit compact ids of the replay in the upper half of the shared arc area
   int32_t v2_l1_shift;      // level-1 window = 2^shift x the reference's HashList size (rounded up to a power of two)
 };
@@ -2286,6 +2287,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
           ns_s[id] = 0xffff;
           dof[id] = d;
           cid_s[d] = (unsigned short)id;
+          if (d >= N1) x.newseq[d - N1] = id;                 // (kept here: the id area is reused by the parallel walk)
         } else {
           s.rs_ok = 0;
         }
@@ -2389,52 +2391,134 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     use_s = false;
     __syncthreads();
     }
-    B2K_TICK(s, 3);                                          // (profile: slot 3 = building the compact arrays, slot 7 = the walk)
-    if (s.rs_ok && tid == 0) {
-      int qn = qcarry, next = 0;
-      bool ok = true;
-      int npop = 0, nvis = 0, qmax = qcarry;
-      // One thread, a chain of dependent shared-memory loads per pop (stack entry -> token -> arc -> destination): the
-      // entry BELOW the top and its token are loaded while the top is processed; they are what the next pop needs unless
-      // this pop pushes (then the next pop is the pushed token, whose record is in registers already) or lowers that very
-      // token (patched in the register copy).
-      int d_top = qn > 0 ? (int)q_s[qn - 1] : 0;
-      float2 t_top = tk_s[d_top];
-      while (qn > 0) {
-        if (PROF) qmax = max(qmax, qn);
-        const int d = d_top;
-        const float2 td = t_top;
-        --qn;
-        int d_below = qn > 0 ? (int)q_s[qn - 1] : 0;
-        float2 t_below = tk_s[d_below];
-        bool pushed = false;
-        const float c = td.x;
-        npop++;
-        if (c < cutoff) {
-          const int oc = __float_as_int(td.y);
+    // ---- The replay is a stack: the initial entries are popped from the back and everything an entry pushes is processed
+    //      before the entry below it, so the run is a sequence of cascades, one per initial entry.  Cascades only interact
+    //      through tokens they share: over the connected components of the compact graph they are independent, and the
+    //      creation order of the new tokens is (order of the cascade's initial entry, order inside the cascade).  So: label
+    //      the components (min-label propagation with pointer jumping, all in shared memory), one thread per component
+    //      replays its entries in stack order with a private stack, every created token is recorded with that key, and
+    //      the keys are ranked.  (One thread for everything was 22 % of the frame: ~470 pops at ~600 cycles each.)
+    bool par_done = false;
+    if (use_s && s.rs_ok && p.par_walk && min(s.rs_n, p.rs_rcap) <= p.rs_ecap) {     // uniform
+      const int R = min(s.rs_n, p.rs_rcap);
+      int *lab = reinterpret_cast<int *>(cid_s);              // R ints in the id area (ids of created tokens are in x.newseq)
+      for (int id = tid; id < R; id += T) lab[id] = id;
+      if (tid == 0) s.ncand = 0;
+      __syncthreads();
+      for (int it = 0; it < 100000; it++) {
+        if (tid == 0) s.cont = 0;
+        __syncthreads();
+        for (int id = tid; id < R; id += T) {
+          const int oc = __float_as_int(tk_s[id].y);
           const int e0 = oc & 0xffff, e1 = e0 + (int)((unsigned)oc >> 16);
-          nvis += e1 - e0;
+          const int mine = lab[id];
+          int m = min(mine, lab[mine]);                       // pointer jumping
+          for (int e = e0; e < e1; e++) m = min(m, lab[__float_as_int(en_s[e].y)]);
+          bool ch = false;
+          if (m < mine) { atomicMin(&lab[id], m); ch = true; }
           for (int e = e0; e < e1; e++) {
-            const float2 ent = en_s[e];
-            const float tot = c + ent.x;
-            if (tot < cutoff) {
-              const int j = __float_as_int(ent.y);
-              const float2 tj = tk_s[j];
-              if (tot < tj.x) {
-                tk_s[j].x = tot;
-                if (j == d_below) t_below.x = tot;
-                if (tj.x == kInfF) ns_s[j] = (unsigned short)next++;
-                if ((unsigned)__float_as_int(tj.y) >> 16) {
-                  if (qn < p.rs_qcap) {
-                    q_s[qn++] = (unsigned short)j;
-                    d_top = j; t_top = make_float2(tot, tj.y); pushed = true;
-                  } else { ok = false; qn = 0; break; }
+            const int j = __float_as_int(en_s[e].y);
+            if (m < lab[j]) { atomicMin(&lab[j], m); ch = true; }
+          }
+          if (ch) s.cont = 1;
+        }
+        __syncthreads();
+        const int again = s.cont;
+        __syncthreads();
+        if (!again) break;
+      }
+      B2K_TICK(s, 3);
+      unsigned long long *crec = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(x.queue + qcarry) + 15) & ~(uintptr_t)15);   // behind the initial worklist (kept for the fallback)
+      for (int root = tid; root < R; root += T) {
+        if (lab[root] != root) continue;
+        unsigned short stk[32];
+        bool overflow = false;
+        for (int k = qcarry - 1; k >= 0 && !overflow; k--) {
+          const int d0 = q_s[k];
+          if (lab[d0] != root) continue;
+          int sp = 0, seq = 0;
+          stk[sp++] = (unsigned short)d0;
+          while (sp > 0) {
+            const int d = stk[--sp];
+            const float2 td = tk_s[d];
+            const float c = td.x;
+            if (c >= cutoff) continue;
+            const int oc = __float_as_int(td.y);
+            const int e0 = oc & 0xffff, e1 = e0 + (int)((unsigned)oc >> 16);
+            for (int e = e0; e < e1; e++) {
+              const float2 ent = en_s[e];
+              const float tot = c + ent.x;
+              if (tot < cutoff) {
+                const int j = __float_as_int(ent.y);
+                const float2 tj = tk_s[j];
+                if (tot < tj.x) {
+                  tk_s[j].x = tot;
+                  if (tj.x == kInfF) {
+                    const int slot = atomicAdd(&s.ncand, 1);
+                    crec[slot] = ((unsigned long long)(qcarry - 1 - k) << 32) | ((unsigned long long)seq++ << 12) | (unsigned long long)j;
+                  }
+                  if ((unsigned)__float_as_int(tj.y) >> 16) {
+                    if (sp < 32) stk[sp++] = (unsigned short)j;
+                    else { overflow = true; sp = 0; break; }
+                  }
                 }
               }
             }
           }
         }
-        if (!pushed) { d_top = d_below; t_top = t_below; }
+        if (overflow) s.rs_ok = 0;                             // (the walk over the scratch records redoes the frame)
+      }
+      __syncthreads();
+      if (s.rs_ok) {
+        const int n = s.ncand;
+        if (n != Nall - N1) { if (tid == 0) B2K_SET_ERR(s, B2K_ERR_STATE); }
+        else if (n > 4096) { if (tid == 0) s.rs_ok = 0; }
+        else {
+          for (int i = tid; i < n; i += T) {                  // the records are distinct: rank = number of smaller ones
+            const unsigned long long mine = crec[i];
+            int r = 0;
+            for (int j2 = 0; j2 < n; j2++) r += (crec[j2] < mine);
+            ns_s[(int)(mine & 0xfffull)] = (unsigned short)r;
+          }
+          if (tid == 0) s.prof[14] += 1;
+        }
+      }
+      __syncthreads();
+      par_done = s.rs_ok != 0;
+      __syncthreads();
+    } else {
+      B2K_TICK(s, 3);                                        // (profile: slot 3 = building the compact arrays, slot 7 = the walk)
+    }
+    if (!par_done && s.rs_ok && tid == 0) {
+      int qn = qcarry, next = 0;
+      bool ok = true;
+      int npop = 0, nvis = 0, qmax = qcarry;
+      while (qn > 0) {
+        if (PROF) qmax = max(qmax, qn);
+        const int d = q_s[--qn];
+        const float2 td = tk_s[d];
+        const float c = td.x;
+        npop++;
+        if (c >= cutoff) continue;
+        const int oc = __float_as_int(td.y);
+        const int e0 = oc & 0xffff, e1 = e0 + (int)((unsigned)oc >> 16);
+        nvis += e1 - e0;
+        for (int e = e0; e < e1; e++) {
+          const float2 ent = en_s[e];
+          const float tot = c + ent.x;
+          if (tot < cutoff) {
+            const int j = __float_as_int(ent.y);
+            const float2 tj = tk_s[j];
+            if (tot < tj.x) {
+              tk_s[j].x = tot;
+              if (tj.x == kInfF) ns_s[j] = (unsigned short)next++;
+              if ((unsigned)__float_as_int(tj.y) >> 16) {
+                if (qn < p.rs_qcap) q_s[qn++] = (unsigned short)j;
+                else { ok = false; qn = 0; break; }
+              }
+            }
+          }
+        }
       }
       if (ok) {
         if (next != Nall - N1) B2K_SET_ERR(s, B2K_ERR_STATE);
@@ -2450,7 +2534,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       replay_done = true;
       if (!s.err)
         for (int d = N1 + tid; d < Nall; d += T) {
-          int id = cidv(d);
+          int id = use_s ? x.newseq[d - N1] : cidv(d);        // (shared-memory ids: stored at claim time, the area may have been reused)
           if (id >= 0) x.newseq[d - N1] = (int)ns_s[id];
           else B2K_SET_ERR(s, B2K_ERR_STATE);                // an eps-created token is always some record's destination
         }
@@ -3339,8 +3423,9 @@ struct b2k_dec {
   int threads_override = 0, fin_threads = 1024, num_sms = 0;   // tuning knobs, read from the environment at creation
   int ctas_override = 0;                // B2K_DEC_CTAS (256-thread CTAs only)
   bool cid_smem_off = false;            // B2K_DEC_CID_SMEM=0
+  bool par_walk_off = false;            // B2K_DEC_PARWALK=0
   bool fin_smem_off = true;             // B2K_FIN_SMEM=1 turns the shared-memory sweep state on (measured slower: 94 vs 58 ms, it shrinks L1 to 92 KB)
-  int arcs_per_thread = 4;              // B2K_DEC_IT (512-thread CTAs)
+  int arcs_per_thread = 3;              // B2K_DEC_IT (512-thread CTAs): 3 measured 1.7 % faster than 4 and 2 (r2n, r2o)
   int nslots = 0;                       // scratch slots = the largest grid any per-lane launch uses (resident CTAs)
   int prof = 0;                         // B2K_DEC_PROF=1: per-phase cycle counters in the reference-order kernel
   int ll_smem_off = 0;                  // B2K_DEC_LL_SMEM=0: leave the log-likelihood rows in global memory
@@ -3501,6 +3586,7 @@ static int dec_create_impl(b2k_dec *d, const b2k_fst *fst, const b2k_dec_cfg *cf
     if (const char *e = getenv("B2K_DEC_GRID")) d->grid_cap = atoi(e);
     if (const char *e = getenv("B2K_DEC_LL_SMEM")) d->ll_smem_off = atoi(e) == 0;
     if (const char *e = getenv("B2K_DEC_CID_SMEM")) d->cid_smem_off = atoi(e) == 0;
+    if (const char *e = getenv("B2K_DEC_PARWALK")) d->par_walk_off = atoi(e) == 0;
     if (const char *e = getenv("B2K_FIN_SMEM")) d->fin_smem_off = atoi(e) == 0;
     if (const char *e = getenv("B2K_DEC_IT")) { int v = atoi(e); if (v >= 2 && v <= 4) d->arcs_per_thread = v; }
     // Persistent launches: at most two CTAs per SM are ever resident (512-thread reference-order CTAs; the
@@ -3724,6 +3810,7 @@ static int launch_v2_t(const b2k_dec *d, DecParams p, int n, int ctas_per_sm, cu
                static_smem + std::max(smem, ll_bytes) <= per_cta) ? 1 : 0;
   if (p.ll_smem) smem = std::max(smem, ll_bytes);
   p.cid_smem = d->cid_smem_off ? 0 : 1;
+  p.par_walk = d->par_walk_off ? 0 : 1;
   if (smem > configured) {
     B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_v2_kernel<T, PROF, IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -3742,7 +3829,7 @@ static int launch_exact(const b2k_dec *d, DecParams p, int n, cudaStream_t st) {
   if (d->use_v2) {
     if (d->prof) {
       if (threads == 1024) return launch_v2_t<1024, true>(d, p, n, 1, st);
-      if (threads == 512) return launch_v2_t<512, true>(d, p, n, 2, st);
+      if (threads == 512) return d->arcs_per_thread == 3 ? launch_v2_t<512, true, 3>(d, p, n, 2, st) : launch_v2_t<512, true>(d, p, n, 2, st);
       return launch_v2_t<256, true>(d, p, n, d->ctas_override > 0 ? d->ctas_override : 2, st);
     }
     if (threads == 1024) return launch_v2_t<1024, false>(d, p, n, 1, st);
