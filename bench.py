@@ -614,6 +614,10 @@ def main():
                          "walk_single_thread", "eps_keys_zero", "list_order_scan", "commit_links_remap", "clear"],
                         [round(float(sum(i[16 + k] for i in infos)) / max(1.0, float(sum(i[16 + 15] for i in infos))), 3)
                          for k in range(12)])),
+                    replay_routes=None if not os.environ.get("B2K_DEC_PROF") else dict(
+                        marking_in_smem=sum(i[16 + 2] & 0xfffff for i in infos) / max(1, sum(i[1] for i in infos)),
+                        ids_in_smem=sum((i[16 + 2] >> 20) & 0xfffff for i in infos) / max(1, sum(i[1] for i in infos)),
+                        walk_by_components=sum((i[16 + 2] >> 40) & 0xfffff for i in infos) / max(1, sum(i[1] for i in infos))),
                     eps_replay_per_frame=dict(zip(["pops", "arc_visits", "in_shared_memory"],
                         [round(float(sum(i[16 + k] for i in infos)) / max(1.0, float(sum(i[1] for i in infos))), 2)
                          for k in (12, 13, 14)])),

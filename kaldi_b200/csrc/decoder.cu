@@ -141,6 +141,7 @@ struct DecParams {
   int32_t *v2_pf;
   int32_t v2_hw_len;
   int32_t fin_scap;         // finalize: tokens of a list whose sweep state is held in shared memory (0 = off)
+  int32_t hash_prefetch;    // second generation: L2 prefetch of the insert's first probe slot (experiment)
   int32_t par_walk;         // second generation: replay by connected components (one thread each)
   int32_t cid_smem;         // second generation: 16-bit compact ids of the replay in the upper half of the shared arc area
   int32_t v2_l1_shift;      // level-1 window = 2^shift x the reference's HashList size (rounded up to a power of two)
@@ -2489,6 +2490,8 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     } else {
       B2K_TICK(s, 3);                                        // (profile: slot 3 = building the compact arrays, slot 7 = the walk)
     }
+    // (profile: which frames take which route -- three 20-bit counters: marking in shared memory, ids in shared memory, walk by components)
+    if (PROF && tid == 0) s.prof[2] += (unsigned long long)owners_marked | ((unsigned long long)use_s << 20) | ((unsigned long long)par_done << 40);
     if (!par_done && s.rs_ok && tid == 0) {
       int qn = qcarry, next = 0;
       bool ok = true;
@@ -2523,8 +2526,6 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
       if (ok) {
         if (next != Nall - N1) B2K_SET_ERR(s, B2K_ERR_STATE);
         s.prof[12] += (unsigned long long)npop; s.prof[13] += (unsigned long long)nvis; s.prof[14] += 1;
-        // sizing data for the shared-memory walk (three 20-bit counters: frames with > 2048 tokens / arcs / worklist entries)
-        if (PROF) s.prof[2] += (unsigned long long)(s.rs_n > 2048) | ((unsigned long long)(s.rs_e > 2048) << 20) | ((unsigned long long)(qmax > 2048) << 40);
       } else {
         s.rs_ok = 0;                                         // worklist outgrew shared memory: redo below
       }
@@ -2921,6 +2922,8 @@ __device__ void dec_advance_v2_lane(const DecParams &p, DecShared<T> &s, const i
             float ac = cost_offset - (p.ll_smem ? ll_s[arc.z] : __ldg(&llg[arc.z]));
             tots[k] = s.chunk_cost[lo] + ac + __int_as_float(arc.y);
             acs[k] = ac; arcid[k] = a; nexts[k] = arc.x; srcs[k] = cb + lo;
+            // (experiment, B2K_DEC_PREFETCH=1) the destination's first probe slot on its way to L2 while the admission scan runs
+            if (p.hash_prefetch) asm volatile("prefetch.global.L2 [%0];" :: "l"(&ctx.hash[probe_slot_b(ctx, bucket_b(ctx, arc.x), 0)]));
           }
         }
         float ex[IT];
@@ -3811,6 +3814,7 @@ static int launch_v2_t(const b2k_dec *d, DecParams p, int n, int ctas_per_sm, cu
   if (p.ll_smem) smem = std::max(smem, ll_bytes);
   p.cid_smem = d->cid_smem_off ? 0 : 1;
   p.par_walk = d->par_walk_off ? 0 : 1;
+  p.hash_prefetch = getenv("B2K_DEC_PREFETCH") && atoi(getenv("B2K_DEC_PREFETCH")) ? 1 : 0;
   if (smem > configured) {
     B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_v2_kernel<T, PROF, IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
