@@ -2392,6 +2392,37 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     use_s = false;
     __syncthreads();
     }
+    // ---- An initial entry none of whose arcs fires under the INITIAL costs never does anything when it is popped: either its
+    //      token's cost is still the initial one then (destinations have only become cheaper), or it was lowered before,
+    //      in which case the token was pushed and processed on the spot and every arc was relaxed with the lowered cost.
+    //      Such entries are dropped (in parallel; the order of the others is kept).
+    int qinit = qcarry;                                      // entries of the shared-memory walks (the scratch walk keeps the full list)
+    if (s.rs_ok && qcarry > 0) {
+      int kept_total = 0;
+      for (int base = 0; base < qcarry; base += T) {
+        const int k = base + tid;
+        int keep = 0, d = 0;
+        if (k < qcarry) {
+          d = q_s[k];
+          const float2 td = tk_s[d];
+          if (td.x < cutoff) {
+            const int oc = __float_as_int(td.y);
+            const int e0 = oc & 0xffff, e1 = e0 + (int)((unsigned)oc >> 16);
+            for (int e = e0; e < e1 && !keep; e++) {
+              const float2 ent = en_s[e];
+              const float tot = td.x + ent.x;
+              keep = (tot < cutoff) && (tot < tk_s[__float_as_int(ent.y)].x);
+            }
+          }
+        }
+        int total;
+        const int off = block_excl_scan<T>(keep, s.redi, &total);   // (barriers inside: every thread has read its q_s[k] of this chunk)
+        if (keep) q_s[kept_total + off] = (unsigned short)d;         // kept_total + off <= k: never ahead of an unread entry of a later chunk
+        kept_total += total;
+        __syncthreads();
+      }
+      qinit = kept_total;
+    }
     // ---- The replay is a stack: the initial entries are popped from the back and everything an entry pushes is processed
     //      before the entry below it, so the run is a sequence of cascades, one per initial entry.  Cascades only interact
     //      through tokens they share: over the connected components of the compact graph they are independent, and the
@@ -2434,7 +2465,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
         if (lab[root] != root) continue;
         unsigned short stk[32];
         bool overflow = false;
-        for (int k = qcarry - 1; k >= 0 && !overflow; k--) {
+        for (int k = qinit - 1; k >= 0 && !overflow; k--) {
           const int d0 = q_s[k];
           if (lab[d0] != root) continue;
           int sp = 0, seq = 0;
@@ -2456,7 +2487,7 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
                   tk_s[j].x = tot;
                   if (tj.x == kInfF) {
                     const int slot = atomicAdd(&s.ncand, 1);
-                    crec[slot] = ((unsigned long long)(qcarry - 1 - k) << 32) | ((unsigned long long)seq++ << 12) | (unsigned long long)j;
+                    crec[slot] = ((unsigned long long)(qinit - 1 - k) << 32) | ((unsigned long long)seq++ << 12) | (unsigned long long)j;
                   }
                   if ((unsigned)__float_as_int(tj.y) >> 16) {
                     if (sp < 32) stk[sp++] = (unsigned short)j;
@@ -2493,11 +2524,10 @@ __device__ void finish_frame_v2(const DecParams &p, DecShared<T> &s, const LaneC
     // (profile: which frames take which route -- three 20-bit counters: marking in shared memory, ids in shared memory, walk by components)
     if (PROF && tid == 0) s.prof[2] += (unsigned long long)owners_marked | ((unsigned long long)use_s << 20) | ((unsigned long long)par_done << 40);
     if (!par_done && s.rs_ok && tid == 0) {
-      int qn = qcarry, next = 0;
+      int qn = qinit, next = 0;
       bool ok = true;
-      int npop = 0, nvis = 0, qmax = qcarry;
+      int npop = 0, nvis = 0;
       while (qn > 0) {
-        if (PROF) qmax = max(qmax, qn);
         const int d = q_s[--qn];
         const float2 td = tk_s[d];
         const float c = td.x;
@@ -2922,7 +2952,7 @@ __device__ void dec_advance_v2_lane(const DecParams &p, DecShared<T> &s, const i
             float ac = cost_offset - (p.ll_smem ? ll_s[arc.z] : __ldg(&llg[arc.z]));
             tots[k] = s.chunk_cost[lo] + ac + __int_as_float(arc.y);
             acs[k] = ac; arcid[k] = a; nexts[k] = arc.x; srcs[k] = cb + lo;
-            // (experiment, B2K_DEC_PREFETCH=1) the destination's first probe slot on its way to L2 while the admission scan runs
+            // the destination's first probe slot is on its way to L2 while the admission scan runs (B2K_DEC_PREFETCH=0 for A/B)
             if (p.hash_prefetch) asm volatile("prefetch.global.L2 [%0];" :: "l"(&ctx.hash[probe_slot_b(ctx, bucket_b(ctx, arc.x), 0)]));
           }
         }
@@ -3426,7 +3456,7 @@ struct b2k_dec {
   int threads_override = 0, fin_threads = 1024, num_sms = 0;   // tuning knobs, read from the environment at creation
   int ctas_override = 0;                // B2K_DEC_CTAS (256-thread CTAs only)
   bool cid_smem_off = false;            // B2K_DEC_CID_SMEM=0
-  bool par_walk_off = false;            // B2K_DEC_PARWALK=0
+  bool par_walk_off = true;             // B2K_DEC_PARWALK=1: replay by connected components (bit-exact, measured no faster: one component holds most of a heavy frame's tokens)
   bool fin_smem_off = true;             // B2K_FIN_SMEM=1 turns the shared-memory sweep state on (measured slower: 94 vs 58 ms, it shrinks L1 to 92 KB)
   int arcs_per_thread = 3;              // B2K_DEC_IT (512-thread CTAs): 3 measured 1.7 % faster than 4 and 2 (r2n, r2o)
   int nslots = 0;                       // scratch slots = the largest grid any per-lane launch uses (resident CTAs)
@@ -3814,7 +3844,7 @@ static int launch_v2_t(const b2k_dec *d, DecParams p, int n, int ctas_per_sm, cu
   if (p.ll_smem) smem = std::max(smem, ll_bytes);
   p.cid_smem = d->cid_smem_off ? 0 : 1;
   p.par_walk = d->par_walk_off ? 0 : 1;
-  p.hash_prefetch = getenv("B2K_DEC_PREFETCH") && atoi(getenv("B2K_DEC_PREFETCH")) ? 1 : 0;
+  p.hash_prefetch = (getenv("B2K_DEC_PREFETCH") && atoi(getenv("B2K_DEC_PREFETCH")) == 0) ? 0 : 1;   // measured 427 -> 422 ms (r2q)
   if (smem > configured) {
     B2K_CUDA_CHECK(cudaFuncSetAttribute(dec_advance_v2_kernel<T, PROF, IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
