@@ -211,15 +211,17 @@ def run_reference_arm(a, wname):
     n_steps = a.warmup + a.steps
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     os.environ["OMP_NUM_THREADS"] = "1"
-    _CPU_STATE["waves"] = [synth.make_audio(NUM_SAMPLES, seed=1000 + i) for i in range(per_step * n_steps + workers)]
+    # one step's worth of distinct utterances (+ one per worker for the warm-up), reused by every step: the CPU path keeps no
+    # state between utterances, and drawing 25 steps x 2 x workers utterances would cost minutes on a many-core box
+    _CPU_STATE["waves"] = [synth.make_audio(NUM_SAMPLES, seed=1000 + i) for i in range(per_step + workers)]
     _cpu_setup(wname)                                               # before the fork: workers share graph and model
     pool = mp.get_context("fork").Pool(workers)
-    base = per_step * n_steps
+    base = per_step
     pool.map(cpu_reference_one, [(base + i, wname) for i in range(workers)], chunksize=1)   # warm every worker
     vals, t_all = [], 0.0
     for s in range(n_steps):
         t0 = time.time()
-        pool.map(cpu_reference_one, [(s * per_step + i, wname) for i in range(per_step)], chunksize=1)
+        pool.map(cpu_reference_one, [(i, wname) for i in range(per_step)], chunksize=1)
         dt = time.time() - t0
         if s >= a.warmup:
             vals.append(per_step * NUM_SAMPLES / 16000.0 / dt)
