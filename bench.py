@@ -329,7 +329,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=6)
     ap.add_argument("--parity-utts", type=int, default=2, help="utterances of the last e2e batch checked against the compiled reference decoder")
-    ap.add_argument("--max-tpf", type=int, default=32768, help="decoder per-frame token capacity (hash = 2x slots)")
+    ap.add_argument("--max-tpf", type=int, default=65536, help="decoder per-frame token capacity (hash = 2x slots)")
     ap.add_argument("--tok-per-frame", type=int, default=9000, help="decoder token arena sizing (avg tokens/frame)")
     ap.add_argument("--links-per-frame", type=int, default=16000, help="decoder link arena sizing (avg links/frame)")
     ap.add_argument("--sweep-arcs", default="")
