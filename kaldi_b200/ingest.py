@@ -43,6 +43,13 @@ def shard_speakers(speakers, lengths, world: int) -> list[np.ndarray]:
     return out
 
 
+def _wire(t):
+    """The tensor as the transport sees it: torch's NCCL wrapper has no 16-bit integer type ("Input tensor data type is not
+    supported for NCCL process group: Short"), so anything but bytes / floats travels as a byte view of the same storage."""
+    import torch
+    return t if t.dtype in (torch.uint8, torch.float32, torch.int64, torch.int32) else t.contiguous().view(torch.uint8)
+
+
 def scatter_rows(rows0, counts, rank: int, world: int, device=None):
     """rank 0: rows0 = [sum(counts) x S] tensor already ordered by destination rank; every rank gets its [counts[rank] x S]
     block.  One group of point-to-point operations (ncclGroupStart / ncclSend... / ncclGroupEnd under NCCL)."""
@@ -52,7 +59,7 @@ def scatter_rows(rows0, counts, rank: int, world: int, device=None):
         return rows0, 0
     offs = np.concatenate([[0], np.cumsum(counts)])
     if rank == 0:
-        ops = [dist.P2POp(dist.isend, rows0[offs[r]:offs[r + 1]], r) for r in range(1, world) if counts[r] > 0]
+        ops = [dist.P2POp(dist.isend, _wire(rows0[offs[r]:offs[r + 1]]), r) for r in range(1, world) if counts[r] > 0]
         sent = int(sum(rows0[offs[r]:offs[r + 1]].numel() * rows0.element_size() for r in range(1, world)))
         reqs = dist.batch_isend_irecv(ops) if ops else []
         for q in reqs:
@@ -61,7 +68,7 @@ def scatter_rows(rows0, counts, rank: int, world: int, device=None):
     shape, dtype = scatter_rows.meta                        # set by broadcast_plan
     mine = torch.empty((int(counts[rank]),) + tuple(shape), dtype=dtype, device=device)
     if counts[rank] > 0:
-        for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, mine, 0)]):
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, _wire(mine), 0)]):       # (a view: the bytes land in `mine`)
             q.wait()
     return mine, 0
 

@@ -96,8 +96,21 @@ def test_two_gpu_ingest_egress_equals_single_gpu():
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
-    ids, shards, nbytes, same, nstates = q.get(timeout=600)
-    [p.join(timeout=120) for p in procs]
+    import queue as _queue
+    import time
+    res, t0 = None, time.time()
+    while res is None and time.time() - t0 < 240:            # a worker that died (exception before the gather) must not hang the test
+        try:
+            res = q.get(timeout=2)
+        except _queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    if res is None:
+        [p.kill() for p in procs if p.is_alive()]
+        pytest.fail("a worker failed or timed out (exit codes %s)" % [p.exitcode for p in procs])
+    ids, shards, nbytes, same, nstates = res
+    [p.join(timeout=60) for p in procs]
+    [p.kill() for p in procs if p.is_alive()]
     assert ids == list(range(8))
     assert len(shards[1]) > 0 and nbytes > len(shards[1]) * 32000 * 2        # PCM out + packed lattices back
     assert nstates > 0
