@@ -3253,9 +3253,18 @@ __device__ void dec_finalize_lane(const DecParams &p, const int lane, const int 
     // ---- lattice-state ids for the surviving tokens of list t (ids grow as we walk
     //      backwards; the host flips them so that id 0 is the start state) and emission of
     //      the surviving states / arcs into the channel's compact lattice region
+    // The ids are flipped when the lattice is packed (the last id becomes state 0) and state 0 must be the START state
+    // (include/b2k.h; the determinizer starts there): on the first token list the token of the graph's start state takes its
+    // id after every other survivor.  (Until round 2 it took whatever the atomic handed it: whenever frame 0 kept an
+    // eps-successor of the start as well, state 0 was one of the two at random -- found as a flaky difference between two
+    // determinizations of the same utterance, tools/determinism_probe.py; the order-free comparisons never saw it.)
+    __shared__ int sh_start_k;
+    if (t == 0 && tid == 0) sh_start_k = -1;
+    if (t == 0) __syncthreads();
     for (int k = tid; k < n; k += T) {
       float ex = tok_extra[tb + k];
       if (ex == kInf) continue;
+      if (t == 0 && tok_state[tb + k] == g.start) { sh_start_k = k; continue; }
       int id = n_states + atomicAdd(&sh_cnt[2], 1);
       ids_cur[k] = id;
       if (in_s) atomicOr(&alive_cur[k >> 5], 1u << (k & 31));
@@ -3269,6 +3278,24 @@ __device__ void dec_finalize_lane(const DecParams &p, const int lane, const int 
       }
     }
     __syncthreads();
+    if (t == 0 && sh_start_k >= 0) {                          // the start state's token: the last id of the lattice
+      if (tid == 0) {
+        const int k = sh_start_k;
+        const int id = n_states + sh_cnt[2];
+        sh_cnt[2] += 1;
+        ids_cur[k] = id;
+        if (in_s) atomicOr(&alive_cur[k >> 5], 1u << (k & 31));
+        if (id < p.cap_ls) ls[id] = make_int4(t, tok_state[tb + k], __float_as_int(tok_cost[tb + k]), __float_as_int(tok_extra[tb + k]));
+        if (t == last) {                                      // (a zero-frame utterance: the first list is the last one too)
+          const float fc = any_final ? __ldg(&g.final_cost[tok_state[tb + k]]) : 0.0f;
+          if (fc != kInf) {
+            const int q = atomicAdd(&sh_nfin, 1);
+            if (q < p.cap_lf) lf[q] = make_int2(id, __float_as_int(fc));
+          }
+        }
+      }
+      __syncthreads();
+    }
     n_states += sh_cnt[2];
     if (t < last) {
       const float coff = p.frame_cost_offset[(size_t)ch * (p.max_frames + 1) + t];

@@ -259,3 +259,31 @@ def test_full_length_utterance_properties():
     assert (ex == 0).sum() >= T + 1          # the best path has extra_cost 0 on every frame
     # and the whole thing equals the oracle too
     _check_against_oracle(g, cfg, ll, dec, 0, frames=False)
+
+
+@pytest.mark.parametrize("seed", [3, 11])
+def test_state_zero_is_the_start_state_and_determinization_is_repeatable(seed):
+    """include/b2k.h promises "state 0 = start" for a raw lattice and b2k_lat_determinize_pruned starts there.  Lattice-state
+    ids are handed out by atomics while the sweep walks backwards: when the first token list keeps an eps-successor of the
+    start beside the start token, either of them used to end up as state 0, and the compact lattice of the same utterance
+    changed from run to run (found with tools/determinism_probe.py; the order-free comparisons above cannot see it)."""
+    from kaldi_b200 import synth
+    from kaldi_b200.lattice import determinize_pruned
+    g = synth.make_hclg(50_000, num_pdfs=64, seed=4)
+    cfg = dict(synth.DEFAULT_DECODER_CFG)
+    ll = synth.make_loglikes(g, 60, seed=seed)
+    beam = float(cfg["lattice_beam"])
+    first = None
+    for rep in range(12):
+        fst, dec = _mk(g, cfg, T=60)
+        _run_gpu(dec, [ll])
+        lat = dec.GetRawLattice(0)
+        assert lat["state_frame"][0] == 0 and lat["state_hclg"][0] == fst.Start()
+        det = determinize_pruned(lat, beam)
+        # (compared as multisets: the numbering of the compact states may follow the order of the raw arrays)
+        cur = {k: np.sort(det[k]) for k in ("arc_word", "arc_graph_cost", "arc_acoustic_cost", "final_graph_cost", "final_acoustic_cost")}
+        cur["num_states"] = np.asarray(det["num_states"])
+        if first is None:
+            first = cur
+        for k in cur:
+            np.testing.assert_array_equal(cur[k], first[k], err_msg=f"run {rep}: {k}")
