@@ -411,6 +411,56 @@ int b2k_nnet_program_info(const b2k_nnet_program *prog, int64_t info[8]);
 /* b2k_nnet_create on a compiled program (needs the device) */
 int b2k_nnet_create_from_program(const b2k_nnet_program *prog, int32_t max_batch, b2k_nnet **out);
 
+/* A window program: outputs at t = first_output_t + k*subsampling, k < num_outputs, of a window of cfg->num_frames input
+ * frames that holds every frame those outputs read (nothing is padded; an output outside that range is an error) and ONE
+ * i-vector for the window -- the computation request BatchedStaticNnet3::SetComputationRequest builds for a chunk with its
+ * context (cudadecoder/batched-static-nnet3.cc:123-152).  Only the rows each layer needs for those outputs are computed.
+ * Host only. */
+int b2k_nnet_compile_window(const b2k_nnet_compile_cfg *cfg, int32_t first_output_t, int32_t num_outputs,
+                            const b2k_nnet_layer *layers, int32_t n_layers, const b2k_nnet_weight *weights,
+                            int32_t n_weights, b2k_nnet_program **out);
+/* ComputeSimpleNnetContext (nnet3/nnet-utils.cc) of the layer list: left / right context in input frames.  Host only. */
+int b2k_nnet_model_context(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers,
+                           int32_t *left, int32_t *right);
+
+/* ------------------------------------------------------------------ chunked nnet3 with carried context
+ *
+ * cuda_decoder::BatchedStaticNnet3 (cudadecoder/batched-static-nnet3.h:59-138, .cc): every call takes at most one chunk of
+ * features per channel, restores the channel's context frames in front of it, runs the network on the batch of windows,
+ * saves the new context, and flushes the right context (last frame repeated) of the channels whose chunk was the last.
+ * cfg->frames_per_chunk is compute_opts.frames_per_chunk (INPUT frames per chunk, >= the right context as the reference
+ * asserts, :172-175); cfg->num_frames is ignored.  Output frame k of a call is the network's output at input time
+ * (first new frame - right context) + k*subsampling, exactly the reference's arithmetic (so frames_per_chunk should be a
+ * multiple of the subsampling factor there as here). */
+typedef struct b2k_nnet_stream b2k_nnet_stream;
+
+/* The frame bookkeeping of BatchContextSwitch for one channel (batched-static-nnet3.cc:151-190): given the frames its
+ * context holds (0 = first chunk), the new frames and whether this is the flush, the frames the context holds afterwards
+ * and the output frames the call produces.  Host only. */
+int b2k_nnet_stream_account(int32_t left_context, int32_t right_context, int32_t subsampling, int32_t frames_in_context,
+                            int32_t n_new_frames, int32_t flush, int32_t *frames_in_context_after,
+                            int32_t *n_output_frames);
+
+int b2k_nnet_stream_create(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers,
+                           const b2k_nnet_weight *weights, int32_t n_weights, int32_t max_batch, int32_t nchannels,
+                           b2k_nnet_stream **out);
+int b2k_nnet_stream_destroy(b2k_nnet_stream *s);
+/* info: {output frames per chunk (GetNOutputFramesPerChunk), total left context, total right context
+ * (GetTotalNnet3RightContext), window frames, input dim, i-vector dim, output dim, channels} */
+int b2k_nnet_stream_info(const b2k_nnet_stream *s, int64_t info[8]);
+/* RunBatch (batched-static-nnet3.cc:293-367).  Batch slot i: channel channels[i]; d_features[i] = n_input_frames_valid[i]
+ * (<= frames_per_chunk) new feature rows, row stride features_stride floats; d_ivectors[i] the i-vector of this run (NULL
+ * array for a model without); is_first_chunk[i] resets the channel's context; is_last_chunk[i] flushes it.  Output frame k
+ * of slot i goes to d_log_post + (i*opc + k)*out_stride, k < n_output_frames[i]; the frames of the flush of slot i to
+ * d_eos_log_post + (i*opc + k)*out_stride, k < n_eos_output_frames[i] (0 for a slot that is not a last chunk), with
+ * opc = output frames per chunk: in FormatOutputPtrs' words (:369-395) frame n_output_frames[i] + k of the channel.
+ * Priors and acoustic scale are applied (:281-286).  Asynchronous on `stream`; the frame counts are final on return. */
+int b2k_nnet_stream_run_batch(b2k_nnet_stream *s, int32_t n, const int32_t *channels, const float *const *d_features,
+                              int32_t features_stride, const float *const *d_ivectors,
+                              const int32_t *n_input_frames_valid, const int32_t *is_first_chunk,
+                              const int32_t *is_last_chunk, float *d_log_post, float *d_eos_log_post,
+                              int32_t out_stride, int32_t *n_output_frames, int32_t *n_eos_output_frames, void *stream);
+
 /* ------------------------------------------------------------------ Kaldi model files (host only)
  *
  * Raw nnet3 models as Nnet::Write emits them (nnet3/nnet-nnet.cc:630-656) and final.mdl = TransitionModel

@@ -395,13 +395,20 @@ struct b2k_nnet_program {
 
 extern "C" {
 
-int b2k_nnet_compile(const b2k_nnet_compile_cfg *cfgp, const b2k_nnet_layer *layers, int32_t n_layers,
-                     const b2k_nnet_weight *weights, int32_t n_weights, b2k_nnet_program **out) {
+// win_n_out <= 0: the whole utterance (outputs at t = 0, sub, ...; the input is padded by repeating its first / last frame).
+// win_n_out > 0: a window program -- outputs at t = win_t0 + k*sub, k < win_n_out, of a window of cfg.num_frames input frames that
+// must hold every frame those outputs read (no padding), one i-vector for the whole window: the computation request of
+// BatchedStaticNnet3::SetComputationRequest (cudadecoder/batched-static-nnet3.cc:123-152).
+static int compile_impl(const b2k_nnet_compile_cfg *cfgp, int win_t0, int win_n_out, const b2k_nnet_layer *layers, int32_t n_layers,
+                        const b2k_nnet_weight *weights, int32_t n_weights, b2k_nnet_program **out) {
   if (!cfgp || !layers || n_layers <= 0 || (!weights && n_weights > 0) || !out)
     return set_error(B2K_ERR_INVALID, "b2k_nnet_compile: bad args");
   const b2k_nnet_compile_cfg &cfg = *cfgp;
+  const bool window = win_n_out > 0;
   const int sub = cfg.frame_subsampling_factor, T = cfg.num_frames, C = cfg.frames_per_chunk;
   if (sub <= 0 || T <= 0 || C <= 0 || C % sub != 0) return set_error(B2K_ERR_INVALID, "b2k_nnet_compile: frames_per_chunk must be a positive multiple of the subsampling factor");
+  if (window && (win_t0 < 0 || (long long)win_t0 + (long long)sub * (win_n_out - 1) >= T))
+    return set_error(B2K_ERR_INVALID, "b2k_nnet_compile_window: the outputs lie outside the window");
   Weights W;
   for (int i = 0; i < n_weights; i++) {
     const b2k_nnet_weight &w = weights[i];
@@ -417,9 +424,10 @@ int b2k_nnet_compile(const b2k_nnet_compile_cfg *cfgp, const b2k_nnet_layer *lay
   std::map<std::string, Node *> by;
   for (auto &n : g.nodes) by[n.name] = &n;
   if (!by.count("output")) return set_error(B2K_ERR_INVALID, "b2k_nnet_compile: no output layer");
-  const int n_out = (T + sub - 1) / sub;
+  const int n_out = window ? win_n_out : (T + sub - 1) / sub;
+  const int out_t0 = window ? win_t0 : 0;
   Node *o = by["output"];
-  o->residues = {0}; o->tmin = 0; o->tmax = sub * (n_out - 1);
+  o->residues = {out_t0 % sub}; o->tmin = out_t0; o->tmax = out_t0 + sub * (n_out - 1);
   std::vector<std::pair<std::string, int>> d;
   // backward pass: required time range and residues (mod sub) of every node
   for (int i = (int)g.nodes.size() - 1; i >= 0; i--) {
@@ -440,8 +448,14 @@ int b2k_nnet_compile(const b2k_nnet_compile_cfg *cfgp, const b2k_nnet_layer *lay
   }
   b2k_nnet_program *P = new b2k_nnet_program();
   P->n_out = n_out;
-  P->left = -by["input"]->tmin;
-  P->right = by["input"]->tmax - sub * (n_out - 1);
+  P->left = out_t0 - by["input"]->tmin;
+  P->right = by["input"]->tmax - (out_t0 + sub * (n_out - 1));
+  if (window && (by["input"]->tmin < 0 || by["input"]->tmax > T - 1)) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "the outputs read input frames [%d, %d] of a window of %d", by["input"]->tmin, by["input"]->tmax, T);
+    delete P;
+    return set_error(B2K_ERR_INVALID, "b2k_nnet_compile_window", msg);
+  }
   for (auto &n : g.nodes) {
     if (n.kind == 0) { n.step = 1; n.t0 = 0; n.rows = T; }
     else if (n.kind == 1) { n.step = 0; n.t0 = 0; n.rows = 0; }
@@ -458,7 +472,7 @@ int b2k_nnet_compile(const b2k_nnet_compile_cfg *cfgp, const b2k_nnet_layer *lay
   // chunk n of the looped computation supplies one i-vector; input time t uses chunk max(0, floor(t / C) - m),
   // m = floor((C + R - 1) / C)   (nnet-compile-looped.cc:179-205)
   const int m = (C + Rk - 1) / C;
-  const int n_chunks = (n_out * sub + C - 1) / C;
+  const int n_chunks = window ? 1 : (n_out * sub + C - 1) / C;
   by["ivector"]->rows = n_chunks;
   P->model_left = Lk; P->model_right = Rk; P->ivector_m = m; P->n_chunks = n_chunks;
   auto put = [&](const float *a, size_t n) -> int64_t {
@@ -611,6 +625,27 @@ int b2k_nnet_compile(const b2k_nnet_compile_cfg *cfgp, const b2k_nnet_layer *lay
   }
   if (P->blob.empty()) P->blob.push_back(0.0f);
   *out = P;
+  return B2K_OK;
+}
+
+int b2k_nnet_compile(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers,
+                     const b2k_nnet_weight *weights, int32_t n_weights, b2k_nnet_program **out) {
+  return compile_impl(cfg, 0, 0, layers, n_layers, weights, n_weights, out);
+}
+
+int b2k_nnet_compile_window(const b2k_nnet_compile_cfg *cfg, int32_t first_output_t, int32_t num_outputs, const b2k_nnet_layer *layers,
+                            int32_t n_layers, const b2k_nnet_weight *weights, int32_t n_weights, b2k_nnet_program **out) {
+  if (num_outputs <= 0) return set_error(B2K_ERR_INVALID, "b2k_nnet_compile_window: num_outputs must be positive");
+  return compile_impl(cfg, first_output_t, num_outputs, layers, n_layers, weights, n_weights, out);
+}
+
+int b2k_nnet_model_context(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers, int32_t *left, int32_t *right) {
+  if (!cfg || !layers || n_layers <= 0 || !left || !right) return set_error(B2K_ERR_INVALID, "b2k_nnet_model_context: bad args");
+  std::string err;
+  if (!validate_layers(*cfg, layers, n_layers, err)) return set_error(B2K_ERR_INVALID, "b2k_nnet_model_context", err.c_str());
+  int L = 0, R = 0;
+  if (!model_context(*cfg, layers, n_layers, &L, &R, err)) return set_error(B2K_ERR_INVALID, "b2k_nnet_model_context", err.c_str());
+  *left = L; *right = R;
   return B2K_OK;
 }
 

@@ -152,3 +152,64 @@ class NnetComputer:
                  [x.data_ptr() for x in d_out], self.output_dim)
         torch.cuda.synchronize()
         return [o.cpu().numpy() for o in d_out]
+
+
+class BatchedStaticNnet3:
+    """cuda_decoder::BatchedStaticNnet3 (cudadecoder/batched-static-nnet3.h:59-138) over b2k_nnet_stream_*: at most one
+    chunk of features per channel and call, context frames carried per channel on the device, right context flushed
+    on the last chunk.  `frames_per_chunk` is compute_opts.frames_per_chunk (input frames)."""
+
+    def __init__(self, arch: dict, W: dict, max_batch: int, nchannels: int = -1, frames_per_chunk: int = 51,
+                 acoustic_scale: float = 1.0, use_priors: bool = True):
+        from .nnet_compile import _Cfg, abi_arrays
+        L = _lib.lib()
+        layers, ws, self._keep = abi_arrays(arch, W)
+        cfg = _Cfg(arch["feat_dim"], arch["ivector_dim"], arch["num_pdfs"], arch["frame_subsampling_factor"], 0,
+                   int(frames_per_chunk), int(use_priors), 0, float(acoustic_scale))
+        self.h = C.c_void_p()
+        L.b2k_nnet_stream_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        _lib.check(L.b2k_nnet_stream_create(C.byref(cfg), layers, len(layers), ws, len(ws), int(max_batch), int(nchannels),
+                                            C.byref(self.h)))
+        info = (C.c_int64 * 8)()
+        L.b2k_nnet_stream_info.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.check(L.b2k_nnet_stream_info(self.h, info))
+        (self.output_frames_per_chunk, self.left_context, self.right_context, self.window, self.input_dim,
+         self.ivector_dim, self.output_dim, self.nchannels) = [int(x) for x in info]
+        self.max_batch = max_batch
+        self.frames_per_chunk = frames_per_chunk
+        L.b2k_nnet_stream_run_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                                C.c_void_p]
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().b2k_nnet_stream_destroy.argtypes = [C.c_void_p]
+                _lib.lib().b2k_nnet_stream_destroy(self.h)
+        except Exception:
+            pass
+
+    def GetNOutputFramesPerChunk(self) -> int:
+        return self.output_frames_per_chunk
+
+    def GetTotalNnet3RightContext(self) -> int:
+        return self.right_context
+
+    def RunBatch(self, channels, d_features, features_stride, d_ivectors, n_input_frames_valid, is_first_chunk,
+                 is_last_chunk, d_all_log_posteriors: int, d_all_eos_log_posteriors: int, out_stride: int, stream: int = 0):
+        """Device pointers as integers.  Returns (n_output_frames, n_eos_output_frames) per batch slot: slot i's frame k
+        is row i*output_frames_per_chunk + k of d_all_log_posteriors, its flush frames the same rows of
+        d_all_eos_log_posteriors (FormatOutputPtrs, batched-static-nnet3.cc:369-395)."""
+        n = len(channels)
+        ch = (C.c_int32 * n)(*[int(c) for c in channels])
+        fp = (C.c_void_p * n)(*[int(p) if p else None for p in d_features])
+        ip = (C.c_void_p * n)(*[int(p) for p in d_ivectors]) if d_ivectors is not None else None
+        nv = (C.c_int32 * n)(*[int(x) for x in n_input_frames_valid])
+        fi = (C.c_int32 * n)(*[int(bool(x)) for x in is_first_chunk])
+        la = (C.c_int32 * n)(*[int(bool(x)) for x in is_last_chunk])
+        no, ne = (C.c_int32 * n)(), (C.c_int32 * n)()
+        _lib.check(_lib.lib().b2k_nnet_stream_run_batch(self.h, n, ch, fp, int(features_stride), ip, nv, fi, la,
+                                                        C.c_void_p(d_all_log_posteriors),
+                                                        C.c_void_p(d_all_eos_log_posteriors) if d_all_eos_log_posteriors else None,
+                                                        int(out_stride), no, ne, C.c_void_p(stream)))
+        return list(no), list(ne)

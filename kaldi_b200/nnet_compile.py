@@ -60,7 +60,9 @@ class CompiledProgram:
     """Owns a b2k_nnet_program; exposes nodes/ops as ctypes arrays (the ABI structs b2k_nnet_create takes) and the blob."""
 
     def __init__(self, arch: dict, W: dict, num_frames: int, frames_per_chunk: int = 21, acoustic_scale: float = 1.0,
-                 use_priors: bool = True, conv_mode: str | None = None):
+                 use_priors: bool = True, conv_mode: str | None = None, window: tuple | None = None):
+        """window = (first_output_t, num_outputs): b2k_nnet_compile_window, the computation request of
+        BatchedStaticNnet3 for a chunk with its context (num_frames = the window's input frames)."""
         L = _lib.lib()
         layers = (_Layer * len(arch["layers"]))(*[_layer(x) for x in arch["layers"]])
         self._keep = {k: np.ascontiguousarray(v, np.float32) for k, v in W.items()}
@@ -73,7 +75,12 @@ class CompiledProgram:
                    float(acoustic_scale))
         self.h = C.c_void_p()
         L.b2k_nnet_compile.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
-        _lib.check(L.b2k_nnet_compile(C.byref(cfg), layers, len(layers), ws, len(ws), C.byref(self.h)))
+        L.b2k_nnet_compile_window.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        if window is None:
+            _lib.check(L.b2k_nnet_compile(C.byref(cfg), layers, len(layers), ws, len(ws), C.byref(self.h)))
+        else:
+            _lib.check(L.b2k_nnet_compile_window(C.byref(cfg), int(window[0]), int(window[1]), layers, len(layers), ws, len(ws),
+                                                 C.byref(self.h)))
         nn, no, bl = C.c_int32(), C.c_int32(), C.c_int64()
         L.b2k_nnet_program_sizes.argtypes = [C.c_void_p] * 4
         _lib.check(L.b2k_nnet_program_sizes(self.h, C.byref(nn), C.byref(no), C.byref(bl)))
@@ -95,3 +102,35 @@ class CompiledProgram:
             _lib.lib().b2k_nnet_program_destroy.argtypes = [C.c_void_p]
             _lib.lib().b2k_nnet_program_destroy(self.h)
             self.h = None
+
+
+def abi_arrays(arch: dict, W: dict):
+    """(layers, weights, keep-alive) as the ABI arrays b2k_nnet_compile / b2k_nnet_stream_create take."""
+    layers = (_Layer * len(arch["layers"]))(*[_layer(x) for x in arch["layers"]])
+    keep = {k: np.ascontiguousarray(v, np.float32) for k, v in W.items()}
+    ws = (_Weight * len(keep))()
+    for i, (k, v) in enumerate(keep.items()):
+        rows, cols = (v.shape if v.ndim == 2 else (v.shape[0], 1))
+        ws[i] = _Weight(k.encode(), v.ctypes.data, v.size, int(rows), int(cols))
+    return layers, ws, keep
+
+
+def model_context(arch: dict) -> tuple:
+    """ComputeSimpleNnetContext of the layer list (b2k_nnet_model_context)."""
+    L = _lib.lib()
+    layers = (_Layer * len(arch["layers"]))(*[_layer(x) for x in arch["layers"]])
+    cfg = _Cfg(arch["feat_dim"], arch["ivector_dim"], arch["num_pdfs"], arch["frame_subsampling_factor"], 1,
+               arch["frame_subsampling_factor"], 0, 0, 1.0)
+    l, r = C.c_int32(), C.c_int32()
+    L.b2k_nnet_model_context.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    _lib.check(L.b2k_nnet_model_context(C.byref(cfg), layers, len(layers), C.byref(l), C.byref(r)))
+    return l.value, r.value
+
+
+def stream_account(left: int, right: int, sub: int, in_ctx: int, n_new: int, flush: bool) -> tuple:
+    """b2k_nnet_stream_account: (frames in context afterwards, output frames) of one BatchContextSwitch."""
+    L = _lib.lib()
+    a, o = C.c_int32(), C.c_int32()
+    L.b2k_nnet_stream_account.argtypes = [C.c_int32] * 6 + [C.c_void_p, C.c_void_p]
+    _lib.check(L.b2k_nnet_stream_account(left, right, sub, in_ctx, n_new, int(flush), C.byref(a), C.byref(o)))
+    return a.value, o.value
