@@ -179,6 +179,29 @@ int b2k_dec_pack_lattices_async(b2k_dec *dec, const int32_t *d_channels, int32_t
 int b2k_dec_unpack_lattices(const void *h_buf, int32_t n, b2k_raw_lattice *out, int64_t *state_offs, int64_t *arc_offs,
                             int64_t *final_offs);
 
+/* The best path of channels that are still decoding (or finalized), without touching their state:
+ * LatticeFasterOnlineDecoderTpl::GetBestPath = BestPathEnd + TraceBackBestPath (decoder/lattice-faster-online-decoder.cc:
+ * 54-167), CudaDecoder::GetBestPath (cudadecoder/cuda-decoder.h:279) -- partial hypotheses, and the best path with
+ * use_final_probs = 0 that endpointing reads (online2/online-endpoint.cc:78-110).  The end token is the cheapest token of
+ * the last frame (with its final cost when use_final_probs and some token of that frame is final); the predecessor of a
+ * token is the link whose source cost + link cost is smallest (ties: lowest arena index).  Arcs come start first, at most
+ * `cap` per channel (arrays [n x cap], any of them may be NULL): ilabel (transition-id, 0 = epsilon), olabel, graph cost,
+ * acoustic cost minus the frame's cost offset (:150-154), the frame index of the arc's destination token list
+ * (0 = before the first frame) and its HCLG state.  final_relative_cost is ComputeFinalCosts' (lattice-faster-decoder.cc:
+ * 545-586) = FinalRelativeCost(); best_cost the end token's cost including final_cost.  Synchronizes `stream`. */
+typedef struct {
+  int32_t status;          /* 0, B2K_ERR_STATE (not decoding / in error / walk did not reach the start), B2K_ERR_OVERFLOW */
+  int32_t n_arcs;          /* 0 with end_state -1: "No final token found" (:111)                                         */
+  int32_t end_state;       /* HCLG state of the end token                                                                */
+  int32_t num_frames;      /* NumFramesDecoded()                                                                         */
+  float final_cost;        /* LatticeWeight(final_cost, 0) of the path's last state (:63)                                */
+  float best_cost;
+  float final_relative_cost;
+} b2k_best_path_info;
+int b2k_dec_best_path(b2k_dec *dec, const int32_t *channels, int32_t n, int32_t use_final_probs, int32_t cap,
+                      int32_t *ilabels, int32_t *olabels, float *graph_costs, float *acoustic_costs,
+                      int32_t *arc_frame, int32_t *arc_state, b2k_best_path_info *info, void *stream);
+
 /* Debug/parity hook: copies the un-pruned token list of frame `frame_plus_one`
  * and the links created by that frame step (tests compare these bit-for-bit
  * against the oracle before any pruning).  links7 rows:

@@ -3457,6 +3457,109 @@ __global__ void dec_pack_body_kernel(DecParams p, const int32_t *channels, int n
   for (int i = gt; i < nf; i += gs) { int2 f = lf[i]; f.x = ns - 1 - f.x; o_finals[fo + i] = f; }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Best path of a channel WITHOUT finalizing it: LatticeFasterOnlineDecoderTpl::BestPathEnd + TraceBackBestPath
+// (decoder/lattice-faster-online-decoder.cc:78-167), ComputeFinalCosts' final_relative_cost (lattice-faster-decoder.cc:
+// 545-586) -- what partial hypotheses, endpointing (online2/online-endpoint.cc:78-110: trailing silence of the best path
+// with use_final_probs = false) and CudaDecoder::GetBestPath (cudadecoder/cuda-decoder.h:279) need mid-utterance.
+// The tokens here carry no back pointer (the reference's non-online Token does not either): the predecessor of a token is
+// the link into it with the smallest (source cost + link cost) -- the link that set the token's cost; ties go to the lowest
+// arena index.  One CTA per channel walks back from the best token of the last list; every step scans the links of one
+// frame (coalesced 16-byte records) and reduces a 64-bit (cost, index) key.
+struct BestPathHdr {
+  int32_t status, n_arcs, end_state, frames;
+  float final_cost, best_cost, final_relative_cost, pad;
+};
+
+template <int T>
+__global__ void __launch_bounds__(T) dec_best_path_kernel(DecParams p, const int32_t *channels, int use_final, int cap,
+                                                          int4 *out_arcs, int2 *out_where, BestPathHdr *out_hdr) {
+  __shared__ unsigned long long sh64[T / 32];
+  const int tid = threadIdx.x;
+  const int ch = channels[blockIdx.x];
+  const FstDev &g = p.fst;
+  const ChanState *cs = &p.chan[ch];
+  const float kInf = __int_as_float(0x7f800000);
+  int4 *oa = out_arcs + (size_t)blockIdx.x * cap;
+  int2 *ow = out_where + (size_t)blockIdx.x * cap;
+  BestPathHdr h;
+  h.status = 0; h.n_arcs = 0; h.end_state = -1; h.frames = cs->frames_decoded;
+  h.final_cost = 0.0f; h.best_cost = kInf; h.final_relative_cost = kInf; h.pad = 0.0f;
+  const int last = cs->frames_decoded;
+  if (last < 0 || last > p.max_frames || cs->status != 0) {
+    h.status = B2K_ERR_STATE;
+    if (tid == 0) out_hdr[blockIdx.x] = h;
+    return;
+  }
+  const int32_t *tok_state = p.tok_state + (size_t)ch * p.max_tokens;
+  const float *tok_cost = p.tok_cost + (size_t)ch * p.max_tokens;
+  const int4 *links = p.links + (size_t)ch * p.max_links;
+  const size_t fo = (size_t)ch * (p.max_frames + 2);
+  const float *coffs = p.frame_cost_offset + (size_t)ch * (p.max_frames + 1);
+  // the end token (BestPathEnd :78-117) and final_relative_cost
+  const int tb = p.frame_tok_begin[fo + last], te = p.frame_tok_begin[fo + last + 1];
+  unsigned long long ka = ~0ull, kb = ~0ull;
+  for (int i = tb + tid; i < te; i += T) {
+    const float c = tok_cost[i], fc = __ldg(&g.final_cost[tok_state[i]]);
+    const unsigned long long a = ((unsigned long long)f2ord(c) << 32) | (uint32_t)(i - tb);
+    const unsigned long long b = ((unsigned long long)f2ord(c + fc) << 32) | (uint32_t)(i - tb);
+    ka = a < ka ? a : ka; kb = b < kb ? b : kb;
+  }
+  ka = block_min_u64<T>(ka, sh64);
+  kb = block_min_u64<T>(kb, sh64);
+  const float best_cost = (ka == ~0ull) ? kInf : ord2f((uint32_t)(ka >> 32));
+  const float best_with_final = (kb == ~0ull) ? kInf : ord2f((uint32_t)(kb >> 32));
+  h.final_relative_cost = (best_cost == kInf && best_with_final == kInf) ? kInf : best_with_final - best_cost;
+  const bool with_final = use_final && best_with_final != kInf;     // "any final tokens were active on the final frame"
+  const unsigned long long kend = with_final ? kb : ka;
+  h.best_cost = with_final ? best_with_final : best_cost;
+  if (kend == ~0ull || h.best_cost == kInf) {                       // "No final token found."
+    if (tid == 0) out_hdr[blockIdx.x] = h;
+    return;
+  }
+  int cur = tb + (int)(uint32_t)(kend & 0xffffffffull);
+  h.end_state = tok_state[cur];
+  h.final_cost = with_final ? __ldg(&g.final_cost[h.end_state]) : 0.0f;
+  int t = last, n = 0;
+  for (;;) {
+    const int lb = p.frame_link_begin[fo + t], lm = p.frame_link_eps[fo + t], le = p.frame_link_begin[fo + t + 1];
+    unsigned long long best = ~0ull;
+    for (int l = lb + tid; l < le; l += T) {
+      const int4 lk = links[l];
+      if (lk.y != cur) continue;
+      float v;
+      if (l < lm) v = (tok_cost[lk.x] + __int_as_float(lk.w)) + __int_as_float(__ldg(&g.e_arcs[lk.z]).y);
+      else v = tok_cost[lk.x] + __int_as_float(__ldg(&g.ne_arcs[(uint32_t)lk.z & B2K_ARC_MASK]).y);
+      const unsigned long long k = ((unsigned long long)f2ord(v) << 32) | (uint32_t)(l - lb);
+      best = k < best ? k : best;
+    }
+    best = block_min_u64<T>(best, sh64);
+    const bool found = best != ~0ull;
+    if (t == 0 && (!found || ord2f((uint32_t)(best >> 32)) > tok_cost[cur])) break;    // the start token: no link made it
+    if (!found) { h.status = B2K_ERR_STATE; break; }
+    if (n >= cap) { h.status = B2K_ERR_OVERFLOW; break; }
+    const int l = lb + (int)(uint32_t)(best & 0xffffffffull);
+    const int4 lk = links[l];
+    if (tid == 0) {
+      if (l < lm) {
+        const int4 arc = __ldg(&g.e_arcs[lk.z]);
+        oa[n] = make_int4(__ldg(&g.e_ilabel[lk.z]), arc.w, arc.y, __float_as_int(__int_as_float(lk.w) - coffs[t - 1]));   // :150-154
+      } else {
+        const int4 arc = __ldg(&g.ne_arcs[(uint32_t)lk.z & B2K_ARC_MASK]);
+        oa[n] = make_int4(0, arc.z & 0x7fffffff, arc.y, 0);
+      }
+      ow[n] = make_int2(t, tok_state[cur]);
+    }
+    n++;
+    cur = lk.x;
+    if (l < lm) t--;
+  }
+  if (h.status == 0 && tok_state[cur] != g.start) h.status = B2K_ERR_STATE;           // the walk must end in the start state
+  h.n_arcs = n;
+  if (tid == 0) out_hdr[blockIdx.x] = h;
+}
+
 }  // namespace b2k
 
 // ====================================================================== host side
@@ -3506,6 +3609,9 @@ struct b2k_dec {
   char *h_pack = nullptr; size_t h_pack_bytes = 0;
   int32_t *d_pack_ch = nullptr; int64_t *d_pack_offs = nullptr;
   ChanState *h_chan = nullptr;
+  // best-path read-back (grow-only scratch)
+  char *d_bp = nullptr; size_t d_bp_bytes = 0;
+  char *h_bp = nullptr; size_t h_bp_bytes = 0;
 };
 
 extern "C" {
@@ -3794,6 +3900,8 @@ int b2k_dec_destroy(b2k_dec *d) {
   if (d->h_chan) cudaFreeHost(d->h_chan);
   if (d->h_pack) cudaFreeHost(d->h_pack);
   if (d->d_pack) cudaFree(d->d_pack);
+  if (d->h_bp) cudaFreeHost(d->h_bp);
+  if (d->d_bp) cudaFree(d->d_bp);
   if (d->staging_free) cudaEventDestroy(d->staging_free);
   delete d;
   return B2K_OK;
@@ -4239,6 +4347,70 @@ int b2k_dec_frame_info(b2k_dec *d, int32_t channel, float *cutoff, float *cost_o
     B2K_CUDA_CHECK(cudaMemcpy(tb.data(), p.frame_tok_begin + (size_t)channel * (p.max_frames + 2), 4 * (size_t)(T + 2), cudaMemcpyDeviceToHost));
     for (int f = 0; f < T; f++) ntoks[f] = tb[f + 2] - tb[f + 1];
   }
+  return B2K_OK;
+}
+
+int b2k_dec_best_path(b2k_dec *d, const int32_t *channels, int32_t n, int32_t use_final_probs, int32_t cap,
+                      int32_t *ilabels, int32_t *olabels, float *graph_costs, float *acoustic_costs, int32_t *arc_frame,
+                      int32_t *arc_state, b2k_best_path_info *info, void *stream) {
+  if (!d || !channels || n <= 0 || cap <= 0 || !info) return set_error(B2K_ERR_INVALID, "b2k_dec_best_path: bad args");
+  for (int i = 0; i < n; i++)
+    if (channels[i] < 0 || channels[i] >= d->nchannels) return set_error(B2K_ERR_INVALID, "b2k_dec_best_path: bad channel id");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t hdr_b = sizeof(BestPathHdr) * (size_t)n, arc_b = sizeof(int4) * (size_t)n * cap, wh_b = sizeof(int2) * (size_t)n * cap;
+  const size_t ch_b = ((sizeof(int32_t) * (size_t)n + 15) / 16) * 16;
+  const size_t need = ch_b + hdr_b + arc_b + wh_b;
+  if (need > d->d_bp_bytes) {
+    B2K_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (d->d_bp) cudaFree(d->d_bp);
+    if (d->h_bp) cudaFreeHost(d->h_bp);
+    d->d_bp = nullptr; d->h_bp = nullptr; d->d_bp_bytes = d->h_bp_bytes = 0;
+    B2K_CUDA_CHECK(cudaMalloc(&d->d_bp, need));
+    B2K_CUDA_CHECK(cudaMallocHost(&d->h_bp, need));
+    d->d_bp_bytes = d->h_bp_bytes = need;
+  }
+  memcpy(d->h_bp, channels, sizeof(int32_t) * (size_t)n);
+  B2K_CUDA_CHECK(cudaMemcpyAsync(d->d_bp, d->h_bp, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+  BestPathHdr *d_hdr = reinterpret_cast<BestPathHdr *>(d->d_bp + ch_b);
+  int4 *d_arcs = reinterpret_cast<int4 *>(d->d_bp + ch_b + hdr_b);
+  int2 *d_where = reinterpret_cast<int2 *>(d->d_bp + ch_b + hdr_b + arc_b);
+  dec_best_path_kernel<512><<<n, 512, 0, st>>>(d->p, reinterpret_cast<const int32_t *>(d->d_bp), use_final_probs ? 1 : 0, cap, d_arcs, d_where, d_hdr);
+  B2K_LAUNCH_CHECK();
+  B2K_CUDA_CHECK(cudaMemcpyAsync(d->h_bp + ch_b, d->d_bp + ch_b, hdr_b, cudaMemcpyDeviceToHost, st));
+  B2K_CUDA_CHECK(cudaStreamSynchronize(st));
+  const BestPathHdr *hh = reinterpret_cast<const BestPathHdr *>(d->h_bp + ch_b);
+  int first_bad = 0;
+  for (int i = 0; i < n; i++) {
+    info[i].status = hh[i].status; info[i].n_arcs = hh[i].n_arcs; info[i].end_state = hh[i].end_state; info[i].num_frames = hh[i].frames;
+    info[i].final_cost = hh[i].final_cost; info[i].best_cost = hh[i].best_cost; info[i].final_relative_cost = hh[i].final_relative_cost;
+    if (hh[i].status != 0 && !first_bad) first_bad = hh[i].status;
+  }
+  // the arcs come back end first; hand them out start first
+  for (int i = 0; i < n; i++) {
+    const int na = std::min(hh[i].n_arcs, cap);
+    if (na <= 0) continue;
+    const size_t ao = ch_b + hdr_b + sizeof(int4) * (size_t)i * cap, wo = ch_b + hdr_b + arc_b + sizeof(int2) * (size_t)i * cap;
+    B2K_CUDA_CHECK(cudaMemcpyAsync(d->h_bp + ao, d->d_bp + ao, sizeof(int4) * (size_t)na, cudaMemcpyDeviceToHost, st));
+    B2K_CUDA_CHECK(cudaMemcpyAsync(d->h_bp + wo, d->d_bp + wo, sizeof(int2) * (size_t)na, cudaMemcpyDeviceToHost, st));
+  }
+  B2K_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; i++) {
+    const int na = std::min(hh[i].n_arcs, cap);
+    const int4 *a = reinterpret_cast<const int4 *>(d->h_bp + ch_b + hdr_b) + (size_t)i * cap;
+    const int2 *w = reinterpret_cast<const int2 *>(d->h_bp + ch_b + hdr_b + arc_b) + (size_t)i * cap;
+    for (int k = 0; k < na; k++) {
+      const int4 x = a[na - 1 - k];
+      const size_t o = (size_t)i * cap + k;
+      if (ilabels) ilabels[o] = x.x;
+      if (olabels) olabels[o] = x.y;
+      if (graph_costs) memcpy(&graph_costs[o], &x.z, 4);
+      if (acoustic_costs) memcpy(&acoustic_costs[o], &x.w, 4);
+      if (arc_frame) arc_frame[o] = w[na - 1 - k].x;
+      if (arc_state) arc_state[o] = w[na - 1 - k].y;
+    }
+  }
+  if (first_bad == B2K_ERR_OVERFLOW) return set_error(B2K_ERR_OVERFLOW, "b2k_dec_best_path: a path is longer than cap arcs");
+  if (first_bad) return set_error(first_bad, "b2k_dec_best_path: a channel is not decoding, is in error, or its traceback did not reach the start state");
   return B2K_OK;
 }
 

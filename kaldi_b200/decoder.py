@@ -250,6 +250,36 @@ class CudaDecoder:
             res.append(d)
         return res
 
+    def GetBestPath(self, channels, use_final_probs: bool = True, cap: int = 8192, stream: int = 0):
+        """Best path of channels that are still decoding (or finalized), without changing them:
+        LatticeFasterOnlineDecoderTpl::GetBestPath (lattice-faster-online-decoder.cc:54-75) / CudaDecoder::GetBestPath
+        (cuda-decoder.h:279).  One dictionary per channel: ilabels, olabels, graph / acoustic costs, the frame and HCLG
+        state each arc leads to, final_cost, best_cost, final_relative_cost, end_state, num_frames."""
+        L = _lib.lib()
+        ch = self._chan(channels)
+        n = len(ch)
+
+        class _Info(C.Structure):
+            _fields_ = [("status", C.c_int32), ("n_arcs", C.c_int32), ("end_state", C.c_int32), ("num_frames", C.c_int32),
+                        ("final_cost", C.c_float), ("best_cost", C.c_float), ("final_relative_cost", C.c_float)]
+        info = (_Info * n)()
+        il = np.zeros((n, cap), np.int32); ol = np.zeros((n, cap), np.int32)
+        gc = np.zeros((n, cap), np.float32); ac = np.zeros((n, cap), np.float32)
+        fr = np.zeros((n, cap), np.int32); st = np.zeros((n, cap), np.int32)
+        L.b2k_dec_best_path.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 8
+        _lib.check(L.b2k_dec_best_path(self.h, ch.ctypes.data, n, int(bool(use_final_probs)), int(cap), il.ctypes.data,
+                                       ol.ctypes.data, gc.ctypes.data, ac.ctypes.data, fr.ctypes.data, st.ctypes.data,
+                                       C.cast(info, C.c_void_p), C.c_void_p(stream)))
+        out = []
+        for i in range(n):
+            k = info[i].n_arcs
+            out.append(dict(ilabels=il[i, :k].copy(), olabels=ol[i, :k].copy(), graph_costs=gc[i, :k].copy(),
+                            acoustic_costs=ac[i, :k].copy(), arc_frame=fr[i, :k].copy(), arc_state=st[i, :k].copy(),
+                            final_cost=float(info[i].final_cost), best_cost=float(info[i].best_cost),
+                            final_relative_cost=float(info[i].final_relative_cost), end_state=int(info[i].end_state),
+                            num_frames=int(info[i].num_frames)))
+        return out
+
     def DebugFrame(self, channel: int, frame_plus_one: int):
         L = _lib.lib()
         nt, nl = C.c_int64(), C.c_int64()
