@@ -304,7 +304,9 @@ int b2k_ivec_destroy(b2k_ivec *iv);
  * <= sched[n] are accumulated (UpdateStatsUntilFrame, online-ivector-feature.cc
  * :248-281) and the i-vector re-estimated by <= num_cg_iters CG iterations from
  * the previous solution.  d_feats[i]: raw base features [num_frames x base_dim];
- * d_out[i]: [n_chunks x ivector_dim] (prior offset removed from dim 0). */
+ * d_out[i]: [n_chunks x ivector_dim] (prior offset removed from dim 0).  sched[n] = -1
+ * (only before the first frame index): no i-vector frame was ready when chunk n ran,
+ * its i-vector is all zeros (decodable-online-looped.cc:188-197). */
 int b2k_ivec_compute_batched(b2k_ivec *iv, int32_t num_lanes, const float *const *d_feats,
                              int32_t feat_stride, int32_t num_frames, const int32_t *sched,
                              int32_t n_chunks, float *const *d_out, int32_t out_stride, void *stream);
@@ -376,7 +378,8 @@ int b2k_nnet_run(b2k_nnet *nn, int32_t batch, const float *const *d_input, int32
 
 /* Which feature frame OnlineIvectorFeature::GetFrame is asked for by each nnet chunk when the CPU tool feeds
  * `chunk_samples` of audio at a time (online2-wav-nnet3-latgen-faster.cc:245-268, decodable-online-looped.cc:
- * 56-84,185-193): the schedule b2k_ivec_compute_batched takes.  Host only. */
+ * 56-84,185-193): the schedule b2k_ivec_compute_batched takes; -1 for a chunk that runs before any i-vector frame is
+ * ready (the reference leaves its i-vector zero, :188-197).  Host only. */
 int b2k_ivec_online_schedule(int64_t num_samples, int32_t chunk_samples, int32_t frame_length, int32_t frame_shift,
                              int32_t num_feature_frames, int32_t nnet_right_context, int32_t frames_per_chunk,
                              int32_t subsampling, int32_t splice_right, int32_t *sched, int32_t max_chunks,

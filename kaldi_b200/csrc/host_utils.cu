@@ -39,7 +39,9 @@ int b2k_ivec_online_schedule(int64_t num_samples, int32_t chunk_samples, int32_t
       const int32_t iv_ready = std::max(0, ready - splice_right);
       iv_frame = std::min(ready - 1, iv_ready - 1);
     }
-    while (done < std::min(chunks_ready, n_chunks)) sched[done++] = std::max(iv_frame, 0);
+    // no i-vector frame is ready yet (tiny chunks at the start of a file): the reference leaves the i-vector zero
+    // (decodable-online-looped.cc:188-197); -1 tells b2k_ivec_compute_batched to do the same
+    while (done < std::min(chunks_ready, n_chunks)) sched[done++] = iv_frame >= 0 ? iv_frame : -1;
   }
   return B2K_OK;
 }

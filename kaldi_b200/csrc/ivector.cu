@@ -250,6 +250,11 @@ __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParam
   int next_t = 0;
   const float *lda_raw = r.lda_raw + (size_t)L * r.T * F;
   for (int n = 0; n < r.n_chunks; n++) {
+    if (r.sched[n] < 0) {          // no i-vector frame was ready when this chunk ran: all zeros (decodable-online-looped.cc:188-197)
+      float *z = r.d_out[L] + (size_t)n * r.out_stride;
+      for (int i = tid; i < D; i += IVS_THREADS) z[i] = 0.0f;
+      continue;
+    }
     const int upto = min(r.sched[n], r.T - 1);
     double tot_weight = 0.0;
     const bool any = next_t <= upto;
@@ -552,7 +557,7 @@ int b2k_ivec_compute_batched(b2k_ivec *iv, int32_t num_lanes, const float *const
     iv->h_featp[i] = d_feats[i]; iv->h_outp[i] = d_out[i];
   }
   for (int n = 0; n < n_chunks; n++) {
-    if (sched[n] < 0 || (n > 0 && sched[n] < sched[n - 1])) return set_error(B2K_ERR_INVALID, "schedule must be non-decreasing");
+    if (sched[n] < -1 || (n > 0 && sched[n] < sched[n - 1])) return set_error(B2K_ERR_INVALID, "schedule must be non-decreasing (-1 = no i-vector ready yet)");
     iv->h_sched[n] = sched[n];
   }
   B2K_CUDA_CHECK(cudaMemcpyAsync(iv->d_clanes, iv->h_clanes, sizeof(CmvnLane) * num_lanes, cudaMemcpyHostToDevice, st));

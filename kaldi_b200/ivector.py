@@ -104,7 +104,7 @@ def online_ivector_schedule(num_samples: int, chunk_samples: int, frame_length: 
             iv_ready = max(0, ready - splice_right)
             iv_frame = min(ready - 1, iv_ready - 1)
         while done_chunks < min(chunks_ready, n_chunks):
-            sched.append(max(iv_frame, 0))
+            sched.append(iv_frame if iv_frame >= 0 else -1)   # -1: no i-vector frame ready, the chunk's i-vector stays zero
             done_chunks += 1
     return np.asarray(sched, np.int32)
 

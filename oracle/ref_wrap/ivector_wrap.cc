@@ -74,6 +74,10 @@ int ref_ivector_run(void *h, const float *feats, int T, int D, const double *glo
     if (debug_lda_norm) for (int t = 0; t < T; t++) { SubVector<BaseFloat> row(debug_lda_norm + (size_t)t * lda_norm.Dim(), lda_norm.Dim()); lda_norm.GetFrame(t, &row); }
     for (int n = 0; n < n_chunks; n++) {
       int frame = sched[n];
+      if (frame < 0) {   // no i-vector frame ready: GetFrame is not called and the i-vector stays zero (decodable-online-looped.cc:188-197)
+        for (int d = 0; d < ivdim; d++) out[(size_t)n * ivdim + d] = 0.0f;
+        continue;
+      }
       // UpdateStatsUntilFrame(frame) with use_most_recent_ivector = true (:248-281)
       std::vector<int32> frames;
       for (; num_frames_stats <= frame; num_frames_stats++) frames.push_back(num_frames_stats);

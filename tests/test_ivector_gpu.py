@@ -46,3 +46,24 @@ def test_schedule_matches_online_tool_bookkeeping():
     # short utterance: everything is flushed at InputFinished
     s2 = IVM.online_ivector_schedule(8000, 2880, 400, 160, 48, 29, 21, 3)
     assert list(s2) == [47] * len(s2)
+
+
+def test_chunks_before_the_first_ivector_frame_get_zeros():
+    """sched[n] = -1 (b2k_ivec_online_schedule for a chunk that runs before any i-vector frame is ready): all zeros for that
+    chunk, and the later chunks are what they are without it (decodable-online-looped.cc:188-197)."""
+    import torch
+    from oracle import ivector_oracle as IO
+    G, D = 64, 20
+    ex = IVM.make_synthetic_extractor(1, num_gauss=G, ivector_dim=D, max_count=100.0)
+    R = IO.RefIvector(ex)
+    f = _feats(5, 32000)
+    T = f.shape[0]
+    sched = np.array([-1, -1, 10, 50, T - 1], np.int32)
+    gpu = IVM.IvectorExtractorGpu(ex, max_lanes=1, max_frames=T)
+    d_f = torch.from_numpy(f).cuda()
+    d_o = torch.full((len(sched), D), 7.0, device="cuda")
+    gpu.Compute([d_f.data_ptr()], 40, T, sched, [d_o.data_ptr()], D)
+    torch.cuda.synchronize()
+    got, ref = d_o.cpu().numpy(), R.run(f, sched)
+    assert not got[:2].any() and not ref[:2].any()
+    assert np.abs(got - ref).max() <= 2e-4 * np.linalg.norm(ref, axis=1).max()
