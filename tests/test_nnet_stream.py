@@ -210,6 +210,8 @@ def test_device_stream_equals_the_window_program_and_the_whole_utterance(which, 
     if (fpc - nn.right_context) % 3 == 0 and fpc % 3 == 0:
         for u in (0, 3):
             T = lens[u]
+            if T > nn.right_context and (T - nn.right_context) % 3 != 0:
+                continue        # the flush continues at (frames so far - right context): off the grid, as in the reference
             whole = NnetComputer(arch, W, T, 1, frames_per_chunk=3 * ((T + 2) // 3) + 3, use_priors=False)
             ref = whole.forward([feats[u]], [ivs[u][None, :]])[0]
             g = np.concatenate(got[u], 0)
