@@ -441,10 +441,17 @@ int b2k_nnet_create_from_program(const b2k_nnet_program *prog, int32_t max_batch
  * frames that holds every frame those outputs read (nothing is padded; an output outside that range is an error) and ONE
  * i-vector for the window -- the computation request BatchedStaticNnet3::SetComputationRequest builds for a chunk with its
  * context (cudadecoder/batched-static-nnet3.cc:123-152).  Only the rows each layer needs for those outputs are computed.
- * Host only. */
+ * ivector_rows = 1: that.  ivector_rows > 1: the window is chunk n of a LOOPED run (DecodableNnetLoopedOnlineBase::
+ * AdvanceChunk, nnet3/decodable-online-looped.cc:118-236): first_output_t is the chunk's first frame, cfg->frames_per_chunk
+ * = C its length, and the "ivector" input holds the i-vectors the chunks n-(rows-1) .. n received (chunk 0's repeated in
+ * front of the utterance); time t reads row floor((t - first_output_t + (rows-1)*C) / C) - m, the Round() / lag arithmetic
+ * of the looped compilation (nnet-compile-looped.cc:179-205), so the window's outputs are the looped computation's.
+ * b2k_nnet_looped_ivector_rows: the rows that needs = ceil(left/C) + m + 1.  Host only. */
 int b2k_nnet_compile_window(const b2k_nnet_compile_cfg *cfg, int32_t first_output_t, int32_t num_outputs,
-                            const b2k_nnet_layer *layers, int32_t n_layers, const b2k_nnet_weight *weights,
-                            int32_t n_weights, b2k_nnet_program **out);
+                            int32_t ivector_rows, const b2k_nnet_layer *layers, int32_t n_layers,
+                            const b2k_nnet_weight *weights, int32_t n_weights, b2k_nnet_program **out);
+int b2k_nnet_looped_ivector_rows(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers,
+                                 int32_t *rows);
 /* ComputeSimpleNnetContext (nnet3/nnet-utils.cc) of the layer list: left / right context in input frames.  Host only. */
 int b2k_nnet_model_context(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers,
                            int32_t *left, int32_t *right);
@@ -467,12 +474,18 @@ int b2k_nnet_stream_account(int32_t left_context, int32_t right_context, int32_t
                             int32_t n_new_frames, int32_t flush, int32_t *frames_in_context_after,
                             int32_t *n_output_frames);
 
+/* looped = 0: one i-vector per window, BatchedStaticNnet3's computation.  looped = 1: the windows are the chunks of
+ * DecodableNnetLoopedOnlineBase::AdvanceChunk (nnet3/decodable-online-looped.cc:118-236) and d_ivectors[i] holds
+ * info[7] rows, the i-vectors chunks n-(rows-1) .. n received (b2k_nnet_compile_window); the caller feeds the frames the
+ * looped schedule reads -- right_context frames in a channel's first call (no output), then frames_per_chunk per call,
+ * indices clamped to the frames that exist (:150-160) and no flush -- and every call's outputs are the looped
+ * computation's for that chunk (kaldi_b200/host/b2k_nnet3_shims.h: DecodableNnetLoopedOnlineB2k). */
 int b2k_nnet_stream_create(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers,
                            const b2k_nnet_weight *weights, int32_t n_weights, int32_t max_batch, int32_t nchannels,
-                           b2k_nnet_stream **out);
+                           int32_t looped, b2k_nnet_stream **out);
 int b2k_nnet_stream_destroy(b2k_nnet_stream *s);
 /* info: {output frames per chunk (GetNOutputFramesPerChunk), total left context, total right context
- * (GetTotalNnet3RightContext), window frames, input dim, i-vector dim, output dim, channels} */
+ * (GetTotalNnet3RightContext), window frames, input dim, i-vector dim, output dim, i-vector rows per slot} */
 int b2k_nnet_stream_info(const b2k_nnet_stream *s, int64_t info[8]);
 /* RunBatch (batched-static-nnet3.cc:293-367).  Batch slot i: channel channels[i]; d_features[i] = n_input_frames_valid[i]
  * (<= frames_per_chunk) new feature rows, row stride features_stride floats; d_ivectors[i] the i-vector of this run (NULL

@@ -399,7 +399,11 @@ extern "C" {
 // win_n_out > 0: a window program -- outputs at t = win_t0 + k*sub, k < win_n_out, of a window of cfg.num_frames input frames that
 // must hold every frame those outputs read (no padding), one i-vector for the whole window: the computation request of
 // BatchedStaticNnet3::SetComputationRequest (cudadecoder/batched-static-nnet3.cc:123-152).
-static int compile_impl(const b2k_nnet_compile_cfg *cfgp, int win_t0, int win_n_out, const b2k_nnet_layer *layers, int32_t n_layers,
+// win_iv_rows > 1 (window programs only): the looped computation's i-vectors -- the window is chunk n of a looped run
+// (its first output is the first frame of the chunk, cfg.frames_per_chunk = C frames per chunk) and the i-vector input holds
+// the i-vectors of chunks n-(rows-1) .. n: time t of the window reads row floor((t - win_t0 + (rows-1)*C) / C) - m, the same
+// Round() / lag arithmetic as the whole-utterance program (nnet-compile-looped.cc:179-205).
+static int compile_impl(const b2k_nnet_compile_cfg *cfgp, int win_t0, int win_n_out, int win_iv_rows, const b2k_nnet_layer *layers, int32_t n_layers,
                         const b2k_nnet_weight *weights, int32_t n_weights, b2k_nnet_program **out) {
   if (!cfgp || !layers || n_layers <= 0 || (!weights && n_weights > 0) || !out)
     return set_error(B2K_ERR_INVALID, "b2k_nnet_compile: bad args");
@@ -472,7 +476,8 @@ static int compile_impl(const b2k_nnet_compile_cfg *cfgp, int win_t0, int win_n_
   // chunk n of the looped computation supplies one i-vector; input time t uses chunk max(0, floor(t / C) - m),
   // m = floor((C + R - 1) / C)   (nnet-compile-looped.cc:179-205)
   const int m = (C + Rk - 1) / C;
-  const int n_chunks = window ? 1 : (n_out * sub + C - 1) / C;
+  const int n_chunks = window ? std::max(1, win_iv_rows) : (n_out * sub + C - 1) / C;
+  const int iv_shift = (window && win_iv_rows > 1) ? (win_iv_rows - 1) * C - out_t0 : 0;
   by["ivector"]->rows = n_chunks;
   P->model_left = Lk; P->model_right = Rk; P->ivector_m = m; P->n_chunks = n_chunks;
   auto put = [&](const float *a, size_t n) -> int64_t {
@@ -498,7 +503,7 @@ static int compile_impl(const b2k_nnet_compile_cfg *cfgp, int win_t0, int win_n_
       const Node *s = by[src];
       memset(t, 0, sizeof(*t));
       t->src = idx[src]; t->C = 1; t->scale = 1.0f;
-      if (kind == 1) { t->ratio = n.step; t->shift = n.t0 + off; t->lo = 0; t->hi = s->rows - 1; t->ivec = 1; t->C = C; t->m = m; return; }
+      if (kind == 1) { t->ratio = n.step; t->shift = n.t0 + off + iv_shift; t->lo = 0; t->hi = s->rows - 1; t->ivec = 1; t->C = C; t->m = m; return; }
       if (s->kind == 0) { t->ratio = n.step; t->shift = n.t0 + off; t->lo = 0; t->hi = T - 1; return; }
       if (s->step == 0 || n.step % s->step != 0 || (n.t0 + off - s->t0) % s->step != 0) { failed = true; return; }
       t->ratio = n.step / s->step; t->shift = (n.t0 + off - s->t0) / s->step; t->lo = 0; t->hi = s->rows - 1;
@@ -630,13 +635,24 @@ static int compile_impl(const b2k_nnet_compile_cfg *cfgp, int win_t0, int win_n_
 
 int b2k_nnet_compile(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers,
                      const b2k_nnet_weight *weights, int32_t n_weights, b2k_nnet_program **out) {
-  return compile_impl(cfg, 0, 0, layers, n_layers, weights, n_weights, out);
+  return compile_impl(cfg, 0, 0, 1, layers, n_layers, weights, n_weights, out);
 }
 
-int b2k_nnet_compile_window(const b2k_nnet_compile_cfg *cfg, int32_t first_output_t, int32_t num_outputs, const b2k_nnet_layer *layers,
-                            int32_t n_layers, const b2k_nnet_weight *weights, int32_t n_weights, b2k_nnet_program **out) {
-  if (num_outputs <= 0) return set_error(B2K_ERR_INVALID, "b2k_nnet_compile_window: num_outputs must be positive");
-  return compile_impl(cfg, first_output_t, num_outputs, layers, n_layers, weights, n_weights, out);
+int b2k_nnet_compile_window(const b2k_nnet_compile_cfg *cfg, int32_t first_output_t, int32_t num_outputs, int32_t ivector_rows,
+                            const b2k_nnet_layer *layers, int32_t n_layers, const b2k_nnet_weight *weights, int32_t n_weights,
+                            b2k_nnet_program **out) {
+  if (num_outputs <= 0 || ivector_rows <= 0) return set_error(B2K_ERR_INVALID, "b2k_nnet_compile_window: num_outputs and ivector_rows must be positive");
+  return compile_impl(cfg, first_output_t, num_outputs, ivector_rows, layers, n_layers, weights, n_weights, out);
+}
+
+int b2k_nnet_looped_ivector_rows(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers, int32_t *rows) {
+  if (!cfg || !rows || cfg->frames_per_chunk <= 0) return set_error(B2K_ERR_INVALID, "b2k_nnet_looped_ivector_rows: bad args");
+  int32_t L = 0, R = 0;
+  const int rc = b2k_nnet_model_context(cfg, layers, n_layers, &L, &R);
+  if (rc) return rc;
+  const int C = cfg->frames_per_chunk;
+  *rows = (L + C - 1) / C + (C + R - 1) / C + 1;        // chunks reached back by the left context + the lag m + the chunk itself
+  return B2K_OK;
 }
 
 int b2k_nnet_model_context(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers, int32_t *left, int32_t *right) {

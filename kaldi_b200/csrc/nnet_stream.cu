@@ -60,7 +60,7 @@ using namespace b2k;
 struct b2k_nnet_stream {
   b2k_nnet *nn = nullptr;
   int L = 0, R = 0, sub = 1, fpc = 0, W = 0, opc = 0, in_dim = 0, iv_dim = 0, out_dim = 0;
-  int max_batch = 0, nchannels = 0;
+  int max_batch = 0, nchannels = 0, iv_rows = 1;
   float *d_ctx = nullptr, *d_win = nullptr;
   SlotAsg *d_asg = nullptr, *h_asg = nullptr;      // 2 * max_batch entries: the main pass, then the flush
   cudaEvent_t staging_free = nullptr;
@@ -84,7 +84,7 @@ int b2k_nnet_stream_account(int32_t L, int32_t R, int32_t sub, int32_t in_ctx, i
 }
 
 int b2k_nnet_stream_create(const b2k_nnet_compile_cfg *cfgp, const b2k_nnet_layer *layers, int32_t n_layers, const b2k_nnet_weight *weights,
-                           int32_t n_weights, int32_t max_batch, int32_t nchannels, b2k_nnet_stream **out) {
+                           int32_t n_weights, int32_t max_batch, int32_t nchannels, int32_t looped, b2k_nnet_stream **out) {
   if (!cfgp || !layers || !out || max_batch <= 0) return set_error(B2K_ERR_INVALID, "b2k_nnet_stream_create: bad args");
   if (nchannels < 0) nchannels = max_batch;
   if (nchannels < max_batch) return set_error(B2K_ERR_INVALID, "b2k_nnet_stream_create: nchannels < max_batch");   // batched-static-nnet3.h:62
@@ -98,8 +98,14 @@ int b2k_nnet_stream_create(const b2k_nnet_compile_cfg *cfgp, const b2k_nnet_laye
   if (fpc < R) return set_error(B2K_ERR_INVALID, "Please set --frames-per-chunk at least as large as the neural net right context");   // :172-175
   const int opc = (sub - 1 + fpc) / sub, W = fpc + L + R;
   cfg.num_frames = W;
+  int iv_rows = 1;
+  if (looped) {                                              // the looped computation's i-vector arithmetic: C = the chunk
+    if (fpc % sub != 0) return set_error(B2K_ERR_INVALID, "b2k_nnet_stream_create: looped chunks must be a multiple of the subsampling factor");
+    cfg.frames_per_chunk = fpc;
+    if (cfg.ivector_dim > 0 && (rc = b2k_nnet_looped_ivector_rows(&cfg, layers, n_layers, &iv_rows))) return rc;
+  }
   b2k_nnet_program *prog = nullptr;
-  rc = b2k_nnet_compile_window(&cfg, L, opc, layers, n_layers, weights, n_weights, &prog);
+  rc = b2k_nnet_compile_window(&cfg, L, opc, iv_rows, layers, n_layers, weights, n_weights, &prog);
   if (rc) return rc;
   if ((rc = require_device())) { b2k_nnet_program_destroy(prog); return rc; }
   b2k_nnet_stream *s = new b2k_nnet_stream();
@@ -108,7 +114,7 @@ int b2k_nnet_stream_create(const b2k_nnet_compile_cfg *cfgp, const b2k_nnet_laye
   if (rc) { delete s; return rc; }
   s->L = L; s->R = R; s->sub = sub; s->fpc = fpc; s->W = W; s->opc = opc;
   s->in_dim = cfg.feat_dim; s->iv_dim = cfg.ivector_dim; s->out_dim = b2k_nnet_output_dim(s->nn);
-  s->max_batch = max_batch; s->nchannels = nchannels;
+  s->max_batch = max_batch; s->nchannels = nchannels; s->iv_rows = iv_rows;
   s->in_ctx.assign(nchannels, -1);
   const size_t ctx_floats = (size_t)nchannels * std::max(1, L + R) * s->in_dim, win_floats = (size_t)max_batch * W * s->in_dim;
   cudaError_t e = cudaMalloc(&s->d_ctx, ctx_floats * sizeof(float));
@@ -136,7 +142,7 @@ int b2k_nnet_stream_destroy(b2k_nnet_stream *s) {
 int b2k_nnet_stream_info(const b2k_nnet_stream *s, int64_t info[8]) {
   if (!s || !info) return set_error(B2K_ERR_INVALID, "b2k_nnet_stream_info: bad args");
   info[0] = s->opc; info[1] = s->L; info[2] = s->R; info[3] = s->W; info[4] = s->in_dim; info[5] = s->iv_dim; info[6] = s->out_dim;
-  info[7] = s->nchannels;
+  info[7] = s->iv_rows;
   return B2K_OK;
 }
 

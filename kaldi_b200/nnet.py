@@ -160,21 +160,22 @@ class BatchedStaticNnet3:
     on the last chunk.  `frames_per_chunk` is compute_opts.frames_per_chunk (input frames)."""
 
     def __init__(self, arch: dict, W: dict, max_batch: int, nchannels: int = -1, frames_per_chunk: int = 51,
-                 acoustic_scale: float = 1.0, use_priors: bool = True):
+                 acoustic_scale: float = 1.0, use_priors: bool = True, looped: bool = False):
         from .nnet_compile import _Cfg, abi_arrays
         L = _lib.lib()
         layers, ws, self._keep = abi_arrays(arch, W)
         cfg = _Cfg(arch["feat_dim"], arch["ivector_dim"], arch["num_pdfs"], arch["frame_subsampling_factor"], 0,
                    int(frames_per_chunk), int(use_priors), 0, float(acoustic_scale))
         self.h = C.c_void_p()
-        L.b2k_nnet_stream_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.b2k_nnet_stream_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_void_p]
         _lib.check(L.b2k_nnet_stream_create(C.byref(cfg), layers, len(layers), ws, len(ws), int(max_batch), int(nchannels),
-                                            C.byref(self.h)))
+                                            int(bool(looped)), C.byref(self.h)))
         info = (C.c_int64 * 8)()
         L.b2k_nnet_stream_info.argtypes = [C.c_void_p, C.c_void_p]
         _lib.check(L.b2k_nnet_stream_info(self.h, info))
         (self.output_frames_per_chunk, self.left_context, self.right_context, self.window, self.input_dim,
-         self.ivector_dim, self.output_dim, self.nchannels) = [int(x) for x in info]
+         self.ivector_dim, self.output_dim, self.ivector_rows) = [int(x) for x in info]
         self.max_batch = max_batch
         self.frames_per_chunk = frames_per_chunk
         L.b2k_nnet_stream_run_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,

@@ -61,8 +61,9 @@ class CompiledProgram:
 
     def __init__(self, arch: dict, W: dict, num_frames: int, frames_per_chunk: int = 21, acoustic_scale: float = 1.0,
                  use_priors: bool = True, conv_mode: str | None = None, window: tuple | None = None):
-        """window = (first_output_t, num_outputs): b2k_nnet_compile_window, the computation request of
-        BatchedStaticNnet3 for a chunk with its context (num_frames = the window's input frames)."""
+        """window = (first_output_t, num_outputs[, ivector_rows]): b2k_nnet_compile_window, the computation request of
+        BatchedStaticNnet3 for a chunk with its context (num_frames = the window's input frames); ivector_rows > 1: chunk n
+        of a looped run with the i-vectors of chunks n-(rows-1) .. n."""
         L = _lib.lib()
         layers = (_Layer * len(arch["layers"]))(*[_layer(x) for x in arch["layers"]])
         self._keep = {k: np.ascontiguousarray(v, np.float32) for k, v in W.items()}
@@ -75,12 +76,12 @@ class CompiledProgram:
                    float(acoustic_scale))
         self.h = C.c_void_p()
         L.b2k_nnet_compile.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
-        L.b2k_nnet_compile_window.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.b2k_nnet_compile_window.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         if window is None:
             _lib.check(L.b2k_nnet_compile(C.byref(cfg), layers, len(layers), ws, len(ws), C.byref(self.h)))
         else:
-            _lib.check(L.b2k_nnet_compile_window(C.byref(cfg), int(window[0]), int(window[1]), layers, len(layers), ws, len(ws),
-                                                 C.byref(self.h)))
+            _lib.check(L.b2k_nnet_compile_window(C.byref(cfg), int(window[0]), int(window[1]), int(window[2]) if len(window) > 2 else 1,
+                                                 layers, len(layers), ws, len(ws), C.byref(self.h)))
         nn, no, bl = C.c_int32(), C.c_int32(), C.c_int64()
         L.b2k_nnet_program_sizes.argtypes = [C.c_void_p] * 4
         _lib.check(L.b2k_nnet_program_sizes(self.h, C.byref(nn), C.byref(no), C.byref(bl)))
@@ -134,3 +135,15 @@ def stream_account(left: int, right: int, sub: int, in_ctx: int, n_new: int, flu
     L.b2k_nnet_stream_account.argtypes = [C.c_int32] * 6 + [C.c_void_p, C.c_void_p]
     _lib.check(L.b2k_nnet_stream_account(left, right, sub, in_ctx, n_new, int(flush), C.byref(a), C.byref(o)))
     return a.value, o.value
+
+
+def looped_ivector_rows(arch: dict, frames_per_chunk: int) -> int:
+    """b2k_nnet_looped_ivector_rows: i-vector rows a looped window program reads (ceil(left / C) + lag + 1)."""
+    L = _lib.lib()
+    layers = (_Layer * len(arch["layers"]))(*[_layer(x) for x in arch["layers"]])
+    cfg = _Cfg(arch["feat_dim"], arch["ivector_dim"], arch["num_pdfs"], arch["frame_subsampling_factor"], 1,
+               int(frames_per_chunk), 0, 0, 1.0)
+    r = C.c_int32()
+    L.b2k_nnet_looped_ivector_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    _lib.check(L.b2k_nnet_looped_ivector_rows(C.byref(cfg), layers, len(layers), C.byref(r)))
+    return r.value

@@ -154,6 +154,84 @@ def test_off_grid_chunks_follow_the_reference_arithmetic():
     assert checked > 20
 
 
+def _looped_windows(arch, feats, chunk_iv, C, L, Rc, k1):
+    """The inputs of the looped schedule, chunk by chunk: window n = input frames [n*C - L, (n+1)*C + Rc) with indices clamped
+    to the utterance (decodable-online-looped.cc:150-160), i-vector rows = the i-vectors of chunks n-(k1-1) .. n (chunk 0's
+    in front of the utterance)."""
+    T = feats.shape[0]
+    n_out = (T + 2) // 3
+    n_chunks = (n_out * 3 + C - 1) // C
+    for n in range(n_chunks):
+        idx = np.clip(np.arange(n * C - L, (n + 1) * C + Rc), 0, T - 1)
+        ivr = np.stack([chunk_iv[max(0, n - (k1 - 1) + r)] for r in range(k1)])
+        yield n, feats[idx], ivr, min(C // 3, n_out - n * (C // 3))
+
+
+@pytest.mark.parametrize("which,T", [("tiny", 100), ("tiny", 21), ("tiny", 5), ("tiny-lda", 77), ("cnn", 64), ("tdnn", 90)])
+def test_looped_windows_reproduce_the_reference_looped_forward(which, T):
+    """Window programs with the looped i-vector arithmetic (ivector_rows > 1): an i-vector that CHANGES with every chunk, the
+    chunks evaluated one window at a time, equal the reference's DecodableNnetSimpleLooped run over the whole utterance
+    (Round(ivector, C) with its lag, nnet-compile-looped.cc:179-205)."""
+    from oracle import program_interp as PI
+    NC = _lib_or_skip()
+    arch = ARCHS[which]()
+    W = NM.random_weights(arch, seed=4)
+    R = _ref_or_skip(arch, W)
+    C = R.frames_per_chunk
+    rng = np.random.default_rng(T + 1)
+    feats = (rng.standard_normal((T, arch["feat_dim"])) * 10).astype(np.float32)
+    iv = rng.standard_normal((T, 100)).astype(np.float32)
+    ref = R.forward(feats, iv, period=1)
+    chunk_iv = iv[R.chunk_ivector_rows(T, T, 1)]
+    L, Rc = NC.model_context(arch)
+    k1 = NC.looped_ivector_rows(arch, C)
+    assert k1 == -(-L // C) + (C + Rc - 1) // C + 1
+    cp = NC.CompiledProgram(arch, W, C + L + Rc, C, use_priors=False, window=(L, C // 3, k1))
+    assert cp.n_chunks == k1
+    prog = PI.program_from_abi(cp.nodes, cp.ops, cp.blob)
+    outs = [PI.run_program(prog, win, ivr)[:keep] for _n, win, ivr, keep in _looped_windows(arch, feats, chunk_iv, C, L, Rc, k1)]
+    got = np.concatenate(outs, 0)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which,T", [("tiny", 100), ("cnn", 64)])
+def test_device_looped_stream_reproduces_the_whole_utterance_run(which, T):
+    """b2k_nnet_stream in looped mode, fed as DecodableNnetLoopedOnlineBase::AdvanceChunk reads its input (right-context frames
+    first, then a chunk per call, indices clamped): the device's own whole-utterance forward with per-chunk i-vectors
+    (b2k_nnet_run, itself pinned to the reference's looped forward) chunk by chunk."""
+    import torch
+    from kaldi_b200.nnet import BatchedStaticNnet3, NnetComputer
+    NC = _lib_or_skip()
+    arch = ARCHS[which]()
+    W = NM.random_weights(arch, seed=4)
+    C = 21
+    rng = np.random.default_rng(T)
+    feats = (rng.standard_normal((T, arch["feat_dim"])) * 10).astype(np.float32)
+    whole = NnetComputer(arch, W, T, 1, frames_per_chunk=C, use_priors=False)
+    chunk_iv = rng.standard_normal((whole.n_chunks, 100)).astype(np.float32)
+    ref = whole.forward([feats], [chunk_iv])[0]
+    nn = BatchedStaticNnet3(arch, W, max_batch=1, frames_per_chunk=C, use_priors=False, looped=True)
+    L, Rc, k1, opc, P = nn.left_context, nn.right_context, nn.ivector_rows, nn.output_frames_per_chunk, nn.output_dim
+    assert k1 == NC.looped_ivector_rows(arch, C) and opc == C // 3
+    d_out = torch.zeros(opc, P, device="cuda")
+    outs = []
+    first = torch.from_numpy(feats[np.clip(np.arange(0, Rc), 0, T - 1)]).cuda()
+    zeros_iv = torch.zeros(k1, 100, device="cuda")
+    no, ne = nn.RunBatch([0], [first.data_ptr()], arch["feat_dim"], [zeros_iv.data_ptr()], [Rc], [True], [False], d_out.data_ptr(), 0, P)
+    assert no == [0] and ne == [0]
+    for n, win, ivr, keep in _looped_windows(arch, feats, chunk_iv, C, L, Rc, k1):
+        new = torch.from_numpy(np.ascontiguousarray(win[L + Rc:])).cuda()          # the C frames this chunk adds
+        d_iv = torch.from_numpy(ivr).cuda()
+        no, ne = nn.RunBatch([0], [new.data_ptr()], arch["feat_dim"], [d_iv.data_ptr()], [C], [False], [False], d_out.data_ptr(), 0, P)
+        torch.cuda.synchronize()
+        assert no == [opc]
+        outs.append(d_out.cpu().numpy()[:keep].copy())
+    got = np.concatenate(outs, 0)
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("which,fpc", [("tiny", 21), ("tiny", 51), ("cnn", 21), ("tdnn", 30)])
 def test_device_stream_equals_the_window_program_and_the_whole_utterance(which, fpc):
