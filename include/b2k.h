@@ -509,6 +509,11 @@ int b2k_nnet_stream_run_batch(b2k_nnet_stream *s, int32_t n, const int32_t *chan
  * kaldi_b200/kaldi_io.py is the Python twin; both are pinned to files written by the reference's own Write(). */
 typedef struct b2k_model b2k_model;
 int b2k_model_read(const char *path, int32_t is_mdl /* 1: final.mdl, 0: raw nnet3 */, b2k_model **out);
+/* The same parse on bytes in memory -- what a Kaldi-side shim gets from Nnet::Write / AmNnetSimple::Write into a string
+ * stream, with or without the "\0B" binary marker in front (kaldi_b200/host/b2k_nnet3_shims.h).  kind 0: raw nnet3
+ * (Nnet::Write); 1: TransitionModel + AmNnetSimple (final.mdl); 2: AmNnetSimple::Write alone (b2k_model_read takes the
+ * same values).  Host only. */
+int b2k_model_read_memory(const void *data, int64_t len, int32_t kind, b2k_model **out);
 int b2k_model_destroy(b2k_model *model);
 /* The same object from arrays the caller already holds (synthetic models; everything is copied; "priors" optional, tid2pdf
  * may be NULL): the input of b2k_pipeline_create without a model file. */

@@ -43,6 +43,9 @@ struct Reader {
   std::vector<unsigned char> d;
   size_t p = 0;
   bool binary = false;
+  Reader(const void *data, size_t len) : d((const unsigned char *)data, (const unsigned char *)data + len) {
+    if (d.size() >= 2 && d[0] == 0 && d[1] == 'B') { binary = true; p = 2; }
+  }
   explicit Reader(const char *path) {
     FILE *f = fopen(path, "rb");
     if (!f) throw FormatError(std::string("cannot open ") + path);
@@ -836,30 +839,47 @@ static void finish(b2k_model *M, const std::vector<float> *priors) {
 
 extern "C" {
 
+// kind 0: raw nnet3 (Nnet::Write); 1: final.mdl (TransitionModel + AmNnetSimple); 2: AmNnetSimple::Write alone
+static void read_model(Reader &r, int kind, b2k_model *M) {
+  ParsedNnet P;
+  std::vector<float> priors;
+  if (kind == 1) read_transition_model(r, &M->tid2pdf, &M->tid2phone);
+  read_nnet3(r, &P);
+  if (kind == 1 || kind == 2) {
+    r.expect("<LeftContext>"); r.read_int();
+    r.expect("<RightContext>"); r.read_int();
+    r.expect("<Priors>");
+    Value pv;
+    r.read_vector(&pv);
+    priors = pv.f;
+  }
+  to_arch(P, M);
+  finish(M, &priors);
+}
+
 int b2k_model_read(const char *path, int32_t is_mdl, b2k_model **out) {
-  if (!path || !out) return b2k::set_error(B2K_ERR_INVALID, "b2k_model_read: bad args");
+  if (!path || !out || is_mdl < 0 || is_mdl > 2) return b2k::set_error(B2K_ERR_INVALID, "b2k_model_read: bad args");
   b2k_model *M = new b2k_model();
   try {
     Reader r(path);
-    ParsedNnet P;
-    std::vector<float> priors;
-    if (is_mdl) {
-      read_transition_model(r, &M->tid2pdf, &M->tid2phone);
-      read_nnet3(r, &P);
-      r.expect("<LeftContext>"); r.read_int();
-      r.expect("<RightContext>"); r.read_int();
-      r.expect("<Priors>");
-      Value pv;
-      r.read_vector(&pv);
-      priors = pv.f;
-    } else {
-      read_nnet3(r, &P);
-    }
-    to_arch(P, M);
-    finish(M, &priors);
+    read_model(r, is_mdl, M);
   } catch (const std::exception &e) {
     delete M;
     return b2k::set_error(B2K_ERR_INVALID, "b2k_model_read", e.what());
+  }
+  *out = M;
+  return B2K_OK;
+}
+
+int b2k_model_read_memory(const void *data, int64_t len, int32_t kind, b2k_model **out) {
+  if (!data || len <= 0 || !out || kind < 0 || kind > 2) return b2k::set_error(B2K_ERR_INVALID, "b2k_model_read_memory: bad args");
+  b2k_model *M = new b2k_model();
+  try {
+    Reader r(data, (size_t)len);
+    read_model(r, kind, M);
+  } catch (const std::exception &e) {
+    delete M;
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_model_read_memory", e.what());
   }
   *out = M;
   return B2K_OK;

@@ -46,6 +46,34 @@ def check() -> bool:
             "  c.Check(); c.ComputeConfig();\n  b2k_dec_cfg d = c.ToB2k(400);\n  return d.max_active + c.main_q_capacity;\n}\n")
         subprocess.check_call(["g++", "-fsyntax-only"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"),
                               "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include"]) + [cc])
+        # the nnet3 surfaces (b2k_nnet3_shims.h) against the reference's own nnet3 / cudadecoder headers, HAVE_CUDA=1 as in a CUDA
+        # build of Kaldi: NnetComputer's members, DecodableAmNnetLoopedOnline as a DecodableInterface, and BatchedStaticNnet3's
+        # RunBatch called with exactly the argument types batched-threaded-nnet3-cuda-online-pipeline.cc:662-668 passes
+        nn = os.path.join(td, "n.cc")
+        open(nn, "w").write(
+            '#include "cudadecoder/batched-static-nnet3.h"\n#include "nnet3/decodable-online-looped.h"\n#include "b2k_nnet3_shims.h"\n'
+            "using namespace kaldi;\n"
+            "typedef b2k_shim::BatchedStaticNnet3B2k<cuda_decoder::BatchedStaticNnet3Config> Static;\n"
+            "void f(const cuda_decoder::BatchedStaticNnet3Config &c, const nnet3::AmNnetSimple &am, const TransitionModel &tm,\n"
+            "       const nnet3::DecodableNnetSimpleLoopedInfo &info, OnlineFeatureInterface *feats, OnlineFeatureInterface *ivecs,\n"
+            "       const nnet3::NnetComputeOptions &co, const nnet3::ComputationRequest &req) {\n"
+            "  Static s(c, am);\n"
+            "  std::vector<int> channels, nvalid; std::vector<BaseFloat *> d_features, d_ivectors; std::vector<bool> first, last;\n"
+            "  CuMatrix<BaseFloat> post; std::vector<std::vector<std::pair<int, const BaseFloat *>>> ptrs;\n"
+            "  s.RunBatch(channels, d_features, 40, d_ivectors, nvalid, first, last, &post, &ptrs);\n"
+            "  int a = s.GetNOutputFramesPerChunk() + s.GetTotalNnet3RightContext(); (void)a;\n"
+            "  b2k_shim::DecodableAmNnetLoopedOnlineB2k d(tm, info, feats, ivecs);\n"
+            "  DecodableInterface *itf = &d;\n"
+            "  BaseFloat l = itf->LogLikelihood(0, 1); (void)l; itf->NumFramesReady(); itf->IsLastFrame(0); itf->NumIndices();\n"
+            "  d.SetFrameOffset(d.GetFrameOffset()); d.FrameSubsamplingFactor();\n"
+            "  b2k_shim::DecodableNnetLoopedOnlineB2k d2(info, feats, ivecs); d2.LogLikelihood(0, 1);\n"
+            "  b2k_shim::NnetComputerB2k comp(co, req, am.GetNnet());\n"
+            "  CuMatrix<BaseFloat> in, out; comp.AcceptInput(\"input\", &in); comp.Run();\n"
+            "  const CuMatrixBase<BaseFloat> &o = comp.GetOutput(\"output\"); (void)o; comp.GetOutputDestructive(\"output\", &out);\n"
+            "}\n")
+        subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"),
+                              "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include",
+                              "-I" + os.path.join(ROOT, "oracle", "_ref", "inc")]) + [nn])
     return True
 
 

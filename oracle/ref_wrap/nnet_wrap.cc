@@ -7,6 +7,7 @@
 //   SetBatchnormTestMode / SetDropoutTestMode / CollapseModel   nnet3/nnet-utils.cc
 //   AmNnetSimple, DecodableNnetSimpleLoopedInfo, DecodableNnetSimpleLooped
 //                                          nnet3/decodable-simple-looped.{h,cc}
+#include <fstream>
 #include <cstring>
 #include <memory>
 #include <sstream>
@@ -192,6 +193,28 @@ int ref_write_final_mdl(void *h, const char *path, int binary, const char *topo_
     for (int t = 1; t <= n; t++) tid2pdf_out[t] = tm.TransitionIdToPdf(t);
     return n;
   } catch (const std::exception &e) { fprintf(stderr, "ref_write_final_mdl: %s\n", e.what()); return -1; }
+}
+
+// AmNnetSimple::Write alone (nnet3/am-nnet-simple.cc:34-57) -- what kaldi_b200/host/b2k_nnet3_shims.h serialises into memory
+// from the AmNnetSimple a Kaldi tool holds; with_header = the "\0B" marker Output writes.
+int ref_write_am_nnet(void *h, const char *path, int binary, int with_header, const float *priors, int num_priors) {
+  try {
+    RefNnet *r = (RefNnet *)h;
+    AmNnetSimple am(r->nnet);
+    if (priors && num_priors > 0) {
+      Vector<BaseFloat> pv(num_priors);
+      for (int i = 0; i < num_priors; i++) pv(i) = priors[i];
+      am.SetPriors(pv);
+    }
+    if (with_header) {
+      Output ko(path, binary != 0);
+      am.Write(ko.Stream(), binary != 0);
+      return ko.Close() ? 0 : -1;
+    }
+    std::ofstream os(path, std::ios::binary);
+    am.Write(os, binary != 0);
+    return os.good() ? 0 : -1;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_write_am_nnet: %s\n", e.what()); return -1; }
 }
 
 // Matrix<float>::Read / Vector<float>::Read through Input (util/kaldi-io.h), binary or text: the reference-side

@@ -218,3 +218,64 @@ def test_trained_recipe_model_with_dropout_and_xent_branch(tmp_path, binary, whi
         L.b2k_nnet_program_destroy(prog)
     assert out.shape == ref.shape
     assert np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("which", ["idct-delta", "cnn"])
+def test_model_from_memory_as_the_nnet3_shims_serialise_it(tmp_path, which):
+    """b2k_model_read_memory on the bytes Nnet::Write / AmNnetSimple::Write / final.mdl produce (kaldi_b200/host/
+    b2k_nnet3_shims.h: ModelB2k writes the reference's object into a string stream): the same layers and weights as the file
+    reader, with and without the binary marker in front of a text stream, and AmNnetSimple alone (kind 2) keeps its priors."""
+    L = _lib()
+    from oracle import nnet_oracle as NO
+    if not (os.path.exists(NO._SO) or os.path.isdir("/root/reference")):
+        pytest.skip("oracle/_ref nnet3 library not present")
+    arch = NM.arch_tiny_cnn() if which == "cnn" else NM.arch_tiny(front=which)
+    Wt = NM.random_weights(arch, seed=5)
+    R = NO.RefNnet(arch, Wt, collapse=False)
+    if not hasattr(R.lib, "ref_write_am_nnet"):
+        pytest.skip("oracle/_ref library predates ref_write_am_nnet")
+    R.lib.ref_nnet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    R.lib.ref_write_am_nnet.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    R.lib.ref_write_final_mdl.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    pri = np.ascontiguousarray(Wt["priors"], np.float32)
+    L.b2k_model_read_memory.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.c_void_p]
+    L.b2k_model_destroy.argtypes = [C.c_void_p]
+
+    def from_memory(data, kind):
+        h = C.c_void_p()
+        rc = L.b2k_model_read_memory(data, len(data), kind, C.byref(h))
+        assert rc == 0, L.b2k_last_error()
+        try:
+            info = (C.c_int32 * 8)()
+            L.b2k_model_info.argtypes = [C.c_void_p, C.c_void_p]
+            assert L.b2k_model_info(h, info) == 0
+            L.b2k_model_weights.restype = C.c_void_p
+            from kaldi_b200.nnet_compile import _Weight
+            ws = C.cast(L.b2k_model_weights(h), C.POINTER(_Weight))
+            W = {ws[i].name.decode(): np.ctypeslib.as_array(C.cast(ws[i].data, C.POINTER(C.c_float)), shape=(ws[i].size,)).copy()
+                 for i in range(info[5])}
+            return list(info), W
+        finally:
+            L.b2k_model_destroy(h)
+
+    for binary in (1, 0):
+        raw, am, am_nohdr, mdl = (str(tmp_path / f"{n}{binary}") for n in ("raw", "am", "am_nohdr", "mdl"))
+        assert R.lib.ref_nnet_write(R.h, raw.encode(), binary) == 0
+        assert R.lib.ref_write_am_nnet(R.h, am.encode(), binary, 1, pri.ctypes.data, pri.size) == 0
+        assert R.lib.ref_write_am_nnet(R.h, am_nohdr.encode(), 0, 0, pri.ctypes.data, pri.size) == 0
+        t2p = np.zeros(64, np.int32)
+        assert R.lib.ref_write_final_mdl(R.h, mdl.encode(), binary, CHAIN_TOPO.encode(), 5, 2, pri.ctypes.data, pri.size,
+                                         t2p.ctypes.data, t2p.size) > 0
+        _h, finfo, _layers, fW, _t = _read(L, mdl, 1)
+        L.b2k_model_destroy(_h)
+        for path, kind, has_priors in ((raw, 0, False), (am, 2, True), (am_nohdr, 2, True), (mdl, 1, True)):
+            info, W = from_memory(open(path, "rb").read(), kind)
+            assert info[:6] == finfo[:6] and info[7] == (1 if has_priors else 0)
+            for k, v in fW.items():
+                if k == "priors" and not has_priors:
+                    continue
+                tol = dict(rtol=0, atol=0) if (binary and path != am_nohdr) else dict(rtol=2e-5, atol=1e-6)
+                np.testing.assert_allclose(W[k], np.asarray(v).ravel(), err_msg=f"{path} {k}", **tol)
+    assert L.b2k_model_read_memory(b"\0Bgarbage", 9, 2, C.byref(C.c_void_p())) != 0
+    assert L.b2k_model_read_memory(None, 0, 2, C.byref(C.c_void_p())) != 0
