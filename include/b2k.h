@@ -311,6 +311,21 @@ int b2k_ivec_compute_batched(b2k_ivec *iv, int32_t num_lanes, const float *const
                              int32_t feat_stride, int32_t num_frames, const int32_t *sched,
                              int32_t n_chunks, float *const *d_out, int32_t out_stride, void *stream);
 
+/* The same with speaker adaptation carried from utterance to utterance: OnlineIvectorFeature::SetAdaptationState before
+ * the utterance and GetAdaptationState after it (online2/online-ivector-feature.cc:386-396,445-453; the tool's
+ * per-speaker loop, online2bin/online2-wav-nnet3-latgen-faster.cc:199-221,287).  A state is
+ * b2k_ivec_adaptation_state_doubles() doubles in device memory: OnlineCmvnState::speaker_cmvn_stats [2 x (base_dim+1)],
+ * then OnlineIvectorEstimationStats {num_frames, linear term [D], quadratic term [D(D+1)/2, packed lower triangle]}.
+ * d_state_in[i] NULL (or the array NULL): lane i starts as a new speaker (no speaker CMVN stats, prior-only i-vector
+ * stats); d_state_out[i] non-NULL: the state after this utterance -- GetState(last frame) of the CMVN (every frame added
+ * to the speaker stats) and the i-vector stats, both limited to max_remembered_frames as LimitFrames does (:109-127;
+ * < 0 = no limit) -- which may be the array d_state_in[i] points to. */
+int64_t b2k_ivec_adaptation_state_doubles(const b2k_ivec *iv);
+int b2k_ivec_compute_batched_adapt(b2k_ivec *iv, int32_t num_lanes, const float *const *d_feats, int32_t feat_stride,
+                                   int32_t num_frames, const int32_t *sched, int32_t n_chunks, float *const *d_out,
+                                   int32_t out_stride, const double *const *d_state_in, double *const *d_state_out,
+                                   float max_remembered_frames, void *stream);
+
 /* -------------------------------------------------------------------- nnet3 */
 
 /* A compiled forward program for one utterance length: the analogue of the

@@ -276,13 +276,20 @@ feat_kernel(FeatParams p, const FeatLane *lanes, int frames_per_cta) {
 __global__ void cmvn_kernel(CmvnParams p, const CmvnLane *lanes) {
   const CmvnLane L = lanes[blockIdx.x];
   const int d = threadIdx.x;
-  if (d >= p.dim) return;
   const int D = p.dim;
-  double s0 = L.state[d], s1 = L.state[(D + 1) + d], cnt = L.state[D];
+  const bool act = d < D;
+  const double *spk = L.speaker ? L.speaker : p.speaker_stats;
+  double s0 = 0.0, s1 = 0.0, cnt = 0.0, sp0 = 0.0, sp1 = 0.0, spc = 0.0, sp1c = 0.0;
+  if (act) {
+    s0 = L.state[d]; s1 = L.state[(D + 1) + d]; cnt = L.state[D];
+    if (spk) { sp0 = spk[d]; sp1 = spk[(D + 1) + d]; spc = spk[D]; sp1c = spk[2 * D + 1]; }
+  }
+  __syncthreads();                 // speaker_out may be the array `speaker` was read from
+  if (!act) return;
   const double g0 = p.global_stats ? p.global_stats[d] : 0.0, g1 = p.global_stats ? p.global_stats[(D + 1) + d] : 0.0,
                gc = p.global_stats ? p.global_stats[D] : 0.0;
-  const double sp0 = p.speaker_stats ? p.speaker_stats[d] : 0.0, sp1 = p.speaker_stats ? p.speaker_stats[(D + 1) + d] : 0.0,
-               spc = p.speaker_stats ? p.speaker_stats[D] : 0.0;
+  // OnlineCmvn::GetState (online-feature.cc:278-300): the speaker stats plus every frame of this utterance, in double
+  double a0 = sp0, a1 = sp1, ac = spc;
   for (int i = 0; i < L.num_frames; i++) {
     const int t = L.first_frame + i;
     const float xf = L.in[(size_t)t * L.in_stride + d];
@@ -300,8 +307,9 @@ __global__ void cmvn_kernel(CmvnParams p, const CmvnLane *lanes) {
     }
     // SmoothOnlineCmvnStats (:372-419)
     double m0 = s0, m1 = s1, c = cnt;
+    if (L.speaker_out) { a0 += x; a1 = __dadd_rn(a1, __dmul_rn(x, x)); ac += 1.0; }
     if (c < (double)p.cmn_window) {
-      if (p.speaker_stats) {
+      if (spk) {
         double cfs = (double)p.cmn_window - c;
         if (cfs > (double)p.speaker_frames) cfs = (double)p.speaker_frames;
         if (cfs > spc) cfs = spc;
@@ -333,6 +341,14 @@ __global__ void cmvn_kernel(CmvnParams p, const CmvnLane *lanes) {
   }
   L.state[d] = s0; L.state[(D + 1) + d] = s1;
   if (d == 0) L.state[D] = cnt;
+  if (L.speaker_out) {
+    // OnlineIvectorExtractorAdaptationState::LimitFrames, CMVN half (online-ivector-feature.cc:113-118): BaseFloat arithmetic
+    double sc = 1.0;
+    const float count = (float)ac;
+    if (L.max_remembered_frames >= 0.0f && count > L.max_remembered_frames) sc = (double)(L.max_remembered_frames / count);
+    L.speaker_out[d] = a0 * sc; L.speaker_out[(D + 1) + d] = a1 * sc;
+    if (d == 0) { L.speaker_out[D] = ac * sc; L.speaker_out[2 * D + 1] = sp1c * sc; }
+  }
 }
 
 int launch_cmvn(const CmvnParams &cp, const CmvnLane *d_lanes, int num_lanes, cudaStream_t st) {
@@ -564,6 +580,7 @@ int b2k_cmvn_apply_batched(b2k_feat *f, const b2k_cmvn_cfg *cfg, int32_t num_lan
     CmvnLane &L = f->h_clanes[i];
     L.in = d_in[i]; L.out = d_out[i]; L.in_stride = in_stride; L.out_stride = out_stride;
     L.first_frame = first_frame ? first_frame[i] : 0; L.num_frames = num_frames[i]; L.state = d_state[i];
+    L.speaker = nullptr; L.speaker_out = nullptr; L.max_remembered_frames = -1.0f;
   }
   B2K_CUDA_CHECK(cudaMemcpyAsync(f->d_clanes, f->h_clanes, sizeof(CmvnLane) * num_lanes, cudaMemcpyHostToDevice, st));
   B2K_CUDA_CHECK(cudaEventRecord(f->staging_free, st));

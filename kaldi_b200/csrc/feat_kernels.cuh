@@ -10,6 +10,11 @@ struct CmvnLane {
   int in_stride, out_stride;
   int first_frame, num_frames;        // frames to produce in this call
   double *state;         // [2*(dim+1)] sliding-window stats after frame first_frame-1 (persisted)
+  // speaker adaptation (OnlineCmvnState::speaker_cmvn_stats): this lane's own speaker stats (null: CmvnParams::speaker_stats),
+  // and where OnlineCmvn::GetState(last frame) + LimitFrames leave them after the call (null: not wanted; may equal `speaker`)
+  const double *speaker;
+  double *speaker_out;
+  float max_remembered_frames;   // < 0: no limit
 };
 struct CmvnParams {
   int dim, cmn_window, speaker_frames, global_frames, normalize_mean, normalize_variance;

@@ -49,6 +49,11 @@ struct IvecRun {
   int *post_cnt;                 // [lanes x T]
   const int *sched; int n_chunks;
   float *const *d_out; int out_stride;
+  // speaker adaptation state per lane (null arrays / null entries: a new speaker, nothing kept): the i-vector half is
+  // {num_frames, linear[D], quadratic[D(D+1)/2]} after the CMVN half (2*(base_dim+1) doubles); in and out may be the same array
+  const double *const *state_in; double *const *state_out;
+  int state_iv_off;              // doubles in front of the i-vector half
+  float max_remembered_frames;
 };
 
 #define IV_WARPS 8
@@ -239,14 +244,23 @@ __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParam
   float *pval_s = reinterpret_cast<float *>(pidx_s + 8 * IVS_STAGE);   // 8 * IVS_STAGE
   float *feat_s = pval_s + 8 * IVS_STAGE;                      // IVS_STAGE * F
   const int tid = threadIdx.x, L = blockIdx.x;
-  // OnlineIvectorEstimationStats ctor (:786-795): linear(0) = prior_offset, quadratic = I
-  for (int k = tid; k < Q; k += IVS_THREADS) quad[k] = 0.0;
-  for (int i = tid; i < D; i += IVS_THREADS) { lin[i] = 0.0; x[i] = 0.0; }
-  __syncthreads();
-  for (int i = tid; i < D; i += IVS_THREADS) quad[(size_t)i * (i + 1) / 2 + i] = 1.0;
-  if (tid == 0) lin[0] = (double)p.prior_offset;
-  __syncthreads();
+  const double *st_in = (r.state_in && r.state_in[L]) ? r.state_in[L] + r.state_iv_off : nullptr;
   double num_frames = 0.0;
+  if (st_in) {
+    // SetAdaptationState (online-ivector-feature.cc:445-453): ivector_stats_ = the speaker's; the i-vector itself starts
+    // from its default again (a new OnlineIvectorFeature object, :438-440)
+    num_frames = st_in[0];
+    for (int i = tid; i < D; i += IVS_THREADS) { lin[i] = st_in[1 + i]; x[i] = 0.0; }
+    for (int k = tid; k < Q; k += IVS_THREADS) quad[k] = st_in[1 + D + k];
+  } else {
+    // OnlineIvectorEstimationStats ctor (:786-795): linear(0) = prior_offset, quadratic = I
+    for (int k = tid; k < Q; k += IVS_THREADS) quad[k] = 0.0;
+    for (int i = tid; i < D; i += IVS_THREADS) { lin[i] = 0.0; x[i] = 0.0; }
+    __syncthreads();
+    for (int i = tid; i < D; i += IVS_THREADS) quad[(size_t)i * (i + 1) / 2 + i] = 1.0;
+    if (tid == 0) lin[0] = (double)p.prior_offset;
+  }
+  __syncthreads();
   int next_t = 0;
   const float *lda_raw = r.lda_raw + (size_t)L * r.T * F;
   for (int n = 0; n < r.n_chunks; n++) {
@@ -437,6 +451,27 @@ __global__ void __launch_bounds__(IVS_THREADS, 3) ivec_stats_cg_kernel(IvecParam
     }
     __syncthreads();
   }
+  if (r.state_out && r.state_out[L]) {
+    // GetAdaptationState (:386-396): the stats as they stand, then LimitFrames' i-vector half (:119-126) =
+    // OnlineIvectorEstimationStats::Scale (ivector-extractor.cc:671-693)
+    double *so = r.state_out[L] + r.state_iv_off;
+    double scale = 1.0, diag_add = 0.0, nf = num_frames;
+    const float limit = r.max_remembered_frames * p.posterior_scale;            // BaseFloat product
+    if (r.max_remembered_frames >= 0.0f && num_frames > (double)limit) {
+      scale = (double)limit / num_frames;
+      nf = num_frames * scale;
+      if (p.max_count == 0.0f) diag_add = 1.0 - scale;
+      else {
+        const double mc = (double)p.max_count;
+        diag_add = fmax(nf, mc) / mc - scale * fmax(num_frames, mc) / mc;
+      }
+    }
+    for (int i = tid; i < D; i += IVS_THREADS) so[1 + i] = lin[i] * scale + (i == 0 ? (double)p.prior_offset * diag_add : 0.0);
+    for (int k = tid; k < Q; k += IVS_THREADS) so[1 + D + k] = quad[k] * scale;
+    __syncthreads();
+    for (int i = tid; i < D; i += IVS_THREADS) so[1 + D + (size_t)i * (i + 1) / 2 + i] += diag_add;
+    if (tid == 0) so[0] = nf;
+  }
 }
 
 }  // namespace b2k
@@ -451,6 +486,7 @@ struct b2k_ivec {
   int *d_post_idx = nullptr, *d_post_cnt = nullptr, *d_sched = nullptr;
   double *d_cmvn_state = nullptr, *d_global = nullptr;
   CmvnLane *d_clanes = nullptr, *h_clanes = nullptr;
+  double **d_stp = nullptr, **h_stp = nullptr;     // [2 * max_lanes]: state in pointers, then state out pointers
   const float **d_featp = nullptr, **h_featp = nullptr;
   float **d_outp = nullptr, **h_outp = nullptr;
   int *h_sched = nullptr;
@@ -518,6 +554,8 @@ int b2k_ivec_create(const b2k_ivec_cfg *cfg, const float *lda, const float *gcon
   if ((rc = al((void **)&iv->d_featp, sizeof(void *) * NL))) return rc;
   if ((rc = al((void **)&iv->d_outp, sizeof(void *) * NL))) return rc;
   B2K_CUDA_CHECK(cudaMallocHost((void **)&iv->h_clanes, sizeof(CmvnLane) * NL));
+  if ((rc = al((void **)&iv->d_stp, sizeof(double *) * 2 * NL))) return rc;
+  B2K_CUDA_CHECK(cudaMallocHost((void **)&iv->h_stp, sizeof(double *) * 2 * NL));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&iv->h_featp, sizeof(void *) * NL));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&iv->h_outp, sizeof(void *) * NL));
   B2K_CUDA_CHECK(cudaMallocHost((void **)&iv->h_sched, 4 * 4096));
@@ -535,15 +573,29 @@ int b2k_ivec_destroy(b2k_ivec *iv) {
   if (!iv) return B2K_OK;
   cudaDeviceSynchronize();
   for (void *p : iv->allocs) cudaFree(p);
-  cudaFreeHost(iv->h_clanes); cudaFreeHost(iv->h_featp); cudaFreeHost(iv->h_outp); cudaFreeHost(iv->h_sched);
+  cudaFreeHost(iv->h_clanes); cudaFreeHost(iv->h_featp); cudaFreeHost(iv->h_outp); cudaFreeHost(iv->h_sched); cudaFreeHost(iv->h_stp);
   if (iv->staging_free) cudaEventDestroy(iv->staging_free);
   delete iv;
   return B2K_OK;
 }
 
+int64_t b2k_ivec_adaptation_state_doubles(const b2k_ivec *iv) {
+  if (!iv) return -1;
+  const int64_t D = iv->cfg.ivector_dim;
+  return 2 * ((int64_t)iv->cfg.base_dim + 1) + 1 + D + D * (D + 1) / 2;
+}
+
 int b2k_ivec_compute_batched(b2k_ivec *iv, int32_t num_lanes, const float *const *d_feats, int32_t feat_stride,
                              int32_t num_frames, const int32_t *sched, int32_t n_chunks, float *const *d_out,
                              int32_t out_stride, void *stream) {
+  return b2k_ivec_compute_batched_adapt(iv, num_lanes, d_feats, feat_stride, num_frames, sched, n_chunks, d_out, out_stride, nullptr,
+                                        nullptr, -1.0f, stream);
+}
+
+int b2k_ivec_compute_batched_adapt(b2k_ivec *iv, int32_t num_lanes, const float *const *d_feats, int32_t feat_stride,
+                                   int32_t num_frames, const int32_t *sched, int32_t n_chunks, float *const *d_out,
+                                   int32_t out_stride, const double *const *d_state_in, double *const *d_state_out,
+                                   float max_remembered_frames, void *stream) {
   if (!iv || num_lanes <= 0 || num_lanes > iv->cfg.max_lanes || !d_feats || !sched || !d_out || n_chunks <= 0 ||
       n_chunks > 4096 || num_frames <= 0 || num_frames > iv->cfg.max_frames)
     return set_error(B2K_ERR_INVALID, "b2k_ivec_compute_batched: bad args");
@@ -554,6 +606,12 @@ int b2k_ivec_compute_batched(b2k_ivec *iv, int32_t num_lanes, const float *const
     CmvnLane &L = iv->h_clanes[i];
     L.in = d_feats[i]; L.out = iv->d_cmvn + (size_t)i * num_frames * bd; L.in_stride = feat_stride; L.out_stride = bd;
     L.first_frame = 0; L.num_frames = num_frames; L.state = iv->d_cmvn_state + (size_t)i * 2 * (bd + 1);
+    // the CMVN half of a speaker's adaptation state lies in front of the i-vector half
+    L.speaker = d_state_in ? d_state_in[i] : nullptr;
+    L.speaker_out = d_state_out ? d_state_out[i] : nullptr;
+    L.max_remembered_frames = max_remembered_frames;
+    iv->h_stp[i] = d_state_in ? const_cast<double *>(d_state_in[i]) : nullptr;
+    iv->h_stp[iv->cfg.max_lanes + i] = d_state_out ? d_state_out[i] : nullptr;
     iv->h_featp[i] = d_feats[i]; iv->h_outp[i] = d_out[i];
   }
   for (int n = 0; n < n_chunks; n++) {
@@ -564,6 +622,7 @@ int b2k_ivec_compute_batched(b2k_ivec *iv, int32_t num_lanes, const float *const
   B2K_CUDA_CHECK(cudaMemcpyAsync((void *)iv->d_featp, iv->h_featp, sizeof(void *) * num_lanes, cudaMemcpyHostToDevice, st));
   B2K_CUDA_CHECK(cudaMemcpyAsync((void *)iv->d_outp, iv->h_outp, sizeof(void *) * num_lanes, cudaMemcpyHostToDevice, st));
   B2K_CUDA_CHECK(cudaMemcpyAsync(iv->d_sched, iv->h_sched, 4 * (size_t)n_chunks, cudaMemcpyHostToDevice, st));
+  B2K_CUDA_CHECK(cudaMemcpyAsync((void *)iv->d_stp, iv->h_stp, sizeof(double *) * 2 * (size_t)iv->cfg.max_lanes, cudaMemcpyHostToDevice, st));
   B2K_CUDA_CHECK(cudaEventRecord(iv->staging_free, st));
   B2K_CUDA_CHECK(cudaMemsetAsync(iv->d_cmvn_state, 0, 8 * (size_t)num_lanes * 2 * (bd + 1), st));
   CmvnParams cp;
@@ -576,6 +635,8 @@ int b2k_ivec_compute_batched(b2k_ivec *iv, int32_t num_lanes, const float *const
   r.d_feats = iv->d_featp; r.feat_stride = feat_stride; r.T = num_frames; r.cmvn = iv->d_cmvn; r.lda_raw = iv->d_lda_raw;
   r.post_idx = iv->d_post_idx; r.post_val = iv->d_post_val; r.post_cnt = iv->d_post_cnt; r.sched = iv->d_sched;
   r.n_chunks = n_chunks; r.d_out = iv->d_outp; r.out_stride = out_stride;
+  r.state_in = d_state_in ? iv->d_stp : nullptr; r.state_out = d_state_out ? iv->d_stp + iv->cfg.max_lanes : nullptr;
+  r.state_iv_off = 2 * (bd + 1); r.max_remembered_frames = max_remembered_frames;
   const int fpc = 64;
   ivec_front_kernel<<<dim3((num_frames + fpc - 1) / fpc, num_lanes), IV_WARPS * 32, iv->smem_front, st>>>(iv->p, r, fpc);
   B2K_LAUNCH_CHECK();

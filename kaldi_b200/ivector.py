@@ -156,6 +156,31 @@ class IvectorExtractorGpu:
             sched.ctypes.data_as(C.POINTER(C.c_int32)), len(sched), C.cast(oa, C.c_void_p), int(out_stride),
             C.c_void_p(stream)))
 
+    def AdaptationStateDoubles(self) -> int:
+        """Doubles in one speaker's adaptation state (speaker CMVN stats, then the i-vector stats)."""
+        L = _lib.lib()
+        L.b2k_ivec_adaptation_state_doubles.restype = C.c_int64
+        L.b2k_ivec_adaptation_state_doubles.argtypes = [C.c_void_p]
+        return int(L.b2k_ivec_adaptation_state_doubles(self.h))
+
+    def ComputeAdapt(self, feat_ptrs, feat_stride: int, num_frames: int, schedule, out_ptrs, out_stride: int,
+                     state_in_ptrs, state_out_ptrs, max_remembered_frames: float = 1000.0, stream: int = 0):
+        """Compute with speaker adaptation: state_in_ptrs[i] (0 / None = a new speaker) is what SetAdaptationState would be
+        given before the utterance, state_out_ptrs[i] receives GetAdaptationState after it (device pointers to
+        AdaptationStateDoubles() doubles; in and out may coincide).  online2-wav-nnet3-latgen-faster.cc:199-221,287."""
+        n = len(feat_ptrs)
+        sched = np.ascontiguousarray(schedule, np.int32)
+        fa = (C.c_void_p * n)(*[int(p) for p in feat_ptrs])
+        oa = (C.c_void_p * n)(*[int(p) for p in out_ptrs])
+        si = (C.c_void_p * n)(*[int(p) if p else None for p in state_in_ptrs]) if state_in_ptrs is not None else None
+        so = (C.c_void_p * n)(*[int(p) if p else None for p in state_out_ptrs]) if state_out_ptrs is not None else None
+        L = _lib.lib()
+        L.b2k_ivec_compute_batched_adapt.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        _lib.check(L.b2k_ivec_compute_batched_adapt(
+            self.h, n, C.cast(fa, C.c_void_p), int(feat_stride), int(num_frames), sched.ctypes.data, len(sched),
+            C.cast(oa, C.c_void_p), int(out_stride), si, so, float(max_remembered_frames), C.c_void_p(stream)))
+
     # pipeline hook
     def compute_chunk_ivectors(self, pipe, n: int, stream: int = 0):
         T, D = pipe.T, pipe.feat.dim

@@ -82,7 +82,22 @@ class RefIvector:
         except Exception:
             pass
 
-    def run(self, feats: np.ndarray, schedule, online_cmvn_iextractor: bool = False, debug: bool = False):
+    def new_speaker(self):
+        """An opaque speaker (OnlineIvectorExtractorAdaptationState on the reference side) for run(..., speaker=)."""
+        self.lib.ref_ivector_speaker_create.restype = C.c_void_p
+        return C.c_void_p(self.lib.ref_ivector_speaker_create())
+
+    def speaker_state(self, speaker) -> np.ndarray:
+        """The speaker's adaptation state as doubles in b2k's layout (b2k_ivec_compute_batched_adapt)."""
+        D, iv = self.ex["base_dim"], self.ex["ivector_dim"]
+        out = np.zeros(2 * (D + 1) + 1 + iv + iv * (iv + 1) // 2, np.float64)
+        self.lib.ref_ivector_speaker_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        if self.lib.ref_ivector_speaker_state(speaker, D, iv, out.ctypes.data) != 0:
+            raise RuntimeError("speaker without a state")
+        return out
+
+    def run(self, feats: np.ndarray, schedule, online_cmvn_iextractor: bool = False, debug: bool = False, speaker=None,
+            max_remembered_frames: float = 1000.0):
         ex = self.ex
         f = np.ascontiguousarray(feats, np.float32)
         T, D = f.shape
@@ -92,12 +107,13 @@ class RefIvector:
         dr = np.zeros((T, ex["feat_dim"]), np.float32) if debug else None
         dn = np.zeros((T, ex["feat_dim"]), np.float32) if debug else None
         fp, dp, ip = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int32)
-        r = self.lib.ref_ivector_run(self.h, f.ctypes.data_as(fp), T, D, g.ctypes.data_as(dp), ex["cmn_window"],
-                                     ex["speaker_frames"], ex["global_frames"], ex["splice"], ex["splice"],
-                                     ex["num_gselect"], C.c_float(ex["min_post"]), C.c_float(ex["posterior_scale"]),
-                                     C.c_float(ex["max_count"]), ex["num_cg_iters"], int(online_cmvn_iextractor),
-                                     sched.ctypes.data_as(ip), len(sched), out.ctypes.data_as(fp),
-                                     dr.ctypes.data_as(fp) if debug else None, dn.ctypes.data_as(fp) if debug else None)
+        r = self.lib.ref_ivector_run_speaker(self.h, f.ctypes.data_as(fp), T, D, g.ctypes.data_as(dp), ex["cmn_window"],
+                                             ex["speaker_frames"], ex["global_frames"], ex["splice"], ex["splice"],
+                                             ex["num_gselect"], C.c_float(ex["min_post"]), C.c_float(ex["posterior_scale"]),
+                                             C.c_float(ex["max_count"]), ex["num_cg_iters"], int(online_cmvn_iextractor),
+                                             sched.ctypes.data_as(ip), len(sched), out.ctypes.data_as(fp),
+                                             dr.ctypes.data_as(fp) if debug else None, dn.ctypes.data_as(fp) if debug else None,
+                                             speaker, C.c_float(max_remembered_frames))
         if r != 0:
             raise RuntimeError("reference i-vector extraction failed")
         return (out, dr, dn) if debug else out

@@ -30,7 +30,41 @@ struct RefIvec {
   Matrix<BaseFloat> lda;
 };
 
+// One speaker across utterances: what OnlineIvectorExtractorAdaptationState holds (online2/online-ivector-feature.h:218-263).
+struct RefSpeaker {
+  bool has = false;
+  OnlineCmvnState cmvn;
+  std::unique_ptr<OnlineIvectorEstimationStats> stats;
+};
+
 extern "C" {
+
+void *ref_ivector_speaker_create() { return new RefSpeaker(); }
+void ref_ivector_speaker_destroy(void *s) { delete (RefSpeaker *)s; }
+// The speaker's state as flat doubles in b2k's layout: speaker_cmvn_stats [2 x (D+1)], num_frames, linear [ivdim], quadratic
+// [packed lower triangle] (read back through the reference's own binary Write / Read: the members are private).
+int ref_ivector_speaker_state(void *sp, int D, int ivdim, double *out) {
+  try {
+    RefSpeaker *s = (RefSpeaker *)sp;
+    if (!s->has) return -1;
+    for (int r = 0; r < 2; r++) for (int c = 0; c <= D; c++) out[r * (D + 1) + c] = s->cmvn.speaker_cmvn_stats.NumRows() ? s->cmvn.speaker_cmvn_stats(r, c) : 0.0;
+    std::stringstream ss(std::ios::in | std::ios::out | std::ios::binary);
+    s->stats->Write(ss, true);
+    double prior_offset, max_count, num_frames;
+    ExpectToken(ss, true, "<OnlineIvectorEstimationStats>");
+    ExpectToken(ss, true, "<PriorOffset>"); ReadBasicType(ss, true, &prior_offset);
+    ExpectToken(ss, true, "<MaxCount>"); ReadBasicType(ss, true, &max_count);
+    ExpectToken(ss, true, "<NumFrames>"); ReadBasicType(ss, true, &num_frames);
+    SpMatrix<double> q; Vector<double> l;
+    ExpectToken(ss, true, "<QuadraticTerm>"); q.Read(ss, true);
+    ExpectToken(ss, true, "<LinearTerm>"); l.Read(ss, true);
+    double *o = out + 2 * (D + 1);
+    o[0] = num_frames;
+    for (int i = 0; i < ivdim; i++) o[1 + i] = l(i);
+    for (int i = 0, k = 0; i < ivdim; i++) for (int j = 0; j <= i; j++, k++) o[1 + ivdim + k] = q(i, j);
+    return 0;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_ivector_speaker_state: %s\n", e.what()); return -1; }
+}
 
 void *ref_ivector_create(const char *extractor_text, const char *ubm_text, const float *lda, int lda_rows, int lda_cols) {
   try {
@@ -46,12 +80,31 @@ void ref_ivector_destroy(void *h) { delete (RefIvec *)h; }
 
 // sched[n] = frame index passed to OnlineIvectorFeature::GetFrame for nnet chunk n
 // (non-decreasing).  out: [n_chunks x ivector_dim], prior offset already subtracted from dim 0.
+int ref_ivector_run_speaker(void *h, const float *feats, int T, int D, const double *global_cmvn, int cmn_window,
+                            int speaker_frames, int global_frames, int splice_left, int splice_right, int num_gselect,
+                            float min_post, float posterior_scale, float max_count, int num_cg_iters,
+                            int online_cmvn_iextractor, const int *sched, int n_chunks, float *out,
+                            float *debug_lda_raw, float *debug_lda_norm, void *speaker, float max_remembered_frames);
+
 int ref_ivector_run(void *h, const float *feats, int T, int D, const double *global_cmvn, int cmn_window,
                     int speaker_frames, int global_frames, int splice_left, int splice_right, int num_gselect,
                     float min_post, float posterior_scale, float max_count, int num_cg_iters,
                     int online_cmvn_iextractor, const int *sched, int n_chunks, float *out,
                     float *debug_lda_raw, float *debug_lda_norm) {
+  return ref_ivector_run_speaker(h, feats, T, D, global_cmvn, cmn_window, speaker_frames, global_frames, splice_left, splice_right,
+                                 num_gselect, min_post, posterior_scale, max_count, num_cg_iters, online_cmvn_iextractor, sched,
+                                 n_chunks, out, debug_lda_raw, debug_lda_norm, nullptr, -1.0f);
+}
+
+// speaker != NULL: SetAdaptationState(speaker) before the utterance when the speaker has a state (online-ivector-feature.cc:
+// 445-453), GetAdaptationState after it (:386-396: OnlineCmvn::GetState of the last frame, the stats, LimitFrames :109-127)
+int ref_ivector_run_speaker(void *h, const float *feats, int T, int D, const double *global_cmvn, int cmn_window,
+                            int speaker_frames, int global_frames, int splice_left, int splice_right, int num_gselect,
+                            float min_post, float posterior_scale, float max_count, int num_cg_iters,
+                            int online_cmvn_iextractor, const int *sched, int n_chunks, float *out,
+                            float *debug_lda_raw, float *debug_lda_norm, void *speaker, float max_remembered_frames) {
   try {
+    RefSpeaker *spk = (RefSpeaker *)speaker;
     RefIvec *r = (RefIvec *)h;
     Matrix<BaseFloat> m(T, D);
     for (int t = 0; t < T; t++) memcpy(m.RowData(t), feats + (size_t)t * D, 4 * D);
@@ -61,6 +114,7 @@ int ref_ivector_run(void *h, const float *feats, int T, int D, const double *glo
     Matrix<double> g(2, D + 1);
     for (int i = 0; i < 2; i++) for (int j = 0; j <= D; j++) g(i, j) = global_cmvn[i * (D + 1) + j];
     OnlineCmvnState cstate(g);
+    if (spk && spk->has) { cstate = spk->cmvn; cstate.global_cmvn_stats = g; }
     OnlineCmvn cmvn(copts, cstate, &base);
     OnlineSpliceOptions sopts;
     sopts.left_context = splice_left; sopts.right_context = splice_right;
@@ -68,6 +122,7 @@ int ref_ivector_run(void *h, const float *feats, int T, int D, const double *glo
     OnlineTransform lda_norm(r->lda, &splice_norm), lda_raw(r->lda, &splice_raw);
     const int ivdim = r->extractor.IvectorDim();
     OnlineIvectorEstimationStats stats(ivdim, r->extractor.PriorOffset(), max_count);
+    if (spk && spk->has) stats = *spk->stats;
     Vector<double> current_ivector(ivdim);
     int num_frames_stats = 0;
     if (debug_lda_raw) for (int t = 0; t < T; t++) { SubVector<BaseFloat> row(debug_lda_raw + (size_t)t * lda_raw.Dim(), lda_raw.Dim()); lda_raw.GetFrame(t, &row); }
@@ -103,6 +158,23 @@ int ref_ivector_run(void *h, const float *feats, int T, int D, const double *glo
       out[(size_t)n * ivdim] = (float)current_ivector(0);
       { Vector<BaseFloat> f(ivdim); f.CopyFromVec(current_ivector); f(0) -= r->extractor.PriorOffset();
         for (int d = 0; d < ivdim; d++) out[(size_t)n * ivdim + d] = f(d); }
+    }
+    if (spk) {
+      OnlineCmvnState ns;
+      cmvn.GetState(cmvn.NumFramesReady() - 1, &ns);
+      // LimitFrames (:109-127), restated with the reference's own Scale() methods
+      if (max_remembered_frames >= 0.0f) {
+        if (ns.speaker_cmvn_stats.NumRows() != 0) {
+          int32 feat_dim = ns.speaker_cmvn_stats.NumCols() - 1;
+          BaseFloat count = ns.speaker_cmvn_stats(0, feat_dim);
+          if (count > max_remembered_frames) ns.speaker_cmvn_stats.Scale(max_remembered_frames / count);
+        }
+        BaseFloat max_remembered_frames_scaled = max_remembered_frames * posterior_scale;
+        if (stats.Count() > max_remembered_frames_scaled) stats.Scale(max_remembered_frames_scaled / stats.Count());
+      }
+      spk->cmvn = ns;
+      spk->stats.reset(new OnlineIvectorEstimationStats(stats));
+      spk->has = true;
     }
     return 0;
   } catch (const std::exception &e) { fprintf(stderr, "ref_ivector_run: %s\n", e.what()); return -1; }
