@@ -74,6 +74,30 @@ def check() -> bool:
         subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"),
                               "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include",
                               "-I" + os.path.join(ROOT, "oracle", "_ref", "inc")]) + [nn])
+        # the online2 feature pipeline (b2k_online2_shims.h) against the reference's own online2 headers; online-ivector-feature.h
+        # pulls in the OpenFst-based decoders for OnlineSilenceWeighting: their guards are pre-defined and the two templates declared
+        o2 = os.path.join(td, "o.cc")
+        open(o2, "w").write(
+            "#define KALDI_DECODER_LATTICE_FASTER_ONLINE_DECODER_H_\n#define KALDI_DECODER_LATTICE_INCREMENTAL_ONLINE_DECODER_H_\n"
+            '#include <queue>\n#include "base/kaldi-common.h"\n'
+            "namespace kaldi { template <class FST> class LatticeFasterOnlineDecoderTpl; template <class FST> class LatticeIncrementalOnlineDecoderTpl; }\n"
+            '#include "b2k_online2_shims.h"\n'
+            "using namespace kaldi;\n"
+            "void f(const OnlineNnet2FeaturePipelineConfig &cfg, const VectorBase<BaseFloat> &wave) {\n"
+            "  OnlineNnet2FeaturePipelineInfo info(cfg);\n"
+            "  b2k_shim::FeatureTablesB2k tables(info);\n"
+            "  b2k_shim::OnlineNnet2FeaturePipelineB2k p(info, tables);\n"
+            "  OnlineFeatureInterface *itf = &p;\n"
+            "  OnlineIvectorExtractorAdaptationState st(info.ivector_extractor_info);\n"
+            "  p.SetAdaptationState(st); p.AcceptWaveform(16000.0f, wave); p.InputFinished(); p.GetAdaptationState(&st);\n"
+            "  OnlineCmvnState cs; p.GetCmvnState(&cs); p.SetCmvnState(cs);\n"
+            "  std::vector<std::pair<int32, BaseFloat> > dw; p.UpdateFrameWeights(dw);\n"
+            "  Vector<BaseFloat> v(itf->Dim()); itf->GetFrame(0, &v); itf->NumFramesReady(); itf->IsLastFrame(0); p.FrameShiftInSeconds();\n"
+            "  OnlineFeatureInterface *in = p.InputFeature(); OnlineIvectorFeature *iv = p.IvectorFeature(); (void)in; (void)iv;\n"
+            "}\n")
+        subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=0"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"),
+                              "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include",
+                              "-I" + os.path.join(ROOT, "oracle", "_ref", "inc")]) + [o2])
     return True
 
 
