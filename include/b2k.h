@@ -803,6 +803,14 @@ double b2k_pipeline_nnet_flops_per_utterance(const b2k_pipeline *p);
 b2k_dec *b2k_pipeline_decoder(b2k_pipeline *p);
 const float *b2k_pipeline_features(const b2k_pipeline *p);
 const float *b2k_pipeline_ivectors(const b2k_pipeline *p);
+/* Speaker adaptation for the NEXT batch this pipeline runs (decode_batch / submit / run_device), then forgotten: slot i
+ * starts from the state d_state_in[i] points to (NULL: a new speaker) and leaves the speaker's state after the utterance in
+ * d_state_out[i] (NULL: not kept) -- b2k_ivec_compute_batched_adapt's arguments; device pointers to
+ * b2k_ivec_adaptation_state_doubles() doubles that must stay valid until the batch has run.  The tool's per-speaker loop
+ * (online2bin/online2-wav-nnet3-latgen-faster.cc:199-221,287) becomes: batch k holds the k-th utterance of every speaker
+ * (kaldi_b200/ingest.py: speaker_waves), so two slots of one batch never share a state (refused). n = 0 clears it. */
+int b2k_pipeline_set_speaker_states(b2k_pipeline *p, int32_t n, const double *const *d_state_in, double *const *d_state_out,
+                                    float max_remembered_frames);
 const float *b2k_pipeline_loglikes(const b2k_pipeline *p);
 
 #ifdef __cplusplus

@@ -33,6 +33,10 @@ struct b2k_pipeline {
   std::vector<const float *> p_wave, p_feats, p_ivec, p_ll;
   std::vector<float *> p_feats_out, p_ivec_out, p_ll_out;
   int32_t last_n = 0;
+  // speaker adaptation of the NEXT batch (b2k_pipeline_set_speaker_states; cleared when the batch has been launched)
+  std::vector<const double *> spk_in;
+  std::vector<double *> spk_out;
+  float spk_max_remembered = -1.0f;
   // pipelined operation (submit / collect): two batches in flight
   struct Slot {
     int16_t *h_wave16 = nullptr;      // pinned [max_batch x num_samples]
@@ -287,6 +291,21 @@ int b2k_pipeline_get_plan(const b2k_pipeline *p, b2k_pipeline_plan *plan) {
   return B2K_OK;
 }
 
+int b2k_pipeline_set_speaker_states(b2k_pipeline *p, int32_t n, const double *const *d_state_in, double *const *d_state_out,
+                                    float max_remembered_frames) {
+  if (!p || n < 0 || n > p->cfg.max_batch || (n > 0 && (!d_state_in || !d_state_out)))
+    return set_error(B2K_ERR_INVALID, "b2k_pipeline_set_speaker_states: bad args");
+  if (n > 0 && !p->ivec) return set_error(B2K_ERR_STATE, "b2k_pipeline_set_speaker_states: the pipeline has no i-vector extractor");
+  for (int32_t i = 0; i < n; i++)
+    for (int32_t j = 0; j < i; j++)
+      if (d_state_out[i] && d_state_out[i] == d_state_out[j])
+        return set_error(B2K_ERR_INVALID, "b2k_pipeline_set_speaker_states: two utterances of one batch write the same speaker state (a speaker's utterances go into successive batches)");
+  p->spk_in.assign(d_state_in, d_state_in + n);
+  p->spk_out.assign(d_state_out, d_state_out + n);
+  p->spk_max_remembered = max_remembered_frames;
+  return B2K_OK;
+}
+
 b2k_dec *b2k_pipeline_decoder(b2k_pipeline *p) { return p ? p->dec : nullptr; }
 const float *b2k_pipeline_loglikes(const b2k_pipeline *p) { return p ? p->d_loglikes : nullptr; }
 const float *b2k_pipeline_features(const b2k_pipeline *p) { return p ? p->d_feats : nullptr; }
@@ -304,9 +323,15 @@ static int run_device(b2k_pipeline *p, int32_t n, void *stream) {
   if (rc) return rc;
   tick(1);
   if (p->ivec) {
-    rc = b2k_ivec_compute_batched(p->ivec, n, p->p_feats.data(), pl.feat_dim, pl.num_feature_frames, p->sched.data(),
-                                  pl.num_chunks, p->p_ivec_out.data(), pl.ivector_dim, stream);
+    const bool adapt = (int32_t)p->spk_in.size() == n;
+    rc = b2k_ivec_compute_batched_adapt(p->ivec, n, p->p_feats.data(), pl.feat_dim, pl.num_feature_frames, p->sched.data(),
+                                        pl.num_chunks, p->p_ivec_out.data(), pl.ivector_dim, adapt ? p->spk_in.data() : nullptr,
+                                        adapt ? p->spk_out.data() : nullptr, p->spk_max_remembered, stream);
+    p->spk_in.clear(); p->spk_out.clear();
     if (rc) return rc;
+  } else if (!p->spk_in.empty()) {
+    p->spk_in.clear(); p->spk_out.clear();
+    return set_error(B2K_ERR_STATE, "speaker states were set on a pipeline without an i-vector extractor");
   }
   if (p->cfg.use_cmvn) {                     // every utterance starts from empty sliding-window stats and no speaker stats
     const size_t SD = 2 * ((size_t)pl.feat_dim + 1);

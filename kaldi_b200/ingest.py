@@ -43,6 +43,19 @@ def shard_speakers(speakers, lengths, world: int) -> list[np.ndarray]:
     return out
 
 
+def speaker_waves(speakers) -> list[np.ndarray]:
+    """The order in which ONE rank decodes its utterances when adaptation state is carried from one utterance of a speaker to
+    the next (online2-wav-nnet3-latgen-faster.cc:199-221,287): wave k = the k-th utterance of every speaker that has one, so
+    the utterances of a wave are independent (one batch, or several) and a speaker's state is final before its next utterance
+    starts.  Positions into `speakers`; speakers in order of first appearance."""
+    seen, nth = {}, []
+    for s in speakers:
+        nth.append(seen.get(s, 0))
+        seen[s] = nth[-1] + 1
+    nth = np.asarray(nth, np.int64)
+    return [np.nonzero(nth == k)[0] for k in range(int(nth.max()) + 1)] if len(nth) else []
+
+
 def _wire(t):
     """The tensor as the transport sees it: torch's NCCL wrapper has no 16-bit integer type ("Input tensor data type is not
     supported for NCCL process group: Short"), so anything but bytes / floats travels as a byte view of the same storage."""

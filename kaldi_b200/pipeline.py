@@ -247,6 +247,18 @@ class NativeBatchedPipeline:
         except Exception:
             pass
 
+    def set_speaker_states(self, state_in_ptrs, state_out_ptrs, max_remembered_frames: float = 1000.0):
+        """Speaker adaptation of the NEXT batch (b2k_pipeline_set_speaker_states): device pointers (0 / None = a new speaker /
+        state not kept) to IvectorExtractorGpu.AdaptationStateDoubles() doubles per batch slot."""
+        import ctypes as C
+        from . import _lib
+        n = len(state_in_ptrs)
+        assert len(state_out_ptrs) == n
+        si = (C.c_void_p * n)(*[int(p) if p else None for p in state_in_ptrs])
+        so = (C.c_void_p * n)(*[int(p) if p else None for p in state_out_ptrs])
+        self._L.b2k_pipeline_set_speaker_states.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float]
+        _lib.check(self._L.b2k_pipeline_set_speaker_states(self.h, n, si, so, float(max_remembered_frames)))
+
     def decode_batch(self, waves, stream: int = 0):
         import ctypes as C
         from . import _lib

@@ -125,3 +125,26 @@ def test_speaker_shards_are_balanced():
             per_spk[s] = per_spk.get(s, 0) + int(lengths[u])
         loads = [int(lengths[s].sum()) for s in shards]
         assert max(loads) - min(loads) <= max(per_spk.values())
+
+
+def test_speaker_waves_keep_a_speakers_utterances_in_successive_batches():
+    """ingest.speaker_waves: wave k holds the k-th utterance of every speaker (so a batch never holds two utterances of one
+    speaker and the adaptation state is final before the speaker's next utterance), every utterance exactly once, a speaker's
+    utterances in their original order (online2-wav-nnet3-latgen-faster.cc:199-221)."""
+    from kaldi_b200.ingest import speaker_waves
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        n = int(rng.integers(1, 40))
+        spk = [f"s{int(rng.integers(0, 7))}" for _ in range(n)]
+        waves = speaker_waves(spk)
+        flat = np.concatenate(waves)
+        assert sorted(flat.tolist()) == list(range(n))
+        when = {}
+        for k, w in enumerate(waves):
+            assert len({spk[u] for u in w}) == len(w), "two utterances of a speaker in one wave"
+            for u in w:
+                when[u] = k
+        for s in set(spk):
+            ids = [u for u in range(n) if spk[u] == s]
+            assert [when[u] for u in ids] == list(range(len(ids)))
+    assert speaker_waves([]) == []
