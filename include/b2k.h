@@ -260,6 +260,13 @@ int b2k_feat_compute_batched(b2k_feat *f, int32_t num_lanes, const float *const 
                              const int32_t *num_frames, float *const *d_out, int32_t row_stride,
                              void *stream);
 
+/* The same on 16-bit PCM as it arrives (WaveData's samples before their conversion to float, feat/wave-reader.cc: Kaldi keeps
+ * the int16 range in its floats, so (float)sample is the value the float form holds): half the bytes per frame. */
+int b2k_feat_compute_batched_i16(b2k_feat *f, int32_t num_lanes, const int16_t *const *d_wave16,
+                                 const int32_t *num_samples, const int32_t *first_frame,
+                                 const int32_t *num_frames, float *const *d_out, int32_t row_stride,
+                                 void *stream);
+
 /* OnlineCmvnOptions (feat/online-feature.h:203-227) */
 typedef struct {
   int32_t cmn_window, speaker_frames, global_frames, normalize_mean, normalize_variance;

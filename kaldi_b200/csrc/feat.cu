@@ -34,6 +34,7 @@ namespace b2k {
 #define FEAT_MAX_BINS 64
 #define FEAT_MAX_MELW 1024
 #define FEAT_WARPS 8
+#define FEAT_FRAMES_PER_CTA 64
 
 struct FeatTables {               // device pointers
   const float *window;            // [frame_length]
@@ -55,7 +56,8 @@ struct FeatParams {
 };
 
 struct FeatLane {                 // per lane descriptor (device array)
-  const float *wave;              // utterance samples (whole utterance so far)
+  const float *wave;              // utterance samples (whole utterance so far), int16-range floats; null when wave16 is given
+  const int16_t *wave16;          // the same as 16-bit PCM (the format audio arrives in: 320 instead of 640 bytes per frame)
   int num_samples;                // valid samples in wave
   int first_frame, num_frames;    // frames to compute in this call
   float *out;                     // &feats[first_frame][0] is out + first_frame*row_stride
@@ -65,7 +67,7 @@ struct FeatLane {                 // per lane descriptor (device array)
 __device__ __forceinline__ int bitrev8(int x) { return (int)(__brev((unsigned)x) >> 24); }
 
 __global__ void __launch_bounds__(FEAT_WARPS * 32)
-feat_kernel(FeatParams p, const FeatLane *lanes, int frames_per_cta) {
+feat_kernel(FeatParams p, const FeatLane *lanes, int frames_per_cta, int stage_cap_bytes) {
   extern __shared__ float smem[];
   // layout
   float *s_window = smem;                                   // frame_length (<=512)
@@ -100,6 +102,55 @@ feat_kernel(FeatParams p, const FeatLane *lanes, int frames_per_cta) {
   const int f_end = min(f_begin + frames_per_cta, L.num_frames);
   const int NL = p.frame_length;
   const float FLT_EPS = 1.1920928955078125e-07f;
+  if (f_begin >= f_end) return;                         // (uniform: nothing below is reached by a part of the CTA only)
+
+  // ---- the samples of this CTA's frames: ONE bulk copy (TMA, cp.async.bulk) of the contiguous span they cover into shared
+  //      memory, completion on an mbarrier; the frames overlap by 60 %, so every sample is fetched from HBM / L2 once per CTA
+  //      instead of 2.5 times.  The span is cut to 16-byte boundaries of the source; what falls outside it (the ragged ends,
+  //      reflected samples of snip_edges = false) is read directly.
+  __shared__ __align__(8) unsigned long long s_bar;
+  unsigned char *s_stage = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<unsigned long long>(s_mel + FEAT_WARPS * FEAT_MAX_BINS) + 15ull) & ~15ull);      // 16 spare bytes are reserved
+  long long st_lo = 0, st_hi = 0;                        // staged samples [st_lo, st_hi)
+  {
+    const int esz = L.wave16 ? 2 : 4;
+    const unsigned char *base = L.wave16 ? reinterpret_cast<const unsigned char *>(L.wave16) : reinterpret_cast<const unsigned char *>(L.wave);
+    const long long fr0 = L.first_frame + f_begin, fr1 = L.first_frame + f_end - 1;
+    long long lo = p.snip_edges ? fr0 * p.frame_shift : (long long)p.frame_shift * fr0 + p.frame_shift / 2 - NL / 2;
+    long long hi = (p.snip_edges ? fr1 * p.frame_shift : (long long)p.frame_shift * fr1 + p.frame_shift / 2 - NL / 2) + NL;
+    lo = max(lo, 0LL); hi = min(hi, (long long)L.num_samples);
+    unsigned long long a0 = 0, a1 = 0;
+    if (hi > lo) {
+      a0 = (reinterpret_cast<unsigned long long>(base) + (unsigned long long)lo * esz + 15ull) & ~15ull;     // first 16-byte boundary inside
+      a1 = (reinterpret_cast<unsigned long long>(base) + (unsigned long long)hi * esz) & ~15ull;             // last one inside
+    }
+    unsigned bytes = 0;
+    if (a1 > a0 && a1 - a0 <= (unsigned long long)stage_cap_bytes) bytes = (unsigned)(a1 - a0);
+    if (bytes) {
+      st_lo = (long long)((a0 - reinterpret_cast<unsigned long long>(base)) / esz);
+      st_hi = st_lo + bytes / esz;
+    }
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (bytes) {
+      if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((unsigned)__cvta_generic_to_shared(s_stage)), "l"(a0), "r"(bytes), "r"(bar) : "memory");
+      }
+      unsigned ok = 0;
+      do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar) : "memory");
+      } while (!ok);
+    }
+  }
+  const float *stage_f = reinterpret_cast<const float *>(s_stage);
+  const int16_t *stage_h = reinterpret_cast<const int16_t *>(s_stage);
 
   for (int fr = f_begin + warp; fr < f_end; fr += FEAT_WARPS) {
     const int frame = L.first_frame + fr;
@@ -119,7 +170,8 @@ feat_kernel(FeatParams p, const FeatLane *lanes, int frames_per_cta) {
           int n = L.num_samples;
           while (s < 0 || s >= n) { if (s < 0) s = -s - 1; else s = 2LL * n - 1 - s; }
         }
-        x = L.wave[s];
+        if (s >= st_lo && s < st_hi) x = L.wave16 ? (float)stage_h[s - st_lo] : stage_f[s - st_lo];
+        else x = L.wave16 ? (float)L.wave16[s] : L.wave[s];
         sum += x;
       }
       v[k] = x;
@@ -370,7 +422,7 @@ struct b2k_feat {
   CmvnLane *d_clanes = nullptr, *h_clanes = nullptr;
   int max_lanes = 0;
   cudaEvent_t staging_free = nullptr;
-  size_t smem_bytes = 0;
+  size_t smem_bytes = 0, stage_bytes = 0;
   int frame_length = 0, frame_shift = 0;
 };
 
@@ -499,6 +551,10 @@ int b2k_feat_create(const b2k_feat_cfg *cfg, b2k_feat **out) {
   f->smem_bytes = sizeof(float) * (FEAT_NFFT + 2 * (FEAT_NFFT / 4) + 2 * (FEAT_NFFT / 2) + FEAT_MAX_MELW +
                                    3 * FEAT_MAX_BINS + FEAT_MAX_BINS * FEAT_MAX_BINS + FEAT_MAX_BINS +
                                    FEAT_WARPS * (FEAT_NFFT + 2) + FEAT_WARPS * FEAT_MAX_BINS);
+  // + the staged samples of one CTA: FEAT_FRAMES_PER_CTA frames of fp32 (int16 needs half)
+  f->stage_bytes = ((size_t)(FEAT_FRAMES_PER_CTA - 1) * shift + NL) * sizeof(float) + 16;
+  f->stage_bytes = (f->stage_bytes + 15) / 16 * 16;
+  f->smem_bytes += f->stage_bytes;
   B2K_CUDA_CHECK(cudaFuncSetAttribute(feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_bytes));
   *out = f;
   return B2K_OK;
@@ -529,18 +585,36 @@ int32_t b2k_feat_num_frames(const b2k_feat *f, int64_t num_samples, int32_t flus
   return n;
 }
 
+static int feat_compute_impl(b2k_feat *f, int32_t num_lanes, const float *const *d_wave, const int16_t *const *d_wave16,
+                             const int32_t *num_samples, const int32_t *first_frame, const int32_t *num_frames, float *const *d_out,
+                             int32_t row_stride, void *stream);
+
 int b2k_feat_compute_batched(b2k_feat *f, int32_t num_lanes, const float *const *d_wave,
                              const int32_t *num_samples, const int32_t *first_frame,
                              const int32_t *num_frames, float *const *d_out, int32_t row_stride,
                              void *stream) {
-  if (!f || num_lanes <= 0 || num_lanes > f->max_lanes || !d_wave || !num_samples || !num_frames || !d_out)
+  return feat_compute_impl(f, num_lanes, d_wave, nullptr, num_samples, first_frame, num_frames, d_out, row_stride, stream);
+}
+
+int b2k_feat_compute_batched_i16(b2k_feat *f, int32_t num_lanes, const int16_t *const *d_wave16,
+                                 const int32_t *num_samples, const int32_t *first_frame,
+                                 const int32_t *num_frames, float *const *d_out, int32_t row_stride,
+                                 void *stream) {
+  return feat_compute_impl(f, num_lanes, nullptr, d_wave16, num_samples, first_frame, num_frames, d_out, row_stride, stream);
+}
+
+static int feat_compute_impl(b2k_feat *f, int32_t num_lanes, const float *const *d_wave, const int16_t *const *d_wave16,
+                             const int32_t *num_samples, const int32_t *first_frame, const int32_t *num_frames, float *const *d_out,
+                             int32_t row_stride, void *stream) {
+  if (!f || num_lanes <= 0 || num_lanes > f->max_lanes || (!d_wave && !d_wave16) || !num_samples || !num_frames || !d_out)
     return set_error(B2K_ERR_INVALID, "b2k_feat_compute_batched: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   B2K_CUDA_CHECK(cudaEventSynchronize(f->staging_free));
   int max_frames = 0;
   for (int i = 0; i < num_lanes; i++) {
     FeatLane &L = f->h_lanes[i];
-    L.wave = d_wave[i]; L.num_samples = num_samples[i];
+    L.wave = d_wave ? d_wave[i] : nullptr; L.wave16 = d_wave16 ? d_wave16[i] : nullptr; L.num_samples = num_samples[i];
+    if (!L.wave && !L.wave16 && num_frames[i] > 0) return set_error(B2K_ERR_INVALID, "b2k_feat_compute_batched: null waveform");
     L.first_frame = first_frame ? first_frame[i] : 0; L.num_frames = num_frames[i];
     L.out = d_out[i]; L.row_stride = row_stride;
     if (L.num_frames < 0 || (L.num_frames > 0 && L.num_samples <= 0))
@@ -553,9 +627,9 @@ int b2k_feat_compute_batched(b2k_feat *f, int32_t num_lanes, const float *const 
   if (max_frames == 0) return B2K_OK;
   B2K_CUDA_CHECK(cudaMemcpyAsync(f->d_lanes, f->h_lanes, sizeof(FeatLane) * num_lanes, cudaMemcpyHostToDevice, st));
   B2K_CUDA_CHECK(cudaEventRecord(f->staging_free, st));
-  const int frames_per_cta = 64;
+  const int frames_per_cta = FEAT_FRAMES_PER_CTA;
   dim3 grid((max_frames + frames_per_cta - 1) / frames_per_cta, num_lanes);
-  feat_kernel<<<grid, FEAT_WARPS * 32, f->smem_bytes, st>>>(f->p, f->d_lanes, frames_per_cta);
+  feat_kernel<<<grid, FEAT_WARPS * 32, f->smem_bytes, st>>>(f->p, f->d_lanes, frames_per_cta, (int)f->stage_bytes);
   B2K_LAUNCH_CHECK();
   return B2K_OK;
 }

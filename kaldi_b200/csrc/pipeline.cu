@@ -31,6 +31,7 @@ struct b2k_pipeline {
   std::vector<double *> p_cmvn_state;
   std::vector<int32_t> sched, channels, ns, zeros, nframes, nout;
   std::vector<const float *> p_wave, p_feats, p_ivec, p_ll;
+  std::vector<const int16_t *> p_wave16;
   std::vector<float *> p_feats_out, p_ivec_out, p_ll_out;
   int32_t last_n = 0;
   // speaker adaptation of the NEXT batch (b2k_pipeline_set_speaker_states; cleared when the batch has been launched)
@@ -313,14 +314,24 @@ const float *b2k_pipeline_ivectors(const b2k_pipeline *p) { return p ? p->d_ivec
 
 }  // extern "C"
 
-// All stages for the first n batch slots, inputs already in d_wave; asynchronous on `stream`.
-static int run_device(b2k_pipeline *p, int32_t n, void *stream) {
+// All stages for the first n batch slots, inputs already in d_wave (or, d_wave16 given, 16-bit PCM [n x num_samples] that the
+// feature kernel reads directly; wave_consumed is recorded once it has); asynchronous on `stream`.
+static int run_device(b2k_pipeline *p, int32_t n, void *stream, const int16_t *d_wave16 = nullptr, cudaEvent_t wave_consumed = nullptr) {
   const b2k_pipeline_plan &pl = p->plan;
   auto tick = [&](int i) { if (p->timing) cudaEventRecord(p->tev[i], (cudaStream_t)stream); };
   tick(0);
-  int rc = b2k_feat_compute_batched(p->feat, n, p->p_wave.data(), p->ns.data(), p->zeros.data(), p->nframes.data(),
-                                    p->p_feats_out.data(), pl.feat_dim, stream);
+  int rc;
+  if (d_wave16) {
+    p->p_wave16.resize(n);
+    for (int32_t i = 0; i < n; i++) p->p_wave16[i] = d_wave16 + (size_t)i * (size_t)p->cfg.num_samples;
+    rc = b2k_feat_compute_batched_i16(p->feat, n, p->p_wave16.data(), p->ns.data(), p->zeros.data(), p->nframes.data(),
+                                      p->p_feats_out.data(), pl.feat_dim, stream);
+  } else {
+    rc = b2k_feat_compute_batched(p->feat, n, p->p_wave.data(), p->ns.data(), p->zeros.data(), p->nframes.data(),
+                                  p->p_feats_out.data(), pl.feat_dim, stream);
+  }
   if (rc) return rc;
+  if (wave_consumed) B2K_CUDA_CHECK(cudaEventRecord(wave_consumed, (cudaStream_t)stream));
   tick(1);
   if (p->ivec) {
     const bool adapt = (int32_t)p->spk_in.size() == n;
@@ -384,20 +395,6 @@ static int decode_batch(b2k_pipeline *p, int32_t n, const S *const *h_waves, voi
 }
 
 // ---------------------------------------------------------------- pipelined operation
-__global__ void i16_to_f32_kernel(const int16_t *__restrict__ src, float *__restrict__ dst, size_t n) {
-  // 8 samples per thread: one 16-byte load, two 16-byte stores (the waveform stays in the int16 range as floats)
-  const size_t i8 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (i8 + 8 <= n) {
-    const uint4 v = *reinterpret_cast<const uint4 *>(src + i8);
-    const int16_t *h = reinterpret_cast<const int16_t *>(&v);
-    float4 a = make_float4(h[0], h[1], h[2], h[3]), b = make_float4(h[4], h[5], h[6], h[7]);
-    *reinterpret_cast<float4 *>(dst + i8) = a;
-    *reinterpret_cast<float4 *>(dst + i8 + 4) = b;
-  } else {
-    for (size_t i = i8; i < n; i++) dst[i] = (float)src[i];
-  }
-}
-
 static int ensure_pipelined(b2k_pipeline *p) {
   if (p->st_copy) return B2K_OK;
   B2K_CUDA_CHECK(cudaStreamCreateWithFlags(&p->st_copy, cudaStreamNonBlocking));
@@ -440,16 +437,10 @@ extern "C" int b2k_pipeline_submit_i16(b2k_pipeline *p, int32_t n, const int16_t
   if (p->n_submitted >= 2) B2K_CUDA_CHECK(cudaStreamWaitEvent(p->st_copy, sl.wave_consumed, 0));
   B2K_CUDA_CHECK(cudaMemcpyAsync(sl.d_wave16, sl.h_wave16, 2 * total, cudaMemcpyHostToDevice, p->st_copy));
   B2K_CUDA_CHECK(cudaEventRecord(sl.h2d_done, p->st_copy));
-  // compute stream: int16 -> float (Kaldi keeps int16-range values in floats), the four stages, finalize, pack
+  // compute stream: the four stages (the feature kernel reads the 16-bit PCM itself), finalize, pack
   B2K_CUDA_CHECK(cudaStreamWaitEvent(p->st_compute, sl.h2d_done, 0));
-  {
-    const size_t threads = (total + 7) / 8;
-    i16_to_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, p->st_compute>>>(sl.d_wave16, p->d_wave, total);
-    B2K_LAUNCH_CHECK();
-  }
-  B2K_CUDA_CHECK(cudaEventRecord(sl.wave_consumed, p->st_compute));
   p->last_n = n;
-  rc = run_device(p, n, (void *)p->st_compute);
+  rc = run_device(p, n, (void *)p->st_compute, sl.d_wave16, sl.wave_consumed);
   if (rc) return rc;
   // packed lattices: capacity from the decoder's own per-channel limits would be far too large; start from 64 MB or
   // 1.5x the last batch's need and grow when the header reports an overflow (collect then falls back to the synchronous copy)
@@ -473,11 +464,8 @@ extern "C" int b2k_pipeline_submit_i16(b2k_pipeline *p, int32_t n, const int16_t
 extern "C" int b2k_pipeline_run_device_i16(b2k_pipeline *p, int32_t n, const int16_t *d_waves, void *stream) {
   if (!p || n <= 0 || n > p->cfg.max_batch || !d_waves) return set_error(B2K_ERR_INVALID, "b2k_pipeline_run_device_i16: bad args");
   if (reinterpret_cast<uintptr_t>(d_waves) & 15) return set_error(B2K_ERR_INVALID, "b2k_pipeline_run_device_i16: the waveform block must be 16-byte aligned");
-  const size_t total = (size_t)n * (size_t)p->cfg.num_samples, threads = (total + 7) / 8;
-  i16_to_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_waves, p->d_wave, total);
-  B2K_LAUNCH_CHECK();
   p->last_n = n;
-  return run_device(p, n, stream);
+  return run_device(p, n, stream, d_waves);
 }
 
 // The finalized lattices of batch slots 0..n-1 packed into a caller-owned device buffer (b2k_dec_pack_lattices_async):

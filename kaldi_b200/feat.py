@@ -97,7 +97,8 @@ class BatchedFeatures:
         return int(_lib.lib().b2k_feat_num_frames(self.h, int(num_samples), int(flush)))
 
     def ComputeFeaturesBatched(self, wave_ptrs, num_samples, first_frame, num_frames, out_ptrs,
-                               row_stride: int, stream: int = 0):
+                               row_stride: int, stream: int = 0, int16: bool = False):
+        """int16 = True: wave_ptrs are device pointers to 16-bit PCM (b2k_feat_compute_batched_i16)."""
         n = len(wave_ptrs)
         ns = np.ascontiguousarray(num_samples, np.int32)
         ff = np.ascontiguousarray(first_frame, np.int32)
@@ -105,9 +106,11 @@ class BatchedFeatures:
         wp, _k1 = _ptr_array(wave_ptrs)
         op, _k2 = _ptr_array(out_ptrs)
         i32p = C.POINTER(C.c_int32)
-        _lib.check(_lib.lib().b2k_feat_compute_batched(
-            self.h, n, wp, ns.ctypes.data_as(i32p), ff.ctypes.data_as(i32p), nf.ctypes.data_as(i32p),
-            op, int(row_stride), C.c_void_p(stream)))
+        L = _lib.lib()
+        L.b2k_feat_compute_batched_i16.argtypes = L.b2k_feat_compute_batched.argtypes
+        fn = L.b2k_feat_compute_batched_i16 if int16 else L.b2k_feat_compute_batched
+        _lib.check(fn(self.h, n, wp, ns.ctypes.data_as(i32p), ff.ctypes.data_as(i32p), nf.ctypes.data_as(i32p),
+                      op, int(row_stride), C.c_void_p(stream)))
 
     def ApplyCmvnBatched(self, cmvn: OnlineCmvnOptions, in_ptrs, out_ptrs, in_stride, out_stride,
                          first_frame, num_frames, state_ptrs, global_stats_ptr, speaker_stats_ptr=0,

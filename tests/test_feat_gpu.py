@@ -130,3 +130,34 @@ def test_full_size_batch_properties(cfgs):
     shifted = bf.compute([base[0][160:]])[0]
     assert np.array_equal(shifted, got[0][1:])
     assert all(g.shape == (998, 40) and np.isfinite(g).all() for g in got)
+
+
+@pytest.mark.parametrize("name", ["mfcc_hires", "mfcc_hires_nosnip", "fbank_mag_energy"])
+def test_int16_input_and_unaligned_sources_give_the_same_bits(cfgs, name):
+    """The kernel stages the samples of a CTA's frames with one bulk copy cut to 16-byte boundaries of the source and reads the
+    ragged ends directly: (a) 16-bit PCM in (b2k_feat_compute_batched_i16) gives exactly the features of its float form,
+    (b) a waveform that starts 1, 2 or 3 samples past a 16-byte boundary gives exactly the features of the aligned copy,
+    (c) frames requested in pieces that start in the middle of a CTA's span do too; short and ragged lengths included."""
+    import torch
+    from kaldi_b200.feat import BatchedFeatures
+    bf = BatchedFeatures(_opts(cfgs[name]))
+    D = bf.Dim()
+    for n_samples, seed in ((48017, 1), (16000, 2), (559, 3), (400, 4), (10480 + 160 * 64, 5)):
+        pcm = np.clip(np.round(synth.make_audio(n_samples, seed=seed)), -32768, 32767).astype(np.int16)
+        want = bf.compute([pcm.astype(np.float32)])[0]
+        T = want.shape[0]
+        if T == 0:
+            continue
+        for shift in (0, 1, 2, 3, 5):
+            for i16 in (False, True):
+                buf = torch.zeros(n_samples + 16, dtype=torch.int16 if i16 else torch.float32, device="cuda")
+                src = torch.from_numpy(pcm if i16 else pcm.astype(np.float32)).cuda()
+                buf[shift:shift + n_samples] = src
+                out = torch.zeros(T, D, device="cuda")
+                ptr = buf.data_ptr() + shift * (2 if i16 else 4)
+                pieces = [(0, T)] if shift != 5 else [(0, min(7, T)), (min(7, T), T - min(7, T))]
+                for f0, k in pieces:
+                    if k > 0:
+                        bf.ComputeFeaturesBatched([ptr], [n_samples], [f0], [k], [out.data_ptr()], D, int16=i16)
+                torch.cuda.synchronize()
+                np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg=f"{name} n={n_samples} shift={shift} int16={i16}")
