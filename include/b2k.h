@@ -820,6 +820,42 @@ int b2k_pipeline_set_speaker_states(b2k_pipeline *p, int32_t n, const double *co
                                     float max_remembered_frames);
 const float *b2k_pipeline_loglikes(const b2k_pipeline *p);
 
+/* ------------------------------------------------------------------ many audio streams, chunk by chunk
+ *
+ * cuda_decoder::BatchedThreadedNnet3CudaOnlinePipeline::DecodeBatch(corr_ids, wave_samples, is_first_chunk, is_last_chunk)
+ * (cudadecoder/batched-threaded-nnet3-cuda-online-pipeline.cc:316-377): every call brings at most one chunk of 16-bit PCM per
+ * channel; the features of the frames that became computable, the chunked network (b2k_nnet_stream_run_batch, context per
+ * channel) and the decoder's frames run for the whole batch of channels; nothing of an utterance is recomputed.  A chunk may
+ * bring at most frames_per_chunk new feature frames.  Partial hypotheses: b2k_dec_best_path on b2k_stream_decoder() with
+ * use_final_probs = 0 (channel ids are the decoder's channel ids); after a channel's last chunk the call has run
+ * FinalizeDecoding and its raw lattice is b2k_dec_get_raw_lattice(b2k_stream_decoder(s), channel). */
+typedef struct {
+  b2k_feat_cfg feat;
+  b2k_dec_cfg dec;              /* max_frames is raised to what max_seconds needs                                  */
+  int32_t nchannels;            /* streams in flight at most (= the largest batch of one call)                      */
+  float max_seconds;            /* per stream                                                                      */
+  int32_t frames_per_chunk;     /* compute_opts.frames_per_chunk of BatchedStaticNnet3 (input frames per call)      */
+  float acoustic_scale;
+  int32_t use_priors;
+} b2k_stream_cfg;
+typedef struct b2k_stream b2k_stream;
+void b2k_stream_cfg_default(b2k_stream_cfg *cfg);
+int b2k_stream_create(const b2k_stream_cfg *cfg, const b2k_model *model, const b2k_fst *fst, b2k_stream **out);
+int b2k_stream_destroy(b2k_stream *s);
+/* info: {channels, max samples, max feature frames, feature dim, pdfs, i-vector dim, output frames per chunk, frames per chunk} */
+int b2k_stream_info(const b2k_stream *s, int64_t info[8]);
+/* Slot i: channel channels[i], num_samples[i] new samples at h_chunks[i] (host), is_first_chunk[i] starts a new utterance on
+ * the channel, is_last_chunk[i] ends it (right context flushed, FinalizeDecoding run).  d_ivectors: NULL (zeros) or one device
+ * i-vector per slot.  Optional outputs per slot: output frames decoded by this call / so far, and where this call's
+ * log-likelihood rows lie ([frames x pdfs], valid until the next call; NULL when there are none).  Asynchronous on `stream`
+ * except for the copy of pageable host chunks. */
+int b2k_stream_decode_batch_i16(b2k_stream *s, int32_t n, const int32_t *channels, const int16_t *const *h_chunks,
+                                const int32_t *num_samples, const int32_t *is_first_chunk, const int32_t *is_last_chunk,
+                                const float *const *d_ivectors, int32_t *new_output_frames, int32_t *output_frames_so_far,
+                                const float **d_new_frames, const float **d_flushed_frames, void *stream);
+b2k_dec *b2k_stream_decoder(b2k_stream *s);
+const float *b2k_stream_features(const b2k_stream *s, int32_t channel);   /* [max feature frames x dim] of a channel */
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,3 +121,94 @@ class StreamingBatchedDecoder:
                 if last:
                     r["lattice"] = self.dec.GetRawLattice(r["channel"])
         return res
+
+
+class NativeStreamingDecoder:
+    """The same through the C ABI alone (b2k_stream_*, kaldi_b200/csrc/stream_pipeline.cu): model.KaldiModel + CudaFst ->
+    b2k_stream_create; DecodeBatch(channels, int16 chunks, is_first_chunk, is_last_chunk) -> b2k_stream_decode_batch_i16;
+    partial hypotheses and lattices come from the stream's decoder handle (b2k_dec_best_path, b2k_dec_get_raw_lattice)."""
+
+    def __init__(self, model, fst: CudaFst, decoder_cfg: dict, nchannels: int, max_seconds: float = 30.0, frames_per_chunk: int = 51,
+                 feature_opts: FeatureOptions | None = None, acoustic_scale: float = 1.0, use_priors: bool = True):
+        import ctypes as C
+        from dataclasses import fields
+        from . import _lib
+        from .decoder import _DecCfg
+        from .feat import _FeatCfg
+        self._C, self._lib_mod = C, _lib
+        L = self._L = _lib.lib()
+        fo = feature_opts or FeatureOptions(max_lanes=max(nchannels, 8))
+
+        class _StreamCfg(C.Structure):
+            _fields_ = [("feat", _FeatCfg), ("dec", _DecCfg), ("nchannels", C.c_int32), ("max_seconds", C.c_float),
+                        ("frames_per_chunk", C.c_int32), ("acoustic_scale", C.c_float), ("use_priors", C.c_int32)]
+        c = _StreamCfg()
+        L.b2k_stream_cfg_default.argtypes = [C.c_void_p]
+        L.b2k_stream_cfg_default.restype = None
+        L.b2k_stream_cfg_default(C.byref(c))
+        c.feat = _FeatCfg(**{f.name: getattr(fo, f.name) for f in fields(fo)})
+        dc = CudaDecoderConfig.from_dict(decoder_cfg)
+        c.dec = _DecCfg(dc.default_beam, dc.lattice_beam, dc.max_active, dc.min_active, dc.beam_delta, dc.prune_interval,
+                        dc.prune_scale, dc.max_tokens_per_frame, dc.max_frames, dc.max_tokens, dc.max_links,
+                        int(dc.reference_order), dc.hash_ratio, dc.max_arcs_per_frame, dc.max_lattice_states, dc.max_lattice_arcs)
+        c.nchannels, c.max_seconds, c.frames_per_chunk = int(nchannels), float(max_seconds), int(frames_per_chunk)
+        c.acoustic_scale, c.use_priors = float(acoustic_scale), int(use_priors)
+        self.model, self.fst = model, fst
+        self.h = C.c_void_p()
+        L.b2k_stream_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.check(L.b2k_stream_create(C.byref(c), model.h, fst.h, C.byref(self.h)))
+        info = (C.c_int64 * 8)()
+        L.b2k_stream_info.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.check(L.b2k_stream_info(self.h, info))
+        (self.nchannels, self.max_samples, self.max_frames, self.D, self.P, self.ivd, self.opc, self.fpc) = [int(x) for x in info]
+        # a CudaDecoder view of the stream's own decoder (not owned: the stream destroys it)
+        L.b2k_stream_decoder.restype = C.c_void_p
+        L.b2k_stream_decoder.argtypes = [C.c_void_p]
+        self.dec = CudaDecoder.__new__(CudaDecoder)
+        self.dec.h = None
+        self._dec_h = C.c_void_p(L.b2k_stream_decoder(self.h))
+        self.dec.fst, self.dec.config, self.dec.nlanes, self.dec.nchannels = fst, dc, nchannels, nchannels
+        L.b2k_stream_decode_batch_i16.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 10 + [C.c_void_p]
+
+    def _with_dec(self):
+        self.dec.h = self._dec_h
+        return self.dec
+
+    def __del__(self):
+        try:
+            if getattr(self, "dec", None) is not None:
+                self.dec.h = None                      # the view must not destroy the stream's decoder
+            if self.h:
+                self._L.b2k_stream_destroy.argtypes = [self._C.c_void_p]
+                self._L.b2k_stream_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def DecodeBatch(self, channels, wave_chunks_i16, is_first_chunk, is_last_chunk, want_partial: bool = True):
+        C = self._C
+        n = len(channels)
+        keep = [np.ascontiguousarray(w, np.int16) for w in wave_chunks_i16]
+        ch = (C.c_int32 * n)(*[int(c) for c in channels])
+        hp = (C.c_void_p * n)(*[w.ctypes.data if len(w) else None for w in keep])
+        ns = (C.c_int32 * n)(*[len(w) for w in keep])
+        fi = (C.c_int32 * n)(*[int(bool(x)) for x in is_first_chunk])
+        la = (C.c_int32 * n)(*[int(bool(x)) for x in is_last_chunk])
+        new, sofar = (C.c_int32 * n)(), (C.c_int32 * n)()
+        pn, pf = (C.c_void_p * n)(), (C.c_void_p * n)()
+        self._lib_mod.check(self._L.b2k_stream_decode_batch_i16(self.h, n, ch, hp, ns, fi, la, None, new, sofar, pn, pf, None))
+        dec = self._with_dec()
+        try:
+            res = []
+            partial = dec.GetBestPath(list(channels), use_final_probs=False) if want_partial else [None] * n
+            for i in range(n):
+                r = dict(channel=int(channels[i]), new_output_frames=int(new[i]), frames_decoded=int(sofar[i]))
+                if want_partial:
+                    r["partial_words"] = partial[i]["olabels"][partial[i]["olabels"] != 0]
+                    r["partial_cost"] = partial[i]["best_cost"]
+                if is_last_chunk[i]:
+                    r["lattice"] = dec.GetRawLattice(int(channels[i]))
+                res.append(r)
+            return res
+        finally:
+            self.dec.h = None

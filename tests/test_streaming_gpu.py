@@ -65,3 +65,48 @@ def test_streams_decode_chunk_by_chunk():
         assert all(np.array_equal(got[k], want[k]) for k in got), f"stream on channel {c}"
         sp = LAT.best_path(lattices[c])
         assert np.isfinite(sp["total_cost"]) and last_partial[c] is not None
+
+
+def test_native_stream_pipeline_equals_the_python_composition():
+    """b2k_stream_* (C++ orchestration, 16-bit PCM in, the feature kernel reading it directly) against StreamingBatchedDecoder
+    (the same stage calls from Python, validated against the reference-order decoder above) on the same chunks: the same number
+    of output frames per call, the same partial hypotheses, bit-identical lattices; and its misuse is refused."""
+    from kaldi_b200 import _lib
+    from kaldi_b200.decoder import CudaFst, lattice_to_canonical
+    from kaldi_b200.model import KaldiModel
+    from kaldi_b200.streaming import NativeStreamingDecoder, StreamingBatchedDecoder
+    P, fpc = 200, 21
+    arch = NM.arch_tiny(P)
+    W = NM.random_weights(arch, seed=2)
+    g = synth.make_hclg(150_000, num_pdfs=P, seed=4)
+    cfg = dict(synth.DEFAULT_DECODER_CFG)
+    py = StreamingBatchedDecoder(arch, W, g, cfg, nchannels=4, max_seconds=6.0, frames_per_chunk=fpc)
+    nat = NativeStreamingDecoder(KaldiModel.from_arch(arch, W), CudaFst(g), cfg, nchannels=4, max_seconds=6.0, frames_per_chunk=fpc)
+    assert (nat.opc, nat.fpc, nat.D, nat.P) == (py.opc, fpc, py.D, P)
+    lens = [40000, 25000]
+    pcm = [np.clip(np.round(synth.make_audio(n, seed=90 + i)), -32768, 32767).astype(np.int16) for i, n in enumerate(lens)]
+    chan, chunk, pos = [2, 0], fpc * 160, [0, 0]
+    lat_py, lat_nat = {}, {}
+    while len(lat_nat) < 2:
+        act = [u for u in range(2) if pos[u] < lens[u]]
+        pieces = [pcm[u][pos[u]:pos[u] + chunk] for u in act]
+        first = [pos[u] == 0 for u in act]
+        last = [pos[u] + chunk >= lens[u] for u in act]
+        ch = [chan[u] for u in act]
+        a = py.DecodeBatch(ch, [p.astype(np.float32) for p in pieces], first, last)
+        b = nat.DecodeBatch(ch, pieces, first, last)
+        for u, ra, rb in zip(act, a, b):
+            assert (ra["new_output_frames"], ra["frames_decoded"]) == (rb["new_output_frames"], rb["frames_decoded"])
+            assert np.array_equal(ra["partial_words"], rb["partial_words"]) and ra["partial_cost"] == rb["partial_cost"]
+            if "lattice" in ra:
+                lat_py[chan[u]], lat_nat[chan[u]] = ra["lattice"], rb["lattice"]
+            pos[u] += chunk
+    for c in chan:
+        x, y = lattice_to_canonical(lat_py[c]), lattice_to_canonical(lat_nat[c])
+        assert all(np.array_equal(x[k], y[k]) for k in x) and len(x["states"]) > 0
+    with pytest.raises(_lib.B2kError):       # a stream must start with is_first_chunk
+        nat.DecodeBatch([1], [pcm[0][:chunk]], [False], [False])
+    with pytest.raises(_lib.B2kError):       # more audio than frames_per_chunk frames in one call
+        nat.DecodeBatch([1], [pcm[0][:chunk * 3]], [True], [False])
+    with pytest.raises(_lib.B2kError):       # the same channel twice
+        nat.DecodeBatch([1, 1], [pcm[0][:chunk]] * 2, [True, True], [False, False])
