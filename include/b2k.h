@@ -221,7 +221,7 @@ int b2k_dec_frame_info(b2k_dec *dec, int32_t channel, float *cutoff, float *cost
  * mel-computations.h:43-58) — what OnlineNnet2FeaturePipelineInfo reads from
  * --mfcc-config / --fbank-config (online2/online-nnet2-feature-pipeline.cc:36-60). */
 typedef struct {
-  int32_t feature_type;        /* 0 = mfcc, 1 = fbank                           */
+  int32_t feature_type;        /* 0 = mfcc, 1 = fbank, 2 = plp (feat/feature-plp.h:38-66: lpc_order, compress_factor, cepstral_scale below) */
   float samp_freq, frame_shift_ms, frame_length_ms;
   float dither;                /* must be 0 (reference dither is unseeded)      */
   float preemph_coeff;
@@ -235,6 +235,9 @@ typedef struct {
   float cepstral_lifter;
   int32_t htk_compat, use_log_fbank, use_power, htk_mode;
   int32_t max_lanes;
+  /* PlpOptions only (defaults 12, 0.33333, 1.0; num_ceps <= lpc_order + 1) */
+  int32_t lpc_order;
+  float compress_factor, cepstral_scale;
 } b2k_feat_cfg;
 
 void b2k_feat_cfg_default(b2k_feat_cfg *cfg);   /* mfcc_hires.conf with --dither=0 */

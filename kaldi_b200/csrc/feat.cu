@@ -44,6 +44,8 @@ struct FeatTables {               // device pointers
   const float *mel_w;             // [mel_w_total]
   const float *dct;               // [num_ceps * num_bins]
   const float *lifter;            // [num_ceps]
+  const float *equal_loudness;    // plp: [num_bins] (GetEqualLoudnessVector, mel-computations.cc:301-313)
+  const float *idft;              // plp: [(lpc_order + 1) x (num_bins + 2)] (InitIdftBases, feature-functions.cc:188-203)
 };
 
 struct FeatParams {
@@ -53,6 +55,7 @@ struct FeatParams {
       use_power, htk_mode, use_lifter;
   float preemph, energy_floor_log, has_energy_floor;
   int dim;
+  int lpc_order; float compress_factor, cepstral_scale;     // plp
 };
 
 struct FeatLane {                 // per lane descriptor (device array)
@@ -291,14 +294,58 @@ feat_kernel(FeatParams p, const FeatLane *lanes, int frames_per_cta, int stage_c
       float e = 0.f;
       for (int i = 0; i < len; i++) e = fmaf(w[i], ps[i], e);
       if (p.htk_mode && e < 1.0f) e = 1.0f;
-      if (p.feature_type == 0 || p.use_log_fbank) e = logf(fmaxf(e, FLT_EPS));
+      if (p.feature_type == 0 || (p.feature_type == 1 && p.use_log_fbank)) e = logf(fmaxf(e, FLT_EPS));
+      if (p.feature_type == 2) e = powf(e * __ldg(&p.t.equal_loudness[b]), p.compress_factor);   // feature-plp.cc:140-142
       mel[b] = e;
     }
     __syncwarp();
     float *orow = L.out + (size_t)frame * L.row_stride;
     if (p.use_energy && p.has_energy_floor != 0.f && log_energy < p.energy_floor_log)
       log_energy = p.energy_floor_log;
-    if (p.feature_type == 1) {
+    if (p.feature_type == 2) {
+      // PlpComputer::Compute (feature-plp.cc:144-182): autocorrelation of the compressed spectrum with its first and last
+      // band repeated, Durbin's recursion, LPC -> cepstrum, lifter, scale, C0 / energy, HTK order.  The frame's scratch
+      // (buf is free again) holds the 13 + 12 + 12 + 12 values; the recursions are short and sequential: lane 0 runs them.
+      const int N2 = p.num_bins + 2, LO = p.lpc_order;
+      float *ac = buf, *lpc = buf + 64, *tmp = buf + 128, *cep = buf + 192;
+      for (int k = lane_id; k <= LO; k += 32) {
+        const float *row = p.t.idft + (size_t)k * N2;
+        float a = __ldg(&row[0]) * mel[0];                                  // AddMatVec: a dot product per row, in order
+        for (int j = 1; j <= p.num_bins; j++) a = fmaf(__ldg(&row[j]), mel[j - 1], a);
+        a = fmaf(__ldg(&row[N2 - 1]), mel[p.num_bins - 1], a);
+        ac[k] = a;
+      }
+      __syncwarp();
+      if (lane_id == 0) {
+        float E = ac[0];                                                    // Durbin (mel-computations.cc:266-297)
+        for (int i = 0; i < LO; i++) {
+          float ki = ac[i + 1];
+          for (int j = 0; j < i; j++) ki += lpc[j] * ac[i - j];
+          ki = ki / E;
+          float c = 1.0f - ki * ki;
+          if (c < 1.0e-5f) c = 1.0e-5f;
+          E *= c;
+          tmp[i] = -ki;
+          for (int j = 0; j < i; j++) tmp[j] = lpc[j] - ki * lpc[i - j - 1];
+          for (int j = 0; j <= i; j++) lpc[j] = tmp[j];
+        }
+        float res = -logf(1.0f / E);                                        // ComputeLpc (:317-329)
+        res = fmaxf(res, 1.17549435e-38f);                                  // std::numeric_limits<float>::min() (:161-162)
+        for (int i = 0; i < LO; i++) {                                      // Lpc2Cepstrum (:300-309), the sum in double
+          double sum = 0.0;
+          for (int j = 0; j < i; j++) sum += (double)((float)(i - j) * lpc[j] * cep[i - j - 1]);
+          cep[i] = (float)((double)(-lpc[i]) - sum / (double)(float)(i + 1));
+        }
+        for (int c = 0; c < p.num_ceps; c++) {
+          float v = (c == 0) ? res : cep[c - 1];
+          v *= s_lifter[c];
+          if (p.cepstral_scale != 1.0f) v *= p.cepstral_scale;
+          if (p.use_energy && c == 0) v = log_energy;
+          if (p.htk_compat) { if (c == 0) orow[p.num_ceps - 1] = v; else orow[c - 1] = v; }
+          else orow[c] = v;
+        }
+      }
+    } else if (p.feature_type == 1) {
       // fbank layout (feature-fbank.cc:103-122)
       int mel_offset = (p.use_energy && !p.htk_compat) ? 1 : 0;
       for (int b = lane_id; b < p.num_bins; b += 32) orow[mel_offset + b] = mel[b];
@@ -438,6 +485,7 @@ void b2k_feat_cfg_default(b2k_feat_cfg *c) {
   c->snip_edges = 1; c->window_type = 0; c->num_bins = 40; c->low_freq = 20.f; c->high_freq = -400.f;
   c->num_ceps = 40; c->use_energy = 0; c->energy_floor = 0.f; c->raw_energy = 1; c->cepstral_lifter = 22.f;
   c->htk_compat = 0; c->use_log_fbank = 1; c->use_power = 1; c->htk_mode = 0; c->max_lanes = 1024;
+  c->lpc_order = 12; c->compress_factor = 0.33333f; c->cepstral_scale = 1.0f;
 }
 
 int b2k_feat_create(const b2k_feat_cfg *cfg, b2k_feat **out) {
@@ -451,8 +499,11 @@ int b2k_feat_create(const b2k_feat_cfg *cfg, b2k_feat **out) {
   int padded = 1; while (padded < NL) padded *= 2;
   if (!cfg->round_to_power_of_two || padded != FEAT_NFFT)
     return set_error(B2K_ERR_INVALID, "only a padded window of 512 samples is supported (16 kHz / 25 ms)");
+  if (cfg->feature_type < 0 || cfg->feature_type > 2) return set_error(B2K_ERR_INVALID, "feature_type must be 0 (mfcc), 1 (fbank) or 2 (plp)");
   if (cfg->num_bins < 3 || cfg->num_bins > FEAT_MAX_BINS || cfg->num_ceps > cfg->num_bins || cfg->num_ceps < 1)
     return set_error(B2K_ERR_INVALID, "need 3 <= num_bins <= 64 and num_ceps <= num_bins");
+  if (cfg->feature_type == 2 && (cfg->lpc_order < 1 || cfg->lpc_order > 63 || cfg->num_ceps > cfg->lpc_order + 1 || cfg->num_ceps < 2))
+    return set_error(B2K_ERR_INVALID, "plp: need 1 <= lpc_order <= 63 and 2 <= num_ceps <= lpc_order + 1");   // feature-plp.cc:124
   b2k_feat *f = new b2k_feat();
   f->cfg = *cfg; f->frame_length = NL; f->frame_shift = shift;
   // --- window (FeatureWindowFunction, feature-window.cc:109-135): double math, float storage
@@ -507,6 +558,32 @@ int b2k_feat_create(const b2k_feat_cfg *cfg, b2k_feat **out) {
     }
     if (melw.size() > FEAT_MAX_MELW) { delete f; return set_error(B2K_ERR_INVALID, "mel weight table too large"); }
   }
+  // --- plp: equal-loudness weights at the bands' centre frequencies (GetEqualLoudnessVector, mel-computations.cc:301-313; the
+  //     centres as MelBanks::MelBanks leaves them, :99-102) and the inverse-DFT bases (InitIdftBases, feature-functions.cc:188-203)
+  std::vector<float> eql(cfg->num_bins, 1.0f), idft(1, 0.0f);
+  if (cfg->feature_type == 2) {
+    const float nyquist = 0.5f * cfg->samp_freq;
+    const float high = cfg->high_freq > 0.0f ? cfg->high_freq : nyquist + cfg->high_freq;
+    const float mel_low = melscale_f(cfg->low_freq), mel_high = melscale_f(high);
+    const float delta = (mel_high - mel_low) / (cfg->num_bins + 1);
+    for (int b = 0; b < cfg->num_bins; b++) {
+      const float center_mel = mel_low + (b + 1) * delta;
+      const float f0 = 700.0f * (expf(center_mel / 1127.0f) - 1.0f);          // InverseMelScale (mel-computations.h:81)
+      const float fsq = f0 * f0;
+      const float fsub = (float)(fsq / (fsq + 1.6e5));
+      eql[b] = (float)(fsub * fsub * ((fsq + 1.44e6) / (fsq + 9.61e6)));
+    }
+    const int nb = cfg->lpc_order + 1, dm = cfg->num_bins + 2;
+    idft.assign((size_t)nb * dm, 0.0f);
+    const float angle = (float)(M_PI / (float)(dm - 1));
+    const float scale = (float)(1.0f / (2.0 * (float)(dm - 1)));
+    for (int i = 0; i < nb; i++) {
+      idft[(size_t)i * dm] = (float)(1.0 * scale);
+      const float i_fl = (float)i;
+      for (int j = 1; j < dm - 1; j++) idft[(size_t)i * dm + j] = (float)(2.0 * scale * cos(angle * i_fl * (float)j));
+      idft[(size_t)i * dm + dm - 1] = (float)(scale * cos(angle * i_fl * (float)(dm - 1)));
+    }
+  }
   // --- DCT rows (ComputeDctMatrix, matrix-functions.cc:592-608, Real = float) and lifter (mel-computations.cc:253-259)
   std::vector<float> dct((size_t)cfg->num_ceps * cfg->num_bins), lifter(cfg->num_ceps, 1.0f);
   {
@@ -532,7 +609,7 @@ int b2k_feat_create(const b2k_feat_cfg *cfg, b2k_feat **out) {
   memset(&p, 0, sizeof(p));
 #define UP(field, vec) if ((rc = up((vec).data(), sizeof((vec)[0]) * (vec).size(), (const void **)&p.t.field))) return rc;
   UP(window, window) UP(tw_half, twh) UP(tw_full, twf) UP(mel_first, mfirst) UP(mel_len, mlen) UP(mel_off, moff)
-  UP(mel_w, melw) UP(dct, dct) UP(lifter, lifter)
+  UP(mel_w, melw) UP(dct, dct) UP(lifter, lifter) UP(equal_loudness, eql) UP(idft, idft)
 #undef UP
   p.frame_length = NL; p.frame_shift = shift; p.num_bins = cfg->num_bins; p.num_ceps = cfg->num_ceps;
   p.mel_w_total = (int)melw.size(); p.feature_type = cfg->feature_type; p.remove_dc = cfg->remove_dc_offset;
@@ -541,7 +618,8 @@ int b2k_feat_create(const b2k_feat_cfg *cfg, b2k_feat **out) {
   p.htk_mode = cfg->htk_mode; p.use_lifter = cfg->cepstral_lifter != 0.0f; p.preemph = cfg->preemph_coeff;
   p.has_energy_floor = cfg->energy_floor > 0.0f ? 1.f : 0.f;
   p.energy_floor_log = cfg->energy_floor > 0.0f ? logf(cfg->energy_floor) : 0.f;
-  p.dim = cfg->feature_type == 0 ? cfg->num_ceps : cfg->num_bins + (cfg->use_energy ? 1 : 0);
+  p.dim = cfg->feature_type != 1 ? cfg->num_ceps : cfg->num_bins + (cfg->use_energy ? 1 : 0);
+  p.lpc_order = cfg->lpc_order; p.compress_factor = cfg->compress_factor; p.cepstral_scale = cfg->cepstral_scale;
   f->max_lanes = cfg->max_lanes > 0 ? cfg->max_lanes : 1024;
   B2K_CUDA_CHECK(cudaMalloc((void **)&f->d_lanes, sizeof(FeatLane) * f->max_lanes)); f->allocs.push_back(f->d_lanes);
   B2K_CUDA_CHECK(cudaMalloc((void **)&f->d_clanes, sizeof(CmvnLane) * f->max_lanes)); f->allocs.push_back(f->d_clanes);

@@ -20,7 +20,8 @@ class _FeatCfg(C.Structure):
                 ("high_freq", C.c_float), ("num_ceps", C.c_int32), ("use_energy", C.c_int32),
                 ("energy_floor", C.c_float), ("raw_energy", C.c_int32), ("cepstral_lifter", C.c_float),
                 ("htk_compat", C.c_int32), ("use_log_fbank", C.c_int32), ("use_power", C.c_int32),
-                ("htk_mode", C.c_int32), ("max_lanes", C.c_int32)]
+                ("htk_mode", C.c_int32), ("max_lanes", C.c_int32),
+                ("lpc_order", C.c_int32), ("compress_factor", C.c_float), ("cepstral_scale", C.c_float)]
 
 
 class _CmvnCfg(C.Structure):
@@ -55,6 +56,9 @@ class FeatureOptions:
     use_power: int = 1
     htk_mode: int = 0
     max_lanes: int = 1024
+    lpc_order: int = 12              # PlpOptions (feature_type 2), feat/feature-plp.h:38-66
+    compress_factor: float = 0.33333
+    cepstral_scale: float = 1.0
 
 
 @dataclass

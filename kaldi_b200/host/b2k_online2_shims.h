@@ -7,7 +7,7 @@
 // Only the base feature object (OnlineMfcc / OnlineFbank, online-nnet2-feature-pipeline.cc:100-108) is replaced -- by
 // OnlineBaseFeatureB2k over b2k_feat_* -- and everything stacked on it is the reference's own OnlineCmvn /
 // OnlineIvectorFeature / OnlineAppendFeature, so adaptation state, CMVN state and frame weights keep their meaning and their
-// types.  PLP and pitch have no kernel here and are refused.
+// types.  Pitch has no kernel here and is refused.
 //
 // online2/online-ivector-feature.h includes the OpenFst-based decoders; a build without OpenFst (this repository's check,
 // oracle/check_shims.py) pre-defines their include guards and forward-declares the two decoder templates.
@@ -23,6 +23,7 @@
 #include "b2k_kaldi_shims.h"
 #include "feat/feature-fbank.h"
 #include "feat/feature-mfcc.h"
+#include "feat/feature-plp.h"
 #include "feat/online-feature.h"
 #include "online2/online-ivector-feature.h"
 #include "online2/online-nnet2-feature-pipeline.h"
@@ -71,6 +72,18 @@ inline b2k_feat_cfg ToB2kFeatCfg(const FbankOptions &o, int32 max_lanes = 1) {
   return c;
 }
 
+inline b2k_feat_cfg ToB2kFeatCfg(const PlpOptions &o, int32 max_lanes = 1) {
+  b2k_feat_cfg c;
+  b2k_feat_cfg_default(&c);
+  c.feature_type = 2;
+  FrameAndMelB2k(o.frame_opts, o.mel_opts, &c);
+  c.lpc_order = o.lpc_order; c.num_ceps = o.num_ceps; c.use_energy = o.use_energy; c.energy_floor = o.energy_floor;
+  c.raw_energy = o.raw_energy; c.compress_factor = o.compress_factor; c.cepstral_lifter = static_cast<float>(o.cepstral_lifter);
+  c.cepstral_scale = o.cepstral_scale; c.htk_compat = o.htk_compat;
+  c.max_lanes = max_lanes;
+  return c;
+}
+
 // One per OnlineNnet2FeaturePipelineInfo: the device tables (window, mel banks, DCT) every utterance's pipeline shares.
 class FeatureTablesB2k {
  public:
@@ -79,7 +92,8 @@ class FeatureTablesB2k {
     b2k_feat_cfg c;
     if (info.feature_type == "mfcc") c = ToB2kFeatCfg(info.mfcc_opts, max_lanes);
     else if (info.feature_type == "fbank") c = ToB2kFeatCfg(info.fbank_opts, max_lanes);
-    else KALDI_ERR << "b2k computes mfcc and fbank features, not " << info.feature_type;
+    else if (info.feature_type == "plp") c = ToB2kFeatCfg(info.plp_opts, max_lanes);
+    else KALDI_ERR << "b2k computes mfcc, fbank and plp features, not " << info.feature_type;
     Check(b2k_feat_create(&c, &feat_), "b2k_feat_create");
   }
   ~FeatureTablesB2k() { b2k_feat_destroy(feat_); }

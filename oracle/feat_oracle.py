@@ -60,6 +60,9 @@ class FeatOpts:
     use_power: int = 1
     window_type: int = 0           # 0 povey, 1 hamming, 2 hanning, 3 rectangular
     htk_mode: int = 0              # MelBanksOptions::htk_mode (mel-computations.h:52-55)
+    lpc_order: int = 12            # PlpOptions (feature_type 2), feat/feature-plp.h:38-66
+    compress_factor: float = 0.33333
+    cepstral_scale: float = 1.0
 
     @property
     def window_shift(self):       # WindowShift  feature-window.h:106
@@ -81,7 +84,7 @@ class FeatOpts:
 
     @property
     def dim(self):
-        if self.feature_type == 0:
+        if self.feature_type in (0, 2):
             return self.num_ceps
         return self.num_bins + (1 if self.use_energy else 0)
 
@@ -94,7 +97,8 @@ class _COpts(C.Structure):
                 ("num_ceps", C.c_int), ("use_energy", C.c_int), ("energy_floor", C.c_float),
                 ("raw_energy", C.c_int), ("cepstral_lifter", C.c_float), ("htk_compat", C.c_int),
                 ("use_log_fbank", C.c_int), ("use_power", C.c_int),
-                ("window_type", C.c_int), ("htk_mode", C.c_int)]
+                ("window_type", C.c_int), ("htk_mode", C.c_int),
+                ("lpc_order", C.c_int), ("compress_factor", C.c_float), ("cepstral_scale", C.c_float)]
 
 
 def _copts(o: FeatOpts) -> _COpts:
@@ -255,6 +259,86 @@ def extract_frames(wave: np.ndarray, o: FeatOpts) -> np.ndarray:
     return np.asarray(wave, np.float32)[idx]
 
 
+def plp_tables(o: FeatOpts):
+    """Equal-loudness weights at the bands' centre frequencies (GetEqualLoudnessVector, mel-computations.cc:301-313; centres as
+    MelBanks::MelBanks leaves them, :99-102) and the inverse-DFT bases (InitIdftBases, feature-functions.cc:188-203), float
+    arithmetic where the reference's is."""
+    nyq = F32(0.5) * F32(o.samp_freq)
+    high = F32(o.high_freq) if o.high_freq > 0.0 else nyq + F32(o.high_freq)
+
+    def mel_scale(f):
+        return F32(1127.0) * np.log(F32(1.0) + F32(f) / F32(700.0)).astype(np.float32)
+    mel_low, mel_high = mel_scale(o.low_freq), mel_scale(high)
+    delta = F32((mel_high - mel_low) / F32(o.num_bins + 1))
+    eql = np.zeros(o.num_bins, np.float32)
+    for b in range(o.num_bins):
+        center_mel = F32(mel_low + F32(b + 1) * delta)
+        f0 = F32(F32(700.0) * (np.exp(F32(center_mel / F32(1127.0)), dtype=np.float32) - F32(1.0)))
+        fsq = F32(f0 * f0)
+        fsub = F32(float(fsq) / (float(fsq) + 1.6e5))
+        eql[b] = F32(float(fsub) * float(fsub) * ((float(fsq) + 1.44e6) / (float(fsq) + 9.61e6)))
+    nb, dm = o.lpc_order + 1, o.num_bins + 2
+    angle = F32(np.pi / float(F32(dm - 1)))
+    scale = F32(1.0 / (2.0 * float(F32(dm - 1))))
+    idft = np.zeros((nb, dm), np.float32)
+    for i in range(nb):
+        idft[i, 0] = F32(1.0 * float(scale))
+        for j in range(1, dm - 1):
+            idft[i, j] = F32(2.0 * float(scale) * np.cos(float(F32(F32(angle * F32(i)) * F32(j)))))
+        idft[i, dm - 1] = F32(float(scale) * np.cos(float(F32(F32(angle * F32(i)) * F32(dm - 1)))))
+    return eql, idft
+
+
+def _plp_tail(mel: np.ndarray, raw_log_energy, o: FeatOpts) -> np.ndarray:
+    """PlpComputer::Compute after the mel bank (feature-plp.cc:140-182): equal loudness, compression, autocorrelation by the
+    inverse-DFT bases, Durbin's recursion (mel-computations.cc:266-297), LPC -> cepstrum (:300-309), lifter, scale, C0 / energy."""
+    eql, idft = plp_tables(o)
+    T = mel.shape[0]
+    comp = np.power((mel * eql[None, :]).astype(np.float32), F32(o.compress_factor)).astype(np.float32)
+    dup = np.concatenate([comp[:, :1], comp, comp[:, -1:]], 1)
+    ac = (dup @ idft.T).astype(np.float32)
+    LO = o.lpc_order
+    out = np.zeros((T, o.num_ceps), np.float32)
+    lift = lifter_coeffs(o) if o.cepstral_lifter != 0.0 else np.ones(o.num_ceps, np.float32)
+    for t in range(T):
+        a = ac[t]
+        lpc = np.zeros(LO, np.float32); tmp = np.zeros(LO, np.float32)
+        E = F32(a[0])
+        for i in range(LO):
+            ki = F32(a[i + 1])
+            for j in range(i):
+                ki = F32(ki + F32(lpc[j] * a[i - j]))
+            ki = F32(ki / E)
+            c = F32(F32(1.0) - F32(ki * ki))
+            if c < F32(1.0e-5):
+                c = F32(1.0e-5)
+            E = F32(E * c)
+            tmp[i] = -ki
+            for j in range(i):
+                tmp[j] = F32(lpc[j] - F32(ki * lpc[i - j - 1]))
+            lpc[:i + 1] = tmp[:i + 1]
+        res = max(F32(-np.log(F32(F32(1.0) / E))), np.finfo(np.float32).tiny)
+        cep = np.zeros(LO, np.float32)
+        for i in range(LO):
+            sm = 0.0
+            for j in range(i):
+                sm += float(F32(F32(F32(i - j) * lpc[j]) * cep[i - j - 1]))
+            cep[i] = F32(float(-lpc[i]) - sm / float(F32(i + 1)))
+        out[t, 0] = res
+        out[t, 1:] = cep[:o.num_ceps - 1]
+    out = (out * lift[None, :]).astype(np.float32)
+    if o.cepstral_scale != 1.0:
+        out = (out * F32(o.cepstral_scale)).astype(np.float32)
+    if o.use_energy:
+        e = raw_log_energy
+        if o.energy_floor > 0.0:
+            e = np.maximum(e, F32(np.log(F32(o.energy_floor))))
+        out[:, 0] = e
+    if o.htk_compat:
+        out = np.concatenate([out[:, 1:], out[:, :1]], 1)
+    return out
+
+
 def mfcc_fbank(wave: np.ndarray, o: FeatOpts) -> np.ndarray:
     """Mfcc/Fbank::ComputeFeatures = ExtractWindow + ProcessWindow
     (feature-window.cc:137-160) + MfccComputer::Compute (feature-mfcc.cc:28-80)
@@ -298,6 +382,8 @@ def mfcc_fbank(wave: np.ndarray, o: FeatOpts) -> np.ndarray:
         mel[:, b] = (power[:, first:first + len(w)] * w[None, :]).sum(axis=1, dtype=np.float32)
     if o.htk_mode:
         mel = np.maximum(mel, F32(1.0))                       # :237 HTK-like flooring
+    if o.feature_type == 2:
+        return _plp_tail(mel, raw_log_energy, o)
     if o.feature_type == 0 or o.use_log_fbank:
         mel = np.log(np.maximum(mel, FLT_EPS)).astype(np.float32)
     if o.feature_type == 1:

@@ -14,6 +14,7 @@
 
 #include "feat/feature-fbank.h"
 #include "feat/feature-mfcc.h"
+#include "feat/feature-plp.h"
 #include "feat/online-feature.h"
 #include "matrix/kaldi-matrix.h"
 #include "feat/resample.h"
@@ -37,6 +38,8 @@ struct ref_feat_opts {
   int htk_compat, use_log_fbank, use_power;
   int window_type;         // 0 povey, 1 hamming, 2 hanning, 3 rectangular
   int htk_mode;            // MelBanksOptions::htk_mode (hidden test option)
+  int lpc_order;           // PlpOptions (feature_type 2)
+  float compress_factor, cepstral_scale;
 };
 
 static void fill_frame(const ref_feat_opts *o, FrameExtractionOptions *f) {
@@ -66,12 +69,24 @@ static FbankOptions fbank_opts(const ref_feat_opts *o) {
   return m;
 }
 
+static PlpOptions plp_opts(const ref_feat_opts *o) {
+  PlpOptions m;
+  fill_frame(o, &m.frame_opts);
+  m.mel_opts.num_bins = o->num_bins; m.mel_opts.low_freq = o->low_freq; m.mel_opts.high_freq = o->high_freq;
+  m.mel_opts.htk_mode = o->htk_mode != 0;
+  m.lpc_order = o->lpc_order; m.num_ceps = o->num_ceps; m.use_energy = o->use_energy != 0; m.energy_floor = o->energy_floor;
+  m.raw_energy = o->raw_energy != 0; m.compress_factor = o->compress_factor; m.cepstral_lifter = (int32)o->cepstral_lifter;
+  m.cepstral_scale = o->cepstral_scale; m.htk_compat = o->htk_compat != 0;
+  return m;
+}
+
 // offline: whole-utterance features.  returns number of frames (or -1), writes dim.
 int ref_feat_compute(const ref_feat_opts *o, const float *wave, int n, float *out, int max_rows, int *dim) {
   try {
     SubVector<BaseFloat> w(const_cast<float *>(wave), n);
     Matrix<BaseFloat> feats;
     if (o->feature_type == 0) { Mfcc m(mfcc_opts(o)); m.ComputeFeatures(w, o->samp_freq, 1.0, &feats); }
+    else if (o->feature_type == 2) { Plp m(plp_opts(o)); m.ComputeFeatures(w, o->samp_freq, 1.0, &feats); }
     else { Fbank m(fbank_opts(o)); m.ComputeFeatures(w, o->samp_freq, 1.0, &feats); }
     *dim = feats.NumCols();
     if (feats.NumRows() > max_rows) return -2;
@@ -86,6 +101,7 @@ int ref_feat_online(const ref_feat_opts *o, const float *wave, int n, int chunk,
   try {
     std::unique_ptr<OnlineBaseFeature> f;
     if (o->feature_type == 0) f.reset(new OnlineMfcc(mfcc_opts(o)));
+    else if (o->feature_type == 2) f.reset(new OnlinePlp(plp_opts(o)));
     else f.reset(new OnlineFbank(fbank_opts(o)));
     for (int off = 0; off < n; off += chunk) {
       int len = std::min(chunk, n - off);

@@ -161,3 +161,33 @@ def test_int16_input_and_unaligned_sources_give_the_same_bits(cfgs, name):
                         bf.ComputeFeaturesBatched([ptr], [n_samples], [f0], [k], [out.data_ptr()], D, int16=i16)
                 torch.cuda.synchronize()
                 np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg=f"{name} n={n_samples} shift={shift} int16={i16}")
+
+
+@pytest.mark.parametrize("kw", [dict(use_energy=1), dict(use_energy=0), dict(use_energy=0, htk_compat=1, cepstral_scale=10.0),
+                                dict(use_energy=1, raw_energy=0, num_ceps=9, lpc_order=10, cepstral_lifter=0.0)])
+def test_plp_kernel_vs_compiled_reference(kw):
+    """feature_type 2: PlpComputer::Compute (feat/feature-plp.cc:112-182, compiled in oracle/_ref) -- the kernel's tail after the
+    mel bank (equal loudness, cube-root compression, inverse-DFT autocorrelation, Durbin, LPC -> cepstrum, lifter, scale, C0 or
+    energy, HTK order).  Durbin's recursion amplifies the ~1e-6 differences between the two FFTs about 40-fold (measured on the
+    reference itself), so the tolerance is 2e-3 per unit of cepstral scale on cepstra of magnitude <= 6 (C0 ~ 20); int16 input
+    gives the same bits as float input."""
+    import torch
+    from kaldi_b200.feat import BatchedFeatures
+    from oracle import feat_oracle as F
+    o = F.FeatOpts(**{**dict(feature_type=2, num_bins=23, num_ceps=13, low_freq=20.0, high_freq=0.0), **kw})
+    bf = BatchedFeatures(_opts(o))
+    assert bf.Dim() == o.num_ceps
+    R = F.RefFeat()
+    waves = [np.clip(np.round(synth.make_audio(n, seed=60 + i)), -32768, 32767).astype(np.float32) for i, n in enumerate((48000, 16000, 559))]
+    got = bf.compute(waves)
+    for w, g in zip(waves, got):
+        want = R.compute(w, o)
+        assert g.shape == want.shape
+        assert np.abs(g - want).max() <= 2e-3 * o.cepstral_scale, (np.abs(g - want).max(), np.abs(want).max())
+    pcm = waves[0].astype(np.int16)
+    d = torch.from_numpy(pcm).cuda()
+    T = got[0].shape[0]
+    out = torch.zeros(T, bf.Dim(), device="cuda")
+    bf.ComputeFeaturesBatched([d.data_ptr()], [len(pcm)], [0], [T], [out.data_ptr()], bf.Dim(), int16=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), got[0])
