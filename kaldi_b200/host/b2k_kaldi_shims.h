@@ -20,6 +20,7 @@
 #include <vector>
 
 #include <functional>
+#include <map>
 
 #include "b2k.h"
 #include "b2k_pipeline_shim.h"
@@ -347,6 +348,149 @@ class BatchedOnlinePipelineB2k {
  private:
   b2k_host::B2kPipelineBackend backend_;
   b2k_host::B2kBatcher batcher_;
+};
+
+// cuda_decoder::BatchedThreadedNnet3CudaOnlinePipeline, STREAMING: every DecodeBatch advances every listed utterance by its
+// chunk (features of the new frames, chunked network, decoder frames) over b2k_stream_*, reports partial hypotheses and
+// end points per call and hands the raw lattice to the utterance's callback after its last chunk -- the reference's call
+// structure (batched-threaded-nnet3-cuda-online-pipeline.h:160-215, .cc:316-377), where BatchedOnlinePipelineB2k above decodes
+// an utterance when its last chunk has arrived.  Utterances hold a channel from TryInitCorrID until their last chunk.
+class StreamingOnlinePipelineB2k {
+ public:
+  using CorrelationID = uint64_t;
+  typedef std::function<void(const std::string &, bool, bool)> BestPathCallback;    // …online-pipeline.h:129: (text, partial, endpoint)
+  typedef std::function<void(CorrelationID, const b2k_raw_lattice &)> RawLatticeCallback;
+
+  // model: for the transition-id -> phone table the end point rules need (may be NULL when no end points are asked for)
+  StreamingOnlinePipelineB2k(const b2k_stream_cfg &config, const b2k_model *model, const b2k_fst *decode_fst) : model_(model) {
+    Check(b2k_stream_create(&config, model, decode_fst, &s_), "b2k_stream_create");
+    int64_t info[8];
+    Check(b2k_stream_info(s_, info), "b2k_stream_info");
+    for (int32 c = (int32)info[0] - 1; c >= 0; c--) free_.push_back(c);
+    frames_per_chunk_ = (int32)info[7];
+    samples_per_chunk_ = (int32)(frames_per_chunk_ * config.feat.samp_freq * 0.001f * config.feat.frame_shift_ms);
+    int32_t mi[8];
+    Check(b2k_model_info(model, mi), "b2k_model_info");
+    decoder_frame_shift_seconds_ = 0.001f * config.feat.frame_shift_ms * mi[3];
+    num_tids_ = mi[6];
+    Check(b2k_endpoint_cfg_default(&endpoint_), "b2k_endpoint_cfg_default");
+  }
+  ~StreamingOnlinePipelineB2k() { b2k_stream_destroy(s_); }
+
+  int32 GetNSampsPerChunk() const { return samples_per_chunk_; }                     // :248-250
+  int32 GetNInputFramesPerChunk() const { return frames_per_chunk_; }
+  BaseFloat GetDecoderFrameShiftSeconds() const { return decoder_frame_shift_seconds_; }
+
+  bool TryInitCorrID(CorrelationID corr_id, int /*wait_for*/ = 0) {                  // :165: false = every channel is taken
+    if (chan_.count(corr_id)) return true;
+    if (free_.empty()) return false;
+    chan_[corr_id] = free_.back();
+    free_.pop_back();
+    return true;
+  }
+  void SetBestPathCallback(CorrelationID corr_id, const BestPathCallback &callback) { best_cb_[corr_id] = callback; }
+  void SetRawLatticeCallback(CorrelationID corr_id, const RawLatticeCallback &callback) { lat_cb_[corr_id] = callback; }
+  // how a word id is spelled in hypotheses (the reference reads its word symbol table); default: the id itself
+  void SetWordMapper(const std::function<std::string(int32)> &f) { word_of_ = f; }
+  void SetEndpointConfig(const b2k_endpoint_cfg &c) { endpoint_ = c; }
+
+  // :209-215.  wave_samples hold 16-bit PCM values (what WaveData::Read leaves in its floats); anything else is refused.
+  void DecodeBatch(const std::vector<CorrelationID> &corr_ids, const std::vector<SubVector<BaseFloat>> &wave_samples,
+                   const std::vector<bool> &is_first_chunk, const std::vector<bool> &is_last_chunk,
+                   std::vector<const std::string *> *partial_hypotheses = nullptr, std::vector<bool> *end_point = nullptr) {
+    const size_t n = corr_ids.size();
+    KALDI_ASSERT(wave_samples.size() == n && is_first_chunk.size() >= n && is_last_chunk.size() >= n);
+    pcm_.resize(n); chans_.resize(n); ptrs_.resize(n); ns_.resize(n); first_.resize(n); last_.resize(n);
+    for (size_t i = 0; i < n; i++) {
+      if (is_first_chunk[i] && !TryInitCorrID(corr_ids[i])) KALDI_ERR << "DecodeBatch: no free channel for a new utterance";
+      auto it = chan_.find(corr_ids[i]);
+      if (it == chan_.end()) KALDI_ERR << "DecodeBatch: unknown correlation id (its first chunk never came)";
+      chans_[i] = it->second;
+      const SubVector<BaseFloat> &w = wave_samples[i];
+      pcm_[i].resize(w.Dim());
+      for (int32 k = 0; k < w.Dim(); k++) {
+        const float v = w(k);
+        const int16_t q = (int16_t)v;
+        if ((float)q != v) KALDI_ERR << "DecodeBatch: sample " << v << " is not a 16-bit PCM value";
+        pcm_[i][k] = q;
+      }
+      ptrs_[i] = pcm_[i].data(); ns_[i] = w.Dim(); first_[i] = is_first_chunk[i] ? 1 : 0; last_[i] = is_last_chunk[i] ? 1 : 0;
+    }
+    Check(b2k_stream_decode_batch_i16(s_, (int32_t)n, chans_.data(), ptrs_.data(), ns_.data(), first_.data(), last_.data(), nullptr,
+                                      nullptr, nullptr, nullptr, nullptr, cudaStreamPerThread), "b2k_stream_decode_batch_i16");
+    b2k_dec *dec = b2k_stream_decoder(s_);
+    const bool want_text = partial_hypotheses != nullptr || end_point != nullptr || !best_cb_.empty();
+    if (partial_hypotheses) partial_hypotheses->assign(n, nullptr);
+    if (end_point) end_point->assign(n, false);
+    if (want_text) {
+      const int32_t cap = 16384;
+      il_.resize(n * (size_t)cap); ol_.resize(n * (size_t)cap); info_.resize(n);
+      Check(b2k_dec_best_path(dec, chans_.data(), (int32_t)n, /*use_final_probs=*/0, cap, il_.data(), ol_.data(), nullptr, nullptr,
+                              nullptr, nullptr, info_.data(), cudaStreamPerThread), "b2k_dec_best_path");
+      for (size_t i = 0; i < n; i++) {
+        std::string &text = text_[corr_ids[i]];
+        text.clear();
+        for (int32_t k = 0; k < info_[i].n_arcs; k++) {
+          const int32 w = ol_[i * (size_t)cap + k];
+          if (w == 0) continue;
+          if (!text.empty()) text += ' ';
+          text += word_of_ ? word_of_(w) : std::to_string(w);
+        }
+        bool ep = false;
+        if ((end_point || !best_cb_.empty()) && model_ && num_tids_ > 0) {
+          int32_t hit = 0;
+          Check(b2k_endpoint_detected_on_path(&endpoint_, b2k_model_tid2phone(model_), num_tids_, il_.data() + i * (size_t)cap, info_[i].n_arcs,
+                                              info_[i].num_frames, decoder_frame_shift_seconds_, info_[i].final_relative_cost, &hit, nullptr),
+                "b2k_endpoint_detected_on_path");
+          ep = hit != 0;
+        }
+        if (partial_hypotheses) (*partial_hypotheses)[i] = &text;
+        if (end_point) (*end_point)[i] = ep;
+        auto cb = best_cb_.find(corr_ids[i]);
+        if (cb != best_cb_.end()) cb->second(text, /*partial=*/!is_last_chunk[i], ep);
+      }
+    }
+    for (size_t i = 0; i < n; i++) {
+      if (!is_last_chunk[i]) continue;
+      auto cb = lat_cb_.find(corr_ids[i]);
+      if (cb != lat_cb_.end()) {
+        b2k_raw_lattice q = {};
+        Check(b2k_dec_get_raw_lattice(dec, chans_[i], &q, cudaStreamPerThread), "b2k_dec_get_raw_lattice");     // sizes
+        st_f_.resize(q.num_states); st_h_.resize(q.num_states); st_t_.resize(q.num_states); st_e_.resize(q.num_states);
+        a_s_.resize(q.num_arcs); a_d_.resize(q.num_arcs); a_i_.resize(q.num_arcs); a_o_.resize(q.num_arcs); a_g_.resize(q.num_arcs); a_a_.resize(q.num_arcs);
+        f_s_.resize(q.num_finals); f_c_.resize(q.num_finals);
+        q.state_frame = st_f_.data(); q.state_hclg = st_h_.data(); q.state_tot_cost = st_t_.data(); q.state_extra_cost = st_e_.data();
+        q.arc_src = a_s_.data(); q.arc_dst = a_d_.data(); q.arc_ilabel = a_i_.data(); q.arc_olabel = a_o_.data();
+        q.arc_graph_cost = a_g_.data(); q.arc_acoustic_cost = a_a_.data(); q.final_state = f_s_.data(); q.final_cost = f_c_.data();
+        Check(b2k_dec_get_raw_lattice(dec, chans_[i], &q, cudaStreamPerThread), "b2k_dec_get_raw_lattice");
+        cb->second(corr_ids[i], q);
+        lat_cb_.erase(cb);
+      }
+      best_cb_.erase(corr_ids[i]);
+      free_.push_back(chans_[i]);
+      chan_.erase(corr_ids[i]);
+    }
+  }
+
+ private:
+  b2k_stream *s_ = NULL;
+  const b2k_model *model_;
+  int32 frames_per_chunk_ = 0, samples_per_chunk_ = 0, num_tids_ = 0;
+  BaseFloat decoder_frame_shift_seconds_ = 0.03f;
+  b2k_endpoint_cfg endpoint_;
+  std::vector<int32> free_;
+  std::map<CorrelationID, int32> chan_;
+  std::map<CorrelationID, BestPathCallback> best_cb_;
+  std::map<CorrelationID, RawLatticeCallback> lat_cb_;
+  std::map<CorrelationID, std::string> text_;
+  std::function<std::string(int32)> word_of_;
+  std::vector<std::vector<int16_t>> pcm_;
+  std::vector<int32_t> chans_, ns_, first_, last_, il_, ol_;
+  std::vector<const int16_t *> ptrs_;
+  std::vector<b2k_best_path_info> info_;
+  std::vector<int32_t> st_f_, st_h_, a_s_, a_d_, a_i_, a_o_, f_s_;
+  std::vector<float> st_t_, st_e_, a_g_, a_a_, f_c_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(StreamingOnlinePipelineB2k);
 };
 
 // ------------------------------------------------------------------------------------------------ endpointing

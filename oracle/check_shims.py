@@ -46,6 +46,24 @@ def check() -> bool:
             "  c.Check(); c.ComputeConfig();\n  b2k_dec_cfg d = c.ToB2k(400);\n  return d.max_active + c.main_q_capacity;\n}\n")
         subprocess.check_call(["g++", "-fsyntax-only"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"),
                               "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include"]) + [cc])
+        # the streaming pipeline shim: DecodeBatch with exactly the argument types the reference's own callers pass
+        # (cudadecoderbin/batched-wav-nnet3-cuda-online.cc), callbacks, end points
+        sp = os.path.join(td, "s.cc")
+        open(sp, "w").write(
+            '#include "b2k_kaldi_shims.h"\nusing namespace kaldi;\n'
+            "void f(const b2k_stream_cfg &c, const b2k_model *m, const b2k_fst *g, const std::vector<SubVector<BaseFloat>> &waves) {\n"
+            "  b2k_shim::StreamingOnlinePipelineB2k p(c, m, g);\n"
+            "  std::vector<b2k_shim::StreamingOnlinePipelineB2k::CorrelationID> ids(1, 7);\n"
+            "  std::vector<bool> first(1, true), last(1, false), ep; std::vector<const std::string *> hyp;\n"
+            "  p.TryInitCorrID(7);\n"
+            "  p.SetBestPathCallback(7, [](const std::string &, bool, bool) {});\n"
+            "  p.SetRawLatticeCallback(7, [](uint64_t, const b2k_raw_lattice &) {});\n"
+            "  p.DecodeBatch(ids, waves, first, last, &hyp, &ep);\n"
+            "  p.DecodeBatch(ids, waves, first, last);\n"
+            "  int x = p.GetNSampsPerChunk() + p.GetNInputFramesPerChunk(); (void)x; p.GetDecoderFrameShiftSeconds();\n"
+            "}\n")
+        subprocess.check_call(["g++", "-fsyntax-only"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"),
+                              "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include"]) + [sp])
         # the nnet3 surfaces (b2k_nnet3_shims.h) against the reference's own nnet3 / cudadecoder headers, HAVE_CUDA=1 as in a CUDA
         # build of Kaldi: NnetComputer's members, DecodableAmNnetLoopedOnline as a DecodableInterface, and BatchedStaticNnet3's
         # RunBatch called with exactly the argument types batched-threaded-nnet3-cuda-online-pipeline.cc:662-668 passes
