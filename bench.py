@@ -8,6 +8,7 @@ Metric (BASELINE.json): real-time factor RTFx = audio-seconds / wall-seconds.  A
   python bench.py --impl reference --gpus N ...             # the reference's own CPU path on the host cores
   python bench.py --workload librispeech_tdnn_1d/hclg50M/batch512   # BASELINE configs[2] (one GPU's share)
   python bench.py --workload decoder_sweep                  # BASELINE configs[4]: Marcs/s per (graph size, beam)
+  python bench.py --workload streaming [--partials]          # serving mode: B streams chunk by chunk through b2k_stream_*
 
 Everything on the GPU side goes through the C ABI (include/b2k.h): b2k_pipeline_* over libb2k.so.
 `value`       : whole-job RTFx with the audio already resident in HBM (b2k_pipeline_run_device, CUDA events).
@@ -318,13 +319,90 @@ def decoder_sweep(a, rank, world, local_rank):
     return 0
 
 
+def streaming_bench(a, rank, world, local_rank):
+    """Serving mode: B audio streams decoded chunk by chunk through b2k_stream_* (the call structure of
+    BatchedThreadedNnet3CudaOnlinePipeline::DecodeBatch): every call brings 0.51 s of 16-bit PCM per stream from HOST memory,
+    computes the new feature frames, the chunked network and the decoder frames of all streams, and the last call finalizes
+    them.  A step = all the calls of B utterances of 10 s.  The network sees zero i-vectors (the device i-vector stage works
+    per utterance).  With --partials every call also asks for every stream's partial hypothesis (b2k_dec_best_path)."""
+    import torch
+    from kaldi_b200.decoder import CudaFst
+    from kaldi_b200.feat import FeatureOptions
+    from kaldi_b200.model import KaldiModel
+    from kaldi_b200.streaming import NativeStreamingDecoder
+    torch.cuda.set_device(local_rank)
+    wname = DEFAULT_WORKLOAD
+    w = WORKLOADS[wname]
+    arch = arch_for(w)
+    W = load_calibrated_weights(arch, 0, w["cal"])
+    graph = graph_for(w["graph_arcs"], w["num_pdfs"])
+    B, fpc = a.batch or w["batch"], 51
+    nf_out = 333 + 24
+    sd = NativeStreamingDecoder(KaldiModel.from_arch(arch, W), CudaFst(graph), dict(synth.DEFAULT_DECODER_CFG), nchannels=B,
+                                max_seconds=NUM_SAMPLES / 16000.0 + 0.1, frames_per_chunk=fpc,
+                                feature_opts=FeatureOptions(max_lanes=max(B, 64)),
+                                decoder_kwargs=dict(max_tokens=nf_out * a.tok_per_frame, max_links=nf_out * a.links_per_frame,
+                                                    max_tokens_per_frame=a.max_tpf, reference_order=True))
+    pcm = np.stack([synth.make_audio(NUM_SAMPLES, seed=10_000 * rank + i) for i in range(B)]).astype(np.int16)
+    chunk = fpc * 160
+    n_calls = (NUM_SAMPLES + chunk - 1) // chunk
+    ch = list(range(B))
+    h2d = 0
+
+    def one_utterance_set():
+        nonlocal h2d
+        res = None
+        for k in range(n_calls):
+            pieces = [pcm[i, k * chunk:(k + 1) * chunk] for i in range(B)]
+            res = sd.DecodeBatch(ch, pieces, [k == 0] * B, [k == n_calls - 1] * B, want_partial=a.partials, lattices="batched")
+            h2d += sum(len(p) for p in pieces) * 2
+        return res
+    for _ in range(max(1, a.warmup)):
+        one_utterance_set()
+    torch.cuda.synchronize()
+    h2d = 0
+    mon = ClockSampler(local_rank); mon.start()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    frames = 0
+    for _ in range(a.steps):
+        res = one_utterance_set()
+        frames = res[0]["frames_decoded"]
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = mon.stop()
+    t_dev = e0.elapsed_time(e1) / 1e3
+    audio = B * NUM_SAMPLES / 16000.0 * a.steps
+    infos = [sd._with_dec().ChannelInfo(c) for c in (0, B // 2, B - 1)]
+    sd.dec.h = None
+    if rank == 0:
+        print(json.dumps(dict(metric="real-time factor (audio-sec/wall-sec)", value=audio / wall, unit="RTFx", n_gpus=world, steps=a.steps,
+                              warmup=max(1, a.warmup), ms_per_step=1e3 * wall / a.steps, higher_is_better=True, scaling="weak",
+                              vs_baseline=None, dtype="f32", data="synthetic",
+                              config=dict(workload="streaming: " + wname, streams=B, seconds_per_stream=NUM_SAMPLES / 16000.0,
+                                          chunk_seconds=chunk / 16000.0, calls_per_utterance=n_calls, frames_per_chunk=fpc,
+                                          partial_hypotheses_every_call=bool(a.partials), ivectors="zeros",
+                                          api="b2k_stream_decode_batch_i16 (C ABI), 16-bit PCM chunks in host memory every call",
+                                          timing="wall clock around the calls (host-paced: every call copies its chunks from "
+                                                 "pageable host memory); device time in e2e.device_s"),
+                              e2e=dict(value=audio / wall, unit="RTFx", h2d_bytes_per_step=h2d // max(1, a.steps),
+                                       d2h_bytes_per_step=int(sum(v.nbytes for v in res[0]["lattices_packed"].values())),
+                                       lattice_states_per_step=int(len(res[0]["lattices_packed"]["state_frame"])),
+                                       device_s=t_dev, wall_s=wall),
+                              output_frames_per_stream=frames, channel_status=[i["status"] for i in infos], clocks=clocks)))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["decoder_sweep"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["decoder_sweep", "streaming"])
+    ap.add_argument("--partials", action="store_true", help="--workload streaming: ask for every stream's partial hypothesis after every call")
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU per step (0 = the workload's own)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts", type=int, default=6)
@@ -347,6 +425,8 @@ def main():
         return 0
     if a.workload == "decoder_sweep":
         return decoder_sweep(a, rank, world, local_rank)
+    if a.workload == "streaming":
+        return streaming_bench(a, rank, world, local_rank)
 
     import torch
     import torch.distributed as dist

@@ -129,7 +129,8 @@ class NativeStreamingDecoder:
     partial hypotheses and lattices come from the stream's decoder handle (b2k_dec_best_path, b2k_dec_get_raw_lattice)."""
 
     def __init__(self, model, fst: CudaFst, decoder_cfg: dict, nchannels: int, max_seconds: float = 30.0, frames_per_chunk: int = 51,
-                 feature_opts: FeatureOptions | None = None, acoustic_scale: float = 1.0, use_priors: bool = True):
+                 feature_opts: FeatureOptions | None = None, acoustic_scale: float = 1.0, use_priors: bool = True,
+                 decoder_kwargs: dict | None = None):
         import ctypes as C
         from dataclasses import fields
         from . import _lib
@@ -147,7 +148,7 @@ class NativeStreamingDecoder:
         L.b2k_stream_cfg_default.restype = None
         L.b2k_stream_cfg_default(C.byref(c))
         c.feat = _FeatCfg(**{f.name: getattr(fo, f.name) for f in fields(fo)})
-        dc = CudaDecoderConfig.from_dict(decoder_cfg)
+        dc = CudaDecoderConfig.from_dict(decoder_cfg, **(decoder_kwargs or {}))
         c.dec = _DecCfg(dc.default_beam, dc.lattice_beam, dc.max_active, dc.min_active, dc.beam_delta, dc.prune_interval,
                         dc.prune_scale, dc.max_tokens_per_frame, dc.max_frames, dc.max_tokens, dc.max_links,
                         int(dc.reference_order), dc.hash_ratio, dc.max_arcs_per_frame, dc.max_lattice_states, dc.max_lattice_arcs)
@@ -185,7 +186,10 @@ class NativeStreamingDecoder:
         except Exception:
             pass
 
-    def DecodeBatch(self, channels, wave_chunks_i16, is_first_chunk, is_last_chunk, want_partial: bool = True):
+    def DecodeBatch(self, channels, wave_chunks_i16, is_first_chunk, is_last_chunk, want_partial: bool = True,
+                    lattices: str = "each"):
+        """lattices: "each" = the raw lattice of every stream that ended in its result; "batched" = one packed read-back of all of
+        them (CudaDecoder.GetRawLattices) in the first result under "lattices_packed"; "none"."""
         C = self._C
         n = len(channels)
         keep = [np.ascontiguousarray(w, np.int16) for w in wave_chunks_i16]
@@ -206,9 +210,13 @@ class NativeStreamingDecoder:
                 if want_partial:
                     r["partial_words"] = partial[i]["olabels"][partial[i]["olabels"] != 0]
                     r["partial_cost"] = partial[i]["best_cost"]
-                if is_last_chunk[i]:
+                if is_last_chunk[i] and lattices == "each":
                     r["lattice"] = dec.GetRawLattice(int(channels[i]))
                 res.append(r)
+            done = [int(c) for c, l in zip(channels, is_last_chunk) if l]
+            if done and lattices == "batched":
+                res[0]["lattices_packed"] = dec.GetRawLattices(done)
+                res[0]["lattices_channels"] = done
             return res
         finally:
             self.dec.h = None
