@@ -502,7 +502,8 @@ int b2k_nnet_stream_account(int32_t left_context, int32_t right_context, int32_t
 /* looped = 0: one i-vector per window, BatchedStaticNnet3's computation.  looped = 1: the windows are the chunks of
  * DecodableNnetLoopedOnlineBase::AdvanceChunk (nnet3/decodable-online-looped.cc:118-236) and d_ivectors[i] holds
  * info[7] rows, the i-vectors chunks n-(rows-1) .. n received (b2k_nnet_compile_window); the caller feeds the frames the
- * looped schedule reads -- right_context frames in a channel's first call (no output), then frames_per_chunk per call,
+ * looped schedule reads -- first the right_context frames (no output yet; in pieces of at most frames_per_chunk when the right
+ * context is longer than a chunk, the first piece with is_first_chunk), then frames_per_chunk per call,
  * indices clamped to the frames that exist (:150-160) and no flush -- and every call's outputs are the looped
  * computation's for that chunk (kaldi_b200/host/b2k_nnet3_shims.h: DecodableNnetLoopedOnlineB2k). */
 int b2k_nnet_stream_create(const b2k_nnet_compile_cfg *cfg, const b2k_nnet_layer *layers, int32_t n_layers,

@@ -95,7 +95,8 @@ int b2k_nnet_stream_create(const b2k_nnet_compile_cfg *cfgp, const b2k_nnet_laye
   cfg.num_frames = 1; cfg.frames_per_chunk = sub;
   int rc = b2k_nnet_model_context(&cfg, layers, n_layers, &L, &R);
   if (rc) return rc;
-  if (fpc < R) return set_error(B2K_ERR_INVALID, "Please set --frames-per-chunk at least as large as the neural net right context");   // :172-175
+  // (the looped schedule has no such limit: its first right-context frames may arrive over several calls, none of which has output yet)
+  if (!looped && fpc < R) return set_error(B2K_ERR_INVALID, "Please set --frames-per-chunk at least as large as the neural net right context");   // :172-175
   const int opc = (sub - 1 + fpc) / sub, W = fpc + L + R;
   cfg.num_frames = W;
   int iv_rows = 1;

@@ -368,6 +368,7 @@ class StreamingOnlinePipelineB2k {
     Check(b2k_stream_info(s_, info), "b2k_stream_info");
     for (int32 c = (int32)info[0] - 1; c >= 0; c--) free_.push_back(c);
     frames_per_chunk_ = (int32)info[7];
+    path_cap_ = (int32)info[2];          // arcs of a best path <= output frames + epsilon arcs: well under the feature frames of a stream
     samples_per_chunk_ = (int32)(frames_per_chunk_ * config.feat.samp_freq * 0.001f * config.feat.frame_shift_ms);
     int32_t mi[8];
     Check(b2k_model_info(model, mi), "b2k_model_info");
@@ -423,7 +424,7 @@ class StreamingOnlinePipelineB2k {
     if (partial_hypotheses) partial_hypotheses->assign(n, nullptr);
     if (end_point) end_point->assign(n, false);
     if (want_text) {
-      const int32_t cap = 16384;
+      const int32_t cap = path_cap_;
       il_.resize(n * (size_t)cap); ol_.resize(n * (size_t)cap); info_.resize(n);
       Check(b2k_dec_best_path(dec, chans_.data(), (int32_t)n, /*use_final_probs=*/0, cap, il_.data(), ol_.data(), nullptr, nullptr,
                               nullptr, nullptr, info_.data(), cudaStreamPerThread), "b2k_dec_best_path");
@@ -475,7 +476,7 @@ class StreamingOnlinePipelineB2k {
  private:
   b2k_stream *s_ = NULL;
   const b2k_model *model_;
-  int32 frames_per_chunk_ = 0, samples_per_chunk_ = 0, num_tids_ = 0;
+  int32 frames_per_chunk_ = 0, samples_per_chunk_ = 0, num_tids_ = 0, path_cap_ = 4096;
   BaseFloat decoder_frame_shift_seconds_ = 0.03f;
   b2k_endpoint_cfg endpoint_;
   std::vector<int32> free_;

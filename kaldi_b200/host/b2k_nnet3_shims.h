@@ -383,16 +383,18 @@ class DecodableNnetLoopedOnlineBaseB2k : public DecodableInterface {
       d_iv_.Resize(ivector_rows_, ivector.Dim(), kUndefined, kStrideEqualNumCols);   // b2k reads the rows back to back
       d_iv_.CopyFromMat(rows);
     }
-    int32_t ch = 0, n_out = 0, n_eos = 0, zero = 0, one = 1;
+    int32_t ch = 0, n_out = 0, n_eos = 0, zero = 0;
     const float *ivp = info_.has_ivectors ? d_iv_.Data() : NULL;
-    if (num_chunks_computed_ == 0) {                                                   // the right context first: no output yet
-      Matrix<BaseFloat> f;
-      gather(0, R, &f);
-      if (R > 0) {
+    if (num_chunks_computed_ == 0) {                               // the right context first, a chunk's worth at a time: no output yet
+      for (int32 b = 0; b < R; b += C) {
+        Matrix<BaseFloat> f;
+        gather(b, std::min(b + C, R), &f);
         d_feats_.Resize(0, 0); d_feats_ = f;
-        const float *fp = d_feats_.Data(); int32_t nv = R;
-        CheckNnet3(b2k_nnet_stream_run_batch(s_, 1, &ch, &fp, d_feats_.Stride(), info_.has_ivectors ? &ivp : NULL, &nv, &one, &zero,
+        const float *fp = d_feats_.Data(); int32_t nv = f.NumRows();
+        const int32_t is_first = b == 0 ? 1 : 0;
+        CheckNnet3(b2k_nnet_stream_run_batch(s_, 1, &ch, &fp, d_feats_.Stride(), info_.has_ivectors ? &ivp : NULL, &nv, &is_first, &zero,
                                              d_out_.Data(), NULL, d_out_.Stride(), &n_out, &n_eos, cudaStreamPerThread), "b2k_nnet_stream_run_batch");
+        KALDI_ASSERT(n_out == 0);
       }
     }
     Matrix<BaseFloat> f;

@@ -217,10 +217,12 @@ def test_device_looped_stream_reproduces_the_whole_utterance_run(which, T):
     assert k1 == NC.looped_ivector_rows(arch, C) and opc == C // 3
     d_out = torch.zeros(opc, P, device="cuda")
     outs = []
-    first = torch.from_numpy(feats[np.clip(np.arange(0, Rc), 0, T - 1)]).cuda()
     zeros_iv = torch.zeros(k1, 100, device="cuda")
-    no, ne = nn.RunBatch([0], [first.data_ptr()], arch["feat_dim"], [zeros_iv.data_ptr()], [Rc], [True], [False], d_out.data_ptr(), 0, P)
-    assert no == [0] and ne == [0]
+    for b in range(0, Rc, C):            # the right-context frames first (in pieces of at most a chunk): no output yet
+        piece = torch.from_numpy(feats[np.clip(np.arange(b, min(b + C, Rc)), 0, T - 1)]).cuda()
+        no, ne = nn.RunBatch([0], [piece.data_ptr()], arch["feat_dim"], [zeros_iv.data_ptr()], [piece.shape[0]], [b == 0], [False],
+                             d_out.data_ptr(), 0, P)
+        assert no == [0] and ne == [0]
     for n, win, ivr, keep in _looped_windows(arch, feats, chunk_iv, C, L, Rc, k1):
         new = torch.from_numpy(np.ascontiguousarray(win[L + Rc:])).cuda()          # the C frames this chunk adds
         d_iv = torch.from_numpy(ivr).cuda()

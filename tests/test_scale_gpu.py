@@ -111,9 +111,10 @@ def test_full_width_looped_stream_vs_compiled_reference():
     L, Rc, k1, opc, P = nn.left_context, nn.right_context, nn.ivector_rows, nn.output_frames_per_chunk, nn.output_dim
     assert (L, Rc) == (R.left_context, R.right_context)
     d_out = torch.zeros(opc, P, device="cuda")
-    first = torch.from_numpy(feats[np.clip(np.arange(0, Rc), 0, T - 1)]).cuda()
     z = torch.zeros(k1, 100, device="cuda")
-    assert nn.RunBatch([0], [first.data_ptr()], 40, [z.data_ptr()], [Rc], [True], [False], d_out.data_ptr(), 0, P) == ([0], [0])
+    for b in range(0, Rc, C):            # the right context (40 frames) is longer than a chunk (21): it arrives in two calls
+        piece = torch.from_numpy(feats[np.clip(np.arange(b, min(b + C, Rc)), 0, T - 1)]).cuda()
+        assert nn.RunBatch([0], [piece.data_ptr()], 40, [z.data_ptr()], [piece.shape[0]], [b == 0], [False], d_out.data_ptr(), 0, P) == ([0], [0])
     outs = []
     for n, win, ivr, keep in _looped_windows(arch, feats, civ, C, L, Rc, k1):
         new = torch.from_numpy(np.ascontiguousarray(win[L + Rc:])).cuda()
