@@ -580,10 +580,11 @@ int b2k_ivec_cfg_from_conf(const char *conf_path, b2k_ivec_cfg *cfg, b2k_ivec_pa
  * groups the tool registers (--endpoint.*, --ivector-silence-weighting.*, decoder and decodable options) are passed
  * through in `rest`, one per line. */
 typedef struct {
-  int32_t feature_type;               /* 0 mfcc, 1 fbank ("plp" is rejected) */
+  int32_t feature_type;               /* 0 mfcc, 1 fbank, 2 plp              */
   int32_t add_pitch;                  /* must be false                       */
   char mfcc_config[512], fbank_config[512], cmvn_config[512], global_cmvn_stats[512], ivector_extraction_config[512];
   char rest[4096];
+  char plp_config[512];
 } b2k_online_conf;
 int b2k_online_conf_read(const char *conf_path, b2k_online_conf *out);
 

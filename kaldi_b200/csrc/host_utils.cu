@@ -162,13 +162,15 @@ static void apply(const char *path, const std::map<std::string, std::pair<std::s
 extern "C" {
 
 int b2k_feat_cfg_from_conf(const char *conf_path, int32_t feature_type, b2k_feat_cfg *cfg) {
-  if (!conf_path || !cfg || (feature_type != 0 && feature_type != 1)) return b2k::set_error(B2K_ERR_INVALID, "b2k_feat_cfg_from_conf: bad args");
-  // the reference's own defaults (NOT mfcc_hires.conf): MfccOptions() / FbankOptions(), FrameExtractionOptions(), MelBanksOptions(23)
+  if (!conf_path || !cfg || feature_type < 0 || feature_type > 2) return b2k::set_error(B2K_ERR_INVALID, "b2k_feat_cfg_from_conf: bad args");
+  // the reference's own defaults (NOT mfcc_hires.conf): MfccOptions() / FbankOptions() / PlpOptions(), FrameExtractionOptions(), MelBanksOptions(23)
   b2k_feat_cfg c;
   memset(&c, 0, sizeof(c));
   c.feature_type = feature_type; c.samp_freq = 16000.f; c.frame_shift_ms = 10.f; c.frame_length_ms = 25.f; c.dither = 1.0f;
   c.preemph_coeff = 0.97f; c.remove_dc_offset = 1; c.round_to_power_of_two = 1; c.snip_edges = 1; c.window_type = 0;
-  c.num_bins = 23; c.low_freq = 20.f; c.high_freq = 0.f; c.num_ceps = 13; c.use_energy = feature_type == 0 ? 1 : 0;
+  c.num_bins = 23; c.low_freq = 20.f; c.high_freq = 0.f; c.num_ceps = 13; c.use_energy = feature_type != 1 ? 1 : 0;
+  c.lpc_order = 12; c.compress_factor = 0.33333f; c.cepstral_scale = 1.0f;       // PlpOptions (feat/feature-plp.h:55-66)
+  int32_t plp_lifter = 22;                                                         // PlpOptions::cepstral_lifter is an int32
   c.energy_floor = 0.f; c.raw_energy = 1; c.cepstral_lifter = 22.f; c.htk_compat = 0; c.use_log_fbank = 1; c.use_power = 1; c.htk_mode = 0;
   c.max_lanes = cfg->max_lanes > 0 ? cfg->max_lanes : 1024;
   char window[512] = "povey";
@@ -183,12 +185,16 @@ int b2k_feat_cfg_from_conf(const char *conf_path, int32_t feature_type, b2k_feat
       {"vtln-low", 'f', &vtln_low}, {"vtln-high", 'f', &vtln_high}, {"debug-mel", 'b', &debug_mel},
       {"use-energy", 'b', &c.use_energy}, {"energy-floor", 'f', &c.energy_floor}, {"raw-energy", 'b', &c.raw_energy}, {"htk-compat", 'b', &c.htk_compat}};
   if (feature_type == 0) { o.push_back({"num-ceps", 'i', &c.num_ceps}); o.push_back({"cepstral-lifter", 'f', &c.cepstral_lifter}); }
-  else { o.push_back({"use-log-fbank", 'b', &c.use_log_fbank}); o.push_back({"use-power", 'b', &c.use_power}); }
+  else if (feature_type == 2) {                                                    // PlpOptions::Register (feature-plp.h:68-90)
+    o.push_back({"lpc-order", 'i', &c.lpc_order}); o.push_back({"num-ceps", 'i', &c.num_ceps}); o.push_back({"compress-factor", 'f', &c.compress_factor});
+    o.push_back({"cepstral-lifter", 'i', &plp_lifter}); o.push_back({"cepstral-scale", 'f', &c.cepstral_scale});
+  } else { o.push_back({"use-log-fbank", 'b', &c.use_log_fbank}); o.push_back({"use-power", 'b', &c.use_power}); }
   try {
     apply(conf_path, read_conf(conf_path), o.data(), o.size());
     const std::string w = window;
     c.window_type = w == "povey" ? 0 : w == "hamming" ? 1 : w == "hanning" ? 2 : w == "rectangular" ? 3 : -1;
     if (c.window_type < 0) throw ConfError{"window type " + w + " is not supported (povey, hamming, hanning, rectangular)"};
+    if (feature_type == 2) c.cepstral_lifter = (float)plp_lifter;
   } catch (const ConfError &e) {
     return b2k::set_error(B2K_ERR_INVALID, "b2k_feat_cfg_from_conf", e.msg.c_str());
   }
@@ -246,8 +252,8 @@ int b2k_online_conf_read(const char *conf_path, b2k_online_conf *out) {
   if (!conf_path || !out) return b2k::set_error(B2K_ERR_INVALID, "b2k_online_conf_read: bad args");
   b2k_online_conf c;
   memset(&c, 0, sizeof(c));
-  char feature_type[512] = "mfcc", plp_config[512] = "", pitch_config[512] = "";
-  const Opt opts[] = {{"feature-type", 's', feature_type}, {"mfcc-config", 's', c.mfcc_config}, {"plp-config", 's', plp_config},
+  char feature_type[512] = "mfcc", pitch_config[512] = "";
+  const Opt opts[] = {{"feature-type", 's', feature_type}, {"mfcc-config", 's', c.mfcc_config}, {"plp-config", 's', c.plp_config},
                       {"fbank-config", 's', c.fbank_config}, {"cmvn-config", 's', c.cmvn_config}, {"global-cmvn-stats", 's', c.global_cmvn_stats},
                       {"add-pitch", 'b', &c.add_pitch}, {"online-pitch-config", 's', pitch_config},
                       {"ivector-extraction-config", 's', c.ivector_extraction_config}};
@@ -263,8 +269,8 @@ int b2k_online_conf_read(const char *conf_path, b2k_online_conf *out) {
     }
     apply(conf_path, mine, opts, sizeof(opts) / sizeof(opts[0]));
     const std::string ft = feature_type;
-    c.feature_type = ft == "mfcc" ? 0 : ft == "fbank" ? 1 : -1;
-    if (c.feature_type < 0) throw ConfError{"feature type " + ft + " is not supported (mfcc, fbank)"};     // "plp": SURVEY section 8(f) row 4
+    c.feature_type = ft == "mfcc" ? 0 : ft == "fbank" ? 1 : ft == "plp" ? 2 : -1;
+    if (c.feature_type < 0) throw ConfError{"Invalid feature type: " + ft + " (expected mfcc, plp or fbank)"};     // online-nnet2-feature-pipeline.cc:49-52
     if (c.add_pitch) throw ConfError{"--add-pitch=true is not supported"};
     if (rest.size() >= sizeof(c.rest)) throw ConfError{"too many other options in the file"};
     memcpy(c.rest, rest.c_str(), rest.size() + 1);

@@ -154,6 +154,21 @@ int ref_feat_opts_from_conf(const char *path, int feature_type, float *out, char
     kaldi::ParseOptions po("");
     kaldi::MfccOptions m;
     kaldi::FbankOptions f;
+    if (feature_type == 2) {          // PlpOptions: the same slots, then lpc_order, compress_factor, cepstral_scale
+      kaldi::PlpOptions q;
+      q.Register(&po);
+      po.ReadConfigFile(path);
+      const kaldi::FrameExtractionOptions &fr = q.frame_opts;
+      int i = 0;
+      out[i++] = fr.samp_freq; out[i++] = fr.frame_shift_ms; out[i++] = fr.frame_length_ms; out[i++] = fr.dither; out[i++] = fr.preemph_coeff;
+      out[i++] = fr.remove_dc_offset; out[i++] = fr.round_to_power_of_two; out[i++] = fr.snip_edges;
+      out[i++] = q.mel_opts.num_bins; out[i++] = q.mel_opts.low_freq; out[i++] = q.mel_opts.high_freq;
+      out[i++] = q.num_ceps; out[i++] = q.use_energy; out[i++] = q.energy_floor; out[i++] = q.raw_energy; out[i++] = q.cepstral_lifter;
+      out[i++] = q.htk_compat; out[i++] = 1; out[i++] = 1;
+      out[i++] = q.lpc_order; out[i++] = q.compress_factor; out[i++] = q.cepstral_scale;
+      snprintf(window, window_cap, "%s", fr.window_type.c_str());
+      return 0;
+    }
     if (feature_type == 0) m.Register(&po); else f.Register(&po);
     po.ReadConfigFile(path);
     const kaldi::FrameExtractionOptions &fr = feature_type == 0 ? m.frame_opts : f.frame_opts;

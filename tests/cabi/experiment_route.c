@@ -20,7 +20,7 @@ int main(int argc, char **argv) {
   b2k_pipeline_cfg cfg;
   b2k_pipeline_cfg_default(&cfg);
   cfg.feat.max_lanes = 1;
-  CHECK(b2k_feat_cfg_from_conf(oc.feature_type == 0 ? oc.mfcc_config : oc.fbank_config, oc.feature_type, &cfg.feat));
+  CHECK(b2k_feat_cfg_from_conf(oc.feature_type == 0 ? oc.mfcc_config : oc.feature_type == 1 ? oc.fbank_config : oc.plp_config, oc.feature_type, &cfg.feat));
   CHECK(b2k_pipeline_cfg_apply_options(oc.rest, &cfg));   /* --beam, --lattice-beam, --acoustic-scale ... if the file carries them */
   cfg.feat.dither = 0.0f;                         /* the reference's dither is unseeded: results are defined only without it */
   b2k_endpoint_cfg ep;                            /* the --endpoint.* group of the same file (online2-wav-nnet3-latgen-faster.cc:128) */

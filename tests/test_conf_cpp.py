@@ -85,6 +85,29 @@ def test_feature_options_equal_the_references_parse(tmp_path, text, feature_type
     assert c.window_type == WINDOWS[win] and c.feature_type == feature_type
 
 
+PLP = "--lpc-order=10\n--num-ceps=9\n--compress-factor=0.25\n--cepstral-lifter=20\n--cepstral-scale=2.5\n--use-energy=false\n--num-mel-bins=21\n--dither=0\n"
+
+
+@pytest.mark.parametrize("text", [PLP, "", ODD], ids=["plp", "defaults-plp", "odd-plp"])
+def test_plp_options_equal_the_references_parse(tmp_path, text):
+    """PlpOptions::Register (feat/feature-plp.h:68-90): the option file of --plp-config through b2k_feat_cfg_from_conf(…, 2, …)
+    and through the reference's own ParseOptions."""
+    L = _lib()
+    p = str(tmp_path / "plp.conf")
+    open(p, "w").write(text)
+    rc, c = _mine(L, p, 2)
+    rrc, ref, win = _reference(p, 2)
+    assert rc == 0 and rrc == 0
+    for i, k in enumerate(FIELDS + ["lpc_order", "compress_factor", "cepstral_scale"]):
+        if k in ("use_log_fbank", "use_power"):
+            continue
+        assert float(getattr(c, k)) == pytest.approx(ref[i], abs=1e-6), k
+    assert c.window_type == WINDOWS[win] and c.feature_type == 2
+    for bad in ("--cepstral-lifter=22.5\n", "--use-power=true\n", "--lpc-order=twelve\n"):      # an int32 option; an fbank option; not a number
+        open(p, "w").write(bad)
+        assert _mine(L, p, 2)[0] != 0 and _reference(p, 2)[0] != 0
+
+
 @pytest.mark.parametrize("text", ["--no-such-option=3\n", "num-ceps=13\n", "--frame-length = 20\n", "--num-ceps=thirteen\n", "--use-energy=maybe\n",
                                   "--use-log-fbank=true\n", "--htk-compat=\n", "--dither=0x10\n", "--dither=1e400\n", "--num-ceps=2147483648\n",
                                   "--num-ceps=3.0\n", "--dither=1.0f\n", "--frame-shift=\n"])
@@ -206,7 +229,7 @@ def test_ivector_option_names_are_the_ones_the_reference_registers():
 class _OnlineConf(C.Structure):
     _fields_ = [("feature_type", C.c_int32), ("add_pitch", C.c_int32)] + \
                [(k, C.c_char * 512) for k in ("mfcc_config", "fbank_config", "cmvn_config", "global_cmvn_stats", "ivector_extraction_config")] + \
-               [("rest", C.c_char * 4096)]
+               [("rest", C.c_char * 4096), ("plp_config", C.c_char * 512)]
 
 
 def test_online_conf_as_prepare_online_decoding_writes_it(tmp_path):
@@ -220,7 +243,9 @@ def test_online_conf_as_prepare_online_decoding_writes_it(tmp_path):
     assert c.feature_type == 0 and c.mfcc_config.decode() == "/exp/conf/mfcc.conf"
     assert c.ivector_extraction_config.decode() == "/exp/conf/ivector_extractor.conf"
     assert sorted(c.rest.decode().split()) == ["--endpoint.rule1.min-trailing-silence=0.5", "--endpoint.silence-phones=1:2:3:4:5"]
-    open(p, "w").write("--feature-type=plp\n")
+    open(p, "w").write("--feature-type=plp\n--plp-config=/exp/conf/plp.conf\n")
+    assert L.b2k_online_conf_read(p.encode(), C.byref(c)) == 0 and c.feature_type == 2 and c.plp_config.decode() == "/exp/conf/plp.conf"
+    open(p, "w").write("--feature-type=spectrogram\n")
     assert L.b2k_online_conf_read(p.encode(), C.byref(c)) != 0
     open(p, "w").write("--feature-type=fbank\n--add-pitch=true\n")
     assert L.b2k_online_conf_read(p.encode(), C.byref(c)) != 0

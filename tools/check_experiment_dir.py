@@ -29,7 +29,7 @@ def check(exp_dir: str, hclg: str, seconds: float = 10.0, batch: int = 64) -> di
     class OnlineConf(C.Structure):
         _fields_ = [("feature_type", C.c_int32), ("add_pitch", C.c_int32)] + \
                    [(k, C.c_char * 512) for k in ("mfcc_config", "fbank_config", "cmvn_config", "global_cmvn_stats", "ivector_extraction_config")] + \
-                   [("rest", C.c_char * 4096)]
+                   [("rest", C.c_char * 4096), ("plp_config", C.c_char * 512)]
 
     class IvecCfg(C.Structure):
         _fields_ = [(k, C.c_int32) for k in ("base_dim", "splice_left", "splice_right", "feat_dim", "num_gauss", "ivector_dim", "num_gselect")] + \
@@ -43,10 +43,10 @@ def check(exp_dir: str, hclg: str, seconds: float = 10.0, batch: int = 64) -> di
     oc = OnlineConf()
     L.b2k_online_conf_read.argtypes = [C.c_char_p, C.c_void_p]
     _lib.check(L.b2k_online_conf_read(os.path.join(exp_dir, "conf", "online.conf").encode(), C.byref(oc)))
-    out["feature_type"] = ["mfcc", "fbank"][oc.feature_type]
+    out["feature_type"] = ["mfcc", "fbank", "plp"][oc.feature_type]
     out["other_options"] = oc.rest.decode().split()
     fc = _FeatCfg()
-    conf = (oc.mfcc_config if oc.feature_type == 0 else oc.fbank_config).decode()
+    conf = (oc.mfcc_config if oc.feature_type == 0 else oc.fbank_config if oc.feature_type == 1 else oc.plp_config).decode()
     L.b2k_feat_cfg_from_conf.argtypes = [C.c_char_p, C.c_int32, C.c_void_p]
     _lib.check(L.b2k_feat_cfg_from_conf(conf.encode(), oc.feature_type, C.byref(fc)))
     feat_dim = fc.num_ceps if oc.feature_type == 0 else fc.num_bins + (1 if fc.use_energy else 0)
