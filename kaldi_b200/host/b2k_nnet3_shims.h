@@ -3,6 +3,8 @@
 //   nnet3::NnetComputer {AcceptInput, Run, GetOutput, GetOutputDestructive}            nnet3/nnet-compute.h:88-200
 //   nnet3::DecodableNnetLoopedOnline / DecodableAmNnetLoopedOnline                     nnet3/decodable-online-looped.h:49-196
 //   cuda_decoder::BatchedStaticNnet3 {RunBatch, FormatOutputPtrs, Get*}                cudadecoder/batched-static-nnet3.h:59-138
+//   SingleUtteranceNnet3Decoder {AdvanceDecoding, FinalizeDecoding, EndpointDetected, GetBestPath, GetLattice}
+//                                                                                       online2/online-nnet3-decoding.h:50-121
 //
 // The model goes from the reference's objects to libb2k.so through the reference's own serialisation
 // (Nnet::Write / AmNnetSimple::Write into memory -> b2k_model_read_memory), so no component walker has to track
@@ -21,6 +23,7 @@
 #include <vector>
 
 #include "b2k.h"
+#include "b2k_kaldi_shims.h"
 #include "base/kaldi-error.h"
 #include "cudamatrix/cu-device.h"
 #include "cudamatrix/cu-matrix.h"
@@ -347,6 +350,17 @@ class DecodableNnetLoopedOnlineBaseB2k : public DecodableInterface {
   }
   int32 GetFrameOffset() const { return frame_offset_; }
 
+  // For a decoder that reads the log-likelihoods where they are: the device rows of `subsampled_frame` and of the frames after
+  // it in the same chunk (priors and acoustic scale applied), `*num_frames` of them, row stride `*stride` floats.
+  const BaseFloat *DeviceFrames(int32 subsampled_frame, int32 *num_frames, int32 *stride) {
+    subsampled_frame += frame_offset_;
+    EnsureFrameIsComputed(subsampled_frame);
+    const int32 row = subsampled_frame - current_log_post_subsampled_offset_;
+    *num_frames = d_log_post_.NumRows() - row;
+    *stride = d_log_post_.Stride();
+    return d_log_post_.Data() + static_cast<size_t>(row) * d_log_post_.Stride();
+  }
+
  protected:
   inline void EnsureFrameIsComputed(int32 subsampled_frame) {
     KALDI_ASSERT(subsampled_frame >= current_log_post_subsampled_offset_ && "Frames must be accessed in order.");
@@ -406,12 +420,12 @@ class DecodableNnetLoopedOnlineBaseB2k : public DecodableInterface {
                                          d_out_.Data(), NULL, d_out_.Stride(), &n_out, &n_eos, cudaStreamPerThread), "b2k_nnet_stream_run_batch");
     if (cudaStreamSynchronize(cudaStreamPerThread) != cudaSuccess) KALDI_ERR << "cudaStreamSynchronize failed";
     KALDI_ASSERT(n_out == d_out_.NumRows());
-    {                                                                                  // :206-230
-      CuMatrix<BaseFloat> output(d_out_);
-      if (info_.log_priors.Dim() != 0) output.AddVecToRows(-1.0, info_.log_priors);
-      output.Scale(info_.opts.acoustic_scale);
-      current_log_post_.Resize(0, 0);
-      current_log_post_.Swap(&output);
+    {                                                                                  // :206-230; the chunk stays on the device too
+      d_log_post_ = d_out_;
+      if (info_.log_priors.Dim() != 0) d_log_post_.AddVecToRows(-1.0, info_.log_priors);
+      d_log_post_.Scale(info_.opts.acoustic_scale);
+      current_log_post_.Resize(d_log_post_.NumRows(), d_log_post_.NumCols(), kUndefined);
+      d_log_post_.CopyToMat(&current_log_post_);
     }
     KALDI_ASSERT(current_log_post_.NumRows() == info_.frames_per_chunk / info_.opts.frame_subsampling_factor &&
                  current_log_post_.NumCols() == info_.output_dim);
@@ -432,7 +446,7 @@ class DecodableNnetLoopedOnlineBaseB2k : public DecodableInterface {
   b2k_nnet_stream *s_ = NULL;
   int32 ivector_rows_ = 1;
   std::vector<Vector<BaseFloat> > chunk_ivectors_;
-  CuMatrix<BaseFloat> d_feats_, d_iv_, d_out_;
+  CuMatrix<BaseFloat> d_feats_, d_iv_, d_out_, d_log_post_;
   KALDI_DISALLOW_COPY_AND_ASSIGN(DecodableNnetLoopedOnlineBaseB2k);
 };
 
@@ -465,6 +479,137 @@ class DecodableAmNnetLoopedOnlineB2k : public DecodableNnetLoopedOnlineBaseB2k {
 
  private:
   const TransitionModel &trans_model_;
+};
+
+// SingleUtteranceNnet3DecoderTpl (online2/online-nnet3-decoding.h:50-121), the object online2-wav-nnet3-latgen-faster drives:
+//   feature_pipeline.AcceptWaveform(...); decoder.AdvanceDecoding(); if (decoder.EndpointDetected(endpoint_opts)) break; ...
+//   decoder.FinalizeDecoding(); decoder.GetLattice(true, &clat);
+// The decodable is DecodableAmNnetLoopedOnlineB2k (its chunks stay on the device), the decoder one lane of b2k_dec.
+//   DecoderConfig  = LatticeFasterDecoderConfig (decoder/lattice-faster-decoder.h:39-99; a template parameter because that
+//                    header needs OpenFst)
+//   Features       = OnlineNnet2FeaturePipeline or OnlineNnet2FeaturePipelineB2k: InputFeature(), IvectorFeature(),
+//                    FrameShiftInSeconds()
+//   graph          = CudaFstB2k(decode_fst, &trans_model).Handle()  (b2k_kaldi_shims.h)
+template <class DecoderConfig, class Features>
+class SingleUtteranceNnet3DecoderB2k {
+ public:
+  SingleUtteranceNnet3DecoderB2k(const DecoderConfig &decoder_opts, const TransitionModel &trans_model,
+                                 const nnet3::DecodableNnetSimpleLoopedInfo &info, const b2k_fst *fst, Features *features,
+                                 int32 max_frames = 4096)
+      : decoder_opts_(decoder_opts),
+        input_feature_frame_shift_in_seconds_(features->FrameShiftInSeconds()),
+        trans_model_(trans_model),
+        decodable_(trans_model, info, features->InputFeature(), features->IvectorFeature()) {
+    b2k_dec_cfg c;
+    b2k_dec_cfg_default(&c);
+    c.beam = decoder_opts.beam; c.lattice_beam = decoder_opts.lattice_beam; c.max_active = decoder_opts.max_active;
+    c.min_active = decoder_opts.min_active; c.beam_delta = decoder_opts.beam_delta; c.prune_interval = decoder_opts.prune_interval;
+    c.prune_scale = decoder_opts.prune_scale; c.hash_ratio = decoder_opts.hash_ratio; c.max_frames = max_frames;
+    CheckNnet3(b2k_dec_create(fst, &c, 1, 1, &dec_), "b2k_dec_create");
+    InitDecoding();
+  }
+  ~SingleUtteranceNnet3DecoderB2k() { b2k_dec_destroy(dec_); }
+
+  void InitDecoding(int32 frame_offset = 0) {                                          // online-nnet3-decoding.cc:39-43
+    const int32_t ch = 0;
+    CheckNnet3(b2k_dec_init_decoding(dec_, &ch, 1, cudaStreamPerThread), "InitDecoding");
+    frames_decoded_ = 0;
+    decodable_.SetFrameOffset(frame_offset);
+  }
+  void AdvanceDecoding() {                                                             // :46-48: every frame that is ready
+    const int32_t ch = 0;
+    while (frames_decoded_ < decodable_.NumFramesReady()) {
+      int32 in_chunk = 0, stride = 0;
+      const float *rows = decodable_.DeviceFrames(frames_decoded_, &in_chunk, &stride);
+      int32_t n = std::min(in_chunk, decodable_.NumFramesReady() - frames_decoded_);
+      CheckNnet3(b2k_dec_advance_decoding_frames(dec_, &ch, &rows, &n, stride, 1, cudaStreamPerThread), "AdvanceDecoding");
+      frames_decoded_ += n;
+    }
+  }
+  void FinalizeDecoding() {                                                            // :51-53
+    const int32_t ch = 0;
+    CheckNnet3(b2k_dec_finalize_decoding(dec_, &ch, 1, cudaStreamPerThread), "FinalizeDecoding");
+  }
+  int32 NumFramesDecoded() const { return frames_decoded_; }
+
+  // EndpointDetected(config, trans_model, frame_shift, decoder) (online-endpoint.cc:116-135) on the LIVE best path
+  template <class EndpointConfig>
+  bool EndpointDetected(const EndpointConfig &config) {                                // :85-92
+    if (frames_decoded_ == 0) return false;
+    std::vector<int32> ilabels;
+    b2k_best_path_info bp;
+    BestPath(false, &ilabels, NULL, NULL, NULL, &bp);
+    const BaseFloat frame_shift = input_feature_frame_shift_in_seconds_ * decodable_.FrameSubsamplingFactor();
+    return EndpointDetectedB2k(config, trans_model_, frame_shift, ilabels, bp.num_frames, bp.final_relative_cost);
+  }
+  BaseFloat FinalRelativeCost() {
+    b2k_best_path_info bp;
+    BestPath(false, NULL, NULL, NULL, NULL, &bp);
+    return bp.final_relative_cost;
+  }
+  // the best path as arrays (what GetBestPath builds its linear lattice from)
+  void BestPath(bool use_final_probs, std::vector<int32> *ilabels, std::vector<int32> *olabels, std::vector<BaseFloat> *graph_costs,
+                std::vector<BaseFloat> *acoustic_costs, b2k_best_path_info *info) {
+    const int32_t ch = 0, cap = 3 * std::max(1, frames_decoded_) + 64;
+    std::vector<int32_t> il(cap), ol(cap);
+    std::vector<float> g(cap), a(cap);
+    CheckNnet3(b2k_dec_best_path(dec_, &ch, 1, use_final_probs ? 1 : 0, cap, il.data(), ol.data(), g.data(), a.data(), NULL, NULL, info,
+                                 cudaStreamPerThread), "b2k_dec_best_path");
+    const int32 n = info->n_arcs;
+    if (ilabels) ilabels->assign(il.begin(), il.begin() + n);
+    if (olabels) olabels->assign(ol.begin(), ol.begin() + n);
+    if (graph_costs) graph_costs->assign(g.begin(), g.begin() + n);
+    if (acoustic_costs) acoustic_costs->assign(a.begin(), a.begin() + n);
+  }
+
+#ifdef B2K_HAVE_OPENFST
+  // GetBestPath(end_of_utterance, Lattice*) (:78-82): LatticeFasterOnlineDecoderTpl::GetBestPath's linear lattice
+  // (lattice-faster-online-decoder.cc:54-75)
+  void GetBestPath(bool end_of_utterance, Lattice *best_path) {
+    std::vector<int32> il, ol;
+    std::vector<BaseFloat> g, a;
+    b2k_best_path_info bp;
+    BestPath(end_of_utterance, &il, &ol, &g, &a, &bp);
+    best_path->DeleteStates();
+    if (bp.end_state < 0) return;
+    for (size_t k = 0; k <= il.size(); k++) best_path->AddState();
+    best_path->SetStart(0);
+    for (size_t k = 0; k < il.size(); k++)
+      best_path->AddArc(static_cast<int32>(k), LatticeArc(il[k], ol[k], LatticeWeight(g[k], a[k]), static_cast<int32>(k + 1)));
+    best_path->SetFinal(static_cast<int32>(il.size()), LatticeWeight(bp.final_cost, 0.0));
+  }
+#if !defined(B2K_OPENFST_IS_STANDIN)
+  // GetLattice(end_of_utterance, CompactLattice*) (:56-75): raw lattice + pruned determinization at lattice_beam.  The raw
+  // lattice of this decoder exists after FinalizeDecoding (final probabilities applied): end_of_utterance must be true.
+  void GetLattice(bool end_of_utterance, CompactLattice *clat) {
+    if (NumFramesDecoded() == 0) KALDI_ERR << "You cannot get a lattice if you decoded no frames.";
+    if (!end_of_utterance) KALDI_ERR << "b2k: the lattice is available at the end of the utterance (use GetBestPath for partial results)";
+    if (!decoder_opts_.determinize_lattice) KALDI_ERR << "--determinize-lattice=false option is not supported at the moment";
+    FinalizeDecoding();
+    b2k_raw_lattice r = {};
+    CheckNnet3(b2k_dec_get_raw_lattice(dec_, 0, &r, cudaStreamPerThread), "GetRawLattice(size)");
+    std::vector<int32> sf(r.num_states), sh(r.num_states), as(r.num_arcs), ad(r.num_arcs), ai(r.num_arcs), ao(r.num_arcs), fs(r.num_finals);
+    std::vector<float> st(r.num_states), se(r.num_states), ag(r.num_arcs), aa(r.num_arcs), fc(r.num_finals);
+    r.state_frame = sf.data(); r.state_hclg = sh.data(); r.state_tot_cost = st.data(); r.state_extra_cost = se.data();
+    r.arc_src = as.data(); r.arc_dst = ad.data(); r.arc_ilabel = ai.data(); r.arc_olabel = ao.data();
+    r.arc_graph_cost = ag.data(); r.arc_acoustic_cost = aa.data(); r.final_state = fs.data(); r.final_cost = fc.data();
+    CheckNnet3(b2k_dec_get_raw_lattice(dec_, 0, &r, cudaStreamPerThread), "GetRawLattice");
+    b2k_clat *c = NULL;
+    CheckNnet3(b2k_lat_determinize_pruned(&r, decoder_opts_.lattice_beam, 0, &c), "b2k_lat_determinize_pruned");
+    BatchedOnlinePipelineB2k::FillCompactLattice(c, clat);
+    b2k_clat_destroy(c);
+  }
+#endif
+#endif
+
+ private:
+  const DecoderConfig &decoder_opts_;
+  BaseFloat input_feature_frame_shift_in_seconds_;
+  const TransitionModel &trans_model_;
+  DecodableAmNnetLoopedOnlineB2k decodable_;
+  b2k_dec *dec_ = NULL;
+  int32 frames_decoded_ = 0;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(SingleUtteranceNnet3DecoderB2k);
 };
 
 }  // namespace b2k_shim

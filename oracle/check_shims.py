@@ -116,6 +116,28 @@ def check() -> bool:
         subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=0"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"),
                               "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include",
                               "-I" + os.path.join(ROOT, "oracle", "_ref", "inc")]) + [o2])
+        # SingleUtteranceNnet3DecoderB2k with the reference's OWN LatticeFasterDecoderConfig (decoder/lattice-faster-decoder.h, compiled
+        # against the container-only OpenFst stand-in as the decoder oracle is) and OnlineEndpointConfig: the calls of
+        # online2bin/online2-wav-nnet3-latgen-faster.cc:246-283
+        su = os.path.join(td, "u.cc")
+        open(su, "w").write(
+            '#include "decoder/lattice-faster-decoder.h"\n'
+            "#define KALDI_DECODER_LATTICE_FASTER_ONLINE_DECODER_H_\n#define KALDI_DECODER_LATTICE_INCREMENTAL_ONLINE_DECODER_H_\n"
+            '#include "online2/online-endpoint.h"\n#include "b2k_nnet3_shims.h"\n'
+            "using namespace kaldi;\n"
+            "struct Feats { OnlineFeatureInterface *InputFeature(); OnlineFeatureInterface *IvectorFeature(); BaseFloat FrameShiftInSeconds() const; };\n"
+            "void f(const LatticeFasterDecoderConfig &opts, const TransitionModel &tm, const nnet3::DecodableNnetSimpleLoopedInfo &info,\n"
+            "       const b2k_fst *g, Feats *feats, const OnlineEndpointConfig &ep) {\n"
+            "  b2k_shim::SingleUtteranceNnet3DecoderB2k<LatticeFasterDecoderConfig, Feats> d(opts, tm, info, g, feats);\n"
+            "  d.InitDecoding(0); d.AdvanceDecoding(); bool e = d.EndpointDetected(ep); (void)e; d.FinalizeDecoding();\n"
+            "  int32 n = d.NumFramesDecoded(); (void)n; BaseFloat c = d.FinalRelativeCost(); (void)c;\n"
+            "  Lattice best; d.GetBestPath(true, &best);\n"
+            "}\n")
+        stub = os.path.join(ROOT, "oracle", "ref_wrap", "fst_stub")
+        flags = RF.cxxflags(["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "kaldi_b200", "host"),
+                             "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "oracle", "_ref", "inc")])
+        flags = [f for f in flags if not f.startswith("-I")] + ["-I" + stub] + [f for f in flags if f.startswith("-I")]
+        subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1", "-DB2K_HAVE_OPENFST", "-DB2K_OPENFST_IS_STANDIN"] + flags + [su])
     return True
 
 
