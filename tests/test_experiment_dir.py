@@ -129,3 +129,34 @@ def test_c99_program_drives_the_directory_through_the_abi(tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
     else:
         assert r.returncode == 3 and "no CUDA device" in r.stderr
+
+
+def test_c99_streaming_program_reaches_the_device_boundary(tmp_path):
+    """tests/cabi/stream_route.c (one utterance chunk by chunk through b2k_stream_*, partial hypotheses and the end-point rules per
+    chunk): compiles as strict C99 against include/b2k.h and runs its host side; without a GPU it stops at the first device call
+    with the library's message."""
+    import shutil
+    import struct
+    import subprocess
+    so = os.path.join(ROOT, "kaldi_b200", "libb2k.so")
+    if not os.path.exists(so) or not shutil.which("gcc"):
+        pytest.skip("libb2k.so or gcc missing")
+    d = str(tmp_path / "exp")
+    hclg, n_tids = _build(d)
+    x = (3000 * np.sin(2 * np.pi * 300 * np.arange(8000) / 8000)).astype("<i2").tobytes()
+    body = b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, 8000, 16000, 2, 16) + b"data" + struct.pack("<I", len(x)) + x
+    wav = str(tmp_path / "utt.wav")
+    open(wav, "wb").write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    exe = str(tmp_path / "stream_route")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "cabi", "stream_route.c"), "-o", exe, "-L" + os.path.dirname(so), "-lb2k",
+                        "-Wl,-rpath," + os.path.dirname(so)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, os.path.join(d, "conf", "online.conf"), os.path.join(d, "final.mdl"), hclg, wav, str(tmp_path / "out.ark")],
+                       capture_output=True, text=True, timeout=300)
+    assert f"host side ready: 16000 samples in chunks of 8160, 10 pdfs, {n_tids} transition-ids, silence phones 1:2" in r.stdout, r.stdout + r.stderr
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "no CUDA device" in r.stderr

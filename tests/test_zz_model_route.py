@@ -266,6 +266,45 @@ def test_c99_program_decodes_a_directory_on_the_device(tmp_path):
 
 
 @pytest.mark.gpu
+def test_c99_streaming_program_decodes_chunk_by_chunk_on_the_device(tmp_path):
+    """tests/cabi/stream_route.c: the same directory, the utterance fed 0.51 s at a time through b2k_stream_*, a partial hypothesis
+    and the end-point rules after every chunk, the compact lattice at the end: one transition-id per decoder frame."""
+    import shutil
+    import struct
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_experiment_dir import _build
+    from kaldi_b200.lattice import compact_best_path, read_lattice_archive
+    if not shutil.which("gcc"):
+        pytest.skip("gcc missing")
+    root = os.path.dirname(HERE)
+    d = str(tmp_path / "exp")
+    hclg, _ = _build(d)
+    n = 40000
+    x = (3000 * np.sin(2 * np.pi * 300 * np.arange(n) / 16000) + np.random.default_rng(1).normal(0, 300, n)).astype("<i2").tobytes()
+    body = b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, 16000, 32000, 2, 16) + b"data" + struct.pack("<I", len(x)) + x
+    wav, ark = str(tmp_path / "utt.wav"), str(tmp_path / "out.ark")
+    open(wav, "wb").write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    so_dir = os.path.join(root, "kaldi_b200")
+    exe = str(tmp_path / "stream_route")
+    r = subprocess.run(["gcc", "-std=c99", "-I" + os.path.join(root, "include"), os.path.join(HERE, "cabi", "stream_route.c"), "-o", exe,
+                        "-L" + so_dir, "-lb2k", "-Wl,-rpath," + so_dir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, os.path.join(d, "conf", "online.conf"), os.path.join(d, "final.mdl"), hclg, wav, ark], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("frames decoded") >= 3 and "streamed in" in r.stdout, r.stdout
+    (key, kind, clat), = read_lattice_archive(open(ark, "rb").read())
+    assert key == "utt" and kind == "compact" and clat["num_states"] > 0 and len(clat["final_state"]) > 0
+    bp = compact_best_path(clat)
+    frames = 1 + (n - 400) // 160
+    if "ended at an end point" not in r.stdout:
+        # every call rounds its own output count up: at least ceil(frames / 3) decoder frames, at most one more per call
+        assert (frames + 2) // 3 <= len(bp["tids"]) <= (frames + 2) // 3 + 6 and np.isfinite(bp["total_cost"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("T", [64, 23])
 def test_chain_tdnn_without_factorisation_on_the_device(T):
     from kaldi_b200.nnet import NnetComputer
