@@ -704,6 +704,14 @@ typedef struct b2k_clat b2k_clat;
 /* max_states > 0: budget of determinized states; when it is exceeded the work is redone with 3/4 of the beam (the
  * reference reduces its beam when max_mem is hit, determinize-lattice-pruned.h:126-160) — see b2k_clat_effective_beam */
 int b2k_lat_determinize_pruned(const b2k_raw_lattice *raw, float beam, int64_t max_states, b2k_clat **out);
+/* DeterminizeLatticePhonePruned's two passes (lat/determinize-lattice-pruned.h:238-283, .cc:1291-1470): phone labels inserted on
+ * the arcs that start a phone, determinization over words and phones, phone labels deleted, determinization over words
+ * (--phone-determinize / --word-determinize; at least one must be set).  The transition model as three arrays over transition-ids
+ * (index 0 unused): TransitionIdToPhone, IsSelfLoop, TransitionIdIsStartOfPhone.  Same accepted sequences, weights and alignments
+ * as b2k_lat_determinize_pruned within the beam; b2k_clat_sizes' counters are the sum of both passes. */
+int b2k_lat_determinize_phone_pruned(const b2k_raw_lattice *raw, float beam, int64_t max_states, const int32_t *phone_of,
+                                     const uint8_t *self_loop, const uint8_t *phone_start, int32_t num_tids,
+                                     int32_t phone_determinize, int32_t word_determinize, b2k_clat **out);
 /* CompactLatticeShortestPath + read-out (online2-wav-nnet3-latgen-faster.cc:43-76): words and transition-ids of the best path
  * of the compact lattice, graph / acoustic cost with the final weight included; too small capacities: sizes + B2K_ERR_OVERFLOW */
 int b2k_clat_best_path(const b2k_clat *clat, int32_t *words, int32_t *n_words, int32_t *tids, int32_t *n_tids, int32_t cap_words,

@@ -13,9 +13,9 @@
 //    (determinize-lattice-pruned.h:126-140: "--beam" relative to the best path).  A sequence outside the beam can survive
 //    where its states are shared with sequences inside it; it then carries the weight of its best SURVIVING derivation,
 //    which is never below its true best cost (pruned determinization does not promise more, in the reference either).
-// Not reproduced: the phone-level first pass of the wrapper (an efficiency device: it does not change the
-// accepted language), max_mem / max_loop early stopping, minimization (off by default, DeterminizeLatticePhone-
-// PrunedOptions), and therefore the STATE NUMBERING of the reference's output.
+// The wrapper's phone-level first pass (an efficiency device: it does not change the accepted language) is
+// b2k_lat_determinize_phone_pruned below.  Not reproduced: max_mem / max_loop early stopping, minimization (off by default,
+// DeterminizeLatticePhonePrunedOptions), and therefore the STATE NUMBERING of the reference's output.
 // PARITY: pinned by equivalence.  The reference's own lat/determinize-lattice-pruned.cc is compiled in oracle/_ref
 // against a container-only OpenFst stand-in (oracle/ref_det.py, oracle/ref_wrap/fst_stub_det/) and run on the same raw
 // lattices, with and without its phone-level pass: same word sequences within the beam, same weights, same
@@ -339,6 +339,103 @@ int b2k_lat_determinize_pruned_batch(const b2k_raw_lattice *in, int32_t n, float
     if (rc[i] && !first) { first = rc[i]; b2k::g_last_error = msg[i]; }
   }
   return first;
+}
+
+// The two-pass form of DeterminizeLatticePhonePruned (lat/determinize-lattice-pruned.cc:1291-1470): first determinize over words
+// AND phone labels -- a phone label is put on every arc that starts a phone (not a self-loop, not leaving the start state), on the
+// arc itself when it carries no word, behind it on an extra arc otherwise (DeterminizeLatticeInsertPhones :1291-1345) -- which
+// merges derivations early, phone by phone, instead of carrying whole-word sets of alternatives; then delete the phone labels
+// (:1347-1370), expand the compact arcs back into transition-id arcs (ConvertLattice) and determinize over words.  Every word
+// sequence within the beam keeps its best derivation through both passes (its phone sequence is within the beam too), so the
+// result accepts the same sequences with the same weights and alignments as the one-pass form.
+int b2k_lat_determinize_phone_pruned(const b2k_raw_lattice *in, float beam, int64_t max_states, const int32_t *phone_of,
+                                     const uint8_t *self_loop, const uint8_t *phone_start, int32_t num_tids, int32_t phone_determinize,
+                                     int32_t word_determinize, b2k_clat **out) {
+  if (!out) return b2k::set_error(B2K_ERR_INVALID, "b2k_lat_determinize_phone_pruned: bad args");
+  *out = nullptr;
+  if (!phone_determinize && !word_determinize)
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_lat_determinize_phone_pruned: both passes are off (the reference copies the lattice then; ask for at least one)");
+  if (!phone_determinize) return b2k_lat_determinize_pruned(in, beam, max_states, out);
+  if (!in || !phone_of || !self_loop || !phone_start || num_tids <= 0 || in->num_states < 0 || in->num_arcs < 0)
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_lat_determinize_phone_pruned: bad args");
+  if (in->num_states > 0 && (!in->arc_src || !in->arc_dst || !in->arc_ilabel || !in->arc_olabel || !in->arc_graph_cost || !in->arc_acoustic_cost))
+    return b2k::set_error(B2K_ERR_INVALID, "b2k_lat_determinize_phone_pruned: the raw lattice arrays are missing");
+  // ---- pass 1 input: phones inserted
+  int32_t first_phone_label = 1;                             // HighestNumberedInputSymbol + 1 (words are the labels here)
+  for (int64_t a = 0; a < in->num_arcs; a++) first_phone_label = std::max(first_phone_label, in->arc_olabel[a] + 1);
+  std::vector<int32_t> src(in->arc_src, in->arc_src + in->num_arcs), dst(in->arc_dst, in->arc_dst + in->num_arcs),
+      il(in->arc_ilabel, in->arc_ilabel + in->num_arcs), ol(in->arc_olabel, in->arc_olabel + in->num_arcs);
+  std::vector<float> g(in->arc_graph_cost, in->arc_graph_cost + in->num_arcs), ac(in->arc_acoustic_cost, in->arc_acoustic_cost + in->num_arcs);
+  int64_t nstates = in->num_states;
+  for (int64_t a = 0; a < in->num_arcs; a++) {
+    const int32_t tid = il[a];
+    if (tid < 0 || tid >= num_tids) return b2k::set_error(B2K_ERR_INVALID, "b2k_lat_determinize_phone_pruned: transition-id outside the table");
+    if (src[a] == 0 || tid == 0 || !phone_start[tid] || self_loop[tid]) continue;     // (:1307-1308 skips the start state's arcs)
+    const int32_t phone = phone_of[tid];
+    if (phone <= 0) return b2k::set_error(B2K_ERR_INVALID, "b2k_lat_determinize_phone_pruned: phone 0 for a transition-id");      // :1321
+    if (ol[a] == 0) { ol[a] = first_phone_label + phone; continue; }
+    const int32_t x = (int32_t)nstates++;                   // word arc first, the phone on an extra arc behind it
+    src.push_back(x); dst.push_back(dst[a]); il.push_back(0); ol.push_back(first_phone_label + phone); g.push_back(0.f); ac.push_back(0.f);
+    dst[a] = x;
+  }
+  b2k_raw_lattice l1 = *in;
+  l1.num_states = nstates; l1.num_arcs = (int64_t)src.size();
+  l1.arc_src = src.data(); l1.arc_dst = dst.data(); l1.arc_ilabel = il.data(); l1.arc_olabel = ol.data();
+  l1.arc_graph_cost = g.data(); l1.arc_acoustic_cost = ac.data();
+  b2k_clat *c1 = nullptr;
+  int rc = b2k_lat_determinize_pruned(&l1, beam, max_states, &c1);
+  if (rc) return rc;
+  // ---- phones deleted, compact arcs expanded into transition-id arcs (word and weight on the first arc of a chain)
+  std::vector<int32_t> s2, d2, i2, o2, fs2;
+  std::vector<float> g2, a2, fc2;
+  int64_t n2 = c1->num_states;
+  auto chain = [&](int32_t from, int32_t to, int32_t label, float wg, float wa, const int32_t *str, int64_t len) {
+    // to < 0: a fresh end state (returned)
+    const int64_t n = std::max<int64_t>(len, 1);
+    int32_t cur = from;
+    for (int64_t j = 0; j < n; j++) {
+      const int32_t nxt = (j + 1 < n || to < 0) ? (int32_t)n2++ : to;
+      s2.push_back(cur); d2.push_back(nxt); i2.push_back(j < len ? str[j] : 0); o2.push_back(j == 0 ? label : 0);
+      g2.push_back(j == 0 ? wg : 0.f); a2.push_back(j == 0 ? wa : 0.f);
+      cur = nxt;
+    }
+    return cur;
+  };
+  for (size_t i = 0; i < c1->arc_src.size(); i++) {
+    const int32_t lab = c1->arc_word[i] >= first_phone_label ? 0 : c1->arc_word[i];
+    chain(c1->arc_src[i], c1->arc_dst[i], lab, c1->arc_g[i], c1->arc_a[i], c1->tids.data() + c1->arc_str_off[i], c1->arc_str_off[i + 1] - c1->arc_str_off[i]);
+  }
+  for (size_t f = 0; f < c1->final_state.size(); f++) {      // a compact final weight has an acoustic part and a string: an arc to a fresh final state
+    const int32_t e = chain(c1->final_state[f], -1, 0, c1->final_g[f], c1->final_a[f], c1->tids.data() + c1->final_str_off[f],
+                            c1->final_str_off[f + 1] - c1->final_str_off[f]);
+    fs2.push_back(e); fc2.push_back(0.f);
+  }
+  const int64_t expanded1 = c1->subsets_expanded, elems1 = c1->elements_total;
+  const float eff1 = c1->effective_beam;
+  if (!word_determinize) {
+    // "ConvertLattice(*ifst, ofst, false)" (:1448-1451): the phone-level result as a compact lattice, one transition-id per arc
+    b2k_clat *C = new b2k_clat();
+    C->num_states = n2; C->arc_src = s2; C->arc_dst = d2; C->arc_word = o2; C->arc_g = g2; C->arc_a = a2;
+    C->arc_str_off.push_back(0);
+    for (size_t i = 0; i < s2.size(); i++) { if (i2[i] != 0) C->tids.push_back(i2[i]); C->arc_str_off.push_back((int64_t)C->tids.size()); }
+    C->final_str_off.push_back((int64_t)C->tids.size());
+    for (size_t f = 0; f < fs2.size(); f++) { C->final_state.push_back(fs2[f]); C->final_g.push_back(0.f); C->final_a.push_back(0.f); C->final_str_off.push_back((int64_t)C->tids.size()); }
+    C->subsets_expanded = expanded1; C->elements_total = elems1; C->effective_beam = eff1;
+    delete c1;
+    *out = C;
+    return B2K_OK;
+  }
+  delete c1;
+  b2k_raw_lattice l2;
+  memset(&l2, 0, sizeof(l2));
+  l2.num_states = n2; l2.num_arcs = (int64_t)s2.size(); l2.num_finals = (int64_t)fs2.size();
+  l2.arc_src = s2.data(); l2.arc_dst = d2.data(); l2.arc_ilabel = i2.data(); l2.arc_olabel = o2.data();
+  l2.arc_graph_cost = g2.data(); l2.arc_acoustic_cost = a2.data(); l2.final_state = fs2.data(); l2.final_cost = fc2.data();
+  rc = b2k_lat_determinize_pruned(&l2, beam, max_states, out);
+  if (rc) return rc;
+  (*out)->subsets_expanded += expanded1; (*out)->elements_total += elems1;
+  (*out)->effective_beam = std::min((*out)->effective_beam, eff1);
+  return B2K_OK;
 }
 
 int b2k_clat_destroy(b2k_clat *c) { delete c; return B2K_OK; }

@@ -594,8 +594,20 @@ class SingleUtteranceNnet3DecoderB2k {
     r.arc_src = as.data(); r.arc_dst = ad.data(); r.arc_ilabel = ai.data(); r.arc_olabel = ao.data();
     r.arc_graph_cost = ag.data(); r.arc_acoustic_cost = aa.data(); r.final_state = fs.data(); r.final_cost = fc.data();
     CheckNnet3(b2k_dec_get_raw_lattice(dec_, 0, &r, cudaStreamPerThread), "GetRawLattice");
+    // DeterminizeLatticePhonePrunedWrapper(trans_model_, &raw_lat, lat_beam, clat, decoder_opts_.det_opts) (:70-73): the
+    // transition model as the three per-transition-id arrays b2k_lat_determinize_phone_pruned takes
+    const int32 nt = trans_model_.NumTransitionIds() + 1;
+    std::vector<int32_t> phone_of(nt, 0);
+    std::vector<uint8_t> self_loop(nt, 0), phone_start(nt, 0);
+    for (int32 t = 1; t < nt; t++) {
+      phone_of[t] = trans_model_.TransitionIdToPhone(t);
+      self_loop[t] = trans_model_.IsSelfLoop(t) ? 1 : 0;
+      phone_start[t] = trans_model_.TransitionIdIsStartOfPhone(t) ? 1 : 0;
+    }
     b2k_clat *c = NULL;
-    CheckNnet3(b2k_lat_determinize_pruned(&r, decoder_opts_.lattice_beam, 0, &c), "b2k_lat_determinize_pruned");
+    CheckNnet3(b2k_lat_determinize_phone_pruned(&r, decoder_opts_.lattice_beam, 0, phone_of.data(), self_loop.data(), phone_start.data(), nt,
+                                                decoder_opts_.det_opts.phone_determinize ? 1 : 0, decoder_opts_.det_opts.word_determinize ? 1 : 0, &c),
+               "b2k_lat_determinize_phone_pruned");
     BatchedOnlinePipelineB2k::FillCompactLattice(c, clat);
     b2k_clat_destroy(c);
   }

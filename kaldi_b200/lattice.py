@@ -146,11 +146,13 @@ def raw_lattice_from_canonical(c: dict) -> dict:
 
 # ---- raw lattice -> compact lattice (kaldi_b200/csrc/lattice_det.cu through the C ABI; host only) -------------------
 
-def determinize_pruned(lat: dict, beam: float, max_states: int = 0) -> dict:
+def determinize_pruned(lat: dict, beam: float, max_states: int = 0, phones: dict | None = None, word_determinize: bool = True) -> dict:
     """DeterminizeLatticePhonePrunedWrapper's role (lat/determinize-lattice-pruned.h:284) for one finalized raw
     lattice: returns the compact lattice as flat arrays — arc_src/arc_dst/arc_word/arc_graph_cost/arc_acoustic_cost,
     arc_tids (list of int32 arrays), final_state/final_graph_cost/final_acoustic_cost/final_tids, num_states (state 0
-    = start) — plus `stats` (subsets expanded, elements).  See include/b2k.h b2k_lat_determinize_pruned."""
+    = start) — plus `stats` (subsets expanded, elements).  See include/b2k.h b2k_lat_determinize_pruned.
+    phones = dict(phone_of, self_loop, phone_start) over transition-ids: the two-pass form with the phone-level first pass
+    (b2k_lat_determinize_phone_pruned)."""
     import ctypes as C
     from . import _lib
     from .decoder import _RawLattice, _p
@@ -164,7 +166,16 @@ def determinize_pruned(lat: dict, beam: float, max_states: int = 0) -> dict:
         setattr(r, k, _p(v, C.c_float if v.dtype == np.float32 else C.c_int32))
     h = C.c_void_p()
     L.b2k_lat_determinize_pruned.argtypes = [C.c_void_p, C.c_float, C.c_int64, C.c_void_p]
-    _lib.check(L.b2k_lat_determinize_pruned(C.byref(r), float(beam), int(max_states), C.byref(h)))
+    if phones is None:
+        _lib.check(L.b2k_lat_determinize_pruned(C.byref(r), float(beam), int(max_states), C.byref(h)))
+    else:
+        po = np.ascontiguousarray(phones["phone_of"], np.int32)
+        sl = np.ascontiguousarray(phones["self_loop"], np.uint8)
+        ps = np.ascontiguousarray(phones["phone_start"], np.uint8)
+        L.b2k_lat_determinize_phone_pruned.argtypes = [C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                                       C.c_int32, C.c_int32, C.c_void_p]
+        _lib.check(L.b2k_lat_determinize_phone_pruned(C.byref(r), float(beam), int(max_states), po.ctypes.data, sl.ctypes.data,
+                                                      ps.ctypes.data, len(po), 1, int(word_determinize), C.byref(h)))
     L.b2k_clat_effective_beam.restype = C.c_float
     L.b2k_clat_effective_beam.argtypes = [C.c_void_p]
     eff = float(L.b2k_clat_effective_beam(h))

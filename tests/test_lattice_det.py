@@ -9,10 +9,10 @@ import numpy as np
 import pytest
 
 
-def _det(lat, beam):
+def _det(lat, beam, phones=None, word_determinize=True):
     try:
         from kaldi_b200.lattice import determinize_pruned
-        return determinize_pruned(lat, beam)
+        return determinize_pruned(lat, beam, phones=phones, word_determinize=word_determinize)
     except OSError as e:
         pytest.skip(str(e))
 
@@ -296,7 +296,8 @@ def test_reference_determinizer_agrees_without_pruning(seed):
     for phone_pass in (False, True):
         r = RD.determinize(lat, 1e9, phone_determinize=phone_pass, **PHONES)
         assert r["ok"] == 1
-        ref, mine = _enumerate_compact(r), _enumerate_compact(_det(lat, 1e9))
+        # ours in the same mode: one pass over words, or the phone-level pass first (b2k_lat_determinize_phone_pruned)
+        ref, mine = _enumerate_compact(r), _enumerate_compact(_det(lat, 1e9, phones=PHONES if phone_pass else None))
         assert set(ref) == set(mine) == set(want)
         for k in want:
             assert ref[k][0] == pytest.approx(mine[k][0], abs=2e-4) and ref[k][1] == pytest.approx(mine[k][1], abs=2e-4)
@@ -314,9 +315,9 @@ def test_reference_determinizer_agrees_within_the_beam(seed):
         pytest.skip("no accepting path")
     best = min(v[0] for v in want.values())
     beam = float(rng.uniform(0.5, 4.0))
-    mine = _enumerate_compact(_det(lat, beam))
     inside = {k for k, v in want.items() if v[0] <= best + beam - 1e-3}
     for phone_pass in (False, True):
+        mine = _enumerate_compact(_det(lat, beam, phones=PHONES if phone_pass else None))
         r = RD.determinize(lat, beam, phone_determinize=phone_pass, **PHONES)
         assert r["ok"] == 1
         ref = _enumerate_compact(r)
@@ -347,9 +348,13 @@ def test_reference_determinizer_agrees_on_decoder_output():
     t = np.arange(ntid)
     phones = dict(phone_of=(1 + np.maximum(t - 1, 0) // 2 % 40).astype(np.int32), self_loop=((t % 2 == 0) & (t > 0)).astype(np.uint8),
                   phone_start=(t % 2 == 1).astype(np.uint8))
+    two_pass = _det(lat, beam, phones=phones)
+    assert compact_best_path(two_pass)["words"].tolist() == compact_best_path(mine)["words"].tolist()
     for phone_pass in (False, True):
         r = RD.determinize(lat, beam, phone_determinize=phone_pass, **phones)
         assert r["ok"] == 1
+        if phone_pass:
+            mine = two_pass
         a, b = compact_best_path(r), compact_best_path(mine)
         assert a["words"].tolist() == b["words"].tolist() and a["tids"].tolist() == b["tids"].tolist()
         assert a["total_cost"] == pytest.approx(b["total_cost"], abs=1e-3)
@@ -445,3 +450,37 @@ def test_threaded_batch_equals_single_calls():
     for i, h in enumerate(out):
         if h:
             L.b2k_clat_destroy(h)
+
+
+def test_phone_level_pass_alone_keeps_the_language_and_the_weights():
+    """--word-determinize=false: the result of the phone-level pass as a compact lattice (one transition-id per arc), not
+    deterministic over words but accepting the same word sequences at the same best costs (determinize-lattice-pruned.cc:1446-1451)."""
+    rng = np.random.default_rng(77)
+    for _ in range(30):
+        lat = _random_lattice(rng, n_states=int(rng.integers(3, 10)), n_arcs=int(rng.integers(3, 22)), vocab=3)
+        want = _enumerate_raw(lat)
+        if not want:
+            continue
+        c = _det(lat, 1e9, phones=PHONES, word_determinize=False)
+        assert all(len(t) <= 1 for t in c["arc_tids"])                       # one transition-id per arc at most
+        out_arcs, fin, got = {}, {int(s): i for i, s in enumerate(c["final_state"])}, {}
+        for a in range(len(c["arc_src"])):
+            out_arcs.setdefault(int(c["arc_src"][a]), []).append(a)
+
+        def walk(st, cost, words):                                            # word epsilons allowed, several paths per sequence
+            if st in fin:
+                tot = cost + float(c["final_graph_cost"][fin[st]]) + float(c["final_acoustic_cost"][fin[st]])
+                got[tuple(words)] = min(got.get(tuple(words), np.inf), tot)
+            for a in out_arcs.get(st, []):
+                w = int(c["arc_word"][a])
+                walk(int(c["arc_dst"][a]), cost + float(c["arc_graph_cost"][a]) + float(c["arc_acoustic_cost"][a]), words + ([w] if w else []))
+        walk(0, 0.0, [])
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k] == pytest.approx(want[k][0], abs=2e-4)
+    from kaldi_b200 import _lib
+    with pytest.raises(_lib.B2kError):
+        bad = dict(PHONES, phone_of=np.zeros_like(PHONES["phone_of"]))       # phone 0 for a transition-id (the reference asserts, :1321)
+        lat = _random_lattice(np.random.default_rng(1), n_states=6, n_arcs=14, vocab=2)
+        lat["arc_ilabel"][:] = 6                                             # a phone-start, non-self-loop transition-id on every arc
+        _det(lat, 1e9, phones=bad)
