@@ -21,6 +21,8 @@
 
 #include "b2k.h"
 #include "b2k_kaldi_shims.h"
+#include "cudamatrix/cu-matrix.h"
+#include "cudamatrix/cu-vector.h"
 #include "feat/feature-fbank.h"
 #include "feat/feature-mfcc.h"
 #include "feat/feature-plp.h"
@@ -162,6 +164,119 @@ class OnlineNnet2FeaturePipelineB2k : public OnlineFeatureInterface {
   std::unique_ptr<OnlineAppendFeature> append_;
   OnlineFeatureInterface *input_ = NULL, *final_ = NULL;
   KALDI_DISALLOW_COPY_AND_ASSIGN(OnlineNnet2FeaturePipelineB2k);
+};
+
+// OnlineBatchedFeaturePipelineCuda (cudafeat/online-batched-feature-pipeline-cuda.h:44-134): one chunk of samples per lane and
+// call, the frames that became computable land in rows [lane * GetMaxChunkFrames(), ...) of `input_features`, online CMVN applied
+// when the configuration asks for it.  The reference stashes the samples a frame still needs between calls; here a channel's
+// samples and raw features so far stay in device memory (the feature kernel reads frames that straddle two chunks from there,
+// the CMVN kernel its sliding window), bounded by max_seconds per utterance.  The streaming i-vector of the reference's class
+// (BatchedIvectorExtractorCuda) has no counterpart: a non-null ivector_features with i-vectors configured is refused.
+class OnlineBatchedFeaturePipelineB2k {
+ public:
+  typedef int32 ChannelId;
+  OnlineBatchedFeaturePipelineB2k(const OnlineNnet2FeaturePipelineConfig &config, int32_t max_chunk_size_samples, int32_t max_lanes,
+                                  int32_t num_channels, BaseFloat max_seconds = 120.0f)
+      : info_(config), tables_(info_, max_lanes), max_chunk_size_samples_(max_chunk_size_samples), max_lanes_(max_lanes),
+        num_channels_(num_channels) {
+    if (info_.feature_type == "mfcc") frame_opts_ = info_.mfcc_opts.frame_opts;
+    else if (info_.feature_type == "fbank") frame_opts_ = info_.fbank_opts.frame_opts;
+    else frame_opts_ = info_.plp_opts.frame_opts;
+    const int32_t shift = frame_opts_.WindowShift();
+    max_chunk_size_frames_ = (max_chunk_size_samples_ + shift - 1) / shift;                  // :63-64
+    dim_ = b2k_feat_dim(tables_.Handle());
+    max_samples_ = static_cast<int32_t>(max_seconds * frame_opts_.samp_freq);
+    max_frames_ = b2k_feat_num_frames(tables_.Handle(), max_samples_, 1) + 1;
+    const size_t sd = 2 * (static_cast<size_t>(dim_) + 1);
+    if (cudaMalloc(&d_wave_, sizeof(float) * static_cast<size_t>(num_channels) * max_samples_) != cudaSuccess ||
+        cudaMalloc(&d_raw_, sizeof(float) * static_cast<size_t>(num_channels) * max_frames_ * dim_) != cudaSuccess ||
+        cudaMalloc(&d_cmvn_state_, sizeof(double) * static_cast<size_t>(num_channels) * sd) != cudaSuccess ||
+        cudaMalloc(&d_global_, sizeof(double) * sd) != cudaSuccess)
+      KALDI_ERR << "cudaMalloc failed";
+    if (info_.use_cmvn) {
+      if (info_.global_cmvn_stats.NumCols() == 0) KALDI_ERR << "global_cmvn_stats for OnlineCmvn must be non-empty.";   // :78-80
+      std::vector<double> g(sd);
+      for (int32 r = 0; r < 2; r++)
+        for (int32 c = 0; c <= dim_; c++) g[r * (dim_ + 1) + c] = info_.global_cmvn_stats(r, c);
+      cudaMemcpy(d_global_, g.data(), sizeof(double) * sd, cudaMemcpyHostToDevice);
+      cmvn_cfg_.cmn_window = info_.cmvn_opts.cmn_window; cmvn_cfg_.speaker_frames = info_.cmvn_opts.speaker_frames;
+      cmvn_cfg_.global_frames = info_.cmvn_opts.global_frames; cmvn_cfg_.normalize_mean = info_.cmvn_opts.normalize_mean;
+      cmvn_cfg_.normalize_variance = info_.cmvn_opts.normalize_variance;
+    }
+    samples_.assign(num_channels, 0);
+  }
+  ~OnlineBatchedFeaturePipelineB2k() { cudaFree(d_wave_); cudaFree(d_raw_); cudaFree(d_cmvn_state_); cudaFree(d_global_); }
+
+  void ComputeFeaturesBatched(int32_t num_lanes, const std::vector<ChannelId> &channels, const std::vector<int32_t> &num_chunk_samples,
+                              const std::vector<bool> &first, const std::vector<bool> &last, BaseFloat sample_freq,
+                              const CuMatrixBase<BaseFloat> &cu_waves, CuMatrix<BaseFloat> *input_features,
+                              CuVector<BaseFloat> *ivector_features, std::vector<int32_t> *num_frames_computed) {
+    KALDI_ASSERT(num_lanes <= max_lanes_);                                                   // :135-136
+    KALDI_ASSERT(num_lanes <= static_cast<int32_t>(num_frames_computed->size()));
+    if (sample_freq != frame_opts_.samp_freq) KALDI_ERR << "Sampling frequency mismatch, expected " << frame_opts_.samp_freq << ", got " << sample_freq;
+    if (info_.use_ivectors && ivector_features != NULL) KALDI_ERR << "b2k computes i-vectors per utterance (b2k_ivec_compute_batched), not per chunk";
+    if (input_features->NumRows() < num_lanes * max_chunk_size_frames_ || input_features->NumCols() != dim_)
+      input_features->Resize(max_lanes_ * max_chunk_size_frames_, dim_, kUndefined);
+    const size_t sd = 2 * (static_cast<size_t>(dim_) + 1);
+    wp_.resize(num_lanes); rawp_.resize(num_lanes); inp_.resize(num_lanes); outp_.resize(num_lanes); statep_.resize(num_lanes);
+    ns_.resize(num_lanes); ff_.resize(num_lanes); nf_.resize(num_lanes);
+    for (int32_t lane = 0; lane < num_lanes; lane++) {
+      const ChannelId ch = channels[lane];
+      KALDI_ASSERT(ch >= 0 && ch < num_channels_);                                           // :145-146
+      KALDI_ASSERT(num_chunk_samples[lane] <= max_chunk_size_samples_);
+      const int32_t current_sample = first[lane] ? 0 : samples_[ch];                         // :153-156
+      const int32_t current_frame = b2k_feat_num_frames(tables_.Handle(), current_sample, 0);
+      const int32_t num_samples = current_sample + num_chunk_samples[lane];
+      if (num_samples > max_samples_) KALDI_ERR << "utterance longer than the configured capacity";
+      const int32_t num_frames = b2k_feat_num_frames(tables_.Handle(), num_samples, last[lane] ? 1 : 0);
+      float *w = d_wave_ + static_cast<size_t>(ch) * max_samples_;
+      if (num_chunk_samples[lane] > 0 &&
+          cudaMemcpyAsync(w + current_sample, cu_waves.Data() + static_cast<size_t>(lane) * cu_waves.Stride(),
+                          sizeof(float) * num_chunk_samples[lane], cudaMemcpyDeviceToDevice, cudaStreamPerThread) != cudaSuccess)
+        KALDI_ERR << "copying the chunk behind the channel's samples failed";
+      if (first[lane]) cudaMemsetAsync(d_cmvn_state_ + static_cast<size_t>(ch) * sd, 0, sizeof(double) * sd, cudaStreamPerThread);
+      samples_[ch] = num_samples;                                                            // :173-174
+      (*num_frames_computed)[lane] = num_frames - current_frame;                             // :177
+      float *raw = d_raw_ + static_cast<size_t>(ch) * max_frames_ * dim_;
+      wp_[lane] = w; rawp_[lane] = raw; ns_[lane] = num_samples; ff_[lane] = current_frame; nf_[lane] = num_frames - current_frame;
+      // frame f of the channel goes to row lane * max_chunk_frames + (f - current_frame): the kernels address frames absolutely
+      inp_[lane] = raw;
+      outp_[lane] = input_features->Data() + (static_cast<ptrdiff_t>(lane) * max_chunk_size_frames_ - current_frame) * input_features->Stride();
+      statep_[lane] = d_cmvn_state_ + static_cast<size_t>(ch) * sd;
+    }
+    Check(b2k_feat_compute_batched(tables_.Handle(), num_lanes, wp_.data(), ns_.data(), ff_.data(), nf_.data(), rawp_.data(), dim_,
+                                   cudaStreamPerThread), "b2k_feat_compute_batched");
+    if (info_.use_cmvn) {
+      Check(b2k_cmvn_apply_batched(tables_.Handle(), &cmvn_cfg_, num_lanes, inp_.data(), outp_.data(), dim_, input_features->Stride(),
+                                   ff_.data(), nf_.data(), statep_.data(), d_global_, NULL, cudaStreamPerThread), "b2k_cmvn_apply_batched");
+    } else {
+      for (int32_t lane = 0; lane < num_lanes; lane++)
+        if (nf_[lane] > 0 &&
+            cudaMemcpy2DAsync(input_features->Data() + static_cast<size_t>(lane) * max_chunk_size_frames_ * input_features->Stride(),
+                              sizeof(float) * input_features->Stride(), rawp_[lane] + static_cast<size_t>(ff_[lane]) * dim_, sizeof(float) * dim_,
+                              sizeof(float) * dim_, nf_[lane], cudaMemcpyDeviceToDevice, cudaStreamPerThread) != cudaSuccess)
+          KALDI_ERR << "copying the new feature frames failed";
+    }
+  }
+
+  int32_t GetMaxChunkFrames() { return max_chunk_size_frames_; }
+  int32_t FeatureDim() { return dim_; }
+  int32_t IvectorDim() { return 0; }
+  const FrameExtractionOptions &GetFrameOptions() { return frame_opts_; }
+
+ private:
+  OnlineNnet2FeaturePipelineInfo info_;
+  FeatureTablesB2k tables_;
+  FrameExtractionOptions frame_opts_;
+  int32_t max_chunk_size_samples_, max_chunk_size_frames_ = 0, max_lanes_, num_channels_, dim_ = 0, max_samples_ = 0, max_frames_ = 0;
+  float *d_wave_ = NULL, *d_raw_ = NULL;
+  double *d_cmvn_state_ = NULL, *d_global_ = NULL;
+  b2k_cmvn_cfg cmvn_cfg_;
+  std::vector<int32_t> samples_, ns_, ff_, nf_;
+  std::vector<const float *> wp_, inp_;
+  std::vector<float *> rawp_, outp_;
+  std::vector<double *> statep_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(OnlineBatchedFeaturePipelineB2k);
 };
 
 }  // namespace b2k_shim

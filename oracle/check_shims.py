@@ -112,6 +112,12 @@ def check() -> bool:
             "  std::vector<std::pair<int32, BaseFloat> > dw; p.UpdateFrameWeights(dw);\n"
             "  Vector<BaseFloat> v(itf->Dim()); itf->GetFrame(0, &v); itf->NumFramesReady(); itf->IsLastFrame(0); p.FrameShiftInSeconds();\n"
             "  OnlineFeatureInterface *in = p.InputFeature(); OnlineIvectorFeature *iv = p.IvectorFeature(); (void)in; (void)iv;\n"
+            "  // OnlineBatchedFeaturePipelineCuda's call as batched-threaded-nnet3-cuda-online-pipeline.cc:272-279 makes it\n"
+            "  b2k_shim::OnlineBatchedFeaturePipelineB2k bp(cfg, 8160, 4, 16);\n"
+            "  std::vector<int32> channels(1, 0), nsamp(1, 8160), nframes(1, 0); std::vector<bool> first(1, true), last(1, false);\n"
+            "  CuMatrix<BaseFloat> waves(4, 8160), feats; CuVector<BaseFloat> ivecs;\n"
+            "  bp.ComputeFeaturesBatched(1, channels, nsamp, first, last, 16000.0f, waves, &feats, NULL, &nframes);\n"
+            "  int32 x = bp.GetMaxChunkFrames() + bp.FeatureDim() + bp.IvectorDim(); (void)x; bp.GetFrameOptions();\n"
             "}\n")
         subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=0"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"),
                               "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include",
