@@ -3,6 +3,7 @@
 //   nnet3::NnetComputer {AcceptInput, Run, GetOutput, GetOutputDestructive}            nnet3/nnet-compute.h:88-200
 //   nnet3::DecodableNnetLoopedOnline / DecodableAmNnetLoopedOnline                     nnet3/decodable-online-looped.h:49-196
 //   cuda_decoder::BatchedStaticNnet3 {RunBatch, FormatOutputPtrs, Get*}                cudadecoder/batched-static-nnet3.h:59-138
+//   nnet3::DecodableNnetSimple / DecodableAmNnetSimple (the offline tools' decodables)  nnet3/nnet-am-decodable-simple.h:185-349
 //   SingleUtteranceNnet3Decoder {AdvanceDecoding, FinalizeDecoding, EndpointDetected, GetBestPath, GetLattice}
 //                                                                                       online2/online-nnet3-decoding.h:50-121
 //
@@ -479,6 +480,158 @@ class DecodableAmNnetLoopedOnlineB2k : public DecodableNnetLoopedOnlineBaseB2k {
 
  private:
   const TransitionModel &trans_model_;
+};
+
+// nnet3::DecodableNnetSimple / DecodableAmNnetSimple (nnet3/nnet-am-decodable-simple.h:185-349), the decodables of the OFFLINE
+// tools (nnet3bin/nnet3-latgen-faster.cc, nnet3-compute.cc): the utterance is cut into chunks of --frames-per-chunk outputs, each
+// computed from its own window of input frames [first output - left, last output + right] (indices clamped to the utterance,
+// nnet-am-decodable-simple.cc:136-166) with ONE i-vector per chunk (the one nearest the chunk's middle frame, :181-211).  The
+// reference computes a chunk when the decoder first asks for one of its frames; here ALL chunks of the utterance are the lanes
+// of one batched run of a window program (b2k_nnet_compile_window) at construction -- same windows, same i-vectors, same outputs.
+//
+// NnetSimpleComputerB2k is the part that is shared between utterances (the role CachingOptimizingCompiler plays in the
+// reference's constructor arguments): the model on the device and the compiled window program.
+class NnetSimpleComputerB2k {
+ public:
+  NnetSimpleComputerB2k(const nnet3::NnetSimpleComputationOptions &opts, const nnet3::Nnet &nnet, int32 max_chunks_per_run = 64)
+      : max_lanes_(max_chunks_per_run) {
+    RequireCuDevice();
+    if (opts.extra_left_context != 0 || opts.extra_right_context != 0 || opts.extra_left_context_initial > 0 || opts.extra_right_context_final > 0)
+      KALDI_ERR << "b2k: extra left / right context is not supported";
+    if (opts.frame_subsampling_factor < 1 || opts.frames_per_chunk < 1)
+      KALDI_ERR << "--frame-subsampling-factor and --frames-per-chunk must be > 0";                      // CheckAndFixConfigs :287-290
+    sf_ = opts.frame_subsampling_factor;
+    frames_per_chunk_ = sf_ * ((opts.frames_per_chunk + sf_ - 1) / sf_);                                  // (:294-296; the supported nets have modulus 1)
+    opc_ = frames_per_chunk_ / sf_;
+    model_.reset(new ModelB2k(nnet, sf_));
+    b2k_nnet_compile_cfg c = model_->CompileConfig(sf_, 1.0f, false);
+    CheckNnet3(b2k_nnet_model_context(&c, b2k_model_layers(model_->Handle()), model_->NumLayers(), &left_, &right_), "b2k_nnet_model_context");
+    window_ = (opc_ - 1) * sf_ + 1 + left_ + right_;                                                     // :137-139 for a full chunk
+    c.num_frames = window_;
+    b2k_nnet_program *prog = NULL;
+    CheckNnet3(b2k_nnet_compile_window(&c, left_, opc_, 1, b2k_model_layers(model_->Handle()), model_->NumLayers(),
+                                       b2k_model_weights(model_->Handle()), model_->NumWeights(), &prog), "b2k_nnet_compile_window");
+    const int rc = b2k_nnet_create_from_program(prog, max_lanes_, &nn_);
+    b2k_nnet_program_destroy(prog);
+    CheckNnet3(rc, "b2k_nnet_create_from_program");
+  }
+  ~NnetSimpleComputerB2k() { if (nn_) b2k_nnet_destroy(nn_); }
+
+  int32 OutputDim() const { return model_->NumPdfs(); }
+  int32 InputDim() const { return model_->FeatDim(); }
+  int32 IvectorDim() const { return model_->IvectorDim(); }
+  int32 FrameSubsamplingFactor() const { return sf_; }
+  void GetSimpleNnetContext(int32 *left, int32 *right) const { *left = left_; *right = right_; }
+
+  // Raw network output for every subsampled frame of the utterance ([ceil(T / sf) x OutputDim()]; priors and acoustic scale are
+  // the caller's, as in DoNnetComputation :258-262)
+  void Compute(const MatrixBase<BaseFloat> &feats, const VectorBase<BaseFloat> *ivector, const MatrixBase<BaseFloat> *online_ivectors,
+               int32 online_ivector_period, CuMatrix<BaseFloat> *output) {
+    const int32 T = feats.NumRows(), dim = feats.NumCols(), ivd = model_->IvectorDim();
+    if (dim != model_->FeatDim())
+      KALDI_ERR << "Neural net expects 'input' features with dimension " << model_->FeatDim() << " but you provided " << dim;       // :103-106
+    const int32 given_ivd = ivector ? ivector->Dim() : (online_ivectors ? online_ivectors->NumCols() : 0);
+    if (given_ivd != ivd) KALDI_ERR << "Neural net expects 'ivector' features with dimension " << ivd << " but you provided " << given_ivd;
+    KALDI_ASSERT(!(ivector != NULL && online_ivectors != NULL));                                          // :52
+    KALDI_ASSERT(!(online_ivectors != NULL && online_ivector_period <= 0 && "You need to set the --online-ivector-period option!"));
+    const int32 num_subsampled = (T + sf_ - 1) / sf_, num_chunks = (num_subsampled + opc_ - 1) / opc_;
+    output->Resize(num_subsampled, model_->NumPdfs(), kUndefined);
+    for (int32 c0 = 0; c0 < num_chunks; c0 += max_lanes_) {
+      const int32 n = std::min(max_lanes_, num_chunks - c0);
+      Matrix<BaseFloat> win(n * window_, dim, kUndefined), ivs(std::max(1, n), std::max(1, ivd));
+      for (int32 k = 0; k < n; k++) {
+        const int32 first_out = (c0 + k) * opc_ * sf_;
+        const int32 outs = std::min(num_subsampled - (c0 + k) * opc_, opc_), last_out = first_out + (outs - 1) * sf_;
+        for (int32 i = 0; i < window_; i++) {                                                            // :150-161 (rows past the chunk's own
+          const int32 t = std::min(std::max(first_out - left_ + i, 0), T - 1);                            //  window feed outputs nobody reads)
+          win.Row(k * window_ + i).CopyFromVec(feats.Row(t));
+        }
+        if (ivector) ivs.Row(k).CopyFromVec(*ivector);                                                    // GetCurrentIvector :181-211
+        else if (online_ivectors) {
+          const int32 frame_to_search = first_out + (last_out - first_out) / 2;
+          int32 ivector_frame = frame_to_search / online_ivector_period;
+          if (ivector_frame >= online_ivectors->NumRows()) {
+            const int32 margin = ivector_frame - (online_ivectors->NumRows() - 1);
+            if (margin * online_ivector_period > 50)
+              KALDI_ERR << "Could not get iVector for frame " << frame_to_search << ", only available till frame " << online_ivectors->NumRows()
+                        << " * ivector-period=" << online_ivector_period << " (mismatched --online-ivector-period?)";
+            ivector_frame = online_ivectors->NumRows() - 1;
+          }
+          ivs.Row(k).CopyFromVec(online_ivectors->Row(ivector_frame));
+        }
+      }
+      d_win_ = win;
+      if (ivd > 0) { d_iv_.Resize(n, ivd, kUndefined, kStrideEqualNumCols); d_iv_.CopyFromMat(ivs.RowRange(0, n)); }
+      d_out_.Resize(n * opc_, model_->NumPdfs(), kUndefined);
+      std::vector<const float *> in(n), iv(n);
+      std::vector<float *> out(n);
+      for (int32 k = 0; k < n; k++) {
+        in[k] = d_win_.Data() + static_cast<size_t>(k) * window_ * d_win_.Stride();
+        iv[k] = ivd > 0 ? d_iv_.Data() + static_cast<size_t>(k) * ivd : NULL;
+        out[k] = d_out_.Data() + static_cast<size_t>(k) * opc_ * d_out_.Stride();
+      }
+      CheckNnet3(b2k_nnet_run(nn_, n, in.data(), d_win_.Stride(), ivd > 0 ? iv.data() : NULL, ivd, out.data(), d_out_.Stride(), cudaStreamPerThread),
+                 "b2k_nnet_run");
+      const int32 rows = std::min(n * opc_, num_subsampled - c0 * opc_);
+      output->RowRange(c0 * opc_, rows).CopyFromMat(d_out_.RowRange(0, rows));
+    }
+  }
+
+ private:
+  int32 max_lanes_, sf_ = 1, frames_per_chunk_ = 0, opc_ = 0, left_ = 0, right_ = 0, window_ = 0;
+  std::unique_ptr<ModelB2k> model_;
+  b2k_nnet *nn_ = NULL;
+  CuMatrix<BaseFloat> d_win_, d_iv_, d_out_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(NnetSimpleComputerB2k);
+};
+
+class DecodableNnetSimpleB2k {                        // nnet-am-decodable-simple.h:185-270
+ public:
+  DecodableNnetSimpleB2k(const nnet3::NnetSimpleComputationOptions &opts, const VectorBase<BaseFloat> &priors,
+                         const MatrixBase<BaseFloat> &feats, NnetSimpleComputerB2k *computer, const VectorBase<BaseFloat> *ivector = NULL,
+                         const MatrixBase<BaseFloat> *online_ivectors = NULL, int32 online_ivector_period = 1) {
+    CuMatrix<BaseFloat> out;
+    computer->Compute(feats, ivector, online_ivectors, online_ivector_period, &out);
+    if (priors.Dim() != 0) {                                                                            // :47,258-260
+      CuVector<BaseFloat> log_priors(priors);
+      log_priors.ApplyLog();
+      out.AddVecToRows(-1.0, log_priors);
+    }
+    out.Scale(opts.acoustic_scale);                                                                     // :262
+    log_post_.Resize(out.NumRows(), out.NumCols(), kUndefined);
+    out.CopyToMat(&log_post_);
+  }
+  inline int32 NumFrames() const { return log_post_.NumRows(); }
+  inline int32 OutputDim() const { return log_post_.NumCols(); }
+  void GetOutputForFrame(int32 frame, VectorBase<BaseFloat> *output) { output->CopyFromVec(log_post_.Row(frame)); }
+  inline BaseFloat GetOutput(int32 subsampled_frame, int32 pdf_id) { return log_post_(subsampled_frame, pdf_id); }
+
+ private:
+  Matrix<BaseFloat> log_post_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(DecodableNnetSimpleB2k);
+};
+
+class DecodableAmNnetSimpleB2k : public DecodableInterface {             // nnet-am-decodable-simple.h:272-349
+ public:
+  DecodableAmNnetSimpleB2k(const nnet3::NnetSimpleComputationOptions &opts, const TransitionModel &trans_model,
+                           const nnet3::AmNnetSimple &am_nnet, const MatrixBase<BaseFloat> &feats, NnetSimpleComputerB2k *computer,
+                           const VectorBase<BaseFloat> *ivector = NULL, const MatrixBase<BaseFloat> *online_ivectors = NULL,
+                           int32 online_ivector_period = 1)
+      : decodable_nnet_(opts, am_nnet.Priors(), feats, computer, ivector, online_ivectors, online_ivector_period), trans_model_(trans_model) {}
+  BaseFloat LogLikelihood(int32 frame, int32 transition_id) override {
+    return decodable_nnet_.GetOutput(frame, trans_model_.TransitionIdToPdfFast(transition_id));
+  }
+  int32 NumFramesReady() const override { return decodable_nnet_.NumFrames(); }
+  int32 NumIndices() const override { return trans_model_.NumTransitionIds(); }
+  bool IsLastFrame(int32 frame) const override {
+    KALDI_ASSERT(frame < NumFramesReady());
+    return frame == NumFramesReady() - 1;
+  }
+
+ private:
+  DecodableNnetSimpleB2k decodable_nnet_;
+  const TransitionModel &trans_model_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(DecodableAmNnetSimpleB2k);
 };
 
 // SingleUtteranceNnet3DecoderTpl (online2/online-nnet3-decoding.h:50-121), the object online2-wav-nnet3-latgen-faster drives:

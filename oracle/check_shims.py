@@ -88,6 +88,13 @@ def check() -> bool:
             "  b2k_shim::NnetComputerB2k comp(co, req, am.GetNnet());\n"
             "  CuMatrix<BaseFloat> in, out; comp.AcceptInput(\"input\", &in); comp.Run();\n"
             "  const CuMatrixBase<BaseFloat> &o = comp.GetOutput(\"output\"); (void)o; comp.GetOutputDestructive(\"output\", &out);\n"
+            "  // the decodable of nnet3bin/nnet3-latgen-faster.cc:212-216, arguments as the tool passes them\n"
+            "  nnet3::NnetSimpleComputationOptions so; Matrix<BaseFloat> features, online_ivectors; Vector<BaseFloat> ivector;\n"
+            "  b2k_shim::NnetSimpleComputerB2k shared(so, am.GetNnet());\n"
+            "  b2k_shim::DecodableAmNnetSimpleB2k offline(so, tm, am, features, &shared, &ivector, &online_ivectors, 10);\n"
+            "  DecodableInterface *oi = &offline; oi->LogLikelihood(0, 1); oi->NumFramesReady(); oi->IsLastFrame(0); oi->NumIndices();\n"
+            "  b2k_shim::DecodableNnetSimpleB2k raw(so, am.Priors(), features, &shared); Vector<BaseFloat> row(raw.OutputDim());\n"
+            "  raw.GetOutputForFrame(0, &row); raw.NumFrames(); raw.GetOutput(0, 0);\n"
             "}\n")
         subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"),
                               "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include",

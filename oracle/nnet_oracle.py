@@ -120,6 +120,24 @@ class RefNnet:
             raise RuntimeError(f"reference forward failed ({r})")
         return out
 
+    def forward_simple(self, feats: np.ndarray, online_ivectors: np.ndarray | None, period: int, frames_per_chunk: int) -> np.ndarray:
+        """DecodableNnetSimple (the offline tools' decodable, nnet3/nnet-am-decodable-simple.cc) over the utterance."""
+        f = np.ascontiguousarray(feats, np.float32)
+        T, D = f.shape
+        sub = self.arch["frame_subsampling_factor"]
+        n_out = (T + sub - 1) // sub
+        out = np.zeros((n_out, self.output_dim), np.float32)
+        self.lib.ref_nnet_forward_simple.argtypes = None
+        if online_ivectors is not None:
+            iv = np.ascontiguousarray(online_ivectors, np.float32)
+            r = self.lib.ref_nnet_forward_simple(self.h, _p(f, C.c_float), T, D, _p(iv, C.c_float), iv.shape[0], iv.shape[1], int(period),
+                                                 int(frames_per_chunk), _p(out, C.c_float), n_out)
+        else:
+            r = self.lib.ref_nnet_forward_simple(self.h, _p(f, C.c_float), T, D, None, 0, 0, 1, int(frames_per_chunk), _p(out, C.c_float), n_out)
+        if r != n_out:
+            raise RuntimeError(f"reference simple forward failed ({r})")
+        return out
+
     def chunk_ivector_rows(self, num_frames: int, num_ivector_rows: int, period: int):
         """Row of the online_ivectors matrix chunk n reads: GetCurrentIvector(end_input_frame)
         (decodable-simple-looped.cc:190,262-279)."""

@@ -20,6 +20,7 @@
 #include "tree/context-dep.h"
 #include "util/kaldi-io.h"
 #include "nnet3/decodable-simple-looped.h"
+#include "nnet3/nnet-am-decodable-simple.h"
 #include "nnet3/nnet-nnet.h"
 #include "nnet3/nnet-normalize-component.h"
 #include "nnet3/nnet-simple-component.h"
@@ -31,6 +32,7 @@ using namespace kaldi::nnet3;
 struct RefNnet {
   Nnet nnet;
   std::unique_ptr<AmNnetSimple> am;
+  std::unique_ptr<AmNnetSimple> am_simple;   // the same model before DecodableNnetSimpleLoopedInfo rewrites its i-vector descriptors in place
   std::unique_ptr<DecodableNnetSimpleLoopedInfo> info;
   NnetSimpleLoopedComputationOptions opts;
   std::string tmp;
@@ -118,6 +120,7 @@ int ref_nnet_prepare(void *h, int frames_per_chunk, int frame_subsampling_factor
     r->opts.frames_per_chunk = frames_per_chunk;
     r->opts.frame_subsampling_factor = frame_subsampling_factor;
     r->opts.acoustic_scale = acoustic_scale;
+    r->am_simple.reset(new AmNnetSimple(*r->am));        // (ModifyNnetIvectorPeriod, decodable-simple-looped.cc:74, changes r->am's nnet)
     r->info.reset(new DecodableNnetSimpleLoopedInfo(r->opts, r->am.get()));
     return 0;
   } catch (const std::exception &e) { fprintf(stderr, "ref_nnet_prepare: %s\n", e.what()); return -1; }
@@ -148,6 +151,30 @@ int ref_nnet_forward(void *h, const float *feats, int T, int D, const float *ive
     for (int t = 0; t < n; t++) { SubVector<BaseFloat> row(out + (size_t)t * P, P); dec.GetOutputForFrame(t, &row); }
     return n;
   } catch (const std::exception &e) { fprintf(stderr, "ref_nnet_forward: %s\n", e.what()); return -1; }
+}
+
+// DecodableNnetSimple over a whole utterance (nnet3/nnet-am-decodable-simple.cc: the decodable of the offline tools): chunks of
+// frames_per_chunk outputs, each from its own clamped window, ONE i-vector per chunk (the row nearest the chunk's middle frame).
+// online_ivectors [M x idim] with the given period, or M = 0 for none.  Uses the options of ref_nnet_prepare.
+int ref_nnet_forward_simple(void *h, const float *feats, int T, int D, const float *ivectors, int M, int idim, int period,
+                            int frames_per_chunk, float *out, int max_rows) {
+  try {
+    RefNnet *r = (RefNnet *)h;
+    Matrix<BaseFloat> f(T, D);
+    for (int t = 0; t < T; t++) memcpy(f.RowData(t), feats + (size_t)t * D, 4 * D);
+    Matrix<BaseFloat> iv;
+    if (M > 0) { iv.Resize(M, idim); for (int m = 0; m < M; m++) memcpy(iv.RowData(m), ivectors + (size_t)m * idim, 4 * idim); }
+    NnetSimpleComputationOptions so;
+    so.frames_per_chunk = frames_per_chunk;
+    so.frame_subsampling_factor = r->opts.frame_subsampling_factor;
+    so.acoustic_scale = r->opts.acoustic_scale;
+    CachingOptimizingCompiler compiler(r->am_simple->GetNnet(), so.optimize_config, so.compiler_config);
+    DecodableNnetSimple dec(so, r->am_simple->GetNnet(), r->am_simple->Priors(), f, &compiler, NULL, M > 0 ? &iv : NULL, M > 0 ? period : 0);
+    int n = dec.NumFrames(), P = dec.OutputDim();
+    if (n > max_rows) return -2;
+    for (int t = 0; t < n; t++) { SubVector<BaseFloat> row(out + (size_t)t * P, P); dec.GetOutputForFrame(t, &row); }
+    return n;
+  } catch (const std::exception &e) { fprintf(stderr, "ref_nnet_forward_simple: %s\n", e.what()); return -1; }
 }
 
 // Nnet::Write (nnet3/nnet-nnet.cc:630) of the model as it stands (call before ref_nnet_prepare for the

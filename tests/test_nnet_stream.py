@@ -195,6 +195,45 @@ def test_looped_windows_reproduce_the_reference_looped_forward(which, T):
     assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("which,T,fpc,period", [("tiny", 100, 50, 10), ("tiny", 37, 21, 1), ("tiny-lda", 77, 50, 7), ("cnn", 64, 30, 10),
+                                                 ("tdnn", 90, 50, 10), ("tiny", 4, 50, 10)])
+def test_offline_chunks_reproduce_the_reference_simple_decodable(which, T, fpc, period):
+    """What NnetSimpleComputerB2k::Compute does (kaldi_b200/host/b2k_nnet3_shims.h: the decodable of nnet3-latgen-faster), restated
+    over the C++-compiled window program: every chunk of --frames-per-chunk outputs from its own clamped window with the online
+    i-vector nearest its middle frame, against the reference's own DecodableNnetSimple (nnet3/nnet-am-decodable-simple.cc,
+    compiled in oracle/_ref)."""
+    from oracle import program_interp as PI
+    NC = _lib_or_skip()
+    arch = ARCHS[which]()
+    W = NM.random_weights(arch, seed=8)
+    R = _ref_or_skip(arch, W)
+    if not hasattr(R.lib, "ref_nnet_forward_simple"):
+        pytest.skip("oracle/_ref library predates ref_nnet_forward_simple")
+    sf = arch["frame_subsampling_factor"]
+    rng = np.random.default_rng(T)
+    feats = (rng.standard_normal((T, arch["feat_dim"])) * 10).astype(np.float32)
+    online_iv = rng.standard_normal(((T + period - 1) // period, 100)).astype(np.float32)
+    ref = R.forward_simple(feats, online_iv, period, fpc)
+    fpc_r = sf * ((fpc + sf - 1) // sf)
+    opc = fpc_r // sf
+    L, Rc = NC.model_context(arch)
+    window = (opc - 1) * sf + 1 + L + Rc
+    cp = NC.CompiledProgram(arch, W, window, sf, use_priors=False, window=(L, opc, 1))
+    prog = PI.program_from_abi(cp.nodes, cp.ops, cp.blob)
+    n_sub = (T + sf - 1) // sf
+    outs = []
+    for c in range((n_sub + opc - 1) // opc):
+        first_out = c * opc * sf
+        n = min(n_sub - c * opc, opc)
+        last_out = first_out + (n - 1) * sf
+        win = feats[np.clip(first_out - L + np.arange(window), 0, T - 1)]
+        iv_frame = min((first_out + (last_out - first_out) // 2) // period, online_iv.shape[0] - 1)
+        outs.append(PI.run_program(prog, win, online_iv[iv_frame][None, :])[:n])
+    got = np.concatenate(outs, 0)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("which,T", [("tiny", 100), ("cnn", 64)])
 def test_device_looped_stream_reproduces_the_whole_utterance_run(which, T):
