@@ -401,6 +401,8 @@ class StreamingOnlinePipelineB2k {
                    std::vector<const std::string *> *partial_hypotheses = nullptr, std::vector<bool> *end_point = nullptr) {
     const size_t n = corr_ids.size();
     KALDI_ASSERT(wave_samples.size() == n && is_first_chunk.size() >= n && is_last_chunk.size() >= n);
+    for (CorrelationID id : finished_) text_.erase(id);       // their hypothesis strings were valid until this call
+    finished_.clear();
     pcm_.resize(n); chans_.resize(n); ptrs_.resize(n); ns_.resize(n); first_.resize(n); last_.resize(n);
     for (size_t i = 0; i < n; i++) {
       if (is_first_chunk[i] && !TryInitCorrID(corr_ids[i])) KALDI_ERR << "DecodeBatch: no free channel for a new utterance";
@@ -470,6 +472,7 @@ class StreamingOnlinePipelineB2k {
       best_cb_.erase(corr_ids[i]);
       free_.push_back(chans_[i]);
       chan_.erase(corr_ids[i]);
+      finished_.push_back(corr_ids[i]);
     }
   }
 
@@ -484,6 +487,7 @@ class StreamingOnlinePipelineB2k {
   std::map<CorrelationID, BestPathCallback> best_cb_;
   std::map<CorrelationID, RawLatticeCallback> lat_cb_;
   std::map<CorrelationID, std::string> text_;
+  std::vector<CorrelationID> finished_;
   std::function<std::string(int32)> word_of_;
   std::vector<std::vector<int16_t>> pcm_;
   std::vector<int32_t> chans_, ns_, first_, last_, il_, ol_;
