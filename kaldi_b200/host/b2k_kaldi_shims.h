@@ -23,6 +23,7 @@
 #include <map>
 
 #include "b2k.h"
+#include "b2k_dynamic_batcher.h"
 #include "b2k_pipeline_shim.h"
 #include "base/kaldi-error.h"
 #include "itf/online-feature-itf.h"
@@ -496,6 +497,46 @@ class StreamingOnlinePipelineB2k {
   std::vector<int32_t> st_f_, st_h_, a_s_, a_d_, a_i_, a_o_, f_s_;
   std::vector<float> st_t_, st_e_, a_g_, a_a_, f_c_;
   KALDI_DISALLOW_COPY_AND_ASSIGN(StreamingOnlinePipelineB2k);
+};
+
+// cuda_decoder::CudaOnlinePipelineDynamicBatcher (cudadecoder/cuda-online-pipeline-dynamic-batcher.h:38-60) in front of
+// StreamingOnlinePipelineB2k: producers Push chunks from any thread, a worker thread forms the batches (at most one chunk per
+// stream and batch, a stream's chunks in order, a batch as soon as it is full or the timeout has passed) and calls DecodeBatch.
+// The scheduling is b2k_host::DynamicBatcher (b2k_dynamic_batcher.h), unit-tested with a mock pipeline.
+class CudaOnlinePipelineDynamicBatcherB2k {
+ public:
+  typedef StreamingOnlinePipelineB2k::CorrelationID CorrelationID;
+  // config.dynamic_batcher_timeout as in CudaOnlinePipelineDynamicBatcherConfig (:34-36)
+  CudaOnlinePipelineDynamicBatcherB2k(double dynamic_batcher_timeout, StreamingOnlinePipelineB2k &pipeline, int32 max_batch_size)
+      : adapter_{&pipeline, max_batch_size}, batcher_(&adapter_, dynamic_batcher_timeout) {}
+  void Push(CorrelationID corr_id, bool is_first_chunk, bool is_last_chunk, const SubVector<BaseFloat> &wave_samples) {
+    batcher_.Push(corr_id, is_first_chunk, is_last_chunk, wave_samples.Data(), wave_samples.Dim());
+  }
+  void WaitForCompletion() {
+    try {
+      batcher_.WaitForCompletion();
+    } catch (const std::exception &e) {
+      KALDI_ERR << "dynamic batcher: " << e.what();
+    }
+  }
+  int GetNumPendingChunks(CorrelationID corr_id) { return batcher_.GetNumPendingChunks(corr_id); }
+
+ private:
+  struct Adapter {
+    StreamingOnlinePipelineB2k *p;
+    int32 max_batch;
+    int MaxBatchSize() const { return max_batch; }
+    bool TryInitCorrID(uint64_t id) { return p->TryInitCorrID(id); }
+    void DecodeBatch(const std::vector<uint64_t> &ids, const std::vector<std::pair<const float *, int64_t>> &chunks,
+                     const std::vector<bool> &first, const std::vector<bool> &last) {
+      std::vector<SubVector<BaseFloat>> waves;
+      static BaseFloat none = 0.0f;
+      for (const auto &c : chunks) waves.push_back(SubVector<BaseFloat>(c.second > 0 ? const_cast<BaseFloat *>(c.first) : &none, (MatrixIndexT)c.second));
+      p->DecodeBatch(ids, waves, first, last);
+    }
+  };
+  Adapter adapter_;
+  b2k_host::DynamicBatcher<Adapter> batcher_;
 };
 
 // ------------------------------------------------------------------------------------------------ endpointing

@@ -61,6 +61,8 @@ def check() -> bool:
             "  p.DecodeBatch(ids, waves, first, last, &hyp, &ep);\n"
             "  p.DecodeBatch(ids, waves, first, last);\n"
             "  int x = p.GetNSampsPerChunk() + p.GetNInputFramesPerChunk(); (void)x; p.GetDecoderFrameShiftSeconds();\n"
+            "  b2k_shim::CudaOnlinePipelineDynamicBatcherB2k batcher(2e-3, p, 64);\n"
+            "  batcher.Push(7, true, false, waves[0]); batcher.WaitForCompletion(); int n = batcher.GetNumPendingChunks(7); (void)n;\n"
             "}\n")
         subprocess.check_call(["g++", "-fsyntax-only"] + RF.cxxflags(["-I" + os.path.join(ROOT, "include"),
                               "-I" + os.path.join(ROOT, "kaldi_b200", "host"), "-I/usr/local/cuda/include"]) + [sp])

@@ -29,6 +29,20 @@ def test_batcher_logic_with_mock_backend(tmp_path):
     assert "batcher ok" in r.stdout
 
 
+def test_dynamic_batcher_with_mock_pipeline(tmp_path):
+    """b2k_host::DynamicBatcher (the role of cuda_decoder::CudaOnlinePipelineDynamicBatcher): four producer threads, 40 streams on
+    12 channels, batches of 8 -- one chunk per stream and batch, chunks in order, nothing lost, channels respected; the timeout
+    path, the full-batch path, empty last chunks, a reused id, an exception from the pipeline."""
+    _gxx()
+    exe = str(tmp_path / "dynamic_batcher_test")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-pthread", "-I" + HOST,
+                        os.path.join(ROOT, "tests", "cabi", "dynamic_batcher_test.cc"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for _ in range(3):
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and "dynamic batcher ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_pipeline_backend_links_and_fails_loudly_without_a_device(tmp_path):
     _gxx()
     so = os.path.join(ROOT, "kaldi_b200", "libb2k.so")
