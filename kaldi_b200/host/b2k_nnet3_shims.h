@@ -700,19 +700,21 @@ class SingleUtteranceNnet3DecoderB2k {
     BestPath(false, NULL, NULL, NULL, NULL, &bp);
     return bp.final_relative_cost;
   }
-  // the best path as arrays (what GetBestPath builds its linear lattice from)
+  // the best path as arrays (what GetBestPath builds its linear lattice from); arc_states: the HCLG state each arc enters
+  // (a token of the decoder is a (frame, state) pair: OnlineSilenceWeightingB2k tells tokens apart by it)
   void BestPath(bool use_final_probs, std::vector<int32> *ilabels, std::vector<int32> *olabels, std::vector<BaseFloat> *graph_costs,
-                std::vector<BaseFloat> *acoustic_costs, b2k_best_path_info *info) {
+                std::vector<BaseFloat> *acoustic_costs, b2k_best_path_info *info, std::vector<int32> *arc_states = NULL) {
     const int32_t ch = 0, cap = 3 * std::max(1, frames_decoded_) + 64;
-    std::vector<int32_t> il(cap), ol(cap);
+    std::vector<int32_t> il(cap), ol(cap), st(arc_states ? cap : 0);
     std::vector<float> g(cap), a(cap);
-    CheckNnet3(b2k_dec_best_path(dec_, &ch, 1, use_final_probs ? 1 : 0, cap, il.data(), ol.data(), g.data(), a.data(), NULL, NULL, info,
-                                 cudaStreamPerThread), "b2k_dec_best_path");
+    CheckNnet3(b2k_dec_best_path(dec_, &ch, 1, use_final_probs ? 1 : 0, cap, il.data(), ol.data(), g.data(), a.data(), NULL,
+                                 arc_states ? st.data() : NULL, info, cudaStreamPerThread), "b2k_dec_best_path");
     const int32 n = info->n_arcs;
     if (ilabels) ilabels->assign(il.begin(), il.begin() + n);
     if (olabels) olabels->assign(ol.begin(), ol.begin() + n);
     if (graph_costs) graph_costs->assign(g.begin(), g.begin() + n);
     if (acoustic_costs) acoustic_costs->assign(a.begin(), a.begin() + n);
+    if (arc_states) arc_states->assign(st.begin(), st.begin() + n);
   }
 
 #ifdef B2K_HAVE_OPENFST

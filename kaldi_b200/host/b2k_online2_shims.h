@@ -21,6 +21,7 @@
 
 #include "b2k.h"
 #include "b2k_kaldi_shims.h"
+#include "b2k_silence_weighting.h"
 #include "cudamatrix/cu-matrix.h"
 #include "cudamatrix/cu-vector.h"
 #include "feat/feature-fbank.h"
@@ -277,6 +278,67 @@ class OnlineBatchedFeaturePipelineB2k {
   std::vector<float *> rawp_, outp_;
   std::vector<double *> statep_;
   KALDI_DISALLOW_COPY_AND_ASSIGN(OnlineBatchedFeaturePipelineB2k);
+};
+
+// OnlineSilenceWeighting (online2/online-ivector-feature.h:460-571) over a b2k decoder.  The loop of the online2 tools stays
+// as it is (online2bin/online2-wav-nnet3-latgen-faster.cc:254-262):
+//     if (silence_weighting.Active() && feature_pipeline.IvectorFeature() != NULL) {
+//       silence_weighting.ComputeCurrentTraceback(decoder);
+//       silence_weighting.GetDeltaWeights(feature_pipeline.NumFramesReady(), frame_offset * subsampling, &delta_weights);
+//       feature_pipeline.UpdateFrameWeights(delta_weights);
+//     }
+// The reference's ComputeCurrentTraceback is a template over its own decoders (instantiated in the .cc for three FST types);
+// this one takes any decoder with NumFramesDecoded() and BestPath(use_final_probs, &ilabels, ..., &info, &arc_states):
+// SingleUtteranceNnet3DecoderB2k (b2k_nnet3_shims.h).  The bookkeeping is b2k_host::SilenceWeighting, pinned to the
+// reference's class call after call (tests/test_silence_weighting.py).
+class OnlineSilenceWeightingB2k {
+ public:
+  OnlineSilenceWeightingB2k(const TransitionModel &trans_model, const OnlineSilenceWeightingConfig &config,
+                            int32 frame_subsampling_factor = 1)
+      : config_(config), core_(TidToPhone(trans_model), config.silence_phones_str, config.silence_weight, config.max_state_duration,
+                               frame_subsampling_factor) {
+    KALDI_ASSERT(frame_subsampling_factor >= 1);
+    if (!core_.SilencePhonesParsed())        // the reference goes on with an empty list without a word
+      KALDI_WARN << "--silence-phones=" << config.silence_phones_str << " is not a list of integers: no phone counts as silence";
+  }
+
+  bool Active() const { return config_.Active(); }
+
+  template <class Decoder>
+  void ComputeCurrentTraceback(Decoder &decoder, bool use_final_probs = false) {
+    const int32 num_frames_decoded = decoder.NumFramesDecoded();
+    ilabels_.clear(); arc_states_.clear();
+    if (num_frames_decoded > 0) {
+      b2k_best_path_info info;
+      decoder.BestPath(use_final_probs, &ilabels_, NULL, NULL, NULL, &info, &arc_states_);
+    }
+    try {
+      if (!core_.SetTracebackFromPath(ilabels_.data(), arc_states_.data(), static_cast<int32>(ilabels_.size()), num_frames_decoded))
+        KALDI_ERR << "the best path does not hold one transition-id per decoded frame (" << num_frames_decoded << " frames)";
+    } catch (const std::runtime_error &e) { KALDI_ERR << e.what(); }
+  }
+
+  void GetDeltaWeights(int32 num_frames_ready, int32 first_decoder_frame, std::vector<std::pair<int32, BaseFloat> > *delta_weights) {
+    KALDI_ASSERT(num_frames_ready > first_decoder_frame || num_frames_ready == 0);
+    core_.GetDeltaWeights(num_frames_ready, first_decoder_frame, delta_weights);
+  }
+  void GetDeltaWeights(int32 num_frames_ready, std::vector<std::pair<int32, BaseFloat> > *delta_weights) {
+    GetDeltaWeights(num_frames_ready, 0, delta_weights);
+  }
+  void GetNonsilenceFrames(int32 num_frames_ready, int32 first_decoder_frame, std::vector<int32> *frames) {
+    KALDI_ASSERT(num_frames_ready > first_decoder_frame || num_frames_ready == 0);
+    core_.GetNonsilenceFrames(num_frames_ready, first_decoder_frame, frames);
+  }
+
+ private:
+  static std::vector<int32_t> TidToPhone(const TransitionModel &trans_model) {
+    std::vector<int32_t> t(trans_model.NumTransitionIds() + 1, 0);
+    for (int32 tid = 1; tid <= trans_model.NumTransitionIds(); tid++) t[tid] = trans_model.TransitionIdToPhone(tid);
+    return t;
+  }
+  const OnlineSilenceWeightingConfig &config_;
+  b2k_host::SilenceWeighting core_;
+  std::vector<int32> ilabels_, arc_states_;
 };
 
 }  // namespace b2k_shim

@@ -138,7 +138,8 @@ def check() -> bool:
         open(su, "w").write(
             '#include "decoder/lattice-faster-decoder.h"\n'
             "#define KALDI_DECODER_LATTICE_FASTER_ONLINE_DECODER_H_\n#define KALDI_DECODER_LATTICE_INCREMENTAL_ONLINE_DECODER_H_\n"
-            '#include "online2/online-endpoint.h"\n#include "b2k_nnet3_shims.h"\n'
+            "namespace kaldi { template <class FST> class LatticeFasterOnlineDecoderTpl; template <class FST> class LatticeIncrementalOnlineDecoderTpl; }\n"
+            '#include <queue>\n#include "online2/online-endpoint.h"\n#include "b2k_nnet3_shims.h"\n#include "b2k_online2_shims.h"\n'
             "using namespace kaldi;\n"
             "struct Feats { OnlineFeatureInterface *InputFeature(); OnlineFeatureInterface *IvectorFeature(); BaseFloat FrameShiftInSeconds() const; };\n"
             "void f(const LatticeFasterDecoderConfig &opts, const TransitionModel &tm, const nnet3::DecodableNnetSimpleLoopedInfo &info,\n"
@@ -147,6 +148,22 @@ def check() -> bool:
             "  d.InitDecoding(0); d.AdvanceDecoding(); bool e = d.EndpointDetected(ep); (void)e; d.FinalizeDecoding();\n"
             "  int32 n = d.NumFramesDecoded(); (void)n; BaseFloat c = d.FinalRelativeCost(); (void)c;\n"
             "  Lattice best; d.GetBestPath(true, &best);\n"
+            "}\n"
+            "// the silence weighting of the tool's loop (online2-wav-nnet3-latgen-faster.cc:222-262) over the b2k decoder and pipeline\n"
+            "void g(const LatticeFasterDecoderConfig &opts, const TransitionModel &tm, const nnet3::DecodableNnetSimpleLoopedInfo &info,\n"
+            "       const b2k_fst *graph, const OnlineNnet2FeaturePipelineInfo &finfo, const b2k_shim::FeatureTablesB2k &tables) {\n"
+            "  b2k_shim::OnlineNnet2FeaturePipelineB2k feature_pipeline(finfo, tables);\n"
+            "  b2k_shim::OnlineSilenceWeightingB2k silence_weighting(tm, finfo.silence_weighting_config, info.opts.frame_subsampling_factor);\n"
+            "  b2k_shim::SingleUtteranceNnet3DecoderB2k<LatticeFasterDecoderConfig, b2k_shim::OnlineNnet2FeaturePipelineB2k> decoder(opts, tm, info, graph, &feature_pipeline);\n"
+            "  std::vector<std::pair<int32, BaseFloat> > delta_weights;\n"
+            "  if (silence_weighting.Active() && feature_pipeline.IvectorFeature() != NULL) {\n"
+            "    silence_weighting.ComputeCurrentTraceback(decoder);\n"
+            "    silence_weighting.GetDeltaWeights(feature_pipeline.NumFramesReady(), 0, &delta_weights);\n"
+            "    silence_weighting.GetDeltaWeights(feature_pipeline.NumFramesReady(), &delta_weights);\n"
+            "    feature_pipeline.UpdateFrameWeights(delta_weights);\n"
+            "    std::vector<int32> ns; silence_weighting.GetNonsilenceFrames(feature_pipeline.NumFramesReady(), 0, &ns);\n"
+            "  }\n"
+            "  decoder.AdvanceDecoding();\n"
             "}\n")
         stub = os.path.join(ROOT, "oracle", "ref_wrap", "fst_stub")
         flags = RF.cxxflags(["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "kaldi_b200", "host"),

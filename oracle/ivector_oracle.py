@@ -118,6 +118,42 @@ class RefIvector:
             raise RuntimeError("reference i-vector extraction failed")
         return (out, dr, dn) if debug else out
 
+    def run_real(self, feats: np.ndarray, schedule, online_cmvn_iextractor: bool = False, speaker=None,
+                 max_remembered_frames: float = 1000.0, delta_weights=None):
+        """The same through the reference's OWN OnlineIvectorFeature (oracle/ref_wrap/silence_wrap.cc: ref_ivector_run_real), which
+        run()'s glue restates.  delta_weights: per chunk a list of (frame, weight difference) handed to UpdateFrameWeights before that
+        chunk's GetFrame (the silence weighting of the online2 tools); None = unweighted."""
+        ex = self.ex
+        if not hasattr(self.lib, "ref_ivector_run_real"):
+            raise RuntimeError("oracle/_ref predates silence_wrap.cc")
+        f = np.ascontiguousarray(feats, np.float32)
+        T, D = f.shape
+        sched = np.ascontiguousarray(schedule, np.int32)
+        out = np.zeros((len(sched), ex["ivector_dim"]), np.float32)
+        g = np.ascontiguousarray(ex["global_cmvn_stats"], np.float64)
+        fp, dp, ip = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        off = fr = w = None
+        if delta_weights is not None:
+            assert len(delta_weights) == len(sched)
+            off = np.zeros(len(sched) + 1, np.int32)
+            off[1:] = np.cumsum([len(d) for d in delta_weights])
+            flat = [p for d in delta_weights for p in d]
+            fr = np.array([p[0] for p in flat] + [0], np.int32)
+            w = np.array([p[1] for p in flat] + [0.0], np.float32)
+        self.lib.ref_ivector_run_real.argtypes = None
+        r = self.lib.ref_ivector_run_real(self.h, f.ctypes.data_as(fp), T, D, g.ctypes.data_as(dp), ex["cmn_window"],
+                                          ex["speaker_frames"], ex["global_frames"], ex["splice"], ex["splice"],
+                                          ex["num_gselect"], C.c_float(ex["min_post"]), C.c_float(ex["posterior_scale"]),
+                                          C.c_float(ex["max_count"]), ex["num_cg_iters"], int(online_cmvn_iextractor),
+                                          sched.ctypes.data_as(ip), len(sched), out.ctypes.data_as(fp),
+                                          speaker, C.c_float(max_remembered_frames),
+                                          off.ctypes.data_as(ip) if off is not None else None,
+                                          fr.ctypes.data_as(ip) if fr is not None else None,
+                                          w.ctypes.data_as(fp) if w is not None else None)
+        if r != 0:
+            raise RuntimeError("reference OnlineIvectorFeature failed")
+        return out
+
     # used by bench.py's CPU arm
     def chunk_ivectors(self, feats, n_chunks, frames_per_chunk, right_context):
         sched = IVM.online_ivector_schedule(160000 if feats.shape[0] == 998 else (feats.shape[0] - 1) * 160 + 400, 2880, 400, 160,

@@ -42,7 +42,8 @@ NNET_SOURCES = [s for s in NNET_SOURCES if s != "tree/tree-renderer.cc"]
 def build(quiet: bool = False, force: bool = False) -> str:
     wrap = os.path.join(HERE, "ref_wrap", "nnet_wrap.cc")
     wraps = [wrap, os.path.join(HERE, "ref_wrap", "ivector_wrap.cc"), os.path.join(HERE, "ref_wrap", "nnet_stubs.cc"),
-             os.path.join(HERE, "ref_wrap", "endpoint_wrap.cc")]
+             os.path.join(HERE, "ref_wrap", "endpoint_wrap.cc"), os.path.join(HERE, "ref_wrap", "silence_wrap.cc"),
+             os.path.join(HERE, "ref_wrap", "replay_decoder.h"), os.path.join(HERE, "ref_wrap", "ivector_ref_types.h")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(w) for w in wraps):
         return SO
     if not os.path.isdir(RF.SRC):
@@ -66,8 +67,11 @@ def build(quiet: bool = False, force: bool = False) -> str:
     subprocess.check_call(["g++"] + flags + ["-c", wrap, "-o", wobj])
     eobj = os.path.join(OUT_DIR, "obj_nnet", "endpoint_wrap.o")
     subprocess.check_call(["g++"] + flags + ["-c", os.path.join(HERE, "ref_wrap", "endpoint_wrap.cc"), "-o", eobj])
+    # OnlineSilenceWeighting: the reference's online-ivector-feature.cc as it lies, over the replay decoder
+    zobj = os.path.join(OUT_DIR, "obj_nnet", "silence_wrap.o")
+    subprocess.check_call(["g++"] + flags + ["-c", os.path.join(HERE, "ref_wrap", "silence_wrap.cc"), "-o", zobj])
     subprocess.check_call(["g++"] + flags + ["-c", os.path.join(HERE, "ref_wrap", "nnet_stubs.cc"), "-o", sobj])
-    subprocess.check_call(["g++", "-shared", "-o", SO] + objs + base_objs + [wobj, sobj, iobj, eobj, blas,
+    subprocess.check_call(["g++", "-shared", "-o", SO] + objs + base_objs + [wobj, sobj, iobj, eobj, zobj, blas,
                           "-Wl,--disable-new-dtags,-rpath," + os.path.dirname(blas), "-lpthread", "-lm", "-ldl"])
     return SO
 

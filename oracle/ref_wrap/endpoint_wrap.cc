@@ -1,51 +1,16 @@
 // TEST INFRASTRUCTURE ONLY (oracle side).  Compiles the reference's OWN online2/online-endpoint.cc where it lies:
 // EndpointDetected (the five rules), TrailingSilenceLength<DEC> and OnlineEndpointConfig::Register run unmodified.
-// The decoder headers that file includes need OpenFst, which this image does not have, so their include guards are
-// pre-defined here and the decoder class templates are declared as a replay device: a decoder that "has decoded" a
-// given best path and hands it back, last arc first, through the BestPathEnd / TraceBackBestPath interface
-// (decoder/lattice-faster-online-decoder.h:88-118).  The endpoint code itself sees the interface it was written for.
+// The decoder it queries is the replay device of replay_decoder.h (the decoder headers need OpenFst, which this image
+// does not have): the endpoint code itself sees the interface it was written for.
 #include <cstdio>
 #include <cstring>
 #include <sstream>
 #include <string>
 #include <vector>
 
-#define KALDI_LAT_KALDI_LATTICE_H_
-#define KALDI_DECODER_LATTICE_FASTER_ONLINE_DECODER_H_
-#define KALDI_DECODER_LATTICE_INCREMENTAL_ONLINE_DECODER_H_
-#define KALDI_DECODER_GRAMMAR_FST_H_
-#include "base/kaldi-common.h"
+#include "replay_decoder.h"
 #include "util/common-utils.h"
 #include "hmm/transition-model.h"
-#include <fst/fst-decl.h>     // forward declarations only (written by oracle/ref_nnet.py)
-
-namespace fst {
-struct ConstGrammarFst {};
-struct VectorGrammarFst {};
-}  // namespace fst
-
-namespace kaldi {
-struct LatticeArc { int ilabel = 0, olabel = 0, nextstate = 0; };
-
-struct ReplayDecoder {
-  std::vector<int> path;                    // ilabels of the best path in time order, epsilons (0) allowed
-  int frames = 0;
-  float final_relative_cost = 0.0f;
-  struct BestPathIterator {
-    int pos;                                // index of the arc handed out next; -1 = done
-    bool Done() const { return pos < 0; }
-  };
-  BestPathIterator BestPathEnd(bool, BaseFloat *) const { return BestPathIterator{(int)path.size() - 1}; }
-  BestPathIterator TraceBackBestPath(BestPathIterator it, LatticeArc *arc) const {
-    arc->ilabel = path[it.pos];
-    return BestPathIterator{it.pos - 1};
-  }
-  int32 NumFramesDecoded() const { return frames; }
-  BaseFloat FinalRelativeCost() const { return final_relative_cost; }
-};
-template <class F> struct LatticeFasterOnlineDecoderTpl : public ReplayDecoder {};
-template <class F> struct LatticeIncrementalOnlineDecoderTpl : public ReplayDecoder {};
-}  // namespace kaldi
 
 #include "online2/online-endpoint.cc"
 

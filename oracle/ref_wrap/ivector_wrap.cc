@@ -10,8 +10,10 @@
 // and this file restates only the glue of OnlineIvectorFeature
 // (online2/online-ivector-feature.cc: ctor :399-443, GetMinPost :188-199,
 // UpdateStatsForFrames :201-245, UpdateStatsUntilFrame :248-281, GetFrame
-// :327-355), which cannot be compiled as is because the same translation unit
-// instantiates OnlineSilenceWeighting over the OpenFst-based decoder.
+// :327-355).  That translation unit also instantiates OnlineSilenceWeighting over the
+// OpenFst-based decoders; silence_wrap.cc compiles it over a replay decoder instead and
+// runs the reference's OWN OnlineIvectorFeature on the same inputs (ref_ivector_run_real):
+// tests/test_ivector_oracle_pin.py holds the glue below to it, bit for bit.
 #include <sstream>
 #include <memory>
 #include <vector>
@@ -24,18 +26,8 @@
 
 using namespace kaldi;
 
-struct RefIvec {
-  IvectorExtractor extractor;
-  DiagGmm ubm;
-  Matrix<BaseFloat> lda;
-};
-
-// One speaker across utterances: what OnlineIvectorExtractorAdaptationState holds (online2/online-ivector-feature.h:218-263).
-struct RefSpeaker {
-  bool has = false;
-  OnlineCmvnState cmvn;
-  std::unique_ptr<OnlineIvectorEstimationStats> stats;
-};
+#include "ivector_ref_types.h"
+using namespace b2k_oracle;
 
 extern "C" {
 
