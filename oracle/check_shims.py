@@ -170,6 +170,20 @@ def check() -> bool:
                              "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "oracle", "_ref", "inc")])
         flags = [f for f in flags if not f.startswith("-I")] + ["-I" + stub] + [f for f in flags if f.startswith("-I")]
         subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1", "-DB2K_HAVE_OPENFST", "-DB2K_OPENFST_IS_STANDIN"] + flags + [su])
+        # The reference's TOOLS, as they lie in the reference tree, against the drop-in header (kaldi_b200/host/b2k_online2_dropin.h
+        # force-included: OnlineNnet2FeaturePipeline, OnlineSilenceWeighting and SingleUtteranceNnet3Decoder become the b2k adapters;
+        # every other statement of the tools is compiled as written).  OpenFst is the container stand-in plus fst_stub_tool/
+        # (CompactLattice as a container, DECLARATIONS of the lattice library calls the tools make after decoding).
+        tool_stub = os.path.join(ROOT, "oracle", "ref_wrap", "fst_stub_tool")
+        tflags = [f for f in flags if not f.startswith("-I")] + ["-I" + tool_stub] + [f for f in flags if f.startswith("-I")]
+        for tool in ("online2bin/online2-wav-nnet3-latgen-faster.cc", "online2bin/online2-tcp-nnet3-decode-faster.cc"):
+            pre = subprocess.run(["g++", "-E", "-DHAVE_CUDA=1", "-include", "b2k_online2_dropin.h"] + tflags + [os.path.join(RF.SRC, tool)],
+                                 check=True, capture_output=True, text=True).stdout
+            for adapter in ("b2k_dropin::OnlineNnet2FeaturePipeline feature_pipeline(", "b2k_dropin::SingleUtteranceNnet3Decoder decoder(",
+                            "b2k_dropin::OnlineSilenceWeighting silence_weighting("):
+                assert adapter in pre, (tool, adapter)          # the tool's own objects ARE the adapters
+            subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1", "-include", "b2k_online2_dropin.h"] + tflags +
+                                  [os.path.join(RF.SRC, tool)])
     return True
 
 

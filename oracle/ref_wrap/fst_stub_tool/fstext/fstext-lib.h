@@ -1,0 +1,15 @@
+// TEST INFRASTRUCTURE ONLY (oracle/check_shims.py, -fsyntax-only): what online2bin/online2-wav-nnet3-latgen-faster.cc uses of
+// fstext-lib.h and of OpenFst's symbol table: declarations (fstext/kaldi-fst-io.h:49, fst/symbol-table.h).
+#ifndef B2K_ORACLE_FST_STUB_TOOL_FSTEXT_LIB_H_
+#define B2K_ORACLE_FST_STUB_TOOL_FSTEXT_LIB_H_
+#include <string>
+#include "fst/fstlib.h"
+namespace fst {
+class SymbolTable {
+ public:
+  static SymbolTable *ReadText(const std::string &filename);
+  std::string Find(long key) const;
+};
+Fst<StdArc> *ReadFstKaldiGeneric(std::string rxfilename, bool throw_on_err = true);
+}  // namespace fst
+#endif
