@@ -184,6 +184,16 @@ def check() -> bool:
                 assert adapter in pre, (tool, adapter)          # the tool's own objects ARE the adapters
             subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1", "-include", "b2k_online2_dropin.h"] + tflags +
                                   [os.path.join(RF.SRC, tool)])
+        # ... and the CUDA online tool against kaldi_b200/host/b2k_cuda_pipeline_dropin.h: BatchedThreadedNnet3CudaOnlinePipeline and
+        # CudaOnlinePipelineDynamicBatcher become adapters over the b2k streaming pipeline; option structs, result and callback
+        # types, the lattice postprocessor and cuda-bin-tools.h stay the reference's
+        tool = os.path.join(RF.SRC, "cudadecoderbin/batched-wav-nnet3-cuda-online.cc")
+        pre = subprocess.run(["g++", "-E", "-DHAVE_CUDA=1", "-include", "b2k_cuda_pipeline_dropin.h"] + tflags + [tool],
+                             check=True, capture_output=True, text=True).stdout
+        for adapter in ("b2k_cuda_dropin::BatchedThreadedNnet3CudaOnlinePipeline cuda_pipeline(",
+                        "b2k_cuda_dropin::CudaOnlinePipelineDynamicBatcher dynamic_batcher("):
+            assert adapter in pre, adapter
+        subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1", "-include", "b2k_cuda_pipeline_dropin.h"] + tflags + [tool])
     return True
 
 

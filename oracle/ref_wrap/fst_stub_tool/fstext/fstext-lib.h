@@ -4,12 +4,8 @@
 #define B2K_ORACLE_FST_STUB_TOOL_FSTEXT_LIB_H_
 #include <string>
 #include "fst/fstlib.h"
+#include "fst/symbol-table.h"
 namespace fst {
-class SymbolTable {
- public:
-  static SymbolTable *ReadText(const std::string &filename);
-  std::string Find(long key) const;
-};
 Fst<StdArc> *ReadFstKaldiGeneric(std::string rxfilename, bool throw_on_err = true);
 }  // namespace fst
 #endif
