@@ -1,9 +1,13 @@
-// b2k_cuda_pipeline_dropin.h -- build cudadecoderbin/batched-wav-nnet3-cuda-online.cc against b2k WITHOUT editing it.
+// b2k_cuda_pipeline_dropin.h -- build cudadecoderbin/batched-wav-nnet3-cuda-online.cc and batched-wav-nnet3-cuda2.cc against
+// b2k WITHOUT editing them.
 //
 //   g++ ... -include b2k_cuda_pipeline_dropin.h cudadecoderbin/batched-wav-nnet3-cuda-online.cc ... -lb2k
+//   g++ ... -include b2k_cuda_pipeline_dropin.h cudadecoderbin/batched-wav-nnet3-cuda2.cc ... -lb2k
 //
-// The tool drives two classes: cuda_decoder::BatchedThreadedNnet3CudaOnlinePipeline (cudadecoder/batched-threaded-nnet3-cuda-
-// online-pipeline.h:119-330) and cuda_decoder::CudaOnlinePipelineDynamicBatcher (cuda-online-pipeline-dynamic-batcher.h:38-60).
+// The online tool drives two classes: cuda_decoder::BatchedThreadedNnet3CudaOnlinePipeline (cudadecoder/batched-threaded-nnet3-
+// cuda-online-pipeline.h:119-330) and cuda_decoder::CudaOnlinePipelineDynamicBatcher (cuda-online-pipeline-dynamic-batcher.h:
+// 38-60); the offline tool (the reference's throughput benchmark) drives cuda_decoder::BatchedThreadedNnet3CudaPipeline2
+// (batched-threaded-nnet3-cuda-pipeline2.h:57-245), which is the online pipeline fed whole utterances chunk by chunk.
 // This header includes the reference's own headers first (so that the tool's later #includes are no-ops and the option
 // structs, CudaPipelineResult, SegmentedLatticeCallbackParams, LatticePostprocessor stay the reference's types), then lets the
 // two names resolve to adapters over the b2k streaming pipeline (b2k_stream_*: features, chunked nnet3 with carried context,
@@ -30,7 +34,9 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <cmath>
 #include <random>                                    // the tool uses std::mt19937 and gets <random> through OpenFst
+#include <set>
 #include <string>
 #include <utility>
 #include <vector>
@@ -47,6 +53,7 @@
 #include "b2k_kaldi_shims.h"
 #include "b2k_nnet3_shims.h"
 #include "b2k_online2_shims.h"
+#include "b2k_utterance_pump.h"
 
 namespace kaldi {
 namespace cuda_decoder {
@@ -218,13 +225,153 @@ class CudaOnlinePipelineDynamicBatcher {
   b2k_shim::CudaOnlinePipelineDynamicBatcherB2k impl_;
 };
 
+// cuda_decoder::BatchedThreadedNnet3CudaPipeline2 (cudadecoder/batched-threaded-nnet3-cuda-pipeline2.h:57-245): whole
+// utterances in, one callback per utterance out.  Like the reference's class it owns an online pipeline and feeds it the
+// utterances chunk by chunk (b2k_host::UtterancePump: the reference's control thread, here on the caller's thread -- a full
+// batch of utterances is decoded as soon as there is one, WaitForAllTasks / WaitForGroup decode what is left, callbacks run on
+// the calling thread).  Segmentation (seg_opts) is the reference's: NumberOfSegments, the per-segment offsets, segments shorter
+// than --min-segment-length dropped (:265-334).
+class BatchedThreadedNnet3CudaPipeline2 {
+ public:
+  typedef kaldi::cuda_decoder::BatchedThreadedNnet3CudaPipeline2Config Config;
+  BatchedThreadedNnet3CudaPipeline2(const Config &config, const fst::Fst<fst::StdArc> &decode_fst,
+                                    const nnet3::AmNnetSimple &am_nnet, const TransitionModel &trans_model)
+      : config_(config), online_(config.cuda_online_pipeline_opts, decode_fst, am_nnet, trans_model), backend_{&online_},
+        pump_(&backend_, online_.GetConfig().max_batch_size, online_.GetNSampsPerChunk()) {
+    config_.Check();
+    model_freq_ = online_.GetModelFrequency();
+    segment_length_nsamples_ = config_.seg_opts.segment_length_s * model_freq_;                                  // :77-83
+    segment_shift_nsamples_ = (config_.seg_opts.segment_length_s - config_.seg_opts.segment_overlap_s) * model_freq_;
+    min_segment_length_nsamples_ = config_.seg_opts.min_segment_length_s * model_freq_;
+  }
+  virtual ~BatchedThreadedNnet3CudaPipeline2() {}
+
+  void SegmentedDecodeWithCallback(const std::shared_ptr<WaveData> &wave_data, const SegmentedResultsCallback &segmented_callback,
+                                   const int result_type = CudaPipelineResult::RESULT_TYPE_LATTICE) {
+    KALDI_ASSERT(result_type && "You must define at least one result type");
+    KALDI_ASSERT("Mismatch in model and utt frequency" && (wave_data->SampFreq() == model_freq_));
+    SubVector<BaseFloat> h_wave(wave_data->Data(), 0);
+    const int total_nsamples = h_wave.Dim();
+    if (total_nsamples == 0) {                       // one empty lattice (:336-345)
+      SegmentedLatticeCallbackParams params;
+      params.results.emplace_back();
+      CompactLattice clat;
+      params.results.back().SetLatticeResult(std::move(clat));
+      segmented_callback(params);
+      return;
+    }
+    const int nsegments = NumberOfSegments(total_nsamples, segment_length_nsamples_, segment_shift_nsamples_);
+    // what the segments of one utterance share: the result slots, how many are still out, the audio
+    struct Shared {
+      std::vector<CudaPipelineResult> results;
+      int not_done;
+      std::shared_ptr<WaveData> wave;
+      SegmentedResultsCallback callback;
+    };
+    std::shared_ptr<Shared> shared = std::make_shared<Shared>();
+    shared->wave = wave_data;
+    shared->callback = segmented_callback;
+    std::vector<std::pair<int, int> > segments;      // (offset, nsamples) of the segments that are decoded
+    int dropped = 0;
+    for (int offset = 0;; offset += segment_shift_nsamples_) {
+      const int nsamples = std::min(total_nsamples - offset, segment_length_nsamples_);
+      if (nsamples >= min_segment_length_nsamples_) segments.push_back(std::make_pair(offset, nsamples));
+      else dropped++;
+      if (offset + nsamples >= total_nsamples) break;
+    }
+    KALDI_ASSERT(nsegments - dropped == static_cast<int>(segments.size()));                  // :333
+    shared->results.resize(segments.size());
+    shared->not_done = static_cast<int>(segments.size());
+    if (segments.empty()) { SegmentedLatticeCallbackParams params; segmented_callback(params); return; }
+    std::shared_ptr<LatticePostprocessor> *postprocessor = &lattice_postprocessor_;
+    for (size_t i = 0; i < segments.size(); i++) {
+      shared->results[i].SetTimeOffsetSeconds(std::floor(static_cast<BaseFloat>(segments[i].first) / model_freq_));
+      shared->results[i].SetSegmentID(static_cast<int>(i));
+      if (i + 1 == segments.size()) shared->results[i].SetAsLastSegment();
+      const uint64_t corr_id = next_corr_id_++;
+      online_.SetLatticeCallback(corr_id, [shared, i, result_type, postprocessor](CompactLattice &clat) {
+        SetResultUsingLattice(clat, result_type, *postprocessor, &shared->results[i]);      // lattice-postprocessor.cc:115
+        if (--shared->not_done == 0) {
+          SegmentedLatticeCallbackParams params;
+          params.results = std::move(shared->results);
+          shared->callback(params);
+        }
+      });
+      pump_.Add(corr_id, h_wave.Data() + segments[i].first, segments[i].second, [shared]() {});   // keeps the audio alive
+    }
+    pump_.Run(false);
+  }
+
+  void DecodeWithCallback(const std::shared_ptr<WaveData> &wave_data, const std::function<void(CompactLattice &)> &callback,
+                          const std::string &group = std::string()) {
+    KALDI_ASSERT("Mismatch in model and utt frequency" && (wave_data->SampFreq() == model_freq_));
+    SubVector<BaseFloat> h_wave(wave_data->Data(), 0);
+    std::shared_ptr<WaveData> keep = wave_data;
+    Submit(h_wave.Data(), h_wave.Dim(), callback, group, [keep]() {});
+  }
+  // the samples must stay valid until the callback has run (the reference keeps a SubVector onto them too, :190-196)
+  void DecodeWithCallback(const VectorBase<BaseFloat> &wave_data, float sample_rate,
+                          const std::function<void(CompactLattice &)> &callback, const std::string &group = std::string()) {
+    KALDI_ASSERT(sample_rate == model_freq_);
+    Submit(wave_data.Data(), wave_data.Dim(), callback, group, std::function<void()>());
+  }
+
+  void SetLatticePostprocessor(const std::shared_ptr<LatticePostprocessor> &lattice_postprocessor) {
+    lattice_postprocessor_ = lattice_postprocessor;
+    lattice_postprocessor_->SetDecoderFrameShift(online_.GetDecoderFrameShiftSeconds());     // …pipeline2.cc:148-154
+    lattice_postprocessor_->SetTransitionInformation(&online_.GetTransitionModel());
+  }
+  // groups exist so that a caller can wait for some of its tasks; on one thread every wait decodes what is pending
+  void CreateTaskGroup(const std::string &group) { KALDI_ASSERT("Group is already in use" && groups_.insert(group).second); }
+  void DestroyTaskGroup(const std::string &group) { KALDI_ASSERT("Group does not exist" && groups_.erase(group) == 1); }
+  void WaitForGroup(const std::string &group) {
+    KALDI_ASSERT("Group does not exist. Call CreateTaskGroup() first" && groups_.count(group));
+    pump_.Run(true);
+  }
+  void WaitForAllTasks() { pump_.Run(true); }
+  void SetSymbolTable(const fst::SymbolTable &word_syms) { online_.SetSymbolTable(word_syms); }
+
+ private:
+  void Submit(const BaseFloat *samples, int32 num_samples, const std::function<void(CompactLattice &)> &callback,
+              const std::string &group, std::function<void()> release) {
+    if (!group.empty()) KALDI_ASSERT("Group does not exist. Call CreateTaskGroup() first" && groups_.count(group));
+    if (num_samples == 0) return;                    // nothing to do (:218)
+    const uint64_t corr_id = next_corr_id_++;
+    online_.SetLatticeCallback(corr_id, callback);
+    pump_.Add(corr_id, samples, num_samples, std::move(release));
+    pump_.Run(false);
+  }
+  struct Backend {                                   // UtterancePump's view of the online pipeline
+    BatchedThreadedNnet3CudaOnlinePipeline *online;
+    void DecodeBatch(const std::vector<uint64_t> &ids, const std::vector<std::pair<const float *, int64_t> > &chunks,
+                     const std::vector<bool> &first, const std::vector<bool> &last) {
+      std::vector<SubVector<BaseFloat> > waves;
+      for (size_t i = 0; i < chunks.size(); i++)
+        waves.push_back(SubVector<BaseFloat>(const_cast<BaseFloat *>(chunks[i].first), static_cast<MatrixIndexT>(chunks[i].second)));
+      online->DecodeBatch(ids, waves, first, last);
+    }
+  };
+
+  const Config &config_;
+  BatchedThreadedNnet3CudaOnlinePipeline online_;
+  Backend backend_;
+  b2k_host::UtterancePump<Backend> pump_;
+  std::shared_ptr<LatticePostprocessor> lattice_postprocessor_;
+  std::set<std::string> groups_;
+  uint64_t next_corr_id_ = 0;
+  BaseFloat model_freq_ = 16000.0f;
+  int segment_length_nsamples_ = 0, segment_shift_nsamples_ = 0, min_segment_length_nsamples_ = 0;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(BatchedThreadedNnet3CudaPipeline2);
+};
+
 }  // namespace b2k_cuda_dropin
 }  // namespace cuda_decoder
 }  // namespace kaldi
 
-// From here on the two names mean the adapters (whole tokens only: ...PipelineConfig and ...DynamicBatcherConfig are other
-// tokens and stay the reference's structs).
+// From here on the three names mean the adapters (whole tokens only: ...PipelineConfig, ...Pipeline2Config and
+// ...DynamicBatcherConfig are other tokens and stay the reference's structs).
 #define BatchedThreadedNnet3CudaOnlinePipeline b2k_cuda_dropin::BatchedThreadedNnet3CudaOnlinePipeline
 #define CudaOnlinePipelineDynamicBatcher b2k_cuda_dropin::CudaOnlinePipelineDynamicBatcher
+#define BatchedThreadedNnet3CudaPipeline2 b2k_cuda_dropin::BatchedThreadedNnet3CudaPipeline2
 
 #endif  // B2K_CUDA_PIPELINE_DROPIN_H_

@@ -187,13 +187,17 @@ def check() -> bool:
         # ... and the CUDA online tool against kaldi_b200/host/b2k_cuda_pipeline_dropin.h: BatchedThreadedNnet3CudaOnlinePipeline and
         # CudaOnlinePipelineDynamicBatcher become adapters over the b2k streaming pipeline; option structs, result and callback
         # types, the lattice postprocessor and cuda-bin-tools.h stay the reference's
-        tool = os.path.join(RF.SRC, "cudadecoderbin/batched-wav-nnet3-cuda-online.cc")
-        pre = subprocess.run(["g++", "-E", "-DHAVE_CUDA=1", "-include", "b2k_cuda_pipeline_dropin.h"] + tflags + [tool],
-                             check=True, capture_output=True, text=True).stdout
-        for adapter in ("b2k_cuda_dropin::BatchedThreadedNnet3CudaOnlinePipeline cuda_pipeline(",
-                        "b2k_cuda_dropin::CudaOnlinePipelineDynamicBatcher dynamic_batcher("):
-            assert adapter in pre, adapter
-        subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1", "-include", "b2k_cuda_pipeline_dropin.h"] + tflags + [tool])
+        for name, adapters in (("cudadecoderbin/batched-wav-nnet3-cuda-online.cc",
+                                ("b2k_cuda_dropin::BatchedThreadedNnet3CudaOnlinePipeline cuda_pipeline(",
+                                 "b2k_cuda_dropin::CudaOnlinePipelineDynamicBatcher dynamic_batcher(")),
+                               # the offline tool (whole utterances, the reference's throughput benchmark): BatchedThreadedNnet3CudaPipeline2
+                               ("cudadecoderbin/batched-wav-nnet3-cuda2.cc", ("b2k_cuda_dropin::BatchedThreadedNnet3CudaPipeline2 cuda_pipeline(",))):
+            tool = os.path.join(RF.SRC, name)
+            pre = subprocess.run(["g++", "-E", "-DHAVE_CUDA=1", "-include", "b2k_cuda_pipeline_dropin.h"] + tflags + [tool],
+                                 check=True, capture_output=True, text=True).stdout
+            for adapter in adapters:
+                assert adapter in pre, (name, adapter)
+            subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1", "-include", "b2k_cuda_pipeline_dropin.h"] + tflags + [tool])
     return True
 
 

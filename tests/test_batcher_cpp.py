@@ -43,6 +43,18 @@ def test_dynamic_batcher_with_mock_pipeline(tmp_path):
         assert r.returncode == 0 and "dynamic batcher ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_utterance_pump_with_mock_pipeline(tmp_path):
+    """b2k_host::UtterancePump (the role of BatchedThreadedNnet3CudaPipeline2's control thread: whole utterances through the
+    chunk-at-a-time pipeline): every sample once and in order, flags, batch sizes, eager and draining runs."""
+    _gxx()
+    exe = str(tmp_path / "utterance_pump_test")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I" + HOST,
+                        os.path.join(ROOT, "tests", "cabi", "utterance_pump_test.cc"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "utterance pump ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_pipeline_backend_links_and_fails_loudly_without_a_device(tmp_path):
     _gxx()
     so = os.path.join(ROOT, "kaldi_b200", "libb2k.so")
