@@ -709,6 +709,12 @@ int b2k_lat_determinize_pruned(const b2k_raw_lattice *raw, float beam, int64_t m
  * (--phone-determinize / --word-determinize; at least one must be set).  The transition model as three arrays over transition-ids
  * (index 0 unused): TransitionIdToPhone, IsSelfLoop, TransitionIdIsStartOfPhone.  Same accepted sequences, weights and alignments
  * as b2k_lat_determinize_pruned within the beam; b2k_clat_sizes' counters are the sum of both passes. */
+/* In place: what DeterminizeLatticePhonePruned adds under --minimize (lat/determinize-lattice-pruned.cc:1459-1465, off by
+ * default): PushCompactLatticeStrings + PushCompactLatticeWeights (lat/push-lattice.cc: transition-ids and costs move as
+ * early as every path allows; the start state keeps what is left) and MinimizeCompactLattice (lat/minimize-lattice.cc:
+ * states with the same words, strings and -- within delta, the reference's default is 1/1024 -- weights ahead of them
+ * become one).  Same language, alignments and path weights (up to float rounding).  State 0 stays the start. */
+int b2k_clat_minimize(b2k_clat *clat, float delta);
 int b2k_lat_determinize_phone_pruned(const b2k_raw_lattice *raw, float beam, int64_t max_states, const int32_t *phone_of,
                                      const uint8_t *self_loop, const uint8_t *phone_start, int32_t num_tids,
                                      int32_t phone_determinize, int32_t word_determinize, b2k_clat **out);

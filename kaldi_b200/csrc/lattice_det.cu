@@ -440,6 +440,246 @@ int b2k_lat_determinize_phone_pruned(const b2k_raw_lattice *in, float beam, int6
 
 int b2k_clat_destroy(b2k_clat *c) { delete c; return B2K_OK; }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Push + minimize: what DeterminizeLatticePhonePruned does after determinization under --minimize
+// (lat/determinize-lattice-pruned.cc:1459-1465): PushCompactLatticeStrings, PushCompactLatticeWeights (lat/push-lattice.cc),
+// MinimizeCompactLattice (lat/minimize-lattice.cc).  The lattice stays an acyclic deterministic acceptor over words with the
+// same language, path weights (up to float rounding of the re-distribution) and alignments; transition-ids move as early and
+// costs as early as they can, after which states with the same future are one state.
+namespace {
+
+struct LW {                                   // LatticeWeight: (graph, acoustic), compared by the sum, then by the first
+  float g, a;
+  static LW Zero() { const float inf = std::numeric_limits<float>::infinity(); return LW{inf, inf}; }
+  bool IsZero() const { const float inf = std::numeric_limits<float>::infinity(); return g == inf && a == inf; }
+};
+inline LW lw_times(const LW &x, const LW &y) { return LW{x.g + y.g, x.a + y.a}; }
+inline LW lw_plus(const LW &x, const LW &y) {            // the better of the two (fstext/lattice-weight.h:295-315)
+  const float fx = x.g + x.a, fy = y.g + y.a;
+  if (fx < fy) return x;
+  if (fx > fy) return y;
+  return x.g <= y.g ? x : y;
+}
+inline LW lw_divide(const LW &x, const LW &y) {          // :371-386: anything that is not a number is Zero
+  const float inf = std::numeric_limits<float>::infinity();
+  const float g = x.g - y.g, a = x.a - y.a;
+  if (g != g || a != a || g == -inf || a == -inf || g == inf || a == inf) return LW::Zero();
+  return LW{g, a};
+}
+inline bool lw_approx_equal(const LW &x, const LW &y, float delta) {       // :390-395
+  if (x.g == y.g && x.a == y.a) return true;
+  return std::fabs((x.g + x.a) - (y.g + y.a)) <= delta;
+}
+
+struct MArc { int32_t dst, word; LW w; std::vector<int32_t> str; };
+struct MState { std::vector<MArc> arcs; bool is_final = false; LW fw = LW::Zero(); std::vector<int32_t> fstr; };
+
+// the first n transition-ids met on a path out of state s (any path: the callers only ask where every path agrees)
+void first_tids(const std::vector<MState> &st, int32_t s, size_t n, std::vector<int32_t> *out) {
+  while (n > 0) {
+    const MState &q = st[s];
+    const std::vector<int32_t> *str;
+    int32_t next = -1;
+    if (q.is_final) str = &q.fstr;
+    else if (!q.arcs.empty()) { str = &q.arcs[0].str; next = q.arcs[0].dst; }
+    else return;                                          // a dead end: nothing more to give
+    const size_t take = std::min(n, str->size());
+    out->insert(out->end(), str->begin(), str->begin() + take);
+    n -= take;
+    if (next < 0) return;
+    s = next;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2k_clat_minimize(b2k_clat *c, float delta) {
+  if (!c || !(delta >= 0.f)) return b2k::set_error(B2K_ERR_INVALID, "b2k_clat_minimize: bad args");
+  const int64_t N = c->num_states, A = (int64_t)c->arc_src.size(), F = (int64_t)c->final_state.size();
+  if (N == 0) return B2K_OK;                               // an empty lattice is pushed and minimal
+  std::vector<MState> st(N);
+  for (int64_t a = 0; a < A; a++) {
+    MArc m;
+    m.dst = c->arc_dst[a]; m.word = c->arc_word[a]; m.w = LW{c->arc_g[a], c->arc_a[a]};
+    m.str.assign(c->tids.begin() + c->arc_str_off[a], c->tids.begin() + c->arc_str_off[a + 1]);
+    st[c->arc_src[a]].arcs.push_back(std::move(m));
+  }
+  for (int64_t f = 0; f < F; f++) {
+    MState &q = st[c->final_state[f]];
+    q.is_final = true; q.fw = LW{c->final_g[f], c->final_a[f]};
+    q.fstr.assign(c->tids.begin() + c->final_str_off[f], c->tids.begin() + c->final_str_off[f + 1]);
+  }
+  // topological order from the start state (0): depth first, a state after everything it reaches, then reversed
+  std::vector<int32_t> order;
+  {
+    std::vector<uint8_t> mark(N, 0);                       // 1 = on the stack, 2 = done
+    std::vector<std::pair<int32_t, size_t> > stack;
+    stack.push_back(std::make_pair(0, (size_t)0));
+    mark[0] = 1;
+    while (!stack.empty()) {
+      const int32_t s = stack.back().first;
+      if (stack.back().second < st[s].arcs.size()) {
+        const int32_t d = st[s].arcs[stack.back().second++].dst;
+        if (mark[d] == 1) return b2k::set_error(B2K_ERR_STATE, "b2k_clat_minimize: the lattice has a cycle");
+        if (mark[d] == 0) { mark[d] = 1; stack.push_back(std::make_pair(d, (size_t)0)); }
+      } else {
+        mark[s] = 2; order.push_back(s); stack.pop_back();
+      }
+    }
+    std::reverse(order.begin(), order.end());              // states the start does not reach are dropped at the end
+  }
+  const size_t R = order.size();
+
+  // 1. strings: shift[s] = how many transition-ids every path out of s starts with, so that they can sit on the arcs INTO s
+  {
+    std::vector<int64_t> shift(N, 0);
+    std::vector<int32_t> ref, cmp;
+    for (size_t k = R; k-- > 1;) {                         // not the start state: nothing comes before it
+      const int32_t s = order[k];
+      const MState &q = st[s];
+      if (q.arcs.empty()) { shift[s] = (int64_t)q.fstr.size(); continue; }
+      int64_t sh = q.is_final ? (int64_t)q.fstr.size() : std::numeric_limits<int64_t>::max();
+      for (const MArc &m : q.arcs) sh = std::min(sh, shift[m.dst] + (int64_t)m.str.size());
+      if (q.arcs.size() + (q.is_final ? 1 : 0) > 1 && sh > 0) {      // several ways on: keep what they have in common
+        ref.clear();
+        size_t from = 0;
+        if (q.is_final) ref.assign(q.fstr.begin(), q.fstr.begin() + sh);
+        else {
+          ref.assign(q.arcs[0].str.begin(), q.arcs[0].str.begin() + std::min<size_t>(sh, q.arcs[0].str.size()));
+          first_tids(st, q.arcs[0].dst, sh - ref.size(), &ref);
+          from = 1;
+        }
+        for (size_t i = from; i < q.arcs.size() && sh > 0; i++) {
+          const MArc &m = q.arcs[i];
+          cmp.assign(m.str.begin(), m.str.begin() + std::min<size_t>(sh, m.str.size()));
+          first_tids(st, m.dst, sh - cmp.size(), &cmp);
+          int64_t same = 0;
+          while (same < sh && same < (int64_t)ref.size() && same < (int64_t)cmp.size() && ref[same] == cmp[same]) same++;
+          sh = same;
+        }
+      }
+      shift[s] = sh;
+    }
+    std::vector<std::vector<std::vector<int32_t> > > new_str(N);     // computed from the old strings, then swapped in
+    for (size_t k = 0; k < R; k++) {
+      const int32_t s = order[k];
+      new_str[s].resize(st[s].arcs.size());
+      for (size_t i = 0; i < st[s].arcs.size(); i++) {
+        const MArc &m = st[s].arcs[i];
+        std::vector<int32_t> full(m.str);
+        first_tids(st, m.dst, (size_t)shift[m.dst], &full);
+        new_str[s][i].assign(full.begin() + shift[s], full.end());
+      }
+    }
+    for (size_t k = 0; k < R; k++) {
+      const int32_t s = order[k];
+      for (size_t i = 0; i < st[s].arcs.size(); i++) st[s].arcs[i].str.swap(new_str[s][i]);
+      if (st[s].is_final) st[s].fstr.erase(st[s].fstr.begin(), st[s].fstr.begin() + shift[s]);
+    }
+  }
+
+  // 2. weights: to_end[s] = the best weight from s to the end; every arc then carries its share, the start keeps the rest
+  {
+    std::vector<LW> to_end(N, LW::Zero());
+    for (size_t k = R; k-- > 0;) {
+      const int32_t s = order[k];
+      LW w = st[s].fw;
+      for (const MArc &m : st[s].arcs) w = lw_plus(w, lw_times(m.w, to_end[m.dst]));
+      to_end[s] = w;
+    }
+    to_end[0] = LW{0.f, 0.f};
+    for (size_t k = 0; k < R; k++) {
+      const int32_t s = order[k];
+      if (to_end[s].IsZero()) continue;
+      for (MArc &m : st[s].arcs)
+        if (!to_end[m.dst].IsZero()) m.w = lw_times(m.w, lw_divide(to_end[m.dst], to_end[s]));
+      if (st[s].is_final) st[s].fw = lw_divide(st[s].fw, to_end[s]);
+    }
+  }
+
+  // 3. states with the same future become one: last states first, so that what an arc leads to is already a class
+  std::vector<int32_t> cls(N);
+  for (int64_t s = 0; s < N; s++) cls[s] = (int32_t)s;
+  {
+    struct Key { int32_t word, dst; const MArc *arc; };
+    auto sorted_arcs = [&](int32_t s, std::vector<Key> *out) {
+      out->clear();
+      for (const MArc &m : st[s].arcs) out->push_back(Key{m.word, cls[m.dst], &m});
+      std::sort(out->begin(), out->end(), [](const Key &x, const Key &y) { return x.word != y.word ? x.word < y.word : x.dst < y.dst; });
+    };
+    // an exact signature (words, classes reached, strings; not the costs) decides who is compared with whom
+    auto signature = [&](int32_t s, const std::vector<Key> &keys) {
+      uint64_t h = st[s].is_final ? 0x9E3779B97F4A7C15ull : 0x632BE59BD9B4E019ull;
+      auto mix = [&h](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+      if (st[s].is_final) { mix(st[s].fstr.size()); for (int32_t t : st[s].fstr) mix((uint64_t)(uint32_t)t); }
+      for (const Key &k : keys) {
+        mix(0xABCDull); mix((uint64_t)(uint32_t)k.word); mix((uint64_t)(uint32_t)k.dst); mix(k.arc->str.size());
+        for (int32_t t : k.arc->str) mix((uint64_t)(uint32_t)t);
+      }
+      return h;
+    };
+    std::unordered_map<uint64_t, std::vector<int32_t> > groups;      // representatives seen so far, latest last
+    std::vector<Key> ks, kt;
+    for (size_t k = R; k-- > 0;) {
+      const int32_t s = order[k];
+      sorted_arcs(s, &ks);
+      std::vector<int32_t> &g = groups[signature(s, ks)];
+      bool merged = false;
+      for (size_t i = g.size(); i-- > 0 && !merged;) {     // candidates in the order the reference meets them: nearest the start first
+        const int32_t t = g[i];
+        if (st[s].is_final != st[t].is_final || st[s].arcs.size() != st[t].arcs.size()) continue;
+        if (st[s].is_final && (!lw_approx_equal(st[s].fw, st[t].fw, delta) || st[s].fstr != st[t].fstr)) continue;
+        sorted_arcs(t, &kt);
+        bool same = true;
+        for (size_t j = 0; j < ks.size() && same; j++)
+          same = ks[j].word == kt[j].word && ks[j].dst == kt[j].dst && lw_approx_equal(ks[j].arc->w, kt[j].arc->w, 1.0f / 1024.0f) &&
+                 ks[j].arc->str == kt[j].arc->str;
+        if (same) { cls[s] = t; merged = true; }
+      }
+      if (!merged) g.push_back(s);
+    }
+  }
+
+  // write back: the states the (possibly merged) start reaches, renumbered from it, arcs in their old order
+  const int32_t start = cls[0];
+  std::vector<int32_t> newid(N, -1), kept;
+  {
+    std::vector<int32_t> todo(1, start);
+    newid[start] = 0; kept.push_back(start);
+    while (!todo.empty()) {
+      const int32_t s = todo.back(); todo.pop_back();
+      for (const MArc &m : st[s].arcs) {
+        const int32_t d = cls[m.dst];
+        if (newid[d] < 0) { newid[d] = (int32_t)kept.size(); kept.push_back(d); todo.push_back(d); }
+      }
+    }
+  }
+  b2k_clat out;
+  out.subsets_expanded = c->subsets_expanded; out.elements_total = c->elements_total; out.effective_beam = c->effective_beam;
+  out.num_states = (int64_t)kept.size();
+  out.arc_str_off.push_back(0);
+  for (int32_t s : kept)
+    for (const MArc &m : st[s].arcs) {
+      out.arc_src.push_back(newid[s]); out.arc_dst.push_back(newid[cls[m.dst]]); out.arc_word.push_back(m.word);
+      out.arc_g.push_back(m.w.g); out.arc_a.push_back(m.w.a);
+      out.tids.insert(out.tids.end(), m.str.begin(), m.str.end());
+      out.arc_str_off.push_back((int64_t)out.tids.size());
+    }
+  out.final_str_off.push_back((int64_t)out.tids.size());
+  for (int32_t s : kept)
+    if (st[s].is_final) {
+      out.final_state.push_back(newid[s]); out.final_g.push_back(st[s].fw.g); out.final_a.push_back(st[s].fw.a);
+      out.tids.insert(out.tids.end(), st[s].fstr.begin(), st[s].fstr.end());
+      out.final_str_off.push_back((int64_t)out.tids.size());
+    }
+  *c = std::move(out);
+  return B2K_OK;
+}
+
 // LatticeFasterDecoderTpl::GetBestPath (decoder/lattice-faster-decoder.cc:102-108 = GetRawLattice + ShortestPath over
 // graph + acoustic) / CudaDecoder::GetBestPath (cudadecoder/cuda-decoder.h): the cheapest path from state 0 to a final
 // state of a finalized raw lattice.  Ties: the first minimum in topological order of states and input order of arcs.

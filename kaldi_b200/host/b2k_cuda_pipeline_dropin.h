@@ -171,6 +171,7 @@ class BatchedThreadedNnet3CudaOnlinePipeline {
                                                           config_.det_opts.phone_determinize ? 1 : 0,
                                                           config_.det_opts.word_determinize ? 1 : 0, &c),
                          "b2k_lat_determinize_phone_pruned");
+    if (config_.det_opts.minimize) b2k_shim::CheckNnet3(b2k_clat_minimize(c, 1.0f / 1024.0f /* fst::kDelta, as the reference calls it */), "b2k_clat_minimize");
     CompactLattice clat;
     b2k_shim::BatchedOnlinePipelineB2k::FillCompactLattice(c, &clat);
     b2k_clat_destroy(c);

@@ -763,6 +763,7 @@ class SingleUtteranceNnet3DecoderB2k {
     CheckNnet3(b2k_lat_determinize_phone_pruned(&r, decoder_opts_.lattice_beam, 0, phone_of.data(), self_loop.data(), phone_start.data(), nt,
                                                 decoder_opts_.det_opts.phone_determinize ? 1 : 0, decoder_opts_.det_opts.word_determinize ? 1 : 0, &c),
                "b2k_lat_determinize_phone_pruned");
+    if (decoder_opts_.det_opts.minimize) CheckNnet3(b2k_clat_minimize(c, 1.0f / 1024.0f /* MinimizeCompactLattice's default delta, fst::kDelta */), "b2k_clat_minimize");   // :1459-1465
     BatchedOnlinePipelineB2k::FillCompactLattice(c, clat);
     b2k_clat_destroy(c);
   }

@@ -146,13 +146,15 @@ def raw_lattice_from_canonical(c: dict) -> dict:
 
 # ---- raw lattice -> compact lattice (kaldi_b200/csrc/lattice_det.cu through the C ABI; host only) -------------------
 
-def determinize_pruned(lat: dict, beam: float, max_states: int = 0, phones: dict | None = None, word_determinize: bool = True) -> dict:
+def determinize_pruned(lat: dict, beam: float, max_states: int = 0, phones: dict | None = None, word_determinize: bool = True,
+                       minimize: bool = False, delta: float = 1.0 / 1024.0) -> dict:
     """DeterminizeLatticePhonePrunedWrapper's role (lat/determinize-lattice-pruned.h:284) for one finalized raw
     lattice: returns the compact lattice as flat arrays — arc_src/arc_dst/arc_word/arc_graph_cost/arc_acoustic_cost,
     arc_tids (list of int32 arrays), final_state/final_graph_cost/final_acoustic_cost/final_tids, num_states (state 0
     = start) — plus `stats` (subsets expanded, elements).  See include/b2k.h b2k_lat_determinize_pruned.
     phones = dict(phone_of, self_loop, phone_start) over transition-ids: the two-pass form with the phone-level first pass
-    (b2k_lat_determinize_phone_pruned)."""
+    (b2k_lat_determinize_phone_pruned).  minimize: push strings and weights, then merge equivalent states (b2k_clat_minimize:
+    DeterminizeLatticePhonePrunedOptions::minimize, off by default in the reference too)."""
     import ctypes as C
     from . import _lib
     from .decoder import _RawLattice, _p
@@ -176,6 +178,13 @@ def determinize_pruned(lat: dict, beam: float, max_states: int = 0, phones: dict
                                                        C.c_int32, C.c_int32, C.c_void_p]
         _lib.check(L.b2k_lat_determinize_phone_pruned(C.byref(r), float(beam), int(max_states), po.ctypes.data, sl.ctypes.data,
                                                       ps.ctypes.data, len(po), 1, int(word_determinize), C.byref(h)))
+    if minimize:
+        L.b2k_clat_minimize.argtypes = [C.c_void_p, C.c_float]
+        rc = L.b2k_clat_minimize(h, float(delta))
+        if rc:
+            L.b2k_clat_destroy.argtypes = [C.c_void_p]
+            L.b2k_clat_destroy(h)
+            _lib.check(rc)
     L.b2k_clat_effective_beam.restype = C.c_float
     L.b2k_clat_effective_beam.argtypes = [C.c_void_p]
     eff = float(L.b2k_clat_effective_beam(h))

@@ -28,7 +28,12 @@ def build(quiet: bool = False, force: bool = False) -> str:
     flags = ref_feat.cxxflags()
     flags = [f for f in flags if not f.startswith("-I")] + ["-I" + stub] + [f for f in flags if f.startswith("-I")]
     objdir = os.path.join(ref_feat.OUT_DIR, "obj_det")
-    objs = ref_feat.compile_objects(BASE_SOURCES + ["lat/determinize-lattice-pruned.cc"], objdir, flags, quiet)
+    for f in ("lat_determinize-lattice-pruned.o", "lat_push-lattice.o", "lat_minimize-lattice.o"):
+        o = os.path.join(objdir, f)         # they depend on the stand-in headers, which the object cache does not track
+        if os.path.exists(o) and os.path.getmtime(o) < newest:
+            os.remove(o)
+    objs = ref_feat.compile_objects(BASE_SOURCES + ["lat/determinize-lattice-pruned.cc", "lat/push-lattice.cc", "lat/minimize-lattice.cc"],
+                                    objdir, flags, quiet)
     wobj = os.path.join(objdir, "det_wrap.o")
     subprocess.check_call(["g++"] + flags + ["-c", wrap, "-o", wobj])
     subprocess.check_call(["g++", "-shared", "-o", SO] + objs + [wobj, "-lpthread", "-lm", "-ldl"])
@@ -49,7 +54,7 @@ def lib():
         _lib = C.CDLL(path)
         _lib.ref_det_run.restype = C.c_void_p
         _lib.ref_det_run.argtypes = [C.c_int32, C.c_int64] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
-                                                                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+                                                                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         _lib.ref_det_sizes.argtypes = [C.c_void_p, C.c_void_p]
         _lib.ref_det_copy.argtypes = [C.c_void_p] * 12
         _lib.ref_det_free.argtypes = [C.c_void_p]
@@ -57,7 +62,7 @@ def lib():
 
 
 def determinize(lat: dict, beam: float, phone_determinize: bool = False, phone_of=None, self_loop=None, phone_start=None,
-                max_mem: int = 0) -> dict:
+                max_mem: int = 0, minimize: bool = False) -> dict:
     L = lib()
     k = {n: np.ascontiguousarray(lat[n], np.float32 if lat[n].dtype.kind == "f" else np.int32) for n in
          ("arc_src", "arc_dst", "arc_ilabel", "arc_olabel", "arc_graph_cost", "arc_acoustic_cost", "final_state", "final_cost")}
@@ -72,7 +77,7 @@ def determinize(lat: dict, beam: float, phone_determinize: bool = False, phone_o
     h = L.ref_det_run(len(lat["state_frame"]), len(k["arc_src"]), p(k["arc_src"]), p(k["arc_dst"]), p(k["arc_ilabel"]),
                       p(k["arc_olabel"]), p(k["arc_graph_cost"]), p(k["arc_acoustic_cost"]), len(k["final_state"]),
                       p(k["final_state"]), p(k["final_cost"]), float(beam), int(phone_determinize), p(ph), p(lo), p(st),
-                      n_tids, int(max_mem))
+                      n_tids, int(max_mem), int(minimize))
     try:
         sz = (C.c_int64 * 5)()
         L.ref_det_sizes(h, sz)

@@ -50,7 +50,7 @@ void *ref_det_run(int32_t num_states, int64_t num_arcs, const int32_t *src, cons
                   const int32_t *olabel, const float *graph, const float *acoustic, int64_t num_finals,
                   const int32_t *final_state, const float *final_cost, double beam, int32_t phone_determinize,
                   const int32_t *phone_of, const uint8_t *self_loop, const uint8_t *phone_start, int32_t num_tids,
-                  int32_t max_mem) {
+                  int32_t max_mem, int32_t minimize) {
   using namespace kaldi;
   Lattice lat;
   for (int32_t s = 0; s < num_states; s++) lat.AddState();
@@ -65,6 +65,8 @@ void *ref_det_run(int32_t num_states, int64_t num_arcs, const int32_t *src, cons
   fst::DeterminizeLatticePhonePrunedOptions opts;           // defaults: delta kDelta, word_determinize, no minimize
   opts.phone_determinize = phone_determinize != 0;
   if (max_mem > 0) opts.max_mem = max_mem;
+  opts.minimize = minimize != 0;                            // push strings, push weights, minimize (:1459-1465; the reference's own
+                                                            // lat/push-lattice.cc and lat/minimize-lattice.cc are compiled in)
   CompactLattice clat;
   Out *o = new Out();
   const auto t0 = std::chrono::steady_clock::now();
@@ -72,24 +74,28 @@ void *ref_det_run(int32_t num_states, int64_t num_arcs, const int32_t *src, cons
   g_last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   o->num_states = clat.NumStates();
   o->arc_off.push_back(0);
-  // the start state is made state 0 (Connect keeps relative order; TopSort put the start first)
-  for (int32_t s = 0; s < clat.NumStates(); s++)
+  // the readers assume state 0 = start: TopSort put it first; after minimization it may have been merged into a later state,
+  // in which case the two numbers are exchanged on the way out
+  const int32_t start = clat.NumStates() > 0 ? clat.Start() : 0;
+  auto id = [start](int32_t s) { return s == start ? 0 : (s == 0 ? start : s); };
+  for (int32_t n = 0; n < clat.NumStates(); n++) {
+    const int32_t s = id(n);                                // the state that is written as number n
     for (fst::ArcIterator<CompactLattice> it(clat, s); !it.Done(); it.Next()) {
       const CompactLatticeArc &a = it.Value();
-      o->arc_src.push_back(s); o->arc_dst.push_back(a.nextstate); o->arc_word.push_back(a.ilabel);
+      o->arc_src.push_back(n); o->arc_dst.push_back(id(a.nextstate)); o->arc_word.push_back(a.ilabel);
       o->arc_g.push_back(a.weight.Weight().Value1()); o->arc_a.push_back(a.weight.Weight().Value2());
       o->tids.insert(o->tids.end(), a.weight.String().begin(), a.weight.String().end());
       o->arc_off.push_back((int64_t)o->tids.size());
     }
+  }
   o->final_off.push_back((int64_t)o->tids.size());
-  for (int32_t s = 0; s < clat.NumStates(); s++) {
-    const CompactLatticeWeight w = clat.Final(s);
+  for (int32_t n = 0; n < clat.NumStates(); n++) {
+    const CompactLatticeWeight w = clat.Final(id(n));
     if (w == CompactLatticeWeight::Zero()) continue;
-    o->final_state.push_back(s); o->final_g.push_back(w.Weight().Value1()); o->final_a.push_back(w.Weight().Value2());
+    o->final_state.push_back(n); o->final_g.push_back(w.Weight().Value1()); o->final_a.push_back(w.Weight().Value2());
     o->tids.insert(o->tids.end(), w.String().begin(), w.String().end());
     o->final_off.push_back((int64_t)o->tids.size());
   }
-  if (clat.NumStates() > 0 && clat.Start() != 0) o->ok = -1;   // the readers assume state 0 = start
   return o;
 }
 

@@ -484,3 +484,140 @@ def test_phone_level_pass_alone_keeps_the_language_and_the_weights():
         lat = _random_lattice(np.random.default_rng(1), n_states=6, n_arcs=14, vocab=2)
         lat["arc_ilabel"][:] = 6                                             # a phone-start, non-self-loop transition-id on every arc
         _det(lat, 1e9, phones=bad)
+
+
+def _strings_are_pushed(c):
+    """After PushCompactLatticeStrings no state other than the start has a transition-id that ALL its ways on begin with."""
+    firsts = {}
+    for a in range(len(c["arc_src"])):
+        t = c["arc_tids"][a]
+        firsts.setdefault(int(c["arc_src"][a]), []).append(int(t[0]) if len(t) else None)
+    for i, s in enumerate(c["final_state"]):
+        t = c["final_tids"][i]
+        firsts.setdefault(int(s), []).append(int(t[0]) if len(t) else None)
+    return firsts
+
+
+@pytest.mark.parametrize("seed", range(300, 360))
+def test_push_and_minimize_agree_with_the_references(seed):
+    """b2k_clat_minimize against the reference's OWN lat/push-lattice.cc + lat/minimize-lattice.cc (compiled in oracle/_ref,
+    run by DeterminizeLatticePhonePruned under opts.minimize): same language, path weights and alignments as before and as the
+    reference's result, and the SAME number of states and arcs as the reference's minimized lattice."""
+    RD = _ref_det()
+    rng = np.random.default_rng(seed)
+    lat = _random_lattice(rng, n_states=int(rng.integers(4, 14)), n_arcs=int(rng.integers(6, 40)), vocab=int(rng.integers(1, 4)),
+                          tid_eps_frac=float(rng.choice([0.0, 0.2, 0.6])))
+    want = _enumerate_raw(lat)
+    if not want:
+        pytest.skip("no accepting path")
+    for phone_pass in (False, True):
+        plain = _det(lat, 1e9, phones=PHONES if phone_pass else None)
+        mine = _det_min(lat, 1e9, phones=PHONES if phone_pass else None)
+        r = RD.determinize(lat, 1e9, phone_determinize=phone_pass, minimize=True, **PHONES)
+        assert r["ok"] == 1
+        em, er, ep = _enumerate_compact(mine), _enumerate_compact(r), _enumerate_compact(plain)
+        assert set(em) == set(er) == set(ep) == set(want)
+        for k in want:
+            assert em[k][0] == pytest.approx(ep[k][0], abs=2e-4) and em[k][1] == pytest.approx(ep[k][1], abs=2e-4)
+            assert em[k][0] == pytest.approx(er[k][0], abs=2e-4) and em[k][1] == pytest.approx(er[k][1], abs=2e-4)
+            if want[k][4] - want[k][0] > 1e-3:
+                assert em[k][3] == er[k][3] == want[k][3], k
+        assert mine["num_states"] <= plain["num_states"]
+        assert (mine["num_states"], len(mine["arc_src"]), len(mine["final_state"])) == (r["num_states"], len(r["arc_src"]), len(r["final_state"]))
+        # pushed alike: the number of transition-ids per arc equals the reference's, as a multiset over (word, length)
+        key = lambda c: sorted((int(c["arc_word"][a]), len(c["arc_tids"][a])) for a in range(len(c["arc_src"])))
+        assert key(mine) == key(r)
+
+
+def _det_min(lat, beam, phones=None):
+    try:
+        from kaldi_b200.lattice import determinize_pruned
+        return determinize_pruned(lat, beam, phones=phones, minimize=True)
+    except OSError as e:
+        pytest.skip(str(e))
+
+
+def test_minimize_merges_identical_tails_and_keeps_the_start_at_zero():
+    """Two words leading into two copies of the same tail: after minimization there is one tail."""
+    # 0 -w1-> 1 -w3-> 3(final) ; 0 -w2-> 2 -w3-> 4(final): the determinized lattice has 5 states, the minimal one 3
+    lat = dict(state_frame=np.zeros(5, np.int32), state_hclg=np.arange(5, dtype=np.int32), state_tot_cost=np.zeros(5, np.float32),
+               state_extra_cost=np.zeros(5, np.float32),
+               arc_src=np.array([0, 0, 1, 2], np.int32), arc_dst=np.array([1, 2, 3, 4], np.int32),
+               arc_ilabel=np.array([11, 12, 13, 13], np.int32), arc_olabel=np.array([1, 2, 3, 3], np.int32),
+               arc_graph_cost=np.array([1.0, 2.0, 0.5, 0.5], np.float32), arc_acoustic_cost=np.array([0.25, 0.5, 1.0, 1.0], np.float32),
+               final_state=np.array([3, 4], np.int32), final_cost=np.array([0.125, 0.125], np.float32))
+    plain, mini = _det(lat, 100.0), _det_min(lat, 100.0)
+    assert plain["num_states"] == 5 and mini["num_states"] == 3
+    assert len(mini["arc_src"]) == 3 and len(mini["final_state"]) == 1
+    a, b = _enumerate_compact(plain), _enumerate_compact(mini)
+    assert set(a) == set(b) == {(1, 3), (2, 3)}
+    for k in a:
+        assert a[k][0] == pytest.approx(b[k][0], abs=1e-5) and a[k][3] == b[k][3]
+    # weights pushed: the best path's whole cost sits on the arcs out of the start; the other start arc carries the difference too
+    assert float(mini["final_graph_cost"][0]) + float(mini["final_acoustic_cost"][0]) == pytest.approx(0.0, abs=1e-6)
+
+
+def _lockstep(x, y, limit):
+    """Every word sequence of x that ends within `limit` is in y at the same cost (both deterministic, walked from state 0)."""
+    xo, yo = {}, {}
+    for i in range(len(x["arc_src"])):
+        xo.setdefault(int(x["arc_src"][i]), []).append(i)
+    for i in range(len(y["arc_src"])):
+        yo[(int(y["arc_src"][i]), int(y["arc_word"][i]))] = i
+    xf = {int(s): i for i, s in enumerate(x["final_state"])}
+    yf = {int(s): i for i, s in enumerate(y["final_state"])}
+    stack, seen, checked = [(0, 0, 0.0, 0.0)], {(0, 0)}, 0
+    while stack:
+        sx, sy, cx, cy = stack.pop()
+        if sx in xf:
+            tx = cx + float(x["final_graph_cost"][xf[sx]]) + float(x["final_acoustic_cost"][xf[sx]])
+            if tx <= limit:
+                assert sy in yf
+                ty = cy + float(y["final_graph_cost"][yf[sy]]) + float(y["final_acoustic_cost"][yf[sy]])
+                assert ty == pytest.approx(tx, abs=2e-3)
+                checked += 1
+        for i in xo.get(sx, []):
+            j = yo.get((sy, int(x["arc_word"][i])))
+            if j is None:
+                continue
+            nxt = (int(x["arc_dst"][i]), int(y["arc_dst"][j]))
+            # a pair of states can be reached at different accumulated costs once costs have been pushed: the DIFFERENCE is what
+            # has to agree, so a pair is expanded once and the difference checked on every other visit
+            ncx = cx + float(x["arc_graph_cost"][i]) + float(x["arc_acoustic_cost"][i])
+            ncy = cy + float(y["arc_graph_cost"][j]) + float(y["arc_acoustic_cost"][j])
+            if nxt in seen:
+                continue
+            seen.add(nxt)
+            stack.append((nxt[0], nxt[1], ncx, ncy))
+    return checked
+
+
+def test_minimize_on_decoder_output():
+    """A real decoder lattice (40 frames, 30 k-arc graph): minimization keeps every word sequence and its cost, the best path and
+    its alignment, and removes states; the reference's push + minimize of ITS determinized lattice has the same best path."""
+    RD = _ref_det()
+    from kaldi_b200 import synth
+    from kaldi_b200.lattice import compact_best_path, raw_lattice_from_canonical
+    from oracle import dec_oracle as D
+    g = synth.make_hclg(30_000, num_pdfs=60, seed=7, olabel_frac=0.3)
+    cfg = dict(synth.DEFAULT_DECODER_CFG)
+    ll = (np.random.default_rng(5).standard_normal((40, 60)) * 2.0).astype(np.float32)
+    o = D.DecoderOracle(g, cfg)
+    o.decode(ll, mode=D.MODE_REFERENCE_ORDER)
+    lat = raw_lattice_from_canonical(o.lattice())
+    beam = float(cfg["lattice_beam"])
+    plain, mini = _det(lat, beam), _det_min(lat, beam)
+    assert mini["num_states"] < plain["num_states"] and len(mini["arc_src"]) < len(plain["arc_src"])
+    a, b = compact_best_path(plain), compact_best_path(mini)
+    assert a["words"].tolist() == b["words"].tolist() and a["tids"].tolist() == b["tids"].tolist()
+    assert a["total_cost"] == pytest.approx(b["total_cost"], abs=1e-3)
+    assert _lockstep(plain, mini, 1e30) > 0 and _lockstep(mini, plain, 1e30) > 0
+    r = RD.determinize(lat, beam, minimize=True, **PHONES)
+    assert r["ok"] == 1
+    c = compact_best_path(r)
+    assert c["words"].tolist() == b["words"].tolist() and c["tids"].tolist() == b["tids"].tolist()
+    assert c["total_cost"] == pytest.approx(b["total_cost"], abs=1e-3)
+    limit = a["total_cost"] + beam - 0.05
+    assert _lockstep(r, mini, limit) > 0 and _lockstep(mini, r, limit) > 0
+    # the two minimal lattices differ at most by what the two determinizers kept just outside the beam
+    assert abs(r["num_states"] - mini["num_states"]) <= 0.1 * mini["num_states"] + 2
