@@ -176,14 +176,21 @@ def check() -> bool:
         # (CompactLattice as a container, DECLARATIONS of the lattice library calls the tools make after decoding).
         tool_stub = os.path.join(ROOT, "oracle", "ref_wrap", "fst_stub_tool")
         tflags = [f for f in flags if not f.startswith("-I")] + ["-I" + tool_stub] + [f for f in flags if f.startswith("-I")]
-        for tool in ("online2bin/online2-wav-nnet3-latgen-faster.cc", "online2bin/online2-tcp-nnet3-decode-faster.cc"):
-            pre = subprocess.run(["g++", "-E", "-DHAVE_CUDA=1", "-include", "b2k_online2_dropin.h"] + tflags + [os.path.join(RF.SRC, tool)],
+        decoding = ("b2k_dropin::OnlineNnet2FeaturePipeline feature_pipeline(", "b2k_dropin::SingleUtteranceNnet3Decoder decoder(",
+                    "b2k_dropin::OnlineSilenceWeighting silence_weighting(")
+        for hdr, tool, adapters in (
+                ("b2k_online2_dropin.h", "online2bin/online2-wav-nnet3-latgen-faster.cc", decoding),
+                ("b2k_online2_dropin.h", "online2bin/online2-tcp-nnet3-decode-faster.cc", decoding),
+                # the feature-side tool: the pipeline alone (features + i-vectors as matrices)
+                ("b2k_online2_dropin.h", "online2bin/online2-wav-dump-features.cc", ("b2k_dropin::OnlineNnet2FeaturePipeline feature_pipeline(",)),
+                # the offline nnet3 tools: DecodableNnetSimple / DecodableAmNnetSimple (kaldi_b200/host/b2k_nnet3_dropin.h)
+                ("b2k_nnet3_dropin.h", "nnet3bin/nnet3-compute.cc", ("b2k_nnet3_dropin::DecodableNnetSimple nnet_computer(",)),
+                ("b2k_nnet3_dropin.h", "nnet3bin/nnet3-latgen-faster.cc", ("b2k_nnet3_dropin::DecodableAmNnetSimple nnet_decodable(",))):
+            pre = subprocess.run(["g++", "-E", "-DHAVE_CUDA=1", "-include", hdr] + tflags + [os.path.join(RF.SRC, tool)],
                                  check=True, capture_output=True, text=True).stdout
-            for adapter in ("b2k_dropin::OnlineNnet2FeaturePipeline feature_pipeline(", "b2k_dropin::SingleUtteranceNnet3Decoder decoder(",
-                            "b2k_dropin::OnlineSilenceWeighting silence_weighting("):
+            for adapter in adapters:
                 assert adapter in pre, (tool, adapter)          # the tool's own objects ARE the adapters
-            subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1", "-include", "b2k_online2_dropin.h"] + tflags +
-                                  [os.path.join(RF.SRC, tool)])
+            subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1", "-include", hdr] + tflags + [os.path.join(RF.SRC, tool)])
         # ... and the CUDA online tool against kaldi_b200/host/b2k_cuda_pipeline_dropin.h: BatchedThreadedNnet3CudaOnlinePipeline and
         # CudaOnlinePipelineDynamicBatcher become adapters over the b2k streaming pipeline; option structs, result and callback
         # types, the lattice postprocessor and cuda-bin-tools.h stay the reference's

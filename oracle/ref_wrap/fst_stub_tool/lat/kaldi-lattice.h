@@ -61,5 +61,19 @@ class CompactLatticeHolder {                                             // lat/
   ~CompactLatticeHolder();
 };
 typedef TableWriter<CompactLatticeHolder> CompactLatticeWriter;
+class LatticeHolder {                                                    // lat/kaldi-lattice.h:132-170, declarations
+ public:
+  typedef Lattice T;
+  LatticeHolder();
+  static bool Write(std::ostream &os, bool binary, const T &t);
+  bool Read(std::istream &is);
+  static bool IsReadInBinary() { return true; }
+  T &Value();
+  void Clear();
+  void Swap(LatticeHolder *other);
+  bool ExtractRange(const LatticeHolder &other, const std::string &range);
+  ~LatticeHolder();
+};
+typedef TableWriter<LatticeHolder> LatticeWriter;
 }  // namespace kaldi
 #endif
