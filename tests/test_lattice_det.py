@@ -621,3 +621,51 @@ def test_minimize_on_decoder_output():
     assert _lockstep(r, mini, limit) > 0 and _lockstep(mini, r, limit) > 0
     # the two minimal lattices differ at most by what the two determinizers kept just outside the beam
     assert abs(r["num_states"] - mini["num_states"]) <= 0.1 * mini["num_states"] + 2
+
+
+@pytest.mark.parametrize("seed", range(400, 420))
+def test_minimize_is_idempotent(seed):
+    """Pushing and minimizing a lattice that is already pushed and minimal changes nothing but float rounding."""
+    import ctypes as C
+    from kaldi_b200 import _lib
+    try:
+        L = _lib.lib()
+    except OSError as e:
+        pytest.skip(str(e))
+    rng = np.random.default_rng(seed)
+    lat = _random_lattice(rng, n_states=int(rng.integers(5, 16)), n_arcs=int(rng.integers(8, 50)), vocab=2)
+    once = _det_min(lat, 1e9)
+    if not once["num_states"]:
+        pytest.skip("no accepting path")
+    # feed the minimized lattice back as a raw lattice (one arc per word arc, its transition-ids folded into a chain is not
+    # needed: determinizing a deterministic lattice keeps it) and minimize again
+    src, dst, il, ol, g, a = [], [], [], [], [], []
+    n = once["num_states"]
+    for i in range(len(once["arc_src"])):
+        tids = once["arc_tids"][i].tolist() or [0]
+        cur = int(once["arc_src"][i])
+        for k, t in enumerate(tids):
+            last = k + 1 == len(tids)
+            nxt = int(once["arc_dst"][i]) if last else n
+            if not last:
+                n += 1
+            src.append(cur); dst.append(nxt); il.append(t); ol.append(int(once["arc_word"][i]) if k == 0 else 0)
+            g.append(float(once["arc_graph_cost"][i]) if k == 0 else 0.0); a.append(float(once["arc_acoustic_cost"][i]) if k == 0 else 0.0)
+            cur = nxt
+    fs, fc = [], []
+    for i, s in enumerate(once["final_state"]):
+        cur = int(s)
+        for t in once["final_tids"][i].tolist():
+            src.append(cur); dst.append(n); il.append(t); ol.append(0); g.append(0.0); a.append(0.0)
+            cur = n; n += 1
+        fs.append(cur); fc.append(float(once["final_graph_cost"][i]) + float(once["final_acoustic_cost"][i]))
+    again = dict(state_frame=np.zeros(n, np.int32), state_hclg=np.arange(n, dtype=np.int32), state_tot_cost=np.zeros(n, np.float32),
+                 state_extra_cost=np.zeros(n, np.float32), arc_src=np.array(src, np.int32), arc_dst=np.array(dst, np.int32),
+                 arc_ilabel=np.array(il, np.int32), arc_olabel=np.array(ol, np.int32), arc_graph_cost=np.array(g, np.float32),
+                 arc_acoustic_cost=np.array(a, np.float32), final_state=np.array(fs, np.int32), final_cost=np.array(fc, np.float32))
+    twice = _det_min(again, 1e9)
+    assert (twice["num_states"], len(twice["arc_src"]), len(twice["final_state"])) == (once["num_states"], len(once["arc_src"]), len(once["final_state"]))
+    x, y = _enumerate_compact(once), _enumerate_compact(twice)
+    assert set(x) == set(y)
+    for k in x:
+        assert x[k][0] == pytest.approx(y[k][0], abs=2e-4) and x[k][3] == y[k][3]
