@@ -74,7 +74,6 @@ class BatchedThreadedNnet3CudaOnlinePipeline {
     if (feature_info_.use_ivectors)
       KALDI_ERR << "the b2k streaming pipeline has no per-chunk i-vector stage (--ivector-extraction-config)";
     if (feature_info_.add_pitch) KALDI_ERR << "b2k has no pitch kernel (--add-pitch)";
-    if (!config_.determinize_lattice) KALDI_ERR << "--determinize-lattice=false is not supported";
     model_.reset(new b2k_shim::ModelB2k(am_nnet, config_.compute_opts.frame_subsampling_factor));
     graph_.reset(new b2k_shim::CudaFstB2k(decode_fst, &trans_model));
 
@@ -165,16 +164,32 @@ class BatchedThreadedNnet3CudaOnlinePipeline {
  private:
   // raw lattice of a finished stream -> determinized CompactLattice (+ CTM) -> the caller's callback
   void FinishStream(const b2k_raw_lattice &raw, const SegmentedResultsCallback &callback, int result_type) {
-    b2k_clat *c = NULL;
-    b2k_shim::CheckNnet3(b2k_lat_determinize_phone_pruned(&raw, config_.decoder_opts.lattice_beam, 0, phone_of_.data(), self_loop_.data(),
-                                                          phone_start_.data(), static_cast<int32>(phone_of_.size()),
-                                                          config_.det_opts.phone_determinize ? 1 : 0,
-                                                          config_.det_opts.word_determinize ? 1 : 0, &c),
-                         "b2k_lat_determinize_phone_pruned");
-    if (config_.det_opts.minimize) b2k_shim::CheckNnet3(b2k_clat_minimize(c, 1.0f / 1024.0f /* fst::kDelta, as the reference calls it */), "b2k_clat_minimize");
     CompactLattice clat;
-    b2k_shim::BatchedOnlinePipelineB2k::FillCompactLattice(c, &clat);
-    b2k_clat_destroy(c);
+    if (config_.determinize_lattice) {                                                   // …online-pipeline.cc:755-760
+      b2k_clat *c = NULL;
+      b2k_shim::CheckNnet3(b2k_lat_determinize_phone_pruned(&raw, config_.decoder_opts.lattice_beam, 0, phone_of_.data(), self_loop_.data(),
+                                                            phone_start_.data(), static_cast<int32>(phone_of_.size()),
+                                                            config_.det_opts.phone_determinize ? 1 : 0,
+                                                            config_.det_opts.word_determinize ? 1 : 0, &c),
+                           "b2k_lat_determinize_phone_pruned");
+      if (config_.det_opts.minimize) b2k_shim::CheckNnet3(b2k_clat_minimize(c, 1.0f / 1024.0f /* fst::kDelta, as the reference calls it */), "b2k_clat_minimize");
+      b2k_shim::BatchedOnlinePipelineB2k::FillCompactLattice(c, &clat);
+      b2k_clat_destroy(c);
+    } else {
+      // ConvertLattice(lat, &clat) (fstext/lattice-utils.h:91): the raw lattice state for state, the word as the label, the
+      // transition-id (if any) as a one-element string
+      for (int64_t s = 0; s < raw.num_states; s++) clat.AddState();
+      if (raw.num_states > 0) clat.SetStart(0);
+      for (int64_t a = 0; a < raw.num_arcs; a++) {
+        std::vector<int32> str;
+        if (raw.arc_ilabel[a] != 0) str.push_back(raw.arc_ilabel[a]);
+        clat.AddArc(raw.arc_src[a], CompactLatticeArc(raw.arc_olabel[a], raw.arc_olabel[a],
+                                                       CompactLatticeWeight(LatticeWeight(raw.arc_graph_cost[a], raw.arc_acoustic_cost[a]), str),
+                                                       raw.arc_dst[a]));
+      }
+      for (int64_t f = 0; f < raw.num_finals; f++)
+        clat.SetFinal(raw.final_state[f], CompactLatticeWeight(LatticeWeight(raw.final_cost[f], 0.0f), std::vector<int32>()));
+    }
     SegmentedLatticeCallbackParams params;
     params.results.emplace_back();
     CudaPipelineResult &result = params.results[0];
