@@ -74,6 +74,7 @@ class BatchedThreadedNnet3CudaOnlinePipeline {
     if (feature_info_.use_ivectors)
       KALDI_ERR << "the b2k streaming pipeline has no per-chunk i-vector stage (--ivector-extraction-config)";
     if (feature_info_.add_pitch) KALDI_ERR << "b2k has no pitch kernel (--add-pitch)";
+    if (config_.reset_on_endpoint) KALDI_ERR << "--reset-on-endpoint is not supported (a stream is one segment)";
     model_.reset(new b2k_shim::ModelB2k(am_nnet, config_.compute_opts.frame_subsampling_factor));
     graph_.reset(new b2k_shim::CudaFstB2k(decode_fst, &trans_model));
 
@@ -94,6 +95,8 @@ class BatchedThreadedNnet3CudaOnlinePipeline {
     c.acoustic_scale = config_.compute_opts.acoustic_scale;
     c.use_priors = 1;
     pipeline_.reset(new b2k_shim::StreamingOnlinePipelineB2k(c, model_->Handle(), graph_->Handle()));
+    // the end-point rules are CudaDecoderConfig's (cuda-decoder.h:64,147: --endpoint.* registered beside the decoder options)
+    pipeline_->SetEndpointConfig(b2k_shim::ToB2kEndpointConfig(config_.decoder_opts.endpointing_config));
     seconds_per_chunk_ = pipeline_->GetNSampsPerChunk() / model_frequency_;
 
     const int32 nt = trans_model.NumTransitionIds() + 1;        // the transition model as the determinizer takes it
