@@ -227,3 +227,28 @@ def test_silence_list_parsing_is_the_references(ref, mine, tid2phone, sil, ok):
     if not ok or not sil:
         assert np.all(a[2] == 1.0)              # nothing is silence
     ref.ref_silw_destroy(r); mine.silw_destroy(m)
+
+
+def test_kaldi_typed_wrapper_beside_the_references_class(tmp_path, ref):
+    """OnlineSilenceWeightingB2k (the Kaldi-typed shim) constructed from the same TransitionModel and OnlineSilenceWeightingConfig as
+    the reference's class, in one C++ program (tests/cabi/silence_weighting_kaldi_test.cc) linked against oracle/_ref: 300 tracebacks,
+    delta weights and non-silence frames equal call after call; a decoder that goes backwards raises KaldiFatalError in both.
+    Needs the reference's headers: this container only."""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("/root/reference not present")
+    so_b2k = os.path.join(ROOT, "kaldi_b200", "libb2k.so")
+    if not os.path.exists(so_b2k):
+        pytest.skip("libb2k.so not built")
+    from oracle import nnet_oracle as NO, ref_feat as RF
+    blas = os.path.dirname(RF.find_openblas())
+    flags = RF.cxxflags(["-DHAVE_CUDA=0", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "kaldi_b200", "host"),
+                         "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "oracle", "_ref", "inc"),
+                         "-I" + os.path.join(ROOT, "oracle", "ref_wrap")])
+    exe = str(tmp_path / "swk")
+    r = subprocess.run(["g++"] + flags + [os.path.join(ROOT, "tests", "cabi", "silence_weighting_kaldi_test.cc"), "-o", exe, NO._SO,
+                        "-Wl,-rpath," + os.path.dirname(NO._SO), "-Wl,-rpath-link," + blas, "-Wl,-rpath," + blas,
+                        "-L" + os.path.dirname(so_b2k), "-lb2k", "-Wl,-rpath," + os.path.dirname(so_b2k), "-Wl,--allow-shlib-undefined"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe, MDL], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "silence weighting wrapper ok" in r.stdout, r.stdout + r.stderr[-2000:]
