@@ -91,8 +91,7 @@ inline b2k_feat_cfg ToB2kFeatCfg(const PlpOptions &o, int32 max_lanes = 1) {
 class FeatureTablesB2k {
  public:
   explicit FeatureTablesB2k(const OnlineNnet2FeaturePipelineInfo &info, int32 max_lanes = 1) {
-    if (info.add_pitch) KALDI_ERR << "b2k has no pitch kernel (--add-pitch)";
-    b2k_feat_cfg c;
+    b2k_feat_cfg c;                                        // (pitch, when asked for, is appended on the host by the pipeline below)
     if (info.feature_type == "mfcc") c = ToB2kFeatCfg(info.mfcc_opts, max_lanes);
     else if (info.feature_type == "fbank") c = ToB2kFeatCfg(info.fbank_opts, max_lanes);
     else if (info.feature_type == "plp") c = ToB2kFeatCfg(info.plp_opts, max_lanes);
@@ -116,10 +115,16 @@ class OnlineNnet2FeaturePipelineB2k : public OnlineFeatureInterface {
     base_.reset(new OnlineBaseFeatureB2k(tables.Handle(), info.FrameShiftInSeconds(),
                                          static_cast<int32>(max_seconds * b2k_feat_samp_freq(tables.Handle()))));
     OnlineFeatureInterface *top = base_.get();
+    if (info.add_pitch) {                                           // :111-116: the reference's own pitch objects, on the host
+      pitch_.reset(new OnlinePitchFeature(info.pitch_opts));        // (b2k has no pitch kernel; the base features come from the device)
+      pitch_feature_.reset(new OnlineProcessPitch(info.pitch_process_opts, pitch_.get()));
+      plus_pitch_.reset(new OnlineAppendFeature(base_.get(), pitch_feature_.get()));
+      top = plus_pitch_.get();
+    }
     if (info.use_cmvn) {                                            // online-nnet2-feature-pipeline.cc:121-131
       if (info.global_cmvn_stats.NumCols() == 0)
         KALDI_ERR << "global_cmvn_stats for OnlineCmvn must be non-empty, please assign it to OnlineNnet2FeaturePipelineInfo.";
-      cmvn_.reset(new OnlineCmvn(info.cmvn_opts, OnlineCmvnState(info.global_cmvn_stats), base_.get()));
+      cmvn_.reset(new OnlineCmvn(info.cmvn_opts, OnlineCmvnState(info.global_cmvn_stats), top));
       top = cmvn_.get();
     }
     input_ = top;                                                   // what the network reads as "input"
@@ -149,8 +154,14 @@ class OnlineNnet2FeaturePipelineB2k : public OnlineFeatureInterface {
   void SetCmvnState(const OnlineCmvnState &cmvn_state) { if (cmvn_) cmvn_->SetState(cmvn_state); }
   void GetCmvnState(OnlineCmvnState *cmvn_state) { if (cmvn_) cmvn_->GetState(cmvn_->NumFramesReady() - 1, cmvn_state); }
 
-  void AcceptWaveform(BaseFloat sampling_rate, const VectorBase<BaseFloat> &waveform) { base_->AcceptWaveform(sampling_rate, waveform); }
-  void InputFinished() { base_->InputFinished(); }
+  void AcceptWaveform(BaseFloat sampling_rate, const VectorBase<BaseFloat> &waveform) {          // :219-225
+    base_->AcceptWaveform(sampling_rate, waveform);
+    if (pitch_) pitch_->AcceptWaveform(sampling_rate, waveform);
+  }
+  void InputFinished() {                                                                          // :227-231
+    base_->InputFinished();
+    if (pitch_) pitch_->InputFinished();
+  }
 
   OnlineIvectorFeature *IvectorFeature() { return ivector_.get(); }
   const OnlineIvectorFeature *IvectorFeature() const { return ivector_.get(); }
@@ -160,6 +171,9 @@ class OnlineNnet2FeaturePipelineB2k : public OnlineFeatureInterface {
   const OnlineNnet2FeaturePipelineInfo &info_;
   // destruction runs bottom-up in reverse order of declaration: the stages on top go first
   std::unique_ptr<OnlineBaseFeatureB2k> base_;
+  std::unique_ptr<OnlinePitchFeature> pitch_;
+  std::unique_ptr<OnlineProcessPitch> pitch_feature_;
+  std::unique_ptr<OnlineAppendFeature> plus_pitch_;
   std::unique_ptr<OnlineCmvn> cmvn_;
   std::unique_ptr<OnlineIvectorFeature> ivector_;
   std::unique_ptr<OnlineAppendFeature> append_;
@@ -180,6 +194,7 @@ class OnlineBatchedFeaturePipelineB2k {
                                   int32_t num_channels, BaseFloat max_seconds = 120.0f)
       : info_(config), tables_(info_, max_lanes), max_chunk_size_samples_(max_chunk_size_samples), max_lanes_(max_lanes),
         num_channels_(num_channels) {
+    if (info_.add_pitch) KALDI_ERR << "b2k has no pitch kernel (--add-pitch); the single-utterance pipeline appends pitch on the host";
     if (info_.feature_type == "mfcc") frame_opts_ = info_.mfcc_opts.frame_opts;
     else if (info_.feature_type == "fbank") frame_opts_ = info_.fbank_opts.frame_opts;
     else frame_opts_ = info_.plp_opts.frame_opts;
