@@ -21,6 +21,7 @@
 
 #include <functional>
 #include <map>
+#include <mutex>
 
 #include "b2k.h"
 #include "b2k_dynamic_batcher.h"
@@ -383,15 +384,24 @@ class StreamingOnlinePipelineB2k {
   int32 GetNInputFramesPerChunk() const { return frames_per_chunk_; }
   BaseFloat GetDecoderFrameShiftSeconds() const { return decoder_frame_shift_seconds_; }
 
+  // Like the reference's (…online-pipeline.cc:107-168: available_channels_m_, map_callbacks_m_), TryInitCorrID and the callback
+  // setters may be called from other threads while ONE thread runs DecodeBatch (the dynamic batcher's worker).
   bool TryInitCorrID(CorrelationID corr_id, int /*wait_for*/ = 0) {                  // :165: false = every channel is taken
+    std::lock_guard<std::mutex> lock(chan_mu_);
     if (chan_.count(corr_id)) return true;
     if (free_.empty()) return false;
     chan_[corr_id] = free_.back();
     free_.pop_back();
     return true;
   }
-  void SetBestPathCallback(CorrelationID corr_id, const BestPathCallback &callback) { best_cb_[corr_id] = callback; }
-  void SetRawLatticeCallback(CorrelationID corr_id, const RawLatticeCallback &callback) { lat_cb_[corr_id] = callback; }
+  void SetBestPathCallback(CorrelationID corr_id, const BestPathCallback &callback) {
+    std::lock_guard<std::mutex> lock(cb_mu_);
+    best_cb_[corr_id] = callback;
+  }
+  void SetRawLatticeCallback(CorrelationID corr_id, const RawLatticeCallback &callback) {
+    std::lock_guard<std::mutex> lock(cb_mu_);
+    lat_cb_[corr_id] = callback;
+  }
   // how a word id is spelled in hypotheses (the reference reads its word symbol table); default: the id itself
   void SetWordMapper(const std::function<std::string(int32)> &f) { word_of_ = f; }
   void SetEndpointConfig(const b2k_endpoint_cfg &c) { endpoint_ = c; }
@@ -407,9 +417,12 @@ class StreamingOnlinePipelineB2k {
     pcm_.resize(n); chans_.resize(n); ptrs_.resize(n); ns_.resize(n); first_.resize(n); last_.resize(n);
     for (size_t i = 0; i < n; i++) {
       if (is_first_chunk[i] && !TryInitCorrID(corr_ids[i])) KALDI_ERR << "DecodeBatch: no free channel for a new utterance";
-      auto it = chan_.find(corr_ids[i]);
-      if (it == chan_.end()) KALDI_ERR << "DecodeBatch: unknown correlation id (its first chunk never came)";
-      chans_[i] = it->second;
+      {
+        std::lock_guard<std::mutex> lock(chan_mu_);
+        auto it = chan_.find(corr_ids[i]);
+        if (it == chan_.end()) KALDI_ERR << "DecodeBatch: unknown correlation id (its first chunk never came)";
+        chans_[i] = it->second;
+      }
       const SubVector<BaseFloat> &w = wave_samples[i];
       pcm_[i].resize(w.Dim());
       for (int32 k = 0; k < w.Dim(); k++) {
@@ -423,7 +436,22 @@ class StreamingOnlinePipelineB2k {
     Check(b2k_stream_decode_batch_i16(s_, (int32_t)n, chans_.data(), ptrs_.data(), ns_.data(), first_.data(), last_.data(), nullptr,
                                       nullptr, nullptr, nullptr, nullptr, cudaStreamPerThread), "b2k_stream_decode_batch_i16");
     b2k_dec *dec = b2k_stream_decoder(s_);
-    const bool want_text = partial_hypotheses != nullptr || end_point != nullptr || !best_cb_.empty();
+    // this batch's callbacks, taken under the lock and called without it (a callback may register callbacks)
+    batch_best_.assign(n, BestPathCallback()); batch_lat_.assign(n, RawLatticeCallback());
+    bool any_best = false;
+    {
+      std::lock_guard<std::mutex> lock(cb_mu_);
+      for (size_t i = 0; i < n; i++) {
+        auto b = best_cb_.find(corr_ids[i]);
+        if (b != best_cb_.end()) { batch_best_[i] = b->second; any_best = true; }
+        if (is_last_chunk[i]) {
+          auto l = lat_cb_.find(corr_ids[i]);
+          if (l != lat_cb_.end()) { batch_lat_[i] = l->second; lat_cb_.erase(l); }
+          if (b != best_cb_.end()) best_cb_.erase(b);
+        }
+      }
+    }
+    const bool want_text = partial_hypotheses != nullptr || end_point != nullptr || any_best;
     if (partial_hypotheses) partial_hypotheses->assign(n, nullptr);
     if (end_point) end_point->assign(n, false);
     if (want_text) {
@@ -441,7 +469,7 @@ class StreamingOnlinePipelineB2k {
           text += word_of_ ? word_of_(w) : std::to_string(w);
         }
         bool ep = false;
-        if ((end_point || !best_cb_.empty()) && model_ && num_tids_ > 0) {
+        if ((end_point || any_best) && model_ && num_tids_ > 0) {
           int32_t hit = 0;
           Check(b2k_endpoint_detected_on_path(&endpoint_, b2k_model_tid2phone(model_), num_tids_, il_.data() + i * (size_t)cap, info_[i].n_arcs,
                                               info_[i].num_frames, decoder_frame_shift_seconds_, info_[i].final_relative_cost, &hit, nullptr),
@@ -450,14 +478,12 @@ class StreamingOnlinePipelineB2k {
         }
         if (partial_hypotheses) (*partial_hypotheses)[i] = &text;
         if (end_point) (*end_point)[i] = ep;
-        auto cb = best_cb_.find(corr_ids[i]);
-        if (cb != best_cb_.end()) cb->second(text, /*partial=*/!is_last_chunk[i], ep);
+        if (batch_best_[i]) batch_best_[i](text, /*partial=*/!is_last_chunk[i], ep);
       }
     }
     for (size_t i = 0; i < n; i++) {
       if (!is_last_chunk[i]) continue;
-      auto cb = lat_cb_.find(corr_ids[i]);
-      if (cb != lat_cb_.end()) {
+      if (batch_lat_[i]) {
         b2k_raw_lattice q = {};
         Check(b2k_dec_get_raw_lattice(dec, chans_[i], &q, cudaStreamPerThread), "b2k_dec_get_raw_lattice");     // sizes
         st_f_.resize(q.num_states); st_h_.resize(q.num_states); st_t_.resize(q.num_states); st_e_.resize(q.num_states);
@@ -467,12 +493,13 @@ class StreamingOnlinePipelineB2k {
         q.arc_src = a_s_.data(); q.arc_dst = a_d_.data(); q.arc_ilabel = a_i_.data(); q.arc_olabel = a_o_.data();
         q.arc_graph_cost = a_g_.data(); q.arc_acoustic_cost = a_a_.data(); q.final_state = f_s_.data(); q.final_cost = f_c_.data();
         Check(b2k_dec_get_raw_lattice(dec, chans_[i], &q, cudaStreamPerThread), "b2k_dec_get_raw_lattice");
-        cb->second(corr_ids[i], q);
-        lat_cb_.erase(cb);
+        batch_lat_[i](corr_ids[i], q);
       }
-      best_cb_.erase(corr_ids[i]);
-      free_.push_back(chans_[i]);
-      chan_.erase(corr_ids[i]);
+      {
+        std::lock_guard<std::mutex> lock(chan_mu_);
+        free_.push_back(chans_[i]);
+        chan_.erase(corr_ids[i]);
+      }
       finished_.push_back(corr_ids[i]);
     }
   }
@@ -485,8 +512,11 @@ class StreamingOnlinePipelineB2k {
   b2k_endpoint_cfg endpoint_;
   std::vector<int32> free_;
   std::map<CorrelationID, int32> chan_;
+  std::mutex chan_mu_, cb_mu_;
   std::map<CorrelationID, BestPathCallback> best_cb_;
   std::map<CorrelationID, RawLatticeCallback> lat_cb_;
+  std::vector<BestPathCallback> batch_best_;
+  std::vector<RawLatticeCallback> batch_lat_;
   std::map<CorrelationID, std::string> text_;
   std::vector<CorrelationID> finished_;
   std::function<std::string(int32)> word_of_;
