@@ -35,6 +35,7 @@
 #include <map>
 #include <memory>
 #include <cmath>
+#include <cstdlib>
 #include <random>                                    // the tool uses std::mt19937 and gets <random> through OpenFst
 #include <set>
 #include <string>
@@ -66,8 +67,11 @@ class BatchedThreadedNnet3CudaOnlinePipeline {
   typedef std::function<void(CompactLattice &)> LatticeCallback;
   typedef kaldi::cuda_decoder::BatchedThreadedNnet3CudaOnlinePipelineConfig Config;
 
+  // max_seconds_per_stream: the device buffers of a channel (samples, features, decoder arenas) are sized for it -- the reference
+  // grows its buffers instead; B2K_STREAM_MAX_SECONDS in the environment overrides it for a tool that cannot pass it
   BatchedThreadedNnet3CudaOnlinePipeline(const Config &config, const fst::Fst<fst::StdArc> &decode_fst,
-                                         const nnet3::AmNnetSimple &am_nnet, const TransitionModel &trans_model)
+                                         const nnet3::AmNnetSimple &am_nnet, const TransitionModel &trans_model,
+                                         BaseFloat max_seconds_per_stream = 60.0f)
       : config_(config), trans_model_(&trans_model), feature_info_(config.feature_opts) {
     config_.compute_opts.CheckAndFixConfigs(am_nnet.GetNnet().Modulus());           // …online-pipeline.h:151-152
     config_.CheckAndFixConfigs();
@@ -91,6 +95,12 @@ class BatchedThreadedNnet3CudaOnlinePipeline {
     d.main_q_capacity = config_.decoder_opts.main_q_capacity; d.aux_q_capacity = config_.decoder_opts.aux_q_capacity;
     c.dec = d.ToB2k(c.dec.max_frames);
     c.nchannels = config_.num_channels;
+    c.max_seconds = max_seconds_per_stream;
+    if (const char *env = std::getenv("B2K_STREAM_MAX_SECONDS")) {
+      const double v = std::atof(env);
+      if (!(v > 0.0)) KALDI_ERR << "B2K_STREAM_MAX_SECONDS=" << env << " is not a positive number";
+      c.max_seconds = static_cast<float>(v);
+    }
     c.frames_per_chunk = config_.compute_opts.frames_per_chunk;
     c.acoustic_scale = config_.compute_opts.acoustic_scale;
     c.use_priors = 1;
@@ -255,7 +265,11 @@ class BatchedThreadedNnet3CudaPipeline2 {
   typedef kaldi::cuda_decoder::BatchedThreadedNnet3CudaPipeline2Config Config;
   BatchedThreadedNnet3CudaPipeline2(const Config &config, const fst::Fst<fst::StdArc> &decode_fst,
                                     const nnet3::AmNnetSimple &am_nnet, const TransitionModel &trans_model)
-      : config_(config), online_(config.cuda_online_pipeline_opts, decode_fst, am_nnet, trans_model), backend_{&online_},
+      : config_(config),
+        // a stream is one segment: with the default segmentation (20 s) the channels are sized for a segment, not for 60 s
+        online_(config.cuda_online_pipeline_opts, decode_fst, am_nnet, trans_model,
+                static_cast<BaseFloat>(std::min(60.0, config.seg_opts.segment_length_s) + 1.0)),
+        backend_{&online_},
         pump_(&backend_, online_.GetConfig().max_batch_size, online_.GetNSampsPerChunk()) {
     config_.Check();
     model_freq_ = online_.GetModelFrequency();
