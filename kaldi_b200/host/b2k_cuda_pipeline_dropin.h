@@ -93,13 +93,33 @@ class BatchedThreadedNnet3CudaOnlinePipeline {
     d.default_beam = config_.decoder_opts.default_beam; d.lattice_beam = config_.decoder_opts.lattice_beam;
     d.max_active = config_.decoder_opts.max_active; d.ntokens_pre_allocated = config_.decoder_opts.ntokens_pre_allocated;
     d.main_q_capacity = config_.decoder_opts.main_q_capacity; d.aux_q_capacity = config_.decoder_opts.aux_q_capacity;
-    c.dec = d.ToB2k(c.dec.max_frames);
     c.nchannels = config_.num_channels;
     c.max_seconds = max_seconds_per_stream;
     if (const char *env = std::getenv("B2K_STREAM_MAX_SECONDS")) {
       const double v = std::atof(env);
       if (!(v > 0.0)) KALDI_ERR << "B2K_STREAM_MAX_SECONDS=" << env << " is not a positive number";
       c.max_seconds = static_cast<float>(v);
+    }
+    // The b2k decoder keeps a stream's tokens and links on the device until its lattice has been read (the reference moves them
+    // to the host as it goes, cuda-decoder.cc:1100-1260), in arenas of a fixed size per channel: 12 bytes a token, 16 a link,
+    // two links a token on average.  With num_channels in the hundreds that is THE memory of the pipeline, so it is sized from
+    // what the device has: half of the free memory over the channels, at most 9000 tokens per decoder frame (what the batched
+    // bench gives a lane), and refused when that leaves fewer than 400 (a stream would overflow its arena).
+    {
+      const int32 sub = std::max(1, config_.compute_opts.frame_subsampling_factor);
+      const int64_t frames = static_cast<int64_t>(c.max_seconds * 1000.0f / c.feat.frame_shift_ms) / sub + 16;
+      size_t free_bytes = 0, total_bytes = 0;
+      if (cudaMemGetInfo(&free_bytes, &total_bytes) != cudaSuccess) KALDI_ERR << "cudaMemGetInfo failed: is a CUDA device selected?";
+      const double per_channel = 0.5 * static_cast<double>(free_bytes) / std::max(1, config_.num_channels);
+      int64_t tokens = static_cast<int64_t>(per_channel / (12.0 + 2.0 * 16.0));
+      tokens = std::min<int64_t>(tokens, frames * 9000);
+      if (tokens < frames * 400)
+        KALDI_ERR << "not enough device memory for " << config_.num_channels << " channels of " << c.max_seconds
+                  << " s each (" << (free_bytes >> 20) << " MB free): lower --num-channels / --max-batch-size, or the stream "
+                  << "length (B2K_STREAM_MAX_SECONDS, --segment-length)";
+      c.dec = d.ToB2k(static_cast<int32>(frames));
+      c.dec.max_tokens = tokens;
+      c.dec.max_links = 2 * tokens;
     }
     c.frames_per_chunk = config_.compute_opts.frames_per_chunk;
     c.acoustic_scale = config_.compute_opts.acoustic_scale;
