@@ -658,6 +658,9 @@ class SingleUtteranceNnet3DecoderB2k {
     c.beam = decoder_opts.beam; c.lattice_beam = decoder_opts.lattice_beam; c.max_active = decoder_opts.max_active;
     c.min_active = decoder_opts.min_active; c.beam_delta = decoder_opts.beam_delta; c.prune_interval = decoder_opts.prune_interval;
     c.prune_scale = decoder_opts.prune_scale; c.hash_ratio = decoder_opts.hash_ratio; c.max_frames = max_frames;
+    // one channel: its arenas hold the whole utterance (no interim pruning): 2000 tokens and 4000 links a frame, ~350 MB at 4096 frames
+    c.max_tokens = std::max<int64_t>(c.max_tokens, static_cast<int64_t>(max_frames) * 2000);
+    c.max_links = std::max<int64_t>(c.max_links, 2 * c.max_tokens);
     CheckNnet3(b2k_dec_create(fst, &c, 1, 1, &dec_), "b2k_dec_create");
     InitDecoding();
   }
