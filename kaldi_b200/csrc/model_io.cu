@@ -590,6 +590,16 @@ static void to_arch(const ParsedNnet &P, b2k_model *M) {
   }
   for (auto &ln : view)
     if (ln.kind == "component-node" && (!have_root || keep.count(ln.kv["name"]))) { inputs[ln.kv["name"]] = ln.kv["input"]; cn.push_back({ln.kv["name"], ln.kv}); }
+  // nnet3::CollapseModel (nnet3/nnet-utils.cc:1793-1796, 1891-1894) replaces two components by one called "<first>.<second>" and
+  // leaves the node its name: such a network is not the model as trained, and the patterns below would misread it
+  for (auto &e : cn) {
+    const std::string &node = e.first, &comp = e.second.at("component");
+    if (comp != node && comp.size() > node.size() + 1 &&
+        (comp.compare(comp.size() - node.size() - 1, std::string::npos, "." + node) == 0 || comp.compare(0, node.size() + 1, node + ".") == 0))
+      throw FormatError("component " + comp + " of node " + node + " is a merged one: the network has been through nnet3::CollapseModel; "
+                        "b2k folds batch-norm and dropout itself and takes the model as it was trained (build the tools with the "
+                        "b2k drop-in headers, which leave CollapseModel out)");
+  }
   A.node_dim["input"] = M->feat_dim; A.node_dim["ivector"] = M->ivector_dim;
   auto comp_of = [&](size_t i) -> const Component & {
     const Component *c = P.get(cn[i].second.at("component"));

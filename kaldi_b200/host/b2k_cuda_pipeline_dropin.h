@@ -423,6 +423,7 @@ class BatchedThreadedNnet3CudaPipeline2 {
 
 // From here on the three names mean the adapters (whole tokens only: ...PipelineConfig, ...Pipeline2Config and
 // ...DynamicBatcherConfig are other tokens and stay the reference's structs).
+#include "b2k_dropin_common.h"                      // leaves nnet3::CollapseModel out: b2k takes the model as trained
 #define BatchedThreadedNnet3CudaOnlinePipeline b2k_cuda_dropin::BatchedThreadedNnet3CudaOnlinePipeline
 #define CudaOnlinePipelineDynamicBatcher b2k_cuda_dropin::CudaOnlinePipelineDynamicBatcher
 #define BatchedThreadedNnet3CudaPipeline2 b2k_cuda_dropin::BatchedThreadedNnet3CudaPipeline2

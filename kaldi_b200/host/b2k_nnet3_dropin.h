@@ -73,6 +73,7 @@ class DecodableAmNnetSimple : public b2k_shim::DecodableAmNnetSimpleB2k {
 }  // namespace kaldi
 
 // From here on the two names mean the adapters (DecodableNnetSimpleLooped... and DecodableAmNnetSimpleParallel are other tokens).
+#include "b2k_dropin_common.h"                      // leaves nnet3::CollapseModel out: b2k takes the model as trained
 #define DecodableNnetSimple b2k_nnet3_dropin::DecodableNnetSimple
 #define DecodableAmNnetSimple b2k_nnet3_dropin::DecodableAmNnetSimple
 

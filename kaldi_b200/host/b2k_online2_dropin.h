@@ -92,6 +92,7 @@ typedef b2k_shim::OnlineSilenceWeightingB2k OnlineSilenceWeighting;
 
 // From here on the three names mean the adapters (whole tokens only: OnlineNnet2FeaturePipelineInfo / ...Config,
 // OnlineSilenceWeightingConfig and SingleUtteranceNnet3DecoderTpl are other tokens and stay the reference's).
+#include "b2k_dropin_common.h"                      // leaves nnet3::CollapseModel out: b2k takes the model as trained
 #define OnlineNnet2FeaturePipeline b2k_dropin::OnlineNnet2FeaturePipeline
 #define OnlineSilenceWeighting b2k_dropin::OnlineSilenceWeighting
 #define SingleUtteranceNnet3Decoder b2k_dropin::SingleUtteranceNnet3Decoder

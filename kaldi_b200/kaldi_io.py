@@ -566,6 +566,11 @@ def nnet3_to_arch(parsed: dict, name: str = "from_file", frame_subsampling_facto
     node_dim = {"input": dims["input"], "ivector": dims.get("ivector", 0)}
     nodes = _inference_view(nodes, comps)
     cn = [(kv["name"], kv) for kind, kv in nodes if kind == "component-node"]
+    for n, kv in cn:     # nnet3::CollapseModel names a merged component "<first>.<second>" and leaves the node its name
+        c = kv.get("component", n)
+        if c != n and (c.endswith("." + n) or c.startswith(n + ".")):
+            raise KaldiFormatError(f"component {c} of node {n} is a merged one: the network has been through nnet3::CollapseModel; "
+                                   "b2k folds batch-norm and dropout itself and takes the model as it was trained")
     names = [n for n, _ in cn]
     inputs = {n: kv["input"] for n, kv in cn}
     i = 0

@@ -190,6 +190,8 @@ def check() -> bool:
                                  check=True, capture_output=True, text=True).stdout
             for adapter in adapters:
                 assert adapter in pre, (tool, adapter)          # the tool's own objects ARE the adapters
+            if "dump-features" not in tool:                     # ... and its CollapseModel call leaves the model as trained
+                assert "B2kLeaveModelAsTrained(nnet3::CollapseModelConfig()" in pre or "B2kLeaveModelAsTrained(CollapseModelConfig()" in pre, tool
             subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1", "-include", hdr] + tflags + [os.path.join(RF.SRC, tool)])
         # ... and the CUDA online tool against kaldi_b200/host/b2k_cuda_pipeline_dropin.h: BatchedThreadedNnet3CudaOnlinePipeline and
         # CudaOnlinePipelineDynamicBatcher become adapters over the b2k streaming pipeline; option structs, result and callback
@@ -204,6 +206,7 @@ def check() -> bool:
                                  check=True, capture_output=True, text=True).stdout
             for adapter in adapters:
                 assert adapter in pre, (name, adapter)
+            assert "B2kLeaveModelAsTrained(nnet3::CollapseModelConfig()" in pre, name
             subprocess.check_call(["g++", "-fsyntax-only", "-DHAVE_CUDA=1", "-include", "b2k_cuda_pipeline_dropin.h"] + tflags + [tool])
     return True
 

@@ -279,3 +279,34 @@ def test_model_from_memory_as_the_nnet3_shims_serialise_it(tmp_path, which):
                 np.testing.assert_allclose(W[k], np.asarray(v).ravel(), err_msg=f"{path} {k}", **tol)
     assert L.b2k_model_read_memory(b"\0Bgarbage", 9, 2, C.byref(C.c_void_p())) != 0
     assert L.b2k_model_read_memory(None, 0, 2, C.byref(C.c_void_p())) != 0
+
+
+@pytest.mark.parametrize("which", ["lda", "tdnn"])
+def test_collapsed_network_is_refused_not_misread(tmp_path, which):
+    """nnet3::CollapseModel merges the LDA front into the first affine ("lda.tdnn1.affine"): such a network is not the model as
+    trained, and both readers say so instead of matching their patterns against it (the tools built with the drop-in headers leave
+    CollapseModel out: kaldi_b200/host/b2k_dropin_common.h).  The same model uncollapsed reads fine."""
+    L = _lib()
+    from oracle import nnet_oracle as NO
+    if not (os.path.exists(NO._SO) or os.path.isdir("/root/reference")):
+        pytest.skip("oracle/_ref nnet3 library not present")
+    arch = NM.arch_tiny_tdnn() if which == "tdnn" else NM.arch_tiny(front=which)
+    Wt = NM.random_weights(arch, seed=3)
+    for collapse in (False, True):
+        R = NO.RefNnet(arch, Wt, collapse=collapse)
+        R.lib.ref_nnet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        p = str(tmp_path / ("c.raw" if collapse else "p.raw"))
+        assert R.lib.ref_nnet_write(R.h, p.encode(), 1) == 0
+        h = C.c_void_p()
+        L.b2k_model_read.argtypes = [C.c_char_p, C.c_int32, C.c_void_p]
+        rc = L.b2k_model_read(p.encode(), 0, C.byref(h))
+        L.b2k_last_error.restype = C.c_char_p
+        if collapse:
+            assert rc != 0 and "CollapseModel" in L.b2k_last_error().decode()
+            from kaldi_b200.kaldi_io import KaldiFormatError
+            with pytest.raises(KaldiFormatError, match="CollapseModel"):
+                NM.load_kaldi_raw(p, frame_subsampling_factor=arch["frame_subsampling_factor"])
+        else:
+            assert rc == 0, L.b2k_last_error().decode()
+            L.b2k_model_destroy.argtypes = [C.c_void_p]
+            L.b2k_model_destroy(h)
