@@ -310,3 +310,30 @@ def test_collapsed_network_is_refused_not_misread(tmp_path, which):
             assert rc == 0, L.b2k_last_error().decode()
             L.b2k_model_destroy.argtypes = [C.c_void_p]
             L.b2k_model_destroy(h)
+
+
+def test_network_as_the_looped_info_leaves_it(tmp_path):
+    """DecodableNnetSimpleLoopedInfo rewrites the i-vector term of the network it is given (nnet-compile-looped.cc:36-75:
+    ReplaceIndex(ivector, t, 0) -> Round(ivector, period)); the looped decodable shim serialises THAT network
+    (b2k_nnet3_shims.h: ModelB2k(info.nnet)).  Both readers take it and see the same layers as before the rewrite."""
+    import re
+    L = _lib()
+    from oracle import nnet_oracle as NO
+    if not (os.path.exists(NO._SO) or os.path.isdir("/root/reference")):
+        pytest.skip("oracle/_ref nnet3 library not present")
+    arch = NM.arch_tiny(front="lda")
+    R = NO.RefNnet(arch, NM.random_weights(arch, seed=3), collapse=False)
+    R.lib.ref_nnet_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    p, q = str(tmp_path / "a.raw"), str(tmp_path / "b.raw")
+    assert R.lib.ref_nnet_write(R.h, p.encode(), 0) == 0
+    txt = open(p, errors="replace").read()
+    assert "ReplaceIndex(ivector, t, 0)" in txt
+    open(q, "w").write(re.sub(r"ReplaceIndex\(ivector, t, 0\)", "Round(ivector, 30)", txt))
+    ha, ia, la, _, _ = _read(L, p, 0)
+    hb, ib, lb, _, _ = _read(L, q, 0)
+    assert ia == ib and [_layer_dict(x) for x in la] == [_layer_dict(x) for x in lb]
+    L.b2k_model_destroy.argtypes = [C.c_void_p]
+    L.b2k_model_destroy(ha); L.b2k_model_destroy(hb)
+    a1, _ = NM.load_kaldi_raw(p, frame_subsampling_factor=3)
+    a2, _ = NM.load_kaldi_raw(q, frame_subsampling_factor=3)
+    assert a1["layers"] == a2["layers"]
